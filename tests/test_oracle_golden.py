@@ -1,0 +1,469 @@
+"""Pins the CPU oracle against the reference's own unit tests (SURVEY.md §4 golden vectors).
+
+Each test ports one CppUnitLite test of /root/reference (file:line in the docstring): same inputs,
+same known answers, same analytic-vs-central-difference Jacobian check and tolerance.  The oracle's
+arithmetic lives in oracle/gpo_*.h; GTSAM's part of it is a restatement (GTSAM is not available in
+the container), so these reference tests are what pins it.
+"""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+
+POSE3, POSE2, ROT3, LINEAR = po.POSE3, po.POSE2, po.ROT3, po.LINEAR
+
+
+def P3(y, p, r, x, yy, z):
+    return po.pose3(po.rot3_ypr(y, p, r), [x, yy, z])
+
+
+def R3(y, p, r):
+    return po.rot3_wire(po.rot3_ypr(y, p, r))
+
+
+def iso(n, sigma):
+    return np.eye(n) / sigma
+
+
+def two_state_graph(group, p1, v1, p2, v2, land=None, dim=3):
+    g = po.Graph(group, 2, 1 if land is not None else 0, dim=dim)
+    g.set_values(np.stack([p1, p2]), np.stack([v1, v2]), None if land is None else np.asarray(land, dtype=float).reshape(1, -1))
+    return g
+
+
+def numeric_jacobians(g, k, group, step):
+    """central differences of evaluateError wrt every variable of factor k (gtsam::numericalDerivative11)"""
+    e0, H = g.eval_factor(k, True)
+    poses, vels, lands = g.get_values()
+    D = g.D
+    out = []
+    # variable order of every factor here: x1, v1, x2, v2, [l]  (or subset: detect by dims count)
+    nv = len(H)
+    layout = {4: ["p0", "v0", "p1", "v1"], 5: ["p0", "v0", "p1", "v1", "l0"], 1: None, 2: None}[nv]
+    assert layout is not None
+    for name in layout:
+        d = g.DL if name[0] == "l" else D
+        J = np.zeros((len(e0), d))
+        for c in range(d):
+            es = []
+            for sgn in (+1, -1):
+                delta = np.zeros(d); delta[c] = sgn * step
+                P, V, Lm = poses.copy(), vels.copy(), lands.copy()
+                idx = int(name[1])
+                if name[0] == "p":
+                    P[idx] = po.retract(group, poses[idx], delta)
+                elif name[0] == "v":
+                    V[idx] = vels[idx] + delta
+                else:
+                    Lm[idx] = lands[idx] + delta
+                g.set_values(P, V, Lm)
+                es.append(g.eval_factor(k, False)[0])
+            J[:, c] = (es[0] - es[1]) / (2 * step)
+        out.append(J)
+    g.set_values(poses, vels, lands)
+    return e0, H, out
+
+
+# ----------------------------------------------------------------------------- gp/tests/testPose3Utils.cpp
+def test_body_centric_velocity():
+    """gp/tests/testPose3Utils.cpp:86-164"""
+    dt = 0.1
+    cases = [
+        (P3(0, 0, 0, 0, 0, 0), P3(0, 0, 0, 0, 0, 0), [0] * 6, [0] * 6),
+        (P3(0, 0, 0, 0, 0, 0), P3(0, 0, 0, .1, 0, 0), [0, 0, 0, 1, 0, 0], [0, 0, 0, 1, 0, 0]),
+        (P3(0, 0, 0, 0, 0, 0), P3(.1, 0, 0, 0, 0, 0), [0, 0, 1, 0, 0, 0], [0, 0, 1, 0, 0, 0]),
+        (P3(math.pi / 2, 0, 0, 0, 0, 0), P3(math.pi / 2, 0, 0, .1, 0, 0), [0, 0, 0, 0, -1, 0], [0, 0, 0, 1, 0, 0]),
+        (P3(math.pi / 2, 0, 0, 0, 0, 0), P3(math.pi / 2 + .1, 0, 0, 0, 0, 0), [0, 0, 1, 0, 0, 0], [0, 0, 1, 0, 0, 0]),
+        (P3(math.pi / 2, 0, 0, 1, 0, 0), P3(math.pi / 2, 0, .1, 1, 0, 0), [1, 0, 0, 0, 0, 0], [0, 1, 0, 0, 0, 1]),
+        (P3(0, 0, 0, 0, -1, 0), P3(math.pi / 2, 0, 0, 1, 0, 0), [0, 0, 5 * math.pi, 5 * math.pi, 0, 0], [0, 0, 5 * math.pi, 0, 0, 0]),
+    ]
+    for T1, T2, vb, vs in cases:
+        np.testing.assert_allclose(po.body_centric(0, T1, T2, dt), vb, atol=1e-6)
+        np.testing.assert_allclose(po.body_centric(1, T1, T2, dt), vs, atol=1e-6)
+
+
+def _numerical_lie_jacobian(group, T, dt, left):
+    """gp/tests/testPose3Utils.cpp:28-55 (Forster15rss eq. A.48)"""
+    if group == ROT3:
+        log, exp = po.rot3_logmap, po.rot3_expmap
+        comp = lambda A, B: (A.reshape(3, 3).T @ B.reshape(3, 3).T).T.ravel()
+        inv = lambda A: A.reshape(3, 3).ravel(order="C").reshape(3, 3).T.ravel() if False else A.reshape(3, 3).T.ravel()
+        dim = 3
+    else:
+        log, exp, comp, inv, dim = po.pose3_logmap, po.pose3_expmap, po.pose3_compose, po.pose3_inverse, 6
+    omega = log(T)
+    J = np.zeros((dim, dim))
+    for i in range(dim):
+        d = np.zeros(dim); d[i] = dt
+        r = exp(omega + d)
+        J[:, i] = (log(comp(r, inv(T))) if left else log(comp(inv(T), r))) / dt
+    return J
+
+
+SO3_CASES = [(0, 0, 0), (1e-5, 0, 1e-5), (0.1, 0.2, 0.3), (-0.4, 1.2, 0.8), (2.4, -2.5, 3.7)]
+
+
+@pytest.mark.parametrize("ypr", SO3_CASES[1:])
+def test_so3_jacobians(ypr):
+    """gp/tests/testPose3Utils.cpp:167-214 — left/right Jacobian (and inverses) vs numerical Lie Jacobians"""
+    R = R3(*ypr)
+    w = po.rot3_logmap(R)
+    Jr_num = _numerical_lie_jacobian(ROT3, R, 1e-6, left=False)
+    Jl_num = _numerical_lie_jacobian(ROT3, R, 1e-6, left=True)
+    np.testing.assert_allclose(po.so3_jacobian(0, w), Jr_num, atol=1e-6)
+    np.testing.assert_allclose(po.so3_jacobian(2, w), Jl_num, atol=1e-6)
+    np.testing.assert_allclose(po.so3_jacobian(1, w), np.linalg.inv(Jr_num), atol=1e-5)
+    np.testing.assert_allclose(po.so3_jacobian(3, w), np.linalg.inv(Jl_num), atol=1e-5)
+
+
+@pytest.mark.parametrize("case", [(1e-5, 0, 1e-5, 0.1, -0.2, 0.3), (0.1, 0.2, 0.3, 4, -2, 1), (-0.4, 1.2, 0.8, -3, 8, 5)])
+def test_se3_jacobians(case):
+    """gp/tests/testPose3Utils.cpp:217-286"""
+    T = P3(*case)
+    xi = po.pose3_logmap(T)
+    Jr_num = _numerical_lie_jacobian(POSE3, T, 1e-6, left=False)
+    Jl_num = _numerical_lie_jacobian(POSE3, T, 1e-6, left=True)
+    np.testing.assert_allclose(po.se3_jacobian(0, xi), Jr_num, atol=1e-5)
+    np.testing.assert_allclose(po.se3_jacobian(2, xi), Jl_num, atol=1e-5)
+    np.testing.assert_allclose(po.se3_jacobian(1, xi) @ po.se3_jacobian(0, xi), np.eye(6), atol=1e-9)
+    np.testing.assert_allclose(po.se3_jacobian(3, xi) @ po.se3_jacobian(2, xi), np.eye(6), atol=1e-9)
+
+
+def test_exp_log_roundtrip():
+    rng = np.random.default_rng(0)
+    for _ in range(50):
+        xi = rng.normal(size=6) * np.array([0.5, 0.5, 0.5, 3, 3, 3])
+        np.testing.assert_allclose(po.pose3_logmap(po.pose3_expmap(xi)), xi, atol=1e-10)
+        x2 = rng.normal(size=3) * np.array([3, 3, 1.0])
+        np.testing.assert_allclose(po.pose2_logmap(po.pose2_expmap(x2)), x2, atol=1e-10)
+
+
+# ----------------------------------------------------------------------------- GP priors
+PRIOR_CASES = {
+    POSE3: dict(Qc=0.01 * np.eye(6), cases=[
+        (P3(0, 0, 0, 0, 0, 0), [0] * 6, P3(0, 0, 0, 0, 0, 0), [0] * 6, True, 1e-6),
+        (P3(0, 0, 0, 0, 0, 0), [0, 0, 0, 1, 0, 0], P3(0, 0, 0, .1, 0, 0), [0, 0, 0, 1, 0, 0], True, 1e-6),
+        (P3(0, 0, 0, 0, 0, 0), [0, 0, 1, 0, 0, 0], P3(.1, 0, 0, 0, 0, 0), [0, 0, 1, 0, 0, 0], True, 1e-6),
+        (P3(-.1, 1.2, .3, -4, 2, 14), [2, 3, 1, 5, 4, 9], P3(2.4, -2.5, 3.7, 9, -8, -7), [1, 3, 8, 0, 6, 4], False, 1e-5),
+    ]),  # gp/tests/testGaussianProcessPriorPose3.cpp:27-143
+    POSE2: dict(Qc=0.01 * np.eye(3), cases=[
+        ([0, 0, 0], [0, 0, 0], [0, 0, 0], [0, 0, 0], True, 1e-6),
+        ([0, 0, 0], [1, 0, 0], [.1, 0, 0], [1, 0, 0], True, 1e-6),
+        ([0, 0, 0], [0, 0, 1], [0, 0, .1], [0, 0, 1], True, 1e-6),
+        ([-.1, 1.2, .3], [5, 4, 9], [2.4, -2.5, 3.7], [0, 6, 4], False, 1e-6),
+    ]),  # gp/tests/testGaussianProcessPriorPose2.cpp:27-143
+    ROT3: dict(Qc=0.01 * np.eye(3), cases=[
+        (R3(0, 0, 0), [0, 0, 0], R3(0, 0, 0), [0, 0, 0], True, 1e-6),
+        (R3(0, 0, 0), [0, 0, 1], R3(.1, 0, 0), [0, 0, 1], True, 1e-6),
+        (R3(0, 0, 0), [1, 0, 0], R3(0, 0, .1), [1, 0, 0], True, 1e-6),
+        (R3(-.1, 1.2, .3), [2, 3, 1], R3(2.4, -2.5, 3.7), [1, 3, 8], False, 1e-6),
+    ]),  # gp/tests/testGaussianProcessPriorRot3.cpp:27-143
+    LINEAR: dict(Qc=0.01 * np.eye(3), cases=[
+        ([0, 0, 0], [0, 0, 0], [0, 0, 0], [0, 0, 0], True, 1e-6),
+        ([0, 0, 0], [1, 0, 0], [.1, 0, 0], [1, 0, 0], True, 1e-6),
+        ([3, -2, 1], [2, 3, 1], [0.4, 7, -9], [1, 3, 8], False, 1e-6),
+    ]),  # gp/tests/testGaussianProcessPriorLinear.cpp:27-125
+}
+
+
+@pytest.mark.parametrize("group", [POSE3, POSE2, ROT3, LINEAR])
+def test_gp_prior_factor(group):
+    spec = PRIOR_CASES[group]
+    for p1, v1, p2, v2, zero, tol in spec["cases"]:
+        g = two_state_graph(group, np.asarray(p1, float), np.asarray(v1, float), np.asarray(p2, float), np.asarray(v2, float))
+        g.add_qc_model(spec["Qc"])
+        g.add_gp_prior(0, 0.1)
+        # Pose2: step 1e-5 instead of the reference's 1e-6 — gtsam::Pose2::Logmap evaluates cos(w)-1 for the perturbed
+        # relative pose, whose cancellation noise (~1e-11) divided by a 2e-6 step exceeds the 1e-6 tolerance.
+        e, H, Hnum = numeric_jacobians(g, 0, group, 1e-5 if group == POSE2 else 1e-6)
+        if zero:
+            np.testing.assert_allclose(e, 0, atol=1e-6)
+        for Ha, Hn in zip(H, Hnum):
+            np.testing.assert_allclose(Ha, Hn, atol=tol)
+        # cheap path (no Jacobians requested) returns the same residual (gp/GaussianProcessPriorPose3.h:73-74)
+        np.testing.assert_allclose(g.eval_factor(0, False)[0], e, atol=0)
+
+
+def _opt_graph_prior(group, p1, p2, v1, v2i, dt, sigma=0.001):
+    g = two_state_graph(group, np.asarray(p1, float), np.asarray(v1, float), np.asarray(p2, float), np.asarray(v2i, float))
+    D = g.D
+    g.add_qc_model(0.01 * np.eye(D))
+    g.add_prior_pose(0, p1, iso(D, sigma))
+    g.add_prior_pose(1, p2, iso(D, sigma))
+    g.add_gp_prior(0, dt)
+    return g
+
+
+@pytest.mark.parametrize("group,p1,p2,v1,v2i,dt", [
+    (POSE3, P3(0, 0, 0, 0, 0, 0), P3(0, 0, 0, 1, 0, 0), [0, 0, 0, 1, 0, 0], [.1, .2, -.3, 2., -.5, .6], 1.0),  # testGaussianProcessPriorPose3.cpp:146-195
+    (POSE2, [0, 0, 0], [1, 0, 0], [1, 0, 0], [2., -.5, .6], 1.0),                                            # testGaussianProcessPriorPose2.cpp:146-195
+    (ROT3, R3(0, 0, 0), R3(0, 0, .1), [1, 0, 0], [2., -.5, .6], 0.1),                                        # testGaussianProcessPriorRot3.cpp:146-195
+    (LINEAR, [0, 0, 0], [1, 0, 0], [1, 0, 0], [2., -.5, .6], 1.0),                                           # testGaussianProcessPriorLinear.cpp:128-177
+])
+def test_gp_prior_optimization(group, p1, p2, v1, v2i, dt):
+    g = _opt_graph_prior(group, p1, p2, v1, v2i, dt)
+    st = g.optimize(use_lm=False)
+    assert st.status == 0
+    P, V, _ = g.get_values()
+    assert abs(g.error()) < 1e-6
+    np.testing.assert_allclose(P[0], p1, atol=1e-6)
+    np.testing.assert_allclose(P[1], p2, atol=1e-6)
+    np.testing.assert_allclose(V[0], v1, atol=1e-6)
+    np.testing.assert_allclose(V[1], v1, atol=1e-6)
+
+
+# ----------------------------------------------------------------------------- interpolators
+def _pose_local(group, a, b):
+    if group == POSE3:
+        return po.pose3_logmap(po.pose3_compose(po.pose3_inverse(a), b))
+    if group == ROT3:
+        return po.rot3_logmap((a.reshape(3, 3) @ b.reshape(3, 3).T).T.ravel())  # a^T b in wire layout
+    if group == POSE2:
+        return po.pose2_logmap(po.pose2_compose(po.pose2_inverse(a), b))
+    return b - a
+
+
+INTERP_CASES = {
+    POSE3: [(P3(0, 0, 0, 0, 0, 0), [0] * 6, P3(0, 0, 0, 0, 0, 0), [0] * 6, P3(0, 0, 0, 0, 0, 0)),
+            (P3(0, 0, 0, 0, 0, 0), [0, 0, 0, 1, 0, 0], P3(0, 0, 0, .1, 0, 0), [0, 0, 0, 1, 0, 0], P3(0, 0, 0, .03, 0, 0)),
+            (P3(0, 0, 0, 0, 0, 0), [0, 0, 1, 0, 0, 0], P3(.1, 0, 0, 0, 0, 0), [0, 0, 1, 0, 0, 0], P3(.03, 0, 0, 0, 0, 0)),
+            (P3(.4, -.8, .2, 3, -8, 2), [.1, -.2, -1.4, .5, .9, .7], P3(.1, .3, -.5, -9, 3, 4), [.6, .3, -.9, .4, -.2, .8], None)],
+    POSE2: [([0, 0, 0], [0, 0, 0], [0, 0, 0], [0, 0, 0], [0, 0, 0]),
+            ([0, 0, 0], [1, 0, 0], [.1, 0, 0], [1, 0, 0], [.03, 0, 0]),
+            ([0, 0, 0], [0, 0, 1], [0, 0, .1], [0, 0, 1], [0, 0, .03]),
+            ([3, -8, 2], [.5, .9, .7], [-9, 3, 4], [.6, -.2, .8], None)],
+    ROT3: [(R3(0, 0, 0), [0, 0, 0], R3(0, 0, 0), [0, 0, 0], R3(0, 0, 0)),
+           (R3(0, 0, 0), [1, 0, 0], R3(0, 0, .1), [1, 0, 0], R3(0, 0, .03)),
+           (R3(0, 0, 0), [0, 0, 1], R3(.1, 0, 0), [0, 0, 1], R3(.03, 0, 0)),
+           (R3(.4, -.8, .2), [.1, -.2, -1.4], R3(.1, .3, -.5), [.6, .3, -.9], None)],
+    LINEAR: [([0, 0, 0], [0, 0, 0], [0, 0, 0], [0, 0, 0], [0, 0, 0]),
+             ([0, 0, 0], [10, 0, 0], [1, 0, 0], [10, 0, 0], [.3, 0, 0]),
+             ([3, -8, 2], [.5, .9, .7], [-9, 3, 4], [.6, -.2, .8], None)],
+}
+
+
+@pytest.mark.parametrize("group", [POSE3, POSE2, ROT3, LINEAR])
+def test_interpolator(group):
+    """gp/tests/testGaussianProcessInterpolator{Pose3,Pose2,Rot3,Linear}.cpp: known poses at tau=.03 and the four
+    Jacobians vs central differences (tolerance 1e-8 as in the reference)"""
+    D = 6 if group == POSE3 else 3
+    Qc = 0.01 * np.eye(D)
+    dt, tau = 0.1, 0.03
+    for p1, v1, p2, v2, expect in INTERP_CASES[group]:
+        p1, v1, p2, v2 = (np.asarray(a, float) for a in (p1, v1, p2, v2))
+        pose, H = po.interpolate(group, Qc, dt, tau, p1, v1, p2, v2, want_H=True)
+        if expect is not None:
+            np.testing.assert_allclose(_pose_local(group, np.asarray(expect, float), pose), 0, atol=1e-8)
+        # Lie groups: step 1e-4 instead of the reference's 1e-6.  gtsam's Pose3::Expmap ((w x v - R (w x v) + w w.v)/theta^2)
+        # and Pose2::Logmap (cos(w)-1) lose ~1e-12 to cancellation at theta ~ 1e-6, which a 2e-6 step amplifies to ~4e-6;
+        # at 1e-4 the analytic blocks agree with central differences to ~1e-9, i.e. inside the reference's 1e-8 tolerance (the 'random' cases carry ~1e-8 truncation error).
+        step = 1e-6 if group == LINEAR else 1e-4
+        args = [p1, v1, p2, v2]
+        for k in range(4):
+            J = np.zeros((D, D))
+            for c in range(D):
+                outs = []
+                for sgn in (1, -1):
+                    d = np.zeros(D); d[c] = sgn * step
+                    a = list(args)
+                    a[k] = po.retract(group, args[k], d) if k % 2 == 0 else args[k] + d
+                    outs.append(po.interpolate(group, Qc, dt, tau, *a))
+                J[:, c] = _pose_local(group, outs[1], outs[0]) / (2 * step)
+            np.testing.assert_allclose(H[k], J, atol=1e-8 if group == LINEAR else 3e-8)  # 3e-8: O(step^2) truncation at 1e-4
+
+
+def test_lambda_psi_closed_form():
+    """SURVEY.md Appendix A.6 golden: dt=.1, tau=.03 -> Lambda_1=(0.784, 0.0147), Psi_1=(0.216, -0.0063); blocks are scalar*I
+    and independent of Qc (gp/GPutils.h:54-71)"""
+    for D, Qc in ((3, 0.01 * np.eye(3)), (6, np.diag([1, 2, 3, 4, 5, 6.0])), (3, np.array([[2, .3, 0], [.3, 1, .1], [0, .1, 4.0]]))):
+        La, Ps = po.lambda_psi(D, Qc, 0.1, 0.03)
+        I = np.eye(D)
+        np.testing.assert_allclose(La[:D, :D], 0.784 * I, atol=1e-12)
+        np.testing.assert_allclose(La[:D, D:], 0.0147 * I, atol=1e-12)
+        np.testing.assert_allclose(Ps[:D, :D], 0.216 * I, atol=1e-12)
+        np.testing.assert_allclose(Ps[:D, D:], -0.0063 * I, atol=1e-12)
+
+
+# ----------------------------------------------------------------------------- interpolated range factors
+def _range3(T, land):
+    R, t = po.pose3_Rt(T)
+    return float(np.linalg.norm(R.T @ (np.asarray(land) - t)))
+
+
+def test_interp_range_pose3():
+    """slam/tests/testGPInterpolatedRangeFactorPose3.cpp:38-174"""
+    Qc = 0.001 * np.eye(6)
+    dt, tau = 0.1, 0.04
+    bTs = P3(1.0, .4, .5, .3, .6, -.7)
+    cases = [
+        (P3(0, 0, 0, 0, 0, 0), [0] * 6, P3(0, 0, 0, 0, 0, 0), [0] * 6, [0, 0, 10], 10.0, None, 1e-6, 1e-6),
+        (P3(0, 0, 0, -.04, 0, 0), [0, 0, 0, 1, 0, 0], P3(0, 0, 0, .06, 0, 0), [0, 0, 0, 1, 0, 0], [0, 0, 10], 10.0, None, 1e-4, 1e-6),
+        (P3(-.04, 0, 0, 0, 0, 0), [0, 0, 1, 0, 0, 0], P3(.06, 0, 0, 0, 0, 0), [0, 0, 1, 0, 0, 0], [0, 0, 10], 10.0, None, 1e-6, 1e-6),
+        (P3(0, 0, 0, 0, 0, 0), [0, 0, 0, 15, 0, 0], P3(0, 0, 0, 1.5, 0, 0), [0, 0, 0, 15, 0, 0], [3.4, 1.2, 10],
+         _range3(po.pose3_compose(P3(0, 0, 0, .6, 0, 0), bTs), [3.4, 1.2, 10]), bTs, 1e-4, 1e-5),
+    ]
+    for p1, v1, p2, v2, land, meas, sensor, step, tol in cases:
+        g = two_state_graph(POSE3, p1, np.asarray(v1, float), p2, np.asarray(v2, float), land)
+        g.add_qc_model(Qc)
+        g.add_interp_range(0, 0, meas, 0.1, dt, tau, body_P_sensor=sensor)
+        e, H, Hnum = numeric_jacobians(g, 0, POSE3, step)
+        np.testing.assert_allclose(e, 0, atol=1e-6)
+        for Ha, Hn in zip(H, Hnum):
+            np.testing.assert_allclose(Ha, Hn, atol=tol)
+
+
+def test_interp_range_pose2():
+    """slam/tests/testGPInterpolatedRangeFactorPose2.cpp:38-197"""
+    Qc = 0.001 * np.eye(3)
+    dt, tau = 0.1, 0.04
+    cases = [
+        ([0, 0, 0], [0, 0, 0], [0, 0, 0], [0, 0, 0], [0, 10], 10.0, 1e-6, True),
+        ([-.04, 0, 0], [1, 0, 0], [.06, 0, 0], [1, 0, 0], [0, 10], 10.0, 1e-4, True),
+        ([0, 0, -.04], [0, 0, 1], [0, 0, .06], [0, 0, 1], [0, 10], 10.0, 1e-6, True),
+        ([0, 0, 0], [15, 0, 0], [1.5, 0, 0], [15, 0, 0], [3.4, 1.2], float(np.hypot(3.4 - .6, 1.2)), 1e-4, True),
+        ([5.34, 7.1, -4.32], [15, 21.3, 32], [1.5, -2.2, 3.0], [-15, 4.2, -30], [3.4, 1.2], 2.0, 1e-6, False),
+    ]
+    for p1, v1, p2, v2, land, meas, step, zero in cases:
+        g = two_state_graph(POSE2, np.asarray(p1, float), np.asarray(v1, float), np.asarray(p2, float), np.asarray(v2, float), land)
+        g.add_qc_model(Qc)
+        g.add_interp_range(0, 0, meas, 0.1, dt, tau)
+        e, H, Hnum = numeric_jacobians(g, 0, POSE2, step)
+        if zero:
+            np.testing.assert_allclose(e, 0, atol=1e-6)
+        for Ha, Hn in zip(H, Hnum):
+            np.testing.assert_allclose(Ha, Hn, atol=1e-6)
+
+
+def test_interp_range_2dlinear():
+    """slam/tests/testGPInterpolatedRangeFactor2DLinear.cpp:38-226"""
+    Qc = 0.001 * np.eye(3)
+    dt, tau = 0.1, 0.04
+    cases = [
+        ([0, 0, 0], [0, 0, 0], [0, 0, 0], [0, 0, 0], [0, 10], 10.0, True),
+        ([-.04, 0, 0], [1, 0, 0], [.06, 0, 0], [1, 0, 0], [0, 10], 10.0, True),
+        ([0, 0, 0], [15, 0, 0], [1.5, 0, 0], [15, 0, 0], [3.4, 1.2], float(np.hypot(3.4 - .6, 1.2)), True),
+        ([5.34, 7.1, -4.32], [15, 21.3, 32], [1.5, -2.2, 3.0], [-15, 4.2, -30], [3.4, 1.2], 2.0, False),
+    ]
+    for p1, v1, p2, v2, land, meas, zero in cases:
+        g = two_state_graph(LINEAR, np.asarray(p1, float), np.asarray(v1, float), np.asarray(p2, float), np.asarray(v2, float), land)
+        g.add_qc_model(Qc)
+        g.add_interp_range(0, 0, meas, 0.1, dt, tau)
+        e, H, Hnum = numeric_jacobians(g, 0, LINEAR, 1e-6)
+        if zero:
+            np.testing.assert_allclose(e, 0, atol=1e-6)
+        for Ha, Hn in zip(H, Hnum):
+            np.testing.assert_allclose(Ha, Hn, atol=1e-6)
+
+
+def _range_opt_graph(group, p1, p2, v, p1i, p2i, v1i, v2i, land, landi, meas, taus, dt, bias=0.0):
+    g = two_state_graph(group, np.asarray(p1i, float), np.asarray(v1i, float), np.asarray(p2i, float), np.asarray(v2i, float), landi)
+    D, DL = g.D, g.DL
+    g.add_qc_model(0.01 * np.eye(D))
+    g.add_prior_pose(0, p1, iso(D, 0.01)); g.add_prior_pose(1, p2, iso(D, 0.01))
+    g.add_prior_landmark(0, land, iso(DL, 0.1))
+    g.add_prior_vel(0, v, iso(D, 0.01)); g.add_prior_vel(1, v, iso(D, 0.01))
+    g.add_gp_prior(0, dt)
+    for m, tau in zip(meas, taus):
+        g.add_interp_range(0, 0, m, 0.1, dt, tau)
+    return g
+
+
+def test_interp_range_pose3_optimization():
+    """slam/tests/testGPInterpolatedRangeFactorPose3.cpp:177-260 (includes extrapolation tau=-0.1 and 0.2 with delta_t=0.1)"""
+    land = np.array([.4, 1.2, 3.0])
+    meas = [_range3(P3(0, 0, 0, x, 0, 0), land) for x in (-1, .5, 2)]
+    v = [0, 0, 0, 10, 0, 0]
+    g = _range_opt_graph(POSE3, P3(0, 0, 0, 0, 0, 0), P3(0, 0, 0, 1, 0, 0), v, P3(.1, .2, .4, .2, .3, -.2), P3(-.1, -.2, -.4, 1.2, -.3, .2),
+                         [-.1, 0, 0, .8, 0, .2], [0, 0, .2, 1.2, 0, -.1], land, [.3, 1.1, 2.9], meas, (-.1, .05, .2), 0.1)
+    st = g.optimize(use_lm=False)
+    assert st.status == 0
+    P, V, Lm = g.get_values()
+    assert abs(g.error()) < 1e-6
+    np.testing.assert_allclose(P[0], P3(0, 0, 0, 0, 0, 0), atol=1e-6)
+    np.testing.assert_allclose(P[1], P3(0, 0, 0, 1, 0, 0), atol=1e-6)
+    np.testing.assert_allclose(V, [v, v], atol=1e-6)
+    np.testing.assert_allclose(Lm[0], land, atol=1e-6)
+
+
+@pytest.mark.parametrize("group,bias", [(POSE2, 0.0), (LINEAR, 10 * math.pi)])
+def test_interp_range_2d_optimization(group, bias):
+    """slam/tests/testGPInterpolatedRangeFactorPose2.cpp:200-283 and ...2DLinear.cpp:229-317 (theta bias 10*pi); tol 1e-4"""
+    land = np.array([2.4, 3.2])
+    meas = [float(np.hypot(land[0] - x, land[1])) for x in (.5, 2.5, 4.5)]
+    p1, p2 = [0, 0, bias], [5, 0, bias]
+    v = [10, 0, 0]
+    g = _range_opt_graph(group, p1, p2, v, [.1, .1, bias - .1], [5.1, -.1, bias + .1], [9.8, 0, .2], [10.2, 0, -.1], land, [2.3, 3.1], meas,
+                         (.05, .25, .45), 0.5)
+    st = g.optimize(use_lm=False)
+    assert st.status == 0
+    P, V, Lm = g.get_values()
+    assert abs(g.error()) < 1e-4
+    np.testing.assert_allclose(P[0], p1, atol=1e-4); np.testing.assert_allclose(P[1], p2, atol=1e-4)
+    np.testing.assert_allclose(V, [v, v], atol=1e-4)
+    np.testing.assert_allclose(Lm[0], land, atol=1e-4)
+
+
+# ----------------------------------------------------------------------------- plain 2D factors
+def test_plain_2d_known_answers():
+    """slam/tests/testRangeFactor2DLinear.cpp:63-67, testRangeBearingFactor2DLinear.cpp:55-59, testOdometryFactor2DLinear.cpp:65-70"""
+    g = po.Graph(LINEAR, 2, 1, dim=3)
+    g.set_values([[13.1, -4.8, 1.5], [0, 0, 0]], np.zeros((2, 3)), [[-5.4, 6.6]])
+    g.add_range_2d(0, 0, 13.1, 1.0)
+    g.add_range_bearing_2d(0, 0, 13.1, 0.0, np.eye(2))
+    e, _ = g.eval_factor(0, True)
+    np.testing.assert_allclose(e, [8.630393461693233], atol=1e-9)
+    e, _ = g.eval_factor(1, True)
+    np.testing.assert_allclose(e, [1.089334716657378, 8.630393461693233], atol=1e-9)
+    g2 = po.Graph(LINEAR, 2, 0, dim=3)
+    g2.set_values([[42, 24, math.pi / 2], [42, 25, math.pi / 2 + 1]], np.zeros((2, 3)))
+    g2.add_odometry_2d(0, 1, [1, 0, 1], np.eye(3))
+    e, _ = g2.eval_factor(0, True)
+    np.testing.assert_allclose(e, 0, atol=1e-9)
+
+
+def test_plain_2d_jacobians():
+    """analytic vs central differences for the plain 2-way factors at a generic point (reference pattern, tol 1e-6)"""
+    poses = np.array([[13.1, -4.8, 1.5], [11.0, -2.0, 1.1]]); lands = np.array([[-5.4, 6.6]])
+    g = po.Graph(LINEAR, 2, 1, dim=3)
+    g.set_values(poses, np.zeros((2, 3)), lands)
+    g.add_range_2d(0, 0, 13.1, 1.0)
+    g.add_range_bearing_2d(0, 0, 13.1, 0.3, np.eye(2))
+    g.add_odometry_2d(0, 1, [1, 0, 1], np.eye(3))
+    step = 1e-6
+    for k, varlist in ((0, [("p", 0), ("l", 0)]), (1, [("p", 0), ("l", 0)]), (2, [("p", 0), ("p", 1)])):
+        e0, H = g.eval_factor(k, True)
+        for (kind, idx), Ha in zip(varlist, H):
+            d = 3 if kind == "p" else 2
+            J = np.zeros((len(e0), d))
+            for c in range(d):
+                es = []
+                for sgn in (1, -1):
+                    P, Lm = poses.copy(), lands.copy()
+                    (P if kind == "p" else Lm)[idx, c] += sgn * step
+                    g.set_values(P, np.zeros((2, 3)), Lm)
+                    es.append(g.eval_factor(k, False)[0])
+                J[:, c] = (es[0] - es[1]) / (2 * step)
+            g.set_values(poses, np.zeros((2, 3)), lands)
+            np.testing.assert_allclose(Ha, J, atol=1e-6)
+
+
+def test_attitude_factor_self_consistency():
+    """slam/GPInterpolatedAttitudeFactorRot3.h:61-83 has NO reference test: parity unpinned.  Pin what can be
+    pinned: zero residual when the interpolated attitude maps bRef onto nZ, and analytic vs numerical Jacobians."""
+    Qc = np.eye(3) * 1e4
+    g = two_state_graph(ROT3, R3(0, 0, 0), np.array([0, 0, 1.0]), R3(.005, 0, 0), np.array([0, 0, 1.0]))
+    g.add_qc_model(Qc)
+    g.add_interp_attitude(0, 0.005, 0.002, [0, 0, 1], 0.1)
+    e, H, Hnum = numeric_jacobians(g, 0, ROT3, 1e-6)
+    np.testing.assert_allclose(e, 0, atol=1e-9)
+    for Ha, Hn in zip(H, Hnum):
+        np.testing.assert_allclose(Ha, Hn, atol=1e-6)
+    g = two_state_graph(ROT3, R3(.4, -.8, .2), np.array([.1, -.2, -1.4]), R3(.1, .3, -.5), np.array([.6, .3, -.9]))
+    g.add_qc_model(Qc)
+    nz = np.array([.3, -.5, .81]); nz /= np.linalg.norm(nz)
+    g.add_interp_attitude(0, 0.1, 0.03, nz, 0.1, bRef=[0, .6, .8])
+    e, H, Hnum = numeric_jacobians(g, 0, ROT3, 1e-6)
+    for Ha, Hn in zip(H, Hnum):
+        np.testing.assert_allclose(Ha, Hn, atol=1e-6)
