@@ -1,0 +1,308 @@
+// Per-factor residual + Jacobian arithmetic of the gpslam factor types, written for one
+// thread per factor (all loops compile-time unrolled so every small matrix stays in registers).
+//
+// Reference semantics reproduced (file:line in /root/reference/gpslam):
+//   gp/GaussianProcessPriorPose3.h:60-98, ...Pose2.h:58-82, ...Rot3.h:58-79, ...Linear.h:63-83
+//   gp/GaussianProcessInterpolatorPose3.h:57-105 (+Pose2/Rot3/Linear), GPutils.h:54-71
+//   slam/GPInterpolatedRangeFactor{Pose3,Pose2,2DLinear}.h, slam/GPInterpolatedAttitudeFactorRot3.h
+//   slam/{RangeFactor2DLinear,RangeBearingFactor2DLinear,OdometryFactor2DLinear,RangeFactorPose2}.h
+//   GTSAM PriorFactor / BetweenFactor
+//
+// Output convention: the whitened GTSAM JacobianFactor payload  A = R*H,  b = -R*e  with R the
+// upper-triangular square-root information.  For GP priors R = chol(calcQ_inv(Qc,dt)) =
+// U (x) Rq with U = chol([[12/dt^3,-6/dt^2],[-6/dt^2,4/dt]]) and Rq = chol(Qc^-1)
+// (gp/GPutils.h:33-41, gp/GaussianProcessPriorPose3.h:46).
+#pragma once
+#include "lie.cuh"
+
+namespace gpb {
+
+enum Group { G_POSE3 = 0, G_POSE2 = 1, G_ROT3 = 2, G_LINEAR = 3 };
+
+template <int G> struct GroupTraits;
+template <> struct GroupTraits<G_POSE3> { static constexpr int D = 6, PS = 12, DL = 3; };
+template <> struct GroupTraits<G_POSE2> { static constexpr int D = 3, PS = 3, DL = 2; };
+template <> struct GroupTraits<G_ROT3> { static constexpr int D = 3, PS = 9, DL = 0; };
+template <> struct GroupTraits<G_LINEAR> { static constexpr int D = 3, PS = 3, DL = 2; };  // Linear<3> ("2DLinear" states)
+
+// chol of the 2x2 GP kernel inverse: u11,u12,u22
+struct GpWhiten { double u11, u12, u22; };
+GPB_HD GpWhiten gp_whiten(double dt) {
+  GpWhiten w;
+  w.u11 = sqrt(12.0 / (dt * dt * dt));
+  w.u12 = (-6.0 / (dt * dt)) / w.u11;
+  w.u22 = sqrt(4.0 / dt - w.u12 * w.u12);
+  return w;
+}
+// Hermite interpolation scalars: Lambda_12, Psi_11, Psi_12 of gp/GPutils.h:54-71
+struct InterpCoef { double lam12, psi11, psi12; };
+GPB_HD InterpCoef interp_coef(double dt, double tau) {
+  const double s = tau / dt, s2 = s * s, s3 = s2 * s;
+  InterpCoef c;
+  c.psi11 = 3 * s2 - 2 * s3;
+  c.psi12 = dt * (s3 - s2);
+  c.lam12 = tau - c.psi11 * dt - c.psi12;
+  return c;
+}
+
+// y = Rq x for upper-triangular Rq (DxD column-major), vectors as arrays
+template <int D> GPB_HD void triu_mul(const double* Rq, const double* x, double* y) {
+#pragma unroll
+  for (int r = 0; r < D; r++) {
+    double s = 0;
+#pragma unroll
+    for (int k = r; k < D; k++) s += Rq[r + k * D] * x[k];
+    y[r] = s;
+  }
+}
+// whiten one (top,bot) column pair of a GP prior: out[0:D] = Rq(u11 top + u12 bot), out[D:2D] = u22 Rq bot
+template <int D> GPB_HD void gp_whiten_col(const GpWhiten& w, const double* Rq, const double* top, const double* bot, double sign, double* out) {
+  double t[D], y[D];
+#pragma unroll
+  for (int k = 0; k < D; k++) t[k] = sign * (w.u11 * top[k] + w.u12 * bot[k]);
+  triu_mul<D>(Rq, t, y);
+#pragma unroll
+  for (int k = 0; k < D; k++) out[k] = y[k];
+#pragma unroll
+  for (int k = 0; k < D; k++) t[k] = sign * w.u22 * bot[k];
+  triu_mul<D>(Rq, t, y);
+#pragma unroll
+  for (int k = 0; k < D; k++) out[D + k] = y[k];
+}
+
+// ================================================================= GP prior, SE(3)
+struct GpPose3 {
+  X6 e_top, e_bot;
+  L6 a, b, Da, Db;  // a = Jl^-1(r) (H1_top = -a), b = Jr^-1(r) (H3_top), Da = D a, Db = D b
+};
+// state record: [pose(12) | vel(6)]
+GPB_HD void gp_prior_pose3_eval(const double* s1, const double* s2, double dt, bool wantJ, GpPose3& o) {
+  const P3 T1 = p3_from_wire(s1), T2 = p3_from_wire(s2);
+  const X6 v1 = x6_from(s1 + 12), v2 = x6_from(s2 + 12);
+  const X6 r = se3_logmap(p3_between(T1, T2));
+  const JrinvCoef c = se3_jrinv_coef(dot(r.w, r.w));
+  o.b = se3_jrinv(r, c);
+  o.e_top = r - dt * v1;
+  o.e_bot = o.b * v2 - v1;
+  if (wantJ) {
+    o.a = o.b - l6_ad(r);  // Jl^-1 = Jr^-1 - ad
+    const L6 D = se3_djrinv(r, v2, c);
+    o.Da = D * o.a;
+    o.Db = D * o.b;
+  }
+}
+// whitened column c (0..24; 24 = rhs) of the 12x25 [A|b]; CV must be a compile-time constant after unrolling
+template <int VAR, int C> GPB_HD void gp_prior_pose3_col(const GpPose3& o, const GpWhiten& w, const double* Rq, double dt, double* out) {
+  double top[6], bot[6];
+  if (VAR == 0) {  // T1: [-a ; -Da]
+#pragma unroll
+    for (int k = 0; k < 6; k++) { top[k] = elem(o.a, k, C); bot[k] = elem(o.Da, k, C); }
+    gp_whiten_col<6>(w, Rq, top, bot, -1.0, out);
+  } else if (VAR == 1) {  // v1: [-dt I ; -I]
+#pragma unroll
+    for (int k = 0; k < 6; k++) { top[k] = (k == C) ? dt : 0.0; bot[k] = (k == C) ? 1.0 : 0.0; }
+    gp_whiten_col<6>(w, Rq, top, bot, -1.0, out);
+  } else if (VAR == 2) {  // T2: [b ; Db]
+#pragma unroll
+    for (int k = 0; k < 6; k++) { top[k] = elem(o.b, k, C); bot[k] = elem(o.Db, k, C); }
+    gp_whiten_col<6>(w, Rq, top, bot, 1.0, out);
+  } else if (VAR == 3) {  // v2: [0 ; b]
+#pragma unroll
+    for (int k = 0; k < 6; k++) { top[k] = 0.0; bot[k] = elem(o.b, k, C); }
+    gp_whiten_col<6>(w, Rq, top, bot, 1.0, out);
+  } else {  // rhs = -R e
+#pragma unroll
+    for (int k = 0; k < 6; k++) { top[k] = elem(o.e_top, k); bot[k] = elem(o.e_bot, k); }
+    gp_whiten_col<6>(w, Rq, top, bot, -1.0, out);
+  }
+}
+
+// ================================================================= GP prior, D = 3 groups
+// Unwhitened: J_top = [Ja, -dt I, Jb, 0], J_bot = [0, -I, 0, +I] (Pose2/Rot3);  Linear: J_top = [I, dt I, -I, 0], J_bot = [0, I, 0, -I]
+struct GpD3 { V3 e_top, e_bot; M3 Ja, Jb; double s_v1, s_v2; };  // s_v1: sign of the v1 blocks (-1 Lie, +1 linear); s_v2 likewise for v2 bottom
+template <int G> GPB_HD void gp_prior_d3_eval(const double* s1, const double* s2, double dt, bool wantJ, GpD3& o) {
+  constexpr int PS = GroupTraits<G>::PS;
+  const V3 v1 = v3(s1[PS], s1[PS + 1], s1[PS + 2]), v2 = v3(s2[PS], s2[PS + 1], s2[PS + 2]);
+  if (G == G_POSE2) {
+    const P2 T1 = p2(s1[0], s1[1], s1[2]), T2 = p2(s2[0], s2[1], s2[2]);
+    const P2 T12 = p2_between(T1, T2);
+    const V3 r = se2_logmap(T12);
+    o.e_top = r - dt * v1; o.e_bot = v2 - v1;
+    if (wantJ) {
+      const M3 Hlog = se2_dlog(r);
+      // Hlog * Hcomp1 * Hinv = Hlog * Ad(T2^-1) * (-Ad(T1)) = -Hlog * Ad(T12^-1)
+      o.Ja = -(Hlog * p2_adjoint(p2_inverse(T12)));
+      o.Jb = Hlog;
+    }
+    o.s_v1 = -1.0; o.s_v2 = 1.0;
+  } else if (G == G_ROT3) {
+    const M3 R1 = m3_from_wire(s1), R2 = m3_from_wire(s2);
+    const M3 R12 = transpose(R1) * R2;
+    const V3 r = so3_logmap(R12);
+    o.e_top = r - dt * v1; o.e_bot = v2 - v1;
+    if (wantJ) {
+      const M3 Hlog = so3_jrinv(r);
+      o.Ja = -(Hlog * transpose(R12));  // Hlog * R2^T * (-R1)
+      o.Jb = Hlog;
+    }
+    o.s_v1 = -1.0; o.s_v2 = 1.0;
+  } else {  // linear: e = Phi(dt) x1 - x2
+    const V3 p1 = v3(s1[0], s1[1], s1[2]), p2_ = v3(s2[0], s2[1], s2[2]);
+    o.e_top = p1 + dt * v1 - p2_; o.e_bot = v1 - v2;
+    o.Ja = m3_identity(); o.Jb = -m3_identity();
+    o.s_v1 = 1.0; o.s_v2 = -1.0;
+  }
+}
+template <int VAR, int C> GPB_HD void gp_prior_d3_col(const GpD3& o, const GpWhiten& w, const double* Rq, double dt, double* out) {
+  double top[3], bot[3];
+  if (VAR == 0) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) { top[k] = o.Ja.m[3 * k + C]; bot[k] = 0.0; }
+  } else if (VAR == 1) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) { top[k] = (k == C) ? o.s_v1 * dt : 0.0; bot[k] = (k == C) ? o.s_v1 : 0.0; }
+  } else if (VAR == 2) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) { top[k] = o.Jb.m[3 * k + C]; bot[k] = 0.0; }
+  } else if (VAR == 3) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) { top[k] = 0.0; bot[k] = (k == C) ? o.s_v2 : 0.0; }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 3; k++) { top[k] = -elem(o.e_top, k); bot[k] = -elem(o.e_bot, k); }
+  }
+  gp_whiten_col<3>(w, Rq, top, bot, 1.0, out);
+}
+
+// ================================================================= "extra" factors (measurement rows attached to an interval)
+// Every extra factor produces m whitened rows over [state_a (2D) | state_b (2D) | landmark (DL) | rhs].
+// state_a / state_b are the two support states (i, i+1) of its interval (or (i, j) for a loop closure).
+enum ExtraKind {
+  X_INTERP_RANGE = 1, X_INTERP_ATTITUDE = 2, X_PRIOR_POSE = 3, X_PRIOR_VEL = 4, X_PRIOR_LANDMARK = 5,
+  X_BETWEEN = 6, X_RANGE_2D = 7, X_RANGE_BEARING_2D = 8, X_ODOMETRY_2D = 9
+};
+constexpr int XP_STRIDE = 56;  // doubles of parameters per extra factor (see ExtraParams below)
+// parameter record (doubles): [0] delta_t [1] tau [2] z [3] z2 [4..15] aux (sensor pose / nZ,bRef / value) [16] has_sensor
+// [20..55] sqrt information R (m x m column-major, upper triangular); for scalar factors R[0] = 1/sigma.
+
+GPB_HD X6 rowmul(const X6& h, const L6& M) { return x6(tmul(M.A, h.w) + tmul(M.B, h.v), tmul(M.C, h.v)); }  // h^T M as a row
+
+// slam/GPInterpolatedRangeFactorPose3.h:64-98 — unwhitened residual and 1x6 Jacobian rows, 1x3 landmark row
+struct Range3Out { double e; X6 H1, H2, H3, H4; V3 H5; };
+GPB_HD void interp_range_pose3(const double* s1, const double* s2, const double* land, const double* prm, bool wantJ, Range3Out& o) {
+  const double dt = prm[0], tau = prm[1], z = prm[2];
+  const P3 T1 = p3_from_wire(s1), T2 = p3_from_wire(s2);
+  const X6 v1 = x6_from(s1 + 12), v2 = x6_from(s2 + 12);
+  const X6 r = se3_logmap(p3_between(T1, T2));
+  const JrinvCoef c = se3_jrinv_coef(dot(r.w, r.w));
+  const L6 b = se3_jrinv(r, c);
+  const X6 f = b * v2;
+  const InterpCoef ic = interp_coef(dt, tau);
+  const X6 xi = ic.lam12 * v1 + ic.psi11 * r + ic.psi12 * f;
+  const P3 dT = se3_expmap(xi);
+  P3 T = p3_compose(T1, dT);
+  const bool has_sensor = prm[16] != 0.0;
+  P3 S;
+  if (has_sensor) { S = p3_from_wire(prm + 4); T = p3_compose(T, S); }
+  const V3 q = tmul(T.R, v3(land[0], land[1], land[2]) - T.t);
+  const double rng = sqrt(dot(q, q));
+  o.e = rng - z;
+  if (!wantJ) return;
+  const V3 qh = (1.0 / rng) * q;
+  X6 hpose = x6(v3(0, 0, 0), -qh);  // qh^T [ [q]x , -I ] = [0, -qh^T]
+  if (has_sensor) hpose = rowmul(hpose, l6_adjoint(p3_inverse(S)));
+  const X6 g = rowmul(hpose, se3_jr(xi));  // Hpose * Hexp
+  const L6 a = b - l6_ad(r);
+  const L6 D = se3_djrinv(r, v2, c);
+  const X6 gD = rowmul(g, D);
+  const X6 k = ic.psi11 * g + ic.psi12 * gD;
+  o.H1 = rowmul(hpose, l6_adjoint(p3_inverse(dT))) - rowmul(k, a);
+  o.H2 = ic.lam12 * g;
+  o.H3 = rowmul(k, b);
+  o.H4 = ic.psi12 * rowmul(g, b);
+  o.H5 = T.R * qh;  // (qh^T R^T)^T
+}
+
+// slam/GPInterpolatedRangeFactorPose2.h:64-98 and slam/GPInterpolatedRangeFactor2DLinear.h:60-88
+struct Range2Out { double e; V3 H1, H2, H3, H4; double H5[2]; };
+template <int G> GPB_HD void interp_range_2d(const double* s1, const double* s2, const double* land, const double* prm, bool wantJ, Range2Out& o) {
+  const double dt = prm[0], tau = prm[1], z = prm[2];
+  const InterpCoef ic = interp_coef(dt, tau);
+  const V3 v1 = v3(s1[3], s1[4], s1[5]), v2 = v3(s2[3], s2[4], s2[5]);
+  if (G == G_POSE2) {
+    const P2 T1 = p2(s1[0], s1[1], s1[2]), T2 = p2(s2[0], s2[1], s2[2]);
+    const P2 T12 = p2_between(T1, T2);
+    const V3 r = se2_logmap(T12);
+    const V3 xi = ic.lam12 * v1 + ic.psi11 * r + ic.psi12 * v2;
+    const P2 dT = se2_expmap(xi);
+    P2 T = p2_compose(T1, dT);
+    const bool has_sensor = prm[16] != 0.0;
+    P2 S = p2(prm[4], prm[5], prm[6]);
+    if (has_sensor) T = p2_compose(T, S);
+    const double dx = land[0] - T.x, dy = land[1] - T.y;
+    const double rng = sqrt(dx * dx + dy * dy);
+    o.e = rng - z;
+    if (!wantJ) return;
+    const double hx = dx / rng, hy = dy / rng, c = cos(T.th), s = sin(T.th);
+    V3 hpose = v3(-(hx * c + hy * s), hx * s - hy * c, 0.0);  // D_r_d * [[-c, s, 0],[-s,-c,0]]
+    if (has_sensor) hpose = tmul(p2_adjoint(p2_inverse(S)), hpose);
+    const V3 g = tmul(se2_dexp(xi), hpose);  // row * Hexp
+    const M3 Hlog = se2_dlog(r);
+    const V3 gl = tmul(Hlog, g);
+    o.H1 = tmul(p2_adjoint(p2_inverse(dT)), hpose) - ic.psi11 * tmul(p2_adjoint(p2_inverse(T12)), gl);
+    o.H2 = ic.lam12 * g;
+    o.H3 = ic.psi11 * gl;
+    o.H4 = ic.psi12 * g;
+    o.H5[0] = hx; o.H5[1] = hy;
+  } else {  // 2DLinear: pose = Lambda_1 x1 + Psi_1 x2 ; theta ignored
+    const double lam11 = 1.0 - ic.psi11;
+    const double px = lam11 * s1[0] + ic.lam12 * v1.x + ic.psi11 * s2[0] + ic.psi12 * v2.x;
+    const double py = lam11 * s1[1] + ic.lam12 * v1.y + ic.psi11 * s2[1] + ic.psi12 * v2.y;
+    const double dx = land[0] - px, dy = land[1] - py;
+    const double rng = sqrt(dx * dx + dy * dy);
+    o.e = rng - z;
+    if (!wantJ) return;
+    double hx, hy;
+    if (fabs(rng) > 1e-10) { hx = dx / rng; hy = dy / rng; } else { hx = 1; hy = 1; }  // gtsam::Point2::norm
+    const V3 hpose = v3(-hx, -hy, 0.0);
+    o.H1 = lam11 * hpose; o.H2 = ic.lam12 * hpose; o.H3 = ic.psi11 * hpose; o.H4 = ic.psi12 * hpose;
+    o.H5[0] = hx; o.H5[1] = hy;
+  }
+}
+
+// slam/GPInterpolatedAttitudeFactorRot3.h:61-83 (+ gtsam::AttitudeFactor::attitudeError): 2 rows
+struct AttOut { double e[2]; V3 H1[2], H2[2], H3[2], H4[2]; };
+GPB_HD void interp_attitude_rot3(const double* s1, const double* s2, const double* prm, bool wantJ, AttOut& o) {
+  const double dt = prm[0], tau = prm[1];
+  const V3 nZ = v3(prm[4], prm[5], prm[6]), bRef = v3(prm[7], prm[8], prm[9]);
+  const InterpCoef ic = interp_coef(dt, tau);
+  const M3 R1 = m3_from_wire(s1), R2 = m3_from_wire(s2);
+  const V3 v1 = v3(s1[9], s1[10], s1[11]), v2 = v3(s2[9], s2[10], s2[11]);
+  const M3 R12 = transpose(R1) * R2;
+  const V3 r = so3_logmap(R12);
+  const V3 xi = ic.lam12 * v1 + ic.psi11 * r + ic.psi12 * v2;
+  const M3 dR = so3_expmap(xi);
+  const M3 R = R1 * dR;
+  const V3 nRef = R * bRef;
+  V3 z1, z2; unit3_basis(nZ, z1, z2);
+  o.e[0] = dot(z1, nRef); o.e[1] = dot(z2, nRef);
+  if (!wantJ) return;
+  // Hrot = Bz^T Bq Bq^T (-R [bRef]x);  Bq Bq^T = I - nRef nRef^T
+  const M3 dn = -(R * skew(bRef));
+  const M3 P = m3_identity() - outer(nRef, nRef);
+  const M3 PM = P * dn;
+  const M3 Hexp = so3_jr(xi), Hlog = so3_jrinv(r);
+  const V3 zz[2] = {z1, z2};
+#pragma unroll
+  for (int k = 0; k < 2; k++) {
+    const V3 hrot = tmul(PM, zz[k]);
+    const V3 g = tmul(Hexp, hrot);
+    const V3 gl = tmul(Hlog, g);
+    o.H1[k] = tmul(transpose(dR), hrot) - ic.psi11 * tmul(transpose(R12), gl);  // Hcomp21 = dR^T ; Hlog*R2^T*(-R1) = -Hlog R12^T
+    o.H2[k] = ic.lam12 * g;
+    o.H3[k] = ic.psi11 * gl;
+    o.H4[k] = ic.psi12 * g;
+  }
+}
+
+}  // namespace gpb

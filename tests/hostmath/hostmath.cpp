@@ -1,0 +1,61 @@
+// TEST HARNESS ONLY: compiles the product's __host__ __device__ factor arithmetic
+// (gpslam_b200/csrc/{lie,factors}.cuh) with g++ so CPU tests can compare it with the oracle
+// without a GPU.  Not part of the product path.
+#include "../../gpslam_b200/csrc/factors.cuh"
+using namespace gpb;
+
+template <int VAR, int C, int N> struct EmitP3 {
+  static void run(const GpPose3& o, const GpWhiten& w, const double* Rq, double dt, double* out) {
+    gp_prior_pose3_col<VAR, C>(o, w, Rq, dt, out + (VAR * 6 + C) * 12);
+    EmitP3<VAR, C + 1, N>::run(o, w, Rq, dt, out);
+  }
+};
+template <int VAR, int N> struct EmitP3<VAR, N, N> { static void run(const GpPose3&, const GpWhiten&, const double*, double, double*) {} };
+template <int VAR, int C, int N> struct EmitD3 {
+  static void run(const GpD3& o, const GpWhiten& w, const double* Rq, double dt, double* out) {
+    gp_prior_d3_col<VAR, C>(o, w, Rq, dt, out + (VAR * 3 + C) * 6);
+    EmitD3<VAR, C + 1, N>::run(o, w, Rq, dt, out);
+  }
+};
+template <int VAR, int N> struct EmitD3<VAR, N, N> { static void run(const GpD3&, const GpWhiten&, const double*, double, double*) {} };
+
+extern "C" {
+// out: m x (4D+1) column-major whitened [A|b]
+void hm_gp_prior(int group, const double* s1, const double* s2, double dt, const double* Rq, double* out) {
+  const GpWhiten w = gp_whiten(dt);
+  if (group == G_POSE3) {
+    GpPose3 o; gp_prior_pose3_eval(s1, s2, dt, true, o);
+    EmitP3<0, 0, 6>::run(o, w, Rq, dt, out); EmitP3<1, 0, 6>::run(o, w, Rq, dt, out);
+    EmitP3<2, 0, 6>::run(o, w, Rq, dt, out); EmitP3<3, 0, 6>::run(o, w, Rq, dt, out);
+    gp_prior_pose3_col<4, 0>(o, w, Rq, dt, out + 24 * 12);
+  } else {
+    GpD3 o;
+    if (group == G_POSE2) gp_prior_d3_eval<G_POSE2>(s1, s2, dt, true, o);
+    else if (group == G_ROT3) gp_prior_d3_eval<G_ROT3>(s1, s2, dt, true, o);
+    else gp_prior_d3_eval<G_LINEAR>(s1, s2, dt, true, o);
+    EmitD3<0, 0, 3>::run(o, w, Rq, dt, out); EmitD3<1, 0, 3>::run(o, w, Rq, dt, out);
+    EmitD3<2, 0, 3>::run(o, w, Rq, dt, out); EmitD3<3, 0, 3>::run(o, w, Rq, dt, out);
+    gp_prior_d3_col<4, 0>(o, w, Rq, dt, out + 12 * 6);
+  }
+}
+// unwhitened rows: out = [H1(D) H2(D) H3(D) H4(D) H5(DL) e] per row
+void hm_interp_range(int group, const double* s1, const double* s2, const double* land, const double* prm, double* out) {
+  if (group == G_POSE3) {
+    Range3Out o; interp_range_pose3(s1, s2, land, prm, true, o);
+    for (int k = 0; k < 6; k++) { out[k] = elem(o.H1, k); out[6 + k] = elem(o.H2, k); out[12 + k] = elem(o.H3, k); out[18 + k] = elem(o.H4, k); }
+    out[24] = o.H5.x; out[25] = o.H5.y; out[26] = o.H5.z; out[27] = o.e;
+  } else {
+    Range2Out o;
+    if (group == G_POSE2) interp_range_2d<G_POSE2>(s1, s2, land, prm, true, o); else interp_range_2d<G_LINEAR>(s1, s2, land, prm, true, o);
+    for (int k = 0; k < 3; k++) { out[k] = elem(o.H1, k); out[3 + k] = elem(o.H2, k); out[6 + k] = elem(o.H3, k); out[9 + k] = elem(o.H4, k); }
+    out[12] = o.H5[0]; out[13] = o.H5[1]; out[14] = o.e;
+  }
+}
+void hm_interp_attitude(const double* s1, const double* s2, const double* prm, double* out) {
+  AttOut o; interp_attitude_rot3(s1, s2, prm, true, o);
+  for (int r = 0; r < 2; r++) {
+    for (int k = 0; k < 3; k++) { out[13 * r + k] = elem(o.H1[r], k); out[13 * r + 3 + k] = elem(o.H2[r], k); out[13 * r + 6 + k] = elem(o.H3[r], k); out[13 * r + 9 + k] = elem(o.H4[r], k); }
+    out[13 * r + 12] = o.e[r];
+  }
+}
+}

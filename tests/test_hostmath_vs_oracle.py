@@ -1,0 +1,132 @@
+"""CPU check of the product's __host__ __device__ factor arithmetic (gpslam_b200/csrc/*.cuh, compiled by g++ through
+tests/hostmath) against the oracle on random inputs: whitened GP-prior [A|b] for every group, interpolated range /
+attitude rows.  Tolerances: residuals 1e-11; Jacobians 1e-6 where the oracle carries the reference's 1e-6-step numerical
+differentiation (SE(3) blocks, gp/Pose3utils.cpp:167-179), 1e-10 elsewhere."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def hm():
+    so = os.path.join(HERE, "hostmath", "libhostmath.so")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++", "-o", so, os.path.join(HERE, "hostmath", "hostmath.cpp")], check=True)
+    return C.CDLL(so)
+
+
+def dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def rand_state(rng, group, scale_rot=1.0, scale_t=3.0):
+    if group == po.POSE3:
+        T = po.pose3_expmap(np.concatenate([rng.normal(size=3) * scale_rot, rng.normal(size=3) * scale_t]))
+        return T, rng.normal(size=6)
+    if group == po.ROT3:
+        return po.rot3_expmap(rng.normal(size=3) * scale_rot), rng.normal(size=3)
+    if group == po.POSE2:
+        return np.array([*(rng.normal(size=2) * scale_t), rng.normal() * scale_rot]), rng.normal(size=3)
+    return rng.normal(size=3) * scale_t, rng.normal(size=3)
+
+
+def rand_spd(rng, n):
+    A = rng.normal(size=(n, n))
+    return A @ A.T + n * np.eye(n)
+
+
+@pytest.mark.parametrize("group", [po.POSE3, po.POSE2, po.ROT3, po.LINEAR])
+@pytest.mark.parametrize("small", [False, True])
+def test_gp_prior_whitened(hm, group, small):
+    rng = np.random.default_rng(100 + group)
+    D = 6 if group == po.POSE3 else 3
+    m, ncol = 2 * D, 4 * D + 1
+    for trial in range(40):
+        dt = float(rng.uniform(0.05, 1.5))
+        Qc = rand_spd(rng, D) if trial % 2 else np.eye(D) * rng.uniform(0.01, 2)
+        p1, v1 = rand_state(rng, group)
+        if small:  # trajectory-like: small relative motion (also theta -> 0 branches)
+            step = rng.normal(size=D) * (1e-9 if trial % 5 == 0 else 0.05)
+            p2 = po.retract(group, p1, step) if group != po.POSE2 else po.pose2_compose(p1, po.pose2_expmap(step))
+            v2 = v1 + rng.normal(size=D) * 0.1
+        else:
+            p2, v2 = rand_state(rng, group)
+        g = po.Graph(group, 2, 0)
+        g.set_values(np.stack([p1, p2]), np.stack([v1, v2]))
+        g.add_qc_model(Qc)
+        g.add_gp_prior(0, dt)
+        A, b = g.linearize_factor(0)
+        Ao = np.concatenate(A + [b.reshape(-1, 1)], axis=1)
+        Rq = np.linalg.cholesky(np.linalg.inv(Qc)).T  # upper, Rq^T Rq = Qc^-1
+        out = np.zeros(m * ncol)
+        s1 = np.concatenate([p1, v1]); s2 = np.concatenate([p2, v2])
+        hm.hm_gp_prior(C.c_int(group), dp(s1), dp(s2), C.c_double(dt), dp(np.ascontiguousarray(Rq.T).ravel()), dp(out))
+        Ag = out.reshape(ncol, m).T
+        scale = max(1.0, np.abs(Ao).max())
+        np.testing.assert_allclose(Ag[:, -1], Ao[:, -1], atol=1e-11 * scale)                      # rhs = -R e
+        np.testing.assert_allclose(Ag[:, :-1], Ao[:, :-1], atol=(1e-6 if group == po.POSE3 else 1e-10) * scale)
+
+
+@pytest.mark.parametrize("group", [po.POSE3, po.POSE2, po.LINEAR])
+def test_interp_range_rows(hm, group):
+    rng = np.random.default_rng(7 + group)
+    D = 6 if group == po.POSE3 else 3
+    DL = 3 if group == po.POSE3 else 2
+    for trial in range(40):
+        dt = float(rng.uniform(0.05, 0.5)); tau = float(rng.uniform(-0.5, 1.5) * dt)
+        p1, v1 = rand_state(rng, group)
+        if trial % 2:
+            p2, v2 = rand_state(rng, group)
+        else:
+            step = rng.normal(size=D) * 0.05
+            p2 = po.retract(group, p1, step) if group != po.POSE2 else po.pose2_compose(p1, po.pose2_expmap(step))
+            v2 = v1 + rng.normal(size=D) * 0.1
+        land = rng.normal(size=DL) * 10
+        sensor = None
+        if trial % 3 == 0 and group != po.LINEAR:
+            sensor = rand_state(rng, group, 0.5, 0.5)[0]
+        g = po.Graph(group, 2, 1)
+        g.set_values(np.stack([p1, p2]), np.stack([v1, v2]), land.reshape(1, -1))
+        g.add_qc_model(np.eye(D))
+        z = float(rng.uniform(1, 20))
+        g.add_interp_range(0, 0, z, 0.1, dt, tau, body_P_sensor=sensor)
+        e, H = g.eval_factor(0, True)
+        prm = np.zeros(56); prm[0] = dt; prm[1] = tau; prm[2] = z
+        if sensor is not None:
+            prm[4:4 + len(sensor)] = sensor; prm[16] = 1.0
+        out = np.zeros(4 * D + DL + 1)
+        hm.hm_interp_range(C.c_int(group), dp(np.concatenate([p1, v1])), dp(np.concatenate([p2, v2])), dp(land), dp(prm), dp(out))
+        Ho = np.concatenate([h.ravel() for h in H])
+        scale = max(1.0, np.abs(Ho).max())
+        assert abs(out[-1] - e[0]) < 1e-10 * max(1.0, abs(e[0]))
+        np.testing.assert_allclose(out[:-1], Ho, atol=(1e-6 if group == po.POSE3 else 1e-10) * scale)
+
+
+def test_interp_attitude_rows(hm):
+    rng = np.random.default_rng(11)
+    for trial in range(40):
+        dt = float(rng.uniform(0.005, 0.5)); tau = float(rng.uniform(0, 1) * dt)
+        p1, v1 = rand_state(rng, po.ROT3)
+        p2 = po.retract(po.ROT3, p1, rng.normal(size=3) * (0.05 if trial % 2 else 1.0)); v2 = v1 + rng.normal(size=3) * 0.1
+        nz = rng.normal(size=3); nz /= np.linalg.norm(nz)
+        br = rng.normal(size=3); br /= np.linalg.norm(br)
+        if trial % 4 == 0:
+            nz, br = np.array([0, 0, 1.0]), np.array([0, 0, 1.0])
+        g = po.Graph(po.ROT3, 2, 0)
+        g.set_values(np.stack([p1, p2]), np.stack([v1, v2]))
+        g.add_qc_model(np.eye(3))
+        g.add_interp_attitude(0, dt, tau, nz, 0.1, bRef=br)
+        e, H = g.eval_factor(0, True)
+        prm = np.zeros(56); prm[0] = dt; prm[1] = tau; prm[4:7] = nz; prm[7:10] = br
+        out = np.zeros(26)
+        hm.hm_interp_attitude(dp(np.concatenate([p1, v1])), dp(np.concatenate([p2, v2])), dp(prm), dp(out))
+        for r in range(2):
+            assert abs(out[13 * r + 12] - e[r]) < 1e-11
+            Ho = np.concatenate([h[r] for h in H])
+            np.testing.assert_allclose(out[13 * r:13 * r + 12], Ho, atol=1e-10 * max(1.0, np.abs(Ho).max()))
