@@ -1,0 +1,234 @@
+"""ctypes binding of the C ABI declared in include/gpb.h (one-to-one; no arithmetic happens in Python)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+_LIB = None
+
+GPB_POSE3, GPB_POSE2, GPB_ROT3, GPB_LINEAR = 0, 1, 2, 3
+_PS = {GPB_POSE3: 12, GPB_POSE2: 3, GPB_ROT3: 9, GPB_LINEAR: 3}
+_D = {GPB_POSE3: 6, GPB_POSE2: 3, GPB_ROT3: 3, GPB_LINEAR: 3}
+_DL = {GPB_POSE3: 3, GPB_POSE2: 2, GPB_ROT3: 0, GPB_LINEAR: 2}
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-shared"]
+
+
+def library_path():
+    return os.path.join(_HERE, "libgpb.so")
+
+
+def build_library(force=False, verbose=False):
+    """nvcc-compile gpslam_b200/csrc/engine.cu for sm_100a into gpslam_b200/libgpb.so (in-tree, so it ships to the GPU box)."""
+    src_dir = os.path.join(_HERE, "csrc")
+    out = library_path()
+    srcs = [os.path.join(src_dir, f) for f in os.listdir(src_dir)] + [os.path.join(_ROOT, "include", "gpb.h")]
+    if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(s) for s in srcs):
+        return out
+    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", out, os.path.join(src_dir, "engine.cu")]
+    subprocess.run(cmd, check=True)
+    return out
+
+
+class Params(C.Structure):
+    _fields_ = [("max_iterations", C.c_int), ("rel_tol", C.c_double), ("abs_tol", C.c_double), ("err_tol", C.c_double),
+                ("lambda_initial", C.c_double), ("lambda_factor", C.c_double), ("lambda_upper", C.c_double), ("lambda_lower", C.c_double),
+                ("min_model_fidelity", C.c_double), ("use_lm", C.c_int)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("iterations", C.c_int), ("error_initial", C.c_double), ("error_final", C.c_double), ("lambda_", C.c_double),
+                ("linearize_ms", C.c_double), ("assemble_ms", C.c_double), ("solve_ms", C.c_double), ("update_ms", C.c_double),
+                ("total_ms", C.c_double), ("status", C.c_int)]
+
+
+class Sizes(C.Structure):
+    _fields_ = [("hbm_bytes", C.c_double), ("linearise_bytes", C.c_double), ("fused_bytes", C.c_double), ("solve_bytes", C.c_double),
+                ("n_gp", C.c_int), ("n_extra", C.c_int), ("n_rows", C.c_int), ("border_dim", C.c_int), ("levels", C.c_int)]
+
+
+class GpbError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load libgpb.so.  Raises (never falls back) if the CUDA library has not been built."""
+    global _LIB
+    if _LIB is None:
+        path = library_path()
+        if not os.path.exists(path):
+            raise GpbError("gpslam_b200: %s is missing — run `python -c 'import __graft_entry__ as g; g.build()'` (nvcc, sm_100a). "
+                           "There is no CPU fallback." % path)
+        L = C.CDLL(path)
+        L.gpb_last_error.restype = C.c_char_p
+        L.gpb_graph_create.restype = C.c_void_p
+        L.gpb_graph_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
+        _LIB = L
+    return _LIB
+
+
+def device_count():
+    return lib().gpb_device_count()
+
+
+def default_params(use_lm=True):
+    p = Params()
+    lib().gpb_default_params(C.byref(p), C.c_int(1 if use_lm else 0))
+    return p
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double)) if a is not None else None
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int)) if a is not None else None
+
+
+def _f64(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+
+
+def _fcol(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float64).T).ravel()
+
+
+class Graph:
+    """Trajectory factor graph resident on one B200.  Construction calls mirror the reference's factor constructors
+    (gpslam.h:31-226); after finalize() everything lives in HBM and the calls below map one-to-one onto the C ABI."""
+
+    def __init__(self, group, n_states, n_landmarks=0, dim=3):
+        self.L = lib()
+        self.group, self.N = group, n_states
+        self.D, self.PS, self.DL = _D[group], _PS[group], _DL[group]
+        self.NL = n_landmarks if self.DL else 0
+        h = self.L.gpb_graph_create(group, dim, n_states, n_landmarks)
+        if not h:
+            raise GpbError(self.L.gpb_last_error().decode())
+        self.h = C.c_void_p(h)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.gpb_graph_destroy(self.h)
+            self.h = None
+
+    def _ck(self, rc):
+        if rc < 0:
+            raise GpbError("gpb error %d: %s" % (rc, self.L.gpb_last_error().decode()))
+        return rc
+
+    # ---- construction
+    def add_qc_model(self, Qc):
+        return self._ck(self.L.gpb_add_qc_model(self.h, _dp(_fcol(Qc))))
+
+    def add_gp_prior(self, i, delta_t, qc=0):
+        i = np.ascontiguousarray(np.atleast_1d(i), dtype=np.int32)
+        dt = _f64(np.broadcast_to(np.atleast_1d(delta_t), i.shape))
+        self._ck(self.L.gpb_add_gp_prior(self.h, C.c_int(len(i)), _ip(i), _dp(dt), C.c_int(qc)))
+
+    def add_interp_range(self, i, l, z, sigma, delta_t, tau, qc=0, body_P_sensor=None):
+        i = np.ascontiguousarray(np.atleast_1d(i), dtype=np.int32)
+        l = np.ascontiguousarray(np.broadcast_to(np.atleast_1d(l), i.shape), dtype=np.int32)
+        b = lambda a: _f64(np.broadcast_to(np.atleast_1d(a), i.shape))
+        bps = _f64(body_P_sensor) if body_P_sensor is not None else None
+        self._ck(self.L.gpb_add_interp_range(self.h, C.c_int(len(i)), _ip(i), _ip(l), _dp(b(z)), _dp(b(sigma)), _dp(b(delta_t)), _dp(b(tau)), C.c_int(qc),
+                                             _dp(bps)))
+
+    def add_interp_attitude(self, i, delta_t, tau, nZ, sigma, bRef=(0, 0, 1), qc=0):
+        i = np.ascontiguousarray(np.atleast_1d(i), dtype=np.int32)
+        b = lambda a: _f64(np.broadcast_to(np.atleast_1d(a), i.shape))
+        nz = _f64(np.broadcast_to(np.asarray(nZ, dtype=np.float64).reshape(-1, 3), (len(i), 3)))
+        br = _f64(np.broadcast_to(np.asarray(bRef, dtype=np.float64).reshape(-1, 3), (len(i), 3)))
+        self._ck(self.L.gpb_add_interp_attitude(self.h, C.c_int(len(i)), _ip(i), _dp(b(delta_t)), _dp(b(tau)), C.c_int(qc), _dp(nz), _dp(br), _dp(b(sigma))))
+
+    def add_prior_pose(self, i, value, sqrt_info):
+        self._ck(self.L.gpb_add_prior_pose(self.h, C.c_int(i), _dp(_f64(value)), _dp(_fcol(sqrt_info))))
+
+    def add_prior_vel(self, i, value, sqrt_info):
+        self._ck(self.L.gpb_add_prior_vel(self.h, C.c_int(i), _dp(_f64(value)), _dp(_fcol(sqrt_info))))
+
+    def add_prior_landmark(self, l, value, sqrt_info):
+        self._ck(self.L.gpb_add_prior_landmark(self.h, C.c_int(l), _dp(_f64(value)), _dp(_fcol(sqrt_info))))
+
+    def add_between(self, i, j, meas, sqrt_info):
+        self._ck(self.L.gpb_add_between(self.h, C.c_int(i), C.c_int(j), _dp(_f64(meas)), _dp(_fcol(sqrt_info))))
+
+    def add_range_2d(self, i, l, z, sigma):
+        self._ck(self.L.gpb_add_range_2d(self.h, C.c_int(i), C.c_int(l), C.c_double(z), C.c_double(sigma)))
+
+    def add_range_bearing_2d(self, i, l, rng, bearing, sqrt_info):
+        self._ck(self.L.gpb_add_range_bearing_2d(self.h, C.c_int(i), C.c_int(l), C.c_double(rng), C.c_double(bearing), _dp(_fcol(sqrt_info))))
+
+    def add_odometry_2d(self, i, j, meas, sqrt_info):
+        self._ck(self.L.gpb_add_odometry_2d(self.h, C.c_int(i), C.c_int(j), _dp(_f64(meas)), _dp(_fcol(sqrt_info))))
+
+    def set_segment_length(self, level0=0, upper=0):
+        self._ck(self.L.gpb_set_segment_length(self.h, C.c_int(level0), C.c_int(upper)))
+
+    def set_values(self, poses=None, vels=None, lands=None):
+        p = _f64(poses).reshape(-1) if poses is not None else None
+        v = _f64(vels).reshape(-1) if vels is not None else None
+        l = _f64(lands).reshape(-1) if lands is not None and self.NL else None
+        self._ck(self.L.gpb_set_values(self.h, _dp(p), _dp(v), _dp(l)))
+
+    def get_values(self):
+        p = np.zeros((self.N, self.PS)); v = np.zeros((self.N, self.D)); l = np.zeros((self.NL, max(self.DL, 1)))
+        self._ck(self.L.gpb_get_values(self.h, _dp(p), _dp(v), _dp(l) if self.NL else None))
+        return p, v, (l[:, :self.DL] if self.NL else np.zeros((0, self.DL)))
+
+    def finalize(self, device=0):
+        self._ck(self.L.gpb_graph_finalize(self.h, C.c_int(device)))
+
+    # ---- hot path
+    def error(self):
+        e = C.c_double()
+        self._ck(self.L.gpb_error(self.h, C.byref(e)))
+        return e.value
+
+    def linearize(self):
+        e = C.c_double()
+        self._ck(self.L.gpb_linearize(self.h, C.byref(e)))
+        return e.value
+
+    def _split(self, flat, m, dims):
+        out, o = [], 0
+        for d in dims:
+            if d == 0:
+                break
+            out.append(flat[o:o + m * d].reshape(d, m).T.copy())
+            o += m * d
+        return out
+
+    def linearized_factor(self, kind, idx):
+        """whitened ([A_1..A_n], b) of one factor after linearize(): kind 0 = GP prior of interval idx, 1 = idx-th other factor"""
+        A = np.zeros(12 * 6 * 5); b = np.zeros(12); dims = np.zeros(5, dtype=np.int32)
+        m = self._ck(self.L.gpb_get_linearized_factor(self.h, C.c_int(kind), C.c_int(idx), _dp(A), _dp(b), _ip(dims)))
+        return self._split(A, m, dims), b[:m].copy()
+
+    def normal_equations_dense(self):
+        n = self.N * 2 * self.D + self.NL * self.DL
+        H = np.zeros((n, n)); g = np.zeros(n)
+        self._ck(self.L.gpb_get_normal_equations(self.h, _dp(H), _dp(g), C.c_int(n)))
+        return H.T.copy(), g
+
+    def solve_delta(self, lam=0.0):
+        ds = np.zeros((self.N, 2 * self.D)); dl = np.zeros(max(self.NL * self.DL, 1))
+        self._ck(self.L.gpb_solve_delta(self.h, C.c_double(lam), _dp(ds), _dp(dl)))
+        return ds, dl[:self.NL * self.DL]
+
+    def optimize(self, params=None, n_iter=0, use_lm=True):
+        p = params if params is not None else default_params(use_lm)
+        st = Stats()
+        self._ck(self.L.gpb_optimize(self.h, C.byref(p), C.c_int(n_iter), C.byref(st)))
+        return st
+
+    def sizes(self):
+        s = Sizes()
+        self._ck(self.L.gpb_get_sizes(self.h, C.byref(s)))
+        return s
+
+    def launches(self):
+        return self.L.gpb_kernel_launches_last_optimize(self.h)

@@ -1,0 +1,809 @@
+// B200-native (sm_100a) sparse-GP factor-graph engine: batched linearise, normal-equation assembly,
+// multi-level segment-parallel bordered block-tridiagonal Cholesky, GN/LM loop.  C ABI in include/gpb.h.
+//
+// Device data layout (all FP64, resident in HBM for the life of the graph):
+//   X      [N][SR]            state records  [pose (PS) | velocity (D)]            (AoS, 16 B-aligned records,
+//                              staged per tile into shared memory by one TMA bulk copy, cp.async.bulk)
+//   AB     [4D+1][D][NFp][2]   whitened GP-prior JacobianFactors [A|b], SoA: column, row-pair, factor  (128-bit stores,
+//                              consecutive lanes -> consecutive 16 B)
+//   XR     [2bs+DL+1][NXRp]    whitened rows of every other factor (range, attitude, priors, between, 2-D factors)
+//   HREC   [N][2bs^2+bs]       assembled normal equations per state: D_i | E_i (= H_{i+1,i}) | g_i
+//   level records / factor records of the solver: see "solver" below.
+//
+// Reference path replaced: NonlinearFactorGraph::linearize -> GaussianFactorGraph ->
+// eliminateMultifrontal (Cholesky) -> back-substitution -> Values::retract -> graph.error, driven by
+// GaussNewtonOptimizer / LevenbergMarquardtOptimizer::iterate.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <type_traits>
+#include <vector>
+
+#include "../../include/gpb.h"
+#include "kernels_lin.cuh"
+#include "kernels_asm.cuh"
+#include "kernels_solve.cuh"
+
+// ===================================================================== errors
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CUDA_TRY(x)                                                                                           \
+  do {                                                                                                        \
+    cudaError_t e_ = (x);                                                                                     \
+    if (e_ != cudaSuccess) return fail(GPB_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(e_));        \
+  } while (0)
+
+
+// ===================================================================== host-side graph
+struct Extra {
+  int kind, sa, sb, l, m, order, interval;
+  double prm[XP_STRIDE];
+};
+
+struct Level {
+  int n = 0, M = 0, S = 0, nseg = 0, ncta = 0;
+  double* rec = nullptr;   // level >= 1: [n][3 bs^2 + 2 bs]  (D1 | D2 | E | g1 | g2)
+  double* brec = nullptr;  // level >= 1: [n][2 bs nb]
+  double* frec = nullptr;  // [n][2 bs^2 + bs w]   (Lii | Le | Y)
+  double* xsol = nullptr;  // [n][bs]
+  double* cseg = nullptr;  // [ncta][nb nb + nb]
+};
+
+struct gpb_graph {
+  int group = 0, D = 0, PS = 0, DL = 0, N = 0, L = 0, bs = 0, SR = 0, nb = 0, w = 0, W = 0;
+  std::vector<std::vector<double>> Rq;  // chol_upper(Qc^-1), D x D column-major
+  std::vector<double> dt;               // per interval (0 = no GP prior)
+  std::vector<int> gp_qc;
+  std::vector<Extra> extras;
+  std::vector<double> h_X, h_land;
+  bool finalized = false, linearized = false, assembled = false;
+  int device = -1;
+  int M0 = 0, Mup = 0;
+  int nint = 0, NFp = 0, NX = 0, NXR = 0, NXRp = 0, ncolsX = 0, ngp = 0;
+  double *d_X = nullptr, *d_Xt = nullptr, *d_land = nullptr, *d_landt = nullptr;
+  double *d_dt = nullptr, *d_Rq = nullptr;
+  int* d_qc = nullptr;
+  double *d_AB[2] = {nullptr, nullptr}, *d_XR[2] = {nullptr, nullptr};
+  int cur = 0;
+  int *d_xkind = nullptr, *d_xsa = nullptr, *d_xsb = nullptr, *d_xl = nullptr, *d_xrow = nullptr;
+  double* d_xprm = nullptr;
+  int *d_rowoff = nullptr, *d_rowland = nullptr, *d_lmoff = nullptr, *d_lmrows = nullptr;
+  std::vector<int> sorted_of_order, h_xrow;
+  std::vector<Extra> sorted;
+  double* d_HREC = nullptr;
+  double *d_errpart = nullptr, *d_scal = nullptr;
+  int nerrpart = 0;
+  int* d_flag = nullptr;
+  double *d_Cbase = nullptr, *d_xlm = nullptr, *d_Cpart = nullptr;
+  std::vector<Level> levels;
+  cudaStream_t stream = nullptr;
+  double cur_error = 0;
+  int launches = 0;
+  size_t hbm_bytes = 0;
+  std::vector<void*> allocs;
+};
+
+static int pose_storage(int group, int D) { return group == GPB_POSE3 ? 12 : group == GPB_ROT3 ? 9 : group == GPB_POSE2 ? 3 : D; }
+static int land_dim(int group) { return group == GPB_POSE3 ? 3 : group == GPB_ROT3 ? 0 : 2; }
+static int extra_rows_of(const gpb_graph* g, int kind) {
+  switch (kind) {
+    case X_INTERP_RANGE: case X_RANGE_2D: return 1;
+    case X_INTERP_ATTITUDE: case X_RANGE_BEARING_2D: return 2;
+    case X_PRIOR_POSE: case X_PRIOR_VEL: case X_BETWEEN: return g->D;
+    case X_PRIOR_LANDMARK: return g->DL;
+    case X_ODOMETRY_2D: return 3;
+  }
+  return 0;
+}
+
+template <class T> static int dev_alloc(gpb_graph* g, T** p, size_t count) {
+  void* q = nullptr;
+  const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+  CUDA_TRY(cudaMalloc(&q, bytes));
+  g->allocs.push_back(q);
+  g->hbm_bytes += bytes;
+  *p = (T*)q;
+  return GPB_OK;
+}
+template <class T> static int dev_upload(gpb_graph* g, T** p, const std::vector<T>& v) {
+  int rc = dev_alloc(g, p, v.size());
+  if (rc) return rc;
+  if (!v.empty()) CUDA_TRY(cudaMemcpy(*p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return GPB_OK;
+}
+
+// upper Cholesky of the inverse of a small SPD matrix (column-major), for Rq = chol(Qc^-1)
+static bool chol_upper_of_inverse(const double* Q, int n, double* R) {
+  std::vector<double> A(Q, Q + n * n), I(n * n, 0.0);
+  for (int k = 0; k < n; k++) I[k + k * n] = 1.0;
+  for (int c = 0; c < n; c++) {  // Gauss-Jordan with partial pivoting
+    int p = c;
+    for (int r = c + 1; r < n; r++) if (std::fabs(A[r + c * n]) > std::fabs(A[p + c * n])) p = r;
+    if (A[p + c * n] == 0.0) return false;
+    if (p != c) for (int k = 0; k < n; k++) { std::swap(A[c + k * n], A[p + k * n]); std::swap(I[c + k * n], I[p + k * n]); }
+    const double d = 1.0 / A[c + c * n];
+    for (int k = 0; k < n; k++) { A[c + k * n] *= d; I[c + k * n] *= d; }
+    for (int r = 0; r < n; r++) if (r != c) { const double f = A[r + c * n]; if (f != 0) for (int k = 0; k < n; k++) { A[r + k * n] -= f * A[c + k * n]; I[r + k * n] -= f * I[c + k * n]; } }
+  }
+  for (int k = 0; k < n * n; k++) R[k] = 0.0;
+  for (int j = 0; j < n; j++) {
+    double d = I[j + j * n];
+    for (int k = 0; k < j; k++) d -= R[k + j * n] * R[k + j * n];
+    if (!(d > 0)) return false;
+    R[j + j * n] = std::sqrt(d);
+    for (int c = j + 1; c < n; c++) { double t = I[j + c * n]; for (int k = 0; k < j; k++) t -= R[k + j * n] * R[k + c * n]; R[j + c * n] = t / R[j + j * n]; }
+  }
+  return true;
+}
+
+// ===================================================================== C ABI: construction
+extern "C" {
+
+const char* gpb_last_error(void) { return g_err.c_str(); }
+int gpb_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; } return n; }
+void gpb_default_params(gpb_params* p, int use_lm) {
+  p->max_iterations = 100; p->rel_tol = 1e-5; p->abs_tol = 1e-5; p->err_tol = 0.0; p->lambda_initial = 1e-5; p->lambda_factor = 10.0;
+  p->lambda_upper = 1e5; p->lambda_lower = 0.0; p->min_model_fidelity = 1e-3; p->use_lm = use_lm;
+}
+
+gpb_graph* gpb_graph_create(int group, int dim, int n_states, int n_landmarks) {
+  if (group < 0 || group > 3 || n_states < 2 || n_landmarks < 0) { fail(GPB_ERR_ARG, "gpb_graph_create: bad arguments (need group 0..3, n_states >= 2)"); return nullptr; }
+  if (group == GPB_LINEAR && dim != 3) { fail(GPB_ERR_UNSUPPORTED, "gpb_graph_create: GPB_LINEAR supports dim 3 (the reference's 2DLinear states)"); return nullptr; }
+  gpb_graph* g = new gpb_graph();
+  g->group = group; g->D = group == GPB_POSE3 ? 6 : 3; g->PS = pose_storage(group, g->D); g->DL = land_dim(group);
+  g->N = n_states; g->L = g->DL ? n_landmarks : 0; g->bs = 2 * g->D; g->SR = g->PS + g->D; g->nint = n_states - 1;
+  g->dt.assign(g->nint, 0.0); g->gp_qc.assign(g->nint, 0);
+  g->h_X.assign((size_t)n_states * g->SR, 0.0); g->h_land.assign((size_t)g->L * std::max(g->DL, 1), 0.0);
+  return g;
+}
+
+void gpb_graph_destroy(gpb_graph* g) {
+  if (!g) return;
+  if (g->device >= 0) cudaSetDevice(g->device);
+  for (void* p : g->allocs) cudaFree(p);
+  if (g->stream) cudaStreamDestroy(g->stream);
+  delete g;
+}
+
+#define CHECK_OPEN(g) do { if (!(g)) return fail(GPB_ERR_ARG, "null graph"); if ((g)->finalized) return fail(GPB_ERR_STATE, "graph already finalized"); } while (0)
+
+int gpb_add_qc_model(gpb_graph* g, const double* Qc) {
+  CHECK_OPEN(g);
+  // getQc (gp/GPutils.cpp:16-20) dereferences a failed dynamic_cast when the model is not Gaussian; here a non-SPD Qc is a checked error
+  std::vector<double> R(g->D * g->D);
+  if (!chol_upper_of_inverse(Qc, g->D, R.data())) return fail(GPB_ERR_ARG, "gpb_add_qc_model: Qc is not symmetric positive definite");
+  g->Rq.push_back(R);
+  return (int)g->Rq.size() - 1;
+}
+
+int gpb_add_gp_prior(gpb_graph* g, int n, const int* i, const double* delta_t, int qc) {
+  CHECK_OPEN(g);
+  if (qc < 0 || qc >= (int)g->Rq.size()) return fail(GPB_ERR_ARG, "gpb_add_gp_prior: unknown Qc model id");
+  for (int k = 0; k < n; k++) {
+    if (i[k] < 0 || i[k] >= g->nint) return fail(GPB_ERR_ARG, "gpb_add_gp_prior: interval index out of range");
+    if (!(delta_t[k] > 0.0)) return fail(GPB_ERR_ARG, "gpb_add_gp_prior: delta_t must be positive");
+    if (g->dt[i[k]] > 0.0) return fail(GPB_ERR_UNSUPPORTED, "gpb_add_gp_prior: at most one GP prior per interval");
+    g->dt[i[k]] = delta_t[k]; g->gp_qc[i[k]] = qc;
+  }
+  return GPB_OK;
+}
+
+static Extra make_extra(int kind) { Extra e; std::memset(&e, 0, sizeof(e)); e.kind = kind; e.sa = e.sb = e.l = -1; return e; }
+static void set_R(Extra& e, int m, const double* R) { for (int k = 0; k < m * m; k++) e.prm[20 + k] = R[k]; }
+// place a single-state factor: a-part of interval s, or b-part of interval N-2 for the last state
+static void place_single(const gpb_graph* g, Extra& e, int s) {
+  if (s <= g->nint - 1) { e.sa = s; e.sb = -1; e.interval = s; } else { e.sa = -1; e.sb = s; e.interval = s - 1; }
+}
+
+int gpb_add_interp_range(gpb_graph* g, int n, const int* i, const int* l, const double* z, const double* sigma, const double* delta_t,
+                         const double* tau, int qc, const double* body_P_sensor) {
+  CHECK_OPEN(g);
+  if (g->group == GPB_ROT3) return fail(GPB_ERR_UNSUPPORTED, "gpb_add_interp_range: no range factor on Rot3 trajectories");
+  if (body_P_sensor && g->group == GPB_LINEAR) return fail(GPB_ERR_UNSUPPORTED, "GPInterpolatedRangeFactor2DLinear has no body_P_sensor");
+  (void)qc;  // Lambda/Psi do not depend on Qc
+  for (int k = 0; k < n; k++) {
+    if (i[k] < 0 || i[k] >= g->nint || l[k] < 0 || l[k] >= g->L) return fail(GPB_ERR_ARG, "gpb_add_interp_range: index out of range");
+    if (!(sigma[k] > 0.0) || !(delta_t[k] > 0.0)) return fail(GPB_ERR_ARG, "gpb_add_interp_range: sigma and delta_t must be positive");
+    Extra e = make_extra(X_INTERP_RANGE);
+    e.sa = i[k]; e.sb = i[k] + 1; e.l = l[k]; e.interval = i[k]; e.m = 1;
+    e.prm[0] = delta_t[k]; e.prm[1] = tau[k]; e.prm[2] = z[k]; e.prm[20] = 1.0 / sigma[k];
+    if (body_P_sensor) { for (int t = 0; t < g->PS; t++) e.prm[4 + t] = body_P_sensor[t]; e.prm[16] = 1.0; }
+    e.order = (int)g->extras.size(); g->extras.push_back(e);
+  }
+  return GPB_OK;
+}
+
+int gpb_add_interp_attitude(gpb_graph* g, int n, const int* i, const double* delta_t, const double* tau, int qc, const double* nZ,
+                            const double* bRef, const double* sigma) {
+  CHECK_OPEN(g);
+  if (g->group != GPB_ROT3) return fail(GPB_ERR_UNSUPPORTED, "gpb_add_interp_attitude: Rot3 trajectories only");
+  (void)qc;
+  for (int k = 0; k < n; k++) {
+    if (i[k] < 0 || i[k] >= g->nint) return fail(GPB_ERR_ARG, "gpb_add_interp_attitude: index out of range");
+    Extra e = make_extra(X_INTERP_ATTITUDE);
+    e.sa = i[k]; e.sb = i[k] + 1; e.interval = i[k]; e.m = 2;
+    e.prm[0] = delta_t[k]; e.prm[1] = tau[k];
+    for (int t = 0; t < 3; t++) { e.prm[4 + t] = nZ[3 * k + t]; e.prm[7 + t] = bRef[3 * k + t]; }
+    e.prm[20] = 1.0 / sigma[k]; e.prm[23] = 1.0 / sigma[k];
+    e.order = (int)g->extras.size(); g->extras.push_back(e);
+  }
+  return GPB_OK;
+}
+
+int gpb_add_prior_pose(gpb_graph* g, int i, const double* value, const double* sqrt_info) {
+  CHECK_OPEN(g);
+  if (i < 0 || i >= g->N) return fail(GPB_ERR_ARG, "gpb_add_prior_pose: index out of range");
+  Extra e = make_extra(X_PRIOR_POSE); place_single(g, e, i); e.m = g->D;
+  for (int t = 0; t < g->PS; t++) e.prm[4 + t] = value[t];
+  set_R(e, g->D, sqrt_info); e.order = (int)g->extras.size(); g->extras.push_back(e);
+  return GPB_OK;
+}
+int gpb_add_prior_vel(gpb_graph* g, int i, const double* value, const double* sqrt_info) {
+  CHECK_OPEN(g);
+  if (i < 0 || i >= g->N) return fail(GPB_ERR_ARG, "gpb_add_prior_vel: index out of range");
+  Extra e = make_extra(X_PRIOR_VEL); place_single(g, e, i); e.m = g->D;
+  for (int t = 0; t < g->D; t++) e.prm[4 + t] = value[t];
+  set_R(e, g->D, sqrt_info); e.order = (int)g->extras.size(); g->extras.push_back(e);
+  return GPB_OK;
+}
+int gpb_add_prior_landmark(gpb_graph* g, int l, const double* value, const double* sqrt_info) {
+  CHECK_OPEN(g);
+  if (l < 0 || l >= g->L) return fail(GPB_ERR_ARG, "gpb_add_prior_landmark: index out of range");
+  Extra e = make_extra(X_PRIOR_LANDMARK); e.l = l; e.interval = 0; e.sa = 0; e.m = g->DL;
+  for (int t = 0; t < g->DL; t++) e.prm[4 + t] = value[t];
+  set_R(e, g->DL, sqrt_info); e.order = (int)g->extras.size(); g->extras.push_back(e);
+  return GPB_OK;
+}
+int gpb_add_between(gpb_graph* g, int i, int j, const double* measured, const double* sqrt_info) {
+  CHECK_OPEN(g);
+  if (i < 0 || i >= g->N || j < 0 || j >= g->N || i == j) return fail(GPB_ERR_ARG, "gpb_add_between: index out of range");
+  if (std::abs(i - j) != 1) return fail(GPB_ERR_UNSUPPORTED, "gpb_add_between: loop closures (|i-j| > 1) are not supported by this build yet");
+  Extra e = make_extra(X_BETWEEN); e.m = g->D;
+  e.sa = std::min(i, j); e.sb = e.sa + 1; e.interval = e.sa; e.prm[17] = (j < i) ? 1.0 : 0.0;
+  for (int t = 0; t < g->PS; t++) e.prm[4 + t] = measured[t];
+  set_R(e, g->D, sqrt_info); e.order = (int)g->extras.size(); g->extras.push_back(e);
+  return GPB_OK;
+}
+int gpb_add_range_2d(gpb_graph* g, int i, int l, double z, double sigma) {
+  CHECK_OPEN(g);
+  if (g->group != GPB_POSE2 && g->group != GPB_LINEAR) return fail(GPB_ERR_UNSUPPORTED, "gpb_add_range_2d: Pose2 / Linear<3> trajectories only");
+  if (i < 0 || i >= g->N || l < 0 || l >= g->L) return fail(GPB_ERR_ARG, "gpb_add_range_2d: index out of range");
+  Extra e = make_extra(X_RANGE_2D); place_single(g, e, i); e.l = l; e.m = 1; e.prm[2] = z; e.prm[20] = 1.0 / sigma;
+  e.order = (int)g->extras.size(); g->extras.push_back(e);
+  return GPB_OK;
+}
+int gpb_add_range_bearing_2d(gpb_graph* g, int i, int l, double range, double bearing, const double* sqrt_info) {
+  CHECK_OPEN(g);
+  if (g->group != GPB_LINEAR) return fail(GPB_ERR_UNSUPPORTED, "gpb_add_range_bearing_2d: Linear<3> trajectories only");
+  if (i < 0 || i >= g->N || l < 0 || l >= g->L) return fail(GPB_ERR_ARG, "gpb_add_range_bearing_2d: index out of range");
+  Extra e = make_extra(X_RANGE_BEARING_2D); place_single(g, e, i); e.l = l; e.m = 2; e.prm[2] = range; e.prm[3] = bearing; set_R(e, 2, sqrt_info);
+  e.order = (int)g->extras.size(); g->extras.push_back(e);
+  return GPB_OK;
+}
+int gpb_add_odometry_2d(gpb_graph* g, int i, int j, const double* measured, const double* sqrt_info) {
+  CHECK_OPEN(g);
+  if (g->group != GPB_LINEAR) return fail(GPB_ERR_UNSUPPORTED, "gpb_add_odometry_2d: Linear<3> trajectories only");
+  if (i < 0 || j != i + 1 || j >= g->N) return fail(GPB_ERR_UNSUPPORTED, "gpb_add_odometry_2d: needs consecutive states (j == i+1)");
+  Extra e = make_extra(X_ODOMETRY_2D); e.sa = i; e.sb = j; e.interval = i; e.m = 3;
+  for (int t = 0; t < 3; t++) e.prm[4 + t] = measured[t];
+  set_R(e, 3, sqrt_info); e.order = (int)g->extras.size(); g->extras.push_back(e);
+  return GPB_OK;
+}
+
+static int upload_values(gpb_graph* g) {
+  CUDA_TRY(cudaMemcpyAsync(g->d_X, g->h_X.data(), g->h_X.size() * sizeof(double), cudaMemcpyHostToDevice, g->stream));
+  if (g->L) CUDA_TRY(cudaMemcpyAsync(g->d_land, g->h_land.data(), (size_t)g->L * g->DL * sizeof(double), cudaMemcpyHostToDevice, g->stream));
+  g->linearized = false; g->assembled = false;
+  return GPB_OK;
+}
+
+int gpb_set_values(gpb_graph* g, const double* poses, const double* vels, const double* landmarks) {
+  if (!g) return fail(GPB_ERR_ARG, "null graph");
+  for (int i = 0; i < g->N; i++) {
+    if (poses) for (int k = 0; k < g->PS; k++) g->h_X[(size_t)i * g->SR + k] = poses[(size_t)i * g->PS + k];
+    if (vels) for (int k = 0; k < g->D; k++) g->h_X[(size_t)i * g->SR + g->PS + k] = vels[(size_t)i * g->D + k];
+  }
+  if (landmarks && g->L) std::copy(landmarks, landmarks + (size_t)g->L * g->DL, g->h_land.begin());
+  if (g->finalized) { CUDA_TRY(cudaSetDevice(g->device)); int rc = upload_values(g); if (rc) return rc; CUDA_TRY(cudaStreamSynchronize(g->stream)); }
+  return GPB_OK;
+}
+
+int gpb_get_values(gpb_graph* g, double* poses, double* vels, double* landmarks) {
+  if (!g) return fail(GPB_ERR_ARG, "null graph");
+  if (g->finalized) {
+    CUDA_TRY(cudaSetDevice(g->device));
+    CUDA_TRY(cudaMemcpyAsync(g->h_X.data(), g->d_X, g->h_X.size() * sizeof(double), cudaMemcpyDeviceToHost, g->stream));
+    if (g->L) CUDA_TRY(cudaMemcpyAsync(g->h_land.data(), g->d_land, (size_t)g->L * g->DL * sizeof(double), cudaMemcpyDeviceToHost, g->stream));
+    CUDA_TRY(cudaStreamSynchronize(g->stream));
+  }
+  for (int i = 0; i < g->N; i++) {
+    if (poses) for (int k = 0; k < g->PS; k++) poses[(size_t)i * g->PS + k] = g->h_X[(size_t)i * g->SR + k];
+    if (vels) for (int k = 0; k < g->D; k++) vels[(size_t)i * g->D + k] = g->h_X[(size_t)i * g->SR + g->PS + k];
+  }
+  if (landmarks && g->L) std::copy(g->h_land.begin(), g->h_land.begin() + (size_t)g->L * g->DL, landmarks);
+  return GPB_OK;
+}
+
+int gpb_set_segment_length(gpb_graph* g, int level0, int upper) {
+  CHECK_OPEN(g);
+  if ((level0 && level0 < 2) || (upper && upper < 2)) return fail(GPB_ERR_ARG, "segment length must be >= 2");
+  g->M0 = level0; g->Mup = upper;
+  return GPB_OK;
+}
+
+// ===================================================================== finalize: build the device-resident graph
+int gpb_graph_finalize(gpb_graph* g, int device) {
+  CHECK_OPEN(g);
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(GPB_ERR_CUDA, "gpb_graph_finalize: no CUDA device available (this engine has no CPU fallback)"); }
+  if (device < 0 || device >= ndev) return fail(GPB_ERR_ARG, "gpb_graph_finalize: bad device index");
+  if (g->Rq.empty()) return fail(GPB_ERR_STATE, "gpb_graph_finalize: no Qc model registered");
+  CUDA_TRY(cudaSetDevice(device));
+  g->device = device;
+  CUDA_TRY(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
+  const int D = g->D, bs = g->bs, DL = g->DL;
+  g->nb = g->L * DL; g->w = bs + g->nb + 1;
+  g->W = g->w <= 16 ? 16 : g->w <= 32 ? 32 : 64;
+  if (g->w > 64) return fail(GPB_ERR_UNSUPPORTED, "gpb_graph_finalize: landmark border wider than 64 - 2D - 1 columns is not supported by this build");
+  g->ngp = 0; for (double h : g->dt) if (h > 0) g->ngp++;
+  g->NFp = (g->nint + 31) & ~31;
+  // ---- sort extras by interval (stable), assign row offsets
+  g->sorted = g->extras;
+  std::stable_sort(g->sorted.begin(), g->sorted.end(), [](const Extra& a, const Extra& b) { return a.interval < b.interval; });
+  g->NX = (int)g->sorted.size();
+  g->sorted_of_order.assign(g->NX, 0);
+  std::vector<int> xkind(g->NX), xsa(g->NX), xsb(g->NX), xl(g->NX), xrow(g->NX), rowoff(g->nint + 1, 0), rowland;
+  std::vector<double> xprm((size_t)g->NX * XP_STRIDE);
+  int nrows = 0;
+  for (int k = 0; k < g->NX; k++) {
+    const Extra& e = g->sorted[k];
+    g->sorted_of_order[e.order] = k;
+    xkind[k] = e.kind; xsa[k] = e.sa; xsb[k] = e.sb; xl[k] = e.l; xrow[k] = nrows;
+    std::copy(e.prm, e.prm + XP_STRIDE, xprm.begin() + (size_t)k * XP_STRIDE);
+    for (int r = 0; r < e.m; r++) rowland.push_back(e.l);
+    nrows += e.m;
+    rowoff[e.interval + 1] += e.m;
+  }
+  for (int t = 0; t < g->nint; t++) rowoff[t + 1] += rowoff[t];
+  g->NXR = nrows; g->NXRp = (nrows + 31) & ~31; g->h_xrow = xrow; g->ncolsX = 2 * bs + DL + 1;
+  // rows per landmark
+  std::vector<int> lmoff(g->L + 1, 0), lmrows;
+  for (int r = 0; r < nrows; r++) if (rowland[r] >= 0) lmoff[rowland[r] + 1]++;
+  for (int l = 0; l < g->L; l++) lmoff[l + 1] += lmoff[l];
+  lmrows.assign(lmoff[g->L], 0);
+  { std::vector<int> fill(lmoff.begin(), lmoff.end() - 1); for (int r = 0; r < nrows; r++) if (rowland[r] >= 0) lmrows[fill[rowland[r]]++] = r; }
+  // ---- device buffers
+  int rc;
+  std::vector<double> rq((size_t)g->Rq.size() * D * D);
+  for (size_t m = 0; m < g->Rq.size(); m++) std::copy(g->Rq[m].begin(), g->Rq[m].end(), rq.begin() + m * D * D);
+  if ((rc = dev_alloc(g, &g->d_X, (size_t)(g->N + 1) * g->SR))) return rc;
+  if ((rc = dev_alloc(g, &g->d_Xt, (size_t)(g->N + 1) * g->SR))) return rc;
+  if ((rc = dev_alloc(g, &g->d_land, (size_t)g->L * std::max(DL, 1)))) return rc;
+  if ((rc = dev_alloc(g, &g->d_landt, (size_t)g->L * std::max(DL, 1)))) return rc;
+  if ((rc = dev_upload(g, &g->d_dt, g->dt))) return rc;
+  if ((rc = dev_upload(g, &g->d_qc, g->gp_qc))) return rc;
+  if ((rc = dev_upload(g, &g->d_Rq, rq))) return rc;
+  for (int b = 0; b < 2; b++) {
+    if ((rc = dev_alloc(g, &g->d_AB[b], (size_t)(4 * D + 1) * D * g->NFp * 2))) return rc;
+    if ((rc = dev_alloc(g, &g->d_XR[b], (size_t)g->ncolsX * std::max(g->NXRp, 32)))) return rc;
+    CUDA_TRY(cudaMemset(g->d_XR[b], 0, (size_t)g->ncolsX * std::max(g->NXRp, 32) * sizeof(double)));
+  }
+  if ((rc = dev_upload(g, &g->d_xkind, xkind))) return rc;
+  if ((rc = dev_upload(g, &g->d_xsa, xsa))) return rc;
+  if ((rc = dev_upload(g, &g->d_xsb, xsb))) return rc;
+  if ((rc = dev_upload(g, &g->d_xl, xl))) return rc;
+  if ((rc = dev_upload(g, &g->d_xrow, xrow))) return rc;
+  if ((rc = dev_upload(g, &g->d_xprm, xprm))) return rc;
+  if ((rc = dev_upload(g, &g->d_rowoff, rowoff))) return rc;
+  if ((rc = dev_upload(g, &g->d_rowland, rowland))) return rc;
+  if ((rc = dev_upload(g, &g->d_lmoff, lmoff))) return rc;
+  if ((rc = dev_upload(g, &g->d_lmrows, lmrows))) return rc;
+  if ((rc = dev_alloc(g, &g->d_HREC, (size_t)g->N * (2 * bs * bs + bs)))) return rc;
+  g->nerrpart = (g->nint + 127) / 128 + (g->NX + 127) / 128 + (g->N + 127) / 128 + 8;
+  if ((rc = dev_alloc(g, &g->d_errpart, (size_t)2 * g->nerrpart))) return rc;
+  if ((rc = dev_alloc(g, &g->d_scal, 8))) return rc;
+  if ((rc = dev_alloc(g, &g->d_flag, 1))) return rc;
+  CUDA_TRY(cudaMemset(g->d_flag, 0, sizeof(int)));
+  const int centries = g->nb * g->nb + g->nb;
+  if ((rc = dev_alloc(g, &g->d_Cbase, (size_t)centries))) return rc;
+  CUDA_TRY(cudaMemset(g->d_Cbase, 0, std::max(centries, 1) * sizeof(double)));
+  if ((rc = dev_alloc(g, &g->d_xlm, (size_t)std::max(g->nb, 1)))) return rc;
+  // ---- elimination levels
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  const int M0 = g->M0 ? g->M0 : (g->nb > 0 ? 32 : 16), Mup = g->Mup ? g->Mup : 8;
+  const int fstride = 2 * bs * bs + bs * g->w;
+  int n = g->N, lev = 0, total_cta = 0;
+  while (true) {
+    Level L;
+    L.n = n; L.M = lev == 0 ? M0 : Mup; L.S = (n - 1) / L.M; L.nseg = L.S + 1;
+    L.ncta = std::min(L.nseg, sms * 8);
+    if ((rc = dev_alloc(g, &L.frec, (size_t)n * fstride))) return rc;
+    if ((rc = dev_alloc(g, &L.xsol, (size_t)n * bs))) return rc;
+    if (g->nb) { if ((rc = dev_alloc(g, &L.cseg, (size_t)L.ncta * centries))) return rc; }
+    if (lev > 0) {
+      if ((rc = dev_alloc(g, &L.rec, (size_t)n * (3 * bs * bs + 2 * bs)))) return rc;
+      if ((rc = dev_alloc(g, &L.brec, (size_t)n * 2 * bs * std::max(g->nb, 1)))) return rc;
+    }
+    total_cta += L.ncta;
+    g->levels.push_back(L);
+    if (L.S == 0) break;
+    n = L.S; lev++;
+  }
+  if ((rc = dev_alloc(g, &g->d_Cpart, (size_t)16 * g->levels.size() * std::max(centries, 1)))) return rc;
+  g->finalized = true;
+  rc = upload_values(g);
+  if (rc) return rc;
+  CUDA_TRY(cudaStreamSynchronize(g->stream));
+  return GPB_OK;
+}
+
+}  // extern "C"
+
+// ===================================================================== launches
+#define CHECK_READY(g) do { if (!(g)) return fail(GPB_ERR_ARG, "null graph"); if (!(g)->finalized) return fail(GPB_ERR_STATE, "graph not finalized"); CUDA_TRY(cudaSetDevice((g)->device)); } while (0)
+
+template <int G> static int launch_linearize(gpb_graph* g, const double* X, const double* land, int buf, int wantJ) {
+  constexpr int NT = 128, SR = GroupTraits<G>::PS + GroupTraits<G>::D;
+  const int nb1 = (g->nint + NT - 1) / NT, nb2 = (g->NX + NT - 1) / NT;
+  const size_t smem = (size_t)(NT + 1) * SR * sizeof(double);
+  k_lin_gp<G, NT><<<nb1, NT, smem, g->stream>>>(X, g->d_dt, g->d_qc, g->d_Rq, g->d_AB[buf], g->d_errpart, g->nint, g->NFp, wantJ);
+  g->launches++;
+  if (nb2 > 0) {
+    k_lin_extra<G, NT><<<nb2, NT, 0, g->stream>>>(X, land, g->d_xkind, g->d_xsa, g->d_xsb, g->d_xl, g->d_xrow, g->d_xprm, g->d_XR[buf], g->d_errpart + nb1, g->NX,
+                                                   g->NXRp, wantJ);
+    g->launches++;
+  }
+  k_sum_partials<<<1, 256, 0, g->stream>>>(g->d_errpart, nb1 + nb2, g->d_scal, 0);
+  g->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return GPB_OK;
+}
+static int linearize_dispatch(gpb_graph* g, const double* X, const double* land, int buf, int wantJ) {
+  switch (g->group) {
+    case GPB_POSE3: return launch_linearize<G_POSE3>(g, X, land, buf, wantJ);
+    case GPB_POSE2: return launch_linearize<G_POSE2>(g, X, land, buf, wantJ);
+    case GPB_ROT3: return launch_linearize<G_ROT3>(g, X, land, buf, wantJ);
+    default: return launch_linearize<G_LINEAR>(g, X, land, buf, wantJ);
+  }
+}
+
+template <int G> static int launch_assemble(gpb_graph* g, int buf) {
+  constexpr int NT = 128, bs = 2 * GroupTraits<G>::D, TILES = bs == 12 ? 4 : 1;
+  const int Npad = (g->N + 31) & ~31;
+  const int nblk = (TILES * Npad + NT - 1) / NT;
+  k_assemble<G, NT><<<nblk, NT, 0, g->stream>>>(g->d_AB[buf], g->d_dt, g->NX ? g->d_XR[buf] : nullptr, g->d_rowoff, g->d_HREC, g->N, g->NFp, g->NXRp);
+  g->launches++;
+  if (g->nb) {
+    CUDA_TRY(cudaMemsetAsync(g->d_Cbase, 0, (size_t)(g->nb * g->nb + g->nb) * sizeof(double), g->stream));
+    k_landmark_base<128><<<g->L, 128, 0, g->stream>>>(g->d_XR[buf], g->d_lmoff, g->d_lmrows, g->NXRp, 2 * bs, g->DL, g->nb, g->d_Cbase);
+    g->launches++;
+  }
+  CUDA_TRY(cudaGetLastError());
+  return GPB_OK;
+}
+static int assemble_dispatch(gpb_graph* g, int buf) {
+  switch (g->group) {
+    case GPB_POSE3: return launch_assemble<G_POSE3>(g, buf);
+    case GPB_POSE2: return launch_assemble<G_POSE2>(g, buf);
+    case GPB_ROT3: return launch_assemble<G_ROT3>(g, buf);
+    default: return launch_assemble<G_LINEAR>(g, buf);
+  }
+}
+
+template <int BS, int W> static void launch_fwd(const FwdArgs& a, int ncta, cudaStream_t s) { k_fwd<BS, W><<<ncta, (W < 32 ? 32 : W), 0, s>>>(a); }
+template <int BS, int W> static void launch_bwd(const BwdArgs& a, int ncta, cudaStream_t s) { k_bwd<BS, W><<<ncta, (W < 32 ? 32 : W), 0, s>>>(a); }
+template <int BS> static void fwd_w(int W, const FwdArgs& a, int ncta, cudaStream_t s) { if (W == 16) launch_fwd<BS, 16>(a, ncta, s); else if (W == 32) launch_fwd<BS, 32>(a, ncta, s); else launch_fwd<BS, 64>(a, ncta, s); }
+template <int BS> static void bwd_w(int W, const BwdArgs& a, int ncta, cudaStream_t s) { if (W == 16) launch_bwd<BS, 16>(a, ncta, s); else if (W == 32) launch_bwd<BS, 32>(a, ncta, s); else launch_bwd<BS, 64>(a, ncta, s); }
+
+// Solve (H + lambda I) delta = g with the current HREC / XR[buf]; delta lands in levels[0].xsol and d_xlm.
+static int solve_system(gpb_graph* g, int buf, double lambda) {
+  const int bs = g->bs, nb = g->nb, fstride = 2 * bs * bs + bs * g->w, centries = nb * nb + nb;
+  const int nlev = (int)g->levels.size();
+  for (int lev = 0; lev < nlev; lev++) {
+    Level& L = g->levels[lev];
+    FwdArgs a;
+    a.n = L.n; a.M = L.M; a.S = L.S; a.nseg = L.nseg; a.first_level = lev == 0;
+    a.rec = lev == 0 ? g->d_HREC : L.rec; a.brec = L.brec;
+    a.XR = g->d_XR[buf]; a.rowoff = g->d_rowoff; a.rowland = g->d_rowland; a.NXRp = g->NXRp; a.nint = g->nint; a.nb = nb; a.DL = std::max(g->DL, 1);
+    a.lambda = lambda;
+    a.rec_out = lev + 1 < nlev ? g->levels[lev + 1].rec : nullptr; a.brec_out = lev + 1 < nlev ? g->levels[lev + 1].brec : nullptr;
+    a.frec = L.frec; a.fstride = fstride; a.cseg = L.cseg; a.flag = g->d_flag;
+    if (bs == 12) fwd_w<12>(g->W, a, L.ncta, g->stream); else fwd_w<6>(g->W, a, L.ncta, g->stream);
+    g->launches++;
+    if (nb) {
+      const int R = std::min(16, L.ncta);
+      dim3 grid((centries + 255) / 256, R);
+      k_cseg_reduce<<<grid, 256, 0, g->stream>>>(L.cseg, L.ncta, centries, R, g->d_Cpart + (size_t)lev * 16 * centries);
+      if (R < 16) CUDA_TRY(cudaMemsetAsync(g->d_Cpart + ((size_t)lev * 16 + R) * centries, 0, (size_t)(16 - R) * centries * sizeof(double), g->stream));
+      g->launches++;
+    }
+  }
+  if (nb) {
+    k_landmark_solve<256><<<1, 256, (size_t)centries * sizeof(double), g->stream>>>(g->d_Cbase, g->d_Cpart, 16 * nlev, nb, lambda, g->d_xlm, g->d_flag);
+    g->launches++;
+  }
+  for (int lev = nlev - 1; lev >= 0; lev--) {
+    Level& L = g->levels[lev];
+    BwdArgs b;
+    b.n = L.n; b.M = L.M; b.S = L.S; b.nseg = L.nseg; b.nb = nb; b.frec = L.frec; b.fstride = fstride;
+    b.xup = lev + 1 < nlev ? g->levels[lev + 1].xsol : nullptr; b.xl = g->d_xlm; b.xsol = L.xsol;
+    if (bs == 12) bwd_w<12>(g->W, b, L.ncta, g->stream); else bwd_w<6>(g->W, b, L.ncta, g->stream);
+    g->launches++;
+  }
+  CUDA_TRY(cudaGetLastError());
+  return GPB_OK;
+}
+
+template <int G> static int launch_retract(gpb_graph* g) {
+  constexpr int NT = 128;
+  const int nblk = (g->N + NT - 1) / NT;
+  double* part = g->d_errpart + g->nerrpart;
+  k_retract<G, NT><<<nblk, NT, 0, g->stream>>>(g->d_X, g->levels[0].xsol, g->d_HREC, g->d_Xt, part, part + nblk, g->N);
+  k_sum_partials<<<1, 256, 0, g->stream>>>(part, nblk, g->d_scal, 1);
+  k_sum_partials<<<1, 256, 0, g->stream>>>(part + nblk, nblk, g->d_scal, 2);
+  g->launches += 3;
+  if (g->nb) { k_retract_land<<<1, 256, 0, g->stream>>>(g->d_land, g->d_xlm, g->d_Cbase + (size_t)g->nb * g->nb, g->d_landt, g->nb, g->d_scal); g->launches++; }
+  CUDA_TRY(cudaGetLastError());
+  return GPB_OK;
+}
+static int retract_dispatch(gpb_graph* g) {
+  switch (g->group) {
+    case GPB_POSE3: return launch_retract<G_POSE3>(g);
+    case GPB_POSE2: return launch_retract<G_POSE2>(g);
+    case GPB_ROT3: return launch_retract<G_ROT3>(g);
+    default: return launch_retract<G_LINEAR>(g);
+  }
+}
+
+static int read_scalars(gpb_graph* g, double* out3, int* flag) {
+  double h[3];
+  CUDA_TRY(cudaMemcpyAsync(h, g->d_scal, 3 * sizeof(double), cudaMemcpyDeviceToHost, g->stream));
+  CUDA_TRY(cudaMemcpyAsync(flag, g->d_flag, sizeof(int), cudaMemcpyDeviceToHost, g->stream));
+  CUDA_TRY(cudaStreamSynchronize(g->stream));
+  out3[0] = h[0]; out3[1] = h[1]; out3[2] = h[2];
+  return GPB_OK;
+}
+
+extern "C" {
+
+int gpb_linearize(gpb_graph* g, double* error_out) {
+  CHECK_READY(g);
+  int rc = linearize_dispatch(g, g->d_X, g->d_land, g->cur, 1);
+  if (rc) return rc;
+  double s[3]; int flag;
+  if ((rc = read_scalars(g, s, &flag))) return rc;
+  g->cur_error = s[0]; g->linearized = true; g->assembled = false;
+  if (error_out) *error_out = s[0];
+  return GPB_OK;
+}
+
+int gpb_error(gpb_graph* g, double* error_out) {
+  CHECK_READY(g);
+  // cheap path: residuals only (the `else` branches of evaluateError, gp/GaussianProcessPriorPose3.h:73-74)
+  int rc = linearize_dispatch(g, g->d_X, g->d_land, g->cur, 0);
+  if (rc) return rc;
+  double s[3]; int flag;
+  if ((rc = read_scalars(g, s, &flag))) return rc;
+  if (error_out) *error_out = s[0];
+  return GPB_OK;
+}
+
+static int ensure_assembled(gpb_graph* g) {
+  int rc;
+  if (!g->linearized && (rc = gpb_linearize(g, nullptr))) return rc;
+  if (!g->assembled) { if ((rc = assemble_dispatch(g, g->cur))) return rc; g->assembled = true; }
+  return GPB_OK;
+}
+
+int gpb_solve_delta(gpb_graph* g, double lambda, double* delta_states, double* delta_landmarks) {
+  CHECK_READY(g);
+  int rc = ensure_assembled(g);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemsetAsync(g->d_flag, 0, sizeof(int), g->stream));
+  if ((rc = solve_system(g, g->cur, lambda))) return rc;
+  int flag = 0;
+  CUDA_TRY(cudaMemcpyAsync(&flag, g->d_flag, sizeof(int), cudaMemcpyDeviceToHost, g->stream));
+  if (delta_states) CUDA_TRY(cudaMemcpyAsync(delta_states, g->levels[0].xsol, (size_t)g->N * g->bs * sizeof(double), cudaMemcpyDeviceToHost, g->stream));
+  if (delta_landmarks && g->nb) CUDA_TRY(cudaMemcpyAsync(delta_landmarks, g->d_xlm, (size_t)g->nb * sizeof(double), cudaMemcpyDeviceToHost, g->stream));
+  CUDA_TRY(cudaStreamSynchronize(g->stream));
+  if (flag) return fail(GPB_ERR_NUMERIC, "gpb_solve_delta: system is not positive definite (indeterminate linear system)");
+  return GPB_OK;
+}
+
+// ===================================================================== GN / LM loop
+int gpb_optimize(gpb_graph* g, const gpb_params* params, int n_iter, gpb_stats* st) {
+  CHECK_READY(g);
+  gpb_params p;
+  if (params) p = *params; else gpb_default_params(&p, 1);
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
+  CUDA_TRY(cudaEventRecord(e0, g->stream));
+  g->launches = 0;
+  int rc;
+  if (!g->linearized && (rc = gpb_linearize(g, nullptr))) return rc;
+  const double error_initial = g->cur_error;
+  double error = error_initial, lambda = p.lambda_initial;
+  int iterations = 0, status = 0;
+  auto one_iteration = [&]() -> int {
+    int r;
+    if (!g->assembled) { if ((r = assemble_dispatch(g, g->cur))) return r; g->assembled = true; }
+    while (true) {
+      CUDA_TRY(cudaMemsetAsync(g->d_flag, 0, sizeof(int), g->stream));
+      if ((r = solve_system(g, g->cur, p.use_lm ? lambda : 0.0))) return r;
+      if ((r = retract_dispatch(g))) return r;
+      // linearise at the trial point into the other buffer: gives the trial error and, if accepted, the next iteration's [A|b]
+      if ((r = linearize_dispatch(g, g->d_Xt, g->d_landt, 1 - g->cur, 1))) return r;
+      double s[3]; int flag;
+      if ((r = read_scalars(g, s, &flag))) return r;
+      const double newError = s[0];
+      bool success = false, stop = false;
+      if (!p.use_lm) {
+        if (flag) { status = 1; return fail(GPB_ERR_NUMERIC, "GaussNewton: indeterminate linear system"); }
+        success = true;
+      } else if (!flag) {
+        // (H + lambda I) d = g  =>  error - linearised_error(d) = g.d - 0.5 d^T H d = 0.5 g.d + 0.5 lambda |d|^2
+        const double linearizedCostChange = 0.5 * s[1] + 0.5 * lambda * s[2];
+        if (linearizedCostChange >= 0) {
+          const double costChange = error - newError;
+          double modelFidelity = 0;
+          if (linearizedCostChange > 1e-20) modelFidelity = costChange / linearizedCostChange;
+          success = modelFidelity > p.min_model_fidelity;
+          if (std::fabs(costChange) < p.rel_tol * error) stop = true;
+        }
+      }
+      if (success) {
+        std::swap(g->d_X, g->d_Xt); std::swap(g->d_land, g->d_landt); g->cur = 1 - g->cur;
+        error = newError; g->cur_error = error; g->assembled = false; g->linearized = true;
+        if (p.use_lm) lambda = std::max(p.lambda_lower, lambda / p.lambda_factor);
+        break;
+      } else if (!stop) {
+        lambda *= p.lambda_factor;
+        if (lambda >= p.lambda_upper) { status = 1; break; }
+      } else break;
+    }
+    iterations++;
+    return GPB_OK;
+  };
+  if (n_iter > 0) {
+    for (int k = 0; k < n_iter && !status; k++) if ((rc = one_iteration())) return rc;
+  } else if (!(error <= p.err_tol)) {
+    do {
+      const double currentError = error;
+      if ((rc = one_iteration())) return rc;
+      if (status) break;
+      if (error <= p.err_tol) break;
+      const double absDec = currentError - error, relDec = absDec / currentError;
+      if ((p.rel_tol && relDec <= p.rel_tol) || absDec <= p.abs_tol) break;
+    } while (iterations < p.max_iterations);
+  }
+  CUDA_TRY(cudaEventRecord(e1, g->stream));
+  CUDA_TRY(cudaEventSynchronize(e1));
+  float ms = 0;
+  CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (st) {
+    std::memset(st, 0, sizeof(*st));
+    st->iterations = iterations; st->error_initial = error_initial; st->error_final = error; st->lambda = lambda; st->total_ms = ms; st->status = status;
+  }
+  return GPB_OK;
+}
+
+int gpb_kernel_launches_last_optimize(gpb_graph* g) { return g ? g->launches : 0; }
+
+// ===================================================================== parity copy-outs
+int gpb_get_linearized_factor(gpb_graph* g, int kind, int idx, double* A_out, double* b_out, int* dims_out) {
+  CHECK_READY(g);
+  if (!g->linearized) return fail(GPB_ERR_STATE, "call gpb_linearize first");
+  const int D = g->D, bs = g->bs, DL = g->DL;
+  for (int v = 0; v < 5; v++) dims_out[v] = 0;
+  if (kind == 0) {
+    if (idx < 0 || idx >= g->nint || !(g->dt[idx] > 0)) return fail(GPB_ERR_ARG, "no GP prior on that interval");
+    const int m = bs, ncol = 4 * D + 1;
+    std::vector<double> col(2);
+    for (int c = 0; c < ncol; c++)
+      for (int rp = 0; rp < D; rp++) {
+        CUDA_TRY(cudaMemcpy(col.data(), g->d_AB[g->cur] + ((size_t)(c * D + rp) * g->NFp + idx) * 2, 2 * sizeof(double), cudaMemcpyDeviceToHost));
+        for (int t = 0; t < 2; t++) { const int r = 2 * rp + t; if (c < 4 * D) A_out[(size_t)c * m + r] = col[t]; else b_out[r] = col[t]; }
+      }
+    for (int v = 0; v < 4; v++) dims_out[v] = D;
+    return m;
+  }
+  if (idx < 0 || idx >= g->NX) return fail(GPB_ERR_ARG, "factor index out of range");
+  const int k = g->sorted_of_order[idx];
+  const Extra& e = g->sorted[k];
+  const int m = e.m, row0 = g->h_xrow[k];
+  std::vector<double> rows((size_t)g->ncolsX * m);
+  for (int c = 0; c < g->ncolsX; c++) CUDA_TRY(cudaMemcpy(rows.data() + (size_t)c * m, g->d_XR[g->cur] + (size_t)c * g->NXRp + row0, m * sizeof(double), cudaMemcpyDeviceToHost));
+  // variable order of the reference's factor
+  int nv = 0, o = 0;
+  auto emit = [&](int col0, int d) { for (int c = 0; c < d; c++) for (int r = 0; r < m; r++) A_out[o++] = rows[(size_t)(col0 + c) * m + r]; dims_out[nv++] = d; };
+  const int offs = e.sa >= 0 ? 0 : bs;
+  switch (e.kind) {
+    case X_INTERP_RANGE: emit(0, D); emit(D, D); emit(bs, D); emit(bs + D, D); emit(2 * bs, DL); break;
+    case X_INTERP_ATTITUDE: emit(0, D); emit(D, D); emit(bs, D); emit(bs + D, D); break;
+    case X_PRIOR_POSE: emit(offs, D); break;
+    case X_PRIOR_VEL: emit(offs + D, D); break;
+    case X_PRIOR_LANDMARK: emit(2 * bs, DL); break;
+    case X_BETWEEN: if (e.prm[17] != 0.0) { emit(bs, D); emit(0, D); } else { emit(0, D); emit(bs, D); } break;
+    case X_ODOMETRY_2D: emit(0, D); emit(bs, D); break;
+    case X_RANGE_2D: case X_RANGE_BEARING_2D: emit(offs, D); emit(2 * bs, DL); break;
+  }
+  for (int r = 0; r < m; r++) b_out[r] = rows[(size_t)(g->ncolsX - 1) * m + r];
+  return m;
+}
+
+int gpb_get_normal_equations(gpb_graph* g, double* H, double* rhs, int n) {
+  CHECK_READY(g);
+  int rc = ensure_assembled(g);
+  if (rc) return rc;
+  const int bs = g->bs, DL = g->DL, nb = g->nb, REC = 2 * bs * bs + bs;
+  if (n != g->N * bs + nb) return fail(GPB_ERR_ARG, "gpb_get_normal_equations: wrong system dimension");
+  std::vector<double> rec((size_t)g->N * REC), XR((size_t)g->ncolsX * g->NXRp, 0.0), Cb((size_t)nb * nb + nb, 0.0);
+  CUDA_TRY(cudaStreamSynchronize(g->stream));
+  CUDA_TRY(cudaMemcpy(rec.data(), g->d_HREC, rec.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  if (g->NX) CUDA_TRY(cudaMemcpy(XR.data(), g->d_XR[g->cur], XR.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  if (nb) CUDA_TRY(cudaMemcpy(Cb.data(), g->d_Cbase, Cb.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  std::fill(H, H + (size_t)n * n, 0.0); std::fill(rhs, rhs + n, 0.0);
+  for (int i = 0; i < g->N; i++) {
+    const double* r = rec.data() + (size_t)i * REC;
+    for (int c = 0; c < bs; c++) for (int rr = 0; rr < bs; rr++) H[(size_t)(i * bs + rr) + (size_t)(i * bs + c) * n] = r[rr + c * bs];
+    if (i + 1 < g->N) for (int c = 0; c < bs; c++) for (int rr = 0; rr < bs; rr++) {
+      const double v = r[bs * bs + rr + c * bs];
+      H[(size_t)((i + 1) * bs + rr) + (size_t)(i * bs + c) * n] = v; H[(size_t)(i * bs + c) + (size_t)((i + 1) * bs + rr) * n] = v;
+    }
+    for (int rr = 0; rr < bs; rr++) rhs[i * bs + rr] = r[2 * bs * bs + rr];
+  }
+  // border from the extra rows (host side, parity only)
+  int row = 0;
+  for (int k = 0; k < g->NX; k++) {
+    const Extra& e = g->sorted[k];
+    for (int r = 0; r < e.m; r++, row++) {
+      if (e.l < 0) continue;
+      const int lo = g->N * bs + e.l * DL;
+      for (int d = 0; d < DL; d++) {
+        const double lv = XR[(size_t)(2 * bs + d) * g->NXRp + row];
+        for (int side = 0; side < 2; side++) {
+          const int s = e.interval + side;
+          if (s >= g->N) continue;
+          for (int c = 0; c < bs; c++) { const double v = XR[(size_t)(side * bs + c) * g->NXRp + row] * lv; H[(size_t)(s * bs + c) + (size_t)(lo + d) * n] += v; H[(size_t)(lo + d) + (size_t)(s * bs + c) * n] += v; }
+        }
+      }
+    }
+  }
+  for (int c = 0; c < nb; c++) { for (int r = 0; r < nb; r++) H[(size_t)(g->N * bs + r) + (size_t)(g->N * bs + c) * n] = Cb[r + (size_t)c * nb]; rhs[g->N * bs + c] = Cb[(size_t)nb * nb + c]; }
+  return GPB_OK;
+}
+
+int gpb_get_sizes(gpb_graph* g, gpb_sizes* s) {
+  if (!g || !s) return fail(GPB_ERR_ARG, "null argument");
+  const int D = g->D, bs = g->bs;
+  const double state_bytes = 8.0 * g->SR, land_bytes = 8.0 * g->DL;
+  // LINEARISE_BYTES = sum_states value_bytes + sum_factors (param_bytes + 8 m (sum_k d_k + 1))
+  double lin = g->N * state_bytes + g->L * land_bytes + g->ngp * (8.0 + 8.0 * bs * (4 * D + 1));
+  for (const Extra& e : g->extras) {
+    int cols = 0; double prm = 0;
+    switch (e.kind) {
+      case X_INTERP_RANGE: cols = 4 * D + g->DL; prm = 44; break;
+      case X_INTERP_ATTITUDE: cols = 4 * D; prm = 80; break;
+      case X_PRIOR_POSE: cols = D; prm = 8.0 * (g->PS + D * D); break;
+      case X_PRIOR_VEL: cols = D; prm = 8.0 * (D + D * D); break;
+      case X_PRIOR_LANDMARK: cols = g->DL; prm = 8.0 * (g->DL + g->DL * g->DL); break;
+      case X_BETWEEN: cols = 2 * D; prm = 8.0 * (g->PS + D * D); break;
+      case X_ODOMETRY_2D: cols = 6; prm = 8.0 * 12; break;
+      case X_RANGE_2D: cols = D + 2; prm = 16; break;
+      case X_RANGE_BEARING_2D: cols = D + 2; prm = 48; break;
+    }
+    lin += prm + 8.0 * e.m * (cols + 1);
+  }
+  s->linearise_bytes = lin;
+  s->fused_bytes = g->N * (state_bytes + 8.0 * (2 * bs * bs + bs));
+  s->solve_bytes = 2.0 * g->N * 8.0 * (2 * bs * bs + bs);
+  s->hbm_bytes = (double)g->hbm_bytes;
+  s->n_gp = g->ngp; s->n_extra = (int)g->extras.size(); s->n_rows = g->NXR; s->border_dim = g->nb; s->levels = (int)g->levels.size();
+  return GPB_OK;
+}
+
+}  // extern "C"

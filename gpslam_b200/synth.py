@@ -1,0 +1,213 @@
+"""Deterministic synthetic trajectory graphs for BASELINE.json's configs.
+
+`build(cfg, make_graph)` constructs the same graph through any object exposing the construction calls shared by
+gpslam_b200.Graph (CUDA engine) and oracle.pyoracle.Graph (CPU oracle), so both sides see identical inputs.
+Pure numpy; no arithmetic of the hot path lives here (ground truth uses its own small Exp maps).
+"""
+import numpy as np
+
+POSE3, POSE2, ROT3, LINEAR = 0, 1, 2, 3
+
+
+def _skew(w):
+    return np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]])
+
+
+def _so3_exp(w):
+    th = np.linalg.norm(w)
+    W = _skew(w)
+    if th < 1e-12:
+        return np.eye(3) + W
+    return np.eye(3) + np.sin(th) / th * W + (1 - np.cos(th)) / th ** 2 * (W @ W)
+
+
+def _se3_exp(xi):
+    w, v = xi[:3], xi[3:]
+    R = _so3_exp(w)
+    th2 = w @ w
+    if th2 < 1e-20:
+        return R, v.copy()
+    wxv = np.cross(w, v)
+    return R, (wxv - R @ wxv + w * (w @ v)) / th2
+
+
+def _se2_exp(xi):
+    w = xi[2]
+    if abs(w) < 1e-12:
+        return xi.copy()
+    c, s = np.cos(w), np.sin(w)
+    ox, oy = -xi[1], xi[0]
+    return np.array([(ox - (c * ox - s * oy)) / w, (oy - (s * ox + c * oy)) / w, w])
+
+
+def _wire3(R, t):
+    return np.concatenate([R.T.ravel(), t])
+
+
+class Config:
+    def __init__(self, name, group, n_states, n_landmarks=0, range_per_state=0.0, dt=0.1, seed=0, qc_sigma=0.1, prior_every=100,
+                 attitude_every=0, odometry=False, init_noise=0.05, zero_rot_fraction=0.01):
+        self.__dict__.update(locals())
+        del self.__dict__["self"]
+
+
+def config(name):
+    """BASELINE.json configs (sizes may be overridden by the caller through attributes)."""
+    base = 20260925
+    if name == "C1":
+        return Config("C1", POSE2, 1000, 4, 0.444, dt=0.1, seed=base + 1, qc_sigma=0.1, prior_every=0, odometry=True)
+    if name == "C2":
+        return Config("C2", POSE3, 10000, 0, 0.0, dt=0.1, seed=base + 2, qc_sigma=0.1)
+    if name == "C3":
+        return Config("C3", POSE3, 100000, 16, 0.5, dt=0.1, seed=base + 3, qc_sigma=0.1)
+    if name == "C4":
+        return Config("C4", ROT3, 1000000, 0, 0.0, dt=0.005, seed=base + 4, qc_sigma=100.0, prior_every=0, attitude_every=4)
+    if name == "C5":
+        return Config("C5", POSE3, 1000000, 16, 0.5, dt=0.1, seed=base + 5, qc_sigma=0.1)
+    raise KeyError(name)
+
+
+def ground_truth(cfg):
+    """constant body twist with a slow sinusoidal modulation: T_{i+1} = T_i Exp(w_i dt), v_i = w_i"""
+    rng = np.random.default_rng(cfg.seed)
+    N, dt = cfg.n_states, cfg.dt
+    t = np.arange(N) * dt
+    if cfg.group == POSE3:
+        w0 = np.array([0.05, -0.1, 0.27, 1.0, 0.1, -0.05])
+        tw = w0[None, :] * (1 + 0.3 * np.sin(0.05 * t)[:, None]) + 0.02 * np.stack([np.sin(0.11 * t + k) for k in range(6)], axis=1)
+        nz = max(1, int(cfg.zero_rot_fraction * N))
+        z0 = N // 3
+        tw[z0:z0 + nz, :3] = 0.0  # slice with exactly zero angular rate: hits the reference's theta -> 0 branches
+        poses = np.zeros((N, 12)); R = np.eye(3); p = np.zeros(3)
+        for i in range(N):
+            poses[i] = _wire3(R, p)
+            dR, dp = _se3_exp(tw[i] * dt)
+            p = R @ dp + p; R = R @ dR
+            if i % 1000 == 0:
+                u, _, vt = np.linalg.svd(R); R = u @ vt
+        return poses, tw
+    if cfg.group == ROT3:
+        w0 = np.array([0.3, -0.2, 0.5])
+        tw = w0[None, :] * (1 + 0.3 * np.sin(0.5 * t)[:, None])
+        poses = np.zeros((N, 9)); R = np.eye(3)
+        for i in range(N):
+            poses[i] = R.T.ravel()
+            R = R @ _so3_exp(tw[i] * dt)
+            if i % 1000 == 0:
+                u, _, vt = np.linalg.svd(R); R = u @ vt
+        return poses, tw
+    # planar groups
+    w0 = np.array([1.0, 0.0, 0.12])
+    tw = w0[None, :] * (1 + 0.3 * np.sin(0.05 * t)[:, None])
+    poses = np.zeros((N, 3)); x = np.zeros(3)
+    for i in range(N):
+        poses[i] = x
+        d = _se2_exp(tw[i] * dt)
+        c, s = np.cos(x[2]), np.sin(x[2])
+        x = np.array([x[0] + c * d[0] - s * d[1], x[1] + s * d[0] + c * d[1], x[2] + d[2]])
+    if cfg.group == LINEAR:  # "linear Pose2" states: velocities are world-frame derivatives of (x, y, theta)
+        v = np.zeros_like(tw)
+        v[:, 0] = np.cos(poses[:, 2]) * tw[:, 0] - np.sin(poses[:, 2]) * tw[:, 1]
+        v[:, 1] = np.sin(poses[:, 2]) * tw[:, 0] + np.cos(poses[:, 2]) * tw[:, 1]
+        v[:, 2] = tw[:, 2]
+        return poses, v
+    return poses, tw
+
+
+def _retract(group, pose, d):
+    if group == POSE3:
+        R = pose[:9].reshape(3, 3).T; t = pose[9:]
+        dR, dp = _se3_exp(d)
+        return _wire3(R @ dR, R @ dp + t)
+    if group == ROT3:
+        return (pose.reshape(3, 3).T @ _so3_exp(d)).T.ravel()
+    if group == POSE2:
+        c, s = np.cos(pose[2]), np.sin(pose[2])
+        return np.array([pose[0] + c * d[0] - s * d[1], pose[1] + s * d[0] + c * d[1], pose[2] + d[2]])
+    return pose + d
+
+
+def build(cfg, make_graph, finalize=True):
+    """Returns (graph, truth dict).  make_graph(group, n_states, n_landmarks) -> Graph-like object."""
+    rng = np.random.default_rng(cfg.seed + 1000)
+    N, dt, group = cfg.n_states, cfg.dt, cfg.group
+    D = 6 if group == POSE3 else 3
+    DL = {POSE3: 3, POSE2: 2, ROT3: 0, LINEAR: 2}[group]
+    poses, vels = ground_truth(cfg)
+    L = cfg.n_landmarks if DL else 0
+    g = make_graph(group, N, L)
+    g.add_qc_model(np.eye(D) * cfg.qc_sigma ** 2)
+    g.add_gp_prior(np.arange(N - 1), np.full(N - 1, dt))
+    iso = lambda n, s: np.eye(n) / s
+    lands = np.zeros((L, max(DL, 1)))
+    if L:
+        if group == POSE3:
+            ctr = poses[:, 9:12].mean(axis=0); span = np.abs(poses[:, 9:12] - ctr).max() + 10.0
+            lands = ctr + rng.uniform(-span, span, size=(L, 3))
+        else:
+            ctr = poses[:, :2].mean(axis=0); span = np.abs(poses[:, :2] - ctr).max() + 10.0
+            lands = ctr + rng.uniform(-span, span, size=(L, 2))
+        nr = int(round(cfg.range_per_state * N))
+        ri = np.sort(rng.integers(0, N - 1, size=nr)); rl = rng.integers(0, L, size=nr); tau = rng.uniform(0, dt, size=nr)
+        sig = 0.1 if group == POSE3 else 0.5
+        z = np.zeros(nr)
+        for k in range(nr):
+            i = ri[k]
+            Ti = _retract(group if group != LINEAR else POSE2, poses[i], (vels[i] if group != LINEAR else _body(poses[i], vels[i])) * tau[k])
+            if group == POSE3:
+                z[k] = np.linalg.norm(lands[rl[k]] - Ti[9:12])
+            else:
+                z[k] = np.linalg.norm(lands[rl[k]] - Ti[:2])
+        z += rng.normal(size=nr) * sig
+        g.add_interp_range(ri, rl, z, np.full(nr, sig), np.full(nr, dt), tau)
+        for l in range(L):
+            g.add_prior_landmark(l, lands[l] + rng.normal(size=DL) * 0.5, iso(DL, 1.0))
+    # gauge: pose + velocity prior on state 0, sparse pose priors along the chain
+    s0 = 1e-3 if group != POSE2 else 1.0
+    g.add_prior_pose(0, poses[0], iso(D, s0))
+    g.add_prior_vel(0, vels[0], iso(D, 1e-3 if group != POSE2 else 1.0))
+    if cfg.prior_every:
+        for i in range(cfg.prior_every, N, cfg.prior_every):
+            g.add_prior_pose(i, _retract(group, poses[i], rng.normal(size=D) * 0.1), iso(D, 0.1))
+    if cfg.attitude_every and group == ROT3:
+        ai = np.arange(0, N - 1, cfg.attitude_every)
+        g.add_interp_attitude(ai, np.full(len(ai), dt), np.full(len(ai), 0.5 * dt), _attitude_meas(poses, vels, ai, dt, rng), np.full(len(ai), 0.1))
+        # gyro-like relative-rotation factors (the reference's AHRSFactor is GTSAM code)
+    if cfg.odometry and group in (POSE2, POSE3, ROT3):
+        for i in range(N - 1):
+            meas = _between(group, poses[i], poses[i + 1], rng, 1e-3)
+            g.add_between(i, i + 1, meas, iso(D, 1e-3) if group != POSE2 else np.diag([1e3, 1e3, 1e3 / np.pi]))
+    # initial values: truth (+) noise on the pose tangent, zero velocities (matlab/PlazaPose2.m:201-202)
+    init = np.stack([_retract(group, poses[i], rng.normal(size=D) * cfg.init_noise) for i in range(N)])
+    g.set_values(init, np.zeros((N, D)), lands + (rng.normal(size=lands.shape) * 0.5 if L else 0))
+    if finalize and hasattr(g, "finalize"):
+        g.finalize()
+    return g, dict(poses=poses, vels=vels, lands=lands)
+
+
+def _body(pose, v):
+    c, s = np.cos(pose[2]), np.sin(pose[2])
+    return np.array([c * v[0] + s * v[1], -s * v[0] + c * v[1], v[2]])
+
+
+def _between(group, a, b, rng, noise):
+    if group == POSE3:
+        Ra = a[:9].reshape(3, 3).T; Rb = b[:9].reshape(3, 3).T
+        R = Ra.T @ Rb; t = Ra.T @ (b[9:] - a[9:])
+        dR, dp = _se3_exp(rng.normal(size=6) * noise)
+        return _wire3(R @ dR, R @ dp + t)
+    if group == ROT3:
+        return ((a.reshape(3, 3).T).T @ b.reshape(3, 3).T @ _so3_exp(rng.normal(size=3) * noise)).T.ravel()
+    c, s = np.cos(a[2]), np.sin(a[2])
+    dx, dy = b[0] - a[0], b[1] - a[1]
+    return np.array([c * dx + s * dy, -s * dx + c * dy, b[2] - a[2]]) + rng.normal(size=3) * noise
+
+
+def _attitude_meas(poses, vels, ai, dt, rng):
+    """accelerometer-style direction measurements nZ = R(t) bRef + noise, bRef = e_z"""
+    out = np.zeros((len(ai), 3))
+    for k, i in enumerate(ai):
+        R = poses[i].reshape(3, 3).T @ _so3_exp(vels[i] * 0.5 * dt)
+        n = R @ np.array([0, 0, 1.0]) + rng.normal(size=3) * 0.02
+        out[k] = n / np.linalg.norm(n)
+    return out

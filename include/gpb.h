@@ -1,0 +1,133 @@
+/* gpb.h — C ABI of the B200-native sparse-GP factor-graph linearise-and-solve engine.
+ *
+ * This is the drop-in boundary for gtrll/gpslam's hot path.  gpslam has no FFI
+ * of its own — its plugin API is GTSAM's factor interface — so each entry point below names the
+ * reference/GTSAM interface it stands in for.  Plain pointers and sizes only; all matrices are
+ * column-major doubles (Eigen's layout); every call returns 0 on success or a negative status,
+ * with gpb_last_error() giving the message.  No CPU fallback exists: without a CUDA device (or
+ * with the CUDA library missing) gpb_graph_finalize() and everything after it fails loudly.
+ *
+ * Wire layouts (shared with the oracle and the kernels):
+ *   Pose3 = 12 doubles [R column-major (9) | t (3)],  Rot3 = 9 (R column-major),
+ *   Pose2 = (x, y, theta),  Linear<D> = D doubles;  velocities = tangent vectors (D doubles);
+ *   Pose3 tangent order (omega, v) [gp/Pose3utils.cpp:116], Pose2 tangent (vx, vy, omega).
+ *   Landmarks: Point3 for Pose3 graphs, Point2 for Pose2 / Linear<3> graphs.
+ */
+#ifndef GPB_H
+#define GPB_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gpb_graph gpb_graph;
+
+/* state manifold of the trajectory; selects the factor family
+ * (gp/GaussianProcessPrior{Pose3,Pose2,Rot3,Linear}.h and the matching interpolators) */
+enum { GPB_POSE3 = 0, GPB_POSE2 = 1, GPB_ROT3 = 2, GPB_LINEAR = 3 };
+
+enum { GPB_OK = 0, GPB_ERR_ARG = -1, GPB_ERR_CUDA = -2, GPB_ERR_STATE = -3, GPB_ERR_UNSUPPORTED = -4, GPB_ERR_NUMERIC = -5 };
+
+/* LevenbergMarquardtParams / GaussNewtonParams (GTSAM defaults) */
+typedef struct gpb_params {
+  int max_iterations;        /* 100 */
+  double rel_tol, abs_tol, err_tol; /* 1e-5, 1e-5, 0 */
+  double lambda_initial, lambda_factor, lambda_upper, lambda_lower; /* 1e-5, 10, 1e5, 0 */
+  double min_model_fidelity; /* 1e-3 */
+  int use_lm;                /* 1 = LevenbergMarquardtOptimizer, 0 = GaussNewtonOptimizer */
+} gpb_params;
+
+typedef struct gpb_stats {
+  int iterations;
+  double error_initial, error_final, lambda;
+  double linearize_ms, assemble_ms, solve_ms, update_ms, total_ms; /* device time (CUDA events) */
+  int status;
+} gpb_stats;
+
+const char* gpb_last_error(void);
+int gpb_device_count(void);
+void gpb_default_params(gpb_params* p, int use_lm);
+
+/* -- graph construction: stands in for NonlinearFactorGraph::add + Values::insert
+ *    (matlab/PlazaPose2.m:90-204).  dim is used by GPB_LINEAR only (supported: 3). */
+gpb_graph* gpb_graph_create(int group, int dim, int n_states, int n_landmarks);
+void gpb_graph_destroy(gpb_graph* g);
+
+/* getQc (gp/GPutils.cpp:16-20): registers a D x D process-noise covariance Qc, returns its id */
+int gpb_add_qc_model(gpb_graph* g, const double* Qc);
+
+/* GaussianProcessPrior{Pose3,Pose2,Rot3,Linear}(x_i, v_i, x_{i+1}, v_{i+1}, delta_t, Qc)
+ * (gp/GaussianProcessPriorPose3.h:43-49): n factors on intervals i[k] -> i[k]+1 */
+int gpb_add_gp_prior(gpb_graph* g, int n, const int* i, const double* delta_t, int qc);
+
+/* GPInterpolatedRangeFactor{Pose3,Pose2,2DLinear}(z, meas_model(sigma), Qc, x_i, v_i, x_{i+1}, v_{i+1}, l, delta_t, tau
+ * [, body_P_sensor])  (slam/GPInterpolatedRangeFactorPose3.h:46-54).  body_P_sensor: one pose shared by the n factors, or NULL. */
+int gpb_add_interp_range(gpb_graph* g, int n, const int* i, const int* l, const double* z, const double* sigma,
+                         const double* delta_t, const double* tau, int qc, const double* body_P_sensor);
+
+/* GPInterpolatedAttitudeFactorRot3(x_i, v_i, x_{i+1}, v_{i+1}, delta_t, tau, Qc, meas_model(sigma), nZ, bRef)
+ * (slam/GPInterpolatedAttitudeFactorRot3.h:44-51).  nZ, bRef: 3 doubles per factor. */
+int gpb_add_interp_attitude(gpb_graph* g, int n, const int* i, const double* delta_t, const double* tau, int qc,
+                            const double* nZ, const double* bRef, const double* sigma);
+
+/* gtsam::PriorFactor<Pose|Vector|Point>: value in wire layout, sqrt_info = upper-triangular R (d x d) */
+int gpb_add_prior_pose(gpb_graph* g, int i, const double* value, const double* sqrt_info);
+int gpb_add_prior_vel(gpb_graph* g, int i, const double* value, const double* sqrt_info);
+int gpb_add_prior_landmark(gpb_graph* g, int l, const double* value, const double* sqrt_info);
+
+/* gtsam::BetweenFactor<Pose>(x_i, x_j, measured, model): odometry when j == i+1, loop closure otherwise */
+int gpb_add_between(gpb_graph* g, int i, int j, const double* measured, const double* sqrt_info);
+
+/* plain 2-way factors of gpslam/slam (Linear<3> states unless noted):
+ * RangeFactor2DLinear (slam/RangeFactor2DLinear.h:43-56) / RangeFactorPose2 (slam/RangeFactorPose2.h:15, Pose2 graphs),
+ * RangeBearingFactor2DLinear (slam/RangeBearingFactor2DLinear.h:47-84), OdometryFactor2DLinear (slam/OdometryFactor2DLinear.h:50-75) */
+int gpb_add_range_2d(gpb_graph* g, int i, int l, double z, double sigma);
+int gpb_add_range_bearing_2d(gpb_graph* g, int i, int l, double range, double bearing, const double* sqrt_info);
+int gpb_add_odometry_2d(gpb_graph* g, int i, int j, const double* measured, const double* sqrt_info);
+
+/* Values::insert / Values::at : host buffers, [n_states x pose_storage], [n_states x D], [n_landmarks x DL] */
+int gpb_set_values(gpb_graph* g, const double* poses, const double* vels, const double* landmarks);
+int gpb_get_values(gpb_graph* g, double* poses, double* vels, double* landmarks);
+
+/* Freezes the graph: sorts factors by interval, builds the device-resident SoA layout, allocates
+ * every solver buffer on `device`.  Must be called once after the last gpb_add_*. */
+int gpb_graph_finalize(gpb_graph* g, int device);
+
+/* NonlinearFactorGraph::error(values): 0.5 * sum |R e|^2 at the current values */
+int gpb_error(gpb_graph* g, double* error_out);
+
+/* NonlinearFactorGraph::linearize(values): batched evaluation of every factor's whitened
+ * [A|b] (the GaussianFactorGraph payload) into device memory; returns the graph error. */
+int gpb_linearize(gpb_graph* g, double* error_out);
+
+/* Copy-out of one factor's whitened JacobianFactor after gpb_linearize (parity checks):
+ * kind 0 = GP prior of interval idx, kind 1 = idx-th measurement/prior/between factor in insertion order.
+ * A_out: concatenated column-major blocks (m x d_v) in the factor's variable order; b_out: m.  Returns m (>0) or a status. */
+int gpb_get_linearized_factor(gpb_graph* g, int kind, int idx, double* A_out, double* b_out, int* dims_out /*[5]*/);
+
+/* Dense copy-out of the assembled normal equations H = A^T A, rhs = A^T b in the variable order
+ * [x_0 v_0 x_1 v_1 ... | landmarks] (small graphs only, parity checks).  n must equal the system dimension. */
+int gpb_get_normal_equations(gpb_graph* g, double* H_out, double* rhs_out, int n);
+
+/* GaussNewtonOptimizer::iterate / LevenbergMarquardtOptimizer::iterate (matlab/PlazaPose2.m:225):
+ * n_iter > 0 runs exactly n_iter iterations; n_iter <= 0 runs NonlinearOptimizer::optimize() to convergence. */
+int gpb_optimize(gpb_graph* g, const gpb_params* params, int n_iter, gpb_stats* stats);
+
+/* Solve the current linearisation once: delta = argmin |A d - b|^2 + lambda |d|^2, copied to the host
+ * as [n_states x 2D] and [n_landmarks x DL] (parity checks of the block solver). */
+int gpb_solve_delta(gpb_graph* g, double lambda, double* delta_states, double* delta_landmarks);
+
+/* solver tuning: segment length per elimination level (>= 2); 0 keeps the default */
+int gpb_set_segment_length(gpb_graph* g, int level0, int upper_levels);
+
+/* bytes of HBM held by the graph, and the algorithmic byte counts of SURVEY.md §8(d) */
+typedef struct gpb_sizes { double hbm_bytes, linearise_bytes, fused_bytes, solve_bytes; int n_gp, n_extra, n_rows, border_dim, levels; } gpb_sizes;
+int gpb_get_sizes(gpb_graph* g, gpb_sizes* s);
+
+/* names and average device milliseconds of the kernels timed during the last gpb_optimize (profiling aid) */
+int gpb_kernel_launches_last_optimize(gpb_graph* g);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPB_H */
