@@ -1,0 +1,183 @@
+#!/usr/bin/env python
+"""bench.py — GN iterations/sec on BASELINE.json's 100k-state SE(3) GP trajectory (config C3) + linearise HBM GB/s.
+
+  python bench.py --gpus N --steps K --warmup W            # CUDA engine (one process per GPU under torchrun for N > 1)
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (restated oracle) on the host cores
+
+A "step" is one Gauss-Newton iteration of the hot path over the whole graph: batched linearise of every factor ->
+normal-equation assembly -> bordered block-tridiagonal Cholesky solve -> retract -> error.  Prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = "C3: SE(3) GP-prior + interpolated range factors, 100k states, 50k ranges, 16 landmarks (BASELINE.json configs[2]; interpolated range only - the reference has no interpolated bearing factor)"
+METRIC = "GN iterations/sec on 100k-state SE(3) GP trajectory"
+CPU_SAMPLE_STATES = 10000
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region"""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush(); self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 7:
+                continue
+            try:
+                sm.append(float(c[0])); mx.append(float(c[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, c[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        os.unlink(self.f.name)
+        return out
+
+
+def cpu_reference_run(steps, warmup, threads, n_sample=CPU_SAMPLE_STATES):
+    """the reference's CPU path (oracle/: restated gpslam factors + GTSAM-style GN over a bordered block-tridiagonal Cholesky)
+    on a bounded sample of the workload: C3 cut to n_sample states (same factor densities).  Per-iteration cost is linear in
+    the number of states, so iterations/sec on the 100k-state graph = sample rate * n_sample / 100000."""
+    from gpslam_b200 import synth
+    from oracle import pyoracle as po
+    cfg = synth.config("C3"); full = cfg.n_states; cfg.n_states = n_sample
+    o, _ = synth.build(cfg, lambda grp, n, l: po.Graph(grp, n, l))
+    o.set_threads(threads)
+    if warmup:
+        o.optimize(n_iter=warmup, use_lm=False)
+    t0 = time.perf_counter()
+    st = o.optimize(n_iter=steps, use_lm=False)
+    dt = time.perf_counter() - t0
+    rate_sample = steps / dt
+    return {"value": rate_sample * n_sample / full, "seconds_per_iteration_sample": dt / steps, "lin_seconds": st.lin_seconds, "solve_seconds": st.solve_seconds,
+            "sample": "C3 cut to %d of %d states (same factor densities), %d GN iterations after %d warm-up; rate scaled by %d/%d (cost is linear in states)"
+                      % (n_sample, full, steps, warmup, n_sample, full)}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    from oracle import pyoracle as po
+    threads = po.hardware_threads()
+    r = cpu_reference_run(args.steps, args.warmup, threads)
+    line = {"metric": METRIC, "value": r["value"], "unit": "iterations/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 / r["value"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "impl": "reference", "config": {"workload": WORKLOAD},
+            "cpu_baseline": {"value": r["value"], "unit": "iterations/s", "cores": threads, "kind": "port", "sample": r["sample"]},
+            "e2e": {"value": r["value"], "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def run_engine(args, rank, world, local_rank):
+    import gpslam_b200 as gb
+    from gpslam_b200 import synth
+    if world > 1:
+        raise SystemExit("bench.py: the trajectory-sharded multi-GPU path is not built yet in this round; run with --gpus 1")
+    if gb.device_count() <= local_rank:
+        raise SystemExit("bench.py: no CUDA device (the engine has no CPU fallback)")
+    cfg = synth.config("C3")
+    if args.states:
+        cfg.n_states = args.states
+    t0 = time.perf_counter()
+    g, _ = synth.build(cfg, lambda grp, n, l: gb.Graph(grp, n, l))
+    build_s = time.perf_counter() - t0
+    sz = g.sizes()
+    err0 = g.linearize()
+    # ---- warm-up, then K timed GN iterations: CUDA events on the engine's stream, synchronised on both sides (gpb_optimize)
+    g.optimize(n_iter=max(args.warmup, 3), use_lm=False)
+    sampler = ClockSampler(local_rank)
+    st = g.optimize(n_iter=args.steps, use_lm=False)
+    launches = g.launches()
+    ms_per_step = st.total_ms / args.steps
+    value = 1e3 / ms_per_step
+    # ---- end to end through the C ABI with host buffers: H2D of the values, one iteration, D2H of the result, every step
+    P, V, Lm = g.get_values()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        g.set_values(P, V, Lm)
+        g.optimize(n_iter=1, use_lm=False)
+        P, V, Lm = g.get_values()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    clocks = sampler.stop()
+    io_bytes = int(P.nbytes + V.nbytes + Lm.nbytes)
+    # ---- per-stage device times and the linearise roofline
+    stages = {n: g.time_stage(k, 20) for k, n in ((0, "linearise_gp"), (1, "linearise_other"), (2, "assemble"), (3, "solve"), (4, "retract"), (5, "solve_fwd_level0"))}
+    peak, peak_src = peaks()
+    gp_bytes = cfg.n_states * 8.0 * 18 + sz.n_gp * (8.0 + 8.0 * 12 * 25)  # states once + per factor (param + [A|b])
+    achieved = gp_bytes / (stages["linearise_gp"] * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": "iterations/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "states": cfg.n_states, "gp_factors": sz.n_gp, "other_factors": sz.n_extra, "landmark_dims": sz.border_dim,
+                   "solver_levels": sz.levels, "optimizer": "Gauss-Newton", "l2": "inputs larger than L2: [A|b] buffers 2 x %.0f MB, solver factors %.0f MB (L2 126 MB)"
+                   % (sz.n_gp * 2400 / 1e6, sz.hbm_bytes / 1e6), "hbm_resident_mb": sz.hbm_bytes / 1e6, "graph_build_s": build_s},
+        "e2e": {"value": 1.0 / e2e_s, "unit": "iterations/s", "h2d_bytes_per_step": io_bytes, "d2h_bytes_per_step": io_bytes},
+        "gpu_launches": launches,
+        "roofline": {"kernel": "k_lin_gp<POSE3> (batched GP-prior linearise)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "peak_source": peak_src, "algorithmic_bytes": gp_bytes, "ms": stages["linearise_gp"], "traffic": None},
+        "stages_ms": stages, "clocks": clocks, "error": {"initial": err0, "final": st.error_final},
+    }
+    if rank == 0 and not args.no_cpu:
+        r = cpu_reference_run(3, 1, 1)
+        line["cpu_baseline"] = {"value": r["value"], "unit": "iterations/s", "cores": 1, "kind": "port", "sample": r["sample"],
+                                "seconds_per_iteration_sample": r["seconds_per_iteration_sample"]}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--states", type=int, default=0, help="override the number of states (parity/debug runs; not a bench value)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_engine(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

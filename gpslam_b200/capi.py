@@ -225,6 +225,11 @@ class Graph:
         self._ck(self.L.gpb_optimize(self.h, C.byref(p), C.c_int(n_iter), C.byref(st)))
         return st
 
+    def time_stage(self, stage, reps=10):
+        ms = C.c_double()
+        self._ck(self.L.gpb_time_stage(self.h, C.c_int(stage), C.c_int(reps), C.byref(ms)))
+        return ms.value
+
     def sizes(self):
         s = Sizes()
         self._ck(self.L.gpb_get_sizes(self.h, C.byref(s)))

@@ -57,7 +57,8 @@ struct gpb_graph {
   std::vector<double> dt;               // per interval (0 = no GP prior)
   std::vector<int> gp_qc;
   std::vector<Extra> extras;
-  std::vector<double> h_X, h_land;
+  std::vector<double> h_X, h_land;   // host values before finalize()
+  bool pinned = false;  // h_X / h_land are page-locked (cudaHostRegister) after finalize()
   bool finalized = false, linearized = false, assembled = false;
   int device = -1;
   int M0 = 0, Mup = 0;
@@ -162,6 +163,7 @@ gpb_graph* gpb_graph_create(int group, int dim, int n_states, int n_landmarks) {
 void gpb_graph_destroy(gpb_graph* g) {
   if (!g) return;
   if (g->device >= 0) cudaSetDevice(g->device);
+  if (g->pinned) { cudaHostUnregister(g->h_X.data()); if (g->L) cudaHostUnregister(g->h_land.data()); }
   for (void* p : g->allocs) cudaFree(p);
   if (g->stream) cudaStreamDestroy(g->stream);
   delete g;
@@ -433,6 +435,11 @@ int gpb_graph_finalize(gpb_graph* g, int device) {
     n = L.S; lev++;
   }
   if ((rc = dev_alloc(g, &g->d_Cpart, (size_t)16 * g->levels.size() * std::max(centries, 1)))) return rc;
+  // page-lock the host staging so the H2D / D2H copies of the values run at full PCIe rate
+  if (cudaHostRegister(g->h_X.data(), g->h_X.size() * sizeof(double), cudaHostRegisterDefault) == cudaSuccess) {
+    g->pinned = true;
+    if (g->L) cudaHostRegister(g->h_land.data(), g->h_land.size() * sizeof(double), cudaHostRegisterDefault);
+  } else cudaGetLastError();
   g->finalized = true;
   rc = upload_values(g);
   if (rc) return rc;
@@ -498,29 +505,35 @@ template <int BS, int W> static void launch_bwd(const BwdArgs& a, int ncta, cuda
 template <int BS> static void fwd_w(int W, const FwdArgs& a, int ncta, cudaStream_t s) { if (W == 16) launch_fwd<BS, 16>(a, ncta, s); else if (W == 32) launch_fwd<BS, 32>(a, ncta, s); else launch_fwd<BS, 64>(a, ncta, s); }
 template <int BS> static void bwd_w(int W, const BwdArgs& a, int ncta, cudaStream_t s) { if (W == 16) launch_bwd<BS, 16>(a, ncta, s); else if (W == 32) launch_bwd<BS, 32>(a, ncta, s); else launch_bwd<BS, 64>(a, ncta, s); }
 
+static int launch_fwd_level(gpb_graph* g, int buf, double lambda, int lev) {
+  const int bs = g->bs, nb = g->nb, fstride = 2 * bs * bs + bs * g->w, centries = nb * nb + nb;
+  const int nlev = (int)g->levels.size();
+  Level& L = g->levels[lev];
+  FwdArgs a;
+  a.n = L.n; a.M = L.M; a.S = L.S; a.nseg = L.nseg; a.first_level = lev == 0;
+  a.rec = lev == 0 ? g->d_HREC : L.rec; a.brec = L.brec;
+  a.XR = g->d_XR[buf]; a.rowoff = g->d_rowoff; a.rowland = g->d_rowland; a.NXRp = g->NXRp; a.nint = g->nint; a.nb = nb; a.DL = std::max(g->DL, 1);
+  a.lambda = lambda;
+  a.rec_out = lev + 1 < nlev ? g->levels[lev + 1].rec : nullptr; a.brec_out = lev + 1 < nlev ? g->levels[lev + 1].brec : nullptr;
+  a.frec = L.frec; a.fstride = fstride; a.cseg = L.cseg; a.flag = g->d_flag;
+  if (bs == 12) fwd_w<12>(g->W, a, L.ncta, g->stream); else fwd_w<6>(g->W, a, L.ncta, g->stream);
+  g->launches++;
+  if (nb) {
+    const int R = std::min(16, L.ncta);
+    dim3 grid((centries + 255) / 256, R);
+    k_cseg_reduce<<<grid, 256, 0, g->stream>>>(L.cseg, L.ncta, centries, R, g->d_Cpart + (size_t)lev * 16 * centries);
+    if (R < 16) CUDA_TRY(cudaMemsetAsync(g->d_Cpart + ((size_t)lev * 16 + R) * centries, 0, (size_t)(16 - R) * centries * sizeof(double), g->stream));
+    g->launches++;
+  }
+  return GPB_OK;
+}
+
 // Solve (H + lambda I) delta = g with the current HREC / XR[buf]; delta lands in levels[0].xsol and d_xlm.
 static int solve_system(gpb_graph* g, int buf, double lambda) {
   const int bs = g->bs, nb = g->nb, fstride = 2 * bs * bs + bs * g->w, centries = nb * nb + nb;
   const int nlev = (int)g->levels.size();
-  for (int lev = 0; lev < nlev; lev++) {
-    Level& L = g->levels[lev];
-    FwdArgs a;
-    a.n = L.n; a.M = L.M; a.S = L.S; a.nseg = L.nseg; a.first_level = lev == 0;
-    a.rec = lev == 0 ? g->d_HREC : L.rec; a.brec = L.brec;
-    a.XR = g->d_XR[buf]; a.rowoff = g->d_rowoff; a.rowland = g->d_rowland; a.NXRp = g->NXRp; a.nint = g->nint; a.nb = nb; a.DL = std::max(g->DL, 1);
-    a.lambda = lambda;
-    a.rec_out = lev + 1 < nlev ? g->levels[lev + 1].rec : nullptr; a.brec_out = lev + 1 < nlev ? g->levels[lev + 1].brec : nullptr;
-    a.frec = L.frec; a.fstride = fstride; a.cseg = L.cseg; a.flag = g->d_flag;
-    if (bs == 12) fwd_w<12>(g->W, a, L.ncta, g->stream); else fwd_w<6>(g->W, a, L.ncta, g->stream);
-    g->launches++;
-    if (nb) {
-      const int R = std::min(16, L.ncta);
-      dim3 grid((centries + 255) / 256, R);
-      k_cseg_reduce<<<grid, 256, 0, g->stream>>>(L.cseg, L.ncta, centries, R, g->d_Cpart + (size_t)lev * 16 * centries);
-      if (R < 16) CUDA_TRY(cudaMemsetAsync(g->d_Cpart + ((size_t)lev * 16 + R) * centries, 0, (size_t)(16 - R) * centries * sizeof(double), g->stream));
-      g->launches++;
-    }
-  }
+  int rc;
+  for (int lev = 0; lev < nlev; lev++) if ((rc = launch_fwd_level(g, buf, lambda, lev))) return rc;
   if (nb) {
     k_landmark_solve<256><<<1, 256, (size_t)centries * sizeof(double), g->stream>>>(g->d_Cbase, g->d_Cpart, 16 * nlev, nb, lambda, g->d_xlm, g->d_flag);
     g->launches++;
@@ -803,6 +816,60 @@ int gpb_get_sizes(gpb_graph* g, gpb_sizes* s) {
   s->solve_bytes = 2.0 * g->N * 8.0 * (2 * bs * bs + bs);
   s->hbm_bytes = (double)g->hbm_bytes;
   s->n_gp = g->ngp; s->n_extra = (int)g->extras.size(); s->n_rows = g->NXR; s->border_dim = g->nb; s->levels = (int)g->levels.size();
+  return GPB_OK;
+}
+
+
+// Average device milliseconds of one stage over `reps` launches (CUDA events on the engine's own stream).
+int gpb_time_stage(gpb_graph* g, int stage, int reps, double* ms_out) {
+  CHECK_READY(g);
+  if (reps < 1 || !ms_out) return fail(GPB_ERR_ARG, "gpb_time_stage: bad arguments");
+  int rc = ensure_assembled(g);
+  if (rc) return rc;
+  if ((rc = solve_system(g, g->cur, 0.0))) return rc;  // valid delta for the retract stage; also warms up
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
+  CUDA_TRY(cudaStreamSynchronize(g->stream));
+  const int other = 1 - g->cur;
+  constexpr int NT = 128;
+  const int nb1 = (g->nint + NT - 1) / NT, nb2 = (g->NX + NT - 1) / NT;
+  auto gp_only = [&](auto tag) {
+    constexpr int G = decltype(tag)::value; constexpr int SR = GroupTraits<G>::PS + GroupTraits<G>::D;
+    k_lin_gp<G, NT><<<nb1, NT, (size_t)(NT + 1) * SR * sizeof(double), g->stream>>>(g->d_X, g->d_dt, g->d_qc, g->d_Rq, g->d_AB[other], g->d_errpart, g->nint, g->NFp, 1);
+  };
+  auto extra_only = [&](auto tag) {
+    constexpr int G = decltype(tag)::value;
+    if (nb2) k_lin_extra<G, NT><<<nb2, NT, 0, g->stream>>>(g->d_X, g->d_land, g->d_xkind, g->d_xsa, g->d_xsb, g->d_xl, g->d_xrow, g->d_xprm, g->d_XR[other], g->d_errpart + nb1, g->NX, g->NXRp, 1);
+  };
+  auto by_group = [&](auto fn) {
+    switch (g->group) {
+      case GPB_POSE3: fn(std::integral_constant<int, G_POSE3>{}); break;
+      case GPB_POSE2: fn(std::integral_constant<int, G_POSE2>{}); break;
+      case GPB_ROT3: fn(std::integral_constant<int, G_ROT3>{}); break;
+      default: fn(std::integral_constant<int, G_LINEAR>{}); break;
+    }
+  };
+  CUDA_TRY(cudaEventRecord(e0, g->stream));
+  for (int r = 0; r < reps; r++) {
+    switch (stage) {
+      case 0: by_group(gp_only); break;
+      case 1: by_group(extra_only); break;
+      case 2: if ((rc = assemble_dispatch(g, g->cur))) return rc; break;
+      case 3: if ((rc = solve_system(g, g->cur, 0.0))) return rc; break;
+      case 4: if ((rc = retract_dispatch(g))) return rc; break;
+      case 5: if ((rc = launch_fwd_level(g, g->cur, 0.0, 0))) return rc; break;
+      default: return fail(GPB_ERR_ARG, "gpb_time_stage: unknown stage");
+    }
+  }
+  CUDA_TRY(cudaEventRecord(e1, g->stream));
+  CUDA_TRY(cudaEventSynchronize(e1));
+  CUDA_TRY(cudaGetLastError());
+  float ms = 0;
+  CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  *ms_out = ms / reps;
+  // stage 5 leaves the upper levels untouched but consistent; restore a complete solve so later calls see a valid state
+  if (stage == 5) { if ((rc = solve_system(g, g->cur, 0.0))) return rc; CUDA_TRY(cudaStreamSynchronize(g->stream)); }
   return GPB_OK;
 }
 

@@ -124,6 +124,11 @@ int gpb_set_segment_length(gpb_graph* g, int level0, int upper_levels);
 typedef struct gpb_sizes { double hbm_bytes, linearise_bytes, fused_bytes, solve_bytes; int n_gp, n_extra, n_rows, border_dim, levels; } gpb_sizes;
 int gpb_get_sizes(gpb_graph* g, gpb_sizes* s);
 
+/* profiling aid: average device milliseconds (CUDA events on the engine's stream) of one stage of the hot path over `reps`
+ * launches at the current values.  stage: 0 batched GP-prior linearise kernel, 1 linearise of the other factors, 2 assembly,
+ * 3 whole block solve (all levels, both sweeps), 4 retract, 5 level-0 forward elimination only. */
+int gpb_time_stage(gpb_graph* g, int stage, int reps, double* ms_out);
+
 /* names and average device milliseconds of the kernels timed during the last gpb_optimize (profiling aid) */
 int gpb_kernel_launches_last_optimize(gpb_graph* g);
 
