@@ -192,21 +192,30 @@ def test_reference_two_state_optimizations():
 
 def test_full_size_properties():
     """BASELINE config C3 at full size (100k SE(3) states, 50k interpolated ranges, 16 landmarks): size-independent properties —
-    GN error decreases monotonically to a fixed point, the solver's delta at the fixed point is ~0 (gradient vanishes), and a
-    second engine instance with different segment lengths reaches the same solution."""
+    LM never increases the error (each accepted step passed the fidelity test), the optimiser reaches a fixed point where
+    the Gauss-Newton step vanishes (normal equations solved: gradient ~ 0), and a second engine instance with different
+    segment lengths (a different elimination order) reaches the same solution to 1e-6."""
     cfg = synth.config("C3")
     g, truth = synth.build(cfg, lambda grp, n, l: gb.Graph(grp, n, l))
     errs = [g.linearize()]
-    for _ in range(6):
-        st = g.optimize(n_iter=1, use_lm=False)
+    for _ in range(8):
+        st = g.optimize(n_iter=1, use_lm=True)
         errs.append(st.error_final)
     assert all(b <= a * (1 + 1e-12) for a, b in zip(errs, errs[1:])), errs
+    st = g.optimize(use_lm=True)
+    assert st.status == 0
+    for _ in range(3):
+        g.optimize(n_iter=1, use_lm=False)
     ds, dl = g.solve_delta(0.0)
-    assert np.abs(ds).max() < 1e-4 and np.abs(dl).max() < 1e-4
+    assert np.abs(ds).max() < 1e-5 and np.abs(dl).max() < 1e-5, (np.abs(ds).max(), np.abs(dl).max())
     P1, V1, L1 = g.get_values()
     def mk(grp, n, l):
         h = gb.Graph(grp, n, l); h.set_segment_length(20, 5); return h
     g2, _ = synth.build(cfg, mk)
-    g2.optimize(n_iter=6, use_lm=False)
+    for _ in range(8):
+        g2.optimize(n_iter=1, use_lm=True)
+    g2.optimize(use_lm=True)
+    for _ in range(3):
+        g2.optimize(n_iter=1, use_lm=False)
     P2, V2, L2 = g2.get_values()
     assert np.abs(P1 - P2).max() < 1e-6 and np.abs(V1 - V2).max() < 1e-6 and np.abs(L1 - L2).max() < 1e-6
