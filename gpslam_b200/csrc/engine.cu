@@ -43,7 +43,8 @@ struct Extra {
 };
 
 struct Level {
-  int n = 0, M = 0, S = 0, nseg = 0, ncta = 0;
+  int n = 0, M = 0, S = 0, nseg = 0, ncta = 0, ncta_bwd = 0;
+  bool top = false;        // storage-only level holding the external separators' Schur complement (sharded graphs)
   double* rec = nullptr;   // level >= 1: [n][3 bs^2 + 2 bs]  (D1 | D2 | E | g1 | g2)
   double* brec = nullptr;  // level >= 1: [n][2 bs nb]
   double* frec = nullptr;  // [n][2 bs^2 + bs w]   (Lii | Le | Y)
@@ -71,6 +72,11 @@ struct gpb_graph {
   int *d_xkind = nullptr, *d_xsa = nullptr, *d_xsb = nullptr, *d_xl = nullptr, *d_xrow = nullptr;
   double* d_xprm = nullptr;
   int *d_rowoff = nullptr, *d_rowland = nullptr, *d_lmoff = nullptr, *d_lmrows = nullptr;
+  int *d_bsoff = nullptr, *d_bsrow = nullptr, *d_bsside = nullptr;  // per-state CSR of landmark-bearing rows (level-0 border gather)
+  int extL = 0, extR = 0;  // shard: first / last state is an external separator (owned by the global reduced system)
+  int *d_listA = nullptr, *d_listB = nullptr;  // extra factors by kind class: interpolated measurements / everything else
+  int nA = 0, nB = 0;
+  double* d_Csum = nullptr;
   std::vector<int> sorted_of_order, h_xrow;
   std::vector<Extra> sorted;
   double* d_HREC = nullptr;
@@ -335,6 +341,26 @@ int gpb_set_segment_length(gpb_graph* g, int level0, int upper) {
   return GPB_OK;
 }
 
+}  // extern "C"
+template <int BS, int W> static int occ_fwd() {
+  int nb = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_fwd<BS, W>, (W < 32 ? 32 : W), 0) != cudaSuccess) { cudaGetLastError(); nb = 4; }
+  return nb < 1 ? 1 : nb;
+}
+template <int BS, int W> static int occ_bwd() {
+  int nb = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_bwd<BS, W>, (W < 32 ? 32 : W), 0) != cudaSuccess) { cudaGetLastError(); nb = 4; }
+  return nb < 1 ? 1 : nb;
+}
+static int bwd_blocks_per_sm(int bs, int W) {
+  if (bs == 12) return W == 16 ? occ_bwd<12, 16>() : W == 32 ? occ_bwd<12, 32>() : occ_bwd<12, 64>();
+  return W == 16 ? occ_bwd<6, 16>() : W == 32 ? occ_bwd<6, 32>() : occ_bwd<6, 64>();
+}
+static int fwd_blocks_per_sm(int bs, int W) {
+  if (bs == 12) return W == 16 ? occ_fwd<12, 16>() : W == 32 ? occ_fwd<12, 32>() : occ_fwd<12, 64>();
+  return W == 16 ? occ_fwd<6, 16>() : W == 32 ? occ_fwd<6, 32>() : occ_fwd<6, 64>();
+}
+extern "C" {
 // ===================================================================== finalize: build the device-resident graph
 int gpb_graph_finalize(gpb_graph* g, int device) {
   CHECK_OPEN(g);
@@ -369,6 +395,22 @@ int gpb_graph_finalize(gpb_graph* g, int device) {
     rowoff[e.interval + 1] += e.m;
   }
   for (int t = 0; t < g->nint; t++) rowoff[t + 1] += rowoff[t];
+  std::vector<int> bsoff(g->N + 1, 0), bsrow, bsside;
+  {
+    std::vector<std::vector<std::pair<int, int>>> per(g->N);
+    for (int k = 0; k < g->NX; k++) {
+      const Extra& e = g->sorted[k];
+      if (e.l < 0) continue;
+      for (int r = 0; r < e.m; r++) {
+        if (e.sa >= 0) per[e.interval].push_back({xrow[k] + r, 0});
+        if (e.sb >= 0) per[e.interval + 1].push_back({xrow[k] + r, 1});
+      }
+    }
+    for (int i = 0; i < g->N; i++) { bsoff[i + 1] = bsoff[i] + (int)per[i].size(); for (auto& pr : per[i]) { bsrow.push_back(pr.first); bsside.push_back(pr.second); } }
+  }
+  std::vector<int> listA, listB;
+  for (int k = 0; k < g->NX; k++) (xkind[k] == X_INTERP_RANGE || xkind[k] == X_INTERP_ATTITUDE ? listA : listB).push_back(k);
+  g->nA = (int)listA.size(); g->nB = (int)listB.size();
   g->NXR = nrows; g->NXRp = (nrows + 31) & ~31; g->h_xrow = xrow; g->ncolsX = 2 * bs + DL + 1;
   // rows per landmark
   std::vector<int> lmoff(g->L + 1, 0), lmrows;
@@ -398,12 +440,17 @@ int gpb_graph_finalize(gpb_graph* g, int device) {
   if ((rc = dev_upload(g, &g->d_xl, xl))) return rc;
   if ((rc = dev_upload(g, &g->d_xrow, xrow))) return rc;
   if ((rc = dev_upload(g, &g->d_xprm, xprm))) return rc;
+  if ((rc = dev_upload(g, &g->d_bsoff, bsoff))) return rc;
+  if ((rc = dev_upload(g, &g->d_bsrow, bsrow))) return rc;
+  if ((rc = dev_upload(g, &g->d_bsside, bsside))) return rc;
+  if ((rc = dev_upload(g, &g->d_listA, listA))) return rc;
+  if ((rc = dev_upload(g, &g->d_listB, listB))) return rc;
   if ((rc = dev_upload(g, &g->d_rowoff, rowoff))) return rc;
   if ((rc = dev_upload(g, &g->d_rowland, rowland))) return rc;
   if ((rc = dev_upload(g, &g->d_lmoff, lmoff))) return rc;
   if ((rc = dev_upload(g, &g->d_lmrows, lmrows))) return rc;
   if ((rc = dev_alloc(g, &g->d_HREC, (size_t)g->N * (2 * bs * bs + bs)))) return rc;
-  g->nerrpart = (g->nint + 127) / 128 + (g->NX + 127) / 128 + (g->N + 127) / 128 + 8;
+  g->nerrpart = (g->nint + 127) / 128 + (g->NX + 127) / 128 + (g->N + 127) / 128 + 16;
   if ((rc = dev_alloc(g, &g->d_errpart, (size_t)2 * g->nerrpart))) return rc;
   if ((rc = dev_alloc(g, &g->d_scal, 8))) return rc;
   if ((rc = dev_alloc(g, &g->d_flag, 1))) return rc;
@@ -417,11 +464,14 @@ int gpb_graph_finalize(gpb_graph* g, int device) {
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
   const int M0 = g->M0 ? g->M0 : (g->nb > 0 ? 32 : 16), Mup = g->Mup ? g->Mup : 8;
   const int fstride = 2 * bs * bs + bs * g->w;
-  int n = g->N, lev = 0, total_cta = 0;
+  int n = g->N, lev = 0;
   while (true) {
     Level L;
-    L.n = n; L.M = lev == 0 ? M0 : Mup; L.S = (n - 1) / L.M; L.nseg = L.S + 1;
-    L.ncta = std::min(L.nseg, sms * 8);
+    const int m = n - g->extL - g->extR;  // ordinary (eliminable) states of this level
+    if (m < 0) return fail(GPB_ERR_ARG, "shard too small for its external separators");
+    L.n = n; L.M = lev == 0 ? M0 : Mup; L.S = m > 0 ? (m - 1) / L.M : 0; L.nseg = L.S + 1;
+    L.ncta = std::min(L.nseg, sms * fwd_blocks_per_sm(bs, g->W));  // persistent CTAs: one resident wave
+    L.ncta_bwd = std::min(L.nseg, sms * bwd_blocks_per_sm(bs, g->W));
     if ((rc = dev_alloc(g, &L.frec, (size_t)n * fstride))) return rc;
     if ((rc = dev_alloc(g, &L.xsol, (size_t)n * bs))) return rc;
     if (g->nb) { if ((rc = dev_alloc(g, &L.cseg, (size_t)L.ncta * centries))) return rc; }
@@ -429,12 +479,23 @@ int gpb_graph_finalize(gpb_graph* g, int device) {
       if ((rc = dev_alloc(g, &L.rec, (size_t)n * (3 * bs * bs + 2 * bs)))) return rc;
       if ((rc = dev_alloc(g, &L.brec, (size_t)n * 2 * bs * std::max(g->nb, 1)))) return rc;
     }
-    total_cta += L.ncta;
     g->levels.push_back(L);
-    if (L.S == 0) break;
-    n = L.S; lev++;
+    const int n_next = g->extL + L.S + g->extR;
+    if (L.S == 0) {
+      if (n_next > 0) {  // storage for the Schur complement on the external separators
+        Level T; T.top = true; T.n = n_next;
+        if ((rc = dev_alloc(g, &T.xsol, (size_t)n_next * bs))) return rc;
+        if ((rc = dev_alloc(g, &T.rec, (size_t)n_next * (3 * bs * bs + 2 * bs)))) return rc;
+        if ((rc = dev_alloc(g, &T.brec, (size_t)n_next * 2 * bs * std::max(g->nb, 1)))) return rc;
+        g->levels.push_back(T);
+      }
+      break;
+    }
+    n = n_next; lev++;
   }
   if ((rc = dev_alloc(g, &g->d_Cpart, (size_t)16 * g->levels.size() * std::max(centries, 1)))) return rc;
+  CUDA_TRY(cudaMemset(g->d_Cpart, 0, (size_t)16 * g->levels.size() * std::max(centries, 1) * sizeof(double)));
+  if ((rc = dev_alloc(g, &g->d_Csum, (size_t)std::max(centries, 1)))) return rc;
   // page-lock the host staging so the H2D / D2H copies of the values run at full PCIe rate
   if (cudaHostRegister(g->h_X.data(), g->h_X.size() * sizeof(double), cudaHostRegisterDefault) == cudaSuccess) {
     g->pinned = true;
@@ -454,16 +515,21 @@ int gpb_graph_finalize(gpb_graph* g, int device) {
 
 template <int G> static int launch_linearize(gpb_graph* g, const double* X, const double* land, int buf, int wantJ) {
   constexpr int NT = 128, SR = GroupTraits<G>::PS + GroupTraits<G>::D;
-  const int nb1 = (g->nint + NT - 1) / NT, nb2 = (g->NX + NT - 1) / NT;
+  const int nb1 = (g->nint + NT - 1) / NT, nbA = (g->nA + NT - 1) / NT, nbB = (g->nB + NT - 1) / NT;
   const size_t smem = (size_t)(NT + 1) * SR * sizeof(double);
   k_lin_gp<G, NT><<<nb1, NT, smem, g->stream>>>(X, g->d_dt, g->d_qc, g->d_Rq, g->d_AB[buf], g->d_errpart, g->nint, g->NFp, wantJ);
   g->launches++;
-  if (nb2 > 0) {
-    k_lin_extra<G, NT><<<nb2, NT, 0, g->stream>>>(X, land, g->d_xkind, g->d_xsa, g->d_xsb, g->d_xl, g->d_xrow, g->d_xprm, g->d_XR[buf], g->d_errpart + nb1, g->NX,
-                                                   g->NXRp, wantJ);
+  if (nbA > 0) {
+    k_lin_extra<G, 0, NT><<<nbA, NT, 0, g->stream>>>(g->d_listA, g->nA, X, land, g->d_xkind, g->d_xsa, g->d_xsb, g->d_xl, g->d_xrow, g->d_xprm, g->d_XR[buf],
+                                                      g->d_errpart + nb1, g->NX, g->NXRp, wantJ);
     g->launches++;
   }
-  k_sum_partials<<<1, 256, 0, g->stream>>>(g->d_errpart, nb1 + nb2, g->d_scal, 0);
+  if (nbB > 0) {
+    k_lin_extra<G, 1, NT><<<nbB, NT, 0, g->stream>>>(g->d_listB, g->nB, X, land, g->d_xkind, g->d_xsa, g->d_xsb, g->d_xl, g->d_xrow, g->d_xprm, g->d_XR[buf],
+                                                      g->d_errpart + nb1 + nbA, g->NX, g->NXRp, wantJ);
+    g->launches++;
+  }
+  k_sum_partials<<<1, 256, 0, g->stream>>>(g->d_errpart, nb1 + nbA + nbB, g->d_scal, 0);
   g->launches++;
   CUDA_TRY(cudaGetLastError());
   return GPB_OK;
@@ -479,8 +545,8 @@ static int linearize_dispatch(gpb_graph* g, const double* X, const double* land,
 
 template <int G> static int launch_assemble(gpb_graph* g, int buf) {
   constexpr int NT = 128, bs = 2 * GroupTraits<G>::D, TILES = bs == 12 ? 4 : 1;
-  const int Npad = (g->N + 31) & ~31;
-  const int nblk = (TILES * Npad + NT - 1) / NT;
+  const int states_per_cta = 32 * (NT / (32 * TILES));
+  const int nblk = (g->N + states_per_cta - 1) / states_per_cta;
   k_assemble<G, NT><<<nblk, NT, 0, g->stream>>>(g->d_AB[buf], g->d_dt, g->NX ? g->d_XR[buf] : nullptr, g->d_rowoff, g->d_HREC, g->N, g->NFp, g->NXRp);
   g->launches++;
   if (g->nb) {
@@ -510,9 +576,9 @@ static int launch_fwd_level(gpb_graph* g, int buf, double lambda, int lev) {
   const int nlev = (int)g->levels.size();
   Level& L = g->levels[lev];
   FwdArgs a;
-  a.n = L.n; a.M = L.M; a.S = L.S; a.nseg = L.nseg; a.first_level = lev == 0;
+  a.n = L.n; a.M = L.M; a.S = L.S; a.nseg = L.nseg; a.first_level = lev == 0; a.extL = g->extL; a.extR = g->extR;
   a.rec = lev == 0 ? g->d_HREC : L.rec; a.brec = L.brec;
-  a.XR = g->d_XR[buf]; a.rowoff = g->d_rowoff; a.rowland = g->d_rowland; a.NXRp = g->NXRp; a.nint = g->nint; a.nb = nb; a.DL = std::max(g->DL, 1);
+  a.XR = g->d_XR[buf]; a.bsoff = g->d_bsoff; a.bsrow = g->d_bsrow; a.bsside = g->d_bsside; a.rowland = g->d_rowland; a.NXRp = g->NXRp; a.nb = nb; a.DL = std::max(g->DL, 1);
   a.lambda = lambda;
   a.rec_out = lev + 1 < nlev ? g->levels[lev + 1].rec : nullptr; a.brec_out = lev + 1 < nlev ? g->levels[lev + 1].brec : nullptr;
   a.frec = L.frec; a.fstride = fstride; a.cseg = L.cseg; a.flag = g->d_flag;
@@ -528,26 +594,45 @@ static int launch_fwd_level(gpb_graph* g, int buf, double lambda, int lev) {
   return GPB_OK;
 }
 
-// Solve (H + lambda I) delta = g with the current HREC / XR[buf]; delta lands in levels[0].xsol and d_xlm.
-static int solve_system(gpb_graph* g, int buf, double lambda) {
-  const int bs = g->bs, nb = g->nb, fstride = 2 * bs * bs + bs * g->w, centries = nb * nb + nb;
-  const int nlev = (int)g->levels.size();
+// number of elimination levels (excluding the storage-only top level of a sharded graph)
+static int num_elim_levels(const gpb_graph* g) { return (int)g->levels.size() - (g->levels.back().top ? 1 : 0); }
+
+static int solve_forward(gpb_graph* g, int buf, double lambda) {
   int rc;
-  for (int lev = 0; lev < nlev; lev++) if ((rc = launch_fwd_level(g, buf, lambda, lev))) return rc;
+  const int nel = num_elim_levels(g);
+  for (int lev = 0; lev < nel; lev++) if ((rc = launch_fwd_level(g, buf, lambda, lev))) return rc;
+  return GPB_OK;
+}
+static int solve_landmarks_local(gpb_graph* g, double lambda) {
+  const int nb = g->nb, centries = nb * nb + nb, nel = num_elim_levels(g);
   if (nb) {
-    k_landmark_solve<256><<<1, 256, (size_t)centries * sizeof(double), g->stream>>>(g->d_Cbase, g->d_Cpart, 16 * nlev, nb, lambda, g->d_xlm, g->d_flag);
-    g->launches++;
+    k_cseg_final<<<(centries + 127) / 128, 128, 0, g->stream>>>(g->d_Cbase, g->d_Cpart, 16 * nel, centries, g->d_Csum);
+    k_landmark_solve<128><<<1, 128, (size_t)centries * sizeof(double), g->stream>>>(g->d_Csum, nb, lambda, g->d_xlm, g->d_flag);
+    g->launches += 2;
   }
-  for (int lev = nlev - 1; lev >= 0; lev--) {
+  return GPB_OK;
+}
+static int solve_backward(gpb_graph* g) {
+  const int bs = g->bs, nb = g->nb, fstride = 2 * bs * bs + bs * g->w;
+  const int nel = num_elim_levels(g), nlev = (int)g->levels.size();
+  for (int lev = nel - 1; lev >= 0; lev--) {
     Level& L = g->levels[lev];
     BwdArgs b;
-    b.n = L.n; b.M = L.M; b.S = L.S; b.nseg = L.nseg; b.nb = nb; b.frec = L.frec; b.fstride = fstride;
+    b.n = L.n; b.M = L.M; b.S = L.S; b.nseg = L.nseg; b.nb = nb; b.extL = g->extL; b.extR = g->extR; b.frec = L.frec; b.fstride = fstride;
     b.xup = lev + 1 < nlev ? g->levels[lev + 1].xsol : nullptr; b.xl = g->d_xlm; b.xsol = L.xsol;
-    if (bs == 12) bwd_w<12>(g->W, b, L.ncta, g->stream); else bwd_w<6>(g->W, b, L.ncta, g->stream);
+    if (bs == 12) bwd_w<12>(g->W, b, L.ncta_bwd, g->stream); else bwd_w<6>(g->W, b, L.ncta_bwd, g->stream);
     g->launches++;
   }
   CUDA_TRY(cudaGetLastError());
   return GPB_OK;
+}
+// Solve (H + lambda I) delta = g with the current HREC / XR[buf]; delta lands in levels[0].xsol and d_xlm.
+static int solve_system(gpb_graph* g, int buf, double lambda) {
+  int rc;
+  if ((rc = solve_forward(g, buf, lambda))) return rc;
+  if (g->extL || g->extR) return fail(GPB_ERR_STATE, "sharded graph: use the distributed solve");
+  if ((rc = solve_landmarks_local(g, lambda))) return rc;
+  return solve_backward(g);
 }
 
 template <int G> static int launch_retract(gpb_graph* g) {
@@ -832,14 +917,16 @@ int gpb_time_stage(gpb_graph* g, int stage, int reps, double* ms_out) {
   CUDA_TRY(cudaStreamSynchronize(g->stream));
   const int other = 1 - g->cur;
   constexpr int NT = 128;
-  const int nb1 = (g->nint + NT - 1) / NT, nb2 = (g->NX + NT - 1) / NT;
+  const int nb1 = (g->nint + NT - 1) / NT;
   auto gp_only = [&](auto tag) {
     constexpr int G = decltype(tag)::value; constexpr int SR = GroupTraits<G>::PS + GroupTraits<G>::D;
     k_lin_gp<G, NT><<<nb1, NT, (size_t)(NT + 1) * SR * sizeof(double), g->stream>>>(g->d_X, g->d_dt, g->d_qc, g->d_Rq, g->d_AB[other], g->d_errpart, g->nint, g->NFp, 1);
   };
+  const int nbA = (g->nA + NT - 1) / NT, nbB = (g->nB + NT - 1) / NT;
   auto extra_only = [&](auto tag) {
     constexpr int G = decltype(tag)::value;
-    if (nb2) k_lin_extra<G, NT><<<nb2, NT, 0, g->stream>>>(g->d_X, g->d_land, g->d_xkind, g->d_xsa, g->d_xsb, g->d_xl, g->d_xrow, g->d_xprm, g->d_XR[other], g->d_errpart + nb1, g->NX, g->NXRp, 1);
+    if (nbA) k_lin_extra<G, 0, NT><<<nbA, NT, 0, g->stream>>>(g->d_listA, g->nA, g->d_X, g->d_land, g->d_xkind, g->d_xsa, g->d_xsb, g->d_xl, g->d_xrow, g->d_xprm, g->d_XR[other], g->d_errpart + nb1, g->NX, g->NXRp, 1);
+    if (nbB) k_lin_extra<G, 1, NT><<<nbB, NT, 0, g->stream>>>(g->d_listB, g->nB, g->d_X, g->d_land, g->d_xkind, g->d_xsa, g->d_xsb, g->d_xl, g->d_xrow, g->d_xprm, g->d_XR[other], g->d_errpart + nb1 + nbA, g->NX, g->NXRp, 1);
   };
   auto by_group = [&](auto fn) {
     switch (g->group) {

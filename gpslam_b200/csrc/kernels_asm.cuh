@@ -13,155 +13,164 @@ __global__ void __launch_bounds__(NT) k_assemble(const double* __restrict__ AB, 
   constexpr int D = GroupTraits<G>::D, DL = GroupTraits<G>::DL, bs = 2 * D, REC = 2 * bs * bs + bs;
   constexpr int TILES = (bs == 12) ? 4 : 1;
   constexpr int XRHS = 2 * bs + DL;
-  // tile-major thread order inside the grid: threads of the same tile class are contiguous, so a warp reads consecutive factors
-  const int gid = blockIdx.x * NT + threadIdx.x;
-  const int Npad = (N + 31) & ~31;  // tile classes start on a warp boundary
-  const int tile = gid / Npad, i = gid % Npad;
-  if (tile >= TILES || i >= N) return;
+  // a warp is one tile class over 32 consecutive states (coalesced 128-bit loads, no divergence); the TILES warps that
+  // work on the same 32 states sit in the same CTA so the [A|b] columns they share are fetched from HBM once (L1 hits)
+  static_assert(NT % (32 * TILES) == 0, "CTA = groups of TILES warps");
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = wid % TILES;
+  const int i = (blockIdx.x * (NT / (32 * TILES)) + wid / TILES) * 32 + lane;
+  if (i >= N) return;
   const int nint = N - 1;
-  const bool doD = (TILES == 1) || tile < 2;
-  const bool doE = (TILES == 1) || tile >= 2;
-  const bool doG = (TILES == 1) || tile == 0;
   const int c0 = (TILES == 1) ? 0 : (tile & 1) * 6;
-  double acc[bs][6];   // D tile (or E tile when this thread only does E)
-  double acc2[TILES == 1 ? bs : 1][6];  // E tile for the single-thread-per-state case
-  double g[bs];
-#pragma unroll
-  for (int r = 0; r < bs; r++) {
-    g[r] = 0;
-#pragma unroll
-    for (int c = 0; c < 6; c++) acc[r][c] = 0;
-  }
-  if constexpr (TILES == 1) {
-#pragma unroll
-    for (int r = 0; r < bs; r++)
-#pragma unroll
-      for (int c = 0; c < 6; c++) acc2[r][c] = 0;
-  }
   auto ld2 = [&](int col, int rp, int f) { return *reinterpret_cast<const double2*>(AB + ((size_t)(col * D + rp) * NFp + f) * 2); };
-  // ---- GP prior of interval i: columns 0..bs-1 belong to state i, bs..2bs-1 to state i+1
-  if (i < nint && dt[i] > 0.0) {
+  double* rec = HREC + (size_t)i * REC;
+
+  // One tile = 6 columns of D_i (DOD) and/or of E_i (DOE); C0, DOD, DOE, DOG are compile-time so every operand array stays in
+  // registers and each tile class only carries the operands it needs.
+  auto run = [&](auto c0tag, auto dtag, auto etag, auto gtag) {
+    constexpr int C0 = decltype(c0tag)::value;
+    constexpr bool DOD = decltype(dtag)::value, DOE = decltype(etag)::value, DOG = decltype(gtag)::value;
+    double accD[DOD ? bs : 1][6], accE[DOE ? bs : 1][6], g[DOG ? bs : 1];
+#pragma unroll
+    for (int r = 0; r < (DOD ? bs : 1); r++)
+#pragma unroll
+      for (int c = 0; c < 6; c++) accD[r][c] = 0;
+#pragma unroll
+    for (int r = 0; r < (DOE ? bs : 1); r++)
+#pragma unroll
+      for (int c = 0; c < 6; c++) accE[r][c] = 0;
+#pragma unroll
+    for (int r = 0; r < (DOG ? bs : 1); r++) g[r] = 0;
+
+    // ---- GP prior of interval i: columns 0..bs-1 belong to state i, bs..2bs-1 to state i+1
+    if (i < nint && dt[i] > 0.0) {
 #pragma unroll 1
-    for (int rp = 0; rp < D; rp++) {
-      double2 a[bs];
+      for (int rp = 0; rp < D; rp++) {
+        if constexpr (DOD) {
+          double2 a[bs];
 #pragma unroll
-      for (int c = 0; c < bs; c++) a[c] = ld2(c, rp, i);
-      if (doD) {
-#pragma unroll
-        for (int r = 0; r < bs; r++)
-#pragma unroll
-          for (int c = 0; c < 6; c++) acc[r][c] += a[r].x * a[c0 + c].x + a[r].y * a[c0 + c].y;
-      }
-      if (doE) {
-        double2 b2[bs];
-#pragma unroll
-        for (int c = 0; c < bs; c++) b2[c] = ld2(bs + c, rp, i);
-        if constexpr (TILES == 1) {
+          for (int c = 0; c < bs; c++) a[c] = ld2(c, rp, i);
 #pragma unroll
           for (int r = 0; r < bs; r++)
 #pragma unroll
-            for (int c = 0; c < 6; c++) acc2[r][c] += b2[r].x * a[c].x + b2[r].y * a[c].y;
-        } else {
+            for (int c = 0; c < 6; c++) accD[r][c] += a[r].x * a[C0 + c].x + a[r].y * a[C0 + c].y;
+          if constexpr (DOG) {
+            const double2 rh = ld2(2 * bs, rp, i);
 #pragma unroll
-          for (int r = 0; r < bs; r++)
-#pragma unroll
-            for (int c = 0; c < 6; c++) acc[r][c] += b2[r].x * a[c0 + c].x + b2[r].y * a[c0 + c].y;
-        }
-      }
-      if (doG) {
-        const double2 rh = ld2(2 * bs, rp, i);
-#pragma unroll
-        for (int r = 0; r < bs; r++) g[r] += a[r].x * rh.x + a[r].y * rh.y;
-      }
-    }
-  }
-  // ---- GP prior of interval i-1: state i is its second state
-  if (doD && i >= 1 && dt[i - 1] > 0.0) {
-#pragma unroll 1
-    for (int rp = 0; rp < D; rp++) {
-      double2 a[bs];
-#pragma unroll
-      for (int c = 0; c < bs; c++) a[c] = ld2(bs + c, rp, i - 1);
-#pragma unroll
-      for (int r = 0; r < bs; r++)
-#pragma unroll
-        for (int c = 0; c < 6; c++) acc[r][c] += a[r].x * a[c0 + c].x + a[r].y * a[c0 + c].y;
-      if (doG) {
-        const double2 rh = ld2(2 * bs, rp, i - 1);
-#pragma unroll
-        for (int r = 0; r < bs; r++) g[r] += a[r].x * rh.x + a[r].y * rh.y;
-      }
-    }
-  }
-  // ---- extra rows of interval i (a-part = state i, b-part = state i+1) and of interval i-1 (b-part = state i)
-  if (XR != nullptr) {
-    if (i < nint) {
-      for (int row = rowoff[i]; row < rowoff[i + 1]; row++) {
-        double a[bs];
-#pragma unroll
-        for (int c = 0; c < bs; c++) a[c] = XR[(size_t)c * NXRp + row];
-        if (doD) {
-#pragma unroll
-          for (int r = 0; r < bs; r++)
-#pragma unroll
-            for (int c = 0; c < 6; c++) acc[r][c] += a[r] * a[c0 + c];
-        }
-        if (doE) {
-          double b2[bs];
-#pragma unroll
-          for (int c = 0; c < bs; c++) b2[c] = XR[(size_t)(bs + c) * NXRp + row];
-          if constexpr (TILES == 1) {
-#pragma unroll
-            for (int r = 0; r < bs; r++)
-#pragma unroll
-              for (int c = 0; c < 6; c++) acc2[r][c] += b2[r] * a[c];
-          } else {
-#pragma unroll
-            for (int r = 0; r < bs; r++)
-#pragma unroll
-              for (int c = 0; c < 6; c++) acc[r][c] += b2[r] * a[c0 + c];
+            for (int r = 0; r < bs; r++) g[r] += a[r].x * rh.x + a[r].y * rh.y;
           }
         }
-        if (doG) {
-          const double rh = XR[(size_t)XRHS * NXRp + row];
+        if constexpr (DOE) {
+          double2 a6[6], b2[bs];
 #pragma unroll
-          for (int r = 0; r < bs; r++) g[r] += a[r] * rh;
+          for (int c = 0; c < 6; c++) a6[c] = ld2(C0 + c, rp, i);
+#pragma unroll
+          for (int c = 0; c < bs; c++) b2[c] = ld2(bs + c, rp, i);
+#pragma unroll
+          for (int r = 0; r < bs; r++)
+#pragma unroll
+            for (int c = 0; c < 6; c++) accE[r][c] += b2[r].x * a6[c].x + b2[r].y * a6[c].y;
         }
       }
     }
-    if (doD && i >= 1) {
-      for (int row = rowoff[i - 1]; row < rowoff[i]; row++) {
-        double b2[bs];
+    // ---- GP prior of interval i-1: state i is its second state
+    if constexpr (DOD) {
+      if (i >= 1 && dt[i - 1] > 0.0) {
+#pragma unroll 1
+        for (int rp = 0; rp < D; rp++) {
+          double2 a[bs];
 #pragma unroll
-        for (int c = 0; c < bs; c++) b2[c] = XR[(size_t)(bs + c) * NXRp + row];
+          for (int c = 0; c < bs; c++) a[c] = ld2(bs + c, rp, i - 1);
 #pragma unroll
-        for (int r = 0; r < bs; r++)
+          for (int r = 0; r < bs; r++)
 #pragma unroll
-          for (int c = 0; c < 6; c++) acc[r][c] += b2[r] * b2[c0 + c];
-        if (doG) {
-          const double rh = XR[(size_t)XRHS * NXRp + row];
+            for (int c = 0; c < 6; c++) accD[r][c] += a[r].x * a[C0 + c].x + a[r].y * a[C0 + c].y;
+          if constexpr (DOG) {
+            const double2 rh = ld2(2 * bs, rp, i - 1);
 #pragma unroll
-          for (int r = 0; r < bs; r++) g[r] += b2[r] * rh;
+            for (int r = 0; r < bs; r++) g[r] += a[r].x * rh.x + a[r].y * rh.y;
+          }
         }
       }
     }
-  }
-  // ---- store: tile = 6 full columns = 6*bs contiguous doubles of the column-major block
-  double* rec = HREC + (size_t)i * REC;
-  double* dst = rec + (doD ? 0 : bs * bs) + c0 * bs;
+    // ---- extra rows of interval i (a-part = state i, b-part = state i+1) and of interval i-1 (b-part = state i)
+    if (XR != nullptr) {
+      if (i < nint) {
+        for (int row = rowoff[i]; row < rowoff[i + 1]; row++) {
+          if constexpr (DOD) {
+            double a[bs];
 #pragma unroll
-  for (int c = 0; c < 6; c++)
+            for (int c = 0; c < bs; c++) a[c] = XR[(size_t)c * NXRp + row];
 #pragma unroll
-    for (int r = 0; r < bs; r += 2) st128(dst + c * bs + r, acc[r][c], acc[r + 1][c]);
+            for (int r = 0; r < bs; r++)
+#pragma unroll
+              for (int c = 0; c < 6; c++) accD[r][c] += a[r] * a[C0 + c];
+            if constexpr (DOG) {
+              const double rh = XR[(size_t)XRHS * NXRp + row];
+#pragma unroll
+              for (int r = 0; r < bs; r++) g[r] += a[r] * rh;
+            }
+          }
+          if constexpr (DOE) {
+            double a6[6], b2[bs];
+#pragma unroll
+            for (int c = 0; c < 6; c++) a6[c] = XR[(size_t)(C0 + c) * NXRp + row];
+#pragma unroll
+            for (int c = 0; c < bs; c++) b2[c] = XR[(size_t)(bs + c) * NXRp + row];
+#pragma unroll
+            for (int r = 0; r < bs; r++)
+#pragma unroll
+              for (int c = 0; c < 6; c++) accE[r][c] += b2[r] * a6[c];
+          }
+        }
+      }
+      if constexpr (DOD) {
+        if (i >= 1) {
+          for (int row = rowoff[i - 1]; row < rowoff[i]; row++) {
+            double b2[bs];
+#pragma unroll
+            for (int c = 0; c < bs; c++) b2[c] = XR[(size_t)(bs + c) * NXRp + row];
+#pragma unroll
+            for (int r = 0; r < bs; r++)
+#pragma unroll
+              for (int c = 0; c < 6; c++) accD[r][c] += b2[r] * b2[C0 + c];
+            if constexpr (DOG) {
+              const double rh = XR[(size_t)XRHS * NXRp + row];
+#pragma unroll
+              for (int r = 0; r < bs; r++) g[r] += b2[r] * rh;
+            }
+          }
+        }
+      }
+    }
+    // ---- store: a tile = 6 full columns = 6*bs contiguous doubles of the column-major block
+    if constexpr (DOD) {
+      double* dst = rec + C0 * bs;
+#pragma unroll
+      for (int c = 0; c < 6; c++)
+#pragma unroll
+        for (int r = 0; r < bs; r += 2) st128(dst + c * bs + r, accD[r][c], accD[r + 1][c]);
+    }
+    if constexpr (DOE) {
+      double* dst = rec + bs * bs + C0 * bs;
+#pragma unroll
+      for (int c = 0; c < 6; c++)
+#pragma unroll
+        for (int r = 0; r < bs; r += 2) st128(dst + c * bs + r, accE[r][c], accE[r + 1][c]);
+    }
+    if constexpr (DOG) {
+#pragma unroll
+      for (int r = 0; r < bs; r += 2) st128(rec + 2 * bs * bs + r, g[r], g[r + 1]);
+    }
+  };
+  using T = std::true_type; using F = std::false_type;
   if constexpr (TILES == 1) {
-    double* dstE = rec + bs * bs;
-#pragma unroll
-    for (int c = 0; c < 6; c++)
-#pragma unroll
-      for (int r = 0; r < bs; r += 2) st128(dstE + c * bs + r, acc2[r][c], acc2[r + 1][c]);
+    run(std::integral_constant<int, 0>{}, T{}, T{}, T{});
+  } else {
+    if (tile == 0) run(std::integral_constant<int, 0>{}, T{}, F{}, T{});
+    else if (tile == 1) run(std::integral_constant<int, 6>{}, T{}, F{}, F{});
+    else if (tile == 2) run(std::integral_constant<int, 0>{}, F{}, T{}, F{});
+    else run(std::integral_constant<int, 6>{}, F{}, T{}, F{});
   }
-  if (doG) {
-#pragma unroll
-    for (int r = 0; r < bs; r += 2) st128(rec + 2 * bs * bs + r, g[r], g[r + 1]);
-  }
+  (void)c0;
 }

@@ -113,7 +113,9 @@ __global__ void __launch_bounds__(NT) k_lin_gp(const double* __restrict__ X, con
 
 // ===================================================================== kernel: measurement / prior / between rows
 // One thread per "extra" factor; writes its m whitened rows over [state a (2D) | state b (2D) | landmark (DL) | rhs].
-template <int G>
+// CLS 0: interpolated measurement factors (range / attitude) — the volume; CLS 1: priors, between, plain 2-D factors.
+// Two kernels so the lean interpolated path does not inherit the generic path's local arrays and divergence.
+template <int G, int CLS>
 __device__ __forceinline__ void extra_rows(int kind, const double* __restrict__ X, const double* __restrict__ land, int sa, int sb, int l,
                                            const double* __restrict__ prm, bool wantJ, double* __restrict__ XR, int NXRp, int row0,
                                            double& err) {
@@ -122,6 +124,7 @@ __device__ __forceinline__ void extra_rows(int kind, const double* __restrict__ 
   const double* Rm = prm + 20;
   // helper: write one full row (coefficients c[NC-1] then rhs)
   auto put = [&](int row, int col, double v) { XR[(size_t)col * NXRp + row] = v; };
+  if constexpr (CLS == 0) {
   if (kind == X_INTERP_RANGE) {
     const double isg = Rm[0];
     if constexpr (G == G_POSE3) {
@@ -168,6 +171,7 @@ __device__ __forceinline__ void extra_rows(int kind, const double* __restrict__ 
     }
     return;
   }
+  } else {
   // ---- factors with dense m x m sqrt information R and m <= 6: unwhitened e[m], H over the row layout, then whiten
   double e[6];
   double H[6][NC - 1];
@@ -300,17 +304,22 @@ __device__ __forceinline__ void extra_rows(int kind, const double* __restrict__ 
       put(row0 + r, NC - 1, -be);
     }
   }
+  }
 }
 
-template <int G, int NT>
-__global__ void __launch_bounds__(NT) k_lin_extra(const double* __restrict__ X, const double* __restrict__ land, const int* __restrict__ xkind,
+template <int G, int CLS, int NT>
+__global__ void __launch_bounds__(NT) k_lin_extra(const int* __restrict__ list, int nlist, const double* __restrict__ X, const double* __restrict__ land, const int* __restrict__ xkind,
                                                   const int* __restrict__ xsa, const int* __restrict__ xsb, const int* __restrict__ xl,
                                                   const int* __restrict__ xrow, const double* __restrict__ xprm, double* __restrict__ XR,
                                                   double* __restrict__ errpart, int nx, int NXRp, int wantJ) {
   __shared__ double sred[NT / 32];
-  const int f = blockIdx.x * NT + threadIdx.x;
+  const int t = blockIdx.x * NT + threadIdx.x;
   double err = 0.0;
-  if (f < nx) extra_rows<G>(xkind[f], X, land, xsa[f], xsb[f], xl[f], xprm + (size_t)f * XP_STRIDE, wantJ != 0, XR, NXRp, xrow[f], err);
+  if (t < nlist) {
+    const int f = list[t];
+    extra_rows<G, CLS>(xkind[f], X, land, xsa[f], xsb[f], xl[f], xprm + (size_t)f * XP_STRIDE, wantJ != 0, XR, NXRp, xrow[f], err);
+  }
+  (void)nx;
   const double tot = block_sum<NT>(err, sred);
   if (threadIdx.x == 0) errpart[blockIdx.x] = tot;
 }

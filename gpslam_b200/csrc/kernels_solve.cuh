@@ -19,13 +19,15 @@
 #include "kernels_lin.cuh"
 
 struct FwdArgs {
-  int n, M, S, nseg, first_level;
+  int n, M, S, nseg, first_level, extL, extR;   // S = number of ordinary separators; nseg = S + 1
   const double* rec;
   const double* brec;
   const double* XR;
-  const int* rowoff;
+  const int* bsoff;    // level 0: per-state CSR of landmark-bearing rows
+  const int* bsrow;    //          row index
+  const int* bsside;   //          0: state is the row's a-part, 1: b-part
   const int* rowland;
-  int NXRp, nint, nb, DL;
+  int NXRp, nb, DL;
   double lambda;
   double* rec_out;
   double* brec_out;
@@ -36,23 +38,58 @@ struct FwdArgs {
 };
 
 struct BwdArgs {
-  int n, M, S, nseg, nb;
+  int n, M, S, nseg, nb, extL, extR;
   const double* frec;
   int fstride;
-  const double* xup;  // solution of the next level [S][BS]
+  const double* xup;  // solution of the next level [extL + S + extR][BS]
   const double* xl;   // landmark solution [nb]
   double* xsol;       // [n][BS]
 };
 
+// Segment geometry shared by the two sweeps.  Chain states 0..n-1; optional external separators (state 0 / state n-1, owned
+// by the neighbouring shard's system) are never eliminated here; ordinary separators sit every M ordinary states.
+struct SegGeom { int p, q, po, qo, i0, i1; };
+__device__ __forceinline__ SegGeom seg_geom(int seg, int n, int M, int S, int extL, int extR) {
+  SegGeom g;
+  const int base = extL ? 1 : 0;
+  g.p = seg > 0 ? base + seg * M - 1 : (extL ? 0 : -1);
+  g.q = seg < S ? base + (seg + 1) * M - 1 : (extR ? n - 1 : -1);
+  g.po = seg > 0 ? extL + seg - 1 : 0;
+  g.qo = seg < S ? extL + seg : extL + S + extR - 1;
+  g.i0 = g.p + 1;
+  g.i1 = g.q >= 0 ? g.q - 1 : n - 1;
+  return g;
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// FP64 tensor-core MMA, D(8x8) = A(8x4, row) * B(4x8, col) + C.  Fragments: a = A[lane>>2][lane&3], b = B[lane&3][lane>>2],
+// c/d = C[lane>>2][2*(lane&3) + {0,1}]   (PTX ISA, mma.m8n8k4 .f64; SASS DMMA)
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+// lower-triangular 8x8 tile grid of the 64x64 Schur block, interleaved over the two warps: tile t = 2u + warp
+__constant__ unsigned char c_tileI[36] = {0, 1, 1, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 4, 5, 5, 5, 5, 5, 5, 6, 6, 6, 6, 6, 6, 6, 7, 7, 7, 7, 7, 7, 7, 7};
+__constant__ unsigned char c_tileJ[36] = {0, 0, 1, 0, 1, 2, 0, 1, 2, 3, 0, 1, 2, 3, 4, 0, 1, 2, 3, 4, 5, 0, 1, 2, 3, 4, 5, 6, 0, 1, 2, 3, 4, 5, 6, 7};
+
 template <int BS, int W>
-__global__ void __launch_bounds__((W < 32 ? 32 : W)) k_fwd(const FwdArgs a) {
+__global__ void __launch_bounds__((W < 32 ? 32 : W), (W == 64 ? 6 : 8)) k_fwd(const FwdArgs a) {
+  constexpr bool MMA = (BS == 12 && W == 64);  // Schur SYRK + panel update on the FP64 tensor pipe
   constexpr int NT = (W < 32 ? 32 : W);
-  constexpr int REC0 = 2 * BS * BS + BS, REC1 = 3 * BS * BS + 2 * BS, YS = BS + 1, NA = W / 2 + 1;
-  __shared__ double Dm[BS * BS], Dn[BS * BS], Em[BS * BS], Ysm[W * YS], invd[BS];
+  constexpr int REC0 = 2 * BS * BS + BS, REC1 = 3 * BS * BS + 2 * BS, YS = MMA ? BS : BS + 1, NA = MMA ? 36 : W / 2 + 1, NBP = W;  // NBP: padded border width
+  __shared__ __align__(16) double Rb[2][REC1];
+  __shared__ double Dm[BS * BS], Dn[BS * BS], Em[BS * BS], Ysm[W * YS], invd[BS], Bn[BS * NBP];
+  __shared__ double Psm[W * BS];  // panel columns P (one per thread), kept in shared memory between phases
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, gi = lane >> 2, ti = lane & 3;
   const int c = threadIdx.x;
   const int nb = a.nb, w = BS + nb + 1, M = a.M;
   const bool first = a.first_level != 0;
   const int RECS = first ? REC0 : REC1;
+  const int oE = first ? BS * BS : 2 * BS * BS, oG = first ? 2 * BS * BS : 3 * BS * BS;
   const bool is_spike = c < BS, is_border = (c >= BS) && (c < BS + nb), is_rhs = (c == BS + nb), active = c < w;
   const int lb = c - BS;
 
@@ -60,115 +97,118 @@ __global__ void __launch_bounds__((W < 32 ? 32 : W)) k_fwd(const FwdArgs a) {
 #pragma unroll
   for (int j = 0; j < NA; j++) acc[j] = 0.0;
 
-  // D of state i (both parts summed, + lambda on the diagonal at level 0), element k
-  auto D_at = [&](int i, int k) -> double {
-    const double* r = a.rec + (size_t)i * RECS;
-    if (first) return r[k] + ((k % (BS + 1)) == 0 ? a.lambda : 0.0);
-    return r[k] + r[BS * BS + k];
+  auto prefetch = [&](int i, int buf) {  // whole record of state i -> Rb[buf] (16-byte cp.async chunks)
+    const double* src = a.rec + (size_t)i * RECS;
+    for (int k = c; k < RECS / 2; k += NT) cp_async16(&Rb[buf][2 * k], src + 2 * k);
   };
-  auto E_ptr = [&](int i) -> const double* { return a.rec + (size_t)i * RECS + (first ? BS * BS : 2 * BS * BS); };
-  // own (not yet eliminated) entries of this thread's panel column for state i, added into P
-  auto add_own = [&](int i, bool with_spike, int p, double* P) {
-    if (is_spike) {
-      if (with_spike) {
-        const double* E = E_ptr(p);  // rows: state p+1, cols: state p
-#pragma unroll
-        for (int r = 0; r < BS; r++) P[r] += E[r + c * BS];
+  // level 0: gather the landmark border of state i into Bn (12 x nb) from the sparse measurement rows; `lane` in [0, 32)
+  auto gather_border = [&](int i, int lane) {
+    for (int e = a.bsoff[i]; e < a.bsoff[i + 1]; e++) {
+      const int row = a.bsrow[e], side = a.bsside[e];
+      const int l = a.rowland[row];
+      if (lane < BS) {
+        const double av = a.XR[(size_t)(side * BS + lane) * a.NXRp + row];
+        for (int d = 0; d < a.DL; d++) Bn[lane + (l * a.DL + d) * BS] += av * a.XR[(size_t)(2 * BS + d) * a.NXRp + row];
       }
-    } else if (is_border) {
+    }
+  };
+  // own (not yet eliminated) entries of this thread's panel column for state i (whose record sits in Rb[buf]), added into P
+  auto add_own = [&](int i, int buf) {
+    double* P = Psm + c * BS;
+    if (is_border) {
       if (first) {
-        const int l = lb / a.DL, d = lb - l * a.DL;
-#pragma unroll 1
-        for (int side = 0; side < 2; side++) {
-          const int t = side == 0 ? i : i - 1;  // interval whose a-part (side 0) / b-part (side 1) is state i
-          if (t < 0 || t >= a.nint) continue;
-          for (int row = a.rowoff[t]; row < a.rowoff[t + 1]; row++) {
-            if (a.rowland[row] != l) continue;
-            const double coef = a.XR[(size_t)(2 * BS + d) * a.NXRp + row];
 #pragma unroll
-            for (int r = 0; r < BS; r++) P[r] += a.XR[(size_t)(side * BS + r) * a.NXRp + row] * coef;
-          }
-        }
+        for (int r = 0; r < BS; r++) { P[r] += Bn[r + lb * BS]; Bn[r + lb * BS] = 0.0; }
       } else {
         const double* B = a.brec + (size_t)i * (2 * BS * nb);
 #pragma unroll
         for (int r = 0; r < BS; r++) P[r] += B[r + lb * BS] + B[BS * nb + r + lb * BS];
       }
     } else if (is_rhs) {
-      const double* r0 = a.rec + (size_t)i * RECS;
-      if (first) {
 #pragma unroll
-        for (int r = 0; r < BS; r++) P[r] += r0[2 * BS * BS + r];
-      } else {
-#pragma unroll
-        for (int r = 0; r < BS; r++) P[r] += r0[3 * BS * BS + r] + r0[3 * BS * BS + BS + r];
-      }
+      for (int r = 0; r < BS; r++) P[r] += Rb[buf][oG + r] + (first ? 0.0 : Rb[buf][oG + BS + r]);
     }
   };
+  auto D_of = [&](int buf, int k) -> double {  // D (parts summed; + lambda on the diagonal at level 0)
+    if (first) return Rb[buf][k] + ((k % (BS + 1)) == 0 ? a.lambda : 0.0);
+    return Rb[buf][k] + Rb[buf][BS * BS + k];
+  };
+
+  if (first) { for (int k = c; k < BS * NBP; k += NT) Bn[k] = 0.0; }
+  __syncthreads();
 
   for (int seg = blockIdx.x; seg < a.nseg; seg += gridDim.x) {
-    const int p = seg > 0 ? seg * M - 1 : -1;
-    const int q = seg < a.S ? (seg + 1) * M - 1 : -1;
-    const int i0 = p + 1, i1 = (q >= 0) ? q - 1 : a.n - 1;
-    double P[BS];
-#pragma unroll
-    for (int r = 0; r < BS; r++) P[r] = 0.0;
+    const SegGeom sg = seg_geom(seg, a.n, M, a.S, a.extL, a.extR);
+    const int p = sg.p, q = sg.q, i0 = sg.i0, i1 = sg.i1;
+    const int ilast = (q >= 0) ? q : i1;  // last record that must be fetched
     for (int k = c; k < BS * BS; k += NT) Dn[k] = 0.0;
+    if (i0 <= ilast) prefetch(i0, 0);
+    cp_async_commit();
+    if (first && nb > 0 && i0 <= ilast && c < 32) gather_border(i0, c);
+    // panel init; spike columns start as the coupling of the first interior state to the left separator, E_p
+    if (c < W) {
+      const bool sp = is_spike && p >= 0 && i0 <= i1;
+      const double* E = a.rec + (size_t)(sp ? p : 0) * RECS + oE;
+#pragma unroll
+      for (int r = 0; r < BS; r++) Psm[c * BS + r] = sp ? E[r + c * BS] : 0.0;
+    }
     __syncthreads();
 
-    for (int i = i0; i <= i1; i++) {
+    int buf = 0;
+    for (int i = i0; i <= i1; i++, buf ^= 1) {
       const bool has_next = (i < i1) || (q >= 0);
-      for (int k = c; k < BS * BS; k += NT) Dm[k] = D_at(i, k) + Dn[k];
-      if (has_next) {
-        const double* E = E_ptr(i);
-        for (int k = c; k < BS * BS; k += NT) Em[k] = E[k];
-      }
-      add_own(i, (i == i0) && (p >= 0), p, P);
+      if (i + 1 <= ilast) prefetch(i + 1, buf ^ 1);
+      cp_async_commit();
+      cp_async_wait<1>();
       __syncthreads();
-      // ---- in-place Cholesky of Dm (lower, column-major) by the first warp
+      for (int k = c; k < BS * BS; k += NT) Dm[k] = D_of(buf, k) + Dn[k];
+      if (has_next) { for (int k = c; k < BS * BS; k += NT) Em[k] = Rb[buf][oE + k]; }
+      add_own(i, buf);
+      __syncthreads();
+      // ---- Cholesky of Dm (lower, column-major, in place) by the first warp, left-looking: lane r computes entry (r, j)
+      //      from the finished columns in shared memory; the pivot travels by one shuffle.  (A register-resident variant
+      //      costs ~60 registers and pushed the kernel into spills.)  Meanwhile the second warp gathers the next state's border.
       if (c < 32) {
+        if (NT == 32 && first && nb > 0 && i + 1 <= ilast) gather_border(i + 1, c);
+        const int rr = c < BS ? c : BS - 1;
+        bool bad = false;
 #pragma unroll 1
-        for (int j = 0; j < BS; j++) {
-          const double djj = Dm[j + j * BS];
-          if (!(djj > 0.0) && c == 0) *a.flag = 1;
-          const double sq = sqrt(djj > 0.0 ? djj : 1.0);
-          const double inv = 1.0 / sq;
-          __syncwarp();
-          if (c == j) { Dm[j + j * BS] = sq; invd[j] = inv; }
-          if (c > j && c < BS) Dm[c + j * BS] *= inv;
-          __syncwarp();
-          if (c > j && c < BS) {
-            const double lrj = Dm[c + j * BS];
-            for (int cc = j + 1; cc <= c; cc++) Dm[c + cc * BS] -= lrj * Dm[cc + j * BS];
-          }
+        for (int j = 0; j < BS; j++) {  // not unrolled: a fully unrolled body lets ptxas hoist ~70 LDS and spill
+          double sj = Dm[rr + j * BS];
+          for (int t = 0; t < j; t++) sj -= Dm[rr + t * BS] * Dm[j + t * BS];
+          const double djj = __shfl_sync(0xffffffffu, sj, j);
+          bad |= !(djj > 0.0);
+          const double inv = rsqrt(djj > 0.0 ? djj : 1.0);
+          if (c >= j && c < BS) Dm[c + j * BS] = (c == j) ? djj * inv : sj * inv;
+          if (c == j) invd[j] = inv;
           __syncwarp();
         }
+        if (bad && c == 0) *a.flag = 1;
+      } else if (c < 64) {
+        if (first && nb > 0 && i + 1 <= ilast) gather_border(i + 1, c - 32);
       }
       __syncthreads();
       // ---- Y = L^-1 P  (one column per thread)
-      double Y[BS];
-#pragma unroll
-      for (int r = 0; r < BS; r++) {
-        double s = P[r];
-#pragma unroll
-        for (int t = 0; t < r; t++) s -= Dm[r + t * BS] * Y[t];
-        Y[r] = s * invd[r];
-      }
-      if (c < W) {
-#pragma unroll
-        for (int r = 0; r < BS; r++) Ysm[c * YS + r] = active ? Y[r] : 0.0;
-      }
       double* F = a.frec + (size_t)i * a.fstride;
-      if (active) {
+      if (c < W) {
+        double* yc = Ysm + c * YS;
+        const double* pc = Psm + c * BS;
+#pragma unroll 1
+        for (int r = 0; r < BS; r++) {  // forward substitution through shared memory (own column: no synchronisation needed)
+          double s = active ? pc[r] : 0.0;
+          for (int t = 0; t < r; t++) s -= Dm[r + t * BS] * yc[t];
+          yc[r] = s * invd[r];
+        }
+        if (active) {
 #pragma unroll
-        for (int r = 0; r < BS; r++) F[2 * BS * BS + c * BS + r] = Y[r];
+          for (int r = 0; r < BS; r += 2) st128(F + 2 * BS * BS + c * BS + r, yc[r], yc[r + 1]);
+        }
       }
       // ---- Le = E L^-T, one row per thread (in place in Em)
       if (has_next && c < BS) {
-#pragma unroll
+#pragma unroll 1
         for (int cc = 0; cc < BS; cc++) {
           double s = Em[c + cc * BS];
-#pragma unroll
           for (int t = 0; t < cc; t++) s -= Em[c + t * BS] * Dm[cc + t * BS];
           Em[c + cc * BS] = s * invd[cc];
         }
@@ -177,14 +217,7 @@ __global__ void __launch_bounds__((W < 32 ? 32 : W)) k_fwd(const FwdArgs a) {
       for (int k = c; k < BS * BS; k += NT) F[k] = Dm[k];
       if (has_next) {
         for (int k = c; k < BS * BS; k += NT) F[BS * BS + k] = Em[k];
-        // next panel column: P = -Le Y ; Schur update of the next diagonal block: Dn = -Le Le^T
-#pragma unroll
-        for (int r = 0; r < BS; r++) {
-          double s = 0.0;
-#pragma unroll
-          for (int t = 0; t < BS; t++) s += Em[r + t * BS] * Y[t];
-          P[r] = -s;
-        }
+        // Schur update of the next diagonal block: Dn = -Le Le^T
         for (int k = c; k < BS * BS; k += NT) {
           const int r = k % BS, cc = k / BS;
           double s = 0.0;
@@ -192,105 +225,228 @@ __global__ void __launch_bounds__((W < 32 ? 32 : W)) k_fwd(const FwdArgs a) {
           for (int t = 0; t < BS; t++) s += Em[r + t * BS] * Em[cc + t * BS];
           Dn[k] = -s;
         }
-      } else {
-#pragma unroll
-        for (int r = 0; r < BS; r++) P[r] = 0.0;
       }
-      // ---- Schur accumulation: acc[j] += Y_c . Y_{(c+j) mod W}
-      if (c < W) {
+      if constexpr (MMA) {
+        // ---- tensor-pipe part.  Y fragments: element (k = 4s + ti) of panel column 8T + gi.
+        // (1) next panel  P' = -Le Y : warp w owns column tiles 4w..4w+3, two row tiles (rows 8..11 of the second are padding)
+        if (has_next) {
+          double aLe[2][3];
 #pragma unroll
-        for (int j = 0; j < NA; j++) {
-          const double* y2 = Ysm + ((c + j) % W) * YS;
-          double s = 0.0;
+          for (int mt = 0; mt < 2; mt++)
 #pragma unroll
-          for (int r = 0; r < BS; r++) s += Y[r] * y2[r];
-          acc[j] += s;
+            for (int sK = 0; sK < 3; sK++) aLe[mt][sK] = (8 * mt + gi < BS) ? Em[(8 * mt + gi) + (4 * sK + ti) * BS] : 0.0;
+#pragma unroll
+          for (int jt = 0; jt < 4; jt++) {
+            const int J = 4 * warp + jt;
+            double d[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+            for (int sK = 0; sK < 3; sK++) {
+              const double bY = Ysm[(8 * J + gi) * YS + 4 * sK + ti];
+              dmma884(d[0][0], d[0][1], aLe[0][sK], bY);
+              dmma884(d[1][0], d[1][1], aLe[1][sK], bY);
+            }
+#pragma unroll
+            for (int mt = 0; mt < 2; mt++)
+              if (8 * mt + gi < BS) { Psm[(8 * J + 2 * ti) * BS + 8 * mt + gi] = -d[mt][0]; Psm[(8 * J + 2 * ti + 1) * BS + 8 * mt + gi] = -d[mt][1]; }
+          }
+        }
+        else {
+#pragma unroll
+          for (int r = 0; r < BS; r++) Psm[c * BS + r] = 0.0;
+        }
+        // (2) Schur accumulation  S += Y^T Y  on the lower-triangular 8x8 tile grid: this warp's tiles t = 2u + warp
+#pragma unroll
+        for (int u = 0; u < 18; u++) {
+          const int t = 2 * u + warp;
+          const int I = c_tileI[t], J = c_tileJ[t];
+#pragma unroll
+          for (int sK = 0; sK < 3; sK++) {
+            const double aY = Ysm[(8 * I + gi) * YS + 4 * sK + ti];
+            const double bY = Ysm[(8 * J + gi) * YS + 4 * sK + ti];
+            dmma884(acc[2 * u], acc[2 * u + 1], aY, bY);
+          }
+          if ((u & 3) == 3) asm volatile("" ::: "memory");  // keep the scheduler from hoisting every tile's fragment loads (register pressure)
+        }
+      } else {
+        double Y[BS];
+#pragma unroll
+        for (int r = 0; r < BS; r++) Y[r] = (c < W) ? Ysm[c * YS + r] : 0.0;
+        if (c < W) {  // next panel column: P = -Le Y
+#pragma unroll
+          for (int r = 0; r < BS; r++) {
+            double s = 0.0;
+            if (has_next) {
+#pragma unroll
+              for (int t = 0; t < BS; t++) s += Em[r + t * BS] * Y[t];
+            }
+            Psm[c * BS + r] = -s;
+          }
+        }
+        // ---- Schur accumulation: acc[j] += Y_c . Y_{(c+j) mod W}
+        if (c < W) {
+#pragma unroll
+          for (int j = 0; j < NA; j++) {
+            const double* y2 = Ysm + ((c + j) % W) * YS;
+            double s = 0.0;
+#pragma unroll
+            for (int r = 0; r < BS; r++) s += Y[r] * y2[r];
+            acc[j] += s;
+          }
         }
       }
       __syncthreads();
     }
 
-    // ---- segment end: hand the Schur complement to the next level
+    // ---- segment end: hand the Schur complement to the next level (record of q is in Rb[buf])
+    cp_async_wait<0>();
+    __syncthreads();
     if (q >= 0) {
-      double* R = a.rec_out + (size_t)seg * REC1;
-      for (int k = c; k < BS * BS; k += NT) R[k] = D_at(q, k) + Dn[k];  // D1
-      add_own(q, false, -1, P);                                          // own border / rhs of q on top of the updates
+      double* R = a.rec_out + (size_t)sg.qo * REC1;
+      for (int k = c; k < BS * BS; k += NT) R[k] = D_of(buf, k) + Dn[k];  // D1
+      add_own(q, buf);                                                      // own border / rhs of q on top of the updates
+      const double* P = Psm + (c < W ? c : 0) * BS;
       if (is_border) {
-        double* B = a.brec_out + (size_t)seg * (2 * BS * nb);
+        double* B = a.brec_out + (size_t)sg.qo * (2 * BS * nb);
 #pragma unroll
         for (int r = 0; r < BS; r++) B[r + lb * BS] = P[r];
       } else if (is_rhs) {
 #pragma unroll
         for (int r = 0; r < BS; r++) R[3 * BS * BS + r] = P[r];
       } else if (is_spike && p >= 0) {
-        double* Ep = a.rec_out + (size_t)(seg - 1) * REC1 + 2 * BS * BS;  // E_{seg-1}: rows separator seg, cols separator seg-1
+        double* Ep = a.rec_out + (size_t)sg.po * REC1 + 2 * BS * BS;  // rows: separator q, cols: separator p
+        if (i0 <= i1) {
 #pragma unroll
-        for (int r = 0; r < BS; r++) Ep[r + c * BS] = P[r];
+          for (int r = 0; r < BS; r++) Ep[r + c * BS] = P[r];
+        } else {  // no interior state: p and q are directly coupled
+          const double* E = a.rec + (size_t)p * RECS + oE;
+#pragma unroll
+          for (int r = 0; r < BS; r++) Ep[r + c * BS] = E[r + c * BS];
+        }
+      }
+      if (a.extR && seg == a.S) {  // external right separator: no segment to its right -> its part 2 is zero
+        for (int k = c; k < BS * BS; k += NT) R[BS * BS + k] = 0.0;
+        if (c < BS) R[3 * BS * BS + BS + c] = 0.0;
+        if (is_border) { double* B = a.brec_out + (size_t)sg.qo * (2 * BS * nb) + BS * nb;
+#pragma unroll
+          for (int r = 0; r < BS; r++) B[r + lb * BS] = 0.0; }
       }
     }
-    if (c < W) {
-      double* Rp = (p >= 0) ? a.rec_out + (size_t)(seg - 1) * REC1 : nullptr;
-      double* Bp = (p >= 0) ? a.brec_out + (size_t)(seg - 1) * (2 * BS * nb) + BS * nb : nullptr;
+    if (a.extL && seg == 0) {
+      // external left separator: nobody is to its left here -> part 1 carries this shard's own (undamped) share of it
+      double* R = a.rec_out;  // po == 0
+      const double* src = a.rec + (size_t)p * RECS;
+      for (int k = c; k < BS * BS; k += NT) R[k] = first ? src[k] : src[k] + src[BS * BS + k];
+      if (c < BS) R[3 * BS * BS + c] = first ? src[oG + c] : src[oG + c] + src[oG + BS + c];
+      __syncthreads();  // Bn is free (q consumed it); gather p's border when it exists
+      if (first && nb > 0) { if (c < 32) gather_border(p, c); }
+      __syncthreads();
+      if (is_border) {
+        double* B = a.brec_out;
+        if (first) {
 #pragma unroll
-      for (int j = 0; j < NA; j++) {
-        const int c2 = (c + j) % W;
-        const int lo = c < c2 ? c : c2, hi = c < c2 ? c2 : c;
-        if (lo < BS) {  // spike involved: belongs to separator p, flushed per segment
+          for (int r = 0; r < BS; r++) { B[r + lb * BS] = Bn[r + lb * BS]; Bn[r + lb * BS] = 0.0; }
+        } else {
+          const double* Bs = a.brec + (size_t)p * (2 * BS * nb);
+#pragma unroll
+          for (int r = 0; r < BS; r++) B[r + lb * BS] = Bs[r + lb * BS] + Bs[BS * nb + r + lb * BS];
+        }
+      }
+    }
+    {
+      double* Rp = (p >= 0) ? a.rec_out + (size_t)sg.po * REC1 : nullptr;
+      double* Bp = (p >= 0) ? a.brec_out + (size_t)sg.po * (2 * BS * nb) + BS * nb : nullptr;
+      // entry (x, y) of the accumulated Y^T Y with a spike column involved belongs to separator p: flush and reset
+      auto flush_spike = [&](int x, int y, double& av) {
+        const int lo = x < y ? x : y, hi = x < y ? y : x;
+        if (lo < BS) {
           if (p >= 0 && hi < w) {
-            const double v = -acc[j];
+            const double v = -av;
             if (hi < BS) { Rp[BS * BS + lo + hi * BS] = v; Rp[BS * BS + hi + lo * BS] = v; }  // D2
             else if (hi < BS + nb) Bp[lo + (hi - BS) * BS] = v;                                // B2
             else Rp[3 * BS * BS + BS + lo] = v;                                                // g2
           }
-          acc[j] = 0.0;
+          av = 0.0;
         }
+      };
+      if constexpr (MMA) {
+#pragma unroll
+        for (int u = 0; u < 18; u++) {
+          const int t = 2 * u + warp;
+          const int x = 8 * c_tileI[t] + gi, y = 8 * c_tileJ[t] + 2 * ti;
+          if (x >= y) flush_spike(x, y, acc[2 * u]); else if (x < BS || y < BS) acc[2 * u] = 0.0;
+          if (x >= y + 1) flush_spike(x, y + 1, acc[2 * u + 1]); else if (x < BS || y + 1 < BS) acc[2 * u + 1] = 0.0;
+        }
+      } else if (c < W) {
+#pragma unroll
+        for (int j = 0; j < NA; j++) flush_spike(c, (c + j) % W, acc[j]);
       }
     }
     __syncthreads();
   }
   // ---- landmark x landmark and landmark x rhs parts stay in registers across this CTA's segments
-  if (nb > 0 && c < W) {
+  if (nb > 0) {
     double* Cs = a.cseg + (size_t)blockIdx.x * (nb * nb + nb);
-#pragma unroll
-    for (int j = 0; j < NA; j++) {
-      const int c2 = (c + j) % W;
-      const int lo = c < c2 ? c : c2, hi = c < c2 ? c2 : c;
+    auto flush_land = [&](int x, int y, double av) {
+      const int lo = x < y ? x : y, hi = x < y ? y : x;
       if (lo >= BS && hi < w) {
-        const double v = -acc[j];
+        const double v = -av;
         if (hi < BS + nb) { Cs[(lo - BS) + (hi - BS) * nb] = v; Cs[(hi - BS) + (lo - BS) * nb] = v; }
         else if (lo < BS + nb) Cs[nb * nb + (lo - BS)] = v;
       }
+    };
+    if constexpr (MMA) {
+#pragma unroll
+      for (int u = 0; u < 18; u++) {
+        const int t = 2 * u + warp;
+        const int x = 8 * c_tileI[t] + gi, y = 8 * c_tileJ[t] + 2 * ti;
+        if (x >= y) flush_land(x, y, acc[2 * u]);
+        if (x >= y + 1) flush_land(x, y + 1, acc[2 * u + 1]);
+      }
+    } else if (c < W) {
+#pragma unroll
+      for (int j = 0; j < NA; j++) flush_land(c, (c + j) % W, acc[j]);
     }
   }
 }
 
 // Back-substitution of one level: x_i = L_ii^-T ( y_i - Yspike_i x_p - Yborder_i x_l - Le_i^T x_{i+1} ), right to left.
+// The factor record of the next state to visit streams into shared memory (cp.async double buffer) while the current one is used.
 template <int BS, int W>
 __global__ void __launch_bounds__((W < 32 ? 32 : W)) k_bwd(const BwdArgs a) {
-  constexpr int NT = (W < 32 ? 32 : W), NP = NT / BS;
-  __shared__ double coef[W], part[NP][BS], Lm[BS * BS], Le[BS * BS], xn[BS], cv[BS];
+  constexpr int NT = (W < 32 ? 32 : W), NP = NT / BS, FSM = 2 * BS * BS + BS * W;
+  __shared__ __align__(16) double Fb[2][FSM];
+  __shared__ double coef[W], part[NP][BS], xn[BS], cv[BS];
   const int c = threadIdx.x;
-  const int nb = a.nb, w = BS + nb + 1, M = a.M;
+  const int nb = a.nb, w = BS + nb + 1, M = a.M, fs = a.fstride;
+  auto prefetch = [&](int i, int buf) {
+    const double* src = a.frec + (size_t)i * fs;
+    for (int k = c; k < fs / 2; k += NT) cp_async16(&Fb[buf][2 * k], src + 2 * k);
+  };
   for (int seg = blockIdx.x; seg < a.nseg; seg += gridDim.x) {
-    const int p = seg > 0 ? seg * M - 1 : -1;
-    const int q = seg < a.S ? (seg + 1) * M - 1 : -1;
-    const int i0 = p + 1, i1 = (q >= 0) ? q - 1 : a.n - 1;
+    const SegGeom sg = seg_geom(seg, a.n, M, a.S, a.extL, a.extR);
+    const int p = sg.p, q = sg.q, i0 = sg.i0, i1 = sg.i1;
+    if (i1 >= i0) prefetch(i1, 0);
+    cp_async_commit();
     if (c < W) {
       double v = 0.0;
-      if (c < BS) v = (p >= 0) ? -a.xup[(size_t)(seg - 1) * BS + c] : 0.0;
+      if (c < BS) v = (p >= 0) ? -a.xup[(size_t)sg.po * BS + c] : 0.0;
       else if (c < BS + nb) v = -a.xl[c - BS];
       else if (c == BS + nb) v = 1.0;
       coef[c] = v;
     }
     if (c < BS) {
-      xn[c] = (q >= 0) ? a.xup[(size_t)seg * BS + c] : 0.0;
+      xn[c] = (q >= 0) ? a.xup[(size_t)sg.qo * BS + c] : 0.0;
       if (q >= 0) a.xsol[(size_t)q * BS + c] = xn[c];
+      if (a.extL && seg == 0) a.xsol[c] = a.xup[c];  // external left separator: copy its solution down
     }
-    __syncthreads();
     bool has_next = (q >= 0);
-    for (int i = i1; i >= i0; i--) {
-      const double* F = a.frec + (size_t)i * a.fstride;
-      for (int k = c; k < BS * BS; k += NT) { Lm[k] = F[k]; if (has_next) Le[k] = F[BS * BS + k]; }
+    int buf = 0;
+    for (int i = i1; i >= i0; i--, buf ^= 1) {
+      if (i - 1 >= i0) prefetch(i - 1, buf ^ 1);
+      cp_async_commit();
+      cp_async_wait<1>();
+      __syncthreads();
+      const double* F = Fb[buf];
       // partial sums of Y * coef over a slice of columns
       if (c < NP * BS) {
         const int r = c % BS, pt = c / BS;
@@ -299,33 +455,33 @@ __global__ void __launch_bounds__((W < 32 ? 32 : W)) k_bwd(const BwdArgs a) {
         part[pt][r] = s;
       }
       __syncthreads();
-      if (c < BS) {
-        double s = 0.0;
-#pragma unroll
-        for (int pt = 0; pt < NP; pt++) s += part[pt][c];
-        if (has_next) {
-#pragma unroll
-          for (int t = 0; t < BS; t++) s -= Le[t + c * BS] * xn[t];
-        }
-        cv[c] = s;
-      }
-      __syncwarp();
-      // L^T x = cv, by lane 0..BS-1 of the first warp (column sweep from the bottom)
+      // first warp: reduce, subtract Le^T x_next, then L^T x = cv by a column sweep from the bottom
       if (c < 32) {
-        double rhs = (c < BS) ? cv[c] : 0.0;
+        double rhs = 0.0;
+        if (c < BS) {
+#pragma unroll
+          for (int pt = 0; pt < NP; pt++) rhs += part[pt][c];
+          if (has_next) {
+#pragma unroll
+            for (int t = 0; t < BS; t++) rhs -= F[BS * BS + t + c * BS] * xn[t];
+          }
+        }
         double xr = 0.0;
 #pragma unroll 1
         for (int r = BS - 1; r >= 0; r--) {
-          const double xv = __shfl_sync(0xffffffffu, rhs, r) / Lm[r + r * BS];
+          const double xv = __shfl_sync(0xffffffffu, rhs, r) / F[r + r * BS];
           if (c == r) xr = xv;
-          if (c < r) rhs -= Lm[r + c * BS] * xv;
+          if (c < r) rhs -= F[r + c * BS] * xv;
         }
         if (c < BS) { xn[c] = xr; a.xsol[(size_t)i * BS + c] = xr; }
       }
       has_next = true;
       __syncthreads();
     }
+    cp_async_wait<0>();
+    __syncthreads();
   }
+  (void)cv;
 }
 
 // landmark x landmark base: C0 = sum_rows l^T l (block diagonal), gl0 = sum_rows l^T rhs.  One CTA per landmark.
@@ -367,17 +523,24 @@ __global__ void k_cseg_reduce(const double* __restrict__ cseg, int nblocks, int 
   out[(size_t)slice * entries + e] = s;
 }
 
-// landmark system: C = Cbase + sum parts + lambda I, Cholesky, solve.  Single CTA.  parts: [nparts][nb*nb+nb]
+// stage 2: C = Cbase + sum over all level/slice partials  (many CTAs; fixed order -> deterministic)
+__global__ void k_cseg_final(const double* __restrict__ Cbase, const double* __restrict__ parts, int nparts, int entries, double* __restrict__ Csum) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= entries) return;
+  double s = Cbase[e];
+  for (int k = 0; k < nparts; k++) s += parts[(size_t)k * entries + e];
+  Csum[e] = s;
+}
+
+// landmark system: (C + lambda I) x = g, Cholesky + two triangular solves in shared memory.  Single CTA (nb <= 64).
 template <int NT>
-__global__ void __launch_bounds__(NT) k_landmark_solve(const double* __restrict__ Cbase, const double* __restrict__ parts, int nparts, int nb,
-                                                       double lambda, double* __restrict__ xl, int* __restrict__ flag) {
+__global__ void __launch_bounds__(NT) k_landmark_solve(const double* __restrict__ Csum, int nb, double lambda, double* __restrict__ xl, int* __restrict__ flag) {
   extern __shared__ double sm[];
   double* C = sm;            // nb x nb column-major
   double* g = sm + nb * nb;  // nb
   const int entries = nb * nb + nb;
   for (int e = threadIdx.x; e < entries; e += NT) {
-    double s = Cbase[e];
-    for (int k = 0; k < nparts; k++) s += parts[(size_t)k * entries + e];
+    double s = Csum[e];
     if (e < nb * nb && (e % (nb + 1)) == 0) s += lambda;
     sm[e] = s;
   }
@@ -385,21 +548,31 @@ __global__ void __launch_bounds__(NT) k_landmark_solve(const double* __restrict_
   for (int j = 0; j < nb; j++) {
     const double djj = C[j + j * nb];
     if (!(djj > 0.0) && threadIdx.x == 0) *flag = 2;
-    const double sq = sqrt(djj > 0.0 ? djj : 1.0);
+    const double inv = rsqrt(djj > 0.0 ? djj : 1.0);
     __syncthreads();
-    for (int r = j + threadIdx.x; r < nb; r += NT) C[r + j * nb] = (r == j) ? sq : C[r + j * nb] / sq;
+    for (int r = j + threadIdx.x; r < nb; r += NT) C[r + j * nb] = (r == j) ? djj * inv : C[r + j * nb] * inv;
     __syncthreads();
-    for (int k = threadIdx.x; k < (nb - j - 1) * (nb - j - 1); k += NT) {
-      const int r = j + 1 + k % (nb - j - 1), cc = j + 1 + k / (nb - j - 1);
+    const int m = nb - j - 1;
+    for (int k = threadIdx.x; k < m * m; k += NT) {
+      const int r = j + 1 + k % m, cc = j + 1 + k / m;
       if (r >= cc) C[r + cc * nb] -= C[r + j * nb] * C[cc + j * nb];
     }
     __syncthreads();
   }
-  if (threadIdx.x == 0) {
-    for (int r = 0; r < nb; r++) { double s = g[r]; for (int t = 0; t < r; t++) s -= C[r + t * nb] * g[t]; g[r] = s / C[r + r * nb]; }
-    for (int r = nb - 1; r >= 0; r--) { double s = g[r]; for (int t = r + 1; t < nb; t++) s -= C[t + r * nb] * g[t]; g[r] = s / C[r + r * nb]; }
-    for (int r = 0; r < nb; r++) xl[r] = g[r];
+  // L y = g (column sweep), then L^T x = y; thread r owns component r (nb <= NT)
+  for (int j = 0; j < nb; j++) {
+    if (threadIdx.x == j) g[j] /= C[j + j * nb];
+    __syncthreads();
+    if (threadIdx.x > j && threadIdx.x < nb) g[threadIdx.x] -= C[threadIdx.x + j * nb] * g[j];
+    __syncthreads();
   }
+  for (int j = nb - 1; j >= 0; j--) {
+    if (threadIdx.x == j) g[j] /= C[j + j * nb];
+    __syncthreads();
+    if (threadIdx.x < j) g[threadIdx.x] -= C[j + threadIdx.x * nb] * g[j];
+    __syncthreads();
+  }
+  if (threadIdx.x < nb) xl[threadIdx.x] = g[threadIdx.x];
 }
 
 // x <- x (+) delta for every state (Pose3 / Rot3: Expmap; Pose2: GTSAM's default chart; vectors: add), plus the two dot
