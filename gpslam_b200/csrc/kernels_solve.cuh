@@ -76,13 +76,72 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
 __constant__ unsigned char c_tileI[36] = {0, 1, 1, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 4, 5, 5, 5, 5, 5, 5, 6, 6, 6, 6, 6, 6, 6, 7, 7, 7, 7, 7, 7, 7, 7};
 __constant__ unsigned char c_tileJ[36] = {0, 0, 1, 0, 1, 2, 0, 1, 2, 3, 0, 1, 2, 3, 4, 0, 1, 2, 3, 4, 5, 0, 1, 2, 3, 4, 5, 6, 0, 1, 2, 3, 4, 5, 6, 7};
 
+// Fused Cholesky + triangular inverse of an SPD block (BS <= 12) by ONE warp, right-looking, with the lower-triangular
+// entries spread over all 32 lanes (entry e = lane + 32k).  Per pivot step j: the pivot travels by one shuffle, the owners of
+// column j of L and of row j of X = L^-1 publish them in shared memory, then every lane applies one FMA per owned entry to the
+// Cholesky trailing block (A[r][c] -= L[r][j] L[c][j]) and to the inverse accumulators (Z[r][c] += L[r][j] X[j][c]).
+// Dsrc: the SPD block (column-major, lower part read).  Outputs: Li = L^-1 (lower, column-major; strictly-upper untouched),
+// Lout (optional) = L, invd[j] = 1 / L[j][j].  colL / rowX: 2 x BS scratch each (double-buffered by step parity).  Returns false if not PD.
+template <int BS>
+__device__ __forceinline__ bool warp_chol_inverse(const double* Dsrc, double* Li, double* Lout, double* invd, double* colL, double* rowX, int lane) {
+  constexpr int NE = BS * (BS + 1) / 2, K = (NE + 31) / 32;
+  int er[K], ec[K];
+  double A[K], Z[K];
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    int e = lane + 32 * k, cidx = 0;
+    if (e >= NE) e = NE - 1;                      // surplus lanes shadow the last entry (their stores are suppressed)
+    while (e >= BS - cidx) { e -= BS - cidx; cidx++; }
+    ec[k] = cidx; er[k] = cidx + e;
+    A[k] = Dsrc[er[k] + ec[k] * BS];
+    Z[k] = 0.0;
+  }
+  bool ok = true;
+#pragma unroll 1
+  for (int j = 0; j < BS; j++) {
+    const int didx = j * BS - (j * (j - 1)) / 2;  // position of (j, j) in the column-major lower enumeration
+    const int dslot = didx >> 5;
+    double mine = A[0];
+#pragma unroll
+    for (int k = 1; k < K; k++) if (dslot == k) mine = A[k];
+    const double piv = __shfl_sync(0xffffffffu, mine, didx & 31);
+    ok &= (piv > 0.0);
+    const double inv = rsqrt(piv > 0.0 ? piv : 1.0);
+    double* cl = colL + (j & 1) * BS;
+    double* rx = rowX + (j & 1) * BS;
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      const bool live = (lane + 32 * k) < NE;
+      if (live && ec[k] == j) {                    // column j of L
+        const double l = (er[k] == j) ? piv * inv : A[k] * inv;
+        cl[er[k]] = l;
+        if (Lout) Lout[er[k] + j * BS] = l;
+      }
+      if (live && er[k] == j) {                    // row j of X = L^-1
+        const double x = (ec[k] == j) ? inv : -Z[k] * inv;
+        rx[ec[k]] = x;
+        Li[j + ec[k] * BS] = x;
+      }
+    }
+    if (lane == 0) invd[j] = inv;
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      if (ec[k] > j) A[k] -= cl[er[k]] * cl[ec[k]];
+      else if (er[k] > j) Z[k] += cl[er[k]] * rx[ec[k]];
+    }
+  }
+  return ok;
+}
+
 template <int BS, int W>
 __global__ void __launch_bounds__((W < 32 ? 32 : W), (W == 64 ? 6 : 8)) k_fwd(const FwdArgs a) {
   constexpr bool MMA = (BS == 12 && W == 64);  // Schur SYRK + panel update on the FP64 tensor pipe
   constexpr int NT = (W < 32 ? 32 : W);
   constexpr int REC0 = 2 * BS * BS + BS, REC1 = 3 * BS * BS + 2 * BS, YS = MMA ? BS : BS + 1, NA = MMA ? 36 : W / 2 + 1, NBP = W;  // NBP: padded border width
   __shared__ __align__(16) double Rb[2][REC1];
-  __shared__ double Dm[BS * BS], Dn[BS * BS], Em[BS * BS], Ysm[W * YS], invd[BS], Bn[BS * NBP];
+  __shared__ double Dm[BS * BS], Dn[BS * BS], Em[BS * BS], Li[BS * BS], Ysm[W * YS], invd[BS], Bn[BS * NBP];
+  __shared__ double colL[2 * BS], rowX[2 * BS];
   __shared__ double Psm[W * BS];  // panel columns P (one per thread), kept in shared memory between phases
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, gi = lane >> 2, ti = lane & 3;
   const int c = threadIdx.x;
@@ -133,6 +192,7 @@ __global__ void __launch_bounds__((W < 32 ? 32 : W), (W == 64 ? 6 : 8)) k_fwd(co
     if (first) return Rb[buf][k] + ((k % (BS + 1)) == 0 ? a.lambda : 0.0);
     return Rb[buf][k] + Rb[buf][BS * BS + k];
   };
+  for (int k = c; k < BS * BS; k += NT) Li[k] = 0.0;  // strictly-upper part of L^-1 stays zero
 
   if (first) { for (int k = c; k < BS * NBP; k += NT) Bn[k] = 0.0; }
   __syncthreads();
@@ -162,59 +222,87 @@ __global__ void __launch_bounds__((W < 32 ? 32 : W), (W == 64 ? 6 : 8)) k_fwd(co
       cp_async_wait<1>();
       __syncthreads();
       for (int k = c; k < BS * BS; k += NT) Dm[k] = D_of(buf, k) + Dn[k];
-      if (has_next) { for (int k = c; k < BS * BS; k += NT) Em[k] = Rb[buf][oE + k]; }
+      if (!MMA && has_next) { for (int k = c; k < BS * BS; k += NT) Em[k] = Rb[buf][oE + k]; }
       add_own(i, buf);
       __syncthreads();
-      // ---- Cholesky of Dm (lower, column-major, in place) by the first warp, left-looking: lane r computes entry (r, j)
-      //      from the finished columns in shared memory; the pivot travels by one shuffle.  (A register-resident variant
-      //      costs ~60 registers and pushed the kernel into spills.)  Meanwhile the second warp gathers the next state's border.
+      // ---- factor phase (the serial critical path of the chain): fused Cholesky + L^-1 by the first warp, entries spread over
+      //      all 32 lanes (warp_chol_inverse).  Meanwhile the second warp gathers the next state's landmark border.
       if (c < 32) {
         if (NT == 32 && first && nb > 0 && i + 1 <= ilast) gather_border(i + 1, c);
-        const int rr = c < BS ? c : BS - 1;
-        bool bad = false;
-#pragma unroll 1
-        for (int j = 0; j < BS; j++) {  // not unrolled: a fully unrolled body lets ptxas hoist ~70 LDS and spill
-          double sj = Dm[rr + j * BS];
-          for (int t = 0; t < j; t++) sj -= Dm[rr + t * BS] * Dm[j + t * BS];
-          const double djj = __shfl_sync(0xffffffffu, sj, j);
-          bad |= !(djj > 0.0);
-          const double inv = rsqrt(djj > 0.0 ? djj : 1.0);
-          if (c >= j && c < BS) Dm[c + j * BS] = (c == j) ? djj * inv : sj * inv;
-          if (c == j) invd[j] = inv;
-          __syncwarp();
-        }
-        if (bad && c == 0) *a.flag = 1;
+        const bool ok = warp_chol_inverse<BS>(Dm, Li, MMA ? nullptr : Dm, invd, colL, rowX, c);
+        if (!ok && c == 0) *a.flag = 1;
       } else if (c < 64) {
         if (first && nb > 0 && i + 1 <= ilast) gather_border(i + 1, c - 32);
       }
       __syncthreads();
       // ---- Y = L^-1 P  (one column per thread)
       double* F = a.frec + (size_t)i * a.fstride;
-      if (c < W) {
-        double* yc = Ysm + c * YS;
-        const double* pc = Psm + c * BS;
-#pragma unroll 1
-        for (int r = 0; r < BS; r++) {  // forward substitution through shared memory (own column: no synchronisation needed)
-          double s = active ? pc[r] : 0.0;
-          for (int t = 0; t < r; t++) s -= Dm[r + t * BS] * yc[t];
-          yc[r] = s * invd[r];
-        }
-        if (active) {
+      if constexpr (MMA) {
+        // ---- Y = L^-1 P on the tensor pipe: warp w owns column tiles 4w..4w+3; row tile 0 skips the zero k-slice 2
+        {
+          double aLi[2][3];
 #pragma unroll
-          for (int r = 0; r < BS; r += 2) st128(F + 2 * BS * BS + c * BS + r, yc[r], yc[r + 1]);
+          for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+            for (int sK = 0; sK < 3; sK++) aLi[mt][sK] = (8 * mt + gi < BS) ? Li[(8 * mt + gi) + (4 * sK + ti) * BS] : 0.0;
+#pragma unroll
+          for (int jt = 0; jt < 4; jt++) {
+            const int J = 4 * warp + jt;
+            double d[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+            for (int sK = 0; sK < 3; sK++) {
+              const double bP = Psm[(8 * J + gi) * BS + 4 * sK + ti];
+              if (sK < 2) dmma884(d[0][0], d[0][1], aLi[0][sK], bP);
+              dmma884(d[1][0], d[1][1], aLi[1][sK], bP);
+            }
+#pragma unroll
+            for (int mt = 0; mt < 2; mt++)
+              if (8 * mt + gi < BS) { Ysm[(8 * J + 2 * ti) * YS + 8 * mt + gi] = d[mt][0]; Ysm[(8 * J + 2 * ti + 1) * YS + 8 * mt + gi] = d[mt][1]; }
+          }
         }
-      }
-      // ---- Le = E L^-T, one row per thread (in place in Em)
-      if (has_next && c < BS) {
+        // ---- Le = E L^-T : warp w owns row tile w; E is still in the record buffer
+        if (has_next) {
+          const double* E0 = &Rb[buf][oE];
+#pragma unroll
+          for (int nt = 0; nt < 2; nt++) {
+            double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+            for (int sK = 0; sK < 3; sK++) {
+              const double aE = (8 * warp + gi < BS) ? E0[(8 * warp + gi) + (4 * sK + ti) * BS] : 0.0;
+              const double bL = (8 * nt + gi < BS) ? Li[(8 * nt + gi) + (4 * sK + ti) * BS] : 0.0;  // (L^-T)[k][j] = L^-1[j][k]
+              dmma884(d0, d1, aE, bL);
+            }
+            if (8 * warp + gi < BS && 8 * nt + 2 * ti < BS) { Em[(8 * warp + gi) + (8 * nt + 2 * ti) * BS] = d0; Em[(8 * warp + gi) + (8 * nt + 2 * ti + 1) * BS] = d1; }
+          }
+        }
+      } else {
+        if (c < W) {
+          double* yc = Ysm + c * YS;
+          const double* pc = Psm + c * BS;
 #pragma unroll 1
-        for (int cc = 0; cc < BS; cc++) {
-          double s = Em[c + cc * BS];
-          for (int t = 0; t < cc; t++) s -= Em[c + t * BS] * Dm[cc + t * BS];
-          Em[c + cc * BS] = s * invd[cc];
+          for (int r = 0; r < BS; r++) {  // forward substitution through shared memory (own column: no synchronisation needed)
+            double sv = active ? pc[r] : 0.0;
+            for (int t = 0; t < r; t++) sv -= Dm[r + t * BS] * yc[t];
+            yc[r] = sv * invd[r];
+          }
+        }
+        // ---- Le = E L^-T, one row per thread (in place in Em)
+        if (has_next && c < BS) {
+#pragma unroll 1
+          for (int cc = 0; cc < BS; cc++) {
+            double sv = Em[c + cc * BS];
+            for (int t = 0; t < cc; t++) sv -= Em[c + t * BS] * Dm[cc + t * BS];
+            Em[c + cc * BS] = sv * invd[cc];
+          }
         }
       }
       __syncthreads();
-      for (int k = c; k < BS * BS; k += NT) F[k] = Dm[k];
+      if (active) {
+        const double* yc = Ysm + c * YS;
+#pragma unroll
+        for (int r = 0; r < BS; r += 2) st128(F + 2 * BS * BS + c * BS + r, yc[r], yc[r + 1]);
+      }
+      for (int k = c; k < BS * BS; k += NT) F[k] = Li[k];  // the back-substitution uses L^-1
       if (has_next) {
         for (int k = c; k < BS * BS; k += NT) F[BS * BS + k] = Em[k];
         // Schur update of the next diagonal block: Dn = -Le Le^T
@@ -466,13 +554,15 @@ __global__ void __launch_bounds__((W < 32 ? 32 : W)) k_bwd(const BwdArgs a) {
             for (int t = 0; t < BS; t++) rhs -= F[BS * BS + t + c * BS] * xn[t];
           }
         }
+        // x = L^-T rhs: the factor record stores L^-1 (lower triangular, column-major), so this is a mat-vec
+        if (c < BS) cv[c] = rhs;
+        __syncwarp();
         double xr = 0.0;
-#pragma unroll 1
-        for (int r = BS - 1; r >= 0; r--) {
-          const double xv = __shfl_sync(0xffffffffu, rhs, r) / F[r + r * BS];
-          if (c == r) xr = xv;
-          if (c < r) rhs -= F[r + c * BS] * xv;
+        if (c < BS) {
+#pragma unroll
+          for (int t = 0; t < BS; t++) xr += F[t + c * BS] * cv[t];
         }
+        __syncwarp();
         if (c < BS) { xn[c] = xr; a.xsol[(size_t)i * BS + c] = xr; }
       }
       has_next = true;
@@ -481,7 +571,6 @@ __global__ void __launch_bounds__((W < 32 ? 32 : W)) k_bwd(const BwdArgs a) {
     cp_async_wait<0>();
     __syncthreads();
   }
-  (void)cv;
 }
 
 // landmark x landmark base: C0 = sum_rows l^T l (block diagonal), gl0 = sum_rows l^T rhs.  One CTA per landmark.
