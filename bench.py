@@ -23,6 +23,9 @@ sys.path.insert(0, ROOT)
 WORKLOAD = "C3: SE(3) GP-prior + interpolated range factors, 100k states, 50k ranges, 16 landmarks (BASELINE.json configs[2]; interpolated range only - the reference has no interpolated bearing factor)"
 METRIC = "GN iterations/sec on 100k-state SE(3) GP trajectory"
 CPU_SAMPLE_STATES = 10000
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_lin_gp launch on C3, from the ncu --set full capture summarised in
+# profiles/r1a_ncu_full_summary.csv (15.7 MB read + 180.7 MB written; the tail of the 240 MB of [A|b] is still in L2 at kernel end)
+TRAFFIC_LIN_GP = 196.4e6
 
 
 def peaks():
@@ -109,58 +112,96 @@ def run_reference(args, rank, world):
 
 def run_engine(args, rank, world, local_rank):
     import gpslam_b200 as gb
-    from gpslam_b200 import synth
-    if world > 1:
-        raise SystemExit("bench.py: the trajectory-sharded multi-GPU path is not built yet in this round; run with --gpus 1")
+    from gpslam_b200 import shard, synth
     if gb.device_count() <= local_rank:
         raise SystemExit("bench.py: no CUDA device (the engine has no CPU fallback)")
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     cfg = synth.config("C3")
     if args.states:
         cfg.n_states = args.states
     t0 = time.perf_counter()
-    g, _ = synth.build(cfg, lambda grp, n, l: gb.Graph(grp, n, l))
+    if world > 1:
+        # strong scaling: the SAME 100k-state graph, cut into contiguous segments, one per GPU; one NCCL all-reduce of the
+        # boundary Schur system per GN iteration and no other collective on the data path
+        g, _ = synth.build(cfg, lambda grp, n, l: shard.ShardBuilder(lambda g_, n_, l_: gb.Graph(g_, n_, l_), grp, n, l, rank, world), finalize=False)
+        g.g.set_allreduce(shard.torch_allreduce(local_rank))
+        g.finalize(local_rank)
+        g = g.g
+    else:
+        g, _ = synth.build(cfg, lambda grp, n, l: gb.Graph(grp, n, l), finalize=False)
+        g.finalize(local_rank)
     build_s = time.perf_counter() - t0
     sz = g.sizes()
     err0 = g.linearize()
-    # ---- warm-up, then K timed GN iterations: CUDA events on the engine's stream, synchronised on both sides (gpb_optimize)
+
+    def sync_all():
+        if dist is not None:
+            import torch
+            dist.barrier(); torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- warm-up, then K timed GN iterations: CUDA events on the engine's stream, synchronised on both sides (gpb_optimize),
+    #      barrier before, max over ranks after
     g.optimize(n_iter=max(args.warmup, 3), use_lm=False)
     sampler = ClockSampler(local_rank)
+    sync_all()
     st = g.optimize(n_iter=args.steps, use_lm=False)
+    sync_all()
     launches = g.launches()
-    ms_per_step = st.total_ms / args.steps
+    n_allreduce = g.allreduces()
+    ms_per_step = max_over_ranks(st.total_ms) / args.steps
     value = 1e3 / ms_per_step
     # ---- end to end through the C ABI with host buffers: H2D of the values, one iteration, D2H of the result, every step
     P, V, Lm = g.get_values()
+    sync_all()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         g.set_values(P, V, Lm)
         g.optimize(n_iter=1, use_lm=False)
         P, V, Lm = g.get_values()
-    e2e_s = (time.perf_counter() - t0) / args.steps
+    e2e_s = max_over_ranks((time.perf_counter() - t0) / args.steps)
     clocks = sampler.stop()
     io_bytes = int(P.nbytes + V.nbytes + Lm.nbytes)
-    # ---- per-stage device times and the linearise roofline
+    # ---- per-stage device times and the linearise roofline (local shard)
     stages = {n: g.time_stage(k, 20) for k, n in ((0, "linearise_gp"), (1, "linearise_other"), (2, "assemble"), (3, "solve"), (4, "retract"), (5, "solve_fwd_level0"))}
     peak, peak_src = peaks()
-    gp_bytes = cfg.n_states * 8.0 * 18 + sz.n_gp * (8.0 + 8.0 * 12 * 25)  # states once + per factor (param + [A|b])
+    gp_bytes = g.N * 8.0 * 18 + sz.n_gp * (8.0 + 8.0 * 12 * 25)  # states once + per factor (param + [A|b])
     achieved = gp_bytes / (stages["linearise_gp"] * 1e-3) / 1e9
     line = {
         "metric": METRIC, "value": value, "unit": "iterations/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "states": cfg.n_states, "gp_factors": sz.n_gp, "other_factors": sz.n_extra, "landmark_dims": sz.border_dim,
-                   "solver_levels": sz.levels, "optimizer": "Gauss-Newton", "l2": "inputs larger than L2: [A|b] buffers 2 x %.0f MB, solver factors %.0f MB (L2 126 MB)"
-                   % (sz.n_gp * 2400 / 1e6, sz.hbm_bytes / 1e6), "hbm_resident_mb": sz.hbm_bytes / 1e6, "graph_build_s": build_s},
-        "e2e": {"value": 1.0 / e2e_s, "unit": "iterations/s", "h2d_bytes_per_step": io_bytes, "d2h_bytes_per_step": io_bytes},
+        "config": {"workload": WORKLOAD, "states": cfg.n_states, "states_per_gpu": g.N, "gp_factors_rank0": sz.n_gp, "other_factors_rank0": sz.n_extra,
+                   "landmark_dims": sz.border_dim, "solver_levels": sz.levels, "optimizer": "Gauss-Newton",
+                   "parallelism": "trajectory segments x%d, one NCCL all-reduce of the boundary Schur system per iteration" % world if world > 1 else "single GPU",
+                   "allreduces_per_step": (n_allreduce - 1) / args.steps if world > 1 else 0,
+                   "l2": "inputs larger than L2: [A|b] buffers 2 x %.0f MB, resident %.0f MB per GPU (L2 126 MB)" % (sz.n_gp * 2400 / 1e6, sz.hbm_bytes / 1e6),
+                   "hbm_resident_mb": sz.hbm_bytes / 1e6, "graph_build_s": build_s},
+        "e2e": {"value": 1.0 / e2e_s, "unit": "iterations/s", "h2d_bytes_per_step": io_bytes * world, "d2h_bytes_per_step": io_bytes * world},
         "gpu_launches": launches,
         "roofline": {"kernel": "k_lin_gp<POSE3> (batched GP-prior linearise)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "peak_source": peak_src, "algorithmic_bytes": gp_bytes, "ms": stages["linearise_gp"], "traffic": None},
+                     "peak_source": peak_src, "algorithmic_bytes": gp_bytes, "ms": stages["linearise_gp"], "traffic": TRAFFIC_LIN_GP},
         "stages_ms": stages, "clocks": clocks, "error": {"initial": err0, "final": st.error_final},
     }
-    if rank == 0 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu:
         r = cpu_reference_run(3, 1, 1)
         line["cpu_baseline"] = {"value": r["value"], "unit": "iterations/s", "cores": 1, "kind": "port", "sample": r["sample"],
                                 "seconds_per_iteration_sample": r["seconds_per_iteration_sample"]}
-    print(json.dumps(line))
+    if rank == 0:
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
 
 
 def main():

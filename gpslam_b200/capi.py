@@ -165,6 +165,18 @@ class Graph:
     def add_odometry_2d(self, i, j, meas, sqrt_info):
         self._ck(self.L.gpb_add_odometry_2d(self.h, C.c_int(i), C.c_int(j), _dp(_f64(meas)), _dp(_fcol(sqrt_info))))
 
+    def set_shard(self, rank, world, ext_left, ext_right):
+        self._ck(self.L.gpb_graph_set_shard(self.h, C.c_int(rank), C.c_int(world), C.c_int(1 if ext_left else 0), C.c_int(1 if ext_right else 0)))
+
+    def set_allreduce(self, fn):
+        """fn(device_ptr:int, count:int) -> 0; in-place SUM over ranks, complete on return"""
+        CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_longlong)
+        self._cb = CB(lambda ctx, ptr, count: int(fn(ptr, count)))
+        self._ck(self.L.gpb_set_allreduce(self.h, self._cb, None))
+
+    def allreduces(self):
+        return self.L.gpb_allreduces_last_optimize(self.h)
+
     def set_segment_length(self, level0=0, upper=0):
         self._ck(self.L.gpb_set_segment_length(self.h, C.c_int(level0), C.c_int(upper)))
 

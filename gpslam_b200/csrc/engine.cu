@@ -73,6 +73,9 @@ struct gpb_graph {
   double* d_xprm = nullptr;
   int *d_rowoff = nullptr, *d_rowland = nullptr, *d_lmoff = nullptr, *d_lmrows = nullptr;
   int *d_bsoff = nullptr, *d_bsrow = nullptr, *d_bsside = nullptr;  // per-state CSR of landmark-bearing rows (level-0 border gather)
+  int rank = 0, world = 1, nsep = 0, R = 0;
+  gpb_allreduce_fn allreduce = nullptr; void* allreduce_ctx = nullptr;
+  double* d_topbuf = nullptr; double cur_error_local = 0; int n_allreduce = 0;
   int extL = 0, extR = 0;  // shard: first / last state is an external separator (owned by the global reduced system)
   int *d_listA = nullptr, *d_listB = nullptr;  // extra factors by kind class: interpolated measurements / everything else
   int nA = 0, nB = 0;
@@ -334,6 +337,20 @@ int gpb_get_values(gpb_graph* g, double* poses, double* vels, double* landmarks)
   return GPB_OK;
 }
 
+int gpb_graph_set_shard(gpb_graph* g, int rank, int world, int ext_left, int ext_right) {
+  CHECK_OPEN(g);
+  if (world < 1 || rank < 0 || rank >= world) return fail(GPB_ERR_ARG, "gpb_graph_set_shard: bad rank/world");
+  if ((rank == 0 && ext_left) || (rank == world - 1 && ext_right)) return fail(GPB_ERR_ARG, "gpb_graph_set_shard: the first shard has no left neighbour, the last no right neighbour");
+  if (world > 1 && ((rank > 0 && !ext_left) || (rank < world - 1 && !ext_right))) return fail(GPB_ERR_ARG, "gpb_graph_set_shard: interior cuts need their separators");
+  g->rank = rank; g->world = world; g->extL = ext_left ? 1 : 0; g->extR = ext_right ? 1 : 0;
+  return GPB_OK;
+}
+int gpb_set_allreduce(gpb_graph* g, gpb_allreduce_fn fn, void* ctx) {
+  if (!g) return fail(GPB_ERR_ARG, "null graph");
+  g->allreduce = fn; g->allreduce_ctx = ctx;
+  return GPB_OK;
+}
+
 int gpb_set_segment_length(gpb_graph* g, int level0, int upper) {
   CHECK_OPEN(g);
   if ((level0 && level0 < 2) || (upper && upper < 2)) return fail(GPB_ERR_ARG, "segment length must be >= 2");
@@ -496,6 +513,11 @@ int gpb_graph_finalize(gpb_graph* g, int device) {
   if ((rc = dev_alloc(g, &g->d_Cpart, (size_t)16 * g->levels.size() * std::max(centries, 1)))) return rc;
   CUDA_TRY(cudaMemset(g->d_Cpart, 0, (size_t)16 * g->levels.size() * std::max(centries, 1) * sizeof(double)));
   if ((rc = dev_alloc(g, &g->d_Csum, (size_t)std::max(centries, 1)))) return rc;
+  g->nsep = g->world - 1; g->R = g->nsep * bs + g->nb;
+  if (g->world > 1) {
+    if (g->R > 256) return fail(GPB_ERR_UNSUPPORTED, "reduced system larger than 256 unknowns");
+    if ((rc = dev_alloc(g, &g->d_topbuf, (size_t)g->R * g->R + g->R + 4))) return rc;
+  }
   // page-lock the host staging so the H2D / D2H copies of the values run at full PCIe rate
   if (cudaHostRegister(g->h_X.data(), g->h_X.size() * sizeof(double), cudaHostRegisterDefault) == cudaSuccess) {
     g->pinned = true;
@@ -626,11 +648,56 @@ static int solve_backward(gpb_graph* g) {
   CUDA_TRY(cudaGetLastError());
   return GPB_OK;
 }
+// in-place sum over ranks of a small device buffer through the registered callback (stream-ordered on both sides)
+static int dist_allreduce(gpb_graph* g, double* dbuf, long long count) {
+  if (!g->allreduce) return fail(GPB_ERR_STATE, "sharded graph: no all-reduce registered (gpb_set_allreduce)");
+  CUDA_TRY(cudaStreamSynchronize(g->stream));
+  if (g->allreduce(g->allreduce_ctx, dbuf, count) != 0) return fail(GPB_ERR_CUDA, "all-reduce callback failed");
+  g->n_allreduce++;
+  return GPB_OK;
+}
+// sharded solve: local elimination down to the external separators -> pack -> ONE all-reduce -> redundant dense solve ->
+// local back-substitution.  global_err_out: sum over ranks of err_local (the error at the current linearisation point).
+static int solve_system_dist(gpb_graph* g, int buf, double lambda, double err_local, double* global_err_out, int* flag_out) {
+  int rc;
+  const int nb = g->nb, centries = nb * nb + nb, nel = num_elim_levels(g), R = g->R;
+  if ((rc = solve_forward(g, buf, lambda))) return rc;
+  if (nb) { k_cseg_final<<<(centries + 127) / 128, 128, 0, g->stream>>>(g->d_Cbase, g->d_Cpart, 16 * nel, centries, g->d_Csum); g->launches++; }
+  PackArgs pa;
+  pa.bs = g->bs; pa.nb = nb; pa.R = R; pa.nsep = g->nsep; pa.rank = g->rank; pa.extL = g->extL; pa.extR = g->extR;
+  pa.rec = g->levels.back().rec; pa.brec = g->levels.back().brec; pa.Csum = g->d_Csum; pa.err_local = err_local; pa.flag = g->d_flag; pa.buf = g->d_topbuf;
+  const long long total = (long long)R * R + R + 4;
+  k_pack_top<<<(int)std::min<long long>((total + 255) / 256, 148), 256, 0, g->stream>>>(pa);
+  g->launches++;
+  if ((rc = dist_allreduce(g, g->d_topbuf, total))) return rc;
+  double sc[4];
+  CUDA_TRY(cudaMemcpyAsync(sc, g->d_topbuf + (size_t)R * R + R, 4 * sizeof(double), cudaMemcpyDeviceToHost, g->stream));
+  k_top_solve<256><<<1, 256, 0, g->stream>>>(g->d_topbuf, R, g->nsep * g->bs, lambda, g->d_flag);
+  k_top_scatter<<<1, 64, 0, g->stream>>>(g->d_topbuf, R, g->bs, nb, g->nsep, g->rank, g->extL, g->extR, g->levels.back().xsol, g->d_xlm);
+  g->launches += 2;
+  if ((rc = solve_backward(g))) return rc;
+  int flag = 0;
+  CUDA_TRY(cudaMemcpyAsync(&flag, g->d_flag, sizeof(int), cudaMemcpyDeviceToHost, g->stream));
+  CUDA_TRY(cudaStreamSynchronize(g->stream));
+  if (global_err_out) *global_err_out = sc[0];
+  if (flag_out) *flag_out = (sc[1] != 0.0 || flag != 0) ? 1 : 0;
+  return GPB_OK;
+}
+// global sums of up to 4 host scalars (one tiny all-reduce; used outside the per-iteration hot loop and by LM trials)
+static int dist_sum_scalars(gpb_graph* g, double* v4) {
+  double* d = g->d_topbuf;  // reuse the head of the exchange buffer
+  CUDA_TRY(cudaMemcpyAsync(d, v4, 4 * sizeof(double), cudaMemcpyHostToDevice, g->stream));
+  int rc = dist_allreduce(g, d, 4);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(v4, d, 4 * sizeof(double), cudaMemcpyDeviceToHost, g->stream));
+  CUDA_TRY(cudaStreamSynchronize(g->stream));
+  return GPB_OK;
+}
 // Solve (H + lambda I) delta = g with the current HREC / XR[buf]; delta lands in levels[0].xsol and d_xlm.
 static int solve_system(gpb_graph* g, int buf, double lambda) {
   int rc;
+  if (g->world > 1) return solve_system_dist(g, buf, lambda, 0.0, nullptr, nullptr);
   if ((rc = solve_forward(g, buf, lambda))) return rc;
-  if (g->extL || g->extR) return fail(GPB_ERR_STATE, "sharded graph: use the distributed solve");
   if ((rc = solve_landmarks_local(g, lambda))) return rc;
   return solve_backward(g);
 }
@@ -639,11 +706,11 @@ template <int G> static int launch_retract(gpb_graph* g) {
   constexpr int NT = 128;
   const int nblk = (g->N + NT - 1) / NT;
   double* part = g->d_errpart + g->nerrpart;
-  k_retract<G, NT><<<nblk, NT, 0, g->stream>>>(g->d_X, g->levels[0].xsol, g->d_HREC, g->d_Xt, part, part + nblk, g->N);
+  k_retract<G, NT><<<nblk, NT, 0, g->stream>>>(g->d_X, g->levels[0].xsol, g->d_HREC, g->d_Xt, part, part + nblk, g->N, g->extL ? 1 : 0);
   k_sum_partials<<<1, 256, 0, g->stream>>>(part, nblk, g->d_scal, 1);
   k_sum_partials<<<1, 256, 0, g->stream>>>(part + nblk, nblk, g->d_scal, 2);
   g->launches += 3;
-  if (g->nb) { k_retract_land<<<1, 256, 0, g->stream>>>(g->d_land, g->d_xlm, g->d_Cbase + (size_t)g->nb * g->nb, g->d_landt, g->nb, g->d_scal); g->launches++; }
+  if (g->nb) { k_retract_land<<<1, 256, 0, g->stream>>>(g->d_land, g->d_xlm, g->d_Cbase + (size_t)g->nb * g->nb, g->d_landt, g->nb, g->d_scal, g->rank == 0 ? 1 : 0); g->launches++; }
   CUDA_TRY(cudaGetLastError());
   return GPB_OK;
 }
@@ -673,6 +740,8 @@ int gpb_linearize(gpb_graph* g, double* error_out) {
   if (rc) return rc;
   double s[3]; int flag;
   if ((rc = read_scalars(g, s, &flag))) return rc;
+  g->cur_error_local = s[0];
+  if (g->world > 1) { double v[4] = {s[0], 0, 0, 0}; if ((rc = dist_sum_scalars(g, v))) return rc; s[0] = v[0]; }
   g->cur_error = s[0]; g->linearized = true; g->assembled = false;
   if (error_out) *error_out = s[0];
   return GPB_OK;
@@ -685,6 +754,7 @@ int gpb_error(gpb_graph* g, double* error_out) {
   if (rc) return rc;
   double s[3]; int flag;
   if ((rc = read_scalars(g, s, &flag))) return rc;
+  if (g->world > 1) { double v[4] = {s[0], 0, 0, 0}; if ((rc = dist_sum_scalars(g, v))) return rc; s[0] = v[0]; }
   if (error_out) *error_out = s[0];
   return GPB_OK;
 }
@@ -719,24 +789,42 @@ int gpb_optimize(gpb_graph* g, const gpb_params* params, int n_iter, gpb_stats* 
   cudaEvent_t e0, e1;
   CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
   CUDA_TRY(cudaEventRecord(e0, g->stream));
-  g->launches = 0;
+  g->launches = 0; g->n_allreduce = 0;
   int rc;
   if (!g->linearized && (rc = gpb_linearize(g, nullptr))) return rc;
   const double error_initial = g->cur_error;
   double error = error_initial, lambda = p.lambda_initial;
   int iterations = 0, status = 0;
+  const bool dist = g->world > 1;
+  // sharded graphs: exactly ONE all-reduce per Gauss-Newton iteration (the boundary Schur system, which also carries the error
+  // of the current point).  LM trials and convergence-tested runs need the trial point's global error before the next
+  // iteration and pay a second, 4-double all-reduce for it.
+  const bool need_trial_error = dist && (p.use_lm || n_iter <= 0);
   auto one_iteration = [&]() -> int {
     int r;
     if (!g->assembled) { if ((r = assemble_dispatch(g, g->cur))) return r; g->assembled = true; }
     while (true) {
       CUDA_TRY(cudaMemsetAsync(g->d_flag, 0, sizeof(int), g->stream));
-      if ((r = solve_system(g, g->cur, p.use_lm ? lambda : 0.0))) return r;
+      int flag = 0;
+      const double lam = p.use_lm ? lambda : 0.0;
+      if (dist) {
+        double gerr = 0;
+        if ((r = solve_system_dist(g, g->cur, lam, g->cur_error_local, &gerr, &flag))) return r;
+        error = gerr;  // exact global error of the current point
+      } else if ((r = solve_system(g, g->cur, lam))) return r;
       if ((r = retract_dispatch(g))) return r;
       // linearise at the trial point into the other buffer: gives the trial error and, if accepted, the next iteration's [A|b]
       if ((r = linearize_dispatch(g, g->d_Xt, g->d_landt, 1 - g->cur, 1))) return r;
-      double s[3]; int flag;
-      if ((r = read_scalars(g, s, &flag))) return r;
-      const double newError = s[0];
+      double s[3]; int lflag;
+      if ((r = read_scalars(g, s, &lflag))) return r;
+      flag |= lflag;
+      const double newErrorLocal = s[0];
+      if (need_trial_error) {
+        double v[4] = {s[0], s[1], s[2], (double)flag};
+        if ((r = dist_sum_scalars(g, v))) return r;
+        s[0] = v[0]; s[1] = v[1]; s[2] = v[2]; flag = v[3] != 0.0;
+      }
+      const double newError = (dist && !need_trial_error) ? error : s[0];  // plain sharded GN: known at the next iteration's all-reduce
       bool success = false, stop = false;
       if (!p.use_lm) {
         if (flag) { status = 1; return fail(GPB_ERR_NUMERIC, "GaussNewton: indeterminate linear system"); }
@@ -754,7 +842,7 @@ int gpb_optimize(gpb_graph* g, const gpb_params* params, int n_iter, gpb_stats* 
       }
       if (success) {
         std::swap(g->d_X, g->d_Xt); std::swap(g->d_land, g->d_landt); g->cur = 1 - g->cur;
-        error = newError; g->cur_error = error; g->assembled = false; g->linearized = true;
+        error = newError; g->cur_error = error; g->cur_error_local = newErrorLocal; g->assembled = false; g->linearized = true;
         if (p.use_lm) lambda = std::max(p.lambda_lower, lambda / p.lambda_factor);
         break;
       } else if (!stop) {
@@ -779,6 +867,11 @@ int gpb_optimize(gpb_graph* g, const gpb_params* params, int n_iter, gpb_stats* 
   }
   CUDA_TRY(cudaEventRecord(e1, g->stream));
   CUDA_TRY(cudaEventSynchronize(e1));
+  if (dist && !need_trial_error) {  // report the exact final error (outside the timed loop: one 4-double all-reduce)
+    double v[4] = {g->cur_error_local, 0, 0, 0};
+    if ((rc = dist_sum_scalars(g, v))) return rc;
+    error = v[0]; g->cur_error = error;
+  }
   float ms = 0;
   CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
   cudaEventDestroy(e0); cudaEventDestroy(e1);
@@ -790,6 +883,12 @@ int gpb_optimize(gpb_graph* g, const gpb_params* params, int n_iter, gpb_stats* 
 }
 
 int gpb_kernel_launches_last_optimize(gpb_graph* g) { return g ? g->launches : 0; }
+int gpb_allreduces_last_optimize(gpb_graph* g) { return g ? g->n_allreduce : 0; }
+// plain cudaMemcpy (kind: 1 host->device, 2 device->host) for callers that implement gpb_allreduce_fn without a CUDA binding of their own
+int gpb_memcpy(void* dst, const void* src, long long bytes, int kind) {
+  CUDA_TRY(cudaMemcpy(dst, src, (size_t)bytes, kind == 1 ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost));
+  return GPB_OK;
+}
 
 // ===================================================================== parity copy-outs
 int gpb_get_linearized_factor(gpb_graph* g, int kind, int idx, double* A_out, double* b_out, int* dims_out) {

@@ -82,20 +82,25 @@ __constant__ unsigned char c_tileJ[36] = {0, 0, 1, 0, 1, 2, 0, 1, 2, 3, 0, 1, 2,
 // Cholesky trailing block (A[r][c] -= L[r][j] L[c][j]) and to the inverse accumulators (Z[r][c] += L[r][j] X[j][c]).
 // Dsrc: the SPD block (column-major, lower part read).  Outputs: Li = L^-1 (lower, column-major; strictly-upper untouched),
 // Lout (optional) = L, invd[j] = 1 / L[j][j].  colL / rowX: 2 x BS scratch each (double-buffered by step parity).  Returns false if not PD.
+template <int BS> struct CholMap { static constexpr int NE = BS * (BS + 1) / 2, K = (NE + 31) / 32; int er[K], ec[K]; };
+template <int BS> __device__ __forceinline__ CholMap<BS> chol_map(int lane) {  // (row, col) of the entries a lane owns; computed once per kernel
+  CholMap<BS> m;
+#pragma unroll
+  for (int k = 0; k < CholMap<BS>::K; k++) {
+    int e = lane + 32 * k, cidx = 0;
+    if (e >= CholMap<BS>::NE) e = CholMap<BS>::NE - 1;  // surplus lanes shadow the last entry (their stores are suppressed)
+    while (e >= BS - cidx) { e -= BS - cidx; cidx++; }
+    m.ec[k] = cidx; m.er[k] = cidx + e;
+  }
+  return m;
+}
 template <int BS>
-__device__ __forceinline__ bool warp_chol_inverse(const double* Dsrc, double* Li, double* Lout, double* invd, double* colL, double* rowX, int lane) {
-  constexpr int NE = BS * (BS + 1) / 2, K = (NE + 31) / 32;
-  int er[K], ec[K];
+__device__ __forceinline__ bool warp_chol_inverse(const CholMap<BS>& cm, const double* Dsrc, double* Li, double* Lout, double* invd, double* colL, double* rowX, int lane) {
+  constexpr int NE = CholMap<BS>::NE, K = CholMap<BS>::K;
+  const int* er = cm.er; const int* ec = cm.ec;
   double A[K], Z[K];
 #pragma unroll
-  for (int k = 0; k < K; k++) {
-    int e = lane + 32 * k, cidx = 0;
-    if (e >= NE) e = NE - 1;                      // surplus lanes shadow the last entry (their stores are suppressed)
-    while (e >= BS - cidx) { e -= BS - cidx; cidx++; }
-    ec[k] = cidx; er[k] = cidx + e;
-    A[k] = Dsrc[er[k] + ec[k] * BS];
-    Z[k] = 0.0;
-  }
+  for (int k = 0; k < K; k++) { A[k] = Dsrc[er[k] + ec[k] * BS]; Z[k] = 0.0; }
   bool ok = true;
 #pragma unroll 1
   for (int j = 0; j < BS; j++) {
@@ -144,6 +149,7 @@ __global__ void __launch_bounds__((W < 32 ? 32 : W), (W == 64 ? 6 : 8)) k_fwd(co
   __shared__ double colL[2 * BS], rowX[2 * BS];
   __shared__ double Psm[W * BS];  // panel columns P (one per thread), kept in shared memory between phases
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, gi = lane >> 2, ti = lane & 3;
+  const CholMap<BS> cmap = chol_map<BS>(lane);
   const int c = threadIdx.x;
   const int nb = a.nb, w = BS + nb + 1, M = a.M;
   const bool first = a.first_level != 0;
@@ -229,7 +235,7 @@ __global__ void __launch_bounds__((W < 32 ? 32 : W), (W == 64 ? 6 : 8)) k_fwd(co
       //      all 32 lanes (warp_chol_inverse).  Meanwhile the second warp gathers the next state's landmark border.
       if (c < 32) {
         if (NT == 32 && first && nb > 0 && i + 1 <= ilast) gather_border(i + 1, c);
-        const bool ok = warp_chol_inverse<BS>(Dm, Li, MMA ? nullptr : Dm, invd, colL, rowX, c);
+        const bool ok = warp_chol_inverse<BS>(cmap, Dm, Li, MMA ? nullptr : Dm, invd, colL, rowX, c);
         if (!ok && c == 0) *a.flag = 1;
       } else if (c < 64) {
         if (first && nb > 0 && i + 1 <= ilast) gather_border(i + 1, c - 32);
@@ -668,7 +674,7 @@ __global__ void __launch_bounds__(NT) k_landmark_solve(const double* __restrict_
 // products LM needs: g.delta and |delta|^2 (block partials).
 template <int G, int NT>
 __global__ void __launch_bounds__(NT) k_retract(const double* __restrict__ X, const double* __restrict__ xsol, const double* __restrict__ HREC,
-                                                double* __restrict__ Xt, double* __restrict__ part_gd, double* __restrict__ part_dd, int N) {
+                                                double* __restrict__ Xt, double* __restrict__ part_gd, double* __restrict__ part_dd, int N, int dd_from) {
   constexpr int D = GroupTraits<G>::D, PS = GroupTraits<G>::PS, SR = PS + D, bs = 2 * D, REC = 2 * bs * bs + bs;
   __shared__ double sred[NT / 32];
   const int i = blockIdx.x * NT + threadIdx.x;
@@ -679,7 +685,7 @@ __global__ void __launch_bounds__(NT) k_retract(const double* __restrict__ X, co
     for (int k = 0; k < bs; k++) d[k] = xsol[(size_t)i * bs + k];
     const double* g = HREC + (size_t)i * REC + 2 * bs * bs;
 #pragma unroll
-    for (int k = 0; k < bs; k++) { gd += g[k] * d[k]; dd += d[k] * d[k]; }
+    for (int k = 0; k < bs; k++) { gd += g[k] * d[k]; if (i >= dd_from) dd += d[k] * d[k]; }  // a halo copy's |delta|^2 is counted by its owner
     const double* x = X + (size_t)i * SR;
     double* y = Xt + (size_t)i * SR;
     if constexpr (G == G_POSE3) {
@@ -704,13 +710,126 @@ __global__ void __launch_bounds__(NT) k_retract(const double* __restrict__ X, co
 }
 
 __global__ void k_retract_land(const double* __restrict__ land, const double* __restrict__ xl, const double* __restrict__ gl, double* __restrict__ landt,
-                               int n, double* __restrict__ scal) {
+                               int n, double* __restrict__ scal, int count_dd) {
   // single block: landmarks are few; also folds their share of g.delta / |delta|^2 into scal[1], scal[2]
   __shared__ double sred[8];
   double gd = 0, dd = 0;
-  for (int k = threadIdx.x; k < n; k += 256) { landt[k] = land[k] + xl[k]; gd += gl[k] * xl[k]; dd += xl[k] * xl[k]; }
+  for (int k = threadIdx.x; k < n; k += 256) { landt[k] = land[k] + xl[k]; gd += gl[k] * xl[k]; if (count_dd) dd += xl[k] * xl[k]; }
   const double t1 = block_sum<256>(gd, sred);
   __syncthreads();
   const double t2 = block_sum<256>(dd, sred);
   if (threadIdx.x == 0) { scal[1] += t1; scal[2] += t2; }
+}
+
+// ===================================================================== sharded graphs: the global reduced system
+// Unknowns: [separator_0 .. separator_{P-2} (bs each) | landmarks (nb)], R = (P-1) bs + nb.  Buffer: T (R x R column-major,
+// full symmetric) | t (R) | scalars[4] = {local error sum, not-PD flag sum, unused, unused}.  Every rank adds the Schur
+// complement of its segment (top-level records of its external separators, its landmark block) at its offsets; ONE
+// all-reduce (sum) over NVLink completes the system; every rank then factors it redundantly.
+struct PackArgs {
+  int bs, nb, R, nsep, rank, extL, extR;
+  const double* rec;    // top-level records [extL + extR][3 bs^2 + 2 bs]
+  const double* brec;   // [extL + extR][2 bs nb]
+  const double* Csum;   // local landmark block nb*nb + nb
+  double err_local;
+  const int* flag;
+  double* buf;
+};
+__global__ void k_pack_top(const PackArgs a) {
+  const int R = a.R, bs = a.bs, nb = a.nb, REC1 = 3 * bs * bs + 2 * bs;
+  const size_t total = (size_t)R * R + R + 4;
+  const int loff = a.nsep * bs;  // landmark offset
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    double v = 0.0;
+    if (e < (size_t)R * R) {
+      const int r = (int)(e % R), c = (int)(e / R);
+      // classify row / column: separator block index or landmark
+      auto local_slot = [&](int sep) -> int {  // slot of global separator `sep` in this rank's top records, or -1
+        if (a.extL && sep == a.rank - 1) return 0;
+        if (a.extR && sep == a.rank) return a.extL;
+        return -1;
+      };
+      const bool rl = r >= loff, cl = c >= loff;
+      if (rl && cl) v = a.Csum[(r - loff) + (size_t)(c - loff) * nb];
+      else if (!rl && !cl) {
+        const int sr = r / bs, sc = c / bs, ir = r % bs, ic = c % bs;
+        const int kr = local_slot(sr), kc = local_slot(sc);
+        if (kr >= 0 && kc >= 0) {
+          if (kr == kc) { const double* D = a.rec + (size_t)kr * REC1; v = D[ir + ic * bs] + D[bs * bs + ir + ic * bs]; }
+          else if (kr == kc + 1) v = a.rec[(size_t)kc * REC1 + 2 * bs * bs + ir + ic * bs];       // E: rows slot kc+1, cols slot kc
+          else if (kc == kr + 1) v = a.rec[(size_t)kr * REC1 + 2 * bs * bs + ic + ir * bs];
+        }
+      } else {
+        const int rs = rl ? c : r, ll = (rl ? r : c) - loff;  // separator row index, landmark column
+        const int k = local_slot(rs / bs);
+        if (k >= 0) { const double* B = a.brec + (size_t)k * (2 * bs * nb); v = B[(rs % bs) + ll * bs] + B[bs * nb + (rs % bs) + ll * bs]; }
+      }
+    } else if (e < (size_t)R * R + R) {
+      const int r = (int)(e - (size_t)R * R);
+      if (r >= loff) v = a.Csum[(size_t)nb * nb + (r - loff)];
+      else {
+        int k = -1;
+        if (a.extL && r / bs == a.rank - 1) k = 0;
+        if (a.extR && r / bs == a.rank) k = a.extL;
+        if (k >= 0) { const double* g = a.rec + (size_t)k * REC1 + 3 * bs * bs; v = g[r % bs] + g[bs + r % bs]; }
+      }
+    } else {
+      const int sidx = (int)(e - ((size_t)R * R + R));
+      v = sidx == 0 ? a.err_local : (sidx == 1 ? (double)(*a.flag) : 0.0);
+    }
+    a.buf[e] = v;
+  }
+}
+
+// Dense Cholesky solve of the all-reduced system (in place in global memory; the working set is L2-resident), single CTA.
+// lambda is added to the landmark diagonal only (separator blocks were damped when their level-0 blocks were handed off).
+template <int NT>
+__global__ void __launch_bounds__(NT) k_top_solve(double* __restrict__ buf, int R, int loff, double lambda, int* __restrict__ flag) {
+  double* T = buf;
+  double* t = buf + (size_t)R * R;
+  __shared__ double colj[256];
+  __shared__ double sinv;
+  for (int r = loff + threadIdx.x; r < R; r += NT) T[r + (size_t)r * R] += lambda;
+  __syncthreads();
+  for (int j = 0; j < R; j++) {
+    if (threadIdx.x == 0) {
+      const double djj = T[j + (size_t)j * R];
+      if (!(djj > 0.0)) *flag = 3;
+      sinv = rsqrt(djj > 0.0 ? djj : 1.0);
+    }
+    __syncthreads();
+    const double inv = sinv;
+    for (int r = j + threadIdx.x; r < R; r += NT) { const double l = (r == j) ? T[j + (size_t)j * R] * inv : T[r + (size_t)j * R] * inv; T[r + (size_t)j * R] = l; colj[r] = l; }
+    __syncthreads();
+    const int m = R - j - 1;
+    for (int k = threadIdx.x; k < m * m; k += NT) {
+      const int r = j + 1 + k % m, cc = j + 1 + k / m;
+      if (r >= cc) T[r + (size_t)cc * R] -= colj[r] * colj[cc];
+    }
+    __syncthreads();
+  }
+  for (int j = 0; j < R; j++) {  // L y = t
+    if (threadIdx.x == 0) t[j] /= T[j + (size_t)j * R];
+    __syncthreads();
+    const double yj = t[j];
+    for (int r = j + 1 + threadIdx.x; r < R; r += NT) t[r] -= T[r + (size_t)j * R] * yj;
+    __syncthreads();
+  }
+  for (int j = R - 1; j >= 0; j--) {  // L^T x = y
+    if (threadIdx.x == 0) t[j] /= T[j + (size_t)j * R];
+    __syncthreads();
+    const double xj = t[j];
+    for (int r = threadIdx.x; r < j; r += NT) t[r] -= T[j + (size_t)r * R] * xj;
+    __syncthreads();
+  }
+}
+
+// scatter the reduced solution: this rank's external separators -> top-level xsol, landmarks -> xl
+__global__ void k_top_scatter(const double* __restrict__ buf, int R, int bs, int nb, int nsep, int rank, int extL, int extR, double* __restrict__ xsol_top,
+                              double* __restrict__ xl) {
+  const double* x = buf + (size_t)R * R;
+  const int tid = threadIdx.x;
+  if (extL && tid < bs) xsol_top[tid] = x[(rank - 1) * bs + tid];
+  if (extR && tid < bs) xsol_top[extL * bs + tid] = x[rank * bs + tid];
+  for (int k = tid; k < nb; k += blockDim.x) xl[k] = x[nsep * bs + k];
 }

@@ -117,6 +117,18 @@ int gpb_optimize(gpb_graph* g, const gpb_params* params, int n_iter, gpb_stats* 
  * as [n_states x 2D] and [n_landmarks x DL] (parity checks of the block solver). */
 int gpb_solve_delta(gpb_graph* g, double lambda, double* delta_states, double* delta_landmarks);
 
+/* -- trajectory sharding across the GPUs of one node.  Each process owns one contiguous segment of the chain
+ * and builds only that sub-graph (local state indices).  ext_left: local state 0 is the last state of the left neighbour
+ * (halo copy; a separator of the global reduced system); ext_right: the local last state is this rank's boundary separator.
+ * Call before gpb_graph_finalize.  Landmarks are replicated; factors attached to interval (t, t+1) belong to the rank
+ * whose local chain contains both states. */
+int gpb_graph_set_shard(gpb_graph* g, int rank, int world, int ext_left, int ext_right);
+
+/* In-place SUM all-reduce of `count` doubles at device pointer `buf` over all ranks, complete on return.  The engine calls it
+ * exactly once per Gauss-Newton iteration, on the packed boundary Schur-complement system (plus the error scalar). */
+typedef int (*gpb_allreduce_fn)(void* ctx, double* device_buf, long long count);
+int gpb_set_allreduce(gpb_graph* g, gpb_allreduce_fn fn, void* ctx);
+
 /* solver tuning: segment length per elimination level (>= 2); 0 keeps the default */
 int gpb_set_segment_length(gpb_graph* g, int level0, int upper_levels);
 
@@ -131,6 +143,10 @@ int gpb_time_stage(gpb_graph* g, int stage, int reps, double* ms_out);
 
 /* names and average device milliseconds of the kernels timed during the last gpb_optimize (profiling aid) */
 int gpb_kernel_launches_last_optimize(gpb_graph* g);
+/* plain cudaMemcpy (kind 1: host->device, 2: device->host), for gpb_allreduce_fn implementations without their own CUDA binding */
+int gpb_memcpy(void* dst, const void* src, long long bytes, int kind);
+/* all-reduce calls issued by the last gpb_optimize (sharded graphs) */
+int gpb_allreduces_last_optimize(gpb_graph* g);
 
 #ifdef __cplusplus
 }
