@@ -1059,4 +1059,60 @@ int gpb_time_stage(gpb_graph* g, int stage, int reps, double* ms_out) {
   return GPB_OK;
 }
 
+
+// Single-factor compatibility path behind NoiseModelFactor::evaluateError: builds a throw-away 2-state graph with unit noise,
+// runs the SAME batched kernels on it and un-whitens the result.  Thread-safe (no shared state); slow by design (allocations).
+int gpb_eval_factor(int group, int kind, const double* x1, const double* v1, const double* x2, const double* v2, const double* landmark,
+                    const double* prm, double* e_out, double* H_out, int* dims_out) {
+  if (group < 0 || group > 3 || !x1 || !prm || !e_out || !dims_out) return fail(GPB_ERR_ARG, "gpb_eval_factor: bad arguments");
+  gpb_graph* g = gpb_graph_create(group, 3, 2, 1);
+  if (!g) return GPB_ERR_ARG;
+  const int D = g->D, PS = g->PS, DL = g->DL;
+  auto done = [&](int rc) { gpb_graph_destroy(g); return rc; };
+  std::vector<double> I(D * D, 0.0), I2(36, 0.0);
+  for (int k = 0; k < D; k++) I[k + k * D] = 1.0;
+  int rc = gpb_add_qc_model(g, I.data());
+  if (rc < 0) return done(rc);
+  const int zero = 0; const double one = 1.0;
+  const double dt = prm[0], tau = prm[1];
+  auto eye = [&](int m) { std::fill(I2.begin(), I2.end(), 0.0); for (int k = 0; k < m; k++) I2[k + k * m] = 1.0; return I2.data(); };
+  switch (kind) {
+    case 0: rc = gpb_add_gp_prior(g, 1, &zero, &dt, 0); break;
+    case X_INTERP_RANGE: rc = gpb_add_interp_range(g, 1, &zero, &zero, &prm[2], &one, &dt, &tau, 0, prm[16] != 0.0 ? prm + 4 : nullptr); break;
+    case X_INTERP_ATTITUDE: rc = gpb_add_interp_attitude(g, 1, &zero, &dt, &tau, 0, prm + 4, prm + 7, &one); break;
+    case X_PRIOR_POSE: rc = gpb_add_prior_pose(g, 0, prm + 4, eye(D)); break;
+    case X_PRIOR_VEL: rc = gpb_add_prior_vel(g, 0, prm + 4, eye(D)); break;
+    case X_PRIOR_LANDMARK: rc = gpb_add_prior_landmark(g, 0, prm + 4, eye(DL)); break;
+    case X_BETWEEN: rc = gpb_add_between(g, 0, 1, prm + 4, eye(D)); break;
+    case X_RANGE_2D: rc = gpb_add_range_2d(g, 0, 0, prm[2], 1.0); break;
+    case X_RANGE_BEARING_2D: rc = gpb_add_range_bearing_2d(g, 0, 0, prm[2], prm[3], eye(2)); break;
+    case X_ODOMETRY_2D: rc = gpb_add_odometry_2d(g, 0, 1, prm + 4, eye(3)); break;
+    default: return done(fail(GPB_ERR_ARG, "gpb_eval_factor: unknown factor kind"));
+  }
+  if (rc < 0) return done(rc);
+  std::vector<double> P(2 * PS, 0.0), V(2 * D, 0.0), Lm(std::max(DL, 1), 0.0);
+  std::copy(x1, x1 + PS, P.begin());
+  if (x2) std::copy(x2, x2 + PS, P.begin() + PS); else std::copy(x1, x1 + PS, P.begin() + PS);
+  if (v1) std::copy(v1, v1 + D, V.begin());
+  if (v2) std::copy(v2, v2 + D, V.begin() + D);
+  if (landmark && DL) std::copy(landmark, landmark + DL, Lm.begin());
+  if ((rc = gpb_set_values(g, P.data(), V.data(), Lm.data())) < 0) return done(rc);
+  if ((rc = gpb_graph_finalize(g, 0)) < 0) return done(rc);
+  if ((rc = gpb_linearize(g, nullptr)) < 0) return done(rc);
+  double A[12 * 6 * 5], b[12];
+  const int m = gpb_get_linearized_factor(g, kind == 0 ? 0 : 1, 0, A, b, dims_out);
+  if (m < 0) return done(m);
+  int ncols = 0;
+  for (int v = 0; v < 5; v++) ncols += dims_out[v];
+  if (kind == 0) {  // un-whiten the GP prior: rows [top; bot] = (U (x) I)^-1 [top'; bot']
+    const GpWhiten w = gp_whiten(dt);
+    auto unw = [&](double* col) { for (int k = 0; k < D; k++) { const double bot = col[D + k] / w.u22; col[D + k] = bot; col[k] = (col[k] - w.u12 * bot) / w.u11; } };
+    for (int c = 0; c < ncols; c++) unw(A + (size_t)c * m);
+    unw(b);
+  }
+  for (int r = 0; r < m; r++) e_out[r] = -b[r];
+  if (H_out) std::copy(A, A + (size_t)m * ncols, H_out);
+  return done(m);
+}
+
 }  // extern "C"

@@ -85,6 +85,17 @@ int gpb_add_range_2d(gpb_graph* g, int i, int l, double z, double sigma);
 int gpb_add_range_bearing_2d(gpb_graph* g, int i, int l, double range, double bearing, const double* sqrt_info);
 int gpb_add_odometry_2d(gpb_graph* g, int i, int j, const double* measured, const double* sqrt_info);
 
+/* Single-factor compatibility path: NoiseModelFactorN::evaluateError(x..., H...) of ONE factor (e.g.
+ * gp/GaussianProcessPriorPose3.h:60-65, slam/GPInterpolatedRangeFactorPose3.h:64-69): unwhitened residual e (m doubles) and,
+ * when H_out != NULL, the Jacobian blocks concatenated column-major in the factor's variable order (dims_out[5] = their widths).
+ * Evaluated by the same device code as the batched path on a throw-away 2-state graph; thread-safe, not fast.
+ * kind: GPB_F_*.  prm[20]: [0] delta_t [1] tau [2] range / z [3] bearing [4..15] body_P_sensor | nZ(3),bRef(3) | prior value |
+ * measured (wire layout) [16] has_sensor.  x2/v2/landmark may be NULL when the factor does not use them.  Returns m or a status. */
+enum { GPB_F_GP_PRIOR = 0, GPB_F_INTERP_RANGE = 1, GPB_F_INTERP_ATTITUDE = 2, GPB_F_PRIOR_POSE = 3, GPB_F_PRIOR_VEL = 4, GPB_F_PRIOR_LANDMARK = 5,
+       GPB_F_BETWEEN = 6, GPB_F_RANGE_2D = 7, GPB_F_RANGE_BEARING_2D = 8, GPB_F_ODOMETRY_2D = 9 };
+int gpb_eval_factor(int group, int kind, const double* x1, const double* v1, const double* x2, const double* v2, const double* landmark,
+                    const double* prm, double* e_out, double* H_out, int* dims_out);
+
 /* Values::insert / Values::at : host buffers, [n_states x pose_storage], [n_states x D], [n_landmarks x DL] */
 int gpb_set_values(gpb_graph* g, const double* poses, const double* vels, const double* landmarks);
 int gpb_get_values(gpb_graph* g, double* poses, double* vels, double* landmarks);

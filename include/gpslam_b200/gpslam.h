@@ -1,0 +1,442 @@
+// gpslam.h — header-only C++ host facade over the C ABI (include/gpb.h): the reference's factor classes, with the
+// reference's names, constructor argument order and evaluateError contract, plus the few GTSAM container / optimiser
+// types its call sites use (matlab/PlazaPose2.m:51-230, the "Optimization" unit tests).  Graphs written against
+// gpslam + GTSAM compile against this header by switching the include and the namespace alias.
+//
+// GTSAM itself is not available where this was built, so the handful of value types the interface needs live in
+// namespace gpslam_b200::gtsam (Key/Symbol, Pose3, Rot3, Pose2, Point2/3, Vector, Matrix, noiseModel).  Differences from
+// the reference signatures, all forced by the absence of Boost/GTSAM: optional Jacobians are `Matrix*` (nullptr = not
+// requested) instead of boost::optional<Matrix&>; shared_ptr is std::shared_ptr.
+//
+// No arithmetic lives here: evaluateError forwards to gpb_eval_factor (the same device code as the batched path) and the
+// optimisers lower the graph to a gpb_graph and call gpb_optimize.  Errors become std::runtime_error carrying gpb_last_error().
+#pragma once
+#include <array>
+#include <cmath>
+#include <cstdint>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../gpb.h"
+
+namespace gpslam_b200 {
+namespace gtsam {
+
+using Key = std::uint64_t;
+inline Key Symbol(char c, std::uint64_t j) { return (static_cast<Key>(static_cast<unsigned char>(c)) << 56) | j; }
+inline char symbolChr(Key k) { return static_cast<char>(k >> 56); }
+inline std::uint64_t symbolIndex(Key k) { return k & ((Key(1) << 56) - 1); }
+
+using Vector = std::vector<double>;
+struct Matrix {  // dynamic, column-major (Eigen's default)
+  int rows = 0, cols = 0;
+  std::vector<double> a;
+  Matrix() {}
+  Matrix(int r, int c) : rows(r), cols(c), a(static_cast<size_t>(r) * c, 0.0) {}
+  double& operator()(int r, int c) { return a[r + static_cast<size_t>(c) * rows]; }
+  double operator()(int r, int c) const { return a[r + static_cast<size_t>(c) * rows]; }
+  static Matrix Identity(int n, int m) { Matrix I(n, m); for (int k = 0; k < (n < m ? n : m); k++) I(k, k) = 1.0; return I; }
+};
+inline Matrix operator*(double s, Matrix m) { for (double& v : m.a) v *= s; return m; }
+
+template <int N> using VectorN = std::array<double, N>;
+using Vector3 = VectorN<3>;
+using Vector6 = VectorN<6>;
+struct Point2 { double x = 0, y = 0; Point2() {} Point2(double x_, double y_) : x(x_), y(y_) {} };
+struct Point3 { double x = 0, y = 0, z = 0; Point3() {} Point3(double x_, double y_, double z_) : x(x_), y(y_), z(z_) {} };
+struct Unit3 { double x = 0, y = 0, z = 1; Unit3() {} Unit3(double x_, double y_, double z_) { const double n = std::sqrt(x_ * x_ + y_ * y_ + z_ * z_); x = x_ / n; y = y_ / n; z = z_ / n; } };
+
+struct Rot3 {
+  double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};  // column-major
+  static Rot3 Ypr(double y, double p, double r) {  // Rz(y) Ry(p) Rx(r)  (gp/tests/testPose3Utils.cpp:126-133)
+    const double cy = std::cos(y), sy = std::sin(y), cp = std::cos(p), sp = std::sin(p), cr = std::cos(r), sr = std::sin(r);
+    Rot3 o;
+    const double m[3][3] = {{cy * cp, cy * sp * sr - sy * cr, cy * sp * cr + sy * sr}, {sy * cp, sy * sp * sr + cy * cr, sy * sp * cr - cy * sr}, {-sp, cp * sr, cp * cr}};
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) o.R[i + 3 * j] = m[i][j];
+    return o;
+  }
+};
+struct Pose3 {
+  Rot3 r; Point3 t;
+  Pose3() {}
+  Pose3(const Rot3& r_, const Point3& t_) : r(r_), t(t_) {}
+  void wire(double* p) const { for (int k = 0; k < 9; k++) p[k] = r.R[k]; p[9] = t.x; p[10] = t.y; p[11] = t.z; }
+  static Pose3 fromWire(const double* p) { Pose3 T; for (int k = 0; k < 9; k++) T.r.R[k] = p[k]; T.t = Point3(p[9], p[10], p[11]); return T; }
+};
+struct Pose2 { double x = 0, y = 0, theta = 0; Pose2() {} Pose2(double x_, double y_, double th) : x(x_), y(y_), theta(th) {} };
+
+namespace noiseModel {
+// Every model the gpslam call sites use reduces to a Gaussian with upper-triangular square-root information R.
+struct Gaussian {
+  int dim = 0;
+  Matrix cov;  // covariance (kept for getQc: gp/GPutils.cpp:16-20)
+  Matrix R;    // upper-triangular sqrt information
+  using shared_ptr = std::shared_ptr<Gaussian>;
+  static shared_ptr Covariance(const Matrix& c) {
+    auto m = std::make_shared<Gaussian>(); m->dim = c.rows; m->cov = c;
+    // R = chol_upper(cov^-1); only needed for measurement models, where the call sites use diagonal covariances
+    m->R = Matrix(c.rows, c.cols);
+    bool diag = true;
+    for (int i = 0; i < c.rows; i++) for (int j = 0; j < c.cols; j++) if (i != j && c(i, j) != 0.0) diag = false;
+    if (diag) for (int i = 0; i < c.rows; i++) m->R(i, i) = 1.0 / std::sqrt(c(i, i));
+    else m->R = Matrix();  // dense covariance: valid as a Qc model (the engine factors it itself), not as a measurement model
+    return m;
+  }
+};
+struct Isotropic { static Gaussian::shared_ptr Sigma(int dim, double sigma) { return Gaussian::Covariance((sigma * sigma) * Matrix::Identity(dim, dim)); } };
+struct Diagonal {
+  static Gaussian::shared_ptr Sigmas(const Vector& s) { Matrix c(static_cast<int>(s.size()), static_cast<int>(s.size())); for (size_t k = 0; k < s.size(); k++) c(static_cast<int>(k), static_cast<int>(k)) = s[k] * s[k]; return Gaussian::Covariance(c); }
+};
+}  // namespace noiseModel
+using SharedNoiseModel = noiseModel::Gaussian::shared_ptr;
+
+}  // namespace gtsam
+
+namespace detail {
+inline void check(int rc) { if (rc < 0) throw std::runtime_error(std::string("gpslam_b200: ") + gpb_last_error()); }
+inline const gtsam::Matrix& sqrtInfo(const gtsam::SharedNoiseModel& m) {
+  if (!m || m->R.rows == 0) throw std::runtime_error("gpslam_b200: measurement noise model must be Gaussian with a diagonal covariance");
+  return m->R;
+}
+inline void wire(const gtsam::Pose3& v, double* p) { v.wire(p); }
+inline void wire(const gtsam::Rot3& v, double* p) { for (int k = 0; k < 9; k++) p[k] = v.R[k]; }
+inline void wire(const gtsam::Pose2& v, double* p) { p[0] = v.x; p[1] = v.y; p[2] = v.theta; }
+inline void wire(const gtsam::Vector3& v, double* p) { for (int k = 0; k < 3; k++) p[k] = v[k]; }
+inline void wire(const gtsam::Vector6& v, double* p) { for (int k = 0; k < 6; k++) p[k] = v[k]; }
+inline void wire(const gtsam::Point3& v, double* p) { p[0] = v.x; p[1] = v.y; p[2] = v.z; }
+inline void wire(const gtsam::Point2& v, double* p) { p[0] = v.x; p[1] = v.y; }
+template <class T> struct GroupOf;
+template <> struct GroupOf<gtsam::Pose3> { static constexpr int group = GPB_POSE3, D = 6, PS = 12, DL = 3; using Vel = gtsam::Vector6; using Land = gtsam::Point3; };
+template <> struct GroupOf<gtsam::Pose2> { static constexpr int group = GPB_POSE2, D = 3, PS = 3, DL = 2; using Vel = gtsam::Vector3; using Land = gtsam::Point2; };
+template <> struct GroupOf<gtsam::Rot3> { static constexpr int group = GPB_ROT3, D = 3, PS = 9, DL = 0; using Vel = gtsam::Vector3; using Land = gtsam::Point2; };
+template <> struct GroupOf<gtsam::Vector3> { static constexpr int group = GPB_LINEAR, D = 3, PS = 3, DL = 2; using Vel = gtsam::Vector3; using Land = gtsam::Point2; };
+
+// evaluateError through the C ABI: returns e, fills the requested Jacobians (in the factor's variable order)
+inline gtsam::Vector eval(int group, int kind, const double* x1, const double* v1, const double* x2, const double* v2, const double* land, const double* prm,
+                          std::initializer_list<gtsam::Matrix*> H) {
+  double e[12], Hbuf[12 * 6 * 5];
+  int dims[5];
+  bool want = false;
+  for (gtsam::Matrix* h : H) want |= (h != nullptr);
+  const int m = gpb_eval_factor(group, kind, x1, v1, x2, v2, land, prm, e, want ? Hbuf : nullptr, dims);
+  check(m);
+  if (want) {
+    int o = 0, v = 0;
+    for (gtsam::Matrix* h : H) {
+      if (h) { *h = gtsam::Matrix(m, dims[v]); for (int k = 0; k < m * dims[v]; k++) h->a[k] = Hbuf[o + k]; }
+      o += m * dims[v]; v++;
+    }
+  }
+  return gtsam::Vector(e, e + m);
+}
+}  // namespace detail
+
+// ================================================================================== factors
+class NonlinearFactor {
+ public:
+  virtual ~NonlinearFactor() {}
+  virtual const std::vector<gtsam::Key>& keys() const = 0;
+  virtual size_t size() const { return keys().size(); }
+  // lowering hook used by the optimisers: add this factor to g; idx maps a state key to its chain index, lidx a landmark key
+  virtual void lower(gpb_graph* g, int qc_of(void*, const gtsam::Matrix&), void* ctx, const std::map<gtsam::Key, int>& sidx,
+                     const std::map<gtsam::Key, int>& lidx) const = 0;
+  using shared_ptr = std::shared_ptr<NonlinearFactor>;
+};
+
+namespace detail {
+inline int stateOf(const std::map<gtsam::Key, int>& m, gtsam::Key k) {
+  auto it = m.find(k);
+  if (it == m.end()) throw std::runtime_error("gpslam_b200: factor refers to a key that is not in Values");
+  return it->second;
+}
+}  // namespace detail
+
+/// 4-way GP prior factors — gp/GaussianProcessPrior{Pose3,Pose2,Rot3,Linear}.h (constructor: :43-49)
+template <class POSE>
+class GaussianProcessPriorT : public NonlinearFactor {
+  using G = detail::GroupOf<POSE>;
+  std::vector<gtsam::Key> keys_;
+  double delta_t_;
+  gtsam::SharedNoiseModel Qc_;
+
+ public:
+  GaussianProcessPriorT(gtsam::Key poseKey1, gtsam::Key velKey1, gtsam::Key poseKey2, gtsam::Key velKey2, double delta_t, const gtsam::SharedNoiseModel& Qc_model)
+      : keys_{poseKey1, velKey1, poseKey2, velKey2}, delta_t_(delta_t), Qc_(Qc_model) {
+    if (!Qc_model) throw std::runtime_error("gpslam_b200: Qc model is not Gaussian");  // getQc dereferences a failed dynamic_cast in the reference (gp/GPutils.cpp:17-19)
+  }
+  const std::vector<gtsam::Key>& keys() const override { return keys_; }
+  size_t size() const override { return 4; }
+  double delta_t() const { return delta_t_; }
+  /// factor error function (gp/GaussianProcessPriorPose3.h:60-98)
+  gtsam::Vector evaluateError(const POSE& pose1, const typename G::Vel& vel1, const POSE& pose2, const typename G::Vel& vel2, gtsam::Matrix* H1 = nullptr,
+                              gtsam::Matrix* H2 = nullptr, gtsam::Matrix* H3 = nullptr, gtsam::Matrix* H4 = nullptr) const {
+    double x1[12], x2[12], v1[6], v2[6], prm[20] = {0};
+    detail::wire(pose1, x1); detail::wire(pose2, x2); detail::wire(vel1, v1); detail::wire(vel2, v2);
+    prm[0] = delta_t_;
+    return detail::eval(G::group, GPB_F_GP_PRIOR, x1, v1, x2, v2, nullptr, prm, {H1, H2, H3, H4});
+  }
+  bool equals(const GaussianProcessPriorT& e, double tol = 1e-9) const { return keys_ == e.keys_ && std::fabs(delta_t_ - e.delta_t_) < tol; }
+  void lower(gpb_graph* g, int qc_of(void*, const gtsam::Matrix&), void* ctx, const std::map<gtsam::Key, int>& sidx, const std::map<gtsam::Key, int>&) const override {
+    const int i = detail::stateOf(sidx, keys_[0]), j = detail::stateOf(sidx, keys_[2]);
+    if (j != i + 1 || detail::stateOf(sidx, keys_[1]) != i || detail::stateOf(sidx, keys_[3]) != j) throw std::runtime_error("gpslam_b200: GP prior must join consecutive states");
+    detail::check(gpb_add_gp_prior(g, 1, &i, &delta_t_, qc_of(ctx, Qc_->cov)));
+  }
+};
+using GaussianProcessPriorPose3 = GaussianProcessPriorT<gtsam::Pose3>;
+using GaussianProcessPriorPose2 = GaussianProcessPriorT<gtsam::Pose2>;
+using GaussianProcessPriorRot3 = GaussianProcessPriorT<gtsam::Rot3>;
+template <int Dim> using GaussianProcessPriorLinear = GaussianProcessPriorT<gtsam::VectorN<Dim>>;
+
+/// 5-way interpolated range factors — slam/GPInterpolatedRangeFactorPose3.h:46-54, ...Pose2.h
+template <class POSE>
+class GPInterpolatedRangeFactorT : public NonlinearFactor {
+  using G = detail::GroupOf<POSE>;
+  std::vector<gtsam::Key> keys_;
+  double measured_, delta_t_, tau_;
+  gtsam::SharedNoiseModel meas_, Qc_;
+  bool has_sensor_ = false;
+  POSE body_P_sensor_;
+
+ public:
+  GPInterpolatedRangeFactorT(double measured, const gtsam::SharedNoiseModel& meas_model, const gtsam::SharedNoiseModel& Qc_model, gtsam::Key poseKey1,
+                             gtsam::Key velKey1, gtsam::Key poseKey2, gtsam::Key velKey2, gtsam::Key pointKey, double delta_t, double tau,
+                             const POSE* body_P_sensor = nullptr)
+      : keys_{poseKey1, velKey1, poseKey2, velKey2, pointKey}, measured_(measured), delta_t_(delta_t), tau_(tau), meas_(meas_model), Qc_(Qc_model) {
+    if (body_P_sensor) { has_sensor_ = true; body_P_sensor_ = *body_P_sensor; }
+  }
+  const std::vector<gtsam::Key>& keys() const override { return keys_; }
+  double measured() const { return measured_; }
+  gtsam::Vector evaluateError(const POSE& pose1, const typename G::Vel& vel1, const POSE& pose2, const typename G::Vel& vel2, const typename G::Land& point,
+                              gtsam::Matrix* H1 = nullptr, gtsam::Matrix* H2 = nullptr, gtsam::Matrix* H3 = nullptr, gtsam::Matrix* H4 = nullptr,
+                              gtsam::Matrix* H5 = nullptr) const {
+    double x1[12], x2[12], v1[6], v2[6], l[3], prm[20] = {0};
+    detail::wire(pose1, x1); detail::wire(pose2, x2); detail::wire(vel1, v1); detail::wire(vel2, v2); detail::wire(point, l);
+    prm[0] = delta_t_; prm[1] = tau_; prm[2] = measured_;
+    if (has_sensor_) { detail::wire(body_P_sensor_, prm + 4); prm[16] = 1.0; }
+    return detail::eval(G::group, GPB_F_INTERP_RANGE, x1, v1, x2, v2, l, prm, {H1, H2, H3, H4, H5});
+  }
+  void lower(gpb_graph* g, int qc_of(void*, const gtsam::Matrix&), void* ctx, const std::map<gtsam::Key, int>& sidx, const std::map<gtsam::Key, int>& lidx) const override {
+    const int i = detail::stateOf(sidx, keys_[0]), l = detail::stateOf(lidx, keys_[4]);
+    const double sigma = 1.0 / detail::sqrtInfo(meas_)(0, 0);
+    double bps[12];
+    if (has_sensor_) detail::wire(body_P_sensor_, bps);
+    detail::check(gpb_add_interp_range(g, 1, &i, &l, &measured_, &sigma, &delta_t_, &tau_, qc_of(ctx, Qc_->cov), has_sensor_ ? bps : nullptr));
+  }
+};
+using GPInterpolatedRangeFactorPose3 = GPInterpolatedRangeFactorT<gtsam::Pose3>;
+using GPInterpolatedRangeFactorPose2 = GPInterpolatedRangeFactorT<gtsam::Pose2>;
+
+/// slam/GPInterpolatedRangeFactor2DLinear.h:42-50 — note the reference's different argument order
+class GPInterpolatedRangeFactor2DLinear : public GPInterpolatedRangeFactorT<gtsam::Vector3> {
+ public:
+  GPInterpolatedRangeFactor2DLinear(double measured, gtsam::Key pose1Key, gtsam::Key vel1Key, gtsam::Key pose2Key, gtsam::Key vel2Key, gtsam::Key pointKey,
+                                    const gtsam::SharedNoiseModel& meas_model, const gtsam::SharedNoiseModel& Qc_model, double delta_t, double tau)
+      : GPInterpolatedRangeFactorT<gtsam::Vector3>(measured, meas_model, Qc_model, pose1Key, vel1Key, pose2Key, vel2Key, pointKey, delta_t, tau) {}
+};
+
+/// slam/GPInterpolatedAttitudeFactorRot3.h:44-51
+class GPInterpolatedAttitudeFactorRot3 : public NonlinearFactor {
+  std::vector<gtsam::Key> keys_;
+  double delta_t_, tau_;
+  gtsam::SharedNoiseModel Qc_, meas_;
+  gtsam::Unit3 nZ_, bRef_;
+
+ public:
+  GPInterpolatedAttitudeFactorRot3(gtsam::Key poseKey1, gtsam::Key velKey1, gtsam::Key poseKey2, gtsam::Key velKey2, double delta_t, double tau,
+                                   const gtsam::SharedNoiseModel& Qc_model, const gtsam::SharedNoiseModel& meas_model, const gtsam::Unit3& nZ,
+                                   const gtsam::Unit3& bRef = gtsam::Unit3(0, 0, 1))
+      : keys_{poseKey1, velKey1, poseKey2, velKey2}, delta_t_(delta_t), tau_(tau), Qc_(Qc_model), meas_(meas_model), nZ_(nZ), bRef_(bRef) {}
+  const std::vector<gtsam::Key>& keys() const override { return keys_; }
+  gtsam::Vector evaluateError(const gtsam::Rot3& pose1, const gtsam::Vector3& vel1, const gtsam::Rot3& pose2, const gtsam::Vector3& vel2, gtsam::Matrix* H1 = nullptr,
+                              gtsam::Matrix* H2 = nullptr, gtsam::Matrix* H3 = nullptr, gtsam::Matrix* H4 = nullptr) const {
+    double x1[9], x2[9], prm[20] = {0};
+    detail::wire(pose1, x1); detail::wire(pose2, x2);
+    prm[0] = delta_t_; prm[1] = tau_; prm[4] = nZ_.x; prm[5] = nZ_.y; prm[6] = nZ_.z; prm[7] = bRef_.x; prm[8] = bRef_.y; prm[9] = bRef_.z;
+    return detail::eval(GPB_ROT3, GPB_F_INTERP_ATTITUDE, x1, vel1.data(), x2, vel2.data(), nullptr, prm, {H1, H2, H3, H4});
+  }
+  void lower(gpb_graph* g, int qc_of(void*, const gtsam::Matrix&), void* ctx, const std::map<gtsam::Key, int>& sidx, const std::map<gtsam::Key, int>&) const override {
+    const int i = detail::stateOf(sidx, keys_[0]);
+    const double sigma = 1.0 / detail::sqrtInfo(meas_)(0, 0), nz[3] = {nZ_.x, nZ_.y, nZ_.z}, br[3] = {bRef_.x, bRef_.y, bRef_.z};
+    detail::check(gpb_add_interp_attitude(g, 1, &i, &delta_t_, &tau_, qc_of(ctx, Qc_->cov), nz, br, &sigma));
+  }
+};
+
+/// gtsam::PriorFactor<T> on a pose ('x'), velocity ('v') or landmark ('l') key
+template <class T>
+class PriorFactor : public NonlinearFactor {
+  std::vector<gtsam::Key> keys_;
+  T prior_;
+  gtsam::SharedNoiseModel model_;
+
+ public:
+  PriorFactor(gtsam::Key key, const T& prior, const gtsam::SharedNoiseModel& model) : keys_{key}, prior_(prior), model_(model) {}
+  const std::vector<gtsam::Key>& keys() const override { return keys_; }
+  void lower(gpb_graph* g, int (*)(void*, const gtsam::Matrix&), void*, const std::map<gtsam::Key, int>& sidx, const std::map<gtsam::Key, int>& lidx) const override {
+    double v[12];
+    detail::wire(prior_, v);
+    const gtsam::Matrix& R = detail::sqrtInfo(model_);
+    const char c = gtsam::symbolChr(keys_[0]);
+    if (c == 'l') detail::check(gpb_add_prior_landmark(g, detail::stateOf(lidx, keys_[0]), v, R.a.data()));
+    else if (c == 'v') detail::check(gpb_add_prior_vel(g, detail::stateOf(sidx, keys_[0]), v, R.a.data()));
+    else detail::check(gpb_add_prior_pose(g, detail::stateOf(sidx, keys_[0]), v, R.a.data()));
+  }
+};
+
+/// gtsam::BetweenFactor<POSE> between consecutive poses (odometry)
+template <class POSE>
+class BetweenFactor : public NonlinearFactor {
+  std::vector<gtsam::Key> keys_;
+  POSE measured_;
+  gtsam::SharedNoiseModel model_;
+
+ public:
+  BetweenFactor(gtsam::Key key1, gtsam::Key key2, const POSE& measured, const gtsam::SharedNoiseModel& model) : keys_{key1, key2}, measured_(measured), model_(model) {}
+  const std::vector<gtsam::Key>& keys() const override { return keys_; }
+  void lower(gpb_graph* g, int (*)(void*, const gtsam::Matrix&), void*, const std::map<gtsam::Key, int>& sidx, const std::map<gtsam::Key, int>&) const override {
+    double v[12];
+    detail::wire(measured_, v);
+    detail::check(gpb_add_between(g, detail::stateOf(sidx, keys_[0]), detail::stateOf(sidx, keys_[1]), v, detail::sqrtInfo(model_).a.data()));
+  }
+};
+
+// ================================================================================== containers and optimisers
+class NonlinearFactorGraph {
+  std::vector<NonlinearFactor::shared_ptr> factors_;
+
+ public:
+  template <class F> void add(const F& f) { factors_.push_back(std::make_shared<F>(f)); }
+  void push_back(const NonlinearFactor::shared_ptr& f) { factors_.push_back(f); }
+  size_t size() const { return factors_.size(); }
+  const std::vector<NonlinearFactor::shared_ptr>& factors() const { return factors_; }
+};
+
+/// gtsam::Values restricted to the variable types of a gpslam trajectory: poses 'x', velocities 'v', landmarks 'l'
+class Values {
+  friend class NonlinearOptimizer;
+  std::map<gtsam::Key, std::vector<double>> v_;  // wire layout per key
+
+ public:
+  template <class T> void insert(gtsam::Key k, const T& value) {
+    if (v_.count(k)) throw std::runtime_error("gpslam_b200: Values::insert: key already exists");
+    double w[12]; detail::wire(value, w);
+    int n = 3;
+    if (std::is_same<T, gtsam::Pose3>::value) n = 12; else if (std::is_same<T, gtsam::Rot3>::value) n = 9; else if (std::is_same<T, gtsam::Vector6>::value) n = 6;
+    else if (std::is_same<T, gtsam::Point2>::value) n = 2;
+    v_[k] = std::vector<double>(w, w + n);
+  }
+  bool exists(gtsam::Key k) const { return v_.count(k) != 0; }
+  size_t size() const { return v_.size(); }
+  const std::vector<double>& wire(gtsam::Key k) const { auto it = v_.find(k); if (it == v_.end()) throw std::runtime_error("gpslam_b200: Values::at: key not found"); return it->second; }
+  template <class T> T at(gtsam::Key k) const;
+  const std::map<gtsam::Key, std::vector<double>>& all() const { return v_; }
+  std::map<gtsam::Key, std::vector<double>>& all() { return v_; }
+};
+template <> inline gtsam::Pose3 Values::at<gtsam::Pose3>(gtsam::Key k) const { return gtsam::Pose3::fromWire(wire(k).data()); }
+template <> inline gtsam::Rot3 Values::at<gtsam::Rot3>(gtsam::Key k) const { gtsam::Rot3 r; for (int i = 0; i < 9; i++) r.R[i] = wire(k)[i]; return r; }
+template <> inline gtsam::Pose2 Values::at<gtsam::Pose2>(gtsam::Key k) const { const auto& w = wire(k); return gtsam::Pose2(w[0], w[1], w[2]); }
+template <> inline gtsam::Vector3 Values::at<gtsam::Vector3>(gtsam::Key k) const { const auto& w = wire(k); return gtsam::Vector3{w[0], w[1], w[2]}; }
+template <> inline gtsam::Vector6 Values::at<gtsam::Vector6>(gtsam::Key k) const { const auto& w = wire(k); return gtsam::Vector6{w[0], w[1], w[2], w[3], w[4], w[5]}; }
+template <> inline gtsam::Point3 Values::at<gtsam::Point3>(gtsam::Key k) const { const auto& w = wire(k); return gtsam::Point3(w[0], w[1], w[2]); }
+template <> inline gtsam::Point2 Values::at<gtsam::Point2>(gtsam::Key k) const { const auto& w = wire(k); return gtsam::Point2(w[0], w[1]); }
+
+struct GaussNewtonParams { int maxIterations = 100; double relativeErrorTol = 1e-5, absoluteErrorTol = 1e-5, errorTol = 0.0; void setVerbosity(const std::string&) {} };
+struct LevenbergMarquardtParams : GaussNewtonParams { double lambdaInitial = 1e-5, lambdaFactor = 10.0, lambdaUpperBound = 1e5, lambdaLowerBound = 0.0, minModelFidelity = 1e-3; };
+
+/// Lowers (graph, values) onto one B200 and drives gpb_optimize; base of GaussNewtonOptimizer / LevenbergMarquardtOptimizer.
+class NonlinearOptimizer {
+ protected:
+  gpb_graph* g_ = nullptr;
+  Values values_;
+  std::vector<gtsam::Key> xkeys_, vkeys_, lkeys_;
+  int PS_ = 0, D_ = 0, DL_ = 0, iterations_ = 0;
+  double error_ = 0.0;
+  gpb_params params_;
+  std::vector<gtsam::Matrix> qc_models_;
+
+  static int qcOf(void* self, const gtsam::Matrix& cov) {
+    auto* o = static_cast<NonlinearOptimizer*>(self);
+    for (size_t k = 0; k < o->qc_models_.size(); k++) if (o->qc_models_[k].a == cov.a) return static_cast<int>(k);
+    const int id = gpb_add_qc_model(o->g_, cov.a.data());
+    detail::check(id);
+    o->qc_models_.push_back(cov);
+    return id;
+  }
+  void pull() {
+    std::vector<double> P(xkeys_.size() * PS_), V(xkeys_.size() * D_), L(lkeys_.size() * (DL_ ? DL_ : 1));
+    detail::check(gpb_get_values(g_, P.data(), V.data(), lkeys_.empty() ? nullptr : L.data()));
+    for (size_t i = 0; i < xkeys_.size(); i++) { values_.all()[xkeys_[i]].assign(P.begin() + i * PS_, P.begin() + (i + 1) * PS_); values_.all()[vkeys_[i]].assign(V.begin() + i * D_, V.begin() + (i + 1) * D_); }
+    for (size_t l = 0; l < lkeys_.size(); l++) values_.all()[lkeys_[l]].assign(L.begin() + l * DL_, L.begin() + (l + 1) * DL_);
+  }
+
+ public:
+  NonlinearOptimizer(const NonlinearFactorGraph& graph, const Values& initial, int group, int device = 0) : values_(initial) {
+    // states: keys 'x' i with consecutive indices, each with its velocity key 'v' i; landmarks 'l'
+    std::map<std::uint64_t, gtsam::Key> xs, ls;
+    for (const auto& kv : initial.all()) {
+      const char c = gtsam::symbolChr(kv.first);
+      if (c == 'x') xs[gtsam::symbolIndex(kv.first)] = kv.first; else if (c == 'l') ls[gtsam::symbolIndex(kv.first)] = kv.first;
+      else if (c != 'v') throw std::runtime_error("gpslam_b200: only 'x', 'v', 'l' keys are supported");
+    }
+    if (xs.size() < 2) throw std::runtime_error("gpslam_b200: need at least two states");
+    std::map<gtsam::Key, int> sidx, lidx;
+    std::uint64_t prev = 0; bool first = true;
+    for (const auto& kv : xs) {
+      if (!first && kv.first != prev + 1) throw std::runtime_error("gpslam_b200: state indices must be consecutive");
+      prev = kv.first; first = false;
+      const int i = static_cast<int>(xkeys_.size());
+      xkeys_.push_back(kv.second); vkeys_.push_back(gtsam::Symbol('v', kv.first));
+      sidx[kv.second] = i; sidx[vkeys_.back()] = i;
+    }
+    for (const auto& kv : ls) { lidx[kv.second] = static_cast<int>(lkeys_.size()); lkeys_.push_back(kv.second); }
+    PS_ = group == GPB_POSE3 ? 12 : group == GPB_ROT3 ? 9 : 3; D_ = group == GPB_POSE3 ? 6 : 3; DL_ = group == GPB_POSE3 ? 3 : group == GPB_ROT3 ? 0 : 2;
+    g_ = gpb_graph_create(group, 3, static_cast<int>(xkeys_.size()), static_cast<int>(lkeys_.size()));
+    if (!g_) throw std::runtime_error(std::string("gpslam_b200: ") + gpb_last_error());
+    for (const auto& f : graph.factors()) f->lower(g_, &NonlinearOptimizer::qcOf, this, sidx, lidx);
+    std::vector<double> P(xkeys_.size() * PS_), V(xkeys_.size() * D_), L(lkeys_.size() * (DL_ ? DL_ : 1));
+    for (size_t i = 0; i < xkeys_.size(); i++) {
+      const auto& p = initial.wire(xkeys_[i]); const auto& v = initial.wire(vkeys_[i]);
+      if (static_cast<int>(p.size()) != PS_ || static_cast<int>(v.size()) != D_) throw std::runtime_error("gpslam_b200: value type does not match the trajectory group");
+      std::copy(p.begin(), p.end(), P.begin() + i * PS_); std::copy(v.begin(), v.end(), V.begin() + i * D_);
+    }
+    for (size_t l = 0; l < lkeys_.size(); l++) { const auto& w = initial.wire(lkeys_[l]); std::copy(w.begin(), w.end(), L.begin() + l * DL_); }
+    detail::check(gpb_set_values(g_, P.data(), V.data(), lkeys_.empty() ? nullptr : L.data()));
+    detail::check(gpb_graph_finalize(g_, device));
+    detail::check(gpb_error(g_, &error_));
+  }
+  NonlinearOptimizer(const NonlinearOptimizer&) = delete;
+  virtual ~NonlinearOptimizer() { if (g_) gpb_graph_destroy(g_); }
+  /// one optimiser iteration (matlab/PlazaPose2.m:225)
+  void iterate() { gpb_stats st; detail::check(gpb_optimize(g_, &params_, 1, &st)); error_ = st.error_final; iterations_ += st.iterations; pull(); }
+  /// NonlinearOptimizer::optimize(): iterate to GTSAM's convergence test
+  const Values& optimize() { gpb_stats st; detail::check(gpb_optimize(g_, &params_, 0, &st)); error_ = st.error_final; iterations_ += st.iterations; pull(); return values_; }
+  const Values& values() const { return values_; }
+  double error() const { return error_; }
+  int iterations() const { return iterations_; }
+};
+
+template <class POSE> int groupOfValues() { return detail::GroupOf<POSE>::group; }
+
+class GaussNewtonOptimizer : public NonlinearOptimizer {
+ public:
+  GaussNewtonOptimizer(const NonlinearFactorGraph& graph, const Values& initial, const GaussNewtonParams& p = GaussNewtonParams(), int group = GPB_POSE3, int device = 0)
+      : NonlinearOptimizer(graph, initial, group, device) {
+    gpb_default_params(&params_, 0);
+    params_.max_iterations = p.maxIterations; params_.rel_tol = p.relativeErrorTol; params_.abs_tol = p.absoluteErrorTol; params_.err_tol = p.errorTol;
+  }
+};
+class LevenbergMarquardtOptimizer : public NonlinearOptimizer {
+ public:
+  LevenbergMarquardtOptimizer(const NonlinearFactorGraph& graph, const Values& initial, const LevenbergMarquardtParams& p = LevenbergMarquardtParams(),
+                              int group = GPB_POSE3, int device = 0)
+      : NonlinearOptimizer(graph, initial, group, device) {
+    gpb_default_params(&params_, 1);
+    params_.max_iterations = p.maxIterations; params_.rel_tol = p.relativeErrorTol; params_.abs_tol = p.absoluteErrorTol; params_.err_tol = p.errorTol;
+    params_.lambda_initial = p.lambdaInitial; params_.lambda_factor = p.lambdaFactor; params_.lambda_upper = p.lambdaUpperBound; params_.lambda_lower = p.lambdaLowerBound;
+    params_.min_model_fidelity = p.minModelFidelity;
+  }
+};
+
+}  // namespace gpslam_b200

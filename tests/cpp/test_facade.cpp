@@ -1,0 +1,176 @@
+// GPU test of the C++ host facade (include/gpslam_b200/gpslam.h), written the way the reference's CppUnitLite tests are:
+//   gp/tests/testGaussianProcessPriorPose3.cpp:27-143  (Factor: known residuals, analytic vs numerical Jacobians)
+//   gp/tests/testGaussianProcessPriorPose3.cpp:146-195 (Optimization: 2-state graph, GaussNewtonOptimizer)
+//   slam/tests/testGPInterpolatedRangeFactorPose3.cpp:177-260 (3 interpolated ranges incl. extrapolated tau)
+// Only the namespace differs from the reference's test code (gpslam_b200 instead of gtsam/gpslam) and Jacobians are passed
+// as pointers.  Exit code 0 = all EXPECTs passed.
+#include <cmath>
+#include <cstdio>
+#include <functional>
+
+#include "gpslam_b200/gpslam.h"
+
+using namespace gpslam_b200;
+using namespace gpslam_b200::gtsam;
+
+static int failures = 0;
+#define EXPECT(cond) do { if (!(cond)) { std::printf("EXPECT failed: %s (line %d)\n", #cond, __LINE__); failures++; } } while (0)
+
+static bool assert_equal(const Vector& a, const Vector& b, double tol) {
+  if (a.size() != b.size()) return false;
+  for (size_t k = 0; k < a.size(); k++) if (std::fabs(a[k] - b[k]) > tol) return false;
+  return true;
+}
+static bool assert_equal(const Matrix& a, const Matrix& b, double tol) {
+  if (a.rows != b.rows || a.cols != b.cols) return false;
+  for (size_t k = 0; k < a.a.size(); k++) if (std::fabs(a.a[k] - b.a[k]) > tol) { std::printf("  |diff| = %g at %zu\n", std::fabs(a.a[k] - b.a[k]), k); return false; }
+  return true;
+}
+// test-side retract: T * Exp(xi) (rotation first), enough for central differences
+static Pose3 retract(const Pose3& T, const double* xi) {
+  const double th = std::sqrt(xi[0] * xi[0] + xi[1] * xi[1] + xi[2] * xi[2]);
+  double W[9] = {0, xi[2], -xi[1], -xi[2], 0, xi[0], xi[1], -xi[0], 0};  // column-major skew
+  double E[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  const double a = th > 1e-12 ? std::sin(th) / th : 1.0, b = th > 1e-12 ? (1 - std::cos(th)) / (th * th) : 0.5;
+  double W2[9];
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { double s = 0; for (int k = 0; k < 3; k++) s += W[i + 3 * k] * W[k + 3 * j]; W2[i + 3 * j] = s; }
+  for (int k = 0; k < 9; k++) E[k] += a * W[k] + b * W2[k];
+  // translation: first order is enough at 1e-6 steps
+  Pose3 o;
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { double s = 0; for (int k = 0; k < 3; k++) s += T.r.R[i + 3 * k] * E[k + 3 * j]; o.r.R[i + 3 * j] = s; }
+  const double v[3] = {xi[3], xi[4], xi[5]};
+  double t[3] = {T.t.x, T.t.y, T.t.z};
+  for (int i = 0; i < 3; i++) for (int k = 0; k < 3; k++) t[i] += T.r.R[i + 3 * k] * v[k];
+  o.t = Point3(t[0], t[1], t[2]);
+  return o;
+}
+static Matrix numericalDerivativePose(const std::function<Vector(const Pose3&)>& f, const Pose3& x, double delta) {
+  Vector f0 = f(x);
+  Matrix H(static_cast<int>(f0.size()), 6);
+  for (int c = 0; c < 6; c++) {
+    double d[6] = {0, 0, 0, 0, 0, 0};
+    d[c] = delta; const Vector fp = f(retract(x, d));
+    d[c] = -delta; const Vector fm = f(retract(x, d));
+    for (size_t r = 0; r < f0.size(); r++) H(static_cast<int>(r), c) = (fp[r] - fm[r]) / (2 * delta);
+  }
+  return H;
+}
+static Matrix numericalDerivativeVec(const std::function<Vector(const Vector6&)>& f, const Vector6& x, double delta) {
+  Vector f0 = f(x);
+  Matrix H(static_cast<int>(f0.size()), 6);
+  for (int c = 0; c < 6; c++) {
+    Vector6 xp = x, xm = x; xp[c] += delta; xm[c] -= delta;
+    const Vector fp = f(xp), fm = f(xm);
+    for (size_t r = 0; r < f0.size(); r++) H(static_cast<int>(r), c) = (fp[r] - fm[r]) / (2 * delta);
+  }
+  return H;
+}
+
+static void testFactor() {
+  const double delta_t = 0.1;
+  Matrix Qc = 0.01 * Matrix::Identity(6, 6);
+  SharedNoiseModel Qc_model = noiseModel::Gaussian::Covariance(Qc);
+  Key key_pose1 = Symbol('x', 1), key_pose2 = Symbol('x', 2), key_vel1 = Symbol('v', 1), key_vel2 = Symbol('v', 2);
+  GaussianProcessPriorPose3 factor(key_pose1, key_vel1, key_pose2, key_vel2, delta_t, Qc_model);
+  Pose3 p1, p2; Vector6 v1, v2;
+  Matrix actualH1, actualH2, actualH3, actualH4;
+  Vector actual, expect(12, 0.0);
+
+  // test at const forward velocity v1 = v2 = 1.0
+  p1 = Pose3(Rot3::Ypr(0.0, 0.0, 0.0), Point3(0.0, 0.0, 0.0)); p2 = Pose3(Rot3::Ypr(0.0, 0.0, 0.0), Point3(0.1, 0.0, 0.0));
+  v1 = Vector6{0, 0, 0, 1, 0, 0}; v2 = Vector6{0, 0, 0, 1, 0, 0};
+  actual = factor.evaluateError(p1, v1, p2, v2, &actualH1, &actualH2, &actualH3, &actualH4);
+  EXPECT(assert_equal(expect, actual, 1e-6));
+  // test at const rotation w1 = w2 = 1.0
+  p2 = Pose3(Rot3::Ypr(0.1, 0.0, 0.0), Point3(0.0, 0.0, 0.0));
+  v1 = Vector6{0, 0, 1, 0, 0, 0}; v2 = Vector6{0, 0, 1, 0, 0, 0};
+  actual = factor.evaluateError(p1, v1, p2, v2);
+  EXPECT(assert_equal(expect, actual, 1e-6));
+
+  // some random stuff just for testing jacobian (error is not zero)
+  p1 = Pose3(Rot3::Ypr(-0.1, 1.2, 0.3), Point3(-4.0, 2.0, 14.0)); p2 = Pose3(Rot3::Ypr(2.4, -2.5, 3.7), Point3(9.0, -8.0, -7.0));
+  v1 = Vector6{2, 3, 1, 5, 4, 9}; v2 = Vector6{1, 3, 8, 0, 6, 4};
+  actual = factor.evaluateError(p1, v1, p2, v2, &actualH1, &actualH2, &actualH3, &actualH4);
+  Matrix expectH1 = numericalDerivativePose([&](const Pose3& x) { return factor.evaluateError(x, v1, p2, v2); }, p1, 1e-6);
+  Matrix expectH2 = numericalDerivativeVec([&](const Vector6& x) { return factor.evaluateError(p1, x, p2, v2); }, v1, 1e-6);
+  Matrix expectH3 = numericalDerivativePose([&](const Pose3& x) { return factor.evaluateError(p1, v1, x, v2); }, p2, 1e-6);
+  Matrix expectH4 = numericalDerivativeVec([&](const Vector6& x) { return factor.evaluateError(p1, v1, p2, x); }, v2, 1e-6);
+  EXPECT(assert_equal(expectH1, actualH1, 1e-5));
+  EXPECT(assert_equal(expectH2, actualH2, 1e-6));
+  EXPECT(assert_equal(expectH3, actualH3, 1e-5));
+  EXPECT(assert_equal(expectH4, actualH4, 1e-6));
+}
+
+static void testOptimization() {
+  SharedNoiseModel model_prior = noiseModel::Isotropic::Sigma(6, 0.001);
+  double delta_t = 1;
+  SharedNoiseModel Qc_model = noiseModel::Gaussian::Covariance(0.01 * Matrix::Identity(6, 6));
+  Pose3 pose1(Rot3(), Point3(0, 0, 0)), pose2(Rot3(), Point3(1, 0, 0));
+  Vector6 v1{0, 0, 0, 1, 0, 0}, v2{0.1, 0.2, -0.3, 2.0, -0.5, 0.6};
+  NonlinearFactorGraph graph;
+  graph.add(PriorFactor<Pose3>(Symbol('x', 1), pose1, model_prior));
+  graph.add(PriorFactor<Pose3>(Symbol('x', 2), pose2, model_prior));
+  graph.add(GaussianProcessPriorPose3(Symbol('x', 1), Symbol('v', 1), Symbol('x', 2), Symbol('v', 2), delta_t, Qc_model));
+  Values init_values;
+  init_values.insert(Symbol('x', 1), pose1); init_values.insert(Symbol('v', 1), v1);
+  init_values.insert(Symbol('x', 2), pose2); init_values.insert(Symbol('v', 2), v2);
+  GaussNewtonParams parameters;
+  GaussNewtonOptimizer optimizer(graph, init_values, parameters);
+  optimizer.optimize();
+  Values values = optimizer.values();
+  EXPECT(std::fabs(optimizer.error()) < 1e-6);
+  double w1[12], w2[12], o1[12], o2[12];
+  pose1.wire(w1); pose2.wire(w2); values.at<Pose3>(Symbol('x', 1)).wire(o1); values.at<Pose3>(Symbol('x', 2)).wire(o2);
+  for (int k = 0; k < 12; k++) { EXPECT(std::fabs(w1[k] - o1[k]) < 1e-6); EXPECT(std::fabs(w2[k] - o2[k]) < 1e-6); }
+  for (int k = 0; k < 6; k++) { EXPECT(std::fabs(values.at<Vector6>(Symbol('v', 1))[k] - v1[k]) < 1e-6); EXPECT(std::fabs(values.at<Vector6>(Symbol('v', 2))[k] - v1[k]) < 1e-6); }
+}
+
+static double range3(double cx, const Point3& l) { return std::sqrt((l.x - cx) * (l.x - cx) + l.y * l.y + l.z * l.z); }
+static void testRangeOptimization() {
+  SharedNoiseModel model_prior = noiseModel::Isotropic::Sigma(6, 0.01), model_prior3_loss = noiseModel::Isotropic::Sigma(3, 0.1), model_cam = noiseModel::Isotropic::Sigma(1, 0.1);
+  double delta_t = 0.1, tau1 = -0.1, tau2 = 0.05, tau3 = 0.2;
+  SharedNoiseModel Qc_model = noiseModel::Gaussian::Covariance(0.01 * Matrix::Identity(6, 6));
+  Pose3 p1(Rot3(), Point3(0, 0, 0)), p2(Rot3(), Point3(1, 0, 0));
+  Vector6 v1{0, 0, 0, 10, 0, 0}, v2{0, 0, 0, 10, 0, 0};
+  Pose3 p1i(Rot3::Ypr(0.1, 0.2, 0.4), Point3(0.2, 0.3, -0.2)), p2i(Rot3::Ypr(-0.1, -0.2, -0.4), Point3(1.2, -0.3, 0.2));
+  Vector6 v1i{-0.1, 0, 0, 0.8, 0, 0.2}, v2i{0, 0, 0.2, 1.2, 0, -0.1};
+  Point3 land(0.4, 1.2, 3), landi(0.3, 1.1, 2.9);
+  NonlinearFactorGraph graph;
+  graph.add(PriorFactor<Pose3>(Symbol('x', 1), p1, model_prior));
+  graph.add(PriorFactor<Pose3>(Symbol('x', 2), p2, model_prior));
+  graph.add(PriorFactor<Point3>(Symbol('l', 1), land, model_prior3_loss));
+  graph.add(PriorFactor<Vector6>(Symbol('v', 1), v1, model_prior));
+  graph.add(PriorFactor<Vector6>(Symbol('v', 2), v2, model_prior));
+  graph.add(GaussianProcessPriorPose3(Symbol('x', 1), Symbol('v', 1), Symbol('x', 2), Symbol('v', 2), delta_t, Qc_model));
+  graph.add(GPInterpolatedRangeFactorPose3(range3(-1, land), model_cam, Qc_model, Symbol('x', 1), Symbol('v', 1), Symbol('x', 2), Symbol('v', 2), Symbol('l', 1), delta_t, tau1));
+  graph.add(GPInterpolatedRangeFactorPose3(range3(0.5, land), model_cam, Qc_model, Symbol('x', 1), Symbol('v', 1), Symbol('x', 2), Symbol('v', 2), Symbol('l', 1), delta_t, tau2));
+  graph.add(GPInterpolatedRangeFactorPose3(range3(2, land), model_cam, Qc_model, Symbol('x', 1), Symbol('v', 1), Symbol('x', 2), Symbol('v', 2), Symbol('l', 1), delta_t, tau3));
+  Values init_values;
+  init_values.insert(Symbol('x', 1), p1i); init_values.insert(Symbol('v', 1), v1i);
+  init_values.insert(Symbol('x', 2), p2i); init_values.insert(Symbol('v', 2), v2i);
+  init_values.insert(Symbol('l', 1), landi);
+  GaussNewtonParams parameters; parameters.setVerbosity("ERROR");
+  GaussNewtonOptimizer optimizer(graph, init_values, parameters);
+  optimizer.optimize();
+  Values values = optimizer.values();
+  EXPECT(std::fabs(optimizer.error()) < 1e-6);
+  double w[12], o[12];
+  p1.wire(w); values.at<Pose3>(Symbol('x', 1)).wire(o); for (int k = 0; k < 12; k++) EXPECT(std::fabs(w[k] - o[k]) < 1e-6);
+  p2.wire(w); values.at<Pose3>(Symbol('x', 2)).wire(o); for (int k = 0; k < 12; k++) EXPECT(std::fabs(w[k] - o[k]) < 1e-6);
+  const Point3 lo = values.at<Point3>(Symbol('l', 1));
+  EXPECT(std::fabs(lo.x - land.x) < 1e-6 && std::fabs(lo.y - land.y) < 1e-6 && std::fabs(lo.z - land.z) < 1e-6);
+  // error behaviour: a key missing from Values is an exception, as in GTSAM
+  bool threw = false;
+  try { NonlinearFactorGraph g2; g2.add(PriorFactor<Pose3>(Symbol('x', 7), p1, model_prior)); GaussNewtonOptimizer bad(g2, init_values, parameters); } catch (const std::runtime_error&) { threw = true; }
+  EXPECT(threw);
+}
+
+int main() {
+  try {
+    testFactor();
+    testOptimization();
+    testRangeOptimization();
+  } catch (const std::exception& e) { std::printf("exception: %s\n", e.what()); return 2; }
+  std::printf(failures ? "FAILED (%d)\n" : "OK (%d failures)\n", failures);
+  return failures ? 1 : 0;
+}
