@@ -374,6 +374,11 @@ static int bwd_blocks_per_sm(int bs, int W) {
   return W == 16 ? occ_bwd<6, 16>() : W == 32 ? occ_bwd<6, 32>() : occ_bwd<6, 64>();
 }
 static int fwd_blocks_per_sm(int bs, int W) {
+  if (bs == 12 && W == 64) {
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_fwd_ws<12>, 96, 0) != cudaSuccess) { cudaGetLastError(); nb = 4; }
+    return nb < 1 ? 1 : nb;
+  }
   if (bs == 12) return W == 16 ? occ_fwd<12, 16>() : W == 32 ? occ_fwd<12, 32>() : occ_fwd<12, 64>();
   return W == 16 ? occ_fwd<6, 16>() : W == 32 ? occ_fwd<6, 32>() : occ_fwd<6, 64>();
 }
@@ -604,7 +609,8 @@ static int launch_fwd_level(gpb_graph* g, int buf, double lambda, int lev) {
   a.lambda = lambda;
   a.rec_out = lev + 1 < nlev ? g->levels[lev + 1].rec : nullptr; a.brec_out = lev + 1 < nlev ? g->levels[lev + 1].brec : nullptr;
   a.frec = L.frec; a.fstride = fstride; a.cseg = L.cseg; a.flag = g->d_flag;
-  if (bs == 12) fwd_w<12>(g->W, a, L.ncta, g->stream); else fwd_w<6>(g->W, a, L.ncta, g->stream);
+  if (bs == 12 && g->W == 64) k_fwd_ws<12><<<L.ncta, 96, 0, g->stream>>>(a);  // warp-specialised pipeline (factor warp + 2 panel warps)
+  else if (bs == 12) fwd_w<12>(g->W, a, L.ncta, g->stream); else fwd_w<6>(g->W, a, L.ncta, g->stream);
   g->launches++;
   if (nb) {
     const int R = std::min(16, L.ncta);

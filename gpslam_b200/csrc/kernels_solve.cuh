@@ -503,6 +503,390 @@ __global__ void __launch_bounds__((W < 32 ? 32 : W), (W == 64 ? 6 : 8)) k_fwd(co
   }
 }
 
+// Register-resident variant for a warp with registers to spare (the factor warp of k_fwd_ws): lane r owns row r of the
+// Cholesky factor (pivot and column entries travel by shuffles, no shared-memory round trips); L is then published once and
+// lane c computes column c of L^-1 by forward substitution with broadcast shared-memory reads.  ~500 instructions per block.
+template <int BS>
+__device__ __forceinline__ bool warp_chol_inverse_regs(const double* Dsrc, double* Lsm, double* Li, int lane) {
+  const int rr = lane < BS ? lane : BS - 1;
+  double arow[BS], invs[BS];
+#pragma unroll
+  for (int cc = 0; cc < BS; cc++) arow[cc] = Dsrc[rr + cc * BS];
+  bool ok = true;
+#pragma unroll
+  for (int j = 0; j < BS; j++) {
+    const double piv = __shfl_sync(0xffffffffu, arow[j], j);
+    ok &= (piv > 0.0);
+    const double inv = rsqrt(piv > 0.0 ? piv : 1.0);
+    invs[j] = inv;
+    const double lrj = (lane == j) ? piv * inv : arow[j] * inv;
+    arow[j] = lrj;
+#pragma unroll
+    for (int cc = j + 1; cc < BS; cc++) {
+      const double lcj = __shfl_sync(0xffffffffu, lrj, cc);
+      arow[cc] -= lrj * lcj;
+    }
+  }
+  if (lane < BS) {
+#pragma unroll
+    for (int cc = 0; cc < BS; cc++) Lsm[lane + cc * BS] = arow[cc];
+  }
+  __syncwarp();
+  if (lane < BS) {
+    double x[BS];
+#pragma unroll
+    for (int r = 0; r < BS; r++) {
+      double sv = 0.0;
+#pragma unroll
+      for (int t = 0; t < r; t++) sv += Lsm[r + t * BS] * x[t];   // x[t] == 0 for t < lane
+      x[r] = (r == lane) ? invs[r] : (r < lane ? 0.0 : -sv * invs[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < BS; r++) Li[r + lane * BS] = x[r];
+  }
+  return ok;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Warp-specialised forward sweep (BS = 12, panel width 64): the production path for SE(3) graphs with landmarks.
+//   warp 0 ("factor warp")  walks the chain's serial recurrence  D'_i = D_i - Le_{i-1} Le_{i-1}^T  ->  L_i^-1  ->  Le_i = E_i L_i^-T
+//                           and publishes (L_i^-1, Le_i, g_i) into a 2-slot shared-memory ring; it never touches the panel.
+//   warps 1-2 ("panel")     consume a slot per state: Y = L^-1 P, P' = own - Le Y, S += Y^T Y, all on the FP64 tensor pipe, and
+//                           stream the factors to HBM.  They lag the factor warp by up to two states, so the panel work of
+//                           state i overlaps the factorisation of states i+1, i+2.
+// Hand-off: named barriers (bar.arrive / bar.sync) full[s] / empty[s]; the two panel warps meet on one 64-thread barrier per state.
+__device__ __forceinline__ void nbar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void nbar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+template <int BS>
+__global__ void __launch_bounds__(96, 4) k_fwd_ws(const FwdArgs a) {
+  constexpr int W = 64, NT = 96, REC0 = 2 * BS * BS + BS, REC1 = 3 * BS * BS + 2 * BS, NBP = W;
+  constexpr int B_FULL = 1, B_EMPTY = 3, B_PANEL = 5;  // named-barrier ids: full[0..1] = 1,2 ; empty[0..1] = 3,4 ; panel = 5
+  __shared__ __align__(16) double Rb[2][REC1];
+  __shared__ double Dm[BS * BS], Dn[BS * BS], Lsm[BS * BS];
+  __shared__ double LiS[2][BS * BS], LeS[2][BS * BS], gS[2][BS];
+  __shared__ double Psm[W * BS], Ysm[2][W * BS], Bn[2][BS * NBP];  // Bn: landmark border of the current / next state (double buffer)
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gi = lane >> 2, ti = lane & 3;
+  const bool isF = warp == 0;
+  const int c = tid - 32, pw = warp - 1;  // panel column / panel warp index (panel threads only)
+  const int nb = a.nb, w = BS + nb + 1, M = a.M;
+  const bool first = a.first_level != 0;
+  const int RECS = first ? REC0 : REC1;
+  const int oE = first ? BS * BS : 2 * BS * BS, oG = first ? 2 * BS * BS : 3 * BS * BS;
+  const bool is_border = !isF && (c >= BS) && (c < BS + nb), is_rhs = !isF && (c == BS + nb), is_spike = !isF && c < BS, active = !isF && c < w;
+  const int lb = c - BS;
+  const CholMap<BS> cmap = chol_map<BS>(lane);
+
+  double acc[36];
+#pragma unroll
+  for (int j = 0; j < 36; j++) acc[j] = 0.0;
+
+  auto prefetch = [&](int i, int buf) {  // factor warp: whole record of state i -> Rb[buf]
+    const double* src = a.rec + (size_t)i * RECS;
+    for (int k = lane; k < RECS / 2; k += 32) cp_async16(&Rb[buf][2 * k], src + 2 * k);
+  };
+  auto gather_border = [&](int i, int ln, double* Bd) {  // level 0: landmark border of state i -> Bd (lanes 0..BS-1 of one warp)
+    for (int e = a.bsoff[i]; e < a.bsoff[i + 1]; e++) {
+      const int row = a.bsrow[e], side = a.bsside[e];
+      const int l = a.rowland[row];
+      if (ln < BS) {
+        const double av = a.XR[(size_t)(side * BS + ln) * a.NXRp + row];
+        for (int d = 0; d < a.DL; d++) Bd[ln + (l * a.DL + d) * BS] += av * a.XR[(size_t)(2 * BS + d) * a.NXRp + row];
+      }
+    }
+  };
+  auto add_own_border = [&](int i, double* Bd) {  // panel thread: landmark column of state i into its panel column
+    if (!is_border) return;
+    double* P = Psm + c * BS;
+    if (first) {
+#pragma unroll
+      for (int r = 0; r < BS; r++) { P[r] += Bd[r + lb * BS]; Bd[r + lb * BS] = 0.0; }
+    } else {
+      const double* B = a.brec + (size_t)i * (2 * BS * nb);
+#pragma unroll
+      for (int r = 0; r < BS; r++) P[r] += B[r + lb * BS] + B[BS * nb + r + lb * BS];
+    }
+  };
+
+  for (int k = tid; k < BS * NBP; k += NT) { Bn[0][k] = 0.0; Bn[1][k] = 0.0; }
+  for (int k = tid; k < BS * BS; k += NT) { LiS[0][k] = 0.0; LiS[1][k] = 0.0; }  // strictly-upper parts of L^-1 stay zero
+  __syncthreads();
+
+  for (int seg = blockIdx.x; seg < a.nseg; seg += gridDim.x) {
+    const SegGeom sg = seg_geom(seg, a.n, M, a.S, a.extL, a.extR);
+    const int p = sg.p, q = sg.q, i0 = sg.i0, i1 = sg.i1;
+    const int ilast = (q >= 0) ? q : i1;
+    // ---- segment prologue
+    if (isF) {
+      for (int k = lane; k < BS * BS; k += 32) Dn[k] = 0.0;
+      if (i0 <= ilast) prefetch(i0, 0);
+      cp_async_commit();
+    } else {
+      const bool sp = is_spike && p >= 0 && i0 <= i1;
+      const double* E = a.rec + (size_t)(sp ? p : 0) * RECS + oE;
+#pragma unroll
+      for (int r = 0; r < BS; r++) Psm[c * BS + r] = sp ? E[r + c * BS] : 0.0;
+      if (first && nb > 0 && i0 <= ilast && pw == 0) gather_border(i0, lane, Bn[0]);
+    }
+    __syncthreads();
+
+    if (isF) {
+      // ================================================= factor warp
+      int buf = 0;
+      for (int i = i0; i <= i1; i++, buf ^= 1) {
+        const int s = (i - i0) & 1;
+        const bool has_next = (i < i1) || (q >= 0);
+        if (i + 1 <= ilast) prefetch(i + 1, buf ^ 1);
+        cp_async_commit();
+        if (i - i0 >= 2) nbar_sync(B_EMPTY + s, NT);  // slot s free again (panel finished state i-2)
+        cp_async_wait<1>();
+        __syncwarp();
+        for (int k = lane; k < BS * BS; k += 32) {
+          double v = Rb[buf][k] + Dn[k];
+          if (first) { if ((k % (BS + 1)) == 0) v += a.lambda; } else v += Rb[buf][BS * BS + k];
+          Dm[k] = v;
+        }
+        if (lane < BS) gS[s][lane] = Rb[buf][oG + lane] + (first ? 0.0 : Rb[buf][oG + BS + lane]);
+        __syncwarp();
+        const bool ok = warp_chol_inverse_regs<BS>(Dm, Lsm, LiS[s], lane);
+        if (!ok && lane == 0) *a.flag = 1;
+        __syncwarp();
+        if (has_next) {
+          // Le = E L^-T (tensor pipe, 4 tiles), then Dn = -Le Le^T
+          const double* E0 = &Rb[buf][oE];
+#pragma unroll
+          for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+            for (int nt = 0; nt < 2; nt++) {
+              double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+              for (int sK = 0; sK < 3; sK++) {
+                const double aE = (8 * mt + gi < BS) ? E0[(8 * mt + gi) + (4 * sK + ti) * BS] : 0.0;
+                const double bL = (8 * nt + gi < BS) ? LiS[s][(8 * nt + gi) + (4 * sK + ti) * BS] : 0.0;
+                dmma884(d0, d1, aE, bL);
+              }
+              if (8 * mt + gi < BS && 8 * nt + 2 * ti < BS) { LeS[s][(8 * mt + gi) + (8 * nt + 2 * ti) * BS] = d0; LeS[s][(8 * mt + gi) + (8 * nt + 2 * ti + 1) * BS] = d1; }
+            }
+          __syncwarp();
+#pragma unroll
+          for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+            for (int nt = 0; nt < 2; nt++) {
+              double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+              for (int sK = 0; sK < 3; sK++) {
+                const double aL = (8 * mt + gi < BS) ? LeS[s][(8 * mt + gi) + (4 * sK + ti) * BS] : 0.0;
+                const double bL = (8 * nt + gi < BS) ? LeS[s][(8 * nt + gi) + (4 * sK + ti) * BS] : 0.0;
+                dmma884(d0, d1, aL, bL);
+              }
+              if (8 * mt + gi < BS && 8 * nt + 2 * ti < BS) { Dn[(8 * mt + gi) + (8 * nt + 2 * ti) * BS] = -d0; Dn[(8 * mt + gi) + (8 * nt + 2 * ti + 1) * BS] = -d1; }
+            }
+        }
+        __syncwarp();
+        nbar_arrive(B_FULL + s, NT);  // publish slot s
+      }
+      // drain: balance the panel's last (up to two) empty-arrivals
+      const int nst = i1 - i0 + 1;
+      if (nst >= 2) nbar_sync(B_EMPTY + ((nst - 2) & 1), NT);
+      if (nst >= 1) nbar_sync(B_EMPTY + ((nst - 1) & 1), NT);
+      cp_async_wait<0>();
+    } else {
+      // ================================================= panel warps
+      for (int i = i0; i <= i1; i++) {
+        const int s = (i - i0) & 1;
+        const bool has_next = (i < i1) || (q >= 0);
+        double* Y = Ysm[s];
+        add_own_border(i, Bn[s]);
+        // next state's landmark border (level 0) into the other buffer; published by this state's panel barrier
+        if (first && nb > 0 && i + 1 <= ilast && pw == 0) gather_border(i + 1, lane, Bn[s ^ 1]);
+        nbar_sync(B_FULL + s, NT);  // L^-1, Le, g of state i are in slot s
+        if (is_rhs) {
+#pragma unroll
+          for (int r = 0; r < BS; r++) Psm[c * BS + r] += gS[s][r];
+        }
+        __syncwarp();
+        // ---- Y = L^-1 P : this warp's column tiles 4pw..4pw+3 (its own threads' columns)
+        {
+          double aLi[2][3];
+#pragma unroll
+          for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+            for (int sK = 0; sK < 3; sK++) aLi[mt][sK] = (8 * mt + gi < BS) ? LiS[s][(8 * mt + gi) + (4 * sK + ti) * BS] : 0.0;
+#pragma unroll
+          for (int jt = 0; jt < 4; jt++) {
+            const int J = 4 * pw + jt;
+            double d[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+            for (int sK = 0; sK < 3; sK++) {
+              const double bP = Psm[(8 * J + gi) * BS + 4 * sK + ti];
+              if (sK < 2) dmma884(d[0][0], d[0][1], aLi[0][sK], bP);
+              dmma884(d[1][0], d[1][1], aLi[1][sK], bP);
+            }
+#pragma unroll
+            for (int mt = 0; mt < 2; mt++)
+              if (8 * mt + gi < BS) { Y[(8 * J + 2 * ti) * BS + 8 * mt + gi] = d[mt][0]; Y[(8 * J + 2 * ti + 1) * BS + 8 * mt + gi] = d[mt][1]; }
+          }
+        }
+        nbar_sync(B_PANEL, 64);  // all 64 Y columns visible to both panel warps
+        // ---- next panel P' = -Le Y (own column tiles), or zero at the end of an open chain
+        if (has_next) {
+          double aLe[2][3];
+#pragma unroll
+          for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+            for (int sK = 0; sK < 3; sK++) aLe[mt][sK] = (8 * mt + gi < BS) ? LeS[s][(8 * mt + gi) + (4 * sK + ti) * BS] : 0.0;
+#pragma unroll
+          for (int jt = 0; jt < 4; jt++) {
+            const int J = 4 * pw + jt;
+            double d[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+            for (int sK = 0; sK < 3; sK++) {
+              const double bY = Y[(8 * J + gi) * BS + 4 * sK + ti];
+              dmma884(d[0][0], d[0][1], aLe[0][sK], bY);
+              dmma884(d[1][0], d[1][1], aLe[1][sK], bY);
+            }
+#pragma unroll
+            for (int mt = 0; mt < 2; mt++)
+              if (8 * mt + gi < BS) { Psm[(8 * J + 2 * ti) * BS + 8 * mt + gi] = -d[mt][0]; Psm[(8 * J + 2 * ti + 1) * BS + 8 * mt + gi] = -d[mt][1]; }
+          }
+        } else {
+#pragma unroll
+          for (int r = 0; r < BS; r++) Psm[c * BS + r] = 0.0;
+        }
+        // ---- factors to HBM: Y column (one per thread), L^-1 and Le (shared between the 64 panel threads)
+        double* F = a.frec + (size_t)i * a.fstride;
+        if (active) {
+          const double* yc = Y + c * BS;
+#pragma unroll
+          for (int r = 0; r < BS; r += 2) st128(F + 2 * BS * BS + c * BS + r, yc[r], yc[r + 1]);
+        }
+        for (int k = c; k < BS * BS; k += 64) { F[k] = LiS[s][k]; if (has_next) F[BS * BS + k] = LeS[s][k]; }
+        // ---- Schur accumulation S += Y^T Y : this warp's share of the lower-triangular 8x8 tile grid
+#pragma unroll
+        for (int u = 0; u < 18; u++) {
+          const int t = 2 * u + pw;
+          const int I = c_tileI[t], J = c_tileJ[t];
+#pragma unroll
+          for (int sK = 0; sK < 3; sK++) {
+            const double aY = Y[(8 * I + gi) * BS + 4 * sK + ti];
+            const double bY = Y[(8 * J + gi) * BS + 4 * sK + ti];
+            dmma884(acc[2 * u], acc[2 * u + 1], aY, bY);
+          }
+        }
+        __syncwarp();
+        nbar_arrive(B_EMPTY + s, NT);  // slot s (and Ysm[s]) may be reused
+      }
+    }
+    __syncthreads();
+
+    // ---- segment end: hand the Schur complement to the next level.  The record of q (if any) is in Rb[(i1 - i0 + 1) & 1].
+    const int qbuf = (i1 - i0 + 1) & 1;
+    auto Dq = [&](int k) -> double {
+      if (first) return Rb[qbuf][k] + ((k % (BS + 1)) == 0 ? a.lambda : 0.0);
+      return Rb[qbuf][k] + Rb[qbuf][BS * BS + k];
+    };
+    if (q >= 0) {
+      double* R = a.rec_out + (size_t)sg.qo * REC1;
+      for (int k = tid; k < BS * BS; k += NT) R[k] = Dq(k) + Dn[k];  // D1
+      if (!isF) {
+        add_own_border(q, Bn[qbuf]);
+        if (is_rhs) {
+#pragma unroll
+          for (int r = 0; r < BS; r++) Psm[c * BS + r] += Rb[qbuf][oG + r] + (first ? 0.0 : Rb[qbuf][oG + BS + r]);
+        }
+        const double* P = Psm + c * BS;
+        if (is_border) {
+          double* B = a.brec_out + (size_t)sg.qo * (2 * BS * nb);
+#pragma unroll
+          for (int r = 0; r < BS; r++) B[r + lb * BS] = P[r];
+        } else if (is_rhs) {
+#pragma unroll
+          for (int r = 0; r < BS; r++) R[3 * BS * BS + r] = P[r];
+        } else if (is_spike && p >= 0) {
+          double* Ep = a.rec_out + (size_t)sg.po * REC1 + 2 * BS * BS;
+          if (i0 <= i1) {
+#pragma unroll
+            for (int r = 0; r < BS; r++) Ep[r + c * BS] = P[r];
+          } else {
+            const double* E = a.rec + (size_t)p * RECS + oE;
+#pragma unroll
+            for (int r = 0; r < BS; r++) Ep[r + c * BS] = E[r + c * BS];
+          }
+        }
+      }
+      if (a.extR && seg == a.S) {
+        for (int k = tid; k < BS * BS; k += NT) R[BS * BS + k] = 0.0;
+        if (tid < BS) R[3 * BS * BS + BS + tid] = 0.0;
+        if (is_border) { double* B = a.brec_out + (size_t)sg.qo * (2 * BS * nb) + BS * nb;
+#pragma unroll
+          for (int r = 0; r < BS; r++) B[r + lb * BS] = 0.0; }
+      }
+    }
+    if (a.extL && seg == 0) {
+      double* R = a.rec_out;
+      const double* src = a.rec + (size_t)p * RECS;
+      for (int k = tid; k < BS * BS; k += NT) R[k] = first ? src[k] : src[k] + src[BS * BS + k];
+      if (tid < BS) R[3 * BS * BS + tid] = first ? src[oG + tid] : src[oG + tid] + src[oG + BS + tid];
+      __syncthreads();
+      if (first && nb > 0 && warp == 1) gather_border(p, lane, Bn[0]);
+      __syncthreads();
+      if (is_border) {
+        double* B = a.brec_out;
+        if (first) {
+#pragma unroll
+          for (int r = 0; r < BS; r++) { B[r + lb * BS] = Bn[0][r + lb * BS]; Bn[0][r + lb * BS] = 0.0; }
+        } else {
+          const double* Bs = a.brec + (size_t)p * (2 * BS * nb);
+#pragma unroll
+          for (int r = 0; r < BS; r++) B[r + lb * BS] = Bs[r + lb * BS] + Bs[BS * nb + r + lb * BS];
+        }
+      }
+    }
+    if (!isF) {
+      double* Rp = (p >= 0) ? a.rec_out + (size_t)sg.po * REC1 : nullptr;
+      double* Bp = (p >= 0) ? a.brec_out + (size_t)sg.po * (2 * BS * nb) + BS * nb : nullptr;
+      auto flush_spike = [&](int x, int y, double& av) {
+        const int lo = x < y ? x : y, hi = x < y ? y : x;
+        if (lo < BS) {
+          if (p >= 0 && hi < w) {
+            const double v = -av;
+            if (hi < BS) { Rp[BS * BS + lo + hi * BS] = v; Rp[BS * BS + hi + lo * BS] = v; }
+            else if (hi < BS + nb) Bp[lo + (hi - BS) * BS] = v;
+            else Rp[3 * BS * BS + BS + lo] = v;
+          }
+          av = 0.0;
+        }
+      };
+#pragma unroll
+      for (int u = 0; u < 18; u++) {
+        const int t = 2 * u + pw;
+        const int x = 8 * c_tileI[t] + gi, y = 8 * c_tileJ[t] + 2 * ti;
+        if (x >= y) flush_spike(x, y, acc[2 * u]); else if (x < BS || y < BS) acc[2 * u] = 0.0;
+        if (x >= y + 1) flush_spike(x, y + 1, acc[2 * u + 1]); else if (x < BS || y + 1 < BS) acc[2 * u + 1] = 0.0;
+      }
+    }
+    __syncthreads();
+  }
+  if (nb > 0 && !isF) {
+    double* Cs = a.cseg + (size_t)blockIdx.x * (nb * nb + nb);
+    auto flush_land = [&](int x, int y, double av) {
+      const int lo = x < y ? x : y, hi = x < y ? y : x;
+      if (lo >= BS && hi < w) {
+        const double v = -av;
+        if (hi < BS + nb) { Cs[(lo - BS) + (hi - BS) * nb] = v; Cs[(hi - BS) + (lo - BS) * nb] = v; }
+        else if (lo < BS + nb) Cs[nb * nb + (lo - BS)] = v;
+      }
+    };
+#pragma unroll
+    for (int u = 0; u < 18; u++) {
+      const int t = 2 * u + pw;
+      const int x = 8 * c_tileI[t] + gi, y = 8 * c_tileJ[t] + 2 * ti;
+      if (x >= y) flush_land(x, y, acc[2 * u]);
+      if (x >= y + 1) flush_land(x, y + 1, acc[2 * u + 1]);
+    }
+  }
+}
+
 // Back-substitution of one level: x_i = L_ii^-T ( y_i - Yspike_i x_p - Yborder_i x_l - Le_i^T x_{i+1} ), right to left.
 // The factor record of the next state to visit streams into shared memory (cp.async double buffer) while the current one is used.
 template <int BS, int W>
