@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <type_traits>
@@ -484,7 +485,9 @@ int gpb_graph_finalize(gpb_graph* g, int device) {
   // ---- elimination levels
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-  const int M0 = g->M0 ? g->M0 : (g->nb > 0 ? 32 : 16), Mup = g->Mup ? g->Mup : 8;
+  // segment lengths: explicit setting > environment (tuning aid) > defaults
+  const char* em0 = getenv("GPB_M0"); const char* emu = getenv("GPB_MUP");
+  const int M0 = g->M0 ? g->M0 : (em0 ? std::max(2, atoi(em0)) : (g->nb > 0 ? 32 : 16)), Mup = g->Mup ? g->Mup : (emu ? std::max(2, atoi(emu)) : 8);
   const int fstride = 2 * bs * bs + bs * g->w;
   int n = g->N, lev = 0;
   while (true) {

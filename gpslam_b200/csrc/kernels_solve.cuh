@@ -565,7 +565,7 @@ __global__ void __launch_bounds__(96, 4) k_fwd_ws(const FwdArgs a) {
   __shared__ __align__(16) double Rb[2][REC1];
   __shared__ double Dm[BS * BS], Dn[BS * BS], Lsm[BS * BS];
   __shared__ double LiS[2][BS * BS], LeS[2][BS * BS], gS[2][BS];
-  __shared__ double Psm[W * BS], Ysm[2][W * BS], Bn[2][BS * NBP];  // Bn: landmark border of the current / next state (double buffer)
+  __shared__ __align__(16) double Psm[W * BS], Ysm[2][W * BS], Bn[2][BS * NBP];  // Bn: landmark border of the current / next state (double buffer)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gi = lane >> 2, ti = lane & 3;
   const bool isF = warp == 0;
   const int c = tid - 32, pw = warp - 1;  // panel column / panel warp index (panel threads only)
@@ -580,6 +580,9 @@ __global__ void __launch_bounds__(96, 4) k_fwd_ws(const FwdArgs a) {
   double acc[36];
 #pragma unroll
   for (int j = 0; j < 36; j++) acc[j] = 0.0;
+  int tI[18], tJ[18];  // shared-memory offsets of this lane's A / B fragment elements for its 18 Schur tiles
+#pragma unroll
+  for (int u = 0; u < 18; u++) { const int t = 2 * u + (warp == 2 ? 1 : 0); tI[u] = (8 * c_tileI[t] + gi) * BS + ti; tJ[u] = (8 * c_tileJ[t] + gi) * BS + ti; }
 
   auto prefetch = [&](int i, int buf) {  // factor warp: whole record of state i -> Rb[buf]
     const double* src = a.rec + (size_t)i * RECS;
@@ -599,8 +602,10 @@ __global__ void __launch_bounds__(96, 4) k_fwd_ws(const FwdArgs a) {
     if (!is_border) return;
     double* P = Psm + c * BS;
     if (first) {
+      double2* P2 = reinterpret_cast<double2*>(P);
+      double2* B2 = reinterpret_cast<double2*>(Bd + lb * BS);
 #pragma unroll
-      for (int r = 0; r < BS; r++) { P[r] += Bd[r + lb * BS]; Bd[r + lb * BS] = 0.0; }
+      for (int r = 0; r < BS / 2; r++) { const double2 bv = B2[r]; double2 pv = P2[r]; pv.x += bv.x; pv.y += bv.y; P2[r] = pv; B2[r] = make_double2(0.0, 0.0); }
     } else {
       const double* B = a.brec + (size_t)i * (2 * BS * nb);
 #pragma unroll
@@ -712,19 +717,23 @@ __global__ void __launch_bounds__(96, 4) k_fwd_ws(const FwdArgs a) {
           for (int mt = 0; mt < 2; mt++)
 #pragma unroll
             for (int sK = 0; sK < 3; sK++) aLi[mt][sK] = (8 * mt + gi < BS) ? LiS[s][(8 * mt + gi) + (4 * sK + ti) * BS] : 0.0;
+          double d[4][2][2];
+#pragma unroll
+          for (int jt = 0; jt < 4; jt++) { d[jt][0][0] = d[jt][0][1] = d[jt][1][0] = d[jt][1][1] = 0.0; }
+#pragma unroll
+          for (int sK = 0; sK < 3; sK++)
+#pragma unroll
+            for (int jt = 0; jt < 4; jt++) {
+              const double bP = Psm[(8 * (4 * pw + jt) + gi) * BS + 4 * sK + ti];
+              if (sK < 2) dmma884(d[jt][0][0], d[jt][0][1], aLi[0][sK], bP);
+              dmma884(d[jt][1][0], d[jt][1][1], aLi[1][sK], bP);
+            }
 #pragma unroll
           for (int jt = 0; jt < 4; jt++) {
             const int J = 4 * pw + jt;
-            double d[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
-#pragma unroll
-            for (int sK = 0; sK < 3; sK++) {
-              const double bP = Psm[(8 * J + gi) * BS + 4 * sK + ti];
-              if (sK < 2) dmma884(d[0][0], d[0][1], aLi[0][sK], bP);
-              dmma884(d[1][0], d[1][1], aLi[1][sK], bP);
-            }
 #pragma unroll
             for (int mt = 0; mt < 2; mt++)
-              if (8 * mt + gi < BS) { Y[(8 * J + 2 * ti) * BS + 8 * mt + gi] = d[mt][0]; Y[(8 * J + 2 * ti + 1) * BS + 8 * mt + gi] = d[mt][1]; }
+              if (8 * mt + gi < BS) { Y[(8 * J + 2 * ti) * BS + 8 * mt + gi] = d[jt][mt][0]; Y[(8 * J + 2 * ti + 1) * BS + 8 * mt + gi] = d[jt][mt][1]; }
           }
         }
         nbar_sync(B_PANEL, 64);  // all 64 Y columns visible to both panel warps
@@ -735,19 +744,23 @@ __global__ void __launch_bounds__(96, 4) k_fwd_ws(const FwdArgs a) {
           for (int mt = 0; mt < 2; mt++)
 #pragma unroll
             for (int sK = 0; sK < 3; sK++) aLe[mt][sK] = (8 * mt + gi < BS) ? LeS[s][(8 * mt + gi) + (4 * sK + ti) * BS] : 0.0;
+          double d[4][2][2];
+#pragma unroll
+          for (int jt = 0; jt < 4; jt++) { d[jt][0][0] = d[jt][0][1] = d[jt][1][0] = d[jt][1][1] = 0.0; }
+#pragma unroll
+          for (int sK = 0; sK < 3; sK++)
+#pragma unroll
+            for (int jt = 0; jt < 4; jt++) {
+              const double bY = Y[(8 * (4 * pw + jt) + gi) * BS + 4 * sK + ti];
+              dmma884(d[jt][0][0], d[jt][0][1], aLe[0][sK], bY);
+              dmma884(d[jt][1][0], d[jt][1][1], aLe[1][sK], bY);
+            }
 #pragma unroll
           for (int jt = 0; jt < 4; jt++) {
             const int J = 4 * pw + jt;
-            double d[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
-#pragma unroll
-            for (int sK = 0; sK < 3; sK++) {
-              const double bY = Y[(8 * J + gi) * BS + 4 * sK + ti];
-              dmma884(d[0][0], d[0][1], aLe[0][sK], bY);
-              dmma884(d[1][0], d[1][1], aLe[1][sK], bY);
-            }
 #pragma unroll
             for (int mt = 0; mt < 2; mt++)
-              if (8 * mt + gi < BS) { Psm[(8 * J + 2 * ti) * BS + 8 * mt + gi] = -d[mt][0]; Psm[(8 * J + 2 * ti + 1) * BS + 8 * mt + gi] = -d[mt][1]; }
+              if (8 * mt + gi < BS) { Psm[(8 * J + 2 * ti) * BS + 8 * mt + gi] = -d[jt][mt][0]; Psm[(8 * J + 2 * ti + 1) * BS + 8 * mt + gi] = -d[jt][mt][1]; }
           }
         } else {
 #pragma unroll
@@ -763,13 +776,11 @@ __global__ void __launch_bounds__(96, 4) k_fwd_ws(const FwdArgs a) {
         for (int k = c; k < BS * BS; k += 64) { F[k] = LiS[s][k]; if (has_next) F[BS * BS + k] = LeS[s][k]; }
         // ---- Schur accumulation S += Y^T Y : this warp's share of the lower-triangular 8x8 tile grid
 #pragma unroll
-        for (int u = 0; u < 18; u++) {
-          const int t = 2 * u + pw;
-          const int I = c_tileI[t], J = c_tileJ[t];
+        for (int sK = 0; sK < 3; sK++) {  // k-slice outer, tiles inner: 18 independent accumulators keep the tensor pipe fed
 #pragma unroll
-          for (int sK = 0; sK < 3; sK++) {
-            const double aY = Y[(8 * I + gi) * BS + 4 * sK + ti];
-            const double bY = Y[(8 * J + gi) * BS + 4 * sK + ti];
+          for (int u = 0; u < 18; u++) {
+            const double aY = Y[tI[u] + 4 * sK];
+            const double bY = Y[tJ[u] + 4 * sK];
             dmma884(acc[2 * u], acc[2 * u + 1], aY, bY);
           }
         }
