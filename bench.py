@@ -205,6 +205,10 @@ def run_engine(args, rank, world, local_rank):
 
 
 def main():
+    # stdout carries exactly ONE JSON line: everything else a library prints (NCCL's version banner, torchrun notices) goes to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
