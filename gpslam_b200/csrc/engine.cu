@@ -74,9 +74,11 @@ struct gpb_graph {
   double* d_xprm = nullptr;
   int *d_rowoff = nullptr, *d_rowland = nullptr, *d_lmoff = nullptr, *d_lmrows = nullptr;
   int *d_bsoff = nullptr, *d_bsrow = nullptr, *d_bsside = nullptr;  // per-state CSR of landmark-bearing rows (level-0 border gather)
-  int rank = 0, world = 1, nsep = 0, R = 0;
+  int rank = 0, world = 1, nsep = 0, R = 0, sms = 148;
   gpb_allreduce_fn allreduce = nullptr; void* allreduce_ctx = nullptr;
   double* d_topbuf = nullptr; double cur_error_local = 0; int n_allreduce = 0;
+  double* d_lambda = nullptr;
+  cudaGraphExec_t iter_graph[2] = {nullptr, nullptr}; int iter_graph_launches[2] = {0, 0};  // captured GN/LM trial per buffer parity
   int extL = 0, extR = 0;  // shard: first / last state is an external separator (owned by the global reduced system)
   int *d_listA = nullptr, *d_listB = nullptr;  // extra factors by kind class: interpolated measurements / everything else
   int nA = 0, nB = 0;
@@ -174,6 +176,7 @@ void gpb_graph_destroy(gpb_graph* g) {
   if (!g) return;
   if (g->device >= 0) cudaSetDevice(g->device);
   if (g->pinned) { cudaHostUnregister(g->h_X.data()); if (g->L) cudaHostUnregister(g->h_land.data()); }
+  for (int k = 0; k < 2; k++) if (g->iter_graph[k]) cudaGraphExecDestroy(g->iter_graph[k]);
   for (void* p : g->allocs) cudaFree(p);
   if (g->stream) cudaStreamDestroy(g->stream);
   delete g;
@@ -377,7 +380,7 @@ static int bwd_blocks_per_sm(int bs, int W) {
 static int fwd_blocks_per_sm(int bs, int W) {
   if (bs == 12 && W == 64) {
     int nb = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_fwd_ws<12>, 96, 0) != cudaSuccess) { cudaGetLastError(); nb = 4; }
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_panel<12>, 64, 0) != cudaSuccess) { cudaGetLastError(); nb = 4; }
     return nb < 1 ? 1 : nb;
   }
   if (bs == 12) return W == 16 ? occ_fwd<12, 16>() : W == 32 ? occ_fwd<12, 32>() : occ_fwd<12, 64>();
@@ -477,6 +480,8 @@ int gpb_graph_finalize(gpb_graph* g, int device) {
   if ((rc = dev_alloc(g, &g->d_errpart, (size_t)2 * g->nerrpart))) return rc;
   if ((rc = dev_alloc(g, &g->d_scal, 8))) return rc;
   if ((rc = dev_alloc(g, &g->d_flag, 1))) return rc;
+  if ((rc = dev_alloc(g, &g->d_lambda, 1))) return rc;
+  CUDA_TRY(cudaMemset(g->d_lambda, 0, sizeof(double)));
   CUDA_TRY(cudaMemset(g->d_flag, 0, sizeof(int)));
   const int centries = g->nb * g->nb + g->nb;
   if ((rc = dev_alloc(g, &g->d_Cbase, (size_t)centries))) return rc;
@@ -485,6 +490,7 @@ int gpb_graph_finalize(gpb_graph* g, int device) {
   // ---- elimination levels
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  g->sms = sms;
   // segment lengths: explicit setting > environment (tuning aid) > defaults
   const char* em0 = getenv("GPB_M0"); const char* emu = getenv("GPB_MUP");
   const int M0 = g->M0 ? g->M0 : (em0 ? std::max(2, atoi(em0)) : (g->nb > 0 ? 32 : 16)), Mup = g->Mup ? g->Mup : (emu ? std::max(2, atoi(emu)) : 8);
@@ -609,12 +615,19 @@ static int launch_fwd_level(gpb_graph* g, int buf, double lambda, int lev) {
   a.n = L.n; a.M = L.M; a.S = L.S; a.nseg = L.nseg; a.first_level = lev == 0; a.extL = g->extL; a.extR = g->extR;
   a.rec = lev == 0 ? g->d_HREC : L.rec; a.brec = L.brec;
   a.XR = g->d_XR[buf]; a.bsoff = g->d_bsoff; a.bsrow = g->d_bsrow; a.bsside = g->d_bsside; a.rowland = g->d_rowland; a.NXRp = g->NXRp; a.nb = nb; a.DL = std::max(g->DL, 1);
-  a.lambda = lambda;
+  a.lambda_ptr = g->d_lambda;
   a.rec_out = lev + 1 < nlev ? g->levels[lev + 1].rec : nullptr; a.brec_out = lev + 1 < nlev ? g->levels[lev + 1].brec : nullptr;
   a.frec = L.frec; a.fstride = fstride; a.cseg = L.cseg; a.flag = g->d_flag;
-  if (bs == 12 && g->W == 64) k_fwd_ws<12><<<L.ncta, 96, 0, g->stream>>>(a);  // warp-specialised pipeline (factor warp + 2 panel warps)
-  else if (bs == 12) fwd_w<12>(g->W, a, L.ncta, g->stream); else fwd_w<6>(g->W, a, L.ncta, g->stream);
-  g->launches++;
+  if (bs == 12 && g->W == 64) {
+    // spine first (warp per segment: the latency-bound 12x12 recurrence wants many independent warps), then the tensor-pipe panel
+    const int spine_ctas = std::min((L.nseg + 7) / 8, 2 * g->sms);
+    k_spine<12><<<spine_ctas, 256, 0, g->stream>>>(a);
+    k_panel<12><<<L.ncta, 64, 0, g->stream>>>(a);
+    g->launches += 2;
+  } else {
+    if (bs == 12) fwd_w<12>(g->W, a, L.ncta, g->stream); else fwd_w<6>(g->W, a, L.ncta, g->stream);
+    g->launches++;
+  }
   if (nb) {
     const int R = std::min(16, L.ncta);
     dim3 grid((centries + 255) / 256, R);
@@ -638,7 +651,7 @@ static int solve_landmarks_local(gpb_graph* g, double lambda) {
   const int nb = g->nb, centries = nb * nb + nb, nel = num_elim_levels(g);
   if (nb) {
     k_cseg_final<<<(centries + 127) / 128, 128, 0, g->stream>>>(g->d_Cbase, g->d_Cpart, 16 * nel, centries, g->d_Csum);
-    k_landmark_solve<128><<<1, 128, (size_t)centries * sizeof(double), g->stream>>>(g->d_Csum, nb, lambda, g->d_xlm, g->d_flag);
+    k_landmark_solve<128><<<1, 128, (size_t)centries * sizeof(double), g->stream>>>(g->d_Csum, nb, g->d_lambda, g->d_xlm, g->d_flag);
     g->launches += 2;
   }
   return GPB_OK;
@@ -670,6 +683,7 @@ static int dist_allreduce(gpb_graph* g, double* dbuf, long long count) {
 static int solve_system_dist(gpb_graph* g, int buf, double lambda, double err_local, double* global_err_out, int* flag_out) {
   int rc;
   const int nb = g->nb, centries = nb * nb + nb, nel = num_elim_levels(g), R = g->R;
+  k_set_scalar<<<1, 1, 0, g->stream>>>(g->d_lambda, lambda);
   if ((rc = solve_forward(g, buf, lambda))) return rc;
   if (nb) { k_cseg_final<<<(centries + 127) / 128, 128, 0, g->stream>>>(g->d_Cbase, g->d_Cpart, 16 * nel, centries, g->d_Csum); g->launches++; }
   PackArgs pa;
@@ -681,7 +695,7 @@ static int solve_system_dist(gpb_graph* g, int buf, double lambda, double err_lo
   if ((rc = dist_allreduce(g, g->d_topbuf, total))) return rc;
   double sc[4];
   CUDA_TRY(cudaMemcpyAsync(sc, g->d_topbuf + (size_t)R * R + R, 4 * sizeof(double), cudaMemcpyDeviceToHost, g->stream));
-  k_top_solve<256><<<1, 256, 0, g->stream>>>(g->d_topbuf, R, g->nsep * g->bs, lambda, g->d_flag);
+  k_top_solve<256><<<1, 256, 0, g->stream>>>(g->d_topbuf, R, g->nsep * g->bs, g->d_lambda, g->d_flag);
   k_top_scatter<<<1, 64, 0, g->stream>>>(g->d_topbuf, R, g->bs, nb, g->nsep, g->rank, g->extL, g->extR, g->levels.back().xsol, g->d_xlm);
   g->launches += 2;
   if ((rc = solve_backward(g))) return rc;
@@ -706,6 +720,7 @@ static int dist_sum_scalars(gpb_graph* g, double* v4) {
 static int solve_system(gpb_graph* g, int buf, double lambda) {
   int rc;
   if (g->world > 1) return solve_system_dist(g, buf, lambda, 0.0, nullptr, nullptr);
+  k_set_scalar<<<1, 1, 0, g->stream>>>(g->d_lambda, lambda);
   if ((rc = solve_forward(g, buf, lambda))) return rc;
   if ((rc = solve_landmarks_local(g, lambda))) return rc;
   return solve_backward(g);
@@ -820,10 +835,37 @@ int gpb_optimize(gpb_graph* g, const gpb_params* params, int n_iter, gpb_stats* 
         double gerr = 0;
         if ((r = solve_system_dist(g, g->cur, lam, g->cur_error_local, &gerr, &flag))) return r;
         error = gerr;  // exact global error of the current point
-      } else if ((r = solve_system(g, g->cur, lam))) return r;
-      if ((r = retract_dispatch(g))) return r;
-      // linearise at the trial point into the other buffer: gives the trial error and, if accepted, the next iteration's [A|b]
-      if ((r = linearize_dispatch(g, g->d_Xt, g->d_landt, 1 - g->cur, 1))) return r;
+      } else {
+        // single GPU: solve -> retract -> linearise(trial) is a fixed launch sequence per buffer parity; replay it as one CUDA
+        // graph (about 45 short kernels; the launch gaps were ~10 % of the iteration).  lambda is read from device memory.
+        const int par = g->cur;
+        if (!g->iter_graph[par]) {
+          cudaGraph_t graph;
+          const int l0 = g->launches;
+          CUDA_TRY(cudaStreamBeginCapture(g->stream, cudaStreamCaptureModeThreadLocal));
+          k_clear_flag<<<1, 1, 0, g->stream>>>(g->d_flag);
+          r = solve_forward(g, par, lam);
+          if (!r) r = solve_landmarks_local(g, lam);
+          if (!r) r = solve_backward(g);
+          if (!r) r = retract_dispatch(g);
+          if (!r) r = linearize_dispatch(g, g->d_Xt, g->d_landt, 1 - par, 1);
+          const cudaError_t ce = cudaStreamEndCapture(g->stream, &graph);
+          if (r) return r;
+          CUDA_TRY(ce);
+          CUDA_TRY(cudaGraphInstantiate(&g->iter_graph[par], graph, 0));
+          cudaGraphDestroy(graph);
+          g->iter_graph_launches[par] = g->launches - l0 + 1;
+          g->launches = l0;
+        }
+        k_set_scalar<<<1, 1, 0, g->stream>>>(g->d_lambda, lam);
+        CUDA_TRY(cudaGraphLaunch(g->iter_graph[par], g->stream));
+        g->launches += g->iter_graph_launches[par] + 1;
+      }
+      if (dist) {
+        if ((r = retract_dispatch(g))) return r;
+        // linearise at the trial point into the other buffer: gives the trial error and, if accepted, the next iteration's [A|b]
+        if ((r = linearize_dispatch(g, g->d_Xt, g->d_landt, 1 - g->cur, 1))) return r;
+      }
       double s[3]; int lflag;
       if ((r = read_scalars(g, s, &lflag))) return r;
       flag |= lflag;

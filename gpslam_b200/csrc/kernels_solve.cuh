@@ -28,7 +28,7 @@ struct FwdArgs {
   const int* bsside;   //          0: state is the row's a-part, 1: b-part
   const int* rowland;
   int NXRp, nb, DL;
-  double lambda;
+  const double* lambda_ptr;  // LM damping lives in device memory so a captured CUDA graph can be replayed with a new value
   double* rec_out;
   double* brec_out;
   double* frec;
@@ -195,7 +195,7 @@ __global__ void __launch_bounds__((W < 32 ? 32 : W), (W == 64 ? 6 : 8)) k_fwd(co
     }
   };
   auto D_of = [&](int buf, int k) -> double {  // D (parts summed; + lambda on the diagonal at level 0)
-    if (first) return Rb[buf][k] + ((k % (BS + 1)) == 0 ? a.lambda : 0.0);
+    if (first) return Rb[buf][k] + ((k % (BS + 1)) == 0 ? (*a.lambda_ptr) : 0.0);
     return Rb[buf][k] + Rb[buf][BS * BS + k];
   };
   for (int k = c; k < BS * BS; k += NT) Li[k] = 0.0;  // strictly-upper part of L^-1 stays zero
@@ -648,7 +648,7 @@ __global__ void __launch_bounds__(96, 4) k_fwd_ws(const FwdArgs a) {
         __syncwarp();
         for (int k = lane; k < BS * BS; k += 32) {
           double v = Rb[buf][k] + Dn[k];
-          if (first) { if ((k % (BS + 1)) == 0) v += a.lambda; } else v += Rb[buf][BS * BS + k];
+          if (first) { if ((k % (BS + 1)) == 0) v += (*a.lambda_ptr); } else v += Rb[buf][BS * BS + k];
           Dm[k] = v;
         }
         if (lane < BS) gS[s][lane] = Rb[buf][oG + lane] + (first ? 0.0 : Rb[buf][oG + BS + lane]);
@@ -793,7 +793,7 @@ __global__ void __launch_bounds__(96, 4) k_fwd_ws(const FwdArgs a) {
     // ---- segment end: hand the Schur complement to the next level.  The record of q (if any) is in Rb[(i1 - i0 + 1) & 1].
     const int qbuf = (i1 - i0 + 1) & 1;
     auto Dq = [&](int k) -> double {
-      if (first) return Rb[qbuf][k] + ((k % (BS + 1)) == 0 ? a.lambda : 0.0);
+      if (first) return Rb[qbuf][k] + ((k % (BS + 1)) == 0 ? (*a.lambda_ptr) : 0.0);
       return Rb[qbuf][k] + Rb[qbuf][BS * BS + k];
     };
     if (q >= 0) {
@@ -879,6 +879,369 @@ __global__ void __launch_bounds__(96, 4) k_fwd_ws(const FwdArgs a) {
     __syncthreads();
   }
   if (nb > 0 && !isF) {
+    double* Cs = a.cseg + (size_t)blockIdx.x * (nb * nb + nb);
+    auto flush_land = [&](int x, int y, double av) {
+      const int lo = x < y ? x : y, hi = x < y ? y : x;
+      if (lo >= BS && hi < w) {
+        const double v = -av;
+        if (hi < BS + nb) { Cs[(lo - BS) + (hi - BS) * nb] = v; Cs[(hi - BS) + (lo - BS) * nb] = v; }
+        else if (lo < BS + nb) Cs[nb * nb + (lo - BS)] = v;
+      }
+    };
+#pragma unroll
+    for (int u = 0; u < 18; u++) {
+      const int t = 2 * u + pw;
+      const int x = 8 * c_tileI[t] + gi, y = 8 * c_tileJ[t] + 2 * ti;
+      if (x >= y) flush_land(x, y, acc[2 * u]);
+      if (x >= y + 1) flush_land(x, y + 1, acc[2 * u + 1]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Two-kernel forward sweep (BS = 12, panel width 64).  The chain "spine"  D'_i = D_i - Le_{i-1} Le_{i-1}^T -> L_i^-1 ->
+// Le_i = E_i L_i^-T  never depends on the panel, so it is factored first by k_spine: ONE WARP PER SEGMENT, ~40 independent warps
+// per SM — the recurrence is latency-bound (12 dependent pivots per state), and only thread-level parallelism hides that.
+// k_panel then streams the stored (L^-1, Le) and does nothing but tensor-pipe products: Y = L^-1 P, P' = own - Le Y, S += Y^T Y.
+template <int BS>
+__global__ void __launch_bounds__(256, 2) k_spine(const FwdArgs a) {
+  constexpr int WPC = 8, REC0 = 2 * BS * BS + BS, REC1 = 3 * BS * BS + 2 * BS, NV = (BS * BS + 31) / 32;
+  __shared__ double sDm[WPC][BS * BS], sDn[WPC][BS * BS], sLi[WPC][BS * BS], sLe[WPC][BS * BS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gi = lane >> 2, ti = lane & 3;
+  double* Dm = sDm[warp]; double* Dn = sDn[warp]; double* Li = sLi[warp]; double* Le = sLe[warp];
+  const bool first = a.first_level != 0;
+  const int RECS = first ? REC0 : REC1, oE = first ? BS * BS : 2 * BS * BS;
+  const double lambda = *a.lambda_ptr;
+  for (int k = lane; k < BS * BS; k += 32) Li[k] = 0.0;  // strictly-upper part of L^-1 stays zero
+  // D (lane-distributed, NV values per lane) and the A-fragments of E of one state, fetched one state ahead into registers
+  double dv[NV], ev[2][3];
+  auto fetch = [&](int i, bool want_e) {
+    const double* r = a.rec + (size_t)i * RECS;
+#pragma unroll
+    for (int m = 0; m < NV; m++) { const int k = lane + 32 * m; dv[m] = (k < BS * BS) ? (first ? r[k] : r[k] + r[BS * BS + k]) : 0.0; }
+#pragma unroll
+    for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+      for (int sK = 0; sK < 3; sK++) ev[mt][sK] = (want_e && 8 * mt + gi < BS) ? r[oE + (8 * mt + gi) + (4 * sK + ti) * BS] : 0.0;
+  };
+  const int nwarps = gridDim.x * WPC;
+  for (int seg = blockIdx.x * WPC + warp; seg < a.nseg; seg += nwarps) {
+    const SegGeom sg = seg_geom(seg, a.n, a.M, a.S, a.extL, a.extR);
+    const int q = sg.q, i0 = sg.i0, i1 = sg.i1;
+    const int ilast = (q >= 0) ? q : i1;
+    for (int k = lane; k < BS * BS; k += 32) Dn[k] = 0.0;
+    if (i0 <= ilast) fetch(i0, (i0 < i1) || (q >= 0 && i0 <= i1));
+    __syncwarp();
+    for (int i = i0; i <= i1; i++) {
+      const bool has_next = (i < i1) || (q >= 0);
+#pragma unroll
+      for (int m = 0; m < NV; m++) {
+        const int k = lane + 32 * m;
+        if (k < BS * BS) Dm[k] = dv[m] + Dn[k] + ((first && (k % (BS + 1)) == 0) ? lambda : 0.0);
+      }
+      double ec[2][3];
+#pragma unroll
+      for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+        for (int sK = 0; sK < 3; sK++) ec[mt][sK] = ev[mt][sK];
+      if (i + 1 <= ilast) fetch(i + 1, (i + 1 < i1) || (q >= 0 && i + 1 <= i1));  // next state's loads fly during this factorisation
+      __syncwarp();
+      const bool ok = warp_chol_inverse_regs<BS>(Dm, Dm, Li, lane);
+      if (!ok && lane == 0) *a.flag = 1;
+      __syncwarp();
+      double* F = a.frec + (size_t)i * a.fstride;
+      for (int k = lane; k < BS * BS; k += 32) F[k] = Li[k];
+      if (has_next) {
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+          for (int nt = 0; nt < 2; nt++) {  // Le = E L^-T
+            double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+            for (int sK = 0; sK < 3; sK++) {
+              const double bL = (8 * nt + gi < BS) ? Li[(8 * nt + gi) + (4 * sK + ti) * BS] : 0.0;
+              dmma884(d0, d1, ec[mt][sK], bL);
+            }
+            if (8 * mt + gi < BS && 8 * nt + 2 * ti < BS) { Le[(8 * mt + gi) + (8 * nt + 2 * ti) * BS] = d0; Le[(8 * mt + gi) + (8 * nt + 2 * ti + 1) * BS] = d1; }
+          }
+        __syncwarp();
+        for (int k = lane; k < BS * BS; k += 32) F[BS * BS + k] = Le[k];
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+          for (int nt = 0; nt < 2; nt++) {  // Dn = -Le Le^T
+            double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+            for (int sK = 0; sK < 3; sK++) {
+              const double aL = (8 * mt + gi < BS) ? Le[(8 * mt + gi) + (4 * sK + ti) * BS] : 0.0;
+              const double bL = (8 * nt + gi < BS) ? Le[(8 * nt + gi) + (4 * sK + ti) * BS] : 0.0;
+              dmma884(d0, d1, aL, bL);
+            }
+            if (8 * mt + gi < BS && 8 * nt + 2 * ti < BS) { Dn[(8 * mt + gi) + (8 * nt + 2 * ti) * BS] = -d0; Dn[(8 * mt + gi) + (8 * nt + 2 * ti + 1) * BS] = -d1; }
+          }
+      }
+      __syncwarp();
+    }
+    if (q >= 0) {  // D1 of the right separator: its own block (fetched last) + the last Schur update (+ damping at level 0)
+      double* R = a.rec_out + (size_t)sg.qo * REC1;
+#pragma unroll
+      for (int m = 0; m < NV; m++) {
+        const int k = lane + 32 * m;
+        if (k < BS * BS) R[k] = dv[m] + Dn[k] + ((first && (k % (BS + 1)) == 0) ? lambda : 0.0);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+template <int BS>
+__global__ void __launch_bounds__(64, 8) k_panel(const FwdArgs a) {
+  constexpr int W = 64, NT = 64, REC0 = 2 * BS * BS + BS, REC1 = 3 * BS * BS + 2 * BS, NBP = W;
+  __shared__ __align__(16) double Fb[2][2 * BS * BS];  // (L^-1 | Le) of the current / next state (cp.async double buffer)
+  __shared__ __align__(16) double Gb[2][2 * BS];       // rhs block(s) g of the current / next state
+  __shared__ __align__(16) double Psm[W * BS], Ysm[W * BS], Bn[2][BS * NBP];
+  const int c = threadIdx.x, pw = c >> 5, lane = c & 31, gi = lane >> 2, ti = lane & 3;
+  const int nb = a.nb, w = BS + nb + 1, M = a.M;
+  const bool first = a.first_level != 0;
+  const int RECS = first ? REC0 : REC1;
+  const int oE = first ? BS * BS : 2 * BS * BS, oG = first ? 2 * BS * BS : 3 * BS * BS;
+  const bool is_border = (c >= BS) && (c < BS + nb), is_rhs = (c == BS + nb), is_spike = c < BS, active = c < w;
+  const int lb = c - BS;
+  double acc[36];
+#pragma unroll
+  for (int j = 0; j < 36; j++) acc[j] = 0.0;
+  int tI[18], tJ[18];
+#pragma unroll
+  for (int u = 0; u < 18; u++) { const int t = 2 * u + pw; tI[u] = (8 * c_tileI[t] + gi) * BS + ti; tJ[u] = (8 * c_tileJ[t] + gi) * BS + ti; }
+
+  auto prefetch = [&](int i, int buf, bool with_le) {
+    const double* src = a.frec + (size_t)i * a.fstride;
+    const int n2 = (with_le ? 2 * BS * BS : BS * BS) / 2;
+    for (int k = c; k < n2; k += NT) cp_async16(&Fb[buf][2 * k], src + 2 * k);
+  };
+  auto prefetch_g = [&](int i, int buf) {
+    const double* g = a.rec + (size_t)i * RECS + oG;
+    if (c < (first ? BS : 2 * BS) / 2) cp_async16(&Gb[buf][2 * c], g + 2 * c);
+  };
+  auto gather_border = [&](int i, int ln, double* Bd) {
+    for (int e = a.bsoff[i]; e < a.bsoff[i + 1]; e++) {
+      const int row = a.bsrow[e], side = a.bsside[e];
+      const int l = a.rowland[row];
+      if (ln < BS) {
+        const double av = a.XR[(size_t)(side * BS + ln) * a.NXRp + row];
+        for (int d = 0; d < a.DL; d++) Bd[ln + (l * a.DL + d) * BS] += av * a.XR[(size_t)(2 * BS + d) * a.NXRp + row];
+      }
+    }
+  };
+  auto add_own = [&](int i, double* Bd) {  // landmark column / rhs of state i into this thread's panel column
+    double* P = Psm + c * BS;
+    if (is_border) {
+      if (first) {
+        double2* P2 = reinterpret_cast<double2*>(P);
+        double2* B2 = reinterpret_cast<double2*>(Bd + lb * BS);
+#pragma unroll
+        for (int r = 0; r < BS / 2; r++) { const double2 bv = B2[r]; double2 pv = P2[r]; pv.x += bv.x; pv.y += bv.y; P2[r] = pv; B2[r] = make_double2(0.0, 0.0); }
+      } else {
+        const double* B = a.brec + (size_t)i * (2 * BS * nb);
+#pragma unroll
+        for (int r = 0; r < BS; r++) P[r] += B[r + lb * BS] + B[BS * nb + r + lb * BS];
+      }
+    }
+  };
+  auto add_rhs = [&](int buf) {  // after the cp.async of this state's g has landed
+    if (is_rhs) {
+#pragma unroll
+      for (int r = 0; r < BS; r++) Psm[c * BS + r] += Gb[buf][r] + (first ? 0.0 : Gb[buf][BS + r]);
+    }
+  };
+  for (int k = c; k < BS * NBP; k += NT) { Bn[0][k] = 0.0; Bn[1][k] = 0.0; }
+  __syncthreads();
+
+  for (int seg = blockIdx.x; seg < a.nseg; seg += gridDim.x) {
+    const SegGeom sg = seg_geom(seg, a.n, M, a.S, a.extL, a.extR);
+    const int p = sg.p, q = sg.q, i0 = sg.i0, i1 = sg.i1;
+    const int ilast = (q >= 0) ? q : i1;
+    if (i0 <= i1) prefetch(i0, 0, (i0 < i1) || (q >= 0));
+    if (i0 <= ilast) prefetch_g(i0, 0);
+    cp_async_commit();
+    {
+      const bool sp = is_spike && p >= 0 && i0 <= i1;
+      const double* E = a.rec + (size_t)(sp ? p : 0) * RECS + oE;
+#pragma unroll
+      for (int r = 0; r < BS; r++) Psm[c * BS + r] = sp ? E[r + c * BS] : 0.0;
+    }
+    if (first && nb > 0 && i0 <= ilast && pw == 0) gather_border(i0, lane, Bn[0]);
+    __syncthreads();
+    int s = 0;
+    for (int i = i0; i <= i1; i++, s ^= 1) {
+      const bool has_next = (i < i1) || (q >= 0);
+      if (i + 1 <= i1) prefetch(i + 1, s ^ 1, (i + 1 < i1) || (q >= 0));
+      if (i + 1 <= ilast) prefetch_g(i + 1, s ^ 1);
+      cp_async_commit();
+      add_own(i, Bn[s]);
+      if (first && nb > 0 && i + 1 <= ilast && pw == 0) gather_border(i + 1, lane, Bn[s ^ 1]);
+      cp_async_wait<1>();
+      __syncthreads();
+      add_rhs(s);   // the rhs column (thread BS + nb) lives in this warp's own column tiles: a warp-level sync is enough
+      __syncwarp();
+      const double* Li = Fb[s];
+      const double* Le = Fb[s] + BS * BS;
+      // ---- Y = L^-1 P (own column tiles)
+      {
+        double aLi[2][3];
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+          for (int sK = 0; sK < 3; sK++) aLi[mt][sK] = (8 * mt + gi < BS) ? Li[(8 * mt + gi) + (4 * sK + ti) * BS] : 0.0;
+        double d[4][2][2];
+#pragma unroll
+        for (int jt = 0; jt < 4; jt++) { d[jt][0][0] = d[jt][0][1] = d[jt][1][0] = d[jt][1][1] = 0.0; }
+#pragma unroll
+        for (int sK = 0; sK < 3; sK++)
+#pragma unroll
+          for (int jt = 0; jt < 4; jt++) {
+            const double bP = Psm[(8 * (4 * pw + jt) + gi) * BS + 4 * sK + ti];
+            if (sK < 2) dmma884(d[jt][0][0], d[jt][0][1], aLi[0][sK], bP);
+            dmma884(d[jt][1][0], d[jt][1][1], aLi[1][sK], bP);
+          }
+#pragma unroll
+        for (int jt = 0; jt < 4; jt++) {
+          const int J = 4 * pw + jt;
+#pragma unroll
+          for (int mt = 0; mt < 2; mt++)
+            if (8 * mt + gi < BS) { Ysm[(8 * J + 2 * ti) * BS + 8 * mt + gi] = d[jt][mt][0]; Ysm[(8 * J + 2 * ti + 1) * BS + 8 * mt + gi] = d[jt][mt][1]; }
+        }
+      }
+      __syncthreads();
+      // ---- P' = -Le Y (own column tiles)
+      if (has_next) {
+        double aLe[2][3];
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+          for (int sK = 0; sK < 3; sK++) aLe[mt][sK] = (8 * mt + gi < BS) ? Le[(8 * mt + gi) + (4 * sK + ti) * BS] : 0.0;
+        double d[4][2][2];
+#pragma unroll
+        for (int jt = 0; jt < 4; jt++) { d[jt][0][0] = d[jt][0][1] = d[jt][1][0] = d[jt][1][1] = 0.0; }
+#pragma unroll
+        for (int sK = 0; sK < 3; sK++)
+#pragma unroll
+          for (int jt = 0; jt < 4; jt++) {
+            const double bY = Ysm[(8 * (4 * pw + jt) + gi) * BS + 4 * sK + ti];
+            dmma884(d[jt][0][0], d[jt][0][1], aLe[0][sK], bY);
+            dmma884(d[jt][1][0], d[jt][1][1], aLe[1][sK], bY);
+          }
+#pragma unroll
+        for (int jt = 0; jt < 4; jt++) {
+          const int J = 4 * pw + jt;
+#pragma unroll
+          for (int mt = 0; mt < 2; mt++)
+            if (8 * mt + gi < BS) { Psm[(8 * J + 2 * ti) * BS + 8 * mt + gi] = -d[jt][mt][0]; Psm[(8 * J + 2 * ti + 1) * BS + 8 * mt + gi] = -d[jt][mt][1]; }
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < BS; r++) Psm[c * BS + r] = 0.0;
+      }
+      // ---- Y column to HBM
+      if (active) {
+        double* F = a.frec + (size_t)i * a.fstride;
+        const double* yc = Ysm + c * BS;
+#pragma unroll
+        for (int r = 0; r < BS; r += 2) st128(F + 2 * BS * BS + c * BS + r, yc[r], yc[r + 1]);
+      }
+      // ---- S += Y^T Y
+#pragma unroll
+      for (int sK = 0; sK < 3; sK++) {
+#pragma unroll
+        for (int u = 0; u < 18; u++) {
+          const double aY = Ysm[tI[u] + 4 * sK];
+          const double bY = Ysm[tJ[u] + 4 * sK];
+          dmma884(acc[2 * u], acc[2 * u + 1], aY, bY);
+        }
+      }
+      __syncthreads();
+    }
+    cp_async_wait<0>();
+    // ---- segment end (D1 of q was written by k_spine)
+    const int qpar = (i1 - i0 + 1) & 1;
+    if (q >= 0) {
+      double* R = a.rec_out + (size_t)sg.qo * REC1;
+      add_own(q, Bn[qpar]);
+      __syncthreads();   // g of q was copied by threads 0..BS-1; the rhs thread reads it
+      add_rhs(qpar);
+      const double* P = Psm + c * BS;
+      if (is_border) {
+        double* B = a.brec_out + (size_t)sg.qo * (2 * BS * nb);
+#pragma unroll
+        for (int r = 0; r < BS; r++) B[r + lb * BS] = P[r];
+      } else if (is_rhs) {
+#pragma unroll
+        for (int r = 0; r < BS; r++) R[3 * BS * BS + r] = P[r];
+      } else if (is_spike && p >= 0) {
+        double* Ep = a.rec_out + (size_t)sg.po * REC1 + 2 * BS * BS;
+        if (i0 <= i1) {
+#pragma unroll
+          for (int r = 0; r < BS; r++) Ep[r + c * BS] = P[r];
+        } else {
+          const double* E = a.rec + (size_t)p * RECS + oE;
+#pragma unroll
+          for (int r = 0; r < BS; r++) Ep[r + c * BS] = E[r + c * BS];
+        }
+      }
+      if (a.extR && seg == a.S) {
+        for (int k = c; k < BS * BS; k += NT) R[BS * BS + k] = 0.0;
+        if (c < BS) R[3 * BS * BS + BS + c] = 0.0;
+        if (is_border) { double* B = a.brec_out + (size_t)sg.qo * (2 * BS * nb) + BS * nb;
+#pragma unroll
+          for (int r = 0; r < BS; r++) B[r + lb * BS] = 0.0; }
+      }
+    }
+    if (a.extL && seg == 0) {
+      double* R = a.rec_out;
+      const double* src = a.rec + (size_t)p * RECS;
+      for (int k = c; k < BS * BS; k += NT) R[k] = first ? src[k] : src[k] + src[BS * BS + k];
+      if (c < BS) R[3 * BS * BS + c] = first ? src[oG + c] : src[oG + c] + src[oG + BS + c];
+      __syncthreads();
+      if (first && nb > 0 && pw == 0) gather_border(p, lane, Bn[0]);
+      __syncthreads();
+      if (is_border) {
+        double* B = a.brec_out;
+        if (first) {
+#pragma unroll
+          for (int r = 0; r < BS; r++) { B[r + lb * BS] = Bn[0][r + lb * BS]; Bn[0][r + lb * BS] = 0.0; }
+        } else {
+          const double* Bs = a.brec + (size_t)p * (2 * BS * nb);
+#pragma unroll
+          for (int r = 0; r < BS; r++) B[r + lb * BS] = Bs[r + lb * BS] + Bs[BS * nb + r + lb * BS];
+        }
+      }
+    }
+    {
+      double* Rp = (p >= 0) ? a.rec_out + (size_t)sg.po * REC1 : nullptr;
+      double* Bp = (p >= 0) ? a.brec_out + (size_t)sg.po * (2 * BS * nb) + BS * nb : nullptr;
+      auto flush_spike = [&](int x, int y, double& av) {
+        const int lo = x < y ? x : y, hi = x < y ? y : x;
+        if (lo < BS) {
+          if (p >= 0 && hi < w) {
+            const double v = -av;
+            if (hi < BS) { Rp[BS * BS + lo + hi * BS] = v; Rp[BS * BS + hi + lo * BS] = v; }
+            else if (hi < BS + nb) Bp[lo + (hi - BS) * BS] = v;
+            else Rp[3 * BS * BS + BS + lo] = v;
+          }
+          av = 0.0;
+        }
+      };
+#pragma unroll
+      for (int u = 0; u < 18; u++) {
+        const int t = 2 * u + pw;
+        const int x = 8 * c_tileI[t] + gi, y = 8 * c_tileJ[t] + 2 * ti;
+        if (x >= y) flush_spike(x, y, acc[2 * u]); else if (x < BS || y < BS) acc[2 * u] = 0.0;
+        if (x >= y + 1) flush_spike(x, y + 1, acc[2 * u + 1]); else if (x < BS || y + 1 < BS) acc[2 * u + 1] = 0.0;
+      }
+    }
+    __syncthreads();
+  }
+  if (nb > 0) {
     double* Cs = a.cseg + (size_t)blockIdx.x * (nb * nb + nb);
     auto flush_land = [&](int x, int y, double av) {
       const int lo = x < y ? x : y, hi = x < y ? y : x;
@@ -1024,7 +1387,8 @@ __global__ void k_cseg_final(const double* __restrict__ Cbase, const double* __r
 
 // landmark system: (C + lambda I) x = g, Cholesky + two triangular solves in shared memory.  Single CTA (nb <= 64).
 template <int NT>
-__global__ void __launch_bounds__(NT) k_landmark_solve(const double* __restrict__ Csum, int nb, double lambda, double* __restrict__ xl, int* __restrict__ flag) {
+__global__ void __launch_bounds__(NT) k_landmark_solve(const double* __restrict__ Csum, int nb, const double* __restrict__ lambda_ptr, double* __restrict__ xl, int* __restrict__ flag) {
+  const double lambda = *lambda_ptr;
   extern __shared__ double sm[];
   double* C = sm;            // nb x nb column-major
   double* g = sm + nb * nb;  // nb
@@ -1179,7 +1543,8 @@ __global__ void k_pack_top(const PackArgs a) {
 // Dense Cholesky solve of the all-reduced system (in place in global memory; the working set is L2-resident), single CTA.
 // lambda is added to the landmark diagonal only (separator blocks were damped when their level-0 blocks were handed off).
 template <int NT>
-__global__ void __launch_bounds__(NT) k_top_solve(double* __restrict__ buf, int R, int loff, double lambda, int* __restrict__ flag) {
+__global__ void __launch_bounds__(NT) k_top_solve(double* __restrict__ buf, int R, int loff, const double* __restrict__ lambda_ptr, int* __restrict__ flag) {
+  const double lambda = *lambda_ptr;
   double* T = buf;
   double* t = buf + (size_t)R * R;
   __shared__ double colj[256];
@@ -1228,3 +1593,6 @@ __global__ void k_top_scatter(const double* __restrict__ buf, int R, int bs, int
   if (extR && tid < bs) xsol_top[extL * bs + tid] = x[rank * bs + tid];
   for (int k = tid; k < nb; k += blockDim.x) xl[k] = x[nsep * bs + k];
 }
+
+__global__ void k_set_scalar(double* p, double v) { *p = v; }
+__global__ void k_clear_flag(int* f) { *f = 0; }
