@@ -8,6 +8,7 @@ A "step" is one Gauss-Newton iteration of the hot path over the whole graph: bat
 normal-equation assembly -> bordered block-tridiagonal Cholesky solve -> retract -> error.  Prints ONE JSON line.
 """
 import argparse
+import datetime
 import json
 import os
 import subprocess
@@ -36,16 +37,25 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region"""
-    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms; started before the graph is built (nvidia-smi needs a second or
+    more to come up on an 8-GPU box) and reduced to the samples whose timestamps fall inside the loaded window
+    [mark_begin, mark_end] = warm-up + timed iterations + end-to-end leg + stage timings"""
+    Q = "timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index=0):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f,
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "50"], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
+        self.t0 = self.t1 = None
+
+    def mark_begin(self):
+        self.t0 = datetime.datetime.now()
+
+    def mark_end(self):
+        self.t1 = datetime.datetime.now()
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
@@ -59,15 +69,22 @@ class ClockSampler:
         self.f.flush(); self.f.seek(0)
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = []
         for line in self.f.read().splitlines():
             c = [x.strip() for x in line.split(",")]
-            if len(c) < 7:
+            if len(c) < 8:
                 continue
             try:
-                sm.append(float(c[0])); mx.append(float(c[1]))
+                ts = datetime.datetime.strptime(c[0], "%Y/%m/%d %H:%M:%S.%f")
+                rows.append((ts, float(c[1]), float(c[2]), c[4:8]))
             except ValueError:
                 continue
-            for n, v in zip(names, c[3:7]):
+        inside = [r for r in rows if self.t0 is not None and self.t1 is not None and self.t0 <= r[0] <= self.t1]
+        if not inside and rows and self.t0 is not None:  # window shorter than the sampling period: the nearest sample to it
+            inside = [min(rows, key=lambda r: abs((r[0] - self.t0).total_seconds()))]
+        for ts, s_, m_, flags in inside:
+            sm.append(s_); mx.append(m_)
+            for n, v in zip(names, flags):
                 if v.lower().startswith("active"):
                     reasons.add(n)
         if sm:
@@ -121,6 +138,7 @@ def run_engine(args, rank, world, local_rank):
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    sampler = ClockSampler(local_rank)
     cfg = synth.config("C3")
     if args.states:
         cfg.n_states = args.states
@@ -154,8 +172,8 @@ def run_engine(args, rank, world, local_rank):
 
     # ---- warm-up, then K timed GN iterations: CUDA events on the engine's stream, synchronised on both sides (gpb_optimize),
     #      barrier before, max over ranks after
+    sampler.mark_begin()
     g.optimize(n_iter=max(args.warmup, 3), use_lm=False)
-    sampler = ClockSampler(local_rank)
     sync_all()
     st = g.optimize(n_iter=args.steps, use_lm=False)
     sync_all()
@@ -164,18 +182,22 @@ def run_engine(args, rank, world, local_rank):
     ms_per_step = max_over_ranks(st.total_ms) / args.steps
     value = 1e3 / ms_per_step
     # ---- end to end through the C ABI with host buffers: H2D of the values, one iteration, D2H of the result, every step
-    P, V, Lm = g.get_values()
+    #      (values live in page-locked host arrays, as a caller that cares about the transfer would hold them)
+    P, V, Lm = g.get_values(out=g.alloc_values())
+    for _ in range(2):
+        g.set_values(P, V, Lm); g.optimize(n_iter=1, use_lm=False); g.get_values(out=(P, V, Lm))
     sync_all()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         g.set_values(P, V, Lm)
         g.optimize(n_iter=1, use_lm=False)
-        P, V, Lm = g.get_values()
+        g.get_values(out=(P, V, Lm))
     e2e_s = max_over_ranks((time.perf_counter() - t0) / args.steps)
-    clocks = sampler.stop()
     io_bytes = int(P.nbytes + V.nbytes + Lm.nbytes)
     # ---- per-stage device times and the linearise roofline (local shard)
     stages = {n: g.time_stage(k, 20) for k, n in ((0, "linearise_gp"), (1, "linearise_other"), (2, "assemble"), (3, "solve"), (4, "retract"), (5, "solve_fwd_level0"))}
+    sampler.mark_end()
+    clocks = sampler.stop()
     peak, peak_src = peaks()
     gp_bytes = g.N * 8.0 * 18 + sz.n_gp * (8.0 + 8.0 * 12 * 25)  # states once + per factor (param + [A|b])
     achieved = gp_bytes / (stages["linearise_gp"] * 1e-3) / 1e9

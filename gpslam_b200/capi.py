@@ -109,9 +109,13 @@ class Graph:
         if not h:
             raise GpbError(self.L.gpb_last_error().decode())
         self.h = C.c_void_p(h)
+        self._pinned = []
 
     def __del__(self):
         if getattr(self, "h", None):
+            for p in getattr(self, "_pinned", []):
+                self.L.gpb_free_host(p)
+            self._pinned = []
             self.L.gpb_graph_destroy(self.h)
             self.h = None
 
@@ -169,9 +173,9 @@ class Graph:
         self._ck(self.L.gpb_graph_set_shard(self.h, C.c_int(rank), C.c_int(world), C.c_int(1 if ext_left else 0), C.c_int(1 if ext_right else 0)))
 
     def set_allreduce(self, fn):
-        """fn(device_ptr:int, count:int) -> 0; in-place SUM over ranks, complete on return"""
-        CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_longlong)
-        self._cb = CB(lambda ctx, ptr, count: int(fn(ptr, count)))
+        """fn(device_ptr:int, count:int, cuda_stream:int) -> 0; in-place SUM over ranks, stream-ordered on cuda_stream (see gpb.h)"""
+        CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p)
+        self._cb = CB(lambda ctx, ptr, count, stream: int(fn(ptr, count, stream or 0)))
         self._ck(self.L.gpb_set_allreduce(self.h, self._cb, None))
 
     def allreduces(self):
@@ -186,10 +190,27 @@ class Graph:
         l = _f64(lands).reshape(-1) if lands is not None and self.NL else None
         self._ck(self.L.gpb_set_values(self.h, _dp(p), _dp(v), _dp(l)))
 
-    def get_values(self):
+    def get_values(self, out=None):
+        """out: optional (poses, vels, lands) arrays to fill in place (e.g. page-locked ones from alloc_values)"""
+        if out is not None:
+            p, v, l = out
+            assert p.shape == (self.N, self.PS) and v.shape == (self.N, self.D) and p.flags.c_contiguous and v.flags.c_contiguous
+            self._ck(self.L.gpb_get_values(self.h, _dp(p), _dp(v), _dp(l) if self.NL else None))
+            return p, v, l
         p = np.zeros((self.N, self.PS)); v = np.zeros((self.N, self.D)); l = np.zeros((self.NL, max(self.DL, 1)))
         self._ck(self.L.gpb_get_values(self.h, _dp(p), _dp(v), _dp(l) if self.NL else None))
         return p, v, (l[:, :self.DL] if self.NL else np.zeros((0, self.DL)))
+
+    def alloc_values(self):
+        """page-locked (poses, vels, lands) arrays for set_values / get_values(out=...); freed with the graph"""
+        out = []
+        for shape in ((self.N, self.PS), (self.N, self.D), (self.NL, max(self.DL, 1))):
+            n = max(int(np.prod(shape)), 1)
+            ptr = C.c_void_p()
+            self._ck(self.L.gpb_alloc_host(C.byref(ptr), C.c_longlong(8 * n)))
+            self._pinned.append(ptr)
+            out.append(np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_double)), shape=(n,))[:int(np.prod(shape))].reshape(shape))
+        return tuple(out)
 
     def finalize(self, device=0):
         self._ck(self.L.gpb_graph_finalize(self.h, C.c_int(device)))

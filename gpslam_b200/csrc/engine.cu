@@ -314,8 +314,48 @@ static int upload_values(gpb_graph* g) {
   return GPB_OK;
 }
 
+// stage the caller's arrays in the (idle) trial buffer and interleave them into state records on the device: with page-locked
+// caller memory (gpb_alloc_host) the copies run at PCIe rate and no host loop touches the 14 MB
+static int values_via_device(gpb_graph* g, double* poses, double* vels, double* landmarks, int dir) {
+  CUDA_TRY(cudaSetDevice(g->device));
+  const size_t np = (size_t)g->N * g->PS, nv = (size_t)g->N * g->D;
+  double *sp = g->d_Xt, *sv = g->d_Xt + np;
+  const int nblk = (int)std::min<size_t>((np + nv + 255) / 256, (size_t)g->sms * 8);
+  if (dir == 0) {
+    CUDA_TRY(cudaMemcpyAsync(sp, poses, np * sizeof(double), cudaMemcpyHostToDevice, g->stream));
+    CUDA_TRY(cudaMemcpyAsync(sv, vels, nv * sizeof(double), cudaMemcpyHostToDevice, g->stream));
+    k_pack_values<<<nblk, 256, 0, g->stream>>>(sp, sv, g->d_X, g->N, g->PS, g->D, 0);
+    if (landmarks && g->L) CUDA_TRY(cudaMemcpyAsync(g->d_land, landmarks, (size_t)g->L * g->DL * sizeof(double), cudaMemcpyHostToDevice, g->stream));
+    g->linearized = false; g->assembled = false;
+  } else {
+    k_pack_values<<<nblk, 256, 0, g->stream>>>(sp, sv, g->d_X, g->N, g->PS, g->D, 1);
+    CUDA_TRY(cudaMemcpyAsync(poses, sp, np * sizeof(double), cudaMemcpyDeviceToHost, g->stream));
+    CUDA_TRY(cudaMemcpyAsync(vels, sv, nv * sizeof(double), cudaMemcpyDeviceToHost, g->stream));
+    if (landmarks && g->L) CUDA_TRY(cudaMemcpyAsync(landmarks, g->d_land, (size_t)g->L * g->DL * sizeof(double), cudaMemcpyDeviceToHost, g->stream));
+  }
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaStreamSynchronize(g->stream));
+  return GPB_OK;
+}
+int gpb_alloc_host(void** ptr, long long bytes) {
+  if (!ptr || bytes <= 0) return fail(GPB_ERR_ARG, "gpb_alloc_host: bad arguments");
+  CUDA_TRY(cudaHostAlloc(ptr, (size_t)bytes, cudaHostAllocDefault));
+  return GPB_OK;
+}
+int gpb_free_host(void* ptr) {
+  if (ptr) CUDA_TRY(cudaFreeHost(ptr));
+  return GPB_OK;
+}
+
 int gpb_set_values(gpb_graph* g, const double* poses, const double* vels, const double* landmarks) {
   if (!g) return fail(GPB_ERR_ARG, "null graph");
+  if (g->finalized && poses && vels) return values_via_device(g, const_cast<double*>(poses), const_cast<double*>(vels), const_cast<double*>(landmarks), 0);
+  if (g->finalized) {  // partial update: refresh the host mirror first
+    CUDA_TRY(cudaSetDevice(g->device));
+    CUDA_TRY(cudaMemcpyAsync(g->h_X.data(), g->d_X, g->h_X.size() * sizeof(double), cudaMemcpyDeviceToHost, g->stream));
+    if (g->L) CUDA_TRY(cudaMemcpyAsync(g->h_land.data(), g->d_land, (size_t)g->L * g->DL * sizeof(double), cudaMemcpyDeviceToHost, g->stream));
+    CUDA_TRY(cudaStreamSynchronize(g->stream));
+  }
   for (int i = 0; i < g->N; i++) {
     if (poses) for (int k = 0; k < g->PS; k++) g->h_X[(size_t)i * g->SR + k] = poses[(size_t)i * g->PS + k];
     if (vels) for (int k = 0; k < g->D; k++) g->h_X[(size_t)i * g->SR + g->PS + k] = vels[(size_t)i * g->D + k];
@@ -327,6 +367,7 @@ int gpb_set_values(gpb_graph* g, const double* poses, const double* vels, const 
 
 int gpb_get_values(gpb_graph* g, double* poses, double* vels, double* landmarks) {
   if (!g) return fail(GPB_ERR_ARG, "null graph");
+  if (g->finalized && poses && vels) return values_via_device(g, poses, vels, landmarks, 1);
   if (g->finalized) {
     CUDA_TRY(cudaSetDevice(g->device));
     CUDA_TRY(cudaMemcpyAsync(g->h_X.data(), g->d_X, g->h_X.size() * sizeof(double), cudaMemcpyDeviceToHost, g->stream));
@@ -673,14 +714,15 @@ static int solve_backward(gpb_graph* g) {
 // in-place sum over ranks of a small device buffer through the registered callback (stream-ordered on both sides)
 static int dist_allreduce(gpb_graph* g, double* dbuf, long long count) {
   if (!g->allreduce) return fail(GPB_ERR_STATE, "sharded graph: no all-reduce registered (gpb_set_allreduce)");
-  CUDA_TRY(cudaStreamSynchronize(g->stream));
-  if (g->allreduce(g->allreduce_ctx, dbuf, count) != 0) return fail(GPB_ERR_CUDA, "all-reduce callback failed");
+  if (g->allreduce(g->allreduce_ctx, dbuf, count, (void*)g->stream) != 0) return fail(GPB_ERR_CUDA, "all-reduce callback failed");
   g->n_allreduce++;
   return GPB_OK;
 }
 // sharded solve: local elimination down to the external separators -> pack -> ONE all-reduce -> redundant dense solve ->
 // local back-substitution.  global_err_out: sum over ranks of err_local (the error at the current linearisation point).
-static int solve_system_dist(gpb_graph* g, int buf, double lambda, double err_local, double* global_err_out, int* flag_out) {
+// async: nothing is read back and the host is not synchronised (plain Gauss-Newton with a fixed iteration count); the local error
+// of the current point is then taken from d_scal[0], where the linearise that produced this point left it.
+static int solve_system_dist(gpb_graph* g, int buf, double lambda, double err_local, double* global_err_out, int* flag_out, bool async = false) {
   int rc;
   const int nb = g->nb, centries = nb * nb + nb, nel = num_elim_levels(g), R = g->R;
   k_set_scalar<<<1, 1, 0, g->stream>>>(g->d_lambda, lambda);
@@ -688,17 +730,18 @@ static int solve_system_dist(gpb_graph* g, int buf, double lambda, double err_lo
   if (nb) { k_cseg_final<<<(centries + 127) / 128, 128, 0, g->stream>>>(g->d_Cbase, g->d_Cpart, 16 * nel, centries, g->d_Csum); g->launches++; }
   PackArgs pa;
   pa.bs = g->bs; pa.nb = nb; pa.R = R; pa.nsep = g->nsep; pa.rank = g->rank; pa.extL = g->extL; pa.extR = g->extR;
-  pa.rec = g->levels.back().rec; pa.brec = g->levels.back().brec; pa.Csum = g->d_Csum; pa.err_local = err_local; pa.flag = g->d_flag; pa.buf = g->d_topbuf;
+  pa.rec = g->levels.back().rec; pa.brec = g->levels.back().brec; pa.Csum = g->d_Csum; pa.err_local = err_local; pa.err_ptr = async ? g->d_scal : nullptr; pa.flag = g->d_flag; pa.buf = g->d_topbuf;
   const long long total = (long long)R * R + R + 4;
   k_pack_top<<<(int)std::min<long long>((total + 255) / 256, 148), 256, 0, g->stream>>>(pa);
   g->launches++;
   if ((rc = dist_allreduce(g, g->d_topbuf, total))) return rc;
-  double sc[4];
-  CUDA_TRY(cudaMemcpyAsync(sc, g->d_topbuf + (size_t)R * R + R, 4 * sizeof(double), cudaMemcpyDeviceToHost, g->stream));
+  double sc[4] = {0, 0, 0, 0};
+  if (!async) CUDA_TRY(cudaMemcpyAsync(sc, g->d_topbuf + (size_t)R * R + R, 4 * sizeof(double), cudaMemcpyDeviceToHost, g->stream));
   k_top_solve<256><<<1, 256, 0, g->stream>>>(g->d_topbuf, R, g->nsep * g->bs, g->d_lambda, g->d_flag);
   k_top_scatter<<<1, 64, 0, g->stream>>>(g->d_topbuf, R, g->bs, nb, g->nsep, g->rank, g->extL, g->extR, g->levels.back().xsol, g->d_xlm);
   g->launches += 2;
   if ((rc = solve_backward(g))) return rc;
+  if (async) return GPB_OK;
   int flag = 0;
   CUDA_TRY(cudaMemcpyAsync(&flag, g->d_flag, sizeof(int), cudaMemcpyDeviceToHost, g->stream));
   CUDA_TRY(cudaStreamSynchronize(g->stream));
@@ -824,9 +867,22 @@ int gpb_optimize(gpb_graph* g, const gpb_params* params, int n_iter, gpb_stats* 
   // of the current point).  LM trials and convergence-tested runs need the trial point's global error before the next
   // iteration and pay a second, 4-double all-reduce for it.
   const bool need_trial_error = dist && (p.use_lm || n_iter <= 0);
+  const bool async_gn = dist && !need_trial_error;
+  if (async_gn) CUDA_TRY(cudaMemsetAsync(g->d_flag, 0, sizeof(int), g->stream));
   auto one_iteration = [&]() -> int {
     int r;
     if (!g->assembled) { if ((r = assemble_dispatch(g, g->cur))) return r; g->assembled = true; }
+    if (async_gn) {
+      // sharded plain Gauss-Newton: the whole iteration, all-reduce included, is enqueued without a host round trip; a failed
+      // factorisation anywhere raises the (sticky) flag, which is checked once after the last iteration
+      if ((r = solve_system_dist(g, g->cur, 0.0, 0.0, nullptr, nullptr, true))) return r;
+      if ((r = retract_dispatch(g))) return r;
+      if ((r = linearize_dispatch(g, g->d_Xt, g->d_landt, 1 - g->cur, 1))) return r;
+      std::swap(g->d_X, g->d_Xt); std::swap(g->d_land, g->d_landt); g->cur = 1 - g->cur;
+      g->assembled = false; g->linearized = true;
+      iterations++;
+      return GPB_OK;
+    }
     while (true) {
       CUDA_TRY(cudaMemsetAsync(g->d_flag, 0, sizeof(int), g->stream));
       int flag = 0;
@@ -918,10 +974,14 @@ int gpb_optimize(gpb_graph* g, const gpb_params* params, int n_iter, gpb_stats* 
   }
   CUDA_TRY(cudaEventRecord(e1, g->stream));
   CUDA_TRY(cudaEventSynchronize(e1));
-  if (dist && !need_trial_error) {  // report the exact final error (outside the timed loop: one 4-double all-reduce)
-    double v[4] = {g->cur_error_local, 0, 0, 0};
+  if (async_gn) {  // report the exact final error and the failure flag (outside the timed loop: one 4-double all-reduce)
+    double s[3]; int lflag = 0;
+    if ((rc = read_scalars(g, s, &lflag))) return rc;
+    if (iterations) g->cur_error_local = s[0];
+    double v[4] = {g->cur_error_local, 0, 0, (double)lflag};
     if ((rc = dist_sum_scalars(g, v))) return rc;
     error = v[0]; g->cur_error = error;
+    if (v[3] != 0.0) { status = 1; cudaEventDestroy(e0); cudaEventDestroy(e1); return fail(GPB_ERR_NUMERIC, "GaussNewton: indeterminate linear system"); }
   }
   float ms = 0;
   CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
@@ -936,6 +996,10 @@ int gpb_optimize(gpb_graph* g, const gpb_params* params, int n_iter, gpb_stats* 
 int gpb_kernel_launches_last_optimize(gpb_graph* g) { return g ? g->launches : 0; }
 int gpb_allreduces_last_optimize(gpb_graph* g) { return g ? g->n_allreduce : 0; }
 // plain cudaMemcpy (kind: 1 host->device, 2 device->host) for callers that implement gpb_allreduce_fn without a CUDA binding of their own
+int gpb_stream_synchronize(void* cuda_stream) {
+  CUDA_TRY(cudaStreamSynchronize((cudaStream_t)cuda_stream));
+  return GPB_OK;
+}
 int gpb_memcpy(void* dst, const void* src, long long bytes, int kind) {
   CUDA_TRY(cudaMemcpy(dst, src, (size_t)bytes, kind == 1 ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost));
   return GPB_OK;

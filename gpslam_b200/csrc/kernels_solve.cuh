@@ -1468,6 +1468,16 @@ __global__ void __launch_bounds__(NT) k_retract(const double* __restrict__ X, co
   if (threadIdx.x == 0) { part_gd[blockIdx.x] = t1; part_dd[blockIdx.x] = t2; }
 }
 
+// values cross the C ABI as separate pose / velocity arrays; HBM holds one AoS record per state.  dir 0: arrays -> records, 1: back.
+__global__ void k_pack_values(double* __restrict__ poses, double* __restrict__ vels, double* __restrict__ X, int N, int PS, int D, int dir) {
+  const int SR = PS + D;
+  const size_t total = (size_t)N * SR;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const size_t i = e / SR; const int k = (int)(e % SR);
+    double* a = k < PS ? poses + i * PS + k : vels + i * D + (k - PS);
+    if (dir == 0) X[e] = *a; else *a = X[e];
+  }
+}
 __global__ void k_retract_land(const double* __restrict__ land, const double* __restrict__ xl, const double* __restrict__ gl, double* __restrict__ landt,
                                int n, double* __restrict__ scal, int count_dd) {
   // single block: landmarks are few; also folds their share of g.delta / |delta|^2 into scal[1], scal[2]
@@ -1491,6 +1501,7 @@ struct PackArgs {
   const double* brec;   // [extL + extR][2 bs nb]
   const double* Csum;   // local landmark block nb*nb + nb
   double err_local;
+  const double* err_ptr;  // when non-null the local error is read from device memory (asynchronous Gauss-Newton) instead of err_local
   const int* flag;
   double* buf;
 };
@@ -1534,7 +1545,7 @@ __global__ void k_pack_top(const PackArgs a) {
       }
     } else {
       const int sidx = (int)(e - ((size_t)R * R + R));
-      v = sidx == 0 ? a.err_local : (sidx == 1 ? (double)(*a.flag) : 0.0);
+      v = sidx == 0 ? (a.err_ptr ? *a.err_ptr : a.err_local) : (sidx == 1 ? (double)(*a.flag) : 0.0);
     }
     a.buf[e] = v;
   }

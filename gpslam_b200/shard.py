@@ -108,7 +108,8 @@ class ShardBuilder:
 
 
 def torch_allreduce(device):
-    """gpb_allreduce_fn over torch.distributed (NCCL over NVLink): wraps the engine's device buffer without a copy"""
+    """gpb_allreduce_fn over torch.distributed (NCCL over NVLink): wraps the engine's device buffer without a copy and enqueues
+    the collective in order on the engine's own stream - no host synchronisation, so the GN loop keeps running ahead"""
     import torch
     import torch.distributed as dist
 
@@ -118,10 +119,16 @@ def torch_allreduce(device):
 
     dev = torch.device("cuda", device)
 
-    def fn(ptr, count):
-        t = torch.as_tensor(_Ptr(ptr, count), device=dev)
-        dist.all_reduce(t)
-        torch.cuda.synchronize(dev)
+    cache = {}
+
+    def fn(ptr, count, stream):
+        key = (ptr, count, stream)
+        ent = cache.get(key)
+        if ent is None:
+            ent = cache[key] = (torch.as_tensor(_Ptr(ptr, count), device=dev), torch.cuda.ExternalStream(stream, device=dev))
+        t, ext = ent
+        with torch.cuda.stream(ext):
+            dist.all_reduce(t)
         return 0
     return fn
 
@@ -152,7 +159,8 @@ class LocalAllreduce:
     def make(self, rank):
         import ctypes as C
 
-        def fn(ptr, count):
+        def fn(ptr, count, stream):
+            self.lib.gpb_stream_synchronize(C.c_void_p(stream))
             self.slots[rank] = (ptr, count)
             self.bar.wait()
             if rank == 0:

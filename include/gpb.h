@@ -99,6 +99,10 @@ int gpb_eval_factor(int group, int kind, const double* x1, const double* v1, con
 /* Values::insert / Values::at : host buffers, [n_states x pose_storage], [n_states x D], [n_landmarks x DL] */
 int gpb_set_values(gpb_graph* g, const double* poses, const double* vels, const double* landmarks);
 int gpb_get_values(gpb_graph* g, double* poses, double* vels, double* landmarks);
+/* page-locked host memory for the value arrays: gpb_set_values / gpb_get_values then move them at PCIe rate (any host pointer
+ * is accepted; pageable memory goes through the driver's staging copies) */
+int gpb_alloc_host(void** ptr, long long bytes);
+int gpb_free_host(void* ptr);
 
 /* Freezes the graph: sorts factors by interval, builds the device-resident SoA layout, allocates
  * every solver buffer on `device`.  Must be called once after the last gpb_add_*. */
@@ -135,9 +139,14 @@ int gpb_solve_delta(gpb_graph* g, double lambda, double* delta_states, double* d
  * whose local chain contains both states. */
 int gpb_graph_set_shard(gpb_graph* g, int rank, int world, int ext_left, int ext_right);
 
-/* In-place SUM all-reduce of `count` doubles at device pointer `buf` over all ranks, complete on return.  The engine calls it
- * exactly once per Gauss-Newton iteration, on the packed boundary Schur-complement system (plus the error scalar). */
-typedef int (*gpb_allreduce_fn)(void* ctx, double* device_buf, long long count);
+/* In-place SUM all-reduce of `count` doubles at device pointer `buf` over all ranks, STREAM-ORDERED on `cuda_stream` (the
+ * engine's cudaStream_t): it must consume the buffer after the work already enqueued on that stream and produce the sums
+ * before work enqueued on it later; it need not be complete on return (NCCL enqueued on that stream is the intended
+ * implementation - the engine never synchronises the host around the call, so a plain Gauss-Newton run stays asynchronous).
+ * An implementation that works on the host instead calls gpb_stream_synchronize(cuda_stream) first and returns when done.
+ * The engine calls it exactly once per Gauss-Newton iteration, on the packed boundary Schur-complement system (which also
+ * carries the error scalar). */
+typedef int (*gpb_allreduce_fn)(void* ctx, double* device_buf, long long count, void* cuda_stream);
 int gpb_set_allreduce(gpb_graph* g, gpb_allreduce_fn fn, void* ctx);
 
 /* solver tuning: segment length per elimination level (>= 2); 0 keeps the default */
@@ -156,6 +165,8 @@ int gpb_time_stage(gpb_graph* g, int stage, int reps, double* ms_out);
 int gpb_kernel_launches_last_optimize(gpb_graph* g);
 /* plain cudaMemcpy (kind 1: host->device, 2: device->host), for gpb_allreduce_fn implementations without their own CUDA binding */
 int gpb_memcpy(void* dst, const void* src, long long bytes, int kind);
+/* cudaStreamSynchronize for the same callers */
+int gpb_stream_synchronize(void* cuda_stream);
 /* all-reduce calls issued by the last gpb_optimize (sharded graphs) */
 int gpb_allreduces_last_optimize(gpb_graph* g);
 
