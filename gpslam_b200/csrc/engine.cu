@@ -74,7 +74,9 @@ struct gpb_graph {
   double* d_xprm = nullptr;
   int *d_rowoff = nullptr, *d_rowland = nullptr, *d_lmoff = nullptr, *d_lmrows = nullptr;
   int *d_bsoff = nullptr, *d_bsrow = nullptr, *d_bsside = nullptr;  // per-state CSR of landmark-bearing rows (level-0 border gather)
+  double* d_bent = nullptr; int nbent = 0;                          // the same rows packed as 128-byte entries (k_border_pack)
   int rank = 0, world = 1, nsep = 0, R = 0, sms = 148;
+  bool old_panel = false;
   gpb_allreduce_fn allreduce = nullptr; void* allreduce_ctx = nullptr;
   double* d_topbuf = nullptr; double cur_error_local = 0; int n_allreduce = 0;
   double* d_lambda = nullptr;
@@ -421,7 +423,7 @@ static int bwd_blocks_per_sm(int bs, int W) {
 static int fwd_blocks_per_sm(int bs, int W) {
   if (bs == 12 && W == 64) {
     int nb = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_panel<12>, 64, 0) != cudaSuccess) { cudaGetLastError(); nb = 4; }
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_panel4<12>, 128, 0) != cudaSuccess) { cudaGetLastError(); nb = 4; }
     return nb < 1 ? 1 : nb;
   }
   if (bs == 12) return W == 16 ? occ_fwd<12, 16>() : W == 32 ? occ_fwd<12, 32>() : occ_fwd<12, 64>();
@@ -510,6 +512,8 @@ int gpb_graph_finalize(gpb_graph* g, int device) {
   if ((rc = dev_upload(g, &g->d_bsoff, bsoff))) return rc;
   if ((rc = dev_upload(g, &g->d_bsrow, bsrow))) return rc;
   if ((rc = dev_upload(g, &g->d_bsside, bsside))) return rc;
+  g->nbent = (int)bsrow.size();
+  if ((rc = dev_alloc(g, &g->d_bent, (size_t)std::max(g->nbent, 1) * 16))) return rc;
   if ((rc = dev_upload(g, &g->d_listA, listA))) return rc;
   if ((rc = dev_upload(g, &g->d_listB, listB))) return rc;
   if ((rc = dev_upload(g, &g->d_rowoff, rowoff))) return rc;
@@ -534,6 +538,7 @@ int gpb_graph_finalize(gpb_graph* g, int device) {
   g->sms = sms;
   // segment lengths: explicit setting > environment (tuning aid) > defaults
   const char* em0 = getenv("GPB_M0"); const char* emu = getenv("GPB_MUP");
+  g->old_panel = getenv("GPB_OLD_PANEL") != nullptr;  // A/B switch while the four-warp panel kernel is being validated
   const int M0 = g->M0 ? g->M0 : (em0 ? std::max(2, atoi(em0)) : (g->nb > 0 ? 32 : 16)), Mup = g->Mup ? g->Mup : (emu ? std::max(2, atoi(emu)) : 8);
   const int fstride = 2 * bs * bs + bs * g->w;
   int n = g->N, lev = 0;
@@ -630,6 +635,10 @@ template <int G> static int launch_assemble(gpb_graph* g, int buf) {
     CUDA_TRY(cudaMemsetAsync(g->d_Cbase, 0, (size_t)(g->nb * g->nb + g->nb) * sizeof(double), g->stream));
     k_landmark_base<128><<<g->L, 128, 0, g->stream>>>(g->d_XR[buf], g->d_lmoff, g->d_lmrows, g->NXRp, 2 * bs, g->DL, g->nb, g->d_Cbase);
     g->launches++;
+    if (bs == 12 && g->W == 64 && g->nbent > 0) {
+      k_border_pack<<<(g->nbent * 16 + 255) / 256, 256, 0, g->stream>>>(g->d_XR[buf], g->d_bsrow, g->d_bsside, g->d_rowland, g->nbent, bs, g->DL, g->NXRp, g->d_bent);
+      g->launches++;
+    }
   }
   CUDA_TRY(cudaGetLastError());
   return GPB_OK;
@@ -655,7 +664,7 @@ static int launch_fwd_level(gpb_graph* g, int buf, double lambda, int lev) {
   FwdArgs a;
   a.n = L.n; a.M = L.M; a.S = L.S; a.nseg = L.nseg; a.first_level = lev == 0; a.extL = g->extL; a.extR = g->extR;
   a.rec = lev == 0 ? g->d_HREC : L.rec; a.brec = L.brec;
-  a.XR = g->d_XR[buf]; a.bsoff = g->d_bsoff; a.bsrow = g->d_bsrow; a.bsside = g->d_bsside; a.rowland = g->d_rowland; a.NXRp = g->NXRp; a.nb = nb; a.DL = std::max(g->DL, 1);
+  a.XR = g->d_XR[buf]; a.bsoff = g->d_bsoff; a.bsrow = g->d_bsrow; a.bsside = g->d_bsside; a.rowland = g->d_rowland; a.bent = g->d_bent; a.NXRp = g->NXRp; a.nb = nb; a.DL = std::max(g->DL, 1);
   a.lambda_ptr = g->d_lambda;
   a.rec_out = lev + 1 < nlev ? g->levels[lev + 1].rec : nullptr; a.brec_out = lev + 1 < nlev ? g->levels[lev + 1].brec : nullptr;
   a.frec = L.frec; a.fstride = fstride; a.cseg = L.cseg; a.flag = g->d_flag;
@@ -663,7 +672,8 @@ static int launch_fwd_level(gpb_graph* g, int buf, double lambda, int lev) {
     // spine first (warp per segment: the latency-bound 12x12 recurrence wants many independent warps), then the tensor-pipe panel
     const int spine_ctas = std::min((L.nseg + 7) / 8, 2 * g->sms);
     k_spine<12><<<spine_ctas, 256, 0, g->stream>>>(a);
-    k_panel<12><<<L.ncta, 64, 0, g->stream>>>(a);
+    if (g->old_panel) k_panel<12><<<L.ncta, 64, 0, g->stream>>>(a);
+    else k_panel4<12><<<L.ncta, 128, 0, g->stream>>>(a);
     g->launches += 2;
   } else {
     if (bs == 12) fwd_w<12>(g->W, a, L.ncta, g->stream); else fwd_w<6>(g->W, a, L.ncta, g->stream);

@@ -27,6 +27,7 @@ struct FwdArgs {
   const int* bsrow;    //          row index
   const int* bsside;   //          0: state is the row's a-part, 1: b-part
   const int* rowland;
+  const double* bent;  // level 0: packed border entries (k_border_pack), 16 doubles each, CSR order of bsoff
   int NXRp, nb, DL;
   const double* lambda_ptr;  // LM damping lives in device memory so a captured CUDA graph can be replayed with a new value
   double* rec_out;
@@ -1258,6 +1259,331 @@ __global__ void __launch_bounds__(64, 8) k_panel(const FwdArgs a) {
       if (x >= y) flush_land(x, y, acc[2 * u]);
       if (x >= y + 1) flush_land(x, y + 1, acc[2 * u + 1]);
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Panel kernel, four warps.  Warp pw owns column tiles 2pw, 2pw+1 of the 12 x 64 panel [spike | border | rhs] for the
+// thread-per-column steps and for Y = L^-1 P, P' = -Le Y; the symmetric update S += Y^T Y (36 lower 8x8 tiles) is split nine
+// tiles per warp with compile-time tile lists, so its fragments and accumulators never leave registers.  ONE block barrier
+// per state (Y of all tiles visible before the rank-12 update; Y is double-buffered so the next state's Y can be written
+// while slower warps still read this one).  (L^-1 | Le), g and the packed border entries of state i+2 stream in with
+// cp.async (three stages) while state i is processed.
+__host__ __device__ constexpr int syrk_tile_I(int pw, int u) {
+  constexpr int t[4][9] = {{0, 1, 1, 2, 2, 2, 3, 3, 3}, {4, 4, 4, 4, 5, 5, 5, 5, 3}, {6, 6, 6, 6, 7, 7, 7, 7, 7}, {4, 5, 5, 6, 6, 6, 7, 7, 7}};
+  return t[pw][u];
+}
+__host__ __device__ constexpr int syrk_tile_J(int pw, int u) {
+  constexpr int t[4][9] = {{0, 0, 1, 0, 1, 2, 1, 2, 3}, {0, 1, 2, 3, 0, 1, 2, 3, 0}, {0, 1, 2, 3, 0, 1, 2, 3, 4}, {4, 4, 5, 4, 5, 6, 5, 6, 7}};
+  return t[pw][u];
+}
+__host__ __device__ constexpr bool syrk_needs(int pw, int t) {
+  for (int u = 0; u < 9; u++) if (syrk_tile_I(pw, u) == t || syrk_tile_J(pw, u) == t) return true;
+  return false;
+}
+template <int PW> __device__ __forceinline__ void syrk_accum(const double* __restrict__ Y, double (&acc)[18], int gi, int ti) {
+  constexpr int BS = 12;
+#pragma unroll
+  for (int sK = 0; sK < 3; sK++) {
+    double yf[8];
+    static_for<0, 8>([&](auto T) {
+      constexpr int t = decltype(T)::value;
+      if constexpr (syrk_needs(PW, t)) yf[t] = Y[(8 * t + gi) * BS + 4 * sK + ti];
+    });
+    static_for<0, 9>([&](auto U) {
+      constexpr int u = decltype(U)::value;
+      dmma884(acc[2 * u], acc[2 * u + 1], yf[syrk_tile_I(PW, u)], yf[syrk_tile_J(PW, u)]);
+    });
+  }
+}
+
+// level-0 border entries, one 128-byte record per landmark-bearing row in per-state CSR order:
+// [0..11] the row's coefficients on the state, [12..12+DL) its coefficients on the landmark, [15] the landmark index
+__global__ void k_border_pack(const double* __restrict__ XR, const int* __restrict__ bsrow, const int* __restrict__ bsside, const int* __restrict__ rowland,
+                              int nent, int BS, int DL, int NXRp, double* __restrict__ bent) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x, e = t >> 4, k = t & 15;
+  if (e >= nent) return;
+  const int row = bsrow[e], side = bsside[e];
+  double v = 0.0;
+  if (k < BS) v = XR[(size_t)(side * BS + k) * NXRp + row];
+  else if (k < BS + DL) v = XR[(size_t)(2 * BS + (k - BS)) * NXRp + row];
+  else if (k == 15) v = (double)rowland[row];
+  bent[(size_t)e * 16 + k] = v;
+}
+
+template <int BS>
+__global__ void __launch_bounds__(128, 5) k_panel4(const FwdArgs a) {
+  static_assert(BS == 12, "panel kernel is specialised for 12 x 12 state blocks");
+  constexpr int W = 64, NT = 128, REC0 = 2 * BS * BS + BS, REC1 = 3 * BS * BS + 2 * BS, NST = 3, MAXE = 6, HB = BS / 2;
+  __shared__ __align__(16) double Fb[NST][2 * BS * BS];  // (L^-1 | Le)
+  __shared__ __align__(16) double Gb[NST][2 * BS];       // rhs block(s) g
+  __shared__ __align__(16) double Eb[NST][MAXE * 16];    // packed border entries (level 0)
+  __shared__ __align__(16) double Psm[W * BS], Ysm[2][W * BS];
+  const int c = threadIdx.x, pw = c >> 5, lane = c & 31, gi = lane >> 2, ti = lane & 3;
+  const int col = 16 * pw + (lane & 15), r0 = HB * (lane >> 4);  // thread-per-half-column steps: column, first row
+  const int nb = a.nb, w = BS + nb + 1, M = a.M;
+  const bool first = a.first_level != 0;
+  const bool ent = first && nb > 0;
+  const int RECS = first ? REC0 : REC1;
+  const int oE = first ? BS * BS : 2 * BS * BS, oG = first ? 2 * BS * BS : 3 * BS * BS;
+  const bool is_border = (col >= BS) && (col < BS + nb), is_rhs = (col == BS + nb), is_spike = col < BS, active = col < w;
+  const int lb = col - BS;
+  const int myl = is_border ? lb / a.DL : -1, myd = is_border ? lb % a.DL : 0;
+  double acc[18];
+#pragma unroll
+  for (int j = 0; j < 18; j++) acc[j] = 0.0;
+  auto with_pw = [&](auto fn) {
+    if (pw == 0) fn(std::integral_constant<int, 0>{});
+    else if (pw == 1) fn(std::integral_constant<int, 1>{});
+    else if (pw == 2) fn(std::integral_constant<int, 2>{});
+    else fn(std::integral_constant<int, 3>{});
+  };
+  auto bso = [&](int i) { return ent ? a.bsoff[i < a.n ? i : a.n] : 0; };
+
+  for (int seg = blockIdx.x; seg < a.nseg; seg += gridDim.x) {
+    const SegGeom sg = seg_geom(seg, a.n, M, a.S, a.extL, a.extR);
+    const int p = sg.p, q = sg.q, i0 = sg.i0, i1 = sg.i1;
+    const int ilast = (q >= 0) ? q : i1;
+    int b0 = bso(i0), b1 = bso(i0 + 1), b2 = bso(i0 + 2), b3 = bso(i0 + 3);  // rolling window of CSR offsets: states i .. i+3
+    auto prefetch = [&](int i, int st, int e0, int e1) {
+      if (i <= i1) {
+        const double* src = a.frec + (size_t)i * a.fstride;
+        const int n2 = (((i < i1) || (q >= 0)) ? 2 * BS * BS : BS * BS) / 2;
+        for (int k = c; k < n2; k += NT) cp_async16(&Fb[st][2 * k], src + 2 * k);
+      }
+      if (i <= ilast) {
+        if (c < (first ? BS : 2 * BS) / 2) cp_async16(&Gb[st][2 * c], a.rec + (size_t)i * RECS + oG + 2 * c);
+        if (ent) { const int ne = min(e1 - e0, MAXE); if (c < 8 * ne) cp_async16(&Eb[st][2 * c], a.bent + (size_t)e0 * 16 + 2 * c); }
+      }
+    };
+    // own half-column of state i: border entries / dense border blocks, rhs
+    auto add_own = [&](int i, int st, int e0, int e1) {
+      double* P = Psm + col * BS + r0;
+      if (is_border) {
+        if (first) {
+          const int ne = e1 - e0;
+          for (int k = 0; k < ne; k++) {
+            if (k < MAXE) {
+              const double* en = &Eb[st][16 * k];
+              if ((int)en[15] == myl) { const double h = en[BS + myd];
+#pragma unroll
+                for (int r = 0; r < HB; r++) P[r] += en[r0 + r] * h; }
+            } else {
+              const double* en = a.bent + (size_t)(e0 + k) * 16;
+              if ((int)en[15] == myl) { const double h = en[BS + myd];
+#pragma unroll
+                for (int r = 0; r < HB; r++) P[r] += en[r0 + r] * h; }
+            }
+          }
+        } else {
+          const double* B = a.brec + (size_t)i * (2 * BS * nb) + r0 + lb * BS;
+#pragma unroll
+          for (int r = 0; r < HB; r++) P[r] += B[r] + B[BS * nb + r];
+        }
+      } else if (is_rhs) {
+#pragma unroll
+        for (int r = 0; r < HB; r++) P[r] += Gb[st][r0 + r] + (first ? 0.0 : Gb[st][BS + r0 + r]);
+      }
+    };
+    prefetch(i0, 0, b0, b1); cp_async_commit();
+    prefetch(i0 + 1, 1, b1, b2); cp_async_commit();
+    {
+      const bool sp = is_spike && p >= 0 && i0 <= i1;
+      const double* E = a.rec + (size_t)(sp ? p : 0) * RECS + oE + r0 + col * BS;
+#pragma unroll
+      for (int r = 0; r < HB; r++) Psm[col * BS + r0 + r] = sp ? E[r] : 0.0;
+    }
+    cp_async_wait<1>();
+    __syncthreads();
+    int st = 0, ys = 0;
+    for (int i = i0; i <= i1; i++) {
+      const bool has_next = (i < i1) || (q >= 0);
+      const int st2 = st == 0 ? 2 : st - 1;  // stage of state i+2 == stage of state i-1, free since the previous barrier
+      prefetch(i + 2, st2, b2, b3);
+      cp_async_commit();
+      const int b4 = bso(i + 4);
+      add_own(i, st, b0, b1);
+      __syncwarp();
+      const double* Li = Fb[st];
+      const double* Le = Fb[st] + BS * BS;
+      double* Y = Ysm[ys];
+      // ---- Y = L^-1 P (own column tiles)
+      {
+        double aLi[2][3];
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+          for (int sK = 0; sK < 3; sK++) aLi[mt][sK] = (8 * mt + gi < BS) ? Li[(8 * mt + gi) + (4 * sK + ti) * BS] : 0.0;
+        double d[2][2][2];
+#pragma unroll
+        for (int jt = 0; jt < 2; jt++) { d[jt][0][0] = d[jt][0][1] = d[jt][1][0] = d[jt][1][1] = 0.0; }
+#pragma unroll
+        for (int sK = 0; sK < 3; sK++)
+#pragma unroll
+          for (int jt = 0; jt < 2; jt++) {
+            const double bP = Psm[(8 * (2 * pw + jt) + gi) * BS + 4 * sK + ti];
+            if (sK < 2) dmma884(d[jt][0][0], d[jt][0][1], aLi[0][sK], bP);
+            dmma884(d[jt][1][0], d[jt][1][1], aLi[1][sK], bP);
+          }
+#pragma unroll
+        for (int jt = 0; jt < 2; jt++) {
+          const int J = 2 * pw + jt;
+#pragma unroll
+          for (int mt = 0; mt < 2; mt++)
+            if (8 * mt + gi < BS) { Y[(8 * J + 2 * ti) * BS + 8 * mt + gi] = d[jt][mt][0]; Y[(8 * J + 2 * ti + 1) * BS + 8 * mt + gi] = d[jt][mt][1]; }
+        }
+      }
+      __syncwarp();
+      // ---- P' = -Le Y (own column tiles)
+      if (has_next) {
+        double aLe[2][3];
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+          for (int sK = 0; sK < 3; sK++) aLe[mt][sK] = (8 * mt + gi < BS) ? Le[(8 * mt + gi) + (4 * sK + ti) * BS] : 0.0;
+        double d[2][2][2];
+#pragma unroll
+        for (int jt = 0; jt < 2; jt++) { d[jt][0][0] = d[jt][0][1] = d[jt][1][0] = d[jt][1][1] = 0.0; }
+#pragma unroll
+        for (int sK = 0; sK < 3; sK++)
+#pragma unroll
+          for (int jt = 0; jt < 2; jt++) {
+            const double bY = Y[(8 * (2 * pw + jt) + gi) * BS + 4 * sK + ti];
+            dmma884(d[jt][0][0], d[jt][0][1], aLe[0][sK], bY);
+            dmma884(d[jt][1][0], d[jt][1][1], aLe[1][sK], bY);
+          }
+#pragma unroll
+        for (int jt = 0; jt < 2; jt++) {
+          const int J = 2 * pw + jt;
+#pragma unroll
+          for (int mt = 0; mt < 2; mt++)
+            if (8 * mt + gi < BS) { Psm[(8 * J + 2 * ti) * BS + 8 * mt + gi] = -d[jt][mt][0]; Psm[(8 * J + 2 * ti + 1) * BS + 8 * mt + gi] = -d[jt][mt][1]; }
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < HB; r++) Psm[col * BS + r0 + r] = 0.0;
+      }
+      // ---- Y half-column to HBM
+      if (active) {
+        double* F = a.frec + (size_t)i * a.fstride + 2 * BS * BS + col * BS + r0;
+        const double* yc = Y + col * BS + r0;
+#pragma unroll
+        for (int r = 0; r < HB; r += 2) st128(F + r, yc[r], yc[r + 1]);
+      }
+      cp_async_wait<1>();
+      __syncthreads();
+      // ---- S += Y^T Y (this warp's nine tiles)
+      with_pw([&](auto PW) { syrk_accum<decltype(PW)::value>(Y, acc, gi, ti); });
+      b0 = b1; b1 = b2; b2 = b3; b3 = b4;
+      st = st == 2 ? 0 : st + 1; ys ^= 1;
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+    // ---- segment end (D1 of q was written by k_spine): the closing separator's own border / rhs, then hand the panel off
+    if (q >= 0) {
+      double* R = a.rec_out + (size_t)sg.qo * REC1;
+      add_own(q, st, b0, b1);
+      const double* P = Psm + col * BS + r0;
+      if (is_border) {
+        double* B = a.brec_out + (size_t)sg.qo * (2 * BS * nb) + r0 + lb * BS;
+#pragma unroll
+        for (int r = 0; r < HB; r++) B[r] = P[r];
+      } else if (is_rhs) {
+#pragma unroll
+        for (int r = 0; r < HB; r++) R[3 * BS * BS + r0 + r] = P[r];
+      } else if (is_spike && p >= 0) {
+        double* Ep = a.rec_out + (size_t)sg.po * REC1 + 2 * BS * BS + r0 + col * BS;
+        if (i0 <= i1) {
+#pragma unroll
+          for (int r = 0; r < HB; r++) Ep[r] = P[r];
+        } else {
+          const double* E = a.rec + (size_t)p * RECS + oE + r0 + col * BS;
+#pragma unroll
+          for (int r = 0; r < HB; r++) Ep[r] = E[r];
+        }
+      }
+      if (a.extR && seg == a.S) {
+        for (int k = c; k < BS * BS; k += NT) R[BS * BS + k] = 0.0;
+        if (c < BS) R[3 * BS * BS + BS + c] = 0.0;
+        if (is_border) { double* B = a.brec_out + (size_t)sg.qo * (2 * BS * nb) + BS * nb + r0 + lb * BS;
+#pragma unroll
+          for (int r = 0; r < HB; r++) B[r] = 0.0; }
+      }
+    }
+    if (a.extL && seg == 0) {  // the left external separator (halo state p): its own blocks pass through to the next level
+      double* R = a.rec_out;
+      const double* src = a.rec + (size_t)p * RECS;
+      for (int k = c; k < BS * BS; k += NT) R[k] = first ? src[k] : src[k] + src[BS * BS + k];
+      if (c < BS) R[3 * BS * BS + c] = first ? src[oG + c] : src[oG + c] + src[oG + BS + c];
+      if (is_border) {
+        double* B = a.brec_out + r0 + lb * BS;
+        double v[HB];
+#pragma unroll
+        for (int r = 0; r < HB; r++) v[r] = 0.0;
+        if (first) {
+          for (int e = a.bsoff[p]; e < a.bsoff[p + 1]; e++) {
+            const double* en = a.bent + (size_t)e * 16;
+            if ((int)en[15] == myl) { const double h = en[BS + myd];
+#pragma unroll
+              for (int r = 0; r < HB; r++) v[r] += en[r0 + r] * h; }
+          }
+        } else {
+          const double* Bs = a.brec + (size_t)p * (2 * BS * nb) + r0 + lb * BS;
+#pragma unroll
+          for (int r = 0; r < HB; r++) v[r] = Bs[r] + Bs[BS * nb + r];
+        }
+#pragma unroll
+        for (int r = 0; r < HB; r++) B[r] = v[r];
+      }
+    }
+    {
+      double* Rp = (p >= 0) ? a.rec_out + (size_t)sg.po * REC1 : nullptr;
+      double* Bp = (p >= 0) ? a.brec_out + (size_t)sg.po * (2 * BS * nb) + BS * nb : nullptr;
+      auto flush_spike = [&](int x, int y, double& av) {
+        const int lo = x < y ? x : y, hi = x < y ? y : x;
+        if (lo < BS) {
+          if (p >= 0 && hi < w) {
+            const double v = -av;
+            if (hi < BS) { Rp[BS * BS + lo + hi * BS] = v; Rp[BS * BS + hi + lo * BS] = v; }
+            else if (hi < BS + nb) Bp[lo + (hi - BS) * BS] = v;
+            else Rp[3 * BS * BS + BS + lo] = v;
+          }
+          av = 0.0;
+        }
+      };
+      with_pw([&](auto PW) {
+        constexpr int pwc = decltype(PW)::value;
+        static_for<0, 9>([&](auto U) {
+          constexpr int u = decltype(U)::value;
+          if constexpr (syrk_tile_J(pwc, u) < 2) {  // only tiles whose columns reach into the spike block (columns 0..11)
+            const int x = 8 * syrk_tile_I(pwc, u) + gi, y = 8 * syrk_tile_J(pwc, u) + 2 * ti;
+            if (x >= y) flush_spike(x, y, acc[2 * u]); else if (x < BS || y < BS) acc[2 * u] = 0.0;
+            if (x >= y + 1) flush_spike(x, y + 1, acc[2 * u + 1]); else if (x < BS || y + 1 < BS) acc[2 * u + 1] = 0.0;
+          }
+        });
+      });
+    }
+    __syncthreads();
+  }
+  if (nb > 0) {
+    double* Cs = a.cseg + (size_t)blockIdx.x * (nb * nb + nb);
+    auto flush_land = [&](int x, int y, double av) {
+      const int lo = x < y ? x : y, hi = x < y ? y : x;
+      if (lo >= BS && hi < w) {
+        const double v = -av;
+        if (hi < BS + nb) { Cs[(lo - BS) + (hi - BS) * nb] = v; Cs[(hi - BS) + (lo - BS) * nb] = v; }
+        else if (lo < BS + nb) Cs[nb * nb + (lo - BS)] = v;
+      }
+    };
+    with_pw([&](auto PW) {
+      constexpr int pwc = decltype(PW)::value;
+      static_for<0, 9>([&](auto U) {
+        constexpr int u = decltype(U)::value;
+        const int x = 8 * syrk_tile_I(pwc, u) + gi, y = 8 * syrk_tile_J(pwc, u) + 2 * ti;
+        if (x >= y) flush_land(x, y, acc[2 * u]);
+        if (x >= y + 1) flush_land(x, y + 1, acc[2 * u + 1]);
+      });
+    });
   }
 }
 
