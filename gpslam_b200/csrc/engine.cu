@@ -93,7 +93,8 @@ struct gpb_graph {
   int* d_flag = nullptr;
   double *d_Cbase = nullptr, *d_xlm = nullptr, *d_Cpart = nullptr;
   std::vector<Level> levels;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, stream2 = nullptr;  // stream2: forked side branch (joined back before anything consumes its output)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   double cur_error = 0;
   int launches = 0;
   size_t hbm_bytes = 0;
@@ -180,6 +181,9 @@ void gpb_graph_destroy(gpb_graph* g) {
   if (g->pinned) { cudaHostUnregister(g->h_X.data()); if (g->L) cudaHostUnregister(g->h_land.data()); }
   for (int k = 0; k < 2; k++) if (g->iter_graph[k]) cudaGraphExecDestroy(g->iter_graph[k]);
   for (void* p : g->allocs) cudaFree(p);
+  if (g->ev_fork) cudaEventDestroy(g->ev_fork);
+  if (g->ev_join) cudaEventDestroy(g->ev_join);
+  if (g->stream2) cudaStreamDestroy(g->stream2);
   if (g->stream) cudaStreamDestroy(g->stream);
   delete g;
 }
@@ -440,6 +444,9 @@ int gpb_graph_finalize(gpb_graph* g, int device) {
   CUDA_TRY(cudaSetDevice(device));
   g->device = device;
   CUDA_TRY(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaStreamCreateWithFlags(&g->stream2, cudaStreamNonBlocking));
+  CUDA_TRY(cudaEventCreateWithFlags(&g->ev_fork, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&g->ev_join, cudaEventDisableTiming));
   const int D = g->D, bs = g->bs, DL = g->DL;
   g->nb = g->L * DL; g->w = bs + g->nb + 1;
   g->W = g->w <= 16 ? 16 : g->w <= 32 ? 32 : 64;
@@ -539,7 +546,20 @@ int gpb_graph_finalize(gpb_graph* g, int device) {
   // segment lengths: explicit setting > environment (tuning aid) > defaults
   const char* em0 = getenv("GPB_M0"); const char* emu = getenv("GPB_MUP");
   g->old_panel = getenv("GPB_OLD_PANEL") != nullptr;  // A/B switch while the four-warp panel kernel is being validated
-  const int M0 = g->M0 ? g->M0 : (em0 ? std::max(2, atoi(em0)) : (g->nb > 0 ? 32 : 16)), Mup = g->Mup ? g->Mup : (emu ? std::max(2, atoi(emu)) : 8);
+  int M0 = g->M0 ? g->M0 : (em0 ? std::max(2, atoi(em0)) : (g->nb > 0 ? 32 : 16));
+  const int Mup = g->Mup ? g->Mup : (emu ? std::max(2, atoi(emu)) : 8);
+  if (!g->M0 && !em0 && bs == 12 && g->W == 64) {
+    // the panel kernel runs one resident wave of persistent CTAs, each walking ceil(nseg / slots) segments of M0 (+ a closing
+    // separator) states one after the other: pick the segment length that minimises that serial depth (whole rounds - a
+    // 100k-state chain on 148 x 5 slots wants 46, not 32); ties go to the longer segment (fewer separators for the next level)
+    const int slots = sms * fwd_blocks_per_sm(bs, g->W), m0 = g->N - g->extL - g->extR;
+    long long best = -1;
+    for (int M = 12; M <= 63; M++) {
+      const int nseg = (m0 > 0 ? (m0 - 1) / M : 0) + 1;
+      const long long cost = (long long)((nseg + slots - 1) / slots) * (M + 2);
+      if (best < 0 || cost <= best) { best = cost; M0 = M; }
+    }
+  }
   const int fstride = 2 * bs * bs + bs * g->w;
   int n = g->N, lev = 0;
   while (true) {
@@ -599,6 +619,15 @@ template <int G> static int launch_linearize(gpb_graph* g, const double* X, cons
   constexpr int NT = 128, SR = GroupTraits<G>::PS + GroupTraits<G>::D;
   const int nb1 = (g->nint + NT - 1) / NT, nbA = (g->nA + NT - 1) / NT, nbB = (g->nB + NT - 1) / NT;
   const size_t smem = (size_t)(NT + 1) * SR * sizeof(double);
+  // the generic (non-interpolated) factors are few but slow per thread: they run on a forked stream beside the two bulk kernels
+  if (nbB > 0) {
+    CUDA_TRY(cudaEventRecord(g->ev_fork, g->stream));
+    CUDA_TRY(cudaStreamWaitEvent(g->stream2, g->ev_fork, 0));
+    k_lin_extra<G, 1, NT><<<nbB, NT, 0, g->stream2>>>(g->d_listB, g->nB, X, land, g->d_xkind, g->d_xsa, g->d_xsb, g->d_xl, g->d_xrow, g->d_xprm, g->d_XR[buf],
+                                                       g->d_errpart + nb1 + nbA, g->NX, g->NXRp, wantJ);
+    CUDA_TRY(cudaEventRecord(g->ev_join, g->stream2));
+    g->launches++;
+  }
   k_lin_gp<G, NT><<<nb1, NT, smem, g->stream>>>(X, g->d_dt, g->d_qc, g->d_Rq, g->d_AB[buf], g->d_errpart, g->nint, g->NFp, wantJ);
   g->launches++;
   if (nbA > 0) {
@@ -606,11 +635,7 @@ template <int G> static int launch_linearize(gpb_graph* g, const double* X, cons
                                                       g->d_errpart + nb1, g->NX, g->NXRp, wantJ);
     g->launches++;
   }
-  if (nbB > 0) {
-    k_lin_extra<G, 1, NT><<<nbB, NT, 0, g->stream>>>(g->d_listB, g->nB, X, land, g->d_xkind, g->d_xsa, g->d_xsb, g->d_xl, g->d_xrow, g->d_xprm, g->d_XR[buf],
-                                                      g->d_errpart + nb1 + nbA, g->NX, g->NXRp, wantJ);
-    g->launches++;
-  }
+  if (nbB > 0) CUDA_TRY(cudaStreamWaitEvent(g->stream, g->ev_join, 0));
   k_sum_partials<<<1, 256, 0, g->stream>>>(g->d_errpart, nb1 + nbA + nbB, g->d_scal, 0);
   g->launches++;
   CUDA_TRY(cudaGetLastError());
@@ -670,8 +695,8 @@ static int launch_fwd_level(gpb_graph* g, int buf, double lambda, int lev) {
   a.frec = L.frec; a.fstride = fstride; a.cseg = L.cseg; a.flag = g->d_flag;
   if (bs == 12 && g->W == 64) {
     // spine first (warp per segment: the latency-bound 12x12 recurrence wants many independent warps), then the tensor-pipe panel
-    const int spine_ctas = std::min((L.nseg + 7) / 8, 2 * g->sms);
-    k_spine<12><<<spine_ctas, 256, 0, g->stream>>>(a);
+    const int spine_ctas = std::min(L.nseg, 16 * g->sms);
+    k_spine<12><<<spine_ctas, 32, 0, g->stream>>>(a);
     if (g->old_panel) k_panel<12><<<L.ncta, 64, 0, g->stream>>>(a);
     else k_panel4<12><<<L.ncta, 128, 0, g->stream>>>(a);
     g->launches += 2;

@@ -548,6 +548,44 @@ __device__ __forceinline__ bool warp_chol_inverse_regs(const double* Dsrc, doubl
   return ok;
 }
 
+// Row-per-lane Cholesky with the triangular inverse fused into the same pivot loop: lane r holds row r of the SPD block AND
+// builds column r of X = L^-1.  At pivot j the column of L travels by shuffles (lcj = L[cc][j]); the same values feed the
+// trailing update  A[r][cc] -= L[r][j] L[cc][j]  and the forward substitution  sv[cc] += L[cc][j] X[j][r], so the inverse costs
+// one extra FMA per shuffle and no data movement of its own.  Only the lower triangle of the input row is used.
+// Output: Li (shared, column-major, full block incl. the zero upper part).  Lanes >= BS shadow row BS-1.
+// 1/sqrt(x) for a positive, normal x: the hardware seed (MUFU.RSQ64H, ~20 bits) and two Newton steps; no special-case branches
+__device__ __forceinline__ double rsqrt_pos(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double hx = 0.5 * x;
+  y = y * fma(-hx * y, y, 1.5);
+  y = y * fma(-hx * y, y, 1.5);
+  return y;
+}
+template <int BS>
+__device__ __forceinline__ bool warp_chol_inverse_fused(double (&arow)[BS], double* __restrict__ Li, int lane) {
+  double sv[BS];
+#pragma unroll
+  for (int cc = 0; cc < BS; cc++) sv[cc] = 0.0;
+  bool ok = true;
+#pragma unroll
+  for (int j = 0; j < BS; j++) {
+    const double piv = __shfl_sync(0xffffffffu, arow[j], j);
+    ok &= (piv > 0.0);
+    const double inv = rsqrt_pos(piv > 0.0 ? piv : 1.0);
+    const double lrj = (lane == j) ? piv * inv : arow[j] * inv;
+    const double xj = (lane == j) ? inv : (lane > j ? 0.0 : -sv[j] * inv);
+    if (lane < BS) Li[j + lane * BS] = xj;
+#pragma unroll
+    for (int cc = j + 1; cc < BS; cc++) {
+      const double lcj = __shfl_sync(0xffffffffu, lrj, cc);
+      arow[cc] -= lrj * lcj;
+      sv[cc] += lcj * xj;
+    }
+  }
+  return ok;
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // Warp-specialised forward sweep (BS = 12, panel width 64): the production path for SE(3) graphs with landmarks.
 //   warp 0 ("factor warp")  walks the chain's serial recurrence  D'_i = D_i - Le_{i-1} Le_{i-1}^T  ->  L_i^-1  ->  Le_i = E_i L_i^-T
@@ -905,49 +943,46 @@ __global__ void __launch_bounds__(96, 4) k_fwd_ws(const FwdArgs a) {
 // per SM — the recurrence is latency-bound (12 dependent pivots per state), and only thread-level parallelism hides that.
 // k_panel then streams the stored (L^-1, Le) and does nothing but tensor-pipe products: Y = L^-1 P, P' = own - Le Y, S += Y^T Y.
 template <int BS>
-__global__ void __launch_bounds__(256, 2) k_spine(const FwdArgs a) {
-  constexpr int WPC = 8, REC0 = 2 * BS * BS + BS, REC1 = 3 * BS * BS + 2 * BS, NV = (BS * BS + 31) / 32;
-  __shared__ double sDm[WPC][BS * BS], sDn[WPC][BS * BS], sLi[WPC][BS * BS], sLe[WPC][BS * BS];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gi = lane >> 2, ti = lane & 3;
-  double* Dm = sDm[warp]; double* Dn = sDn[warp]; double* Li = sLi[warp]; double* Le = sLe[warp];
+__global__ void __launch_bounds__(32, 16) k_spine(const FwdArgs a) {
+  // ONE WARP PER CTA: segment and state loops then depend on blockIdx only, so the compiler can prove the warp converged at
+  // every shuffle (with several warps per CTA each __shfl_sync was wrapped in WARPSYNC / BSSY / ENDCOLLECTIVE sequences)
+  constexpr int REC0 = 2 * BS * BS + BS, REC1 = 3 * BS * BS + 2 * BS;
+  __shared__ double Dn[BS * BS], Li[BS * BS], Le[BS * BS];
+  const int lane = threadIdx.x, gi = lane >> 2, ti = lane & 3;
+  const int rr = lane < BS ? lane : BS - 1;
   const bool first = a.first_level != 0;
   const int RECS = first ? REC0 : REC1, oE = first ? BS * BS : 2 * BS * BS;
-  const double lambda = *a.lambda_ptr;
-  for (int k = lane; k < BS * BS; k += 32) Li[k] = 0.0;  // strictly-upper part of L^-1 stays zero
-  // D (lane-distributed, NV values per lane) and the A-fragments of E of one state, fetched one state ahead into registers
-  double dv[NV], ev[2][3];
+  const double lambda = first ? *a.lambda_ptr : 0.0;
+  // row rr of D (the layout the factorisation wants) and the A-fragments of E of one state, fetched one state ahead into registers
+  double drow[BS], ev[2][3];
   auto fetch = [&](int i, bool want_e) {
     const double* r = a.rec + (size_t)i * RECS;
 #pragma unroll
-    for (int m = 0; m < NV; m++) { const int k = lane + 32 * m; dv[m] = (k < BS * BS) ? (first ? r[k] : r[k] + r[BS * BS + k]) : 0.0; }
+    for (int cc = 0; cc < BS; cc++) drow[cc] = first ? r[rr + cc * BS] : r[rr + cc * BS] + r[BS * BS + rr + cc * BS];
 #pragma unroll
     for (int mt = 0; mt < 2; mt++)
 #pragma unroll
       for (int sK = 0; sK < 3; sK++) ev[mt][sK] = (want_e && 8 * mt + gi < BS) ? r[oE + (8 * mt + gi) + (4 * sK + ti) * BS] : 0.0;
   };
-  const int nwarps = gridDim.x * WPC;
-  for (int seg = blockIdx.x * WPC + warp; seg < a.nseg; seg += nwarps) {
+  for (int seg = blockIdx.x; seg < a.nseg; seg += gridDim.x) {
     const SegGeom sg = seg_geom(seg, a.n, a.M, a.S, a.extL, a.extR);
     const int q = sg.q, i0 = sg.i0, i1 = sg.i1;
     const int ilast = (q >= 0) ? q : i1;
     for (int k = lane; k < BS * BS; k += 32) Dn[k] = 0.0;
     if (i0 <= ilast) fetch(i0, (i0 < i1) || (q >= 0 && i0 <= i1));
     __syncwarp();
+#pragma unroll 1
     for (int i = i0; i <= i1; i++) {
       const bool has_next = (i < i1) || (q >= 0);
+      double arow[BS], ec[2][3];
 #pragma unroll
-      for (int m = 0; m < NV; m++) {
-        const int k = lane + 32 * m;
-        if (k < BS * BS) Dm[k] = dv[m] + Dn[k] + ((first && (k % (BS + 1)) == 0) ? lambda : 0.0);
-      }
-      double ec[2][3];
+      for (int cc = 0; cc < BS; cc++) arow[cc] = drow[cc] + Dn[rr + cc * BS] + (cc == rr ? lambda : 0.0);
 #pragma unroll
       for (int mt = 0; mt < 2; mt++)
 #pragma unroll
         for (int sK = 0; sK < 3; sK++) ec[mt][sK] = ev[mt][sK];
       if (i + 1 <= ilast) fetch(i + 1, (i + 1 < i1) || (q >= 0 && i + 1 <= i1));  // next state's loads fly during this factorisation
-      __syncwarp();
-      const bool ok = warp_chol_inverse_regs<BS>(Dm, Dm, Li, lane);
+      const bool ok = warp_chol_inverse_fused<BS>(arow, Li, lane);
       if (!ok && lane == 0) *a.flag = 1;
       __syncwarp();
       double* F = a.frec + (size_t)i * a.fstride;
@@ -983,13 +1018,10 @@ __global__ void __launch_bounds__(256, 2) k_spine(const FwdArgs a) {
       }
       __syncwarp();
     }
-    if (q >= 0) {  // D1 of the right separator: its own block (fetched last) + the last Schur update (+ damping at level 0)
+    if (q >= 0 && lane < BS) {  // D1 of the right separator: its own block (fetched last) + the last Schur update (+ damping at level 0)
       double* R = a.rec_out + (size_t)sg.qo * REC1;
 #pragma unroll
-      for (int m = 0; m < NV; m++) {
-        const int k = lane + 32 * m;
-        if (k < BS * BS) R[k] = dv[m] + Dn[k] + ((first && (k % (BS + 1)) == 0) ? lambda : 0.0);
-      }
+      for (int cc = 0; cc < BS; cc++) R[rr + cc * BS] = drow[cc] + Dn[rr + cc * BS] + (cc == rr ? lambda : 0.0);
     }
     __syncwarp();
   }
