@@ -76,7 +76,7 @@ struct gpb_graph {
   int *d_bsoff = nullptr, *d_bsrow = nullptr, *d_bsside = nullptr;  // per-state CSR of landmark-bearing rows (level-0 border gather)
   double* d_bent = nullptr; int nbent = 0;                          // the same rows packed as 128-byte entries (k_border_pack)
   int rank = 0, world = 1, nsep = 0, R = 0, sms = 148;
-  bool old_panel = false;
+  bool old_panel = false, generic_fwd = false;
   gpb_allreduce_fn allreduce = nullptr; void* allreduce_ctx = nullptr;
   double* d_topbuf = nullptr; double cur_error_local = 0; int n_allreduce = 0;
   double* d_lambda = nullptr;
@@ -545,6 +545,7 @@ int gpb_graph_finalize(gpb_graph* g, int device) {
   g->sms = sms;
   // segment lengths: explicit setting > environment (tuning aid) > defaults
   const char* em0 = getenv("GPB_M0"); const char* emu = getenv("GPB_MUP");
+  g->generic_fwd = getenv("GPB_GENERIC_FWD") != nullptr;  // A/B switch: one-kernel generic forward sweep (k_fwd<12,64>)
   g->old_panel = getenv("GPB_OLD_PANEL") != nullptr;  // A/B switch while the four-warp panel kernel is being validated
   int M0 = g->M0 ? g->M0 : (em0 ? std::max(2, atoi(em0)) : (g->nb > 0 ? 32 : 16));
   const int Mup = g->Mup ? g->Mup : (emu ? std::max(2, atoi(emu)) : 8);
@@ -693,7 +694,7 @@ static int launch_fwd_level(gpb_graph* g, int buf, double lambda, int lev) {
   a.lambda_ptr = g->d_lambda;
   a.rec_out = lev + 1 < nlev ? g->levels[lev + 1].rec : nullptr; a.brec_out = lev + 1 < nlev ? g->levels[lev + 1].brec : nullptr;
   a.frec = L.frec; a.fstride = fstride; a.cseg = L.cseg; a.flag = g->d_flag;
-  if (bs == 12 && g->W == 64) {
+  if (bs == 12 && g->W == 64 && !g->generic_fwd) {
     // spine first (warp per segment: the latency-bound 12x12 recurrence wants many independent warps), then the tensor-pipe panel
     const int spine_ctas = std::min(L.nseg, 16 * g->sms);
     k_spine<12><<<spine_ctas, 32, 0, g->stream>>>(a);

@@ -36,6 +36,8 @@ def small_cfg(name, n, **kw):
 
 CASES = {
     "pose3": dict(name="C3", n=300, n_landmarks=4, prior_every=40),
+    # 16 landmarks -> 64-column panel: the production SE(3) kernels (k_spine + k_panel4), which narrower borders never reach
+    "pose3_wide": dict(name="C3", n=333, n_landmarks=16, prior_every=40),
     "pose3_chain": dict(name="C2", n=257, prior_every=30),
     "pose2": dict(name="C1", n=200),
     "rot3": dict(name="C4", n=301),
@@ -86,7 +88,7 @@ def make_pair(case):
     return g, o
 
 
-ALL = ["pose3", "pose3_chain", "pose2", "rot3", "linear"]
+ALL = ["pose3", "pose3_wide", "pose3_chain", "pose2", "rot3", "linear"]
 
 
 @pytest.mark.parametrize("case", ALL)
@@ -145,11 +147,13 @@ def test_optimize_matches_oracle(case, use_lm):
         assert np.abs(Lg - Lo).max() <= 1e-6
 
 
+@pytest.mark.parametrize("n_landmarks", [2, 16])
 @pytest.mark.parametrize("n", [2, 3, 16, 17, 18, 33, 129, 130])
-def test_segment_boundaries(n):
-    """chain lengths around the segment cuts, several segment lengths: same delta as a dense solve"""
+def test_segment_boundaries(n, n_landmarks):
+    """chain lengths around the segment cuts, several segment lengths, narrow (generic kernel) and 64-column (spine + panel
+    kernels) borders: same delta as a dense solve"""
     for seglen in ((2, 2), (4, 3), (16, 8), None):
-        cfg = small_cfg("C3", n, n_landmarks=2, prior_every=5, range_per_state=0.7)
+        cfg = small_cfg("C3", n, n_landmarks=n_landmarks, prior_every=5, range_per_state=0.7)
         g, o, _ = both(cfg, seglen)
         g.linearize()
         Hg, gg = g.normal_equations_dense()
@@ -191,31 +195,40 @@ def test_reference_two_state_optimizations():
 
 
 def test_full_size_properties():
-    """BASELINE config C3 at full size (100k SE(3) states, 50k interpolated ranges, 16 landmarks): size-independent properties —
-    LM never increases the error (each accepted step passed the fidelity test), the optimiser reaches a fixed point where
-    the Gauss-Newton step vanishes (normal equations solved: gradient ~ 0), and a second engine instance with different
-    segment lengths (a different elimination order) reaches the same solution to 1e-6."""
+    """BASELINE config C3 at full size (100k SE(3) states, 50k interpolated ranges, 16 landmarks), size-independent properties:
+    (i) two engine instances with different segment lengths (= different elimination orders of the same normal equations)
+    return the same Gauss-Newton / damped step; (ii) LM never increases the error (every accepted step passed the fidelity
+    test); (iii) both instances converge (GTSAM's stop rule) to the same solution to 1e-6; (iv) one Gauss-Newton iteration
+    from the initial values lands where the CPU oracle's does (<= 1e-6, north_star's tolerance).
+    Not asserted: that the GN step vanishes at the LM optimum - the tail of the trajectory (range-only beyond the last pose
+    prior) holds a weakly observable mode on which plain GN converges linearly, identically in the oracle and in the engine."""
     cfg = synth.config("C3")
     g, truth = synth.build(cfg, lambda grp, n, l: gb.Graph(grp, n, l))
-    errs = [g.linearize()]
-    for _ in range(8):
-        st = g.optimize(n_iter=1, use_lm=True)
-        errs.append(st.error_final)
-    assert all(b <= a * (1 + 1e-12) for a, b in zip(errs, errs[1:])), errs
-    st = g.optimize(use_lm=True)
-    assert st.status == 0
-    for _ in range(3):
-        g.optimize(n_iter=1, use_lm=False)
-    ds, dl = g.solve_delta(0.0)
-    assert np.abs(ds).max() < 1e-5 and np.abs(dl).max() < 1e-5, (np.abs(ds).max(), np.abs(dl).max())
-    P1, V1, L1 = g.get_values()
     def mk(grp, n, l):
         h = gb.Graph(grp, n, l); h.set_segment_length(20, 5); return h
     g2, _ = synth.build(cfg, mk)
+    e1, e2 = g.linearize(), g2.linearize()
+    assert e1 == e2
+    for lam in (0.0, 1e-3):
+        ds1, dl1 = g.solve_delta(lam); ds2, dl2 = g2.solve_delta(lam)
+        assert np.abs(ds1 - ds2).max() <= 1e-8 * max(1.0, np.abs(ds1).max()), (lam, np.abs(ds1 - ds2).max())
+        assert np.abs(dl1 - dl2).max() <= 1e-8 * max(1.0, np.abs(dl1).max())
+    # (iv) first: one GN iteration of a third instance against the oracle at full size
+    g3, _ = synth.build(cfg, lambda grp, n, l: gb.Graph(grp, n, l))
+    o, _ = synth.build(cfg, lambda grp, n, l: po.Graph(grp, n, l))
+    o.set_threads(po.hardware_threads())
+    sg = g3.optimize(n_iter=1, use_lm=False); so = o.optimize(n_iter=1, use_lm=False)
+    assert abs(sg.error_final - so.error_final) <= 1e-7 * so.error_final
+    Pg, Vg, Lg = g3.get_values(); Po, Vo, Lo = o.get_values()
+    assert np.abs(Pg - Po).max() <= 1e-6 and np.abs(Vg - Vo).max() <= 1e-6 and np.abs(Lg - Lo).max() <= 1e-6
+    del g3, o
+    errs = [e1]
     for _ in range(8):
-        g2.optimize(n_iter=1, use_lm=True)
-    g2.optimize(use_lm=True)
-    for _ in range(3):
-        g2.optimize(n_iter=1, use_lm=False)
-    P2, V2, L2 = g2.get_values()
+        st = g.optimize(n_iter=1, use_lm=True); g2.optimize(n_iter=1, use_lm=True)
+        errs.append(st.error_final)
+    assert all(b <= a * (1 + 1e-12) for a, b in zip(errs, errs[1:])), errs
+    st = g.optimize(use_lm=True); st2 = g2.optimize(use_lm=True)
+    assert st.status == 0 and st2.status == 0 and st.iterations == st2.iterations
+    assert abs(st.error_final - st2.error_final) <= 1e-9 * st.error_final
+    P1, V1, L1 = g.get_values(); P2, V2, L2 = g2.get_values()
     assert np.abs(P1 - P2).max() < 1e-6 and np.abs(V1 - V2).max() < 1e-6 and np.abs(L1 - L2).max() < 1e-6
