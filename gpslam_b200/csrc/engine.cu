@@ -76,7 +76,7 @@ struct gpb_graph {
   int *d_bsoff = nullptr, *d_bsrow = nullptr, *d_bsside = nullptr;  // per-state CSR of landmark-bearing rows (level-0 border gather)
   double* d_bent = nullptr; int nbent = 0;                          // the same rows packed as 128-byte entries (k_border_pack)
   int rank = 0, world = 1, nsep = 0, R = 0, sms = 148;
-  bool old_panel = false, generic_fwd = false;
+  bool old_panel = false, generic_fwd = false, old_spine = false;
   gpb_allreduce_fn allreduce = nullptr; void* allreduce_ctx = nullptr;
   double* d_topbuf = nullptr; double cur_error_local = 0; int n_allreduce = 0;
   double* d_lambda = nullptr;
@@ -447,6 +447,7 @@ int gpb_graph_finalize(gpb_graph* g, int device) {
   CUDA_TRY(cudaStreamCreateWithFlags(&g->stream2, cudaStreamNonBlocking));
   CUDA_TRY(cudaEventCreateWithFlags(&g->ev_fork, cudaEventDisableTiming));
   CUDA_TRY(cudaEventCreateWithFlags(&g->ev_join, cudaEventDisableTiming));
+  CUDA_TRY(cudaFuncSetAttribute(k_small_solve<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_solve_smem(SMALL_SOLVE_MAX)));
   const int D = g->D, bs = g->bs, DL = g->DL;
   g->nb = g->L * DL; g->w = bs + g->nb + 1;
   g->W = g->w <= 16 ? 16 : g->w <= 32 ? 32 : 64;
@@ -528,7 +529,7 @@ int gpb_graph_finalize(gpb_graph* g, int device) {
   if ((rc = dev_upload(g, &g->d_lmoff, lmoff))) return rc;
   if ((rc = dev_upload(g, &g->d_lmrows, lmrows))) return rc;
   if ((rc = dev_alloc(g, &g->d_HREC, (size_t)g->N * (2 * bs * bs + bs)))) return rc;
-  g->nerrpart = (g->nint + 127) / 128 + (g->NX + 127) / 128 + (g->N + 127) / 128 + 16;
+  g->nerrpart = (g->nint + 127) / 128 + (g->NX + 127) / 128 + (g->NX + 3) / 4 + (g->N + 127) / 128 + 16;
   if ((rc = dev_alloc(g, &g->d_errpart, (size_t)2 * g->nerrpart))) return rc;
   if ((rc = dev_alloc(g, &g->d_scal, 8))) return rc;
   if ((rc = dev_alloc(g, &g->d_flag, 1))) return rc;
@@ -546,6 +547,7 @@ int gpb_graph_finalize(gpb_graph* g, int device) {
   // segment lengths: explicit setting > environment (tuning aid) > defaults
   const char* em0 = getenv("GPB_M0"); const char* emu = getenv("GPB_MUP");
   g->generic_fwd = getenv("GPB_GENERIC_FWD") != nullptr;  // A/B switch: one-kernel generic forward sweep (k_fwd<12,64>)
+  g->old_spine = getenv("GPB_OLD_SPINE") != nullptr;
   g->old_panel = getenv("GPB_OLD_PANEL") != nullptr;  // A/B switch while the four-warp panel kernel is being validated
   int M0 = g->M0 ? g->M0 : (em0 ? std::max(2, atoi(em0)) : (g->nb > 0 ? 32 : 16));
   const int Mup = g->Mup ? g->Mup : (emu ? std::max(2, atoi(emu)) : 8);
@@ -596,7 +598,7 @@ int gpb_graph_finalize(gpb_graph* g, int device) {
   if ((rc = dev_alloc(g, &g->d_Csum, (size_t)std::max(centries, 1)))) return rc;
   g->nsep = g->world - 1; g->R = g->nsep * bs + g->nb;
   if (g->world > 1) {
-    if (g->R > 256) return fail(GPB_ERR_UNSUPPORTED, "reduced system larger than 256 unknowns");
+    if (g->R > SMALL_SOLVE_MAX) return fail(GPB_ERR_UNSUPPORTED, "reduced system larger than SMALL_SOLVE_MAX unknowns");
     if ((rc = dev_alloc(g, &g->d_topbuf, (size_t)g->R * g->R + g->R + 4))) return rc;
   }
   // page-lock the host staging so the H2D / D2H copies of the values run at full PCIe rate
@@ -618,7 +620,7 @@ int gpb_graph_finalize(gpb_graph* g, int device) {
 
 template <int G> static int launch_linearize(gpb_graph* g, const double* X, const double* land, int buf, int wantJ) {
   constexpr int NT = 128, SR = GroupTraits<G>::PS + GroupTraits<G>::D;
-  const int nb1 = (g->nint + NT - 1) / NT, nbA = (g->nA + NT - 1) / NT, nbB = (g->nB + NT - 1) / NT;
+  const int nb1 = (g->nint + NT - 1) / NT, nbA = (g->nA + NT - 1) / NT, nbB = (int)(((size_t)g->nB * 32 + NT - 1) / NT);  // generic factors: one warp each
   const size_t smem = (size_t)(NT + 1) * SR * sizeof(double);
   // the generic (non-interpolated) factors are few but slow per thread: they run on a forked stream beside the two bulk kernels
   if (nbB > 0) {
@@ -659,7 +661,7 @@ template <int G> static int launch_assemble(gpb_graph* g, int buf) {
   g->launches++;
   if (g->nb) {
     CUDA_TRY(cudaMemsetAsync(g->d_Cbase, 0, (size_t)(g->nb * g->nb + g->nb) * sizeof(double), g->stream));
-    k_landmark_base<128><<<g->L, 128, 0, g->stream>>>(g->d_XR[buf], g->d_lmoff, g->d_lmrows, g->NXRp, 2 * bs, g->DL, g->nb, g->d_Cbase);
+    k_landmark_base<512><<<g->L, 512, 0, g->stream>>>(g->d_XR[buf], g->d_lmoff, g->d_lmrows, g->NXRp, 2 * bs, g->DL, g->nb, g->d_Cbase);
     g->launches++;
     if (bs == 12 && g->W == 64 && g->nbent > 0) {
       k_border_pack<<<(g->nbent * 16 + 255) / 256, 256, 0, g->stream>>>(g->d_XR[buf], g->d_bsrow, g->d_bsside, g->d_rowland, g->nbent, bs, g->DL, g->NXRp, g->d_bent);
@@ -697,7 +699,8 @@ static int launch_fwd_level(gpb_graph* g, int buf, double lambda, int lev) {
   if (bs == 12 && g->W == 64 && !g->generic_fwd) {
     // spine first (warp per segment: the latency-bound 12x12 recurrence wants many independent warps), then the tensor-pipe panel
     const int spine_ctas = std::min(L.nseg, 16 * g->sms);
-    k_spine<12><<<spine_ctas, 32, 0, g->stream>>>(a);
+    if (g->old_spine) k_spine_v1<12><<<spine_ctas, 32, 0, g->stream>>>(a);
+    else k_spine<12><<<spine_ctas, 32, 0, g->stream>>>(a);
     if (g->old_panel) k_panel<12><<<L.ncta, 64, 0, g->stream>>>(a);
     else k_panel4<12><<<L.ncta, 128, 0, g->stream>>>(a);
     g->launches += 2;
@@ -728,7 +731,7 @@ static int solve_landmarks_local(gpb_graph* g, double lambda) {
   const int nb = g->nb, centries = nb * nb + nb, nel = num_elim_levels(g);
   if (nb) {
     k_cseg_final<<<(centries + 127) / 128, 128, 0, g->stream>>>(g->d_Cbase, g->d_Cpart, 16 * nel, centries, g->d_Csum);
-    k_landmark_solve<128><<<1, 128, (size_t)centries * sizeof(double), g->stream>>>(g->d_Csum, nb, g->d_lambda, g->d_xlm, g->d_flag);
+    k_small_solve<256><<<1, 256, small_solve_smem(nb), g->stream>>>(g->d_Csum, g->d_Csum + (size_t)nb * nb, nb, 0, g->d_lambda, g->d_xlm, g->d_flag, 2);
     g->launches += 2;
   }
   return GPB_OK;
@@ -773,7 +776,7 @@ static int solve_system_dist(gpb_graph* g, int buf, double lambda, double err_lo
   if ((rc = dist_allreduce(g, g->d_topbuf, total))) return rc;
   double sc[4] = {0, 0, 0, 0};
   if (!async) CUDA_TRY(cudaMemcpyAsync(sc, g->d_topbuf + (size_t)R * R + R, 4 * sizeof(double), cudaMemcpyDeviceToHost, g->stream));
-  k_top_solve<256><<<1, 256, 0, g->stream>>>(g->d_topbuf, R, g->nsep * g->bs, g->d_lambda, g->d_flag);
+  k_small_solve<256><<<1, 256, small_solve_smem(R), g->stream>>>(g->d_topbuf, g->d_topbuf + (size_t)R * R, R, g->nsep * g->bs, g->d_lambda, g->d_topbuf + (size_t)R * R, g->d_flag, 3);
   k_top_scatter<<<1, 64, 0, g->stream>>>(g->d_topbuf, R, g->bs, nb, g->nsep, g->rank, g->extL, g->extR, g->levels.back().xsol, g->d_xlm);
   g->launches += 2;
   if ((rc = solve_backward(g))) return rc;
@@ -1172,7 +1175,7 @@ int gpb_time_stage(gpb_graph* g, int stage, int reps, double* ms_out) {
     constexpr int G = decltype(tag)::value; constexpr int SR = GroupTraits<G>::PS + GroupTraits<G>::D;
     k_lin_gp<G, NT><<<nb1, NT, (size_t)(NT + 1) * SR * sizeof(double), g->stream>>>(g->d_X, g->d_dt, g->d_qc, g->d_Rq, g->d_AB[other], g->d_errpart, g->nint, g->NFp, 1);
   };
-  const int nbA = (g->nA + NT - 1) / NT, nbB = (g->nB + NT - 1) / NT;
+  const int nbA = (g->nA + NT - 1) / NT, nbB = (int)(((size_t)g->nB * 32 + NT - 1) / NT);  // generic factors: one warp each
   auto extra_only = [&](auto tag) {
     constexpr int G = decltype(tag)::value;
     if (nbA) k_lin_extra<G, 0, NT><<<nbA, NT, 0, g->stream>>>(g->d_listA, g->nA, g->d_X, g->d_land, g->d_xkind, g->d_xsa, g->d_xsb, g->d_xl, g->d_xrow, g->d_xprm, g->d_XR[other], g->d_errpart + nb1, g->NX, g->NXRp, 1);

@@ -171,37 +171,53 @@ __device__ __forceinline__ void extra_rows(int kind, const double* __restrict__ 
     }
     return;
   }
-  } else {
-  // ---- factors with dense m x m sqrt information R and m <= 6: unwhitened e[m], H over the row layout, then whiten
-  double e[6];
-  double H[6][NC - 1];
+  }
+}
+
+// CLS 1 (priors, between incl. loop closures, plain 2-D factors): ONE WARP PER FACTOR.  Every lane evaluates the factor's
+// residual e (m <= 6) and its small core Jacobian in registers (uniform across the warp - same factor, no divergence), lane c
+// then forms column c of the unwhitened Jacobian over the row layout [state a | state b | landmark] (lane NC-1: the rhs),
+// whitens it with the dense m x m sqrt information R and stores its m entries.  No local arrays, ~30x more parallelism than
+// a thread per factor - these factors are few (priors every 100th state) but sit on the iteration's critical path.
+template <int G>
+__device__ __forceinline__ void extra_rows_warp(int kind, const double* __restrict__ X, const double* __restrict__ land, int sa, int sb, int l,
+                                                const double* __restrict__ prm, bool wantJ, double* __restrict__ XR, int NXRp, int row0,
+                                                int lane, double& err) {
+  constexpr int D = GroupTraits<G>::D, PS = GroupTraits<G>::PS, SR = PS + D, DL = GroupTraits<G>::DL, bs = 2 * D;
+  constexpr int NC = 2 * bs + DL + 1;
+  static_assert(NC <= 32, "one lane per column of the row layout");
+  const double* Rm = prm + 20;
+  const int c = lane;
+  double e[6], h[6];
+#pragma unroll
+  for (int k = 0; k < 6; k++) { e[k] = 0.0; h[k] = 0.0; }
   int m = 0;
-#pragma unroll
-  for (int r = 0; r < 6; r++)
-#pragma unroll
-    for (int c = 0; c < NC - 1; c++) H[r][c] = 0.0;
   const int side = (sa >= 0) ? 0 : 1;          // single-state factors: a-part when sa valid, else b-part
   const int s = (sa >= 0) ? sa : sb;
   const int off = side * bs;
   if (kind == X_PRIOR_POSE) {
     m = D;
     const double* x = X + (size_t)s * SR;
-    if constexpr (G == G_POSE3) { const X6 d = se3_logmap(p3_between(p3_from_wire(prm + 4), p3_from_wire(x))); for (int k = 0; k < 6; k++) e[k] = elem(d, k); }
+    if constexpr (G == G_POSE3) { const X6 d = se3_logmap(p3_between(p3_from_wire(prm + 4), p3_from_wire(x)));
+#pragma unroll
+      for (int k = 0; k < 6; k++) e[k] = elem(d, k); }
     else if constexpr (G == G_ROT3) { const V3 d = so3_logmap(transpose(m3_from_wire(prm + 4)) * m3_from_wire(x)); e[0] = d.x; e[1] = d.y; e[2] = d.z; }
     else if constexpr (G == G_POSE2) { const P2 d = p2_between(p2(x[0], x[1], x[2]), p2(prm[4], prm[5], prm[6])); e[0] = -d.x; e[1] = -d.y; e[2] = -p2_theta(d); }
-    else { for (int k = 0; k < 3; k++) e[k] = x[k] - prm[4 + k]; }
+    else {
 #pragma unroll
-    for (int k = 0; k < D; k++) H[k][off + k] = 1.0;
+      for (int k = 0; k < 3; k++) e[k] = x[k] - prm[4 + k]; }
+#pragma unroll
+    for (int k = 0; k < D; k++) h[k] = (c == off + k) ? 1.0 : 0.0;
   } else if (kind == X_PRIOR_VEL) {
     m = D;
     const double* x = X + (size_t)s * SR + PS;
 #pragma unroll
-    for (int k = 0; k < D; k++) { e[k] = x[k] - prm[4 + k]; H[k][off + D + k] = 1.0; }
+    for (int k = 0; k < D; k++) { e[k] = x[k] - prm[4 + k]; h[k] = (c == off + D + k) ? 1.0 : 0.0; }
   } else if (kind == X_PRIOR_LANDMARK) {
     if constexpr (DL > 0) {
       m = DL;
 #pragma unroll
-      for (int k = 0; k < DL; k++) { e[k] = land[(size_t)l * DL + k] - prm[4 + k]; H[k][2 * bs + k] = 1.0; }
+      for (int k = 0; k < DL; k++) { e[k] = land[(size_t)l * DL + k] - prm[4 + k]; h[k] = (c == 2 * bs + k) ? 1.0 : 0.0; }
     }
   } else if (kind == X_BETWEEN) {
     m = D;
@@ -214,32 +230,39 @@ __device__ __forceinline__ void extra_rows(int kind, const double* __restrict__ 
     if constexpr (G == G_POSE3) {
       const P3 hx = p3_between(p3_from_wire(p), p3_from_wire(q));
       const X6 d = se3_logmap(p3_between(p3_from_wire(prm + 4), hx));
+#pragma unroll
       for (int k = 0; k < 6; k++) e[k] = elem(d, k);
       const L6 A = l6_adjoint(p3_inverse(hx));
 #pragma unroll
-      for (int r = 0; r < 6; r++)
+      for (int r = 0; r < 6; r++) {
 #pragma unroll
-        for (int c = 0; c < 6; c++) { H[r][o1 + c] = -elem(A, r, c); H[r][o2 + c] = (r == c) ? 1.0 : 0.0; }
+        for (int cc = 0; cc < 6; cc++) if (c == o1 + cc) h[r] = -elem(A, r, cc);
+        if (c == o2 + r) h[r] = 1.0;
+      }
     } else if constexpr (G == G_ROT3) {
       const M3 hx = transpose(m3_from_wire(p)) * m3_from_wire(q);
       const V3 d = so3_logmap(transpose(m3_from_wire(prm + 4)) * hx);
       e[0] = d.x; e[1] = d.y; e[2] = d.z;
 #pragma unroll
-      for (int r = 0; r < 3; r++)
+      for (int r = 0; r < 3; r++) {
 #pragma unroll
-        for (int c = 0; c < 3; c++) { H[r][o1 + c] = -hx.m[3 * c + r]; H[r][o2 + c] = (r == c) ? 1.0 : 0.0; }
+        for (int cc = 0; cc < 3; cc++) if (c == o1 + cc) h[r] = -hx.m[3 * cc + r];
+        if (c == o2 + r) h[r] = 1.0;
+      }
     } else if constexpr (G == G_POSE2) {
       const P2 hx = p2_between(p2(p[0], p[1], p[2]), p2(q[0], q[1], q[2]));
       const P2 d = p2_between(p2(prm[4], prm[5], prm[6]), hx);
       e[0] = d.x; e[1] = d.y; e[2] = p2_theta(d);
       const M3 A = p2_adjoint(p2_inverse(hx));
 #pragma unroll
-      for (int r = 0; r < 3; r++)
+      for (int r = 0; r < 3; r++) {
 #pragma unroll
-        for (int c = 0; c < 3; c++) { H[r][o1 + c] = -A.m[3 * r + c]; H[r][o2 + c] = (r == c) ? 1.0 : 0.0; }
+        for (int cc = 0; cc < 3; cc++) if (c == o1 + cc) h[r] = -A.m[3 * r + cc];
+        if (c == o2 + r) h[r] = 1.0;
+      }
     } else {
 #pragma unroll
-      for (int k = 0; k < 3; k++) { e[k] = (q[k] - p[k]) - prm[4 + k]; H[k][o1 + k] = -1.0; H[k][o2 + k] = 1.0; }
+      for (int k = 0; k < 3; k++) { e[k] = (q[k] - p[k]) - prm[4 + k]; h[k] = (c == o1 + k) ? -1.0 : ((c == o2 + k) ? 1.0 : 0.0); }
     }
   } else if (kind == X_RANGE_2D) {
     if constexpr (G == G_POSE2 || G == G_LINEAR) {
@@ -248,19 +271,19 @@ __device__ __forceinline__ void extra_rows(int kind, const double* __restrict__ 
       const double dx = land[(size_t)l * 2] - x[0], dy = land[(size_t)l * 2 + 1] - x[1];
       const double r = sqrt(dx * dx + dy * dy);
       e[0] = r - prm[2];
-      double hx, hy;
+      double hx, hy, h0, h1;
       if (G == G_LINEAR && !(fabs(r) > 1e-10)) { hx = 1; hy = 1; } else { hx = dx / r; hy = dy / r; }
-      if constexpr (G == G_POSE2) { const double c = cos(x[2]), sn = sin(x[2]); H[0][off] = -(hx * c + hy * sn); H[0][off + 1] = hx * sn - hy * c; }
-      else { H[0][off] = -hx; H[0][off + 1] = -hy; }
-      H[0][2 * bs] = hx; H[0][2 * bs + 1] = hy;
+      if constexpr (G == G_POSE2) { const double cs = cos(x[2]), sn = sin(x[2]); h0 = -(hx * cs + hy * sn); h1 = hx * sn - hy * cs; }
+      else { h0 = -hx; h1 = -hy; }
+      h[0] = (c == off) ? h0 : (c == off + 1) ? h1 : (c == 2 * bs) ? hx : (c == 2 * bs + 1) ? hy : 0.0;
     }
   } else if (kind == X_RANGE_BEARING_2D) {
     if constexpr (G == G_LINEAR) {
       m = 2;
       const double* x = X + (size_t)s * SR;
-      const double c = cos(x[2]), sn = sin(x[2]);
+      const double cs = cos(x[2]), sn = sin(x[2]);
       const double dx = land[(size_t)l * 2] - x[0], dy = land[(size_t)l * 2 + 1] - x[1];
-      const double rx = c * dx + sn * dy, ry = -sn * dx + c * dy;
+      const double rx = cs * dx + sn * dy, ry = -sn * dx + cs * dy;
       const double n = sqrt(rx * rx + ry * ry);
       const double ec = rx / n, es = ry / n, bc = cos(prm[3]), bsn = sin(prm[3]);
       const double d = sqrt(dx * dx + dy * dy);
@@ -271,39 +294,37 @@ __device__ __forceinline__ void extra_rows(int kind, const double* __restrict__ 
       double t0 = 0, t1 = 0;
       if (d > 1e-5) { t0 = -ry / (d * d); t1 = rx / (d * d); }
       // H11 = tmp * [ -R^T , (ry, -rx)^T ],  H12 = tmp * R^T ; R^T = [[c, s],[-s, c]]
-      H[0][off] = -(t0 * c - t1 * sn); H[0][off + 1] = -(t0 * sn + t1 * c); H[0][off + 2] = t0 * ry - t1 * rx;
-      H[1][off] = -hx; H[1][off + 1] = -hy;
-      H[0][2 * bs] = t0 * c - t1 * sn; H[0][2 * bs + 1] = t0 * sn + t1 * c;
-      H[1][2 * bs] = hx; H[1][2 * bs + 1] = hy;
+      const double g0 = t0 * cs - t1 * sn, g1 = t0 * sn + t1 * cs;
+      h[0] = (c == off) ? -g0 : (c == off + 1) ? -g1 : (c == off + 2) ? (t0 * ry - t1 * rx) : (c == 2 * bs) ? g0 : (c == 2 * bs + 1) ? g1 : 0.0;
+      h[1] = (c == off) ? -hx : (c == off + 1) ? -hy : (c == 2 * bs) ? hx : (c == 2 * bs + 1) ? hy : 0.0;
     }
   } else if (kind == X_ODOMETRY_2D) {
     if constexpr (G == G_LINEAR) {
       m = 3;
       const double* x1 = X + (size_t)sa * SR;
       const double* x2 = X + (size_t)sb * SR;
-      const double c = cos(x1[2]), sn = sin(x1[2]);
+      const double cs = cos(x1[2]), sn = sin(x1[2]);
       const double vx = x2[0] - x1[0], vy = x2[1] - x1[1];
-      const double qx = c * vx + sn * vy, qy = -sn * vx + c * vy;
+      const double qx = cs * vx + sn * vy, qy = -sn * vx + cs * vy;
       e[0] = qx - prm[4]; e[1] = qy - prm[5]; e[2] = (x2[2] - x1[2]) - prm[6];
-      H[0][0] = -c; H[0][1] = -sn; H[0][2] = qy; H[1][0] = sn; H[1][1] = -c; H[1][2] = -qx; H[2][2] = -1;
-      H[0][bs] = c; H[0][bs + 1] = sn; H[1][bs] = -sn; H[1][bs + 1] = c; H[2][bs + 2] = 1;
+      h[0] = (c == 0) ? -cs : (c == 1) ? -sn : (c == 2) ? qy : (c == bs) ? cs : (c == bs + 1) ? sn : 0.0;
+      h[1] = (c == 0) ? sn : (c == 1) ? -cs : (c == 2) ? -qx : (c == bs) ? -sn : (c == bs + 1) ? cs : 0.0;
+      h[2] = (c == 2) ? -1.0 : (c == bs + 2) ? 1.0 : 0.0;
     }
   }
-  // whiten: rows r: sum_{k>=r} R[r,k] (.)
-  for (int r = 0; r < m; r++) {
-    double be = 0;
-    for (int k = r; k < m; k++) be += Rm[r + k * m] * e[k];
-    err += 0.5 * be * be;
-    if (wantJ) {
+  // whiten: row r = sum_{k >= r} R[r,k] (.)   (R upper triangular, m x m column-major)
 #pragma unroll
-      for (int c = 0; c < NC - 1; c++) {
-        double a = 0;
-        for (int k = r; k < m; k++) a += Rm[r + k * m] * H[k][c];
-        put(row0 + r, c, a);
+  for (int r = 0; r < 6; r++) {
+    if (r < m) {
+      double be = 0.0, a = 0.0;
+#pragma unroll
+      for (int k = r; k < 6; k++) if (k < m) { const double rk = Rm[r + k * m]; be += rk * e[k]; a += rk * h[k]; }
+      if (lane == 0) err += 0.5 * be * be;
+      if (wantJ) {
+        if (c < NC - 1) XR[(size_t)c * NXRp + row0 + r] = a;
+        else if (c == NC - 1) XR[(size_t)c * NXRp + row0 + r] = -be;
       }
-      put(row0 + r, NC - 1, -be);
     }
-  }
   }
 }
 
@@ -315,9 +336,16 @@ __global__ void __launch_bounds__(NT) k_lin_extra(const int* __restrict__ list, 
   __shared__ double sred[NT / 32];
   const int t = blockIdx.x * NT + threadIdx.x;
   double err = 0.0;
-  if (t < nlist) {
-    const int f = list[t];
-    extra_rows<G, CLS>(xkind[f], X, land, xsa[f], xsb[f], xl[f], xprm + (size_t)f * XP_STRIDE, wantJ != 0, XR, NXRp, xrow[f], err);
+  if constexpr (CLS == 0) {
+    if (t < nlist) {
+      const int f = list[t];
+      extra_rows<G, CLS>(xkind[f], X, land, xsa[f], xsb[f], xl[f], xprm + (size_t)f * XP_STRIDE, wantJ != 0, XR, NXRp, xrow[f], err);
+    }
+  } else {
+    if ((t >> 5) < nlist) {  // one warp per factor
+      const int f = list[t >> 5];
+      extra_rows_warp<G>(xkind[f], X, land, xsa[f], xsb[f], xl[f], xprm + (size_t)f * XP_STRIDE, wantJ != 0, XR, NXRp, xrow[f], threadIdx.x & 31, err);
+    }
   }
   (void)nx;
   const double tot = block_sum<NT>(err, sred);

@@ -943,7 +943,7 @@ __global__ void __launch_bounds__(96, 4) k_fwd_ws(const FwdArgs a) {
 // per SM — the recurrence is latency-bound (12 dependent pivots per state), and only thread-level parallelism hides that.
 // k_panel then streams the stored (L^-1, Le) and does nothing but tensor-pipe products: Y = L^-1 P, P' = own - Le Y, S += Y^T Y.
 template <int BS>
-__global__ void __launch_bounds__(32, 16) k_spine(const FwdArgs a) {
+__global__ void __launch_bounds__(32, 16) k_spine_v1(const FwdArgs a) {
   // ONE WARP PER CTA: segment and state loops then depend on blockIdx only, so the compiler can prove the warp converged at
   // every shuffle (with several warps per CTA each __shfl_sync was wrapped in WARPSYNC / BSSY / ENDCOLLECTIVE sequences)
   constexpr int REC0 = 2 * BS * BS + BS, REC1 = 3 * BS * BS + 2 * BS;
@@ -1022,6 +1022,118 @@ __global__ void __launch_bounds__(32, 16) k_spine(const FwdArgs a) {
       double* R = a.rec_out + (size_t)sg.qo * REC1;
 #pragma unroll
       for (int cc = 0; cc < BS; cc++) R[rr + cc * BS] = drow[cc] + Dn[rr + cc * BS] + (cc == rr ? lambda : 0.0);
+    }
+    __syncwarp();
+  }
+}
+
+
+// Spine, second version: the block column [D_i ; E_i] (24 x 12) is factored as ONE panel.  Lanes 0..11 own the rows of D_i,
+// lanes 12..23 the rows of E_i = H_{i+1,i}; the right-looking pivot loop (one shuffle per column entry) then leaves the rows of
+// L_i in lanes 0..11 and the rows of Le_i = E_i L_i^-T in lanes 12..23 - Le costs no instruction of its own, and it no longer
+// waits for the inverse.  Lanes 0..11 also build column `lane` of L_i^-1 with one extra FMA per shuffle (needed by the panel
+// kernel and the back-substitution) and stream it straight to HBM from registers.  Only the Schur update Dn = -Le Le^T goes
+// through shared memory (Le out, 9 DMMA on the lower tiles, Dn back in the row-per-lane layout, read as 128-bit column loads
+// thanks to symmetry).  The next pivot is broadcast from an early copy (arow[j+1] - l^2 on its owner lane) so the pivot chain
+// is  shfl -> rsqrt -> mul  per column instead of waiting for the column broadcast.
+template <int BS>
+__global__ void __launch_bounds__(32, 16) k_spine(const FwdArgs a) {
+  static_assert(BS == 12, "spine kernel is specialised for 12 x 12 state blocks");
+  constexpr int REC0 = 2 * BS * BS + BS, REC1 = 3 * BS * BS + 2 * BS;
+  __shared__ __align__(16) double Les[BS * BS], Dn[BS * BS];
+  const int lane = threadIdx.x, gi = lane >> 2, ti = lane & 3;
+  const bool dl = lane < BS, el = lane >= BS && lane < 2 * BS;
+  const int rr = dl ? lane : (el ? lane - BS : 0);
+  const bool first = a.first_level != 0;
+  const int RECS = first ? REC0 : REC1, oE = first ? BS * BS : 2 * BS * BS;
+  const double lambda = first ? *a.lambda_ptr : 0.0;
+  double nrow[BS];  // next state's row: D (+ D2 above level 0) on lanes 0..11, E on lanes 12..23, zero elsewhere
+  auto fetch = [&](int i, bool want_e) {
+    const double* r = a.rec + (size_t)i * RECS;
+    const bool ld = dl || (el && want_e);
+    const double* p0 = r + (dl ? rr : oE + rr);
+#pragma unroll
+    for (int cc = 0; cc < BS; cc++) {
+      double v = ld ? p0[cc * BS] : 0.0;
+      if (!first && dl) v += r[BS * BS + rr + cc * BS];
+      nrow[cc] = v;
+    }
+  };
+  for (int seg = blockIdx.x; seg < a.nseg; seg += gridDim.x) {
+    const SegGeom sg = seg_geom(seg, a.n, a.M, a.S, a.extL, a.extR);
+    const int q = sg.q, i0 = sg.i0, i1 = sg.i1;
+    const int ilast = (q >= 0) ? q : i1;
+    for (int k = lane; k < BS * BS; k += 32) Dn[k] = 0.0;
+    if (i0 <= ilast) fetch(i0, (i0 < i1) || (q >= 0 && i0 <= i1));
+    __syncwarp();
+    bool ok = true;
+#pragma unroll 1
+    for (int i = i0; i <= i1; i++) {
+      const bool has_next = (i < i1) || (q >= 0);
+      double arow[BS], sv[BS];
+      {
+        const double* dn = Dn + rr * BS;  // column rr == row rr (symmetric)
+#pragma unroll
+        for (int cc = 0; cc < BS; cc += 2) {
+          const double2 t = *reinterpret_cast<const double2*>(dn + cc);
+          arow[cc] = nrow[cc] + (dl ? t.x : 0.0) + ((dl && cc == rr) ? lambda : 0.0);
+          arow[cc + 1] = nrow[cc + 1] + (dl ? t.y : 0.0) + ((dl && cc + 1 == rr) ? lambda : 0.0);
+        }
+      }
+      if (i + 1 <= ilast) fetch(i + 1, (i + 1 < i1) || (q >= 0 && i + 1 <= i1));  // next state's loads fly during this factorisation
+      double* F = a.frec + (size_t)i * a.fstride;
+#pragma unroll
+      for (int cc = 0; cc < BS; cc++) sv[cc] = 0.0;
+      double piv = __shfl_sync(0xffffffffu, arow[0], 0), xprev = 0.0;
+#pragma unroll
+      for (int j = 0; j < BS; j++) {
+        ok &= (piv > 0.0);
+        const double inv = rsqrt_pos(piv > 0.0 ? piv : 1.0);
+        const double lrj = (lane == j) ? piv * inv : arow[j] * inv;   // lanes 0..11: L[lane][j] (lane >= j); lanes 12..23: Le[rr][j]
+        if (j + 1 < BS) piv = __shfl_sync(0xffffffffu, fma(-lrj, lrj, arow[j + 1 < BS ? j + 1 : j]), j + 1);  // early copy of the next pivot
+        const double xj = (lane == j) ? inv : ((lane > j) ? 0.0 : -sv[j] * inv);   // X[j][lane], X = L^-1 (lanes 0..11)
+        if (j & 1) { if (dl) st128(F + (j - 1) + lane * BS, xprev, xj); } else xprev = xj;
+        if (el && has_next) { Les[rr + j * BS] = lrj; F[BS * BS + rr + j * BS] = lrj; }
+#pragma unroll
+        for (int cc = j + 1; cc < BS; cc++) {
+          const double lcj = __shfl_sync(0xffffffffu, lrj, cc);
+          arow[cc] = fma(-lrj, lcj, arow[cc]);
+          sv[cc] = fma(lcj, xj, sv[cc]);
+        }
+      }
+      __syncwarp();
+      if (has_next) {
+        // Dn = -Le Le^T on the lower 8x8 tiles; written back symmetric so that lane r reads its row as a contiguous column
+        double f[2][3];
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+          for (int sK = 0; sK < 3; sK++) f[mt][sK] = (8 * mt + gi < BS) ? Les[(8 * mt + gi) + (4 * sK + ti) * BS] : 0.0;
+        double c00a = 0.0, c00b = 0.0, c10a = 0.0, c10b = 0.0, c11a = 0.0, c11b = 0.0;
+#pragma unroll
+        for (int sK = 0; sK < 3; sK++) {
+          dmma884(c00a, c00b, f[0][sK], f[0][sK]);
+          dmma884(c10a, c10b, f[1][sK], f[0][sK]);
+          dmma884(c11a, c11b, f[1][sK], f[1][sK]);
+        }
+        __syncwarp();
+        // tile (0,0): element (gi, 2ti + {0,1}) -> stored at its transposed position (a contiguous pair)
+        st128(Dn + 2 * ti + gi * BS, -c00a, -c00b);
+        if (gi < 4) {
+          // tile (1,0): element (8 + gi, 2ti + {0,1}): upper copy as a pair, lower copy as two scalars
+          st128(Dn + 2 * ti + (8 + gi) * BS, -c10a, -c10b);
+          Dn[(8 + gi) + (2 * ti) * BS] = -c10a; Dn[(8 + gi) + (2 * ti + 1) * BS] = -c10b;
+          // tile (1,1): element (8 + gi, 8 + 2ti + {0,1}), 2ti + 1 < 4
+          if (ti < 2) st128(Dn + 8 + 2 * ti + (8 + gi) * BS, -c11a, -c11b);
+        }
+      }
+      __syncwarp();
+    }
+    if (!ok && lane == 0) *a.flag = 1;
+    if (q >= 0 && dl) {  // D1 of the right separator: its own block (fetched last) + the last Schur update (+ damping at level 0)
+      double* R = a.rec_out + (size_t)sg.qo * REC1;
+#pragma unroll
+      for (int cc = 0; cc < BS; cc++) R[rr + cc * BS] = nrow[cc] + Dn[cc + rr * BS] + (cc == rr ? lambda : 0.0);
     }
     __syncwarp();
   }
@@ -1695,32 +1807,42 @@ __global__ void __launch_bounds__((W < 32 ? 32 : W)) k_bwd(const BwdArgs a) {
   }
 }
 
-// landmark x landmark base: C0 = sum_rows l^T l (block diagonal), gl0 = sum_rows l^T rhs.  One CTA per landmark.
+// landmark x landmark base: C0 = sum_rows l^T l (block diagonal), gl0 = sum_rows l^T rhs.  One CTA per landmark; each thread
+// takes a few of the landmark's rows, the 12 sums are reduced by warp shuffles and one shared-memory pass (fixed order).
 template <int NT>
 __global__ void __launch_bounds__(NT) k_landmark_base(const double* __restrict__ XR, const int* __restrict__ lmoff, const int* __restrict__ lmrows,
                                                       int NXRp, int colL, int DL, int nb, double* __restrict__ Cbase) {
-  __shared__ double sred[NT / 32];
-  const int l = blockIdx.x;
+  __shared__ double sred[NT / 32][12];
+  const int l = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   double a[12];
 #pragma unroll
   for (int k = 0; k < 12; k++) a[k] = 0.0;
   for (int t = lmoff[l] + threadIdx.x; t < lmoff[l + 1]; t += NT) {
     const int row = lmrows[t];
     double lv[3] = {0, 0, 0};
-    for (int d = 0; d < DL; d++) lv[d] = XR[(size_t)(colL + d) * NXRp + row];
+#pragma unroll
+    for (int d = 0; d < 3; d++) if (d < DL) lv[d] = XR[(size_t)(colL + d) * NXRp + row];
     const double rh = XR[(size_t)(colL + DL) * NXRp + row];
-    for (int d1 = 0; d1 < DL; d1++) {
-      for (int d2 = 0; d2 < DL; d2++) a[d1 * 3 + d2] += lv[d1] * lv[d2];
+#pragma unroll
+    for (int d1 = 0; d1 < 3; d1++) {
+#pragma unroll
+      for (int d2 = 0; d2 < 3; d2++) a[d1 * 3 + d2] += lv[d1] * lv[d2];
       a[9 + d1] += lv[d1] * rh;
     }
   }
+#pragma unroll
   for (int k = 0; k < 12; k++) {
-    const double t = block_sum<NT>(a[k], sred);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      if (k < 9) { const int d1 = k / 3, d2 = k % 3; if (d1 < DL && d2 < DL) Cbase[(l * DL + d1) + (size_t)(l * DL + d2) * nb] = t; }
-      else { const int d1 = k - 9; if (d1 < DL) Cbase[(size_t)nb * nb + l * DL + d1] = t; }
-    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a[k] += __shfl_down_sync(0xffffffffu, a[k], o);
+    if (lane == 0) sred[wid][k] = a[k];
+  }
+  __syncthreads();
+  if (threadIdx.x < 12) {
+    const int k = threadIdx.x;
+    double t = 0.0;
+    for (int w = 0; w < NT / 32; w++) t += sred[w][k];
+    if (k < 9) { const int d1 = k / 3, d2 = k % 3; if (d1 < DL && d2 < DL) Cbase[(l * DL + d1) + (size_t)(l * DL + d2) * nb] = t; }
+    else { const int d1 = k - 9; if (d1 < DL) Cbase[(size_t)nb * nb + l * DL + d1] = t; }
   }
 }
 
@@ -1743,49 +1865,61 @@ __global__ void k_cseg_final(const double* __restrict__ Cbase, const double* __r
   Csum[e] = s;
 }
 
-// landmark system: (C + lambda I) x = g, Cholesky + two triangular solves in shared memory.  Single CTA (nb <= 64).
+// Small dense SPD solve in shared memory, single CTA:  (A + lambda * diag[loff..R)) x = rhs,  R <= SMALL_SOLVE_MAX.
+// Used for the landmark system (no pinned states; loff = 0) and for reduced systems of a few separators + landmarks (sharded
+// graphs, a handful of loop closures).  The right-hand side rides along as row R of the lower triangle, so the Cholesky
+// factorisation performs the forward substitution; one block barrier per column (the trailing update reads the unscaled
+// pivot column and scales on the fly, the column itself is scaled afterwards by other threads).  Back-substitution is done by
+// one warp, row-oriented, the solution entries living in registers (entry r on lane r mod 32).
+constexpr int SMALL_SOLVE_MAX = 160;
 template <int NT>
-__global__ void __launch_bounds__(NT) k_landmark_solve(const double* __restrict__ Csum, int nb, const double* __restrict__ lambda_ptr, double* __restrict__ xl, int* __restrict__ flag) {
-  const double lambda = *lambda_ptr;
+__global__ void __launch_bounds__(NT) k_small_solve(const double* __restrict__ A, const double* rhs, int R, int loff,
+                                                    const double* __restrict__ lambda_ptr, double* x, int* __restrict__ flag, int flagval) {
   extern __shared__ double sm[];
-  double* C = sm;            // nb x nb column-major
-  double* g = sm + nb * nb;  // nb
-  const int entries = nb * nb + nb;
-  for (int e = threadIdx.x; e < entries; e += NT) {
-    double s = Csum[e];
-    if (e < nb * nb && (e % (nb + 1)) == 0) s += lambda;
-    sm[e] = s;
+  const int ld = R + 1 + ((R & 1) ? 1 : 0);  // odd leading dimension: row walks are bank-conflict free
+  double* dinv = sm + (size_t)ld * R;        // 1 / L[j][j]
+  const double lambda = *lambda_ptr;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4, TY = NT / 16;
+  for (int c = ty; c < R; c += TY) {
+    for (int r = c + tx; r < R; r += 16) sm[r + c * ld] = A[r + (size_t)c * R] + ((r == c && r >= loff) ? lambda : 0.0);
+    if (tx == 0) sm[R + c * ld] = rhs[c];
   }
   __syncthreads();
-  for (int j = 0; j < nb; j++) {
-    const double djj = C[j + j * nb];
-    if (!(djj > 0.0) && threadIdx.x == 0) *flag = 2;
-    const double inv = rsqrt(djj > 0.0 ? djj : 1.0);
-    __syncthreads();
-    for (int r = j + threadIdx.x; r < nb; r += NT) C[r + j * nb] = (r == j) ? djj * inv : C[r + j * nb] * inv;
-    __syncthreads();
-    const int m = nb - j - 1;
-    for (int k = threadIdx.x; k < m * m; k += NT) {
-      const int r = j + 1 + k % m, cc = j + 1 + k / m;
-      if (r >= cc) C[r + cc * nb] -= C[r + j * nb] * C[cc + j * nb];
+  for (int j = 0; j < R; j++) {
+    const double djj = sm[j + j * ld];
+    if (!(djj > 0.0) && tid == 0) *flag = flagval;
+    const double inv = rsqrt_pos(djj > 0.0 ? djj : 1.0);
+    for (int cc = j + 1 + ty; cc < R; cc += TY) {
+      const double lc = sm[cc + j * ld] * inv;
+      for (int r = cc + tx; r <= R; r += 16) sm[r + cc * ld] = fma(-(sm[r + j * ld] * inv), lc, sm[r + cc * ld]);
     }
     __syncthreads();
+    for (int r = j + tid; r <= R; r += NT) sm[r + j * ld] *= inv;
+    if (tid == 0) dinv[j] = inv;
   }
-  // L y = g (column sweep), then L^T x = y; thread r owns component r (nb <= NT)
-  for (int j = 0; j < nb; j++) {
-    if (threadIdx.x == j) g[j] /= C[j + j * nb];
-    __syncthreads();
-    if (threadIdx.x > j && threadIdx.x < nb) g[threadIdx.x] -= C[threadIdx.x + j * nb] * g[j];
-    __syncthreads();
+  __syncthreads();
+  if (tid < 32) {
+    constexpr int KMAX = SMALL_SOLVE_MAX / 32;
+    double yv[KMAX];
+#pragma unroll
+    for (int k = 0; k < KMAX; k++) { const int r = tid + 32 * k; yv[k] = r < R ? sm[R + r * ld] : 0.0; }
+    for (int j = R - 1; j >= 0; j--) {
+      double mine = 0.0;
+#pragma unroll
+      for (int k = 0; k < KMAX; k++) if ((j >> 5) == k) mine = yv[k];
+      const double xj = __shfl_sync(0xffffffffu, mine, j & 31) * dinv[j];
+#pragma unroll
+      for (int k = 0; k < KMAX; k++) {
+        const int r = tid + 32 * k;
+        if (r < j) yv[k] = fma(-sm[j + r * ld], xj, yv[k]);
+        else if (r == j) yv[k] = xj;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < KMAX; k++) { const int r = tid + 32 * k; if (r < R) x[r] = yv[k]; }
   }
-  for (int j = nb - 1; j >= 0; j--) {
-    if (threadIdx.x == j) g[j] /= C[j + j * nb];
-    __syncthreads();
-    if (threadIdx.x < j) g[threadIdx.x] -= C[j + threadIdx.x * nb] * g[j];
-    __syncthreads();
-  }
-  if (threadIdx.x < nb) xl[threadIdx.x] = g[threadIdx.x];
 }
+static size_t small_solve_smem(int R) { return ((size_t)(R + 2) * R + R) * sizeof(double); }
 
 // x <- x (+) delta for every state (Pose3 / Rot3: Expmap; Pose2: GTSAM's default chart; vectors: add), plus the two dot
 // products LM needs: g.delta and |delta|^2 (block partials).
@@ -1906,50 +2040,6 @@ __global__ void k_pack_top(const PackArgs a) {
       v = sidx == 0 ? (a.err_ptr ? *a.err_ptr : a.err_local) : (sidx == 1 ? (double)(*a.flag) : 0.0);
     }
     a.buf[e] = v;
-  }
-}
-
-// Dense Cholesky solve of the all-reduced system (in place in global memory; the working set is L2-resident), single CTA.
-// lambda is added to the landmark diagonal only (separator blocks were damped when their level-0 blocks were handed off).
-template <int NT>
-__global__ void __launch_bounds__(NT) k_top_solve(double* __restrict__ buf, int R, int loff, const double* __restrict__ lambda_ptr, int* __restrict__ flag) {
-  const double lambda = *lambda_ptr;
-  double* T = buf;
-  double* t = buf + (size_t)R * R;
-  __shared__ double colj[256];
-  __shared__ double sinv;
-  for (int r = loff + threadIdx.x; r < R; r += NT) T[r + (size_t)r * R] += lambda;
-  __syncthreads();
-  for (int j = 0; j < R; j++) {
-    if (threadIdx.x == 0) {
-      const double djj = T[j + (size_t)j * R];
-      if (!(djj > 0.0)) *flag = 3;
-      sinv = rsqrt(djj > 0.0 ? djj : 1.0);
-    }
-    __syncthreads();
-    const double inv = sinv;
-    for (int r = j + threadIdx.x; r < R; r += NT) { const double l = (r == j) ? T[j + (size_t)j * R] * inv : T[r + (size_t)j * R] * inv; T[r + (size_t)j * R] = l; colj[r] = l; }
-    __syncthreads();
-    const int m = R - j - 1;
-    for (int k = threadIdx.x; k < m * m; k += NT) {
-      const int r = j + 1 + k % m, cc = j + 1 + k / m;
-      if (r >= cc) T[r + (size_t)cc * R] -= colj[r] * colj[cc];
-    }
-    __syncthreads();
-  }
-  for (int j = 0; j < R; j++) {  // L y = t
-    if (threadIdx.x == 0) t[j] /= T[j + (size_t)j * R];
-    __syncthreads();
-    const double yj = t[j];
-    for (int r = j + 1 + threadIdx.x; r < R; r += NT) t[r] -= T[r + (size_t)j * R] * yj;
-    __syncthreads();
-  }
-  for (int j = R - 1; j >= 0; j--) {  // L^T x = y
-    if (threadIdx.x == 0) t[j] /= T[j + (size_t)j * R];
-    __syncthreads();
-    const double xj = t[j];
-    for (int r = threadIdx.x; r < j; r += NT) t[r] -= T[j + (size_t)r * R] * xj;
-    __syncthreads();
   }
 }
 
