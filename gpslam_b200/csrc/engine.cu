@@ -39,13 +39,14 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 
 // ===================================================================== host-side graph
 struct Extra {
-  int kind, sa, sb, l, m, order, interval;
+  int kind, sa, sb, l, m, order, interval, closure;  // closure: BetweenFactor between non-adjacent states (rows at the tail of the row table)
   double prm[XP_STRIDE];
 };
 
 struct Level {
   int n = 0, M = 0, S = 0, nseg = 0, ncta = 0, ncta_bwd = 0;
-  bool top = false;        // storage-only level holding the external separators' Schur complement (sharded graphs)
+  bool top = false;        // storage-only level holding the Schur complement on the pinned states (external separators, loop-closure endpoints)
+  int* d_sep = nullptr;    // [S] positions of the interior separators in this level's chain
   double* rec = nullptr;   // level >= 1: [n][3 bs^2 + 2 bs]  (D1 | D2 | E | g1 | g2)
   double* brec = nullptr;  // level >= 1: [n][2 bs nb]
   double* frec = nullptr;  // [n][2 bs^2 + bs w]   (Lii | Le | Y)
@@ -75,8 +76,15 @@ struct gpb_graph {
   int *d_rowoff = nullptr, *d_rowland = nullptr, *d_lmoff = nullptr, *d_lmrows = nullptr;
   int *d_bsoff = nullptr, *d_bsrow = nullptr, *d_bsside = nullptr;  // per-state CSR of landmark-bearing rows (level-0 border gather)
   double* d_bent = nullptr; int nbent = 0;                          // the same rows packed as 128-byte entries (k_border_pack)
-  int rank = 0, world = 1, nsep = 0, R = 0, sms = 148;
-  bool old_panel = false, generic_fwd = false, old_spine = false;
+  int rank = 0, world = 1, R = 0, sms = 148;
+  int ntop = 0, P = 0;            // top states of the global reduced system / of this graph's top-level chain
+  int pinL = 0, pinR = 0;         // first / last state of the chain is pinned (external separator or loop-closure endpoint)
+  int* d_gtop = nullptr;          // [P] global top index of local top state k
+  double* d_topx = nullptr;       // [R] solution of the reduced system
+  int nclos = 0, nep = 0, npair = 0;  // loop closures: factors, endpoint states, unique endpoint pairs
+  int *d_epstate = nullptr, *d_epoff = nullptr, *d_eprow = nullptr, *d_epside = nullptr;
+  int *d_pair_a = nullptr, *d_pair_b = nullptr, *d_pairoff = nullptr, *d_pairrow = nullptr;
+  bool generic_fwd = false, force_blocked = false;
   gpb_allreduce_fn allreduce = nullptr; void* allreduce_ctx = nullptr;
   double* d_topbuf = nullptr; double cur_error_local = 0; int n_allreduce = 0;
   double* d_lambda = nullptr;
@@ -280,9 +288,11 @@ int gpb_add_prior_landmark(gpb_graph* g, int l, const double* value, const doubl
 int gpb_add_between(gpb_graph* g, int i, int j, const double* measured, const double* sqrt_info) {
   CHECK_OPEN(g);
   if (i < 0 || i >= g->N || j < 0 || j >= g->N || i == j) return fail(GPB_ERR_ARG, "gpb_add_between: index out of range");
-  if (std::abs(i - j) != 1) return fail(GPB_ERR_UNSUPPORTED, "gpb_add_between: loop closures (|i-j| > 1) are not supported by this build yet");
+  if (std::abs(i - j) != 1 && g->group == GPB_LINEAR) return fail(GPB_ERR_UNSUPPORTED, "gpb_add_between: loop closures need a pose group");
   Extra e = make_extra(X_BETWEEN); e.m = g->D;
-  e.sa = std::min(i, j); e.sb = e.sa + 1; e.interval = e.sa; e.prm[17] = (j < i) ? 1.0 : 0.0;
+  // odometry (|i-j| == 1) lives on its interval; a loop closure couples two distant states: both become pinned separators of the
+  // elimination and its rows go to the tail of the row table (interval == nint)
+  e.sa = std::min(i, j); e.sb = std::max(i, j); e.closure = std::abs(i - j) != 1; e.interval = e.closure ? g->nint : e.sa; e.prm[17] = (j < i) ? 1.0 : 0.0;
   for (int t = 0; t < g->PS; t++) e.prm[4 + t] = measured[t];
   set_R(e, g->D, sqrt_info); e.order = (int)g->extras.size(); g->extras.push_back(e);
   return GPB_OK;
@@ -469,7 +479,7 @@ int gpb_graph_finalize(gpb_graph* g, int device) {
     std::copy(e.prm, e.prm + XP_STRIDE, xprm.begin() + (size_t)k * XP_STRIDE);
     for (int r = 0; r < e.m; r++) rowland.push_back(e.l);
     nrows += e.m;
-    rowoff[e.interval + 1] += e.m;
+    if (e.interval < g->nint) rowoff[e.interval + 1] += e.m;  // loop-closure rows (interval == nint) sit behind every interval's range
   }
   for (int t = 0; t < g->nint; t++) rowoff[t + 1] += rowoff[t];
   std::vector<int> bsoff(g->N + 1, 0), bsrow, bsside;
@@ -488,6 +498,27 @@ int gpb_graph_finalize(gpb_graph* g, int device) {
   std::vector<int> listA, listB;
   for (int k = 0; k < g->NX; k++) (xkind[k] == X_INTERP_RANGE || xkind[k] == X_INTERP_ATTITUDE ? listA : listB).push_back(k);
   g->nA = (int)listA.size(); g->nB = (int)listB.size();
+  // ---- loop closures: endpoint states (pinned separators), per-endpoint and per-pair row lists
+  std::vector<char> pin(g->N, 0);
+  std::vector<int> epstate, epoff, eprow, epside, clos;
+  for (int k = 0; k < g->NX; k++) if (g->sorted[k].closure) clos.push_back(k);
+  g->nclos = (int)clos.size();
+  if (g->nclos && g->world > 1) return fail(GPB_ERR_UNSUPPORTED, "gpb_graph_finalize: loop closures on a sharded graph are not supported by this build");
+  for (int k : clos) { pin[g->sorted[k].sa] = 1; pin[g->sorted[k].sb] = 1; }
+  if (g->extL) pin[0] = 1;
+  if (g->extR) pin[g->N - 1] = 1;
+  g->pinL = pin[0]; g->pinR = pin[g->N - 1];
+  {
+    std::vector<std::vector<std::pair<int, int>>> per(g->N);
+    for (int k : clos) { per[g->sorted[k].sa].push_back({xrow[k], 0}); per[g->sorted[k].sb].push_back({xrow[k], 1}); }
+    epoff.push_back(0);
+    for (int i = 0; i < g->N; i++) if (!per[i].empty()) {
+      epstate.push_back(i);
+      for (auto& pr : per[i]) { eprow.push_back(pr.first); epside.push_back(pr.second); }
+      epoff.push_back((int)eprow.size());
+    }
+    g->nep = (int)epstate.size();
+  }
   g->NXR = nrows; g->NXRp = (nrows + 31) & ~31; g->h_xrow = xrow; g->ncolsX = 2 * bs + DL + 1;
   // rows per landmark
   std::vector<int> lmoff(g->L + 1, 0), lmrows;
@@ -547,15 +578,13 @@ int gpb_graph_finalize(gpb_graph* g, int device) {
   // segment lengths: explicit setting > environment (tuning aid) > defaults
   const char* em0 = getenv("GPB_M0"); const char* emu = getenv("GPB_MUP");
   g->generic_fwd = getenv("GPB_GENERIC_FWD") != nullptr;  // A/B switch: one-kernel generic forward sweep (k_fwd<12,64>)
-  g->old_spine = getenv("GPB_OLD_SPINE") != nullptr;
-  g->old_panel = getenv("GPB_OLD_PANEL") != nullptr;  // A/B switch while the four-warp panel kernel is being validated
   int M0 = g->M0 ? g->M0 : (em0 ? std::max(2, atoi(em0)) : (g->nb > 0 ? 32 : 16));
   const int Mup = g->Mup ? g->Mup : (emu ? std::max(2, atoi(emu)) : 8);
   if (!g->M0 && !em0 && bs == 12 && g->W == 64) {
     // the panel kernel runs one resident wave of persistent CTAs, each walking ceil(nseg / slots) segments of M0 (+ a closing
     // separator) states one after the other: pick the segment length that minimises that serial depth (whole rounds - a
     // 100k-state chain on 148 x 5 slots wants 46, not 32); ties go to the longer segment (fewer separators for the next level)
-    const int slots = sms * fwd_blocks_per_sm(bs, g->W), m0 = g->N - g->extL - g->extR;
+    const int slots = sms * fwd_blocks_per_sm(bs, g->W), m0 = g->N - g->pinL - g->pinR;
     long long best = -1;
     for (int M = 12; M <= 63; M++) {
       const int nseg = (m0 > 0 ? (m0 - 1) / M : 0) + 1;
@@ -564,42 +593,111 @@ int gpb_graph_finalize(gpb_graph* g, int device) {
     }
   }
   const int fstride = 2 * bs * bs + bs * g->w;
-  int n = g->N, lev = 0;
-  while (true) {
-    Level L;
-    const int m = n - g->extL - g->extR;  // ordinary (eliminable) states of this level
-    if (m < 0) return fail(GPB_ERR_ARG, "shard too small for its external separators");
-    L.n = n; L.M = lev == 0 ? M0 : Mup; L.S = m > 0 ? (m - 1) / L.M : 0; L.nseg = L.S + 1;
-    L.ncta = std::min(L.nseg, sms * fwd_blocks_per_sm(bs, g->W));  // persistent CTAs: one resident wave
-    L.ncta_bwd = std::min(L.nseg, sms * bwd_blocks_per_sm(bs, g->W));
-    if ((rc = dev_alloc(g, &L.frec, (size_t)n * fstride))) return rc;
-    if ((rc = dev_alloc(g, &L.xsol, (size_t)n * bs))) return rc;
-    if (g->nb) { if ((rc = dev_alloc(g, &L.cseg, (size_t)L.ncta * centries))) return rc; }
-    if (lev > 0) {
-      if ((rc = dev_alloc(g, &L.rec, (size_t)n * (3 * bs * bs + 2 * bs)))) return rc;
-      if ((rc = dev_alloc(g, &L.brec, (size_t)n * 2 * bs * std::max(g->nb, 1)))) return rc;
-    }
-    g->levels.push_back(L);
-    const int n_next = g->extL + L.S + g->extR;
-    if (L.S == 0) {
-      if (n_next > 0) {  // storage for the Schur complement on the external separators
-        Level T; T.top = true; T.n = n_next;
-        if ((rc = dev_alloc(g, &T.xsol, (size_t)n_next * bs))) return rc;
-        if ((rc = dev_alloc(g, &T.rec, (size_t)n_next * (3 * bs * bs + 2 * bs)))) return rc;
-        if ((rc = dev_alloc(g, &T.brec, (size_t)n_next * 2 * bs * std::max(g->nb, 1)))) return rc;
-        g->levels.push_back(T);
+  // Level recursion.  Each level's chain is cut at its interior separators: every pinned state (never eliminated: it stays a
+  // separator at every level and ends up in the top system) and, inside every run of g ordinary states between two cuts, every
+  // M-th state ((g - 1) / M of them).  The separators (plus the pinned chain ends) form the next level's chain; when no
+  // ordinary separator is left, what remains is the top level: the pinned states only.
+  std::vector<int> top_state;  // original state index of each top-level chain entry
+  {
+    std::vector<char> cpin = pin;                 // pinned flag per entry of the current chain
+    std::vector<int> corig(g->N);                 // original state index per entry
+    for (int i = 0; i < g->N; i++) corig[i] = i;
+    int lev = 0;
+    while (true) {
+      const int n = (int)cpin.size();
+      if (n - g->pinL - g->pinR < 0) return fail(GPB_ERR_ARG, "shard too small for its external separators");
+      Level L;
+      L.n = n; L.M = lev == 0 ? M0 : Mup;
+      std::vector<int> sep;
+      bool ordinary_sep = false;
+      int a = g->pinL ? 0 : -1;                    // position of the last cut
+      const int end = g->pinR ? n - 1 : n;         // position of the closing cut
+      for (int pos = a + 1; pos <= end; pos++) {
+        if (pos == end || cpin[pos]) {
+          const int gap = pos - a - 1;
+          const int ns = gap > 0 ? (gap - 1) / L.M : 0;
+          for (int t = 0; t < ns; t++) { sep.push_back(a + (t + 1) * L.M); ordinary_sep = true; }
+          if (pos < end) sep.push_back(pos);
+          a = pos;
+        }
       }
-      break;
+      std::sort(sep.begin(), sep.end());
+      L.S = (int)sep.size(); L.nseg = L.S + 1;
+      L.ncta = std::min(L.nseg, sms * fwd_blocks_per_sm(bs, g->W));  // persistent CTAs: one resident wave
+      L.ncta_bwd = std::min(L.nseg, sms * bwd_blocks_per_sm(bs, g->W));
+      if ((rc = dev_upload(g, &L.d_sep, sep))) return rc;
+      if ((rc = dev_alloc(g, &L.frec, (size_t)n * fstride))) return rc;
+      if ((rc = dev_alloc(g, &L.xsol, (size_t)n * bs))) return rc;
+      if (g->nb) { if ((rc = dev_alloc(g, &L.cseg, (size_t)L.ncta * centries))) return rc; }
+      if (lev > 0) {
+        if ((rc = dev_alloc(g, &L.rec, (size_t)n * (3 * bs * bs + 2 * bs)))) return rc;
+        if ((rc = dev_alloc(g, &L.brec, (size_t)n * 2 * bs * std::max(g->nb, 1)))) return rc;
+      }
+      g->levels.push_back(L);
+      // next chain: [pinned first] + separators + [pinned last]
+      std::vector<char> npin; std::vector<int> norig;
+      if (g->pinL) { npin.push_back(1); norig.push_back(corig[0]); }
+      for (int sp : sep) { npin.push_back(cpin[sp]); norig.push_back(corig[sp]); }
+      if (g->pinR) { npin.push_back(1); norig.push_back(corig[n - 1]); }
+      const int n_next = (int)npin.size();
+      if (!ordinary_sep) {
+        if (n_next > 0) {  // storage for the Schur complement on the pinned states
+          Level T; T.top = true; T.n = n_next;
+          if ((rc = dev_alloc(g, &T.xsol, (size_t)n_next * bs))) return rc;
+          if ((rc = dev_alloc(g, &T.rec, (size_t)n_next * (3 * bs * bs + 2 * bs)))) return rc;
+          if ((rc = dev_alloc(g, &T.brec, (size_t)n_next * 2 * bs * std::max(g->nb, 1)))) return rc;
+          g->levels.push_back(T);
+          top_state = norig;
+        }
+        break;
+      }
+      cpin.swap(npin); corig.swap(norig); lev++;
     }
-    n = n_next; lev++;
   }
   if ((rc = dev_alloc(g, &g->d_Cpart, (size_t)16 * g->levels.size() * std::max(centries, 1)))) return rc;
   CUDA_TRY(cudaMemset(g->d_Cpart, 0, (size_t)16 * g->levels.size() * std::max(centries, 1) * sizeof(double)));
   if ((rc = dev_alloc(g, &g->d_Csum, (size_t)std::max(centries, 1)))) return rc;
-  g->nsep = g->world - 1; g->R = g->nsep * bs + g->nb;
-  if (g->world > 1) {
-    if (g->R > SMALL_SOLVE_MAX) return fail(GPB_ERR_UNSUPPORTED, "reduced system larger than SMALL_SOLVE_MAX unknowns");
-    if ((rc = dev_alloc(g, &g->d_topbuf, (size_t)g->R * g->R + g->R + 4))) return rc;
+  // ---- the reduced (top) system: global top indices of this graph's pinned states
+  g->P = (int)top_state.size();
+  {
+    std::vector<int> gtop(g->P);
+    if (g->world > 1) {  // sharded: global separator r-1 is this rank's halo, r its own last state
+      g->ntop = g->world - 1;
+      int k = 0;
+      if (g->extL) gtop[k++] = g->rank - 1;
+      if (g->extR) gtop[k++] = g->rank;
+    } else {
+      g->ntop = g->P;
+      for (int k = 0; k < g->P; k++) gtop[k] = k;
+    }
+    g->R = g->ntop * bs + g->nb;
+    if ((rc = dev_upload(g, &g->d_gtop, gtop))) return rc;
+    // unique endpoint pairs of the loop closures, in top indices
+    std::vector<int> top_of(g->N, -1);
+    for (int k = 0; k < g->P; k++) top_of[top_state[k]] = gtop[k];
+    std::vector<std::pair<std::pair<int, int>, int>> pr;  // ((top a, top b), first row)
+    for (int k : clos) pr.push_back({{top_of[g->sorted[k].sa], top_of[g->sorted[k].sb]}, xrow[k]});
+    std::sort(pr.begin(), pr.end());
+    std::vector<int> pair_a, pair_b, pairoff(1, 0), pairrow;
+    for (size_t t = 0; t < pr.size(); t++) {
+      if (pr[t].first.first < 0 || pr[t].first.second < 0) return fail(GPB_ERR_STATE, "internal: loop-closure endpoint missing from the top level");
+      if (t == 0 || pr[t].first != pr[t - 1].first) { if (t) pairoff.push_back((int)pairrow.size()); pair_a.push_back(pr[t].first.first); pair_b.push_back(pr[t].first.second); }
+      pairrow.push_back(pr[t].second);
+    }
+    if (!pr.empty()) pairoff.push_back((int)pairrow.size());
+    g->npair = (int)pair_a.size();
+    if ((rc = dev_upload(g, &g->d_epstate, epstate))) return rc;
+    if ((rc = dev_upload(g, &g->d_epoff, epoff))) return rc;
+    if ((rc = dev_upload(g, &g->d_eprow, eprow))) return rc;
+    if ((rc = dev_upload(g, &g->d_epside, epside))) return rc;
+    if ((rc = dev_upload(g, &g->d_pair_a, pair_a))) return rc;
+    if ((rc = dev_upload(g, &g->d_pair_b, pair_b))) return rc;
+    if ((rc = dev_upload(g, &g->d_pairoff, pairoff))) return rc;
+    if ((rc = dev_upload(g, &g->d_pairrow, pairrow))) return rc;
+  }
+  if (g->world > 1 || g->P > 0) {
+    if ((rc = dev_alloc(g, &g->d_topbuf, (size_t)(g->R + 1) * g->R + 4))) return rc;
+    if ((rc = dev_alloc(g, &g->d_topx, (size_t)std::max(g->R, 1)))) return rc;
   }
   // page-lock the host staging so the H2D / D2H copies of the values run at full PCIe rate
   if (cudaHostRegister(g->h_X.data(), g->h_X.size() * sizeof(double), cudaHostRegisterDefault) == cudaSuccess) {
@@ -659,6 +757,10 @@ template <int G> static int launch_assemble(gpb_graph* g, int buf) {
   const int nblk = (g->N + states_per_cta - 1) / states_per_cta;
   k_assemble<G, NT><<<nblk, NT, 0, g->stream>>>(g->d_AB[buf], g->d_dt, g->NX ? g->d_XR[buf] : nullptr, g->d_rowoff, g->d_HREC, g->N, g->NFp, g->NXRp);
   g->launches++;
+  if (g->nep) {  // loop closures: diagonal blocks / rhs of their endpoint states
+    k_assemble_closures<<<g->nep, 64, 0, g->stream>>>(g->d_XR[buf], g->NXRp, bs, GroupTraits<G>::D, g->ncolsX - 1, g->d_epstate, g->d_epoff, g->d_eprow, g->d_epside, g->d_HREC);
+    g->launches++;
+  }
   if (g->nb) {
     CUDA_TRY(cudaMemsetAsync(g->d_Cbase, 0, (size_t)(g->nb * g->nb + g->nb) * sizeof(double), g->stream));
     k_landmark_base<512><<<g->L, 512, 0, g->stream>>>(g->d_XR[buf], g->d_lmoff, g->d_lmrows, g->NXRp, 2 * bs, g->DL, g->nb, g->d_Cbase);
@@ -690,7 +792,8 @@ static int launch_fwd_level(gpb_graph* g, int buf, double lambda, int lev) {
   const int nlev = (int)g->levels.size();
   Level& L = g->levels[lev];
   FwdArgs a;
-  a.n = L.n; a.M = L.M; a.S = L.S; a.nseg = L.nseg; a.first_level = lev == 0; a.extL = g->extL; a.extR = g->extR;
+  a.n = L.n; a.M = L.M; a.S = L.S; a.nseg = L.nseg; a.first_level = lev == 0; a.extL = g->pinL; a.extR = g->pinR; a.sep = L.d_sep;
+  a.lamL = (g->pinL && !g->extL) ? 1 : 0;  // a pinned first state that is not a neighbour's halo is damped here
   a.rec = lev == 0 ? g->d_HREC : L.rec; a.brec = L.brec;
   a.XR = g->d_XR[buf]; a.bsoff = g->d_bsoff; a.bsrow = g->d_bsrow; a.bsside = g->d_bsside; a.rowland = g->d_rowland; a.bent = g->d_bent; a.NXRp = g->NXRp; a.nb = nb; a.DL = std::max(g->DL, 1);
   a.lambda_ptr = g->d_lambda;
@@ -699,10 +802,8 @@ static int launch_fwd_level(gpb_graph* g, int buf, double lambda, int lev) {
   if (bs == 12 && g->W == 64 && !g->generic_fwd) {
     // spine first (warp per segment: the latency-bound 12x12 recurrence wants many independent warps), then the tensor-pipe panel
     const int spine_ctas = std::min(L.nseg, 16 * g->sms);
-    if (g->old_spine) k_spine_v1<12><<<spine_ctas, 32, 0, g->stream>>>(a);
-    else k_spine<12><<<spine_ctas, 32, 0, g->stream>>>(a);
-    if (g->old_panel) k_panel<12><<<L.ncta, 64, 0, g->stream>>>(a);
-    else k_panel4<12><<<L.ncta, 128, 0, g->stream>>>(a);
+    k_spine<12><<<spine_ctas, 32, 0, g->stream>>>(a);
+    k_panel4<12><<<L.ncta, 128, 0, g->stream>>>(a);
     g->launches += 2;
   } else {
     if (bs == 12) fwd_w<12>(g->W, a, L.ncta, g->stream); else fwd_w<6>(g->W, a, L.ncta, g->stream);
@@ -727,22 +828,13 @@ static int solve_forward(gpb_graph* g, int buf, double lambda) {
   for (int lev = 0; lev < nel; lev++) if ((rc = launch_fwd_level(g, buf, lambda, lev))) return rc;
   return GPB_OK;
 }
-static int solve_landmarks_local(gpb_graph* g, double lambda) {
-  const int nb = g->nb, centries = nb * nb + nb, nel = num_elim_levels(g);
-  if (nb) {
-    k_cseg_final<<<(centries + 127) / 128, 128, 0, g->stream>>>(g->d_Cbase, g->d_Cpart, 16 * nel, centries, g->d_Csum);
-    k_small_solve<256><<<1, 256, small_solve_smem(nb), g->stream>>>(g->d_Csum, g->d_Csum + (size_t)nb * nb, nb, 0, g->d_lambda, g->d_xlm, g->d_flag, 2);
-    g->launches += 2;
-  }
-  return GPB_OK;
-}
 static int solve_backward(gpb_graph* g) {
   const int bs = g->bs, nb = g->nb, fstride = 2 * bs * bs + bs * g->w;
   const int nel = num_elim_levels(g), nlev = (int)g->levels.size();
   for (int lev = nel - 1; lev >= 0; lev--) {
     Level& L = g->levels[lev];
     BwdArgs b;
-    b.n = L.n; b.M = L.M; b.S = L.S; b.nseg = L.nseg; b.nb = nb; b.extL = g->extL; b.extR = g->extR; b.frec = L.frec; b.fstride = fstride;
+    b.n = L.n; b.M = L.M; b.S = L.S; b.nseg = L.nseg; b.nb = nb; b.extL = g->pinL; b.extR = g->pinR; b.sep = L.d_sep; b.frec = L.frec; b.fstride = fstride;
     b.xup = lev + 1 < nlev ? g->levels[lev + 1].xsol : nullptr; b.xl = g->d_xlm; b.xsol = L.xsol;
     if (bs == 12) bwd_w<12>(g->W, b, L.ncta_bwd, g->stream); else bwd_w<6>(g->W, b, L.ncta_bwd, g->stream);
     g->launches++;
@@ -757,28 +849,73 @@ static int dist_allreduce(gpb_graph* g, double* dbuf, long long count) {
   g->n_allreduce++;
   return GPB_OK;
 }
+// Dense solve of the reduced system in d_topbuf ((R+1) x R, row R = rhs) into d_topx.
+static int solve_top_dense(gpb_graph* g) {
+  const int R = g->R, ld = R + 1, loff = g->ntop * g->bs;
+  if (R <= SMALL_SOLVE_MAX && !g->force_blocked) {
+    k_small_solve<256><<<1, 256, small_solve_smem(R), g->stream>>>(g->d_topbuf, ld, g->d_topbuf + R, ld, R, loff, g->d_lambda, g->d_topx, g->d_flag, 3);
+    g->launches++;
+    return GPB_OK;
+  }
+  for (int j0 = 0; j0 < R; j0 += DNB) {
+    const int n = std::min(DNB, R - j0), below = R + 1 - (j0 + n);  // rows below the diagonal tile, rhs row included
+    k_dense_diag<<<1, 256, 0, g->stream>>>(g->d_topbuf, ld, R, j0, loff, g->d_lambda, g->d_flag);
+    k_dense_trsm<<<(below + 127) / 128, 128, 0, g->stream>>>(g->d_topbuf, ld, R, j0);
+    g->launches += 2;
+    if (j0 + n < R) {
+      const int nt = (below + DNB - 1) / DNB;
+      k_dense_syrk<<<dim3(nt, nt), 256, 0, g->stream>>>(g->d_topbuf, ld, R, j0);
+      g->launches++;
+    }
+  }
+  for (int j0 = ((R - 1) / DNB) * DNB; j0 >= 0; j0 -= DNB) {
+    k_dense_bwd<<<std::max(1, (j0 + 255) / 256), 256, 0, g->stream>>>(g->d_topbuf, ld, R, j0, g->d_topx);
+    g->launches++;
+  }
+  CUDA_TRY(cudaGetLastError());
+  return GPB_OK;
+}
+// The part of the solve between the two sweeps.  No pinned states and a single GPU: the landmark system alone.  Otherwise the
+// Schur complement on {pinned states, landmarks} is packed into the reduced system -> (sharded graphs) ONE all-reduce ->
+// dense solve (redundantly on every rank) -> scatter to the top-level solution and the landmark solution.
+// err_local / async: see solve_system_dist.
+static int solve_top(gpb_graph* g, int buf, double err_local, bool async, double* sc_out /*[4] or null*/) {
+  int rc;
+  const int nb = g->nb, centries = nb * nb + nb, nel = num_elim_levels(g), R = g->R;
+  if (nb) { k_cseg_final<<<(centries + 127) / 128, 128, 0, g->stream>>>(g->d_Cbase, g->d_Cpart, 16 * nel, centries, g->d_Csum); g->launches++; }
+  if (g->world == 1 && g->P == 0) {
+    if (nb) { k_small_solve<256><<<1, 256, small_solve_smem(nb), g->stream>>>(g->d_Csum, nb, g->d_Csum + (size_t)nb * nb, 1, nb, 0, g->d_lambda, g->d_xlm, g->d_flag, 2); g->launches++; }
+    return GPB_OK;
+  }
+  const long long total = (long long)(R + 1) * R + 4;
+  CUDA_TRY(cudaMemsetAsync(g->d_topbuf, 0, (size_t)total * sizeof(double), g->stream));
+  PackArgs pa;
+  pa.bs = g->bs; pa.nb = nb; pa.R = R; pa.ntop = g->ntop; pa.P = g->P; pa.gtop = g->d_gtop;
+  pa.rec = g->levels.back().rec; pa.brec = g->levels.back().brec; pa.Csum = g->d_Csum; pa.err_local = err_local; pa.err_ptr = async ? g->d_scal : nullptr; pa.flag = g->d_flag; pa.buf = g->d_topbuf;
+  k_pack_top<<<g->P + 1, 128, 0, g->stream>>>(pa);
+  g->launches++;
+  if (g->npair) {
+    k_pack_closures<<<g->npair, 64, 0, g->stream>>>(g->d_XR[buf], g->NXRp, g->bs, g->D, R + 1, g->d_pair_a, g->d_pair_b, g->d_pairoff, g->d_pairrow, g->d_topbuf);
+    g->launches++;
+  }
+  if (g->world > 1 && (rc = dist_allreduce(g, g->d_topbuf, total))) return rc;
+  if (sc_out) CUDA_TRY(cudaMemcpyAsync(sc_out, g->d_topbuf + (size_t)(R + 1) * R, 4 * sizeof(double), cudaMemcpyDeviceToHost, g->stream));
+  if ((rc = solve_top_dense(g))) return rc;
+  const int nthr = std::max(g->P * g->bs, nb);
+  k_top_scatter<<<(nthr + 127) / 128, 128, 0, g->stream>>>(g->d_topx, g->bs, nb, g->ntop, g->P, g->d_gtop, g->levels.back().xsol, g->d_xlm);
+  g->launches++;
+  return GPB_OK;
+}
 // sharded solve: local elimination down to the external separators -> pack -> ONE all-reduce -> redundant dense solve ->
 // local back-substitution.  global_err_out: sum over ranks of err_local (the error at the current linearisation point).
 // async: nothing is read back and the host is not synchronised (plain Gauss-Newton with a fixed iteration count); the local error
 // of the current point is then taken from d_scal[0], where the linearise that produced this point left it.
 static int solve_system_dist(gpb_graph* g, int buf, double lambda, double err_local, double* global_err_out, int* flag_out, bool async = false) {
   int rc;
-  const int nb = g->nb, centries = nb * nb + nb, nel = num_elim_levels(g), R = g->R;
   k_set_scalar<<<1, 1, 0, g->stream>>>(g->d_lambda, lambda);
   if ((rc = solve_forward(g, buf, lambda))) return rc;
-  if (nb) { k_cseg_final<<<(centries + 127) / 128, 128, 0, g->stream>>>(g->d_Cbase, g->d_Cpart, 16 * nel, centries, g->d_Csum); g->launches++; }
-  PackArgs pa;
-  pa.bs = g->bs; pa.nb = nb; pa.R = R; pa.nsep = g->nsep; pa.rank = g->rank; pa.extL = g->extL; pa.extR = g->extR;
-  pa.rec = g->levels.back().rec; pa.brec = g->levels.back().brec; pa.Csum = g->d_Csum; pa.err_local = err_local; pa.err_ptr = async ? g->d_scal : nullptr; pa.flag = g->d_flag; pa.buf = g->d_topbuf;
-  const long long total = (long long)R * R + R + 4;
-  k_pack_top<<<(int)std::min<long long>((total + 255) / 256, 148), 256, 0, g->stream>>>(pa);
-  g->launches++;
-  if ((rc = dist_allreduce(g, g->d_topbuf, total))) return rc;
   double sc[4] = {0, 0, 0, 0};
-  if (!async) CUDA_TRY(cudaMemcpyAsync(sc, g->d_topbuf + (size_t)R * R + R, 4 * sizeof(double), cudaMemcpyDeviceToHost, g->stream));
-  k_small_solve<256><<<1, 256, small_solve_smem(R), g->stream>>>(g->d_topbuf, g->d_topbuf + (size_t)R * R, R, g->nsep * g->bs, g->d_lambda, g->d_topbuf + (size_t)R * R, g->d_flag, 3);
-  k_top_scatter<<<1, 64, 0, g->stream>>>(g->d_topbuf, R, g->bs, nb, g->nsep, g->rank, g->extL, g->extR, g->levels.back().xsol, g->d_xlm);
-  g->launches += 2;
+  if ((rc = solve_top(g, buf, err_local, async, async ? nullptr : sc))) return rc;
   if ((rc = solve_backward(g))) return rc;
   if (async) return GPB_OK;
   int flag = 0;
@@ -804,7 +941,7 @@ static int solve_system(gpb_graph* g, int buf, double lambda) {
   if (g->world > 1) return solve_system_dist(g, buf, lambda, 0.0, nullptr, nullptr);
   k_set_scalar<<<1, 1, 0, g->stream>>>(g->d_lambda, lambda);
   if ((rc = solve_forward(g, buf, lambda))) return rc;
-  if ((rc = solve_landmarks_local(g, lambda))) return rc;
+  if ((rc = solve_top(g, buf, 0.0, false, nullptr))) return rc;
   return solve_backward(g);
 }
 
@@ -940,7 +1077,7 @@ int gpb_optimize(gpb_graph* g, const gpb_params* params, int n_iter, gpb_stats* 
           CUDA_TRY(cudaStreamBeginCapture(g->stream, cudaStreamCaptureModeThreadLocal));
           k_clear_flag<<<1, 1, 0, g->stream>>>(g->d_flag);
           r = solve_forward(g, par, lam);
-          if (!r) r = solve_landmarks_local(g, lam);
+          if (!r) r = solve_top(g, par, 0.0, false, nullptr);
           if (!r) r = solve_backward(g);
           if (!r) r = retract_dispatch(g);
           if (!r) r = linearize_dispatch(g, g->d_Xt, g->d_landt, 1 - par, 1);
@@ -1030,6 +1167,39 @@ int gpb_optimize(gpb_graph* g, const gpb_params* params, int n_iter, gpb_stats* 
     st->iterations = iterations; st->error_initial = error_initial; st->error_final = error; st->lambda = lambda; st->total_ms = ms; st->status = status;
   }
   return GPB_OK;
+}
+
+// testing aid: the reduced-system solver alone.  Solves (A + lambda * diag[loff..R)) x = b on `device` with the shared-memory
+// solver (R <= SMALL_SOLVE_MAX and !force_blocked) or the blocked multi-CTA Cholesky.  A: R x R column-major, symmetric.
+int gpb_debug_dense_solve(int device, int R, const double* A, const double* b, double lambda, int loff, int force_blocked, double* x_out) {
+  if (R < 1 || !A || !b || !x_out) return fail(GPB_ERR_ARG, "gpb_debug_dense_solve: bad arguments");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(GPB_ERR_CUDA, "gpb_debug_dense_solve: no CUDA device available"); }
+  CUDA_TRY(cudaSetDevice(device));
+  CUDA_TRY(cudaFuncSetAttribute(k_small_solve<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_solve_smem(SMALL_SOLVE_MAX)));
+  gpb_graph g;
+  g.R = R; g.bs = 1; g.ntop = loff; g.force_blocked = force_blocked != 0;
+  CUDA_TRY(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+  int rc = GPB_OK;
+  std::vector<double> T((size_t)(R + 1) * R + 4, 0.0);
+  for (int c = 0; c < R; c++) { for (int r = 0; r < R; r++) T[r + (size_t)c * (R + 1)] = A[r + (size_t)c * R]; T[R + (size_t)c * (R + 1)] = b[c]; }
+  if (!(rc = dev_upload(&g, &g.d_topbuf, T)) && !(rc = dev_alloc(&g, &g.d_topx, (size_t)R)) && !(rc = dev_alloc(&g, &g.d_lambda, 1)) && !(rc = dev_alloc(&g, &g.d_flag, 1))) {
+    cudaMemcpy(g.d_lambda, &lambda, sizeof(double), cudaMemcpyHostToDevice);
+    cudaMemset(g.d_flag, 0, sizeof(int));
+    rc = solve_top_dense(&g);
+    int flag = 0;
+    if (!rc) {
+      cudaStreamSynchronize(g.stream);
+      cudaMemcpy(x_out, g.d_topx, (size_t)R * sizeof(double), cudaMemcpyDeviceToHost);
+      cudaMemcpy(&flag, g.d_flag, sizeof(int), cudaMemcpyDeviceToHost);
+      const cudaError_t ce = cudaGetLastError();
+      if (ce != cudaSuccess) rc = fail(GPB_ERR_CUDA, std::string("gpb_debug_dense_solve: ") + cudaGetErrorString(ce));
+      else if (flag) rc = fail(GPB_ERR_NUMERIC, "gpb_debug_dense_solve: matrix is not positive definite");
+    }
+  }
+  for (void* q : g.allocs) cudaFree(q);
+  cudaStreamDestroy(g.stream);
+  return rc;
 }
 
 int gpb_kernel_launches_last_optimize(gpb_graph* g) { return g ? g->launches : 0; }
@@ -1125,6 +1295,18 @@ int gpb_get_normal_equations(gpb_graph* g, double* H, double* rhs, int n) {
     }
   }
   for (int c = 0; c < nb; c++) { for (int r = 0; r < nb; r++) H[(size_t)(g->N * bs + r) + (size_t)(g->N * bs + c) * n] = Cb[r + (size_t)c * nb]; rhs[g->N * bs + c] = Cb[(size_t)nb * nb + c]; }
+  // loop closures: their diagonal shares are already in the records (k_assemble_closures); add the cross blocks H(j, i) = A_j^T A_i
+  for (int k = 0; k < g->NX; k++) {
+    const Extra& e = g->sorted[k];
+    if (!e.closure) continue;
+    for (int q = 0; q < e.m; q++) {
+      const int rw = g->h_xrow[k] + q;
+      for (int r = 0; r < bs; r++) for (int c = 0; c < bs; c++) {
+        const double v = XR[(size_t)(bs + r) * g->NXRp + rw] * XR[(size_t)c * g->NXRp + rw];
+        H[(size_t)(e.sb * bs + r) + (size_t)(e.sa * bs + c) * n] += v; H[(size_t)(e.sa * bs + c) + (size_t)(e.sb * bs + r) * n] += v;
+      }
+    }
+  }
   return GPB_OK;
 }
 

@@ -19,7 +19,9 @@
 #include "kernels_lin.cuh"
 
 struct FwdArgs {
-  int n, M, S, nseg, first_level, extL, extR;   // S = number of ordinary separators; nseg = S + 1
+  int n, M, S, nseg, first_level, extL, extR;   // S = number of interior separators; nseg = S + 1
+  int lamL;            // level 0: the pinned first state is owned by this graph -> its pass-through block gets the LM damping here
+  const int* sep;      // [S] positions of the interior separators in this level's chain (ascending)
   const double* rec;
   const double* brec;
   const double* XR;
@@ -40,6 +42,7 @@ struct FwdArgs {
 
 struct BwdArgs {
   int n, M, S, nseg, nb, extL, extR;
+  const int* sep;
   const double* frec;
   int fstride;
   const double* xup;  // solution of the next level [extL + S + extR][BS]
@@ -47,14 +50,15 @@ struct BwdArgs {
   double* xsol;       // [n][BS]
 };
 
-// Segment geometry shared by the two sweeps.  Chain states 0..n-1; optional external separators (state 0 / state n-1, owned
-// by the neighbouring shard's system) are never eliminated here; ordinary separators sit every M ordinary states.
+// Segment geometry shared by the two sweeps.  Chain states 0..n-1; a pinned first / last state (extL / extR: a shard's external
+// separators, or loop-closure endpoints sitting on the chain ends) is never eliminated; interior separators are listed in
+// sep[] - every M-th ordinary state plus every pinned state (loop-closure endpoint), which stays a separator at every level
+// and so reaches the reduced top system.
 struct SegGeom { int p, q, po, qo, i0, i1; };
-__device__ __forceinline__ SegGeom seg_geom(int seg, int n, int M, int S, int extL, int extR) {
+__device__ __forceinline__ SegGeom seg_geom(int seg, int n, const int* __restrict__ sep, int S, int extL, int extR) {
   SegGeom g;
-  const int base = extL ? 1 : 0;
-  g.p = seg > 0 ? base + seg * M - 1 : (extL ? 0 : -1);
-  g.q = seg < S ? base + (seg + 1) * M - 1 : (extR ? n - 1 : -1);
+  g.p = seg > 0 ? sep[seg - 1] : (extL ? 0 : -1);
+  g.q = seg < S ? sep[seg] : (extR ? n - 1 : -1);
   g.po = seg > 0 ? extL + seg - 1 : 0;
   g.qo = seg < S ? extL + seg : extL + S + extR - 1;
   g.i0 = g.p + 1;
@@ -205,7 +209,7 @@ __global__ void __launch_bounds__((W < 32 ? 32 : W), (W == 64 ? 6 : 8)) k_fwd(co
   __syncthreads();
 
   for (int seg = blockIdx.x; seg < a.nseg; seg += gridDim.x) {
-    const SegGeom sg = seg_geom(seg, a.n, M, a.S, a.extL, a.extR);
+    const SegGeom sg = seg_geom(seg, a.n, a.sep, a.S, a.extL, a.extR);
     const int p = sg.p, q = sg.q, i0 = sg.i0, i1 = sg.i1;
     const int ilast = (q >= 0) ? q : i1;  // last record that must be fetched
     for (int k = c; k < BS * BS; k += NT) Dn[k] = 0.0;
@@ -430,7 +434,7 @@ __global__ void __launch_bounds__((W < 32 ? 32 : W), (W == 64 ? 6 : 8)) k_fwd(co
       // external left separator: nobody is to its left here -> part 1 carries this shard's own (undamped) share of it
       double* R = a.rec_out;  // po == 0
       const double* src = a.rec + (size_t)p * RECS;
-      for (int k = c; k < BS * BS; k += NT) R[k] = first ? src[k] : src[k] + src[BS * BS + k];
+      for (int k = c; k < BS * BS; k += NT) R[k] = first ? src[k] + ((a.lamL && (k % (BS + 1)) == 0) ? (*a.lambda_ptr) : 0.0) : src[k] + src[BS * BS + k];
       if (c < BS) R[3 * BS * BS + c] = first ? src[oG + c] : src[oG + c] + src[oG + BS + c];
       __syncthreads();  // Bn is free (q consumed it); gather p's border when it exists
       if (first && nb > 0) { if (c < 32) gather_border(p, c); }
@@ -504,55 +508,6 @@ __global__ void __launch_bounds__((W < 32 ? 32 : W), (W == 64 ? 6 : 8)) k_fwd(co
   }
 }
 
-// Register-resident variant for a warp with registers to spare (the factor warp of k_fwd_ws): lane r owns row r of the
-// Cholesky factor (pivot and column entries travel by shuffles, no shared-memory round trips); L is then published once and
-// lane c computes column c of L^-1 by forward substitution with broadcast shared-memory reads.  ~500 instructions per block.
-template <int BS>
-__device__ __forceinline__ bool warp_chol_inverse_regs(const double* Dsrc, double* Lsm, double* Li, int lane) {
-  const int rr = lane < BS ? lane : BS - 1;
-  double arow[BS], invs[BS];
-#pragma unroll
-  for (int cc = 0; cc < BS; cc++) arow[cc] = Dsrc[rr + cc * BS];
-  bool ok = true;
-#pragma unroll
-  for (int j = 0; j < BS; j++) {
-    const double piv = __shfl_sync(0xffffffffu, arow[j], j);
-    ok &= (piv > 0.0);
-    const double inv = rsqrt(piv > 0.0 ? piv : 1.0);
-    invs[j] = inv;
-    const double lrj = (lane == j) ? piv * inv : arow[j] * inv;
-    arow[j] = lrj;
-#pragma unroll
-    for (int cc = j + 1; cc < BS; cc++) {
-      const double lcj = __shfl_sync(0xffffffffu, lrj, cc);
-      arow[cc] -= lrj * lcj;
-    }
-  }
-  if (lane < BS) {
-#pragma unroll
-    for (int cc = 0; cc < BS; cc++) Lsm[lane + cc * BS] = arow[cc];
-  }
-  __syncwarp();
-  if (lane < BS) {
-    double x[BS];
-#pragma unroll
-    for (int r = 0; r < BS; r++) {
-      double sv = 0.0;
-#pragma unroll
-      for (int t = 0; t < r; t++) sv += Lsm[r + t * BS] * x[t];   // x[t] == 0 for t < lane
-      x[r] = (r == lane) ? invs[r] : (r < lane ? 0.0 : -sv * invs[r]);
-    }
-#pragma unroll
-    for (int r = 0; r < BS; r++) Li[r + lane * BS] = x[r];
-  }
-  return ok;
-}
-
-// Row-per-lane Cholesky with the triangular inverse fused into the same pivot loop: lane r holds row r of the SPD block AND
-// builds column r of X = L^-1.  At pivot j the column of L travels by shuffles (lcj = L[cc][j]); the same values feed the
-// trailing update  A[r][cc] -= L[r][j] L[cc][j]  and the forward substitution  sv[cc] += L[cc][j] X[j][r], so the inverse costs
-// one extra FMA per shuffle and no data movement of its own.  Only the lower triangle of the input row is used.
-// Output: Li (shared, column-major, full block incl. the zero upper part).  Lanes >= BS shadow row BS-1.
 // 1/sqrt(x) for a positive, normal x: the hardware seed (MUFU.RSQ64H, ~20 bits) and two Newton steps; no special-case branches
 __device__ __forceinline__ double rsqrt_pos(double x) {
   double y;
@@ -562,472 +517,12 @@ __device__ __forceinline__ double rsqrt_pos(double x) {
   y = y * fma(-hx * y, y, 1.5);
   return y;
 }
-template <int BS>
-__device__ __forceinline__ bool warp_chol_inverse_fused(double (&arow)[BS], double* __restrict__ Li, int lane) {
-  double sv[BS];
-#pragma unroll
-  for (int cc = 0; cc < BS; cc++) sv[cc] = 0.0;
-  bool ok = true;
-#pragma unroll
-  for (int j = 0; j < BS; j++) {
-    const double piv = __shfl_sync(0xffffffffu, arow[j], j);
-    ok &= (piv > 0.0);
-    const double inv = rsqrt_pos(piv > 0.0 ? piv : 1.0);
-    const double lrj = (lane == j) ? piv * inv : arow[j] * inv;
-    const double xj = (lane == j) ? inv : (lane > j ? 0.0 : -sv[j] * inv);
-    if (lane < BS) Li[j + lane * BS] = xj;
-#pragma unroll
-    for (int cc = j + 1; cc < BS; cc++) {
-      const double lcj = __shfl_sync(0xffffffffu, lrj, cc);
-      arow[cc] -= lrj * lcj;
-      sv[cc] += lcj * xj;
-    }
-  }
-  return ok;
-}
-
-// ---------------------------------------------------------------------------------------------------------------------
-// Warp-specialised forward sweep (BS = 12, panel width 64): the production path for SE(3) graphs with landmarks.
-//   warp 0 ("factor warp")  walks the chain's serial recurrence  D'_i = D_i - Le_{i-1} Le_{i-1}^T  ->  L_i^-1  ->  Le_i = E_i L_i^-T
-//                           and publishes (L_i^-1, Le_i, g_i) into a 2-slot shared-memory ring; it never touches the panel.
-//   warps 1-2 ("panel")     consume a slot per state: Y = L^-1 P, P' = own - Le Y, S += Y^T Y, all on the FP64 tensor pipe, and
-//                           stream the factors to HBM.  They lag the factor warp by up to two states, so the panel work of
-//                           state i overlaps the factorisation of states i+1, i+2.
-// Hand-off: named barriers (bar.arrive / bar.sync) full[s] / empty[s]; the two panel warps meet on one 64-thread barrier per state.
-__device__ __forceinline__ void nbar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-__device__ __forceinline__ void nbar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-
-template <int BS>
-__global__ void __launch_bounds__(96, 4) k_fwd_ws(const FwdArgs a) {
-  constexpr int W = 64, NT = 96, REC0 = 2 * BS * BS + BS, REC1 = 3 * BS * BS + 2 * BS, NBP = W;
-  constexpr int B_FULL = 1, B_EMPTY = 3, B_PANEL = 5;  // named-barrier ids: full[0..1] = 1,2 ; empty[0..1] = 3,4 ; panel = 5
-  __shared__ __align__(16) double Rb[2][REC1];
-  __shared__ double Dm[BS * BS], Dn[BS * BS], Lsm[BS * BS];
-  __shared__ double LiS[2][BS * BS], LeS[2][BS * BS], gS[2][BS];
-  __shared__ __align__(16) double Psm[W * BS], Ysm[2][W * BS], Bn[2][BS * NBP];  // Bn: landmark border of the current / next state (double buffer)
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gi = lane >> 2, ti = lane & 3;
-  const bool isF = warp == 0;
-  const int c = tid - 32, pw = warp - 1;  // panel column / panel warp index (panel threads only)
-  const int nb = a.nb, w = BS + nb + 1, M = a.M;
-  const bool first = a.first_level != 0;
-  const int RECS = first ? REC0 : REC1;
-  const int oE = first ? BS * BS : 2 * BS * BS, oG = first ? 2 * BS * BS : 3 * BS * BS;
-  const bool is_border = !isF && (c >= BS) && (c < BS + nb), is_rhs = !isF && (c == BS + nb), is_spike = !isF && c < BS, active = !isF && c < w;
-  const int lb = c - BS;
-  const CholMap<BS> cmap = chol_map<BS>(lane);
-
-  double acc[36];
-#pragma unroll
-  for (int j = 0; j < 36; j++) acc[j] = 0.0;
-  int tI[18], tJ[18];  // shared-memory offsets of this lane's A / B fragment elements for its 18 Schur tiles
-#pragma unroll
-  for (int u = 0; u < 18; u++) { const int t = 2 * u + (warp == 2 ? 1 : 0); tI[u] = (8 * c_tileI[t] + gi) * BS + ti; tJ[u] = (8 * c_tileJ[t] + gi) * BS + ti; }
-
-  auto prefetch = [&](int i, int buf) {  // factor warp: whole record of state i -> Rb[buf]
-    const double* src = a.rec + (size_t)i * RECS;
-    for (int k = lane; k < RECS / 2; k += 32) cp_async16(&Rb[buf][2 * k], src + 2 * k);
-  };
-  auto gather_border = [&](int i, int ln, double* Bd) {  // level 0: landmark border of state i -> Bd (lanes 0..BS-1 of one warp)
-    for (int e = a.bsoff[i]; e < a.bsoff[i + 1]; e++) {
-      const int row = a.bsrow[e], side = a.bsside[e];
-      const int l = a.rowland[row];
-      if (ln < BS) {
-        const double av = a.XR[(size_t)(side * BS + ln) * a.NXRp + row];
-        for (int d = 0; d < a.DL; d++) Bd[ln + (l * a.DL + d) * BS] += av * a.XR[(size_t)(2 * BS + d) * a.NXRp + row];
-      }
-    }
-  };
-  auto add_own_border = [&](int i, double* Bd) {  // panel thread: landmark column of state i into its panel column
-    if (!is_border) return;
-    double* P = Psm + c * BS;
-    if (first) {
-      double2* P2 = reinterpret_cast<double2*>(P);
-      double2* B2 = reinterpret_cast<double2*>(Bd + lb * BS);
-#pragma unroll
-      for (int r = 0; r < BS / 2; r++) { const double2 bv = B2[r]; double2 pv = P2[r]; pv.x += bv.x; pv.y += bv.y; P2[r] = pv; B2[r] = make_double2(0.0, 0.0); }
-    } else {
-      const double* B = a.brec + (size_t)i * (2 * BS * nb);
-#pragma unroll
-      for (int r = 0; r < BS; r++) P[r] += B[r + lb * BS] + B[BS * nb + r + lb * BS];
-    }
-  };
-
-  for (int k = tid; k < BS * NBP; k += NT) { Bn[0][k] = 0.0; Bn[1][k] = 0.0; }
-  for (int k = tid; k < BS * BS; k += NT) { LiS[0][k] = 0.0; LiS[1][k] = 0.0; }  // strictly-upper parts of L^-1 stay zero
-  __syncthreads();
-
-  for (int seg = blockIdx.x; seg < a.nseg; seg += gridDim.x) {
-    const SegGeom sg = seg_geom(seg, a.n, M, a.S, a.extL, a.extR);
-    const int p = sg.p, q = sg.q, i0 = sg.i0, i1 = sg.i1;
-    const int ilast = (q >= 0) ? q : i1;
-    // ---- segment prologue
-    if (isF) {
-      for (int k = lane; k < BS * BS; k += 32) Dn[k] = 0.0;
-      if (i0 <= ilast) prefetch(i0, 0);
-      cp_async_commit();
-    } else {
-      const bool sp = is_spike && p >= 0 && i0 <= i1;
-      const double* E = a.rec + (size_t)(sp ? p : 0) * RECS + oE;
-#pragma unroll
-      for (int r = 0; r < BS; r++) Psm[c * BS + r] = sp ? E[r + c * BS] : 0.0;
-      if (first && nb > 0 && i0 <= ilast && pw == 0) gather_border(i0, lane, Bn[0]);
-    }
-    __syncthreads();
-
-    if (isF) {
-      // ================================================= factor warp
-      int buf = 0;
-      for (int i = i0; i <= i1; i++, buf ^= 1) {
-        const int s = (i - i0) & 1;
-        const bool has_next = (i < i1) || (q >= 0);
-        if (i + 1 <= ilast) prefetch(i + 1, buf ^ 1);
-        cp_async_commit();
-        if (i - i0 >= 2) nbar_sync(B_EMPTY + s, NT);  // slot s free again (panel finished state i-2)
-        cp_async_wait<1>();
-        __syncwarp();
-        for (int k = lane; k < BS * BS; k += 32) {
-          double v = Rb[buf][k] + Dn[k];
-          if (first) { if ((k % (BS + 1)) == 0) v += (*a.lambda_ptr); } else v += Rb[buf][BS * BS + k];
-          Dm[k] = v;
-        }
-        if (lane < BS) gS[s][lane] = Rb[buf][oG + lane] + (first ? 0.0 : Rb[buf][oG + BS + lane]);
-        __syncwarp();
-        const bool ok = warp_chol_inverse_regs<BS>(Dm, Lsm, LiS[s], lane);
-        if (!ok && lane == 0) *a.flag = 1;
-        __syncwarp();
-        if (has_next) {
-          // Le = E L^-T (tensor pipe, 4 tiles), then Dn = -Le Le^T
-          const double* E0 = &Rb[buf][oE];
-#pragma unroll
-          for (int mt = 0; mt < 2; mt++)
-#pragma unroll
-            for (int nt = 0; nt < 2; nt++) {
-              double d0 = 0.0, d1 = 0.0;
-#pragma unroll
-              for (int sK = 0; sK < 3; sK++) {
-                const double aE = (8 * mt + gi < BS) ? E0[(8 * mt + gi) + (4 * sK + ti) * BS] : 0.0;
-                const double bL = (8 * nt + gi < BS) ? LiS[s][(8 * nt + gi) + (4 * sK + ti) * BS] : 0.0;
-                dmma884(d0, d1, aE, bL);
-              }
-              if (8 * mt + gi < BS && 8 * nt + 2 * ti < BS) { LeS[s][(8 * mt + gi) + (8 * nt + 2 * ti) * BS] = d0; LeS[s][(8 * mt + gi) + (8 * nt + 2 * ti + 1) * BS] = d1; }
-            }
-          __syncwarp();
-#pragma unroll
-          for (int mt = 0; mt < 2; mt++)
-#pragma unroll
-            for (int nt = 0; nt < 2; nt++) {
-              double d0 = 0.0, d1 = 0.0;
-#pragma unroll
-              for (int sK = 0; sK < 3; sK++) {
-                const double aL = (8 * mt + gi < BS) ? LeS[s][(8 * mt + gi) + (4 * sK + ti) * BS] : 0.0;
-                const double bL = (8 * nt + gi < BS) ? LeS[s][(8 * nt + gi) + (4 * sK + ti) * BS] : 0.0;
-                dmma884(d0, d1, aL, bL);
-              }
-              if (8 * mt + gi < BS && 8 * nt + 2 * ti < BS) { Dn[(8 * mt + gi) + (8 * nt + 2 * ti) * BS] = -d0; Dn[(8 * mt + gi) + (8 * nt + 2 * ti + 1) * BS] = -d1; }
-            }
-        }
-        __syncwarp();
-        nbar_arrive(B_FULL + s, NT);  // publish slot s
-      }
-      // drain: balance the panel's last (up to two) empty-arrivals
-      const int nst = i1 - i0 + 1;
-      if (nst >= 2) nbar_sync(B_EMPTY + ((nst - 2) & 1), NT);
-      if (nst >= 1) nbar_sync(B_EMPTY + ((nst - 1) & 1), NT);
-      cp_async_wait<0>();
-    } else {
-      // ================================================= panel warps
-      for (int i = i0; i <= i1; i++) {
-        const int s = (i - i0) & 1;
-        const bool has_next = (i < i1) || (q >= 0);
-        double* Y = Ysm[s];
-        add_own_border(i, Bn[s]);
-        // next state's landmark border (level 0) into the other buffer; published by this state's panel barrier
-        if (first && nb > 0 && i + 1 <= ilast && pw == 0) gather_border(i + 1, lane, Bn[s ^ 1]);
-        nbar_sync(B_FULL + s, NT);  // L^-1, Le, g of state i are in slot s
-        if (is_rhs) {
-#pragma unroll
-          for (int r = 0; r < BS; r++) Psm[c * BS + r] += gS[s][r];
-        }
-        __syncwarp();
-        // ---- Y = L^-1 P : this warp's column tiles 4pw..4pw+3 (its own threads' columns)
-        {
-          double aLi[2][3];
-#pragma unroll
-          for (int mt = 0; mt < 2; mt++)
-#pragma unroll
-            for (int sK = 0; sK < 3; sK++) aLi[mt][sK] = (8 * mt + gi < BS) ? LiS[s][(8 * mt + gi) + (4 * sK + ti) * BS] : 0.0;
-          double d[4][2][2];
-#pragma unroll
-          for (int jt = 0; jt < 4; jt++) { d[jt][0][0] = d[jt][0][1] = d[jt][1][0] = d[jt][1][1] = 0.0; }
-#pragma unroll
-          for (int sK = 0; sK < 3; sK++)
-#pragma unroll
-            for (int jt = 0; jt < 4; jt++) {
-              const double bP = Psm[(8 * (4 * pw + jt) + gi) * BS + 4 * sK + ti];
-              if (sK < 2) dmma884(d[jt][0][0], d[jt][0][1], aLi[0][sK], bP);
-              dmma884(d[jt][1][0], d[jt][1][1], aLi[1][sK], bP);
-            }
-#pragma unroll
-          for (int jt = 0; jt < 4; jt++) {
-            const int J = 4 * pw + jt;
-#pragma unroll
-            for (int mt = 0; mt < 2; mt++)
-              if (8 * mt + gi < BS) { Y[(8 * J + 2 * ti) * BS + 8 * mt + gi] = d[jt][mt][0]; Y[(8 * J + 2 * ti + 1) * BS + 8 * mt + gi] = d[jt][mt][1]; }
-          }
-        }
-        nbar_sync(B_PANEL, 64);  // all 64 Y columns visible to both panel warps
-        // ---- next panel P' = -Le Y (own column tiles), or zero at the end of an open chain
-        if (has_next) {
-          double aLe[2][3];
-#pragma unroll
-          for (int mt = 0; mt < 2; mt++)
-#pragma unroll
-            for (int sK = 0; sK < 3; sK++) aLe[mt][sK] = (8 * mt + gi < BS) ? LeS[s][(8 * mt + gi) + (4 * sK + ti) * BS] : 0.0;
-          double d[4][2][2];
-#pragma unroll
-          for (int jt = 0; jt < 4; jt++) { d[jt][0][0] = d[jt][0][1] = d[jt][1][0] = d[jt][1][1] = 0.0; }
-#pragma unroll
-          for (int sK = 0; sK < 3; sK++)
-#pragma unroll
-            for (int jt = 0; jt < 4; jt++) {
-              const double bY = Y[(8 * (4 * pw + jt) + gi) * BS + 4 * sK + ti];
-              dmma884(d[jt][0][0], d[jt][0][1], aLe[0][sK], bY);
-              dmma884(d[jt][1][0], d[jt][1][1], aLe[1][sK], bY);
-            }
-#pragma unroll
-          for (int jt = 0; jt < 4; jt++) {
-            const int J = 4 * pw + jt;
-#pragma unroll
-            for (int mt = 0; mt < 2; mt++)
-              if (8 * mt + gi < BS) { Psm[(8 * J + 2 * ti) * BS + 8 * mt + gi] = -d[jt][mt][0]; Psm[(8 * J + 2 * ti + 1) * BS + 8 * mt + gi] = -d[jt][mt][1]; }
-          }
-        } else {
-#pragma unroll
-          for (int r = 0; r < BS; r++) Psm[c * BS + r] = 0.0;
-        }
-        // ---- factors to HBM: Y column (one per thread), L^-1 and Le (shared between the 64 panel threads)
-        double* F = a.frec + (size_t)i * a.fstride;
-        if (active) {
-          const double* yc = Y + c * BS;
-#pragma unroll
-          for (int r = 0; r < BS; r += 2) st128(F + 2 * BS * BS + c * BS + r, yc[r], yc[r + 1]);
-        }
-        for (int k = c; k < BS * BS; k += 64) { F[k] = LiS[s][k]; if (has_next) F[BS * BS + k] = LeS[s][k]; }
-        // ---- Schur accumulation S += Y^T Y : this warp's share of the lower-triangular 8x8 tile grid
-#pragma unroll
-        for (int sK = 0; sK < 3; sK++) {  // k-slice outer, tiles inner: 18 independent accumulators keep the tensor pipe fed
-#pragma unroll
-          for (int u = 0; u < 18; u++) {
-            const double aY = Y[tI[u] + 4 * sK];
-            const double bY = Y[tJ[u] + 4 * sK];
-            dmma884(acc[2 * u], acc[2 * u + 1], aY, bY);
-          }
-        }
-        __syncwarp();
-        nbar_arrive(B_EMPTY + s, NT);  // slot s (and Ysm[s]) may be reused
-      }
-    }
-    __syncthreads();
-
-    // ---- segment end: hand the Schur complement to the next level.  The record of q (if any) is in Rb[(i1 - i0 + 1) & 1].
-    const int qbuf = (i1 - i0 + 1) & 1;
-    auto Dq = [&](int k) -> double {
-      if (first) return Rb[qbuf][k] + ((k % (BS + 1)) == 0 ? (*a.lambda_ptr) : 0.0);
-      return Rb[qbuf][k] + Rb[qbuf][BS * BS + k];
-    };
-    if (q >= 0) {
-      double* R = a.rec_out + (size_t)sg.qo * REC1;
-      for (int k = tid; k < BS * BS; k += NT) R[k] = Dq(k) + Dn[k];  // D1
-      if (!isF) {
-        add_own_border(q, Bn[qbuf]);
-        if (is_rhs) {
-#pragma unroll
-          for (int r = 0; r < BS; r++) Psm[c * BS + r] += Rb[qbuf][oG + r] + (first ? 0.0 : Rb[qbuf][oG + BS + r]);
-        }
-        const double* P = Psm + c * BS;
-        if (is_border) {
-          double* B = a.brec_out + (size_t)sg.qo * (2 * BS * nb);
-#pragma unroll
-          for (int r = 0; r < BS; r++) B[r + lb * BS] = P[r];
-        } else if (is_rhs) {
-#pragma unroll
-          for (int r = 0; r < BS; r++) R[3 * BS * BS + r] = P[r];
-        } else if (is_spike && p >= 0) {
-          double* Ep = a.rec_out + (size_t)sg.po * REC1 + 2 * BS * BS;
-          if (i0 <= i1) {
-#pragma unroll
-            for (int r = 0; r < BS; r++) Ep[r + c * BS] = P[r];
-          } else {
-            const double* E = a.rec + (size_t)p * RECS + oE;
-#pragma unroll
-            for (int r = 0; r < BS; r++) Ep[r + c * BS] = E[r + c * BS];
-          }
-        }
-      }
-      if (a.extR && seg == a.S) {
-        for (int k = tid; k < BS * BS; k += NT) R[BS * BS + k] = 0.0;
-        if (tid < BS) R[3 * BS * BS + BS + tid] = 0.0;
-        if (is_border) { double* B = a.brec_out + (size_t)sg.qo * (2 * BS * nb) + BS * nb;
-#pragma unroll
-          for (int r = 0; r < BS; r++) B[r + lb * BS] = 0.0; }
-      }
-    }
-    if (a.extL && seg == 0) {
-      double* R = a.rec_out;
-      const double* src = a.rec + (size_t)p * RECS;
-      for (int k = tid; k < BS * BS; k += NT) R[k] = first ? src[k] : src[k] + src[BS * BS + k];
-      if (tid < BS) R[3 * BS * BS + tid] = first ? src[oG + tid] : src[oG + tid] + src[oG + BS + tid];
-      __syncthreads();
-      if (first && nb > 0 && warp == 1) gather_border(p, lane, Bn[0]);
-      __syncthreads();
-      if (is_border) {
-        double* B = a.brec_out;
-        if (first) {
-#pragma unroll
-          for (int r = 0; r < BS; r++) { B[r + lb * BS] = Bn[0][r + lb * BS]; Bn[0][r + lb * BS] = 0.0; }
-        } else {
-          const double* Bs = a.brec + (size_t)p * (2 * BS * nb);
-#pragma unroll
-          for (int r = 0; r < BS; r++) B[r + lb * BS] = Bs[r + lb * BS] + Bs[BS * nb + r + lb * BS];
-        }
-      }
-    }
-    if (!isF) {
-      double* Rp = (p >= 0) ? a.rec_out + (size_t)sg.po * REC1 : nullptr;
-      double* Bp = (p >= 0) ? a.brec_out + (size_t)sg.po * (2 * BS * nb) + BS * nb : nullptr;
-      auto flush_spike = [&](int x, int y, double& av) {
-        const int lo = x < y ? x : y, hi = x < y ? y : x;
-        if (lo < BS) {
-          if (p >= 0 && hi < w) {
-            const double v = -av;
-            if (hi < BS) { Rp[BS * BS + lo + hi * BS] = v; Rp[BS * BS + hi + lo * BS] = v; }
-            else if (hi < BS + nb) Bp[lo + (hi - BS) * BS] = v;
-            else Rp[3 * BS * BS + BS + lo] = v;
-          }
-          av = 0.0;
-        }
-      };
-#pragma unroll
-      for (int u = 0; u < 18; u++) {
-        const int t = 2 * u + pw;
-        const int x = 8 * c_tileI[t] + gi, y = 8 * c_tileJ[t] + 2 * ti;
-        if (x >= y) flush_spike(x, y, acc[2 * u]); else if (x < BS || y < BS) acc[2 * u] = 0.0;
-        if (x >= y + 1) flush_spike(x, y + 1, acc[2 * u + 1]); else if (x < BS || y + 1 < BS) acc[2 * u + 1] = 0.0;
-      }
-    }
-    __syncthreads();
-  }
-  if (nb > 0 && !isF) {
-    double* Cs = a.cseg + (size_t)blockIdx.x * (nb * nb + nb);
-    auto flush_land = [&](int x, int y, double av) {
-      const int lo = x < y ? x : y, hi = x < y ? y : x;
-      if (lo >= BS && hi < w) {
-        const double v = -av;
-        if (hi < BS + nb) { Cs[(lo - BS) + (hi - BS) * nb] = v; Cs[(hi - BS) + (lo - BS) * nb] = v; }
-        else if (lo < BS + nb) Cs[nb * nb + (lo - BS)] = v;
-      }
-    };
-#pragma unroll
-    for (int u = 0; u < 18; u++) {
-      const int t = 2 * u + pw;
-      const int x = 8 * c_tileI[t] + gi, y = 8 * c_tileJ[t] + 2 * ti;
-      if (x >= y) flush_land(x, y, acc[2 * u]);
-      if (x >= y + 1) flush_land(x, y + 1, acc[2 * u + 1]);
-    }
-  }
-}
-
 // ---------------------------------------------------------------------------------------------------------------------
 // Two-kernel forward sweep (BS = 12, panel width 64).  The chain "spine"  D'_i = D_i - Le_{i-1} Le_{i-1}^T -> L_i^-1 ->
-// Le_i = E_i L_i^-T  never depends on the panel, so it is factored first by k_spine: ONE WARP PER SEGMENT, ~40 independent warps
-// per SM — the recurrence is latency-bound (12 dependent pivots per state), and only thread-level parallelism hides that.
-// k_panel then streams the stored (L^-1, Le) and does nothing but tensor-pipe products: Y = L^-1 P, P' = own - Le Y, S += Y^T Y.
-template <int BS>
-__global__ void __launch_bounds__(32, 16) k_spine_v1(const FwdArgs a) {
-  // ONE WARP PER CTA: segment and state loops then depend on blockIdx only, so the compiler can prove the warp converged at
-  // every shuffle (with several warps per CTA each __shfl_sync was wrapped in WARPSYNC / BSSY / ENDCOLLECTIVE sequences)
-  constexpr int REC0 = 2 * BS * BS + BS, REC1 = 3 * BS * BS + 2 * BS;
-  __shared__ double Dn[BS * BS], Li[BS * BS], Le[BS * BS];
-  const int lane = threadIdx.x, gi = lane >> 2, ti = lane & 3;
-  const int rr = lane < BS ? lane : BS - 1;
-  const bool first = a.first_level != 0;
-  const int RECS = first ? REC0 : REC1, oE = first ? BS * BS : 2 * BS * BS;
-  const double lambda = first ? *a.lambda_ptr : 0.0;
-  // row rr of D (the layout the factorisation wants) and the A-fragments of E of one state, fetched one state ahead into registers
-  double drow[BS], ev[2][3];
-  auto fetch = [&](int i, bool want_e) {
-    const double* r = a.rec + (size_t)i * RECS;
-#pragma unroll
-    for (int cc = 0; cc < BS; cc++) drow[cc] = first ? r[rr + cc * BS] : r[rr + cc * BS] + r[BS * BS + rr + cc * BS];
-#pragma unroll
-    for (int mt = 0; mt < 2; mt++)
-#pragma unroll
-      for (int sK = 0; sK < 3; sK++) ev[mt][sK] = (want_e && 8 * mt + gi < BS) ? r[oE + (8 * mt + gi) + (4 * sK + ti) * BS] : 0.0;
-  };
-  for (int seg = blockIdx.x; seg < a.nseg; seg += gridDim.x) {
-    const SegGeom sg = seg_geom(seg, a.n, a.M, a.S, a.extL, a.extR);
-    const int q = sg.q, i0 = sg.i0, i1 = sg.i1;
-    const int ilast = (q >= 0) ? q : i1;
-    for (int k = lane; k < BS * BS; k += 32) Dn[k] = 0.0;
-    if (i0 <= ilast) fetch(i0, (i0 < i1) || (q >= 0 && i0 <= i1));
-    __syncwarp();
-#pragma unroll 1
-    for (int i = i0; i <= i1; i++) {
-      const bool has_next = (i < i1) || (q >= 0);
-      double arow[BS], ec[2][3];
-#pragma unroll
-      for (int cc = 0; cc < BS; cc++) arow[cc] = drow[cc] + Dn[rr + cc * BS] + (cc == rr ? lambda : 0.0);
-#pragma unroll
-      for (int mt = 0; mt < 2; mt++)
-#pragma unroll
-        for (int sK = 0; sK < 3; sK++) ec[mt][sK] = ev[mt][sK];
-      if (i + 1 <= ilast) fetch(i + 1, (i + 1 < i1) || (q >= 0 && i + 1 <= i1));  // next state's loads fly during this factorisation
-      const bool ok = warp_chol_inverse_fused<BS>(arow, Li, lane);
-      if (!ok && lane == 0) *a.flag = 1;
-      __syncwarp();
-      double* F = a.frec + (size_t)i * a.fstride;
-      for (int k = lane; k < BS * BS; k += 32) F[k] = Li[k];
-      if (has_next) {
-#pragma unroll
-        for (int mt = 0; mt < 2; mt++)
-#pragma unroll
-          for (int nt = 0; nt < 2; nt++) {  // Le = E L^-T
-            double d0 = 0.0, d1 = 0.0;
-#pragma unroll
-            for (int sK = 0; sK < 3; sK++) {
-              const double bL = (8 * nt + gi < BS) ? Li[(8 * nt + gi) + (4 * sK + ti) * BS] : 0.0;
-              dmma884(d0, d1, ec[mt][sK], bL);
-            }
-            if (8 * mt + gi < BS && 8 * nt + 2 * ti < BS) { Le[(8 * mt + gi) + (8 * nt + 2 * ti) * BS] = d0; Le[(8 * mt + gi) + (8 * nt + 2 * ti + 1) * BS] = d1; }
-          }
-        __syncwarp();
-        for (int k = lane; k < BS * BS; k += 32) F[BS * BS + k] = Le[k];
-#pragma unroll
-        for (int mt = 0; mt < 2; mt++)
-#pragma unroll
-          for (int nt = 0; nt < 2; nt++) {  // Dn = -Le Le^T
-            double d0 = 0.0, d1 = 0.0;
-#pragma unroll
-            for (int sK = 0; sK < 3; sK++) {
-              const double aL = (8 * mt + gi < BS) ? Le[(8 * mt + gi) + (4 * sK + ti) * BS] : 0.0;
-              const double bL = (8 * nt + gi < BS) ? Le[(8 * nt + gi) + (4 * sK + ti) * BS] : 0.0;
-              dmma884(d0, d1, aL, bL);
-            }
-            if (8 * mt + gi < BS && 8 * nt + 2 * ti < BS) { Dn[(8 * mt + gi) + (8 * nt + 2 * ti) * BS] = -d0; Dn[(8 * mt + gi) + (8 * nt + 2 * ti + 1) * BS] = -d1; }
-          }
-      }
-      __syncwarp();
-    }
-    if (q >= 0 && lane < BS) {  // D1 of the right separator: its own block (fetched last) + the last Schur update (+ damping at level 0)
-      double* R = a.rec_out + (size_t)sg.qo * REC1;
-#pragma unroll
-      for (int cc = 0; cc < BS; cc++) R[rr + cc * BS] = drow[cc] + Dn[rr + cc * BS] + (cc == rr ? lambda : 0.0);
-    }
-    __syncwarp();
-  }
-}
-
-
+// Le_i = E_i L_i^-T  never depends on the panel, so it is factored first by k_spine: ONE WARP PER SEGMENT, 16 independent warps
+// per SM - the recurrence is latency-bound (12 dependent pivots per state), and only thread-level parallelism hides that.
+// k_panel4 then streams the stored (L^-1, Le) and does nothing but tensor-pipe products: Y = L^-1 P, P' = own - Le Y, S += Y^T Y.
+//
 // Spine, second version: the block column [D_i ; E_i] (24 x 12) is factored as ONE panel.  Lanes 0..11 own the rows of D_i,
 // lanes 12..23 the rows of E_i = H_{i+1,i}; the right-looking pivot loop (one shuffle per column entry) then leaves the rows of
 // L_i in lanes 0..11 and the rows of Le_i = E_i L_i^-T in lanes 12..23 - Le costs no instruction of its own, and it no longer
@@ -1060,7 +555,7 @@ __global__ void __launch_bounds__(32, 16) k_spine(const FwdArgs a) {
     }
   };
   for (int seg = blockIdx.x; seg < a.nseg; seg += gridDim.x) {
-    const SegGeom sg = seg_geom(seg, a.n, a.M, a.S, a.extL, a.extR);
+    const SegGeom sg = seg_geom(seg, a.n, a.sep, a.S, a.extL, a.extR);
     const int q = sg.q, i0 = sg.i0, i1 = sg.i1;
     const int ilast = (q >= 0) ? q : i1;
     for (int k = lane; k < BS * BS; k += 32) Dn[k] = 0.0;
@@ -1139,272 +634,6 @@ __global__ void __launch_bounds__(32, 16) k_spine(const FwdArgs a) {
   }
 }
 
-template <int BS>
-__global__ void __launch_bounds__(64, 8) k_panel(const FwdArgs a) {
-  constexpr int W = 64, NT = 64, REC0 = 2 * BS * BS + BS, REC1 = 3 * BS * BS + 2 * BS, NBP = W;
-  __shared__ __align__(16) double Fb[2][2 * BS * BS];  // (L^-1 | Le) of the current / next state (cp.async double buffer)
-  __shared__ __align__(16) double Gb[2][2 * BS];       // rhs block(s) g of the current / next state
-  __shared__ __align__(16) double Psm[W * BS], Ysm[W * BS], Bn[2][BS * NBP];
-  const int c = threadIdx.x, pw = c >> 5, lane = c & 31, gi = lane >> 2, ti = lane & 3;
-  const int nb = a.nb, w = BS + nb + 1, M = a.M;
-  const bool first = a.first_level != 0;
-  const int RECS = first ? REC0 : REC1;
-  const int oE = first ? BS * BS : 2 * BS * BS, oG = first ? 2 * BS * BS : 3 * BS * BS;
-  const bool is_border = (c >= BS) && (c < BS + nb), is_rhs = (c == BS + nb), is_spike = c < BS, active = c < w;
-  const int lb = c - BS;
-  double acc[36];
-#pragma unroll
-  for (int j = 0; j < 36; j++) acc[j] = 0.0;
-  int tI[18], tJ[18];
-#pragma unroll
-  for (int u = 0; u < 18; u++) { const int t = 2 * u + pw; tI[u] = (8 * c_tileI[t] + gi) * BS + ti; tJ[u] = (8 * c_tileJ[t] + gi) * BS + ti; }
-
-  auto prefetch = [&](int i, int buf, bool with_le) {
-    const double* src = a.frec + (size_t)i * a.fstride;
-    const int n2 = (with_le ? 2 * BS * BS : BS * BS) / 2;
-    for (int k = c; k < n2; k += NT) cp_async16(&Fb[buf][2 * k], src + 2 * k);
-  };
-  auto prefetch_g = [&](int i, int buf) {
-    const double* g = a.rec + (size_t)i * RECS + oG;
-    if (c < (first ? BS : 2 * BS) / 2) cp_async16(&Gb[buf][2 * c], g + 2 * c);
-  };
-  auto gather_border = [&](int i, int ln, double* Bd) {
-    for (int e = a.bsoff[i]; e < a.bsoff[i + 1]; e++) {
-      const int row = a.bsrow[e], side = a.bsside[e];
-      const int l = a.rowland[row];
-      if (ln < BS) {
-        const double av = a.XR[(size_t)(side * BS + ln) * a.NXRp + row];
-        for (int d = 0; d < a.DL; d++) Bd[ln + (l * a.DL + d) * BS] += av * a.XR[(size_t)(2 * BS + d) * a.NXRp + row];
-      }
-    }
-  };
-  auto add_own = [&](int i, double* Bd) {  // landmark column / rhs of state i into this thread's panel column
-    double* P = Psm + c * BS;
-    if (is_border) {
-      if (first) {
-        double2* P2 = reinterpret_cast<double2*>(P);
-        double2* B2 = reinterpret_cast<double2*>(Bd + lb * BS);
-#pragma unroll
-        for (int r = 0; r < BS / 2; r++) { const double2 bv = B2[r]; double2 pv = P2[r]; pv.x += bv.x; pv.y += bv.y; P2[r] = pv; B2[r] = make_double2(0.0, 0.0); }
-      } else {
-        const double* B = a.brec + (size_t)i * (2 * BS * nb);
-#pragma unroll
-        for (int r = 0; r < BS; r++) P[r] += B[r + lb * BS] + B[BS * nb + r + lb * BS];
-      }
-    }
-  };
-  auto add_rhs = [&](int buf) {  // after the cp.async of this state's g has landed
-    if (is_rhs) {
-#pragma unroll
-      for (int r = 0; r < BS; r++) Psm[c * BS + r] += Gb[buf][r] + (first ? 0.0 : Gb[buf][BS + r]);
-    }
-  };
-  for (int k = c; k < BS * NBP; k += NT) { Bn[0][k] = 0.0; Bn[1][k] = 0.0; }
-  __syncthreads();
-
-  for (int seg = blockIdx.x; seg < a.nseg; seg += gridDim.x) {
-    const SegGeom sg = seg_geom(seg, a.n, M, a.S, a.extL, a.extR);
-    const int p = sg.p, q = sg.q, i0 = sg.i0, i1 = sg.i1;
-    const int ilast = (q >= 0) ? q : i1;
-    if (i0 <= i1) prefetch(i0, 0, (i0 < i1) || (q >= 0));
-    if (i0 <= ilast) prefetch_g(i0, 0);
-    cp_async_commit();
-    {
-      const bool sp = is_spike && p >= 0 && i0 <= i1;
-      const double* E = a.rec + (size_t)(sp ? p : 0) * RECS + oE;
-#pragma unroll
-      for (int r = 0; r < BS; r++) Psm[c * BS + r] = sp ? E[r + c * BS] : 0.0;
-    }
-    if (first && nb > 0 && i0 <= ilast && pw == 0) gather_border(i0, lane, Bn[0]);
-    __syncthreads();
-    int s = 0;
-    for (int i = i0; i <= i1; i++, s ^= 1) {
-      const bool has_next = (i < i1) || (q >= 0);
-      if (i + 1 <= i1) prefetch(i + 1, s ^ 1, (i + 1 < i1) || (q >= 0));
-      if (i + 1 <= ilast) prefetch_g(i + 1, s ^ 1);
-      cp_async_commit();
-      add_own(i, Bn[s]);
-      if (first && nb > 0 && i + 1 <= ilast && pw == 0) gather_border(i + 1, lane, Bn[s ^ 1]);
-      cp_async_wait<1>();
-      __syncthreads();
-      add_rhs(s);   // the rhs column (thread BS + nb) lives in this warp's own column tiles: a warp-level sync is enough
-      __syncwarp();
-      const double* Li = Fb[s];
-      const double* Le = Fb[s] + BS * BS;
-      // ---- Y = L^-1 P (own column tiles)
-      {
-        double aLi[2][3];
-#pragma unroll
-        for (int mt = 0; mt < 2; mt++)
-#pragma unroll
-          for (int sK = 0; sK < 3; sK++) aLi[mt][sK] = (8 * mt + gi < BS) ? Li[(8 * mt + gi) + (4 * sK + ti) * BS] : 0.0;
-        double d[4][2][2];
-#pragma unroll
-        for (int jt = 0; jt < 4; jt++) { d[jt][0][0] = d[jt][0][1] = d[jt][1][0] = d[jt][1][1] = 0.0; }
-#pragma unroll
-        for (int sK = 0; sK < 3; sK++)
-#pragma unroll
-          for (int jt = 0; jt < 4; jt++) {
-            const double bP = Psm[(8 * (4 * pw + jt) + gi) * BS + 4 * sK + ti];
-            if (sK < 2) dmma884(d[jt][0][0], d[jt][0][1], aLi[0][sK], bP);
-            dmma884(d[jt][1][0], d[jt][1][1], aLi[1][sK], bP);
-          }
-#pragma unroll
-        for (int jt = 0; jt < 4; jt++) {
-          const int J = 4 * pw + jt;
-#pragma unroll
-          for (int mt = 0; mt < 2; mt++)
-            if (8 * mt + gi < BS) { Ysm[(8 * J + 2 * ti) * BS + 8 * mt + gi] = d[jt][mt][0]; Ysm[(8 * J + 2 * ti + 1) * BS + 8 * mt + gi] = d[jt][mt][1]; }
-        }
-      }
-      __syncthreads();
-      // ---- P' = -Le Y (own column tiles)
-      if (has_next) {
-        double aLe[2][3];
-#pragma unroll
-        for (int mt = 0; mt < 2; mt++)
-#pragma unroll
-          for (int sK = 0; sK < 3; sK++) aLe[mt][sK] = (8 * mt + gi < BS) ? Le[(8 * mt + gi) + (4 * sK + ti) * BS] : 0.0;
-        double d[4][2][2];
-#pragma unroll
-        for (int jt = 0; jt < 4; jt++) { d[jt][0][0] = d[jt][0][1] = d[jt][1][0] = d[jt][1][1] = 0.0; }
-#pragma unroll
-        for (int sK = 0; sK < 3; sK++)
-#pragma unroll
-          for (int jt = 0; jt < 4; jt++) {
-            const double bY = Ysm[(8 * (4 * pw + jt) + gi) * BS + 4 * sK + ti];
-            dmma884(d[jt][0][0], d[jt][0][1], aLe[0][sK], bY);
-            dmma884(d[jt][1][0], d[jt][1][1], aLe[1][sK], bY);
-          }
-#pragma unroll
-        for (int jt = 0; jt < 4; jt++) {
-          const int J = 4 * pw + jt;
-#pragma unroll
-          for (int mt = 0; mt < 2; mt++)
-            if (8 * mt + gi < BS) { Psm[(8 * J + 2 * ti) * BS + 8 * mt + gi] = -d[jt][mt][0]; Psm[(8 * J + 2 * ti + 1) * BS + 8 * mt + gi] = -d[jt][mt][1]; }
-        }
-      } else {
-#pragma unroll
-        for (int r = 0; r < BS; r++) Psm[c * BS + r] = 0.0;
-      }
-      // ---- Y column to HBM
-      if (active) {
-        double* F = a.frec + (size_t)i * a.fstride;
-        const double* yc = Ysm + c * BS;
-#pragma unroll
-        for (int r = 0; r < BS; r += 2) st128(F + 2 * BS * BS + c * BS + r, yc[r], yc[r + 1]);
-      }
-      // ---- S += Y^T Y
-#pragma unroll
-      for (int sK = 0; sK < 3; sK++) {
-#pragma unroll
-        for (int u = 0; u < 18; u++) {
-          const double aY = Ysm[tI[u] + 4 * sK];
-          const double bY = Ysm[tJ[u] + 4 * sK];
-          dmma884(acc[2 * u], acc[2 * u + 1], aY, bY);
-        }
-      }
-      __syncthreads();
-    }
-    cp_async_wait<0>();
-    // ---- segment end (D1 of q was written by k_spine)
-    const int qpar = (i1 - i0 + 1) & 1;
-    if (q >= 0) {
-      double* R = a.rec_out + (size_t)sg.qo * REC1;
-      add_own(q, Bn[qpar]);
-      __syncthreads();   // g of q was copied by threads 0..BS-1; the rhs thread reads it
-      add_rhs(qpar);
-      const double* P = Psm + c * BS;
-      if (is_border) {
-        double* B = a.brec_out + (size_t)sg.qo * (2 * BS * nb);
-#pragma unroll
-        for (int r = 0; r < BS; r++) B[r + lb * BS] = P[r];
-      } else if (is_rhs) {
-#pragma unroll
-        for (int r = 0; r < BS; r++) R[3 * BS * BS + r] = P[r];
-      } else if (is_spike && p >= 0) {
-        double* Ep = a.rec_out + (size_t)sg.po * REC1 + 2 * BS * BS;
-        if (i0 <= i1) {
-#pragma unroll
-          for (int r = 0; r < BS; r++) Ep[r + c * BS] = P[r];
-        } else {
-          const double* E = a.rec + (size_t)p * RECS + oE;
-#pragma unroll
-          for (int r = 0; r < BS; r++) Ep[r + c * BS] = E[r + c * BS];
-        }
-      }
-      if (a.extR && seg == a.S) {
-        for (int k = c; k < BS * BS; k += NT) R[BS * BS + k] = 0.0;
-        if (c < BS) R[3 * BS * BS + BS + c] = 0.0;
-        if (is_border) { double* B = a.brec_out + (size_t)sg.qo * (2 * BS * nb) + BS * nb;
-#pragma unroll
-          for (int r = 0; r < BS; r++) B[r + lb * BS] = 0.0; }
-      }
-    }
-    if (a.extL && seg == 0) {
-      double* R = a.rec_out;
-      const double* src = a.rec + (size_t)p * RECS;
-      for (int k = c; k < BS * BS; k += NT) R[k] = first ? src[k] : src[k] + src[BS * BS + k];
-      if (c < BS) R[3 * BS * BS + c] = first ? src[oG + c] : src[oG + c] + src[oG + BS + c];
-      __syncthreads();
-      if (first && nb > 0 && pw == 0) gather_border(p, lane, Bn[0]);
-      __syncthreads();
-      if (is_border) {
-        double* B = a.brec_out;
-        if (first) {
-#pragma unroll
-          for (int r = 0; r < BS; r++) { B[r + lb * BS] = Bn[0][r + lb * BS]; Bn[0][r + lb * BS] = 0.0; }
-        } else {
-          const double* Bs = a.brec + (size_t)p * (2 * BS * nb);
-#pragma unroll
-          for (int r = 0; r < BS; r++) B[r + lb * BS] = Bs[r + lb * BS] + Bs[BS * nb + r + lb * BS];
-        }
-      }
-    }
-    {
-      double* Rp = (p >= 0) ? a.rec_out + (size_t)sg.po * REC1 : nullptr;
-      double* Bp = (p >= 0) ? a.brec_out + (size_t)sg.po * (2 * BS * nb) + BS * nb : nullptr;
-      auto flush_spike = [&](int x, int y, double& av) {
-        const int lo = x < y ? x : y, hi = x < y ? y : x;
-        if (lo < BS) {
-          if (p >= 0 && hi < w) {
-            const double v = -av;
-            if (hi < BS) { Rp[BS * BS + lo + hi * BS] = v; Rp[BS * BS + hi + lo * BS] = v; }
-            else if (hi < BS + nb) Bp[lo + (hi - BS) * BS] = v;
-            else Rp[3 * BS * BS + BS + lo] = v;
-          }
-          av = 0.0;
-        }
-      };
-#pragma unroll
-      for (int u = 0; u < 18; u++) {
-        const int t = 2 * u + pw;
-        const int x = 8 * c_tileI[t] + gi, y = 8 * c_tileJ[t] + 2 * ti;
-        if (x >= y) flush_spike(x, y, acc[2 * u]); else if (x < BS || y < BS) acc[2 * u] = 0.0;
-        if (x >= y + 1) flush_spike(x, y + 1, acc[2 * u + 1]); else if (x < BS || y + 1 < BS) acc[2 * u + 1] = 0.0;
-      }
-    }
-    __syncthreads();
-  }
-  if (nb > 0) {
-    double* Cs = a.cseg + (size_t)blockIdx.x * (nb * nb + nb);
-    auto flush_land = [&](int x, int y, double av) {
-      const int lo = x < y ? x : y, hi = x < y ? y : x;
-      if (lo >= BS && hi < w) {
-        const double v = -av;
-        if (hi < BS + nb) { Cs[(lo - BS) + (hi - BS) * nb] = v; Cs[(hi - BS) + (lo - BS) * nb] = v; }
-        else if (lo < BS + nb) Cs[nb * nb + (lo - BS)] = v;
-      }
-    };
-#pragma unroll
-    for (int u = 0; u < 18; u++) {
-      const int t = 2 * u + pw;
-      const int x = 8 * c_tileI[t] + gi, y = 8 * c_tileJ[t] + 2 * ti;
-      if (x >= y) flush_land(x, y, acc[2 * u]);
-      if (x >= y + 1) flush_land(x, y + 1, acc[2 * u + 1]);
-    }
-  }
-}
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Panel kernel, four warps.  Warp pw owns column tiles 2pw, 2pw+1 of the 12 x 64 panel [spike | border | rhs] for the
@@ -1485,7 +714,7 @@ __global__ void __launch_bounds__(128, 5) k_panel4(const FwdArgs a) {
   auto bso = [&](int i) { return ent ? a.bsoff[i < a.n ? i : a.n] : 0; };
 
   for (int seg = blockIdx.x; seg < a.nseg; seg += gridDim.x) {
-    const SegGeom sg = seg_geom(seg, a.n, M, a.S, a.extL, a.extR);
+    const SegGeom sg = seg_geom(seg, a.n, a.sep, a.S, a.extL, a.extR);
     const int p = sg.p, q = sg.q, i0 = sg.i0, i1 = sg.i1;
     const int ilast = (q >= 0) ? q : i1;
     int b0 = bso(i0), b1 = bso(i0 + 1), b2 = bso(i0 + 2), b3 = bso(i0 + 3);  // rolling window of CSR offsets: states i .. i+3
@@ -1657,7 +886,7 @@ __global__ void __launch_bounds__(128, 5) k_panel4(const FwdArgs a) {
     if (a.extL && seg == 0) {  // the left external separator (halo state p): its own blocks pass through to the next level
       double* R = a.rec_out;
       const double* src = a.rec + (size_t)p * RECS;
-      for (int k = c; k < BS * BS; k += NT) R[k] = first ? src[k] : src[k] + src[BS * BS + k];
+      for (int k = c; k < BS * BS; k += NT) R[k] = first ? src[k] + ((a.lamL && (k % (BS + 1)) == 0) ? (*a.lambda_ptr) : 0.0) : src[k] + src[BS * BS + k];
       if (c < BS) R[3 * BS * BS + c] = first ? src[oG + c] : src[oG + c] + src[oG + BS + c];
       if (is_border) {
         double* B = a.brec_out + r0 + lb * BS;
@@ -1745,7 +974,7 @@ __global__ void __launch_bounds__((W < 32 ? 32 : W)) k_bwd(const BwdArgs a) {
     for (int k = c; k < fs / 2; k += NT) cp_async16(&Fb[buf][2 * k], src + 2 * k);
   };
   for (int seg = blockIdx.x; seg < a.nseg; seg += gridDim.x) {
-    const SegGeom sg = seg_geom(seg, a.n, M, a.S, a.extL, a.extR);
+    const SegGeom sg = seg_geom(seg, a.n, a.sep, a.S, a.extL, a.extR);
     const int p = sg.p, q = sg.q, i0 = sg.i0, i1 = sg.i1;
     if (i1 >= i0) prefetch(i1, 0);
     cp_async_commit();
@@ -1873,7 +1102,7 @@ __global__ void k_cseg_final(const double* __restrict__ Cbase, const double* __r
 // one warp, row-oriented, the solution entries living in registers (entry r on lane r mod 32).
 constexpr int SMALL_SOLVE_MAX = 160;
 template <int NT>
-__global__ void __launch_bounds__(NT) k_small_solve(const double* __restrict__ A, const double* rhs, int R, int loff,
+__global__ void __launch_bounds__(NT) k_small_solve(const double* __restrict__ A, int lda, const double* rhs, int rstride, int R, int loff,
                                                     const double* __restrict__ lambda_ptr, double* x, int* __restrict__ flag, int flagval) {
   extern __shared__ double sm[];
   const int ld = R + 1 + ((R & 1) ? 1 : 0);  // odd leading dimension: row walks are bank-conflict free
@@ -1881,8 +1110,8 @@ __global__ void __launch_bounds__(NT) k_small_solve(const double* __restrict__ A
   const double lambda = *lambda_ptr;
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4, TY = NT / 16;
   for (int c = ty; c < R; c += TY) {
-    for (int r = c + tx; r < R; r += 16) sm[r + c * ld] = A[r + (size_t)c * R] + ((r == c && r >= loff) ? lambda : 0.0);
-    if (tx == 0) sm[R + c * ld] = rhs[c];
+    for (int r = c + tx; r < R; r += 16) sm[r + c * ld] = A[r + (size_t)c * lda] + ((r == c && r >= loff) ? lambda : 0.0);
+    if (tx == 0) sm[R + c * ld] = rhs[(size_t)c * rstride];
   }
   __syncthreads();
   for (int j = 0; j < R; j++) {
@@ -1982,75 +1211,216 @@ __global__ void k_retract_land(const double* __restrict__ land, const double* __
   if (threadIdx.x == 0) { scal[1] += t1; scal[2] += t2; }
 }
 
-// ===================================================================== sharded graphs: the global reduced system
-// Unknowns: [separator_0 .. separator_{P-2} (bs each) | landmarks (nb)], R = (P-1) bs + nb.  Buffer: T (R x R column-major,
-// full symmetric) | t (R) | scalars[4] = {local error sum, not-PD flag sum, unused, unused}.  Every rank adds the Schur
-// complement of its segment (top-level records of its external separators, its landmark block) at its offsets; ONE
-// all-reduce (sum) over NVLink completes the system; every rank then factors it redundantly.
+// ===================================================================== the reduced ("top") system
+// Unknowns: [top states (bs each) | landmarks (nb)], R = ntop * bs + nb.  Top states are the pinned states of the chain: the
+// external separators of a shard (its halo and its last state) and the endpoints of loop closures - states the level recursion
+// never eliminates.  Buffer: T ((R+1) x R column-major, leading dimension R+1: rows 0..R-1 the symmetric matrix, row R the
+// right-hand side) | scalars[4] = {local error sum, not-PD flag sum, unused, unused}.  A graph adds the Schur complement of its
+// chain (top-level records of its pinned states at their global top indices gtop[], its landmark block, its loop-closure cross
+// blocks); on sharded graphs ONE all-reduce (sum) over NVLink completes the system and every rank factors it redundantly.
 struct PackArgs {
-  int bs, nb, R, nsep, rank, extL, extR;
-  const double* rec;    // top-level records [extL + extR][3 bs^2 + 2 bs]
-  const double* brec;   // [extL + extR][2 bs nb]
-  const double* Csum;   // local landmark block nb*nb + nb
+  int bs, nb, R, ntop, P;   // ntop: top states of the whole (global) system; P: this graph's top-level chain length
+  const int* gtop;          // [P] global top index of local top state k
+  const double* rec;        // top-level records [P][3 bs^2 + 2 bs]
+  const double* brec;       // [P][2 bs nb]
+  const double* Csum;       // local landmark block nb*nb + nb
   double err_local;
-  const double* err_ptr;  // when non-null the local error is read from device memory (asynchronous Gauss-Newton) instead of err_local
+  const double* err_ptr;    // when non-null the local error is read from device memory (asynchronous Gauss-Newton) instead of err_local
   const int* flag;
-  double* buf;
+  double* buf;              // zero-filled before the launch
 };
+// one CTA per local top state (+ one for the landmark block and the scalars)
 __global__ void k_pack_top(const PackArgs a) {
-  const int R = a.R, bs = a.bs, nb = a.nb, REC1 = 3 * bs * bs + 2 * bs;
-  const size_t total = (size_t)R * R + R + 4;
-  const int loff = a.nsep * bs;  // landmark offset
-  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
-    double v = 0.0;
-    if (e < (size_t)R * R) {
-      const int r = (int)(e % R), c = (int)(e / R);
-      // classify row / column: separator block index or landmark
-      auto local_slot = [&](int sep) -> int {  // slot of global separator `sep` in this rank's top records, or -1
-        if (a.extL && sep == a.rank - 1) return 0;
-        if (a.extR && sep == a.rank) return a.extL;
-        return -1;
-      };
-      const bool rl = r >= loff, cl = c >= loff;
-      if (rl && cl) v = a.Csum[(r - loff) + (size_t)(c - loff) * nb];
-      else if (!rl && !cl) {
-        const int sr = r / bs, sc = c / bs, ir = r % bs, ic = c % bs;
-        const int kr = local_slot(sr), kc = local_slot(sc);
-        if (kr >= 0 && kc >= 0) {
-          if (kr == kc) { const double* D = a.rec + (size_t)kr * REC1; v = D[ir + ic * bs] + D[bs * bs + ir + ic * bs]; }
-          else if (kr == kc + 1) v = a.rec[(size_t)kc * REC1 + 2 * bs * bs + ir + ic * bs];       // E: rows slot kc+1, cols slot kc
-          else if (kc == kr + 1) v = a.rec[(size_t)kr * REC1 + 2 * bs * bs + ic + ir * bs];
-        }
-      } else {
-        const int rs = rl ? c : r, ll = (rl ? r : c) - loff;  // separator row index, landmark column
-        const int k = local_slot(rs / bs);
-        if (k >= 0) { const double* B = a.brec + (size_t)k * (2 * bs * nb); v = B[(rs % bs) + ll * bs] + B[bs * nb + (rs % bs) + ll * bs]; }
-      }
-    } else if (e < (size_t)R * R + R) {
-      const int r = (int)(e - (size_t)R * R);
-      if (r >= loff) v = a.Csum[(size_t)nb * nb + (r - loff)];
-      else {
-        int k = -1;
-        if (a.extL && r / bs == a.rank - 1) k = 0;
-        if (a.extR && r / bs == a.rank) k = a.extL;
-        if (k >= 0) { const double* g = a.rec + (size_t)k * REC1 + 3 * bs * bs; v = g[r % bs] + g[bs + r % bs]; }
-      }
-    } else {
-      const int sidx = (int)(e - ((size_t)R * R + R));
-      v = sidx == 0 ? (a.err_ptr ? *a.err_ptr : a.err_local) : (sidx == 1 ? (double)(*a.flag) : 0.0);
+  const int R = a.R, ld = R + 1, bs = a.bs, nb = a.nb, REC1 = 3 * bs * bs + 2 * bs, loff = a.ntop * bs;
+  const int k = blockIdx.x, tid = threadIdx.x, NT = blockDim.x;
+  double* T = a.buf;
+  if (k < a.P) {
+    const double* rec = a.rec + (size_t)k * REC1;
+    const int o = a.gtop[k] * bs;
+    for (int e = tid; e < bs * bs; e += NT) { const int r = e % bs, c = e / bs; T[(o + r) + (size_t)(o + c) * ld] = rec[e] + rec[bs * bs + e]; }
+    if (k + 1 < a.P) {  // E: rows top state k+1, cols top state k (the segment between them wrote it)
+      const int o1 = a.gtop[k + 1] * bs;
+      for (int e = tid; e < bs * bs; e += NT) { const int r = e % bs, c = e / bs; const double v = rec[2 * bs * bs + e]; T[(o1 + r) + (size_t)(o + c) * ld] = v; T[(o + c) + (size_t)(o1 + r) * ld] = v; }
     }
-    a.buf[e] = v;
+    const double* B = a.brec + (size_t)k * (2 * bs * nb);
+    for (int e = tid; e < bs * nb; e += NT) { const int r = e % bs, l = e / bs; const double v = B[e] + B[bs * nb + e]; T[(o + r) + (size_t)(loff + l) * ld] = v; T[(loff + l) + (size_t)(o + r) * ld] = v; }
+    for (int r = tid; r < bs; r += NT) T[R + (size_t)(o + r) * ld] = rec[3 * bs * bs + r] + rec[3 * bs * bs + bs + r];
+  } else {
+    for (int e = tid; e < nb * nb; e += NT) { const int r = e % nb, c = e / nb; T[(loff + r) + (size_t)(loff + c) * ld] = a.Csum[e]; }
+    for (int r = tid; r < nb; r += NT) T[R + (size_t)(loff + r) * ld] = a.Csum[(size_t)nb * nb + r];
+    if (tid == 0) { double* sc = T + (size_t)ld * R; sc[0] = a.err_ptr ? *a.err_ptr : a.err_local; sc[1] = (double)(*a.flag); sc[2] = 0.0; sc[3] = 0.0; }
   }
 }
 
-// scatter the reduced solution: this rank's external separators -> top-level xsol, landmarks -> xl
-__global__ void k_top_scatter(const double* __restrict__ buf, int R, int bs, int nb, int nsep, int rank, int extL, int extR, double* __restrict__ xsol_top,
+// Loop closures (BetweenFactor between non-adjacent states i < j; their whitened rows sit at the tail of the extra-row table,
+// a-part = state i, b-part = state j, pose columns only).  Diagonal share: one CTA per endpoint state adds sum A_s^T A_s and
+// sum A_s^T b into the state's assembled record (after k_assemble; fixed order -> deterministic).
+__global__ void k_assemble_closures(const double* __restrict__ XR, int NXRp, int bs, int m, int xrhs, const int* __restrict__ epstate, const int* __restrict__ epoff,
+                                    const int* __restrict__ eprow, const int* __restrict__ epside, double* __restrict__ HREC) {
+  const int s = epstate[blockIdx.x], REC = 2 * bs * bs + bs, tid = threadIdx.x;
+  double* rec = HREC + (size_t)s * REC;
+  for (int e = tid; e < bs * bs + bs; e += blockDim.x) {
+    const bool isg = e >= bs * bs;
+    const int r = isg ? e - bs * bs : e % bs, c = isg ? 0 : e / bs;
+    double acc = 0.0;
+    for (int t = epoff[blockIdx.x]; t < epoff[blockIdx.x + 1]; t++) {
+      const int row0 = eprow[t], o = epside[t] * bs;
+      for (int q = 0; q < m; q++) {
+        const double ar = XR[(size_t)(o + r) * NXRp + row0 + q];
+        acc += ar * (isg ? XR[(size_t)xrhs * NXRp + row0 + q] : XR[(size_t)(o + c) * NXRp + row0 + q]);
+      }
+    }
+    rec[isg ? 2 * bs * bs + r : e] += acc;
+  }
+}
+// Cross share: one CTA per unique endpoint pair adds sum A_j^T A_i at (rows top(j), cols top(i)) of the packed top system and
+// its transpose (+= : a pair adjacent in the top chain already holds its chain coupling there).
+__global__ void k_pack_closures(const double* __restrict__ XR, int NXRp, int bs, int m, int ld, const int* __restrict__ pair_a, const int* __restrict__ pair_b,
+                                const int* __restrict__ pairoff, const int* __restrict__ pairrow, double* __restrict__ T) {
+  const int oa = pair_a[blockIdx.x] * bs, ob = pair_b[blockIdx.x] * bs;  // global top offsets of the a-side (state i) and b-side (state j)
+  for (int e = threadIdx.x; e < bs * bs; e += blockDim.x) {
+    const int r = e % bs, c = e / bs;  // r: column of the b-part, c: column of the a-part
+    double acc = 0.0;
+    for (int t = pairoff[blockIdx.x]; t < pairoff[blockIdx.x + 1]; t++) {
+      const int row0 = pairrow[t];
+      for (int q = 0; q < m; q++) acc += XR[(size_t)(bs + r) * NXRp + row0 + q] * XR[(size_t)c * NXRp + row0 + q];
+    }
+    T[(ob + r) + (size_t)(oa + c) * ld] += acc;
+    T[(oa + c) + (size_t)(ob + r) * ld] += acc;
+  }
+}
+
+// scatter the reduced solution: this graph's top states -> top-level xsol, landmarks -> xl
+__global__ void k_top_scatter(const double* __restrict__ x, int bs, int nb, int ntop, int P, const int* __restrict__ gtop, double* __restrict__ xsol_top,
                               double* __restrict__ xl) {
-  const double* x = buf + (size_t)R * R;
-  const int tid = threadIdx.x;
-  if (extL && tid < bs) xsol_top[tid] = x[(rank - 1) * bs + tid];
-  if (extR && tid < bs) xsol_top[extL * bs + tid] = x[rank * bs + tid];
-  for (int k = tid; k < nb; k += blockDim.x) xl[k] = x[nsep * bs + k];
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < P * bs) xsol_top[t] = x[gtop[t / bs] * bs + t % bs];
+  if (t < nb) xl[t] = x[ntop * bs + t];
+}
+
+// ---- blocked dense Cholesky solve for reduced systems beyond the shared-memory solver (many loop closures).  Right-looking,
+// block size 64, in place on the lower triangle of T (leading dimension ld = R + 1; row R = right-hand side, so the
+// factorisation also performs the forward substitution).  Per block column: k_dense_diag (one CTA: Cholesky of the 64 x 64
+// diagonal tile) -> k_dense_trsm (one thread per row below: row <- row * L_jj^-T) -> k_dense_syrk (64 x 64 tiles of the trailing
+// matrix, 4 x 4 register micro-tiles).  Back-substitution walks the block columns in reverse (k_dense_bwd).
+constexpr int DNB = 64;
+__global__ void __launch_bounds__(256) k_dense_diag(double* __restrict__ T, int ld, int R, int j0, int loff, const double* __restrict__ lambda_ptr, int* __restrict__ flag) {
+  __shared__ double sm[DNB * (DNB + 1)];
+  const int n = min(DNB, R - j0), tid = threadIdx.x, tx = tid & 15, ty = tid >> 4, ldt = DNB + 1;
+  const double lambda = *lambda_ptr;
+  // the LM damping of the landmark diagonal is applied when a diagonal tile is first touched (entries were only updated, never read, before)
+  for (int c = ty; c < n; c += 16) for (int r = c + tx; r < n; r += 16) sm[r + c * ldt] = T[(j0 + r) + (size_t)(j0 + c) * ld] + ((r == c && j0 + r >= loff) ? lambda : 0.0);
+  __syncthreads();
+  for (int j = 0; j < n; j++) {
+    const double djj = sm[j + j * ldt];
+    if (!(djj > 0.0) && tid == 0) *flag = 3;
+    const double inv = rsqrt_pos(djj > 0.0 ? djj : 1.0);
+    for (int cc = j + 1 + ty; cc < n; cc += 16) {
+      const double lc = sm[cc + j * ldt] * inv;
+      for (int r = cc + tx; r < n; r += 16) sm[r + cc * ldt] = fma(-(sm[r + j * ldt] * inv), lc, sm[r + cc * ldt]);
+    }
+    __syncthreads();
+    for (int r = j + tid; r < n; r += 256) sm[r + j * ldt] *= inv;
+  }
+  __syncthreads();
+  for (int c = ty; c < n; c += 16) for (int r = c + tx; r < n; r += 16) T[(j0 + r) + (size_t)(j0 + c) * ld] = sm[r + c * ldt];
+}
+// rows j0+n .. R (inclusive: the rhs row) of block column j0: X L^T = A, one row per thread, L_jj broadcast from shared memory
+__global__ void __launch_bounds__(128) k_dense_trsm(double* __restrict__ T, int ld, int R, int j0) {
+  __shared__ double L[DNB * DNB], dinv[DNB];
+  const int n = min(DNB, R - j0), tid = threadIdx.x;
+  for (int e = tid; e < n * n; e += 128) { const int r = e % n, c = e / n; L[r + c * DNB] = (r >= c) ? T[(j0 + r) + (size_t)(j0 + c) * ld] : 0.0; }
+  __syncthreads();
+  if (tid < n) dinv[tid] = 1.0 / L[tid + tid * DNB];
+  __syncthreads();
+  const int row = j0 + n + blockIdx.x * 128 + tid;
+  if (row > R) return;
+  double x[DNB];
+  if (n == DNB) {
+#pragma unroll
+    for (int c = 0; c < DNB; c++) {
+      double v = T[row + (size_t)(j0 + c) * ld];
+#pragma unroll
+      for (int k = 0; k < c; k++) v = fma(-x[k], L[c + k * DNB], v);
+      x[c] = v * dinv[c];
+    }
+#pragma unroll
+    for (int c = 0; c < DNB; c++) T[row + (size_t)(j0 + c) * ld] = x[c];
+  } else {  // ragged last block column: in place through global memory
+    for (int c = 0; c < n; c++) {
+      double v = T[row + (size_t)(j0 + c) * ld];
+      for (int k = 0; k < c; k++) v = fma(-T[row + (size_t)(j0 + k) * ld], L[c + k * DNB], v);
+      T[row + (size_t)(j0 + c) * ld] = v * dinv[c];
+    }
+  }
+}
+// trailing update C[I][J] -= A_I A_J^T over the rows / columns beyond block column j0 (rows up to R inclusive, columns < R), I >= J
+__global__ void __launch_bounds__(256) k_dense_syrk(double* __restrict__ T, int ld, int R, int j0) {
+  if (blockIdx.y > blockIdx.x) return;
+  __shared__ double As[16][DNB + 1], Bs[16][DNB + 1];
+  const int n = min(DNB, R - j0), base = j0 + n;
+  const int r0 = base + blockIdx.x * DNB, c0 = base + blockIdx.y * DNB;  // tile origin (rows, cols)
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  double acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) acc[i][j] = 0.0;
+  for (int k0 = 0; k0 < n; k0 += 16) {
+    for (int e = tid; e < 16 * DNB; e += 256) {
+      const int rr = e % DNB, kk = e / DNB;
+      const bool kv = k0 + kk < n;
+      As[kk][rr] = (kv && r0 + rr <= R) ? T[(r0 + rr) + (size_t)(j0 + k0 + kk) * ld] : 0.0;
+      Bs[kk][rr] = (kv && c0 + rr <= R) ? T[(c0 + rr) + (size_t)(j0 + k0 + kk) * ld] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; kk++) {
+      double av[4], bv[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) { av[i] = As[kk][tx + 16 * i]; bv[i] = Bs[kk][ty + 16 * i]; }
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int r = r0 + tx + 16 * i, c = c0 + ty + 16 * j;
+      if (r <= R && c < R && r >= c) T[r + (size_t)c * ld] -= acc[i][j];
+    }
+}
+// back-substitution step for block column j0: x_j = L_jj^-T y_j (every CTA, redundantly, by its first warp), then
+// y_c -= L[j-rows][c]^T x_j for the columns c < j0 (one per thread).  y lives in row R of T; x goes to xout.
+__global__ void __launch_bounds__(256) k_dense_bwd(double* __restrict__ T, int ld, int R, int j0, double* __restrict__ xout) {
+  __shared__ double L[DNB * (DNB + 1)], xs[DNB];
+  const int n = min(DNB, R - j0), tid = threadIdx.x, ldt = DNB + 1;
+  for (int e = tid; e < n * n; e += 256) { const int r = e % n, c = e / n; L[r + c * ldt] = (r >= c) ? T[(j0 + r) + (size_t)(j0 + c) * ld] : 0.0; }
+  __syncthreads();
+  if (tid < 32) {
+    double y0 = tid < n ? T[R + (size_t)(j0 + tid) * ld] : 0.0, y1 = tid + 32 < n ? T[R + (size_t)(j0 + tid + 32) * ld] : 0.0;
+    for (int r = n - 1; r >= 0; r--) {
+      const double xr = __shfl_sync(0xffffffffu, r < 32 ? y0 : y1, r & 31) / L[r + r * ldt];
+      // row r of L: L[r][k], k < r
+      if (tid < r) y0 = fma(-L[r + tid * ldt], xr, y0); else if (tid == r) y0 = xr;
+      if (tid + 32 < r) y1 = fma(-L[r + (tid + 32) * ldt], xr, y1); else if (tid + 32 == r) y1 = xr;
+    }
+    if (tid < n) xs[tid] = y0;
+    if (tid + 32 < n) xs[tid + 32] = y1;
+  }
+  __syncthreads();
+  if (blockIdx.x == 0 && tid < n) xout[j0 + tid] = xs[tid];
+  const int c = blockIdx.x * 256 + tid;
+  if (c < j0) {
+    const double* col = T + (size_t)c * ld + j0;
+    double acc = 0.0;
+    for (int r = 0; r < n; r++) acc = fma(col[r], xs[r], acc);
+    T[R + (size_t)c * ld] -= acc;
+  }
 }
 
 __global__ void k_set_scalar(double* p, double v) { *p = v; }

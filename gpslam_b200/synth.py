@@ -46,7 +46,7 @@ def _wire3(R, t):
 
 class Config:
     def __init__(self, name, group, n_states, n_landmarks=0, range_per_state=0.0, dt=0.1, seed=0, qc_sigma=0.1, prior_every=100,
-                 attitude_every=0, odometry=False, init_noise=0.05, zero_rot_fraction=0.01):
+                 attitude_every=0, odometry=False, init_noise=0.05, zero_rot_fraction=0.01, n_closures=0, closure_min_gap=0, closure_ends=False):
         self.__dict__.update(locals())
         del self.__dict__["self"]
 
@@ -63,7 +63,8 @@ def config(name):
     if name == "C4":
         return Config("C4", ROT3, 1000000, 0, 0.0, dt=0.005, seed=base + 4, qc_sigma=100.0, prior_every=0, attitude_every=4)
     if name == "C5":
-        return Config("C5", POSE3, 1000000, 16, 0.5, dt=0.1, seed=base + 5, qc_sigma=0.1)
+        # K = 128 loop closures (BetweenFactor<Pose3>, sigma 0.05) between random state pairs >= 10 000 states apart
+        return Config("C5", POSE3, 1000000, 16, 0.5, dt=0.1, seed=base + 5, qc_sigma=0.1, n_closures=128, closure_min_gap=10000)
     raise KeyError(name)
 
 
@@ -177,6 +178,21 @@ def build(cfg, make_graph, finalize=True):
         for i in range(N - 1):
             meas = _between(group, poses[i], poses[i + 1], rng, 1e-3)
             g.add_between(i, i + 1, meas, iso(D, 1e-3) if group != POSE2 else np.diag([1e3, 1e3, 1e3 / np.pi]))
+    # loop closures: BetweenFactor between distant states (GTSAM type; C5).  Uses its own generator so that the rest of the graph
+    # (and the initial values below) do not depend on the number of closures.
+    if cfg.n_closures and group in (POSE2, POSE3, ROT3):
+        crng = np.random.default_rng(cfg.seed + 2000)
+        gap = min(cfg.closure_min_gap if cfg.closure_min_gap else max(2, N // 10), max(2, N - 2))
+        for k in range(cfg.n_closures):
+            i = int(crng.integers(0, N - gap)); j = int(crng.integers(i + gap, N))
+            if cfg.closure_ends and k == 0:
+                i, j = 0, N - 1  # first and last state of the chain as endpoints
+            if cfg.closure_ends and k == 1:
+                i, j = 1, N - 2  # endpoints adjacent to other endpoints (segments without interior)
+            if crng.random() < 0.25:
+                i, j = j, i  # also exercise the (later -> earlier) argument order
+            meas = _between(group, poses[i], poses[j], crng, 0.05)
+            g.add_between(i, j, meas, iso(D, 0.05))
     # initial values: truth (+) noise on the pose tangent, zero velocities (matlab/PlazaPose2.m:201-202)
     init = np.stack([_retract(group, poses[i], rng.normal(size=D) * cfg.init_noise) for i in range(N)])
     g.set_values(init, np.zeros((N, D)), lands + (rng.normal(size=lands.shape) * 0.5 if L else 0))

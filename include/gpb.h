@@ -75,7 +75,8 @@ int gpb_add_prior_pose(gpb_graph* g, int i, const double* value, const double* s
 int gpb_add_prior_vel(gpb_graph* g, int i, const double* value, const double* sqrt_info);
 int gpb_add_prior_landmark(gpb_graph* g, int l, const double* value, const double* sqrt_info);
 
-/* gtsam::BetweenFactor<Pose>(x_i, x_j, measured, model): odometry when j == i+1, loop closure otherwise */
+/* gtsam::BetweenFactor<Pose>(x_i, x_j, measured, model): odometry when |i-j| == 1; otherwise a loop closure - both states
+ * become pinned separators of the elimination and join the dense reduced system (single-GPU graphs) */
 int gpb_add_between(gpb_graph* g, int i, int j, const double* measured, const double* sqrt_info);
 
 /* plain 2-way factors of gpslam/slam (Linear<3> states unless noted):
@@ -167,6 +168,9 @@ int gpb_kernel_launches_last_optimize(gpb_graph* g);
 int gpb_memcpy(void* dst, const void* src, long long bytes, int kind);
 /* cudaStreamSynchronize for the same callers */
 int gpb_stream_synchronize(void* cuda_stream);
+/* testing aid: the reduced-system solver alone - (A + lambda * diag[loff..R)) x = b, A symmetric R x R column-major; the
+ * shared-memory single-CTA solver for small R, the blocked multi-CTA Cholesky beyond (or when force_blocked != 0) */
+int gpb_debug_dense_solve(int device, int R, const double* A, const double* b, double lambda, int loff, int force_blocked, double* x_out);
 /* all-reduce calls issued by the last gpb_optimize (sharded graphs) */
 int gpb_allreduces_last_optimize(gpb_graph* g);
 

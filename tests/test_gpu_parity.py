@@ -41,6 +41,12 @@ CASES = {
     "pose3_chain": dict(name="C2", n=257, prior_every=30),
     "pose2": dict(name="C1", n=200),
     "rot3": dict(name="C4", n=301),
+    # loop closures (BetweenFactor between distant states, BASELINE config C5): endpoint states become pinned separators and
+    # the Schur complement on {endpoints, landmarks} is solved densely
+    "pose3_loops": dict(name="C5", n=400, n_landmarks=4, prior_every=40, n_closures=5, closure_min_gap=40),
+    "pose3_wide_loops": dict(name="C5", n=500, n_landmarks=16, prior_every=40, n_closures=8, closure_min_gap=60, closure_ends=True),
+    "pose2_loops": dict(name="C1", n=200, n_closures=4, closure_min_gap=30, closure_ends=True),
+    "rot3_loops": dict(name="C4", n=301, n_closures=3, closure_min_gap=50),
 }
 
 
@@ -88,7 +94,7 @@ def make_pair(case):
     return g, o
 
 
-ALL = ["pose3", "pose3_wide", "pose3_chain", "pose2", "rot3", "linear"]
+ALL = ["pose3", "pose3_wide", "pose3_chain", "pose2", "rot3", "linear", "pose3_loops", "pose3_wide_loops", "pose2_loops", "rot3_loops"]
 
 
 @pytest.mark.parametrize("case", ALL)
@@ -161,6 +167,40 @@ def test_segment_boundaries(n, n_landmarks):
         ref = np.linalg.solve(Hg, gg)
         x = np.concatenate([ds.ravel(), dl])
         assert np.abs(x - ref).max() <= 1e-8 * max(1.0, np.abs(ref).max()), (n, seglen)
+
+
+@pytest.mark.parametrize("seglen", [None, (7, 3)])
+def test_many_loop_closures_blocked_top_solve(seglen):
+    """C5 shape with enough closures that the reduced system (40 endpoint states x 12 + landmarks = 492 unknowns) goes through
+    the blocked multi-CTA Cholesky: one damped step against a solve of the same system by the oracle's bordered solver is not
+    available as a dense matrix at this size, so compare the Gauss-Newton / LM trajectories instead."""
+    cfg = small_cfg("C5", 3000, n_landmarks=4, prior_every=100, n_closures=20, closure_min_gap=300)
+    g, o, _ = both(cfg, seglen)
+    assert g.sizes().levels >= 2
+    sg = g.optimize(n_iter=1, use_lm=False); so = o.optimize(n_iter=1, use_lm=False)
+    assert abs(sg.error_final - so.error_final) <= 1e-7 * max(1.0, so.error_final)
+    Pg, Vg, Lg = g.get_values(); Po, Vo, Lo = o.get_values()
+    assert np.abs(Pg - Po).max() <= 1e-6 and np.abs(Vg - Vo).max() <= 1e-6 and np.abs(Lg - Lo).max() <= 1e-6
+    sg = g.optimize(use_lm=True); so = o.optimize(use_lm=True)
+    assert sg.status == 0 and sg.iterations == so.iterations
+    assert abs(sg.error_final - so.error_final) <= 1e-7 * max(1.0, so.error_final)
+    Pg, Vg, Lg = g.get_values(); Po, Vo, Lo = o.get_values()
+    assert np.abs(Pg - Po).max() <= 1e-6 and np.abs(Vg - Vo).max() <= 1e-6 and np.abs(Lg - Lo).max() <= 1e-6
+
+
+@pytest.mark.parametrize("R", [1, 2, 31, 64, 65, 128, 160, 161, 200, 449, 1000])
+def test_reduced_system_solvers(R):
+    """the reduced-system solvers alone (shared-memory single-CTA solver, blocked multi-CTA Cholesky) against numpy"""
+    from gpslam_b200 import capi
+    rng = np.random.default_rng(R)
+    B = rng.normal(size=(R, R + 5)); A = B @ B.T + 0.1 * np.eye(R); b = rng.normal(size=R)
+    for lam, loff in ((0.0, 0), (0.7, R // 2)):
+        ref = np.linalg.solve(A + lam * np.diag((np.arange(R) >= loff).astype(float)), b)
+        for blocked in ((False, True) if R <= 160 else (True,)):
+            x = capi.dense_solve(A, b, lam, loff, blocked)
+            assert np.abs(x - ref).max() <= 1e-9 * max(1.0, np.abs(ref).max()), (R, lam, blocked, np.abs(x - ref).max())
+    with pytest.raises(capi.GpbError):
+        capi.dense_solve(-A, b, 0.0, 0, R > 160)
 
 
 def test_reference_two_state_optimizations():
