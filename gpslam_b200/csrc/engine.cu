@@ -89,6 +89,7 @@ struct gpb_graph {
   double* d_topbuf = nullptr; double cur_error_local = 0; int n_allreduce = 0;
   double* d_lambda = nullptr;
   cudaGraphExec_t iter_graph[2] = {nullptr, nullptr}; int iter_graph_launches[2] = {0, 0};  // captured GN/LM trial per buffer parity
+  cudaGraphExec_t dist_graph[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}}; int dist_graph_launches[2] = {0, 0};  // sharded GN: [parity][before / after the all-reduce]
   int extL = 0, extR = 0;  // shard: first / last state is an external separator (owned by the global reduced system)
   int *d_listA = nullptr, *d_listB = nullptr;  // extra factors by kind class: interpolated measurements / everything else
   int nA = 0, nB = 0;
@@ -188,6 +189,7 @@ void gpb_graph_destroy(gpb_graph* g) {
   if (g->device >= 0) cudaSetDevice(g->device);
   if (g->pinned) { cudaHostUnregister(g->h_X.data()); if (g->L) cudaHostUnregister(g->h_land.data()); }
   for (int k = 0; k < 2; k++) if (g->iter_graph[k]) cudaGraphExecDestroy(g->iter_graph[k]);
+  for (int k = 0; k < 2; k++) for (int h = 0; h < 2; h++) if (g->dist_graph[k][h]) cudaGraphExecDestroy(g->dist_graph[k][h]);
   for (void* p : g->allocs) cudaFree(p);
   if (g->ev_fork) cudaEventDestroy(g->ev_fork);
   if (g->ev_join) cudaEventDestroy(g->ev_join);
@@ -802,7 +804,7 @@ static int launch_fwd_level(gpb_graph* g, int buf, double lambda, int lev) {
   if (bs == 12 && g->W == 64 && !g->generic_fwd) {
     // spine first (warp per segment: the latency-bound 12x12 recurrence wants many independent warps), then the tensor-pipe panel
     const int spine_ctas = std::min(L.nseg, 16 * g->sms);
-    k_spine<12><<<spine_ctas, 32, 0, g->stream>>>(a);
+    if (lev == 0) k_spine<12, true><<<spine_ctas, 32, 0, g->stream>>>(a); else k_spine<12, false><<<spine_ctas, 32, 0, g->stream>>>(a);
     k_panel4<12><<<L.ncta, 128, 0, g->stream>>>(a);
     g->launches += 2;
   } else {
@@ -876,17 +878,14 @@ static int solve_top_dense(gpb_graph* g) {
   return GPB_OK;
 }
 // The part of the solve between the two sweeps.  No pinned states and a single GPU: the landmark system alone.  Otherwise the
-// Schur complement on {pinned states, landmarks} is packed into the reduced system -> (sharded graphs) ONE all-reduce ->
-// dense solve (redundantly on every rank) -> scatter to the top-level solution and the landmark solution.
+// Schur complement on {pinned states, landmarks} is packed into the reduced system (top_pack) -> (sharded graphs) ONE
+// all-reduce -> dense solve, redundantly on every rank, and scatter to the top-level and landmark solutions (top_finish).
 // err_local / async: see solve_system_dist.
-static int solve_top(gpb_graph* g, int buf, double err_local, bool async, double* sc_out /*[4] or null*/) {
-  int rc;
+static bool top_is_landmarks_only(const gpb_graph* g) { return g->world == 1 && g->P == 0; }
+static int top_pack(gpb_graph* g, int buf, double err_local, bool async) {
   const int nb = g->nb, centries = nb * nb + nb, nel = num_elim_levels(g), R = g->R;
   if (nb) { k_cseg_final<<<(centries + 127) / 128, 128, 0, g->stream>>>(g->d_Cbase, g->d_Cpart, 16 * nel, centries, g->d_Csum); g->launches++; }
-  if (g->world == 1 && g->P == 0) {
-    if (nb) { k_small_solve<256><<<1, 256, small_solve_smem(nb), g->stream>>>(g->d_Csum, nb, g->d_Csum + (size_t)nb * nb, 1, nb, 0, g->d_lambda, g->d_xlm, g->d_flag, 2); g->launches++; }
-    return GPB_OK;
-  }
+  if (top_is_landmarks_only(g)) return GPB_OK;
   const long long total = (long long)(R + 1) * R + 4;
   CUDA_TRY(cudaMemsetAsync(g->d_topbuf, 0, (size_t)total * sizeof(double), g->stream));
   PackArgs pa;
@@ -898,13 +897,27 @@ static int solve_top(gpb_graph* g, int buf, double err_local, bool async, double
     k_pack_closures<<<g->npair, 64, 0, g->stream>>>(g->d_XR[buf], g->NXRp, g->bs, g->D, R + 1, g->d_pair_a, g->d_pair_b, g->d_pairoff, g->d_pairrow, g->d_topbuf);
     g->launches++;
   }
-  if (g->world > 1 && (rc = dist_allreduce(g, g->d_topbuf, total))) return rc;
+  return GPB_OK;
+}
+static int top_finish(gpb_graph* g, double* sc_out /*[4] or null*/) {
+  int rc;
+  const int nb = g->nb, R = g->R;
+  if (top_is_landmarks_only(g)) {
+    if (nb) { k_small_solve<256><<<1, 256, small_solve_smem(nb), g->stream>>>(g->d_Csum, nb, g->d_Csum + (size_t)nb * nb, 1, nb, 0, g->d_lambda, g->d_xlm, g->d_flag, 2); g->launches++; }
+    return GPB_OK;
+  }
   if (sc_out) CUDA_TRY(cudaMemcpyAsync(sc_out, g->d_topbuf + (size_t)(R + 1) * R, 4 * sizeof(double), cudaMemcpyDeviceToHost, g->stream));
   if ((rc = solve_top_dense(g))) return rc;
   const int nthr = std::max(g->P * g->bs, nb);
   k_top_scatter<<<(nthr + 127) / 128, 128, 0, g->stream>>>(g->d_topx, g->bs, nb, g->ntop, g->P, g->d_gtop, g->levels.back().xsol, g->d_xlm);
   g->launches++;
   return GPB_OK;
+}
+static int solve_top(gpb_graph* g, int buf, double err_local, bool async, double* sc_out) {
+  int rc;
+  if ((rc = top_pack(g, buf, err_local, async))) return rc;
+  if (g->world > 1 && (rc = dist_allreduce(g, g->d_topbuf, (long long)(g->R + 1) * g->R + 4))) return rc;
+  return top_finish(g, sc_out);
 }
 // sharded solve: local elimination down to the external separators -> pack -> ONE all-reduce -> redundant dense solve ->
 // local back-substitution.  global_err_out: sum over ranks of err_local (the error at the current linearisation point).
@@ -1047,13 +1060,42 @@ int gpb_optimize(gpb_graph* g, const gpb_params* params, int n_iter, gpb_stats* 
   if (async_gn) CUDA_TRY(cudaMemsetAsync(g->d_flag, 0, sizeof(int), g->stream));
   auto one_iteration = [&]() -> int {
     int r;
-    if (!g->assembled) { if ((r = assemble_dispatch(g, g->cur))) return r; g->assembled = true; }
+    if (!async_gn && !g->assembled) { if ((r = assemble_dispatch(g, g->cur))) return r; g->assembled = true; }
     if (async_gn) {
       // sharded plain Gauss-Newton: the whole iteration, all-reduce included, is enqueued without a host round trip; a failed
       // factorisation anywhere raises the (sticky) flag, which is checked once after the last iteration
-      if ((r = solve_system_dist(g, g->cur, 0.0, 0.0, nullptr, nullptr, true))) return r;
-      if ((r = retract_dispatch(g))) return r;
-      if ((r = linearize_dispatch(g, g->d_Xt, g->d_landt, 1 - g->cur, 1))) return r;
+      // The launch sequence is fixed per buffer parity: it is replayed as two CUDA graphs around the all-reduce, so the host
+      // issues 2 graph launches + 1 collective per iteration instead of ~50 kernel launches (a shard's iteration is short).
+      const int par = g->cur;
+      if (!g->dist_graph[par][0]) {
+        const int l0 = g->launches;
+        for (int half = 0; half < 2; half++) {
+          cudaGraph_t graph;
+          CUDA_TRY(cudaStreamBeginCapture(g->stream, cudaStreamCaptureModeThreadLocal));
+          if (half == 0) {
+            r = assemble_dispatch(g, par);
+            k_set_scalar<<<1, 1, 0, g->stream>>>(g->d_lambda, 0.0);
+            if (!r) r = solve_forward(g, par, 0.0);
+            if (!r) r = top_pack(g, par, 0.0, true);
+          } else {
+            r = top_finish(g, nullptr);
+            if (!r) r = solve_backward(g);
+            if (!r) r = retract_dispatch(g);
+            if (!r) r = linearize_dispatch(g, g->d_Xt, g->d_landt, 1 - par, 1);
+          }
+          const cudaError_t ce = cudaStreamEndCapture(g->stream, &graph);
+          if (r) return r;
+          CUDA_TRY(ce);
+          CUDA_TRY(cudaGraphInstantiate(&g->dist_graph[par][half], graph, 0));
+          cudaGraphDestroy(graph);
+        }
+        g->dist_graph_launches[par] = g->launches - l0 + 1;
+        g->launches = l0;
+      }
+      CUDA_TRY(cudaGraphLaunch(g->dist_graph[par][0], g->stream));
+      if ((r = dist_allreduce(g, g->d_topbuf, (long long)(g->R + 1) * g->R + 4))) return r;
+      CUDA_TRY(cudaGraphLaunch(g->dist_graph[par][1], g->stream));
+      g->launches += g->dist_graph_launches[par];
       std::swap(g->d_X, g->d_Xt); std::swap(g->d_land, g->d_landt); g->cur = 1 - g->cur;
       g->assembled = false; g->linearized = true;
       iterations++;

@@ -508,14 +508,13 @@ __global__ void __launch_bounds__((W < 32 ? 32 : W), (W == 64 ? 6 : 8)) k_fwd(co
   }
 }
 
-// 1/sqrt(x) for a positive, normal x: the hardware seed (MUFU.RSQ64H, ~20 bits) and two Newton steps; no special-case branches
+// 1/sqrt(x) for a positive, normal x: the hardware seed (MUFU.RSQ64H, ~20 bits) and one cubically convergent step; no special-case branches
 __device__ __forceinline__ double rsqrt_pos(double x) {
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  const double hx = 0.5 * x;
-  y = y * fma(-hx * y, y, 1.5);
-  y = y * fma(-hx * y, y, 1.5);
-  return y;
+  // one third-order step  y <- y (1 + e/2 + 3 e^2 / 8),  e = 1 - x y^2 : seed error 2^-21 -> e^3 ~ 2^-63, four dependent operations
+  const double e = fma(-(x * y), y, 1.0);
+  return fma(y * e, fma(0.375, e, 0.5), y);
 }
 // ---------------------------------------------------------------------------------------------------------------------
 // Two-kernel forward sweep (BS = 12, panel width 64).  The chain "spine"  D'_i = D_i - Le_{i-1} Le_{i-1}^T -> L_i^-1 ->
@@ -531,7 +530,7 @@ __device__ __forceinline__ double rsqrt_pos(double x) {
 // through shared memory (Le out, 9 DMMA on the lower tiles, Dn back in the row-per-lane layout, read as 128-bit column loads
 // thanks to symmetry).  The next pivot is broadcast from an early copy (arow[j+1] - l^2 on its owner lane) so the pivot chain
 // is  shfl -> rsqrt -> mul  per column instead of waiting for the column broadcast.
-template <int BS>
+template <int BS, bool FIRST>
 __global__ void __launch_bounds__(32, 16) k_spine(const FwdArgs a) {
   static_assert(BS == 12, "spine kernel is specialised for 12 x 12 state blocks");
   constexpr int REC0 = 2 * BS * BS + BS, REC1 = 3 * BS * BS + 2 * BS;
@@ -539,19 +538,22 @@ __global__ void __launch_bounds__(32, 16) k_spine(const FwdArgs a) {
   const int lane = threadIdx.x, gi = lane >> 2, ti = lane & 3;
   const bool dl = lane < BS, el = lane >= BS && lane < 2 * BS;
   const int rr = dl ? lane : (el ? lane - BS : 0);
-  const bool first = a.first_level != 0;
-  const int RECS = first ? REC0 : REC1, oE = first ? BS * BS : 2 * BS * BS;
+  constexpr bool first = FIRST;
+  constexpr int RECS = first ? REC0 : REC1, oE = first ? BS * BS : 2 * BS * BS;
   const double lambda = first ? *a.lambda_ptr : 0.0;
-  double nrow[BS];  // next state's row: D (+ D2 above level 0) on lanes 0..11, E on lanes 12..23, zero elsewhere
+  // next state's row, fetched one state ahead: D on lanes 0..11, E on lanes 12..23 (every other lane re-reads lane 0's row and is
+  // masked when the row is consumed - nothing may depend on the loaded values here, or the warp would wait for HBM on the spot);
+  // above level 0 the second part of D arrives in nrow2
+  double nrow[BS], nrow2[first ? 1 : BS];
+  bool nact = false;
   auto fetch = [&](int i, bool want_e) {
     const double* r = a.rec + (size_t)i * RECS;
-    const bool ld = dl || (el && want_e);
-    const double* p0 = r + (dl ? rr : oE + rr);
+    nact = dl || (el && want_e);
+    const double* p0 = r + (el ? oE + rr : rr);
 #pragma unroll
     for (int cc = 0; cc < BS; cc++) {
-      double v = ld ? p0[cc * BS] : 0.0;
-      if (!first && dl) v += r[BS * BS + rr + cc * BS];
-      nrow[cc] = v;
+      nrow[cc] = p0[cc * BS];
+      if constexpr (!first) nrow2[cc] = r[BS * BS + rr + cc * BS];
     }
   };
   for (int seg = blockIdx.x; seg < a.nseg; seg += gridDim.x) {
@@ -571,8 +573,10 @@ __global__ void __launch_bounds__(32, 16) k_spine(const FwdArgs a) {
 #pragma unroll
         for (int cc = 0; cc < BS; cc += 2) {
           const double2 t = *reinterpret_cast<const double2*>(dn + cc);
-          arow[cc] = nrow[cc] + (dl ? t.x : 0.0) + ((dl && cc == rr) ? lambda : 0.0);
-          arow[cc + 1] = nrow[cc + 1] + (dl ? t.y : 0.0) + ((dl && cc + 1 == rr) ? lambda : 0.0);
+          double v0 = nrow[cc], v1 = nrow[cc + 1];
+          if constexpr (!first) { v0 += dl ? nrow2[cc] : 0.0; v1 += dl ? nrow2[cc + 1] : 0.0; }
+          arow[cc] = (nact ? v0 : 0.0) + (dl ? t.x : 0.0) + ((dl && cc == rr) ? lambda : 0.0);
+          arow[cc + 1] = (nact ? v1 : 0.0) + (dl ? t.y : 0.0) + ((dl && cc + 1 == rr) ? lambda : 0.0);
         }
       }
       if (i + 1 <= ilast) fetch(i + 1, (i + 1 < i1) || (q >= 0 && i + 1 <= i1));  // next state's loads fly during this factorisation
@@ -628,7 +632,7 @@ __global__ void __launch_bounds__(32, 16) k_spine(const FwdArgs a) {
     if (q >= 0 && dl) {  // D1 of the right separator: its own block (fetched last) + the last Schur update (+ damping at level 0)
       double* R = a.rec_out + (size_t)sg.qo * REC1;
 #pragma unroll
-      for (int cc = 0; cc < BS; cc++) R[rr + cc * BS] = nrow[cc] + Dn[cc + rr * BS] + (cc == rr ? lambda : 0.0);
+      for (int cc = 0; cc < BS; cc++) { double v = nrow[cc]; if constexpr (!first) v += nrow2[cc]; R[rr + cc * BS] = v + Dn[cc + rr * BS] + (cc == rr ? lambda : 0.0); }
     }
     __syncwarp();
   }

@@ -27,7 +27,7 @@ def _se3_exp(xi):
     th2 = w @ w
     if th2 < 1e-20:
         return R, v.copy()
-    wxv = np.cross(w, v)
+    wxv = np.array([w[1] * v[2] - w[2] * v[1], w[2] * v[0] - w[0] * v[2], w[0] * v[1] - w[1] * v[0]])  # np.cross, without its per-call overhead
     return R, (wxv - R @ wxv + w * (w @ v)) / th2
 
 
