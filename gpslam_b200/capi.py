@@ -182,6 +182,10 @@ class Graph:
     def set_shard(self, rank, world, ext_left, ext_right):
         self._ck(self.L.gpb_graph_set_shard(self.h, C.c_int(rank), C.c_int(world), C.c_int(1 if ext_left else 0), C.c_int(1 if ext_right else 0)))
 
+    def set_top_map(self, n_real, ntop_global, pinned_local, pinned_gtop):
+        pl = np.ascontiguousarray(np.asarray(pinned_local, dtype=np.int32)); pg = np.ascontiguousarray(np.asarray(pinned_gtop, dtype=np.int32))
+        self._ck(self.L.gpb_graph_set_top_map(self.h, C.c_int(n_real), C.c_int(ntop_global), C.c_int(len(pl)), _ip(pl), _ip(pg)))
+
     def set_allreduce(self, fn):
         """fn(device_ptr:int, count:int, cuda_stream:int) -> 0; in-place SUM over ranks, stream-ordered on cuda_stream (see gpb.h)"""
         CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p)

@@ -81,6 +81,8 @@ struct gpb_graph {
   int pinL = 0, pinR = 0;         // first / last state of the chain is pinned (external separator or loop-closure endpoint)
   int* d_gtop = nullptr;          // [P] global top index of local top state k
   double* d_topx = nullptr;       // [R] solution of the reduced system
+  int n_real = 0;                 // chain entries [n_real, N) are ghost replicas of remote loop-closure endpoints (sharded graphs)
+  int map_ntop = -1; std::vector<int> map_local, map_gtop;  // explicit top map of a shard (gpb_graph_set_top_map)
   int nclos = 0, nep = 0, npair = 0;  // loop closures: factors, endpoint states, unique endpoint pairs
   int *d_epstate = nullptr, *d_epoff = nullptr, *d_eprow = nullptr, *d_epside = nullptr;
   int *d_pair_a = nullptr, *d_pair_b = nullptr, *d_pairoff = nullptr, *d_pairrow = nullptr;
@@ -408,6 +410,17 @@ int gpb_graph_set_shard(gpb_graph* g, int rank, int world, int ext_left, int ext
   g->rank = rank; g->world = world; g->extL = ext_left ? 1 : 0; g->extR = ext_right ? 1 : 0;
   return GPB_OK;
 }
+int gpb_graph_set_top_map(gpb_graph* g, int n_real, int ntop_global, int n_pinned, const int* pinned_local, const int* pinned_gtop) {
+  CHECK_OPEN(g);
+  if (n_real < 2 || n_real > g->N || ntop_global < n_pinned || n_pinned < 0) return fail(GPB_ERR_ARG, "gpb_graph_set_top_map: bad sizes");
+  for (int k = 0; k < n_pinned; k++) {
+    if (pinned_local[k] < 0 || pinned_local[k] >= g->N || (k && pinned_local[k] <= pinned_local[k - 1])) return fail(GPB_ERR_ARG, "gpb_graph_set_top_map: local indices must be ascending and in range");
+    if (pinned_gtop[k] < 0 || pinned_gtop[k] >= ntop_global) return fail(GPB_ERR_ARG, "gpb_graph_set_top_map: global top index out of range");
+  }
+  g->n_real = n_real; g->map_ntop = ntop_global;
+  g->map_local.assign(pinned_local, pinned_local + n_pinned); g->map_gtop.assign(pinned_gtop, pinned_gtop + n_pinned);
+  return GPB_OK;
+}
 int gpb_set_allreduce(gpb_graph* g, gpb_allreduce_fn fn, void* ctx) {
   if (!g) return fail(GPB_ERR_ARG, "null graph");
   g->allreduce = fn; g->allreduce_ctx = ctx;
@@ -505,10 +518,17 @@ int gpb_graph_finalize(gpb_graph* g, int device) {
   std::vector<int> epstate, epoff, eprow, epside, clos;
   for (int k = 0; k < g->NX; k++) if (g->sorted[k].closure) clos.push_back(k);
   g->nclos = (int)clos.size();
-  if (g->nclos && g->world > 1) return fail(GPB_ERR_UNSUPPORTED, "gpb_graph_finalize: loop closures on a sharded graph are not supported by this build");
+  const int n_real = g->n_real ? g->n_real : g->N;
+  if ((g->nclos || n_real < g->N) && g->world > 1 && g->map_ntop < 0) return fail(GPB_ERR_STATE, "gpb_graph_finalize: a sharded graph with loop closures needs gpb_graph_set_top_map");
   for (int k : clos) { pin[g->sorted[k].sa] = 1; pin[g->sorted[k].sb] = 1; }
   if (g->extL) pin[0] = 1;
-  if (g->extR) pin[g->N - 1] = 1;
+  if (g->extR) pin[n_real - 1] = 1;
+  for (int i = n_real; i < g->N; i++) pin[i] = 1;
+  if (g->map_ntop >= 0) {
+    std::vector<char> mapped(g->N, 0);
+    for (int s_ : g->map_local) { mapped[s_] = 1; pin[s_] = 1; }
+    for (int i = 0; i < g->N; i++) if (pin[i] && !mapped[i]) return fail(GPB_ERR_ARG, "gpb_graph_set_top_map: a pinned state (external separator, loop-closure endpoint or ghost) has no global top index");
+  }
   g->pinL = pin[0]; g->pinR = pin[g->N - 1];
   {
     std::vector<std::vector<std::pair<int, int>>> per(g->N);
@@ -663,7 +683,13 @@ int gpb_graph_finalize(gpb_graph* g, int device) {
   g->P = (int)top_state.size();
   {
     std::vector<int> gtop(g->P);
-    if (g->world > 1) {  // sharded: global separator r-1 is this rank's halo, r its own last state
+    if (g->map_ntop >= 0) {  // explicit map (sharded graph with loop closures)
+      g->ntop = g->map_ntop;
+      for (int k = 0; k < g->P; k++) {
+        const auto it = std::lower_bound(g->map_local.begin(), g->map_local.end(), top_state[k]);
+        gtop[k] = g->map_gtop[it - g->map_local.begin()];
+      }
+    } else if (g->world > 1) {  // sharded: global separator r-1 is this rank's halo, r its own last state
       g->ntop = g->world - 1;
       int k = 0;
       if (g->extL) gtop[k++] = g->rank - 1;
@@ -796,6 +822,7 @@ static int launch_fwd_level(gpb_graph* g, int buf, double lambda, int lev) {
   FwdArgs a;
   a.n = L.n; a.M = L.M; a.S = L.S; a.nseg = L.nseg; a.first_level = lev == 0; a.extL = g->pinL; a.extR = g->pinR; a.sep = L.d_sep;
   a.lamL = (g->pinL && !g->extL) ? 1 : 0;  // a pinned first state that is not a neighbour's halo is damped here
+  a.nreal = g->n_real ? g->n_real : g->N;   // ghost entries beyond are damped by their owner rank
   a.rec = lev == 0 ? g->d_HREC : L.rec; a.brec = L.brec;
   a.XR = g->d_XR[buf]; a.bsoff = g->d_bsoff; a.bsrow = g->d_bsrow; a.bsside = g->d_bsside; a.rowland = g->d_rowland; a.bent = g->d_bent; a.NXRp = g->NXRp; a.nb = nb; a.DL = std::max(g->DL, 1);
   a.lambda_ptr = g->d_lambda;
@@ -962,7 +989,7 @@ template <int G> static int launch_retract(gpb_graph* g) {
   constexpr int NT = 128;
   const int nblk = (g->N + NT - 1) / NT;
   double* part = g->d_errpart + g->nerrpart;
-  k_retract<G, NT><<<nblk, NT, 0, g->stream>>>(g->d_X, g->levels[0].xsol, g->d_HREC, g->d_Xt, part, part + nblk, g->N, g->extL ? 1 : 0);
+  k_retract<G, NT><<<nblk, NT, 0, g->stream>>>(g->d_X, g->levels[0].xsol, g->d_HREC, g->d_Xt, part, part + nblk, g->N, g->extL ? 1 : 0, g->n_real ? g->n_real : g->N);
   k_sum_partials<<<1, 256, 0, g->stream>>>(part, nblk, g->d_scal, 1);
   k_sum_partials<<<1, 256, 0, g->stream>>>(part + nblk, nblk, g->d_scal, 2);
   g->launches += 3;

@@ -20,6 +20,7 @@
 
 struct FwdArgs {
   int n, M, S, nseg, first_level, extL, extR;   // S = number of interior separators; nseg = S + 1
+  int nreal;           // level 0: chain entries >= nreal are ghost replicas (damped by their owner rank, not here)
   int lamL;            // level 0: the pinned first state is owned by this graph -> its pass-through block gets the LM damping here
   const int* sep;      // [S] positions of the interior separators in this level's chain (ascending)
   const double* rec;
@@ -401,7 +402,7 @@ __global__ void __launch_bounds__((W < 32 ? 32 : W), (W == 64 ? 6 : 8)) k_fwd(co
     __syncthreads();
     if (q >= 0) {
       double* R = a.rec_out + (size_t)sg.qo * REC1;
-      for (int k = c; k < BS * BS; k += NT) R[k] = D_of(buf, k) + Dn[k];  // D1
+      for (int k = c; k < BS * BS; k += NT) R[k] = D_of(buf, k) + Dn[k] - ((first && q >= a.nreal && (k % (BS + 1)) == 0) ? (*a.lambda_ptr) : 0.0);  // D1 (a ghost is damped by its owner)
       add_own(q, buf);                                                      // own border / rhs of q on top of the updates
       const double* P = Psm + (c < W ? c : 0) * BS;
       if (is_border) {
@@ -632,7 +633,7 @@ __global__ void __launch_bounds__(32, 16) k_spine(const FwdArgs a) {
     if (q >= 0 && dl) {  // D1 of the right separator: its own block (fetched last) + the last Schur update (+ damping at level 0)
       double* R = a.rec_out + (size_t)sg.qo * REC1;
 #pragma unroll
-      for (int cc = 0; cc < BS; cc++) { double v = nrow[cc]; if constexpr (!first) v += nrow2[cc]; R[rr + cc * BS] = v + Dn[cc + rr * BS] + (cc == rr ? lambda : 0.0); }
+      for (int cc = 0; cc < BS; cc++) { double v = nrow[cc]; if constexpr (!first) v += nrow2[cc]; R[rr + cc * BS] = v + Dn[cc + rr * BS] + ((cc == rr && q < a.nreal) ? lambda : 0.0); }
     }
     __syncwarp();
   }
@@ -1158,7 +1159,7 @@ static size_t small_solve_smem(int R) { return ((size_t)(R + 2) * R + R) * sizeo
 // products LM needs: g.delta and |delta|^2 (block partials).
 template <int G, int NT>
 __global__ void __launch_bounds__(NT) k_retract(const double* __restrict__ X, const double* __restrict__ xsol, const double* __restrict__ HREC,
-                                                double* __restrict__ Xt, double* __restrict__ part_gd, double* __restrict__ part_dd, int N, int dd_from) {
+                                                double* __restrict__ Xt, double* __restrict__ part_gd, double* __restrict__ part_dd, int N, int dd_from, int dd_to) {
   constexpr int D = GroupTraits<G>::D, PS = GroupTraits<G>::PS, SR = PS + D, bs = 2 * D, REC = 2 * bs * bs + bs;
   __shared__ double sred[NT / 32];
   const int i = blockIdx.x * NT + threadIdx.x;
@@ -1169,7 +1170,7 @@ __global__ void __launch_bounds__(NT) k_retract(const double* __restrict__ X, co
     for (int k = 0; k < bs; k++) d[k] = xsol[(size_t)i * bs + k];
     const double* g = HREC + (size_t)i * REC + 2 * bs * bs;
 #pragma unroll
-    for (int k = 0; k < bs; k++) { gd += g[k] * d[k]; if (i >= dd_from) dd += d[k] * d[k]; }  // a halo copy's |delta|^2 is counted by its owner
+    for (int k = 0; k < bs; k++) { gd += g[k] * d[k]; if (i >= dd_from && i < dd_to) dd += d[k] * d[k]; }  // a halo / ghost copy's |delta|^2 is counted by its owner
     const double* x = X + (size_t)i * SR;
     double* y = Xt + (size_t)i * SR;
     if constexpr (G == G_POSE3) {

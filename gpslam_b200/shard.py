@@ -19,20 +19,71 @@ def local_range(n_states, rank, world):
     return a - (1 if rank > 0 else 0), b
 
 
-def reduced_dim(world, bs, nb):
-    return (world - 1) * bs + nb
+def reduced_dim(world, bs, nb, ntop=None):
+    return (world - 1 if ntop is None else ntop) * bs + nb
+
+
+def top_states(n_states, world, closures):
+    """global list of top states (the unknowns of the reduced system besides the landmarks), in trajectory order: the last
+    state of every shard but the final one, and every loop-closure endpoint"""
+    s = {owned_range(n_states, r, world)[1] - 1 for r in range(world - 1)}
+    for i, j in closures:
+        s.add(int(i)); s.add(int(j))
+    return sorted(s)
+
+
+def owner_of(n_states, world, state):
+    for r in range(world):
+        a, b = owned_range(n_states, r, world)
+        if a <= state < b:
+            return r
+    raise ValueError(state)
 
 
 class ShardBuilder:
     """Accepts the construction calls of the GLOBAL graph (same API as gpslam_b200.Graph / the oracle) and forwards this
-    rank's part, re-indexed to local state numbers, to a local graph object."""
+    rank's part, re-indexed to local state numbers, to a local graph object.
+
+    Calls are recorded and replayed when the local graph is first needed (`.g`, `finalize`): the graph's size depends on
+    the loop closures, which arrive among the other factors.  A closure (i, j) is evaluated by the rank owning min(i, j);
+    when max(i, j) lives elsewhere that rank carries it as a ghost entry behind its own states.  Every closure endpoint is
+    a top state on the rank that owns it (and wherever it is a ghost)."""
 
     def __init__(self, make_graph, group, n_states, n_landmarks, rank, world):
-        self.N, self.rank, self.world = n_states, rank, world
+        self.make_graph, self.group, self.N, self.NL, self.rank, self.world = make_graph, group, n_states, n_landmarks, rank, world
         self.lo, self.hi = local_range(n_states, rank, world)
-        self.g = make_graph(group, self.hi - self.lo, n_landmarks)
-        if world > 1 and hasattr(self.g, "set_shard"):
-            self.g.set_shard(rank, world, rank > 0, rank < world - 1)
+        self._calls, self._closures, self._values, self._g = [], [], None, None
+
+    # ---- recorded construction calls
+    def _rec(self, name, *args):
+        if self._g is not None:
+            raise RuntimeError("ShardBuilder: the local graph has already been materialised")
+        self._calls.append((name, args))
+
+    def add_qc_model(self, Qc):
+        self._rec("add_qc_model", Qc)
+        return sum(1 for c in self._calls if c[0] == "add_qc_model") - 1
+
+    def add_gp_prior(self, i, delta_t, qc=0): self._rec("add_gp_prior", i, delta_t, qc)
+    def add_interp_range(self, i, l, z, sigma, delta_t, tau, qc=0, body_P_sensor=None): self._rec("add_interp_range", i, l, z, sigma, delta_t, tau, qc, body_P_sensor)
+    def add_interp_attitude(self, i, delta_t, tau, nZ, sigma, bRef=(0, 0, 1), qc=0): self._rec("add_interp_attitude", i, delta_t, tau, nZ, sigma, bRef, qc)
+    def add_prior_pose(self, i, value, sqrt_info): self._rec("add_prior_pose", i, value, sqrt_info)
+    def add_prior_vel(self, i, value, sqrt_info): self._rec("add_prior_vel", i, value, sqrt_info)
+    def add_prior_landmark(self, l, value, sqrt_info): self._rec("add_prior_landmark", l, value, sqrt_info)
+    def add_range_2d(self, i, l, z, sigma): self._rec("add_range_2d", i, l, z, sigma)
+    def add_range_bearing_2d(self, i, l, rng, bearing, sqrt_info): self._rec("add_range_bearing_2d", i, l, rng, bearing, sqrt_info)
+    def add_odometry_2d(self, i, j, meas, sqrt_info): self._rec("add_odometry_2d", i, j, meas, sqrt_info)
+
+    def add_between(self, i, j, meas, sqrt_info):
+        if abs(i - j) != 1:
+            self._closures.append((int(i), int(j)))
+        self._rec("add_between", i, j, meas, sqrt_info)
+
+    def set_values(self, poses=None, vels=None, lands=None):
+        if self._g is not None:
+            self._apply_values(poses, vels, lands)
+        else:
+            self._values = (poses, vels, lands)
 
     # interval t (states t, t+1) is local iff lo <= t <= hi - 2
     def _own_interval(self, t):
@@ -43,67 +94,104 @@ class ShardBuilder:
         t = s if s <= self.N - 2 else self.N - 2
         return self.lo <= t <= self.hi - 2
 
-    def add_qc_model(self, Qc):
-        return self.g.add_qc_model(Qc)
+    # ---- materialisation
+    @property
+    def g(self):
+        if self._g is None:
+            self._materialise()
+        return self._g
 
-    def add_gp_prior(self, i, delta_t, qc=0):
+    def _local(self, s):
+        """local chain index of global state s: a real entry, or a ghost"""
+        return s - self.lo if self.lo <= s < self.hi else self.n_real + self.ghosts.index(s)
+
+    def _materialise(self):
+        rank, world = self.rank, self.world
+        self.n_real = self.hi - self.lo
+        self.top = top_states(self.N, world, self._closures)
+        self.ghosts = []   # global states replicated here
+        for i, j in self._closures:
+            if owner_of(self.N, world, min(i, j)) == rank:
+                far = max(i, j)
+                if not (self.lo <= far < self.hi) and far not in self.ghosts:
+                    self.ghosts.append(far)
+        g = self._g = self.make_graph(self.group, self.n_real + len(self.ghosts), self.NL)
+        if world > 1 and hasattr(g, "set_shard"):
+            g.set_shard(rank, world, rank > 0, rank < world - 1)
+        # this rank's entries of the reduced system, in local chain order
+        pinned = sorted([(s - self.lo, k) for k, s in enumerate(self.top) if self.lo <= s < self.hi] + [(self.n_real + q, self.top.index(s)) for q, s in enumerate(self.ghosts)])
+        self.pinned_local = [p for p, _ in pinned]; self.pinned_gtop = [k for _, k in pinned]
+        if self._closures and hasattr(g, "set_top_map"):
+            g.set_top_map(self.n_real, len(self.top), self.pinned_local, self.pinned_gtop)
+        for name, a in self._calls:
+            getattr(self, "_do_" + name)(*a)
+        if self._values is not None:
+            self._apply_values(*self._values)
+
+    def _do_add_qc_model(self, Qc): self._g.add_qc_model(Qc)
+
+    def _do_add_gp_prior(self, i, delta_t, qc):
         i = np.atleast_1d(i); dt = np.broadcast_to(np.atleast_1d(delta_t), i.shape)
         m = self._own_interval(i)
         if m.any():
-            self.g.add_gp_prior(i[m] - self.lo, dt[m], qc)
+            self._g.add_gp_prior(i[m] - self.lo, dt[m], qc)
 
-    def add_interp_range(self, i, l, z, sigma, delta_t, tau, qc=0, body_P_sensor=None):
+    def _do_add_interp_range(self, i, l, z, sigma, delta_t, tau, qc, body_P_sensor):
         i = np.atleast_1d(i); m = self._own_interval(i)
         b = lambda a: np.broadcast_to(np.atleast_1d(a), i.shape)[m]
         if m.any():
-            self.g.add_interp_range(i[m] - self.lo, b(l), b(z), b(sigma), b(delta_t), b(tau), qc, body_P_sensor)
+            self._g.add_interp_range(i[m] - self.lo, b(l), b(z), b(sigma), b(delta_t), b(tau), qc, body_P_sensor)
 
-    def add_interp_attitude(self, i, delta_t, tau, nZ, sigma, bRef=(0, 0, 1), qc=0):
+    def _do_add_interp_attitude(self, i, delta_t, tau, nZ, sigma, bRef, qc):
         i = np.atleast_1d(i); m = self._own_interval(i)
         b = lambda a: np.broadcast_to(np.atleast_1d(a), i.shape)[m]
         nz = np.broadcast_to(np.asarray(nZ, dtype=float).reshape(-1, 3), (len(i), 3))[m]
         br = np.broadcast_to(np.asarray(bRef, dtype=float).reshape(-1, 3), (len(i), 3))[m]
         if m.any():
-            self.g.add_interp_attitude(i[m] - self.lo, b(delta_t), b(tau), nz, b(sigma), br, qc)
+            self._g.add_interp_attitude(i[m] - self.lo, b(delta_t), b(tau), nz, b(sigma), br, qc)
 
-    def add_prior_pose(self, i, value, sqrt_info):
+    def _do_add_prior_pose(self, i, value, sqrt_info):
         if self._single_state_owner(i):
-            self.g.add_prior_pose(i - self.lo, value, sqrt_info)
+            self._g.add_prior_pose(i - self.lo, value, sqrt_info)
 
-    def add_prior_vel(self, i, value, sqrt_info):
+    def _do_add_prior_vel(self, i, value, sqrt_info):
         if self._single_state_owner(i):
-            self.g.add_prior_vel(i - self.lo, value, sqrt_info)
+            self._g.add_prior_vel(i - self.lo, value, sqrt_info)
 
-    def add_prior_landmark(self, l, value, sqrt_info):
+    def _do_add_prior_landmark(self, l, value, sqrt_info):
         if self.rank == 0:
-            self.g.add_prior_landmark(l, value, sqrt_info)
+            self._g.add_prior_landmark(l, value, sqrt_info)
 
-    def add_between(self, i, j, meas, sqrt_info):
-        if abs(i - j) == 1 and self._own_interval(min(i, j)):
-            self.g.add_between(i - self.lo, j - self.lo, meas, sqrt_info)
-        elif abs(i - j) != 1:
-            raise NotImplementedError("loop closures are not supported by the sharded build")
+    def _do_add_between(self, i, j, meas, sqrt_info):
+        if abs(i - j) == 1:
+            if self._own_interval(min(i, j)):
+                self._g.add_between(i - self.lo, j - self.lo, meas, sqrt_info)
+        elif owner_of(self.N, self.world, min(i, j)) == self.rank:
+            self._g.add_between(self._local(i), self._local(j), meas, sqrt_info)
 
-    def add_range_2d(self, i, l, z, sigma):
+    def _do_add_range_2d(self, i, l, z, sigma):
         if self._single_state_owner(i):
-            self.g.add_range_2d(i - self.lo, l, z, sigma)
+            self._g.add_range_2d(i - self.lo, l, z, sigma)
 
-    def add_range_bearing_2d(self, i, l, rng, bearing, sqrt_info):
+    def _do_add_range_bearing_2d(self, i, l, rng, bearing, sqrt_info):
         if self._single_state_owner(i):
-            self.g.add_range_bearing_2d(i - self.lo, l, rng, bearing, sqrt_info)
+            self._g.add_range_bearing_2d(i - self.lo, l, rng, bearing, sqrt_info)
 
-    def add_odometry_2d(self, i, j, meas, sqrt_info):
+    def _do_add_odometry_2d(self, i, j, meas, sqrt_info):
         if self._own_interval(i):
-            self.g.add_odometry_2d(i - self.lo, j - self.lo, meas, sqrt_info)
+            self._g.add_odometry_2d(i - self.lo, j - self.lo, meas, sqrt_info)
 
-    def set_values(self, poses=None, vels=None, lands=None):
-        self.g.set_values(None if poses is None else np.asarray(poses)[self.lo:self.hi], None if vels is None else np.asarray(vels)[self.lo:self.hi], lands)
+    def _apply_values(self, poses, vels, lands):
+        sel = list(range(self.lo, self.hi)) + self.ghosts
+        self._g.set_values(None if poses is None else np.asarray(poses)[sel], None if vels is None else np.asarray(vels)[sel], lands)
 
     def finalize(self, device=0):
         if hasattr(self.g, "finalize"):
             self.g.finalize(device)
 
     def __getattr__(self, name):  # everything else (optimize, linearize, get_values, ...) goes to the local graph
+        if name.startswith("_"):
+            raise AttributeError(name)
         return getattr(self.g, name)
 
 
@@ -133,15 +221,17 @@ def torch_allreduce(device):
     return fn
 
 
-def reduced_index(world, rank, bs, nb):
-    """global indices (in the all-reduced system [sep_0..sep_{P-2} | landmarks]) of a rank's top-level variables, in the local
-    order [left external separator (if rank > 0), right external separator (if rank < P-1), landmarks]"""
+def reduced_index(world, rank, bs, nb, pinned_gtop=None, ntop=None):
+    """global indices (in the all-reduced system [top states | landmarks]) of a rank's top-level variables, in the local order
+    [its pinned chain entries..., landmarks].  Without loop closures the top states are the world-1 shard boundaries and a
+    rank's pinned entries are its halo (rank > 0) and its last state (rank < world-1)."""
+    if pinned_gtop is None:
+        pinned_gtop = ([rank - 1] if rank > 0 else []) + ([rank] if rank < world - 1 else [])
+        ntop = world - 1
     idx = []
-    if rank > 0:
-        idx += list(range((rank - 1) * bs, rank * bs))
-    if rank < world - 1:
-        idx += list(range(rank * bs, (rank + 1) * bs))
-    idx += list(range((world - 1) * bs, (world - 1) * bs + nb))
+    for k in pinned_gtop:
+        idx += list(range(k * bs, (k + 1) * bs))
+    idx += list(range(ntop * bs, ntop * bs + nb))
     return np.asarray(idx, dtype=np.int64)
 
 

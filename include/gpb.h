@@ -140,6 +140,16 @@ int gpb_solve_delta(gpb_graph* g, double lambda, double* delta_states, double* d
  * whose local chain contains both states. */
 int gpb_graph_set_shard(gpb_graph* g, int rank, int world, int ext_left, int ext_right);
 
+/* Sharded graphs WITH loop closures.  A closure (i, j) is evaluated by the rank that owns state min(i, j); a remote endpoint is
+ * carried as a GHOST: an extra chain entry after the shard's own states (create the graph with n_real + n_ghost states; no
+ * factor but the closures touches a ghost; its values are set like any state's and must equal the owner's).  Every rank applies
+ * the same reduced-system solution to its ghosts, so replicas stay bit-identical without any exchange of values.
+ * pinned_local (ascending): every local chain entry that belongs to the global reduced system - the halo (0) and the shard's
+ * last own state when they are external separators, every loop-closure endpoint owned by this shard (whether or not the
+ * closure is evaluated here), every ghost; pinned_gtop: their indices in the global list of top states (ntop_global long:
+ * shard boundaries and closure endpoints in trajectory order). */
+int gpb_graph_set_top_map(gpb_graph* g, int n_real, int ntop_global, int n_pinned, const int* pinned_local, const int* pinned_gtop);
+
 /* In-place SUM all-reduce of `count` doubles at device pointer `buf` over all ranks, STREAM-ORDERED on `cuda_stream` (the
  * engine's cudaStream_t): it must consume the buffer after the work already enqueued on that stream and produce the sums
  * before work enqueued on it later; it need not be complete on return (NCCL enqueued on that stream is the intended

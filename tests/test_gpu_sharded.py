@@ -38,6 +38,10 @@ def run_sharded(cfg, world, n_iter, use_lm):
     P = V = None
     for r, sb in enumerate(shards):
         p, v, l = sb.g.get_values()
+        for q, s_ in enumerate(sb.ghosts):  # ghost replicas of remote loop-closure endpoints equal their owner's state bit for bit
+            o = shard.owner_of(N, world, s_)
+            po_, vo_, _ = shards[o].g.get_values()
+            assert np.array_equal(p[sb.n_real + q], po_[s_ - shards[o].lo]) and np.array_equal(v[sb.n_real + q], vo_[s_ - shards[o].lo])
         if P is None:
             P = np.zeros((N, p.shape[1])); V = np.zeros((N, v.shape[1]))
         a, b = shard.owned_range(N, r, world)
@@ -70,3 +74,27 @@ def test_sharded_lm_matches_single():
     assert stats[0].iterations == st.iterations
     assert abs(stats[0].error_final - st.error_final) <= 1e-8 * max(1.0, st.error_final)
     assert np.abs(P - P0).max() < 1e-7 and np.abs(V - V0).max() < 1e-7 and np.abs(Lm - L0).max() < 1e-7
+
+
+@pytest.mark.parametrize("name,n,world,ncl,nl", [("C5", 400, 2, 4, 4), ("C5", 500, 3, 7, 16), ("C1", 240, 2, 5, 4), ("C4", 500, 4, 6, 0)])
+def test_sharded_loop_closures_match_single(name, n, world, ncl, nl):
+    """loop closures across shards: endpoints join the global reduced system, the evaluating rank carries remote endpoints as ghosts"""
+    cfg = synth.config(name); cfg.n_states = n; cfg.n_landmarks = min(cfg.n_landmarks, nl); cfg.prior_every = 30
+    cfg.n_closures = ncl; cfg.closure_min_gap = n // 5; cfg.closure_ends = True
+    g, _ = synth.build(cfg, lambda grp, N, L: gb.Graph(grp, N, L))
+    st = g.optimize(n_iter=3, use_lm=False)
+    P0, V0, L0 = g.get_values()
+    P, V, Lm, stats, nar = run_sharded(cfg, world, 3, False)
+    assert all(k == 3 + 2 for k in nar), nar
+    assert abs(stats[0].error_final - st.error_final) <= 1e-9 * max(1.0, st.error_final)
+    assert np.abs(P - P0).max() < 1e-9 and np.abs(V - V0).max() < 1e-9
+    if L0.size:
+        assert np.abs(Lm - L0).max() < 1e-9
+    # LM: damping of pinned / ghost entries happens exactly once
+    g, _ = synth.build(cfg, lambda grp, N, L: gb.Graph(grp, N, L))
+    st = g.optimize(use_lm=True)
+    P0, V0, L0 = g.get_values()
+    P, V, Lm, stats, _ = run_sharded(cfg, world, 0, True)
+    assert stats[0].iterations == st.iterations
+    assert abs(stats[0].error_final - st.error_final) <= 1e-8 * max(1.0, st.error_final)
+    assert np.abs(P - P0).max() < 1e-7 and np.abs(V - V0).max() < 1e-7

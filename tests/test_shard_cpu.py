@@ -17,26 +17,31 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
-def _worker(rank, world, port, name, n, out):
+def _cfg(name, n, ncl):
+    cfg = synth.config(name); cfg.n_states = n; cfg.n_landmarks = min(cfg.n_landmarks, 3); cfg.prior_every = 7
+    cfg.n_closures = ncl; cfg.closure_min_gap = max(3, n // 6); cfg.closure_ends = ncl >= 2
+    return cfg
+
+
+def _worker(rank, world, port, name, n, out, ncl=0):
     import torch
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    cfg = synth.config(name); cfg.n_states = n; cfg.n_landmarks = min(cfg.n_landmarks, 3); cfg.prior_every = 7
+    cfg = _cfg(name, n, ncl)
     sb, _ = synth.build(cfg, lambda grp, N, L: shard.ShardBuilder(lambda g_, n_, l_: po.Graph(g_, n_, l_), grp, N, L, rank, world))
     g = sb.g
     bs, nb = 2 * g.D, g.NL * g.DL
-    H, rhs = g.normal_equations_dense()                      # local variables: [local states..., landmarks]
+    H, rhs = g.normal_equations_dense()                      # local variables: [local chain entries (own states, ghosts)..., landmarks]
     nloc = g.N
-    extL, extR = rank > 0, rank < world - 1
-    top = ([0] if extL else []) + ([nloc - 1] if extR else [])
+    top = sb.pinned_local                                     # halo / last own state / loop-closure endpoints / ghosts
     top_idx = np.concatenate([np.arange(s * bs, (s + 1) * bs) for s in top] + [np.arange(nloc * bs, nloc * bs + nb)]).astype(int)
     int_idx = np.setdiff1d(np.arange(nloc * bs + nb), top_idx)
     Hii, Hit, Htt = H[np.ix_(int_idx, int_idx)], H[np.ix_(int_idx, top_idx)], H[np.ix_(top_idx, top_idx)]
     S = Htt - Hit.T @ np.linalg.solve(Hii, Hit)
     s = rhs[top_idx] - Hit.T @ np.linalg.solve(Hii, rhs[int_idx])
-    R = shard.reduced_dim(world, bs, nb)
-    gi = shard.reduced_index(world, rank, bs, nb)
+    R = shard.reduced_dim(world, bs, nb, len(sb.top))
+    gi = shard.reduced_index(world, rank, bs, nb, sb.pinned_gtop, len(sb.top))
     T = np.zeros((R, R)); t = np.zeros(R)
     T[np.ix_(gi, gi)] = S; t[gi] = s
     buf = torch.from_numpy(np.concatenate([T.ravel(), t]))
@@ -52,12 +57,14 @@ def _worker(rank, world, port, name, n, out):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("name,world,n", [("C3", 2, 41), ("C3", 3, 50), ("C1", 2, 37), ("C4", 3, 46)])
-def test_sharded_schur_matches_full(tmp_path, name, world, n):
+@pytest.mark.parametrize("name,world,n,ncl", [("C3", 2, 41, 0), ("C3", 3, 50, 0), ("C1", 2, 37, 0), ("C4", 3, 46, 0),
+                                              ("C5", 2, 40, 3), ("C5", 3, 52, 5), ("C1", 3, 45, 4)])
+def test_sharded_schur_matches_full(tmp_path, name, world, n, ncl):
+    """ncl > 0: loop closures - endpoints join the reduced system, remote endpoints are carried as ghosts by the evaluating rank"""
     import torch.multiprocessing as mp
     port = _free_port()
-    mp.spawn(_worker, args=(world, port, name, n, str(tmp_path)), nprocs=world, join=True)
-    cfg = synth.config(name); cfg.n_states = n; cfg.n_landmarks = min(cfg.n_landmarks, 3); cfg.prior_every = 7
+    mp.spawn(_worker, args=(world, port, name, n, str(tmp_path), ncl), nprocs=world, join=True)
+    cfg = _cfg(name, n, ncl)
     o, _ = synth.build(cfg, lambda grp, N, L: po.Graph(grp, N, L))
     H, rhs = o.normal_equations_dense()
     ref = np.linalg.solve(H, rhs)
@@ -74,9 +81,9 @@ def test_sharded_schur_matches_full(tmp_path, name, world, n):
 
 
 def test_every_factor_owned_once():
-    for name, n in (("C3", 97), ("C1", 64), ("C4", 80)):
+    for name, n, ncl in (("C3", 97, 0), ("C1", 64, 0), ("C4", 80, 0), ("C5", 90, 6)):
         for world in (2, 3, 5):
-            cfg = synth.config(name); cfg.n_states = n; cfg.n_landmarks = min(cfg.n_landmarks, 3); cfg.prior_every = 7
+            cfg = _cfg(name, n, ncl)
             full, _ = synth.build(cfg, lambda grp, N, L: po.Graph(grp, N, L))
             total = 0; err = 0.0
             for r in range(world):
