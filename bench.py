@@ -24,9 +24,14 @@ sys.path.insert(0, ROOT)
 WORKLOAD = "C3: SE(3) GP-prior + interpolated range factors, 100k states, 50k ranges, 16 landmarks (BASELINE.json configs[2]; interpolated range only - the reference has no interpolated bearing factor)"
 METRIC = "GN iterations/sec on 100k-state SE(3) GP trajectory"
 CPU_SAMPLE_STATES = 10000
-# dram__bytes_read.sum + dram__bytes_write.sum of one k_lin_gp launch on C3, from the ncu --set full capture summarised in
-# profiles/r1a_ncu_full_summary.csv (15.7 MB read + 180.7 MB written; the tail of the 240 MB of [A|b] is still in L2 at kernel end)
-TRAFFIC_LIN_GP = 196.4e6
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch on C3, from the ncu --set full captures summarised in
+# profiles/r1b_ncu_full_summary.csv: k_lin_gp 15.7 MB read + 181.6 MB written (the tail of the 240 MB of [A|b] is still in L2 at
+# kernel end); k_panel4 (level 0) 270.2 MB read + 558.3 MB written
+TRAFFIC_LIN_GP = 197.3e6
+TRAFFIC_PANEL = 828.5e6
+# algorithmic FLOPs of the level-0 panel per state (SE(3), w = 61 columns): Y = L^-1 P (12*13/2*61 MAC), P' = Le Y (12*12*61),
+# S += Y^T Y (61*62/2*12)
+PANEL_FLOP_PER_STATE = 2.0 * (78 * 61 + 144 * 61 + 61 * 62 // 2 * 12)
 
 
 def peaks():
@@ -195,7 +200,10 @@ def run_engine(args, rank, world, local_rank):
     e2e_s = max_over_ranks((time.perf_counter() - t0) / args.steps)
     io_bytes = int(P.nbytes + V.nbytes + Lm.nbytes)
     # ---- per-stage device times and the linearise roofline (local shard)
-    stages = {n: g.time_stage(k, 20) for k, n in ((0, "linearise_gp"), (1, "linearise_other"), (2, "assemble"), (3, "solve"), (4, "retract"), (5, "solve_fwd_level0"))}
+    stages = {n: g.time_stage(k, 20) for k, n in ((0, "linearise_gp"), (1, "linearise_other"), (2, "assemble"), (3, "solve"), (4, "retract"), (5, "solve_fwd_level0"),
+                                                   (6, "solve_spine_level0"), (7, "solve_panel_level0"), (8, "solve_backward"))}
+    from gpslam_b200 import capi
+    dmma_peak = capi.dmma_peak(local_rank)
     sampler.mark_end()
     clocks = sampler.stop()
     peak, peak_src = peaks()
@@ -213,7 +221,12 @@ def run_engine(args, rank, world, local_rank):
         "e2e": {"value": 1.0 / e2e_s, "unit": "iterations/s", "h2d_bytes_per_step": io_bytes * world, "d2h_bytes_per_step": io_bytes * world},
         "gpu_launches": launches,
         "roofline": {"kernel": "k_lin_gp<POSE3> (batched GP-prior linearise)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "peak_source": peak_src, "algorithmic_bytes": gp_bytes, "ms": stages["linearise_gp"], "traffic": TRAFFIC_LIN_GP},
+                     "peak_source": peak_src, "algorithmic_bytes": gp_bytes, "ms": stages["linearise_gp"], "traffic": TRAFFIC_LIN_GP if world == 1 else None},
+        # the kernel that dominates the iteration by time: the level-0 panel, bound by the FP64 tensor pipe
+        "roofline_solver": {"kernel": "k_panel4<12> (level-0 panel: Y = L^-1 P, P' = -Le Y, S += Y^T Y on mma.sync.m8n8k4.f64)", "bound": "tensor", "achieved": PANEL_FLOP_PER_STATE * g.N / (stages["solve_panel_level0"] * 1e-3) / 1e12,
+                            "peak": dmma_peak, "unit": "TFLOP/s", "frac": PANEL_FLOP_PER_STATE * g.N / (stages["solve_panel_level0"] * 1e-3) / 1e12 / dmma_peak,
+                            "peak_source": "measured in this run: FP64 mma.sync m8n8k4 issue loop on all SMs (gpb_debug_dmma_peak); MEASURED_PEAKS.json has no FP64 figure",
+                            "algorithmic_flops": PANEL_FLOP_PER_STATE * g.N, "ms": stages["solve_panel_level0"], "traffic": TRAFFIC_PANEL if world == 1 else None},
         "stages_ms": stages, "clocks": clocks, "error": {"initial": err0, "final": st.error_final},
     }
     if rank == 0 and world == 1 and not args.no_cpu:

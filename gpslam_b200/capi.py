@@ -84,6 +84,14 @@ def dense_solve(A, b, lam=0.0, loff=0, force_blocked=False, device=0):
     return x
 
 
+def dmma_peak(device=0):
+    """measured FP64 tensor-pipe peak (TFLOP/s)"""
+    v = C.c_double()
+    if lib().gpb_debug_dmma_peak(C.c_int(device), C.byref(v)) != 0:
+        raise GpbError(lib().gpb_last_error().decode())
+    return v.value
+
+
 def default_params(use_lm=True):
     p = Params()
     lib().gpb_default_params(C.byref(p), C.c_int(1 if use_lm else 0))

@@ -86,7 +86,7 @@ struct gpb_graph {
   int nclos = 0, nep = 0, npair = 0;  // loop closures: factors, endpoint states, unique endpoint pairs
   int *d_epstate = nullptr, *d_epoff = nullptr, *d_eprow = nullptr, *d_epside = nullptr;
   int *d_pair_a = nullptr, *d_pair_b = nullptr, *d_pairoff = nullptr, *d_pairrow = nullptr;
-  bool generic_fwd = false, force_blocked = false;
+  bool generic_fwd = false, force_blocked = false, old_assemble = false;
   gpb_allreduce_fn allreduce = nullptr; void* allreduce_ctx = nullptr;
   double* d_topbuf = nullptr; double cur_error_local = 0; int n_allreduce = 0;
   double* d_lambda = nullptr;
@@ -561,6 +561,7 @@ int gpb_graph_finalize(gpb_graph* g, int device) {
   if ((rc = dev_upload(g, &g->d_Rq, rq))) return rc;
   for (int b = 0; b < 2; b++) {
     if ((rc = dev_alloc(g, &g->d_AB[b], (size_t)(4 * D + 1) * D * g->NFp * 2))) return rc;
+    CUDA_TRY(cudaMemset(g->d_AB[b], 0, (size_t)(4 * D + 1) * D * g->NFp * 2 * sizeof(double)));  // intervals without a GP prior are never written: they stay zero
     if ((rc = dev_alloc(g, &g->d_XR[b], (size_t)g->ncolsX * std::max(g->NXRp, 32)))) return rc;
     CUDA_TRY(cudaMemset(g->d_XR[b], 0, (size_t)g->ncolsX * std::max(g->NXRp, 32) * sizeof(double)));
   }
@@ -599,6 +600,7 @@ int gpb_graph_finalize(gpb_graph* g, int device) {
   g->sms = sms;
   // segment lengths: explicit setting > environment (tuning aid) > defaults
   const char* em0 = getenv("GPB_M0"); const char* emu = getenv("GPB_MUP");
+  g->old_assemble = getenv("GPB_OLD_ASSEMBLE") != nullptr;  // A/B switch: thread-per-tile assembly instead of the DMMA kernel
   g->generic_fwd = getenv("GPB_GENERIC_FWD") != nullptr;  // A/B switch: one-kernel generic forward sweep (k_fwd<12,64>)
   int M0 = g->M0 ? g->M0 : (em0 ? std::max(2, atoi(em0)) : (g->nb > 0 ? 32 : 16));
   const int Mup = g->Mup ? g->Mup : (emu ? std::max(2, atoi(emu)) : 8);
@@ -783,7 +785,8 @@ template <int G> static int launch_assemble(gpb_graph* g, int buf) {
   constexpr int NT = 128, bs = 2 * GroupTraits<G>::D, TILES = bs == 12 ? 4 : 1;
   const int states_per_cta = 32 * (NT / (32 * TILES));
   const int nblk = (g->N + states_per_cta - 1) / states_per_cta;
-  k_assemble<G, NT><<<nblk, NT, 0, g->stream>>>(g->d_AB[buf], g->d_dt, g->NX ? g->d_XR[buf] : nullptr, g->d_rowoff, g->d_HREC, g->N, g->NFp, g->NXRp);
+  if (G == G_POSE3 && !g->old_assemble) k_assemble_mma<<<(g->N + 7) / 8, 128, 0, g->stream>>>(g->d_AB[buf], g->NX ? g->d_XR[buf] : nullptr, g->d_rowoff, g->d_HREC, g->N, g->NFp, g->NXRp, g->ncolsX - 1);
+  else k_assemble<G, NT><<<nblk, NT, 0, g->stream>>>(g->d_AB[buf], g->d_dt, g->NX ? g->d_XR[buf] : nullptr, g->d_rowoff, g->d_HREC, g->N, g->NFp, g->NXRp);
   g->launches++;
   if (g->nep) {  // loop closures: diagonal blocks / rhs of their endpoint states
     k_assemble_closures<<<g->nep, 64, 0, g->stream>>>(g->d_XR[buf], g->NXRp, bs, GroupTraits<G>::D, g->ncolsX - 1, g->d_epstate, g->d_epoff, g->d_eprow, g->d_epside, g->d_HREC);
@@ -815,7 +818,7 @@ template <int BS, int W> static void launch_bwd(const BwdArgs& a, int ncta, cuda
 template <int BS> static void fwd_w(int W, const FwdArgs& a, int ncta, cudaStream_t s) { if (W == 16) launch_fwd<BS, 16>(a, ncta, s); else if (W == 32) launch_fwd<BS, 32>(a, ncta, s); else launch_fwd<BS, 64>(a, ncta, s); }
 template <int BS> static void bwd_w(int W, const BwdArgs& a, int ncta, cudaStream_t s) { if (W == 16) launch_bwd<BS, 16>(a, ncta, s); else if (W == 32) launch_bwd<BS, 32>(a, ncta, s); else launch_bwd<BS, 64>(a, ncta, s); }
 
-static int launch_fwd_level(gpb_graph* g, int buf, double lambda, int lev) {
+static int launch_fwd_level(gpb_graph* g, int buf, double lambda, int lev, int parts = 3) {
   const int bs = g->bs, nb = g->nb, fstride = 2 * bs * bs + bs * g->w, centries = nb * nb + nb;
   const int nlev = (int)g->levels.size();
   Level& L = g->levels[lev];
@@ -831,9 +834,8 @@ static int launch_fwd_level(gpb_graph* g, int buf, double lambda, int lev) {
   if (bs == 12 && g->W == 64 && !g->generic_fwd) {
     // spine first (warp per segment: the latency-bound 12x12 recurrence wants many independent warps), then the tensor-pipe panel
     const int spine_ctas = std::min(L.nseg, 16 * g->sms);
-    if (lev == 0) k_spine<12, true><<<spine_ctas, 32, 0, g->stream>>>(a); else k_spine<12, false><<<spine_ctas, 32, 0, g->stream>>>(a);
-    k_panel4<12><<<L.ncta, 128, 0, g->stream>>>(a);
-    g->launches += 2;
+    if (parts & 1) { if (lev == 0) k_spine<12, true><<<spine_ctas, 32, 0, g->stream>>>(a); else k_spine<12, false><<<spine_ctas, 32, 0, g->stream>>>(a); g->launches++; }
+    if (parts & 2) { k_panel4<12><<<L.ncta, 128, 0, g->stream>>>(a); g->launches++; }
   } else {
     if (bs == 12) fwd_w<12>(g->W, a, L.ncta, g->stream); else fwd_w<6>(g->W, a, L.ncta, g->stream);
     g->launches++;
@@ -1271,6 +1273,50 @@ int gpb_debug_dense_solve(int device, int R, const double* A, const double* b, d
   return rc;
 }
 
+// profiling aid: FP64 tensor-pipe (mma.sync m8n8k4 / DMMA) issue-rate peak of the device, TFLOP/s, best of 5 launches - the
+// roofline denominator for k_panel4 (MEASURED_PEAKS.json holds HBM and bf16 peaks only)
+__global__ void __launch_bounds__(128) k_dmma_peak(double* out, int iters) {
+  double c[8][2];
+#pragma unroll
+  for (int k = 0; k < 8; k++) { c[k][0] = 0.0; c[k][1] = 0.0; }
+  const double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) dmma884(c[k][0], c[k][1], a, b);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) s += c[k][0] + c[k][1];
+  if (s == 123.456) out[0] = s;
+}
+int gpb_debug_dmma_peak(int device, double* tflops_out) {
+  if (!tflops_out) return fail(GPB_ERR_ARG, "gpb_debug_dmma_peak: null argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(GPB_ERR_CUDA, "gpb_debug_dmma_peak: no CUDA device available"); }
+  CUDA_TRY(cudaSetDevice(device));
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  double* d = nullptr;
+  CUDA_TRY(cudaMalloc(&d, sizeof(double)));
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
+  const int iters = 20000, grid = sms * 8;
+  double best = 0.0;
+  for (int r = 0; r < 6; r++) {
+    CUDA_TRY(cudaEventRecord(e0, 0));
+    k_dmma_peak<<<grid, 128>>>(d, iters);
+    CUDA_TRY(cudaEventRecord(e1, 0));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    const double tf = (double)grid * 4 * iters * 8 * 512.0 / (ms * 1e-3) / 1e12;
+    if (r > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+  *tflops_out = best;
+  return GPB_OK;
+}
+
 int gpb_kernel_launches_last_optimize(gpb_graph* g) { return g ? g->launches : 0; }
 int gpb_allreduces_last_optimize(gpb_graph* g) { return g ? g->n_allreduce : 0; }
 // plain cudaMemcpy (kind: 1 host->device, 2 device->host) for callers that implement gpb_allreduce_fn without a CUDA binding of their own
@@ -1449,6 +1495,9 @@ int gpb_time_stage(gpb_graph* g, int stage, int reps, double* ms_out) {
       case 3: if ((rc = solve_system(g, g->cur, 0.0))) return rc; break;
       case 4: if ((rc = retract_dispatch(g))) return rc; break;
       case 5: if ((rc = launch_fwd_level(g, g->cur, 0.0, 0))) return rc; break;
+      case 6: if ((rc = launch_fwd_level(g, g->cur, 0.0, 0, 1))) return rc; break;  // spine only (SE(3), 64-column panel)
+      case 7: if ((rc = launch_fwd_level(g, g->cur, 0.0, 0, 2))) return rc; break;  // panel only
+      case 8: if ((rc = solve_backward(g))) return rc; break;
       default: return fail(GPB_ERR_ARG, "gpb_time_stage: unknown stage");
     }
   }
@@ -1460,7 +1509,7 @@ int gpb_time_stage(gpb_graph* g, int stage, int reps, double* ms_out) {
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   *ms_out = ms / reps;
   // stage 5 leaves the upper levels untouched but consistent; restore a complete solve so later calls see a valid state
-  if (stage == 5) { if ((rc = solve_system(g, g->cur, 0.0))) return rc; CUDA_TRY(cudaStreamSynchronize(g->stream)); }
+  if (stage >= 5) { if ((rc = solve_system(g, g->cur, 0.0))) return rc; CUDA_TRY(cudaStreamSynchronize(g->stream)); }
   return GPB_OK;
 }
 

@@ -174,3 +174,136 @@ __global__ void __launch_bounds__(NT) k_assemble(const double* __restrict__ AB, 
   }
   (void)c0;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// SE(3) assembly on the FP64 tensor pipe.  One CTA (4 warps) builds the records of TS = 8 consecutive states.
+//   load    : the whitened [A|b] of the 9 GP priors touching those states is staged from the SoA linearisation buffer into
+//             shared memory, factor-major, with cp.async (LDGSTS: ~11 independent 16-byte copies per thread in flight, no
+//             register staging).  Intervals without a GP prior hold zeros in the buffer (cleared once at finalize).
+//   compute : per state (two per warp)  D_i | g_i = Fa_a^T [Fa_a | b] + Fp_b^T [Fp_b | b]  and  E_i = Fa_b^T Fa_a  as
+//             mma.sync.m8n8k4.f64 tiles (36 DMMA), Fa / Fp = priors of the intervals i / i-1, _a / _b their columns on the first /
+//             second state; the rhs rides along as column 12 of the second column tile.  The few measurement / prior rows of
+//             the two intervals are further k-steps of the same products, their fragments read straight from the row table.
+//   store   : the 8 finished records (8 x 2400 B, contiguous in HBM) leave through shared memory as coalesced 128-bit stores
+// This replaces the thread-per-tile kernel for SE(3) (255 registers, 8 warps per SM: latency-bound at a quarter of the HBM rate).
+__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsrc, bool valid) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(valid ? 16 : 0) : "memory");
+}
+__global__ void __launch_bounds__(128) k_assemble_mma(const double* __restrict__ AB, const double* __restrict__ XR,
+                                                      const int* __restrict__ rowoff, double* __restrict__ HREC, int N, int NFp, int NXRp, int xrhs) {
+  constexpr int D = 6, bs = 12, REC = 2 * bs * bs + bs, TS = 8, NF = TS + 1, NCOL = 4 * D + 1, FS = NCOL * bs + 2;  // FS: doubles per staged factor (padded)
+  __shared__ __align__(16) double Fsm[NF * FS];   // staged factors [factor][column][row]; re-used for the finished records
+  static_assert(TS * REC <= NF * FS, "record staging must fit the factor staging");
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gi = lane >> 2, ti = lane & 3;
+  const int i0 = blockIdx.x * TS, nint = N - 1;
+  // ---- load: item = (column c, row pair rp, factor ff); consecutive threads take consecutive factors (16 contiguous bytes each)
+  {
+    constexpr int NITEM = NCOL * D * NF;
+#pragma unroll
+    for (int j = 0; j < (NITEM + 127) / 128; j++) {
+      const int it = tid + 128 * j;
+      if (it < NITEM) {
+        const int ff = it % NF, pr = it / NF, c = pr / D, rp = pr % D;
+        const int f = i0 - 1 + ff;
+        const bool ok = f >= 0 && f < NFp;
+        cp_async16_zfill(&Fsm[ff * FS + c * bs + 2 * rp], AB + ((size_t)pr * NFp + (ok ? f : 0)) * 2, ok);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  // row ranges of this warp's two states (interval i-1: [r0, r1), interval i: [r1, r2)) while the copies fly
+  int rr0[2], rr1[2], rr2[2];
+#pragma unroll
+  for (int sidx = 0; sidx < 2; sidx++) {
+    const int i = i0 + 2 * warp + sidx;
+    rr0[sidx] = rr1[sidx] = rr2[sidx] = 0;
+    if (XR != nullptr && i < N) {
+      rr1[sidx] = rowoff[i < nint ? i : nint];
+      rr0[sidx] = i >= 1 ? rowoff[i - 1] : rr1[sidx];
+      rr2[sidx] = i < nint ? rowoff[i + 1] : rr1[sidx];
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  double accD[2][2][2][2], accE[2][2][2][2];  // [state][mt][nt][2]
+#pragma unroll
+  for (int sidx = 0; sidx < 2; sidx++) {
+    const int sl = 2 * warp + sidx;             // state slot in the tile
+    const double* Fp = Fsm + sl * FS;           // prior of interval i-1
+    const double* Fa = Fsm + (sl + 1) * FS;     // prior of interval i
+#pragma unroll
+    for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+      for (int nt = 0; nt < 2; nt++) { accD[sidx][mt][nt][0] = accD[sidx][mt][nt][1] = 0.0; accE[sidx][mt][nt][0] = accE[sidx][mt][nt][1] = 0.0; }
+    // one k-step (4 rows) of the products; a*: columns of the first state, b*: of the second state, *1b: second column tile
+    // carrying the rhs as column 12.  cur: rows of interval i (all three products); else rows of interval i-1 (their second-
+    // state columns feed D and g only)
+    auto kstep_cur = [&](double a0, double a1, double a1b, double b0, double b1) {
+      dmma884(accD[sidx][0][0][0], accD[sidx][0][0][1], a0, a0);
+      dmma884(accD[sidx][0][1][0], accD[sidx][0][1][1], a0, a1b);
+      dmma884(accD[sidx][1][0][0], accD[sidx][1][0][1], a1, a0);
+      dmma884(accD[sidx][1][1][0], accD[sidx][1][1][1], a1, a1b);
+      dmma884(accE[sidx][0][0][0], accE[sidx][0][0][1], b0, a0);
+      dmma884(accE[sidx][0][1][0], accE[sidx][0][1][1], b0, a1);
+      dmma884(accE[sidx][1][0][0], accE[sidx][1][0][1], b1, a0);
+      dmma884(accE[sidx][1][1][0], accE[sidx][1][1][1], b1, a1);
+    };
+    auto kstep_prev = [&](double p0, double p1, double p1b) {
+      dmma884(accD[sidx][0][0][0], accD[sidx][0][0][1], p0, p0);
+      dmma884(accD[sidx][0][1][0], accD[sidx][0][1][1], p0, p1b);
+      dmma884(accD[sidx][1][0][0], accD[sidx][1][0][1], p1, p0);
+      dmma884(accD[sidx][1][1][0], accD[sidx][1][1][1], p1, p1b);
+    };
+#pragma unroll
+    for (int ks = 0; ks < 3; ks++) {
+      const int k = 4 * ks + ti;
+      const double a0 = Fa[gi * bs + k], a1 = (gi < 4) ? Fa[(8 + gi) * bs + k] : 0.0, a1b = (gi < 4) ? a1 : (gi == 4 ? Fa[24 * bs + k] : 0.0);
+      const double b0 = Fa[(12 + gi) * bs + k], b1 = (gi < 4) ? Fa[(20 + gi) * bs + k] : 0.0;
+      kstep_cur(a0, a1, a1b, b0, b1);
+      const double p0 = Fp[(12 + gi) * bs + k], p1 = (gi < 4) ? Fp[(20 + gi) * bs + k] : 0.0, p1b = (gi < 4) ? p1 : (gi == 4 ? Fp[24 * bs + k] : 0.0);
+      kstep_prev(p0, p1, p1b);
+    }
+    // extra rows, four per k-step, fragments straight from the row table XR[column][row]
+    for (int base = rr1[sidx]; base < rr2[sidx]; base += 4) {
+      const int row = base + ti;
+      const bool v = row < rr2[sidx];
+      const double* x = XR + (v ? row : base);
+      const double a0 = v ? x[(size_t)gi * NXRp] : 0.0, a1 = (v && gi < 4) ? x[(size_t)(8 + gi) * NXRp] : 0.0;
+      const double a1b = (gi < 4) ? a1 : ((v && gi == 4) ? x[(size_t)xrhs * NXRp] : 0.0);
+      const double b0 = v ? x[(size_t)(12 + gi) * NXRp] : 0.0, b1 = (v && gi < 4) ? x[(size_t)(20 + gi) * NXRp] : 0.0;
+      kstep_cur(a0, a1, a1b, b0, b1);
+    }
+    for (int base = rr0[sidx]; base < rr1[sidx]; base += 4) {
+      const int row = base + ti;
+      const bool v = row < rr1[sidx];
+      const double* x = XR + (v ? row : base);
+      const double p0 = v ? x[(size_t)(12 + gi) * NXRp] : 0.0, p1 = (v && gi < 4) ? x[(size_t)(20 + gi) * NXRp] : 0.0;
+      const double p1b = (gi < 4) ? p1 : ((v && gi == 4) ? x[(size_t)xrhs * NXRp] : 0.0);
+      kstep_prev(p0, p1, p1b);
+    }
+  }
+  __syncthreads();  // every warp is done reading the staged factors: the buffer becomes the record staging
+  double* Osm = Fsm;
+#pragma unroll
+  for (int sidx = 0; sidx < 2; sidx++) {
+    double* O = Osm + (2 * warp + sidx) * REC;
+#pragma unroll
+    for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+      for (int nt = 0; nt < 2; nt++)
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          const int row = 8 * mt + gi, col = 8 * nt + 2 * ti + h;
+          if (row < bs) {
+            if (col < bs) { O[row + col * bs] = accD[sidx][mt][nt][h]; O[bs * bs + row + col * bs] = accE[sidx][mt][nt][h]; }
+            else if (col == bs) O[2 * bs * bs + row] = accD[sidx][mt][nt][h];
+          }
+        }
+  }
+  __syncthreads();
+  // ---- store: TS records are contiguous in HBM
+  const int nst = min(TS, N - i0);
+  double* dst = HREC + (size_t)i0 * REC;
+#pragma unroll 4
+  for (int k = tid; k < nst * REC / 2; k += 128) *reinterpret_cast<double2*>(dst + 2 * k) = *reinterpret_cast<const double2*>(Osm + 2 * k);
+}

@@ -32,6 +32,11 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
       "r"(parity)
       : "memory");
 }
+// FP64 tensor-core MMA, D(8x8) = A(8x4, row) * B(4x8, col) + C.  Fragments: a = A[lane>>2][lane&3], b = B[lane&3][lane>>2],
+// c/d = C[lane>>2][2*(lane&3) + {0,1}]   (PTX ISA, mma.m8n8k4 .f64; SASS DMMA)
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
 __device__ __forceinline__ void st128(double* p, double a, double b) { *reinterpret_cast<double2*>(p) = make_double2(a, b); }
 
 // block-wide sum, result valid in thread 0 (deterministic order)

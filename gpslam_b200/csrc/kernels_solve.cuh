@@ -73,11 +73,6 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// FP64 tensor-core MMA, D(8x8) = A(8x4, row) * B(4x8, col) + C.  Fragments: a = A[lane>>2][lane&3], b = B[lane&3][lane>>2],
-// c/d = C[lane>>2][2*(lane&3) + {0,1}]   (PTX ISA, mma.m8n8k4 .f64; SASS DMMA)
-__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
-}
 // lower-triangular 8x8 tile grid of the 64x64 Schur block, interleaved over the two warps: tile t = 2u + warp
 __constant__ unsigned char c_tileI[36] = {0, 1, 1, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 4, 5, 5, 5, 5, 5, 5, 6, 6, 6, 6, 6, 6, 6, 7, 7, 7, 7, 7, 7, 7, 7};
 __constant__ unsigned char c_tileJ[36] = {0, 0, 1, 0, 1, 2, 0, 1, 2, 3, 0, 1, 2, 3, 4, 0, 1, 2, 3, 4, 5, 0, 1, 2, 3, 4, 5, 6, 0, 1, 2, 3, 4, 5, 6, 7};

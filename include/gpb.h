@@ -169,7 +169,8 @@ int gpb_get_sizes(gpb_graph* g, gpb_sizes* s);
 
 /* profiling aid: average device milliseconds (CUDA events on the engine's stream) of one stage of the hot path over `reps`
  * launches at the current values.  stage: 0 batched GP-prior linearise kernel, 1 linearise of the other factors, 2 assembly,
- * 3 whole block solve (all levels, both sweeps), 4 retract, 5 level-0 forward elimination only. */
+ * 3 whole block solve (all levels, both sweeps), 4 retract, 5 level-0 forward elimination only, 6 / 7 its spine / panel kernel
+ * alone (SE(3) graphs with a 64-column panel), 8 back-substitution (all levels). */
 int gpb_time_stage(gpb_graph* g, int stage, int reps, double* ms_out);
 
 /* names and average device milliseconds of the kernels timed during the last gpb_optimize (profiling aid) */
@@ -178,6 +179,9 @@ int gpb_kernel_launches_last_optimize(gpb_graph* g);
 int gpb_memcpy(void* dst, const void* src, long long bytes, int kind);
 /* cudaStreamSynchronize for the same callers */
 int gpb_stream_synchronize(void* cuda_stream);
+/* profiling aid: measured FP64 tensor-pipe (mma.sync m8n8k4, SASS DMMA) peak of the device in TFLOP/s - the roofline
+ * denominator of the panel kernel */
+int gpb_debug_dmma_peak(int device, double* tflops_out);
 /* testing aid: the reduced-system solver alone - (A + lambda * diag[loff..R)) x = b, A symmetric R x R column-major; the
  * shared-memory single-CTA solver for small R, the blocked multi-CTA Cholesky beyond (or when force_blocked != 0) */
 int gpb_debug_dense_solve(int device, int R, const double* A, const double* b, double lambda, int loff, int force_blocked, double* x_out);
