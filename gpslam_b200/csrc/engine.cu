@@ -86,7 +86,7 @@ struct gpb_graph {
   int nclos = 0, nep = 0, npair = 0;  // loop closures: factors, endpoint states, unique endpoint pairs
   int *d_epstate = nullptr, *d_epoff = nullptr, *d_eprow = nullptr, *d_epside = nullptr;
   int *d_pair_a = nullptr, *d_pair_b = nullptr, *d_pairoff = nullptr, *d_pairrow = nullptr;
-  bool generic_fwd = false, force_blocked = false, old_assemble = false;
+  bool generic_fwd = false, force_blocked = false, old_assemble = false, split_levels = false;
   gpb_allreduce_fn allreduce = nullptr; void* allreduce_ctx = nullptr;
   double* d_topbuf = nullptr; double cur_error_local = 0; int n_allreduce = 0;
   double* d_lambda = nullptr;
@@ -600,6 +600,7 @@ int gpb_graph_finalize(gpb_graph* g, int device) {
   g->sms = sms;
   // segment lengths: explicit setting > environment (tuning aid) > defaults
   const char* em0 = getenv("GPB_M0"); const char* emu = getenv("GPB_MUP");
+  g->split_levels = getenv("GPB_SPLIT_LEVELS") != nullptr;  // A/B switch: spine and panel as two launches on the upper levels too
   g->old_assemble = getenv("GPB_OLD_ASSEMBLE") != nullptr;  // A/B switch: thread-per-tile assembly instead of the DMMA kernel
   g->generic_fwd = getenv("GPB_GENERIC_FWD") != nullptr;  // A/B switch: one-kernel generic forward sweep (k_fwd<12,64>)
   int M0 = g->M0 ? g->M0 : (em0 ? std::max(2, atoi(em0)) : (g->nb > 0 ? 32 : 16));
@@ -834,8 +835,13 @@ static int launch_fwd_level(gpb_graph* g, int buf, double lambda, int lev, int p
   if (bs == 12 && g->W == 64 && !g->generic_fwd) {
     // spine first (warp per segment: the latency-bound 12x12 recurrence wants many independent warps), then the tensor-pipe panel
     const int spine_ctas = std::min(L.nseg, 16 * g->sms);
-    if (parts & 1) { if (lev == 0) k_spine<12, true><<<spine_ctas, 32, 0, g->stream>>>(a); else k_spine<12, false><<<spine_ctas, 32, 0, g->stream>>>(a); g->launches++; }
-    if (parts & 2) { k_panel4<12><<<L.ncta, 128, 0, g->stream>>>(a); g->launches++; }
+    if (lev > 0 && parts == 3 && L.nseg <= 2 * g->sms && !g->split_levels) {
+      // small level: spine and panel pipelined inside one kernel (every CTA resident at once)
+      k_level_ws<12><<<L.nseg, 160, 0, g->stream>>>(a); g->launches++;
+    } else {
+      if (parts & 1) { if (lev == 0) k_spine<12, true><<<spine_ctas, 32, 0, g->stream>>>(a); else k_spine<12, false><<<spine_ctas, 32, 0, g->stream>>>(a); g->launches++; }
+      if (parts & 2) { k_panel4<12><<<L.ncta, 128, 0, g->stream>>>(a); g->launches++; }
+    }
   } else {
     if (bs == 12) fwd_w<12>(g->W, a, L.ncta, g->stream); else fwd_w<6>(g->W, a, L.ncta, g->stream);
     g->launches++;

@@ -526,12 +526,15 @@ __device__ __forceinline__ double rsqrt_pos(double x) {
 // through shared memory (Le out, 9 DMMA on the lower tiles, Dn back in the row-per-lane layout, read as 128-bit column loads
 // thanks to symmetry).  The next pivot is broadcast from an early copy (arow[j+1] - l^2 on its owner lane) so the pivot chain
 // is  shfl -> rsqrt -> mul  per column instead of waiting for the column broadcast.
-template <int BS, bool FIRST>
-__global__ void __launch_bounds__(32, 16) k_spine(const FwdArgs a) {
+// `ready` (fused upper-level kernel only): shared-memory counter of the states this warp has finished, published after a
+// fence so that the panel warps of the same CTA may fetch their (L^-1, Le) from HBM / L2.
+template <int BS, bool FIRST, bool FUSED>
+__device__ __forceinline__ void spine_body(const FwdArgs& a, const int lane, volatile int* ready) {
   static_assert(BS == 12, "spine kernel is specialised for 12 x 12 state blocks");
   constexpr int REC0 = 2 * BS * BS + BS, REC1 = 3 * BS * BS + 2 * BS;
   __shared__ __align__(16) double Les[BS * BS], Dn[BS * BS];
-  const int lane = threadIdx.x, gi = lane >> 2, ti = lane & 3;
+  const int gi = lane >> 2, ti = lane & 3;
+  int done = 0;
   const bool dl = lane < BS, el = lane >= BS && lane < 2 * BS;
   const int rr = dl ? lane : (el ? lane - BS : 0);
   constexpr bool first = FIRST;
@@ -623,6 +626,12 @@ __global__ void __launch_bounds__(32, 16) k_spine(const FwdArgs a) {
         }
       }
       __syncwarp();
+      if constexpr (FUSED) {  // L^-1 and Le of state i are in HBM / L2: let the panel warps go
+        __threadfence();
+        __syncwarp();
+        done++;
+        if (lane == 0) *ready = done;
+      }
     }
     if (!ok && lane == 0) *a.flag = 1;
     if (q >= 0 && dl) {  // D1 of the right separator: its own block (fetched last) + the last Schur update (+ damping at level 0)
@@ -633,6 +642,8 @@ __global__ void __launch_bounds__(32, 16) k_spine(const FwdArgs a) {
     __syncwarp();
   }
 }
+template <int BS, bool FIRST>
+__global__ void __launch_bounds__(32, 16) k_spine(const FwdArgs a) { spine_body<BS, FIRST, false>(a, threadIdx.x, nullptr); }
 
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -684,8 +695,13 @@ __global__ void k_border_pack(const double* __restrict__ XR, const int* __restri
   bent[(size_t)e * 16 + k] = v;
 }
 
-template <int BS>
-__global__ void __launch_bounds__(128, 5) k_panel4(const FwdArgs a) {
+// FUSED (upper-level kernel): the 128 panel threads share the CTA with a spine warp; block barriers become a named barrier of
+// the panel threads, and a state's (L^-1, Le) is fetched only after the spine warp has published it (`ready`).
+template <bool FUSED> __device__ __forceinline__ void panel_sync() {
+  if constexpr (FUSED) asm volatile("bar.sync 1, 128;" ::: "memory"); else __syncthreads();
+}
+template <int BS, bool FUSED>
+__device__ __forceinline__ void panel_body(const FwdArgs& a, volatile const int* ready) {
   static_assert(BS == 12, "panel kernel is specialised for 12 x 12 state blocks");
   constexpr int W = 64, NT = 128, REC0 = 2 * BS * BS + BS, REC1 = 3 * BS * BS + 2 * BS, NST = 3, MAXE = 6, HB = BS / 2;
   __shared__ __align__(16) double Fb[NST][2 * BS * BS];  // (L^-1 | Le)
@@ -713,6 +729,7 @@ __global__ void __launch_bounds__(128, 5) k_panel4(const FwdArgs a) {
   };
   auto bso = [&](int i) { return ent ? a.bsoff[i < a.n ? i : a.n] : 0; };
 
+  int seg_base = 0;  // states the spine warp finished before this segment (it walks the same segments in the same order)
   for (int seg = blockIdx.x; seg < a.nseg; seg += gridDim.x) {
     const SegGeom sg = seg_geom(seg, a.n, a.sep, a.S, a.extL, a.extR);
     const int p = sg.p, q = sg.q, i0 = sg.i0, i1 = sg.i1;
@@ -720,6 +737,7 @@ __global__ void __launch_bounds__(128, 5) k_panel4(const FwdArgs a) {
     int b0 = bso(i0), b1 = bso(i0 + 1), b2 = bso(i0 + 2), b3 = bso(i0 + 3);  // rolling window of CSR offsets: states i .. i+3
     auto prefetch = [&](int i, int st, int e0, int e1) {
       if (i <= i1) {
+        if constexpr (FUSED) { while (*ready <= seg_base + (i - i0)) { } }  // the spine warp has published state i
         const double* src = a.frec + (size_t)i * a.fstride;
         const int n2 = (((i < i1) || (q >= 0)) ? 2 * BS * BS : BS * BS) / 2;
         for (int k = c; k < n2; k += NT) cp_async16(&Fb[st][2 * k], src + 2 * k);
@@ -767,7 +785,7 @@ __global__ void __launch_bounds__(128, 5) k_panel4(const FwdArgs a) {
       for (int r = 0; r < HB; r++) Psm[col * BS + r0 + r] = sp ? E[r] : 0.0;
     }
     cp_async_wait<1>();
-    __syncthreads();
+    panel_sync<FUSED>();
     int st = 0, ys = 0;
     for (int i = i0; i <= i1; i++) {
       const bool has_next = (i < i1) || (q >= 0);
@@ -844,14 +862,14 @@ __global__ void __launch_bounds__(128, 5) k_panel4(const FwdArgs a) {
         for (int r = 0; r < HB; r += 2) st128(F + r, yc[r], yc[r + 1]);
       }
       cp_async_wait<1>();
-      __syncthreads();
+      panel_sync<FUSED>();
       // ---- S += Y^T Y (this warp's nine tiles)
       with_pw([&](auto PW) { syrk_accum<decltype(PW)::value>(Y, acc, gi, ti); });
       b0 = b1; b1 = b2; b2 = b3; b3 = b4;
       st = st == 2 ? 0 : st + 1; ys ^= 1;
     }
     cp_async_wait<0>();
-    __syncthreads();
+    panel_sync<FUSED>();
     // ---- segment end (D1 of q was written by k_spine): the closing separator's own border / rhs, then hand the panel off
     if (q >= 0) {
       double* R = a.rec_out + (size_t)sg.qo * REC1;
@@ -936,7 +954,8 @@ __global__ void __launch_bounds__(128, 5) k_panel4(const FwdArgs a) {
         });
       });
     }
-    __syncthreads();
+    panel_sync<FUSED>();
+    if (i1 >= i0) seg_base += i1 - i0 + 1;
   }
   if (nb > 0) {
     double* Cs = a.cseg + (size_t)blockIdx.x * (nb * nb + nb);
@@ -958,6 +977,20 @@ __global__ void __launch_bounds__(128, 5) k_panel4(const FwdArgs a) {
       });
     });
   }
+}
+template <int BS>
+__global__ void __launch_bounds__(128, 5) k_panel4(const FwdArgs a) { panel_body<BS, false>(a, nullptr); }
+
+// Upper elimination levels (a few hundred segments at most: latency, not throughput): ONE kernel per level.  Warp 4 of each
+// CTA walks the spine of the CTA's segments and never waits; warps 0-3 run the panel a couple of states behind it, so a level
+// costs about one spine pass instead of a spine launch followed by a panel launch.
+template <int BS>
+__global__ void __launch_bounds__(160) k_level_ws(const FwdArgs a) {
+  __shared__ int ready;
+  if (threadIdx.x == 0) ready = 0;
+  __syncthreads();
+  if (threadIdx.x >= 128) spine_body<BS, false, true>(a, threadIdx.x - 128, &ready);
+  else panel_body<BS, true>(a, &ready);
 }
 
 // Back-substitution of one level: x_i = L_ii^-T ( y_i - Yspike_i x_p - Yborder_i x_l - Le_i^T x_{i+1} ), right to left.
