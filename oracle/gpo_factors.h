@@ -269,6 +269,53 @@ inline double gpRangePose3(const InterpolatorPose3& gp, double measured, const P
   return hx - measured;
 }
 
+// slam/GPInterpolatedGPSFactorPose3.h:67-95.  body_P_sensor may be null.
+inline Vec3 gpGPSPose3(const InterpolatorPose3& gp, const Vec3& measured, const Pose3* body_P_sensor,
+                       const Pose3& pose1, const Vec6& vel1, const Pose3& pose2, const Vec6& vel2,
+                       Mat<3, 6>* H1, Mat<3, 6>* H2, Mat<3, 6>* H3, Mat<3, 6>* H4) {
+  const bool wantH = H1 || H2 || H3 || H4;
+  Mat6 Hint1, Hint2, Hint3, Hint4;
+  const Pose3 pose = wantH ? gp.interpolatePose(pose1, vel1, pose2, vel2, &Hint1, &Hint2, &Hint3, &Hint4)
+                           : gp.interpolatePose(pose1, vel1, pose2, vel2, nullptr, nullptr, nullptr, nullptr);
+  Mat<3, 6> Hpose;
+  Vec3 point_err;
+  if (body_P_sensor) {
+    point_err = pose3_translation(pose.compose(*body_P_sensor), &Hpose) - measured;
+    if (wantH) Hpose = Hpose * pose3_Hcompose1(*body_P_sensor);
+  } else {
+    point_err = pose3_translation(pose, &Hpose) - measured;
+  }
+  if (wantH) {  // updatePoseJacobians, gp/GaussianProcessInterpolatorPose3.h:108-116
+    if (H1) *H1 = Hpose * Hint1; if (H2) *H2 = Hpose * Hint2; if (H3) *H3 = Hpose * Hint3; if (H4) *H4 = Hpose * Hint4;
+  }
+  return point_err;
+}
+
+// slam/GPInterpolatedProjectionFactorPose3.h:82-139 with CALIBRATION = Cal3_S2, K = (fx, fy, s, u0, v0).  A landmark behind
+// the camera (CheiralityException, :123-138): zero Jacobians and the residual (2 fx, 2 fx); throwCheirality is not restated.
+inline Vec2 gpProjectionPose3(const InterpolatorPose3& gp, const Vec2& measured, const double* K, const Pose3* body_P_sensor,
+                              const Pose3& pose1, const Vec6& vel1, const Pose3& pose2, const Vec6& vel2, const Vec3& point,
+                              Mat<2, 6>* H1, Mat<2, 6>* H2, Mat<2, 6>* H3, Mat<2, 6>* H4, Mat<2, 3>* H5) {
+  const bool wantH = H1 || H2 || H3 || H4;
+  Mat6 Hint1, Hint2, Hint3, Hint4;
+  const Pose3 pose = wantH ? gp.interpolatePose(pose1, vel1, pose2, vel2, &Hint1, &Hint2, &Hint3, &Hint4)
+                           : gp.interpolatePose(pose1, vel1, pose2, vel2, nullptr, nullptr, nullptr, nullptr);
+  Mat<2, 6> Hpose;
+  Vec2 pi;
+  const Pose3 cam = body_P_sensor ? pose.compose(*body_P_sensor) : pose;
+  if (!pinhole_project(cam, K, point, pi, &Hpose, H5)) {
+    if (H1) *H1 = Mat<2, 6>::Zero(); if (H2) *H2 = Mat<2, 6>::Zero(); if (H3) *H3 = Mat<2, 6>::Zero(); if (H4) *H4 = Mat<2, 6>::Zero();
+    if (H5) *H5 = Mat<2, 3>::Zero();
+    Vec2 e; e[0] = 2.0 * K[0]; e[1] = 2.0 * K[0];
+    return e;
+  }
+  if (wantH) {
+    if (body_P_sensor) Hpose = Hpose * pose3_Hcompose1(*body_P_sensor);
+    if (H1) *H1 = Hpose * Hint1; if (H2) *H2 = Hpose * Hint2; if (H3) *H3 = Hpose * Hint3; if (H4) *H4 = Hpose * Hint4;
+  }
+  return pi - measured;
+}
+
 // slam/GPInterpolatedRangeFactorPose2.h:64-98
 inline double gpRangePose2(const InterpolatorPose2& gp, double measured, const Pose2* body_P_sensor,
                            const Pose2& pose1, const Vec3& vel1, const Pose2& pose2, const Vec3& vel2, const Vec2& point,

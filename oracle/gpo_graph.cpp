@@ -30,7 +30,8 @@ namespace {
 enum Group { G_POSE3 = 0, G_POSE2 = 1, G_ROT3 = 2, G_LINEAR = 3 };
 enum FactorKind {
   F_GP_PRIOR = 0, F_INTERP_RANGE = 1, F_INTERP_ATTITUDE = 2, F_PRIOR_POSE = 3, F_PRIOR_VEL = 4,
-  F_PRIOR_LANDMARK = 5, F_BETWEEN = 6, F_RANGE_2D = 7, F_RANGE_BEARING_2D = 8, F_ODOMETRY_2D = 9
+  F_PRIOR_LANDMARK = 5, F_BETWEEN = 6, F_RANGE_2D = 7, F_RANGE_BEARING_2D = 8, F_ODOMETRY_2D = 9,
+  F_INTERP_GPS = 10, F_INTERP_PROJECTION = 11
 };
 
 struct Factor {
@@ -40,6 +41,8 @@ struct Factor {
   double delta_t = 0, tau = 0, z = 0, z2 = 0;
   bool has_sensor = false;
   double aux[12] = {0};     // body_P_sensor (Pose3 12 / Pose2 3) | nZ,bRef | measurement value
+  double meas[3] = {0};     // GPS point / image point
+  double K[5] = {0};        // Cal3_S2 (fx, fy, s, u0, v0)
   double R[36] = {0};       // sqrt information (m x m, column-major, upper triangular)
   int m = 0;
 };
@@ -139,6 +142,33 @@ void eval_factor(const Graph& g, const Factor& f, const double* P, const double*
                             wantH ? &H4 : nullptr, wantH ? &H5 : nullptr);
         if (wantH) { put(out.A[0], H1); put(out.A[1], H2); put(out.A[2], H3); put(out.A[3], H4); put(out.A[4], H5); }
       } else std::abort();
+      return;
+    }
+    case F_INTERP_GPS: {  // slam/GPInterpolatedGPSFactorPose3.h
+      const int i = f.i, j = f.i + 1;
+      addv(0, i, D); addv(1, i, D); addv(0, j, D); addv(1, j, D);
+      out.m = 3;
+      if (g.group != G_POSE3) std::abort();
+      const InterpolatorPose3 gp(get<6, 6>(g.Qc[f.qc].data()), f.delta_t, f.tau);
+      Pose3 sensor; if (f.has_sensor) sensor = Pose3::from(f.aux);
+      Mat<3, 6> H1, H2, H3, H4;
+      put(e, gpGPSPose3(gp, vec<3>(f.meas), f.has_sensor ? &sensor : nullptr, Pose3::from(P + i * PS), vec<6>(V + i * D), Pose3::from(P + j * PS), vec<6>(V + j * D),
+                        wantH ? &H1 : nullptr, wantH ? &H2 : nullptr, wantH ? &H3 : nullptr, wantH ? &H4 : nullptr));
+      if (wantH) { put(out.A[0], H1); put(out.A[1], H2); put(out.A[2], H3); put(out.A[3], H4); }
+      return;
+    }
+    case F_INTERP_PROJECTION: {  // slam/GPInterpolatedProjectionFactorPose3.h
+      const int i = f.i, j = f.i + 1;
+      addv(0, i, D); addv(1, i, D); addv(0, j, D); addv(1, j, D); addv(2, f.l, DL);
+      out.m = 2;
+      if (g.group != G_POSE3) std::abort();
+      const InterpolatorPose3 gp(get<6, 6>(g.Qc[f.qc].data()), f.delta_t, f.tau);
+      Pose3 sensor; if (f.has_sensor) sensor = Pose3::from(f.aux);
+      Mat<2, 6> H1, H2, H3, H4; Mat<2, 3> H5;
+      put(e, gpProjectionPose3(gp, vec<2>(f.meas), f.K, f.has_sensor ? &sensor : nullptr, Pose3::from(P + i * PS), vec<6>(V + i * D), Pose3::from(P + j * PS),
+                               vec<6>(V + j * D), vec<3>(Lm + f.l * DL), wantH ? &H1 : nullptr, wantH ? &H2 : nullptr, wantH ? &H3 : nullptr,
+                               wantH ? &H4 : nullptr, wantH ? &H5 : nullptr));
+      if (wantH) { put(out.A[0], H1); put(out.A[1], H2); put(out.A[2], H3); put(out.A[3], H4); put(out.A[4], H5); }
       return;
     }
     case F_INTERP_ATTITUDE: {
@@ -649,6 +679,32 @@ int gpo_add_interp_range(void* h, int n, const int* i, const int* l, const doubl
   for (int k = 0; k < n; k++) {
     Factor f; f.kind = F_INTERP_RANGE; f.i = i[k]; f.l = l[k]; f.z = z[k]; f.delta_t = delta_t[k]; f.tau = tau[k]; f.qc = qc; f.m = 1; f.R[0] = 1.0 / sigma[k];
     if (body_P_sensor) { f.has_sensor = true; for (int t = 0; t < ps; t++) f.aux[t] = body_P_sensor[t]; }
+    g->factors.push_back(f);
+  }
+  return 0;
+}
+int gpo_add_interp_gps(void* h, int n, const int* i, const double* meas, const double* sqrt_info, const double* delta_t, const double* tau, int qc, const double* body_P_sensor) {
+  Graph* g = (Graph*)h;
+  if (g->group != G_POSE3) return -1;
+  for (int k = 0; k < n; k++) {
+    Factor f; f.kind = F_INTERP_GPS; f.i = i[k]; f.delta_t = delta_t[k]; f.tau = tau[k]; f.qc = qc;
+    for (int t = 0; t < 3; t++) f.meas[t] = meas[3 * k + t];
+    set_R(f, 3, sqrt_info);
+    if (body_P_sensor) { f.has_sensor = true; for (int t = 0; t < 12; t++) f.aux[t] = body_P_sensor[t]; }
+    g->factors.push_back(f);
+  }
+  return 0;
+}
+int gpo_add_interp_projection(void* h, int n, const int* i, const int* l, const double* meas, const double* sqrt_info, const double* delta_t, const double* tau, int qc,
+                              const double* K, const double* body_P_sensor) {
+  Graph* g = (Graph*)h;
+  if (g->group != G_POSE3) return -1;
+  for (int k = 0; k < n; k++) {
+    Factor f; f.kind = F_INTERP_PROJECTION; f.i = i[k]; f.l = l[k]; f.delta_t = delta_t[k]; f.tau = tau[k]; f.qc = qc;
+    for (int t = 0; t < 2; t++) f.meas[t] = meas[2 * k + t];
+    for (int t = 0; t < 5; t++) f.K[t] = K[t];
+    set_R(f, 2, sqrt_info);
+    if (body_P_sensor) { f.has_sensor = true; for (int t = 0; t < 12; t++) f.aux[t] = body_P_sensor[t]; }
     g->factors.push_back(f);
   }
   return 0;

@@ -251,6 +251,40 @@ inline double pose3_range(const Pose3& T, const Vec3& p, Mat<1, 6>* H1, Mat<1, 3
   return r;
 }
 
+// gtsam::Pose3::translation(H): t, d/dT = [0, R]
+inline Vec3 pose3_translation(const Pose3& T, Mat<3, 6>* H) {
+  if (H) { *H = Mat<3, 6>::Zero(); H->set(0, 3, T.R); }
+  return T.t;
+}
+
+// gtsam::PinholeCamera<Cal3_S2>(pose, K).project(point, Dpose, Dpoint)  (GTSAM 4.0 PinholePose / CalibratedCamera):
+// q = R^T (p - t); cheirality: q.z <= 0 -> behind the camera (returns false; GTSAM throws CheiralityException);
+// pn = (q.x, q.y) / q.z; pi = (fx pn.x + s pn.y + u0, fy pn.y + v0);
+// Dpn/Dpose = [[uv, -1-uu, v, -d, 0, du], [1+vv, -uv, -u, 0, -d, dv]], d = 1/q.z;  Dpn/Dpoint = d [[1,0,-u],[0,1,-v]] R^T.
+// K = (fx, fy, s, u0, v0).
+inline bool pinhole_project(const Pose3& T, const double* K, const Vec3& p, Vec2& pi, Mat<2, 6>* Dpose, Mat<2, 3>* Dpoint) {
+  const Mat3 Rt = T.R.t();
+  const Vec3 q = Rt * (p - T.t);
+  if (q[2] <= 0) return false;
+  const double d = 1.0 / q[2], u = q[0] * d, v = q[1] * d;
+  pi[0] = K[0] * u + K[2] * v + K[3];
+  pi[1] = K[1] * v + K[4];
+  Mat2 Dpi = Mat2::Zero();
+  Dpi(0, 0) = K[0]; Dpi(0, 1) = K[2]; Dpi(1, 1) = K[1];
+  if (Dpose) {
+    Mat<2, 6> Dn;
+    Dn(0, 0) = u * v; Dn(0, 1) = -1 - u * u; Dn(0, 2) = v; Dn(0, 3) = -d; Dn(0, 4) = 0; Dn(0, 5) = d * u;
+    Dn(1, 0) = 1 + v * v; Dn(1, 1) = -u * v; Dn(1, 2) = -u; Dn(1, 3) = 0; Dn(1, 4) = -d; Dn(1, 5) = d * v;
+    *Dpose = Dpi * Dn;
+  }
+  if (Dpoint) {
+    Mat<2, 3> Dq;
+    Dq(0, 0) = d; Dq(0, 1) = 0; Dq(0, 2) = -d * u; Dq(1, 0) = 0; Dq(1, 1) = d; Dq(1, 2) = -d * v;
+    *Dpoint = Dpi * (Dq * Rt);
+  }
+  return true;
+}
+
 // ---------------------------------------------------------------- SE(2)
 struct Pose2 {
   double x, y, th;
