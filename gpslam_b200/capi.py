@@ -159,6 +159,24 @@ class Graph:
         self._ck(self.L.gpb_add_interp_range(self.h, C.c_int(len(i)), _ip(i), _ip(l), _dp(b(z)), _dp(b(sigma)), _dp(b(delta_t)), _dp(b(tau)), C.c_int(qc),
                                              _dp(bps)))
 
+    def add_interp_gps(self, i, meas, sqrt_info, delta_t, tau, qc=0, body_P_sensor=None):
+        """GPInterpolatedGPSFactorPose3: meas [n x 3] points, sqrt_info 3x3 upper-triangular R shared by the n factors"""
+        i = np.ascontiguousarray(np.atleast_1d(i), dtype=np.int32)
+        b = lambda a: _f64(np.broadcast_to(np.atleast_1d(a), i.shape))
+        m = _f64(np.broadcast_to(np.asarray(meas, dtype=np.float64).reshape(-1, 3), (len(i), 3)))
+        bps = _f64(body_P_sensor) if body_P_sensor is not None else None
+        self._ck(self.L.gpb_add_interp_gps(self.h, C.c_int(len(i)), _ip(i), _dp(m), _dp(_fcol(sqrt_info)), _dp(b(delta_t)), _dp(b(tau)), C.c_int(qc), _dp(bps)))
+
+    def add_interp_projection(self, i, l, meas, sqrt_info, delta_t, tau, K, qc=0, body_P_sensor=None):
+        """GPInterpolatedProjectionFactorPose3<Cal3_S2>: meas [n x 2] image points, K = (fx, fy, s, u0, v0)"""
+        i = np.ascontiguousarray(np.atleast_1d(i), dtype=np.int32)
+        l = np.ascontiguousarray(np.broadcast_to(np.atleast_1d(l), i.shape), dtype=np.int32)
+        b = lambda a: _f64(np.broadcast_to(np.atleast_1d(a), i.shape))
+        m = _f64(np.broadcast_to(np.asarray(meas, dtype=np.float64).reshape(-1, 2), (len(i), 2)))
+        bps = _f64(body_P_sensor) if body_P_sensor is not None else None
+        self._ck(self.L.gpb_add_interp_projection(self.h, C.c_int(len(i)), _ip(i), _ip(l), _dp(m), _dp(_fcol(sqrt_info)), _dp(b(delta_t)), _dp(b(tau)), C.c_int(qc),
+                                                   _dp(_f64(K)), _dp(bps)))
+
     def add_interp_attitude(self, i, delta_t, tau, nZ, sigma, bRef=(0, 0, 1), qc=0):
         i = np.ascontiguousarray(np.atleast_1d(i), dtype=np.int32)
         b = lambda a: _f64(np.broadcast_to(np.atleast_1d(a), i.shape))

@@ -93,8 +93,8 @@ struct gpb_graph {
   cudaGraphExec_t iter_graph[2] = {nullptr, nullptr}; int iter_graph_launches[2] = {0, 0};  // captured GN/LM trial per buffer parity
   cudaGraphExec_t dist_graph[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}}; int dist_graph_launches[2] = {0, 0};  // sharded GN: [parity][before / after the all-reduce]
   int extL = 0, extR = 0;  // shard: first / last state is an external separator (owned by the global reduced system)
-  int *d_listA = nullptr, *d_listB = nullptr;  // extra factors by kind class: interpolated measurements / everything else
-  int nA = 0, nB = 0;
+  int *d_listA = nullptr, *d_listB = nullptr, *d_listC = nullptr;  // extra factors by kind class: interpolated range / attitude, generic, GPS / projection
+  int nA = 0, nB = 0, nC = 0;
   double* d_Csum = nullptr;
   std::vector<int> sorted_of_order, h_xrow;
   std::vector<Extra> sorted;
@@ -117,7 +117,8 @@ static int land_dim(int group) { return group == GPB_POSE3 ? 3 : group == GPB_RO
 static int extra_rows_of(const gpb_graph* g, int kind) {
   switch (kind) {
     case X_INTERP_RANGE: case X_RANGE_2D: return 1;
-    case X_INTERP_ATTITUDE: case X_RANGE_BEARING_2D: return 2;
+    case X_INTERP_ATTITUDE: case X_RANGE_BEARING_2D: case X_INTERP_PROJECTION: return 2;
+    case X_INTERP_GPS: return 3;
     case X_PRIOR_POSE: case X_PRIOR_VEL: case X_BETWEEN: return g->D;
     case X_PRIOR_LANDMARK: return g->DL;
     case X_ODOMETRY_2D: return 3;
@@ -243,6 +244,46 @@ int gpb_add_interp_range(gpb_graph* g, int n, const int* i, const int* l, const 
     e.sa = i[k]; e.sb = i[k] + 1; e.l = l[k]; e.interval = i[k]; e.m = 1;
     e.prm[0] = delta_t[k]; e.prm[1] = tau[k]; e.prm[2] = z[k]; e.prm[20] = 1.0 / sigma[k];
     if (body_P_sensor) { for (int t = 0; t < g->PS; t++) e.prm[4 + t] = body_P_sensor[t]; e.prm[16] = 1.0; }
+    e.order = (int)g->extras.size(); g->extras.push_back(e);
+  }
+  return GPB_OK;
+}
+
+int gpb_add_interp_gps(gpb_graph* g, int n, const int* i, const double* measured, const double* sqrt_info, const double* delta_t, const double* tau, int qc,
+                       const double* body_P_sensor) {
+  CHECK_OPEN(g);
+  if (g->group != GPB_POSE3) return fail(GPB_ERR_UNSUPPORTED, "gpb_add_interp_gps: Pose3 trajectories only (GPInterpolatedGPSFactorPose3)");
+  (void)qc;  // Lambda/Psi do not depend on Qc
+  for (int k = 0; k < n; k++) {
+    if (i[k] < 0 || i[k] >= g->nint) return fail(GPB_ERR_ARG, "gpb_add_interp_gps: index out of range");
+    if (!(delta_t[k] > 0.0)) return fail(GPB_ERR_ARG, "gpb_add_interp_gps: delta_t must be positive");
+    Extra e = make_extra(X_INTERP_GPS);
+    e.sa = i[k]; e.sb = i[k] + 1; e.interval = i[k]; e.m = 3;
+    e.prm[0] = delta_t[k]; e.prm[1] = tau[k];
+    for (int t = 0; t < 3; t++) e.prm[40 + t] = measured[3 * k + t];
+    set_R(e, 3, sqrt_info);
+    if (body_P_sensor) { for (int t = 0; t < 12; t++) e.prm[4 + t] = body_P_sensor[t]; e.prm[16] = 1.0; }
+    e.order = (int)g->extras.size(); g->extras.push_back(e);
+  }
+  return GPB_OK;
+}
+
+int gpb_add_interp_projection(gpb_graph* g, int n, const int* i, const int* l, const double* measured, const double* sqrt_info, const double* delta_t,
+                              const double* tau, int qc, const double* K, const double* body_P_sensor) {
+  CHECK_OPEN(g);
+  if (g->group != GPB_POSE3) return fail(GPB_ERR_UNSUPPORTED, "gpb_add_interp_projection: Pose3 trajectories only (GPInterpolatedProjectionFactorPose3)");
+  if (!K) return fail(GPB_ERR_ARG, "gpb_add_interp_projection: null calibration");
+  (void)qc;
+  for (int k = 0; k < n; k++) {
+    if (i[k] < 0 || i[k] >= g->nint || l[k] < 0 || l[k] >= g->L) return fail(GPB_ERR_ARG, "gpb_add_interp_projection: index out of range");
+    if (!(delta_t[k] > 0.0)) return fail(GPB_ERR_ARG, "gpb_add_interp_projection: delta_t must be positive");
+    Extra e = make_extra(X_INTERP_PROJECTION);
+    e.sa = i[k]; e.sb = i[k] + 1; e.l = l[k]; e.interval = i[k]; e.m = 2;
+    e.prm[0] = delta_t[k]; e.prm[1] = tau[k];
+    for (int t = 0; t < 2; t++) e.prm[40 + t] = measured[2 * k + t];
+    for (int t = 0; t < 5; t++) e.prm[43 + t] = K[t];
+    set_R(e, 2, sqrt_info);
+    if (body_P_sensor) { for (int t = 0; t < 12; t++) e.prm[4 + t] = body_P_sensor[t]; e.prm[16] = 1.0; }
     e.order = (int)g->extras.size(); g->extras.push_back(e);
   }
   return GPB_OK;
@@ -510,9 +551,9 @@ int gpb_graph_finalize(gpb_graph* g, int device) {
     }
     for (int i = 0; i < g->N; i++) { bsoff[i + 1] = bsoff[i] + (int)per[i].size(); for (auto& pr : per[i]) { bsrow.push_back(pr.first); bsside.push_back(pr.second); } }
   }
-  std::vector<int> listA, listB;
-  for (int k = 0; k < g->NX; k++) (xkind[k] == X_INTERP_RANGE || xkind[k] == X_INTERP_ATTITUDE ? listA : listB).push_back(k);
-  g->nA = (int)listA.size(); g->nB = (int)listB.size();
+  std::vector<int> listA, listB, listC;
+  for (int k = 0; k < g->NX; k++) (xkind[k] == X_INTERP_RANGE || xkind[k] == X_INTERP_ATTITUDE ? listA : (xkind[k] == X_INTERP_GPS || xkind[k] == X_INTERP_PROJECTION ? listC : listB)).push_back(k);
+  g->nA = (int)listA.size(); g->nB = (int)listB.size(); g->nC = (int)listC.size();
   // ---- loop closures: endpoint states (pinned separators), per-endpoint and per-pair row lists
   std::vector<char> pin(g->N, 0);
   std::vector<int> epstate, epoff, eprow, epside, clos;
@@ -578,12 +619,13 @@ int gpb_graph_finalize(gpb_graph* g, int device) {
   if ((rc = dev_alloc(g, &g->d_bent, (size_t)std::max(g->nbent, 1) * 16))) return rc;
   if ((rc = dev_upload(g, &g->d_listA, listA))) return rc;
   if ((rc = dev_upload(g, &g->d_listB, listB))) return rc;
+  if ((rc = dev_upload(g, &g->d_listC, listC))) return rc;
   if ((rc = dev_upload(g, &g->d_rowoff, rowoff))) return rc;
   if ((rc = dev_upload(g, &g->d_rowland, rowland))) return rc;
   if ((rc = dev_upload(g, &g->d_lmoff, lmoff))) return rc;
   if ((rc = dev_upload(g, &g->d_lmrows, lmrows))) return rc;
   if ((rc = dev_alloc(g, &g->d_HREC, (size_t)g->N * (2 * bs * bs + bs)))) return rc;
-  g->nerrpart = (g->nint + 127) / 128 + (g->NX + 127) / 128 + (g->NX + 3) / 4 + (g->N + 127) / 128 + 16;
+  g->nerrpart = (g->nint + 127) / 128 + 2 * ((g->NX + 127) / 128) + (g->NX + 3) / 4 + (g->N + 127) / 128 + 16;
   if ((rc = dev_alloc(g, &g->d_errpart, (size_t)2 * g->nerrpart))) return rc;
   if ((rc = dev_alloc(g, &g->d_scal, 8))) return rc;
   if ((rc = dev_alloc(g, &g->d_flag, 1))) return rc;
@@ -767,8 +809,16 @@ template <int G> static int launch_linearize(gpb_graph* g, const double* X, cons
                                                       g->d_errpart + nb1, g->NX, g->NXRp, wantJ);
     g->launches++;
   }
+  const int nbC = (g->nC + NT - 1) / NT;
+  if constexpr (G == G_POSE3) {
+    if (nbC > 0) {  // GPS / projection factors
+      k_lin_extra<G, 2, NT><<<nbC, NT, 0, g->stream>>>(g->d_listC, g->nC, X, land, g->d_xkind, g->d_xsa, g->d_xsb, g->d_xl, g->d_xrow, g->d_xprm, g->d_XR[buf],
+                                                        g->d_errpart + nb1 + nbA + nbB, g->NX, g->NXRp, wantJ);
+      g->launches++;
+    }
+  }
   if (nbB > 0) CUDA_TRY(cudaStreamWaitEvent(g->stream, g->ev_join, 0));
-  k_sum_partials<<<1, 256, 0, g->stream>>>(g->d_errpart, nb1 + nbA + nbB, g->d_scal, 0);
+  k_sum_partials<<<1, 256, 0, g->stream>>>(g->d_errpart, nb1 + nbA + nbB + (G == G_POSE3 ? nbC : 0), g->d_scal, 0);
   g->launches++;
   CUDA_TRY(cudaGetLastError());
   return GPB_OK;
@@ -1365,7 +1415,8 @@ int gpb_get_linearized_factor(gpb_graph* g, int kind, int idx, double* A_out, do
   const int offs = e.sa >= 0 ? 0 : bs;
   switch (e.kind) {
     case X_INTERP_RANGE: emit(0, D); emit(D, D); emit(bs, D); emit(bs + D, D); emit(2 * bs, DL); break;
-    case X_INTERP_ATTITUDE: emit(0, D); emit(D, D); emit(bs, D); emit(bs + D, D); break;
+    case X_INTERP_ATTITUDE: case X_INTERP_GPS: emit(0, D); emit(D, D); emit(bs, D); emit(bs + D, D); break;
+    case X_INTERP_PROJECTION: emit(0, D); emit(D, D); emit(bs, D); emit(bs + D, D); emit(2 * bs, DL); break;
     case X_PRIOR_POSE: emit(offs, D); break;
     case X_PRIOR_VEL: emit(offs + D, D); break;
     case X_PRIOR_LANDMARK: emit(2 * bs, DL); break;
@@ -1442,6 +1493,8 @@ int gpb_get_sizes(gpb_graph* g, gpb_sizes* s) {
     switch (e.kind) {
       case X_INTERP_RANGE: cols = 4 * D + g->DL; prm = 44; break;
       case X_INTERP_ATTITUDE: cols = 4 * D; prm = 80; break;
+      case X_INTERP_GPS: cols = 4 * D; prm = 8.0 * (2 + 3 + 9) + 20; break;
+      case X_INTERP_PROJECTION: cols = 4 * D + g->DL; prm = 8.0 * (2 + 2 + 4 + 5) + 20; break;
       case X_PRIOR_POSE: cols = D; prm = 8.0 * (g->PS + D * D); break;
       case X_PRIOR_VEL: cols = D; prm = 8.0 * (D + D * D); break;
       case X_PRIOR_LANDMARK: cols = g->DL; prm = 8.0 * (g->DL + g->DL * g->DL); break;
@@ -1483,6 +1536,7 @@ int gpb_time_stage(gpb_graph* g, int stage, int reps, double* ms_out) {
     constexpr int G = decltype(tag)::value;
     if (nbA) k_lin_extra<G, 0, NT><<<nbA, NT, 0, g->stream>>>(g->d_listA, g->nA, g->d_X, g->d_land, g->d_xkind, g->d_xsa, g->d_xsb, g->d_xl, g->d_xrow, g->d_xprm, g->d_XR[other], g->d_errpart + nb1, g->NX, g->NXRp, 1);
     if (nbB) k_lin_extra<G, 1, NT><<<nbB, NT, 0, g->stream>>>(g->d_listB, g->nB, g->d_X, g->d_land, g->d_xkind, g->d_xsa, g->d_xsb, g->d_xl, g->d_xrow, g->d_xprm, g->d_XR[other], g->d_errpart + nb1 + nbA, g->NX, g->NXRp, 1);
+    if constexpr (G == G_POSE3) { if (g->nC) k_lin_extra<G, 2, NT><<<(g->nC + NT - 1) / NT, NT, 0, g->stream>>>(g->d_listC, g->nC, g->d_X, g->d_land, g->d_xkind, g->d_xsa, g->d_xsb, g->d_xl, g->d_xrow, g->d_xprm, g->d_XR[other], g->d_errpart + nb1 + nbA + nbB, g->NX, g->NXRp, 1); }
   };
   auto by_group = [&](auto fn) {
     switch (g->group) {
@@ -1540,6 +1594,8 @@ int gpb_eval_factor(int group, int kind, const double* x1, const double* v1, con
     case 0: rc = gpb_add_gp_prior(g, 1, &zero, &dt, 0); break;
     case X_INTERP_RANGE: rc = gpb_add_interp_range(g, 1, &zero, &zero, &prm[2], &one, &dt, &tau, 0, prm[16] != 0.0 ? prm + 4 : nullptr); break;
     case X_INTERP_ATTITUDE: rc = gpb_add_interp_attitude(g, 1, &zero, &dt, &tau, 0, prm + 4, prm + 7, &one); break;
+    case X_INTERP_GPS: rc = gpb_add_interp_gps(g, 1, &zero, prm + 40, eye(3), &dt, &tau, 0, prm[16] != 0.0 ? prm + 4 : nullptr); break;
+    case X_INTERP_PROJECTION: rc = gpb_add_interp_projection(g, 1, &zero, &zero, prm + 40, eye(2), &dt, &tau, 0, prm + 43, prm[16] != 0.0 ? prm + 4 : nullptr); break;
     case X_PRIOR_POSE: rc = gpb_add_prior_pose(g, 0, prm + 4, eye(D)); break;
     case X_PRIOR_VEL: rc = gpb_add_prior_vel(g, 0, prm + 4, eye(D)); break;
     case X_PRIOR_LANDMARK: rc = gpb_add_prior_landmark(g, 0, prm + 4, eye(DL)); break;

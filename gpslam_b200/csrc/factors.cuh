@@ -179,11 +179,12 @@ template <int VAR, int C> GPB_HD void gp_prior_d3_col(const GpD3& o, const GpWhi
 // state_a / state_b are the two support states (i, i+1) of its interval (or (i, j) for a loop closure).
 enum ExtraKind {
   X_INTERP_RANGE = 1, X_INTERP_ATTITUDE = 2, X_PRIOR_POSE = 3, X_PRIOR_VEL = 4, X_PRIOR_LANDMARK = 5,
-  X_BETWEEN = 6, X_RANGE_2D = 7, X_RANGE_BEARING_2D = 8, X_ODOMETRY_2D = 9
+  X_BETWEEN = 6, X_RANGE_2D = 7, X_RANGE_BEARING_2D = 8, X_ODOMETRY_2D = 9, X_INTERP_GPS = 10, X_INTERP_PROJECTION = 11
 };
 constexpr int XP_STRIDE = 56;  // doubles of parameters per extra factor (see ExtraParams below)
 // parameter record (doubles): [0] delta_t [1] tau [2] z [3] z2 [4..15] aux (sensor pose / nZ,bRef / value) [16] has_sensor
-// [20..55] sqrt information R (m x m column-major, upper triangular); for scalar factors R[0] = 1/sigma.
+// [17] between: arguments swapped  [20..55] sqrt information R (m x m column-major, upper triangular); for scalar factors
+// R[0] = 1/sigma.  GPS / projection factors (R needs 9 / 4 entries): [40..42] measured point, [43..47] Cal3_S2 (fx, fy, s, u0, v0).
 
 GPB_HD X6 rowmul(const X6& h, const L6& M) { return x6(tmul(M.A, h.w) + tmul(M.B, h.v), tmul(M.C, h.v)); }  // h^T M as a row
 
@@ -221,6 +222,83 @@ GPB_HD void interp_range_pose3(const double* s1, const double* s2, const double*
   o.H3 = rowmul(k, b);
   o.H4 = ic.psi12 * rowmul(g, b);
   o.H5 = T.R * qh;  // (qh^T R^T)^T
+}
+
+// Shared pipeline of the SE(3) interpolated measurement factors with several residual rows (GPS, projection): the interpolated
+// pose T(tau) [x body_P_sensor] once, then the four 1x6 Jacobian rows of ANY row `hpose` of d h / d T(tau) through
+// updatePoseJacobians (gp/GaussianProcessInterpolatorPose3.h:57-116), exactly as interp_range_pose3 does for its single row.
+struct Interp3 {
+  P3 T, dT, S; bool has_sensor;
+  X6 r, xi; L6 b, a, Dd, jr, adS, adT; InterpCoef ic;
+};
+GPB_HD void interp3_setup(const double* s1, const double* s2, const double* prm, bool wantJ, Interp3& c) {
+  const double dt = prm[0], tau = prm[1];
+  const P3 T1 = p3_from_wire(s1), T2 = p3_from_wire(s2);
+  const X6 v1 = x6_from(s1 + 12), v2 = x6_from(s2 + 12);
+  c.r = se3_logmap(p3_between(T1, T2));
+  const JrinvCoef cf = se3_jrinv_coef(dot(c.r.w, c.r.w));
+  c.b = se3_jrinv(c.r, cf);
+  const X6 f = c.b * v2;
+  c.ic = interp_coef(dt, tau);
+  c.xi = c.ic.lam12 * v1 + c.ic.psi11 * c.r + c.ic.psi12 * f;
+  c.dT = se3_expmap(c.xi);
+  c.T = p3_compose(T1, c.dT);
+  c.has_sensor = prm[16] != 0.0;
+  if (c.has_sensor) { c.S = p3_from_wire(prm + 4); c.T = p3_compose(c.T, c.S); }
+  if (!wantJ) return;
+  if (c.has_sensor) c.adS = l6_adjoint(p3_inverse(c.S));
+  c.jr = se3_jr(c.xi);
+  c.a = c.b - l6_ad(c.r);
+  c.Dd = se3_djrinv(c.r, v2, cf);
+  c.adT = l6_adjoint(p3_inverse(c.dT));
+}
+// hpose: one row of d h / d(sensor pose); out: the row's Jacobians wrt (x1, v1, x2, v2)
+GPB_HD void interp3_row(const Interp3& c, X6 hpose, X6& H1, X6& H2, X6& H3, X6& H4) {
+  if (c.has_sensor) hpose = rowmul(hpose, c.adS);
+  const X6 g = rowmul(hpose, c.jr);
+  const X6 gD = rowmul(g, c.Dd);
+  const X6 k = c.ic.psi11 * g + c.ic.psi12 * gD;
+  H1 = rowmul(hpose, c.adT) - rowmul(k, c.a);
+  H2 = c.ic.lam12 * g;
+  H3 = rowmul(k, c.b);
+  H4 = c.ic.psi12 * rowmul(g, c.b);
+}
+// slam/GPInterpolatedGPSFactorPose3.h:67-95: e = translation(T(tau) [body_P_sensor]) - measured; d translation / dT = [0, R]
+struct Gps3Out { V3 e; X6 H[3][4]; };
+GPB_HD void interp_gps_pose3(const double* s1, const double* s2, const double* prm, bool wantJ, Gps3Out& o) {
+  Interp3 c;
+  interp3_setup(s1, s2, prm, wantJ, c);
+  o.e = c.T.t - v3(prm[40], prm[41], prm[42]);
+  if (!wantJ) return;
+#pragma unroll
+  for (int k = 0; k < 3; k++) interp3_row(c, x6(v3(0, 0, 0), v3(c.T.R.m[3 * k], c.T.R.m[3 * k + 1], c.T.R.m[3 * k + 2])), o.H[k][0], o.H[k][1], o.H[k][2], o.H[k][3]);
+}
+// slam/GPInterpolatedProjectionFactorPose3.h:82-139 with Cal3_S2: e = K(pi(T^-1 l)) - measured; a landmark behind the camera
+// (gtsam::CheiralityException, :123-138) gives zero Jacobians and the residual (2 fx, 2 fx).
+struct Proj3Out { double e[2]; X6 H[2][4]; V3 H5[2]; };
+GPB_HD void interp_projection_pose3(const double* s1, const double* s2, const double* land, const double* prm, bool wantJ, Proj3Out& o) {
+  Interp3 c;
+  interp3_setup(s1, s2, prm, wantJ, c);
+  const double fx = prm[43], fy = prm[44], sk = prm[45], u0 = prm[46], v0 = prm[47];
+  const V3 q = tmul(c.T.R, v3(land[0], land[1], land[2]) - c.T.t);
+  if (!(q.z > 0.0)) {
+    o.e[0] = o.e[1] = 2.0 * fx;
+#pragma unroll
+    for (int k = 0; k < 2; k++) { for (int v = 0; v < 4; v++) o.H[k][v] = x6(v3(0, 0, 0), v3(0, 0, 0)); o.H5[k] = v3(0, 0, 0); }
+    return;
+  }
+  const double d = 1.0 / q.z, u = q.x * d, v = q.y * d;
+  o.e[0] = fx * u + sk * v + u0 - prm[40];
+  o.e[1] = fy * v + v0 - prm[41];
+  if (!wantJ) return;
+  // d pn / d pose = [[uv, -1-uu, v, -d, 0, du], [1+vv, -uv, -u, 0, -d, dv]];  d pn / d q = d [[1, 0, -u], [0, 1, -v]]
+  const X6 n0 = x6(v3(u * v, -1.0 - u * u, v), v3(-d, 0.0, d * u)), n1 = x6(v3(1.0 + v * v, -u * v, -u), v3(0.0, -d, d * v));
+  const V3 q0 = v3(d, 0.0, -d * u), q1 = v3(0.0, d, -d * v);
+  const X6 h0 = fx * n0 + sk * n1, h1 = fy * n1;
+  interp3_row(c, h0, o.H[0][0], o.H[0][1], o.H[0][2], o.H[0][3]);
+  interp3_row(c, h1, o.H[1][0], o.H[1][1], o.H[1][2], o.H[1][3]);
+  o.H5[0] = c.T.R * (fx * q0 + sk * q1);  // (row * R^T)^T
+  o.H5[1] = c.T.R * (fy * q1);
 }
 
 // slam/GPInterpolatedRangeFactorPose2.h:64-98 and slam/GPInterpolatedRangeFactor2DLinear.h:60-88

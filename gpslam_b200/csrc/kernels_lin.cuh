@@ -118,7 +118,8 @@ __global__ void __launch_bounds__(NT) k_lin_gp(const double* __restrict__ X, con
 
 // ===================================================================== kernel: measurement / prior / between rows
 // One thread per "extra" factor; writes its m whitened rows over [state a (2D) | state b (2D) | landmark (DL) | rhs].
-// CLS 0: interpolated measurement factors (range / attitude) — the volume; CLS 1: priors, between, plain 2-D factors.
+// CLS 0: interpolated measurement factors (range / attitude) — the volume; CLS 1: priors, between, plain 2-D factors;
+// CLS 2: the multi-row SE(3) interpolated factors (GPS, projection), kept out of CLS 0 so the range path keeps its registers.
 // Two kernels so the lean interpolated path does not inherit the generic path's local arrays and divergence.
 template <int G, int CLS>
 __device__ __forceinline__ void extra_rows(int kind, const double* __restrict__ X, const double* __restrict__ land, int sa, int sb, int l,
@@ -172,6 +173,70 @@ __device__ __forceinline__ void extra_rows(int kind, const double* __restrict__ 
           for (int v = 0; v < 4; v++) { put(row0, 3 * v + k, r00 * a0[v] + r01 * a1[v]); put(row0 + 1, 3 * v + k, r11 * a1[v]); }
         }
         put(row0, 12, -w0); put(row0 + 1, 12, -w1);
+      }
+    }
+    return;
+  }
+  }
+  if constexpr (CLS == 2) {
+  if (kind == X_INTERP_GPS) {
+    if constexpr (G == G_POSE3) {
+      Gps3Out o;
+      interp_gps_pose3(X + (size_t)sa * SR, X + (size_t)sb * SR, prm, wantJ, o);
+      // whiten with the dense upper-triangular 3x3 sqrt information: row r = sum_{k >= r} R[r,k] (.)
+      const double ev[3] = {o.e.x, o.e.y, o.e.z};
+#pragma unroll
+      for (int r = 0; r < 3; r++) {
+        double be = 0.0;
+#pragma unroll
+        for (int k = r; k < 3; k++) be += Rm[r + 3 * k] * ev[k];
+        err += 0.5 * be * be;
+        if (wantJ) {
+#pragma unroll
+          for (int v = 0; v < 4; v++)
+#pragma unroll
+            for (int c = 0; c < 6; c++) {
+              double a = 0.0;
+#pragma unroll
+              for (int k = r; k < 3; k++) a += Rm[r + 3 * k] * elem(o.H[k][v], c);
+              put(row0 + r, 6 * v + c, a);
+            }
+          put(row0 + r, 24, 0.0); put(row0 + r, 25, 0.0); put(row0 + r, 26, 0.0);
+          put(row0 + r, 27, -be);
+        }
+      }
+    }
+    return;
+  }
+  if (kind == X_INTERP_PROJECTION) {
+    if constexpr (G == G_POSE3) {
+      Proj3Out o;
+      interp_projection_pose3(X + (size_t)sa * SR, X + (size_t)sb * SR, land + (size_t)l * 3, prm, wantJ, o);
+#pragma unroll
+      for (int r = 0; r < 2; r++) {
+        double be = 0.0;
+#pragma unroll
+        for (int k = r; k < 2; k++) be += Rm[r + 2 * k] * o.e[k];
+        err += 0.5 * be * be;
+        if (wantJ) {
+#pragma unroll
+          for (int v = 0; v < 4; v++)
+#pragma unroll
+            for (int c = 0; c < 6; c++) {
+              double a = 0.0;
+#pragma unroll
+              for (int k = r; k < 2; k++) a += Rm[r + 2 * k] * elem(o.H[k][v], c);
+              put(row0 + r, 6 * v + c, a);
+            }
+#pragma unroll
+          for (int c = 0; c < 3; c++) {
+            double a = 0.0;
+#pragma unroll
+            for (int k = r; k < 2; k++) a += Rm[r + 2 * k] * elem(o.H5[k], c);
+            put(row0 + r, 24 + c, a);
+          }
+          put(row0 + r, 27, -be);
+        }
       }
     }
     return;
@@ -341,7 +406,7 @@ __global__ void __launch_bounds__(NT) k_lin_extra(const int* __restrict__ list, 
   __shared__ double sred[NT / 32];
   const int t = blockIdx.x * NT + threadIdx.x;
   double err = 0.0;
-  if constexpr (CLS == 0) {
+  if constexpr (CLS != 1) {
     if (t < nlist) {
       const int f = list[t];
       extra_rows<G, CLS>(xkind[f], X, land, xsa[f], xsb[f], xl[f], xprm + (size_t)f * XP_STRIDE, wantJ != 0, XR, NXRp, xrow[f], err);

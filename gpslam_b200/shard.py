@@ -66,6 +66,8 @@ class ShardBuilder:
 
     def add_gp_prior(self, i, delta_t, qc=0): self._rec("add_gp_prior", i, delta_t, qc)
     def add_interp_range(self, i, l, z, sigma, delta_t, tau, qc=0, body_P_sensor=None): self._rec("add_interp_range", i, l, z, sigma, delta_t, tau, qc, body_P_sensor)
+    def add_interp_gps(self, i, meas, sqrt_info, delta_t, tau, qc=0, body_P_sensor=None): self._rec("add_interp_gps", i, meas, sqrt_info, delta_t, tau, qc, body_P_sensor)
+    def add_interp_projection(self, i, l, meas, sqrt_info, delta_t, tau, K, qc=0, body_P_sensor=None): self._rec("add_interp_projection", i, l, meas, sqrt_info, delta_t, tau, K, qc, body_P_sensor)
     def add_interp_attitude(self, i, delta_t, tau, nZ, sigma, bRef=(0, 0, 1), qc=0): self._rec("add_interp_attitude", i, delta_t, tau, nZ, sigma, bRef, qc)
     def add_prior_pose(self, i, value, sqrt_info): self._rec("add_prior_pose", i, value, sqrt_info)
     def add_prior_vel(self, i, value, sqrt_info): self._rec("add_prior_vel", i, value, sqrt_info)
@@ -141,6 +143,19 @@ class ShardBuilder:
         b = lambda a: np.broadcast_to(np.atleast_1d(a), i.shape)[m]
         if m.any():
             self._g.add_interp_range(i[m] - self.lo, b(l), b(z), b(sigma), b(delta_t), b(tau), qc, body_P_sensor)
+
+    def _do_add_interp_gps(self, i, meas, sqrt_info, delta_t, tau, qc, body_P_sensor):
+        i = np.atleast_1d(i); m = self._own_interval(i)
+        b = lambda a: np.broadcast_to(np.atleast_1d(a), i.shape)[m]
+        if m.any():
+            self._g.add_interp_gps(i[m] - self.lo, np.broadcast_to(np.asarray(meas, dtype=float).reshape(-1, 3), (len(i), 3))[m], sqrt_info, b(delta_t), b(tau), qc, body_P_sensor)
+
+    def _do_add_interp_projection(self, i, l, meas, sqrt_info, delta_t, tau, K, qc, body_P_sensor):
+        i = np.atleast_1d(i); m = self._own_interval(i)
+        b = lambda a: np.broadcast_to(np.atleast_1d(a), i.shape)[m]
+        if m.any():
+            self._g.add_interp_projection(i[m] - self.lo, b(l), np.broadcast_to(np.asarray(meas, dtype=float).reshape(-1, 2), (len(i), 2))[m], sqrt_info, b(delta_t), b(tau), K, qc,
+                                          body_P_sensor)
 
     def _do_add_interp_attitude(self, i, delta_t, tau, nZ, sigma, bRef, qc):
         i = np.atleast_1d(i); m = self._own_interval(i)

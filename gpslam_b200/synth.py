@@ -46,7 +46,7 @@ def _wire3(R, t):
 
 class Config:
     def __init__(self, name, group, n_states, n_landmarks=0, range_per_state=0.0, dt=0.1, seed=0, qc_sigma=0.1, prior_every=100,
-                 attitude_every=0, odometry=False, init_noise=0.05, zero_rot_fraction=0.01, n_closures=0, closure_min_gap=0, closure_ends=False):
+                 attitude_every=0, odometry=False, init_noise=0.05, zero_rot_fraction=0.01, n_closures=0, closure_min_gap=0, closure_ends=False, gps_every=0, proj_per_state=0.0):
         self.__dict__.update(locals())
         del self.__dict__["self"]
 
@@ -163,6 +163,39 @@ def build(cfg, make_graph, finalize=True):
         g.add_interp_range(ri, rl, z, np.full(nr, sig), np.full(nr, dt), tau)
         for l in range(L):
             g.add_prior_landmark(l, lands[l] + rng.normal(size=DL) * 0.5, iso(DL, 1.0))
+    # SE(3) only: interpolated GPS fixes (every gps_every-th interval, sensor offset, correlated noise model) and interpolated
+    # pinhole projections of the landmarks (Cal3_S2 with skew); SURVEY.md §8f rank 2.  Own generator: the rest of the graph does
+    # not change when they are switched on.
+    if group == POSE3 and (cfg.gps_every or cfg.proj_per_state):
+        mrng = np.random.default_rng(cfg.seed + 3000)
+        bTs = _wire3(_so3_exp(np.array([0.1, -0.2, 0.3])), np.array([0.3, 0.6, -0.7]))
+        def sensor_pose(i, tau_):
+            Ti = _retract(POSE3, poses[i], vels[i] * tau_)
+            R = Ti[:9].reshape(3, 3).T; t = Ti[9:]
+            Rs = bTs[:9].reshape(3, 3).T; ts = bTs[9:]
+            return R @ Rs, R @ ts + t
+        if cfg.gps_every:
+            gi = np.arange(0, N - 1, cfg.gps_every); gtau = mrng.uniform(0, dt, size=len(gi))
+            gmeas = np.stack([sensor_pose(i, t_)[1] for i, t_ in zip(gi, gtau)]) + mrng.normal(size=(len(gi), 3)) * 0.05
+            g.add_interp_gps(gi, gmeas, np.array([[20.0, 2.0, -1.0], [0.0, 15.0, 3.0], [0.0, 0.0, 25.0]]), np.full(len(gi), dt), gtau, body_P_sensor=bTs)
+        if cfg.proj_per_state and L:
+            K = np.array([50.0, 45.0, 0.5, 40.0, 30.0])
+            pi_, pl_, ptau, pmeas = [], [], [], []
+            behind = None
+            for i in mrng.integers(0, N - 1, size=int(round(cfg.proj_per_state * N)) * 4):
+                tau_ = float(mrng.uniform(0, dt)); l = int(mrng.integers(0, L))
+                Rc, tc = sensor_pose(int(i), tau_)
+                q = Rc.T @ (lands[l] - tc)
+                if q[2] < -5.0 and behind is None:
+                    behind = (int(i), l, tau_)   # one factor whose landmark is behind the camera: the cheirality path
+                if q[2] > 5.0 and len(pi_) < int(round(cfg.proj_per_state * N)):
+                    u, v = q[0] / q[2], q[1] / q[2]
+                    pi_.append(int(i)); pl_.append(l); ptau.append(tau_)
+                    pmeas.append([K[0] * u + K[2] * v + K[3] + mrng.normal() * 0.3, K[1] * v + K[4] + mrng.normal() * 0.3])
+            if behind is not None:
+                pi_.append(behind[0]); pl_.append(behind[1]); ptau.append(behind[2]); pmeas.append([40.0, 30.0])
+            if pi_:
+                g.add_interp_projection(np.array(pi_), np.array(pl_), np.array(pmeas), np.array([[3.0, 0.4], [0.0, 2.5]]), np.full(len(pi_), dt), np.array(ptau), K, body_P_sensor=bTs)
     # gauge: pose + velocity prior on state 0, sparse pose priors along the chain
     s0 = 1e-3 if group != POSE2 else 1.0
     g.add_prior_pose(0, poses[0], iso(D, s0))

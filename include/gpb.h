@@ -70,6 +70,19 @@ int gpb_add_interp_range(gpb_graph* g, int n, const int* i, const int* l, const 
 int gpb_add_interp_attitude(gpb_graph* g, int n, const int* i, const double* delta_t, const double* tau, int qc,
                             const double* nZ, const double* bRef, const double* sigma);
 
+/* GPInterpolatedGPSFactorPose3(measured_point3, meas_model, Qc, x_i, v_i, x_{i+1}, v_{i+1}, delta_t, tau [, body_P_sensor])
+ * (slam/GPInterpolatedGPSFactorPose3.h:47-56).  measured: 3 doubles per factor; sqrt_info: upper-triangular 3 x 3 R of the
+ * measurement model, shared by the n factors; body_P_sensor: one pose or NULL.  Pose3 trajectories only. */
+int gpb_add_interp_gps(gpb_graph* g, int n, const int* i, const double* measured, const double* sqrt_info, const double* delta_t, const double* tau, int qc,
+                       const double* body_P_sensor);
+
+/* GPInterpolatedProjectionFactorPose3<Cal3_S2>(measured_point2, cam_model, Qc, x_i, v_i, x_{i+1}, v_{i+1}, l, delta_t, tau, K
+ * [, body_P_sensor])  (slam/GPInterpolatedProjectionFactorPose3.h:60-75).  measured: 2 doubles per factor; sqrt_info: 2 x 2 R;
+ * K = (fx, fy, s, u0, v0).  A landmark behind the camera follows the reference's no-throw path (:123-138): zero Jacobians and
+ * the residual (2 fx, 2 fx); throwCheirality is not offered. */
+int gpb_add_interp_projection(gpb_graph* g, int n, const int* i, const int* l, const double* measured, const double* sqrt_info, const double* delta_t,
+                              const double* tau, int qc, const double* K, const double* body_P_sensor);
+
 /* gtsam::PriorFactor<Pose|Vector|Point>: value in wire layout, sqrt_info = upper-triangular R (d x d) */
 int gpb_add_prior_pose(gpb_graph* g, int i, const double* value, const double* sqrt_info);
 int gpb_add_prior_vel(gpb_graph* g, int i, const double* value, const double* sqrt_info);
@@ -90,10 +103,11 @@ int gpb_add_odometry_2d(gpb_graph* g, int i, int j, const double* measured, cons
  * gp/GaussianProcessPriorPose3.h:60-65, slam/GPInterpolatedRangeFactorPose3.h:64-69): unwhitened residual e (m doubles) and,
  * when H_out != NULL, the Jacobian blocks concatenated column-major in the factor's variable order (dims_out[5] = their widths).
  * Evaluated by the same device code as the batched path on a throw-away 2-state graph; thread-safe, not fast.
- * kind: GPB_F_*.  prm[20]: [0] delta_t [1] tau [2] range / z [3] bearing [4..15] body_P_sensor | nZ(3),bRef(3) | prior value |
- * measured (wire layout) [16] has_sensor.  x2/v2/landmark may be NULL when the factor does not use them.  Returns m or a status. */
+ * kind: GPB_F_*.  prm[48]: [0] delta_t [1] tau [2] range / z [3] bearing [4..15] body_P_sensor | nZ(3),bRef(3) | prior value |
+ * measured (wire layout) [16] has_sensor [40..42] GPS point / image point [43..47] Cal3_S2 (fx, fy, s, u0, v0).
+ * x2/v2/landmark may be NULL when the factor does not use them.  Returns m or a status. */
 enum { GPB_F_GP_PRIOR = 0, GPB_F_INTERP_RANGE = 1, GPB_F_INTERP_ATTITUDE = 2, GPB_F_PRIOR_POSE = 3, GPB_F_PRIOR_VEL = 4, GPB_F_PRIOR_LANDMARK = 5,
-       GPB_F_BETWEEN = 6, GPB_F_RANGE_2D = 7, GPB_F_RANGE_BEARING_2D = 8, GPB_F_ODOMETRY_2D = 9 };
+       GPB_F_BETWEEN = 6, GPB_F_RANGE_2D = 7, GPB_F_RANGE_BEARING_2D = 8, GPB_F_ODOMETRY_2D = 9, GPB_F_INTERP_GPS = 10, GPB_F_INTERP_PROJECTION = 11 };
 int gpb_eval_factor(int group, int kind, const double* x1, const double* v1, const double* x2, const double* v2, const double* landmark,
                     const double* prm, double* e_out, double* H_out, int* dims_out);
 

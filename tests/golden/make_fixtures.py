@@ -25,6 +25,7 @@ POSE3, POSE2, ROT3, LINEAR = 0, 1, 2, 3
 # name -> (synthetic config, size overrides); "linear" uses the hand-built 2DLinear graph of tests/test_gpu_parity.py
 CASES = {
     "pose3": ("C3", dict(n_states=12, n_landmarks=3, prior_every=5, range_per_state=0.8)),
+    "pose3_gps_proj": ("C3", dict(n_states=14, n_landmarks=4, prior_every=5, range_per_state=0.4, gps_every=3, proj_per_state=0.5)),
     "pose3_loops": ("C5", dict(n_states=14, n_landmarks=2, prior_every=6, range_per_state=0.6, n_closures=2, closure_min_gap=5, closure_ends=True)),
     "pose2": ("C1", dict(n_states=12)),
     "pose2_loops": ("C1", dict(n_states=13, n_closures=2, closure_min_gap=4)),

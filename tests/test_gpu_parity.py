@@ -43,6 +43,8 @@ CASES = {
     "rot3": dict(name="C4", n=301),
     # loop closures (BetweenFactor between distant states, BASELINE config C5): endpoint states become pinned separators and
     # the Schur complement on {endpoints, landmarks} is solved densely
+    # GPS fixes and pinhole projections through the GP interpolator, incl. one landmark behind its camera
+    "pose3_gps_proj": dict(name="C3", n=260, n_landmarks=6, prior_every=40, gps_every=7, proj_per_state=0.3),
     "pose3_loops": dict(name="C5", n=400, n_landmarks=4, prior_every=40, n_closures=5, closure_min_gap=40),
     "pose3_wide_loops": dict(name="C5", n=500, n_landmarks=16, prior_every=40, n_closures=8, closure_min_gap=60, closure_ends=True),
     "pose2_loops": dict(name="C1", n=200, n_closures=4, closure_min_gap=30, closure_ends=True),
@@ -94,7 +96,7 @@ def make_pair(case):
     return g, o
 
 
-ALL = ["pose3", "pose3_wide", "pose3_chain", "pose2", "rot3", "linear", "pose3_loops", "pose3_wide_loops", "pose2_loops", "rot3_loops"]
+ALL = ["pose3", "pose3_wide", "pose3_chain", "pose2", "rot3", "linear", "pose3_gps_proj", "pose3_loops", "pose3_wide_loops", "pose2_loops", "rot3_loops"]
 
 
 @pytest.mark.parametrize("case", ALL)
@@ -216,6 +218,31 @@ def test_reference_two_state_optimizations():
     P, V, _ = g.get_values()
     assert st.error_final < 1e-6
     np.testing.assert_allclose(P, [p1, p2], atol=1e-6); np.testing.assert_allclose(V, [[0, 0, 0, 1, 0, 0]] * 2, atol=1e-6)
+
+    # slam/tests/testGPInterpolatedGPSFactorPose3.cpp:179-255 and testGPInterpolatedProjectionFactorPose3.cpp:191-268
+    from tests.test_oracle_golden import _project
+    v = [0, 0, 0, 10, 0, 0]
+    g = gb.Graph(POSE3, 2, 0)
+    g.add_qc_model(0.01 * np.eye(6)); g.add_prior_pose(0, p1, iso(6, 100.0)); g.add_prior_vel(0, v, iso(6, 0.01)); g.add_prior_vel(1, v, iso(6, 0.01)); g.add_gp_prior(0, 0.1)
+    for x, tau in zip((-1, .5, 2), (-.1, .05, .2)):
+        g.add_interp_gps(0, [x, 0, 0], iso(3, 0.1), 0.1, tau)
+    g.set_values(np.stack([P3(.1, .1, -.1, .04, .1, -.06), P3(-.1, .1, -.1, 1.05, -.1, .1)]), np.array([[-.1, 0, 0, 9.8, 0, .2], [0, 0, .2, 9.7, 0, -.1]]))
+    g.finalize()
+    st = g.optimize(use_lm=False)
+    P, V, _ = g.get_values()
+    assert st.error_final < 1e-6
+    np.testing.assert_allclose(P, [p1, p2], atol=1e-6); np.testing.assert_allclose(V, [v, v], atol=1e-6)
+    K = [50, 50, 0, 40, 30]; land = [3.4, 1.2, 20]
+    g = gb.Graph(POSE3, 2, 1)
+    g.add_qc_model(0.01 * np.eye(6)); g.add_prior_pose(0, p1, iso(6, 0.01)); g.add_prior_pose(1, p2, iso(6, 0.01)); g.add_gp_prior(0, 0.1)
+    for x, tau in zip((.2, .6, .9), (.02, .06, .09)):
+        g.add_interp_projection(0, 0, _project(P3(0, 0, 0, x, 0, 0), K, land), iso(2, 0.1), 0.1, tau, K)
+    g.set_values(np.stack([P3(.1, .2, .4, .2, .3, -.2), P3(-.1, -.2, -.4, 1.2, -.3, .2)]), np.array([[-.3, 0, 0, .7, 0, .2], [0, 0, .4, 1.2, 0, -.1]]), np.array([[3.3, 1.3, 18]]))
+    g.finalize()
+    st = g.optimize(use_lm=False)
+    P, V, Lm = g.get_values()
+    assert st.error_final < 1e-6
+    np.testing.assert_allclose(P, [p1, p2], atol=1e-6); np.testing.assert_allclose(V, [v, v], atol=1e-6); np.testing.assert_allclose(Lm[0], land, atol=1e-6)
 
     land = np.array([.4, 1.2, 3.0]); v = [0, 0, 0, 10, 0, 0]
     meas = [_range3(P3(0, 0, 0, x, 0, 0), land) for x in (-1, .5, 2)]

@@ -405,6 +405,111 @@ def test_interp_range_2d_optimization(group, bias):
     np.testing.assert_allclose(Lm[0], land, atol=1e-4)
 
 
+# ----------------------------------------------------------------------------- GPS and projection factors
+def _project(T, K, land):
+    """PinholeCamera<Cal3_S2>(T, K).project(land); K = (fx, fy, s, u0, v0)"""
+    R, t = po.pose3_Rt(T)
+    q = R.T @ (np.asarray(land, float) - t)
+    u, v = q[0] / q[2], q[1] / q[2]
+    return np.array([K[0] * u + K[2] * v + K[3], K[1] * v + K[4]])
+
+
+def test_interp_gps_pose3():
+    """slam/tests/testGPInterpolatedGPSFactorPose3.cpp:38-176: zero residual at the interpolated ground truth and analytic vs
+    central-difference Jacobians (the reference's steps: 1e-6 for the first case, 1e-4 otherwise; tolerance 1e-6)"""
+    Qc = 0.001 * np.eye(6)
+    dt, tau = 0.1, 0.04
+    bTs = P3(1.0, .4, .5, .3, .6, -.7)
+    true_t = po.pose3_Rt(po.pose3_compose(P3(0, 0, 0, .6, 0, 0), bTs))[1]
+    cases = [
+        (P3(0, 0, 0, 0, 0, 0), [0] * 6, P3(0, 0, 0, 0, 0, 0), [0] * 6, [0, 0, 0], None, 1e-6, True),
+        (P3(0, 0, 0, -.04, 0, 0), [0, 0, 0, 1, 0, 0], P3(0, 0, 0, .06, 0, 0), [0, 0, 0, 1, 0, 0], [0, 0, 0], None, 1e-4, True),
+        (P3(-.04, 0, 0, 0, 0, 0), [0, 0, 1, 0, 0, 0], P3(.06, 0, 0, 0, 0, 0), [0, 0, 1, 0, 0, 0], [0, 0, 0], None, 1e-4, True),
+        (P3(0, 0, 0, 0, 0, 0), [0, 0, 0, 15, 0, 0], P3(0, 0, 0, 1.5, 0, 0), [0, 0, 0, 15, 0, 0], true_t, bTs, 1e-4, True),
+        (P3(1.3, 2.4, 1.2, .2, .3, .4), [1.0, 2.0, .4, 15, .3, .2], P3(.5, 6.5, 1.1, 1.5, .7, .5), [2.0, .2, .1, 17, .4, .7], [0, 0, 0], bTs, 1e-4, False),
+    ]
+    for p1, v1, p2, v2, meas, sensor, step, zero in cases:
+        g = two_state_graph(POSE3, p1, np.asarray(v1, float), p2, np.asarray(v2, float))
+        g.add_qc_model(Qc)
+        g.add_interp_gps(0, meas, iso(3, 0.1), dt, tau, body_P_sensor=sensor)
+        e, H, Hnum = numeric_jacobians(g, 0, POSE3, step)
+        assert e.shape == (3,) and len(H) == 4
+        if zero:
+            np.testing.assert_allclose(e, 0, atol=1e-6)
+        for Ha, Hn in zip(H, Hnum):
+            np.testing.assert_allclose(Ha, Hn, atol=1e-6)
+
+
+def test_interp_gps_pose3_optimization():
+    """slam/tests/testGPInterpolatedGPSFactorPose3.cpp:179-255 (tau = -0.1, 0.05, 0.2 with delta_t = 0.1: extrapolation)"""
+    p1, p2, v = P3(0, 0, 0, 0, 0, 0), P3(0, 0, 0, 1, 0, 0), [0, 0, 0, 10, 0, 0]
+    g = two_state_graph(POSE3, P3(.1, .1, -.1, .04, .1, -.06), np.array([-.1, 0, 0, 9.8, 0, .2]), P3(-.1, .1, -.1, 1.05, -.1, .1), np.array([0, 0, .2, 9.7, 0, -.1]))
+    g.add_qc_model(0.01 * np.eye(6))
+    g.add_prior_pose(0, p1, iso(6, 100.0))
+    g.add_prior_vel(0, v, iso(6, 0.01)); g.add_prior_vel(1, v, iso(6, 0.01))
+    g.add_gp_prior(0, 0.1)
+    for x, tau in zip((-1, .5, 2), (-.1, .05, .2)):
+        g.add_interp_gps(0, [x, 0, 0], iso(3, 0.1), 0.1, tau)
+    st = g.optimize(use_lm=False)
+    assert st.status == 0
+    P, V, _ = g.get_values()
+    assert abs(g.error()) < 1e-6
+    np.testing.assert_allclose(P[0], p1, atol=1e-6); np.testing.assert_allclose(P[1], p2, atol=1e-6)
+    np.testing.assert_allclose(V, [v, v], atol=1e-6)
+
+
+def test_interp_projection_pose3():
+    """slam/tests/testGPInterpolatedProjectionFactorPose3.cpp:37-188: Cal3_S2() and Cal3_S2(50, 50, 0, 40, 30), with body_P_sensor"""
+    Qc = 0.001 * np.eye(6)
+    dt, tau = 0.1, 0.04
+    K1, K2 = [1, 1, 0, 0, 0], [50, 50, 0, 40, 30]
+    bTs = P3(1.0, .4, .5, .3, .6, -.7)
+    land2 = [3.4, 1.2, 10]
+    meas2 = _project(po.pose3_compose(P3(0, 0, 0, .6, 0, 0), bTs), K2, land2)
+    cases = [
+        (P3(0, 0, 0, 0, 0, 0), [0] * 6, P3(0, 0, 0, 0, 0, 0), [0] * 6, [0, 0, 10], [0, 0], K1, None, 1e-6, 1e-6),
+        (P3(0, 0, 0, -.04, 0, 0), [0, 0, 0, 1, 0, 0], P3(0, 0, 0, .06, 0, 0), [0, 0, 0, 1, 0, 0], [0, 0, 10], [0, 0], K1, None, 1e-4, 1e-6),
+        (P3(-.04, 0, 0, 0, 0, 0), [0, 0, 1, 0, 0, 0], P3(.06, 0, 0, 0, 0, 0), [0, 0, 1, 0, 0, 0], [0, 0, 10], [0, 0], K1, None, 1e-4, 1e-6),
+        (P3(0, 0, 0, 0, 0, 0), [0, 0, 0, 15, 0, 0], P3(0, 0, 0, 1.5, 0, 0), [0, 0, 0, 15, 0, 0], land2, meas2, K2, bTs, 1e-4, 1e-5),
+    ]
+    for p1, v1, p2, v2, land, meas, K, sensor, step, tol in cases:
+        g = two_state_graph(POSE3, p1, np.asarray(v1, float), p2, np.asarray(v2, float), land)
+        g.add_qc_model(Qc)
+        g.add_interp_projection(0, 0, meas, iso(2, 0.1), dt, tau, K, body_P_sensor=sensor)
+        e, H, Hnum = numeric_jacobians(g, 0, POSE3, step)
+        assert e.shape == (2,) and len(H) == 5
+        np.testing.assert_allclose(e, 0, atol=1e-6)
+        for Ha, Hn in zip(H, Hnum):
+            np.testing.assert_allclose(Ha, Hn, atol=tol)
+    # landmark behind the camera: CheiralityException path (slam/GPInterpolatedProjectionFactorPose3.h:123-138)
+    g = two_state_graph(POSE3, P3(0, 0, 0, 0, 0, 0), np.zeros(6), P3(0, 0, 0, 0, 0, 0), np.zeros(6), [0, 0, -10])
+    g.add_qc_model(Qc)
+    g.add_interp_projection(0, 0, [0, 0], iso(2, 0.1), dt, tau, K2)
+    e, H = g.eval_factor(0, True)
+    np.testing.assert_allclose(e, [100.0, 100.0])
+    assert all(np.all(h == 0) for h in H)
+
+
+def test_interp_projection_pose3_optimization():
+    """slam/tests/testGPInterpolatedProjectionFactorPose3.cpp:191-268"""
+    K = [50, 50, 0, 40, 30]
+    p1, p2, v = P3(0, 0, 0, 0, 0, 0), P3(0, 0, 0, 1, 0, 0), [0, 0, 0, 10, 0, 0]
+    land = [3.4, 1.2, 20]
+    g = two_state_graph(POSE3, P3(.1, .2, .4, .2, .3, -.2), np.array([-.3, 0, 0, .7, 0, .2]), P3(-.1, -.2, -.4, 1.2, -.3, .2), np.array([0, 0, .4, 1.2, 0, -.1]), [3.3, 1.3, 18])
+    g.add_qc_model(0.01 * np.eye(6))
+    g.add_prior_pose(0, p1, iso(6, 0.01)); g.add_prior_pose(1, p2, iso(6, 0.01))
+    g.add_gp_prior(0, 0.1)
+    for x, tau in zip((.2, .6, .9), (.02, .06, .09)):
+        g.add_interp_projection(0, 0, _project(P3(0, 0, 0, x, 0, 0), K, land), iso(2, 0.1), 0.1, tau, K)
+    st = g.optimize(use_lm=False)
+    assert st.status == 0
+    P, V, Lm = g.get_values()
+    assert abs(g.error()) < 1e-6
+    np.testing.assert_allclose(P[0], p1, atol=1e-6); np.testing.assert_allclose(P[1], p2, atol=1e-6)
+    np.testing.assert_allclose(V, [v, v], atol=1e-6)
+    np.testing.assert_allclose(Lm[0], land, atol=1e-6)
+
+
 # ----------------------------------------------------------------------------- plain 2D factors
 def test_plain_2d_known_answers():
     """slam/tests/testRangeFactor2DLinear.cpp:63-67, testRangeBearingFactor2DLinear.cpp:55-59, testOdometryFactor2DLinear.cpp:65-70"""
