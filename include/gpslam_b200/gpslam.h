@@ -237,6 +237,91 @@ class GPInterpolatedRangeFactor2DLinear : public GPInterpolatedRangeFactorT<gtsa
       : GPInterpolatedRangeFactorT<gtsam::Vector3>(measured, meas_model, Qc_model, pose1Key, vel1Key, pose2Key, vel2Key, pointKey, delta_t, tau) {}
 };
 
+/// gtsam::Cal3_S2 (fx, fy, s, u0, v0) — the calibration the reference's projection-factor tests use
+namespace gtsam {
+struct Cal3_S2 {
+  double fx = 1, fy = 1, s = 0, u0 = 0, v0 = 0;
+  Cal3_S2() {}
+  Cal3_S2(double fx_, double fy_, double s_, double u0_, double v0_) : fx(fx_), fy(fy_), s(s_), u0(u0_), v0(v0_) {}
+};
+}  // namespace gtsam
+
+/// slam/GPInterpolatedGPSFactorPose3.h:47-56
+class GPInterpolatedGPSFactorPose3 : public NonlinearFactor {
+  std::vector<gtsam::Key> keys_;
+  gtsam::Point3 measured_;
+  double delta_t_, tau_;
+  gtsam::SharedNoiseModel meas_, Qc_;
+  bool has_sensor_ = false;
+  gtsam::Pose3 body_P_sensor_;
+
+ public:
+  GPInterpolatedGPSFactorPose3(const gtsam::Point3& measured_point3, const gtsam::SharedNoiseModel& meas_model, const gtsam::SharedNoiseModel& Qc_model,
+                               gtsam::Key poseKey1, gtsam::Key velKey1, gtsam::Key poseKey2, gtsam::Key velKey2, double delta_t, double tau,
+                               const gtsam::Pose3* body_P_sensor = nullptr)
+      : keys_{poseKey1, velKey1, poseKey2, velKey2}, measured_(measured_point3), delta_t_(delta_t), tau_(tau), meas_(meas_model), Qc_(Qc_model) {
+    if (body_P_sensor) { has_sensor_ = true; body_P_sensor_ = *body_P_sensor; }
+  }
+  const std::vector<gtsam::Key>& keys() const override { return keys_; }
+  gtsam::Point3 measured() const { return measured_; }
+  gtsam::Vector evaluateError(const gtsam::Pose3& pose1, const gtsam::Vector6& vel1, const gtsam::Pose3& pose2, const gtsam::Vector6& vel2,
+                              gtsam::Matrix* H1 = nullptr, gtsam::Matrix* H2 = nullptr, gtsam::Matrix* H3 = nullptr, gtsam::Matrix* H4 = nullptr) const {
+    double x1[12], x2[12], v1[6], v2[6], prm[48] = {0};
+    detail::wire(pose1, x1); detail::wire(pose2, x2); detail::wire(vel1, v1); detail::wire(vel2, v2);
+    prm[0] = delta_t_; prm[1] = tau_; detail::wire(measured_, prm + 40);
+    if (has_sensor_) { detail::wire(body_P_sensor_, prm + 4); prm[16] = 1.0; }
+    return detail::eval(GPB_POSE3, GPB_F_INTERP_GPS, x1, v1, x2, v2, nullptr, prm, {H1, H2, H3, H4});
+  }
+  void lower(gpb_graph* g, int qc_of(void*, const gtsam::Matrix&), void* ctx, const std::map<gtsam::Key, int>& sidx, const std::map<gtsam::Key, int>&) const override {
+    const int i = detail::stateOf(sidx, keys_[0]);
+    double m[3], bps[12];
+    detail::wire(measured_, m);
+    if (has_sensor_) detail::wire(body_P_sensor_, bps);
+    detail::check(gpb_add_interp_gps(g, 1, &i, m, detail::sqrtInfo(meas_).a.data(), &delta_t_, &tau_, qc_of(ctx, Qc_->cov), has_sensor_ ? bps : nullptr));
+  }
+};
+
+/// slam/GPInterpolatedProjectionFactorPose3.h:60-75 (CALIBRATION = Cal3_S2; the no-throw cheirality path of :123-138)
+template <class CALIBRATION = gtsam::Cal3_S2>
+class GPInterpolatedProjectionFactorPose3 : public NonlinearFactor {
+  std::vector<gtsam::Key> keys_;
+  gtsam::Point2 measured_;
+  double delta_t_, tau_;
+  gtsam::SharedNoiseModel meas_, Qc_;
+  std::shared_ptr<CALIBRATION> K_;
+  bool has_sensor_ = false;
+  gtsam::Pose3 body_P_sensor_;
+  void calib(double* k) const { k[0] = K_->fx; k[1] = K_->fy; k[2] = K_->s; k[3] = K_->u0; k[4] = K_->v0; }
+
+ public:
+  GPInterpolatedProjectionFactorPose3(const gtsam::Point2& measured, const gtsam::SharedNoiseModel& cam_model, const gtsam::SharedNoiseModel& Qc_model,
+                                      gtsam::Key poseKey1, gtsam::Key velKey1, gtsam::Key poseKey2, gtsam::Key velKey2, gtsam::Key pointKey, double delta_t,
+                                      double tau, const std::shared_ptr<CALIBRATION>& K, const gtsam::Pose3* body_P_sensor = nullptr)
+      : keys_{poseKey1, velKey1, poseKey2, velKey2, pointKey}, measured_(measured), delta_t_(delta_t), tau_(tau), meas_(cam_model), Qc_(Qc_model), K_(K) {
+    if (!K_) throw std::runtime_error("gpslam_b200: projection factor needs a calibration");
+    if (body_P_sensor) { has_sensor_ = true; body_P_sensor_ = *body_P_sensor; }
+  }
+  const std::vector<gtsam::Key>& keys() const override { return keys_; }
+  const gtsam::Point2& measured() const { return measured_; }
+  const std::shared_ptr<CALIBRATION> calibration() const { return K_; }
+  gtsam::Vector evaluateError(const gtsam::Pose3& pose1, const gtsam::Vector6& vel1, const gtsam::Pose3& pose2, const gtsam::Vector6& vel2, const gtsam::Point3& point,
+                              gtsam::Matrix* H1 = nullptr, gtsam::Matrix* H2 = nullptr, gtsam::Matrix* H3 = nullptr, gtsam::Matrix* H4 = nullptr,
+                              gtsam::Matrix* H5 = nullptr) const {
+    double x1[12], x2[12], v1[6], v2[6], l[3], prm[48] = {0};
+    detail::wire(pose1, x1); detail::wire(pose2, x2); detail::wire(vel1, v1); detail::wire(vel2, v2); detail::wire(point, l);
+    prm[0] = delta_t_; prm[1] = tau_; detail::wire(measured_, prm + 40); calib(prm + 43);
+    if (has_sensor_) { detail::wire(body_P_sensor_, prm + 4); prm[16] = 1.0; }
+    return detail::eval(GPB_POSE3, GPB_F_INTERP_PROJECTION, x1, v1, x2, v2, l, prm, {H1, H2, H3, H4, H5});
+  }
+  void lower(gpb_graph* g, int qc_of(void*, const gtsam::Matrix&), void* ctx, const std::map<gtsam::Key, int>& sidx, const std::map<gtsam::Key, int>& lidx) const override {
+    const int i = detail::stateOf(sidx, keys_[0]), l = detail::stateOf(lidx, keys_[4]);
+    double m[2], k[5], bps[12];
+    detail::wire(measured_, m); calib(k);
+    if (has_sensor_) detail::wire(body_P_sensor_, bps);
+    detail::check(gpb_add_interp_projection(g, 1, &i, &l, m, detail::sqrtInfo(meas_).a.data(), &delta_t_, &tau_, qc_of(ctx, Qc_->cov), k, has_sensor_ ? bps : nullptr));
+  }
+};
+
 /// slam/GPInterpolatedAttitudeFactorRot3.h:44-51
 class GPInterpolatedAttitudeFactorRot3 : public NonlinearFactor {
   std::vector<gtsam::Key> keys_;

@@ -165,11 +165,72 @@ static void testRangeOptimization() {
   EXPECT(threw);
 }
 
+// slam/tests/testGPInterpolatedGPSFactorPose3.cpp:179-255 and slam/tests/testGPInterpolatedProjectionFactorPose3.cpp:191-268
+static void testGpsAndProjectionOptimization() {
+  SharedNoiseModel model_prior = noiseModel::Isotropic::Sigma(6, 0.01), model_prior_loss = noiseModel::Isotropic::Sigma(6, 100), model_gps = noiseModel::Isotropic::Sigma(3, 0.1),
+                   model_cam = noiseModel::Isotropic::Sigma(2, 0.1);
+  const double delta_t = 0.1;
+  SharedNoiseModel Qc_model = noiseModel::Gaussian::Covariance(0.01 * Matrix::Identity(6, 6));
+  Pose3 p1(Rot3(), Point3(0, 0, 0)), p2(Rot3(), Point3(1, 0, 0));
+  Vector6 v{0, 0, 0, 10, 0, 0};
+  double w[12], o[12];
+  {
+    NonlinearFactorGraph graph;
+    graph.add(PriorFactor<Pose3>(Symbol('x', 1), p1, model_prior_loss));
+    graph.add(PriorFactor<Vector6>(Symbol('v', 1), v, model_prior));
+    graph.add(PriorFactor<Vector6>(Symbol('v', 2), v, model_prior));
+    graph.add(GaussianProcessPriorPose3(Symbol('x', 1), Symbol('v', 1), Symbol('x', 2), Symbol('v', 2), delta_t, Qc_model));
+    const double xs[3] = {-1, 0.5, 2}, taus[3] = {-0.1, 0.05, 0.2};
+    for (int k = 0; k < 3; k++) graph.add(GPInterpolatedGPSFactorPose3(Point3(xs[k], 0, 0), model_gps, Qc_model, Symbol('x', 1), Symbol('v', 1), Symbol('x', 2), Symbol('v', 2), delta_t, taus[k]));
+    Values init_values;
+    init_values.insert(Symbol('x', 1), Pose3(Rot3::Ypr(0.1, 0.1, -0.1), Point3(0.04, 0.1, -0.06))); init_values.insert(Symbol('v', 1), Vector6{-0.1, 0, 0, 9.8, 0, 0.2});
+    init_values.insert(Symbol('x', 2), Pose3(Rot3::Ypr(-0.1, 0.1, -0.1), Point3(1.05, -0.1, 0.1))); init_values.insert(Symbol('v', 2), Vector6{0, 0, 0.2, 9.7, 0, -0.1});
+    GaussNewtonParams parameters;
+    GaussNewtonOptimizer optimizer(graph, init_values, parameters);
+    optimizer.optimize();
+    Values values = optimizer.values();
+    EXPECT(std::fabs(optimizer.error()) < 1e-6);
+    p1.wire(w); values.at<Pose3>(Symbol('x', 1)).wire(o); for (int k = 0; k < 12; k++) EXPECT(std::fabs(w[k] - o[k]) < 1e-6);
+    p2.wire(w); values.at<Pose3>(Symbol('x', 2)).wire(o); for (int k = 0; k < 12; k++) EXPECT(std::fabs(w[k] - o[k]) < 1e-6);
+  }
+  {
+    auto K = std::make_shared<Cal3_S2>(50, 50, 0, 40, 30);
+    const Point3 land(3.4, 1.2, 20), landi(3.3, 1.3, 18);
+    auto project = [&](double cx) { const double u = (land.x - cx) / land.z, vv = land.y / land.z; return Point2(K->fx * u + K->s * vv + K->u0, K->fy * vv + K->v0); };
+    NonlinearFactorGraph graph;
+    graph.add(PriorFactor<Pose3>(Symbol('x', 1), p1, model_prior));
+    graph.add(PriorFactor<Pose3>(Symbol('x', 2), p2, model_prior));
+    graph.add(GaussianProcessPriorPose3(Symbol('x', 1), Symbol('v', 1), Symbol('x', 2), Symbol('v', 2), delta_t, Qc_model));
+    const double xs[3] = {0.2, 0.6, 0.9}, taus[3] = {0.02, 0.06, 0.09};
+    for (int k = 0; k < 3; k++)
+      graph.add(GPInterpolatedProjectionFactorPose3<Cal3_S2>(project(xs[k]), model_cam, Qc_model, Symbol('x', 1), Symbol('v', 1), Symbol('x', 2), Symbol('v', 2), Symbol('l', 1), delta_t, taus[k], K));
+    Values init_values;
+    init_values.insert(Symbol('x', 1), Pose3(Rot3::Ypr(0.1, 0.2, 0.4), Point3(0.2, 0.3, -0.2))); init_values.insert(Symbol('v', 1), Vector6{-0.3, 0, 0, 0.7, 0, 0.2});
+    init_values.insert(Symbol('x', 2), Pose3(Rot3::Ypr(-0.1, -0.2, -0.4), Point3(1.2, -0.3, 0.2))); init_values.insert(Symbol('v', 2), Vector6{0, 0, 0.4, 1.2, 0, -0.1});
+    init_values.insert(Symbol('l', 1), landi);
+    GaussNewtonParams parameters;
+    GaussNewtonOptimizer optimizer(graph, init_values, parameters);
+    optimizer.optimize();
+    Values values = optimizer.values();
+    EXPECT(std::fabs(optimizer.error()) < 1e-6);
+    p1.wire(w); values.at<Pose3>(Symbol('x', 1)).wire(o); for (int k = 0; k < 12; k++) EXPECT(std::fabs(w[k] - o[k]) < 1e-6);
+    p2.wire(w); values.at<Pose3>(Symbol('x', 2)).wire(o); for (int k = 0; k < 12; k++) EXPECT(std::fabs(w[k] - o[k]) < 1e-6);
+    const Point3 lo = values.at<Point3>(Symbol('l', 1));
+    EXPECT(std::fabs(lo.x - land.x) < 1e-6 && std::fabs(lo.y - land.y) < 1e-6 && std::fabs(lo.z - land.z) < 1e-6);
+    // single-factor path: residual of a projection factor at the ground truth is zero
+    GPInterpolatedProjectionFactorPose3<Cal3_S2> f(project(0.6), model_cam, Qc_model, 0, 0, 0, 0, 0, delta_t, 0.06, K);
+    Matrix H1, H5;
+    const Vector e = f.evaluateError(p1, v, p2, v, land, &H1, nullptr, nullptr, nullptr, &H5);
+    EXPECT(e.size() == 2 && std::fabs(e[0]) < 1e-9 && std::fabs(e[1]) < 1e-9 && H1.rows == 2 && H1.cols == 6 && H5.rows == 2 && H5.cols == 3);
+  }
+}
+
 int main() {
   try {
     testFactor();
     testOptimization();
     testRangeOptimization();
+    testGpsAndProjectionOptimization();
   } catch (const std::exception& e) { std::printf("exception: %s\n", e.what()); return 2; }
   std::printf(failures ? "FAILED (%d)\n" : "OK (%d failures)\n", failures);
   return failures ? 1 : 0;
