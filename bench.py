@@ -135,6 +135,11 @@ def run_reference(args, rank, world):
 def run_engine(args, rank, world, local_rank):
     import gpslam_b200 as gb
     from gpslam_b200 import shard, synth
+    # GPB_BENCH_ONE_DEVICE=1: debugging aid - every rank on cuda:0 with the gloo backend, to walk the N-rank code path on a
+    # one-GPU box (NCCL refuses two ranks on one device).  Its line is marked "debug_one_device" and is not a bench value.
+    one_device = world > 1 and os.environ.get("GPB_BENCH_ONE_DEVICE") == "1"
+    if one_device:
+        local_rank = 0
     if gb.device_count() <= local_rank:
         raise SystemExit("bench.py: no CUDA device (the engine has no CPU fallback)")
     dist = None
@@ -142,7 +147,10 @@ def run_engine(args, rank, world, local_rank):
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        if one_device:
+            dist.init_process_group("gloo")
+        else:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     sampler = ClockSampler(local_rank)
     cfg = synth.config("C3")
     if args.states:
@@ -233,6 +241,8 @@ def run_engine(args, rank, world, local_rank):
         r = cpu_reference_run(3, 1, 1)
         line["cpu_baseline"] = {"value": r["value"], "unit": "iterations/s", "cores": 1, "kind": "port", "sample": r["sample"],
                                 "seconds_per_iteration_sample": r["seconds_per_iteration_sample"]}
+    if one_device:
+        line["debug_one_device"] = True
     if rank == 0:
         print(json.dumps(line))
     if dist is not None:

@@ -70,6 +70,59 @@ inline Vec12 gpPriorPose3(const Pose3& pose1, const Vec6& vel1, const Pose3& pos
   return e;
 }
 
+// ---------------------------------------------------------------- Pose3 "VW" family
+// State = (Pose3, linear velocity v, angular velocity w), v and w both expressed in the WORLD frame: convertVWtoVb rotates them
+// into the body frame (gp/Pose3utils.cpp:47-64; gtsam::Rot3::unrotate: q = R^T p, dq/dR = [q]x, dq/dp = R^T).
+// The oracle carries (v, w) as ONE 6-vector velocity variable [v; w] per state, so the reference's H2|H3 (and H5|H6) sit side
+// by side in one 12x6 (or 6x6) block.
+inline Vec6 convertVWtoVb(const Vec3& v, const Vec3& w, const Pose3& pose, Mat<6, 3>* Hv, Mat<6, 3>* Hw, Mat6* Hpose) {
+  const Mat3 Rt = pose.R.t();
+  const Vec3 qw = Rt * w, qv = Rt * v;
+  Vec6 v6; v6.set(0, 0, qw); v6.set(3, 0, qv);
+  if (Hv) { *Hv = Mat<6, 3>::Zero(); Hv->set(3, 0, Rt); }
+  if (Hw) { *Hw = Mat<6, 3>::Zero(); Hw->set(0, 0, Rt); }
+  if (Hpose) { *Hpose = Mat6::Zero(); Hpose->set(0, 0, skew(qw)); Hpose->set(3, 0, skew(qv)); }
+  return v6;
+}
+// gp/Pose3utils.cpp:27-45
+inline void convertVbtoVW(const Vec6& v6, const Pose3& pose, Vec3& v, Vec3& w) {
+  v = pose.R * v6.block<3, 1>(3, 0); w = pose.R * v6.block<3, 1>(0, 0);
+}
+
+// gp/GaussianProcessPriorPose3VW.h:62-117.  Hvw1 = [H2 | H3] (12x6 over [v1; w1]), Hvw2 = [H5 | H6].
+inline Vec12 gpPriorPose3VW(const Pose3& pose1, const Vec3& vel1, const Vec3& omega1, const Pose3& pose2, const Vec3& vel2, const Vec3& omega2,
+                            double delta_t, Mat<12, 6>* H1, Mat<12, 6>* Hvw1, Mat<12, 6>* H4, Mat<12, 6>* Hvw2) {
+  const bool wantH = H1 || Hvw1 || H4 || Hvw2;
+  Mat6 Hinv, Hcomp1, Hcomp2, Hlogmap;
+  const Vec6 r = pose3_logmap(pose1.inverse().compose(pose2));
+  if (wantH) { Hinv = pose3_Hinverse(pose1); Hcomp1 = pose3_Hcompose1(pose2); Hcomp2 = Mat6::Identity(); Hlogmap = rightJacobianPose3inv(r); }
+  const Mat6 Jinv = rightJacobianPose3inv(r);
+  Mat<6, 3> H1v, H1w, H2v, H2w; Mat6 H1p, H2p;
+  const Vec6 v1 = convertVWtoVb(vel1, omega1, pose1, wantH ? &H1v : nullptr, wantH ? &H1w : nullptr, wantH ? &H1p : nullptr);
+  const Vec6 v2 = convertVWtoVb(vel2, omega2, pose2, wantH ? &H2v : nullptr, wantH ? &H2w : nullptr, wantH ? &H2p : nullptr);
+  if (wantH) {
+    Mat<12, 6> Hv1, Hv2;
+    Hv1.set(0, 0, -delta_t * Mat6::Identity()); Hv1.set(6, 0, -Mat6::Identity());
+    Hv2.set(0, 0, Mat6::Zero()); Hv2.set(6, 0, Jinv);
+    if (H1) {
+      const Mat6 J_Ti = Hlogmap * Hcomp1 * Hinv;
+      const Mat6 Jdiff_Ti = jacobianMethodNumercialDiff(rightJacobianPose3inv, r, v2) * J_Ti;
+      H1->set(0, 0, J_Ti - delta_t * H1p); H1->set(6, 0, Jdiff_Ti - H1p);
+    }
+    if (Hvw1) { Hvw1->set(0, 0, Hv1 * H1v); Hvw1->set(0, 3, Hv1 * H1w); }
+    if (H4) {
+      const Mat6 J_Ti1 = Hlogmap * Hcomp2;
+      const Mat6 Jdiff_Ti1 = jacobianMethodNumercialDiff(rightJacobianPose3inv, r, v2) * J_Ti1;
+      H4->set(0, 0, J_Ti1); H4->set(6, 0, Jdiff_Ti1 + Jinv * H2p);
+    }
+    if (Hvw2) { Hvw2->set(0, 0, Hv2 * H2v); Hvw2->set(0, 3, Hv2 * H2w); }
+  }
+  Vec12 e;
+  e.set(0, 0, r - v1 * delta_t);
+  e.set(6, 0, Jinv * v2 - v1);
+  return e;
+}
+
 // gp/GaussianProcessPriorPose2.h:58-82
 inline Vec6 gpPriorPose2(const Pose2& pose1, const Vec3& vel1, const Pose2& pose2, const Vec3& vel2, double delta_t,
                          Mat<6, 3>* H1, Mat<6, 3>* H2, Mat<6, 3>* H3, Mat<6, 3>* H4) {
@@ -157,6 +210,54 @@ struct InterpolatorPose3 {
         *H3 = Hexpr1 * Psi1 * dr2_dT2;
       }
       if (H4) *H4 = Hexpr1 * Psi.block<6, 6>(0, 6) * Jinv;
+    }
+    return pose;
+  }
+};
+
+// gp/GaussianProcessInterpolatorPose3VW.h:43-124 (all six Jacobians requested or none - the only two ways the reference's factor
+// calls it, slam/GPInterpolatedGPSFactorPose3VW.h:80-84).  Hvw1 = [H2 | H3], Hvw2 = [H5 | H6].
+struct InterpolatorPose3VW {
+  double delta_t, tau; Mat6 Qc; Mat12 Lambda, Psi;
+  InterpolatorPose3VW(const Mat6& Qc_, double dt, double tau_) : delta_t(dt), tau(tau_), Qc(Qc_) {
+    Lambda = calcLambda<6>(Qc, dt, tau); Psi = calcPsi<6>(Qc, dt, tau);
+  }
+  Pose3 interpolatePose(const Pose3& pose1, const Vec3& v1, const Vec3& omega1, const Pose3& pose2, const Vec3& v2, const Vec3& omega2,
+                        Mat6* H1, Mat6* Hvw1, Mat6* H4, Mat6* Hvw2) const {
+    const bool wantH = H1 || Hvw1 || H4 || Hvw2;
+    const Vec6 r = pose3_logmap(pose1.inverse().compose(pose2));
+    const Mat6 Jinv = rightJacobianPose3inv(r);
+    Mat<6, 3> H1v, H1w, H2v, H2w; Mat6 H1p, H2p;
+    const Vec6 vel1 = convertVWtoVb(v1, omega1, pose1, wantH ? &H1v : nullptr, wantH ? &H1w : nullptr, wantH ? &H1p : nullptr);
+    const Vec6 vel2 = convertVWtoVb(v2, omega2, pose2, wantH ? &H2v : nullptr, wantH ? &H2w : nullptr, wantH ? &H2p : nullptr);
+    Vec12 r1 = Vec12::Zero(); r1.set(6, 0, vel1);
+    Vec12 r2; r2.set(0, 0, r); r2.set(6, 0, Jinv * vel2);
+    const Mat<6, 12> Lam1 = Lambda.block<6, 12>(0, 0), Psi1 = Psi.block<6, 12>(0, 0);
+    const Vec6 xi = Lam1 * r1 + Psi1 * r2;
+    const Pose3 dT = pose3_expmap(xi);
+    const Pose3 pose = pose1.compose(dT);
+    if (wantH) {
+      const Mat6 Hinv = pose3_Hinverse(pose1), Hcomp11 = pose3_Hcompose1(pose2), Hcomp12 = Mat6::Identity();
+      const Mat6 Hlogmap = rightJacobianPose3inv(r);
+      const Mat6 Hexp = rightJacobianPose3(xi);
+      const Mat6 Hcomp21 = pose3_Hcompose1(dT), Hcomp22 = Mat6::Identity();
+      const Mat6 Hexpr1 = Hcomp22 * Hexp;
+      const Mat6 Hvel1 = Hexpr1 * Lambda.block<6, 6>(0, 6);
+      const Mat6 Hvel2 = Hexpr1 * Psi.block<6, 6>(0, 6) * Jinv;
+      if (H1) {
+        const Mat6 tmp = Hlogmap * Hcomp11 * Hinv;
+        Mat<12, 6> dr2_dT1; dr2_dT1.set(0, 0, tmp);
+        dr2_dT1.set(6, 0, jacobianMethodNumercialDiff(rightJacobianPose3inv, r, vel2) * tmp);
+        *H1 = Hcomp21 + Hexpr1 * Psi1 * dr2_dT1 + Hvel1 * H1p;
+      }
+      if (Hvw1) { Hvw1->set(0, 0, Hvel1 * H1v); Hvw1->set(0, 3, Hvel1 * H1w); }
+      if (H4) {
+        const Mat6 tmp = Hlogmap * Hcomp12;
+        Mat<12, 6> dr2_dT2; dr2_dT2.set(0, 0, tmp);
+        dr2_dT2.set(6, 0, jacobianMethodNumercialDiff(rightJacobianPose3inv, r, vel2) * tmp);
+        *H4 = Hexpr1 * Psi1 * dr2_dT2 + Hvel2 * H2p;
+      }
+      if (Hvw2) { Hvw2->set(0, 0, Hvel2 * H2v); Hvw2->set(0, 3, Hvel2 * H2w); }
     }
     return pose;
   }
@@ -287,6 +388,28 @@ inline Vec3 gpGPSPose3(const InterpolatorPose3& gp, const Vec3& measured, const 
   }
   if (wantH) {  // updatePoseJacobians, gp/GaussianProcessInterpolatorPose3.h:108-116
     if (H1) *H1 = Hpose * Hint1; if (H2) *H2 = Hpose * Hint2; if (H3) *H3 = Hpose * Hint3; if (H4) *H4 = Hpose * Hint4;
+  }
+  return point_err;
+}
+
+// slam/GPInterpolatedGPSFactorPose3VW.h:71-106.  Hvw1 = [H2 | H3], Hvw2 = [H5 | H6].
+inline Vec3 gpGPSPose3VW(const InterpolatorPose3VW& gp, const Vec3& measured, const Pose3* body_P_sensor,
+                         const Pose3& pose1, const Vec3& vel1, const Vec3& omega1, const Pose3& pose2, const Vec3& vel2, const Vec3& omega2,
+                         Mat<3, 6>* H1, Mat<3, 6>* Hvw1, Mat<3, 6>* H4, Mat<3, 6>* Hvw2) {
+  const bool wantH = H1 || Hvw1 || H4 || Hvw2;
+  Mat6 Hint1, Hintvw1, Hint4, Hintvw2;
+  const Pose3 pose = wantH ? gp.interpolatePose(pose1, vel1, omega1, pose2, vel2, omega2, &Hint1, &Hintvw1, &Hint4, &Hintvw2)
+                           : gp.interpolatePose(pose1, vel1, omega1, pose2, vel2, omega2, nullptr, nullptr, nullptr, nullptr);
+  Mat<3, 6> Hpose;
+  Vec3 point_err;
+  if (body_P_sensor) {
+    point_err = pose3_translation(pose.compose(*body_P_sensor), &Hpose) - measured;
+    if (wantH) Hpose = Hpose * pose3_Hcompose1(*body_P_sensor);
+  } else {
+    point_err = pose3_translation(pose, &Hpose) - measured;
+  }
+  if (wantH) {  // updatePoseJacobians, gp/GaussianProcessInterpolatorPose3VW.h:111-124
+    if (H1) *H1 = Hpose * Hint1; if (Hvw1) *Hvw1 = Hpose * Hintvw1; if (H4) *H4 = Hpose * Hint4; if (Hvw2) *Hvw2 = Hpose * Hintvw2;
   }
   return point_err;
 }

@@ -31,7 +31,8 @@ enum Group { G_POSE3 = 0, G_POSE2 = 1, G_ROT3 = 2, G_LINEAR = 3 };
 enum FactorKind {
   F_GP_PRIOR = 0, F_INTERP_RANGE = 1, F_INTERP_ATTITUDE = 2, F_PRIOR_POSE = 3, F_PRIOR_VEL = 4,
   F_PRIOR_LANDMARK = 5, F_BETWEEN = 6, F_RANGE_2D = 7, F_RANGE_BEARING_2D = 8, F_ODOMETRY_2D = 9,
-  F_INTERP_GPS = 10, F_INTERP_PROJECTION = 11
+  F_INTERP_GPS = 10, F_INTERP_PROJECTION = 11,
+  F_GP_PRIOR_VW = 12, F_INTERP_GPS_VW = 13  // Pose3 "VW" family: the velocity variable of a state is [v_world; w_world]
 };
 
 struct Factor {
@@ -154,6 +155,30 @@ void eval_factor(const Graph& g, const Factor& f, const double* P, const double*
       Mat<3, 6> H1, H2, H3, H4;
       put(e, gpGPSPose3(gp, vec<3>(f.meas), f.has_sensor ? &sensor : nullptr, Pose3::from(P + i * PS), vec<6>(V + i * D), Pose3::from(P + j * PS), vec<6>(V + j * D),
                         wantH ? &H1 : nullptr, wantH ? &H2 : nullptr, wantH ? &H3 : nullptr, wantH ? &H4 : nullptr));
+      if (wantH) { put(out.A[0], H1); put(out.A[1], H2); put(out.A[2], H3); put(out.A[3], H4); }
+      return;
+    }
+    case F_GP_PRIOR_VW: {  // gp/GaussianProcessPriorPose3VW.h
+      const int i = f.i, j = f.i + 1;
+      addv(0, i, D); addv(1, i, D); addv(0, j, D); addv(1, j, D);
+      out.m = 12;
+      if (g.group != G_POSE3) std::abort();
+      Mat<12, 6> H1, H2, H3, H4;
+      put(e, gpPriorPose3VW(Pose3::from(P + i * PS), vec<3>(V + i * D), vec<3>(V + i * D + 3), Pose3::from(P + j * PS), vec<3>(V + j * D), vec<3>(V + j * D + 3), f.delta_t,
+                            wantH ? &H1 : nullptr, wantH ? &H2 : nullptr, wantH ? &H3 : nullptr, wantH ? &H4 : nullptr));
+      if (wantH) { put(out.A[0], H1); put(out.A[1], H2); put(out.A[2], H3); put(out.A[3], H4); }
+      return;
+    }
+    case F_INTERP_GPS_VW: {  // slam/GPInterpolatedGPSFactorPose3VW.h
+      const int i = f.i, j = f.i + 1;
+      addv(0, i, D); addv(1, i, D); addv(0, j, D); addv(1, j, D);
+      out.m = 3;
+      if (g.group != G_POSE3) std::abort();
+      const InterpolatorPose3VW gp(get<6, 6>(g.Qc[f.qc].data()), f.delta_t, f.tau);
+      Pose3 sensor; if (f.has_sensor) sensor = Pose3::from(f.aux);
+      Mat<3, 6> H1, H2, H3, H4;
+      put(e, gpGPSPose3VW(gp, vec<3>(f.meas), f.has_sensor ? &sensor : nullptr, Pose3::from(P + i * PS), vec<3>(V + i * D), vec<3>(V + i * D + 3), Pose3::from(P + j * PS),
+                          vec<3>(V + j * D), vec<3>(V + j * D + 3), wantH ? &H1 : nullptr, wantH ? &H2 : nullptr, wantH ? &H3 : nullptr, wantH ? &H4 : nullptr));
       if (wantH) { put(out.A[0], H1); put(out.A[1], H2); put(out.A[2], H3); put(out.A[3], H4); }
       return;
     }
@@ -312,7 +337,7 @@ template <int D> void gp_prior_R(const double* Qc, double dt, double* R) {
   put(R, U);
 }
 void factor_R(const Graph& g, const Factor& f, double* R /*12x12 max*/) {
-  if (f.kind == F_GP_PRIOR) {
+  if (f.kind == F_GP_PRIOR || f.kind == F_GP_PRIOR_VW) {
     switch (g.D) {
       case 1: gp_prior_R<1>(g.Qc[f.qc].data(), f.delta_t, R); break;
       case 2: gp_prior_R<2>(g.Qc[f.qc].data(), f.delta_t, R); break;
@@ -695,6 +720,25 @@ int gpo_add_interp_gps(void* h, int n, const int* i, const double* meas, const d
   }
   return 0;
 }
+// Pose3 "VW" family: vels of the graph are read as [v_world(3); w_world(3)] by these two factor kinds
+int gpo_add_gp_prior_vw(void* h, int n, const int* i, const double* delta_t, int qc) {
+  Graph* g = (Graph*)h;
+  if (g->group != G_POSE3) return -1;
+  for (int k = 0; k < n; k++) { Factor f; f.kind = F_GP_PRIOR_VW; f.i = i[k]; f.delta_t = delta_t[k]; f.qc = qc; f.m = 12; g->factors.push_back(f); }
+  return 0;
+}
+int gpo_add_interp_gps_vw(void* h, int n, const int* i, const double* meas, const double* sqrt_info, const double* delta_t, const double* tau, int qc, const double* body_P_sensor) {
+  Graph* g = (Graph*)h;
+  if (g->group != G_POSE3) return -1;
+  for (int k = 0; k < n; k++) {
+    Factor f; f.kind = F_INTERP_GPS_VW; f.i = i[k]; f.delta_t = delta_t[k]; f.tau = tau[k]; f.qc = qc;
+    for (int t = 0; t < 3; t++) f.meas[t] = meas[3 * k + t];
+    set_R(f, 3, sqrt_info);
+    if (body_P_sensor) { f.has_sensor = true; for (int t = 0; t < 12; t++) f.aux[t] = body_P_sensor[t]; }
+    g->factors.push_back(f);
+  }
+  return 0;
+}
 int gpo_add_interp_projection(void* h, int n, const int* i, const int* l, const double* meas, const double* sqrt_info, const double* delta_t, const double* tau, int qc,
                               const double* K, const double* body_P_sensor) {
   Graph* g = (Graph*)h;
@@ -869,7 +913,12 @@ void gpo_calcQ(int D, const double* Qc, double tau, double* Q, double* Qinv) {
 // interpolatePose for any group at the current wire formats; H1..H4 (D x D col-major) or null
 void gpo_interpolate(int group, int D, const double* Qc, double delta_t, double tau, const double* p1, const double* v1, const double* p2, const double* v2,
                      double* pose_out, double* H /* 4*D*D or null */) {
-  if (group == G_POSE3) {
+  if (group == 4) {  // Pose3 "VW": v1, v2 are [v_world; w_world]; H = [H1 | H2,H3 | H4 | H5,H6]
+    const InterpolatorPose3VW gp(get<6, 6>(Qc), delta_t, tau); Mat6 h[4];
+    gp.interpolatePose(Pose3::from(p1), vec<3>(v1), vec<3>(v1 + 3), Pose3::from(p2), vec<3>(v2), vec<3>(v2 + 3), H ? &h[0] : nullptr, H ? &h[1] : nullptr, H ? &h[2] : nullptr,
+                       H ? &h[3] : nullptr).to(pose_out);
+    if (H) for (int k = 0; k < 4; k++) put(H + 36 * k, h[k]);
+  } else if (group == G_POSE3) {
     const InterpolatorPose3 gp(get<6, 6>(Qc), delta_t, tau); Mat6 h[4];
     gp.interpolatePose(Pose3::from(p1), vec<6>(v1), Pose3::from(p2), vec<6>(v2), H ? &h[0] : nullptr, H ? &h[1] : nullptr, H ? &h[2] : nullptr, H ? &h[3] : nullptr).to(pose_out);
     if (H) for (int k = 0; k < 4; k++) put(H + 36 * k, h[k]);
@@ -889,6 +938,9 @@ void gpo_interpolate(int group, int D, const double* Qc, double delta_t, double 
     if (H) for (int k = 0; k < 4; k++) put(H + 9 * k, h[k]);
   }
 }
+// gp/Pose3utils.cpp:27-64
+void gpo_convert_vw_to_vb(const double* v, const double* w, const double* pose, double* v6) { put(v6, convertVWtoVb(vec<3>(v), vec<3>(w), Pose3::from(pose), nullptr, nullptr, nullptr)); }
+void gpo_convert_vb_to_vw(const double* v6, const double* pose, double* v, double* w) { Vec3 a, b; convertVbtoVW(vec<6>(v6), Pose3::from(pose), a, b); put(v, a); put(w, b); }
 int gpo_hardware_threads() { const unsigned n = std::thread::hardware_concurrency(); return n ? (int)n : 1; }
 
 }  // extern "C"

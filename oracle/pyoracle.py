@@ -63,7 +63,7 @@ def lib():
         L.gpo_graph_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
         L.gpo_error.restype = C.c_double
         for name in ("gpo_graph_destroy", "gpo_set_threads", "gpo_add_qc_model", "gpo_add_gp_prior", "gpo_add_interp_range",
-                     "gpo_add_interp_attitude", "gpo_add_interp_gps", "gpo_add_interp_projection", "gpo_add_prior_pose", "gpo_add_prior_vel", "gpo_add_prior_landmark", "gpo_add_between",
+                     "gpo_add_interp_attitude", "gpo_add_interp_gps", "gpo_add_interp_projection", "gpo_add_gp_prior_vw", "gpo_add_interp_gps_vw", "gpo_add_prior_pose", "gpo_add_prior_vel", "gpo_add_prior_landmark", "gpo_add_between",
                      "gpo_add_range_2d", "gpo_add_range_bearing_2d", "gpo_add_odometry_2d", "gpo_set_values", "gpo_get_values",
                      "gpo_num_factors", "gpo_error", "gpo_linearize_factor", "gpo_eval_factor", "gpo_normal_equations_dense", "gpo_optimize"):
             getattr(L, name).argtypes = None
@@ -119,6 +119,22 @@ class Graph:
         m = _f64(np.broadcast_to(np.asarray(meas, dtype=np.float64).reshape(-1, 3), (len(i), 3)))
         bps = _f64(body_P_sensor) if body_P_sensor is not None else None
         rc = self.L.gpo_add_interp_gps(self.h, C.c_int(len(i)), _ip(i), _dp(m), _dp(_fcol(sqrt_info)), _dp(b(delta_t)), _dp(b(tau)), C.c_int(qc), _dp(bps))
+        assert rc == 0
+
+    def add_gp_prior_vw(self, i, delta_t, qc=0):
+        """GaussianProcessPriorPose3VW: the graph's velocities are [v_world; w_world] (Pose3 graphs only)"""
+        i = np.ascontiguousarray(np.atleast_1d(i), dtype=np.int32)
+        dt = _f64(np.broadcast_to(np.atleast_1d(delta_t), i.shape))
+        rc = self.L.gpo_add_gp_prior_vw(self.h, C.c_int(len(i)), _ip(i), _dp(dt), C.c_int(qc))
+        assert rc == 0
+
+    def add_interp_gps_vw(self, i, meas, sqrt_info, delta_t, tau, qc=0, body_P_sensor=None):
+        """GPInterpolatedGPSFactorPose3VW"""
+        i = np.ascontiguousarray(np.atleast_1d(i), dtype=np.int32)
+        b = lambda a: _f64(np.broadcast_to(np.atleast_1d(a), i.shape))
+        m = _f64(np.broadcast_to(np.asarray(meas, dtype=np.float64).reshape(-1, 3), (len(i), 3)))
+        bps = _f64(body_P_sensor) if body_P_sensor is not None else None
+        rc = self.L.gpo_add_interp_gps_vw(self.h, C.c_int(len(i)), _ip(i), _dp(m), _dp(_fcol(sqrt_info)), _dp(b(delta_t)), _dp(b(tau)), C.c_int(qc), _dp(bps))
         assert rc == 0
 
     def add_interp_projection(self, i, l, meas, sqrt_info, delta_t, tau, K, qc=0, body_P_sensor=None):
@@ -293,8 +309,21 @@ def lambda_psi(D, Qc, delta_t, tau):
     return La.reshape(2 * D, 2 * D).T.copy(), Ps.reshape(2 * D, 2 * D).T.copy()
 
 
+POSE3VW = 4  # interpolate() only: Pose3 with [v_world; w_world] velocities (gp/GaussianProcessInterpolatorPose3VW.h)
+
+
+def convert_vw_to_vb(v, w, pose):
+    out = np.zeros(6); _call("gpo_convert_vw_to_vb", _dp(_f64(v)), _dp(_f64(w)), _dp(_f64(pose)), _dp(out)); return out
+
+
+def convert_vb_to_vw(v6, pose):
+    v = np.zeros(3); w = np.zeros(3); _call("gpo_convert_vb_to_vw", _dp(_f64(v6)), _dp(_f64(pose)), _dp(v), _dp(w)); return v, w
+
+
 def interpolate(group, Qc, delta_t, tau, p1, v1, p2, v2, want_H=False, D=3):
     ps = POSE_STORAGE.get(group, D); d = TANGENT_DIM.get(group, D)
+    if group == POSE3VW:
+        ps, d = 12, 6
     out = np.zeros(ps); H = np.zeros(4 * d * d) if want_H else None
     _call("gpo_interpolate", C.c_int(group), C.c_int(d), _dp(_fcol(Qc)), C.c_double(delta_t), C.c_double(tau), _dp(_f64(p1)), _dp(_f64(v1)),
           _dp(_f64(p2)), _dp(_f64(v2)), _dp(out), _dp(H))

@@ -458,6 +458,147 @@ def test_interp_gps_pose3_optimization():
     np.testing.assert_allclose(V, [v, v], atol=1e-6)
 
 
+# ----------------------------------------------------------------------------- Pose3 "VW" family
+def _vw(v, w):
+    """the oracle's velocity variable of a VW state: [v_world; w_world]"""
+    return np.asarray(list(v) + list(w), float)
+
+
+def test_convert_vw_vb_roundtrip():
+    """gp/Pose3utils.cpp:27-64: Vb = [R^T w; R^T v] and back"""
+    T = P3(.4, -.8, .2, 3, -8, 2)
+    R, _ = po.pose3_Rt(T)
+    v, w = np.array([.1, -.2, -1.4]), np.array([.5, .9, .7])
+    vb = po.convert_vw_to_vb(v, w, T)
+    np.testing.assert_allclose(vb, np.concatenate([R.T @ w, R.T @ v]), atol=1e-14)
+    v2, w2 = po.convert_vb_to_vw(vb, T)
+    np.testing.assert_allclose(v2, v, atol=1e-14); np.testing.assert_allclose(w2, w, atol=1e-14)
+
+
+def test_gp_prior_pose3vw_factor():
+    """gp/tests/testGaussianProcessPriorPose3VW.cpp:33-149: zero residual at rest / constant forward velocity / constant rotation,
+    analytic vs central-difference Jacobians (step 1e-6, tolerance 1e-6) incl. the 'random' point (w2 keeps its previous value
+    (0,0,1) there and w1 is assigned twice, as in the reference)"""
+    cases = [
+        (P3(0, 0, 0, 0, 0, 0), _vw([0, 0, 0], [0, 0, 0]), P3(0, 0, 0, 0, 0, 0), _vw([0, 0, 0], [0, 0, 0]), True),
+        (P3(0, 0, 0, 0, 0, 0), _vw([1, 0, 0], [0, 0, 0]), P3(0, 0, 0, .1, 0, 0), _vw([1, 0, 0], [0, 0, 0]), True),
+        (P3(0, 0, 0, 0, 0, 0), _vw([0, 0, 0], [0, 0, 1]), P3(.1, 0, 0, 0, 0, 0), _vw([0, 0, 0], [0, 0, 1]), True),
+        (P3(-.1, 1.2, .3, -4, 2, 14), _vw([2, 3, 1], [0, 6, 4]), P3(2.4, -2.5, 3.7, 9, -8, -7), _vw([1, 3, 8], [0, 0, 1]), False),
+    ]
+    for p1, vw1, p2, vw2, zero in cases:
+        g = two_state_graph(POSE3, p1, vw1, p2, vw2)
+        g.add_qc_model(0.01 * np.eye(6))
+        g.add_gp_prior_vw(0, 0.1)
+        e, H, Hnum = numeric_jacobians(g, 0, POSE3, 1e-6)
+        assert e.shape == (12,) and [h.shape for h in H] == [(12, 6)] * 4
+        if zero:
+            np.testing.assert_allclose(e, 0, atol=1e-6)
+        for Ha, Hn in zip(H, Hnum):
+            np.testing.assert_allclose(Ha, Hn, atol=1e-6)
+        np.testing.assert_allclose(g.eval_factor(0, False)[0], e, atol=0)
+        # same residual as the body-velocity prior fed with the converted velocities (gp/GaussianProcessPriorPose3VW.h:85-91,116)
+        gb = two_state_graph(POSE3, p1, po.convert_vw_to_vb(vw1[:3], vw1[3:], p1), p2, po.convert_vw_to_vb(vw2[:3], vw2[3:], p2))
+        gb.add_qc_model(0.01 * np.eye(6)); gb.add_gp_prior(0, 0.1)
+        np.testing.assert_allclose(gb.eval_factor(0, False)[0], e, atol=1e-13)
+
+
+def test_gp_prior_pose3vw_optimization():
+    """gp/tests/testGaussianProcessPriorPose3VW.cpp:152-211 (started away from the solution so that GN has something to do)"""
+    p1, p2, vw = P3(0, 0, 0, 0, 0, 0), P3(0, 0, 0, 1, 0, 0), _vw([1, 0, 0], [0, 0, 0])
+    for vw2i in (vw, _vw([2., -.5, .6], [.1, .2, -.3])):
+        g = two_state_graph(POSE3, p1, vw, p2, vw2i)
+        g.add_qc_model(0.01 * np.eye(6))
+        g.add_prior_pose(0, p1, iso(6, 0.001)); g.add_prior_pose(1, p2, iso(6, 0.001))
+        g.add_gp_prior_vw(0, 1.0)
+        st = g.optimize(use_lm=False)
+        assert st.status == 0
+        P, V, _ = g.get_values()
+        assert abs(g.error()) < 1e-6
+        np.testing.assert_allclose(P[0], p1, atol=1e-6); np.testing.assert_allclose(P[1], p2, atol=1e-6)
+        np.testing.assert_allclose(V, [vw, vw], atol=1e-6)
+
+
+def test_interpolator_pose3vw():
+    """gp/tests/testGaussianProcessInterpolatorPose3VW.cpp:30-137: known poses at tau = .03 and the six Jacobians (H2|H3 and
+    H5|H6 side by side) vs central differences; step 1e-4 / tolerance 3e-8 for the reason given in test_interpolator"""
+    Qc, dt, tau = 0.01 * np.eye(6), 0.1, 0.03
+    cases = [
+        (P3(0, 0, 0, 0, 0, 0), _vw([0, 0, 0], [0, 0, 0]), P3(0, 0, 0, 0, 0, 0), _vw([0, 0, 0], [0, 0, 0]), P3(0, 0, 0, 0, 0, 0)),
+        (P3(0, 0, 0, 0, 0, 0), _vw([1, 2, 0], [0, 0, 0]), P3(0, 0, 0, .1, .2, 0), _vw([1, 2, 0], [0, 0, 0]), P3(0, 0, 0, .03, .06, 0)),
+        (P3(0, 0, 0, 0, 0, 0), _vw([0, 0, 0], [0, 0, 1]), P3(.1, 0, 0, 0, 0, 0), _vw([0, 0, 0], [0, 0, 1]), P3(.03, 0, 0, 0, 0, 0)),
+        (P3(.4, -.8, .2, 3, -8, 2), _vw([.6, .3, -.9], [.4, -.2, .8]), P3(.1, .3, -.5, -9, 3, 4), _vw([0, 0, 0], [0, 0, 1]), None),
+    ]
+    for p1, v1, p2, v2, expect in cases:
+        pose, H = po.interpolate(po.POSE3VW, Qc, dt, tau, p1, v1, p2, v2, want_H=True)
+        if expect is not None:
+            np.testing.assert_allclose(_pose_local(POSE3, np.asarray(expect, float), pose), 0, atol=1e-8)
+        # equals the body-velocity interpolator on the converted velocities
+        ref = po.interpolate(POSE3, Qc, dt, tau, p1, po.convert_vw_to_vb(v1[:3], v1[3:], p1), p2, po.convert_vw_to_vb(v2[:3], v2[3:], p2))
+        np.testing.assert_allclose(pose, ref, atol=1e-13)
+        # two steps, the better one counts: at zero rotation the Expmap/Logmap cancellation noise (~1e-12 / step) needs 1e-3,
+        # the 'random' point's O(step^2) truncation needs 1e-4
+        args = [p1, v1, p2, v2]
+        for k in range(4):
+            errs = []
+            for step in (1e-3, 1e-4):
+                J = np.zeros((6, 6))
+                for c in range(6):
+                    outs = []
+                    for sgn in (1, -1):
+                        d = np.zeros(6); d[c] = sgn * step
+                        a = list(args)
+                        a[k] = po.retract(POSE3, args[k], d) if k % 2 == 0 else args[k] + d
+                        outs.append(po.interpolate(po.POSE3VW, Qc, dt, tau, *a))
+                    J[:, c] = _pose_local(POSE3, outs[1], outs[0]) / (2 * step)
+                errs.append(np.abs(H[k] - J).max())
+            assert min(errs) < 3e-8, (k, errs)
+
+
+def test_interp_gps_pose3vw():
+    """slam/tests/testGPInterpolatedGPSFactorPose3VW.cpp:34-263: zero residual at the interpolated ground truth (with and
+    without body_P_sensor), the known non-zero residual (1.6, 0.2, 0), analytic vs central-difference Jacobians (tolerance 1e-6)"""
+    Qc, dt, tau = 0.001 * np.eye(6), 0.1, 0.04
+    bTs = P3(1.4, 4.4, -.5, .3, .6, -.7)
+    bTs_rot = P3(1.4, 4.4, -.5, 0, 0, 0)
+    t_of = lambda T: po.pose3_Rt(po.pose3_compose(T, bTs))[1]
+    cases = [
+        (P3(0, 0, 0, 0, 0, 0), _vw([0, 0, 0], [0, 0, 0]), P3(0, 0, 0, 0, 0, 0), _vw([0, 0, 0], [0, 0, 0]), [0, 0, 0], None, [0, 0, 0]),
+        (P3(0, 0, 0, -.04, .04, 0), _vw([1, -1, 0], [0, 0, 0]), P3(0, 0, 0, .06, -.06, 0), _vw([1, -1, 0], [0, 0, 0]), [0, 0, 0], None, [0, 0, 0]),
+        (P3(-.04, 0, 0, 0, 0, 0), _vw([0, 0, 0], [0, 0, 1]), P3(.06, 0, 0, 0, 0, 0), _vw([0, 0, 0], [0, 0, 1]), [0, 0, 0], None, [0, 0, 0]),
+        (P3(0, 0, 0, 1, 0, 0), _vw([15, 5, 0], [0, 0, 0]), P3(0, 0, 0, 2.5, .5, 0), _vw([15, 5, 0], [0, 0, 0]), t_of(P3(0, 0, 0, 1.6, .2, 0)), bTs, [0, 0, 0]),
+        (P3(0, 0, 0, 1, 0, 0), _vw([15, 5, 0], [0, 0, 0]), P3(0, 0, 0, 2.5, .5, 0), _vw([15, 5, 0], [0, 0, 0]), [0, 0, 0], bTs_rot, [1.6, .2, 0]),
+        (P3(0, 0, 0, 0, 0, 0), _vw([0, 0, 0], [0, 0, 10]), P3(1.0, 0, 0, 0, 0, 0), _vw([0, 0, 0], [0, 0, 10]), t_of(P3(.4, 0, 0, 0, 0, 0)), bTs, [0, 0, 0]),
+        (P3(.4, -.8, .2, 3, -8, 2), _vw([.6, .3, -.9], [.4, -.2, .8]), P3(.1, .3, -.5, -9, 3, 4), _vw([0, 0, 0], [0, 0, 10]), [0, 0, 0], bTs, None),
+    ]
+    for p1, v1, p2, v2, meas, sensor, expect in cases:
+        g = two_state_graph(POSE3, p1, v1, p2, v2)
+        g.add_qc_model(Qc)
+        g.add_interp_gps_vw(0, meas, iso(3, 0.1), dt, tau, body_P_sensor=sensor)
+        e, H, Hnum = numeric_jacobians(g, 0, POSE3, 1e-4)
+        assert e.shape == (3,) and len(H) == 4
+        if expect is not None:
+            np.testing.assert_allclose(e, expect, atol=1e-6)
+        for Ha, Hn in zip(H, Hnum):
+            np.testing.assert_allclose(Ha, Hn, atol=1e-6)
+
+
+def test_interp_gps_pose3vw_optimization():
+    """slam/tests/testGPInterpolatedGPSFactorPose3VW.cpp:266-337 (tau = -0.1, 0.05, 0.2 with delta_t = 0.1: extrapolation)"""
+    p1, p2, vw = P3(0, 0, 0, 0, 0, 0), P3(0, 0, 0, 1, 0, 0), _vw([10, 0, 0], [0, 0, 0])
+    g = two_state_graph(POSE3, P3(.1, -.1, -.1, .1, .1, -.1), _vw([9.8, -.1, -.05], [.1, -.1, .1]), P3(-.1, .1, -.1, 1.1, -.1, .1), _vw([10.2, .03, -.1], [-.1, .1, .1]))
+    g.add_qc_model(0.01 * np.eye(6))
+    g.add_prior_pose(0, p1, iso(6, 0.1)); g.add_prior_pose(1, p2, iso(6, 0.1))
+    g.add_gp_prior_vw(0, 0.1)
+    for x, tau in zip((-1, .5, 2), (-.1, .05, .2)):
+        g.add_interp_gps_vw(0, [x, 0, 0], iso(3, 0.01), 0.1, tau)
+    st = g.optimize(use_lm=False)
+    assert st.status == 0
+    P, V, _ = g.get_values()
+    assert abs(g.error()) < 1e-6
+    np.testing.assert_allclose(P[0], p1, atol=1e-6); np.testing.assert_allclose(P[1], p2, atol=1e-6)
+    np.testing.assert_allclose(V, [vw, vw], atol=1e-6)
+
+
 def test_interp_projection_pose3():
     """slam/tests/testGPInterpolatedProjectionFactorPose3.cpp:37-188: Cal3_S2() and Cal3_S2(50, 50, 0, 40, 30), with body_P_sensor"""
     Qc = 0.001 * np.eye(6)
