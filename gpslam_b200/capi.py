@@ -9,10 +9,10 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 _LIB = None
 
-GPB_POSE3, GPB_POSE2, GPB_ROT3, GPB_LINEAR = 0, 1, 2, 3
-_PS = {GPB_POSE3: 12, GPB_POSE2: 3, GPB_ROT3: 9, GPB_LINEAR: 3}
-_D = {GPB_POSE3: 6, GPB_POSE2: 3, GPB_ROT3: 3, GPB_LINEAR: 3}
-_DL = {GPB_POSE3: 3, GPB_POSE2: 2, GPB_ROT3: 0, GPB_LINEAR: 2}
+GPB_POSE3, GPB_POSE2, GPB_ROT3, GPB_LINEAR, GPB_POSE3VW = 0, 1, 2, 3, 4
+_PS = {GPB_POSE3: 12, GPB_POSE2: 3, GPB_ROT3: 9, GPB_LINEAR: 3, GPB_POSE3VW: 12}
+_D = {GPB_POSE3: 6, GPB_POSE2: 3, GPB_ROT3: 3, GPB_LINEAR: 3, GPB_POSE3VW: 6}
+_DL = {GPB_POSE3: 3, GPB_POSE2: 2, GPB_ROT3: 0, GPB_LINEAR: 2, GPB_POSE3VW: 3}
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-shared"]
 

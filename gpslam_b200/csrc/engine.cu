@@ -56,6 +56,7 @@ struct Level {
 
 struct gpb_graph {
   int group = 0, D = 0, PS = 0, DL = 0, N = 0, L = 0, bs = 0, SR = 0, nb = 0, w = 0, W = 0;
+  int vw = 0;  // GPB_POSE3VW: a GPB_POSE3 graph whose velocities are [v_world | w_world] (selects the VW linearise kernels only)
   std::vector<std::vector<double>> Rq;  // chol_upper(Qc^-1), D x D column-major
   std::vector<double> dt;               // per interval (0 = no GP prior)
   std::vector<int> gp_qc;
@@ -118,7 +119,7 @@ static int extra_rows_of(const gpb_graph* g, int kind) {
   switch (kind) {
     case X_INTERP_RANGE: case X_RANGE_2D: return 1;
     case X_INTERP_ATTITUDE: case X_RANGE_BEARING_2D: case X_INTERP_PROJECTION: return 2;
-    case X_INTERP_GPS: return 3;
+    case X_INTERP_GPS: case X_INTERP_GPS_VW: return 3;
     case X_PRIOR_POSE: case X_PRIOR_VEL: case X_BETWEEN: return g->D;
     case X_PRIOR_LANDMARK: return g->DL;
     case X_ODOMETRY_2D: return 3;
@@ -177,15 +178,18 @@ void gpb_default_params(gpb_params* p, int use_lm) {
 }
 
 gpb_graph* gpb_graph_create(int group, int dim, int n_states, int n_landmarks) {
-  if (group < 0 || group > 3 || n_states < 2 || n_landmarks < 0) { fail(GPB_ERR_ARG, "gpb_graph_create: bad arguments (need group 0..3, n_states >= 2)"); return nullptr; }
+  if (group < 0 || group > GPB_POSE3VW || n_states < 2 || n_landmarks < 0) { fail(GPB_ERR_ARG, "gpb_graph_create: bad arguments (need group 0..4, n_states >= 2)"); return nullptr; }
   if (group == GPB_LINEAR && dim != 3) { fail(GPB_ERR_UNSUPPORTED, "gpb_graph_create: GPB_LINEAR supports dim 3 (the reference's 2DLinear states)"); return nullptr; }
   gpb_graph* g = new gpb_graph();
+  if (group == GPB_POSE3VW) { g->vw = 1; group = GPB_POSE3; }
   g->group = group; g->D = group == GPB_POSE3 ? 6 : 3; g->PS = pose_storage(group, g->D); g->DL = land_dim(group);
   g->N = n_states; g->L = g->DL ? n_landmarks : 0; g->bs = 2 * g->D; g->SR = g->PS + g->D; g->nint = n_states - 1;
   g->dt.assign(g->nint, 0.0); g->gp_qc.assign(g->nint, 0);
   g->h_X.assign((size_t)n_states * g->SR, 0.0); g->h_land.assign((size_t)g->L * std::max(g->DL, 1), 0.0);
   return g;
 }
+
+int gpb_graph_group(const gpb_graph* g) { return !g ? GPB_ERR_ARG : (g->vw ? GPB_POSE3VW : g->group); }
 
 void gpb_graph_destroy(gpb_graph* g) {
   if (!g) return;
@@ -235,6 +239,7 @@ int gpb_add_interp_range(gpb_graph* g, int n, const int* i, const int* l, const 
                          const double* tau, int qc, const double* body_P_sensor) {
   CHECK_OPEN(g);
   if (g->group == GPB_ROT3) return fail(GPB_ERR_UNSUPPORTED, "gpb_add_interp_range: no range factor on Rot3 trajectories");
+  if (g->vw) return fail(GPB_ERR_UNSUPPORTED, "gpb_add_interp_range: the reference has no range factor for Pose3 VW states");
   if (body_P_sensor && g->group == GPB_LINEAR) return fail(GPB_ERR_UNSUPPORTED, "GPInterpolatedRangeFactor2DLinear has no body_P_sensor");
   (void)qc;  // Lambda/Psi do not depend on Qc
   for (int k = 0; k < n; k++) {
@@ -257,7 +262,7 @@ int gpb_add_interp_gps(gpb_graph* g, int n, const int* i, const double* measured
   for (int k = 0; k < n; k++) {
     if (i[k] < 0 || i[k] >= g->nint) return fail(GPB_ERR_ARG, "gpb_add_interp_gps: index out of range");
     if (!(delta_t[k] > 0.0)) return fail(GPB_ERR_ARG, "gpb_add_interp_gps: delta_t must be positive");
-    Extra e = make_extra(X_INTERP_GPS);
+    Extra e = make_extra(g->vw ? X_INTERP_GPS_VW : X_INTERP_GPS);  // GPInterpolatedGPSFactorPose3VW on a GPB_POSE3VW graph
     e.sa = i[k]; e.sb = i[k] + 1; e.interval = i[k]; e.m = 3;
     e.prm[0] = delta_t[k]; e.prm[1] = tau[k];
     for (int t = 0; t < 3; t++) e.prm[40 + t] = measured[3 * k + t];
@@ -271,7 +276,7 @@ int gpb_add_interp_gps(gpb_graph* g, int n, const int* i, const double* measured
 int gpb_add_interp_projection(gpb_graph* g, int n, const int* i, const int* l, const double* measured, const double* sqrt_info, const double* delta_t,
                               const double* tau, int qc, const double* K, const double* body_P_sensor) {
   CHECK_OPEN(g);
-  if (g->group != GPB_POSE3) return fail(GPB_ERR_UNSUPPORTED, "gpb_add_interp_projection: Pose3 trajectories only (GPInterpolatedProjectionFactorPose3)");
+  if (g->group != GPB_POSE3 || g->vw) return fail(GPB_ERR_UNSUPPORTED, "gpb_add_interp_projection: Pose3 trajectories only (GPInterpolatedProjectionFactorPose3; no VW variant in the reference)");
   if (!K) return fail(GPB_ERR_ARG, "gpb_add_interp_projection: null calibration");
   (void)qc;
   for (int k = 0; k < n; k++) {
@@ -552,7 +557,7 @@ int gpb_graph_finalize(gpb_graph* g, int device) {
     for (int i = 0; i < g->N; i++) { bsoff[i + 1] = bsoff[i] + (int)per[i].size(); for (auto& pr : per[i]) { bsrow.push_back(pr.first); bsside.push_back(pr.second); } }
   }
   std::vector<int> listA, listB, listC;
-  for (int k = 0; k < g->NX; k++) (xkind[k] == X_INTERP_RANGE || xkind[k] == X_INTERP_ATTITUDE ? listA : (xkind[k] == X_INTERP_GPS || xkind[k] == X_INTERP_PROJECTION ? listC : listB)).push_back(k);
+  for (int k = 0; k < g->NX; k++) (xkind[k] == X_INTERP_RANGE || xkind[k] == X_INTERP_ATTITUDE ? listA : (xkind[k] == X_INTERP_GPS || xkind[k] == X_INTERP_PROJECTION || xkind[k] == X_INTERP_GPS_VW ? listC : listB)).push_back(k);
   g->nA = (int)listA.size(); g->nB = (int)listB.size(); g->nC = (int)listC.size();
   // ---- loop closures: endpoint states (pinned separators), per-endpoint and per-pair row lists
   std::vector<char> pin(g->N, 0);
@@ -802,7 +807,8 @@ template <int G> static int launch_linearize(gpb_graph* g, const double* X, cons
     CUDA_TRY(cudaEventRecord(g->ev_join, g->stream2));
     g->launches++;
   }
-  k_lin_gp<G, NT><<<nb1, NT, smem, g->stream>>>(X, g->d_dt, g->d_qc, g->d_Rq, g->d_AB[buf], g->d_errpart, g->nint, g->NFp, wantJ);
+  if (G == G_POSE3 && g->vw) k_lin_gp<G_POSE3VW, NT><<<nb1, NT, smem, g->stream>>>(X, g->d_dt, g->d_qc, g->d_Rq, g->d_AB[buf], g->d_errpart, g->nint, g->NFp, wantJ);
+  else k_lin_gp<G, NT><<<nb1, NT, smem, g->stream>>>(X, g->d_dt, g->d_qc, g->d_Rq, g->d_AB[buf], g->d_errpart, g->nint, g->NFp, wantJ);
   g->launches++;
   if (nbA > 0) {
     k_lin_extra<G, 0, NT><<<nbA, NT, 0, g->stream>>>(g->d_listA, g->nA, X, land, g->d_xkind, g->d_xsa, g->d_xsb, g->d_xl, g->d_xrow, g->d_xprm, g->d_XR[buf],
@@ -1415,7 +1421,7 @@ int gpb_get_linearized_factor(gpb_graph* g, int kind, int idx, double* A_out, do
   const int offs = e.sa >= 0 ? 0 : bs;
   switch (e.kind) {
     case X_INTERP_RANGE: emit(0, D); emit(D, D); emit(bs, D); emit(bs + D, D); emit(2 * bs, DL); break;
-    case X_INTERP_ATTITUDE: case X_INTERP_GPS: emit(0, D); emit(D, D); emit(bs, D); emit(bs + D, D); break;
+    case X_INTERP_ATTITUDE: case X_INTERP_GPS: case X_INTERP_GPS_VW: emit(0, D); emit(D, D); emit(bs, D); emit(bs + D, D); break;
     case X_INTERP_PROJECTION: emit(0, D); emit(D, D); emit(bs, D); emit(bs + D, D); emit(2 * bs, DL); break;
     case X_PRIOR_POSE: emit(offs, D); break;
     case X_PRIOR_VEL: emit(offs + D, D); break;
@@ -1493,7 +1499,7 @@ int gpb_get_sizes(gpb_graph* g, gpb_sizes* s) {
     switch (e.kind) {
       case X_INTERP_RANGE: cols = 4 * D + g->DL; prm = 44; break;
       case X_INTERP_ATTITUDE: cols = 4 * D; prm = 80; break;
-      case X_INTERP_GPS: cols = 4 * D; prm = 8.0 * (2 + 3 + 9) + 20; break;
+      case X_INTERP_GPS: case X_INTERP_GPS_VW: cols = 4 * D; prm = 8.0 * (2 + 3 + 9) + 20; break;
       case X_INTERP_PROJECTION: cols = 4 * D + g->DL; prm = 8.0 * (2 + 2 + 4 + 5) + 20; break;
       case X_PRIOR_POSE: cols = D; prm = 8.0 * (g->PS + D * D); break;
       case X_PRIOR_VEL: cols = D; prm = 8.0 * (D + D * D); break;
@@ -1529,7 +1535,8 @@ int gpb_time_stage(gpb_graph* g, int stage, int reps, double* ms_out) {
   const int nb1 = (g->nint + NT - 1) / NT;
   auto gp_only = [&](auto tag) {
     constexpr int G = decltype(tag)::value; constexpr int SR = GroupTraits<G>::PS + GroupTraits<G>::D;
-    k_lin_gp<G, NT><<<nb1, NT, (size_t)(NT + 1) * SR * sizeof(double), g->stream>>>(g->d_X, g->d_dt, g->d_qc, g->d_Rq, g->d_AB[other], g->d_errpart, g->nint, g->NFp, 1);
+    if (G == G_POSE3 && g->vw) k_lin_gp<G_POSE3VW, NT><<<nb1, NT, (size_t)(NT + 1) * SR * sizeof(double), g->stream>>>(g->d_X, g->d_dt, g->d_qc, g->d_Rq, g->d_AB[other], g->d_errpart, g->nint, g->NFp, 1);
+    else k_lin_gp<G, NT><<<nb1, NT, (size_t)(NT + 1) * SR * sizeof(double), g->stream>>>(g->d_X, g->d_dt, g->d_qc, g->d_Rq, g->d_AB[other], g->d_errpart, g->nint, g->NFp, 1);
   };
   const int nbA = (g->nA + NT - 1) / NT, nbB = (int)(((size_t)g->nB * 32 + NT - 1) / NT);  // generic factors: one warp each
   auto extra_only = [&](auto tag) {
@@ -1578,7 +1585,7 @@ int gpb_time_stage(gpb_graph* g, int stage, int reps, double* ms_out) {
 // runs the SAME batched kernels on it and un-whitens the result.  Thread-safe (no shared state); slow by design (allocations).
 int gpb_eval_factor(int group, int kind, const double* x1, const double* v1, const double* x2, const double* v2, const double* landmark,
                     const double* prm, double* e_out, double* H_out, int* dims_out) {
-  if (group < 0 || group > 3 || !x1 || !prm || !e_out || !dims_out) return fail(GPB_ERR_ARG, "gpb_eval_factor: bad arguments");
+  if (group < 0 || group > GPB_POSE3VW || !x1 || !prm || !e_out || !dims_out) return fail(GPB_ERR_ARG, "gpb_eval_factor: bad arguments");
   gpb_graph* g = gpb_graph_create(group, 3, 2, 1);
   if (!g) return GPB_ERR_ARG;
   const int D = g->D, PS = g->PS, DL = g->DL;

@@ -17,10 +17,13 @@
 
 namespace gpb {
 
-enum Group { G_POSE3 = 0, G_POSE2 = 1, G_ROT3 = 2, G_LINEAR = 3 };
+// G_POSE3VW: SE(3) states whose velocity is [v_world(3) | w_world(3)] (the reference's "VW" family, gp/GaussianProcessPriorPose3VW.h);
+// a kernel class of G_POSE3, not a graph group of its own - record layout, block sizes, assembly, solver and retraction are G_POSE3's.
+enum Group { G_POSE3 = 0, G_POSE2 = 1, G_ROT3 = 2, G_LINEAR = 3, G_POSE3VW = 4 };
 
 template <int G> struct GroupTraits;
 template <> struct GroupTraits<G_POSE3> { static constexpr int D = 6, PS = 12, DL = 3; };
+template <> struct GroupTraits<G_POSE3VW> { static constexpr int D = 6, PS = 12, DL = 3; };
 template <> struct GroupTraits<G_POSE2> { static constexpr int D = 3, PS = 3, DL = 2; };
 template <> struct GroupTraits<G_ROT3> { static constexpr int D = 3, PS = 9, DL = 0; };
 template <> struct GroupTraits<G_LINEAR> { static constexpr int D = 3, PS = 3, DL = 2; };  // Linear<3> ("2DLinear" states)
@@ -117,6 +120,53 @@ template <int VAR, int C> GPB_HD void gp_prior_pose3_col(const GpPose3& o, const
   }
 }
 
+// ================================================================= GP prior, SE(3) "VW" (gp/GaussianProcessPriorPose3VW.h:62-117)
+// state record: [pose(12) | v_world(3) | w_world(3)], tangent order of a state [pose(6) | v(3) | w(3)].  convertVWtoVb
+// (gp/Pose3utils.cpp:47-64): vb = [R^T w; R^T v], d vb / d pose = [[vb.w]x 0; [vb.v]x 0], d vb / d v = [0; R^T], d vb / d w = [R^T; 0].
+// With those, the 12x25 [A|b] keeps the body-velocity factor's shape: p.a / p.Da / p.Db carry the extra pose terms
+// (H1 = -[a + dt H1p; D a + H1p], H4 = [b; D b + b H2p]) and only the velocity columns need the rotations.
+struct GpPose3VW { GpPose3 p; M3 R1, R2; };
+GPB_HD X6 vw_to_vb(const M3& R, const double* vw) { return x6(tmul(R, v3(vw[3], vw[4], vw[5])), tmul(R, v3(vw[0], vw[1], vw[2]))); }
+GPB_HD L6 vw_dpose(const X6& vb) { L6 r; r.A = skew(vb.w); r.B = skew(vb.v); r.C = m3_zero(); return r; }
+GPB_HD void gp_prior_pose3vw_eval(const double* s1, const double* s2, double dt, bool wantJ, GpPose3VW& o) {
+  const P3 T1 = p3_from_wire(s1), T2 = p3_from_wire(s2);
+  const X6 v1 = vw_to_vb(T1.R, s1 + 12), v2 = vw_to_vb(T2.R, s2 + 12);
+  const X6 r = se3_logmap(p3_between(T1, T2));
+  const JrinvCoef c = se3_jrinv_coef(dot(r.w, r.w));
+  o.p.b = se3_jrinv(r, c);
+  o.p.e_top = r - dt * v1;
+  o.p.e_bot = o.p.b * v2 - v1;
+  if (wantJ) {
+    o.R1 = T1.R; o.R2 = T2.R;
+    const L6 a = o.p.b - l6_ad(r);
+    const L6 D = se3_djrinv(r, v2, c);
+    const L6 H1p = vw_dpose(v1), H2p = vw_dpose(v2);
+    o.p.a = a + dt * H1p;
+    o.p.Da = D * a + H1p;
+    o.p.Db = D * o.p.b + o.p.b * H2p;
+  }
+}
+template <int VAR, int C> GPB_HD void gp_prior_pose3vw_col(const GpPose3VW& o, const GpWhiten& w, const double* Rq, double dt, double* out) {
+  if (VAR == 1 || VAR == 3) {  // [v | w] columns: u = d vb / d(v_C) = [0; R^T e_C]  or  d vb / d(w_{C-3}) = [R^T e_{C-3}; 0]
+    const M3& R = VAR == 1 ? o.R1 : o.R2;
+    const V3 rc = v3(R.m[3 * (C % 3)], R.m[3 * (C % 3) + 1], R.m[3 * (C % 3) + 2]);  // row C of R = column C of R^T
+    const X6 u = C < 3 ? x6(v3(0, 0, 0), rc) : x6(rc, v3(0, 0, 0));
+    double top[6], bot[6];
+    if (VAR == 1) {  // [-dt u; -u]
+#pragma unroll
+      for (int k = 0; k < 6; k++) { top[k] = dt * elem(u, k); bot[k] = elem(u, k); }
+      gp_whiten_col<6>(w, Rq, top, bot, -1.0, out);
+    } else {  // [0; Jr^-1 u]
+      const X6 bu = o.p.b * u;
+#pragma unroll
+      for (int k = 0; k < 6; k++) { top[k] = 0.0; bot[k] = elem(bu, k); }
+      gp_whiten_col<6>(w, Rq, top, bot, 1.0, out);
+    }
+  } else {
+    gp_prior_pose3_col<VAR, C>(o.p, w, Rq, dt, out);
+  }
+}
+
 // ================================================================= GP prior, D = 3 groups
 // Unwhitened: J_top = [Ja, -dt I, Jb, 0], J_bot = [0, -I, 0, +I] (Pose2/Rot3);  Linear: J_top = [I, dt I, -I, 0], J_bot = [0, I, 0, -I]
 struct GpD3 { V3 e_top, e_bot; M3 Ja, Jb; double s_v1, s_v2; };  // s_v1: sign of the v1 blocks (-1 Lie, +1 linear); s_v2 likewise for v2 bottom
@@ -179,7 +229,8 @@ template <int VAR, int C> GPB_HD void gp_prior_d3_col(const GpD3& o, const GpWhi
 // state_a / state_b are the two support states (i, i+1) of its interval (or (i, j) for a loop closure).
 enum ExtraKind {
   X_INTERP_RANGE = 1, X_INTERP_ATTITUDE = 2, X_PRIOR_POSE = 3, X_PRIOR_VEL = 4, X_PRIOR_LANDMARK = 5,
-  X_BETWEEN = 6, X_RANGE_2D = 7, X_RANGE_BEARING_2D = 8, X_ODOMETRY_2D = 9, X_INTERP_GPS = 10, X_INTERP_PROJECTION = 11
+  X_BETWEEN = 6, X_RANGE_2D = 7, X_RANGE_BEARING_2D = 8, X_ODOMETRY_2D = 9, X_INTERP_GPS = 10, X_INTERP_PROJECTION = 11,
+  X_INTERP_GPS_VW = 12  // GPInterpolatedGPSFactorPose3VW (velocities [v_world | w_world])
 };
 constexpr int XP_STRIDE = 56;  // doubles of parameters per extra factor (see ExtraParams below)
 // parameter record (doubles): [0] delta_t [1] tau [2] z [3] z2 [4..15] aux (sensor pose / nZ,bRef / value) [16] has_sensor
@@ -272,6 +323,56 @@ GPB_HD void interp_gps_pose3(const double* s1, const double* s2, const double* p
   if (!wantJ) return;
 #pragma unroll
   for (int k = 0; k < 3; k++) interp3_row(c, x6(v3(0, 0, 0), v3(c.T.R.m[3 * k], c.T.R.m[3 * k + 1], c.T.R.m[3 * k + 2])), o.H[k][0], o.H[k][1], o.H[k][2], o.H[k][3]);
+}
+// The same pipeline for the "VW" states (gp/GaussianProcessInterpolatorPose3VW.h:58-124): body velocities through convertVWtoVb,
+// two extra pose terms (Hvel1 H1p, Hvel2 H2p) and the velocity rows rotated into the world frame.  Output rows are in the
+// tangent order of a VW state: H2 = [d/dv1 | d/dw1], H4 = [d/dv2 | d/dw2] (stored in the (w, v) slots of an X6 in that order).
+struct Interp3VW { Interp3 c; M3 R1, R2; L6 H1p, bH2p; };
+GPB_HD void interp3vw_setup(const double* s1, const double* s2, const double* prm, bool wantJ, Interp3VW& o) {
+  Interp3& c = o.c;
+  const double dt = prm[0], tau = prm[1];
+  const P3 T1 = p3_from_wire(s1), T2 = p3_from_wire(s2);
+  const X6 v1 = vw_to_vb(T1.R, s1 + 12), v2 = vw_to_vb(T2.R, s2 + 12);
+  c.r = se3_logmap(p3_between(T1, T2));
+  const JrinvCoef cf = se3_jrinv_coef(dot(c.r.w, c.r.w));
+  c.b = se3_jrinv(c.r, cf);
+  const X6 f = c.b * v2;
+  c.ic = interp_coef(dt, tau);
+  c.xi = c.ic.lam12 * v1 + c.ic.psi11 * c.r + c.ic.psi12 * f;
+  c.dT = se3_expmap(c.xi);
+  c.T = p3_compose(T1, c.dT);
+  c.has_sensor = prm[16] != 0.0;
+  if (c.has_sensor) { c.S = p3_from_wire(prm + 4); c.T = p3_compose(c.T, c.S); }
+  if (!wantJ) return;
+  if (c.has_sensor) c.adS = l6_adjoint(p3_inverse(c.S));
+  c.jr = se3_jr(c.xi);
+  c.a = c.b - l6_ad(c.r);
+  c.Dd = se3_djrinv(c.r, v2, cf);
+  c.adT = l6_adjoint(p3_inverse(c.dT));
+  o.R1 = T1.R; o.R2 = T2.R;
+  o.H1p = vw_dpose(v1);
+  o.bH2p = c.b * vw_dpose(v2);
+}
+GPB_HD void interp3vw_row(const Interp3VW& o, X6 hpose, X6& H1, X6& H2, X6& H3, X6& H4) {
+  const Interp3& c = o.c;
+  if (c.has_sensor) hpose = rowmul(hpose, c.adS);
+  const X6 g = rowmul(hpose, c.jr);
+  const X6 gD = rowmul(g, c.Dd);
+  const X6 k = c.ic.psi11 * g + c.ic.psi12 * gD;
+  H1 = rowmul(hpose, c.adT) - rowmul(k, c.a) + c.ic.lam12 * rowmul(g, o.H1p);
+  H2 = c.ic.lam12 * x6(o.R1 * g.v, o.R1 * g.w);          // row (g.v)^T R1^T over v1, (g.w)^T R1^T over w1
+  H3 = rowmul(k, c.b) + c.ic.psi12 * rowmul(g, o.bH2p);
+  const X6 gb = rowmul(g, c.b);
+  H4 = c.ic.psi12 * x6(o.R2 * gb.v, o.R2 * gb.w);
+}
+// slam/GPInterpolatedGPSFactorPose3VW.h:71-106
+GPB_HD void interp_gps_pose3vw(const double* s1, const double* s2, const double* prm, bool wantJ, Gps3Out& o) {
+  Interp3VW c;
+  interp3vw_setup(s1, s2, prm, wantJ, c);
+  o.e = c.c.T.t - v3(prm[40], prm[41], prm[42]);
+  if (!wantJ) return;
+#pragma unroll
+  for (int k = 0; k < 3; k++) interp3vw_row(c, x6(v3(0, 0, 0), v3(c.c.T.R.m[3 * k], c.c.T.R.m[3 * k + 1], c.c.T.R.m[3 * k + 2])), o.H[k][0], o.H[k][1], o.H[k][2], o.H[k][3]);
 }
 // slam/GPInterpolatedProjectionFactorPose3.h:82-139 with Cal3_S2: e = K(pi(T^-1 l)) - measured; a landmark behind the camera
 // (gtsam::CheiralityException, :123-138) gives zero Jacobians and the residual (2 fx, 2 fx).

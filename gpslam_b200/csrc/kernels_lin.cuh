@@ -96,6 +96,19 @@ __global__ void __launch_bounds__(NT) k_lin_gp(const double* __restrict__ X, con
           static_for<0, 6>([&](auto c) { gp_prior_pose3_col<2, decltype(c)::value>(o, w, Rq, h, col); store(12 + decltype(c)::value); });
           static_for<0, 6>([&](auto c) { gp_prior_pose3_col<3, decltype(c)::value>(o, w, Rq, h, col); store(18 + decltype(c)::value); });
         }
+      } else if constexpr (G == G_POSE3VW) {
+        GpPose3VW o;
+        gp_prior_pose3vw_eval(s1, s2, h, wantJ != 0, o);
+        gp_prior_pose3vw_col<4, 0>(o, w, Rq, h, col);
+#pragma unroll
+        for (int k = 0; k < 12; k++) err += col[k] * col[k];
+        if (wantJ) {
+          store(24);
+          static_for<0, 6>([&](auto c) { gp_prior_pose3vw_col<0, decltype(c)::value>(o, w, Rq, h, col); store(decltype(c)::value); });
+          static_for<0, 6>([&](auto c) { gp_prior_pose3vw_col<1, decltype(c)::value>(o, w, Rq, h, col); store(6 + decltype(c)::value); });
+          static_for<0, 6>([&](auto c) { gp_prior_pose3vw_col<2, decltype(c)::value>(o, w, Rq, h, col); store(12 + decltype(c)::value); });
+          static_for<0, 6>([&](auto c) { gp_prior_pose3vw_col<3, decltype(c)::value>(o, w, Rq, h, col); store(18 + decltype(c)::value); });
+        }
       } else {
         GpD3 o;
         gp_prior_d3_eval<G>(s1, s2, h, wantJ != 0, o);
@@ -179,10 +192,11 @@ __device__ __forceinline__ void extra_rows(int kind, const double* __restrict__ 
   }
   }
   if constexpr (CLS == 2) {
-  if (kind == X_INTERP_GPS) {
+  if (kind == X_INTERP_GPS || kind == X_INTERP_GPS_VW) {
     if constexpr (G == G_POSE3) {
       Gps3Out o;
-      interp_gps_pose3(X + (size_t)sa * SR, X + (size_t)sb * SR, prm, wantJ, o);
+      if (kind == X_INTERP_GPS) interp_gps_pose3(X + (size_t)sa * SR, X + (size_t)sb * SR, prm, wantJ, o);
+      else interp_gps_pose3vw(X + (size_t)sa * SR, X + (size_t)sb * SR, prm, wantJ, o);
       // whiten with the dense upper-triangular 3x3 sqrt information: row r = sum_{k >= r} R[r,k] (.)
       const double ev[3] = {o.e.x, o.e.y, o.e.z};
 #pragma unroll

@@ -7,6 +7,7 @@ Pure numpy; no arithmetic of the hot path lives here (ground truth uses its own 
 import numpy as np
 
 POSE3, POSE2, ROT3, LINEAR = 0, 1, 2, 3
+POSE3VW = 4  # graph group of SE(3) states with [v_world | w_world] velocities (Config.vw); cfg.group stays POSE3
 
 
 def _skew(w):
@@ -46,7 +47,7 @@ def _wire3(R, t):
 
 class Config:
     def __init__(self, name, group, n_states, n_landmarks=0, range_per_state=0.0, dt=0.1, seed=0, qc_sigma=0.1, prior_every=100,
-                 attitude_every=0, odometry=False, init_noise=0.05, zero_rot_fraction=0.01, n_closures=0, closure_min_gap=0, closure_ends=False, gps_every=0, proj_per_state=0.0):
+                 attitude_every=0, odometry=False, init_noise=0.05, zero_rot_fraction=0.01, n_closures=0, closure_min_gap=0, closure_ends=False, gps_every=0, proj_per_state=0.0, vw=False):
         self.__dict__.update(locals())
         del self.__dict__["self"]
 
@@ -62,6 +63,10 @@ def config(name):
         return Config("C3", POSE3, 100000, 16, 0.5, dt=0.1, seed=base + 3, qc_sigma=0.1)
     if name == "C4":
         return Config("C4", ROT3, 1000000, 0, 0.0, dt=0.005, seed=base + 4, qc_sigma=100.0, prior_every=0, attitude_every=4)
+    if name == "VW":
+        # SE(3) "VW" family: GaussianProcessPriorPose3VW chain + GPInterpolatedGPSFactorPose3VW fixes; the
+        # reference has no range / projection factor for these states, so no landmarks
+        return Config("VW", POSE3, 10000, 0, 0.0, dt=0.1, seed=base + 6, qc_sigma=0.1, gps_every=5, vw=True)
     if name == "C5":
         # K = 128 loop closures (BetweenFactor<Pose3>, sigma 0.05) between random state pairs >= 10 000 states apart
         return Config("C5", POSE3, 1000000, 16, 0.5, dt=0.1, seed=base + 5, qc_sigma=0.1, n_closures=128, closure_min_gap=10000)
@@ -136,11 +141,19 @@ def build(cfg, make_graph, finalize=True):
     DL = {POSE3: 3, POSE2: 2, ROT3: 0, LINEAR: 2}[group]
     poses, vels = ground_truth(cfg)
     L = cfg.n_landmarks if DL else 0
-    g = make_graph(group, N, L)
+    vw = bool(getattr(cfg, "vw", False)) and group == POSE3
+    g = make_graph(POSE3VW if vw else group, N, L)
+    # wire velocities: the body twist (w, v), or for VW states [v_world | w_world] = [R v | R w] (gp/Pose3utils.cpp:27-45)
+    wire_vels = vels
+    if vw:
+        Rs = poses[:, :9].reshape(N, 3, 3).transpose(0, 2, 1)
+        wire_vels = np.concatenate([np.einsum("nij,nj->ni", Rs, vels[:, 3:]), np.einsum("nij,nj->ni", Rs, vels[:, :3])], axis=1)
     g.add_qc_model(np.eye(D) * cfg.qc_sigma ** 2)
     g.add_gp_prior(np.arange(N - 1), np.full(N - 1, dt))
     iso = lambda n, s: np.eye(n) / s
     lands = np.zeros((L, max(DL, 1)))
+    if L and vw:
+        raise ValueError("synth: Pose3 VW graphs carry no landmarks (no range / projection factor in the reference)")
     if L:
         if group == POSE3:
             ctr = poses[:, 9:12].mean(axis=0); span = np.abs(poses[:, 9:12] - ctr).max() + 10.0
@@ -199,7 +212,7 @@ def build(cfg, make_graph, finalize=True):
     # gauge: pose + velocity prior on state 0, sparse pose priors along the chain
     s0 = 1e-3 if group != POSE2 else 1.0
     g.add_prior_pose(0, poses[0], iso(D, s0))
-    g.add_prior_vel(0, vels[0], iso(D, 1e-3 if group != POSE2 else 1.0))
+    g.add_prior_vel(0, wire_vels[0], iso(D, 1e-3 if group != POSE2 else 1.0))
     if cfg.prior_every:
         for i in range(cfg.prior_every, N, cfg.prior_every):
             g.add_prior_pose(i, _retract(group, poses[i], rng.normal(size=D) * 0.1), iso(D, 0.1))
@@ -231,7 +244,7 @@ def build(cfg, make_graph, finalize=True):
     g.set_values(init, np.zeros((N, D)), lands + (rng.normal(size=lands.shape) * 0.5 if L else 0))
     if finalize and hasattr(g, "finalize"):
         g.finalize()
-    return g, dict(poses=poses, vels=vels, lands=lands)
+    return g, dict(poses=poses, vels=wire_vels, lands=lands)
 
 
 def _body(pose, v):

@@ -24,7 +24,14 @@ typedef struct gpb_graph gpb_graph;
 
 /* state manifold of the trajectory; selects the factor family
  * (gp/GaussianProcessPrior{Pose3,Pose2,Rot3,Linear}.h and the matching interpolators) */
-enum { GPB_POSE3 = 0, GPB_POSE2 = 1, GPB_ROT3 = 2, GPB_LINEAR = 3 };
+/* GPB_POSE3VW: the reference's Pose3 "VW" family (gp/GaussianProcessPriorPose3VW.h, gp/GaussianProcessInterpolatorPose3VW.h,
+ * slam/GPInterpolatedGPSFactorPose3VW.h): states (Pose3 x, Vector3 v, Vector3 w) with v, w in the world frame.  Wire layout of a
+ * velocity: [v(3) | w(3)]; tangent order of a state: [pose(6) | v(3) | w(3)].  On such a graph gpb_add_gp_prior adds
+ * GaussianProcessPriorPose3VW(x_i, v_i, w_i, x_{i+1}, v_{i+1}, w_{i+1}, delta_t, Qc) and gpb_add_interp_gps adds
+ * GPInterpolatedGPSFactorPose3VW; PriorFactor / BetweenFactor work as on GPB_POSE3 (gpb_add_prior_vel: one 6x6 sqrt information
+ * over [v | w], i.e. the reference's two PriorFactor<Vector3> as a block-diagonal); range / projection factors have no VW
+ * variant in the reference and are rejected. */
+enum { GPB_POSE3 = 0, GPB_POSE2 = 1, GPB_ROT3 = 2, GPB_LINEAR = 3, GPB_POSE3VW = 4 };
 
 enum { GPB_OK = 0, GPB_ERR_ARG = -1, GPB_ERR_CUDA = -2, GPB_ERR_STATE = -3, GPB_ERR_UNSUPPORTED = -4, GPB_ERR_NUMERIC = -5 };
 
@@ -51,6 +58,8 @@ void gpb_default_params(gpb_params* p, int use_lm);
 /* -- graph construction: stands in for NonlinearFactorGraph::add + Values::insert
  *    (matlab/PlazaPose2.m:90-204).  dim is used by GPB_LINEAR only (supported: 3). */
 gpb_graph* gpb_graph_create(int group, int dim, int n_states, int n_landmarks);
+/* the group the graph was created with (GPB_POSE3VW for a VW graph) */
+int gpb_graph_group(const gpb_graph* g);
 void gpb_graph_destroy(gpb_graph* g);
 
 /* getQc (gp/GPutils.cpp:16-20): registers a D x D process-noise covariance Qc, returns its id */

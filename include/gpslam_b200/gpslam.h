@@ -322,6 +322,124 @@ class GPInterpolatedProjectionFactorPose3 : public NonlinearFactor {
   }
 };
 
+// ---------------------------------------------------------------------------------- Pose3 "VW" family
+// States (Pose3 'x', Vector3 'v', Vector3 'w'): linear and angular velocity in the world frame (gp/Pose3utils.cpp:27-64).  The
+// C ABI carries them as one graph group (GPB_POSE3VW, velocity wire [v | w]); the 12x6 / 3x6 velocity blocks it returns are
+// split back into the reference's separate H2|H3 and H5|H6 here.
+namespace detail {
+inline void splitVW(const gtsam::Matrix& H, gtsam::Matrix* Hv, gtsam::Matrix* Hw) {
+  for (int half = 0; half < 2; half++) {
+    gtsam::Matrix* o = half ? Hw : Hv;
+    if (!o) continue;
+    *o = gtsam::Matrix(H.rows, 3);
+    for (int c = 0; c < 3; c++) for (int r = 0; r < H.rows; r++) (*o)(r, c) = H(r, 3 * half + c);
+  }
+}
+inline gtsam::Vector evalVW(int kind, const gtsam::Pose3& pose1, const gtsam::Vector3& vel1, const gtsam::Vector3& omega1, const gtsam::Pose3& pose2,
+                            const gtsam::Vector3& vel2, const gtsam::Vector3& omega2, const double* prm, gtsam::Matrix* H1, gtsam::Matrix* H2, gtsam::Matrix* H3,
+                            gtsam::Matrix* H4, gtsam::Matrix* H5, gtsam::Matrix* H6) {
+  double x1[12], x2[12], v1[6], v2[6];
+  wire(pose1, x1); wire(pose2, x2); wire(vel1, v1); wire(omega1, v1 + 3); wire(vel2, v2); wire(omega2, v2 + 3);
+  gtsam::Matrix Hvw1, Hvw2;
+  const gtsam::Vector e = eval(GPB_POSE3VW, kind, x1, v1, x2, v2, nullptr, prm, {H1, (H2 || H3) ? &Hvw1 : nullptr, H4, (H5 || H6) ? &Hvw2 : nullptr});
+  if (H2 || H3) splitVW(Hvw1, H2, H3);
+  if (H5 || H6) splitVW(Hvw2, H5, H6);
+  return e;
+}
+inline void checkVWKeys(const std::map<gtsam::Key, int>& sidx, const std::vector<gtsam::Key>& k) {
+  const int i = stateOf(sidx, k[0]), j = stateOf(sidx, k[3]);
+  if (j != i + 1 || stateOf(sidx, k[1]) != i || stateOf(sidx, k[2]) != i || stateOf(sidx, k[4]) != j || stateOf(sidx, k[5]) != j)
+    throw std::runtime_error("gpslam_b200: a Pose3VW factor must join consecutive states (x_i, v_i, w_i, x_{i+1}, v_{i+1}, w_{i+1})");
+}
+}  // namespace detail
+
+/// gp/GaussianProcessPriorPose3VW.h:43-51 (6-way factor; evaluateError :62-117)
+class GaussianProcessPriorPose3VW : public NonlinearFactor {
+  std::vector<gtsam::Key> keys_;
+  double delta_t_;
+  gtsam::SharedNoiseModel Qc_;
+
+ public:
+  GaussianProcessPriorPose3VW(gtsam::Key poseKey1, gtsam::Key velKey1, gtsam::Key omegaKey1, gtsam::Key poseKey2, gtsam::Key velKey2, gtsam::Key omegaKey2, double delta_t,
+                              const gtsam::SharedNoiseModel& Qc_model)
+      : keys_{poseKey1, velKey1, omegaKey1, poseKey2, velKey2, omegaKey2}, delta_t_(delta_t), Qc_(Qc_model) {
+    if (!Qc_model) throw std::runtime_error("gpslam_b200: Qc model is not Gaussian");
+  }
+  const std::vector<gtsam::Key>& keys() const override { return keys_; }
+  size_t size() const override { return 6; }
+  gtsam::Vector evaluateError(const gtsam::Pose3& pose1, const gtsam::Vector3& vel1, const gtsam::Vector3& omega1, const gtsam::Pose3& pose2, const gtsam::Vector3& vel2,
+                              const gtsam::Vector3& omega2, gtsam::Matrix* H1 = nullptr, gtsam::Matrix* H2 = nullptr, gtsam::Matrix* H3 = nullptr, gtsam::Matrix* H4 = nullptr,
+                              gtsam::Matrix* H5 = nullptr, gtsam::Matrix* H6 = nullptr) const {
+    double prm[48] = {0};
+    prm[0] = delta_t_;
+    return detail::evalVW(GPB_F_GP_PRIOR, pose1, vel1, omega1, pose2, vel2, omega2, prm, H1, H2, H3, H4, H5, H6);
+  }
+  bool equals(const GaussianProcessPriorPose3VW& e, double tol = 1e-9) const { return keys_ == e.keys_ && std::fabs(delta_t_ - e.delta_t_) < tol; }
+  void lower(gpb_graph* g, int qc_of(void*, const gtsam::Matrix&), void* ctx, const std::map<gtsam::Key, int>& sidx, const std::map<gtsam::Key, int>&) const override {
+    if (gpb_graph_group(g) != GPB_POSE3VW) throw std::runtime_error("gpslam_b200: GaussianProcessPriorPose3VW needs an optimiser created with group GPB_POSE3VW");
+    detail::checkVWKeys(sidx, keys_);
+    const int i = detail::stateOf(sidx, keys_[0]);
+    detail::check(gpb_add_gp_prior(g, 1, &i, &delta_t_, qc_of(ctx, Qc_->cov)));
+  }
+};
+
+/// gp/GaussianProcessInterpolatorPose3VW.h:43-124 as a value type: interpolatePose through the GPS factor's device pipeline
+/// (translation of T(tau) = its residual against a zero measurement) is not exposed; the class carries (Qc, delta_t, tau) for
+/// equals() and for the factors below.
+class GaussianProcessInterpolatorPose3VW {
+  double delta_t_ = 0, tau_ = 0;
+  gtsam::SharedNoiseModel Qc_;
+
+ public:
+  GaussianProcessInterpolatorPose3VW() {}
+  GaussianProcessInterpolatorPose3VW(const gtsam::SharedNoiseModel& Qc_model, double delta_t, double tau) : delta_t_(delta_t), tau_(tau), Qc_(Qc_model) {}
+  double delta_t() const { return delta_t_; }
+  double tau() const { return tau_; }
+  const gtsam::SharedNoiseModel& Qc() const { return Qc_; }
+  bool equals(const GaussianProcessInterpolatorPose3VW& e, double tol = 1e-9) const {
+    return std::fabs(delta_t_ - e.delta_t_) < tol && std::fabs(tau_ - e.tau_) < tol && Qc_ && e.Qc_ && Qc_->cov.a == e.Qc_->cov.a;
+  }
+};
+
+/// slam/GPInterpolatedGPSFactorPose3VW.h:50-61 (evaluateError :71-106)
+class GPInterpolatedGPSFactorPose3VW : public NonlinearFactor {
+  std::vector<gtsam::Key> keys_;
+  gtsam::Point3 measured_;
+  GaussianProcessInterpolatorPose3VW GPbase_;
+  gtsam::SharedNoiseModel meas_;
+  bool has_sensor_ = false;
+  gtsam::Pose3 body_P_sensor_;
+
+ public:
+  GPInterpolatedGPSFactorPose3VW(const gtsam::Point3& measured_point3, const gtsam::SharedNoiseModel& meas_model, const gtsam::SharedNoiseModel& Qc_model,
+                                 gtsam::Key poseKey1, gtsam::Key velKey1, gtsam::Key omegaKey1, gtsam::Key poseKey2, gtsam::Key velKey2, gtsam::Key omegaKey2, double delta_t,
+                                 double tau, const gtsam::Pose3* body_P_sensor = nullptr)
+      : keys_{poseKey1, velKey1, omegaKey1, poseKey2, velKey2, omegaKey2}, measured_(measured_point3), GPbase_(Qc_model, delta_t, tau), meas_(meas_model) {
+    if (body_P_sensor) { has_sensor_ = true; body_P_sensor_ = *body_P_sensor; }
+  }
+  const std::vector<gtsam::Key>& keys() const override { return keys_; }
+  size_t size() const override { return 6; }
+  gtsam::Point3 measured() const { return measured_; }
+  gtsam::Vector evaluateError(const gtsam::Pose3& pose1, const gtsam::Vector3& vel1, const gtsam::Vector3& omega1, const gtsam::Pose3& pose2, const gtsam::Vector3& vel2,
+                              const gtsam::Vector3& omega2, gtsam::Matrix* H1 = nullptr, gtsam::Matrix* H2 = nullptr, gtsam::Matrix* H3 = nullptr, gtsam::Matrix* H4 = nullptr,
+                              gtsam::Matrix* H5 = nullptr, gtsam::Matrix* H6 = nullptr) const {
+    double prm[48] = {0};
+    prm[0] = GPbase_.delta_t(); prm[1] = GPbase_.tau(); detail::wire(measured_, prm + 40);
+    if (has_sensor_) { detail::wire(body_P_sensor_, prm + 4); prm[16] = 1.0; }
+    return detail::evalVW(GPB_F_INTERP_GPS, pose1, vel1, omega1, pose2, vel2, omega2, prm, H1, H2, H3, H4, H5, H6);
+  }
+  void lower(gpb_graph* g, int qc_of(void*, const gtsam::Matrix&), void* ctx, const std::map<gtsam::Key, int>& sidx, const std::map<gtsam::Key, int>&) const override {
+    if (gpb_graph_group(g) != GPB_POSE3VW) throw std::runtime_error("gpslam_b200: GPInterpolatedGPSFactorPose3VW needs an optimiser created with group GPB_POSE3VW");
+    detail::checkVWKeys(sidx, keys_);
+    const int i = detail::stateOf(sidx, keys_[0]);
+    double m[3], bps[12];
+    detail::wire(measured_, m);
+    if (has_sensor_) detail::wire(body_P_sensor_, bps);
+    const double dt = GPbase_.delta_t(), tau = GPbase_.tau();
+    detail::check(gpb_add_interp_gps(g, 1, &i, m, detail::sqrtInfo(meas_).a.data(), &dt, &tau, qc_of(ctx, GPbase_.Qc()->cov), has_sensor_ ? bps : nullptr));
+  }
+};
+
 /// slam/GPInterpolatedAttitudeFactorRot3.h:44-51
 class GPInterpolatedAttitudeFactorRot3 : public NonlinearFactor {
   std::vector<gtsam::Key> keys_;
@@ -365,6 +483,15 @@ class PriorFactor : public NonlinearFactor {
     const gtsam::Matrix& R = detail::sqrtInfo(model_);
     const char c = gtsam::symbolChr(keys_[0]);
     if (c == 'l') detail::check(gpb_add_prior_landmark(g, detail::stateOf(lidx, keys_[0]), v, R.a.data()));
+    else if ((c == 'v' || c == 'w') && gpb_graph_group(g) == GPB_POSE3VW) {
+      // PriorFactor<Vector3> on the linear ('v') or angular ('w') velocity of a VW state: a 6x6 sqrt information over [v | w] whose
+      // other half is zero (zero rows add nothing to the error or the normal equations)
+      if (R.rows != 3) throw std::runtime_error("gpslam_b200: PriorFactor on a VW velocity key needs a 3-dimensional model");
+      const int o = c == 'w' ? 3 : 0;
+      double v6[6] = {0}, R6[36] = {0};
+      for (int k = 0; k < 3; k++) { v6[o + k] = v[k]; for (int r = 0; r < 3; r++) R6[(o + r) + 6 * (o + k)] = R(r, k); }
+      detail::check(gpb_add_prior_vel(g, detail::stateOf(sidx, keys_[0]), v6, R6));
+    }
     else if (c == 'v') detail::check(gpb_add_prior_vel(g, detail::stateOf(sidx, keys_[0]), v, R.a.data()));
     else detail::check(gpb_add_prior_pose(g, detail::stateOf(sidx, keys_[0]), v, R.a.data()));
   }
@@ -435,7 +562,8 @@ class NonlinearOptimizer {
  protected:
   gpb_graph* g_ = nullptr;
   Values values_;
-  std::vector<gtsam::Key> xkeys_, vkeys_, lkeys_;
+  std::vector<gtsam::Key> xkeys_, vkeys_, wkeys_, lkeys_;  // wkeys_: angular-velocity keys of a GPB_POSE3VW graph
+  bool vw_ = false;
   int PS_ = 0, D_ = 0, DL_ = 0, iterations_ = 0;
   double error_ = 0.0;
   gpb_params params_;
@@ -452,18 +580,22 @@ class NonlinearOptimizer {
   void pull() {
     std::vector<double> P(xkeys_.size() * PS_), V(xkeys_.size() * D_), L(lkeys_.size() * (DL_ ? DL_ : 1));
     detail::check(gpb_get_values(g_, P.data(), V.data(), lkeys_.empty() ? nullptr : L.data()));
-    for (size_t i = 0; i < xkeys_.size(); i++) { values_.all()[xkeys_[i]].assign(P.begin() + i * PS_, P.begin() + (i + 1) * PS_); values_.all()[vkeys_[i]].assign(V.begin() + i * D_, V.begin() + (i + 1) * D_); }
+    for (size_t i = 0; i < xkeys_.size(); i++) {
+      values_.all()[xkeys_[i]].assign(P.begin() + i * PS_, P.begin() + (i + 1) * PS_);
+      if (vw_) { values_.all()[vkeys_[i]].assign(V.begin() + i * 6, V.begin() + i * 6 + 3); values_.all()[wkeys_[i]].assign(V.begin() + i * 6 + 3, V.begin() + i * 6 + 6); }
+      else values_.all()[vkeys_[i]].assign(V.begin() + i * D_, V.begin() + (i + 1) * D_);
+    }
     for (size_t l = 0; l < lkeys_.size(); l++) values_.all()[lkeys_[l]].assign(L.begin() + l * DL_, L.begin() + (l + 1) * DL_);
   }
 
  public:
-  NonlinearOptimizer(const NonlinearFactorGraph& graph, const Values& initial, int group, int device = 0) : values_(initial) {
-    // states: keys 'x' i with consecutive indices, each with its velocity key 'v' i; landmarks 'l'
+  NonlinearOptimizer(const NonlinearFactorGraph& graph, const Values& initial, int group, int device = 0) : values_(initial), vw_(group == GPB_POSE3VW) {
+    // states: keys 'x' i with consecutive indices, each with its velocity key 'v' i (and 'w' i on a VW graph); landmarks 'l'
     std::map<std::uint64_t, gtsam::Key> xs, ls;
     for (const auto& kv : initial.all()) {
       const char c = gtsam::symbolChr(kv.first);
       if (c == 'x') xs[gtsam::symbolIndex(kv.first)] = kv.first; else if (c == 'l') ls[gtsam::symbolIndex(kv.first)] = kv.first;
-      else if (c != 'v') throw std::runtime_error("gpslam_b200: only 'x', 'v', 'l' keys are supported");
+      else if (c != 'v' && !(c == 'w' && vw_)) throw std::runtime_error("gpslam_b200: only 'x', 'v', 'l' keys are supported ('w' on GPB_POSE3VW graphs)");
     }
     if (xs.size() < 2) throw std::runtime_error("gpslam_b200: need at least two states");
     std::map<gtsam::Key, int> sidx, lidx;
@@ -474,17 +606,24 @@ class NonlinearOptimizer {
       const int i = static_cast<int>(xkeys_.size());
       xkeys_.push_back(kv.second); vkeys_.push_back(gtsam::Symbol('v', kv.first));
       sidx[kv.second] = i; sidx[vkeys_.back()] = i;
+      if (vw_) { wkeys_.push_back(gtsam::Symbol('w', kv.first)); sidx[wkeys_.back()] = i; }
     }
     for (const auto& kv : ls) { lidx[kv.second] = static_cast<int>(lkeys_.size()); lkeys_.push_back(kv.second); }
-    PS_ = group == GPB_POSE3 ? 12 : group == GPB_ROT3 ? 9 : 3; D_ = group == GPB_POSE3 ? 6 : 3; DL_ = group == GPB_POSE3 ? 3 : group == GPB_ROT3 ? 0 : 2;
+    const bool se3 = group == GPB_POSE3 || vw_;
+    PS_ = se3 ? 12 : group == GPB_ROT3 ? 9 : 3; D_ = se3 ? 6 : 3; DL_ = se3 ? 3 : group == GPB_ROT3 ? 0 : 2;
     g_ = gpb_graph_create(group, 3, static_cast<int>(xkeys_.size()), static_cast<int>(lkeys_.size()));
     if (!g_) throw std::runtime_error(std::string("gpslam_b200: ") + gpb_last_error());
     for (const auto& f : graph.factors()) f->lower(g_, &NonlinearOptimizer::qcOf, this, sidx, lidx);
     std::vector<double> P(xkeys_.size() * PS_), V(xkeys_.size() * D_), L(lkeys_.size() * (DL_ ? DL_ : 1));
     for (size_t i = 0; i < xkeys_.size(); i++) {
       const auto& p = initial.wire(xkeys_[i]); const auto& v = initial.wire(vkeys_[i]);
-      if (static_cast<int>(p.size()) != PS_ || static_cast<int>(v.size()) != D_) throw std::runtime_error("gpslam_b200: value type does not match the trajectory group");
+      if (static_cast<int>(p.size()) != PS_ || static_cast<int>(v.size()) != (vw_ ? 3 : D_)) throw std::runtime_error("gpslam_b200: value type does not match the trajectory group");
       std::copy(p.begin(), p.end(), P.begin() + i * PS_); std::copy(v.begin(), v.end(), V.begin() + i * D_);
+      if (vw_) {
+        const auto& w = initial.wire(wkeys_[i]);
+        if (w.size() != 3) throw std::runtime_error("gpslam_b200: 'w' values must be Vector3");
+        std::copy(w.begin(), w.end(), V.begin() + i * D_ + 3);
+      }
     }
     for (size_t l = 0; l < lkeys_.size(); l++) { const auto& w = initial.wire(lkeys_[l]); std::copy(w.begin(), w.end(), L.begin() + l * DL_); }
     detail::check(gpb_set_values(g_, P.data(), V.data(), lkeys_.empty() ? nullptr : L.data()));

@@ -13,10 +13,12 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
-POSE3, POSE2, ROT3, LINEAR = 0, 1, 2, 3
-POSE_STORAGE = {POSE3: 12, POSE2: 3, ROT3: 9}
-TANGENT_DIM = {POSE3: 6, POSE2: 3, ROT3: 3}
-LANDMARK_DIM = {POSE3: 3, POSE2: 2, ROT3: 0, LINEAR: 2}
+# POSE3VW: Pose3 with [v_world; w_world] velocities (the reference's "VW" family); the C side keeps it as a POSE3 graph whose
+# GP-prior / GPS factors are the VW kinds, exactly like the engine's GPB_POSE3VW
+POSE3, POSE2, ROT3, LINEAR, POSE3VW = 0, 1, 2, 3, 4
+POSE_STORAGE = {POSE3: 12, POSE2: 3, ROT3: 9, POSE3VW: 12}
+TANGENT_DIM = {POSE3: 6, POSE2: 3, ROT3: 3, POSE3VW: 6}
+LANDMARK_DIM = {POSE3: 3, POSE2: 2, ROT3: 0, LINEAR: 2, POSE3VW: 3}
 
 
 def build():
@@ -87,7 +89,8 @@ class Graph:
         self.PS = POSE_STORAGE.get(group, dim)
         self.DL = LANDMARK_DIM[group]
         self.NL = n_landmarks if self.DL else 0
-        self.h = C.c_void_p(self.L.gpo_graph_create(group, dim, n_states, n_landmarks))
+        self.vw = group == POSE3VW
+        self.h = C.c_void_p(self.L.gpo_graph_create(POSE3 if self.vw else group, dim, n_states, n_landmarks))
 
     def __del__(self):
         if getattr(self, "h", None):
@@ -103,6 +106,8 @@ class Graph:
     def add_gp_prior(self, i, delta_t, qc=0):
         i = np.ascontiguousarray(np.atleast_1d(i), dtype=np.int32)
         dt = _f64(np.broadcast_to(np.atleast_1d(delta_t), i.shape))
+        if self.vw:
+            return self.add_gp_prior_vw(i, delta_t, qc)
         self.L.gpo_add_gp_prior(self.h, C.c_int(len(i)), _ip(i), _dp(dt), C.c_int(qc))
 
     def add_interp_range(self, i, l, z, sigma, delta_t, tau, qc=0, body_P_sensor=None):
@@ -110,10 +115,13 @@ class Graph:
         l = np.ascontiguousarray(np.broadcast_to(np.atleast_1d(l), i.shape), dtype=np.int32)
         b = lambda a: _f64(np.broadcast_to(np.atleast_1d(a), i.shape))
         bps = _f64(body_P_sensor) if body_P_sensor is not None else None
+        assert not self.vw, "no range factor for Pose3 VW states in the reference"
         self.L.gpo_add_interp_range(self.h, C.c_int(len(i)), _ip(i), _ip(l), _dp(b(z)), _dp(b(sigma)), _dp(b(delta_t)), _dp(b(tau)), C.c_int(qc), _dp(bps))
 
     def add_interp_gps(self, i, meas, sqrt_info, delta_t, tau, qc=0, body_P_sensor=None):
         """GPInterpolatedGPSFactorPose3: meas [n x 3] points, sqrt_info 3x3 upper-triangular R shared by the n factors"""
+        if self.vw:
+            return self.add_interp_gps_vw(i, meas, sqrt_info, delta_t, tau, qc, body_P_sensor)
         i = np.ascontiguousarray(np.atleast_1d(i), dtype=np.int32)
         b = lambda a: _f64(np.broadcast_to(np.atleast_1d(a), i.shape))
         m = _f64(np.broadcast_to(np.asarray(meas, dtype=np.float64).reshape(-1, 3), (len(i), 3)))
@@ -309,9 +317,6 @@ def lambda_psi(D, Qc, delta_t, tau):
     return La.reshape(2 * D, 2 * D).T.copy(), Ps.reshape(2 * D, 2 * D).T.copy()
 
 
-POSE3VW = 4  # interpolate() only: Pose3 with [v_world; w_world] velocities (gp/GaussianProcessInterpolatorPose3VW.h)
-
-
 def convert_vw_to_vb(v, w, pose):
     out = np.zeros(6); _call("gpo_convert_vw_to_vb", _dp(_f64(v)), _dp(_f64(w)), _dp(_f64(pose)), _dp(out)); return out
 
@@ -334,7 +339,7 @@ def interpolate(group, Qc, delta_t, tau, p1, v1, p2, v2, want_H=False, D=3):
 
 def retract(group, pose, delta):
     """x (+) delta with the oracle's chart: Pose3/Rot3 Expmap, Pose2 first-order (GTSAM default), vector add"""
-    if group == POSE3:
+    if group in (POSE3, POSE3VW):
         return pose3_compose(pose, pose3_expmap(delta))
     if group == ROT3:
         R = np.asarray(pose).reshape(3, 3).T @ rot3_expmap(delta).reshape(3, 3).T

@@ -225,12 +225,87 @@ static void testGpsAndProjectionOptimization() {
   }
 }
 
+// gp/tests/testGaussianProcessPriorPose3VW.cpp:33-211 and slam/tests/testGPInterpolatedGPSFactorPose3VW.cpp:266-337
+static Matrix numericalDerivativeVec3(const std::function<Vector(const Vector3&)>& f, const Vector3& x, double delta) {
+  Vector f0 = f(x);
+  Matrix H(static_cast<int>(f0.size()), 3);
+  for (int c = 0; c < 3; c++) {
+    Vector3 xp = x, xm = x; xp[c] += delta; xm[c] -= delta;
+    const Vector fp = f(xp), fm = f(xm);
+    for (size_t r = 0; r < f0.size(); r++) H(static_cast<int>(r), c) = (fp[r] - fm[r]) / (2 * delta);
+  }
+  return H;
+}
+static void testPose3VW() {
+  const double delta_t = 0.1;
+  SharedNoiseModel Qc_model = noiseModel::Gaussian::Covariance(0.01 * Matrix::Identity(6, 6));
+  Key key_pose1 = Symbol('x', 1), key_pose2 = Symbol('x', 2), key_vel1 = Symbol('v', 1), key_vel2 = Symbol('v', 2), key_omega1 = Symbol('w', 1), key_omega2 = Symbol('w', 2);
+  {
+    GaussianProcessPriorPose3VW factor(key_pose1, key_vel1, key_omega1, key_pose2, key_vel2, key_omega2, delta_t, Qc_model);
+    // constant rotation w1 = w2 = 1: zero residual
+    Pose3 p1(Rot3::Ypr(0, 0, 0), Point3(0, 0, 0)), p2(Rot3::Ypr(0.1, 0, 0), Point3(0, 0, 0));
+    Vector3 v1{0, 0, 0}, w1{0, 0, 1}, v2{0, 0, 0}, w2{0, 0, 1};
+    Vector actual = factor.evaluateError(p1, v1, w1, p2, v2, w2);
+    EXPECT(assert_equal(Vector(12, 0.0), actual, 1e-6));
+    // the "random" point: all six analytic Jacobians against central differences (1e-6, as the reference)
+    p1 = Pose3(Rot3::Ypr(-0.1, 1.2, 0.3), Point3(-4.0, 2.0, 14.0)); p2 = Pose3(Rot3::Ypr(2.4, -2.5, 3.7), Point3(9.0, -8.0, -7.0));
+    v1 = Vector3{2, 3, 1}; w1 = Vector3{0, 6, 4}; v2 = Vector3{1, 3, 8};
+    Matrix H1, H2, H3, H4, H5, H6;
+    factor.evaluateError(p1, v1, w1, p2, v2, w2, &H1, &H2, &H3, &H4, &H5, &H6);
+    EXPECT(H1.rows == 12 && H1.cols == 6 && H2.rows == 12 && H2.cols == 3 && H6.cols == 3);
+    EXPECT(assert_equal(numericalDerivativePose([&](const Pose3& x) { return factor.evaluateError(x, v1, w1, p2, v2, w2); }, p1, 1e-6), H1, 1e-6));
+    EXPECT(assert_equal(numericalDerivativeVec3([&](const Vector3& x) { return factor.evaluateError(p1, x, w1, p2, v2, w2); }, v1, 1e-6), H2, 1e-6));
+    EXPECT(assert_equal(numericalDerivativeVec3([&](const Vector3& x) { return factor.evaluateError(p1, v1, x, p2, v2, w2); }, w1, 1e-6), H3, 1e-6));
+    EXPECT(assert_equal(numericalDerivativePose([&](const Pose3& x) { return factor.evaluateError(p1, v1, w1, x, v2, w2); }, p2, 1e-6), H4, 1e-6));
+    EXPECT(assert_equal(numericalDerivativeVec3([&](const Vector3& x) { return factor.evaluateError(p1, v1, w1, p2, x, w2); }, v2, 1e-6), H5, 1e-6));
+    EXPECT(assert_equal(numericalDerivativeVec3([&](const Vector3& x) { return factor.evaluateError(p1, v1, w1, p2, v2, x); }, w2, 1e-6), H6, 1e-6));
+    // only a subset requested
+    Matrix H3only;
+    factor.evaluateError(p1, v1, w1, p2, v2, w2, nullptr, nullptr, &H3only);
+    EXPECT(assert_equal(H3, H3only, 0.0));
+  }
+  {
+    SharedNoiseModel model_prior = noiseModel::Isotropic::Sigma(6, 0.1), model_gps = noiseModel::Isotropic::Sigma(3, 0.01);
+    const double taus[3] = {-0.1, 0.05, 0.2}, xs[3] = {-1, 0.5, 2};
+    Pose3 p1(Rot3(), Point3(0, 0, 0)), p2(Rot3(), Point3(1, 0, 0));
+    Vector3 v{10, 0, 0}, w{0, 0, 0};
+    NonlinearFactorGraph graph;
+    graph.add(PriorFactor<Pose3>(Symbol('x', 1), p1, model_prior));
+    graph.add(PriorFactor<Pose3>(Symbol('x', 2), p2, model_prior));
+    graph.add(GaussianProcessPriorPose3VW(key_pose1, key_vel1, key_omega1, key_pose2, key_vel2, key_omega2, delta_t, Qc_model));
+    for (int k = 0; k < 3; k++)
+      graph.add(GPInterpolatedGPSFactorPose3VW(Point3(xs[k], 0, 0), model_gps, Qc_model, key_pose1, key_vel1, key_omega1, key_pose2, key_vel2, key_omega2, delta_t, taus[k]));
+    // a deliberately weak PriorFactor<Vector3> on one angular velocity: exercises the half-velocity prior path
+    graph.add(PriorFactor<Vector3>(key_omega1, w, noiseModel::Isotropic::Sigma(3, 100.0)));
+    Values init_values;
+    init_values.insert(key_pose1, Pose3(Rot3::Ypr(0.1, -0.1, -0.1), Point3(0.1, 0.1, -0.1))); init_values.insert(key_vel1, Vector3{9.8, -0.1, -0.05}); init_values.insert(key_omega1, Vector3{0.1, -0.1, 0.1});
+    init_values.insert(key_pose2, Pose3(Rot3::Ypr(-0.1, 0.1, -0.1), Point3(1.1, -0.1, 0.1))); init_values.insert(key_vel2, Vector3{10.2, 0.03, -0.1}); init_values.insert(key_omega2, Vector3{-0.1, 0.1, 0.1});
+    GaussNewtonParams parameters;
+    GaussNewtonOptimizer optimizer(graph, init_values, parameters, GPB_POSE3VW);
+    optimizer.optimize();
+    Values values = optimizer.values();
+    EXPECT(std::fabs(optimizer.error()) < 1e-6);
+    double a[12], b[12];
+    p1.wire(a); values.at<Pose3>(key_pose1).wire(b); for (int k = 0; k < 12; k++) EXPECT(std::fabs(a[k] - b[k]) < 1e-6);
+    p2.wire(a); values.at<Pose3>(key_pose2).wire(b); for (int k = 0; k < 12; k++) EXPECT(std::fabs(a[k] - b[k]) < 1e-6);
+    for (int k = 0; k < 3; k++) {
+      EXPECT(std::fabs(values.at<Vector3>(key_vel1)[k] - v[k]) < 1e-6 && std::fabs(values.at<Vector3>(key_vel2)[k] - v[k]) < 1e-6);
+      EXPECT(std::fabs(values.at<Vector3>(key_omega1)[k] - w[k]) < 1e-6 && std::fabs(values.at<Vector3>(key_omega2)[k] - w[k]) < 1e-6);
+    }
+    // VW factors on a body-velocity graph are a checked error
+    bool threw = false;
+    try { GaussNewtonOptimizer bad(graph, init_values, parameters, GPB_POSE3); } catch (const std::runtime_error&) { threw = true; }
+    EXPECT(threw);
+  }
+}
+
 int main() {
   try {
     testFactor();
     testOptimization();
     testRangeOptimization();
     testGpsAndProjectionOptimization();
+    testPose3VW();
   } catch (const std::exception& e) { std::printf("exception: %s\n", e.what()); return 2; }
   std::printf(failures ? "FAILED (%d)\n" : "OK (%d failures)\n", failures);
   return failures ? 1 : 0;

@@ -27,6 +27,7 @@ CASES = {
     "pose3": ("C3", dict(n_states=12, n_landmarks=3, prior_every=5, range_per_state=0.8)),
     "pose3_gps_proj": ("C3", dict(n_states=14, n_landmarks=4, prior_every=5, range_per_state=0.4, gps_every=3, proj_per_state=0.5)),
     "pose3_loops": ("C5", dict(n_states=14, n_landmarks=2, prior_every=6, range_per_state=0.6, n_closures=2, closure_min_gap=5, closure_ends=True)),
+    "pose3vw": ("VW", dict(n_states=13, prior_every=5, gps_every=2, n_closures=1, closure_min_gap=6)),
     "pose2": ("C1", dict(n_states=12)),
     "pose2_loops": ("C1", dict(n_states=13, n_closures=2, closure_min_gap=4)),
     "rot3": ("C4", dict(n_states=13)),
@@ -70,7 +71,7 @@ def generate(name):
 
 
 if __name__ == "__main__":
-    for name in CASES:
+    for name in (sys.argv[1:] or CASES):  # optional: only the named cases (existing fixtures stay byte-identical)
         d = generate(name)
         np.savez_compressed(os.path.join(HERE, "graph_%s.npz" % name), **d)
         print(name, "factors", len(d["Ab_off"]) - 1, "error0 %.6e -> %.6e (LM %d iterations after one GN step)" % (d["error0"][0], d["errorc"][0], d["iters"][0]))

@@ -59,3 +59,42 @@ void hm_interp_attitude(const double* s1, const double* s2, const double* prm, d
   }
 }
 }
+
+// ---- SE(3) "VW" family and the multi-row SE(3) interpolated factors
+template <int VAR, int C, int N> struct EmitVW {
+  static void run(const GpPose3VW& o, const GpWhiten& w, const double* Rq, double dt, double* out) {
+    gp_prior_pose3vw_col<VAR, C>(o, w, Rq, dt, out + (VAR * 6 + C) * 12);
+    EmitVW<VAR, C + 1, N>::run(o, w, Rq, dt, out);
+  }
+};
+template <int VAR, int N> struct EmitVW<VAR, N, N> { static void run(const GpPose3VW&, const GpWhiten&, const double*, double, double*) {} };
+
+extern "C" {
+// out: 12 x 25 column-major whitened [A|b] over [x1(6) | v1,w1 | x2(6) | v2,w2 | rhs]
+void hm_gp_prior_vw(const double* s1, const double* s2, double dt, const double* Rq, double* out) {
+  const GpWhiten w = gp_whiten(dt);
+  GpPose3VW o; gp_prior_pose3vw_eval(s1, s2, dt, true, o);
+  EmitVW<0, 0, 6>::run(o, w, Rq, dt, out); EmitVW<1, 0, 6>::run(o, w, Rq, dt, out);
+  EmitVW<2, 0, 6>::run(o, w, Rq, dt, out); EmitVW<3, 0, 6>::run(o, w, Rq, dt, out);
+  gp_prior_pose3vw_col<4, 0>(o, w, Rq, dt, out + 24 * 12);
+}
+// unwhitened rows of the GPS factors: out[r] = [H1(6) H2(6) H3(6) H4(6) e] for r = 0..2; vw selects GPInterpolatedGPSFactorPose3VW
+void hm_interp_gps(int vw, const double* s1, const double* s2, const double* prm, double* out) {
+  Gps3Out o;
+  if (vw) interp_gps_pose3vw(s1, s2, prm, true, o); else interp_gps_pose3(s1, s2, prm, true, o);
+  const double e[3] = {o.e.x, o.e.y, o.e.z};
+  for (int r = 0; r < 3; r++) {
+    for (int v = 0; v < 4; v++) for (int k = 0; k < 6; k++) out[25 * r + 6 * v + k] = elem(o.H[r][v], k);
+    out[25 * r + 24] = e[r];
+  }
+}
+// out[r] = [H1 H2 H3 H4 (6 each) H5(3) e] for r = 0..1
+void hm_interp_projection(const double* s1, const double* s2, const double* land, const double* prm, double* out) {
+  Proj3Out o; interp_projection_pose3(s1, s2, land, prm, true, o);
+  for (int r = 0; r < 2; r++) {
+    for (int v = 0; v < 4; v++) for (int k = 0; k < 6; k++) out[28 * r + 6 * v + k] = elem(o.H[r][v], k);
+    out[28 * r + 24] = o.H5[r].x; out[28 * r + 25] = o.H5[r].y; out[28 * r + 26] = o.H5[r].z;
+    out[28 * r + 27] = o.e[r];
+  }
+}
+}

@@ -45,6 +45,10 @@ CASES = {
     # the Schur complement on {endpoints, landmarks} is solved densely
     # GPS fixes and pinhole projections through the GP interpolator, incl. one landmark behind its camera
     "pose3_gps_proj": dict(name="C3", n=260, n_landmarks=6, prior_every=40, gps_every=7, proj_per_state=0.3),
+    # SE(3) "VW" family: GaussianProcessPriorPose3VW + GPInterpolatedGPSFactorPose3VW, velocities
+    # [v_world | w_world]; with and without loop closures (no landmarks: the generic k_fwd<12,16> solver path)
+    "pose3vw": dict(name="VW", n=280, prior_every=40, gps_every=3),
+    "pose3vw_loops": dict(name="VW", n=300, prior_every=50, gps_every=4, n_closures=4, closure_min_gap=40),
     "pose3_loops": dict(name="C5", n=400, n_landmarks=4, prior_every=40, n_closures=5, closure_min_gap=40),
     "pose3_wide_loops": dict(name="C5", n=500, n_landmarks=16, prior_every=40, n_closures=8, closure_min_gap=60, closure_ends=True),
     "pose2_loops": dict(name="C1", n=200, n_closures=4, closure_min_gap=30, closure_ends=True),
@@ -96,7 +100,7 @@ def make_pair(case):
     return g, o
 
 
-ALL = ["pose3", "pose3_wide", "pose3_chain", "pose2", "rot3", "linear", "pose3_gps_proj", "pose3_loops", "pose3_wide_loops", "pose2_loops", "rot3_loops"]
+ALL = ["pose3", "pose3_wide", "pose3_chain", "pose2", "rot3", "linear", "pose3_gps_proj", "pose3vw", "pose3vw_loops", "pose3_loops", "pose3_wide_loops", "pose2_loops", "rot3_loops"]
 
 
 @pytest.mark.parametrize("case", ALL)

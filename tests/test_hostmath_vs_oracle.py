@@ -130,3 +130,86 @@ def test_interp_attitude_rows(hm):
             assert abs(out[13 * r + 12] - e[r]) < 1e-11
             Ho = np.concatenate([h[r] for h in H])
             np.testing.assert_allclose(out[13 * r:13 * r + 12], Ho, atol=1e-10 * max(1.0, np.abs(Ho).max()))
+
+
+@pytest.mark.parametrize("small", [False, True])
+def test_gp_prior_vw_whitened(hm, small):
+    """GaussianProcessPriorPose3VW: velocities [v_world | w_world]; same 12x25 [A|b] shape as the body-velocity prior"""
+    rng = np.random.default_rng(321)
+    for trial in range(40):
+        dt = float(rng.uniform(0.05, 1.5))
+        Qc = rand_spd(rng, 6) if trial % 2 else np.eye(6) * rng.uniform(0.01, 2)
+        p1, v1 = rand_state(rng, po.POSE3)
+        if small:
+            p2 = po.retract(po.POSE3, p1, rng.normal(size=6) * (1e-9 if trial % 5 == 0 else 0.05)); v2 = v1 + rng.normal(size=6) * 0.1
+        else:
+            p2, v2 = rand_state(rng, po.POSE3)
+        g = po.Graph(po.POSE3VW, 2, 0)
+        g.set_values(np.stack([p1, p2]), np.stack([v1, v2]))
+        g.add_qc_model(Qc)
+        g.add_gp_prior(0, dt)
+        A, b = g.linearize_factor(0)
+        Ao = np.concatenate(A + [b.reshape(-1, 1)], axis=1)
+        Rq = np.linalg.cholesky(np.linalg.inv(Qc)).T
+        out = np.zeros(12 * 25)
+        hm.hm_gp_prior_vw(dp(np.concatenate([p1, v1])), dp(np.concatenate([p2, v2])), C.c_double(dt), dp(np.ascontiguousarray(Rq.T).ravel()), dp(out))
+        Ag = out.reshape(25, 12).T
+        scale = max(1.0, np.abs(Ao).max())
+        np.testing.assert_allclose(Ag[:, -1], Ao[:, -1], atol=1e-11 * scale)
+        np.testing.assert_allclose(Ag[:, :-1], Ao[:, :-1], atol=1e-6 * scale)
+
+
+@pytest.mark.parametrize("vw", [0, 1])
+def test_interp_gps_rows(hm, vw):
+    """GPInterpolatedGPSFactorPose3 / ...Pose3VW rows (the oracle carries the reference's numerical differentiation: 1e-6)"""
+    rng = np.random.default_rng(55 + vw)
+    for trial in range(40):
+        dt = float(rng.uniform(0.05, 0.5)); tau = float(rng.uniform(-0.5, 1.5) * dt)
+        p1, v1 = rand_state(rng, po.POSE3)
+        if trial % 2:
+            p2, v2 = rand_state(rng, po.POSE3)
+        else:
+            p2 = po.retract(po.POSE3, p1, rng.normal(size=6) * 0.05); v2 = v1 + rng.normal(size=6) * 0.1
+        sensor = rand_state(rng, po.POSE3, 0.5, 0.5)[0] if trial % 3 == 0 else None
+        meas = rng.normal(size=3) * 5
+        g = po.Graph(po.POSE3VW if vw else po.POSE3, 2, 0)
+        g.set_values(np.stack([p1, p2]), np.stack([v1, v2]))
+        g.add_qc_model(np.eye(6))
+        g.add_interp_gps(0, meas, np.eye(3), dt, tau, body_P_sensor=sensor)
+        e, H = g.eval_factor(0, True)
+        prm = np.zeros(56); prm[0] = dt; prm[1] = tau; prm[40:43] = meas
+        if sensor is not None:
+            prm[4:16] = sensor; prm[16] = 1.0
+        out = np.zeros(75)
+        hm.hm_interp_gps(C.c_int(vw), dp(np.concatenate([p1, v1])), dp(np.concatenate([p2, v2])), dp(prm), dp(out))
+        for r in range(3):
+            assert abs(out[25 * r + 24] - e[r]) < 1e-10 * max(1.0, abs(e[r]))
+            Ho = np.concatenate([h[r] for h in H])
+            np.testing.assert_allclose(out[25 * r:25 * r + 24], Ho, atol=1e-6 * max(1.0, np.abs(Ho).max()))
+
+
+def test_interp_projection_rows(hm):
+    rng = np.random.default_rng(77)
+    K = np.array([50.0, 45.0, 0.3, 40.0, 30.0])
+    for trial in range(40):
+        dt = float(rng.uniform(0.05, 0.5)); tau = float(rng.uniform(-0.5, 1.5) * dt)
+        p1, v1 = rand_state(rng, po.POSE3, 0.3)
+        p2 = po.retract(po.POSE3, p1, rng.normal(size=6) * 0.05); v2 = v1 + rng.normal(size=6) * 0.1
+        sensor = rand_state(rng, po.POSE3, 0.2, 0.5)[0] if trial % 3 == 0 else None
+        R, t = po.pose3_Rt(p1)
+        land = t + R @ np.array([rng.normal(), rng.normal(), rng.uniform(-3, 12)])  # some behind the camera: cheirality branch
+        meas = rng.normal(size=2) * 20
+        g = po.Graph(po.POSE3, 2, 1)
+        g.set_values(np.stack([p1, p2]), np.stack([v1, v2]), land.reshape(1, 3))
+        g.add_qc_model(np.eye(6))
+        g.add_interp_projection(0, 0, meas, np.eye(2), dt, tau, K, body_P_sensor=sensor)
+        e, H = g.eval_factor(0, True)
+        prm = np.zeros(56); prm[0] = dt; prm[1] = tau; prm[40:42] = meas; prm[43:48] = K
+        if sensor is not None:
+            prm[4:16] = sensor; prm[16] = 1.0
+        out = np.zeros(56)
+        hm.hm_interp_projection(dp(np.concatenate([p1, v1])), dp(np.concatenate([p2, v2])), dp(land), dp(prm), dp(out))
+        for r in range(2):
+            assert abs(out[28 * r + 27] - e[r]) < 1e-9 * max(1.0, abs(e[r]))
+            Ho = np.concatenate([h[r] for h in H])
+            np.testing.assert_allclose(out[28 * r:28 * r + 27], Ho, atol=1e-6 * max(1.0, np.abs(Ho).max()))
