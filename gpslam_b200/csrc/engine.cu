@@ -56,6 +56,8 @@ struct Level {
 
 struct gpb_graph {
   int group = 0, D = 0, PS = 0, DL = 0, N = 0, L = 0, bs = 0, SR = 0, nb = 0, w = 0, W = 0;
+  int qc_diag = 0;   // every Qc model is diagonal: SE(3) priors use the element-wise whitening kernel class
+  int lin_variant = 0;  // k_lin_gp<G_POSE3> instantiation (see launch_lin_gp_pose3)
   int vw = 0;  // GPB_POSE3VW: a GPB_POSE3 graph whose velocities are [v_world | w_world] (selects the VW linearise kernels only)
   std::vector<std::vector<double>> Rq;  // chol_upper(Qc^-1), D x D column-major
   std::vector<double> dt;               // per interval (0 = no GP prior)
@@ -649,7 +651,14 @@ int gpb_graph_finalize(gpb_graph* g, int device) {
   const char* em0 = getenv("GPB_M0"); const char* emu = getenv("GPB_MUP");
   g->split_levels = getenv("GPB_SPLIT_LEVELS") != nullptr;  // A/B switch: spine and panel as two launches on the upper levels too
   g->old_assemble = getenv("GPB_OLD_ASSEMBLE") != nullptr;  // A/B switch: thread-per-tile assembly instead of the DMMA kernel
-  g->generic_fwd = getenv("GPB_GENERIC_FWD") != nullptr;  // A/B switch: one-kernel generic forward sweep (k_fwd<12,64>)
+  g->generic_fwd = getenv("GPB_GENERIC_FWD") != nullptr;
+  g->qc_diag = 1;
+  for (const auto& R : g->Rq) for (int c = 0; c < D; c++) for (int r = 0; r < D; r++) if (r != c && R[r + c * D] != 0.0) g->qc_diag = 0;
+  g->lin_variant = g->qc_diag ? 1 : 0;
+  if (const char* ev = getenv("GPB_LIN_VARIANT")) {  // A/B switch: 0 dense Rq, 1 diagonal Rq, +2: three CTAs per SM (<= 168 registers)
+    const int v = atoi(ev);
+    if (v >= 0 && v <= 3 && (!(v & 1) || g->qc_diag)) g->lin_variant = v;
+  }  // A/B switch: one-kernel generic forward sweep (k_fwd<12,64>)
   int M0 = g->M0 ? g->M0 : (em0 ? std::max(2, atoi(em0)) : (g->nb > 0 ? 32 : 16));
   const int Mup = g->Mup ? g->Mup : (emu ? std::max(2, atoi(emu)) : 8);
   if (!g->M0 && !em0 && bs == 12 && g->W == 64) {
@@ -794,27 +803,44 @@ int gpb_graph_finalize(gpb_graph* g, int device) {
 // ===================================================================== launches
 #define CHECK_READY(g) do { if (!(g)) return fail(GPB_ERR_ARG, "null graph"); if (!(g)->finalized) return fail(GPB_ERR_STATE, "graph not finalized"); CUDA_TRY(cudaSetDevice((g)->device)); } while (0)
 
+// k_lin_gp for SE(3) states: VW kernel class, or the body-velocity prior in its dense-Rq / diagonal-Rq instantiation
+template <int NT> static void launch_lin_gp_pose3(gpb_graph* g, const double* X, double* AB, int wantJ) {
+  const int nb1 = (g->nint + NT - 1) / NT;
+  const size_t smem = (size_t)(NT + 1) * g->SR * sizeof(double);
+  if (g->vw) { k_lin_gp<G_POSE3VW, NT><<<nb1, NT, smem, g->stream>>>(X, g->d_dt, g->d_qc, g->d_Rq, AB, g->d_errpart, g->nint, g->NFp, wantJ); return; }
+  switch (g->lin_variant) {
+    case 1: k_lin_gp<G_POSE3, NT, true, 1><<<nb1, NT, smem, g->stream>>>(X, g->d_dt, g->d_qc, g->d_Rq, AB, g->d_errpart, g->nint, g->NFp, wantJ); break;
+    case 2: k_lin_gp<G_POSE3, NT, false, 3><<<nb1, NT, smem, g->stream>>>(X, g->d_dt, g->d_qc, g->d_Rq, AB, g->d_errpart, g->nint, g->NFp, wantJ); break;
+    case 3: k_lin_gp<G_POSE3, NT, true, 3><<<nb1, NT, smem, g->stream>>>(X, g->d_dt, g->d_qc, g->d_Rq, AB, g->d_errpart, g->nint, g->NFp, wantJ); break;
+    default: k_lin_gp<G_POSE3, NT, false, 1><<<nb1, NT, smem, g->stream>>>(X, g->d_dt, g->d_qc, g->d_Rq, AB, g->d_errpart, g->nint, g->NFp, wantJ); break;
+  }
+}
+
 template <int G> static int launch_linearize(gpb_graph* g, const double* X, const double* land, int buf, int wantJ) {
   constexpr int NT = 128, SR = GroupTraits<G>::PS + GroupTraits<G>::D;
   const int nb1 = (g->nint + NT - 1) / NT, nbA = (g->nA + NT - 1) / NT, nbB = (int)(((size_t)g->nB * 32 + NT - 1) / NT);  // generic factors: one warp each
   const size_t smem = (size_t)(NT + 1) * SR * sizeof(double);
-  // the generic (non-interpolated) factors are few but slow per thread: they run on a forked stream beside the two bulk kernels
-  if (nbB > 0) {
+  // every measurement / prior / between factor runs on a forked stream beside the GP-prior kernel: the generic factors first
+  // (few, a warp each), then the interpolated ones, whose CTAs fill the SMs the prior kernel's last partial wave leaves idle
+  const bool fork = nbB > 0 || nbA > 0;
+  if (fork) {
     CUDA_TRY(cudaEventRecord(g->ev_fork, g->stream));
     CUDA_TRY(cudaStreamWaitEvent(g->stream2, g->ev_fork, 0));
-    k_lin_extra<G, 1, NT><<<nbB, NT, 0, g->stream2>>>(g->d_listB, g->nB, X, land, g->d_xkind, g->d_xsa, g->d_xsb, g->d_xl, g->d_xrow, g->d_xprm, g->d_XR[buf],
-                                                       g->d_errpart + nb1 + nbA, g->NX, g->NXRp, wantJ);
-    CUDA_TRY(cudaEventRecord(g->ev_join, g->stream2));
-    g->launches++;
+    if (nbB > 0) {
+      k_lin_extra<G, 1, NT><<<nbB, NT, 0, g->stream2>>>(g->d_listB, g->nB, X, land, g->d_xkind, g->d_xsa, g->d_xsb, g->d_xl, g->d_xrow, g->d_xprm, g->d_XR[buf],
+                                                         g->d_errpart + nb1 + nbA, g->NX, g->NXRp, wantJ);
+      g->launches++;
+    }
   }
-  if (G == G_POSE3 && g->vw) k_lin_gp<G_POSE3VW, NT><<<nb1, NT, smem, g->stream>>>(X, g->d_dt, g->d_qc, g->d_Rq, g->d_AB[buf], g->d_errpart, g->nint, g->NFp, wantJ);
+  if constexpr (G == G_POSE3) launch_lin_gp_pose3<NT>(g, X, g->d_AB[buf], wantJ);
   else k_lin_gp<G, NT><<<nb1, NT, smem, g->stream>>>(X, g->d_dt, g->d_qc, g->d_Rq, g->d_AB[buf], g->d_errpart, g->nint, g->NFp, wantJ);
   g->launches++;
   if (nbA > 0) {
-    k_lin_extra<G, 0, NT><<<nbA, NT, 0, g->stream>>>(g->d_listA, g->nA, X, land, g->d_xkind, g->d_xsa, g->d_xsb, g->d_xl, g->d_xrow, g->d_xprm, g->d_XR[buf],
-                                                      g->d_errpart + nb1, g->NX, g->NXRp, wantJ);
+    k_lin_extra<G, 0, NT><<<nbA, NT, 0, g->stream2>>>(g->d_listA, g->nA, X, land, g->d_xkind, g->d_xsa, g->d_xsb, g->d_xl, g->d_xrow, g->d_xprm, g->d_XR[buf],
+                                                       g->d_errpart + nb1, g->NX, g->NXRp, wantJ);
     g->launches++;
   }
+  if (fork) CUDA_TRY(cudaEventRecord(g->ev_join, g->stream2));
   const int nbC = (g->nC + NT - 1) / NT;
   if constexpr (G == G_POSE3) {
     if (nbC > 0) {  // GPS / projection factors
@@ -823,7 +849,7 @@ template <int G> static int launch_linearize(gpb_graph* g, const double* X, cons
       g->launches++;
     }
   }
-  if (nbB > 0) CUDA_TRY(cudaStreamWaitEvent(g->stream, g->ev_join, 0));
+  if (fork) CUDA_TRY(cudaStreamWaitEvent(g->stream, g->ev_join, 0));
   k_sum_partials<<<1, 256, 0, g->stream>>>(g->d_errpart, nb1 + nbA + nbB + (G == G_POSE3 ? nbC : 0), g->d_scal, 0);
   g->launches++;
   CUDA_TRY(cudaGetLastError());
@@ -1535,7 +1561,7 @@ int gpb_time_stage(gpb_graph* g, int stage, int reps, double* ms_out) {
   const int nb1 = (g->nint + NT - 1) / NT;
   auto gp_only = [&](auto tag) {
     constexpr int G = decltype(tag)::value; constexpr int SR = GroupTraits<G>::PS + GroupTraits<G>::D;
-    if (G == G_POSE3 && g->vw) k_lin_gp<G_POSE3VW, NT><<<nb1, NT, (size_t)(NT + 1) * SR * sizeof(double), g->stream>>>(g->d_X, g->d_dt, g->d_qc, g->d_Rq, g->d_AB[other], g->d_errpart, g->nint, g->NFp, 1);
+    if constexpr (G == G_POSE3) launch_lin_gp_pose3<NT>(g, g->d_X, g->d_AB[other], 1);
     else k_lin_gp<G, NT><<<nb1, NT, (size_t)(NT + 1) * SR * sizeof(double), g->stream>>>(g->d_X, g->d_dt, g->d_qc, g->d_Rq, g->d_AB[other], g->d_errpart, g->nint, g->NFp, 1);
   };
   const int nbA = (g->nA + NT - 1) / NT, nbB = (int)(((size_t)g->nB * 32 + NT - 1) / NT);  // generic factors: one warp each

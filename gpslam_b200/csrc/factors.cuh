@@ -21,6 +21,10 @@ namespace gpb {
 // a kernel class of G_POSE3, not a graph group of its own - record layout, block sizes, assembly, solver and retraction are G_POSE3's.
 enum Group { G_POSE3 = 0, G_POSE2 = 1, G_ROT3 = 2, G_LINEAR = 3, G_POSE3VW = 4 };
 
+template <int I, int N, class F> GPB_HD void static_for(F&& f) {
+  if constexpr (I < N) { f(std::integral_constant<int, I>{}); static_for<I + 1, N>(f); }
+}
+
 template <int G> struct GroupTraits;
 template <> struct GroupTraits<G_POSE3> { static constexpr int D = 6, PS = 12, DL = 3; };
 template <> struct GroupTraits<G_POSE3VW> { static constexpr int D = 6, PS = 12, DL = 3; };
@@ -118,6 +122,100 @@ template <int VAR, int C> GPB_HD void gp_prior_pose3_col(const GpPose3& o, const
     for (int k = 0; k < 6; k++) { top[k] = elem(o.e_top, k); bot[k] = elem(o.e_bot, k); }
     gp_whiten_col<6>(w, Rq, top, bot, -1.0, out);
   }
+}
+
+// ---- production emitter of the SE(3) prior's 25 whitened columns (k_lin_gp<G_POSE3>).  Same arithmetic as
+// gp_prior_pose3_eval + gp_prior_pose3_col, organised around what is structurally zero and what is live:
+//  * every Jacobian block is [[A,0],[B,C]]: the translation columns (C >= 3) have zero rotation rows, so their whitening
+//    sums start at k = 3; the v1 columns are plain columns of Rq; the v2 columns need ONE product Rq b[:,C];
+//  * DIAG: every Qc model of the graph is diagonal (the reference's tests and scripts use Qc = sigma^2 I throughout), so Rq is
+//    diagonal and whitening a column is an element-wise scale - identical results, ~half the FP64 work of the kernel;
+//  * order rhs, v1, v2, T2, T1: b and D are live throughout, D b only for T2, a = b - ad(r) and D a only for T1 (the
+//    all-at-once struct keeps four 6x6 blocks live and pins the kernel at 255 registers).
+// sink(c, col): column c (0..24, variable order T1 v1 T2 v2 rhs) as 12 doubles.
+template <int D, int K0, bool DIAG> GPB_HD void rq_mul(const double* __restrict__ Rq, const double* t, double* y) {
+#pragma unroll
+  for (int r = 0; r < D; r++) {
+    if (DIAG) {
+      y[r] = r >= K0 ? Rq[r + r * D] * t[r] : 0.0;
+    } else {
+      const int k0 = r > K0 ? r : K0;
+      double s = Rq[r + k0 * D] * t[k0];
+#pragma unroll
+      for (int k = k0 + 1; k < D; k++) s += Rq[r + k * D] * t[k];
+      y[r] = s;
+    }
+  }
+}
+// column C of sign * [[u11 I, u12 I],[0, u22 I]] (x) Rq applied to [Top; Bot][:, C]
+template <int C, bool DIAG> GPB_HD void gp_col_pair(const L6& Top, const L6& Bot, double sign, const GpWhiten& w, const double* __restrict__ Rq, double* out) {
+  constexpr int K0 = C < 3 ? 0 : 3;
+  double t[6], tb[6];
+#pragma unroll
+  for (int k = 0; k < 6; k++) {
+    if (k >= K0) { const double tp = elem(Top, k, C), bt = elem(Bot, k, C); t[k] = sign * (w.u11 * tp + w.u12 * bt); tb[k] = (sign * w.u22) * bt; }
+    else { t[k] = 0.0; tb[k] = 0.0; }
+  }
+  rq_mul<6, K0, DIAG>(Rq, t, out);
+  rq_mul<6, K0, DIAG>(Rq, tb, out + 6);
+}
+template <bool DIAG, class Sink>
+GPB_HD double gp_prior_pose3_emit(const double* s1, const double* s2, double dt, bool wantJ, const GpWhiten& w, const double* __restrict__ Rq, Sink&& sink) {
+  const P3 T1 = p3_from_wire(s1), T2 = p3_from_wire(s2);
+  const X6 v1 = x6_from(s1 + 12), v2 = x6_from(s2 + 12);
+  const X6 r = se3_logmap(p3_between(T1, T2));
+  const JrinvCoef c = se3_jrinv_coef(dot(r.w, r.w));
+  const L6 b = se3_jrinv(r, c);
+  double col[12];
+  double err = 0.0;
+  {  // rhs = -R e,  e = [r - dt v1; Jr^-1(r) v2 - v1]
+    const X6 et = r - dt * v1, eb = b * v2 - v1;
+    double t[6], tb[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) { t[k] = -(w.u11 * elem(et, k) + w.u12 * elem(eb, k)); tb[k] = -w.u22 * elem(eb, k); }
+    rq_mul<6, 0, DIAG>(Rq, t, col); rq_mul<6, 0, DIAG>(Rq, tb, col + 6);
+#pragma unroll
+    for (int k = 0; k < 12; k++) err += col[k] * col[k];
+    if (!wantJ) return err;
+    sink(24, col);
+  }
+  {  // v1: [-dt I; -I] -> column C of Rq scaled
+    const double st = -(w.u11 * dt + w.u12), sb = -w.u22;
+    static_for<0, 6>([&](auto cc) {
+      constexpr int C = decltype(cc)::value;
+#pragma unroll
+      for (int rr = 0; rr < 6; rr++) {
+        if (DIAG ? rr == C : rr <= C) { const double q = Rq[rr + C * 6]; col[rr] = st * q; col[6 + rr] = sb * q; }
+        else { col[rr] = 0.0; col[6 + rr] = 0.0; }
+      }
+      sink(6 + C, col);
+    });
+  }
+  // v2: [0; b] -> one product y = Rq b[:, C], top u12 y, bottom u22 y
+  static_for<0, 6>([&](auto cc) {
+    constexpr int C = decltype(cc)::value; constexpr int K0 = C < 3 ? 0 : 3;
+    double bc[6], y[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) bc[k] = k >= K0 ? elem(b, k, C) : 0.0;
+    rq_mul<6, K0, DIAG>(Rq, bc, y);
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+      if (DIAG && k < K0) { col[k] = 0.0; col[6 + k] = 0.0; }
+      else { col[k] = w.u12 * y[k]; col[6 + k] = w.u22 * y[k]; }
+    }
+    sink(18 + C, col);
+  });
+  const L6 Dm = se3_djrinv(r, v2, c);
+  {  // T2: [b; D b]
+    const L6 Db = Dm * b;
+    static_for<0, 6>([&](auto cc) { constexpr int C = decltype(cc)::value; gp_col_pair<C, DIAG>(b, Db, 1.0, w, Rq, col); sink(12 + C, col); });
+  }
+  {  // T1: -[a; D a],  a = Jl^-1(r) = Jr^-1(r) - ad(r)
+    const L6 a = b - l6_ad(r);
+    const L6 Da = Dm * a;
+    static_for<0, 6>([&](auto cc) { constexpr int C = decltype(cc)::value; gp_col_pair<C, DIAG>(a, Da, -1.0, w, Rq, col); sink(C, col); });
+  }
+  return err;
 }
 
 // ================================================================= GP prior, SE(3) "VW" (gp/GaussianProcessPriorPose3VW.h:62-117)

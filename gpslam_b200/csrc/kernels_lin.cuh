@@ -6,9 +6,6 @@
 
 using namespace gpb;
 
-template <int I, int N, class F> __host__ __device__ __forceinline__ void static_for(F&& f) {
-  if constexpr (I < N) { f(std::integral_constant<int, I>{}); static_for<I + 1, N>(f); }
-}
 
 // ===================================================================== device helpers
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -55,8 +52,9 @@ template <int NT> __device__ __forceinline__ double block_sum(double v, double* 
 // One thread per GP prior factor (interval i -> i+1).  The tile's NT+1 state records arrive in shared memory through one
 // TMA bulk copy; every whitened column of [A|b] is produced in registers and stored as 128-bit row pairs into the SoA
 // layout, so a warp's store instruction covers 512 contiguous bytes.
-template <int G, int NT>
-__global__ void __launch_bounds__(NT) k_lin_gp(const double* __restrict__ X, const double* __restrict__ dt, const int* __restrict__ qc,
+// DIAG (SE(3) only): every Qc model of the graph is diagonal - whitening is an element-wise scale (gp_prior_pose3_emit).
+template <int G, int NT, bool DIAG = false, int MINB = 1>
+__global__ void __launch_bounds__(NT, MINB) k_lin_gp(const double* __restrict__ X, const double* __restrict__ dt, const int* __restrict__ qc,
                                                const double* __restrict__ RqTab, double* __restrict__ AB, double* __restrict__ errpart,
                                                int nint, int NFp, int wantJ) {
   constexpr int D = GroupTraits<G>::D, SR = GroupTraits<G>::PS + D;
@@ -79,23 +77,16 @@ __global__ void __launch_bounds__(NT) k_lin_gp(const double* __restrict__ X, con
       const double* Rq = RqTab + qc[f] * D * D;
       const GpWhiten w = gp_whiten(h);
       double col[2 * D];
-      auto store = [&](int c) {
+      // entry (column c, row pair rp) of factor f sits at byte ((c D + rp) NFp + f) 16: one 32 x 32 + 64-bit multiply-add per store
+      char* const abase = reinterpret_cast<char*>(AB) + (size_t)f * 16;
+      const unsigned strideB = (unsigned)NFp * 16u;
+      auto store_col = [&](int c, const double* v) {
 #pragma unroll
-        for (int rp = 0; rp < D; rp++) st128(AB + ((size_t)(c * D + rp) * NFp + f) * 2, col[2 * rp], col[2 * rp + 1]);
+        for (int rp = 0; rp < D; rp++) *reinterpret_cast<double2*>(abase + (size_t)((unsigned)(c * D + rp)) * strideB) = make_double2(v[2 * rp], v[2 * rp + 1]);
       };
+      auto store = [&](int c) { store_col(c, col); };
       if constexpr (G == G_POSE3) {
-        GpPose3 o;
-        gp_prior_pose3_eval(s1, s2, h, wantJ != 0, o);
-        gp_prior_pose3_col<4, 0>(o, w, Rq, h, col);
-#pragma unroll
-        for (int k = 0; k < 12; k++) err += col[k] * col[k];
-        if (wantJ) {
-          store(24);
-          static_for<0, 6>([&](auto c) { gp_prior_pose3_col<0, decltype(c)::value>(o, w, Rq, h, col); store(decltype(c)::value); });
-          static_for<0, 6>([&](auto c) { gp_prior_pose3_col<1, decltype(c)::value>(o, w, Rq, h, col); store(6 + decltype(c)::value); });
-          static_for<0, 6>([&](auto c) { gp_prior_pose3_col<2, decltype(c)::value>(o, w, Rq, h, col); store(12 + decltype(c)::value); });
-          static_for<0, 6>([&](auto c) { gp_prior_pose3_col<3, decltype(c)::value>(o, w, Rq, h, col); store(18 + decltype(c)::value); });
-        }
+        err = gp_prior_pose3_emit<DIAG>(s1, s2, h, wantJ != 0, w, Rq, store_col);
       } else if constexpr (G == G_POSE3VW) {
         GpPose3VW o;
         gp_prior_pose3vw_eval(s1, s2, h, wantJ != 0, o);

@@ -47,7 +47,7 @@ def _wire3(R, t):
 
 class Config:
     def __init__(self, name, group, n_states, n_landmarks=0, range_per_state=0.0, dt=0.1, seed=0, qc_sigma=0.1, prior_every=100,
-                 attitude_every=0, odometry=False, init_noise=0.05, zero_rot_fraction=0.01, n_closures=0, closure_min_gap=0, closure_ends=False, gps_every=0, proj_per_state=0.0, vw=False):
+                 attitude_every=0, odometry=False, init_noise=0.05, zero_rot_fraction=0.01, n_closures=0, closure_min_gap=0, closure_ends=False, gps_every=0, proj_per_state=0.0, vw=False, qc_dense=False):
         self.__dict__.update(locals())
         del self.__dict__["self"]
 
@@ -148,7 +148,11 @@ def build(cfg, make_graph, finalize=True):
     if vw:
         Rs = poses[:, :9].reshape(N, 3, 3).transpose(0, 2, 1)
         wire_vels = np.concatenate([np.einsum("nij,nj->ni", Rs, vels[:, 3:]), np.einsum("nij,nj->ni", Rs, vels[:, :3])], axis=1)
-    g.add_qc_model(np.eye(D) * cfg.qc_sigma ** 2)
+    Qc = np.eye(D) * cfg.qc_sigma ** 2
+    if getattr(cfg, "qc_dense", False):  # a correlated Qc: the dense-Rq whitening path of the linearise kernels
+        B = np.fromfunction(lambda i, j: 0.3 / (1.0 + np.abs(i - j)), (D, D)) + np.eye(D) * 0.7
+        Qc = cfg.qc_sigma ** 2 * (B @ B.T)
+    g.add_qc_model(Qc)
     g.add_gp_prior(np.arange(N - 1), np.full(N - 1, dt))
     iso = lambda n, s: np.eye(n) / s
     lands = np.zeros((L, max(DL, 1)))

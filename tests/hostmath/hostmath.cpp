@@ -23,7 +23,11 @@ extern "C" {
 // out: m x (4D+1) column-major whitened [A|b]
 void hm_gp_prior(int group, const double* s1, const double* s2, double dt, const double* Rq, double* out) {
   const GpWhiten w = gp_whiten(dt);
-  if (group == G_POSE3) {
+  if (group == G_POSE3) {  // the production emitter (k_lin_gp<G_POSE3>), dense-Rq instantiation
+    gp_prior_pose3_emit<false>(s1, s2, dt, true, w, Rq, [&](int c, const double* col) { for (int k = 0; k < 12; k++) out[c * 12 + k] = col[k]; });
+  } else if (group == 100) {  // same, diagonal-Rq instantiation (caller guarantees a diagonal Rq)
+    gp_prior_pose3_emit<true>(s1, s2, dt, true, w, Rq, [&](int c, const double* col) { for (int k = 0; k < 12; k++) out[c * 12 + k] = col[k]; });
+  } else if (group == 101) {  // the struct-based reference form of the same arithmetic (used by the VW kernel class)
     GpPose3 o; gp_prior_pose3_eval(s1, s2, dt, true, o);
     EmitP3<0, 0, 6>::run(o, w, Rq, dt, out); EmitP3<1, 0, 6>::run(o, w, Rq, dt, out);
     EmitP3<2, 0, 6>::run(o, w, Rq, dt, out); EmitP3<3, 0, 6>::run(o, w, Rq, dt, out);

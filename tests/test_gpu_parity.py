@@ -49,6 +49,9 @@ CASES = {
     # [v_world | w_world]; with and without loop closures (no landmarks: the generic k_fwd<12,16> solver path)
     "pose3vw": dict(name="VW", n=280, prior_every=40, gps_every=3),
     "pose3vw_loops": dict(name="VW", n=300, prior_every=50, gps_every=4, n_closures=4, closure_min_gap=40),
+    # a correlated (dense) Qc: the dense-Rq instantiation of k_lin_gp (diagonal Qc models take the element-wise one)
+    "pose3_dense_qc": dict(name="C3", n=200, n_landmarks=4, prior_every=40, qc_dense=True),
+    "pose2_dense_qc": dict(name="C1", n=150, qc_dense=True),
     "pose3_loops": dict(name="C5", n=400, n_landmarks=4, prior_every=40, n_closures=5, closure_min_gap=40),
     "pose3_wide_loops": dict(name="C5", n=500, n_landmarks=16, prior_every=40, n_closures=8, closure_min_gap=60, closure_ends=True),
     "pose2_loops": dict(name="C1", n=200, n_closures=4, closure_min_gap=30, closure_ends=True),
@@ -100,7 +103,7 @@ def make_pair(case):
     return g, o
 
 
-ALL = ["pose3", "pose3_wide", "pose3_chain", "pose2", "rot3", "linear", "pose3_gps_proj", "pose3vw", "pose3vw_loops", "pose3_loops", "pose3_wide_loops", "pose2_loops", "rot3_loops"]
+ALL = ["pose3", "pose3_wide", "pose3_chain", "pose2", "rot3", "linear", "pose3_gps_proj", "pose3vw", "pose3vw_loops", "pose3_dense_qc", "pose2_dense_qc", "pose3_loops", "pose3_wide_loops", "pose2_loops", "rot3_loops"]
 
 
 @pytest.mark.parametrize("case", ALL)
@@ -157,6 +160,24 @@ def test_optimize_matches_oracle(case, use_lm):
     assert np.abs(Vg - Vo).max() <= 1e-6
     if Lo.size:
         assert np.abs(Lg - Lo).max() <= 1e-6
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+def test_lin_gp_instantiations_agree(variant, monkeypatch):
+    """k_lin_gp<G_POSE3> instantiations (GPB_LIN_VARIANT: dense / diagonal Rq, two / three CTAs per SM) produce the same [A|b]"""
+    cfg = small_cfg("C3", 300, n_landmarks=4, prior_every=40)
+    g0, o, _ = both(cfg)
+    e0 = g0.linearize()
+    monkeypatch.setenv("GPB_LIN_VARIANT", str(variant))
+    g1, _ = synth.build(cfg, lambda grp, n, l: gb.Graph(grp, n, l))
+    e1 = g1.linearize()
+    assert abs(e1 - e0) <= 1e-12 * abs(e0) and abs(e1 - o.error()) <= 1e-9 * abs(e0)
+    for k in range(0, g0.N - 1, 7):
+        A0, b0 = g0.linearized_factor(0, k); A1, b1 = g1.linearized_factor(0, k)
+        sc = max(1.0, max(np.abs(a).max() for a in A0))
+        np.testing.assert_allclose(b1, b0, atol=1e-12 * max(1.0, np.abs(b0).max()))
+        for x, y in zip(A1, A0):
+            np.testing.assert_allclose(x, y, atol=1e-12 * sc)
 
 
 @pytest.mark.parametrize("n_landmarks", [2, 16])

@@ -71,6 +71,13 @@ def test_gp_prior_whitened(hm, group, small):
         scale = max(1.0, np.abs(Ao).max())
         np.testing.assert_allclose(Ag[:, -1], Ao[:, -1], atol=1e-11 * scale)                      # rhs = -R e
         np.testing.assert_allclose(Ag[:, :-1], Ao[:, :-1], atol=(1e-6 if group == po.POSE3 else 1e-10) * scale)
+        if group == po.POSE3:
+            # the SE(3) kernel's instantiations agree with each other to rounding: struct form (101) always, diagonal-Rq form
+            # (100) when Qc is diagonal
+            for code in (101,) + ((100,) if trial % 2 == 0 else ()):
+                out2 = np.zeros(m * ncol)
+                hm.hm_gp_prior(C.c_int(code), dp(s1), dp(s2), C.c_double(dt), dp(np.ascontiguousarray(Rq.T).ravel()), dp(out2))
+                np.testing.assert_allclose(out2, out, atol=1e-12 * scale, rtol=1e-12)
 
 
 @pytest.mark.parametrize("group", [po.POSE3, po.POSE2, po.LINEAR])
