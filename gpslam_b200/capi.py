@@ -92,6 +92,14 @@ def dmma_peak(device=0):
     return v.value
 
 
+def store_peak(mode, n_factors, device=0):
+    """profiling aid (gpb_debug_store_peak): microseconds to write n_factors SE(3) [A|b] records in k_lin_gp's store pattern"""
+    v = C.c_double()
+    if lib().gpb_debug_store_peak(C.c_int(device), C.c_int(mode), C.c_int(n_factors), C.byref(v)) != 0:
+        raise GpbError(lib().gpb_last_error().decode())
+    return v.value
+
+
 def default_params(use_lm=True):
     p = Params()
     lib().gpb_default_params(C.byref(p), C.c_int(1 if use_lm else 0))

@@ -4,7 +4,8 @@
 // Device data layout (all FP64, resident in HBM for the life of the graph):
 //   X      [N][SR]            state records  [pose (PS) | velocity (D)]            (AoS, 16 B-aligned records,
 //                              staged per tile into shared memory by one TMA bulk copy, cp.async.bulk)
-//   AB     [4D+1][D][NFp][2]   whitened GP-prior JacobianFactors [A|b], SoA: column, row-pair, factor  (128-bit stores,
+//   AB     [NFp/128][(4D+1) D][128][2]   whitened GP-prior JacobianFactors [A|b]: tiles of 128 factors, inside a tile SoA by
+//          (column, row pair) - factors.cuh:ab_off  (128-bit stores,
 //                              consecutive lanes -> consecutive 16 B)
 //   XR     [2bs+DL+1][NXRp]    whitened rows of every other factor (range, attitude, priors, between, 2-D factors)
 //   HREC   [N][2bs^2+bs]       assembled normal equations per state: D_i | E_i (= H_{i+1,i}) | g_i
@@ -526,7 +527,7 @@ int gpb_graph_finalize(gpb_graph* g, int device) {
   g->W = g->w <= 16 ? 16 : g->w <= 32 ? 32 : 64;
   if (g->w > 64) return fail(GPB_ERR_UNSUPPORTED, "gpb_graph_finalize: landmark border wider than 64 - 2D - 1 columns is not supported by this build");
   g->ngp = 0; for (double h : g->dt) if (h > 0) g->ngp++;
-  g->NFp = (g->nint + 31) & ~31;
+  g->NFp = (g->nint + AB_TF - 1) / AB_TF * AB_TF;  // whole tiles of the [A|b] layout (ab_off)
   // ---- sort extras by interval (stable), assign row offsets
   g->sorted = g->extras;
   std::stable_sort(g->sorted.begin(), g->sorted.end(), [](const Extra& a, const Extra& b) { return a.interval < b.interval; });
@@ -1405,6 +1406,56 @@ int gpb_debug_dmma_peak(int device, double* tflops_out) {
   return GPB_OK;
 }
 
+// profiling aid: what the [A|b] store pattern of k_lin_gp<SE(3)> costs with no arithmetic in front of it - the floor the
+// linearise kernel can reach with this layout.  mode 0: cudaMemsetAsync of the same bytes; 1: one thread per factor, 150
+// 128-bit stores at ((c 6 + rp) NFp + f) 16 (k_lin_gp's pattern); 2: the same with st.global.cs (streaming) stores;
+// 3: mode 1 with 256 threads per CTA.  Two buffers alternate (each larger than L2), best of 6.
+__global__ void k_store_pattern(double* AB, int nint, int NFp, double seed, int CS) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= nint) return;
+  // CS 2: the tiled layout (ab_off) - consecutive row pairs 2 KB apart inside the CTA's own tile; else row pairs NFp * 16 B apart
+  char* const abase = reinterpret_cast<char*>(AB) + (CS == 2 ? ab_off(0, f, 150) * 8 : (size_t)f * 16);
+  const unsigned strideB = CS == 2 ? (unsigned)(AB_TF * 16) : (unsigned)NFp * 16u;
+  double v = seed + f;
+#pragma unroll 25
+  for (int k = 0; k < 150; k++) {
+    double2 d = make_double2(v, v + 0.5); v += 1.0;
+    double2* p = reinterpret_cast<double2*>(abase + (size_t)((unsigned)k) * strideB);
+    if (CS == 1) __stcs(p, d); else *p = d;
+  }
+}
+int gpb_debug_store_peak(int device, int mode, int n_factors, double* us_out) {
+  if (!us_out || n_factors < 1 || mode < 0 || mode > 4) return fail(GPB_ERR_ARG, "gpb_debug_store_peak: bad arguments");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(GPB_ERR_CUDA, "gpb_debug_store_peak: no CUDA device available"); }
+  CUDA_TRY(cudaSetDevice(device));
+  const int NFp = (n_factors + AB_TF - 1) / AB_TF * AB_TF;
+  const size_t bytes = (size_t)150 * NFp * 16;
+  double* buf[2] = {nullptr, nullptr};
+  CUDA_TRY(cudaMalloc(&buf[0], bytes)); CUDA_TRY(cudaMalloc(&buf[1], bytes));
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
+  double best = 1e30;
+  for (int r = 0; r < 7; r++) {
+    double* b = buf[r & 1];
+    CUDA_TRY(cudaEventRecord(e0, 0));
+    const int nt = mode == 3 ? 256 : 128;
+    if (mode == 0) CUDA_TRY(cudaMemsetAsync(b, 0, bytes, 0));
+    else if (mode == 2) k_store_pattern<<<(n_factors + nt - 1) / nt, nt>>>(b, n_factors, NFp, (double)r, 1);
+    else if (mode == 4) k_store_pattern<<<(n_factors + nt - 1) / nt, nt>>>(b, n_factors, NFp, (double)r, 2);
+    else k_store_pattern<<<(n_factors + nt - 1) / nt, nt>>>(b, n_factors, NFp, (double)r, 0);
+    CUDA_TRY(cudaEventRecord(e1, 0));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    if (r > 0 && ms * 1e3 < best) best = ms * 1e3;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(buf[0]); cudaFree(buf[1]);
+  CUDA_TRY(cudaGetLastError());
+  *us_out = best;
+  return GPB_OK;
+}
+
 int gpb_kernel_launches_last_optimize(gpb_graph* g) { return g ? g->launches : 0; }
 int gpb_allreduces_last_optimize(gpb_graph* g) { return g ? g->n_allreduce : 0; }
 // plain cudaMemcpy (kind: 1 host->device, 2 device->host) for callers that implement gpb_allreduce_fn without a CUDA binding of their own
@@ -1429,7 +1480,7 @@ int gpb_get_linearized_factor(gpb_graph* g, int kind, int idx, double* A_out, do
     std::vector<double> col(2);
     for (int c = 0; c < ncol; c++)
       for (int rp = 0; rp < D; rp++) {
-        CUDA_TRY(cudaMemcpy(col.data(), g->d_AB[g->cur] + ((size_t)(c * D + rp) * g->NFp + idx) * 2, 2 * sizeof(double), cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(col.data(), g->d_AB[g->cur] + ab_off(c * D + rp, idx, (4 * D + 1) * D), 2 * sizeof(double), cudaMemcpyDeviceToHost));
         for (int t = 0; t < 2; t++) { const int r = 2 * rp + t; if (c < 4 * D) A_out[(size_t)c * m + r] = col[t]; else b_out[r] = col[t]; }
       }
     for (int v = 0; v < 4; v++) dims_out[v] = D;

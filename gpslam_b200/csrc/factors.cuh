@@ -21,6 +21,13 @@ namespace gpb {
 // a kernel class of G_POSE3, not a graph group of its own - record layout, block sizes, assembly, solver and retraction are G_POSE3's.
 enum Group { G_POSE3 = 0, G_POSE2 = 1, G_ROT3 = 2, G_LINEAR = 3, G_POSE3VW = 4 };
 
+// Layout of the whitened GP-prior JacobianFactors [A|b] in HBM: tiles of AB_TF consecutive factors; inside a tile
+// [row pair p = column * D + rp][factor in tile][2 doubles].  A linearise CTA (AB_TF threads) writes ONE contiguous tile
+// (NP x 2 KB: its 128-bit stores are base + compile-time offsets, and the tile sits in one or two 2 MB pages instead of NP of
+// them); an assembly CTA reads 16-byte entries of 8-9 consecutive factors per row pair, all inside one tile.
+constexpr int AB_TF = 128;
+GPB_HD size_t ab_off(int p, int f, int NP) { return ((size_t)(f / AB_TF) * NP + p) * (size_t)(AB_TF * 2) + (size_t)(f % AB_TF) * 2; }
+
 template <int I, int N, class F> GPB_HD void static_for(F&& f) {
   if constexpr (I < N) { f(std::integral_constant<int, I>{}); static_for<I + 1, N>(f); }
 }

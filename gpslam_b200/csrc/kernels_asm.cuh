@@ -22,7 +22,7 @@ __global__ void __launch_bounds__(NT) k_assemble(const double* __restrict__ AB, 
   if (i >= N) return;
   const int nint = N - 1;
   const int c0 = (TILES == 1) ? 0 : (tile & 1) * 6;
-  auto ld2 = [&](int col, int rp, int f) { return *reinterpret_cast<const double2*>(AB + ((size_t)(col * D + rp) * NFp + f) * 2); };
+  auto ld2 = [&](int col, int rp, int f) { return *reinterpret_cast<const double2*>(AB + ab_off(col * D + rp, f, (4 * D + 1) * D)); };
   double* rec = HREC + (size_t)i * REC;
 
   // One tile = 6 columns of D_i (DOD) and/or of E_i (DOE); C0, DOD, DOE, DOG are compile-time so every operand array stays in
@@ -196,18 +196,21 @@ __global__ void __launch_bounds__(128) k_assemble_mma(const double* __restrict__
   static_assert(TS * REC <= NF * FS, "record staging must fit the factor staging");
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gi = lane >> 2, ti = lane & 3;
   const int i0 = blockIdx.x * TS, nint = N - 1;
-  // ---- load: item = (column c, row pair rp, factor ff); consecutive threads take consecutive factors (16 contiguous bytes each)
+  // ---- load: item = (row pair pr = column * D + rp, factor ff), 16 bytes each; consecutive threads take consecutive factors.
+  // Thread (ff, g) = (tid % NF, tid / NF) of the first 14 * NF = 126 threads copies row pairs g, g + 14, ...: its source
+  // (ab_off: + one row of the tile per row pair) and destination (Fsm[ff][2 pr]) advance by constants - no index arithmetic
+  // per copy (the straightforward item -> (ff, c, rp) decode was a quarter of this kernel's instructions)
   {
-    constexpr int NITEM = NCOL * D * NF;
+    constexpr int NPR = NCOL * D, NG = 128 / NF;
+    const int ff = tid % NF, g = tid / NF;
+    if (g < NG) {
+      const int f = i0 - 1 + ff;
+      const bool ok = f >= 0 && f < NFp;
+      const double* src = AB + ab_off(g, ok ? f : 0, NPR);
+      double* dst = &Fsm[ff * FS + 2 * g];
 #pragma unroll
-    for (int j = 0; j < (NITEM + 127) / 128; j++) {
-      const int it = tid + 128 * j;
-      if (it < NITEM) {
-        const int ff = it % NF, pr = it / NF, c = pr / D, rp = pr % D;
-        const int f = i0 - 1 + ff;
-        const bool ok = f >= 0 && f < NFp;
-        cp_async16_zfill(&Fsm[ff * FS + c * bs + 2 * rp], AB + ((size_t)pr * NFp + (ok ? f : 0)) * 2, ok);
-      }
+      for (int j = 0; j < (NPR + NG - 1) / NG; j++)
+        if (g + NG * j < NPR) cp_async16_zfill(dst + 2 * NG * j, src + (size_t)(AB_TF * 2) * NG * j, ok);
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   }
@@ -307,3 +310,4 @@ __global__ void __launch_bounds__(128) k_assemble_mma(const double* __restrict__
 #pragma unroll 4
   for (int k = tid; k < nst * REC / 2; k += 128) *reinterpret_cast<double2*>(dst + 2 * k) = *reinterpret_cast<const double2*>(Osm + 2 * k);
 }
+

@@ -66,23 +66,25 @@ __global__ void __launch_bounds__(NT, MINB) k_lin_gp(const double* __restrict__ 
   if (threadIdx.x == 0) mbar_init(&bar, 1);
   __syncthreads();
   if (threadIdx.x == 0) tma_load_tile(sm, X + (size_t)tile0 * SR, (unsigned)((cnt + 1) * SR * sizeof(double)), &bar);
-  mbar_wait(&bar, 0);
   const int f = tile0 + threadIdx.x;
+  // the factor's own parameters are fetched while the tile is in flight (nothing below the wait depends on a fresh global load)
+  const double h = threadIdx.x < cnt ? dt[f] : 0.0;
+  const int qi = threadIdx.x < cnt ? qc[f] : 0;
+  mbar_wait(&bar, 0);
   double err = 0.0;
   if (threadIdx.x < cnt) {
-    const double h = dt[f];
     if (h > 0.0) {
       const double* s1 = sm + threadIdx.x * SR;
       const double* s2 = s1 + SR;
-      const double* Rq = RqTab + qc[f] * D * D;
+      const double* Rq = RqTab + qi * D * D;
       const GpWhiten w = gp_whiten(h);
       double col[2 * D];
-      // entry (column c, row pair rp) of factor f sits at byte ((c D + rp) NFp + f) 16: one 32 x 32 + 64-bit multiply-add per store
-      char* const abase = reinterpret_cast<char*>(AB) + (size_t)f * 16;
-      const unsigned strideB = (unsigned)NFp * 16u;
+      // this CTA's factors are one tile of the [A|b] layout (ab_off): entry (column c, row pair rp) = base + a compile-time offset
+      static_assert(NT == AB_TF, "one linearise CTA per [A|b] tile");
+      double* const abase = AB + ab_off(0, f, (4 * D + 1) * D);
       auto store_col = [&](int c, const double* v) {
 #pragma unroll
-        for (int rp = 0; rp < D; rp++) *reinterpret_cast<double2*>(abase + (size_t)((unsigned)(c * D + rp)) * strideB) = make_double2(v[2 * rp], v[2 * rp + 1]);
+        for (int rp = 0; rp < D; rp++) st128(abase + (size_t)(c * D + rp) * (AB_TF * 2), v[2 * rp], v[2 * rp + 1]);
       };
       auto store = [&](int c) { store_col(c, col); };
       if constexpr (G == G_POSE3) {

@@ -205,6 +205,10 @@ int gpb_stream_synchronize(void* cuda_stream);
 /* profiling aid: measured FP64 tensor-pipe (mma.sync m8n8k4, SASS DMMA) peak of the device in TFLOP/s - the roofline
  * denominator of the panel kernel */
 int gpb_debug_dmma_peak(int device, double* tflops_out);
+/* profiling aid: microseconds to write n_factors SE(3) [A|b] records (2400 B each) in k_lin_gp's store pattern with no arithmetic
+ * in front (mode 4: the tiled layout the engine uses; 1: untiled SoA, row pairs NFp*16 B apart; 2: 1 with streaming stores; 3: 1 with
+ * 256-thread CTAs) or with cudaMemsetAsync (mode 0) - the floor of the layout */
+int gpb_debug_store_peak(int device, int mode, int n_factors, double* us_out);
 /* testing aid: the reduced-system solver alone - (A + lambda * diag[loff..R)) x = b, A symmetric R x R column-major; the
  * shared-memory single-CTA solver for small R, the blocked multi-CTA Cholesky beyond (or when force_blocked != 0) */
 int gpb_debug_dense_solve(int device, int R, const double* A, const double* b, double lambda, int loff, int force_blocked, double* x_out);

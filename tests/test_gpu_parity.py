@@ -180,6 +180,19 @@ def test_lin_gp_instantiations_agree(variant, monkeypatch):
             np.testing.assert_allclose(x, y, atol=1e-12 * sc)
 
 
+@pytest.mark.parametrize("n", [5, 8, 9, 127, 128, 129, 130, 300])
+def test_assembly_kernels_agree(n, monkeypatch):
+    """SE(3) assembly: the tensor-pipe kernel (k_assemble_mma, default) against the thread-per-tile kernel (GPB_OLD_ASSEMBLE) on
+    chains that end inside / at / just behind a tile of the [A|b] layout (128 factors) and of the kernel (8 states)"""
+    cfg = small_cfg("C3", n, n_landmarks=4, prior_every=max(2, min(40, n // 2)))
+    g0, _ = synth.build(cfg, lambda grp, nn, l: gb.Graph(grp, nn, l))
+    monkeypatch.setenv("GPB_OLD_ASSEMBLE", "1")
+    g1, _ = synth.build(cfg, lambda grp, nn, l: gb.Graph(grp, nn, l))
+    g0.linearize(); g1.linearize()
+    H0, r0 = g0.normal_equations_dense(); H1, r1 = g1.normal_equations_dense()
+    np.testing.assert_allclose(H0, H1, atol=1e-12 * np.abs(H1).max()); np.testing.assert_allclose(r0, r1, atol=1e-12 * np.abs(r1).max())
+
+
 @pytest.mark.parametrize("n_landmarks", [2, 16])
 @pytest.mark.parametrize("n", [2, 3, 16, 17, 18, 33, 129, 130])
 def test_segment_boundaries(n, n_landmarks):
