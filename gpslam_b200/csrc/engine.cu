@@ -90,7 +90,7 @@ struct gpb_graph {
   int nclos = 0, nep = 0, npair = 0;  // loop closures: factors, endpoint states, unique endpoint pairs
   int *d_epstate = nullptr, *d_epoff = nullptr, *d_eprow = nullptr, *d_epside = nullptr;
   int *d_pair_a = nullptr, *d_pair_b = nullptr, *d_pairoff = nullptr, *d_pairrow = nullptr;
-  bool generic_fwd = false, force_blocked = false, old_assemble = false, split_levels = false;
+  bool generic_fwd = false, force_blocked = false, old_assemble = false, split_levels = false, no_tiny = false;
   gpb_allreduce_fn allreduce = nullptr; void* allreduce_ctx = nullptr;
   double* d_topbuf = nullptr; double cur_error_local = 0; int n_allreduce = 0;
   double* d_lambda = nullptr;
@@ -521,7 +521,8 @@ int gpb_graph_finalize(gpb_graph* g, int device) {
   CUDA_TRY(cudaStreamCreateWithFlags(&g->stream2, cudaStreamNonBlocking));
   CUDA_TRY(cudaEventCreateWithFlags(&g->ev_fork, cudaEventDisableTiming));
   CUDA_TRY(cudaEventCreateWithFlags(&g->ev_join, cudaEventDisableTiming));
-  CUDA_TRY(cudaFuncSetAttribute(k_small_solve<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_solve_smem(SMALL_SOLVE_MAX)));
+  CUDA_TRY(cudaFuncSetAttribute(k_small_solve<256, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_solve_smem(SMALL_SOLVE_MAX)));
+  CUDA_TRY(cudaFuncSetAttribute(k_small_solve<256, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_solve_smem(95)));
   const int D = g->D, bs = g->bs, DL = g->DL;
   g->nb = g->L * DL; g->w = bs + g->nb + 1;
   g->W = g->w <= 16 ? 16 : g->w <= 32 ? 32 : 64;
@@ -653,6 +654,7 @@ int gpb_graph_finalize(gpb_graph* g, int device) {
   g->split_levels = getenv("GPB_SPLIT_LEVELS") != nullptr;  // A/B switch: spine and panel as two launches on the upper levels too
   g->old_assemble = getenv("GPB_OLD_ASSEMBLE") != nullptr;  // A/B switch: thread-per-tile assembly instead of the DMMA kernel
   g->generic_fwd = getenv("GPB_GENERIC_FWD") != nullptr;
+  g->no_tiny = getenv("GPB_NO_TINY_SOLVE") != nullptr;  // A/B switch: the plain-loop instantiation of k_small_solve instead of the register-blocked ones
   g->qc_diag = 1;
   for (const auto& R : g->Rq) for (int c = 0; c < D; c++) for (int r = 0; r < D; r++) if (r != c && R[r + c * D] != 0.0) g->qc_diag = 0;
   g->lin_variant = g->qc_diag ? 1 : 0;
@@ -973,7 +975,7 @@ static int dist_allreduce(gpb_graph* g, double* dbuf, long long count) {
 static int solve_top_dense(gpb_graph* g) {
   const int R = g->R, ld = R + 1, loff = g->ntop * g->bs;
   if (R <= SMALL_SOLVE_MAX && !g->force_blocked) {
-    k_small_solve<256><<<1, 256, small_solve_smem(R), g->stream>>>(g->d_topbuf, ld, g->d_topbuf + R, ld, R, loff, g->d_lambda, g->d_topx, g->d_flag, 3);
+    launch_small_solve(g->stream, g->d_topbuf, ld, g->d_topbuf + R, ld, R, loff, g->d_lambda, g->d_topx, g->d_flag, 3, !g->no_tiny);
     g->launches++;
     return GPB_OK;
   }
@@ -1021,7 +1023,7 @@ static int top_finish(gpb_graph* g, double* sc_out /*[4] or null*/) {
   int rc;
   const int nb = g->nb, R = g->R;
   if (top_is_landmarks_only(g)) {
-    if (nb) { k_small_solve<256><<<1, 256, small_solve_smem(nb), g->stream>>>(g->d_Csum, nb, g->d_Csum + (size_t)nb * nb, 1, nb, 0, g->d_lambda, g->d_xlm, g->d_flag, 2); g->launches++; }
+    if (nb) { launch_small_solve(g->stream, g->d_Csum, nb, g->d_Csum + (size_t)nb * nb, 1, nb, 0, g->d_lambda, g->d_xlm, g->d_flag, 2, !g->no_tiny); g->launches++; }
     return GPB_OK;
   }
   if (sc_out) CUDA_TRY(cudaMemcpyAsync(sc_out, g->d_topbuf + (size_t)(R + 1) * R, 4 * sizeof(double), cudaMemcpyDeviceToHost, g->stream));
@@ -1336,9 +1338,10 @@ int gpb_debug_dense_solve(int device, int R, const double* A, const double* b, d
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(GPB_ERR_CUDA, "gpb_debug_dense_solve: no CUDA device available"); }
   CUDA_TRY(cudaSetDevice(device));
-  CUDA_TRY(cudaFuncSetAttribute(k_small_solve<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_solve_smem(SMALL_SOLVE_MAX)));
+  CUDA_TRY(cudaFuncSetAttribute(k_small_solve<256, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_solve_smem(SMALL_SOLVE_MAX)));
+  CUDA_TRY(cudaFuncSetAttribute(k_small_solve<256, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_solve_smem(95)));
   gpb_graph g;
-  g.R = R; g.bs = 1; g.ntop = loff; g.force_blocked = force_blocked != 0;
+  g.R = R; g.bs = 1; g.ntop = loff; g.force_blocked = force_blocked == 1; g.no_tiny = force_blocked == 2;  // 2: the plain-loop instantiation of the shared-memory solver
   CUDA_TRY(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
   int rc = GPB_OK;
   std::vector<double> T((size_t)(R + 1) * R + 4, 0.0);

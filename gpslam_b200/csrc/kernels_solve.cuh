@@ -1133,8 +1133,12 @@ __global__ void k_cseg_final(const double* __restrict__ Cbase, const double* __r
 // factorisation performs the forward substitution; one block barrier per column (the trailing update reads the unscaled
 // pivot column and scales on the fly, the column itself is scaled afterwards by other threads).  Back-substitution is done by
 // one warp, row-oriented, the solution entries living in registers (entry r on lane r mod 32).
+// KB > 0 (R + 1 <= 16 KB): the trailing update of a column is register-blocked - a thread's (up to KB x KB) targets, the 2 KB - 1
+// pivot-column entries and KB multipliers they need are all loaded before the first FMA, so the column costs one shared-memory
+// latency instead of KB^2 dependent load-FMA-store round trips (R = 48, the landmark system of C3: 44 us -> see DESIGN.md).
+// KB = 0: plain loops, any R <= SMALL_SOLVE_MAX.  Same operations on the same operands in every instantiation.
 constexpr int SMALL_SOLVE_MAX = 160;
-template <int NT>
+template <int NT, int KB = 0>
 __global__ void __launch_bounds__(NT) k_small_solve(const double* __restrict__ A, int lda, const double* rhs, int rstride, int R, int loff,
                                                     const double* __restrict__ lambda_ptr, double* x, int* __restrict__ flag, int flagval) {
   extern __shared__ double sm[];
@@ -1151,9 +1155,31 @@ __global__ void __launch_bounds__(NT) k_small_solve(const double* __restrict__ A
     const double djj = sm[j + j * ld];
     if (!(djj > 0.0) && tid == 0) *flag = flagval;
     const double inv = rsqrt_pos(djj > 0.0 ? djj : 1.0);
-    for (int cc = j + 1 + ty; cc < R; cc += TY) {
-      const double lc = sm[cc + j * ld] * inv;
-      for (int r = cc + tx; r <= R; r += 16) sm[r + cc * ld] = fma(-(sm[r + j * ld] * inv), lc, sm[r + cc * ld]);
+    if constexpr (KB > 0) {
+      static_assert(NT == 256, "16 x 16 thread tile");
+      // targets (r, cc) = (j + 1 + ty + tx + 16 (a + b), j + 1 + ty + 16 a): pivot-column rows depend on a + b only
+      const int base = j + 1 + ty;
+      double pv[2 * KB - 1], lc[KB], tv[KB][KB];
+#pragma unroll
+      for (int m = 0; m < 2 * KB - 1; m++) { const int r = base + tx + 16 * m; pv[m] = r <= R ? sm[r + j * ld] : 0.0; }
+#pragma unroll
+      for (int a = 0; a < KB; a++) { const int cc = base + 16 * a; lc[a] = cc < R ? sm[cc + j * ld] : 0.0; }
+#pragma unroll
+      for (int a = 0; a < KB; a++)
+#pragma unroll
+        for (int b = 0; b + a < KB; b++) { const int cc = base + 16 * a, r = cc + tx + 16 * b; tv[a][b] = (cc < R && r <= R) ? sm[r + cc * ld] : 0.0; }
+#pragma unroll
+      for (int a = 0; a < KB; a++)
+#pragma unroll
+        for (int b = 0; b + a < KB; b++) {
+          const int cc = base + 16 * a, r = cc + tx + 16 * b;
+          if (cc < R && r <= R) sm[r + cc * ld] = fma(-(pv[a + b] * inv), lc[a] * inv, tv[a][b]);
+        }
+    } else {
+      for (int cc = j + 1 + ty; cc < R; cc += TY) {
+        const double lc = sm[cc + j * ld] * inv;
+        for (int r = cc + tx; r <= R; r += 16) sm[r + cc * ld] = fma(-(sm[r + j * ld] * inv), lc, sm[r + cc * ld]);
+      }
     }
     __syncthreads();
     for (int r = j + tid; r <= R; r += NT) sm[r + j * ld] *= inv;
@@ -1182,6 +1208,15 @@ __global__ void __launch_bounds__(NT) k_small_solve(const double* __restrict__ A
   }
 }
 static size_t small_solve_smem(int R) { return ((size_t)(R + 2) * R + R) * sizeof(double); }
+// the instantiation that fits R (allow_blocked = false: the plain-loop form, for A/B and tests)
+static void launch_small_solve(cudaStream_t stream, const double* A, int lda, const double* rhs, int rstride, int R, int loff, const double* lambda_ptr, double* x,
+                               int* flag, int flagval, bool allow_blocked = true) {
+  if (allow_blocked && R + 1 <= 16 * 2) k_small_solve<256, 2><<<1, 256, small_solve_smem(R), stream>>>(A, lda, rhs, rstride, R, loff, lambda_ptr, x, flag, flagval);
+  else if (allow_blocked && R + 1 <= 16 * 4) k_small_solve<256, 4><<<1, 256, small_solve_smem(R), stream>>>(A, lda, rhs, rstride, R, loff, lambda_ptr, x, flag, flagval);
+  else if (allow_blocked && R + 1 <= 16 * 6) k_small_solve<256, 6><<<1, 256, small_solve_smem(R), stream>>>(A, lda, rhs, rstride, R, loff, lambda_ptr, x, flag, flagval);
+  else k_small_solve<256, 0><<<1, 256, small_solve_smem(R), stream>>>(A, lda, rhs, rstride, R, loff, lambda_ptr, x, flag, flagval);
+}
+
 
 // x <- x (+) delta for every state (Pose3 / Rot3: Expmap; Pose2: GTSAM's default chart; vectors: add), plus the two dot
 // products LM needs: g.delta and |delta|^2 (block partials).
