@@ -523,6 +523,7 @@ int gpb_graph_finalize(gpb_graph* g, int device) {
   CUDA_TRY(cudaEventCreateWithFlags(&g->ev_join, cudaEventDisableTiming));
   CUDA_TRY(cudaFuncSetAttribute(k_small_solve<256, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_solve_smem(SMALL_SOLVE_MAX)));
   CUDA_TRY(cudaFuncSetAttribute(k_small_solve<256, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_solve_smem(95)));
+  CUDA_TRY(cudaFuncSetAttribute(k_small_solve<256, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_solve_smem(143)));
   const int D = g->D, bs = g->bs, DL = g->DL;
   g->nb = g->L * DL; g->w = bs + g->nb + 1;
   g->W = g->w <= 16 ? 16 : g->w <= 32 ? 32 : 64;
@@ -1340,6 +1341,7 @@ int gpb_debug_dense_solve(int device, int R, const double* A, const double* b, d
   CUDA_TRY(cudaSetDevice(device));
   CUDA_TRY(cudaFuncSetAttribute(k_small_solve<256, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_solve_smem(SMALL_SOLVE_MAX)));
   CUDA_TRY(cudaFuncSetAttribute(k_small_solve<256, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_solve_smem(95)));
+  CUDA_TRY(cudaFuncSetAttribute(k_small_solve<256, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_solve_smem(143)));
   gpb_graph g;
   g.R = R; g.bs = 1; g.ntop = loff; g.force_blocked = force_blocked == 1; g.no_tiny = force_blocked == 2;  // 2: the plain-loop instantiation of the shared-memory solver
   CUDA_TRY(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));

@@ -1133,7 +1133,7 @@ __global__ void k_cseg_final(const double* __restrict__ Cbase, const double* __r
 // factorisation performs the forward substitution; one block barrier per column (the trailing update reads the unscaled
 // pivot column and scales on the fly, the column itself is scaled afterwards by other threads).  Back-substitution is done by
 // one warp, row-oriented, the solution entries living in registers (entry r on lane r mod 32).
-// KB > 0 (R + 1 <= 16 KB): the trailing update of a column is register-blocked - a thread's (up to KB x KB) targets, the 2 KB - 1
+// KB > 0 (R + 1 <= 16 KB; instantiated for KB = 2, 4, 6, 9): the trailing update of a column is register-blocked - a thread's (up to KB x KB) targets, the 2 KB - 1
 // pivot-column entries and KB multipliers they need are all loaded before the first FMA, so the column costs one shared-memory
 // latency instead of KB^2 dependent load-FMA-store round trips (R = 48, the landmark system of C3: 44 us -> see DESIGN.md).
 // KB = 0: plain loops, any R <= SMALL_SOLVE_MAX.  Same operations on the same operands in every instantiation.
@@ -1214,6 +1214,7 @@ static void launch_small_solve(cudaStream_t stream, const double* A, int lda, co
   if (allow_blocked && R + 1 <= 16 * 2) k_small_solve<256, 2><<<1, 256, small_solve_smem(R), stream>>>(A, lda, rhs, rstride, R, loff, lambda_ptr, x, flag, flagval);
   else if (allow_blocked && R + 1 <= 16 * 4) k_small_solve<256, 4><<<1, 256, small_solve_smem(R), stream>>>(A, lda, rhs, rstride, R, loff, lambda_ptr, x, flag, flagval);
   else if (allow_blocked && R + 1 <= 16 * 6) k_small_solve<256, 6><<<1, 256, small_solve_smem(R), stream>>>(A, lda, rhs, rstride, R, loff, lambda_ptr, x, flag, flagval);
+  else if (allow_blocked && R + 1 <= 16 * 9) k_small_solve<256, 9><<<1, 256, small_solve_smem(R), stream>>>(A, lda, rhs, rstride, R, loff, lambda_ptr, x, flag, flagval);  // 8 shards: R = 7 * 12 + 48 = 132
   else k_small_solve<256, 0><<<1, 256, small_solve_smem(R), stream>>>(A, lda, rhs, rstride, R, loff, lambda_ptr, x, flag, flagval);
 }
 

@@ -228,9 +228,9 @@ def test_many_loop_closures_blocked_top_solve(seglen):
     assert np.abs(Pg - Po).max() <= 1e-6 and np.abs(Vg - Vo).max() <= 1e-6 and np.abs(Lg - Lo).max() <= 1e-6
 
 
-@pytest.mark.parametrize("R", [1, 2, 15, 16, 17, 31, 32, 47, 48, 49, 63, 64, 65, 95, 96, 128, 160, 161, 200, 449, 1000])
+@pytest.mark.parametrize("R", [1, 2, 15, 16, 17, 31, 32, 47, 48, 49, 63, 64, 65, 95, 96, 128, 132, 143, 144, 160, 161, 200, 449, 1000])
 def test_reduced_system_solvers(R):
-    """the reduced-system solvers alone (shared-memory single-CTA solver in its register-blocked (R <= 95) and plain-loop
+    """the reduced-system solvers alone (shared-memory single-CTA solver in its register-blocked (R <= 143) and plain-loop
     instantiations, blocked multi-CTA Cholesky) against numpy"""
     from gpslam_b200 import capi
     rng = np.random.default_rng(R)
@@ -240,12 +240,12 @@ def test_reduced_system_solvers(R):
         for blocked in ((False, True) if R <= 160 else (True,)):
             x = capi.dense_solve(A, b, lam, loff, blocked)
             assert np.abs(x - ref).max() <= 1e-9 * max(1.0, np.abs(ref).max()), (R, lam, blocked, np.abs(x - ref).max())
-        if R <= 95:
+        if R <= 143:
             x = capi.dense_solve(A, b, lam, loff, force_small=True)
             assert np.abs(x - ref).max() <= 1e-9 * max(1.0, np.abs(ref).max()), (R, lam, "small", np.abs(x - ref).max())
     with pytest.raises(capi.GpbError):
         capi.dense_solve(-A, b, 0.0, 0, R > 160)
-    if R <= 95:
+    if R <= 143:
         with pytest.raises(capi.GpbError):
             capi.dense_solve(-A, b, 0.0, 0, force_small=True)
 
