@@ -24,11 +24,11 @@ sys.path.insert(0, ROOT)
 WORKLOAD = "C3: SE(3) GP-prior + interpolated range factors, 100k states, 50k ranges, 16 landmarks (BASELINE.json configs[2]; interpolated range only - the reference has no interpolated bearing factor)"
 METRIC = "GN iterations/sec on 100k-state SE(3) GP trajectory"
 CPU_SAMPLE_STATES = 10000
-# dram__bytes_read.sum + dram__bytes_write.sum of one launch on C3, from the ncu --set full captures summarised in
-# profiles/r1b_ncu_full_summary.csv: k_lin_gp 15.7 MB read + 181.6 MB written (the tail of the 240 MB of [A|b] is still in L2 at
-# kernel end); k_panel4 (level 0) 270.2 MB read + 558.3 MB written
-TRAFFIC_LIN_GP = 197.3e6
-TRAFFIC_PANEL = 828.5e6
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch on C3, from the ncu --set full capture summarised in
+# profiles/r1x_ncu_full_summary.csv: k_lin_gp 15.7 MB read + 180.6 MB written (the tail of the 240 MB of [A|b] is still in L2 at
+# kernel end); k_panel4 (level 0) 270.2 MB read + 557.1 MB written
+TRAFFIC_LIN_GP = 196.3e6
+TRAFFIC_PANEL = 827.3e6
 # algorithmic FLOPs of the level-0 panel per state (SE(3), w = 61 columns): Y = L^-1 P (12*13/2*61 MAC), P' = Le Y (12*12*61),
 # S += Y^T Y (61*62/2*12)
 PANEL_FLOP_PER_STATE = 2.0 * (78 * 61 + 144 * 61 + 61 * 62 // 2 * 12)
@@ -212,6 +212,9 @@ def run_engine(args, rank, world, local_rank):
                                                    (6, "solve_spine_level0"), (7, "solve_panel_level0"), (8, "solve_backward"))}
     from gpslam_b200 import capi
     dmma_peak = capi.dmma_peak(local_rank)
+    # what the [A|b] store pattern costs with no arithmetic in front of it, and a plain memset of the same bytes (context for
+    # the linearise roofline: the kernel is bound by its stores)
+    store_floor_us = capi.store_peak(4, sz.n_gp, local_rank); memset_us = capi.store_peak(0, sz.n_gp, local_rank)
     sampler.mark_end()
     clocks = sampler.stop()
     peak, peak_src = peaks()
@@ -228,8 +231,9 @@ def run_engine(args, rank, world, local_rank):
                    "hbm_resident_mb": sz.hbm_bytes / 1e6, "graph_build_s": build_s},
         "e2e": {"value": 1.0 / e2e_s, "unit": "iterations/s", "h2d_bytes_per_step": io_bytes * world, "d2h_bytes_per_step": io_bytes * world},
         "gpu_launches": launches,
-        "roofline": {"kernel": "k_lin_gp<POSE3> (batched GP-prior linearise)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "peak_source": peak_src, "algorithmic_bytes": gp_bytes, "ms": stages["linearise_gp"], "traffic": TRAFFIC_LIN_GP if world == 1 else None},
+        "roofline": {"kernel": "k_lin_gp<POSE3> (batched GP-prior linearise; diagonal-Qc instantiation)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "peak_source": peak_src, "algorithmic_bytes": gp_bytes, "ms": stages["linearise_gp"], "traffic": TRAFFIC_LIN_GP if world == 1 else None,
+                     "store_pattern_floor_ms": store_floor_us * 1e-3, "memset_same_bytes_ms": memset_us * 1e-3},
         # the kernel that dominates the iteration by time: the level-0 panel, bound by the FP64 tensor pipe
         "roofline_solver": {"kernel": "k_panel4<12> (level-0 panel: Y = L^-1 P, P' = -Le Y, S += Y^T Y on mma.sync.m8n8k4.f64)", "bound": "tensor", "achieved": PANEL_FLOP_PER_STATE * g.N / (stages["solve_panel_level0"] * 1e-3) / 1e12,
                             "peak": dmma_peak, "unit": "TFLOP/s", "frac": PANEL_FLOP_PER_STATE * g.N / (stages["solve_panel_level0"] * 1e-3) / 1e12 / dmma_peak,
