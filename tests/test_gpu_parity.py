@@ -344,3 +344,84 @@ def test_full_size_properties():
     assert abs(st.error_final - st2.error_final) <= 1e-9 * st.error_final
     P1, V1, L1 = g.get_values(); P2, V2, L2 = g2.get_values()
     assert np.abs(P1 - P2).max() < 1e-6 and np.abs(V1 - V2).max() < 1e-6 and np.abs(L1 - L2).max() < 1e-6
+
+
+# ----------------------------------------------------------------------------- edge cases
+def _ragged_graph(make, n=90, seed=11):
+    """SE(3) chain with holes: every 7th interval has NO GP prior (odometry BetweenFactors keep the chain connected), intervals
+    with several measurements and intervals with none, one landmark nobody observes (prior only), tau outside [0, dt]"""
+    rng = np.random.default_rng(seed)
+    cfg = small_cfg("C3", n, n_landmarks=3)
+    poses, vels = synth.ground_truth(cfg)
+    g = make(POSE3, n, 3)
+    g.add_qc_model(np.eye(6) * 0.01)
+    keep = np.array([i for i in range(n - 1) if i % 7 != 3])
+    g.add_gp_prior(keep, np.full(len(keep), cfg.dt))
+    for i in range(n - 1):
+        if i % 7 == 3 or i % 5 == 0:
+            g.add_between(i, i + 1, synth._between(POSE3, poses[i], poses[i + 1], rng, 1e-3), np.eye(6) / 1e-2)
+    lands = poses[:, 9:12].mean(axis=0) + rng.uniform(-15, 15, size=(3, 3))
+    ri = np.array([0, 0, 0, 10, 11, 40, 40, 41, 88]); rl = np.array([0, 1, 0, 1, 1, 0, 0, 1, 0]); tau = rng.uniform(-0.03, cfg.dt + 0.03, size=len(ri))
+    z = np.array([np.linalg.norm(lands[l] - synth._retract(POSE3, poses[i], vels[i] * t)[9:12]) for i, l, t in zip(ri, rl, tau)]) + rng.normal(size=len(ri)) * 0.1
+    g.add_interp_range(ri, rl, z, np.full(len(ri), 0.1), np.full(len(ri), cfg.dt), tau)
+    for l in range(3):
+        g.add_prior_landmark(l, lands[l] + rng.normal(size=3) * 0.3, np.eye(3))       # landmark 2: prior only
+    g.add_prior_pose(0, poses[0], np.eye(6) / 1e-3); g.add_prior_vel(0, vels[0], np.eye(6) / 1e-2)
+    g.add_prior_vel(n - 1, vels[n - 1], np.eye(6) / 1e-1)
+    for i in (4, 5, 46):  # states right behind a missing prior need their velocity tied down by something
+        g.add_prior_vel(i, vels[i], np.eye(6))
+    g.set_values(np.stack([synth._retract(POSE3, poses[i], rng.normal(size=6) * 0.03) for i in range(n)]), np.zeros((n, 6)), lands + rng.normal(size=lands.shape) * 0.3)
+    if hasattr(g, "finalize"):
+        g.finalize()
+    return g
+
+
+def test_ragged_graph_matches_oracle():
+    g = _ragged_graph(lambda grp, n, l: gb.Graph(grp, n, l)); o = _ragged_graph(lambda grp, n, l: po.Graph(grp, n, l))
+    assert abs(g.linearize() - o.error()) <= 1e-9 * o.error()
+    Hg, gg = g.normal_equations_dense(); Ho, go = o.normal_equations_dense()
+    np.testing.assert_allclose(Hg, Ho, atol=2e-6 * np.abs(Ho).max()); np.testing.assert_allclose(gg, go, atol=2e-6 * np.abs(go).max())
+    for use_lm in (False, True):
+        g = _ragged_graph(lambda grp, n, l: gb.Graph(grp, n, l)); o = _ragged_graph(lambda grp, n, l: po.Graph(grp, n, l))
+        sg = g.optimize(use_lm=use_lm); so = o.optimize(use_lm=use_lm)
+        assert sg.status == 0 and so.status == 0 and sg.iterations == so.iterations
+        Pg, Vg, Lg = g.get_values(); Po, Vo, Lo = o.get_values()
+        assert np.abs(Pg - Po).max() <= 1e-6 and np.abs(Vg - Vo).max() <= 1e-6 and np.abs(Lg - Lo).max() <= 1e-6
+
+
+def test_indeterminate_system_is_reported():
+    """a GP chain with no prior at all has a free gauge: Gauss-Newton must fail loudly (GTSAM throws
+    IndeterminantLinearSystemException), LM must cope through its damping - in the engine as in the oracle"""
+    from gpslam_b200 import capi
+    n = 40
+    cfg = small_cfg("C2", n); cfg.prior_every = 0
+    poses, vels = synth.ground_truth(cfg)
+
+    def build(make):
+        g = make(POSE3, n, 0)
+        g.add_qc_model(np.eye(6) * 0.01); g.add_gp_prior(np.arange(n - 1), np.full(n - 1, cfg.dt)); g.set_values(poses, vels * 1.01, None)
+        if hasattr(g, "finalize"):
+            g.finalize()
+        return g
+    o = build(lambda grp, nn, l: po.Graph(grp, nn, l))
+    assert o.optimize(use_lm=False).status != 0
+    g = build(lambda grp, nn, l: gb.Graph(grp, nn, l))
+    with pytest.raises(capi.GpbError, match="indeterminate"):
+        g.optimize(use_lm=False)
+    g = build(lambda grp, nn, l: gb.Graph(grp, nn, l)); o = build(lambda grp, nn, l: po.Graph(grp, nn, l))
+    sg = g.optimize(use_lm=True); so = o.optimize(use_lm=True)
+    assert sg.status == 0 and so.status == 0 and sg.error_final < 1e-6 and so.error_final < 1e-6
+
+
+def test_landmark_border_limit():
+    """17 3-D landmarks (51 border columns) is the widest supported border; 18 are refused at finalize, not mis-solved"""
+    from gpslam_b200 import capi
+    cfg = small_cfg("C3", 150, n_landmarks=17, prior_every=30, range_per_state=1.5)
+    g, o, _ = both(cfg)
+    sg = g.optimize(use_lm=True); so = o.optimize(use_lm=True)
+    assert sg.status == 0 and sg.iterations == so.iterations
+    Pg, Vg, Lg = g.get_values(); Po, Vo, Lo = o.get_values()
+    assert np.abs(Pg - Po).max() <= 1e-6 and np.abs(Lg - Lo).max() <= 1e-6
+    cfg = small_cfg("C3", 150, n_landmarks=18, prior_every=30, range_per_state=1.5)
+    with pytest.raises(capi.GpbError):
+        synth.build(cfg, lambda grp, n, l: gb.Graph(grp, n, l))
