@@ -664,7 +664,9 @@ int gpb_graph_finalize(gpb_graph* g, int device) {
     if (v >= 0 && v <= 3 && (!(v & 1) || g->qc_diag)) g->lin_variant = v;
   }  // A/B switch: one-kernel generic forward sweep (k_fwd<12,64>)
   int M0 = g->M0 ? g->M0 : (em0 ? std::max(2, atoi(em0)) : (g->nb > 0 ? 32 : 16));
-  const int Mup = g->Mup ? g->Mup : (emu ? std::max(2, atoi(emu)) : 8);
+  // upper levels: 8 states per segment; 6 on short chains (shards of a few 10k states), where one more level of shorter
+  // segments wins (measured on 12.5k / 25k / 50k / 100k states: -3 %, -2 %, 0, +1 %; gpurun_out/r1z_small_sweep2.jsonl)
+  const int Mup = g->Mup ? g->Mup : (emu ? std::max(2, atoi(emu)) : (g->N <= 40000 ? 6 : 8));
   if (!g->M0 && !em0 && bs == 12 && g->W == 64) {
     // the panel kernel runs one resident wave of persistent CTAs, each walking ceil(nseg / slots) segments of M0 (+ a closing
     // separator) states one after the other: pick the segment length that minimises that serial depth (whole rounds - a
