@@ -23,7 +23,15 @@ sys.path.insert(0, ROOT)
 
 WORKLOAD = "C3: SE(3) GP-prior + interpolated range factors, 100k states, 50k ranges, 16 landmarks (BASELINE.json configs[2]; interpolated range only - the reference has no interpolated bearing factor)"
 METRIC = "GN iterations/sec on 100k-state SE(3) GP trajectory"
-CPU_SAMPLE_STATES = 10000
+# CPU legs: the sample is the largest cut of C3 (same factor densities) whose (warm-up + timed) iterations fit CPU_BUDGET_S at
+# ~30 us per state and iteration on one core - the whole 100k-state workload for the default 1 + 3 iterations (about 12 s),
+# never less than 10k states
+CPU_BUDGET_S = 120.0
+CPU_US_PER_STATE = 30.0
+
+
+def cpu_sample_states(iterations, full=100000):
+    return int(max(10000, min(full, CPU_BUDGET_S / (max(1, iterations) * CPU_US_PER_STATE * 1e-6))))
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch on C3, from the ncu --set full capture summarised in
 # profiles/r1x_ncu_full_summary.csv: k_lin_gp 15.7 MB read + 180.6 MB written (the tail of the 240 MB of [A|b] is still in L2 at
 # kernel end); k_panel4 (level 0) 270.2 MB read + 557.1 MB written
@@ -98,13 +106,16 @@ class ClockSampler:
         return out
 
 
-def cpu_reference_run(steps, warmup, threads, n_sample=CPU_SAMPLE_STATES):
+def cpu_reference_run(steps, warmup, threads, n_sample=None):
     """the reference's CPU path (oracle/: restated gpslam factors + GTSAM-style GN over a bordered block-tridiagonal Cholesky)
     on a bounded sample of the workload: C3 cut to n_sample states (same factor densities).  Per-iteration cost is linear in
     the number of states, so iterations/sec on the 100k-state graph = sample rate * n_sample / 100000."""
     from gpslam_b200 import synth
     from oracle import pyoracle as po
-    cfg = synth.config("C3"); full = cfg.n_states; cfg.n_states = n_sample
+    cfg = synth.config("C3"); full = cfg.n_states
+    if n_sample is None:
+        n_sample = cpu_sample_states(steps + warmup, full)
+    cfg.n_states = n_sample
     o, _ = synth.build(cfg, lambda grp, n, l: po.Graph(grp, n, l))
     o.set_threads(threads)
     if warmup:
@@ -114,8 +125,9 @@ def cpu_reference_run(steps, warmup, threads, n_sample=CPU_SAMPLE_STATES):
     dt = time.perf_counter() - t0
     rate_sample = steps / dt
     return {"value": rate_sample * n_sample / full, "seconds_per_iteration_sample": dt / steps, "lin_seconds": st.lin_seconds, "solve_seconds": st.solve_seconds,
-            "sample": "C3 cut to %d of %d states (same factor densities), %d GN iterations after %d warm-up; rate scaled by %d/%d (cost is linear in states)"
-                      % (n_sample, full, steps, warmup, n_sample, full)}
+            "sample": ("the whole workload (C3, %d states), %d GN iterations after %d warm-up" % (full, steps, warmup)) if n_sample == full else
+                      ("C3 cut to %d of %d states (same factor densities), %d GN iterations after %d warm-up; rate scaled by %d/%d (cost is linear in states)"
+                       % (n_sample, full, steps, warmup, n_sample, full))}
 
 
 def run_reference(args, rank, world):
