@@ -100,6 +100,22 @@ def store_peak(mode, n_factors, device=0):
     return v.value
 
 
+def interpolate_poses(group, x1, v1, x2, v2, delta_t, tau, want_H=False, device=0):
+    """GaussianProcessInterpolator*::interpolatePose for n queries (gpb_interpolate_poses).  Returns poses [n x PS] and, with want_H,
+    H [n, 4, D, D] (Hint1..Hint4)."""
+    x1 = _f64(x1).reshape(-1, _PS[group]); n = len(x1)
+    v1 = _f64(v1).reshape(n, _D[group]); x2 = _f64(x2).reshape(n, _PS[group]); v2 = _f64(v2).reshape(n, _D[group])
+    dt = _f64(np.broadcast_to(np.atleast_1d(delta_t), (n,))); ta = _f64(np.broadcast_to(np.atleast_1d(tau), (n,)))
+    D = _D[group]
+    poses = np.zeros((n, _PS[group])); H = np.zeros((n, 4, D, D)) if want_H else None
+    rc = lib().gpb_interpolate_poses(C.c_int(group), C.c_int(device), C.c_int(n), _dp(x1), _dp(v1), _dp(x2), _dp(v2), _dp(dt), _dp(ta), _dp(poses), _dp(H))
+    if rc != 0:
+        raise GpbError(lib().gpb_last_error().decode())
+    if want_H:
+        return poses, np.ascontiguousarray(H.transpose(0, 1, 3, 2))   # column-major blocks -> [row, col]
+    return poses
+
+
 def default_params(use_lm=True):
     p = Params()
     lib().gpb_default_params(C.byref(p), C.c_int(1 if use_lm else 0))
@@ -259,6 +275,14 @@ class Graph:
             self._pinned.append(ptr)
             out.append(np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_double)), shape=(n,))[:int(np.prod(shape))].reshape(shape))
         return tuple(out)
+
+    def interpolate(self, interval, tau):
+        """poses of the current estimate at time tau[k] into interval[k] (gpb_graph_interpolate): dense trajectory output"""
+        iv = np.ascontiguousarray(np.atleast_1d(interval), dtype=np.int32)
+        ta = _f64(np.broadcast_to(np.atleast_1d(tau), iv.shape))
+        out = np.zeros((len(iv), self.PS))
+        self._ck(self.L.gpb_graph_interpolate(self.h, C.c_int(len(iv)), _ip(iv), _dp(ta), _dp(out)))
+        return out
 
     def finalize(self, device=0):
         self._ck(self.L.gpb_graph_finalize(self.h, C.c_int(device)))

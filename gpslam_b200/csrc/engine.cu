@@ -1723,3 +1723,85 @@ int gpb_eval_factor(int group, int kind, const double* x1, const double* v1, con
 }
 
 }  // extern "C"
+
+// ---- interpolatePose as a query (GaussianProcessInterpolator*::interpolatePose): slow-path helpers, plain allocations per call
+template <int G> static void launch_interp_query(const double* X, const int* ia, const int* ib, const double* dt, const double* tau, int n, double* poses, double* H,
+                                                 cudaStream_t stream) {
+  k_interp_query<G><<<(n + 127) / 128, 128, 0, stream>>>(X, ia, ib, dt, tau, n, poses, H);
+}
+static int interp_query_device(int group, bool vw, const double* dX, const int* dia, const int* dib, const double* ddt, const double* dtau, int n, double* dposes, double* dH,
+                               cudaStream_t stream) {
+  if (group == GPB_POSE3 && vw) launch_interp_query<G_POSE3VW>(dX, dia, dib, ddt, dtau, n, dposes, dH, stream);
+  else if (group == GPB_POSE3) launch_interp_query<G_POSE3>(dX, dia, dib, ddt, dtau, n, dposes, dH, stream);
+  else if (group == GPB_POSE2) launch_interp_query<G_POSE2>(dX, dia, dib, ddt, dtau, n, dposes, dH, stream);
+  else if (group == GPB_ROT3) launch_interp_query<G_ROT3>(dX, dia, dib, ddt, dtau, n, dposes, dH, stream);
+  else launch_interp_query<G_LINEAR>(dX, dia, dib, ddt, dtau, n, dposes, dH, stream);
+  CUDA_TRY(cudaGetLastError());
+  return GPB_OK;
+}
+namespace {
+struct DevBufs {  // frees whatever was allocated, on every exit path
+  std::vector<void*> p;
+  ~DevBufs() { for (void* q : p) cudaFree(q); }
+  template <class T> int up(T** d, const T* h, size_t count) {
+    void* q = nullptr;
+    CUDA_TRY(cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T)));
+    p.push_back(q); *d = (T*)q;
+    if (h && count) CUDA_TRY(cudaMemcpy(q, h, count * sizeof(T), cudaMemcpyHostToDevice));
+    return GPB_OK;
+  }
+};
+}  // namespace
+
+extern "C" {
+
+int gpb_interpolate_poses(int group, int device, int n, const double* x1, const double* v1, const double* x2, const double* v2, const double* delta_t, const double* tau,
+                          double* poses_out, double* H_out) {
+  if (group < 0 || group > GPB_POSE3VW || n < 1 || !x1 || !v1 || !x2 || !v2 || !delta_t || !tau || !poses_out) return fail(GPB_ERR_ARG, "gpb_interpolate_poses: bad arguments");
+  for (int k = 0; k < n; k++) if (!(delta_t[k] > 0.0)) return fail(GPB_ERR_ARG, "gpb_interpolate_poses: delta_t must be positive");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(GPB_ERR_CUDA, "gpb_interpolate_poses: no CUDA device available (this engine has no CPU fallback)"); }
+  CUDA_TRY(cudaSetDevice(device));
+  const bool vw = group == GPB_POSE3VW;
+  const int grp = vw ? GPB_POSE3 : group;
+  const int D = grp == GPB_POSE3 ? 6 : 3, PS = pose_storage(grp, D), SR = PS + D;
+  std::vector<double> X((size_t)2 * n * SR);
+  std::vector<int> ia(n), ib(n);
+  for (int k = 0; k < n; k++) {
+    double* a = X.data() + (size_t)(2 * k) * SR; double* b = a + SR;
+    std::copy(x1 + (size_t)k * PS, x1 + (size_t)(k + 1) * PS, a); std::copy(v1 + (size_t)k * D, v1 + (size_t)(k + 1) * D, a + PS);
+    std::copy(x2 + (size_t)k * PS, x2 + (size_t)(k + 1) * PS, b); std::copy(v2 + (size_t)k * D, v2 + (size_t)(k + 1) * D, b + PS);
+    ia[k] = 2 * k; ib[k] = 2 * k + 1;
+  }
+  DevBufs B; int rc;
+  double *dX, *ddt, *dtau, *dP, *dH = nullptr; int *dia, *dib;
+  if ((rc = B.up(&dX, X.data(), X.size())) || (rc = B.up(&dia, ia.data(), (size_t)n)) || (rc = B.up(&dib, ib.data(), (size_t)n)) || (rc = B.up(&ddt, delta_t, (size_t)n)) ||
+      (rc = B.up(&dtau, tau, (size_t)n)) || (rc = B.up(&dP, (const double*)nullptr, (size_t)n * PS))) return rc;
+  if (H_out && (rc = B.up(&dH, (const double*)nullptr, (size_t)n * 4 * D * D))) return rc;
+  if ((rc = interp_query_device(grp, vw, dX, dia, dib, ddt, dtau, n, dP, dH, 0))) return rc;
+  CUDA_TRY(cudaMemcpy(poses_out, dP, (size_t)n * PS * sizeof(double), cudaMemcpyDeviceToHost));
+  if (H_out) CUDA_TRY(cudaMemcpy(H_out, dH, (size_t)n * 4 * D * D * sizeof(double), cudaMemcpyDeviceToHost));
+  return GPB_OK;
+}
+
+int gpb_graph_interpolate(gpb_graph* g, int n, const int* interval, const double* tau, double* poses_out) {
+  CHECK_READY(g);
+  if (n < 1 || !interval || !tau || !poses_out) return fail(GPB_ERR_ARG, "gpb_graph_interpolate: bad arguments");
+  std::vector<int> ia(n), ib(n); std::vector<double> dts(n);
+  for (int k = 0; k < n; k++) {
+    if (interval[k] < 0 || interval[k] >= g->nint) return fail(GPB_ERR_ARG, "gpb_graph_interpolate: interval out of range");
+    if (!(g->dt[interval[k]] > 0.0)) return fail(GPB_ERR_ARG, "gpb_graph_interpolate: no GP prior on that interval (its delta_t is unknown)");
+    ia[k] = interval[k]; ib[k] = interval[k] + 1; dts[k] = g->dt[interval[k]];
+  }
+  DevBufs B; int rc;
+  double *ddt, *dtau, *dP; int *dia, *dib;
+  if ((rc = B.up(&dia, ia.data(), (size_t)n)) || (rc = B.up(&dib, ib.data(), (size_t)n)) || (rc = B.up(&ddt, dts.data(), (size_t)n)) || (rc = B.up(&dtau, tau, (size_t)n)) ||
+      (rc = B.up(&dP, (const double*)nullptr, (size_t)n * g->PS))) return rc;
+  CUDA_TRY(cudaStreamSynchronize(g->stream));
+  if ((rc = interp_query_device(g->group, g->vw != 0, g->d_X, dia, dib, ddt, dtau, n, dP, nullptr, g->stream))) return rc;
+  CUDA_TRY(cudaStreamSynchronize(g->stream));
+  CUDA_TRY(cudaMemcpy(poses_out, dP, (size_t)n * g->PS * sizeof(double), cudaMemcpyDeviceToHost));
+  return GPB_OK;
+}
+
+}  // extern "C"

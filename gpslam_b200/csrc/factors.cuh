@@ -589,4 +589,86 @@ GPB_HD void interp_attitude_rot3(const double* s1, const double* s2, const doubl
   }
 }
 
+// ================================================================= interpolatePose as a query (all groups)
+// GaussianProcessInterpolator{Pose3,Pose3VW,Pose2,Rot3,Linear}::interpolatePose (gp/GaussianProcessInterpolatorPose3.h:57-105,
+// ...Pose3VW.h:58-108, ...Pose2.h:56-89, ...Rot3.h:56-86, ...Linear.h:70-90): the pose at tau from the two support states, and
+// on request the four D x D Jacobians Hint1..Hint4 (column-major, one after the other) - the same pipelines the interpolated
+// measurement factors use, evaluated on unit rows.  pose_out: wire layout (12 / 9 / 3 doubles).
+template <int G> GPB_HD void interp_pose(const double* s1, const double* s2, double dt, double tau, bool wantJ, double* pose_out, double* H) {
+  constexpr int D = GroupTraits<G>::D;
+  if constexpr (G == G_POSE3 || G == G_POSE3VW) {
+    double prm[20];
+#pragma unroll
+    for (int k = 0; k < 20; k++) prm[k] = 0.0;
+    prm[0] = dt; prm[1] = tau;
+    auto rows = [&](auto& c, auto rowfn) {
+#pragma unroll
+      for (int k = 0; k < 6; k++) {
+        const X6 ek = x6(v3(k == 0 ? 1.0 : 0.0, k == 1 ? 1.0 : 0.0, k == 2 ? 1.0 : 0.0), v3(k == 3 ? 1.0 : 0.0, k == 4 ? 1.0 : 0.0, k == 5 ? 1.0 : 0.0));
+        X6 h[4];
+        rowfn(c, ek, h[0], h[1], h[2], h[3]);
+#pragma unroll
+        for (int v = 0; v < 4; v++)
+#pragma unroll
+          for (int col = 0; col < 6; col++) H[v * 36 + k + 6 * col] = elem(h[v], col);
+      }
+    };
+    if constexpr (G == G_POSE3) {
+      Interp3 c; interp3_setup(s1, s2, prm, wantJ, c);
+      p3_to_wire(c.T, pose_out);
+      if (wantJ) rows(c, [](const Interp3& cc, const X6& e, X6& a, X6& b, X6& cx, X6& d) { interp3_row(cc, e, a, b, cx, d); });
+    } else {
+      Interp3VW c; interp3vw_setup(s1, s2, prm, wantJ, c);
+      p3_to_wire(c.c.T, pose_out);
+      if (wantJ) rows(c, [](const Interp3VW& cc, const X6& e, X6& a, X6& b, X6& cx, X6& d) { interp3vw_row(cc, e, a, b, cx, d); });
+    }
+  } else {
+    const InterpCoef ic = interp_coef(dt, tau);
+    constexpr int PS = GroupTraits<G>::PS;
+    const V3 v1 = v3(s1[PS], s1[PS + 1], s1[PS + 2]), v2 = v3(s2[PS], s2[PS + 1], s2[PS + 2]);
+    M3 H1, H2, H3, H4;
+    if constexpr (G == G_POSE2) {
+      const P2 T1 = p2(s1[0], s1[1], s1[2]), T2 = p2(s2[0], s2[1], s2[2]);
+      const P2 T12 = p2_between(T1, T2);
+      const V3 r = se2_logmap(T12);
+      const V3 xi = ic.lam12 * v1 + ic.psi11 * r + ic.psi12 * v2;
+      const P2 dT = se2_expmap(xi);
+      const P2 T = p2_compose(T1, dT);
+      pose_out[0] = T.x; pose_out[1] = T.y; pose_out[2] = T.th;
+      if (wantJ) {
+        const M3 Hexp = se2_dexp(xi), HexpHlog = Hexp * se2_dlog(r);
+        H1 = p2_adjoint(p2_inverse(dT)) - ic.psi11 * (HexpHlog * p2_adjoint(p2_inverse(T12)));
+        H2 = ic.lam12 * Hexp; H3 = ic.psi11 * HexpHlog; H4 = ic.psi12 * Hexp;
+      }
+    } else if constexpr (G == G_ROT3) {
+      const M3 R1 = m3_from_wire(s1), R2 = m3_from_wire(s2);
+      const M3 R12 = transpose(R1) * R2;
+      const V3 r = so3_logmap(R12);
+      const V3 xi = ic.lam12 * v1 + ic.psi11 * r + ic.psi12 * v2;
+      const M3 dR = so3_expmap(xi);
+      m3_to_wire(R1 * dR, pose_out);
+      if (wantJ) {
+        const M3 Hexp = so3_jr(xi), HexpHlog = Hexp * so3_jrinv(r);
+        H1 = transpose(dR) - ic.psi11 * (HexpHlog * transpose(R12));
+        H2 = ic.lam12 * Hexp; H3 = ic.psi11 * HexpHlog; H4 = ic.psi12 * Hexp;
+      }
+    } else {
+      const double lam11 = 1.0 - ic.psi11;
+#pragma unroll
+      for (int k = 0; k < 3; k++) pose_out[k] = lam11 * s1[k] + ic.lam12 * s1[3 + k] + ic.psi11 * s2[k] + ic.psi12 * s2[3 + k];
+      if (wantJ) { const M3 I = m3_identity(); H1 = lam11 * I; H2 = ic.lam12 * I; H3 = ic.psi11 * I; H4 = ic.psi12 * I; }
+    }
+    if (wantJ) {
+      const M3* Hs[4] = {&H1, &H2, &H3, &H4};
+#pragma unroll
+      for (int v = 0; v < 4; v++)
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+#pragma unroll
+          for (int col = 0; col < 3; col++) H[v * 9 + r + 3 * col] = Hs[v]->m[3 * r + col];
+    }
+  }
+  (void)D;
+}
+
 }  // namespace gpb

@@ -429,6 +429,23 @@ __global__ void __launch_bounds__(NT) k_lin_extra(const int* __restrict__ list, 
   if (threadIdx.x == 0) errpart[blockIdx.x] = tot;
 }
 
+// interpolatePose queries (gpb_interpolate_poses / gpb_graph_interpolate): one thread per query, support records ia[k], ib[k] of X
+template <int G>
+__global__ void __launch_bounds__(128) k_interp_query(const double* __restrict__ X, const int* __restrict__ ia, const int* __restrict__ ib, const double* __restrict__ dt,
+                                                      const double* __restrict__ tau, int n, double* __restrict__ poses, double* __restrict__ H) {
+  constexpr int D = GroupTraits<G>::D, PS = GroupTraits<G>::PS, SR = PS + D;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  double pose[PS], Hl[4 * D * D];
+  interp_pose<G>(X + (size_t)ia[k] * SR, X + (size_t)ib[k] * SR, dt[k], tau[k], H != nullptr, pose, Hl);
+#pragma unroll
+  for (int t = 0; t < PS; t++) poses[(size_t)k * PS + t] = pose[t];
+  if (H != nullptr) {
+#pragma unroll
+    for (int t = 0; t < 4 * D * D; t++) H[(size_t)k * 4 * D * D + t] = Hl[t];
+  }
+}
+
 // deterministic final sum of block partials (single block)
 __global__ void k_sum_partials(const double* __restrict__ part, int n, double* __restrict__ out, int slot) {
   __shared__ double sred[8];

@@ -120,6 +120,18 @@ enum { GPB_F_GP_PRIOR = 0, GPB_F_INTERP_RANGE = 1, GPB_F_INTERP_ATTITUDE = 2, GP
 int gpb_eval_factor(int group, int kind, const double* x1, const double* v1, const double* x2, const double* v2, const double* landmark,
                     const double* prm, double* e_out, double* H_out, int* dims_out);
 
+/* GaussianProcessInterpolator{Pose3,Pose3VW,Pose2,Rot3,Linear}(Qc, delta_t, tau).interpolatePose(pose1, vel1, pose2, vel2, H1..H4)
+ * (gp/GaussianProcessInterpolatorPose3.h:57-105, ...Pose3VW.h:58-108, ...Pose2.h:56-89, ...Rot3.h:56-86, ...Linear.h:70-90) for n
+ * independent queries.  Host buffers in the wire layouts of gpb_set_values; poses_out [n x pose_storage]; H_out (or NULL)
+ * [n][4][D x D column-major] = Hint1..Hint4 (GPB_POSE3VW: Hint2 = [H2 | H3] over [v | w], Hint4 = [H5 | H6]).  Lambda and Psi do not
+ * depend on Qc, so no Qc is passed.  tau may lie outside [0, delta_t].  Slow path (allocations per call). */
+int gpb_interpolate_poses(int group, int device, int n, const double* x1, const double* v1, const double* x2, const double* v2, const double* delta_t, const double* tau,
+                          double* poses_out, double* H_out);
+/* The pose of the graph's CURRENT estimate at time tau[k] into interval[k] (between states interval[k] and interval[k] + 1, which
+ * must carry a GP prior: its delta_t is used) - dense trajectory output after gpb_optimize, what the reference's scripts do with
+ * interpolatePose on the optimised Values.  poses_out [n x pose_storage]. */
+int gpb_graph_interpolate(gpb_graph* g, int n, const int* interval, const double* tau, double* poses_out);
+
 /* Values::insert / Values::at : host buffers, [n_states x pose_storage], [n_states x D], [n_landmarks x DL] */
 int gpb_set_values(gpb_graph* g, const double* poses, const double* vels, const double* landmarks);
 int gpb_get_values(gpb_graph* g, double* poses, double* vels, double* landmarks);

@@ -190,6 +190,60 @@ using GaussianProcessPriorPose2 = GaussianProcessPriorT<gtsam::Pose2>;
 using GaussianProcessPriorRot3 = GaussianProcessPriorT<gtsam::Rot3>;
 template <int Dim> using GaussianProcessPriorLinear = GaussianProcessPriorT<gtsam::VectorN<Dim>>;
 
+/// GP interpolators as value types — gp/GaussianProcessInterpolator{Pose3,Pose2,Rot3,Linear}.h (constructor :43-50, interpolatePose
+/// :57-105).  interpolatePose runs on the device through gpb_interpolate_poses (one query; the batched forms are
+/// gpb_interpolate_poses with n > 1 and gpb_graph_interpolate on an optimised graph).
+namespace detail {
+inline void unwire(const double* p, gtsam::Pose3& o) { o = gtsam::Pose3::fromWire(p); }
+inline void unwire(const double* p, gtsam::Rot3& o) { for (int k = 0; k < 9; k++) o.R[k] = p[k]; }
+inline void unwire(const double* p, gtsam::Pose2& o) { o = gtsam::Pose2(p[0], p[1], p[2]); }
+inline void unwire(const double* p, gtsam::Vector3& o) { o = gtsam::Vector3{p[0], p[1], p[2]}; }
+// one interpolatePose query; Hs: up to four D x D Jacobians (nullptr = not requested)
+inline void interpolate(int group, int D, const double* x1, const double* v1, const double* x2, const double* v2, double delta_t, double tau, double* pose_out,
+                        std::initializer_list<gtsam::Matrix*> Hs) {
+  bool want = false;
+  for (gtsam::Matrix* h : Hs) want |= (h != nullptr);
+  double Hbuf[4 * 36];
+  check(gpb_interpolate_poses(group, 0, 1, x1, v1, x2, v2, &delta_t, &tau, pose_out, want ? Hbuf : nullptr));
+  int v = 0;
+  for (gtsam::Matrix* h : Hs) {
+    if (h) { *h = gtsam::Matrix(D, D); for (int k = 0; k < D * D; k++) h->a[k] = Hbuf[v * D * D + k]; }
+    v++;
+  }
+}
+}  // namespace detail
+
+template <class POSE>
+class GaussianProcessInterpolatorT {
+  using G = detail::GroupOf<POSE>;
+  double delta_t_ = 0, tau_ = 0;
+  gtsam::SharedNoiseModel Qc_;
+
+ public:
+  GaussianProcessInterpolatorT() {}
+  GaussianProcessInterpolatorT(const gtsam::SharedNoiseModel& Qc_model, double delta_t, double tau) : delta_t_(delta_t), tau_(tau), Qc_(Qc_model) {
+    if (!Qc_model) throw std::runtime_error("gpslam_b200: Qc model is not Gaussian");
+  }
+  double delta_t() const { return delta_t_; }
+  double tau() const { return tau_; }
+  /// interpolate pose with Jacobians (gp/GaussianProcessInterpolatorPose3.h:57-105)
+  POSE interpolatePose(const POSE& pose1, const typename G::Vel& vel1, const POSE& pose2, const typename G::Vel& vel2, gtsam::Matrix* H1 = nullptr,
+                       gtsam::Matrix* H2 = nullptr, gtsam::Matrix* H3 = nullptr, gtsam::Matrix* H4 = nullptr) const {
+    double x1[12], x2[12], v1[6], v2[6], out[12];
+    detail::wire(pose1, x1); detail::wire(pose2, x2); detail::wire(vel1, v1); detail::wire(vel2, v2);
+    detail::interpolate(G::group, G::D, x1, v1, x2, v2, delta_t_, tau_, out, {H1, H2, H3, H4});
+    POSE p; detail::unwire(out, p);
+    return p;
+  }
+  bool equals(const GaussianProcessInterpolatorT& e, double tol = 1e-9) const {
+    return std::fabs(delta_t_ - e.delta_t_) < tol && std::fabs(tau_ - e.tau_) < tol && Qc_ && e.Qc_ && Qc_->cov.a == e.Qc_->cov.a;
+  }
+};
+using GaussianProcessInterpolatorPose3 = GaussianProcessInterpolatorT<gtsam::Pose3>;
+using GaussianProcessInterpolatorPose2 = GaussianProcessInterpolatorT<gtsam::Pose2>;
+using GaussianProcessInterpolatorRot3 = GaussianProcessInterpolatorT<gtsam::Rot3>;
+template <int Dim> using GaussianProcessInterpolatorLinear = GaussianProcessInterpolatorT<gtsam::VectorN<Dim>>;
+
 /// 5-way interpolated range factors — slam/GPInterpolatedRangeFactorPose3.h:46-54, ...Pose2.h
 template <class POSE>
 class GPInterpolatedRangeFactorT : public NonlinearFactor {
@@ -383,9 +437,7 @@ class GaussianProcessPriorPose3VW : public NonlinearFactor {
   }
 };
 
-/// gp/GaussianProcessInterpolatorPose3VW.h:43-124 as a value type: interpolatePose through the GPS factor's device pipeline
-/// (translation of T(tau) = its residual against a zero measurement) is not exposed; the class carries (Qc, delta_t, tau) for
-/// equals() and for the factors below.
+/// gp/GaussianProcessInterpolatorPose3VW.h:43-124 as a value type (interpolatePose :58-108 through gpb_interpolate_poses)
 class GaussianProcessInterpolatorPose3VW {
   double delta_t_ = 0, tau_ = 0;
   gtsam::SharedNoiseModel Qc_;
@@ -396,6 +448,17 @@ class GaussianProcessInterpolatorPose3VW {
   double delta_t() const { return delta_t_; }
   double tau() const { return tau_; }
   const gtsam::SharedNoiseModel& Qc() const { return Qc_; }
+  gtsam::Pose3 interpolatePose(const gtsam::Pose3& pose1, const gtsam::Vector3& v1, const gtsam::Vector3& omega1, const gtsam::Pose3& pose2, const gtsam::Vector3& v2,
+                               const gtsam::Vector3& omega2, gtsam::Matrix* H1 = nullptr, gtsam::Matrix* H2 = nullptr, gtsam::Matrix* H3 = nullptr,
+                               gtsam::Matrix* H4 = nullptr, gtsam::Matrix* H5 = nullptr, gtsam::Matrix* H6 = nullptr) const {
+    double x1[12], x2[12], vw1[6], vw2[6], out[12];
+    detail::wire(pose1, x1); detail::wire(pose2, x2); detail::wire(v1, vw1); detail::wire(omega1, vw1 + 3); detail::wire(v2, vw2); detail::wire(omega2, vw2 + 3);
+    gtsam::Matrix Hvw1, Hvw2;
+    detail::interpolate(GPB_POSE3VW, 6, x1, vw1, x2, vw2, delta_t_, tau_, out, {H1, (H2 || H3) ? &Hvw1 : nullptr, H4, (H5 || H6) ? &Hvw2 : nullptr});
+    if (H2 || H3) detail::splitVW(Hvw1, H2, H3);
+    if (H5 || H6) detail::splitVW(Hvw2, H5, H6);
+    return gtsam::Pose3::fromWire(out);
+  }
   bool equals(const GaussianProcessInterpolatorPose3VW& e, double tol = 1e-9) const {
     return std::fabs(delta_t_ - e.delta_t_) < tol && std::fabs(tau_ - e.tau_) < tol && Qc_ && e.Qc_ && Qc_->cov.a == e.Qc_->cov.a;
   }

@@ -299,6 +299,56 @@ static void testPose3VW() {
   }
 }
 
+// gp/tests/testGaussianProcessInterpolatorPose3.cpp:30-120, ...Pose2.cpp, ...Pose3VW.cpp: known interpolated poses at tau = 0.03
+static Vector poseVec(const Pose3& p) { double w[12]; p.wire(w); return Vector(w, w + 12); }
+static void testInterpolators() {
+  SharedNoiseModel Qc_model = noiseModel::Gaussian::Covariance(0.01 * Matrix::Identity(6, 6));
+  const double dt = 0.1, tau = 0.03;
+  {
+    GaussianProcessInterpolatorPose3 base(Qc_model, dt, tau);
+    // forward
+    Pose3 p1(Rot3::Ypr(0, 0, 0), Point3(0, 0, 0)), p2(Rot3::Ypr(0, 0, 0), Point3(0.1, 0, 0));
+    Vector6 v1{0, 0, 0, 1, 0, 0}, v2{0, 0, 0, 1, 0, 0};
+    EXPECT(assert_equal(poseVec(Pose3(Rot3::Ypr(0, 0, 0), Point3(0.03, 0, 0))), poseVec(base.interpolatePose(p1, v1, p2, v2)), 1e-6));
+    // rotate
+    p2 = Pose3(Rot3::Ypr(0.1, 0, 0), Point3(0, 0, 0)); v1 = Vector6{0, 0, 1, 0, 0, 0}; v2 = v1;
+    EXPECT(assert_equal(poseVec(Pose3(Rot3::Ypr(0.03, 0, 0), Point3(0, 0, 0))), poseVec(base.interpolatePose(p1, v1, p2, v2)), 1e-6));
+    // the "random" point: Jacobians wrt the two velocities against central differences of the interpolated translation / rotation
+    p1 = Pose3(Rot3::Ypr(0.4, -0.8, 0.2), Point3(3, -8, 2)); p2 = Pose3(Rot3::Ypr(0.1, 0.3, -0.5), Point3(-9, 3, 4));
+    v1 = Vector6{0.1, -0.2, -1.4, 0.5, 0.9, 0.7}; v2 = Vector6{0.6, 0.3, -0.9, 0.4, -0.2, 0.8};
+    Matrix H1, H2, H3, H4;
+    const Pose3 T = base.interpolatePose(p1, v1, p2, v2, &H1, &H2, &H3, &H4);
+    EXPECT(H1.rows == 6 && H1.cols == 6 && H4.rows == 6 && H4.cols == 6);
+    // d translation = R * (H rows 3..5) delta: check the translation part for v1 and v2
+    auto transOf = [&](const Vector6& a, const Vector6& b) { const Pose3 q = base.interpolatePose(p1, a, p2, b); return Vector{q.t.x, q.t.y, q.t.z}; };
+    for (int which = 0; which < 2; which++) {
+      const Matrix& H = which ? H4 : H2;
+      const Matrix J = numericalDerivativeVec([&](const Vector6& x) { return which ? transOf(v1, x) : transOf(x, v2); }, which ? v2 : v1, 1e-5);
+      for (int c = 0; c < 6; c++)
+        for (int r = 0; r < 3; r++) {
+          double s = 0;  // world-frame translation rate = R(T) * body-frame rows 3..5
+          for (int k = 0; k < 3; k++) s += T.r.R[r + 3 * k] * H(3 + k, c);
+          EXPECT(std::fabs(s - J(r, c)) < 1e-6);
+        }
+    }
+  }
+  {
+    GaussianProcessInterpolatorPose2 base(noiseModel::Gaussian::Covariance(0.01 * Matrix::Identity(3, 3)), dt, tau);
+    const Pose2 q = base.interpolatePose(Pose2(0, 0, 0), Vector3{1, 0, 0}, Pose2(0.1, 0, 0), Vector3{1, 0, 0});
+    EXPECT(std::fabs(q.x - 0.03) < 1e-6 && std::fabs(q.y) < 1e-6 && std::fabs(q.theta) < 1e-6);
+    const Pose2 r = base.interpolatePose(Pose2(0, 0, 0), Vector3{0, 0, 1}, Pose2(0, 0, 0.1), Vector3{0, 0, 1});
+    EXPECT(std::fabs(r.theta - 0.03) < 1e-6 && std::fabs(r.x) < 1e-6);
+  }
+  {
+    GaussianProcessInterpolatorPose3VW base(Qc_model, dt, tau);
+    Pose3 p1(Rot3::Ypr(0, 0, 0), Point3(0, 0, 0)), p2(Rot3::Ypr(0, 0, 0), Point3(0.1, 0.2, 0));
+    Matrix H2, H3;
+    const Pose3 q = base.interpolatePose(p1, Vector3{1, 2, 0}, Vector3{0, 0, 0}, p2, Vector3{1, 2, 0}, Vector3{0, 0, 0}, nullptr, &H2, &H3);
+    EXPECT(assert_equal(poseVec(Pose3(Rot3::Ypr(0, 0, 0), Point3(0.03, 0.06, 0))), poseVec(q), 1e-6));
+    EXPECT(H2.rows == 6 && H2.cols == 3 && H3.rows == 6 && H3.cols == 3);
+  }
+}
+
 int main() {
   try {
     testFactor();
@@ -306,6 +356,7 @@ int main() {
     testRangeOptimization();
     testGpsAndProjectionOptimization();
     testPose3VW();
+    testInterpolators();
   } catch (const std::exception& e) { std::printf("exception: %s\n", e.what()); return 2; }
   std::printf(failures ? "FAILED (%d)\n" : "OK (%d failures)\n", failures);
   return failures ? 1 : 0;

@@ -102,3 +102,14 @@ void hm_interp_projection(const double* s1, const double* s2, const double* land
   }
 }
 }
+
+// ---- interpolatePose as a query: pose (wire) and the four D x D Jacobians, group codes of include/gpb.h (4 = Pose3 VW)
+extern "C" void hm_interp_pose(int group, const double* s1, const double* s2, double dt, double tau, double* pose_out, double* H) {
+  switch (group) {
+    case 0: interp_pose<G_POSE3>(s1, s2, dt, tau, H != nullptr, pose_out, H); break;
+    case 1: interp_pose<G_POSE2>(s1, s2, dt, tau, H != nullptr, pose_out, H); break;
+    case 2: interp_pose<G_ROT3>(s1, s2, dt, tau, H != nullptr, pose_out, H); break;
+    case 3: interp_pose<G_LINEAR>(s1, s2, dt, tau, H != nullptr, pose_out, H); break;
+    default: interp_pose<G_POSE3VW>(s1, s2, dt, tau, H != nullptr, pose_out, H); break;
+  }
+}

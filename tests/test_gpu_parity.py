@@ -425,3 +425,66 @@ def test_landmark_border_limit():
     cfg = small_cfg("C3", 150, n_landmarks=18, prior_every=30, range_per_state=1.5)
     with pytest.raises(capi.GpbError):
         synth.build(cfg, lambda grp, n, l: gb.Graph(grp, n, l))
+
+
+# ----------------------------------------------------------------------------- interpolatePose queries
+@pytest.mark.parametrize("group", [POSE3, POSE2, ROT3, LINEAR, 4])
+def test_interpolate_pose_queries(group):
+    """gpb_interpolate_poses (GaussianProcessInterpolator*::interpolatePose, incl. Pose3VW = group 4) against the oracle: poses
+    1e-11, Jacobians 1e-6 for SE(3) (the oracle keeps the reference's numerical differentiation) and 1e-10 otherwise"""
+    from gpslam_b200 import capi
+    from tests.test_hostmath_vs_oracle import rand_state
+    rng = np.random.default_rng(1200 + group)
+    base = POSE3 if group == 4 else group
+    D = 6 if base == POSE3 else 3
+    n = 48
+    X1, V1, X2, V2, DT, TAU = [], [], [], [], [], []
+    for k in range(n):
+        p1, v1 = rand_state(rng, base)
+        if k % 2:
+            p2, v2 = rand_state(rng, base)
+        else:
+            step = rng.normal(size=D) * (1e-9 if k % 6 == 0 else 0.05)
+            p2 = po.retract(base, p1, step) if base != POSE2 else po.pose2_compose(p1, po.pose2_expmap(step))
+            v2 = v1 + rng.normal(size=D) * 0.1
+        dt = float(rng.uniform(0.05, 0.5))
+        X1.append(p1); V1.append(v1); X2.append(p2); V2.append(v2); DT.append(dt); TAU.append(float(rng.uniform(-0.5, 1.5) * dt))
+    poses, H = capi.interpolate_poses(group, np.stack(X1), np.stack(V1), np.stack(X2), np.stack(V2), np.array(DT), np.array(TAU), want_H=True)
+    only = capi.interpolate_poses(group, np.stack(X1), np.stack(V1), np.stack(X2), np.stack(V2), np.array(DT), np.array(TAU))
+    assert np.array_equal(poses, only)
+    for k in range(n):
+        ref, Href = po.interpolate(group, np.eye(D), DT[k], TAU[k], X1[k], V1[k], X2[k], V2[k], want_H=True)
+        np.testing.assert_allclose(poses[k], ref, atol=1e-11 * max(1.0, np.abs(ref).max()))
+        for v in range(4):
+            np.testing.assert_allclose(H[k, v], Href[v], atol=(1e-6 if D == 6 else 1e-10) * max(1.0, np.abs(Href[v]).max()))
+    with pytest.raises(capi.GpbError):
+        capi.interpolate_poses(group, X1[0], V1[0], X2[0], V2[0], -0.1, 0.0)
+
+
+@pytest.mark.parametrize("case", ["pose3", "pose2", "rot3", "pose3vw"])
+def test_graph_interpolate_dense_output(case):
+    """gpb_graph_interpolate: the optimised trajectory queried between its states equals interpolatePose on the optimised values;
+    tau = 0 and tau = delta_t reproduce the support states"""
+    from gpslam_b200 import capi
+    g, o = make_pair(case)
+    g.optimize(use_lm=True)
+    P, V, _ = g.get_values()
+    rng = np.random.default_rng(5)
+    iv = rng.integers(0, g.N - 1, size=40); dt = synth.config(CASES[case]["name"]).dt
+    tau = rng.uniform(0, dt, size=40)
+    got = g.interpolate(iv, tau)
+    ref = capi.interpolate_poses(g.group, P[iv], V[iv], P[iv + 1], V[iv + 1], dt, tau)
+    assert np.array_equal(got, ref)
+    for k in range(0, 40, 7):
+        r = po.interpolate(g.group, np.eye(g.D), dt, tau[k], P[iv[k]], V[iv[k]], P[iv[k] + 1], V[iv[k] + 1])
+        np.testing.assert_allclose(got[k], r, atol=1e-11 * max(1.0, np.abs(r).max()))
+    def same(a, b, tol):
+        d = a - b
+        if case == "pose2":   # headings compare modulo 2 pi (Logmap wraps the relative heading)
+            d[:, 2] = np.arctan2(np.sin(d[:, 2]), np.cos(d[:, 2]))
+        assert np.abs(d).max() <= tol * max(1.0, np.abs(P).max())
+    same(g.interpolate(iv, np.zeros(40)), P[iv], 1e-12)
+    same(g.interpolate(iv, np.full(40, dt)), P[iv + 1], 1e-9)
+    with pytest.raises(capi.GpbError):
+        g.interpolate([g.N - 1], [0.0])
+

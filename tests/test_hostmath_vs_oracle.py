@@ -220,3 +220,31 @@ def test_interp_projection_rows(hm):
             assert abs(out[28 * r + 27] - e[r]) < 1e-9 * max(1.0, abs(e[r]))
             Ho = np.concatenate([h[r] for h in H])
             np.testing.assert_allclose(out[28 * r:28 * r + 27], Ho, atol=1e-6 * max(1.0, np.abs(Ho).max()))
+
+
+@pytest.mark.parametrize("group", [po.POSE3, po.POSE2, po.ROT3, po.LINEAR, po.POSE3VW])
+def test_interpolate_pose_query(hm, group):
+    """interpolatePose as a query (gpb_interpolate_poses / GaussianProcessInterpolator*::interpolatePose): pose and Hint1..4"""
+    rng = np.random.default_rng(900 + group)
+    base = po.POSE3 if group == po.POSE3VW else group
+    D = 6 if base == po.POSE3 else 3
+    PS = {po.POSE3: 12, po.POSE2: 3, po.ROT3: 9, po.LINEAR: 3}[base]
+    for trial in range(40):
+        dt = float(rng.uniform(0.05, 0.5)); tau = float(rng.uniform(-0.5, 1.5) * dt)
+        p1, v1 = rand_state(rng, base)
+        if trial % 2:
+            p2, v2 = rand_state(rng, base)
+        else:
+            step = rng.normal(size=D) * (1e-9 if trial % 6 == 0 else 0.05)
+            p2 = po.retract(base, p1, step) if base != po.POSE2 else po.pose2_compose(p1, po.pose2_expmap(step))
+            v2 = v1 + rng.normal(size=D) * 0.1
+        ref, Href = po.interpolate(group, np.eye(D), dt, tau, p1, v1, p2, v2, want_H=True)
+        out = np.zeros(PS); H = np.zeros(4 * D * D)
+        hm.hm_interp_pose(C.c_int(group), dp(np.concatenate([p1, v1])), dp(np.concatenate([p2, v2])), C.c_double(dt), C.c_double(tau), dp(out), dp(H))
+        np.testing.assert_allclose(out, ref, atol=1e-11 * max(1.0, np.abs(ref).max()))
+        for k in range(4):
+            Hk = H[k * D * D:(k + 1) * D * D].reshape(D, D).T
+            np.testing.assert_allclose(Hk, Href[k], atol=(1e-6 if D == 6 else 1e-10) * max(1.0, np.abs(Href[k]).max()))
+        out2 = np.zeros(PS)
+        hm.hm_interp_pose(C.c_int(group), dp(np.concatenate([p1, v1])), dp(np.concatenate([p2, v2])), C.c_double(dt), C.c_double(tau), dp(out2), None)
+        assert np.array_equal(out, out2)     # pose-only path
