@@ -58,7 +58,7 @@ def _worker(rank, world, port, name, n, out, ncl=0):
 
 
 @pytest.mark.parametrize("name,world,n,ncl", [("C3", 2, 41, 0), ("C3", 3, 50, 0), ("C1", 2, 37, 0), ("C4", 3, 46, 0),
-                                              ("C5", 2, 40, 3), ("C5", 3, 52, 5), ("C1", 3, 45, 4)])
+                                              ("C5", 2, 40, 3), ("C5", 3, 52, 5), ("C1", 3, 45, 4), ("VW", 2, 41, 0), ("VW", 3, 52, 3)])
 def test_sharded_schur_matches_full(tmp_path, name, world, n, ncl):
     """ncl > 0: loop closures - endpoints join the reduced system, remote endpoints are carried as ghosts by the evaluating rank"""
     import torch.multiprocessing as mp
@@ -81,7 +81,7 @@ def test_sharded_schur_matches_full(tmp_path, name, world, n, ncl):
 
 
 def test_every_factor_owned_once():
-    for name, n, ncl in (("C3", 97, 0), ("C1", 64, 0), ("C4", 80, 0), ("C5", 90, 6)):
+    for name, n, ncl in (("C3", 97, 0), ("C1", 64, 0), ("C4", 80, 0), ("C5", 90, 6), ("VW", 75, 4)):
         for world in (2, 3, 5):
             cfg = _cfg(name, n, ncl)
             full, _ = synth.build(cfg, lambda grp, N, L: po.Graph(grp, N, L))
