@@ -530,6 +530,89 @@ class GPInterpolatedAttitudeFactorRot3 : public NonlinearFactor {
   }
 };
 
+// ---------------------------------------------------------------------------------- plain 2-way factors of gpslam/slam
+/// gtsam::Rot2 as the reference's bearing measurement uses it (an angle)
+namespace gtsam {
+struct Rot2 {
+  double theta_ = 0;
+  Rot2() {}
+  explicit Rot2(double theta) : theta_(theta) {}
+  static Rot2 fromAngle(double theta) { return Rot2(theta); }
+  double theta() const { return theta_; }
+};
+}  // namespace gtsam
+
+/// slam/RangeFactor2DLinear.h:30-34 (Vector3 "linear Pose2" state, Point2 landmark; evaluateError :43-56) and
+/// slam/RangeFactorPose2.h:15 (= gtsam::RangeFactor<Pose2, Point2>): one class template over the pose type
+template <class POSE>
+class RangeFactor2DT : public NonlinearFactor {
+  using G = detail::GroupOf<POSE>;
+  std::vector<gtsam::Key> keys_;
+  double measured_;
+  gtsam::SharedNoiseModel model_;
+
+ public:
+  RangeFactor2DT(gtsam::Key poseKey, gtsam::Key pointKey, double measured, const gtsam::SharedNoiseModel& model)
+      : keys_{poseKey, pointKey}, measured_(measured), model_(model) {}
+  const std::vector<gtsam::Key>& keys() const override { return keys_; }
+  double measured() const { return measured_; }
+  gtsam::Vector evaluateError(const POSE& pose, const gtsam::Point2& point, gtsam::Matrix* H1 = nullptr, gtsam::Matrix* H2 = nullptr) const {
+    double x[3], l[2], prm[48] = {0};
+    detail::wire(pose, x); detail::wire(point, l);
+    prm[2] = measured_;
+    return detail::eval(G::group, GPB_F_RANGE_2D, x, nullptr, nullptr, nullptr, l, prm, {H1, H2});
+  }
+  void lower(gpb_graph* g, int (*)(void*, const gtsam::Matrix&), void*, const std::map<gtsam::Key, int>& sidx, const std::map<gtsam::Key, int>& lidx) const override {
+    detail::check(gpb_add_range_2d(g, detail::stateOf(sidx, keys_[0]), detail::stateOf(lidx, keys_[1]), measured_, 1.0 / detail::sqrtInfo(model_)(0, 0)));
+  }
+};
+using RangeFactor2DLinear = RangeFactor2DT<gtsam::Vector3>;
+using RangeFactorPose2 = RangeFactor2DT<gtsam::Pose2>;
+
+/// slam/RangeBearingFactor2DLinear.h:33-38 (evaluateError :47-84): residual (bearing, range)
+class RangeBearingFactor2DLinear : public NonlinearFactor {
+  std::vector<gtsam::Key> keys_;
+  double range_;
+  gtsam::Rot2 bearing_;
+  gtsam::SharedNoiseModel model_;
+
+ public:
+  RangeBearingFactor2DLinear(gtsam::Key poseKey, gtsam::Key pointKey, double range, const gtsam::Rot2& bearing, const gtsam::SharedNoiseModel& model)
+      : keys_{poseKey, pointKey}, range_(range), bearing_(bearing), model_(model) {}
+  const std::vector<gtsam::Key>& keys() const override { return keys_; }
+  gtsam::Vector evaluateError(const gtsam::Vector3& pose, const gtsam::Point2& point, gtsam::Matrix* H1 = nullptr, gtsam::Matrix* H2 = nullptr) const {
+    double x[3], l[2], prm[48] = {0};
+    detail::wire(pose, x); detail::wire(point, l);
+    prm[2] = range_; prm[3] = bearing_.theta();
+    return detail::eval(GPB_LINEAR, GPB_F_RANGE_BEARING_2D, x, nullptr, nullptr, nullptr, l, prm, {H1, H2});
+  }
+  void lower(gpb_graph* g, int (*)(void*, const gtsam::Matrix&), void*, const std::map<gtsam::Key, int>& sidx, const std::map<gtsam::Key, int>& lidx) const override {
+    detail::check(gpb_add_range_bearing_2d(g, detail::stateOf(sidx, keys_[0]), detail::stateOf(lidx, keys_[1]), range_, bearing_.theta(), detail::sqrtInfo(model_).a.data()));
+  }
+};
+
+/// slam/OdometryFactor2DLinear.h:36-40 (evaluateError :50-75): body-frame odometry (dx, dy, dtheta) between two Vector3 states
+class OdometryFactor2DLinear : public NonlinearFactor {
+  std::vector<gtsam::Key> keys_;
+  gtsam::Vector3 measured_;
+  gtsam::SharedNoiseModel model_;
+
+ public:
+  OdometryFactor2DLinear(gtsam::Key pose1Key, gtsam::Key pose2Key, const gtsam::Vector3& betweenMeasured, const gtsam::SharedNoiseModel& model)
+      : keys_{pose1Key, pose2Key}, measured_(betweenMeasured), model_(model) {}
+  const std::vector<gtsam::Key>& keys() const override { return keys_; }
+  gtsam::Vector evaluateError(const gtsam::Vector3& pose1, const gtsam::Vector3& pose2, gtsam::Matrix* H1 = nullptr, gtsam::Matrix* H2 = nullptr) const {
+    double x1[3], x2[3], prm[48] = {0};
+    detail::wire(pose1, x1); detail::wire(pose2, x2); detail::wire(measured_, prm + 4);
+    return detail::eval(GPB_LINEAR, GPB_F_ODOMETRY_2D, x1, nullptr, x2, nullptr, nullptr, prm, {H1, H2});
+  }
+  void lower(gpb_graph* g, int (*)(void*, const gtsam::Matrix&), void*, const std::map<gtsam::Key, int>& sidx, const std::map<gtsam::Key, int>&) const override {
+    double m[3];
+    detail::wire(measured_, m);
+    detail::check(gpb_add_odometry_2d(g, detail::stateOf(sidx, keys_[0]), detail::stateOf(sidx, keys_[1]), m, detail::sqrtInfo(model_).a.data()));
+  }
+};
+
 /// gtsam::PriorFactor<T> on a pose ('x'), velocity ('v') or landmark ('l') key
 template <class T>
 class PriorFactor : public NonlinearFactor {

@@ -349,6 +349,63 @@ static void testInterpolators() {
   }
 }
 
+// slam/tests/testRangeFactor2DLinear.cpp:63-67, testRangeBearingFactor2DLinear.cpp:55-59, testOdometryFactor2DLinear.cpp:65-70
+// (the known answers) and a small Linear<3> trajectory built from these factors and optimised
+static void testPlain2DFactors() {
+  SharedNoiseModel m1 = noiseModel::Isotropic::Sigma(1, 1.0), m2 = noiseModel::Isotropic::Sigma(2, 1.0), m3 = noiseModel::Isotropic::Sigma(3, 1.0);
+  const Vector3 pose{13.1, -4.8, 1.5};
+  const Point2 point(-5.4, 6.6);
+  {
+    RangeFactor2DLinear f(Symbol('x', 1), Symbol('l', 1), 13.1, m1);
+    Matrix H1, H2;
+    const Vector e = f.evaluateError(pose, point, &H1, &H2);
+    EXPECT(e.size() == 1 && std::fabs(e[0] - 8.630393461693233) < 1e-9);
+    EXPECT(H1.rows == 1 && H1.cols == 3 && H2.rows == 1 && H2.cols == 2 && std::fabs(H1(0, 0) + H2(0, 0)) < 1e-12 && std::fabs(H1(0, 2)) < 1e-12);
+  }
+  {
+    RangeBearingFactor2DLinear f(Symbol('x', 1), Symbol('l', 1), 13.1, Rot2(0.0), m2);
+    const Vector e = f.evaluateError(pose, point);
+    EXPECT(e.size() == 2 && std::fabs(e[0] - 1.089334716657378) < 1e-9 && std::fabs(e[1] - 8.630393461693233) < 1e-9);
+  }
+  {
+    const double pi = 3.14159265358979323846;
+    OdometryFactor2DLinear f(Symbol('x', 1), Symbol('x', 2), Vector3{1, 0, 1}, m3);
+    Matrix H1, H2;
+    const Vector e = f.evaluateError(Vector3{42, 24, pi / 2}, Vector3{42, 25, pi / 2 + 1}, &H1, &H2);
+    EXPECT(e.size() == 3 && std::fabs(e[0]) < 1e-9 && std::fabs(e[1]) < 1e-9 && std::fabs(e[2]) < 1e-9 && H1.rows == 3 && H1.cols == 3 && H2.cols == 3);
+  }
+  {
+    // four Linear<3> states on a line, odometry between them, ranges to two beacons, GP priors: the noise-free optimum is the truth
+    SharedNoiseModel Qc = noiseModel::Gaussian::Covariance(0.01 * Matrix::Identity(3, 3));
+    NonlinearFactorGraph graph;
+    Values init;
+    const Point2 l1(2, 5), l2(-1, -4);
+    init.insert(Symbol('l', 1), Point2(2.3, 4.6)); init.insert(Symbol('l', 2), Point2(-1.2, -3.9));
+    graph.add(PriorFactor<Point2>(Symbol('l', 1), l1, noiseModel::Isotropic::Sigma(2, 0.01)));
+    graph.add(PriorFactor<Point2>(Symbol('l', 2), l2, noiseModel::Isotropic::Sigma(2, 0.01)));
+    graph.add(PriorFactor<Vector3>(Symbol('x', 1), Vector3{0, 0, 0}, noiseModel::Isotropic::Sigma(3, 0.01)));
+    for (int i = 1; i <= 4; i++) {
+      const double x = i - 1.0;
+      init.insert(Symbol('x', i), Vector3{x + 0.1 * (i % 2 ? 1 : -1), 0.05 * i, 0.02 * (i - 2)}); init.insert(Symbol('v', i), Vector3{0.8, 0.1, 0});
+      graph.add(RangeFactor2DLinear(Symbol('x', i), Symbol('l', 1), std::sqrt((l1.x - x) * (l1.x - x) + l1.y * l1.y), noiseModel::Isotropic::Sigma(1, 0.1)));
+      graph.add(RangeBearingFactor2DLinear(Symbol('x', i), Symbol('l', 2), std::sqrt((l2.x - x) * (l2.x - x) + l2.y * l2.y), Rot2(std::atan2(l2.y, l2.x - x)),
+                                           noiseModel::Isotropic::Sigma(2, 0.1)));
+      if (i > 1) {
+        graph.add(OdometryFactor2DLinear(Symbol('x', i - 1), Symbol('x', i), Vector3{1, 0, 0}, noiseModel::Isotropic::Sigma(3, 0.01)));
+        graph.add(GaussianProcessPriorLinear<3>(Symbol('x', i - 1), Symbol('v', i - 1), Symbol('x', i), Symbol('v', i), 1.0, Qc));
+      }
+    }
+    LevenbergMarquardtOptimizer optimizer(graph, init, LevenbergMarquardtParams(), GPB_LINEAR);
+    const double e0 = optimizer.error();
+    optimizer.optimize();
+    EXPECT(optimizer.error() < 1e-6 && optimizer.error() < e0);
+    for (int i = 1; i <= 4; i++) {
+      const Vector3 x = optimizer.values().at<Vector3>(Symbol('x', i)), v = optimizer.values().at<Vector3>(Symbol('v', i));
+      EXPECT(std::fabs(x[0] - (i - 1.0)) < 1e-4 && std::fabs(x[1]) < 1e-4 && std::fabs(x[2]) < 1e-4 && std::fabs(v[0] - 1.0) < 1e-3);
+    }
+  }
+}
+
 int main() {
   try {
     testFactor();
@@ -357,6 +414,7 @@ int main() {
     testGpsAndProjectionOptimization();
     testPose3VW();
     testInterpolators();
+    testPlain2DFactors();
   } catch (const std::exception& e) { std::printf("exception: %s\n", e.what()); return 2; }
   std::printf(failures ? "FAILED (%d)\n" : "OK (%d failures)\n", failures);
   return failures ? 1 : 0;
