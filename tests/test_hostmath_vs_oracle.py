@@ -248,3 +248,46 @@ def test_interpolate_pose_query(hm, group):
         out2 = np.zeros(PS)
         hm.hm_interp_pose(C.c_int(group), dp(np.concatenate([p1, v1])), dp(np.concatenate([p2, v2])), C.c_double(dt), C.c_double(tau), dp(out2), None)
         assert np.array_equal(out, out2)     # pose-only path
+
+
+def test_se3_prior_and_interpolator_by_rotation_regime(hm):
+    """The SE(3) prior's [A|b] and interpolatePose across the regimes of the relative rotation angle theta between the two states:
+    1e-7 (series branches), 1e-4 and 1e-6 (around the reference's theta = 1e-5 switch of rightJacobianPose3Q, gp/Pose3utils.cpp:98,
+    where its 1e-6-step numerical differentiation is itself only good to ~1e-6), 0.3 (typical), 2.5-3.1 (large).  Residuals and
+    poses agree with the oracle to rounding everywhere; Jacobians to 1e-8 where the reference's numerical derivative is clean and to
+    2e-6 around the switch.  (theta within 1e-3 of pi is excluded: Logmap is ill-conditioned there in the reference as well, and
+    adjacent states of a trajectory are never half a turn apart.)"""
+    rng = np.random.default_rng(2024)
+    tolJ = {0: 1e-8, 1: 2e-6, 2: 1e-8, 3: 1e-7, 4: 2e-6}
+    for trial in range(500):
+        mode = trial % 5
+        dt = float(rng.uniform(0.01, 1.0))
+        p1, v1 = rand_state(rng, po.POSE3, scale_rot=2.0)
+        if mode == 0:
+            step = rng.normal(size=6) * 1e-7
+        elif mode == 1:
+            step = rng.normal(size=6) * 1e-4
+        elif mode == 2:
+            step = rng.normal(size=6) * 0.3
+        elif mode == 3:
+            ax = rng.normal(size=3); ax /= np.linalg.norm(ax)
+            step = np.concatenate([ax * rng.uniform(2.5, 3.1), rng.normal(size=3) * 5])
+        else:
+            step = np.concatenate([rng.normal(size=3) * 1e-6, rng.normal(size=3)])
+        p2 = po.retract(po.POSE3, p1, step); v2 = v1 + rng.normal(size=6) * (0.1 if mode < 3 else 2.0)
+        g = po.Graph(po.POSE3, 2, 0); g.set_values(np.stack([p1, p2]), np.stack([v1, v2])); g.add_qc_model(np.eye(6)); g.add_gp_prior(0, dt)
+        A, b = g.linearize_factor(0)
+        Ao = np.concatenate(A + [b.reshape(-1, 1)], axis=1)
+        out = np.zeros(12 * 25); s1 = np.concatenate([p1, v1]); s2 = np.concatenate([p2, v2])
+        hm.hm_gp_prior(C.c_int(0), dp(s1), dp(s2), C.c_double(dt), dp(np.eye(6).ravel()), dp(out))
+        Ag = out.reshape(25, 12).T; sc = max(1.0, np.abs(Ao).max())
+        assert np.abs(Ag[:, -1] - Ao[:, -1]).max() <= 1e-11 * sc, (trial, mode)
+        assert np.abs(Ag[:, :-1] - Ao[:, :-1]).max() <= tolJ[mode] * sc, (trial, mode)
+        tau = float(rng.uniform(-0.5, 1.5) * dt)
+        ref, Href = po.interpolate(po.POSE3, np.eye(6), dt, tau, p1, v1, p2, v2, want_H=True)
+        o2 = np.zeros(12); H = np.zeros(144)
+        hm.hm_interp_pose(C.c_int(0), dp(s1), dp(s2), C.c_double(dt), C.c_double(tau), dp(o2), dp(H))
+        assert np.abs(o2 - ref).max() <= 1e-11 * max(1.0, np.abs(ref).max()), (trial, mode)
+        for k in range(4):
+            Hk = H[k * 36:(k + 1) * 36].reshape(6, 6).T
+            assert np.abs(Hk - Href[k]).max() <= tolJ[mode] * max(1.0, np.abs(Href[k]).max()), (trial, mode, k)
