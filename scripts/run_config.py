@@ -24,7 +24,6 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--lm", action="store_true", help="after the timed GN iterations, run LM to convergence and report it")
-    ap.add_argument("--oracle", action="store_true", help="compare one GN iteration with the CPU oracle (small sizes)")
     args = ap.parse_args()
     import numpy as np
     import gpslam_b200 as gb
@@ -43,17 +42,6 @@ def main():
     err0 = g.linearize()
     out = {"config": args.config, "states": cfg.n_states, "closures": cfg.n_closures, "landmark_dims": sz.border_dim, "gp_factors": sz.n_gp,
            "other_factors": sz.n_extra, "solver_levels": sz.levels, "hbm_resident_mb": sz.hbm_bytes / 1e6, "graph_build_s": build_s, "error_initial": err0}
-    if args.oracle:
-        from oracle import pyoracle as po
-        o, _ = synth.build(cfg, lambda grp, n, l: po.Graph(grp, n, l))
-        o.set_threads(po.hardware_threads())
-        g2, _ = synth.build(cfg, lambda grp, n, l: gb.Graph(grp, n, l))
-        sg = g2.optimize(n_iter=1, use_lm=False); so = o.optimize(n_iter=1, use_lm=False)
-        Pg, Vg, Lg = g2.get_values(); Po, Vo, Lo = o.get_values()
-        out["oracle_one_gn"] = {"max_pose_diff": float(np.abs(Pg - Po).max()), "max_vel_diff": float(np.abs(Vg - Vo).max()),
-                                "max_landmark_diff": float(np.abs(Lg - Lo).max()) if Lo.size else 0.0,
-                                "error_gpu": sg.error_final, "error_cpu": so.error_final}
-        del g2, o
     g.optimize(n_iter=max(args.warmup, 1), use_lm=False)
     st = g.optimize(n_iter=args.steps, use_lm=False)
     out.update({"gn_iterations_per_s": 1e3 * args.steps / st.total_ms, "ms_per_iteration": st.total_ms / args.steps, "launches_per_iteration": g.launches() / args.steps,
