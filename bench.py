@@ -106,7 +106,7 @@ class ClockSampler:
         return out
 
 
-def cpu_reference_run(steps, warmup, threads, n_sample=None):
+def cpu_reference_run(steps, warmup, threads, n_sample=None, keep_first=False):
     """the reference's CPU path (oracle/: restated gpslam factors + GTSAM-style GN over a bordered block-tridiagonal Cholesky)
     on a bounded sample of the workload: C3 cut to n_sample states (same factor densities).  Per-iteration cost is linear in
     the number of states, so iterations/sec on the 100k-state graph = sample rate * n_sample / 100000."""
@@ -118,16 +118,37 @@ def cpu_reference_run(steps, warmup, threads, n_sample=None):
     cfg.n_states = n_sample
     o, _ = synth.build(cfg, lambda grp, n, l: po.Graph(grp, n, l))
     o.set_threads(threads)
+    first = None
     if warmup:
-        o.optimize(n_iter=warmup, use_lm=False)
+        if keep_first:  # the values after the FIRST Gauss-Newton iteration: what the engine's parity gate is compared with
+            o.optimize(n_iter=1, use_lm=False)
+            first = o.get_values()
+            if warmup > 1:
+                o.optimize(n_iter=warmup - 1, use_lm=False)
+        else:
+            o.optimize(n_iter=warmup, use_lm=False)
     t0 = time.perf_counter()
     st = o.optimize(n_iter=steps, use_lm=False)
     dt = time.perf_counter() - t0
     rate_sample = steps / dt
-    return {"value": rate_sample * n_sample / full, "seconds_per_iteration_sample": dt / steps, "lin_seconds": st.lin_seconds, "solve_seconds": st.solve_seconds,
+    return {"value": rate_sample * n_sample / full, "n_sample": n_sample, "first_iteration_values": first, "seconds_per_iteration_sample": dt / steps, "lin_seconds": st.lin_seconds, "solve_seconds": st.solve_seconds,
             "sample": ("the whole workload (C3, %d states), %d GN iterations after %d warm-up" % (full, steps, warmup)) if n_sample == full else
                       ("C3 cut to %d of %d states (same factor densities), %d GN iterations after %d warm-up; rate scaled by %d/%d (cost is linear in states)"
                        % (n_sample, full, steps, warmup, n_sample, full))}
+
+
+def parity_after_one_gn(make_graph, n_states, oracle_values):
+    """SURVEY.md §8(d) parity gate next to the throughput number: a fresh engine graph of the same workload, ONE Gauss-Newton
+    iteration from the same initial values, compared with the oracle's values after its first iteration (largest absolute
+    difference of the wire entries; the tests hold this to 1e-6, north_star's tolerance)"""
+    from gpslam_b200 import synth
+    cfg = synth.config("C3"); cfg.n_states = n_states
+    g, _ = synth.build(cfg, make_graph)
+    g.optimize(n_iter=1, use_lm=False)
+    P, V, L = g.get_values()
+    Po, Vo, Lo = oracle_values
+    return {"after_gn_iterations": 1, "states": n_states, "max_pose_diff": float(np.abs(P - Po).max()), "max_velocity_diff": float(np.abs(V - Vo).max()),
+            "max_landmark_diff": float(np.abs(L - Lo).max()) if np.size(Lo) else 0.0, "tolerance": 1e-6}
 
 
 def run_reference(args, rank, world):
@@ -254,9 +275,13 @@ def run_engine(args, rank, world, local_rank):
         "stages_ms": stages, "clocks": clocks, "error": {"initial": err0, "final": st.error_final},
     }
     if rank == 0 and world == 1 and not args.no_cpu:
-        r = cpu_reference_run(3, 1, 1)
+        r = cpu_reference_run(3, 1, 1, keep_first=True)
         line["cpu_baseline"] = {"value": r["value"], "unit": "iterations/s", "cores": 1, "kind": "port", "sample": r["sample"],
                                 "seconds_per_iteration_sample": r["seconds_per_iteration_sample"]}
+        try:  # reported beside the numbers, never allowed to cost them
+            line["parity"] = parity_after_one_gn(lambda grp, n, l: gb.Graph(grp, n, l), r["n_sample"], r["first_iteration_values"])
+        except Exception as e:  # noqa: BLE001
+            line["parity"] = {"error": "%s: %s" % (type(e).__name__, e)}
     if one_device:
         line["debug_one_device"] = True
     if rank == 0:
