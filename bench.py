@@ -42,6 +42,11 @@ TRAFFIC_PANEL = 827.3e6
 PANEL_FLOP_PER_STATE = 2.0 * (78 * 61 + 144 * 61 + 61 * 62 // 2 * 12)
 
 
+def po_threads():
+    from oracle import pyoracle as po
+    return po.hardware_threads()
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -151,6 +156,25 @@ def parity_after_one_gn(make_graph, n_states, oracle_values):
             "max_landmark_diff": float(np.abs(L - Lo).max()) if np.size(Lo) else 0.0, "tolerance": 1e-6}
 
 
+def parity_converged(make_graph, threads):
+    """north_star's parity criterion beside the throughput number: the engine's and the oracle's LevenbergMarquardtOptimizer runs
+    to convergence (GTSAM's stop rule, matlab/PlazaPose2.m:208-230) from the same initial values on the whole workload;
+    per-state |Log(T_cpu^-1 T_gpu)|_inf, velocity and landmark differences of the two converged solutions"""
+    from gpslam_b200 import synth
+    from oracle import pyoracle as po
+    from tests.test_gpu_fullsize import pose_error
+    rec, _ = synth.record(synth.config("C3"))
+    g = rec.replay(make_graph); o = rec.replay(lambda grp, n, l: po.Graph(grp, n, l))
+    o.set_threads(threads)
+    t0 = time.perf_counter(); sg = g.optimize(use_lm=True); tg = time.perf_counter() - t0
+    t0 = time.perf_counter(); so = o.optimize(use_lm=True); to = time.perf_counter() - t0
+    P, V, L = g.get_values(); Po, Vo, Lo = o.get_values()
+    return {"after": "converged", "optimizer": "LevenbergMarquardt", "states": g.N, "iterations_engine": sg.iterations, "iterations_oracle": so.iterations,
+            "error_engine": sg.error_final, "error_oracle": so.error_final, "max_pose_log_err": float(pose_error(0, Po, P).max()),
+            "max_velocity_diff": float(np.abs(V - Vo).max()), "max_landmark_diff": float(np.abs(L - Lo).max()), "tolerance": 1e-6,
+            "engine_seconds": tg, "oracle_seconds": to, "oracle_threads": threads}
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -160,7 +184,9 @@ def run_reference(args, rank, world):
     line = {"metric": METRIC, "value": r["value"], "unit": "iterations/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 / r["value"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "impl": "reference", "config": {"workload": WORKLOAD},
-            "cpu_baseline": {"value": r["value"], "unit": "iterations/s", "cores": threads, "kind": "port", "sample": r["sample"]},
+            "cpu_baseline": {"value": r["value"], "unit": "iterations/s", "cores": threads, "kind": "port", "sample": r["sample"],
+                             "linearise_s_per_iteration_sample": r["lin_seconds"] / args.steps, "solve_s_per_iteration_sample": r["solve_seconds"] / args.steps,
+                             "note": "linearise is threaded over factors; the bordered block-tridiagonal Cholesky of the restated reference is sequential scalar C++ (no Eigen / BLAS)"},
             "e2e": {"value": r["value"], "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line))
 
@@ -193,11 +219,18 @@ def run_engine(args, rank, world, local_rank):
         # strong scaling: the SAME 100k-state graph, cut into contiguous segments, one per GPU; one NCCL all-reduce of the
         # boundary Schur system per GN iteration and no other collective on the data path
         g, _ = synth.build(cfg, lambda grp, n, l: shard.ShardBuilder(lambda g_, n_, l_: gb.Graph(g_, n_, l_), grp, n, l, rank, world), finalize=False)
-        g.g.set_allreduce(shard.torch_allreduce(local_rank))
+        gen_s = time.perf_counter() - t0
         g.finalize(local_rank)
         g = g.g
+        if one_device:
+            g.set_allreduce(shard.torch_allreduce(local_rank))
+        else:
+            # the engine's own NCCL communicator: the all-reduce is enqueued by the engine inside the captured CUDA graph of an
+            # iteration (no Python, no torch dispatch on the hot loop); torch.distributed only carries the 128-byte unique id
+            shard.init_engine_nccl(g, rank, world)
     else:
         g, _ = synth.build(cfg, lambda grp, n, l: gb.Graph(grp, n, l), finalize=False)
+        gen_s = time.perf_counter() - t0
         g.finalize(local_rank)
     build_s = time.perf_counter() - t0
     sz = g.sizes()
@@ -229,17 +262,25 @@ def run_engine(args, rank, world, local_rank):
     value = 1e3 / ms_per_step
     # ---- end to end through the C ABI with host buffers: H2D of the values, one iteration, D2H of the result, every step
     #      (values live in page-locked host arrays, as a caller that cares about the transfer would hold them)
-    P, V, Lm = g.get_values(out=g.alloc_values())
+    #      through gpb_optimize_batch: step k+1's H2D and step k-1's D2H run on copy streams while step k computes.  Every step
+    #      uploads its own input values (two page-locked input sets, alternating) and downloads its result and error.
+    ins = [g.get_values(out=g.alloc_values()) for _ in range(2)]
+    outs = [g.alloc_values() for _ in range(2)]
+    P, V, Lm = ins[0]
+    g.optimize_batch([ins[k & 1] for k in range(3)], [outs[k & 1] for k in range(3)])
+    sync_all()
+    t0 = time.perf_counter()
+    st_b, errs_b = g.optimize_batch([ins[k & 1] for k in range(args.steps)], [outs[k & 1] for k in range(args.steps)])
+    e2e_s = max_over_ranks((time.perf_counter() - t0) / args.steps)
+    io_bytes = int(P.nbytes + V.nbytes + Lm.nbytes)
+    # the same steps one call at a time (Values in, iterate, Values out; nothing overlapped) for comparison
     for _ in range(2):
-        g.set_values(P, V, Lm); g.optimize(n_iter=1, use_lm=False); g.get_values(out=(P, V, Lm))
+        g.set_values(P, V, Lm); g.optimize(n_iter=1, use_lm=False); g.get_values(out=outs[0])
     sync_all()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        g.set_values(P, V, Lm)
-        g.optimize(n_iter=1, use_lm=False)
-        g.get_values(out=(P, V, Lm))
-    e2e_s = max_over_ranks((time.perf_counter() - t0) / args.steps)
-    io_bytes = int(P.nbytes + V.nbytes + Lm.nbytes)
+        g.set_values(P, V, Lm); g.optimize(n_iter=1, use_lm=False); g.get_values(out=outs[0])
+    e2e_serial_s = max_over_ranks((time.perf_counter() - t0) / args.steps)
     # ---- per-stage device times and the linearise roofline (local shard)
     stages = {n: g.time_stage(k, 20) for k, n in ((0, "linearise_gp"), (1, "linearise_other"), (2, "assemble"), (3, "solve"), (4, "retract"), (5, "solve_fwd_level0"),
                                                    (6, "solve_spine_level0"), (7, "solve_panel_level0"), (8, "solve_backward"))}
@@ -261,8 +302,10 @@ def run_engine(args, rank, world, local_rank):
                    "parallelism": "trajectory segments x%d, one NCCL all-reduce of the boundary Schur system per iteration" % world if world > 1 else "single GPU",
                    "allreduces_per_step": (n_allreduce - 1) / args.steps if world > 1 else 0,
                    "l2": "inputs larger than L2: [A|b] buffers 2 x %.0f MB, resident %.0f MB per GPU (L2 126 MB)" % (sz.n_gp * 2400 / 1e6, sz.hbm_bytes / 1e6),
-                   "hbm_resident_mb": sz.hbm_bytes / 1e6, "graph_build_s": build_s},
-        "e2e": {"value": 1.0 / e2e_s, "unit": "iterations/s", "h2d_bytes_per_step": io_bytes * world, "d2h_bytes_per_step": io_bytes * world},
+                   "hbm_resident_mb": sz.hbm_bytes / 1e6, "graph_build_s": build_s, "generator_s": gen_s, "finalize_s": build_s - gen_s},
+        "e2e": {"value": 1.0 / e2e_s, "unit": "iterations/s", "h2d_bytes_per_step": io_bytes * world, "d2h_bytes_per_step": io_bytes * world + 8 * world,
+                "api": "gpb_optimize_batch (host values in -> one GN iteration -> host values + error out, every step; copies double-buffered against compute)",
+                "unpipelined_value": 1.0 / e2e_serial_s, "unpipelined_api": "gpb_set_values + gpb_optimize(1) + gpb_get_values per step"},
         "gpu_launches": launches,
         "roofline": {"kernel": "k_lin_gp<POSE3> (batched GP-prior linearise; diagonal-Qc instantiation)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "peak_source": peak_src, "algorithmic_bytes": gp_bytes, "ms": stages["linearise_gp"], "traffic": TRAFFIC_LIN_GP if world == 1 else None,
@@ -277,11 +320,14 @@ def run_engine(args, rank, world, local_rank):
     if rank == 0 and world == 1 and not args.no_cpu:
         r = cpu_reference_run(3, 1, 1, keep_first=True)
         line["cpu_baseline"] = {"value": r["value"], "unit": "iterations/s", "cores": 1, "kind": "port", "sample": r["sample"],
-                                "seconds_per_iteration_sample": r["seconds_per_iteration_sample"]}
+                                "seconds_per_iteration_sample": r["seconds_per_iteration_sample"],
+                                "linearise_s_per_iteration_sample": r["lin_seconds"] / 3, "solve_s_per_iteration_sample": r["solve_seconds"] / 3}
         try:  # reported beside the numbers, never allowed to cost them
             line["parity"] = parity_after_one_gn(lambda grp, n, l: gb.Graph(grp, n, l), r["n_sample"], r["first_iteration_values"])
+            if not args.no_converged:
+                line["parity"].update(parity_converged(lambda grp, n, l: gb.Graph(grp, n, l), po_threads()))
         except Exception as e:  # noqa: BLE001
-            line["parity"] = {"error": "%s: %s" % (type(e).__name__, e)}
+            line["parity"] = dict(line.get("parity") or {}, error="%s: %s" % (type(e).__name__, e))
     if one_device:
         line["debug_one_device"] = True
     if rank == 0:
@@ -302,6 +348,7 @@ def main():
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--states", type=int, default=0, help="override the number of states (parity/debug runs; not a bench value)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-converged", action="store_true", help="skip the converged-LM parity run against the oracle (about 1.5 minutes of host time)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":

@@ -116,6 +116,27 @@ def interpolate_poses(group, x1, v1, x2, v2, delta_t, tau, want_H=False, device=
     return poses
 
 
+def interpolate_velocities(x1, v1, x2, v2, delta_t, tau, want_H=False, device=0):
+    """GaussianProcessInterpolatorLinear::interpolateVelocity for n queries (gpb_interpolate_velocities): vels [n x dim] and, with
+    want_H, the four scalars (Lambda21, Lambda22, Psi21, Psi22) per query - H1..H4 are those multiples of the identity"""
+    x1 = _f64(np.atleast_2d(x1)); n, dim = x1.shape
+    v1 = _f64(v1).reshape(n, dim); x2 = _f64(x2).reshape(n, dim); v2 = _f64(v2).reshape(n, dim)
+    dt = _f64(np.broadcast_to(np.atleast_1d(delta_t), (n,))); ta = _f64(np.broadcast_to(np.atleast_1d(tau), (n,)))
+    out = np.zeros((n, dim)); H = np.zeros((n, 4)) if want_H else None
+    rc = lib().gpb_interpolate_velocities(C.c_int(GPB_LINEAR), C.c_int(device), C.c_int(n), C.c_int(dim), _dp(x1), _dp(v1), _dp(x2), _dp(v2), _dp(dt), _dp(ta), _dp(out), _dp(H))
+    if rc != 0:
+        raise GpbError(lib().gpb_last_error().decode())
+    return (out, H) if want_H else out
+
+
+def nccl_unique_id():
+    """128-byte ncclUniqueId for gpb_graph_init_nccl (rank 0 creates it, every rank passes the same bytes)"""
+    buf = (C.c_ubyte * 128)()
+    if lib().gpb_nccl_unique_id(buf) != 0:
+        raise GpbError(lib().gpb_last_error().decode())
+    return bytes(buf)
+
+
 def default_params(use_lm=True):
     p = Params()
     lib().gpb_default_params(C.byref(p), C.c_int(1 if use_lm else 0))
@@ -242,6 +263,11 @@ class Graph:
         self._cb = CB(lambda ctx, ptr, count, stream: int(fn(ptr, count, stream or 0)))
         self._ck(self.L.gpb_set_allreduce(self.h, self._cb, None))
 
+    def init_nccl(self, unique_id, rank, world):
+        """the engine's own NCCL communicator (gpb_graph_init_nccl): collective over all ranks, after finalize()"""
+        buf = (C.c_ubyte * 128).from_buffer_copy(unique_id)
+        self._ck(self.L.gpb_graph_init_nccl(self.h, buf, C.c_int(rank), C.c_int(world)))
+
     def allreduces(self):
         return self.L.gpb_allreduces_last_optimize(self.h)
 
@@ -329,6 +355,24 @@ class Graph:
         st = Stats()
         self._ck(self.L.gpb_optimize(self.h, C.byref(p), C.c_int(n_iter), C.byref(st)))
         return st
+
+    def optimize_batch(self, ins, outs):
+        """gpb_optimize_batch: ins / outs are lists of (poses, vels, lands) array triples (page-locked ones from alloc_values for
+        full copy / compute overlap); one Gauss-Newton iteration per step.  Returns (stats, this rank's error after each step)."""
+        K = len(ins)
+        assert K == len(outs) and K >= 1
+        PP = C.POINTER(C.c_double)
+        def arr(trip, idx):
+            a = (PP * K)()
+            for k, t in enumerate(trip):
+                x = t[idx]
+                assert x.dtype == np.float64 and x.flags.c_contiguous
+                a[k] = _dp(x)
+            return a
+        st = Stats(); errs = np.zeros(K)
+        keep = [arr(ins, 0), arr(ins, 1), arr(ins, 2) if self.NL else None, arr(outs, 0), arr(outs, 1), arr(outs, 2) if self.NL else None]
+        self._ck(self.L.gpb_optimize_batch(self.h, C.c_int(K), keep[0], keep[1], keep[2], keep[3], keep[4], keep[5], _dp(errs), C.byref(st)))
+        return st, errs
 
     def time_stage(self, stage, reps=10):
         ms = C.c_double()

@@ -15,7 +15,9 @@
 // eliminateMultifrontal (Cholesky) -> back-substitution -> Values::retract -> graph.error, driven by
 // GaussNewtonOptimizer / LevenbergMarquardtOptimizer::iterate.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -37,6 +39,43 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
     if (e_ != cudaSuccess) return fail(GPB_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(e_));        \
   } while (0)
 
+
+// ===================================================================== NCCL (optional, bound at run time)
+// The boundary all-reduce of a sharded graph is issued by the engine itself on its own stream, so that a whole
+// Gauss-Newton iteration - collective included - is ONE captured CUDA graph.  libnccl is bound with dlopen when a communicator is
+// first requested (gpb_graph_init_nccl): a process that already holds NCCL (torch.distributed) shares that copy, single-GPU
+// users never load it.  Only the five entry points below are used; types follow nccl.h (ncclUniqueId = 128 opaque bytes,
+// ncclDouble = 8, ncclSum = 0).
+namespace nccl_rt {
+struct UniqueId { char internal[128]; };
+typedef void* Comm;
+typedef int (*GetUniqueId_t)(UniqueId*);
+typedef int (*CommInitRank_t)(Comm*, int, UniqueId, int);
+typedef int (*AllReduce_t)(const void*, void*, size_t, int, int, Comm, cudaStream_t);
+typedef int (*CommDestroy_t)(Comm);
+typedef const char* (*GetErrorString_t)(int);
+static void* handle = nullptr;
+static GetUniqueId_t GetUniqueId = nullptr;
+static CommInitRank_t CommInitRank = nullptr;
+static AllReduce_t AllReduce = nullptr;
+static CommDestroy_t CommDestroy = nullptr;
+static GetErrorString_t GetErrorString = nullptr;
+static const char* load() {  // returns nullptr on success, else what went wrong
+  if (handle) return nullptr;
+  void* h = nullptr;
+  if (const char* env = getenv("GPB_NCCL_LIB")) h = dlopen(env, RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);  // the copy this process already holds (torch's)
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) return "libnccl.so.2 not found (set GPB_NCCL_LIB)";
+  GetUniqueId = (GetUniqueId_t)dlsym(h, "ncclGetUniqueId"); CommInitRank = (CommInitRank_t)dlsym(h, "ncclCommInitRank");
+  AllReduce = (AllReduce_t)dlsym(h, "ncclAllReduce"); CommDestroy = (CommDestroy_t)dlsym(h, "ncclCommDestroy");
+  GetErrorString = (GetErrorString_t)dlsym(h, "ncclGetErrorString");
+  if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy || !GetErrorString) return "libnccl lacks an expected symbol";
+  handle = h;
+  return nullptr;
+}
+}  // namespace nccl_rt
 
 // ===================================================================== host-side graph
 struct Extra {
@@ -90,8 +129,15 @@ struct gpb_graph {
   int nclos = 0, nep = 0, npair = 0;  // loop closures: factors, endpoint states, unique endpoint pairs
   int *d_epstate = nullptr, *d_epoff = nullptr, *d_eprow = nullptr, *d_epside = nullptr;
   int *d_pair_a = nullptr, *d_pair_b = nullptr, *d_pairoff = nullptr, *d_pairrow = nullptr;
-  bool generic_fwd = false, force_blocked = false, old_assemble = false, split_levels = false, no_tiny = false;
+  bool generic_fwd = false, force_blocked = false, old_assemble = false, split_levels = false, no_tiny = false, fuse_l0 = false;
   gpb_allreduce_fn allreduce = nullptr; void* allreduce_ctx = nullptr;
+  nccl_rt::Comm nccl = nullptr;   // engine-owned communicator (gpb_graph_init_nccl): the all-reduce is captured inside the iteration graph
+  cudaGraphExec_t gn_graph[2] = {nullptr, nullptr}; int gn_graph_launches[2] = {0, 0};  // whole asynchronous GN iteration per buffer parity
+  bool failed = false;            // gpb_graph_finalize failed half-way: the graph can only be destroyed
+  // pipelined batch interface (gpb_optimize_batch): staging buffers, copy streams, events
+  double* d_stage_in[2] = {nullptr, nullptr}; double* d_stage_out[2] = {nullptr, nullptr}; double* h_batch_err = nullptr;
+  cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+  cudaEvent_t ev_in_ready[2] = {nullptr, nullptr}, ev_in_free[2] = {nullptr, nullptr}, ev_out_ready[2] = {nullptr, nullptr}, ev_out_free[2] = {nullptr, nullptr};
   double* d_topbuf = nullptr; double cur_error_local = 0; int n_allreduce = 0;
   double* d_lambda = nullptr;
   cudaGraphExec_t iter_graph[2] = {nullptr, nullptr}; int iter_graph_launches[2] = {0, 0};  // captured GN/LM trial per buffer parity
@@ -200,6 +246,17 @@ void gpb_graph_destroy(gpb_graph* g) {
   if (g->pinned) { cudaHostUnregister(g->h_X.data()); if (g->L) cudaHostUnregister(g->h_land.data()); }
   for (int k = 0; k < 2; k++) if (g->iter_graph[k]) cudaGraphExecDestroy(g->iter_graph[k]);
   for (int k = 0; k < 2; k++) for (int h = 0; h < 2; h++) if (g->dist_graph[k][h]) cudaGraphExecDestroy(g->dist_graph[k][h]);
+  for (int k = 0; k < 2; k++) if (g->gn_graph[k]) cudaGraphExecDestroy(g->gn_graph[k]);
+  if (g->nccl && nccl_rt::CommDestroy) { if (g->stream) cudaStreamSynchronize(g->stream); nccl_rt::CommDestroy(g->nccl); }
+  for (int k = 0; k < 2; k++) {
+    if (g->ev_in_ready[k]) cudaEventDestroy(g->ev_in_ready[k]);
+    if (g->ev_in_free[k]) cudaEventDestroy(g->ev_in_free[k]);
+    if (g->ev_out_ready[k]) cudaEventDestroy(g->ev_out_ready[k]);
+    if (g->ev_out_free[k]) cudaEventDestroy(g->ev_out_free[k]);
+  }
+  if (g->s_h2d) cudaStreamDestroy(g->s_h2d);
+  if (g->s_d2h) cudaStreamDestroy(g->s_d2h);
+  if (g->h_batch_err) cudaFreeHost(g->h_batch_err);
   for (void* p : g->allocs) cudaFree(p);
   if (g->ev_fork) cudaEventDestroy(g->ev_fork);
   if (g->ev_join) cudaEventDestroy(g->ev_join);
@@ -498,9 +555,10 @@ static int bwd_blocks_per_sm(int bs, int W) {
   if (bs == 12) return W == 16 ? occ_bwd<12, 16>() : W == 32 ? occ_bwd<12, 32>() : occ_bwd<12, 64>();
   return W == 16 ? occ_bwd<6, 16>() : W == 32 ? occ_bwd<6, 32>() : occ_bwd<6, 64>();
 }
-static int fwd_blocks_per_sm(int bs, int W) {
+static int fwd_blocks_per_sm(int bs, int W, bool fuse_l0 = false) {
   if (bs == 12 && W == 64) {
     int nb = 0;
+    if (fuse_l0) { if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_level0_ws<12>, 160, 0) != cudaSuccess) { cudaGetLastError(); nb = 4; } return nb < 1 ? 1 : nb; }
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_panel4<12>, 128, 0) != cudaSuccess) { cudaGetLastError(); nb = 4; }
     return nb < 1 ? 1 : nb;
   }
@@ -515,6 +573,16 @@ int gpb_graph_finalize(gpb_graph* g, int device) {
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(GPB_ERR_CUDA, "gpb_graph_finalize: no CUDA device available (this engine has no CPU fallback)"); }
   if (device < 0 || device >= ndev) return fail(GPB_ERR_ARG, "gpb_graph_finalize: bad device index");
   if (g->Rq.empty()) return fail(GPB_ERR_STATE, "gpb_graph_finalize: no Qc model registered");
+  if (g->failed) return fail(GPB_ERR_STATE, "gpb_graph_finalize: an earlier finalize of this graph failed; destroy it");
+  // every shape check comes before the first CUDA resource is created: a refused graph holds nothing and may be finalized again
+  if (2 * g->D + g->L * g->DL + 1 > 64) return fail(GPB_ERR_UNSUPPORTED, "gpb_graph_finalize: landmark border wider than 64 - 2D - 1 columns is not supported by this build");
+  if ((g->n_real ? g->n_real : g->N) - (g->extL ? 1 : 0) - (g->extR ? 1 : 0) < 0) return fail(GPB_ERR_ARG, "shard too small for its external separators");
+  {
+    bool any_closure = false;
+    for (const Extra& e : g->extras) any_closure |= e.closure != 0;
+    if ((any_closure || (g->n_real && g->n_real < g->N)) && g->world > 1 && g->map_ntop < 0) return fail(GPB_ERR_STATE, "gpb_graph_finalize: a sharded graph with loop closures needs gpb_graph_set_top_map");
+  }
+  struct FailGuard { gpb_graph* g; ~FailGuard() { if (!g->finalized) g->failed = true; } } fail_guard{g};  // anything failing from here on poisons the graph
   CUDA_TRY(cudaSetDevice(device));
   g->device = device;
   CUDA_TRY(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
@@ -655,6 +723,7 @@ int gpb_graph_finalize(gpb_graph* g, int device) {
   g->split_levels = getenv("GPB_SPLIT_LEVELS") != nullptr;  // A/B switch: spine and panel as two launches on the upper levels too
   g->old_assemble = getenv("GPB_OLD_ASSEMBLE") != nullptr;  // A/B switch: thread-per-tile assembly instead of the DMMA kernel
   g->generic_fwd = getenv("GPB_GENERIC_FWD") != nullptr;
+  g->fuse_l0 = getenv("GPB_FUSE_L0") != nullptr;  // A/B switch: level 0 as ONE warp-specialised kernel (spine warp + panel warps per CTA)
   g->no_tiny = getenv("GPB_NO_TINY_SOLVE") != nullptr;  // A/B switch: the plain-loop instantiation of k_small_solve instead of the register-blocked ones
   g->qc_diag = 1;
   for (const auto& R : g->Rq) for (int c = 0; c < D; c++) for (int r = 0; r < D; r++) if (r != c && R[r + c * D] != 0.0) g->qc_diag = 0;
@@ -671,7 +740,7 @@ int gpb_graph_finalize(gpb_graph* g, int device) {
     // the panel kernel runs one resident wave of persistent CTAs, each walking ceil(nseg / slots) segments of M0 (+ a closing
     // separator) states one after the other: pick the segment length that minimises that serial depth (whole rounds - a
     // 100k-state chain on 148 x 5 slots wants 46, not 32); ties go to the longer segment (fewer separators for the next level)
-    const int slots = sms * fwd_blocks_per_sm(bs, g->W), m0 = g->N - g->pinL - g->pinR;
+    const int slots = sms * fwd_blocks_per_sm(bs, g->W, g->fuse_l0), m0 = g->N - g->pinL - g->pinR;
     long long best = -1;
     for (int M = 12; M <= 63; M++) {
       const int nseg = (m0 > 0 ? (m0 - 1) / M : 0) + 1;
@@ -710,7 +779,7 @@ int gpb_graph_finalize(gpb_graph* g, int device) {
       }
       std::sort(sep.begin(), sep.end());
       L.S = (int)sep.size(); L.nseg = L.S + 1;
-      L.ncta = std::min(L.nseg, sms * fwd_blocks_per_sm(bs, g->W));  // persistent CTAs: one resident wave
+      L.ncta = std::min(L.nseg, sms * fwd_blocks_per_sm(bs, g->W, g->fuse_l0 && lev == 0));  // persistent CTAs: one resident wave
       L.ncta_bwd = std::min(L.nseg, sms * bwd_blocks_per_sm(bs, g->W));
       if ((rc = dev_upload(g, &L.d_sep, sep))) return rc;
       if ((rc = dev_alloc(g, &L.frec, (size_t)n * fstride))) return rc;
@@ -923,7 +992,9 @@ static int launch_fwd_level(gpb_graph* g, int buf, double lambda, int lev, int p
   if (bs == 12 && g->W == 64 && !g->generic_fwd) {
     // spine first (warp per segment: the latency-bound 12x12 recurrence wants many independent warps), then the tensor-pipe panel
     const int spine_ctas = std::min(L.nseg, 16 * g->sms);
-    if (lev > 0 && parts == 3 && L.nseg <= 2 * g->sms && !g->split_levels) {
+    if (lev == 0 && parts == 3 && g->fuse_l0) {
+      k_level0_ws<12><<<L.ncta, 160, 0, g->stream>>>(a); g->launches++;
+    } else if (lev > 0 && parts == 3 && L.nseg <= 2 * g->sms && !g->split_levels) {
       // small level: spine and panel pipelined inside one kernel (every CTA resident at once)
       k_level_ws<12><<<L.nseg, 160, 0, g->stream>>>(a); g->launches++;
     } else {
@@ -969,7 +1040,13 @@ static int solve_backward(gpb_graph* g) {
 }
 // in-place sum over ranks of a small device buffer through the registered callback (stream-ordered on both sides)
 static int dist_allreduce(gpb_graph* g, double* dbuf, long long count) {
-  if (!g->allreduce) return fail(GPB_ERR_STATE, "sharded graph: no all-reduce registered (gpb_set_allreduce)");
+  if (g->nccl) {  // the engine's own communicator: enqueued on the engine stream (and captured with it)
+    const int rc = nccl_rt::AllReduce(dbuf, dbuf, (size_t)count, /*ncclDouble*/ 8, /*ncclSum*/ 0, g->nccl, g->stream);
+    if (rc != 0) return fail(GPB_ERR_CUDA, std::string("ncclAllReduce: ") + nccl_rt::GetErrorString(rc));
+    g->n_allreduce++;
+    return GPB_OK;
+  }
+  if (!g->allreduce) return fail(GPB_ERR_STATE, "sharded graph: no all-reduce registered (gpb_graph_init_nccl or gpb_set_allreduce)");
   if (g->allreduce(g->allreduce_ctx, dbuf, count, (void*)g->stream) != 0) return fail(GPB_ERR_CUDA, "all-reduce callback failed");
   g->n_allreduce++;
   return GPB_OK;
@@ -1160,14 +1237,104 @@ int gpb_solve_delta(gpb_graph* g, double lambda, double* delta_states, double* d
   return GPB_OK;
 }
 
+}  // extern "C"
+
 // ===================================================================== GN / LM loop
-int gpb_optimize(gpb_graph* g, const gpb_params* params, int n_iter, gpb_stats* st) {
+namespace {
+struct EventPair {  // timing events, destroyed on every exit path
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  ~EventPair() { if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); }
+};
+// stream capture that always ends: the captured graph is destroyed, the executable graph survives only on success
+struct Capture {
+  cudaStream_t s; bool open = false;
+  explicit Capture(cudaStream_t s_) : s(s_) {}
+  int begin(cudaStreamCaptureMode mode) { CUDA_TRY(cudaStreamBeginCapture(s, mode)); open = true; return GPB_OK; }
+  int end(int body_rc, cudaGraphExec_t* exec) {
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(s, &graph);
+    open = false;
+    if (body_rc) { if (graph) cudaGraphDestroy(graph); cudaGetLastError(); return body_rc; }
+    if (ce != cudaSuccess) { if (graph) cudaGraphDestroy(graph); return fail(GPB_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce)); }
+    const cudaError_t ci = cudaGraphInstantiate(exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ci != cudaSuccess) return fail(GPB_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ci));
+    return GPB_OK;
+  }
+  ~Capture() { if (open) { cudaGraph_t graph = nullptr; cudaStreamEndCapture(s, &graph); if (graph) cudaGraphDestroy(graph); cudaGetLastError(); } }
+};
+}  // namespace
+
+// One asynchronous Gauss-Newton iteration (no damping, no host round trip): assemble -> eliminate -> [sharded: ONE all-reduce of
+// the boundary Schur system, which also carries the error of the current point] -> reduced solve -> back-substitute -> retract ->
+// linearise at the new point, then the buffers swap.  A failed factorisation anywhere raises the sticky device flag, which the
+// caller checks after its last iteration.  The launch sequence is fixed per buffer parity and is replayed as ONE CUDA graph
+// (single GPU, or sharded with the engine's own NCCL communicator: the collective is captured with the kernels), or as two graphs
+// around a caller-supplied all-reduce callback (gpb_set_allreduce).
+static int gn_iteration_async(gpb_graph* g) {
+  int r = GPB_OK;
+  const int par = g->cur;
+  const bool dist = g->world > 1;
+  const long long top_count = (long long)(g->R + 1) * g->R + 4;
+  auto first_half = [&]() -> int {
+    int rr = assemble_dispatch(g, par);
+    k_set_scalar<<<1, 1, 0, g->stream>>>(g->d_lambda, 0.0); g->launches++;
+    if (!rr) rr = solve_forward(g, par, 0.0);
+    if (!rr) rr = top_pack(g, par, 0.0, true);
+    return rr;
+  };
+  auto second_half = [&]() -> int {
+    int rr = top_finish(g, nullptr);
+    if (!rr) rr = solve_backward(g);
+    if (!rr) rr = retract_dispatch(g);
+    if (!rr) rr = linearize_dispatch(g, g->d_Xt, g->d_landt, 1 - par, 1);
+    return rr;
+  };
+  if (!dist || g->nccl) {
+    if (!g->gn_graph[par]) {
+      const int l0 = g->launches;
+      Capture cap(g->stream);
+      if ((r = cap.begin(dist ? cudaStreamCaptureModeRelaxed : cudaStreamCaptureModeThreadLocal))) return r;
+      r = first_half();
+      if (!r && dist) r = dist_allreduce(g, g->d_topbuf, top_count);
+      if (!r) r = second_half();
+      if ((r = cap.end(r, &g->gn_graph[par]))) return r;
+      g->gn_graph_launches[par] = g->launches - l0;
+      g->launches = l0;
+      if (dist) g->n_allreduce--;  // counted per replay below
+    }
+    CUDA_TRY(cudaGraphLaunch(g->gn_graph[par], g->stream));
+    g->launches += g->gn_graph_launches[par];
+    if (dist) g->n_allreduce++;
+  } else {
+    if (!g->dist_graph[par][0]) {
+      const int l0 = g->launches;
+      for (int half = 0; half < 2; half++) {
+        Capture cap(g->stream);
+        if ((r = cap.begin(cudaStreamCaptureModeThreadLocal))) return r;
+        r = half == 0 ? first_half() : second_half();
+        if ((r = cap.end(r, &g->dist_graph[par][half]))) return r;
+      }
+      g->dist_graph_launches[par] = g->launches - l0;
+      g->launches = l0;
+    }
+    CUDA_TRY(cudaGraphLaunch(g->dist_graph[par][0], g->stream));
+    if ((r = dist_allreduce(g, g->d_topbuf, top_count))) return r;
+    CUDA_TRY(cudaGraphLaunch(g->dist_graph[par][1], g->stream));
+    g->launches += g->dist_graph_launches[par];
+  }
+  std::swap(g->d_X, g->d_Xt); std::swap(g->d_land, g->d_landt); g->cur = 1 - g->cur;
+  g->assembled = false; g->linearized = true;
+  return GPB_OK;
+}
+
+extern "C" int gpb_optimize(gpb_graph* g, const gpb_params* params, int n_iter, gpb_stats* st) {
   CHECK_READY(g);
   gpb_params p;
   if (params) p = *params; else gpb_default_params(&p, 1);
-  cudaEvent_t e0, e1;
-  CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
-  CUDA_TRY(cudaEventRecord(e0, g->stream));
+  EventPair ev;
+  CUDA_TRY(cudaEventCreate(&ev.e0)); CUDA_TRY(cudaEventCreate(&ev.e1));
+  CUDA_TRY(cudaEventRecord(ev.e0, g->stream));
   g->launches = 0; g->n_allreduce = 0;
   int rc;
   if (!g->linearized && (rc = gpb_linearize(g, nullptr))) return rc;
@@ -1175,55 +1342,17 @@ int gpb_optimize(gpb_graph* g, const gpb_params* params, int n_iter, gpb_stats* 
   double error = error_initial, lambda = p.lambda_initial;
   int iterations = 0, status = 0;
   const bool dist = g->world > 1;
-  // sharded graphs: exactly ONE all-reduce per Gauss-Newton iteration (the boundary Schur system, which also carries the error
-  // of the current point).  LM trials and convergence-tested runs need the trial point's global error before the next
-  // iteration and pay a second, 4-double all-reduce for it.
-  const bool need_trial_error = dist && (p.use_lm || n_iter <= 0);
-  const bool async_gn = dist && !need_trial_error;
+  // Plain Gauss-Newton with a fixed iteration count needs nothing from the device between iterations: it runs asynchronously
+  // (gn_iteration_async), on one GPU as on a sharded graph - there with exactly ONE all-reduce per iteration (the boundary Schur
+  // system, which also carries the error of the current point).  LM trials and convergence-tested runs need the trial point's
+  // (global) error before the next decision: one host sync per trial and, sharded, a second 4-double all-reduce for it.
+  const bool need_trial_error = p.use_lm || n_iter <= 0;
+  const bool async_gn = !need_trial_error;
   if (async_gn) CUDA_TRY(cudaMemsetAsync(g->d_flag, 0, sizeof(int), g->stream));
   auto one_iteration = [&]() -> int {
     int r;
-    if (!async_gn && !g->assembled) { if ((r = assemble_dispatch(g, g->cur))) return r; g->assembled = true; }
-    if (async_gn) {
-      // sharded plain Gauss-Newton: the whole iteration, all-reduce included, is enqueued without a host round trip; a failed
-      // factorisation anywhere raises the (sticky) flag, which is checked once after the last iteration
-      // The launch sequence is fixed per buffer parity: it is replayed as two CUDA graphs around the all-reduce, so the host
-      // issues 2 graph launches + 1 collective per iteration instead of ~50 kernel launches (a shard's iteration is short).
-      const int par = g->cur;
-      if (!g->dist_graph[par][0]) {
-        const int l0 = g->launches;
-        for (int half = 0; half < 2; half++) {
-          cudaGraph_t graph;
-          CUDA_TRY(cudaStreamBeginCapture(g->stream, cudaStreamCaptureModeThreadLocal));
-          if (half == 0) {
-            r = assemble_dispatch(g, par);
-            k_set_scalar<<<1, 1, 0, g->stream>>>(g->d_lambda, 0.0);
-            if (!r) r = solve_forward(g, par, 0.0);
-            if (!r) r = top_pack(g, par, 0.0, true);
-          } else {
-            r = top_finish(g, nullptr);
-            if (!r) r = solve_backward(g);
-            if (!r) r = retract_dispatch(g);
-            if (!r) r = linearize_dispatch(g, g->d_Xt, g->d_landt, 1 - par, 1);
-          }
-          const cudaError_t ce = cudaStreamEndCapture(g->stream, &graph);
-          if (r) return r;
-          CUDA_TRY(ce);
-          CUDA_TRY(cudaGraphInstantiate(&g->dist_graph[par][half], graph, 0));
-          cudaGraphDestroy(graph);
-        }
-        g->dist_graph_launches[par] = g->launches - l0 + 1;
-        g->launches = l0;
-      }
-      CUDA_TRY(cudaGraphLaunch(g->dist_graph[par][0], g->stream));
-      if ((r = dist_allreduce(g, g->d_topbuf, (long long)(g->R + 1) * g->R + 4))) return r;
-      CUDA_TRY(cudaGraphLaunch(g->dist_graph[par][1], g->stream));
-      g->launches += g->dist_graph_launches[par];
-      std::swap(g->d_X, g->d_Xt); std::swap(g->d_land, g->d_landt); g->cur = 1 - g->cur;
-      g->assembled = false; g->linearized = true;
-      iterations++;
-      return GPB_OK;
-    }
+    if (async_gn) { if ((r = gn_iteration_async(g))) return r; iterations++; return GPB_OK; }
+    if (!g->assembled) { if ((r = assemble_dispatch(g, g->cur))) return r; g->assembled = true; }
     while (true) {
       CUDA_TRY(cudaMemsetAsync(g->d_flag, 0, sizeof(int), g->stream));
       int flag = 0;
@@ -1237,20 +1366,16 @@ int gpb_optimize(gpb_graph* g, const gpb_params* params, int n_iter, gpb_stats* 
         // graph (about 45 short kernels; the launch gaps were ~10 % of the iteration).  lambda is read from device memory.
         const int par = g->cur;
         if (!g->iter_graph[par]) {
-          cudaGraph_t graph;
           const int l0 = g->launches;
-          CUDA_TRY(cudaStreamBeginCapture(g->stream, cudaStreamCaptureModeThreadLocal));
+          Capture cap(g->stream);
+          if ((r = cap.begin(cudaStreamCaptureModeThreadLocal))) return r;
           k_clear_flag<<<1, 1, 0, g->stream>>>(g->d_flag);
           r = solve_forward(g, par, lam);
           if (!r) r = solve_top(g, par, 0.0, false, nullptr);
           if (!r) r = solve_backward(g);
           if (!r) r = retract_dispatch(g);
           if (!r) r = linearize_dispatch(g, g->d_Xt, g->d_landt, 1 - par, 1);
-          const cudaError_t ce = cudaStreamEndCapture(g->stream, &graph);
-          if (r) return r;
-          CUDA_TRY(ce);
-          CUDA_TRY(cudaGraphInstantiate(&g->iter_graph[par], graph, 0));
-          cudaGraphDestroy(graph);
+          if ((r = cap.end(r, &g->iter_graph[par]))) return r;
           g->iter_graph_launches[par] = g->launches - l0 + 1;
           g->launches = l0;
         }
@@ -1267,12 +1392,12 @@ int gpb_optimize(gpb_graph* g, const gpb_params* params, int n_iter, gpb_stats* 
       if ((r = read_scalars(g, s, &lflag))) return r;
       flag |= lflag;
       const double newErrorLocal = s[0];
-      if (need_trial_error) {
+      if (dist) {
         double v[4] = {s[0], s[1], s[2], (double)flag};
         if ((r = dist_sum_scalars(g, v))) return r;
         s[0] = v[0]; s[1] = v[1]; s[2] = v[2]; flag = v[3] != 0.0;
       }
-      const double newError = (dist && !need_trial_error) ? error : s[0];  // plain sharded GN: known at the next iteration's all-reduce
+      const double newError = s[0];
       bool success = false, stop = false;
       if (!p.use_lm) {
         if (flag) { status = 1; return fail(GPB_ERR_NUMERIC, "GaussNewton: indeterminate linear system"); }
@@ -1313,24 +1438,120 @@ int gpb_optimize(gpb_graph* g, const gpb_params* params, int n_iter, gpb_stats* 
       if ((p.rel_tol && relDec <= p.rel_tol) || absDec <= p.abs_tol) break;
     } while (iterations < p.max_iterations);
   }
-  CUDA_TRY(cudaEventRecord(e1, g->stream));
-  CUDA_TRY(cudaEventSynchronize(e1));
-  if (async_gn) {  // report the exact final error and the failure flag (outside the timed loop: one 4-double all-reduce)
+  CUDA_TRY(cudaEventRecord(ev.e1, g->stream));
+  CUDA_TRY(cudaEventSynchronize(ev.e1));
+  if (async_gn) {  // the exact final error and the failure flag, outside the timed loop (sharded: one 4-double all-reduce)
     double s[3]; int lflag = 0;
     if ((rc = read_scalars(g, s, &lflag))) return rc;
     if (iterations) g->cur_error_local = s[0];
     double v[4] = {g->cur_error_local, 0, 0, (double)lflag};
-    if ((rc = dist_sum_scalars(g, v))) return rc;
+    if (dist && (rc = dist_sum_scalars(g, v))) return rc;
     error = v[0]; g->cur_error = error;
-    if (v[3] != 0.0) { status = 1; cudaEventDestroy(e0); cudaEventDestroy(e1); return fail(GPB_ERR_NUMERIC, "GaussNewton: indeterminate linear system"); }
+    if (v[3] != 0.0) return fail(GPB_ERR_NUMERIC, "GaussNewton: indeterminate linear system");
   }
   float ms = 0;
-  CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  CUDA_TRY(cudaEventElapsedTime(&ms, ev.e0, ev.e1));
   if (st) {
     std::memset(st, 0, sizeof(*st));
     st->iterations = iterations; st->error_initial = error_initial; st->error_final = error; st->lambda = lambda; st->total_ms = ms; st->status = status;
   }
+  return GPB_OK;
+}
+
+extern "C" {
+// ---- the engine's own NCCL communicator (sharded graphs)
+int gpb_nccl_unique_id(unsigned char* id128) {
+  if (!id128) return fail(GPB_ERR_ARG, "gpb_nccl_unique_id: null argument");
+  if (const char* why = nccl_rt::load()) return fail(GPB_ERR_UNSUPPORTED, std::string("gpb_nccl_unique_id: ") + why);
+  nccl_rt::UniqueId id;
+  const int rc = nccl_rt::GetUniqueId(&id);
+  if (rc != 0) return fail(GPB_ERR_CUDA, std::string("ncclGetUniqueId: ") + nccl_rt::GetErrorString(rc));
+  std::memcpy(id128, id.internal, 128);
+  return GPB_OK;
+}
+int gpb_graph_init_nccl(gpb_graph* g, const unsigned char* id128, int rank, int world) {
+  CHECK_READY(g);
+  if (!id128 || world != g->world || rank != g->rank) return fail(GPB_ERR_ARG, "gpb_graph_init_nccl: rank / world must match gpb_graph_set_shard");
+  if (g->nccl) return fail(GPB_ERR_STATE, "gpb_graph_init_nccl: communicator already created");
+  if (const char* why = nccl_rt::load()) return fail(GPB_ERR_UNSUPPORTED, std::string("gpb_graph_init_nccl: ") + why);
+  nccl_rt::UniqueId id;
+  std::memcpy(id.internal, id128, 128);
+  int rc = nccl_rt::CommInitRank(&g->nccl, world, id, rank);
+  if (rc != 0) { g->nccl = nullptr; return fail(GPB_ERR_CUDA, std::string("ncclCommInitRank: ") + nccl_rt::GetErrorString(rc)); }
+  // one eager all-reduce of the exchange buffer: NCCL finishes its lazy set-up (channels, buffers) outside any stream capture
+  if (g->d_topbuf) {
+    const long long count = (long long)(g->R + 1) * g->R + 4;
+    CUDA_TRY(cudaMemsetAsync(g->d_topbuf, 0, (size_t)count * sizeof(double), g->stream));
+    if ((rc = dist_allreduce(g, g->d_topbuf, count))) return rc;
+    CUDA_TRY(cudaStreamSynchronize(g->stream));
+  }
+  return GPB_OK;
+}
+
+// ---- pipelined batch interface: K independent (values in -> one Gauss-Newton iteration -> values out) steps on the resident graph.
+// The host->device copy of step k+1 and the device->host copy of step k-1 run on their own streams while step k computes
+// (double-buffered device staging; all host buffers should be page-locked, gpb_alloc_host).
+int gpb_optimize_batch(gpb_graph* g, int K, const double* const* poses_in, const double* const* vels_in, const double* const* land_in,
+                       double* const* poses_out, double* const* vels_out, double* const* land_out, double* errors_out, gpb_stats* st) {
+  CHECK_READY(g);
+  if (K < 1 || !poses_in || !vels_in || !poses_out || !vels_out) return fail(GPB_ERR_ARG, "gpb_optimize_batch: bad arguments");
+  if (g->L && (!land_in || !land_out)) return fail(GPB_ERR_ARG, "gpb_optimize_batch: the graph has landmarks: land_in / land_out required");
+  const size_t np = (size_t)g->N * g->PS, nv = (size_t)g->N * g->D, nl = (size_t)g->L * g->DL;
+  int rc;
+  if (!g->s_h2d) {
+    for (int b = 0; b < 2; b++) {
+      if ((rc = dev_alloc(g, &g->d_stage_in[b], np + nv))) return rc;
+      if ((rc = dev_alloc(g, &g->d_stage_out[b], np + nv))) return rc;
+      CUDA_TRY(cudaEventCreateWithFlags(&g->ev_in_ready[b], cudaEventDisableTiming)); CUDA_TRY(cudaEventCreateWithFlags(&g->ev_in_free[b], cudaEventDisableTiming));
+      CUDA_TRY(cudaEventCreateWithFlags(&g->ev_out_ready[b], cudaEventDisableTiming)); CUDA_TRY(cudaEventCreateWithFlags(&g->ev_out_free[b], cudaEventDisableTiming));
+    }
+    CUDA_TRY(cudaStreamCreateWithFlags(&g->s_d2h, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&g->s_h2d, cudaStreamNonBlocking));
+  }
+  double* herr = nullptr;
+  CUDA_TRY(cudaHostAlloc((void**)&herr, (size_t)K * sizeof(double), cudaHostAllocDefault));
+  struct Free { double* p; ~Free() { cudaFreeHost(p); } } free_herr{herr};
+  const int nblk = (int)std::min<size_t>((np + nv + 255) / 256, (size_t)g->sms * 8);
+  g->launches = 0; g->n_allreduce = 0;
+  CUDA_TRY(cudaStreamSynchronize(g->stream));
+  const auto t0 = std::chrono::steady_clock::now();
+  CUDA_TRY(cudaMemsetAsync(g->d_flag, 0, sizeof(int), g->stream));
+  for (int k = 0; k < K; k++) {
+    const int b = k & 1;
+    if (k >= 2) CUDA_TRY(cudaStreamWaitEvent(g->s_h2d, g->ev_in_free[b], 0));
+    CUDA_TRY(cudaMemcpyAsync(g->d_stage_in[b], poses_in[k], np * sizeof(double), cudaMemcpyHostToDevice, g->s_h2d));
+    CUDA_TRY(cudaMemcpyAsync(g->d_stage_in[b] + np, vels_in[k], nv * sizeof(double), cudaMemcpyHostToDevice, g->s_h2d));
+    CUDA_TRY(cudaEventRecord(g->ev_in_ready[b], g->s_h2d));
+    CUDA_TRY(cudaStreamWaitEvent(g->stream, g->ev_in_ready[b], 0));
+    k_pack_values<<<nblk, 256, 0, g->stream>>>(g->d_stage_in[b], g->d_stage_in[b] + np, g->d_X, g->N, g->PS, g->D, 0); g->launches++;
+    CUDA_TRY(cudaEventRecord(g->ev_in_free[b], g->stream));
+    if (nl) CUDA_TRY(cudaMemcpyAsync(g->d_land, land_in[k], nl * sizeof(double), cudaMemcpyHostToDevice, g->stream));
+    if ((rc = linearize_dispatch(g, g->d_X, g->d_land, g->cur, 1))) return rc;
+    g->linearized = true; g->assembled = false;
+    if ((rc = gn_iteration_async(g))) return rc;
+    if (k >= 2) CUDA_TRY(cudaStreamWaitEvent(g->stream, g->ev_out_free[b], 0));
+    k_pack_values<<<nblk, 256, 0, g->stream>>>(g->d_stage_out[b], g->d_stage_out[b] + np, g->d_X, g->N, g->PS, g->D, 1); g->launches++;
+    CUDA_TRY(cudaMemcpyAsync(herr + k, g->d_scal, sizeof(double), cudaMemcpyDeviceToHost, g->stream));  // local error at the new point
+    if (nl) CUDA_TRY(cudaMemcpyAsync(land_out[k], g->d_land, nl * sizeof(double), cudaMemcpyDeviceToHost, g->stream));
+    CUDA_TRY(cudaEventRecord(g->ev_out_ready[b], g->stream));
+    CUDA_TRY(cudaStreamWaitEvent(g->s_d2h, g->ev_out_ready[b], 0));
+    CUDA_TRY(cudaMemcpyAsync(poses_out[k], g->d_stage_out[b], np * sizeof(double), cudaMemcpyDeviceToHost, g->s_d2h));
+    CUDA_TRY(cudaMemcpyAsync(vels_out[k], g->d_stage_out[b] + np, nv * sizeof(double), cudaMemcpyDeviceToHost, g->s_d2h));
+    CUDA_TRY(cudaEventRecord(g->ev_out_free[b], g->s_d2h));
+  }
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaStreamSynchronize(g->stream));
+  CUDA_TRY(cudaStreamSynchronize(g->s_d2h));
+  const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  int flag = 0;
+  CUDA_TRY(cudaMemcpy(&flag, g->d_flag, sizeof(int), cudaMemcpyDeviceToHost));
+  g->cur_error_local = herr[K - 1];
+  double v[4] = {herr[K - 1], 0, 0, (double)flag};
+  if (g->world > 1 && (rc = dist_sum_scalars(g, v))) return rc;
+  g->cur_error = v[0];
+  if (errors_out) for (int k = 0; k < K; k++) errors_out[k] = herr[k];  // this rank's share of the error after step k
+  if (st) { std::memset(st, 0, sizeof(*st)); st->iterations = K; st->error_final = v[0]; st->total_ms = ms; st->status = v[3] != 0.0; }
+  if (v[3] != 0.0) return fail(GPB_ERR_NUMERIC, "GaussNewton: indeterminate linear system");
   return GPB_OK;
 }
 
@@ -1611,8 +1832,9 @@ int gpb_time_stage(gpb_graph* g, int stage, int reps, double* ms_out) {
   int rc = ensure_assembled(g);
   if (rc) return rc;
   if ((rc = solve_system(g, g->cur, 0.0))) return rc;  // valid delta for the retract stage; also warms up
-  cudaEvent_t e0, e1;
-  CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
+  EventPair evp;
+  CUDA_TRY(cudaEventCreate(&evp.e0)); CUDA_TRY(cudaEventCreate(&evp.e1));
+  const cudaEvent_t e0 = evp.e0, e1 = evp.e1;
   CUDA_TRY(cudaStreamSynchronize(g->stream));
   const int other = 1 - g->cur;
   constexpr int NT = 128;
@@ -1657,7 +1879,6 @@ int gpb_time_stage(gpb_graph* g, int stage, int reps, double* ms_out) {
   CUDA_TRY(cudaGetLastError());
   float ms = 0;
   CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
   *ms_out = ms / reps;
   // stage 5 leaves the upper levels untouched but consistent; restore a complete solve so later calls see a valid state
   if (stage >= 5) { if ((rc = solve_system(g, g->cur, 0.0))) return rc; CUDA_TRY(cudaStreamSynchronize(g->stream)); }
@@ -1781,6 +2002,30 @@ int gpb_interpolate_poses(int group, int device, int n, const double* x1, const 
   if ((rc = interp_query_device(grp, vw, dX, dia, dib, ddt, dtau, n, dP, dH, 0))) return rc;
   CUDA_TRY(cudaMemcpy(poses_out, dP, (size_t)n * PS * sizeof(double), cudaMemcpyDeviceToHost));
   if (H_out) CUDA_TRY(cudaMemcpy(H_out, dH, (size_t)n * 4 * D * D * sizeof(double), cudaMemcpyDeviceToHost));
+  return GPB_OK;
+}
+
+int gpb_interpolate_velocities(int group, int device, int n, int dim, const double* x1, const double* v1, const double* x2, const double* v2, const double* delta_t, const double* tau,
+                               double* vels_out, double* H_out) {
+  if (n < 1 || !x1 || !v1 || !x2 || !v2 || !delta_t || !tau || !vels_out) return fail(GPB_ERR_ARG, "gpb_interpolate_velocities: bad arguments");
+  // the reference implements interpolateVelocity for the Linear interpolator only; the Lie-group ones are declared and never defined
+  // (gp/GaussianProcessInterpolatorPose3.h:118-123)
+  if (group != GPB_LINEAR) return fail(GPB_ERR_UNSUPPORTED, "gpb_interpolate_velocities: GaussianProcessInterpolatorLinear only (the reference defines no other interpolateVelocity)");
+  if (dim < 1 || dim > 16) return fail(GPB_ERR_ARG, "gpb_interpolate_velocities: dim out of range");
+  for (int k = 0; k < n; k++) if (!(delta_t[k] > 0.0)) return fail(GPB_ERR_ARG, "gpb_interpolate_velocities: delta_t must be positive");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(GPB_ERR_CUDA, "gpb_interpolate_velocities: no CUDA device available (this engine has no CPU fallback)"); }
+  CUDA_TRY(cudaSetDevice(device));
+  DevBufs B; int rc;
+  double *d1, *dv1, *d2, *dv2, *ddt, *dtau, *dV, *dH = nullptr;
+  const size_t nd = (size_t)n * dim;
+  if ((rc = B.up(&d1, x1, nd)) || (rc = B.up(&dv1, v1, nd)) || (rc = B.up(&d2, x2, nd)) || (rc = B.up(&dv2, v2, nd)) || (rc = B.up(&ddt, delta_t, (size_t)n)) ||
+      (rc = B.up(&dtau, tau, (size_t)n)) || (rc = B.up(&dV, (const double*)nullptr, nd))) return rc;
+  if (H_out && (rc = B.up(&dH, (const double*)nullptr, (size_t)n * 4))) return rc;
+  k_interp_velocity_linear<<<(n + 127) / 128, 128>>>(d1, dv1, d2, dv2, ddt, dtau, n, dim, dV, dH);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpy(vels_out, dV, nd * sizeof(double), cudaMemcpyDeviceToHost));
+  if (H_out) CUDA_TRY(cudaMemcpy(H_out, dH, (size_t)n * 4 * sizeof(double), cudaMemcpyDeviceToHost));
   return GPB_OK;
 }
 

@@ -446,6 +446,24 @@ __global__ void __launch_bounds__(128) k_interp_query(const double* __restrict__
   }
 }
 
+// GaussianProcessInterpolatorLinear::interpolateVelocity (gp/GaussianProcessInterpolatorLinear.h:106-126): the lower D rows of
+// Lambda x1 + Psi x2.  Like the upper rows (interp_coef) every D x D block is a scalar times I and does not depend on Qc: with
+// s = tau / dt,  Psi21 = 6 (s - s^2) / dt,  Psi22 = 3 s^2 - 2 s,  Lambda21 = -Psi21,  Lambda22 = 1 - 4 s + 3 s^2
+// (Q(tau) Phi(dt - tau)^T Q(dt)^-1 and Phi(tau) - Psi Phi(dt) of gp/GPutils.h:54-71 multiplied out).
+// One thread per query; H (or null): the four scalars (H1 = Lambda21 I, H2 = Lambda22 I, H3 = Psi21 I, H4 = Psi22 I).
+__global__ void __launch_bounds__(128) k_interp_velocity_linear(const double* __restrict__ x1, const double* __restrict__ v1, const double* __restrict__ x2, const double* __restrict__ v2,
+                                                                const double* __restrict__ dt, const double* __restrict__ tau, int n, int D, double* __restrict__ vel, double* __restrict__ H) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const double s = tau[k] / dt[k];
+  const double psi21 = 6.0 * (s - s * s) / dt[k], psi22 = 3.0 * s * s - 2.0 * s, lam21 = -psi21, lam22 = 1.0 - 4.0 * s + 3.0 * s * s;
+  for (int d = 0; d < D; d++) {
+    const size_t o = (size_t)k * D + d;
+    vel[o] = lam21 * x1[o] + lam22 * v1[o] + psi21 * x2[o] + psi22 * v2[o];
+  }
+  if (H != nullptr) { H[4 * k] = lam21; H[4 * k + 1] = lam22; H[4 * k + 2] = psi21; H[4 * k + 3] = psi22; }
+}
+
 // deterministic final sum of block partials (single block)
 __global__ void k_sum_partials(const double* __restrict__ part, int n, double* __restrict__ out, int slot) {
   __shared__ double sred[8];

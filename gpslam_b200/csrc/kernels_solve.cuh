@@ -993,6 +993,17 @@ __global__ void __launch_bounds__(160) k_level_ws(const FwdArgs a) {
   else panel_body<BS, true>(a, &ready);
 }
 
+// The same warp-specialised kernel at level 0 (A/B switch GPB_FUSE_L0): persistent CTAs, one resident wave; the spine warp's
+// (L^-1, Le) reach the panel warps through L2 (they are written to HBM anyway: the back-substitution needs them).
+template <int BS>
+__global__ void __launch_bounds__(160, 4) k_level0_ws(const FwdArgs a) {
+  __shared__ int ready;
+  if (threadIdx.x == 0) ready = 0;
+  __syncthreads();
+  if (threadIdx.x >= 128) spine_body<BS, true, true>(a, threadIdx.x - 128, &ready);
+  else panel_body<BS, true>(a, &ready);
+}
+
 // Back-substitution of one level: x_i = L_ii^-T ( y_i - Yspike_i x_p - Yborder_i x_l - Le_i^T x_{i+1} ), right to left.
 // The factor record of the next state to visit streams into shared memory (cp.async double buffer) while the current one is used.
 template <int BS, int W>

@@ -236,6 +236,17 @@ def torch_allreduce(device):
     return fn
 
 
+def init_engine_nccl(graph, rank, world):
+    """Create the engine's own NCCL communicator on a finalized shard graph (gpb_graph_init_nccl): rank 0 draws the ncclUniqueId,
+    one torch.distributed broadcast hands it to the other ranks, every rank joins.  After this the engine issues the boundary
+    all-reduce itself, on its own stream, inside the captured CUDA graph of a Gauss-Newton iteration - Python is out of the loop."""
+    import torch.distributed as dist
+    from . import capi
+    box = [capi.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    graph.init_nccl(box[0], rank, world)
+
+
 def reduced_index(world, rank, bs, nb, pinned_gtop=None, ntop=None):
     """global indices (in the all-reduced system [top states | landmarks]) of a rank's top-level variables, in the local order
     [its pinned chain entries..., landmarks].  Without loop closures the top states are the world-1 shard boundaries and a

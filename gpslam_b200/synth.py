@@ -251,6 +251,39 @@ def build(cfg, make_graph, finalize=True):
     return g, dict(poses=poses, vels=wire_vels, lands=lands)
 
 
+class Recorder:
+    """Records the construction calls of build() once so that the same graph can be replayed into several graph objects (the CUDA
+    engine and the CPU oracle of a parity test) without running the generator - a Python loop over every state - twice."""
+
+    def __init__(self, group, n_states, n_landmarks):
+        self.group, self.n_states, self.n_landmarks, self.calls = group, n_states, n_landmarks, []
+
+    def __getattr__(self, name):
+        if name.startswith("_") or name == "finalize":
+            raise AttributeError(name)
+        def rec(*a, **kw):
+            self.calls.append((name, a, kw))
+            return sum(1 for c in self.calls if c[0] == name) - 1   # add_qc_model returns the model id
+        return rec
+
+    def replay(self, make_graph, finalize=True):
+        g = make_graph(self.group, self.n_states, self.n_landmarks)
+        for name, a, kw in self.calls:
+            getattr(g, name)(*a, **kw)
+        if finalize and hasattr(g, "finalize"):
+            g.finalize()
+        return g
+
+
+def record(cfg):
+    """(Recorder, truth) of build(cfg, ...): replay it into as many graph objects as needed"""
+    box = []
+    def mk(grp, n, l):
+        box.append(Recorder(grp, n, l)); return box[0]
+    _, truth = build(cfg, mk, finalize=False)
+    return box[0], truth
+
+
 def _body(pose, v):
     c, s = np.cos(pose[2]), np.sin(pose[2])
     return np.array([c * v[0] + s * v[1], -s * v[0] + c * v[1], v[2]])

@@ -127,6 +127,12 @@ int gpb_eval_factor(int group, int kind, const double* x1, const double* v1, con
  * depend on Qc, so no Qc is passed.  tau may lie outside [0, delta_t].  Slow path (allocations per call). */
 int gpb_interpolate_poses(int group, int device, int n, const double* x1, const double* v1, const double* x2, const double* v2, const double* delta_t, const double* tau,
                           double* poses_out, double* H_out);
+/* GaussianProcessInterpolatorLinear<dim>(Qc, delta_t, tau).interpolateVelocity(pose1, vel1, pose2, vel2, H1..H4)
+ * (gp/GaussianProcessInterpolatorLinear.h:106-126) for n queries: vels_out [n x dim]; H_out (or NULL) [n][4] - H1..H4 are scalar
+ * multiples of the identity (Lambda21, Lambda22, Psi21, Psi22), returned as those four scalars.  group must be GPB_LINEAR: the
+ * reference declares interpolateVelocity for its Lie-group interpolators but never defines it. */
+int gpb_interpolate_velocities(int group, int device, int n, int dim, const double* x1, const double* v1, const double* x2, const double* v2,
+                               const double* delta_t, const double* tau, double* vels_out, double* H_out);
 /* The pose of the graph's CURRENT estimate at time tau[k] into interval[k] (between states interval[k] and interval[k] + 1, which
  * must carry a GP prior: its delta_t is used) - dense trajectory output after gpb_optimize, what the reference's scripts do with
  * interpolatePose on the optimised Values.  poses_out [n x pose_storage]. */
@@ -194,6 +200,24 @@ int gpb_graph_set_top_map(gpb_graph* g, int n_real, int ntop_global, int n_pinne
  * carries the error scalar). */
 typedef int (*gpb_allreduce_fn)(void* ctx, double* device_buf, long long count, void* cuda_stream);
 int gpb_set_allreduce(gpb_graph* g, gpb_allreduce_fn fn, void* ctx);
+
+/* The engine's own all-reduce: an NCCL communicator over the ranks of the sharded graph, created from a ncclUniqueId (128 bytes)
+ * that rank 0 obtains with gpb_nccl_unique_id and hands to the other ranks by whatever means the host program has (the Python
+ * host uses one torch.distributed broadcast).  libnccl.so.2 is bound at run time (the copy the process already holds, else the
+ * system one; GPB_NCCL_LIB overrides).  With it the boundary all-reduce is enqueued by the engine on its own stream and a whole
+ * Gauss-Newton iteration - collective included - is replayed as ONE CUDA graph.  Collective call: every rank, after
+ * gpb_graph_finalize.  Takes precedence over gpb_set_allreduce. */
+int gpb_nccl_unique_id(unsigned char* id128_out);
+int gpb_graph_init_nccl(gpb_graph* g, const unsigned char* id128, int rank, int world);
+
+/* Pipelined batch of K independent steps on the resident graph (same factors, new values each step), each step =
+ * Values::insert (host -> device) + GaussNewtonOptimizer::iterate() once + Values::at (device -> host), the usage of
+ * matlab/PlazaPose2.m:224-233 with values crossing the boundary every step.  Step k+1's host->device copy and step k-1's
+ * device->host copy run on their own streams while step k computes.  poses_in[k] / vels_in[k] / land_in[k] and the *_out[k]
+ * are host buffers in the layouts of gpb_set_values (page-locked ones from gpb_alloc_host for full overlap; an out buffer must
+ * not alias an in buffer of a later step).  errors_out (or NULL) [K]: this rank's graph error after each step.  Gauss-Newton only. */
+int gpb_optimize_batch(gpb_graph* g, int K, const double* const* poses_in, const double* const* vels_in, const double* const* land_in,
+                       double* const* poses_out, double* const* vels_out, double* const* land_out, double* errors_out, gpb_stats* stats);
 
 /* solver tuning: segment length per elimination level (>= 2); 0 keeps the default */
 int gpb_set_segment_length(gpb_graph* g, int level0, int upper_levels);

@@ -67,7 +67,7 @@ def lib():
         for name in ("gpo_graph_destroy", "gpo_set_threads", "gpo_add_qc_model", "gpo_add_gp_prior", "gpo_add_interp_range",
                      "gpo_add_interp_attitude", "gpo_add_interp_gps", "gpo_add_interp_projection", "gpo_add_gp_prior_vw", "gpo_add_interp_gps_vw", "gpo_add_prior_pose", "gpo_add_prior_vel", "gpo_add_prior_landmark", "gpo_add_between",
                      "gpo_add_range_2d", "gpo_add_range_bearing_2d", "gpo_add_odometry_2d", "gpo_set_values", "gpo_get_values",
-                     "gpo_num_factors", "gpo_error", "gpo_linearize_factor", "gpo_eval_factor", "gpo_normal_equations_dense", "gpo_optimize"):
+                     "gpo_num_factors", "gpo_check_step", "gpo_error", "gpo_linearize_factor", "gpo_eval_factor", "gpo_normal_equations_dense", "gpo_optimize"):
             getattr(L, name).argtypes = None
         _LIB = L
     return _LIB
@@ -229,6 +229,15 @@ class Graph:
         rc = self.L.gpo_normal_equations_dense(self.h, _dp(H), _dp(g), C.c_int(n))
         assert rc == 0
         return H.T.copy(), g
+
+    def check_step(self, delta_states, delta_lands, lam=0.0):
+        """residual of a step against the oracle's own normal equations at the current values (any size):
+        dict(residual = max |(J^T J + lam I) delta - J^T b|, rhs = max |J^T b|, step = max |delta|, linearized_error)"""
+        ds = _f64(delta_states).reshape(-1); dl = _f64(delta_lands).reshape(-1) if self.NL else np.zeros(1)
+        assert ds.size == self.N * 2 * self.D
+        out = np.zeros(4)
+        self.L.gpo_check_step(self.h, _dp(ds), _dp(dl), C.c_double(lam), _dp(out))
+        return dict(residual=out[0], rhs=out[1], step=out[2], linearized_error=out[3])
 
     def optimize(self, params=None, n_iter=0, use_lm=True):
         p = params if params is not None else default_params(use_lm)

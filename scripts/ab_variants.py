@@ -15,7 +15,7 @@ sys.path.insert(0, ROOT)
 import gpslam_b200 as gb  # noqa: E402
 from gpslam_b200 import synth  # noqa: E402
 
-STAGES = ((0, "lin_gp"), (1, "lin_other"), (2, "assemble"), (3, "solve"), (4, "retract"), (6, "spine0"), (7, "panel0"), (8, "bwd"))
+STAGES = ((0, "lin_gp"), (1, "lin_other"), (2, "assemble"), (3, "solve"), (4, "retract"), (5, "fwd0"), (6, "spine0"), (7, "panel0"), (8, "bwd"))
 
 
 def main():

@@ -1,0 +1,15 @@
+#!/bin/bash
+# one GPU session: parity tests, bench, A/B of the solver switches, compute-sanitizer.  usage: scripts/gpu_round.sh <tag> [steps...]
+TAG=${1:-r2a}; shift
+STEPS=${@:-"tests bench ab san"}
+mkdir -p gpurun_out
+for s in $STEPS; do
+  case $s in
+    tests) timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/${TAG}_pytest.log;;
+    tests_fast) timeout 900 python -m pytest tests -m gpu -x -q --deselect tests/test_gpu_fullsize.py > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/${TAG}_pytest.log;;
+    bench) timeout 900 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"; cat gpurun_out/${TAG}_bench.json | head -c 6000; tail -3 gpurun_out/${TAG}_bench.err;;
+    benchfast) timeout 600 python bench.py --no-cpu > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"; cat gpurun_out/${TAG}_bench.json | head -c 6000; tail -3 gpurun_out/${TAG}_bench.err;;
+    ab) timeout 600 python scripts/ab_variants.py "" "GPB_FUSE_L0=1" > gpurun_out/${TAG}_ab.jsonl 2> gpurun_out/${TAG}_ab.err; echo "ab rc=$?"; cat gpurun_out/${TAG}_ab.jsonl; tail -3 gpurun_out/${TAG}_ab.err;;
+    san) bash scripts/sanitize.sh ${TAG};;
+  esac
+done

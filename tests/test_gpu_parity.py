@@ -95,7 +95,37 @@ def linear_graph(make, n=120, seed=5):
     return g
 
 
+def pose2_range2d_graph(make, n=160, seed=9):
+    """Pose2 trajectory (Plaza shape) whose range measurements are plain RangeFactorPose2 (slam/RangeFactorPose2.h:15 =
+    gtsam::RangeFactor<Pose2, Point2>) at the states themselves, beside interpolated ranges between them"""
+    rng = np.random.default_rng(seed)
+    cfg = small_cfg("C1", n)
+    poses, vels = synth.ground_truth(cfg)
+    L = 4
+    g = make(POSE2, n, L)
+    g.add_qc_model(np.eye(3) * cfg.qc_sigma ** 2)
+    g.add_gp_prior(np.arange(n - 1), np.full(n - 1, cfg.dt))
+    lands = poses[:, :2].mean(axis=0) + rng.uniform(-25, 25, size=(L, 2))
+    for i in list(range(0, n, 3)) + [n - 1]:   # incl. the last state (the b-part of the last interval)
+        l = int(rng.integers(0, L))
+        g.add_range_2d(i, l, float(np.linalg.norm(lands[l] - poses[i, :2]) + rng.normal() * 0.3), 0.5)
+    ri = np.sort(rng.integers(0, n - 1, size=n // 4)); rl = rng.integers(0, L, size=len(ri)); tau = rng.uniform(0, cfg.dt, size=len(ri))
+    z = np.array([np.linalg.norm(lands[l] - synth._retract(POSE2, poses[i], vels[i] * t)[:2]) for i, l, t in zip(ri, rl, tau)]) + rng.normal(size=len(ri)) * 0.3
+    g.add_interp_range(ri, rl, z, np.full(len(ri), 0.5), np.full(len(ri), cfg.dt), tau)
+    for i in range(n - 1):
+        g.add_between(i, i + 1, synth._between(POSE2, poses[i], poses[i + 1], rng, 1e-3), np.diag([1e3, 1e3, 1e3 / np.pi]))
+    for l in range(L):
+        g.add_prior_landmark(l, lands[l] + rng.normal(size=2) * 0.5, np.eye(2))
+    g.add_prior_pose(0, poses[0], np.eye(3)); g.add_prior_vel(0, vels[0], np.eye(3))
+    g.set_values(np.stack([synth._retract(POSE2, poses[i], rng.normal(size=3) * 0.05) for i in range(n)]), np.zeros((n, 3)), lands + rng.normal(size=lands.shape) * 0.5)
+    if hasattr(g, "finalize"):
+        g.finalize()
+    return g
+
+
 def make_pair(case):
+    if case == "pose2_range2d":
+        return pose2_range2d_graph(lambda grp, n, l: gb.Graph(grp, n, l)), pose2_range2d_graph(lambda grp, n, l: po.Graph(grp, n, l))
     if case == "linear":
         return linear_graph(lambda grp, n, l: gb.Graph(grp, n, l)), linear_graph(lambda grp, n, l: po.Graph(grp, n, l))
     kw = dict(CASES[case]); name = kw.pop("name"); n = kw.pop("n")
@@ -103,7 +133,7 @@ def make_pair(case):
     return g, o
 
 
-ALL = ["pose3", "pose3_wide", "pose3_chain", "pose2", "rot3", "linear", "pose3_gps_proj", "pose3vw", "pose3vw_loops", "pose3_dense_qc", "pose2_dense_qc", "pose3_loops", "pose3_wide_loops", "pose2_loops", "rot3_loops"]
+ALL = ["pose3", "pose3_wide", "pose3_chain", "pose2", "pose2_range2d", "rot3", "linear", "pose3_gps_proj", "pose3vw", "pose3vw_loops", "pose3_dense_qc", "pose2_dense_qc", "pose3_loops", "pose3_wide_loops", "pose2_loops", "rot3_loops"]
 
 
 @pytest.mark.parametrize("case", ALL)
