@@ -129,7 +129,8 @@ struct gpb_graph {
   int nclos = 0, nep = 0, npair = 0;  // loop closures: factors, endpoint states, unique endpoint pairs
   int *d_epstate = nullptr, *d_epoff = nullptr, *d_eprow = nullptr, *d_epside = nullptr;
   int *d_pair_a = nullptr, *d_pair_b = nullptr, *d_pairoff = nullptr, *d_pairrow = nullptr;
-  bool generic_fwd = false, force_blocked = false, old_assemble = false, split_levels = false, no_tiny = false, fuse_l0 = false;
+  bool generic_fwd = false, force_blocked = false, old_assemble = false, split_levels = false, no_tiny = false, fuse_l0 = false, old_bwd = false;
+  int fstride = 0;  // doubles per state of a level's factor record: (L^-1 | Le), + Y for the Y-reading back-substitution
   gpb_allreduce_fn allreduce = nullptr; void* allreduce_ctx = nullptr;
   nccl_rt::Comm nccl = nullptr;   // engine-owned communicator (gpb_graph_init_nccl): the all-reduce is captured inside the iteration graph
   cudaGraphExec_t gn_graph[2] = {nullptr, nullptr}; int gn_graph_launches[2] = {0, 0};  // whole asynchronous GN iteration per buffer parity
@@ -723,7 +724,8 @@ int gpb_graph_finalize(gpb_graph* g, int device) {
   g->split_levels = getenv("GPB_SPLIT_LEVELS") != nullptr;  // A/B switch: spine and panel as two launches on the upper levels too
   g->old_assemble = getenv("GPB_OLD_ASSEMBLE") != nullptr;  // A/B switch: thread-per-tile assembly instead of the DMMA kernel
   g->generic_fwd = getenv("GPB_GENERIC_FWD") != nullptr;
-  g->fuse_l0 = getenv("GPB_FUSE_L0") != nullptr;  // A/B switch: level 0 as ONE warp-specialised kernel (spine warp + panel warps per CTA)
+  g->fuse_l0 = getenv("GPB_FUSE_L0") != nullptr;
+  g->old_bwd = getenv("GPB_OLD_BWD") != nullptr;  // A/B switch: back-substitution from a stored Y (k_bwd) instead of re-eliminating the right-hand side (k_bwd2)  // A/B switch: level 0 as ONE warp-specialised kernel (spine warp + panel warps per CTA)
   g->no_tiny = getenv("GPB_NO_TINY_SOLVE") != nullptr;  // A/B switch: the plain-loop instantiation of k_small_solve instead of the register-blocked ones
   g->qc_diag = 1;
   for (const auto& R : g->Rq) for (int c = 0; c < D; c++) for (int r = 0; r < D; r++) if (r != c && R[r + c * D] != 0.0) g->qc_diag = 0;
@@ -748,7 +750,7 @@ int gpb_graph_finalize(gpb_graph* g, int device) {
       if (best < 0 || cost <= best) { best = cost; M0 = M; }
     }
   }
-  const int fstride = 2 * bs * bs + bs * g->w;
+  const int fstride = g->fstride = 2 * bs * bs + (g->old_bwd ? bs * g->w : 0);
   // Level recursion.  Each level's chain is cut at its interior separators: every pinned state (never eliminated: it stays a
   // separator at every level and ends up in the top system) and, inside every run of g ordinary states between two cuts, every
   // M-th state ((g - 1) / M of them).  The separators (plus the pinned chain ends) form the next level's chain; when no
@@ -954,7 +956,7 @@ template <int G> static int launch_assemble(gpb_graph* g, int buf) {
     CUDA_TRY(cudaMemsetAsync(g->d_Cbase, 0, (size_t)(g->nb * g->nb + g->nb) * sizeof(double), g->stream));
     k_landmark_base<512><<<g->L, 512, 0, g->stream>>>(g->d_XR[buf], g->d_lmoff, g->d_lmrows, g->NXRp, 2 * bs, g->DL, g->nb, g->d_Cbase);
     g->launches++;
-    if (bs == 12 && g->W == 64 && g->nbent > 0) {
+    if (g->nbent > 0) {  // consumed by the level-0 panel kernel (64-column panels) and by the back-substitution
       k_border_pack<<<(g->nbent * 16 + 255) / 256, 256, 0, g->stream>>>(g->d_XR[buf], g->d_bsrow, g->d_bsside, g->d_rowland, g->nbent, bs, g->DL, g->NXRp, g->d_bent);
       g->launches++;
     }
@@ -977,7 +979,7 @@ template <int BS> static void fwd_w(int W, const FwdArgs& a, int ncta, cudaStrea
 template <int BS> static void bwd_w(int W, const BwdArgs& a, int ncta, cudaStream_t s) { if (W == 16) launch_bwd<BS, 16>(a, ncta, s); else if (W == 32) launch_bwd<BS, 32>(a, ncta, s); else launch_bwd<BS, 64>(a, ncta, s); }
 
 static int launch_fwd_level(gpb_graph* g, int buf, double lambda, int lev, int parts = 3) {
-  const int bs = g->bs, nb = g->nb, fstride = 2 * bs * bs + bs * g->w, centries = nb * nb + nb;
+  const int bs = g->bs, nb = g->nb, fstride = g->fstride, centries = nb * nb + nb;
   const int nlev = (int)g->levels.size();
   Level& L = g->levels[lev];
   FwdArgs a;
@@ -988,7 +990,7 @@ static int launch_fwd_level(gpb_graph* g, int buf, double lambda, int lev, int p
   a.XR = g->d_XR[buf]; a.bsoff = g->d_bsoff; a.bsrow = g->d_bsrow; a.bsside = g->d_bsside; a.rowland = g->d_rowland; a.bent = g->d_bent; a.NXRp = g->NXRp; a.nb = nb; a.DL = std::max(g->DL, 1);
   a.lambda_ptr = g->d_lambda;
   a.rec_out = lev + 1 < nlev ? g->levels[lev + 1].rec : nullptr; a.brec_out = lev + 1 < nlev ? g->levels[lev + 1].brec : nullptr;
-  a.frec = L.frec; a.fstride = fstride; a.cseg = L.cseg; a.flag = g->d_flag;
+  a.frec = L.frec; a.fstride = fstride; a.cseg = L.cseg; a.flag = g->d_flag; a.store_y = g->old_bwd ? 1 : 0;
   if (bs == 12 && g->W == 64 && !g->generic_fwd) {
     // spine first (warp per segment: the latency-bound 12x12 recurrence wants many independent warps), then the tensor-pipe panel
     const int spine_ctas = std::min(L.nseg, 16 * g->sms);
@@ -1025,14 +1027,20 @@ static int solve_forward(gpb_graph* g, int buf, double lambda) {
   return GPB_OK;
 }
 static int solve_backward(gpb_graph* g) {
-  const int bs = g->bs, nb = g->nb, fstride = 2 * bs * bs + bs * g->w;
+  const int bs = g->bs, nb = g->nb, fstride = g->fstride;
   const int nel = num_elim_levels(g), nlev = (int)g->levels.size();
   for (int lev = nel - 1; lev >= 0; lev--) {
     Level& L = g->levels[lev];
     BwdArgs b;
     b.n = L.n; b.M = L.M; b.S = L.S; b.nseg = L.nseg; b.nb = nb; b.extL = g->pinL; b.extR = g->pinR; b.sep = L.d_sep; b.frec = L.frec; b.fstride = fstride;
     b.xup = lev + 1 < nlev ? g->levels[lev + 1].xsol : nullptr; b.xl = g->d_xlm; b.xsol = L.xsol;
-    if (bs == 12) bwd_w<12>(g->W, b, L.ncta_bwd, g->stream); else bwd_w<6>(g->W, b, L.ncta_bwd, g->stream);
+    b.first_level = lev == 0; b.DL = std::max(g->DL, 1); b.rec = lev == 0 ? g->d_HREC : L.rec; b.brec = L.brec; b.bsoff = g->d_bsoff; b.bent = g->d_bent;
+    if (g->old_bwd) { if (bs == 12) bwd_w<12>(g->W, b, L.ncta_bwd, g->stream); else bwd_w<6>(g->W, b, L.ncta_bwd, g->stream); }
+    else {
+      // one warp per segment, four per CTA; up to 16 resident warps per SM
+      const int nblk = std::min((L.nseg + 3) / 4, g->sms * 4);
+      if (bs == 12) k_bwd2<12><<<nblk, 128, 0, g->stream>>>(b); else k_bwd2<6><<<nblk, 128, 0, g->stream>>>(b);
+    }
     g->launches++;
   }
   CUDA_TRY(cudaGetLastError());

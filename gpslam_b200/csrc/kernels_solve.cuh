@@ -39,6 +39,7 @@ struct FwdArgs {
   int fstride;
   double* cseg;
   int* flag;
+  int store_y;         // 1: Y = L^-1 [spike | border | rhs] is written behind (L^-1 | Le) for the Y-reading back-substitution k_bwd (A/B switch GPB_OLD_BWD)
 };
 
 struct BwdArgs {
@@ -49,6 +50,12 @@ struct BwdArgs {
   const double* xup;  // solution of the next level [extL + S + extR][BS]
   const double* xl;   // landmark solution [nb]
   double* xsol;       // [n][BS]
+  // k_bwd2 only: the level's own records (right-hand side, border, coupling to the left separator) are re-read instead of a stored Y
+  int first_level, DL;
+  const double* rec;    // level 0: HREC; above: [n][3 BS^2 + 2 BS]
+  const double* brec;   // level >= 1: [n][2 BS nb]
+  const int* bsoff;     // level 0: per-state CSR of the packed border entries
+  const double* bent;   // level 0: packed border entries (k_border_pack)
 };
 
 // Segment geometry shared by the two sweeps.  Chain states 0..n-1; a pinned first / last state (extL / extR: a shard's external
@@ -304,7 +311,7 @@ __global__ void __launch_bounds__((W < 32 ? 32 : W), (W == 64 ? 6 : 8)) k_fwd(co
         }
       }
       __syncthreads();
-      if (active) {
+      if (active && a.store_y) {
         const double* yc = Ysm + c * YS;
 #pragma unroll
         for (int r = 0; r < BS; r += 2) st128(F + 2 * BS * BS + c * BS + r, yc[r], yc[r + 1]);
@@ -630,7 +637,7 @@ __device__ __forceinline__ void spine_body(const FwdArgs& a, const int lane, vol
         __threadfence();
         __syncwarp();
         done++;
-        if (lane == 0) *ready = done;
+        if (lane == 0) atomicExch(const_cast<int*>(ready), done);   // published with an atomic: the counter is a flag, not barrier-protected data
       }
     }
     if (!ok && lane == 0) *a.flag = 1;
@@ -737,7 +744,10 @@ __device__ __forceinline__ void panel_body(const FwdArgs& a, volatile const int*
     int b0 = bso(i0), b1 = bso(i0 + 1), b2 = bso(i0 + 2), b3 = bso(i0 + 3);  // rolling window of CSR offsets: states i .. i+3
     auto prefetch = [&](int i, int st, int e0, int e1) {
       if (i <= i1) {
-        if constexpr (FUSED) { while (*ready <= seg_base + (i - i0)) { } }  // the spine warp has published state i
+        if constexpr (FUSED) {  // the spine warp has published state i (one poller per warp, atomic read of the flag)
+          if (lane == 0) { while (atomicAdd(const_cast<int*>(ready), 0) <= seg_base + (i - i0)) { } }
+          __syncwarp();
+        }
         const double* src = a.frec + (size_t)i * a.fstride;
         const int n2 = (((i < i1) || (q >= 0)) ? 2 * BS * BS : BS * BS) / 2;
         for (int k = c; k < n2; k += NT) cp_async16(&Fb[st][2 * k], src + 2 * k);
@@ -854,8 +864,8 @@ __device__ __forceinline__ void panel_body(const FwdArgs& a, volatile const int*
 #pragma unroll
         for (int r = 0; r < HB; r++) Psm[col * BS + r0 + r] = 0.0;
       }
-      // ---- Y half-column to HBM
-      if (active) {
+      // ---- Y half-column to HBM (only for the Y-reading back-substitution)
+      if (active && a.store_y) {
         double* F = a.frec + (size_t)i * a.fstride + 2 * BS * BS + col * BS + r0;
         const double* yc = Y + col * BS + r0;
 #pragma unroll
@@ -1077,6 +1087,159 @@ __global__ void __launch_bounds__((W < 32 ? 32 : W)) k_bwd(const BwdArgs a) {
     }
     cp_async_wait<0>();
     __syncthreads();
+  }
+}
+
+// Back-substitution without a stored Y (default).  With the separator and landmark solutions known, the interior of a segment
+// solves  A_II x_I = b_I - A_Ip x_p - A_Iq x_q - A_Il x_l  through its block-bidiagonal factor: a forward sweep
+//   z_i = [g_i - B_i x_l - (i == i0) E_p x_p] - Le_{i-1} y_{i-1},   y_i = L_i^-1 z_i
+// and a backward sweep  x_i = L_i^-T (y_i - Le_i^T x_{i+1}),  x_{i1+1} = x_q.  Only (L^-1 | Le) (2 BS^2 doubles per state, twice), the
+// right-hand side and the SPARSE border entries of a state are read: 0.5 GB on C3 instead of the 0.8 GB of [L^-1 | Le | Y] - and the
+// forward elimination no longer writes Y (0.6 GB).  One WARP per segment (the sweeps are 12-pivot-free mat-vec chains: latency,
+// hidden by 16 independent warps per SM); lane r owns row r; (L^-1 | Le) stream through a per-warp cp.async ring; y_i waits in
+// xsol[i] between the sweeps.  The same arithmetic as eliminating the right-hand side column with the known separator values
+// substituted, i.e. the result equals the Y-based form up to rounding order.
+template <int BS>
+__global__ void __launch_bounds__(128) k_bwd2(const BwdArgs a) {
+  constexpr int NW = 4, NST = 3, F2 = 2 * BS * BS, REC0 = 2 * BS * BS + BS, REC1 = 3 * BS * BS + 2 * BS;
+  __shared__ __align__(16) double Fb[NW][NST][F2];
+  __shared__ double vec[NW][BS];
+  __shared__ double xls[64];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nb = a.nb;
+  const bool first = a.first_level != 0, rl = lane < BS;
+  const int RECS = first ? REC0 : REC1, oE = first ? BS * BS : 2 * BS * BS, oG = first ? 2 * BS * BS : 3 * BS * BS;
+  for (int k = threadIdx.x; k < nb; k += 128) xls[k] = a.xl[k];
+  __syncthreads();
+  double* const v = vec[warp];
+  for (int seg = blockIdx.x * NW + warp; seg < a.nseg; seg += gridDim.x * NW) {
+    const SegGeom sg = seg_geom(seg, a.n, a.sep, a.S, a.extL, a.extR);
+    const int p = sg.p, q = sg.q, i0 = sg.i0, i1 = sg.i1;
+    double xq = 0.0, xp = 0.0;   // lane c: entry c of the right / left separator solution
+    if (rl) {
+      if (q >= 0) { xq = a.xup[(size_t)sg.qo * BS + lane]; a.xsol[(size_t)q * BS + lane] = xq; }
+      if (p >= 0) xp = a.xup[(size_t)sg.po * BS + lane];
+      if (a.extL && seg == 0) a.xsol[lane] = a.xup[lane];  // external left separator: copy its solution down
+    }
+    if (i1 < i0) continue;
+    auto fetch = [&](int i, int st) {
+      const double* src = a.frec + (size_t)i * a.fstride;
+      const int n2 = (((i < i1) || (q >= 0)) ? F2 : BS * BS) / 2;   // Le of the last interior state exists only in front of a right separator
+      for (int k = lane; k < n2; k += 32) cp_async16(&Fb[warp][st][2 * k], src + 2 * k);
+    };
+    // right-hand side of state i with the known landmark / left-separator solutions substituted (row `lane`); independent of the sweep
+    auto own_of = [&](int i) -> double {
+      double o = 0.0;
+      if (rl) {
+        const double* r = a.rec + (size_t)i * RECS;
+        o = r[oG + lane] + (first ? 0.0 : r[oG + BS + lane]);
+        if (nb) {
+          if (first) {
+            for (int e = a.bsoff[i]; e < a.bsoff[i + 1]; e++) {
+              const double* en = a.bent + (size_t)e * 16;
+              const int l = (int)en[15];
+              double sc = 0.0;
+              for (int d = 0; d < a.DL; d++) sc += en[BS + d] * xls[l * a.DL + d];
+              o -= en[lane] * sc;
+            }
+          } else {
+            const double* B = a.brec + (size_t)i * (2 * BS * nb);
+            for (int l = 0; l < nb; l++) o -= (B[lane + l * BS] + B[BS * nb + lane + l * BS]) * xls[l];
+          }
+        }
+      }
+      return o;
+    };
+    // ---- forward sweep
+    fetch(i0, 0); cp_async_commit();
+    if (i0 + 1 <= i1) fetch(i0 + 1, 1);
+    cp_async_commit();
+    double own = own_of(i0), t = 0.0;
+    if (p >= 0) {  // coupling of the first interior state to the left separator: E_p x_p
+      const double* E = a.rec + (size_t)p * RECS + oE;
+      __syncwarp();
+      if (rl) v[lane] = xp;
+      __syncwarp();
+      if (rl) {
+#pragma unroll
+        for (int c = 0; c < BS; c++) own -= E[lane + c * BS] * v[c];
+      }
+    }
+    int st = 0;
+    for (int i = i0; i <= i1; i++) {
+      if (i + 2 <= i1) fetch(i + 2, st == 0 ? 2 : st - 1);
+      cp_async_commit();
+      const double own_next = (i + 1 <= i1) ? own_of(i + 1) : 0.0;
+      cp_async_wait<2>();
+      __syncwarp();
+      const double* Li = Fb[warp][st];
+      if (rl) v[lane] = own - t;
+      __syncwarp();
+      double y0 = 0.0, y1 = 0.0;
+      if (rl) {
+#pragma unroll
+        for (int c = 0; c < BS; c += 2) { y0 = fma(Li[lane + c * BS], v[c], y0); y1 = fma(Li[lane + (c + 1) * BS], v[c + 1], y1); }  // strictly-upper part of L^-1 is stored as zeros
+      }
+      const double y = y0 + y1;
+      __syncwarp();
+      if (rl) { v[lane] = y; a.xsol[(size_t)i * BS + lane] = y; }
+      __syncwarp();
+      t = 0.0;
+      if (rl && i < i1) {
+        const double* Le = Li + BS * BS;
+        double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+        for (int c = 0; c < BS; c += 2) { t0 = fma(Le[lane + c * BS], v[c], t0); t1 = fma(Le[lane + (c + 1) * BS], v[c + 1], t1); }
+        t = t0 + t1;
+      }
+      own = own_next;
+      st = st == 2 ? 0 : st + 1;
+      __syncwarp();   // every lane is done with this state's stage before the next iteration's prefetch may overwrite an older one
+    }
+    cp_async_wait<0>();
+    __syncwarp();
+    // ---- backward sweep
+    fetch(i1, 0); cp_async_commit();
+    if (i1 - 1 >= i0) fetch(i1 - 1, 1);
+    cp_async_commit();
+    bool hn = q >= 0;
+    double xn = xq;   // lane r: entry r of x_{i+1}
+    double ycur = rl ? a.xsol[(size_t)i1 * BS + lane] : 0.0;
+    st = 0;
+    for (int i = i1; i >= i0; i--) {
+      if (i - 2 >= i0) fetch(i - 2, st == 0 ? 2 : st - 1);
+      cp_async_commit();
+      const double ynext = (rl && i - 1 >= i0) ? a.xsol[(size_t)(i - 1) * BS + lane] : 0.0;
+      cp_async_wait<2>();
+      __syncwarp();
+      const double* Li = Fb[warp][st];
+      const double* Le = Li + BS * BS;
+      if (rl) v[lane] = xn;
+      __syncwarp();
+      double w = ycur;
+      if (rl && hn) {
+        double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+        for (int r = 0; r < BS; r += 2) { t0 = fma(Le[r + lane * BS], v[r], t0); t1 = fma(Le[r + 1 + lane * BS], v[r + 1], t1); }   // (Le^T x_{i+1})[lane]
+        w -= t0 + t1;
+      }
+      __syncwarp();
+      if (rl) v[lane] = w;
+      __syncwarp();
+      double x0 = 0.0, x1 = 0.0;
+      if (rl) {
+#pragma unroll
+        for (int r = 0; r < BS; r += 2) { x0 = fma(Li[r + lane * BS], v[r], x0); x1 = fma(Li[r + 1 + lane * BS], v[r + 1], x1); }   // (L^-T w)[lane]; zeros above the diagonal
+      }
+      xn = x0 + x1;
+      if (rl) a.xsol[(size_t)i * BS + lane] = xn;
+      hn = true;
+      ycur = ynext;
+      __syncwarp();
+      st = st == 2 ? 0 : st + 1;
+    }
+    cp_async_wait<0>();
+    __syncwarp();
   }
 }
 

@@ -824,14 +824,15 @@ int gpo_eval_factor(void* h, int k, double* e_out, double* H_out, int* dims_out)
 // Step check at any size (test infrastructure; O(non-zeros), threaded over factors): given a step delta in the oracle's variable
 // order (states [x_i, v_i] then landmarks), evaluates r = (J^T J + lambda I) delta - J^T b with the oracle's own whitened
 // Jacobians at the current values.  out[0] = max |r|, out[1] = max |J^T b|, out[2] = max |delta|, out[3] = 0.5 |J delta - b|^2
-// (the linearised error at delta).  A direct solver's step satisfies out[0] <= eps * cond-independent * out[1]: this is how the
+// (the linearised error at delta), out[4] = max (|J|^T |J| |delta|) - the scale a backward-stable solver's residual is measured
+// against (|r| <= c eps (|H| |delta| + |g|)).  This is how the
 // full-size configs (C5: 10^6 states, 128 loop closures) are held to the oracle without the oracle's dense-border solve.
 int gpo_check_step(void* h, const double* delta_states, const double* delta_lands, double lambda, double* out) {
   Graph* g = (Graph*)h;
   const int bs = 2 * g->D, nf = (int)g->factors.size();
   const size_t n = (size_t)g->N * bs + (size_t)g->L * g->DL;
   const int T = std::min(16, std::max(1, g->threads));  // per-thread accumulators of the full system size: bounded
-  std::vector<std::vector<double>> acc(T, std::vector<double>(n, 0.0)), gacc(T, std::vector<double>(n, 0.0));
+  std::vector<std::vector<double>> acc(T, std::vector<double>(n, 0.0)), gacc(T, std::vector<double>(n, 0.0)), aacc(T, std::vector<double>(n, 0.0));
   std::vector<double> lin_err(T, 0.0);
   auto dptr = [&](const VarRef& v) -> const double* { return v.type == 2 ? delta_lands + (size_t)v.idx * g->DL : delta_states + (size_t)v.idx * bs + (v.type == 1 ? g->D : 0); };
   auto off = [&](const VarRef& v) -> size_t { return v.type == 2 ? (size_t)g->N * bs + (size_t)v.idx * g->DL : (size_t)v.idx * bs + (v.type == 1 ? g->D : 0); };
@@ -839,31 +840,32 @@ int gpo_check_step(void* h, const double* delta_states, const double* delta_land
     const int lo = (int)((long long)nf * w / T), hi = (int)((long long)nf * (w + 1) / T);
     for (int k = lo; k < hi; k++) {
       Lin lin; linearize_factor(*g, g->factors[k], g->poses.data(), g->vels.data(), g->lands.data(), true, lin);
-      double jd[12];
-      for (int r = 0; r < lin.m; r++) jd[r] = 0.0;
-      for (int v = 0; v < lin.nv; v++) { const double* d = dptr(lin.v[v]); for (int c = 0; c < lin.d[v]; c++) for (int r = 0; r < lin.m; r++) jd[r] += lin.A[v][r + c * lin.m] * d[c]; }
+      double jd[12], ja[12];
+      for (int r = 0; r < lin.m; r++) { jd[r] = 0.0; ja[r] = 0.0; }
+      for (int v = 0; v < lin.nv; v++) { const double* d = dptr(lin.v[v]); for (int c = 0; c < lin.d[v]; c++) for (int r = 0; r < lin.m; r++) { jd[r] += lin.A[v][r + c * lin.m] * d[c]; ja[r] += std::fabs(lin.A[v][r + c * lin.m] * d[c]); } }
       for (int r = 0; r < lin.m; r++) lin_err[w] += 0.5 * (jd[r] - lin.b[r]) * (jd[r] - lin.b[r]);
       for (int v = 0; v < lin.nv; v++) {
         const size_t o = off(lin.v[v]);
         for (int c = 0; c < lin.d[v]; c++) {
-          double s1 = 0, s2 = 0;
-          for (int r = 0; r < lin.m; r++) { s1 += lin.A[v][r + c * lin.m] * jd[r]; s2 += lin.A[v][r + c * lin.m] * lin.b[r]; }
-          acc[w][o + c] += s1; gacc[w][o + c] += s2;
+          double s1 = 0, s2 = 0, s3 = 0;
+          for (int r = 0; r < lin.m; r++) { s1 += lin.A[v][r + c * lin.m] * jd[r]; s2 += lin.A[v][r + c * lin.m] * lin.b[r]; s3 += std::fabs(lin.A[v][r + c * lin.m]) * ja[r]; }
+          acc[w][o + c] += s1; gacc[w][o + c] += s2; aacc[w][o + c] += s3;
         }
       }
     }
   };
   if (T == 1) work(0);
   else { std::vector<std::thread> pool; for (int w = 0; w < T; w++) pool.emplace_back(work, w); for (auto& t : pool) t.join(); }
-  double rmax = 0, gmax = 0, dmax = 0, le = 0;
+  double rmax = 0, gmax = 0, dmax = 0, le = 0, hmax = 0;
   for (int w = 0; w < T; w++) le += lin_err[w];
   for (size_t t = 0; t < n; t++) {
-    double a = 0, gg = 0;
-    for (int w = 0; w < T; w++) { a += acc[w][t]; gg += gacc[w][t]; }
+    double a = 0, gg = 0, ha = 0;
+    for (int w = 0; w < T; w++) { a += acc[w][t]; gg += gacc[w][t]; ha += aacc[w][t]; }
+    hmax = std::max(hmax, ha);
     const double d = t < (size_t)g->N * bs ? delta_states[t] : delta_lands[t - (size_t)g->N * bs];
     rmax = std::max(rmax, std::fabs(a + lambda * d - gg)); gmax = std::max(gmax, std::fabs(gg)); dmax = std::max(dmax, std::fabs(d));
   }
-  out[0] = rmax; out[1] = gmax; out[2] = dmax; out[3] = le;
+  out[0] = rmax; out[1] = gmax; out[2] = dmax; out[3] = le; out[4] = hmax;
   return 0;
 }
 

@@ -232,12 +232,13 @@ class Graph:
 
     def check_step(self, delta_states, delta_lands, lam=0.0):
         """residual of a step against the oracle's own normal equations at the current values (any size):
-        dict(residual = max |(J^T J + lam I) delta - J^T b|, rhs = max |J^T b|, step = max |delta|, linearized_error)"""
+        dict(residual = max |(J^T J + lam I) delta - J^T b|, rhs = max |J^T b|, step = max |delta|, linearized_error,
+        scale = max(|J|^T |J| |delta|) + rhs: what a backward-stable solver's residual is small against)"""
         ds = _f64(delta_states).reshape(-1); dl = _f64(delta_lands).reshape(-1) if self.NL else np.zeros(1)
         assert ds.size == self.N * 2 * self.D
-        out = np.zeros(4)
+        out = np.zeros(5)
         self.L.gpo_check_step(self.h, _dp(ds), _dp(dl), C.c_double(lam), _dp(out))
-        return dict(residual=out[0], rhs=out[1], step=out[2], linearized_error=out[3])
+        return dict(residual=out[0], rhs=out[1], step=out[2], linearized_error=out[3], scale=out[4] + out[1] + lam * out[2])
 
     def optimize(self, params=None, n_iter=0, use_lm=True):
         p = params if params is not None else default_params(use_lm)
