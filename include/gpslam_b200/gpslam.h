@@ -14,6 +14,8 @@
 #include <array>
 #include <cmath>
 #include <cstdint>
+#include <functional>
+#include <iostream>
 #include <map>
 #include <memory>
 #include <stdexcept>
@@ -29,6 +31,11 @@ using Key = std::uint64_t;
 inline Key Symbol(char c, std::uint64_t j) { return (static_cast<Key>(static_cast<unsigned char>(c)) << 56) | j; }
 inline char symbolChr(Key k) { return static_cast<char>(k >> 56); }
 inline std::uint64_t symbolIndex(Key k) { return k & ((Key(1) << 56) - 1); }
+using KeyFormatter = std::function<std::string(Key)>;
+inline std::string DefaultKeyFormatter(Key k) {  // gtsam's default: Symbol keys print as <chr><index>, plain integers as the number
+  const char c = symbolChr(k);
+  return (c >= 33 && c < 127) ? std::string(1, c) + std::to_string(symbolIndex(k)) : std::to_string(k);
+}
 
 using Vector = std::vector<double>;
 struct Matrix {  // dynamic, column-major (Eigen's default)
@@ -109,10 +116,10 @@ inline void wire(const gtsam::Vector6& v, double* p) { for (int k = 0; k < 6; k+
 inline void wire(const gtsam::Point3& v, double* p) { p[0] = v.x; p[1] = v.y; p[2] = v.z; }
 inline void wire(const gtsam::Point2& v, double* p) { p[0] = v.x; p[1] = v.y; }
 template <class T> struct GroupOf;
-template <> struct GroupOf<gtsam::Pose3> { static constexpr int group = GPB_POSE3, D = 6, PS = 12, DL = 3; using Vel = gtsam::Vector6; using Land = gtsam::Point3; };
-template <> struct GroupOf<gtsam::Pose2> { static constexpr int group = GPB_POSE2, D = 3, PS = 3, DL = 2; using Vel = gtsam::Vector3; using Land = gtsam::Point2; };
-template <> struct GroupOf<gtsam::Rot3> { static constexpr int group = GPB_ROT3, D = 3, PS = 9, DL = 0; using Vel = gtsam::Vector3; using Land = gtsam::Point2; };
-template <> struct GroupOf<gtsam::Vector3> { static constexpr int group = GPB_LINEAR, D = 3, PS = 3, DL = 2; using Vel = gtsam::Vector3; using Land = gtsam::Point2; };
+template <> struct GroupOf<gtsam::Pose3> { static constexpr int group = GPB_POSE3, D = 6, PS = 12, DL = 3; using Vel = gtsam::Vector6; using Land = gtsam::Point3; static const char* name() { return "Pose3"; } };
+template <> struct GroupOf<gtsam::Pose2> { static constexpr int group = GPB_POSE2, D = 3, PS = 3, DL = 2; using Vel = gtsam::Vector3; using Land = gtsam::Point2; static const char* name() { return "Pose2"; } };
+template <> struct GroupOf<gtsam::Rot3> { static constexpr int group = GPB_ROT3, D = 3, PS = 9, DL = 0; using Vel = gtsam::Vector3; using Land = gtsam::Point2; static const char* name() { return "Rot3"; } };
+template <> struct GroupOf<gtsam::Vector3> { static constexpr int group = GPB_LINEAR, D = 3, PS = 3, DL = 2; using Vel = gtsam::Vector3; using Land = gtsam::Point2; static const char* name() { return "Linear<3>"; } };
 
 // evaluateError through the C ABI: returns e, fills the requested Jacobians (in the factor's variable order)
 inline gtsam::Vector eval(int group, int kind, const double* x1, const double* v1, const double* x2, const double* v2, const double* land, const double* prm,
@@ -140,11 +147,26 @@ class NonlinearFactor {
   virtual ~NonlinearFactor() {}
   virtual const std::vector<gtsam::Key>& keys() const = 0;
   virtual size_t size() const { return keys().size(); }
+  using shared_ptr = std::shared_ptr<NonlinearFactor>;
+  /// deep copy (gp/GaussianProcessPriorPose3.h:55-57)
+  virtual shared_ptr clone() const = 0;
+  /// print contents (gp/GaussianProcessPriorPose3.h:112-115): the factor's description, then its keys
+  virtual void print(const std::string& s = "", const gtsam::KeyFormatter& keyFormatter = gtsam::DefaultKeyFormatter) const {
+    std::cout << s << describe() << "\n  keys = {";
+    for (gtsam::Key k : keys()) std::cout << " " << keyFormatter(k);
+    std::cout << " }" << std::endl;
+  }
+  virtual std::string describe() const { return "NonlinearFactor"; }
+  /// a GP prior ties (pose, velocity[, angular velocity]) of one state to the next: the optimiser reads the chain order from these links
+  struct ChainLink { gtsam::Key x1, v1, w1, x2, v2, w2; bool vw; };
+  virtual bool chainLink(ChainLink&) const { return false; }
   // lowering hook used by the optimisers: add this factor to g; idx maps a state key to its chain index, lidx a landmark key
   virtual void lower(gpb_graph* g, int qc_of(void*, const gtsam::Matrix&), void* ctx, const std::map<gtsam::Key, int>& sidx,
                      const std::map<gtsam::Key, int>& lidx) const = 0;
-  using shared_ptr = std::shared_ptr<NonlinearFactor>;
 };
+#define GPSLAM_B200_FACTOR(CLASS, TEXT)                                                                   \
+  NonlinearFactor::shared_ptr clone() const override { return std::make_shared<CLASS>(*this); }           \
+  std::string describe() const override { return TEXT; }
 
 namespace detail {
 inline int stateOf(const std::map<gtsam::Key, int>& m, gtsam::Key k) {
@@ -168,8 +190,10 @@ class GaussianProcessPriorT : public NonlinearFactor {
     if (!Qc_model) throw std::runtime_error("gpslam_b200: Qc model is not Gaussian");  // getQc dereferences a failed dynamic_cast in the reference (gp/GPutils.cpp:17-19)
   }
   const std::vector<gtsam::Key>& keys() const override { return keys_; }
+  GPSLAM_B200_FACTOR(GaussianProcessPriorT, std::string("4-way Gaussian Process Factor ") + G::name())
   size_t size() const override { return 4; }
   double delta_t() const { return delta_t_; }
+  bool chainLink(ChainLink& c) const override { c = ChainLink{keys_[0], keys_[1], 0, keys_[2], keys_[3], 0, false}; return true; }
   /// factor error function (gp/GaussianProcessPriorPose3.h:60-98)
   gtsam::Vector evaluateError(const POSE& pose1, const typename G::Vel& vel1, const POSE& pose2, const typename G::Vel& vel2, gtsam::Matrix* H1 = nullptr,
                               gtsam::Matrix* H2 = nullptr, gtsam::Matrix* H3 = nullptr, gtsam::Matrix* H4 = nullptr) const {
@@ -198,6 +222,7 @@ inline void unwire(const double* p, gtsam::Pose3& o) { o = gtsam::Pose3::fromWir
 inline void unwire(const double* p, gtsam::Rot3& o) { for (int k = 0; k < 9; k++) o.R[k] = p[k]; }
 inline void unwire(const double* p, gtsam::Pose2& o) { o = gtsam::Pose2(p[0], p[1], p[2]); }
 inline void unwire(const double* p, gtsam::Vector3& o) { o = gtsam::Vector3{p[0], p[1], p[2]}; }
+inline void unwire(const double* p, gtsam::Vector6& o) { o = gtsam::Vector6{p[0], p[1], p[2], p[3], p[4], p[5]}; }
 // one interpolatePose query; Hs: up to four D x D Jacobians (nullptr = not requested)
 inline void interpolate(int group, int D, const double* x1, const double* v1, const double* x2, const double* v2, double delta_t, double tau, double* pose_out,
                         std::initializer_list<gtsam::Matrix*> Hs) {
@@ -235,6 +260,19 @@ class GaussianProcessInterpolatorT {
     POSE p; detail::unwire(out, p);
     return p;
   }
+  /// interpolate velocity with Jacobians (gp/GaussianProcessInterpolatorLinear.h:106-126).  Defined for the Linear interpolator only,
+  /// as in the reference (its Lie-group interpolators declare interpolateVelocity and never define it): other groups throw.
+  typename G::Vel interpolateVelocity(const POSE& pose1, const typename G::Vel& vel1, const POSE& pose2, const typename G::Vel& vel2, gtsam::Matrix* H1 = nullptr,
+                                      gtsam::Matrix* H2 = nullptr, gtsam::Matrix* H3 = nullptr, gtsam::Matrix* H4 = nullptr) const {
+    double x1[12], x2[12], v1[6], v2[6], out[6], h[4];
+    detail::wire(pose1, x1); detail::wire(pose2, x2); detail::wire(vel1, v1); detail::wire(vel2, v2);
+    detail::check(gpb_interpolate_velocities(G::group, 0, 1, G::D, x1, v1, x2, v2, &delta_t_, &tau_, out, h));
+    gtsam::Matrix* Hs[4] = {H1, H2, H3, H4};
+    for (int k = 0; k < 4; k++) if (Hs[k]) { *Hs[k] = gtsam::Matrix(G::D, G::D); for (int d = 0; d < G::D; d++) (*Hs[k])(d, d) = h[k]; }
+    typename G::Vel v; detail::unwire(out, v);
+    return v;
+  }
+  void print(const std::string& s = "") const { std::cout << s << "GaussianProcessInterpolator" << G::name() << std::endl; }
   bool equals(const GaussianProcessInterpolatorT& e, double tol = 1e-9) const {
     return std::fabs(delta_t_ - e.delta_t_) < tol && std::fabs(tau_ - e.tau_) < tol && Qc_ && e.Qc_ && Qc_->cov.a == e.Qc_->cov.a;
   }
@@ -262,6 +300,7 @@ class GPInterpolatedRangeFactorT : public NonlinearFactor {
     if (body_P_sensor) { has_sensor_ = true; body_P_sensor_ = *body_P_sensor; }
   }
   const std::vector<gtsam::Key>& keys() const override { return keys_; }
+  GPSLAM_B200_FACTOR(GPInterpolatedRangeFactorT, "RangeFactor, range = " + std::to_string(measured_))
   double measured() const { return measured_; }
   gtsam::Vector evaluateError(const POSE& pose1, const typename G::Vel& vel1, const POSE& pose2, const typename G::Vel& vel2, const typename G::Land& point,
                               gtsam::Matrix* H1 = nullptr, gtsam::Matrix* H2 = nullptr, gtsam::Matrix* H3 = nullptr, gtsam::Matrix* H4 = nullptr,
@@ -289,6 +328,7 @@ class GPInterpolatedRangeFactor2DLinear : public GPInterpolatedRangeFactorT<gtsa
   GPInterpolatedRangeFactor2DLinear(double measured, gtsam::Key pose1Key, gtsam::Key vel1Key, gtsam::Key pose2Key, gtsam::Key vel2Key, gtsam::Key pointKey,
                                     const gtsam::SharedNoiseModel& meas_model, const gtsam::SharedNoiseModel& Qc_model, double delta_t, double tau)
       : GPInterpolatedRangeFactorT<gtsam::Vector3>(measured, meas_model, Qc_model, pose1Key, vel1Key, pose2Key, vel2Key, pointKey, delta_t, tau) {}
+  GPSLAM_B200_FACTOR(GPInterpolatedRangeFactor2DLinear, "RangeFactor, range = " + std::to_string(measured()))
 };
 
 /// gtsam::Cal3_S2 (fx, fy, s, u0, v0) — the calibration the reference's projection-factor tests use
@@ -317,6 +357,7 @@ class GPInterpolatedGPSFactorPose3 : public NonlinearFactor {
     if (body_P_sensor) { has_sensor_ = true; body_P_sensor_ = *body_P_sensor; }
   }
   const std::vector<gtsam::Key>& keys() const override { return keys_; }
+  GPSLAM_B200_FACTOR(GPInterpolatedGPSFactorPose3, "GPSFactor, point = (" + std::to_string(measured_.x) + ", " + std::to_string(measured_.y) + ", " + std::to_string(measured_.z) + ")")
   gtsam::Point3 measured() const { return measured_; }
   gtsam::Vector evaluateError(const gtsam::Pose3& pose1, const gtsam::Vector6& vel1, const gtsam::Pose3& pose2, const gtsam::Vector6& vel2,
                               gtsam::Matrix* H1 = nullptr, gtsam::Matrix* H2 = nullptr, gtsam::Matrix* H3 = nullptr, gtsam::Matrix* H4 = nullptr) const {
@@ -356,6 +397,7 @@ class GPInterpolatedProjectionFactorPose3 : public NonlinearFactor {
     if (body_P_sensor) { has_sensor_ = true; body_P_sensor_ = *body_P_sensor; }
   }
   const std::vector<gtsam::Key>& keys() const override { return keys_; }
+  GPSLAM_B200_FACTOR(GPInterpolatedProjectionFactorPose3, "GPInterpolatedProjectionFactor, z = (" + std::to_string(measured_.x) + ", " + std::to_string(measured_.y) + ")")
   const gtsam::Point2& measured() const { return measured_; }
   const std::shared_ptr<CALIBRATION> calibration() const { return K_; }
   gtsam::Vector evaluateError(const gtsam::Pose3& pose1, const gtsam::Vector6& vel1, const gtsam::Pose3& pose2, const gtsam::Vector6& vel2, const gtsam::Point3& point,
@@ -420,6 +462,8 @@ class GaussianProcessPriorPose3VW : public NonlinearFactor {
     if (!Qc_model) throw std::runtime_error("gpslam_b200: Qc model is not Gaussian");
   }
   const std::vector<gtsam::Key>& keys() const override { return keys_; }
+  GPSLAM_B200_FACTOR(GaussianProcessPriorPose3VW, "4-way Gaussian Process Factor Pose3 VW")
+  bool chainLink(ChainLink& c) const override { c = ChainLink{keys_[0], keys_[1], keys_[2], keys_[3], keys_[4], keys_[5], true}; return true; }
   size_t size() const override { return 6; }
   gtsam::Vector evaluateError(const gtsam::Pose3& pose1, const gtsam::Vector3& vel1, const gtsam::Vector3& omega1, const gtsam::Pose3& pose2, const gtsam::Vector3& vel2,
                               const gtsam::Vector3& omega2, gtsam::Matrix* H1 = nullptr, gtsam::Matrix* H2 = nullptr, gtsam::Matrix* H3 = nullptr, gtsam::Matrix* H4 = nullptr,
@@ -481,6 +525,7 @@ class GPInterpolatedGPSFactorPose3VW : public NonlinearFactor {
     if (body_P_sensor) { has_sensor_ = true; body_P_sensor_ = *body_P_sensor; }
   }
   const std::vector<gtsam::Key>& keys() const override { return keys_; }
+  GPSLAM_B200_FACTOR(GPInterpolatedGPSFactorPose3VW, "GPSFactor, point = (" + std::to_string(measured_.x) + ", " + std::to_string(measured_.y) + ", " + std::to_string(measured_.z) + ")")
   size_t size() const override { return 6; }
   gtsam::Point3 measured() const { return measured_; }
   gtsam::Vector evaluateError(const gtsam::Pose3& pose1, const gtsam::Vector3& vel1, const gtsam::Vector3& omega1, const gtsam::Pose3& pose2, const gtsam::Vector3& vel2,
@@ -516,6 +561,7 @@ class GPInterpolatedAttitudeFactorRot3 : public NonlinearFactor {
                                    const gtsam::Unit3& bRef = gtsam::Unit3(0, 0, 1))
       : keys_{poseKey1, velKey1, poseKey2, velKey2}, delta_t_(delta_t), tau_(tau), Qc_(Qc_model), meas_(meas_model), nZ_(nZ), bRef_(bRef) {}
   const std::vector<gtsam::Key>& keys() const override { return keys_; }
+  GPSLAM_B200_FACTOR(GPInterpolatedAttitudeFactorRot3, "GP Interpolated AttitudeFactor")
   gtsam::Vector evaluateError(const gtsam::Rot3& pose1, const gtsam::Vector3& vel1, const gtsam::Rot3& pose2, const gtsam::Vector3& vel2, gtsam::Matrix* H1 = nullptr,
                               gtsam::Matrix* H2 = nullptr, gtsam::Matrix* H3 = nullptr, gtsam::Matrix* H4 = nullptr) const {
     double x1[9], x2[9], prm[20] = {0};
@@ -555,6 +601,7 @@ class RangeFactor2DT : public NonlinearFactor {
   RangeFactor2DT(gtsam::Key poseKey, gtsam::Key pointKey, double measured, const gtsam::SharedNoiseModel& model)
       : keys_{poseKey, pointKey}, measured_(measured), model_(model) {}
   const std::vector<gtsam::Key>& keys() const override { return keys_; }
+  GPSLAM_B200_FACTOR(RangeFactor2DT, "RangeFactor, range = " + std::to_string(measured_))
   double measured() const { return measured_; }
   gtsam::Vector evaluateError(const POSE& pose, const gtsam::Point2& point, gtsam::Matrix* H1 = nullptr, gtsam::Matrix* H2 = nullptr) const {
     double x[3], l[2], prm[48] = {0};
@@ -580,6 +627,7 @@ class RangeBearingFactor2DLinear : public NonlinearFactor {
   RangeBearingFactor2DLinear(gtsam::Key poseKey, gtsam::Key pointKey, double range, const gtsam::Rot2& bearing, const gtsam::SharedNoiseModel& model)
       : keys_{poseKey, pointKey}, range_(range), bearing_(bearing), model_(model) {}
   const std::vector<gtsam::Key>& keys() const override { return keys_; }
+  GPSLAM_B200_FACTOR(RangeBearingFactor2DLinear, "RangeBearingFactor, range = " + std::to_string(range_))
   gtsam::Vector evaluateError(const gtsam::Vector3& pose, const gtsam::Point2& point, gtsam::Matrix* H1 = nullptr, gtsam::Matrix* H2 = nullptr) const {
     double x[3], l[2], prm[48] = {0};
     detail::wire(pose, x); detail::wire(point, l);
@@ -601,6 +649,7 @@ class OdometryFactor2DLinear : public NonlinearFactor {
   OdometryFactor2DLinear(gtsam::Key pose1Key, gtsam::Key pose2Key, const gtsam::Vector3& betweenMeasured, const gtsam::SharedNoiseModel& model)
       : keys_{pose1Key, pose2Key}, measured_(betweenMeasured), model_(model) {}
   const std::vector<gtsam::Key>& keys() const override { return keys_; }
+  GPSLAM_B200_FACTOR(OdometryFactor2DLinear, "2-way projected odometry factor")
   gtsam::Vector evaluateError(const gtsam::Vector3& pose1, const gtsam::Vector3& pose2, gtsam::Matrix* H1 = nullptr, gtsam::Matrix* H2 = nullptr) const {
     double x1[3], x2[3], prm[48] = {0};
     detail::wire(pose1, x1); detail::wire(pose2, x2); detail::wire(measured_, prm + 4);
@@ -623,6 +672,7 @@ class PriorFactor : public NonlinearFactor {
  public:
   PriorFactor(gtsam::Key key, const T& prior, const gtsam::SharedNoiseModel& model) : keys_{key}, prior_(prior), model_(model) {}
   const std::vector<gtsam::Key>& keys() const override { return keys_; }
+  GPSLAM_B200_FACTOR(PriorFactor, "PriorFactor")
   void lower(gpb_graph* g, int (*)(void*, const gtsam::Matrix&), void*, const std::map<gtsam::Key, int>& sidx, const std::map<gtsam::Key, int>& lidx) const override {
     double v[12];
     detail::wire(prior_, v);
@@ -653,6 +703,7 @@ class BetweenFactor : public NonlinearFactor {
  public:
   BetweenFactor(gtsam::Key key1, gtsam::Key key2, const POSE& measured, const gtsam::SharedNoiseModel& model) : keys_{key1, key2}, measured_(measured), model_(model) {}
   const std::vector<gtsam::Key>& keys() const override { return keys_; }
+  GPSLAM_B200_FACTOR(BetweenFactor, "BetweenFactor")
   void lower(gpb_graph* g, int (*)(void*, const gtsam::Matrix&), void*, const std::map<gtsam::Key, int>& sidx, const std::map<gtsam::Key, int>&) const override {
     double v[12];
     detail::wire(measured_, v);
@@ -736,29 +787,65 @@ class NonlinearOptimizer {
 
  public:
   NonlinearOptimizer(const NonlinearFactorGraph& graph, const Values& initial, int group, int device = 0) : values_(initial), vw_(group == GPB_POSE3VW) {
-    // states: keys 'x' i with consecutive indices, each with its velocity key 'v' i (and 'w' i on a VW graph); landmarks 'l'
-    std::map<std::uint64_t, gtsam::Key> xs, ls;
-    for (const auto& kv : initial.all()) {
-      const char c = gtsam::symbolChr(kv.first);
-      if (c == 'x') xs[gtsam::symbolIndex(kv.first)] = kv.first; else if (c == 'l') ls[gtsam::symbolIndex(kv.first)] = kv.first;
-      else if (c != 'v' && !(c == 'w' && vw_)) throw std::runtime_error("gpslam_b200: only 'x', 'v', 'l' keys are supported ('w' on GPB_POSE3VW graphs)");
-    }
-    if (xs.size() < 2) throw std::runtime_error("gpslam_b200: need at least two states");
+    // The trajectory order comes from the graph, not from key names: every GP prior links (pose, velocity[, omega]) of one state to
+    // the next, so the chain is the path these links form (any keys, any numbering).  Keys outside the chain are landmarks.
+    // Graphs without GP priors fall back to the naming convention 'x' i / 'v' i / 'l' j with consecutive i.
     std::map<gtsam::Key, int> sidx, lidx;
-    std::uint64_t prev = 0; bool first = true;
-    for (const auto& kv : xs) {
-      if (!first && kv.first != prev + 1) throw std::runtime_error("gpslam_b200: state indices must be consecutive");
-      prev = kv.first; first = false;
-      const int i = static_cast<int>(xkeys_.size());
-      xkeys_.push_back(kv.second); vkeys_.push_back(gtsam::Symbol('v', kv.first));
-      sidx[kv.second] = i; sidx[vkeys_.back()] = i;
-      if (vw_) { wkeys_.push_back(gtsam::Symbol('w', kv.first)); sidx[wkeys_.back()] = i; }
+    std::map<gtsam::Key, NonlinearFactor::ChainLink> next;   // by first pose key
+    std::map<gtsam::Key, int> has_pred;
+    for (const auto& f : graph.factors()) {
+      NonlinearFactor::ChainLink c;
+      if (!f->chainLink(c)) continue;
+      if (c.vw != vw_) throw std::runtime_error("gpslam_b200: GP prior family does not match the trajectory group");
+      if (next.count(c.x1)) throw std::runtime_error("gpslam_b200: two GP priors start at the same state");
+      next[c.x1] = c; has_pred[c.x2] = 1;
     }
-    for (const auto& kv : ls) { lidx[kv.second] = static_cast<int>(lkeys_.size()); lkeys_.push_back(kv.second); }
+    if (!next.empty()) {
+      gtsam::Key start = 0; int nstart = 0;
+      for (const auto& kv : next) if (!has_pred.count(kv.first)) { start = kv.first; nstart++; }
+      if (nstart != 1) throw std::runtime_error("gpslam_b200: the GP priors must form one chain (found " + std::to_string(nstart) + " chain starts)");
+      auto push = [&](gtsam::Key x, gtsam::Key v, gtsam::Key w) {
+        const int i = static_cast<int>(xkeys_.size());
+        xkeys_.push_back(x); vkeys_.push_back(v); sidx[x] = i; sidx[v] = i;
+        if (vw_) { wkeys_.push_back(w); sidx[w] = i; }
+      };
+      gtsam::Key cur = start;
+      while (true) {
+        auto it = next.find(cur);
+        if (it == next.end()) break;
+        const auto& c = it->second;
+        if (xkeys_.empty()) push(c.x1, c.v1, c.w1);
+        else if (vkeys_.back() != c.v1 || (vw_ && wkeys_.back() != c.w1)) throw std::runtime_error("gpslam_b200: a state's pose key is paired with two different velocity keys");
+        push(c.x2, c.v2, c.w2);
+        cur = c.x2;
+        if (xkeys_.size() > next.size() + 1) throw std::runtime_error("gpslam_b200: the GP priors form a cycle");
+      }
+      if (xkeys_.size() != next.size() + 1) throw std::runtime_error("gpslam_b200: the GP priors must form one chain");
+      for (const auto& kv : initial.all()) if (!sidx.count(kv.first)) { lidx[kv.first] = static_cast<int>(lkeys_.size()); lkeys_.push_back(kv.first); }
+    } else {
+      std::map<std::uint64_t, gtsam::Key> xs, ls;
+      for (const auto& kv : initial.all()) {
+        const char c = gtsam::symbolChr(kv.first);
+        if (c == 'x') xs[gtsam::symbolIndex(kv.first)] = kv.first; else if (c == 'l') ls[gtsam::symbolIndex(kv.first)] = kv.first;
+        else if (c != 'v' && !(c == 'w' && vw_)) throw std::runtime_error("gpslam_b200: a graph without GP priors needs 'x', 'v', 'l' keys ('w' on GPB_POSE3VW graphs)");
+      }
+      std::uint64_t prev = 0; bool first = true;
+      for (const auto& kv : xs) {
+        if (!first && kv.first != prev + 1) throw std::runtime_error("gpslam_b200: state indices must be consecutive");
+        prev = kv.first; first = false;
+        const int i = static_cast<int>(xkeys_.size());
+        xkeys_.push_back(kv.second); vkeys_.push_back(gtsam::Symbol('v', kv.first));
+        sidx[kv.second] = i; sidx[vkeys_.back()] = i;
+        if (vw_) { wkeys_.push_back(gtsam::Symbol('w', kv.first)); sidx[wkeys_.back()] = i; }
+      }
+      for (const auto& kv : ls) { lidx[kv.second] = static_cast<int>(lkeys_.size()); lkeys_.push_back(kv.second); }
+    }
+    if (xkeys_.size() < 2) throw std::runtime_error("gpslam_b200: need at least two states");
     const bool se3 = group == GPB_POSE3 || vw_;
     PS_ = se3 ? 12 : group == GPB_ROT3 ? 9 : 3; D_ = se3 ? 6 : 3; DL_ = se3 ? 3 : group == GPB_ROT3 ? 0 : 2;
     g_ = gpb_graph_create(group, 3, static_cast<int>(xkeys_.size()), static_cast<int>(lkeys_.size()));
     if (!g_) throw std::runtime_error(std::string("gpslam_b200: ") + gpb_last_error());
+    struct Guard { gpb_graph*& g; bool armed = true; ~Guard() { if (armed && g) { gpb_graph_destroy(g); g = nullptr; } } } guard{g_};  // a throwing constructor runs no destructor
     for (const auto& f : graph.factors()) f->lower(g_, &NonlinearOptimizer::qcOf, this, sidx, lidx);
     std::vector<double> P(xkeys_.size() * PS_), V(xkeys_.size() * D_), L(lkeys_.size() * (DL_ ? DL_ : 1));
     for (size_t i = 0; i < xkeys_.size(); i++) {
@@ -775,11 +862,16 @@ class NonlinearOptimizer {
     detail::check(gpb_set_values(g_, P.data(), V.data(), lkeys_.empty() ? nullptr : L.data()));
     detail::check(gpb_graph_finalize(g_, device));
     detail::check(gpb_error(g_, &error_));
+    guard.armed = false;
   }
   NonlinearOptimizer(const NonlinearOptimizer&) = delete;
   virtual ~NonlinearOptimizer() { if (g_) gpb_graph_destroy(g_); }
   /// one optimiser iteration (matlab/PlazaPose2.m:225)
-  void iterate() { gpb_stats st; detail::check(gpb_optimize(g_, &params_, 1, &st)); error_ = st.error_final; iterations_ += st.iterations; pull(); }
+  /// LM keeps its damping between calls, as GTSAM's iterate() keeps state_.lambda: N calls equal one optimize of N iterations
+  void iterate() { gpb_stats st; detail::check(gpb_optimize(g_, &params_, 1, &st)); error_ = st.error_final; iterations_ += st.iterations; if (params_.use_lm) params_.lambda_initial = st.lambda; pull(); }
+  double lambda() const { return params_.lambda_initial; }
+  /// n iterations in one call (same result as n calls of iterate(); values are pulled once)
+  void iterate(int n) { gpb_stats st; detail::check(gpb_optimize(g_, &params_, n, &st)); error_ = st.error_final; iterations_ += st.iterations; if (params_.use_lm) params_.lambda_initial = st.lambda; pull(); }
   /// NonlinearOptimizer::optimize(): iterate to GTSAM's convergence test
   const Values& optimize() { gpb_stats st; detail::check(gpb_optimize(g_, &params_, 0, &st)); error_ = st.error_final; iterations_ += st.iterations; pull(); return values_; }
   const Values& values() const { return values_; }

@@ -46,6 +46,8 @@
 #include <gpslam/slam/GPInterpolatedRangeFactorPose3.h>
 
 #include <cstdlib>
+#include <algorithm>
+#include <cmath>
 #include <map>
 #include <stdexcept>
 #include <string>
@@ -89,6 +91,14 @@ inline double priorDeltaT(const gtsam::SharedNoiseModel& model, int D, std::vect
   const double dt = 2.0 * S(0, D) / S(D, D);
   Qc.assign(static_cast<size_t>(D) * D, 0.0);
   for (int c = 0; c < D; c++) for (int r = 0; r < D; r++) Qc[r + static_cast<size_t>(c) * D] = S(D + r, D + c) / dt;
+  // covariance() is (R^T R)^-1 recomputed by GTSAM: a diagonal Qc comes back with off-diagonals of rounding size.  Snap them to
+  // zero (relative 1e-12) so the engine keeps its diagonal-Qc linearise kernel, and symmetrise what remains.
+  for (int c = 0; c < D; c++) for (int r = 0; r < c; r++) {
+    double& a = Qc[r + static_cast<size_t>(c) * D]; double& b = Qc[c + static_cast<size_t>(r) * D];
+    const double scale = std::sqrt(std::fabs(Qc[r + static_cast<size_t>(r) * D] * Qc[c + static_cast<size_t>(c) * D]));
+    const double m = 0.5 * (a + b);
+    a = b = (std::fabs(m) <= 1e-12 * scale) ? 0.0 : m;
+  }
   return dt;
 }
 
@@ -106,7 +116,15 @@ struct Lowering {
   std::map<gtsam::Key, int> state, land;       // 'x' / 'v' key -> chain index, 'l' key -> landmark index
   std::vector<std::vector<double>> qcs;        // Qc models registered so far
   int qcId(const std::vector<double>& Qc) {
-    for (size_t k = 0; k < qcs.size(); k++) if (qcs[k] == Qc) return static_cast<int>(k);
+    // models recovered from different factors' covariances agree to rounding only: de-duplicate with a relative tolerance, or every
+    // distinct delta_t would register its own Qc
+    for (size_t k = 0; k < qcs.size(); k++) {
+      bool same = qcs[k].size() == Qc.size();
+      double scale = 0.0;
+      for (double v : qcs[k]) scale = std::max(scale, std::fabs(v));
+      for (size_t t = 0; same && t < Qc.size(); t++) same = std::fabs(qcs[k][t] - Qc[t]) <= 1e-9 * scale;
+      if (same) return static_cast<int>(k);
+    }
     const int id = gpb_add_qc_model(g, Qc.data());
     check(id);
     qcs.push_back(Qc);
@@ -120,6 +138,7 @@ struct Lowering {
     if (!p) return false;
     const int i = stateOf(p->keys()[0]);
     if (stateOf(p->keys()[2]) != i + 1) throw std::runtime_error("gpslam_b200: GP prior must join consecutive states");
+    if (stateOf(p->keys()[1]) != i || stateOf(p->keys()[3]) != i + 1) throw std::runtime_error("gpslam_b200: GP prior velocity keys do not belong to its pose keys");
     std::vector<double> Qc;
     const double dt = priorDeltaT(p->noiseModel(), D, Qc);
     check(gpb_add_gp_prior(g, 1, &i, &dt, qcId(Qc)));

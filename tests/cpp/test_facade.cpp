@@ -406,6 +406,66 @@ static void testPlain2DFactors() {
   }
 }
 
+// Boundary behaviour beyond the arithmetic: clone() / print(), a chain whose keys follow no
+// naming convention, LM damping carried across iterate() calls, GaussianProcessInterpolatorLinear::interpolateVelocity
+static void testBoundary() {
+  SharedNoiseModel Qc = noiseModel::Isotropic::Sigma(3, 0.1);
+  // ---- clone / print / equals (gp/GaussianProcessPriorPose2.h:52-54,88-99)
+  GaussianProcessPriorPose2 f(Symbol('x', 1), Symbol('v', 1), Symbol('x', 2), Symbol('v', 2), 0.5, Qc);
+  NonlinearFactor::shared_ptr c = f.clone();
+  EXPECT(c.get() != &f && c->keys() == f.keys() && c->size() == 4);
+  EXPECT(dynamic_cast<GaussianProcessPriorPose2*>(c.get()) && dynamic_cast<GaussianProcessPriorPose2*>(c.get())->equals(f));
+  EXPECT(c->describe() == "4-way Gaussian Process Factor Pose2");
+  c->print("clone: ");
+  EXPECT(DefaultKeyFormatter(Symbol('x', 12)) == "x12");
+  // ---- interpolateVelocity (gp/GaussianProcessInterpolatorLinear.h:106-126) against Lambda / Psi multiplied out by hand
+  {
+    const double dt = 0.4, tau = 0.15, s_ = tau / dt;
+    GaussianProcessInterpolatorLinear<3> gp(Qc, dt, tau);
+    const Vector3 p1{0.3, -1.2, 0.5}, v1{1.0, 0.2, -0.4}, p2{0.8, -1.0, 0.3}, v2{1.4, 0.6, -0.5};
+    Matrix H1, H2, H3, H4;
+    const Vector3 v = gp.interpolateVelocity(p1, v1, p2, v2, &H1, &H2, &H3, &H4);
+    const double psi21 = 6 * (s_ - s_ * s_) / dt, psi22 = 3 * s_ * s_ - 2 * s_, lam21 = -psi21, lam22 = 1 - 4 * s_ + 3 * s_ * s_;
+    for (int k = 0; k < 3; k++) EXPECT(std::fabs(v[k] - (lam21 * p1[k] + lam22 * v1[k] + psi21 * p2[k] + psi22 * v2[k])) < 1e-12);
+    EXPECT(std::fabs(H1(0, 0) - lam21) < 1e-12 && std::fabs(H2(1, 1) - lam22) < 1e-12 && std::fabs(H3(2, 2) - psi21) < 1e-12 && std::fabs(H4(0, 0) - psi22) < 1e-12 && H1(0, 1) == 0.0);
+    // tau = 0 / tau = dt reproduce the support velocities
+    EXPECT(std::fabs(GaussianProcessInterpolatorLinear<3>(Qc, dt, 0.0).interpolateVelocity(p1, v1, p2, v2)[1] - v1[1]) < 1e-12);
+    EXPECT(std::fabs(GaussianProcessInterpolatorLinear<3>(Qc, dt, dt).interpolateVelocity(p1, v1, p2, v2)[1] - v2[1]) < 1e-12);
+    bool threw = false;
+    try { GaussianProcessInterpolatorPose2(Qc, dt, tau).interpolateVelocity(Pose2(0, 0, 0), v1, Pose2(1, 0, 0), v2); } catch (const std::exception&) { threw = true; }
+    EXPECT(threw);   // declared, never defined in the reference for the Lie-group interpolators
+  }
+  // ---- a Pose2 chain under two key namings: 'x'/'v' with consecutive indices, and arbitrary keys in scrambled numeric order
+  auto build = [&](const std::function<Key(int)>& xk, const std::function<Key(int)>& vk, NonlinearFactorGraph& graph, Values& init) {
+    const int n = 6;
+    SharedNoiseModel prior = noiseModel::Isotropic::Sigma(3, 0.01), odo = noiseModel::Isotropic::Sigma(3, 0.05);
+    graph.add(PriorFactor<Pose2>(xk(0), Pose2(0, 0, 0), prior));
+    graph.add(PriorFactor<Vector3>(vk(0), Vector3{1, 0, 0.1}, prior));
+    for (int i = 0; i < n; i++) {
+      init.insert(xk(i), Pose2(0.9 * i + 0.05 * (i % 3), 0.04 * i, 0.12 * i));
+      init.insert(vk(i), Vector3{0, 0, 0});
+      if (i) {
+        graph.add(GaussianProcessPriorPose2(xk(i - 1), vk(i - 1), xk(i), vk(i), 1.0, Qc));
+        graph.add(BetweenFactor<Pose2>(xk(i - 1), xk(i), Pose2(1.0, 0.05, 0.1), odo));
+      }
+    }
+  };
+  NonlinearFactorGraph ga, gb_; Values ia, ib;
+  build([](int i) { return Symbol('x', i); }, [](int i) { return Symbol('v', i); }, ga, ia);
+  build([](int i) { return Symbol('p', 1000 - 7 * i); }, [](int i) { return Key(50 + ((i * 5) % 6)); }, gb_, ib);
+  LevenbergMarquardtOptimizer A(ga, ia, LevenbergMarquardtParams(), GPB_POSE2), B(gb_, ib, LevenbergMarquardtParams(), GPB_POSE2), Cc(ga, ia, LevenbergMarquardtParams(), GPB_POSE2);
+  // iterate() x 4 keeps its damping between calls: same iterates, same lambda as 4 iterations in one call
+  for (int k = 0; k < 4; k++) { A.iterate(); B.iterate(); }
+  Cc.iterate(4);
+  EXPECT(std::fabs(A.lambda() - Cc.lambda()) <= 1e-15 * Cc.lambda() && std::fabs(A.error() - Cc.error()) <= 1e-12 * (1.0 + Cc.error()));
+  EXPECT(std::fabs(A.error() - B.error()) <= 1e-12 * (1.0 + A.error()));
+  for (int i = 0; i < 6; i++) {
+    const Pose2 a = A.values().at<Pose2>(Symbol('x', i)), b = B.values().at<Pose2>(Symbol('p', 1000 - 7 * i)), c2 = Cc.values().at<Pose2>(Symbol('x', i));
+    EXPECT(std::fabs(a.x - b.x) < 1e-12 && std::fabs(a.y - b.y) < 1e-12 && std::fabs(a.theta - b.theta) < 1e-12);
+    EXPECT(std::fabs(a.x - c2.x) < 1e-12 && std::fabs(a.theta - c2.theta) < 1e-12);
+  }
+}
+
 int main() {
   try {
     testFactor();
@@ -415,6 +475,7 @@ int main() {
     testPose3VW();
     testInterpolators();
     testPlain2DFactors();
+    testBoundary();
   } catch (const std::exception& e) { std::printf("exception: %s\n", e.what()); return 2; }
   std::printf(failures ? "FAILED (%d)\n" : "OK (%d failures)\n", failures);
   return failures ? 1 : 0;

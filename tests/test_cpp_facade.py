@@ -32,6 +32,12 @@ def test_facade_reference_style_tests():
     assert r.returncode == 0, r.stdout + r.stderr
 
 
+@pytest.mark.gpu
+def test_gtsam_adapter_lowering_optimises_on_gpu():
+    """the same adapter run, in the driver's GPU tier (the unmarked twin below is deselected by -m gpu)"""
+    test_gtsam_adapter_compiles_against_api_stubs()
+
+
 def test_gtsam_adapter_compiles_against_api_stubs():
     """include/gpslam_b200/gtsam_adapter.h cannot meet the real GTSAM here (absent: SURVEY.md §8c); it is
     type-checked, warning-free, against tests/cpp/gtsam_stub (declarations of the GTSAM / gpslam entry points it calls) and its
