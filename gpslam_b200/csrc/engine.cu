@@ -130,6 +130,8 @@ struct gpb_graph {
   int *d_epstate = nullptr, *d_epoff = nullptr, *d_eprow = nullptr, *d_epside = nullptr;
   int *d_pair_a = nullptr, *d_pair_b = nullptr, *d_pairoff = nullptr, *d_pairrow = nullptr;
   bool generic_fwd = false, force_blocked = false, old_assemble = false, split_levels = false, no_tiny = false, fuse_l0 = false, old_bwd = false;
+  bool dense_panel = false;   // A/B switch GPB_DENSE_PANEL: k_panel4 (all 64 columns at every state) instead of k_panel0 (active columns only)
+  unsigned char *d_lorder = nullptr, *d_ntile = nullptr;  // k_panel0: per-segment landmark order [nseg][17], active column tiles per state [N]
   int fstride = 0;  // doubles per state of a level's factor record: (L^-1 | Le), + Y for the Y-reading back-substitution
   gpb_allreduce_fn allreduce = nullptr; void* allreduce_ctx = nullptr;
   nccl_rt::Comm nccl = nullptr;   // engine-owned communicator (gpb_graph_init_nccl): the all-reduce is captured inside the iteration graph
@@ -163,6 +165,7 @@ struct gpb_graph {
   std::vector<void*> allocs;
 };
 
+constexpr int BS_PANEL_C0 = 13;  // k_panel0: first landmark column (12 spike columns + the right-hand side)
 static int pose_storage(int group, int D) { return group == GPB_POSE3 ? 12 : group == GPB_ROT3 ? 9 : group == GPB_POSE2 ? 3 : D; }
 static int land_dim(int group) { return group == GPB_POSE3 ? 3 : group == GPB_ROT3 ? 0 : 2; }
 static int extra_rows_of(const gpb_graph* g, int kind) {
@@ -560,7 +563,10 @@ static int fwd_blocks_per_sm(int bs, int W, bool fuse_l0 = false) {
   if (bs == 12 && W == 64) {
     int nb = 0;
     if (fuse_l0) { if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_level0_ws<12>, 160, 0) != cudaSuccess) { cudaGetLastError(); nb = 4; } return nb < 1 ? 1 : nb; }
+    int nb0 = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb0, k_panel0<12>, 128, 0) != cudaSuccess) { cudaGetLastError(); nb0 = 4; }
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_panel4<12>, 128, 0) != cudaSuccess) { cudaGetLastError(); nb = 4; }
+    nb = std::min(nb, nb0);   // one resident wave must hold for either level-0 panel kernel
     return nb < 1 ? 1 : nb;
   }
   if (bs == 12) return W == 16 ? occ_fwd<12, 16>() : W == 32 ? occ_fwd<12, 32>() : occ_fwd<12, 64>();
@@ -725,7 +731,8 @@ int gpb_graph_finalize(gpb_graph* g, int device) {
   g->old_assemble = getenv("GPB_OLD_ASSEMBLE") != nullptr;  // A/B switch: thread-per-tile assembly instead of the DMMA kernel
   g->generic_fwd = getenv("GPB_GENERIC_FWD") != nullptr;
   g->fuse_l0 = getenv("GPB_FUSE_L0") != nullptr;
-  g->old_bwd = getenv("GPB_OLD_BWD") != nullptr;  // A/B switch: back-substitution from a stored Y (k_bwd) instead of re-eliminating the right-hand side (k_bwd2)  // A/B switch: level 0 as ONE warp-specialised kernel (spine warp + panel warps per CTA)
+  g->old_bwd = getenv("GPB_OLD_BWD") != nullptr;
+  g->dense_panel = getenv("GPB_DENSE_PANEL") != nullptr || g->old_bwd;  // the Y-reading back-substitution needs the dense kernel's Y layout  // A/B switch: back-substitution from a stored Y (k_bwd) instead of re-eliminating the right-hand side (k_bwd2)  // A/B switch: level 0 as ONE warp-specialised kernel (spine warp + panel warps per CTA)
   g->no_tiny = getenv("GPB_NO_TINY_SOLVE") != nullptr;  // A/B switch: the plain-loop instantiation of k_small_solve instead of the register-blocked ones
   g->qc_diag = 1;
   for (const auto& R : g->Rq) for (int c = 0; c < D; c++) for (int r = 0; r < D; r++) if (r != c && R[r + c * D] != 0.0) g->qc_diag = 0;
@@ -781,6 +788,25 @@ int gpb_graph_finalize(gpb_graph* g, int device) {
       }
       std::sort(sep.begin(), sep.end());
       L.S = (int)sep.size(); L.nseg = L.S + 1;
+      if (lev == 0 && bs == 12 && g->W == 64) {
+        // k_panel0: per segment, the landmarks in order of first appearance (then the ones it never meets), and per interior
+        // state the number of 8-column tiles [spike 12 | rhs 1 | 3 per landmark seen so far] holds
+        constexpr int LMAX = 17;
+        std::vector<unsigned char> lorder((size_t)L.nseg * LMAX, 0), ntile(n, 2);
+        std::vector<int> rank(std::max(g->L, 1));
+        for (int s_ = 0; s_ < L.nseg; s_++) {
+          const int p_ = s_ > 0 ? sep[s_ - 1] : (g->pinL ? 0 : -1), q_ = s_ < L.S ? sep[s_] : (g->pinR ? n - 1 : -1);
+          const int i0_ = p_ + 1, i1_ = q_ >= 0 ? q_ - 1 : n - 1;
+          std::fill(rank.begin(), rank.end(), -1);
+          int seen = 0;
+          auto visit = [&](int i) { for (int e = bsoff[i]; e < bsoff[i + 1]; e++) { const int l = rowland[bsrow[e]]; if (rank[l] < 0) { rank[l] = seen; lorder[(size_t)s_ * LMAX + seen] = (unsigned char)l; seen++; } } };
+          for (int i = i0_; i <= i1_; i++) { visit(i); ntile[i] = (unsigned char)((BS_PANEL_C0 + 3 * seen + 7) / 8); }
+          if (q_ >= 0) visit(q_);
+          for (int l = 0; l < g->L; l++) if (rank[l] < 0) { lorder[(size_t)s_ * LMAX + seen] = (unsigned char)l; seen++; }
+        }
+        if ((rc = dev_upload(g, &g->d_lorder, lorder))) return rc;
+        if ((rc = dev_upload(g, &g->d_ntile, ntile))) return rc;
+      }
       L.ncta = std::min(L.nseg, sms * fwd_blocks_per_sm(bs, g->W, g->fuse_l0 && lev == 0));  // persistent CTAs: one resident wave
       L.ncta_bwd = std::min(L.nseg, sms * bwd_blocks_per_sm(bs, g->W));
       if ((rc = dev_upload(g, &L.d_sep, sep))) return rc;
@@ -1001,7 +1027,11 @@ static int launch_fwd_level(gpb_graph* g, int buf, double lambda, int lev, int p
       k_level_ws<12><<<L.nseg, 160, 0, g->stream>>>(a); g->launches++;
     } else {
       if (parts & 1) { if (lev == 0) k_spine<12, true><<<spine_ctas, 32, 0, g->stream>>>(a); else k_spine<12, false><<<spine_ctas, 32, 0, g->stream>>>(a); g->launches++; }
-      if (parts & 2) { k_panel4<12><<<L.ncta, 128, 0, g->stream>>>(a); g->launches++; }
+      if (parts & 2) {
+        if (lev == 0 && !g->dense_panel) k_panel0<12><<<L.ncta, 128, 0, g->stream>>>(a, g->d_lorder, g->d_ntile);
+        else k_panel4<12><<<L.ncta, 128, 0, g->stream>>>(a);
+        g->launches++;
+      }
     }
   } else {
     if (bs == 12) fwd_w<12>(g->W, a, L.ncta, g->stream); else fwd_w<6>(g->W, a, L.ncta, g->stream);

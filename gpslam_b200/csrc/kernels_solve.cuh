@@ -991,6 +991,269 @@ __device__ __forceinline__ void panel_body(const FwdArgs& a, volatile const int*
 template <int BS>
 __global__ void __launch_bounds__(128, 5) k_panel4(const FwdArgs a) { panel_body<BS, false>(a, nullptr); }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Level-0 panel kernel with ACTIVE-COLUMN tracking (default for SE(3) graphs with a 64-column panel).  A segment's panel starts
+// as [coupling to the left separator | 0 | 0 ...]: the columns of a landmark stay exactly zero in P, Y and S until the first
+// state of the segment that observes it.  The columns are therefore ordered per segment as
+//   [ spike (12) | rhs (1) | landmarks in order of first appearance in this segment (3 each) | landmarks it never meets ]
+// (lorder[seg][k] = landmark of rank k, a permutation computed once at finalize: the factor structure is static), and state i
+// touches only the first ntile[i] = ceil((13 + 3 seen_i) / 8) column tiles: Y = L^-1 P and P' = -Le Y on those tiles, S += Y^T Y on
+// the lower-triangular tile pairs among them.  Skipped work multiplies exact zeros, so the results equal the dense kernel's
+// (k_panel4) bit for bit up to the order of the landmark sums.  On C3 (16 landmarks, one range factor per two states, 46-state
+// segments) this executes 52 % of the dense kernel's DMMAs.  Column tiles are dealt to the four warps round-robin (tile T ->
+// warp T mod 4) and the Schur tiles by their index in the row-major enumeration of the lower triangle (t -> warp t mod 4), so the
+// warps stay balanced for every ntile.  The landmark x landmark part of S is un-permuted into a shared-memory accumulator at
+// the end of each segment (each entry owned by one thread: deterministic), which persists across the CTA's segments.
+__host__ __device__ constexpr int tri_I(int t) { int i = 0; while ((i + 1) * (i + 2) / 2 <= t) i++; return i; }
+__host__ __device__ constexpr int tri_J(int t) { return t - tri_I(t) * (tri_I(t) + 1) / 2; }
+template <int BS>
+__global__ void __launch_bounds__(128, 5) k_panel0(const FwdArgs a, const unsigned char* __restrict__ lorder, const unsigned char* __restrict__ ntile) {
+  static_assert(BS == 12, "panel kernel is specialised for 12 x 12 state blocks");
+  constexpr int W = 64, NT = 128, REC0 = 2 * BS * BS + BS, REC1 = 3 * BS * BS + 2 * BS, NST = 3, MAXE = 6, HB = BS / 2, C0 = BS + 1, DL = 3, LMAX = 17;
+  constexpr int CSN = LMAX * DL * (LMAX * DL + 1) / 2 + LMAX * DL;   // packed lower triangle of the landmark block + landmark x rhs
+  __shared__ __align__(16) double Fb[NST][2 * BS * BS];  // (L^-1 | Le)
+  __shared__ __align__(16) double Gb[NST][BS];           // rhs block g
+  __shared__ __align__(16) double Eb[NST][MAXE * 16];    // packed border entries
+  __shared__ __align__(16) double Psm[W * BS], Ysm[2][W * BS];
+  __shared__ double Csm[CSN];
+  __shared__ int gdim[W];                                // physical column -> global landmark dimension (or -1), per segment
+  const int c = threadIdx.x, pw = c >> 5, lane = c & 31, gi = lane >> 2, ti = lane & 3;
+  const int ctile = pw + 4 * ((lane & 15) >> 3);         // thread-per-half-column steps: this thread's column tile, column, first row
+  const int col = 8 * ctile + (lane & 7), r0 = HB * (lane >> 4);
+  const int nb = a.nb, w = BS + nb + 1, nl = nb / DL;
+  const bool is_rhs = (col == BS), is_spike = col < BS, is_border = (col >= C0) && (col < C0 + nb), active = col < w;
+  const int myk = is_border ? (col - C0) / DL : 0, myd = is_border ? (col - C0) % DL : 0;
+  double acc[18];
+#pragma unroll
+  for (int j = 0; j < 18; j++) acc[j] = 0.0;
+  for (int k = c; k < CSN; k += NT) Csm[k] = 0.0;
+  auto bso = [&](int i) { return nb > 0 ? a.bsoff[i < a.n ? i : a.n] : 0; };
+
+  for (int seg = blockIdx.x; seg < a.nseg; seg += gridDim.x) {
+    const SegGeom sg = seg_geom(seg, a.n, a.sep, a.S, a.extL, a.extR);
+    const int p = sg.p, q = sg.q, i0 = sg.i0, i1 = sg.i1;
+    const int ilast = (q >= 0) ? q : i1;
+    const int myl = is_border ? (int)lorder[(size_t)seg * LMAX + myk] : -1;   // landmark of this thread's column in this segment
+    const int mygd = is_border ? myl * DL + myd : -1;                         // its global border dimension
+    if (c < W) gdim[c] = (c >= C0 && c < C0 + nb) ? (int)lorder[(size_t)seg * LMAX + (c - C0) / DL] * DL + (c - C0) % DL : -1;
+    int b0 = bso(i0), b1 = bso(i0 + 1), b2 = bso(i0 + 2), b3 = bso(i0 + 3);
+    auto prefetch = [&](int i, int st, int e0, int e1) {
+      if (i <= i1) {
+        const double* src = a.frec + (size_t)i * a.fstride;
+        const int n2 = (((i < i1) || (q >= 0)) ? 2 * BS * BS : BS * BS) / 2;
+        for (int k = c; k < n2; k += NT) cp_async16(&Fb[st][2 * k], src + 2 * k);
+      }
+      if (i <= ilast) {
+        if (c < BS / 2) cp_async16(&Gb[st][2 * c], a.rec + (size_t)i * REC0 + 2 * BS * BS + 2 * c);
+        if (nb > 0) { const int ne = min(e1 - e0, MAXE); if (c < 8 * ne) cp_async16(&Eb[st][2 * c], a.bent + (size_t)e0 * 16 + 2 * c); }
+      }
+    };
+    // own half-column of state i: border entries of this column's landmark, rhs
+    auto add_own = [&](int st, int e0, int e1) {
+      double* P = Psm + col * BS + r0;
+      if (is_border) {
+        const int ne = e1 - e0;
+        for (int k = 0; k < ne; k++) {
+          const double* en = (k < MAXE) ? &Eb[st][16 * k] : a.bent + (size_t)(e0 + k) * 16;
+          if ((int)en[15] == myl) { const double h = en[BS + myd];
+#pragma unroll
+            for (int r = 0; r < HB; r++) P[r] += en[r0 + r] * h; }
+        }
+      } else if (is_rhs) {
+#pragma unroll
+        for (int r = 0; r < HB; r++) P[r] += Gb[st][r0 + r];
+      }
+    };
+    prefetch(i0, 0, b0, b1); cp_async_commit();
+    prefetch(i0 + 1, 1, b1, b2); cp_async_commit();
+    {
+      const bool sp = is_spike && p >= 0 && i0 <= i1;
+      const double* E = a.rec + (size_t)(sp ? p : 0) * REC0 + BS * BS + r0 + col * BS;
+#pragma unroll
+      for (int r = 0; r < HB; r++) Psm[col * BS + r0 + r] = sp ? E[r] : 0.0;
+    }
+    cp_async_wait<1>();
+    __syncthreads();
+    int st = 0, ys = 0, ntmax = 2;
+    for (int i = i0; i <= i1; i++) {
+      const bool has_next = (i < i1) || (q >= 0);
+      const int nt = (int)ntile[i];   // active column tiles at this state (uniform over the CTA)
+      ntmax = nt;
+      const int st2 = st == 0 ? 2 : st - 1;
+      prefetch(i + 2, st2, b2, b3);
+      cp_async_commit();
+      const int b4 = bso(i + 4);
+      add_own(st, b0, b1);
+      __syncwarp();
+      const double* Li = Fb[st];
+      const double* Le = Fb[st] + BS * BS;
+      double* Y = Ysm[ys];
+      // ---- Y = L^-1 P and P' = -Le Y on this warp's active column tiles (pw and pw + 4)
+#pragma unroll
+      for (int jt = 0; jt < 2; jt++) {
+        const int J = pw + 4 * jt;
+        if (J < nt) {
+          double d[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+          for (int sK = 0; sK < 3; sK++) {
+            const double bP = Psm[(8 * J + gi) * BS + 4 * sK + ti];
+            const double a0 = Li[gi + (4 * sK + ti) * BS], a1 = (8 + gi < BS) ? Li[(8 + gi) + (4 * sK + ti) * BS] : 0.0;
+            if (sK < 2) dmma884(d[0][0], d[0][1], a0, bP);   // rows 0..7 of L^-1 have no entries in columns 8..11
+            dmma884(d[1][0], d[1][1], a1, bP);
+          }
+          Y[(8 * J + 2 * ti) * BS + gi] = d[0][0]; Y[(8 * J + 2 * ti + 1) * BS + gi] = d[0][1];
+          if (8 + gi < BS) { Y[(8 * J + 2 * ti) * BS + 8 + gi] = d[1][0]; Y[(8 * J + 2 * ti + 1) * BS + 8 + gi] = d[1][1]; }
+        }
+      }
+      __syncwarp();
+      if (has_next) {
+#pragma unroll
+        for (int jt = 0; jt < 2; jt++) {
+          const int J = pw + 4 * jt;
+          if (J < nt) {
+            double d[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+            for (int sK = 0; sK < 3; sK++) {
+              const double bY = Y[(8 * J + gi) * BS + 4 * sK + ti];
+              const double a0 = Le[gi + (4 * sK + ti) * BS], a1 = (8 + gi < BS) ? Le[(8 + gi) + (4 * sK + ti) * BS] : 0.0;
+              dmma884(d[0][0], d[0][1], a0, bY);
+              dmma884(d[1][0], d[1][1], a1, bY);
+            }
+            Psm[(8 * J + 2 * ti) * BS + gi] = -d[0][0]; Psm[(8 * J + 2 * ti + 1) * BS + gi] = -d[0][1];
+            if (8 + gi < BS) { Psm[(8 * J + 2 * ti) * BS + 8 + gi] = -d[1][0]; Psm[(8 * J + 2 * ti + 1) * BS + 8 + gi] = -d[1][1]; }
+          }
+        }
+      } else if (ctile < nt) {
+#pragma unroll
+        for (int r = 0; r < HB; r++) Psm[col * BS + r0 + r] = 0.0;
+      }
+      cp_async_wait<1>();
+      __syncthreads();
+      // ---- S += Y^T Y on the active lower-triangular tile pairs; this warp's tiles: t = 4 u + pw in row-major order of the triangle
+      {
+        double yf[8][3];
+#pragma unroll
+        for (int T = 0; T < 8; T++)
+          if (T < nt) {
+#pragma unroll
+            for (int sK = 0; sK < 3; sK++) yf[T][sK] = Y[(8 * T + gi) * BS + 4 * sK + ti];
+          }
+        auto tiles = [&](auto PW) {
+          constexpr int pwc = decltype(PW)::value;
+          static_for<0, 9>([&](auto U) {
+            constexpr int u = decltype(U)::value, t = 4 * u + pwc, I = tri_I(t), J = tri_J(t);
+            if (I < nt) {
+#pragma unroll
+              for (int sK = 0; sK < 3; sK++) dmma884(acc[2 * u], acc[2 * u + 1], yf[I][sK], yf[J][sK]);
+            }
+          });
+        };
+        if (pw == 0) tiles(std::integral_constant<int, 0>{});
+        else if (pw == 1) tiles(std::integral_constant<int, 1>{});
+        else if (pw == 2) tiles(std::integral_constant<int, 2>{});
+        else tiles(std::integral_constant<int, 3>{});
+      }
+      b0 = b1; b1 = b2; b2 = b3; b3 = b4;
+      st = st == 2 ? 0 : st + 1; ys ^= 1;
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+    // ---- segment end (D1 of q was written by k_spine): the closing separator's own border / rhs, then hand the panel off
+    if (q >= 0) {
+      double* R = a.rec_out + (size_t)sg.qo * REC1;
+      add_own(st, b0, b1);
+      const double* P = Psm + col * BS + r0;
+      if (is_border) {
+        double* B = a.brec_out + (size_t)sg.qo * (2 * BS * nb) + r0 + mygd * BS;
+#pragma unroll
+        for (int r = 0; r < HB; r++) B[r] = P[r];
+      } else if (is_rhs) {
+#pragma unroll
+        for (int r = 0; r < HB; r++) R[3 * BS * BS + r0 + r] = P[r];
+      } else if (is_spike && p >= 0) {
+        double* Ep = a.rec_out + (size_t)sg.po * REC1 + 2 * BS * BS + r0 + col * BS;
+        if (i0 <= i1) {
+#pragma unroll
+          for (int r = 0; r < HB; r++) Ep[r] = P[r];
+        } else {
+          const double* E = a.rec + (size_t)p * REC0 + BS * BS + r0 + col * BS;
+#pragma unroll
+          for (int r = 0; r < HB; r++) Ep[r] = E[r];
+        }
+      }
+      if (a.extR && seg == a.S) {
+        for (int k = c; k < BS * BS; k += NT) R[BS * BS + k] = 0.0;
+        if (c < BS) R[3 * BS * BS + BS + c] = 0.0;
+        if (is_border) { double* B = a.brec_out + (size_t)sg.qo * (2 * BS * nb) + BS * nb + r0 + mygd * BS;
+#pragma unroll
+          for (int r = 0; r < HB; r++) B[r] = 0.0; }
+      }
+    }
+    if (a.extL && seg == 0) {  // the left external separator (halo state p): its own blocks pass through to the next level
+      double* R = a.rec_out;
+      const double* src = a.rec + (size_t)p * REC0;
+      for (int k = c; k < BS * BS; k += NT) R[k] = src[k] + ((a.lamL && (k % (BS + 1)) == 0) ? (*a.lambda_ptr) : 0.0);
+      if (c < BS) R[3 * BS * BS + c] = src[2 * BS * BS + c];
+      if (is_border) {
+        double* B = a.brec_out + r0 + mygd * BS;
+        double v[HB];
+#pragma unroll
+        for (int r = 0; r < HB; r++) v[r] = 0.0;
+        for (int e = a.bsoff[p]; e < a.bsoff[p + 1]; e++) {
+          const double* en = a.bent + (size_t)e * 16;
+          if ((int)en[15] == myl) { const double h = en[BS + myd];
+#pragma unroll
+            for (int r = 0; r < HB; r++) v[r] += en[r0 + r] * h; }
+        }
+#pragma unroll
+        for (int r = 0; r < HB; r++) B[r] = v[r];
+      }
+    }
+    {
+      // flush the accumulated Y^T Y of this segment: entries touching a spike column belong to separator p (D2 | B2 | g2); the
+      // rest (landmark x landmark, landmark x rhs) is un-permuted into the CTA's accumulator.  Every accumulator is reset.
+      double* Rp = (p >= 0) ? a.rec_out + (size_t)sg.po * REC1 : nullptr;
+      double* Bp = (p >= 0) ? a.brec_out + (size_t)sg.po * (2 * BS * nb) + BS * nb : nullptr;
+      auto flush = [&](int x, int y, double& av) {   // x >= y: physical columns
+        const double v = -av;
+        av = 0.0;
+        if (y < BS) {            // a spike column
+          if (p < 0) return;
+          if (x < BS) { Rp[BS * BS + y + x * BS] = v; Rp[BS * BS + x + y * BS] = v; }            // D2
+          else if (x == BS) Rp[3 * BS * BS + BS + y] = v;                                        // g2
+          else if (x < C0 + nb) Bp[y + gdim[x] * BS] = v;                                        // B2
+        } else if (x < C0 + nb && x > BS) {
+          const int gx = gdim[x];
+          if (y == BS) Csm[nl * DL * (nl * DL + 1) / 2 + gx] += v;                               // landmark x rhs
+          else { const int gy = gdim[y]; const int hi = gx > gy ? gx : gy, lo = gx > gy ? gy : gx; Csm[hi * (hi + 1) / 2 + lo] += v; }
+        }
+      };
+      auto tiles = [&](auto PW) {
+        constexpr int pwc = decltype(PW)::value;
+        static_for<0, 9>([&](auto U) {
+          constexpr int u = decltype(U)::value, t = 4 * u + pwc, I = tri_I(t), J = tri_J(t);
+          // tiles that were never active hold zeros: spike-related ones are still written (B2 of unseen landmarks must read zero)
+          if (I < ntmax || J < 2) {
+            const int x = 8 * I + gi, y = 8 * J + 2 * ti;
+            if (x >= y) flush(x, y, acc[2 * u]); else acc[2 * u] = 0.0;
+            if (x >= y + 1) flush(x, y + 1, acc[2 * u + 1]); else acc[2 * u + 1] = 0.0;
+          }
+        });
+      };
+      if (pw == 0) tiles(std::integral_constant<int, 0>{});
+      else if (pw == 1) tiles(std::integral_constant<int, 1>{});
+      else if (pw == 2) tiles(std::integral_constant<int, 2>{});
+      else tiles(std::integral_constant<int, 3>{});
+    }
+    __syncthreads();
+  }
+  if (nb > 0) {  // expand the packed accumulator into this CTA's full symmetric slot
+    double* Cs = a.cseg + (size_t)blockIdx.x * (nb * nb + nb);
+    for (int e = c; e < nb * nb; e += NT) { const int r = e % nb, cc = e / nb, hi = r > cc ? r : cc, lo = r > cc ? cc : r; Cs[e] = Csm[hi * (hi + 1) / 2 + lo]; }
+    for (int e = c; e < nb; e += NT) Cs[nb * nb + e] = Csm[nb * (nb + 1) / 2 + e];
+  }
+}
+
 // Upper elimination levels (a few hundred segments at most: latency, not throughput): ONE kernel per level.  Warp 4 of each
 // CTA walks the spine of the CTA's segments and never waits; warps 0-3 run the panel a couple of states behind it, so a level
 // costs about one spine pass instead of a spine launch followed by a panel launch.
@@ -1100,8 +1363,10 @@ __global__ void __launch_bounds__((W < 32 ? 32 : W)) k_bwd(const BwdArgs a) {
 // xsol[i] between the sweeps.  The same arithmetic as eliminating the right-hand side column with the known separator values
 // substituted, i.e. the result equals the Y-based form up to rounding order.
 template <int BS>
-__global__ void __launch_bounds__(128) k_bwd2(const BwdArgs a) {
-  constexpr int NW = 4, NST = 3, F2 = 2 * BS * BS, REC0 = 2 * BS * BS + BS, REC1 = 3 * BS * BS + 2 * BS;
+__global__ void __launch_bounds__(128, 4) k_bwd2(const BwdArgs a) {
+  constexpr int NW = 4, NST = 4, F2 = 2 * BS * BS, REC0 = 2 * BS * BS + BS, REC1 = 3 * BS * BS + 2 * BS;
+  constexpr int DLC = BS == 12 ? 3 : 2;   // landmark dimension of the groups with this block size (SO(3) chains carry no border)
+  constexpr int NPART = 32 / BS, KMAX = (64 + NPART - 1) / NPART, KH = (KMAX + 1) / 2;   // upper levels: the dense border product is split over NPART lane groups
   __shared__ __align__(16) double Fb[NW][NST][F2];
   __shared__ double vec[NW][BS];
   __shared__ double xls[64];
@@ -1109,7 +1374,7 @@ __global__ void __launch_bounds__(128) k_bwd2(const BwdArgs a) {
   const int nb = a.nb;
   const bool first = a.first_level != 0, rl = lane < BS;
   const int RECS = first ? REC0 : REC1, oE = first ? BS * BS : 2 * BS * BS, oG = first ? 2 * BS * BS : 3 * BS * BS;
-  for (int k = threadIdx.x; k < nb; k += 128) xls[k] = a.xl[k];
+  for (int k = threadIdx.x; k < 64; k += 128) xls[k] = k < nb ? a.xl[k] : 0.0;
   __syncthreads();
   double* const v = vec[warp];
   for (int seg = blockIdx.x * NW + warp; seg < a.nseg; seg += gridDim.x * NW) {
@@ -1127,50 +1392,89 @@ __global__ void __launch_bounds__(128) k_bwd2(const BwdArgs a) {
       const int n2 = (((i < i1) || (q >= 0)) ? F2 : BS * BS) / 2;   // Le of the last interior state exists only in front of a right separator
       for (int k = lane; k < n2; k += 32) cp_async16(&Fb[warp][st][2 * k], src + 2 * k);
     };
-    // right-hand side of state i with the known landmark / left-separator solutions substituted (row `lane`); independent of the sweep
-    auto own_of = [&](int i) -> double {
-      double o = 0.0;
-      if (rl) {
-        const double* r = a.rec + (size_t)i * RECS;
-        o = r[oG + lane] + (first ? 0.0 : r[oG + BS + lane]);
-        if (nb) {
-          if (first) {
-            for (int e = a.bsoff[i]; e < a.bsoff[i + 1]; e++) {
-              const double* en = a.bent + (size_t)e * 16;
-              const int l = (int)en[15];
-              double sc = 0.0;
-              for (int d = 0; d < a.DL; d++) sc += en[BS + d] * xls[l * a.DL + d];
-              o -= en[lane] * sc;
-            }
-          } else {
-            const double* B = a.brec + (size_t)i * (2 * BS * nb);
-            for (int l = 0; l < nb; l++) o -= (B[lane + l * BS] + B[BS * nb + lane + l * BS]) * xls[l];
-          }
-        }
-      }
-      return o;
-    };
-    // ---- forward sweep
+    // the (L^-1 | Le) of the first states start streaming in while the right-hand sides are formed
     fetch(i0, 0); cp_async_commit();
     if (i0 + 1 <= i1) fetch(i0 + 1, 1);
     cp_async_commit();
-    double own = own_of(i0), t = 0.0;
+    if (i0 + 2 <= i1) fetch(i0 + 2, 2);
+    cp_async_commit();
+    // ---- pass A: o_i = g_i - B_i x_l for every interior state (no recurrence: all loads of the segment are in flight together);
+    //      parked in xsol[i] until the sweep picks it up
+    if (first) {
+      // level 0: one LANE per state; the border is sparse (packed 128-byte entries, CSR by state)
+      for (int i = i0 + lane; i <= i1; i += 32) {
+        const double* r = a.rec + (size_t)i * REC0 + oG;
+        double o[BS];
+#pragma unroll
+        for (int k = 0; k < BS; k += 2) { const double2 t = *reinterpret_cast<const double2*>(r + k); o[k] = t.x; o[k + 1] = t.y; }
+        if (nb) {
+          for (int e = a.bsoff[i]; e < a.bsoff[i + 1]; e++) {
+            const double* en = a.bent + (size_t)e * 16;
+            double ev[16];
+#pragma unroll
+            for (int k = 0; k < 16; k += 2) { const double2 t = *reinterpret_cast<const double2*>(en + k); ev[k] = t.x; ev[k + 1] = t.y; }
+            const int l = (int)ev[15];
+            double sc = 0.0;
+#pragma unroll
+            for (int d = 0; d < DLC; d++) sc += ev[BS + d] * xls[l * DLC + d];
+#pragma unroll
+            for (int k = 0; k < BS; k++) o[k] -= ev[k] * sc;
+          }
+        }
+        double* dst = a.xsol + (size_t)i * BS;
+#pragma unroll
+        for (int k = 0; k < BS; k += 2) st128(dst + k, o[k], o[k + 1]);
+      }
+    } else {
+      // upper levels: dense border blocks B1 + B2 (BS x nb); lane = (row r, column group part), all loads of a state issued before its FMAs
+      const int r = lane % BS, part = lane / BS;
+      for (int i = i0; i <= i1; i++) {
+        const double* B = a.brec + (size_t)i * (2 * BS * nb);
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {   // two batches of KH columns: every load of a batch is issued before its first FMA
+          double b1[KH], b2[KH];
+#pragma unroll
+          for (int k = 0; k < KH; k++) {
+            const int l = part + NPART * (h * KH + k);
+            const bool ok = part < NPART && l < nb;
+            b1[k] = ok ? B[r + l * BS] : 0.0; b2[k] = ok ? B[BS * nb + r + l * BS] : 0.0;
+          }
+#pragma unroll
+          for (int k = 0; k < KH; k++) {
+            const double x = xls[(part + NPART * (h * KH + k)) & 63];   // xls is zero beyond nb
+            if (k & 1) s1 = fma(b1[k] + b2[k], x, s1); else s0 = fma(b1[k] + b2[k], x, s0);
+          }
+        }
+        double tot = s0 + s1;
+        if (part >= NPART) tot = 0.0;
+        double sum = 0.0;
+#pragma unroll
+        for (int pp = 0; pp < NPART; pp++) sum += __shfl_sync(0xffffffffu, tot, (r + pp * BS) & 31);
+        if (rl) { const double* g = a.rec + (size_t)i * REC1 + oG; a.xsol[(size_t)i * BS + lane] = g[lane] + g[BS + lane] - sum; }
+      }
+    }
+    __syncwarp();
+    // ---- forward sweep
+    double own = rl ? a.xsol[(size_t)i0 * BS + lane] : 0.0, t = 0.0;
     if (p >= 0) {  // coupling of the first interior state to the left separator: E_p x_p
       const double* E = a.rec + (size_t)p * RECS + oE;
-      __syncwarp();
       if (rl) v[lane] = xp;
       __syncwarp();
       if (rl) {
+        double e0 = 0.0, e1 = 0.0;
 #pragma unroll
-        for (int c = 0; c < BS; c++) own -= E[lane + c * BS] * v[c];
+        for (int c = 0; c < BS; c += 2) { e0 = fma(E[lane + c * BS], v[c], e0); e1 = fma(E[lane + (c + 1) * BS], v[c + 1], e1); }
+        own -= e0 + e1;
       }
+      __syncwarp();
     }
     int st = 0;
     for (int i = i0; i <= i1; i++) {
-      if (i + 2 <= i1) fetch(i + 2, st == 0 ? 2 : st - 1);
+      if (i + 3 <= i1) fetch(i + 3, st == 0 ? 3 : st - 1);
       cp_async_commit();
-      const double own_next = (i + 1 <= i1) ? own_of(i + 1) : 0.0;
-      cp_async_wait<2>();
+      const double own_next = (rl && i + 1 <= i1) ? a.xsol[(size_t)(i + 1) * BS + lane] : 0.0;
+      cp_async_wait<3>();
       __syncwarp();
       const double* Li = Fb[warp][st];
       if (rl) v[lane] = own - t;
@@ -1193,8 +1497,8 @@ __global__ void __launch_bounds__(128) k_bwd2(const BwdArgs a) {
         t = t0 + t1;
       }
       own = own_next;
-      st = st == 2 ? 0 : st + 1;
-      __syncwarp();   // every lane is done with this state's stage before the next iteration's prefetch may overwrite an older one
+      st = st == NST - 1 ? 0 : st + 1;
+      __syncwarp();   // every lane is done with this state's stage before a later prefetch may overwrite it
     }
     cp_async_wait<0>();
     __syncwarp();
@@ -1202,15 +1506,17 @@ __global__ void __launch_bounds__(128) k_bwd2(const BwdArgs a) {
     fetch(i1, 0); cp_async_commit();
     if (i1 - 1 >= i0) fetch(i1 - 1, 1);
     cp_async_commit();
+    if (i1 - 2 >= i0) fetch(i1 - 2, 2);
+    cp_async_commit();
     bool hn = q >= 0;
     double xn = xq;   // lane r: entry r of x_{i+1}
     double ycur = rl ? a.xsol[(size_t)i1 * BS + lane] : 0.0;
     st = 0;
     for (int i = i1; i >= i0; i--) {
-      if (i - 2 >= i0) fetch(i - 2, st == 0 ? 2 : st - 1);
+      if (i - 3 >= i0) fetch(i - 3, st == 0 ? 3 : st - 1);
       cp_async_commit();
       const double ynext = (rl && i - 1 >= i0) ? a.xsol[(size_t)(i - 1) * BS + lane] : 0.0;
-      cp_async_wait<2>();
+      cp_async_wait<3>();
       __syncwarp();
       const double* Li = Fb[warp][st];
       const double* Le = Li + BS * BS;
@@ -1236,7 +1542,7 @@ __global__ void __launch_bounds__(128) k_bwd2(const BwdArgs a) {
       hn = true;
       ycur = ynext;
       __syncwarp();
-      st = st == 2 ? 0 : st + 1;
+      st = st == NST - 1 ? 0 : st + 1;
     }
     cp_async_wait<0>();
     __syncwarp();
