@@ -92,6 +92,14 @@ def dmma_peak(device=0):
     return v.value
 
 
+def latencies(device=0):
+    """profiling aid (gpb_debug_latency): clocks per dependent operation"""
+    out = np.zeros(8)
+    if lib().gpb_debug_latency(C.c_int(device), _dp(out)) != 0:
+        raise GpbError(lib().gpb_last_error().decode())
+    return dict(zip(("dfma", "dmul", "dmma", "shfl64", "lds", "rsqrt_plus_add", "dadd", "ldg_l2"), out.tolist()))
+
+
 def store_peak(mode, n_factors, device=0):
     """profiling aid (gpb_debug_store_peak): microseconds to write n_factors SE(3) [A|b] records in k_lin_gp's store pattern"""
     v = C.c_double()

@@ -130,6 +130,7 @@ struct gpb_graph {
   int *d_epstate = nullptr, *d_epoff = nullptr, *d_eprow = nullptr, *d_epside = nullptr;
   int *d_pair_a = nullptr, *d_pair_b = nullptr, *d_pairoff = nullptr, *d_pairrow = nullptr;
   bool generic_fwd = false, force_blocked = false, old_assemble = false, split_levels = false, no_tiny = false, fuse_l0 = false, old_bwd = false;
+  int panel0_occ = 5;         // CTAs per SM the level-0 active-column panel kernel is compiled for (GPB_PANEL0_OCC = 4: 128 registers, no spills)
   bool dense_panel = false;   // A/B switch GPB_DENSE_PANEL: k_panel4 (all 64 columns at every state) instead of k_panel0 (active columns only)
   unsigned char *d_lorder = nullptr, *d_ntile = nullptr;  // k_panel0: per-segment landmark order [nseg][17], active column tiles per state [N]
   int fstride = 0;  // doubles per state of a level's factor record: (L^-1 | Le), + Y for the Y-reading back-substitution
@@ -559,12 +560,12 @@ static int bwd_blocks_per_sm(int bs, int W) {
   if (bs == 12) return W == 16 ? occ_bwd<12, 16>() : W == 32 ? occ_bwd<12, 32>() : occ_bwd<12, 64>();
   return W == 16 ? occ_bwd<6, 16>() : W == 32 ? occ_bwd<6, 32>() : occ_bwd<6, 64>();
 }
-static int fwd_blocks_per_sm(int bs, int W, bool fuse_l0 = false) {
+static int fwd_blocks_per_sm(int bs, int W, bool fuse_l0 = false, int panel0_occ = 5) {
   if (bs == 12 && W == 64) {
     int nb = 0;
     if (fuse_l0) { if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_level0_ws<12>, 160, 0) != cudaSuccess) { cudaGetLastError(); nb = 4; } return nb < 1 ? 1 : nb; }
     int nb0 = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb0, k_panel0<12>, 128, 0) != cudaSuccess) { cudaGetLastError(); nb0 = 4; }
+    if ((panel0_occ == 4 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb0, k_panel0<12, 4>, 128, 0) : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb0, k_panel0<12, 5>, 128, 0)) != cudaSuccess) { cudaGetLastError(); nb0 = 4; }
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_panel4<12>, 128, 0) != cudaSuccess) { cudaGetLastError(); nb = 4; }
     nb = std::min(nb, nb0);   // one resident wave must hold for either level-0 panel kernel
     return nb < 1 ? 1 : nb;
@@ -732,7 +733,8 @@ int gpb_graph_finalize(gpb_graph* g, int device) {
   g->generic_fwd = getenv("GPB_GENERIC_FWD") != nullptr;
   g->fuse_l0 = getenv("GPB_FUSE_L0") != nullptr;
   g->old_bwd = getenv("GPB_OLD_BWD") != nullptr;
-  g->dense_panel = getenv("GPB_DENSE_PANEL") != nullptr || g->old_bwd;  // the Y-reading back-substitution needs the dense kernel's Y layout  // A/B switch: back-substitution from a stored Y (k_bwd) instead of re-eliminating the right-hand side (k_bwd2)  // A/B switch: level 0 as ONE warp-specialised kernel (spine warp + panel warps per CTA)
+  g->dense_panel = getenv("GPB_DENSE_PANEL") != nullptr || g->old_bwd;
+  if (const char* ev = getenv("GPB_PANEL0_OCC")) g->panel0_occ = atoi(ev) == 4 ? 4 : 5;  // the Y-reading back-substitution needs the dense kernel's Y layout  // A/B switch: back-substitution from a stored Y (k_bwd) instead of re-eliminating the right-hand side (k_bwd2)  // A/B switch: level 0 as ONE warp-specialised kernel (spine warp + panel warps per CTA)
   g->no_tiny = getenv("GPB_NO_TINY_SOLVE") != nullptr;  // A/B switch: the plain-loop instantiation of k_small_solve instead of the register-blocked ones
   g->qc_diag = 1;
   for (const auto& R : g->Rq) for (int c = 0; c < D; c++) for (int r = 0; r < D; r++) if (r != c && R[r + c * D] != 0.0) g->qc_diag = 0;
@@ -749,7 +751,7 @@ int gpb_graph_finalize(gpb_graph* g, int device) {
     // the panel kernel runs one resident wave of persistent CTAs, each walking ceil(nseg / slots) segments of M0 (+ a closing
     // separator) states one after the other: pick the segment length that minimises that serial depth (whole rounds - a
     // 100k-state chain on 148 x 5 slots wants 46, not 32); ties go to the longer segment (fewer separators for the next level)
-    const int slots = sms * fwd_blocks_per_sm(bs, g->W, g->fuse_l0), m0 = g->N - g->pinL - g->pinR;
+    const int slots = sms * fwd_blocks_per_sm(bs, g->W, g->fuse_l0, g->panel0_occ), m0 = g->N - g->pinL - g->pinR;
     long long best = -1;
     for (int M = 12; M <= 63; M++) {
       const int nseg = (m0 > 0 ? (m0 - 1) / M : 0) + 1;
@@ -807,7 +809,7 @@ int gpb_graph_finalize(gpb_graph* g, int device) {
         if ((rc = dev_upload(g, &g->d_lorder, lorder))) return rc;
         if ((rc = dev_upload(g, &g->d_ntile, ntile))) return rc;
       }
-      L.ncta = std::min(L.nseg, sms * fwd_blocks_per_sm(bs, g->W, g->fuse_l0 && lev == 0));  // persistent CTAs: one resident wave
+      L.ncta = std::min(L.nseg, sms * fwd_blocks_per_sm(bs, g->W, g->fuse_l0 && lev == 0, g->panel0_occ));  // persistent CTAs: one resident wave
       L.ncta_bwd = std::min(L.nseg, sms * bwd_blocks_per_sm(bs, g->W));
       if ((rc = dev_upload(g, &L.d_sep, sep))) return rc;
       if ((rc = dev_alloc(g, &L.frec, (size_t)n * fstride))) return rc;
@@ -1028,7 +1030,7 @@ static int launch_fwd_level(gpb_graph* g, int buf, double lambda, int lev, int p
     } else {
       if (parts & 1) { if (lev == 0) k_spine<12, true><<<spine_ctas, 32, 0, g->stream>>>(a); else k_spine<12, false><<<spine_ctas, 32, 0, g->stream>>>(a); g->launches++; }
       if (parts & 2) {
-        if (lev == 0 && !g->dense_panel) k_panel0<12><<<L.ncta, 128, 0, g->stream>>>(a, g->d_lorder, g->d_ntile);
+        if (lev == 0 && !g->dense_panel) { if (g->panel0_occ == 4) k_panel0<12, 4><<<L.ncta, 128, 0, g->stream>>>(a, g->d_lorder, g->d_ntile); else k_panel0<12, 5><<<L.ncta, 128, 0, g->stream>>>(a, g->d_lorder, g->d_ntile); }
         else k_panel4<12><<<L.ncta, 128, 0, g->stream>>>(a);
         g->launches++;
       }
@@ -1669,6 +1671,68 @@ int gpb_debug_dmma_peak(int device, double* tflops_out) {
   }
   cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
   *tflops_out = best;
+  return GPB_OK;
+}
+
+// profiling aid: dependent-issue latencies (clocks per operation in a chain of dependent operations, one warp on an idle SM) of the
+// instructions the latency-bound solver kernels are made of: [0] DFMA, [1] DMUL, [2] DMMA m8n8k4 accumulating into the same
+// fragment, [3] 64-bit __shfl_sync, [4] shared-memory load -> address of the next load, [5] rsqrt_pos (MUFU.RSQ64H + its
+// third-order correction), [6] DADD, [7] global (L2-resident) load -> address of the next load
+__global__ void k_latency(double* out, int iters, const int* chase) {
+  __shared__ int sidx[256];
+  __shared__ double res[8];
+  for (int k = threadIdx.x; k < 256; k += blockDim.x) sidx[k] = (k + 1) & 255;
+  __syncthreads();
+  double x = 1.0 + 1e-9 * threadIdx.x, y = 0.999999, z = 1e-12;
+  long long t0, t1;
+  t0 = clock64();
+  for (int i = 0; i < iters; i++) x = fma(x, y, z);
+  t1 = clock64(); if (threadIdx.x == 0) res[0] = double(t1 - t0) / iters;
+  t0 = clock64();
+  for (int i = 0; i < iters; i++) x = x * y;
+  t1 = clock64(); if (threadIdx.x == 0) res[1] = double(t1 - t0) / iters;
+  double c0 = x, c1 = y;
+  t0 = clock64();
+  for (int i = 0; i < iters; i++) dmma884(c0, c1, z, y);
+  t1 = clock64(); if (threadIdx.x == 0) res[2] = double(t1 - t0) / iters;
+  x += c0 + c1;
+  t0 = clock64();
+  for (int i = 0; i < iters; i++) x = __shfl_sync(0xffffffffu, x, (threadIdx.x + 1) & 31);
+  t1 = clock64(); if (threadIdx.x == 0) res[3] = double(t1 - t0) / iters;
+  int j = threadIdx.x;
+  t0 = clock64();
+  for (int i = 0; i < iters; i++) j = sidx[j];
+  t1 = clock64(); if (threadIdx.x == 0) res[4] = double(t1 - t0) / iters;
+  x = fabs(x) + 1.0 + j * 1e-30;
+  t0 = clock64();
+  for (int i = 0; i < iters; i++) x = rsqrt_pos(x) + 1.0;
+  t1 = clock64(); if (threadIdx.x == 0) res[5] = double(t1 - t0) / iters;   // includes one DADD
+  t0 = clock64();
+  for (int i = 0; i < iters; i++) x = x + y;
+  t1 = clock64(); if (threadIdx.x == 0) res[6] = double(t1 - t0) / iters;
+  int g = threadIdx.x;
+  t0 = clock64();
+  for (int i = 0; i < iters; i++) g = chase[g];
+  t1 = clock64(); if (threadIdx.x == 0) res[7] = double(t1 - t0) / iters;
+  __syncthreads();
+  if (threadIdx.x < 8) out[threadIdx.x] = res[threadIdx.x];
+  if (x == 123.456 || g == -7) out[8] = x;
+}
+int gpb_debug_latency(int device, double* out8) {
+  if (!out8) return fail(GPB_ERR_ARG, "gpb_debug_latency: null argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(GPB_ERR_CUDA, "gpb_debug_latency: no CUDA device available"); }
+  CUDA_TRY(cudaSetDevice(device));
+  double* d = nullptr; int* ch = nullptr;
+  CUDA_TRY(cudaMalloc(&d, 9 * sizeof(double)));
+  std::vector<int> h(4096);
+  for (int k = 0; k < 4096; k++) h[k] = (k * 33 + 17) & 4095;
+  CUDA_TRY(cudaMalloc(&ch, h.size() * sizeof(int)));
+  CUDA_TRY(cudaMemcpy(ch, h.data(), h.size() * sizeof(int), cudaMemcpyHostToDevice));
+  for (int rep = 0; rep < 2; rep++) k_latency<<<1, 32>>>(d, 2000, ch);
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemcpy(out8, d, 8 * sizeof(double), cudaMemcpyDeviceToHost));
+  cudaFree(d); cudaFree(ch);
   return GPB_OK;
 }
 

@@ -1006,8 +1006,8 @@ __global__ void __launch_bounds__(128, 5) k_panel4(const FwdArgs a) { panel_body
 // the end of each segment (each entry owned by one thread: deterministic), which persists across the CTA's segments.
 __host__ __device__ constexpr int tri_I(int t) { int i = 0; while ((i + 1) * (i + 2) / 2 <= t) i++; return i; }
 __host__ __device__ constexpr int tri_J(int t) { return t - tri_I(t) * (tri_I(t) + 1) / 2; }
-template <int BS>
-__global__ void __launch_bounds__(128, 5) k_panel0(const FwdArgs a, const unsigned char* __restrict__ lorder, const unsigned char* __restrict__ ntile) {
+template <int BS, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_panel0(const FwdArgs a, const unsigned char* __restrict__ lorder, const unsigned char* __restrict__ ntile) {
   static_assert(BS == 12, "panel kernel is specialised for 12 x 12 state blocks");
   constexpr int W = 64, NT = 128, REC0 = 2 * BS * BS + BS, REC1 = 3 * BS * BS + 2 * BS, NST = 3, MAXE = 6, HB = BS / 2, C0 = BS + 1, DL = 3, LMAX = 17;
   constexpr int CSN = LMAX * DL * (LMAX * DL + 1) / 2 + LMAX * DL;   // packed lower triangle of the landmark block + landmark x rhs
@@ -1017,6 +1017,7 @@ __global__ void __launch_bounds__(128, 5) k_panel0(const FwdArgs a, const unsign
   __shared__ __align__(16) double Psm[W * BS], Ysm[2][W * BS];
   __shared__ double Csm[CSN];
   __shared__ int gdim[W];                                // physical column -> global landmark dimension (or -1), per segment
+  __shared__ unsigned char nts[64];                      // active column tiles of the segment's first 64 states (a global load per state would sit on the critical path)
   const int c = threadIdx.x, pw = c >> 5, lane = c & 31, gi = lane >> 2, ti = lane & 3;
   const int ctile = pw + 4 * ((lane & 15) >> 3);         // thread-per-half-column steps: this thread's column tile, column, first row
   const int col = 8 * ctile + (lane & 7), r0 = HB * (lane >> 4);
@@ -1036,6 +1037,7 @@ __global__ void __launch_bounds__(128, 5) k_panel0(const FwdArgs a, const unsign
     const int myl = is_border ? (int)lorder[(size_t)seg * LMAX + myk] : -1;   // landmark of this thread's column in this segment
     const int mygd = is_border ? myl * DL + myd : -1;                         // its global border dimension
     if (c < W) gdim[c] = (c >= C0 && c < C0 + nb) ? (int)lorder[(size_t)seg * LMAX + (c - C0) / DL] * DL + (c - C0) % DL : -1;
+    if (c >= 64 && i0 + (c - 64) <= i1) nts[c - 64] = ntile[i0 + (c - 64)];
     int b0 = bso(i0), b1 = bso(i0 + 1), b2 = bso(i0 + 2), b3 = bso(i0 + 3);
     auto prefetch = [&](int i, int st, int e0, int e1) {
       if (i <= i1) {
@@ -1077,7 +1079,7 @@ __global__ void __launch_bounds__(128, 5) k_panel0(const FwdArgs a, const unsign
     int st = 0, ys = 0, ntmax = 2;
     for (int i = i0; i <= i1; i++) {
       const bool has_next = (i < i1) || (q >= 0);
-      const int nt = (int)ntile[i];   // active column tiles at this state (uniform over the CTA)
+      const int nt = (i - i0 < 64) ? (int)nts[i - i0] : (int)ntile[i];   // active column tiles at this state (uniform over the CTA)
       ntmax = nt;
       const int st2 = st == 0 ? 2 : st - 1;
       prefetch(i + 2, st2, b2, b3);
@@ -1364,19 +1366,37 @@ __global__ void __launch_bounds__((W < 32 ? 32 : W)) k_bwd(const BwdArgs a) {
 // substituted, i.e. the result equals the Y-based form up to rounding order.
 template <int BS>
 __global__ void __launch_bounds__(128, 4) k_bwd2(const BwdArgs a) {
-  constexpr int NW = 4, NST = 4, F2 = 2 * BS * BS, REC0 = 2 * BS * BS + BS, REC1 = 3 * BS * BS + 2 * BS;
+  constexpr int NW = 4, NST = 3, F2 = 2 * BS * BS, REC0 = 2 * BS * BS + BS, REC1 = 3 * BS * BS + 2 * BS, YC = 48, HC = BS / 2;
   constexpr int DLC = BS == 12 ? 3 : 2;   // landmark dimension of the groups with this block size (SO(3) chains carry no border)
-  constexpr int NPART = 32 / BS, KMAX = (64 + NPART - 1) / NPART, KH = (KMAX + 1) / 2;   // upper levels: the dense border product is split over NPART lane groups
+  constexpr int NPART = 32 / BS, KMAX = (64 + NPART - 1) / NPART, KH = (KMAX + 1) / 2;
   __shared__ __align__(16) double Fb[NW][NST][F2];
+  __shared__ __align__(16) double ysm[NW][YC * BS];   // right-hand sides, then y, of the segment's first YC states (later ones wait in xsol)
   __shared__ double vec[NW][BS];
   __shared__ double xls[64];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nb = a.nb;
   const bool first = a.first_level != 0, rl = lane < BS;
+  // mat-vec lanes: (row or column rr, half hh of the summation index); the two halves meet through one shuffle
+  const int rr = lane % BS, hh = (lane / BS) & 1;
+  const bool mv = lane < 2 * BS;
   const int RECS = first ? REC0 : REC1, oE = first ? BS * BS : 2 * BS * BS, oG = first ? 2 * BS * BS : 3 * BS * BS;
   for (int k = threadIdx.x; k < 64; k += 128) xls[k] = k < nb ? a.xl[k] : 0.0;
   __syncthreads();
   double* const v = vec[warp];
+  // y = M v (row form) or M^T v (column form) for a BS x BS column-major block in shared memory; valid on lanes < BS
+  auto matvec = [&](const double* M, bool transposed) -> double {
+    double s0 = 0.0, s1 = 0.0;
+    if (mv) {
+#pragma unroll
+      for (int k = 0; k < HC; k++) {
+        const int c = hh * HC + k;
+        const double m = transposed ? M[c + rr * BS] : M[rr + c * BS];
+        if (k & 1) s1 = fma(m, v[c], s1); else s0 = fma(m, v[c], s0);
+      }
+    }
+    const double s = s0 + s1;
+    return s + __shfl_down_sync(0xffffffffu, s, BS);
+  };
   for (int seg = blockIdx.x * NW + warp; seg < a.nseg; seg += gridDim.x * NW) {
     const SegGeom sg = seg_geom(seg, a.n, a.sep, a.S, a.extL, a.extR);
     const int p = sg.p, q = sg.q, i0 = sg.i0, i1 = sg.i1;
@@ -1392,14 +1412,12 @@ __global__ void __launch_bounds__(128, 4) k_bwd2(const BwdArgs a) {
       const int n2 = (((i < i1) || (q >= 0)) ? F2 : BS * BS) / 2;   // Le of the last interior state exists only in front of a right separator
       for (int k = lane; k < n2; k += 32) cp_async16(&Fb[warp][st][2 * k], src + 2 * k);
     };
+    auto slot = [&](int i) -> double* { return (i - i0 < YC) ? &ysm[warp][(i - i0) * BS] : a.xsol + (size_t)i * BS; };
     // the (L^-1 | Le) of the first states start streaming in while the right-hand sides are formed
     fetch(i0, 0); cp_async_commit();
     if (i0 + 1 <= i1) fetch(i0 + 1, 1);
     cp_async_commit();
-    if (i0 + 2 <= i1) fetch(i0 + 2, 2);
-    cp_async_commit();
-    // ---- pass A: o_i = g_i - B_i x_l for every interior state (no recurrence: all loads of the segment are in flight together);
-    //      parked in xsol[i] until the sweep picks it up
+    // ---- pass A: o_i = g_i - B_i x_l for every interior state (no recurrence: all loads of the segment are in flight together)
     if (first) {
       // level 0: one LANE per state; the border is sparse (packed 128-byte entries, CSR by state)
       for (int i = i0 + lane; i <= i1; i += 32) {
@@ -1421,18 +1439,18 @@ __global__ void __launch_bounds__(128, 4) k_bwd2(const BwdArgs a) {
             for (int k = 0; k < BS; k++) o[k] -= ev[k] * sc;
           }
         }
-        double* dst = a.xsol + (size_t)i * BS;
+        double* dst = slot(i);
 #pragma unroll
         for (int k = 0; k < BS; k += 2) st128(dst + k, o[k], o[k + 1]);
       }
     } else {
-      // upper levels: dense border blocks B1 + B2 (BS x nb); lane = (row r, column group part), all loads of a state issued before its FMAs
+      // upper levels: dense border blocks B1 + B2 (BS x nb); lane = (row r, column group part), every load of a batch issued before its FMAs
       const int r = lane % BS, part = lane / BS;
       for (int i = i0; i <= i1; i++) {
         const double* B = a.brec + (size_t)i * (2 * BS * nb);
         double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-        for (int h = 0; h < 2; h++) {   // two batches of KH columns: every load of a batch is issued before its first FMA
+        for (int h = 0; h < 2; h++) {
           double b1[KH], b2[KH];
 #pragma unroll
           for (int k = 0; k < KH; k++) {
@@ -1451,96 +1469,65 @@ __global__ void __launch_bounds__(128, 4) k_bwd2(const BwdArgs a) {
         double sum = 0.0;
 #pragma unroll
         for (int pp = 0; pp < NPART; pp++) sum += __shfl_sync(0xffffffffu, tot, (r + pp * BS) & 31);
-        if (rl) { const double* g = a.rec + (size_t)i * REC1 + oG; a.xsol[(size_t)i * BS + lane] = g[lane] + g[BS + lane] - sum; }
+        if (rl) { const double* g = a.rec + (size_t)i * REC1 + oG; slot(i)[lane] = g[lane] + g[BS + lane] - sum; }
       }
     }
     __syncwarp();
-    // ---- forward sweep
-    double own = rl ? a.xsol[(size_t)i0 * BS + lane] : 0.0, t = 0.0;
-    if (p >= 0) {  // coupling of the first interior state to the left separator: E_p x_p
-      const double* E = a.rec + (size_t)p * RECS + oE;
+    // ---- forward sweep:  z_i = o_i - [i == i0] E_p x_p - Le_{i-1} y_{i-1},  y_i = L_i^-1 z_i
+    double t = 0.0;
+    if (p >= 0) {  // coupling of the first interior state to the left separator
       if (rl) v[lane] = xp;
       __syncwarp();
-      if (rl) {
-        double e0 = 0.0, e1 = 0.0;
-#pragma unroll
-        for (int c = 0; c < BS; c += 2) { e0 = fma(E[lane + c * BS], v[c], e0); e1 = fma(E[lane + (c + 1) * BS], v[c + 1], e1); }
-        own -= e0 + e1;
-      }
+      t = matvec(a.rec + (size_t)p * RECS + oE, false);
       __syncwarp();
     }
     int st = 0;
     for (int i = i0; i <= i1; i++) {
-      if (i + 3 <= i1) fetch(i + 3, st == 0 ? 3 : st - 1);
+      if (i + 2 <= i1) fetch(i + 2, st == 0 ? 2 : st - 1);
       cp_async_commit();
-      const double own_next = (rl && i + 1 <= i1) ? a.xsol[(size_t)(i + 1) * BS + lane] : 0.0;
-      cp_async_wait<3>();
+      double* ys = slot(i);
+      const double own = rl ? ys[lane] : 0.0;
+      cp_async_wait<2>();
       __syncwarp();
       const double* Li = Fb[warp][st];
       if (rl) v[lane] = own - t;
       __syncwarp();
-      double y0 = 0.0, y1 = 0.0;
-      if (rl) {
-#pragma unroll
-        for (int c = 0; c < BS; c += 2) { y0 = fma(Li[lane + c * BS], v[c], y0); y1 = fma(Li[lane + (c + 1) * BS], v[c + 1], y1); }  // strictly-upper part of L^-1 is stored as zeros
-      }
-      const double y = y0 + y1;
+      const double y = matvec(Li, false);   // the strictly-upper part of L^-1 is stored as zeros
       __syncwarp();
-      if (rl) { v[lane] = y; a.xsol[(size_t)i * BS + lane] = y; }
+      if (rl) { v[lane] = y; ys[lane] = y; }
       __syncwarp();
-      t = 0.0;
-      if (rl && i < i1) {
-        const double* Le = Li + BS * BS;
-        double t0 = 0.0, t1 = 0.0;
-#pragma unroll
-        for (int c = 0; c < BS; c += 2) { t0 = fma(Le[lane + c * BS], v[c], t0); t1 = fma(Le[lane + (c + 1) * BS], v[c + 1], t1); }
-        t = t0 + t1;
-      }
-      own = own_next;
+      t = (i < i1) ? matvec(Li + BS * BS, false) : 0.0;
       st = st == NST - 1 ? 0 : st + 1;
       __syncwarp();   // every lane is done with this state's stage before a later prefetch may overwrite it
     }
     cp_async_wait<0>();
     __syncwarp();
-    // ---- backward sweep
+    // ---- backward sweep:  x_i = L_i^-T (y_i - Le_i^T x_{i+1}),  x_{i1+1} = x_q
     fetch(i1, 0); cp_async_commit();
     if (i1 - 1 >= i0) fetch(i1 - 1, 1);
     cp_async_commit();
-    if (i1 - 2 >= i0) fetch(i1 - 2, 2);
-    cp_async_commit();
     bool hn = q >= 0;
     double xn = xq;   // lane r: entry r of x_{i+1}
-    double ycur = rl ? a.xsol[(size_t)i1 * BS + lane] : 0.0;
     st = 0;
     for (int i = i1; i >= i0; i--) {
-      if (i - 3 >= i0) fetch(i - 3, st == 0 ? 3 : st - 1);
+      if (i - 2 >= i0) fetch(i - 2, st == 0 ? 2 : st - 1);
       cp_async_commit();
-      const double ynext = (rl && i - 1 >= i0) ? a.xsol[(size_t)(i - 1) * BS + lane] : 0.0;
-      cp_async_wait<3>();
+      const double ycur = rl ? slot(i)[lane] : 0.0;
+      cp_async_wait<2>();
       __syncwarp();
       const double* Li = Fb[warp][st];
-      const double* Le = Li + BS * BS;
-      if (rl) v[lane] = xn;
-      __syncwarp();
       double w = ycur;
-      if (rl && hn) {
-        double t0 = 0.0, t1 = 0.0;
-#pragma unroll
-        for (int r = 0; r < BS; r += 2) { t0 = fma(Le[r + lane * BS], v[r], t0); t1 = fma(Le[r + 1 + lane * BS], v[r + 1], t1); }   // (Le^T x_{i+1})[lane]
-        w -= t0 + t1;
+      if (hn) {
+        if (rl) v[lane] = xn;
+        __syncwarp();
+        w -= matvec(Li + BS * BS, true);   // (Le^T x_{i+1})[lane]
+        __syncwarp();
       }
-      __syncwarp();
       if (rl) v[lane] = w;
       __syncwarp();
-      double x0 = 0.0, x1 = 0.0;
-      if (rl) {
-#pragma unroll
-        for (int r = 0; r < BS; r += 2) { x0 = fma(Li[r + lane * BS], v[r], x0); x1 = fma(Li[r + 1 + lane * BS], v[r + 1], x1); }   // (L^-T w)[lane]; zeros above the diagonal
-      }
-      xn = x0 + x1;
+      xn = matvec(Li, true);               // (L^-T w)[lane]
       if (rl) a.xsol[(size_t)i * BS + lane] = xn;
       hn = true;
-      ycur = ynext;
       __syncwarp();
       st = st == NST - 1 ? 0 : st + 1;
     }

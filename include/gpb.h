@@ -241,6 +241,10 @@ int gpb_stream_synchronize(void* cuda_stream);
 /* profiling aid: measured FP64 tensor-pipe (mma.sync m8n8k4, SASS DMMA) peak of the device in TFLOP/s - the roofline
  * denominator of the panel kernel */
 int gpb_debug_dmma_peak(int device, double* tflops_out);
+/* profiling aid: dependent-issue latency, in SM clocks per operation, of the instructions the latency-bound solver kernels chain:
+ * out[0] DFMA, [1] DMUL, [2] DMMA m8n8k4 (same accumulator), [3] 64-bit shuffle, [4] shared-memory load, [5] rsqrt (MUFU seed +
+ * third-order correction + 1 add), [6] DADD, [7] global load served by L2 */
+int gpb_debug_latency(int device, double* out8);
 /* profiling aid: microseconds to write n_factors SE(3) [A|b] records (2400 B each) in k_lin_gp's store pattern with no arithmetic
  * in front (mode 4: the tiled layout the engine uses; 1: untiled SoA, row pairs NFp*16 B apart; 2: 1 with streaming stores; 3: 1 with
  * 256-thread CTAs) or with cudaMemsetAsync (mode 0) - the floor of the layout */

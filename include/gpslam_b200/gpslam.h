@@ -677,7 +677,10 @@ class PriorFactor : public NonlinearFactor {
     double v[12];
     detail::wire(prior_, v);
     const gtsam::Matrix& R = detail::sqrtInfo(model_);
-    const char c = gtsam::symbolChr(keys_[0]);
+    // the role of the key comes from the optimiser's maps, not from its name: lidx holds landmarks (index >= 0) and tags
+    // velocity keys with -1, angular-velocity keys of a VW graph with -2; any other key is a pose
+    const auto lit = lidx.find(keys_[0]);
+    const char c = lit == lidx.end() ? 'x' : (lit->second >= 0 ? 'l' : (lit->second == -2 ? 'w' : 'v'));
     if (c == 'l') detail::check(gpb_add_prior_landmark(g, detail::stateOf(lidx, keys_[0]), v, R.a.data()));
     else if ((c == 'v' || c == 'w') && gpb_graph_group(g) == GPB_POSE3VW) {
       // PriorFactor<Vector3> on the linear ('v') or angular ('w') velocity of a VW state: a 6x6 sqrt information over [v | w] whose
@@ -841,6 +844,7 @@ class NonlinearOptimizer {
       for (const auto& kv : ls) { lidx[kv.second] = static_cast<int>(lkeys_.size()); lkeys_.push_back(kv.second); }
     }
     if (xkeys_.size() < 2) throw std::runtime_error("gpslam_b200: need at least two states");
+    for (size_t i = 0; i < xkeys_.size(); i++) { lidx[vkeys_[i]] = -1; if (vw_) lidx[wkeys_[i]] = -2; }   // key roles for PriorFactor (see its lower())
     const bool se3 = group == GPB_POSE3 || vw_;
     PS_ = se3 ? 12 : group == GPB_ROT3 ? 9 : 3; D_ = se3 ? 6 : 3; DL_ = se3 ? 3 : group == GPB_ROT3 ? 0 : 2;
     g_ = gpb_graph_create(group, 3, static_cast<int>(xkeys_.size()), static_cast<int>(lkeys_.size()));

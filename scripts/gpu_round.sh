@@ -9,7 +9,8 @@ for s in $STEPS; do
     tests_fast) timeout 900 python -m pytest tests -m gpu -x -q --deselect tests/test_gpu_fullsize.py > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/${TAG}_pytest.log;;
     bench) timeout 900 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"; cat gpurun_out/${TAG}_bench.json | head -c 6000; tail -3 gpurun_out/${TAG}_bench.err;;
     benchfast) timeout 600 python bench.py --no-cpu > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"; cat gpurun_out/${TAG}_bench.json | head -c 6000; tail -3 gpurun_out/${TAG}_bench.err;;
-    ab) timeout 600 python scripts/ab_variants.py ${AB_SPECS:-"" "GPB_OLD_BWD=1"} > gpurun_out/${TAG}_ab.jsonl 2> gpurun_out/${TAG}_ab.err; echo "ab rc=$?"; cat gpurun_out/${TAG}_ab.jsonl; tail -3 gpurun_out/${TAG}_ab.err;;
+    ab) eval timeout 600 python scripts/ab_variants.py ${AB_SPECS:-'"" "GPB_DENSE_PANEL=1"'} > gpurun_out/${TAG}_ab.jsonl 2> gpurun_out/${TAG}_ab.err; echo "ab rc=$?"; cat gpurun_out/${TAG}_ab.jsonl; tail -3 gpurun_out/${TAG}_ab.err;;
+    lat) python -c "from gpslam_b200 import capi; import json; print(json.dumps(capi.latencies()))" | tee gpurun_out/${TAG}_latency.json;;
     san) bash scripts/sanitize.sh ${TAG};;
     race) CS=/usr/local/cuda/bin/compute-sanitizer
           timeout 420 $CS --tool racecheck --racecheck-report all --error-exitcode 9 python scripts/sanitize_cases.py pose3_wide 1 > gpurun_out/${TAG}_racecheck.log 2>&1; echo "racecheck pose3_wide rc=$?"
