@@ -973,6 +973,21 @@ template <int G> static int launch_assemble(gpb_graph* g, int buf) {
   constexpr int NT = 128, bs = 2 * GroupTraits<G>::D, TILES = bs == 12 ? 4 : 1;
   const int states_per_cta = 32 * (NT / (32 * TILES));
   const int nblk = (g->N + states_per_cta - 1) / states_per_cta;
+  // the landmark block and the packed border entries depend on the measurement rows only: they run on the side stream beside
+  // the state-record assembly and are joined before the solve
+  const bool fork = g->nb > 0;
+  if (fork) {
+    CUDA_TRY(cudaEventRecord(g->ev_fork, g->stream));
+    CUDA_TRY(cudaStreamWaitEvent(g->stream2, g->ev_fork, 0));
+    CUDA_TRY(cudaMemsetAsync(g->d_Cbase, 0, (size_t)(g->nb * g->nb + g->nb) * sizeof(double), g->stream2));
+    k_landmark_base<512><<<g->L, 512, 0, g->stream2>>>(g->d_XR[buf], g->d_lmoff, g->d_lmrows, g->NXRp, 2 * bs, g->DL, g->nb, g->d_Cbase);
+    g->launches++;
+    if (g->nbent > 0) {  // consumed by the level-0 panel kernel (64-column panels) and by the back-substitution
+      k_border_pack<<<(g->nbent * 16 + 255) / 256, 256, 0, g->stream2>>>(g->d_XR[buf], g->d_bsrow, g->d_bsside, g->d_rowland, g->nbent, bs, g->DL, g->NXRp, g->d_bent);
+      g->launches++;
+    }
+    CUDA_TRY(cudaEventRecord(g->ev_join, g->stream2));
+  }
   if (G == G_POSE3 && !g->old_assemble) k_assemble_mma<<<(g->N + 7) / 8, 128, 0, g->stream>>>(g->d_AB[buf], g->NX ? g->d_XR[buf] : nullptr, g->d_rowoff, g->d_HREC, g->N, g->NFp, g->NXRp, g->ncolsX - 1);
   else k_assemble<G, NT><<<nblk, NT, 0, g->stream>>>(g->d_AB[buf], g->d_dt, g->NX ? g->d_XR[buf] : nullptr, g->d_rowoff, g->d_HREC, g->N, g->NFp, g->NXRp);
   g->launches++;
@@ -980,15 +995,7 @@ template <int G> static int launch_assemble(gpb_graph* g, int buf) {
     k_assemble_closures<<<g->nep, 64, 0, g->stream>>>(g->d_XR[buf], g->NXRp, bs, GroupTraits<G>::D, g->ncolsX - 1, g->d_epstate, g->d_epoff, g->d_eprow, g->d_epside, g->d_HREC);
     g->launches++;
   }
-  if (g->nb) {
-    CUDA_TRY(cudaMemsetAsync(g->d_Cbase, 0, (size_t)(g->nb * g->nb + g->nb) * sizeof(double), g->stream));
-    k_landmark_base<512><<<g->L, 512, 0, g->stream>>>(g->d_XR[buf], g->d_lmoff, g->d_lmrows, g->NXRp, 2 * bs, g->DL, g->nb, g->d_Cbase);
-    g->launches++;
-    if (g->nbent > 0) {  // consumed by the level-0 panel kernel (64-column panels) and by the back-substitution
-      k_border_pack<<<(g->nbent * 16 + 255) / 256, 256, 0, g->stream>>>(g->d_XR[buf], g->d_bsrow, g->d_bsside, g->d_rowland, g->nbent, bs, g->DL, g->NXRp, g->d_bent);
-      g->launches++;
-    }
-  }
+  if (fork) CUDA_TRY(cudaStreamWaitEvent(g->stream, g->ev_join, 0));
   CUDA_TRY(cudaGetLastError());
   return GPB_OK;
 }
@@ -1039,13 +1046,7 @@ static int launch_fwd_level(gpb_graph* g, int buf, double lambda, int lev, int p
     if (bs == 12) fwd_w<12>(g->W, a, L.ncta, g->stream); else fwd_w<6>(g->W, a, L.ncta, g->stream);
     g->launches++;
   }
-  if (nb) {
-    const int R = std::min(16, L.ncta);
-    dim3 grid((centries + 255) / 256, R);
-    k_cseg_reduce<<<grid, 256, 0, g->stream>>>(L.cseg, L.ncta, centries, R, g->d_Cpart + (size_t)lev * 16 * centries);
-    if (R < 16) CUDA_TRY(cudaMemsetAsync(g->d_Cpart + ((size_t)lev * 16 + R) * centries, 0, (size_t)(16 - R) * centries * sizeof(double), g->stream));
-    g->launches++;
-  }
+  (void)centries;  // the per-CTA landmark blocks of every level are summed once, in top_pack (k_cseg_reduce_all)
   return GPB_OK;
 }
 
@@ -1124,7 +1125,14 @@ static int solve_top_dense(gpb_graph* g) {
 static bool top_is_landmarks_only(const gpb_graph* g) { return g->world == 1 && g->P == 0; }
 static int top_pack(gpb_graph* g, int buf, double err_local, bool async) {
   const int nb = g->nb, centries = nb * nb + nb, nel = num_elim_levels(g), R = g->R;
-  if (nb) { k_cseg_final<<<(centries + 127) / 128, 128, 0, g->stream>>>(g->d_Cbase, g->d_Cpart, 16 * nel, centries, g->d_Csum); g->launches++; }
+  if (nb) {
+    CsegLevels lv; lv.n = 0;
+    for (int v = 0; v < nel && lv.n < 24; v++) { lv.ptr[lv.n] = g->levels[v].cseg; lv.ncta[lv.n] = g->levels[v].ncta; lv.n++; }
+    if (nel > 24) return fail(GPB_ERR_UNSUPPORTED, "more than 24 elimination levels (raise the upper segment length)");
+    k_cseg_reduce_all<<<dim3((centries + 255) / 256, 16), 256, 0, g->stream>>>(lv, centries, 16, g->d_Cpart);
+    k_cseg_final<<<(centries + 127) / 128, 128, 0, g->stream>>>(g->d_Cbase, g->d_Cpart, 16, centries, g->d_Csum);
+    g->launches += 2;
+  }
   if (top_is_landmarks_only(g)) return GPB_OK;
   const long long total = (long long)(R + 1) * R + 4;
   CUDA_TRY(cudaMemsetAsync(g->d_topbuf, 0, (size_t)total * sizeof(double), g->stream));

@@ -1585,6 +1585,24 @@ __global__ void k_cseg_reduce(const double* __restrict__ cseg, int nblocks, int 
   out[(size_t)slice * entries + e] = s;
 }
 
+// the same over every level at once (one launch per solve instead of one per level): slice s sums block b of level v when
+// (b + first block of v) mod R == s, walking the levels in order - fixed order, deterministic
+struct CsegLevels { const double* ptr[24]; int ncta[24]; int n; };
+__global__ void k_cseg_reduce_all(const CsegLevels lv, int entries, int R, double* __restrict__ out) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int slice = blockIdx.y;
+  if (e >= entries) return;
+  double s = 0.0;
+  int base = 0;
+  for (int v = 0; v < lv.n; v++) {
+    const double* c = lv.ptr[v];
+    int b = slice - base % R; if (b < 0) b += R;
+    for (; b < lv.ncta[v]; b += R) s += c[(size_t)b * entries + e];
+    base += lv.ncta[v];
+  }
+  out[(size_t)slice * entries + e] = s;
+}
+
 // stage 2: C = Cbase + sum over all level/slice partials  (many CTAs; fixed order -> deterministic)
 __global__ void k_cseg_final(const double* __restrict__ Cbase, const double* __restrict__ parts, int nparts, int entries, double* __restrict__ Csum) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;

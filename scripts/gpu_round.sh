@@ -11,6 +11,7 @@ for s in $STEPS; do
     benchfast) timeout 600 python bench.py --no-cpu > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"; cat gpurun_out/${TAG}_bench.json | head -c 6000; tail -3 gpurun_out/${TAG}_bench.err;;
     ab) eval timeout 600 python scripts/ab_variants.py ${AB_SPECS:-'"" "GPB_DENSE_PANEL=1"'} > gpurun_out/${TAG}_ab.jsonl 2> gpurun_out/${TAG}_ab.err; echo "ab rc=$?"; cat gpurun_out/${TAG}_ab.jsonl; tail -3 gpurun_out/${TAG}_ab.err;;
     lat) python -c "from gpslam_b200 import capi; import json; print(json.dumps(capi.latencies()))" | tee gpurun_out/${TAG}_latency.json;;
+    launches) timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv python scripts/one_iter.py ${NCU_CFG:-C3} ${NCU_STATES:-0} 3 > gpurun_out/${TAG}_launches.log 2>&1; echo "ncu launches rc=$?"; python scripts/ncu_summaries.py ${TAG} > /dev/null 2>&1; cat profiles/${TAG}_launch_shares.txt | head -30; cp profiles/${TAG}_launch_shares.txt gpurun_out/;;
     san) bash scripts/sanitize.sh ${TAG};;
     race) CS=/usr/local/cuda/bin/compute-sanitizer
           timeout 420 $CS --tool racecheck --racecheck-report all --error-exitcode 9 python scripts/sanitize_cases.py pose3_wide 1 > gpurun_out/${TAG}_racecheck.log 2>&1; echo "racecheck pose3_wide rc=$?"
