@@ -840,8 +840,8 @@ int gpb_graph_finalize(gpb_graph* g, int device) {
       cpin.swap(npin); corig.swap(norig); lev++;
     }
   }
-  if ((rc = dev_alloc(g, &g->d_Cpart, (size_t)16 * g->levels.size() * std::max(centries, 1)))) return rc;
-  CUDA_TRY(cudaMemset(g->d_Cpart, 0, (size_t)16 * g->levels.size() * std::max(centries, 1) * sizeof(double)));
+  if ((rc = dev_alloc(g, &g->d_Cpart, (size_t)64 * std::max(centries, 1)))) return rc;
+  CUDA_TRY(cudaMemset(g->d_Cpart, 0, (size_t)64 * std::max(centries, 1) * sizeof(double)));
   if ((rc = dev_alloc(g, &g->d_Csum, (size_t)std::max(centries, 1)))) return rc;
   // ---- the reduced (top) system: global top indices of this graph's pinned states
   g->P = (int)top_state.size();
@@ -1071,8 +1071,14 @@ static int solve_backward(gpb_graph* g) {
     if (g->old_bwd) { if (bs == 12) bwd_w<12>(g->W, b, L.ncta_bwd, g->stream); else bwd_w<6>(g->W, b, L.ncta_bwd, g->stream); }
     else {
       // one warp per segment, four per CTA; up to 16 resident warps per SM
-      const int nblk = std::min((L.nseg + 3) / 4, g->sms * 4);
-      if (bs == 12) k_bwd2<12><<<nblk, 128, 0, g->stream>>>(b); else k_bwd2<6><<<nblk, 128, 0, g->stream>>>(b);
+      // level 0: one warp per segment, four per CTA; above: a CTA per segment (dense border blocks: the warps share the rhs pass)
+      if (lev == 0) {
+        const int nblk = std::min((L.nseg + 3) / 4, g->sms * 4);
+        if (bs == 12) k_bwd2<12, false><<<nblk, 128, 0, g->stream>>>(b); else k_bwd2<6, false><<<nblk, 128, 0, g->stream>>>(b);
+      } else {
+        const int nblk = std::min(L.nseg, g->sms * 4);
+        if (bs == 12) k_bwd2<12, true><<<nblk, 128, 0, g->stream>>>(b); else k_bwd2<6, true><<<nblk, 128, 0, g->stream>>>(b);
+      }
     }
     g->launches++;
   }
@@ -1129,8 +1135,8 @@ static int top_pack(gpb_graph* g, int buf, double err_local, bool async) {
     CsegLevels lv; lv.n = 0;
     for (int v = 0; v < nel && lv.n < 24; v++) { lv.ptr[lv.n] = g->levels[v].cseg; lv.ncta[lv.n] = g->levels[v].ncta; lv.n++; }
     if (nel > 24) return fail(GPB_ERR_UNSUPPORTED, "more than 24 elimination levels (raise the upper segment length)");
-    k_cseg_reduce_all<<<dim3((centries + 255) / 256, 16), 256, 0, g->stream>>>(lv, centries, 16, g->d_Cpart);
-    k_cseg_final<<<(centries + 127) / 128, 128, 0, g->stream>>>(g->d_Cbase, g->d_Cpart, 16, centries, g->d_Csum);
+    k_cseg_reduce_all<<<dim3((centries + 127) / 128, 64), 128, 0, g->stream>>>(lv, centries, 64, g->d_Cpart);
+    k_cseg_final<<<(centries + 63) / 64, 64, 0, g->stream>>>(g->d_Cbase, g->d_Cpart, 64, centries, g->d_Csum);
     g->launches += 2;
   }
   if (top_is_landmarks_only(g)) return GPB_OK;

@@ -1364,7 +1364,9 @@ __global__ void __launch_bounds__((W < 32 ? 32 : W)) k_bwd(const BwdArgs a) {
 // hidden by 16 independent warps per SM); lane r owns row r; (L^-1 | Le) stream through a per-warp cp.async ring; y_i waits in
 // xsol[i] between the sweeps.  The same arithmetic as eliminating the right-hand side column with the known separator values
 // substituted, i.e. the result equals the Y-based form up to rounding order.
-template <int BS>
+// CTASEG (upper levels: few segments, dense border blocks): one CTA per segment - the four warps share the right-hand-side pass
+// (a state each at a time), warp 0 then runs the two sweeps.  Otherwise (level 0) one warp per segment, four segments per CTA.
+template <int BS, bool CTASEG>
 __global__ void __launch_bounds__(128, 4) k_bwd2(const BwdArgs a) {
   constexpr int NW = 4, NST = 3, F2 = 2 * BS * BS, REC0 = 2 * BS * BS + BS, REC1 = 3 * BS * BS + 2 * BS, YC = 48, HC = BS / 2;
   constexpr int DLC = BS == 12 ? 3 : 2;   // landmark dimension of the groups with this block size (SO(3) chains carry no border)
@@ -1383,6 +1385,8 @@ __global__ void __launch_bounds__(128, 4) k_bwd2(const BwdArgs a) {
   for (int k = threadIdx.x; k < 64; k += 128) xls[k] = k < nb ? a.xl[k] : 0.0;
   __syncthreads();
   double* const v = vec[warp];
+  const int yw = CTASEG ? 0 : warp;           // whose y slots / staging ring the segment uses
+  const bool sweeper = !CTASEG || warp == 0;  // this warp runs the sweeps of the segment
   // y = M v (row form) or M^T v (column form) for a BS x BS column-major block in shared memory; valid on lanes < BS
   auto matvec = [&](const double* M, bool transposed) -> double {
     double s0 = 0.0, s1 = 0.0;
@@ -1397,11 +1401,11 @@ __global__ void __launch_bounds__(128, 4) k_bwd2(const BwdArgs a) {
     const double s = s0 + s1;
     return s + __shfl_down_sync(0xffffffffu, s, BS);
   };
-  for (int seg = blockIdx.x * NW + warp; seg < a.nseg; seg += gridDim.x * NW) {
+  for (int seg = CTASEG ? blockIdx.x : blockIdx.x * NW + warp; seg < a.nseg; seg += CTASEG ? gridDim.x : gridDim.x * NW) {
     const SegGeom sg = seg_geom(seg, a.n, a.sep, a.S, a.extL, a.extR);
     const int p = sg.p, q = sg.q, i0 = sg.i0, i1 = sg.i1;
     double xq = 0.0, xp = 0.0;   // lane c: entry c of the right / left separator solution
-    if (rl) {
+    if (rl && sweeper) {
       if (q >= 0) { xq = a.xup[(size_t)sg.qo * BS + lane]; a.xsol[(size_t)q * BS + lane] = xq; }
       if (p >= 0) xp = a.xup[(size_t)sg.po * BS + lane];
       if (a.extL && seg == 0) a.xsol[lane] = a.xup[lane];  // external left separator: copy its solution down
@@ -1410,17 +1414,19 @@ __global__ void __launch_bounds__(128, 4) k_bwd2(const BwdArgs a) {
     auto fetch = [&](int i, int st) {
       const double* src = a.frec + (size_t)i * a.fstride;
       const int n2 = (((i < i1) || (q >= 0)) ? F2 : BS * BS) / 2;   // Le of the last interior state exists only in front of a right separator
-      for (int k = lane; k < n2; k += 32) cp_async16(&Fb[warp][st][2 * k], src + 2 * k);
+      for (int k = lane; k < n2; k += 32) cp_async16(&Fb[yw][st][2 * k], src + 2 * k);
     };
-    auto slot = [&](int i) -> double* { return (i - i0 < YC) ? &ysm[warp][(i - i0) * BS] : a.xsol + (size_t)i * BS; };
+    auto slot = [&](int i) -> double* { return (i - i0 < YC) ? &ysm[yw][(i - i0) * BS] : a.xsol + (size_t)i * BS; };
     // the (L^-1 | Le) of the first states start streaming in while the right-hand sides are formed
-    fetch(i0, 0); cp_async_commit();
-    if (i0 + 1 <= i1) fetch(i0 + 1, 1);
-    cp_async_commit();
+    if (sweeper) {
+      fetch(i0, 0); cp_async_commit();
+      if (i0 + 1 <= i1) fetch(i0 + 1, 1);
+      cp_async_commit();
+    }
     // ---- pass A: o_i = g_i - B_i x_l for every interior state (no recurrence: all loads of the segment are in flight together)
     if (first) {
       // level 0: one LANE per state; the border is sparse (packed 128-byte entries, CSR by state)
-      for (int i = i0 + lane; i <= i1; i += 32) {
+      for (int i = i0 + lane + (sweeper ? 0 : a.n); i <= i1; i += 32) {
         const double* r = a.rec + (size_t)i * REC0 + oG;
         double o[BS];
 #pragma unroll
@@ -1446,7 +1452,7 @@ __global__ void __launch_bounds__(128, 4) k_bwd2(const BwdArgs a) {
     } else {
       // upper levels: dense border blocks B1 + B2 (BS x nb); lane = (row r, column group part), every load of a batch issued before its FMAs
       const int r = lane % BS, part = lane / BS;
-      for (int i = i0; i <= i1; i++) {
+      for (int i = i0 + (CTASEG ? warp : 0); i <= i1; i += CTASEG ? NW : 1) {
         const double* B = a.brec + (size_t)i * (2 * BS * nb);
         double s0 = 0.0, s1 = 0.0;
 #pragma unroll
@@ -1472,7 +1478,8 @@ __global__ void __launch_bounds__(128, 4) k_bwd2(const BwdArgs a) {
         if (rl) { const double* g = a.rec + (size_t)i * REC1 + oG; slot(i)[lane] = g[lane] + g[BS + lane] - sum; }
       }
     }
-    __syncwarp();
+    if constexpr (CTASEG) __syncthreads(); else __syncwarp();
+    if (sweeper) {
     // ---- forward sweep:  z_i = o_i - [i == i0] E_p x_p - Le_{i-1} y_{i-1},  y_i = L_i^-1 z_i
     double t = 0.0;
     if (p >= 0) {  // coupling of the first interior state to the left separator
@@ -1489,7 +1496,7 @@ __global__ void __launch_bounds__(128, 4) k_bwd2(const BwdArgs a) {
       const double own = rl ? ys[lane] : 0.0;
       cp_async_wait<2>();
       __syncwarp();
-      const double* Li = Fb[warp][st];
+      const double* Li = Fb[yw][st];
       if (rl) v[lane] = own - t;
       __syncwarp();
       const double y = matvec(Li, false);   // the strictly-upper part of L^-1 is stored as zeros
@@ -1515,7 +1522,7 @@ __global__ void __launch_bounds__(128, 4) k_bwd2(const BwdArgs a) {
       const double ycur = rl ? slot(i)[lane] : 0.0;
       cp_async_wait<2>();
       __syncwarp();
-      const double* Li = Fb[warp][st];
+      const double* Li = Fb[yw][st];
       double w = ycur;
       if (hn) {
         if (rl) v[lane] = xn;
@@ -1533,6 +1540,8 @@ __global__ void __launch_bounds__(128, 4) k_bwd2(const BwdArgs a) {
     }
     cp_async_wait<0>();
     __syncwarp();
+    }  // sweeper
+    if constexpr (CTASEG) __syncthreads();   // the y slots and the staging ring are free for the CTA's next segment
   }
 }
 
@@ -1592,24 +1601,30 @@ __global__ void k_cseg_reduce_all(const CsegLevels lv, int entries, int R, doubl
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   const int slice = blockIdx.y;
   if (e >= entries) return;
-  double s = 0.0;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;   // four independent chains: the loads of a batch are in flight together
   int base = 0;
   for (int v = 0; v < lv.n; v++) {
-    const double* c = lv.ptr[v];
+    const double* c = lv.ptr[v] + e;
+    const int n = lv.ncta[v];
     int b = slice - base % R; if (b < 0) b += R;
-    for (; b < lv.ncta[v]; b += R) s += c[(size_t)b * entries + e];
-    base += lv.ncta[v];
+    for (; b + 3 * R < n; b += 4 * R) {
+      s0 += c[(size_t)b * entries]; s1 += c[(size_t)(b + R) * entries]; s2 += c[(size_t)(b + 2 * R) * entries]; s3 += c[(size_t)(b + 3 * R) * entries];
+    }
+    for (; b < n; b += R) s0 += c[(size_t)b * entries];
+    base += n;
   }
-  out[(size_t)slice * entries + e] = s;
+  out[(size_t)slice * entries + e] = (s0 + s1) + (s2 + s3);
 }
 
 // stage 2: C = Cbase + sum over all level/slice partials  (many CTAs; fixed order -> deterministic)
 __global__ void k_cseg_final(const double* __restrict__ Cbase, const double* __restrict__ parts, int nparts, int entries, double* __restrict__ Csum) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= entries) return;
-  double s = Cbase[e];
-  for (int k = 0; k < nparts; k++) s += parts[(size_t)k * entries + e];
-  Csum[e] = s;
+  double s0 = Cbase[e], s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  int k = 0;
+  for (; k + 3 < nparts; k += 4) { s0 += parts[(size_t)k * entries + e]; s1 += parts[(size_t)(k + 1) * entries + e]; s2 += parts[(size_t)(k + 2) * entries + e]; s3 += parts[(size_t)(k + 3) * entries + e]; }
+  for (; k < nparts; k++) s0 += parts[(size_t)k * entries + e];
+  Csum[e] = (s0 + s1) + (s2 + s3);
 }
 
 // Small dense SPD solve in shared memory, single CTA:  (A + lambda * diag[loff..R)) x = rhs,  R <= SMALL_SOLVE_MAX.
