@@ -130,7 +130,8 @@ struct gpb_graph {
   int *d_epstate = nullptr, *d_epoff = nullptr, *d_eprow = nullptr, *d_epside = nullptr;
   int *d_pair_a = nullptr, *d_pair_b = nullptr, *d_pairoff = nullptr, *d_pairrow = nullptr;
   bool generic_fwd = false, force_blocked = false, old_assemble = false, split_levels = false, no_tiny = false, fuse_l0 = false, old_bwd = false;
-  int panel0_occ = 5;         // CTAs per SM the level-0 active-column panel kernel is compiled for (GPB_PANEL0_OCC = 4: 128 registers, no spills)
+  bool thread_chain = false;  // 6 x 6 chains without a landmark border: thread-per-segment kernels (k_fwd6t / k_bwd6t); GPB_NO_THREAD_CHAIN = generic kernels
+  int panel0_occ = 4;         // CTAs per SM the level-0 active-column panel kernel is compiled for (GPB_PANEL0_OCC = 4: 128 registers, no spills)
   bool dense_panel = false;   // A/B switch GPB_DENSE_PANEL: k_panel4 (all 64 columns at every state) instead of k_panel0 (active columns only)
   unsigned char *d_lorder = nullptr, *d_ntile = nullptr;  // k_panel0: per-segment landmark order [nseg][17], active column tiles per state [N]
   int fstride = 0;  // doubles per state of a level's factor record: (L^-1 | Le), + Y for the Y-reading back-substitution
@@ -560,7 +561,7 @@ static int bwd_blocks_per_sm(int bs, int W) {
   if (bs == 12) return W == 16 ? occ_bwd<12, 16>() : W == 32 ? occ_bwd<12, 32>() : occ_bwd<12, 64>();
   return W == 16 ? occ_bwd<6, 16>() : W == 32 ? occ_bwd<6, 32>() : occ_bwd<6, 64>();
 }
-static int fwd_blocks_per_sm(int bs, int W, bool fuse_l0 = false, int panel0_occ = 5) {
+static int fwd_blocks_per_sm(int bs, int W, bool fuse_l0 = false, int panel0_occ = 4) {
   if (bs == 12 && W == 64) {
     int nb = 0;
     if (fuse_l0) { if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_level0_ws<12>, 160, 0) != cudaSuccess) { cudaGetLastError(); nb = 4; } return nb < 1 ? 1 : nb; }
@@ -734,7 +735,7 @@ int gpb_graph_finalize(gpb_graph* g, int device) {
   g->fuse_l0 = getenv("GPB_FUSE_L0") != nullptr;
   g->old_bwd = getenv("GPB_OLD_BWD") != nullptr;
   g->dense_panel = getenv("GPB_DENSE_PANEL") != nullptr || g->old_bwd;
-  if (const char* ev = getenv("GPB_PANEL0_OCC")) g->panel0_occ = atoi(ev) == 4 ? 4 : 5;  // the Y-reading back-substitution needs the dense kernel's Y layout  // A/B switch: back-substitution from a stored Y (k_bwd) instead of re-eliminating the right-hand side (k_bwd2)  // A/B switch: level 0 as ONE warp-specialised kernel (spine warp + panel warps per CTA)
+  if (const char* ev = getenv("GPB_PANEL0_OCC")) g->panel0_occ = atoi(ev) == 5 ? 5 : 4;  // the Y-reading back-substitution needs the dense kernel's Y layout  // A/B switch: back-substitution from a stored Y (k_bwd) instead of re-eliminating the right-hand side (k_bwd2)  // A/B switch: level 0 as ONE warp-specialised kernel (spine warp + panel warps per CTA)
   g->no_tiny = getenv("GPB_NO_TINY_SOLVE") != nullptr;  // A/B switch: the plain-loop instantiation of k_small_solve instead of the register-blocked ones
   g->qc_diag = 1;
   for (const auto& R : g->Rq) for (int c = 0; c < D; c++) for (int r = 0; r < D; r++) if (r != c && R[r + c * D] != 0.0) g->qc_diag = 0;
@@ -744,6 +745,9 @@ int gpb_graph_finalize(gpb_graph* g, int device) {
     if (v >= 0 && v <= 3 && (!(v & 1) || g->qc_diag)) g->lin_variant = v;
   }  // A/B switch: one-kernel generic forward sweep (k_fwd<12,64>)
   int M0 = g->M0 ? g->M0 : (em0 ? std::max(2, atoi(em0)) : (g->nb > 0 ? 32 : 16));
+  g->thread_chain = bs == 6 && g->nb == 0 && !g->generic_fwd && !g->old_bwd && getenv("GPB_NO_THREAD_CHAIN") == nullptr;
+  // one thread per segment: about one resident wave of 256 threads per SM, segments of 8 .. 64 states
+  if (g->thread_chain && !g->M0 && !em0) M0 = std::min(64, std::max(8, (g->N + sms * 256 - 1) / (sms * 256)));
   // upper levels: 8 states per segment; 6 on short chains (shards of a few 10k states), where one more level of shorter
   // segments wins (measured on 12.5k / 25k / 50k / 100k states: -3 %, -2 %, 0, +1 %; gpurun_out/r1z_small_sweep2.jsonl)
   const int Mup = g->Mup ? g->Mup : (emu ? std::max(2, atoi(emu)) : (g->N <= 40000 ? 6 : 8));
@@ -1026,7 +1030,10 @@ static int launch_fwd_level(gpb_graph* g, int buf, double lambda, int lev, int p
   a.lambda_ptr = g->d_lambda;
   a.rec_out = lev + 1 < nlev ? g->levels[lev + 1].rec : nullptr; a.brec_out = lev + 1 < nlev ? g->levels[lev + 1].brec : nullptr;
   a.frec = L.frec; a.fstride = fstride; a.cseg = L.cseg; a.flag = g->d_flag; a.store_y = g->old_bwd ? 1 : 0;
-  if (bs == 12 && g->W == 64 && !g->generic_fwd) {
+  if (g->thread_chain) {
+    if (lev == 0) k_fwd6t<true><<<(L.nseg + 63) / 64, 64, 0, g->stream>>>(a); else k_fwd6t<false><<<(L.nseg + 63) / 64, 64, 0, g->stream>>>(a);
+    g->launches++;
+  } else if (bs == 12 && g->W == 64 && !g->generic_fwd) {
     // spine first (warp per segment: the latency-bound 12x12 recurrence wants many independent warps), then the tensor-pipe panel
     const int spine_ctas = std::min(L.nseg, 16 * g->sms);
     if (lev == 0 && parts == 3 && g->fuse_l0) {
@@ -1069,7 +1076,9 @@ static int solve_backward(gpb_graph* g) {
     b.xup = lev + 1 < nlev ? g->levels[lev + 1].xsol : nullptr; b.xl = g->d_xlm; b.xsol = L.xsol;
     b.first_level = lev == 0; b.DL = std::max(g->DL, 1); b.rec = lev == 0 ? g->d_HREC : L.rec; b.brec = L.brec; b.bsoff = g->d_bsoff; b.bent = g->d_bent;
     if (g->old_bwd) { if (bs == 12) bwd_w<12>(g->W, b, L.ncta_bwd, g->stream); else bwd_w<6>(g->W, b, L.ncta_bwd, g->stream); }
-    else {
+    else if (g->thread_chain) {
+      if (lev == 0) k_bwd6t<true><<<(L.nseg + 127) / 128, 128, 0, g->stream>>>(b); else k_bwd6t<false><<<(L.nseg + 127) / 128, 128, 0, g->stream>>>(b);
+    } else {
       // one warp per segment, four per CTA; up to 16 resident warps per SM
       // level 0: one warp per segment, four per CTA; above: a CTA per segment (dense border blocks: the warps share the rhs pass)
       if (lev == 0) {

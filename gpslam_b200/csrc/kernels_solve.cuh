@@ -1545,6 +1545,281 @@ __global__ void __launch_bounds__(128, 4) k_bwd2(const BwdArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Chains of 6 x 6 blocks without a landmark border (SO(3) AHRS graphs - BASELINE config C4 -, Pose2 / Linear chains with no
+// landmarks): ONE THREAD PER SEGMENT, everything in registers.  The panel is 7 columns (6 spike + the right-hand side), a state costs
+// about 900 FMAs and no synchronisation at all; a million states in 26-state segments are 38 000 independent threads - one
+// resident wave of the chip.  Same elimination, record formats and end-of-segment hand-off as k_fwd<6, 16> (which needed a CTA and
+// ~5 us per state for the same work).  tri(r, c): packed lower triangle.
+__host__ __device__ constexpr int tri(int r, int c) { return r * (r + 1) / 2 + c; }
+template <bool FIRST>
+__global__ void __launch_bounds__(64) k_fwd6t(const FwdArgs a) {
+  constexpr int BS = 6, REC0 = 2 * BS * BS + BS, REC1 = 3 * BS * BS + 2 * BS, RECS = FIRST ? REC0 : REC1;
+  constexpr int oE = FIRST ? BS * BS : 2 * BS * BS, oG = FIRST ? 2 * BS * BS : 3 * BS * BS;
+  const int seg = blockIdx.x * blockDim.x + threadIdx.x;
+  if (seg >= a.nseg) return;
+  const SegGeom sg = seg_geom(seg, a.n, a.sep, a.S, a.extL, a.extR);
+  const int p = sg.p, q = sg.q, i0 = sg.i0, i1 = sg.i1;
+  const double lambda = FIRST ? *a.lambda_ptr : 0.0;
+  double Dn[21], P[7][BS], acc[27];
+#pragma unroll
+  for (int k = 0; k < 21; k++) Dn[k] = 0.0;
+#pragma unroll
+  for (int k = 0; k < 27; k++) acc[k] = 0.0;
+  {
+    const bool sp = p >= 0 && i0 <= i1;
+    const double* E = a.rec + (size_t)(sp ? p : 0) * RECS + oE;
+#pragma unroll
+    for (int c = 0; c < BS; c++)
+#pragma unroll
+      for (int r = 0; r < BS; r++) P[c][r] = sp ? E[r + c * BS] : 0.0;
+#pragma unroll
+    for (int r = 0; r < BS; r++) P[6][r] = 0.0;
+  }
+  bool ok = true;
+  for (int i = i0; i <= i1; i++) {
+    const double* rec = a.rec + (size_t)i * RECS;
+    const bool has_next = (i < i1) || (q >= 0);
+    double L[21], X[21], dinv[BS];
+#pragma unroll
+    for (int c = 0; c < BS; c++)
+#pragma unroll
+      for (int r = c; r < BS; r++) L[tri(r, c)] = rec[r + c * BS] + (FIRST ? 0.0 : rec[BS * BS + r + c * BS]) + Dn[tri(r, c)] + (r == c ? lambda : 0.0);
+    // Cholesky, right-looking, in place
+#pragma unroll
+    for (int j = 0; j < BS; j++) {
+      const double piv = L[tri(j, j)];
+      ok &= piv > 0.0;
+      const double inv = rsqrt_pos(piv > 0.0 ? piv : 1.0);
+      dinv[j] = inv;
+      L[tri(j, j)] = piv * inv;
+#pragma unroll
+      for (int r = j + 1; r < BS; r++) L[tri(r, j)] *= inv;
+#pragma unroll
+      for (int c = j + 1; c < BS; c++)
+#pragma unroll
+        for (int r = c; r < BS; r++) L[tri(r, c)] = fma(-L[tri(r, j)], L[tri(c, j)], L[tri(r, c)]);
+    }
+    // X = L^-1 (lower): column by column
+#pragma unroll
+    for (int c = 0; c < BS; c++) {
+      X[tri(c, c)] = dinv[c];
+#pragma unroll
+      for (int r = c + 1; r < BS; r++) {
+        double sacc = 0.0;
+#pragma unroll
+        for (int k = c; k < r; k++) sacc = fma(L[tri(r, k)], X[tri(k, c)], sacc);
+        X[tri(r, c)] = -sacc * dinv[r];
+      }
+    }
+    double* F = a.frec + (size_t)i * a.fstride;
+#pragma unroll
+    for (int c = 0; c < BS; c++)
+#pragma unroll
+      for (int r = 0; r < BS; r += 2) st128(F + c * BS + r, r >= c ? X[tri(r, c)] : 0.0, r + 1 >= c ? X[tri(r + 1, c)] : 0.0);
+    double Le[BS][BS];   // Le[c][r]: column c
+    if (has_next) {
+      // Le L^T = E: column c of Le from columns < c
+#pragma unroll
+      for (int c = 0; c < BS; c++)
+#pragma unroll
+        for (int r = 0; r < BS; r++) {
+          double v = rec[oE + r + c * BS];
+#pragma unroll
+          for (int k = 0; k < c; k++) v = fma(-Le[k][r], L[tri(c, k)], v);
+          Le[c][r] = v * dinv[c];
+        }
+#pragma unroll
+      for (int c = 0; c < BS; c++)
+#pragma unroll
+        for (int r = 0; r < BS; r += 2) st128(F + BS * BS + c * BS + r, Le[c][r], Le[c][r + 1]);
+#pragma unroll
+      for (int c = 0; c < BS; c++)
+#pragma unroll
+        for (int r = c; r < BS; r++) {
+          double sacc = 0.0;
+#pragma unroll
+          for (int k = 0; k < BS; k++) sacc = fma(Le[k][r], Le[k][c], sacc);
+          Dn[tri(r, c)] = -sacc;
+        }
+    }
+    // own right-hand side, then Y = L^-1 P in place (rows from the bottom: y_r needs p_k, k <= r)
+#pragma unroll
+    for (int r = 0; r < BS; r++) P[6][r] += rec[oG + r] + (FIRST ? 0.0 : rec[oG + BS + r]);
+#pragma unroll
+    for (int c = 0; c < 7; c++)
+#pragma unroll
+      for (int r = BS - 1; r >= 0; r--) {
+        double sacc = 0.0;
+#pragma unroll
+        for (int k = 0; k <= r; k++) sacc = fma(X[tri(r, k)], P[c][k], sacc);
+        P[c][r] = sacc;
+      }
+    // S += Y^T Y: spike x spike (lower) and spike x rhs
+#pragma unroll
+    for (int x = 0; x < BS; x++) {
+#pragma unroll
+      for (int y = 0; y <= x; y++) {
+        double sacc = acc[tri(x, y)];
+#pragma unroll
+        for (int k = 0; k < BS; k++) sacc = fma(P[x][k], P[y][k], sacc);
+        acc[tri(x, y)] = sacc;
+      }
+      double sr = acc[21 + x];
+#pragma unroll
+      for (int k = 0; k < BS; k++) sr = fma(P[x][k], P[6][k], sr);
+      acc[21 + x] = sr;
+    }
+    // P' = -Le Y
+#pragma unroll
+    for (int c = 0; c < 7; c++) {
+      double t[BS];
+#pragma unroll
+      for (int r = 0; r < BS; r++) {
+        double sacc = 0.0;
+        if (has_next) {
+#pragma unroll
+          for (int k = 0; k < BS; k++) sacc = fma(Le[k][r], P[c][k], sacc);
+        }
+        t[r] = -sacc;
+      }
+#pragma unroll
+      for (int r = 0; r < BS; r++) P[c][r] = t[r];
+    }
+  }
+  if (!ok) *a.flag = 1;
+  // ---- segment end: the same hand-off as k_fwd (nb = 0)
+  if (q >= 0) {
+    const double* rq = a.rec + (size_t)q * RECS;
+    double* R = a.rec_out + (size_t)sg.qo * REC1;
+    const double lamq = (FIRST && q < a.nreal) ? lambda : 0.0;   // a ghost is damped by its owner
+#pragma unroll
+    for (int c = 0; c < BS; c++)
+#pragma unroll
+      for (int r = 0; r < BS; r++)
+        R[r + c * BS] = rq[r + c * BS] + (FIRST ? 0.0 : rq[BS * BS + r + c * BS]) + Dn[r >= c ? tri(r, c) : tri(c, r)] + (r == c ? lamq : 0.0);   // D1
+#pragma unroll
+    for (int r = 0; r < BS; r++) R[3 * BS * BS + r] = P[6][r] + rq[oG + r] + (FIRST ? 0.0 : rq[oG + BS + r]);                                   // g1
+    if (p >= 0) {
+      double* Ep = a.rec_out + (size_t)sg.po * REC1 + 2 * BS * BS;   // rows: separator q, cols: separator p
+      if (i0 <= i1) {
+#pragma unroll
+        for (int c = 0; c < BS; c++)
+#pragma unroll
+          for (int r = 0; r < BS; r++) Ep[r + c * BS] = P[c][r];
+      } else {  // no interior state: p and q are directly coupled
+        const double* E = a.rec + (size_t)p * RECS + oE;
+#pragma unroll
+        for (int k = 0; k < BS * BS; k++) Ep[k] = E[k];
+      }
+    }
+    if (a.extR && seg == a.S) {  // external right separator: no segment to its right -> its part 2 is zero
+#pragma unroll
+      for (int k = 0; k < BS * BS; k++) R[BS * BS + k] = 0.0;
+#pragma unroll
+      for (int r = 0; r < BS; r++) R[3 * BS * BS + BS + r] = 0.0;
+    }
+  }
+  if (a.extL && seg == 0) {  // external left separator: part 1 carries this shard's own (undamped unless owned) share of it
+    double* R = a.rec_out;
+    const double* src = a.rec + (size_t)p * RECS;
+#pragma unroll
+    for (int k = 0; k < BS * BS; k++) R[k] = FIRST ? src[k] + ((a.lamL && (k % (BS + 1)) == 0) ? lambda : 0.0) : src[k] + src[BS * BS + k];
+#pragma unroll
+    for (int r = 0; r < BS; r++) R[3 * BS * BS + r] = FIRST ? src[oG + r] : src[oG + r] + src[oG + BS + r];
+  }
+  if (p >= 0) {  // Schur complement onto the left separator: D2, g2
+    double* Rp = a.rec_out + (size_t)sg.po * REC1;
+#pragma unroll
+    for (int x = 0; x < BS; x++) {
+#pragma unroll
+      for (int y = 0; y <= x; y++) { Rp[BS * BS + y + x * BS] = -acc[tri(x, y)]; Rp[BS * BS + x + y * BS] = -acc[tri(x, y)]; }
+      Rp[3 * BS * BS + BS + x] = -acc[21 + x];
+    }
+  }
+}
+
+// Back-substitution of the same chains, one thread per segment (the recurrences of k_bwd2 on 6-vectors in registers; y_i waits in xsol[i])
+template <bool FIRST>
+__global__ void __launch_bounds__(128) k_bwd6t(const BwdArgs a) {
+  constexpr int BS = 6, REC0 = 2 * BS * BS + BS, REC1 = 3 * BS * BS + 2 * BS, RECS = FIRST ? REC0 : REC1;
+  constexpr int oE = FIRST ? BS * BS : 2 * BS * BS, oG = FIRST ? 2 * BS * BS : 3 * BS * BS;
+  const int seg = blockIdx.x * blockDim.x + threadIdx.x;
+  if (seg >= a.nseg) return;
+  const SegGeom sg = seg_geom(seg, a.n, a.sep, a.S, a.extL, a.extR);
+  const int p = sg.p, q = sg.q, i0 = sg.i0, i1 = sg.i1;
+  double xq[BS], t[BS];
+#pragma unroll
+  for (int k = 0; k < BS; k++) { xq[k] = q >= 0 ? a.xup[(size_t)sg.qo * BS + k] : 0.0; t[k] = 0.0; }
+  if (q >= 0) {
+#pragma unroll
+    for (int k = 0; k < BS; k++) a.xsol[(size_t)q * BS + k] = xq[k];
+  }
+  if (a.extL && seg == 0) {
+#pragma unroll
+    for (int k = 0; k < BS; k++) a.xsol[k] = a.xup[k];
+  }
+  if (i1 < i0) return;
+  if (p >= 0) {  // E_p x_p enters the first interior state
+    const double* E = a.rec + (size_t)p * RECS + oE;
+#pragma unroll
+    for (int c = 0; c < BS; c++) {
+      const double xc = a.xup[(size_t)sg.po * BS + c];
+#pragma unroll
+      for (int r = 0; r < BS; r++) t[r] = fma(E[r + c * BS], xc, t[r]);
+    }
+  }
+  for (int i = i0; i <= i1; i++) {   // forward: z = g_i - t, y = L^-1 z, t = Le y
+    const double* rec = a.rec + (size_t)i * RECS;
+    const double* F = a.frec + (size_t)i * a.fstride;
+    double z[BS], y[BS];
+#pragma unroll
+    for (int r = 0; r < BS; r++) z[r] = rec[oG + r] + (FIRST ? 0.0 : rec[oG + BS + r]) - t[r];
+#pragma unroll
+    for (int r = 0; r < BS; r++) {
+      double sacc = 0.0;
+#pragma unroll
+      for (int k = 0; k <= r; k++) sacc = fma(F[r + k * BS], z[k], sacc);
+      y[r] = sacc;
+    }
+#pragma unroll
+    for (int r = 0; r < BS; r++) a.xsol[(size_t)i * BS + r] = y[r];
+    if (i < i1) {
+#pragma unroll
+      for (int r = 0; r < BS; r++) {
+        double sacc = 0.0;
+#pragma unroll
+        for (int k = 0; k < BS; k++) sacc = fma(F[BS * BS + r + k * BS], y[k], sacc);
+        t[r] = sacc;
+      }
+    }
+  }
+  bool hn = q >= 0;
+  for (int i = i1; i >= i0; i--) {   // backward: x = L^-T (y - Le^T x_next)
+    const double* F = a.frec + (size_t)i * a.fstride;
+    double w[BS], x[BS];
+#pragma unroll
+    for (int c = 0; c < BS; c++) {
+      double sacc = a.xsol[(size_t)i * BS + c];
+      if (hn) {
+#pragma unroll
+        for (int r = 0; r < BS; r++) sacc = fma(-F[BS * BS + r + c * BS], xq[r], sacc);
+      }
+      w[c] = sacc;
+    }
+#pragma unroll
+    for (int c = 0; c < BS; c++) {
+      double sacc = 0.0;
+#pragma unroll
+      for (int r = c; r < BS; r++) sacc = fma(F[r + c * BS], w[r], sacc);
+      x[c] = sacc;
+    }
+#pragma unroll
+    for (int c = 0; c < BS; c++) { a.xsol[(size_t)i * BS + c] = x[c]; xq[c] = x[c]; }
+    hn = true;
+  }
+}
+
 // landmark x landmark base: C0 = sum_rows l^T l (block diagonal), gl0 = sum_rows l^T rhs.  One CTA per landmark; each thread
 // takes a few of the landmark's rows, the 12 sums are reduced by warp shuffles and one shared-memory pass (fixed order).
 template <int NT>

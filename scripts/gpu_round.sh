@@ -13,6 +13,9 @@ for s in $STEPS; do
     lat) python -c "from gpslam_b200 import capi; import json; print(json.dumps(capi.latencies()))" | tee gpurun_out/${TAG}_latency.json;;
     launches) timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv python scripts/one_iter.py ${NCU_CFG:-C3} ${NCU_STATES:-0} 3 > gpurun_out/${TAG}_launches.log 2>&1; echo "ncu launches rc=$?"; python scripts/ncu_summaries.py ${TAG} > /dev/null 2>&1; cat profiles/${TAG}_launch_shares.txt | head -30; cp profiles/${TAG}_launch_shares.txt gpurun_out/;;
     full) timeout 900 ncu --set full --clock-control none --import-source on -k regex:"${NCU_K:-k_level_ws|k_panel0|k_spine|k_bwd2}" -c ${NCU_C:-12} -o gpurun_out/${TAG}_full -f python scripts/one_iter.py ${NCU_CFG:-C3} ${NCU_STATES:-0} 1 > gpurun_out/${TAG}_full.log 2>&1; echo "ncu full rc=$?"; tail -3 gpurun_out/${TAG}_full.log; ls -la gpurun_out/${TAG}_full.ncu-rep;;
+    c4) timeout 600 python scripts/run_config.py --config C4 --steps 10 > gpurun_out/${TAG}_c4.json 2> gpurun_out/${TAG}_c4.err; echo "c4 rc=$?"; cat gpurun_out/${TAG}_c4.json; tail -3 gpurun_out/${TAG}_c4.err;;
+    c5) timeout 900 python scripts/run_config.py --config C5 --steps 10 > gpurun_out/${TAG}_c5.json 2> gpurun_out/${TAG}_c5.err; echo "c5 rc=$?"; cat gpurun_out/${TAG}_c5.json; tail -3 gpurun_out/${TAG}_c5.err;;
+    c4tests) timeout 900 python -m pytest tests/test_gpu_fullsize.py -m gpu -x -q -k "c4" > gpurun_out/${TAG}_c4tests.log 2>&1; echo "c4tests rc=$?"; tail -5 gpurun_out/${TAG}_c4tests.log;;
     san) bash scripts/sanitize.sh ${TAG};;
     race) CS=/usr/local/cuda/bin/compute-sanitizer
           timeout 420 $CS --tool racecheck --racecheck-report all --error-exitcode 9 python scripts/sanitize_cases.py pose3_wide 1 > gpurun_out/${TAG}_racecheck.log 2>&1; echo "racecheck pose3_wide rc=$?"
