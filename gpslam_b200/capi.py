@@ -74,11 +74,13 @@ def device_count():
     return lib().gpb_device_count()
 
 
-def dense_solve(A, b, lam=0.0, loff=0, force_blocked=False, device=0, force_small=False):
-    """testing aid: the reduced-system solver alone (gpb_debug_dense_solve)"""
+def dense_solve(A, b, lam=0.0, loff=0, force_blocked=False, device=0, force_small=False, old_tiny=False):
+    """testing aid: the reduced-system solver alone (gpb_debug_dense_solve).  Default: the shared-memory blocked factorisation up to
+    160 unknowns, the multi-CTA blocked Cholesky beyond; force_blocked: the multi-CTA one at any size; force_small / old_tiny: the
+    per-column shared-memory kernels (plain loops / register-blocked trailing update)"""
     A = np.asarray(A, dtype=np.float64); R = A.shape[0]
     Af = np.ascontiguousarray(A.T).ravel(); bf = _f64(b); x = np.zeros(R)
-    rc = lib().gpb_debug_dense_solve(C.c_int(device), C.c_int(R), _dp(Af), _dp(bf), C.c_double(lam), C.c_int(loff), C.c_int(1 if force_blocked else (2 if force_small else 0)), _dp(x))
+    rc = lib().gpb_debug_dense_solve(C.c_int(device), C.c_int(R), _dp(Af), _dp(bf), C.c_double(lam), C.c_int(loff), C.c_int(1 if force_blocked else (2 if force_small else (3 if old_tiny else 0))), _dp(x))
     if rc != 0:
         raise GpbError(lib().gpb_last_error().decode())
     return x

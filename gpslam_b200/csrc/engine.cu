@@ -130,6 +130,7 @@ struct gpb_graph {
   int *d_epstate = nullptr, *d_epoff = nullptr, *d_eprow = nullptr, *d_epside = nullptr;
   int *d_pair_a = nullptr, *d_pair_b = nullptr, *d_pairoff = nullptr, *d_pairrow = nullptr;
   bool generic_fwd = false, force_blocked = false, old_assemble = false, split_levels = false, no_tiny = false, fuse_l0 = false, old_bwd = false;
+  int tiny_mode = 0;
   bool thread_chain = false;  // 6 x 6 chains without a landmark border: thread-per-segment kernels (k_fwd6t / k_bwd6t); GPB_NO_THREAD_CHAIN = generic kernels
   int panel0_occ = 4;         // CTAs per SM the level-0 active-column panel kernel is compiled for (GPB_PANEL0_OCC = 4: 128 registers, no spills)
   bool dense_panel = false;   // A/B switch GPB_DENSE_PANEL: k_panel4 (all 64 columns at every state) instead of k_panel0 (active columns only)
@@ -599,6 +600,7 @@ int gpb_graph_finalize(gpb_graph* g, int device) {
   CUDA_TRY(cudaEventCreateWithFlags(&g->ev_fork, cudaEventDisableTiming));
   CUDA_TRY(cudaEventCreateWithFlags(&g->ev_join, cudaEventDisableTiming));
   CUDA_TRY(cudaFuncSetAttribute(k_small_solve<256, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_solve_smem(SMALL_SOLVE_MAX)));
+  CUDA_TRY(cudaFuncSetAttribute(k_small_solve<256, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_solve_smem(SMALL_SOLVE_MAX)));
   CUDA_TRY(cudaFuncSetAttribute(k_small_solve<256, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_solve_smem(95)));
   CUDA_TRY(cudaFuncSetAttribute(k_small_solve<256, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_solve_smem(143)));
   const int D = g->D, bs = g->bs, DL = g->DL;
@@ -736,7 +738,8 @@ int gpb_graph_finalize(gpb_graph* g, int device) {
   g->old_bwd = getenv("GPB_OLD_BWD") != nullptr;
   g->dense_panel = getenv("GPB_DENSE_PANEL") != nullptr || g->old_bwd;
   if (const char* ev = getenv("GPB_PANEL0_OCC")) g->panel0_occ = atoi(ev) == 5 ? 5 : 4;  // the Y-reading back-substitution needs the dense kernel's Y layout  // A/B switch: back-substitution from a stored Y (k_bwd) instead of re-eliminating the right-hand side (k_bwd2)  // A/B switch: level 0 as ONE warp-specialised kernel (spine warp + panel warps per CTA)
-  g->no_tiny = getenv("GPB_NO_TINY_SOLVE") != nullptr;  // A/B switch: the plain-loop instantiation of k_small_solve instead of the register-blocked ones
+  g->no_tiny = getenv("GPB_NO_TINY_SOLVE") != nullptr;
+  g->tiny_mode = g->no_tiny ? 2 : (getenv("GPB_OLD_TINY") != nullptr ? 1 : 0);  // reduced-system solver in shared memory: blocked (default) / register-blocked per column / plain per column  // A/B switch: the plain-loop instantiation of k_small_solve instead of the register-blocked ones
   g->qc_diag = 1;
   for (const auto& R : g->Rq) for (int c = 0; c < D; c++) for (int r = 0; r < D; r++) if (r != c && R[r + c * D] != 0.0) g->qc_diag = 0;
   g->lin_variant = g->qc_diag ? 1 : 0;
@@ -1111,7 +1114,7 @@ static int dist_allreduce(gpb_graph* g, double* dbuf, long long count) {
 static int solve_top_dense(gpb_graph* g) {
   const int R = g->R, ld = R + 1, loff = g->ntop * g->bs;
   if (R <= SMALL_SOLVE_MAX && !g->force_blocked) {
-    launch_small_solve(g->stream, g->d_topbuf, ld, g->d_topbuf + R, ld, R, loff, g->d_lambda, g->d_topx, g->d_flag, 3, !g->no_tiny);
+    launch_small_solve(g->stream, g->d_topbuf, ld, g->d_topbuf + R, ld, R, loff, g->d_lambda, g->d_topx, g->d_flag, 3, g->tiny_mode);
     g->launches++;
     return GPB_OK;
   }
@@ -1166,7 +1169,7 @@ static int top_finish(gpb_graph* g, double* sc_out /*[4] or null*/) {
   int rc;
   const int nb = g->nb, R = g->R;
   if (top_is_landmarks_only(g)) {
-    if (nb) { launch_small_solve(g->stream, g->d_Csum, nb, g->d_Csum + (size_t)nb * nb, 1, nb, 0, g->d_lambda, g->d_xlm, g->d_flag, 2, !g->no_tiny); g->launches++; }
+    if (nb) { launch_small_solve(g->stream, g->d_Csum, nb, g->d_Csum + (size_t)nb * nb, 1, nb, 0, g->d_lambda, g->d_xlm, g->d_flag, 2, g->tiny_mode); g->launches++; }
     return GPB_OK;
   }
   if (sc_out) CUDA_TRY(cudaMemcpyAsync(sc_out, g->d_topbuf + (size_t)(R + 1) * R, 4 * sizeof(double), cudaMemcpyDeviceToHost, g->stream));
@@ -1626,10 +1629,11 @@ int gpb_debug_dense_solve(int device, int R, const double* A, const double* b, d
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(GPB_ERR_CUDA, "gpb_debug_dense_solve: no CUDA device available"); }
   CUDA_TRY(cudaSetDevice(device));
   CUDA_TRY(cudaFuncSetAttribute(k_small_solve<256, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_solve_smem(SMALL_SOLVE_MAX)));
+  CUDA_TRY(cudaFuncSetAttribute(k_small_solve<256, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_solve_smem(SMALL_SOLVE_MAX)));
   CUDA_TRY(cudaFuncSetAttribute(k_small_solve<256, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_solve_smem(95)));
   CUDA_TRY(cudaFuncSetAttribute(k_small_solve<256, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_solve_smem(143)));
   gpb_graph g;
-  g.R = R; g.bs = 1; g.ntop = loff; g.force_blocked = force_blocked == 1; g.no_tiny = force_blocked == 2;  // 2: the plain-loop instantiation of the shared-memory solver
+  g.R = R; g.bs = 1; g.ntop = loff; g.force_blocked = force_blocked == 1; g.no_tiny = force_blocked == 2; g.tiny_mode = force_blocked == 2 ? 2 : (force_blocked == 3 ? 1 : 0);  // 2: plain per-column loops, 3: register-blocked per-column kernel, 0: blocked factorisation
   CUDA_TRY(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
   int rc = GPB_OK;
   std::vector<double> T((size_t)(R + 1) * R + 4, 0.0);

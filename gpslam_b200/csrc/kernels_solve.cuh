@@ -1902,6 +1902,94 @@ __global__ void k_cseg_final(const double* __restrict__ Cbase, const double* __r
   Csum[e] = (s0 + s1) + (s2 + s3);
 }
 
+// Blocked Cholesky of a matrix held in shared memory (lower triangle, column-major, leading dimension ld; nrows >= R rows: row R,
+// when present, is a right-hand side riding along, so the factorisation also forward-substitutes it).  8-column block steps:
+//   (1) warp 0 factors the 8 x 8 diagonal block in registers (lane r = row r; pivots and column multipliers travel by shuffles),
+//   (2) every row below is forward-substituted against it (one thread per row, L broadcast from shared memory),
+//   (3) the trailing matrix gets C[I][J] -= X_I X_J^T as 8 x 8 tiles on the FP64 tensor pipe (two m8n8k4 per tile), tiles dealt to warps.
+// Three block barriers per 8 columns instead of one per column with a whole-CTA rank-1 update in between: the sequential part
+// of a 48-unknown landmark system drops from 48 to 6 steps.  dinv[j] = 1 / L[j][j].  Called by all NT threads of the CTA.
+template <int NT>
+__device__ __forceinline__ void chol_blocked_smem(double* sm, int ld, int R, int nrows, double* dinv, int* flag, int flagval) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gi = lane >> 2, ti = lane & 3;
+  constexpr int NWARP = NT / 32;
+  for (int c0 = 0; c0 < R; c0 += 8) {
+    const int nc = min(8, R - c0);
+    if (warp == 0) {
+      // ---- (1) diagonal block; rows / columns beyond R are padded with the identity
+      const int r = lane & 7;
+      double a[8];
+#pragma unroll
+      for (int c = 0; c < 8; c++) a[c] = (r < nc && c <= r && c < nc) ? sm[(c0 + r) + (c0 + c) * ld] : ((r == c) ? 1.0 : 0.0);
+      bool ok = true;
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const double piv = __shfl_sync(0xffffffffu, a[j], j);
+        ok &= piv > 0.0;
+        const double inv = rsqrt_pos(piv > 0.0 ? piv : 1.0);
+        const double lrj = (r == j) ? piv * inv : a[j] * inv;   // L[r][j], r >= j
+        a[j] = lrj;
+        if (lane == j && j < nc) dinv[c0 + j] = inv;
+#pragma unroll
+        for (int c = j + 1; c < 8; c++) {
+          const double lcj = __shfl_sync(0xffffffffu, lrj, c);
+          a[c] = fma(-lrj, lcj, a[c]);
+        }
+      }
+      if (!ok && lane == 0) *flag = flagval;
+      if (lane < nc) {
+#pragma unroll
+        for (int c = 0; c < 8; c++) if (c <= r && c < nc) sm[(c0 + r) + (c0 + c) * ld] = a[c];
+      }
+    }
+    __syncthreads();
+    // ---- (2) rows below: x L^T = a, in place
+    for (int row = c0 + nc + tid; row < nrows; row += NT) {
+      double x[8];
+#pragma unroll
+      for (int c = 0; c < 8; c++) {
+        if (c < nc) {
+          double v = sm[row + (c0 + c) * ld];
+#pragma unroll
+          for (int k = 0; k < c; k++) v = fma(-x[k], sm[(c0 + c) + (c0 + k) * ld], v);
+          x[c] = v * dinv[c0 + c];
+        } else x[c] = 0.0;
+      }
+#pragma unroll
+      for (int c = 0; c < 8; c++) if (c < nc) sm[row + (c0 + c) * ld] = x[c];
+    }
+    __syncthreads();
+    // ---- (3) trailing update on 8 x 8 tiles (I >= J) of the rows / columns behind this block column
+    const int b0 = c0 + nc;                       // first trailing row / column
+    const int ntr = (nrows - b0 + 7) / 8;         // row tiles (the rhs row included)
+    const int ntc = (R - b0 + 7) / 8;             // column tiles
+    if (ntc > 0) {
+      const int ntiles = ntc * (ntc + 1) / 2 + (ntr - ntc) * ntc;   // lower triangle of the square part + the rows below it
+      for (int t = warp; t < ntiles; t += NWARP) {
+        int I, J;
+        const int tri_n = ntc * (ntc + 1) / 2;
+        if (t < tri_n) { I = 0; while ((I + 1) * (I + 2) / 2 <= t) I++; J = t - I * (I + 1) / 2; }
+        else { const int u = t - tri_n; I = ntc + u / ntc; J = u % ntc; }
+        const int ra = b0 + 8 * I + gi, rb = b0 + 8 * J + gi;      // fragment rows of X_I (A operand) and X_J (B operand: B[k][n] = X_J[n][k])
+        double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+        for (int sK = 0; sK < 2; sK++) {
+          const int k = 4 * sK + ti;
+          const double fa = (ra < nrows && k < nc) ? sm[ra + (c0 + k) * ld] : 0.0;
+          const double fb = (rb < R && k < nc) ? sm[rb + (c0 + k) * ld] : 0.0;
+          dmma884(d0, d1, fa, fb);
+        }
+        const int cr = b0 + 8 * I + gi, cc = b0 + 8 * J + 2 * ti;   // C fragment: (cr, cc), (cr, cc + 1)
+        if (cr < nrows) {
+          if (cc < R && cc <= cr) sm[cr + cc * ld] -= d0;
+          if (cc + 1 < R && cc + 1 <= cr) sm[cr + (cc + 1) * ld] -= d1;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // Small dense SPD solve in shared memory, single CTA:  (A + lambda * diag[loff..R)) x = rhs,  R <= SMALL_SOLVE_MAX.
 // Used for the landmark system (no pinned states; loff = 0) and for reduced systems of a few separators + landmarks (sharded
 // graphs, a handful of loop closures).  The right-hand side rides along as row R of the lower triangle, so the Cholesky
@@ -1926,6 +2014,9 @@ __global__ void __launch_bounds__(NT) k_small_solve(const double* __restrict__ A
     if (tx == 0) sm[R + c * ld] = rhs[(size_t)c * rstride];
   }
   __syncthreads();
+  if constexpr (KB < 0) {   // blocked factorisation: 8-column steps, tensor-pipe trailing updates
+    chol_blocked_smem<NT>(sm, ld, R, R + 1, dinv, flag, flagval);
+  } else
   for (int j = 0; j < R; j++) {
     const double djj = sm[j + j * ld];
     if (!(djj > 0.0) && tid == 0) *flag = flagval;
@@ -1984,12 +2075,15 @@ __global__ void __launch_bounds__(NT) k_small_solve(const double* __restrict__ A
 }
 static size_t small_solve_smem(int R) { return ((size_t)(R + 2) * R + R) * sizeof(double); }
 // the instantiation that fits R (allow_blocked = false: the plain-loop form, for A/B and tests)
+// mode 0 (default): blocked factorisation (8-column steps, tensor-pipe trailing updates); 1: the per-column kernel with a register-
+// blocked trailing update (round 1; A/B switch GPB_OLD_TINY); 2: the per-column kernel with plain loops (tests)
 static void launch_small_solve(cudaStream_t stream, const double* A, int lda, const double* rhs, int rstride, int R, int loff, const double* lambda_ptr, double* x,
-                               int* flag, int flagval, bool allow_blocked = true) {
-  if (allow_blocked && R + 1 <= 16 * 2) k_small_solve<256, 2><<<1, 256, small_solve_smem(R), stream>>>(A, lda, rhs, rstride, R, loff, lambda_ptr, x, flag, flagval);
-  else if (allow_blocked && R + 1 <= 16 * 4) k_small_solve<256, 4><<<1, 256, small_solve_smem(R), stream>>>(A, lda, rhs, rstride, R, loff, lambda_ptr, x, flag, flagval);
-  else if (allow_blocked && R + 1 <= 16 * 6) k_small_solve<256, 6><<<1, 256, small_solve_smem(R), stream>>>(A, lda, rhs, rstride, R, loff, lambda_ptr, x, flag, flagval);
-  else if (allow_blocked && R + 1 <= 16 * 9) k_small_solve<256, 9><<<1, 256, small_solve_smem(R), stream>>>(A, lda, rhs, rstride, R, loff, lambda_ptr, x, flag, flagval);  // 8 shards: R = 7 * 12 + 48 = 132
+                               int* flag, int flagval, int mode = 0) {
+  if (mode == 0) k_small_solve<256, -1><<<1, 256, small_solve_smem(R), stream>>>(A, lda, rhs, rstride, R, loff, lambda_ptr, x, flag, flagval);
+  else if (mode == 1 && R + 1 <= 16 * 2) k_small_solve<256, 2><<<1, 256, small_solve_smem(R), stream>>>(A, lda, rhs, rstride, R, loff, lambda_ptr, x, flag, flagval);
+  else if (mode == 1 && R + 1 <= 16 * 4) k_small_solve<256, 4><<<1, 256, small_solve_smem(R), stream>>>(A, lda, rhs, rstride, R, loff, lambda_ptr, x, flag, flagval);
+  else if (mode == 1 && R + 1 <= 16 * 6) k_small_solve<256, 6><<<1, 256, small_solve_smem(R), stream>>>(A, lda, rhs, rstride, R, loff, lambda_ptr, x, flag, flagval);
+  else if (mode == 1 && R + 1 <= 16 * 9) k_small_solve<256, 9><<<1, 256, small_solve_smem(R), stream>>>(A, lda, rhs, rstride, R, loff, lambda_ptr, x, flag, flagval);  // 8 shards: R = 7 * 12 + 48 = 132
   else k_small_solve<256, 0><<<1, 256, small_solve_smem(R), stream>>>(A, lda, rhs, rstride, R, loff, lambda_ptr, x, flag, flagval);
 }
 
@@ -2150,23 +2244,13 @@ __global__ void k_top_scatter(const double* __restrict__ x, int bs, int nb, int 
 constexpr int DNB = 64;
 __global__ void __launch_bounds__(256) k_dense_diag(double* __restrict__ T, int ld, int R, int j0, int loff, const double* __restrict__ lambda_ptr, int* __restrict__ flag) {
   __shared__ double sm[DNB * (DNB + 1)];
+  __shared__ double dinv_s[DNB];
   const int n = min(DNB, R - j0), tid = threadIdx.x, tx = tid & 15, ty = tid >> 4, ldt = DNB + 1;
   const double lambda = *lambda_ptr;
   // the LM damping of the landmark diagonal is applied when a diagonal tile is first touched (entries were only updated, never read, before)
   for (int c = ty; c < n; c += 16) for (int r = c + tx; r < n; r += 16) sm[r + c * ldt] = T[(j0 + r) + (size_t)(j0 + c) * ld] + ((r == c && j0 + r >= loff) ? lambda : 0.0);
   __syncthreads();
-  for (int j = 0; j < n; j++) {
-    const double djj = sm[j + j * ldt];
-    if (!(djj > 0.0) && tid == 0) *flag = 3;
-    const double inv = rsqrt_pos(djj > 0.0 ? djj : 1.0);
-    for (int cc = j + 1 + ty; cc < n; cc += 16) {
-      const double lc = sm[cc + j * ldt] * inv;
-      for (int r = cc + tx; r < n; r += 16) sm[r + cc * ldt] = fma(-(sm[r + j * ldt] * inv), lc, sm[r + cc * ldt]);
-    }
-    __syncthreads();
-    for (int r = j + tid; r < n; r += 256) sm[r + j * ldt] *= inv;
-  }
-  __syncthreads();
+  chol_blocked_smem<256>(sm, ldt, n, n, dinv_s, flag, 3);   // 8-column block steps (was: one block barrier and a whole-CTA rank-1 update per column)
   for (int c = ty; c < n; c += 16) for (int r = c + tx; r < n; r += 16) T[(j0 + r) + (size_t)(j0 + c) * ld] = sm[r + c * ldt];
 }
 // rows j0+n .. R (inclusive: the rhs row) of block column j0: X L^T = A, one row per thread, L_jj broadcast from shared memory

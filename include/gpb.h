@@ -250,8 +250,9 @@ int gpb_debug_latency(int device, double* out8);
  * 256-thread CTAs) or with cudaMemsetAsync (mode 0) - the floor of the layout */
 int gpb_debug_store_peak(int device, int mode, int n_factors, double* us_out);
 /* testing aid: the reduced-system solver alone - (A + lambda * diag[loff..R)) x = b, A symmetric R x R column-major; the
- * shared-memory single-CTA solver up to R = 160 (register-blocked instantiations up to 143; force_blocked == 2: the plain-loop one),
- * the blocked multi-CTA Cholesky beyond (or when force_blocked == 1) */
+ * shared-memory single-CTA solver up to R = 160 (blocked factorisation in 8-column steps with tensor-pipe trailing updates;
+ * force_blocked == 2 / 3: the per-column kernels with plain loops / a register-blocked trailing update), the blocked multi-CTA
+ * Cholesky beyond (or when force_blocked == 1) */
 int gpb_debug_dense_solve(int device, int R, const double* A, const double* b, double lambda, int loff, int force_blocked, double* x_out);
 /* all-reduce calls issued by the last gpb_optimize (sharded graphs) */
 int gpb_allreduces_last_optimize(gpb_graph* g);

@@ -271,8 +271,9 @@ def test_reduced_system_solvers(R):
             x = capi.dense_solve(A, b, lam, loff, blocked)
             assert np.abs(x - ref).max() <= 1e-9 * max(1.0, np.abs(ref).max()), (R, lam, blocked, np.abs(x - ref).max())
         if R <= 143:
-            x = capi.dense_solve(A, b, lam, loff, force_small=True)
-            assert np.abs(x - ref).max() <= 1e-9 * max(1.0, np.abs(ref).max()), (R, lam, "small", np.abs(x - ref).max())
+            for kw in (dict(force_small=True), dict(old_tiny=True)):
+                x = capi.dense_solve(A, b, lam, loff, **kw)
+                assert np.abs(x - ref).max() <= 1e-9 * max(1.0, np.abs(ref).max()), (R, lam, kw, np.abs(x - ref).max())
     with pytest.raises(capi.GpbError):
         capi.dense_solve(-A, b, 0.0, 0, R > 160)
     if R <= 143:
