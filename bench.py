@@ -36,7 +36,8 @@ def cpu_sample_states(iterations, full=100000):
 # profiles/r1x_ncu_full_summary.csv: k_lin_gp 15.7 MB read + 180.6 MB written (the tail of the 240 MB of [A|b] is still in L2 at
 # kernel end); k_panel4 (level 0) 270.2 MB read + 557.1 MB written
 TRAFFIC_LIN_GP = 196.3e6
-TRAFFIC_PANEL = 827.3e6
+TRAFFIC_PANEL = 282.2e6        # k_panel0<12,4>: 261.4 MB read + 20.9 MB written (profiles/r2f_ncu_full_summary.csv); k_panel4 in round 1: 827.3 MB
+PANEL_EXECUTED_FRACTION = 0.58  # 11.38 M DMMA executed by k_panel0 on C3 (ncu source page, r2f) of the dense panel's 19.6 M
 # algorithmic FLOPs of the level-0 panel per state (SE(3), w = 61 columns): Y = L^-1 P (12*13/2*61 MAC), P' = Le Y (12*12*61),
 # S += Y^T Y (61*62/2*12)
 PANEL_FLOP_PER_STATE = 2.0 * (78 * 61 + 144 * 61 + 61 * 62 // 2 * 12)
@@ -211,9 +212,12 @@ def run_engine(args, rank, world, local_rank):
         else:
             dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     sampler = ClockSampler(local_rank)
-    cfg = synth.config("C3")
+    cfg = synth.config(args.config)
     if args.states:
         cfg.n_states = args.states
+        if cfg.n_closures:
+            cfg.closure_min_gap = min(cfg.closure_min_gap, max(2, cfg.n_states // 10))
+    se3_wide = cfg.group == 0 and 11 <= cfg.n_landmarks <= 17   # SE(3) with a 64-column panel: the spine / panel stage timers exist
     t0 = time.perf_counter()
     if world > 1:
         # strong scaling: the SAME 100k-state graph, cut into contiguous segments, one per GPU; one NCCL all-reduce of the
@@ -283,7 +287,7 @@ def run_engine(args, rank, world, local_rank):
     e2e_serial_s = max_over_ranks((time.perf_counter() - t0) / args.steps)
     # ---- per-stage device times and the linearise roofline (local shard)
     stages = {n: g.time_stage(k, 20) for k, n in ((0, "linearise_gp"), (1, "linearise_other"), (2, "assemble"), (3, "solve"), (4, "retract"), (5, "solve_fwd_level0"),
-                                                   (6, "solve_spine_level0"), (7, "solve_panel_level0"), (8, "solve_backward"))}
+                                                   (6, "solve_spine_level0"), (7, "solve_panel_level0"), (8, "solve_backward")) if se3_wide or k not in (6, 7)}
     from gpslam_b200 import capi
     dmma_peak = capi.dmma_peak(local_rank)
     # what the [A|b] store pattern costs with no arithmetic in front of it, and a plain memset of the same bytes (context for
@@ -292,12 +296,15 @@ def run_engine(args, rank, world, local_rank):
     sampler.mark_end()
     clocks = sampler.stop()
     peak, peak_src = peaks()
-    gp_bytes = g.N * 8.0 * 18 + sz.n_gp * (8.0 + 8.0 * 12 * 25)  # states once + per factor (param + [A|b])
+    D_ = 6 if cfg.group == 0 else 3
+    SR_ = {0: 18, 1: 6, 2: 12, 3: 6}[cfg.group]
+    gp_bytes = g.N * 8.0 * SR_ + sz.n_gp * (8.0 + 8.0 * 2 * D_ * (4 * D_ + 1))  # states once + per factor (param + [A|b])
     achieved = gp_bytes / (stages["linearise_gp"] * 1e-3) / 1e9
     line = {
         "metric": METRIC, "value": value, "unit": "iterations/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "states": cfg.n_states, "states_per_gpu": g.N, "gp_factors_rank0": sz.n_gp, "other_factors_rank0": sz.n_extra,
+        "config": {"workload": WORKLOAD if args.config == "C3" and not args.states else "%s shape, %d states%s (bench.py --config / --states: not the headline workload)" % (args.config, cfg.n_states, ", %d loop closures" % cfg.n_closures if cfg.n_closures else ""),
+                   "states": cfg.n_states, "states_per_gpu": g.N, "gp_factors_rank0": sz.n_gp, "other_factors_rank0": sz.n_extra,
                    "landmark_dims": sz.border_dim, "solver_levels": sz.levels, "optimizer": "Gauss-Newton",
                    "parallelism": "trajectory segments x%d, one NCCL all-reduce of the boundary Schur system per iteration" % world if world > 1 else "single GPU",
                    "allreduces_per_step": (n_allreduce - 1) / args.steps if world > 1 else 0,
@@ -307,17 +314,24 @@ def run_engine(args, rank, world, local_rank):
                 "api": "gpb_optimize_batch (host values in -> one GN iteration -> host values + error out, every step; copies double-buffered against compute)",
                 "unpipelined_value": 1.0 / e2e_serial_s, "unpipelined_api": "gpb_set_values + gpb_optimize(1) + gpb_get_values per step"},
         "gpu_launches": launches,
-        "roofline": {"kernel": "k_lin_gp<POSE3> (batched GP-prior linearise; diagonal-Qc instantiation)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "peak_source": peak_src, "algorithmic_bytes": gp_bytes, "ms": stages["linearise_gp"], "traffic": TRAFFIC_LIN_GP if world == 1 else None,
+        "roofline": {"kernel": "k_lin_gp<%s> (batched GP-prior linearise%s)" % ({0: "POSE3", 1: "POSE2", 2: "ROT3", 3: "LINEAR"}[cfg.group], "; diagonal-Qc instantiation" if cfg.group == 0 else ""), "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "peak_source": peak_src, "algorithmic_bytes": gp_bytes, "ms": stages["linearise_gp"], "traffic": TRAFFIC_LIN_GP if world == 1 and args.config == "C3" and not args.states else None,
                      "store_pattern_floor_ms": store_floor_us * 1e-3, "memset_same_bytes_ms": memset_us * 1e-3},
         # the kernel that dominates the iteration by time: the level-0 panel, bound by the FP64 tensor pipe
-        "roofline_solver": {"kernel": "k_panel4<12> (level-0 panel: Y = L^-1 P, P' = -Le Y, S += Y^T Y on mma.sync.m8n8k4.f64)", "bound": "tensor", "achieved": PANEL_FLOP_PER_STATE * g.N / (stages["solve_panel_level0"] * 1e-3) / 1e12,
-                            "peak": dmma_peak, "unit": "TFLOP/s", "frac": PANEL_FLOP_PER_STATE * g.N / (stages["solve_panel_level0"] * 1e-3) / 1e12 / dmma_peak,
-                            "peak_source": "measured in this run: FP64 mma.sync m8n8k4 issue loop on all SMs (gpb_debug_dmma_peak); MEASURED_PEAKS.json has no FP64 figure",
-                            "algorithmic_flops": PANEL_FLOP_PER_STATE * g.N, "ms": stages["solve_panel_level0"], "traffic": TRAFFIC_PANEL if world == 1 else None},
         "stages_ms": stages, "clocks": clocks, "error": {"initial": err0, "final": st.error_final},
     }
-    if rank == 0 and world == 1 and not args.no_cpu:
+    if se3_wide:
+        # the kernel that dominates the iteration by time: the level-0 panel.  `achieved` counts the DENSE panel's flops (every one of
+        # the 61 columns at every state: what the elimination order costs on paper and what k_panel4 executed in round 1); k_panel0
+        # skips the column tiles that are still exactly zero, so it executes fewer (executed_fraction, from the ncu DMMA count)
+        pf = PANEL_FLOP_PER_STATE * g.N
+        line["roofline_solver"] = {"kernel": "k_panel0<12,4> (level-0 panel on the active columns: Y = L^-1 P, P' = -Le Y, S += Y^T Y on mma.sync.m8n8k4.f64)", "bound": "tensor",
+                                   "achieved": pf / (stages["solve_panel_level0"] * 1e-3) / 1e12, "peak": dmma_peak, "unit": "TFLOP/s",
+                                   "frac": pf / (stages["solve_panel_level0"] * 1e-3) / 1e12 / dmma_peak,
+                                   "peak_source": "measured in this run: FP64 mma.sync m8n8k4 issue loop on all SMs (gpb_debug_dmma_peak); MEASURED_PEAKS.json has no FP64 figure",
+                                   "algorithmic_flops": pf, "executed_fraction": PANEL_EXECUTED_FRACTION if args.config == "C3" and not args.states and world == 1 else None,
+                                   "ms": stages["solve_panel_level0"], "traffic": TRAFFIC_PANEL if world == 1 and args.config == "C3" and not args.states else None}
+    if rank == 0 and world == 1 and not args.no_cpu and args.config == "C3" and not args.states:
         r = cpu_reference_run(3, 1, 1, keep_first=True)
         line["cpu_baseline"] = {"value": r["value"], "unit": "iterations/s", "cores": 1, "kind": "port", "sample": r["sample"],
                                 "seconds_per_iteration_sample": r["seconds_per_iteration_sample"],
@@ -347,6 +361,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--states", type=int, default=0, help="override the number of states (parity/debug runs; not a bench value)")
+    ap.add_argument("--config", default="C3", choices=["C1", "C2", "C3", "C4", "C5"], help="BASELINE.json config shape (default C3, the headline workload; others are side runs)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-converged", action="store_true", help="skip the converged-LM parity run against the oracle (about 1.5 minutes of host time)")
     args = ap.parse_args()

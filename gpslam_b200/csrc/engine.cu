@@ -559,8 +559,8 @@ template <int BS, int W> static int occ_bwd() {
   return nb < 1 ? 1 : nb;
 }
 static int bwd_blocks_per_sm(int bs, int W) {
-  if (bs == 12) return W == 16 ? occ_bwd<12, 16>() : W == 32 ? occ_bwd<12, 32>() : occ_bwd<12, 64>();
-  return W == 16 ? occ_bwd<6, 16>() : W == 32 ? occ_bwd<6, 32>() : occ_bwd<6, 64>();
+  if (bs == 12) return W == 16 ? occ_bwd<12, 16>() : W == 32 ? occ_bwd<12, 32>() : W == 64 ? occ_bwd<12, 64>() : occ_bwd<12, 128>();
+  return W == 16 ? occ_bwd<6, 16>() : W == 32 ? occ_bwd<6, 32>() : W == 64 ? occ_bwd<6, 64>() : occ_bwd<6, 128>();
 }
 static int fwd_blocks_per_sm(int bs, int W, bool fuse_l0 = false, int panel0_occ = 4) {
   if (bs == 12 && W == 64) {
@@ -572,8 +572,8 @@ static int fwd_blocks_per_sm(int bs, int W, bool fuse_l0 = false, int panel0_occ
     nb = std::min(nb, nb0);   // one resident wave must hold for either level-0 panel kernel
     return nb < 1 ? 1 : nb;
   }
-  if (bs == 12) return W == 16 ? occ_fwd<12, 16>() : W == 32 ? occ_fwd<12, 32>() : occ_fwd<12, 64>();
-  return W == 16 ? occ_fwd<6, 16>() : W == 32 ? occ_fwd<6, 32>() : occ_fwd<6, 64>();
+  if (bs == 12) return W == 16 ? occ_fwd<12, 16>() : W == 32 ? occ_fwd<12, 32>() : W == 64 ? occ_fwd<12, 64>() : occ_fwd<12, 128>();
+  return W == 16 ? occ_fwd<6, 16>() : W == 32 ? occ_fwd<6, 32>() : W == 64 ? occ_fwd<6, 64>() : occ_fwd<6, 128>();
 }
 extern "C" {
 // ===================================================================== finalize: build the device-resident graph
@@ -585,7 +585,7 @@ int gpb_graph_finalize(gpb_graph* g, int device) {
   if (g->Rq.empty()) return fail(GPB_ERR_STATE, "gpb_graph_finalize: no Qc model registered");
   if (g->failed) return fail(GPB_ERR_STATE, "gpb_graph_finalize: an earlier finalize of this graph failed; destroy it");
   // every shape check comes before the first CUDA resource is created: a refused graph holds nothing and may be finalized again
-  if (2 * g->D + g->L * g->DL + 1 > 64) return fail(GPB_ERR_UNSUPPORTED, "gpb_graph_finalize: landmark border wider than 64 - 2D - 1 columns is not supported by this build");
+  if (2 * g->D + g->L * g->DL + 1 > 128) return fail(GPB_ERR_UNSUPPORTED, "gpb_graph_finalize: landmark border wider than 128 - 2D - 1 columns (38 3-D / 60 2-D landmarks) is not supported by this build");
   if ((g->n_real ? g->n_real : g->N) - (g->extL ? 1 : 0) - (g->extR ? 1 : 0) < 0) return fail(GPB_ERR_ARG, "shard too small for its external separators");
   {
     bool any_closure = false;
@@ -605,8 +605,7 @@ int gpb_graph_finalize(gpb_graph* g, int device) {
   CUDA_TRY(cudaFuncSetAttribute(k_small_solve<256, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_solve_smem(143)));
   const int D = g->D, bs = g->bs, DL = g->DL;
   g->nb = g->L * DL; g->w = bs + g->nb + 1;
-  g->W = g->w <= 16 ? 16 : g->w <= 32 ? 32 : 64;
-  if (g->w > 64) return fail(GPB_ERR_UNSUPPORTED, "gpb_graph_finalize: landmark border wider than 64 - 2D - 1 columns is not supported by this build");
+  g->W = g->w <= 16 ? 16 : g->w <= 32 ? 32 : g->w <= 64 ? 64 : 128;   // panel width class: 64 runs the SE(3) production kernels, 128 the generic one-kernel sweep
   g->ngp = 0; for (double h : g->dt) if (h > 0) g->ngp++;
   g->NFp = (g->nint + AB_TF - 1) / AB_TF * AB_TF;  // whole tiles of the [A|b] layout (ab_off)
   // ---- sort extras by interval (stable), assign row offsets
@@ -1017,8 +1016,8 @@ static int assemble_dispatch(gpb_graph* g, int buf) {
 
 template <int BS, int W> static void launch_fwd(const FwdArgs& a, int ncta, cudaStream_t s) { k_fwd<BS, W><<<ncta, (W < 32 ? 32 : W), 0, s>>>(a); }
 template <int BS, int W> static void launch_bwd(const BwdArgs& a, int ncta, cudaStream_t s) { k_bwd<BS, W><<<ncta, (W < 32 ? 32 : W), 0, s>>>(a); }
-template <int BS> static void fwd_w(int W, const FwdArgs& a, int ncta, cudaStream_t s) { if (W == 16) launch_fwd<BS, 16>(a, ncta, s); else if (W == 32) launch_fwd<BS, 32>(a, ncta, s); else launch_fwd<BS, 64>(a, ncta, s); }
-template <int BS> static void bwd_w(int W, const BwdArgs& a, int ncta, cudaStream_t s) { if (W == 16) launch_bwd<BS, 16>(a, ncta, s); else if (W == 32) launch_bwd<BS, 32>(a, ncta, s); else launch_bwd<BS, 64>(a, ncta, s); }
+template <int BS> static void fwd_w(int W, const FwdArgs& a, int ncta, cudaStream_t s) { if (W == 16) launch_fwd<BS, 16>(a, ncta, s); else if (W == 32) launch_fwd<BS, 32>(a, ncta, s); else if (W == 64) launch_fwd<BS, 64>(a, ncta, s); else launch_fwd<BS, 128>(a, ncta, s); }
+template <int BS> static void bwd_w(int W, const BwdArgs& a, int ncta, cudaStream_t s) { if (W == 16) launch_bwd<BS, 16>(a, ncta, s); else if (W == 32) launch_bwd<BS, 32>(a, ncta, s); else if (W == 64) launch_bwd<BS, 64>(a, ncta, s); else launch_bwd<BS, 128>(a, ncta, s); }
 
 static int launch_fwd_level(gpb_graph* g, int buf, double lambda, int lev, int parts = 3) {
   const int bs = g->bs, nb = g->nb, fstride = g->fstride, centries = nb * nb + nb;

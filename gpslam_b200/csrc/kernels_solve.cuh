@@ -148,10 +148,10 @@ __device__ __forceinline__ bool warp_chol_inverse(const CholMap<BS>& cm, const d
 }
 
 template <int BS, int W>
-__global__ void __launch_bounds__((W < 32 ? 32 : W), (W == 64 ? 6 : 8)) k_fwd(const FwdArgs a) {
+__global__ void __launch_bounds__((W < 32 ? 32 : W), (W == 128 ? 3 : W == 64 ? 6 : 8)) k_fwd(const FwdArgs a) {
   constexpr bool MMA = (BS == 12 && W == 64);  // Schur SYRK + panel update on the FP64 tensor pipe
   constexpr int NT = (W < 32 ? 32 : W);
-  constexpr int REC0 = 2 * BS * BS + BS, REC1 = 3 * BS * BS + 2 * BS, YS = MMA ? BS : BS + 1, NA = MMA ? 36 : W / 2 + 1, NBP = W;  // NBP: padded border width
+  constexpr int REC0 = 2 * BS * BS + BS, REC1 = 3 * BS * BS + 2 * BS, YS = (MMA || W == 128) ? BS : BS + 1, NA = MMA ? 36 : W / 2 + 1, NBP = W == 128 ? W - BS : W;  // NBP: padded border width (W = 128: trimmed so the static shared memory stays under 48 KB)
   __shared__ __align__(16) double Rb[2][REC1];
   __shared__ double Dm[BS * BS], Dn[BS * BS], Em[BS * BS], Li[BS * BS], Ysm[W * YS], invd[BS], Bn[BS * NBP];
   __shared__ double colL[2 * BS], rowX[2 * BS];
@@ -728,6 +728,9 @@ __device__ __forceinline__ void panel_body(const FwdArgs& a, volatile const int*
   double acc[18];
 #pragma unroll
   for (int j = 0; j < 18; j++) acc[j] = 0.0;
+  double bn1[HB], bn2[HB];   // upper levels: the next state's dense border half-column, in flight
+#pragma unroll
+  for (int r = 0; r < HB; r++) { bn1[r] = 0.0; bn2[r] = 0.0; }
   auto with_pw = [&](auto fn) {
     if (pw == 0) fn(std::integral_constant<int, 0>{});
     else if (pw == 1) fn(std::integral_constant<int, 1>{});
@@ -777,15 +780,26 @@ __device__ __forceinline__ void panel_body(const FwdArgs& a, volatile const int*
             }
           }
         } else {
-          const double* B = a.brec + (size_t)i * (2 * BS * nb) + r0 + lb * BS;
+          // dense border blocks of the upper levels: this state's half-column was loaded one state ahead (a global load issued here
+          // would sit on the per-state critical path: it was the largest stall of k_level_ws); fetch the next state's now
 #pragma unroll
-          for (int r = 0; r < HB; r++) P[r] += B[r] + B[BS * nb + r];
+          for (int r = 0; r < HB; r++) P[r] += bn1[r] + bn2[r];
+          if (i + 1 <= ilast) {
+            const double* B = a.brec + (size_t)(i + 1) * (2 * BS * nb) + r0 + lb * BS;
+#pragma unroll
+            for (int r = 0; r < HB; r++) { bn1[r] = B[r]; bn2[r] = B[BS * nb + r]; }
+          }
         }
       } else if (is_rhs) {
 #pragma unroll
         for (int r = 0; r < HB; r++) P[r] += Gb[st][r0 + r] + (first ? 0.0 : Gb[st][BS + r0 + r]);
       }
     };
+    if (!first && is_border && i0 <= ilast) {
+      const double* B = a.brec + (size_t)i0 * (2 * BS * nb) + r0 + lb * BS;
+#pragma unroll
+      for (int r = 0; r < HB; r++) { bn1[r] = B[r]; bn2[r] = B[BS * nb + r]; }
+    }
     prefetch(i0, 0, b0, b1); cp_async_commit();
     prefetch(i0 + 1, 1, b1, b2); cp_async_commit();
     {
@@ -1374,7 +1388,7 @@ __global__ void __launch_bounds__(128, 4) k_bwd2(const BwdArgs a) {
   __shared__ __align__(16) double Fb[NW][NST][F2];
   __shared__ __align__(16) double ysm[NW][YC * BS];   // right-hand sides, then y, of the segment's first YC states (later ones wait in xsol)
   __shared__ double vec[NW][BS];
-  __shared__ double xls[64];
+  __shared__ double xls[128];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nb = a.nb;
   const bool first = a.first_level != 0, rl = lane < BS;
@@ -1382,7 +1396,7 @@ __global__ void __launch_bounds__(128, 4) k_bwd2(const BwdArgs a) {
   const int rr = lane % BS, hh = (lane / BS) & 1;
   const bool mv = lane < 2 * BS;
   const int RECS = first ? REC0 : REC1, oE = first ? BS * BS : 2 * BS * BS, oG = first ? 2 * BS * BS : 3 * BS * BS;
-  for (int k = threadIdx.x; k < 64; k += 128) xls[k] = k < nb ? a.xl[k] : 0.0;
+  for (int k = threadIdx.x; k < 128; k += 128) xls[k] = k < nb ? a.xl[k] : 0.0;
   __syncthreads();
   double* const v = vec[warp];
   const int yw = CTASEG ? 0 : warp;           // whose y slots / staging ring the segment uses
@@ -1455,6 +1469,9 @@ __global__ void __launch_bounds__(128, 4) k_bwd2(const BwdArgs a) {
       for (int i = i0 + (CTASEG ? warp : 0); i <= i1; i += CTASEG ? NW : 1) {
         const double* B = a.brec + (size_t)i * (2 * BS * nb);
         double s0 = 0.0, s1 = 0.0;
+        if (nb > 64) {   // wide borders (the 128-column panel): plain loop over this lane group's columns
+          if (part < NPART) for (int l = part; l < nb; l += NPART) s0 = fma(B[r + l * BS] + B[BS * nb + r + l * BS], xls[l], s0);
+        } else
 #pragma unroll
         for (int h = 0; h < 2; h++) {
           double b1[KH], b2[KH];

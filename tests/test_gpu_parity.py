@@ -444,18 +444,26 @@ def test_indeterminate_system_is_reported():
     assert sg.status == 0 and so.status == 0 and sg.error_final < 1e-6 and so.error_final < 1e-6
 
 
+@pytest.mark.parametrize("name,n_landmarks", [("C3", 17), ("C3", 18), ("C3", 38), ("C1", 60)])
+def test_wide_landmark_borders(name, n_landmarks):
+    """17 3-D landmarks is the widest border of the 64-column SE(3) production kernels; up to 38 3-D / 60 2-D landmarks run the
+    128-column generic sweep (the reference has no landmark limit) - GN and LM against the oracle"""
+    cfg = small_cfg(name, 150, n_landmarks=n_landmarks, prior_every=30, range_per_state=1.5)
+    for use_lm in (False, True):
+        g, o, _ = both(cfg)
+        sg = g.optimize(use_lm=use_lm); so = o.optimize(use_lm=use_lm)
+        assert sg.status == 0 and sg.iterations == so.iterations
+        Pg, Vg, Lg = g.get_values(); Po, Vo, Lo = o.get_values()
+        assert np.abs(Pg - Po).max() <= 1e-6 and np.abs(Vg - Vo).max() <= 1e-6 and np.abs(Lg - Lo).max() <= 1e-6
+
+
 def test_landmark_border_limit():
-    """17 3-D landmarks (51 border columns) is the widest supported border; 18 are refused at finalize, not mis-solved"""
+    """beyond 128 - 2D - 1 border columns the graph is refused at finalize, not mis-solved"""
     from gpslam_b200 import capi
-    cfg = small_cfg("C3", 150, n_landmarks=17, prior_every=30, range_per_state=1.5)
-    g, o, _ = both(cfg)
-    sg = g.optimize(use_lm=True); so = o.optimize(use_lm=True)
-    assert sg.status == 0 and sg.iterations == so.iterations
-    Pg, Vg, Lg = g.get_values(); Po, Vo, Lo = o.get_values()
-    assert np.abs(Pg - Po).max() <= 1e-6 and np.abs(Lg - Lo).max() <= 1e-6
-    cfg = small_cfg("C3", 150, n_landmarks=18, prior_every=30, range_per_state=1.5)
-    with pytest.raises(capi.GpbError):
-        synth.build(cfg, lambda grp, n, l: gb.Graph(grp, n, l))
+    for name, n_landmarks in (("C3", 39), ("C1", 61)):
+        cfg = small_cfg(name, 150, n_landmarks=n_landmarks, prior_every=30, range_per_state=1.5)
+        with pytest.raises(capi.GpbError):
+            synth.build(cfg, lambda grp, n, l: gb.Graph(grp, n, l))
 
 
 # ----------------------------------------------------------------------------- interpolatePose queries
