@@ -752,7 +752,8 @@ int gpb_graph_finalize(gpb_graph* g, int device) {
   if (g->thread_chain && !g->M0 && !em0) M0 = std::min(64, std::max(8, (g->N + sms * 256 - 1) / (sms * 256)));
   // upper levels: 8 states per segment; 6 on short chains (shards of a few 10k states), where one more level of shorter
   // segments wins (measured on 12.5k / 25k / 50k / 100k states: -3 %, -2 %, 0, +1 %; gpurun_out/r1z_small_sweep2.jsonl)
-  const int Mup = g->Mup ? g->Mup : (emu ? std::max(2, atoi(emu)) : (g->N <= 40000 ? 6 : 8));
+  // (thread-per-segment chains: every upper level is a latency-bound pass of M states per thread - 4 measured best on C4, 1M states)
+  const int Mup = g->Mup ? g->Mup : (emu ? std::max(2, atoi(emu)) : (g->thread_chain ? 4 : (g->N <= 40000 ? 6 : 8)));
   if (!g->M0 && !em0 && bs == 12 && g->W == 64) {
     // the panel kernel runs one resident wave of persistent CTAs, each walking ceil(nseg / slots) segments of M0 (+ a closing
     // separator) states one after the other: pick the segment length that minimises that serial depth (whole rounds - a

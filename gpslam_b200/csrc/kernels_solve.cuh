@@ -1598,10 +1598,17 @@ __global__ void __launch_bounds__(64) k_fwd6t(const FwdArgs a) {
     const double* rec = a.rec + (size_t)i * RECS;
     const bool has_next = (i < i1) || (q >= 0);
     double L[21], X[21], dinv[BS];
+    // the record is read with 128-bit loads (a thread's records are not coalesced with its neighbours': every load instruction
+    // touches 32 sectors, so their number is what the load / store unit feels)
 #pragma unroll
     for (int c = 0; c < BS; c++)
 #pragma unroll
-      for (int r = c; r < BS; r++) L[tri(r, c)] = rec[r + c * BS] + (FIRST ? 0.0 : rec[BS * BS + r + c * BS]) + Dn[tri(r, c)] + (r == c ? lambda : 0.0);
+      for (int r = 0; r < BS; r += 2) {
+        double2 d = *reinterpret_cast<const double2*>(rec + r + c * BS);
+        if constexpr (!FIRST) { const double2 d2 = *reinterpret_cast<const double2*>(rec + BS * BS + r + c * BS); d.x += d2.x; d.y += d2.y; }
+        if (r >= c) L[tri(r, c)] = d.x + Dn[tri(r, c)] + (r == c ? lambda : 0.0);
+        if (r + 1 >= c) L[tri(r + 1, c)] = d.y + Dn[tri(r + 1, c)] + (r + 1 == c ? lambda : 0.0);
+      }
     // Cholesky, right-looking, in place
 #pragma unroll
     for (int j = 0; j < BS; j++) {
@@ -1640,11 +1647,12 @@ __global__ void __launch_bounds__(64) k_fwd6t(const FwdArgs a) {
 #pragma unroll
       for (int c = 0; c < BS; c++)
 #pragma unroll
-        for (int r = 0; r < BS; r++) {
-          double v = rec[oE + r + c * BS];
+        for (int r = 0; r < BS; r += 2) {
+          const double2 e = *reinterpret_cast<const double2*>(rec + oE + r + c * BS);
+          double v0 = e.x, v1 = e.y;
 #pragma unroll
-          for (int k = 0; k < c; k++) v = fma(-Le[k][r], L[tri(c, k)], v);
-          Le[c][r] = v * dinv[c];
+          for (int k = 0; k < c; k++) { v0 = fma(-Le[k][r], L[tri(c, k)], v0); v1 = fma(-Le[k][r + 1], L[tri(c, k)], v1); }
+          Le[c][r] = v0 * dinv[c]; Le[c][r + 1] = v1 * dinv[c];
         }
 #pragma unroll
       for (int c = 0; c < BS; c++)
@@ -1662,7 +1670,11 @@ __global__ void __launch_bounds__(64) k_fwd6t(const FwdArgs a) {
     }
     // own right-hand side, then Y = L^-1 P in place (rows from the bottom: y_r needs p_k, k <= r)
 #pragma unroll
-    for (int r = 0; r < BS; r++) P[6][r] += rec[oG + r] + (FIRST ? 0.0 : rec[oG + BS + r]);
+    for (int r = 0; r < BS; r += 2) {
+      double2 gq = *reinterpret_cast<const double2*>(rec + oG + r);
+      if constexpr (!FIRST) { const double2 g2 = *reinterpret_cast<const double2*>(rec + oG + BS + r); gq.x += g2.x; gq.y += g2.y; }
+      P[6][r] += gq.x; P[6][r + 1] += gq.y;
+    }
 #pragma unroll
     for (int c = 0; c < 7; c++)
 #pragma unroll
@@ -1789,24 +1801,32 @@ __global__ void __launch_bounds__(128) k_bwd6t(const BwdArgs a) {
   for (int i = i0; i <= i1; i++) {   // forward: z = g_i - t, y = L^-1 z, t = Le y
     const double* rec = a.rec + (size_t)i * RECS;
     const double* F = a.frec + (size_t)i * a.fstride;
-    double z[BS], y[BS];
+    double z[BS], y[BS], M[BS * BS];
 #pragma unroll
-    for (int r = 0; r < BS; r++) z[r] = rec[oG + r] + (FIRST ? 0.0 : rec[oG + BS + r]) - t[r];
+    for (int k = 0; k < BS * BS; k += 2) { const double2 m = *reinterpret_cast<const double2*>(F + k); M[k] = m.x; M[k + 1] = m.y; }   // L^-1
+#pragma unroll
+    for (int r = 0; r < BS; r += 2) {
+      double2 gq = *reinterpret_cast<const double2*>(rec + oG + r);
+      if constexpr (!FIRST) { const double2 g2 = *reinterpret_cast<const double2*>(rec + oG + BS + r); gq.x += g2.x; gq.y += g2.y; }
+      z[r] = gq.x - t[r]; z[r + 1] = gq.y - t[r + 1];
+    }
 #pragma unroll
     for (int r = 0; r < BS; r++) {
       double sacc = 0.0;
 #pragma unroll
-      for (int k = 0; k <= r; k++) sacc = fma(F[r + k * BS], z[k], sacc);
+      for (int k = 0; k <= r; k++) sacc = fma(M[r + k * BS], z[k], sacc);
       y[r] = sacc;
     }
 #pragma unroll
-    for (int r = 0; r < BS; r++) a.xsol[(size_t)i * BS + r] = y[r];
+    for (int r = 0; r < BS; r += 2) st128(a.xsol + (size_t)i * BS + r, y[r], y[r + 1]);
     if (i < i1) {
+#pragma unroll
+      for (int k = 0; k < BS * BS; k += 2) { const double2 m = *reinterpret_cast<const double2*>(F + BS * BS + k); M[k] = m.x; M[k + 1] = m.y; }   // Le
 #pragma unroll
       for (int r = 0; r < BS; r++) {
         double sacc = 0.0;
 #pragma unroll
-        for (int k = 0; k < BS; k++) sacc = fma(F[BS * BS + r + k * BS], y[k], sacc);
+        for (int k = 0; k < BS; k++) sacc = fma(M[r + k * BS], y[k], sacc);
         t[r] = sacc;
       }
     }
@@ -1814,25 +1834,31 @@ __global__ void __launch_bounds__(128) k_bwd6t(const BwdArgs a) {
   bool hn = q >= 0;
   for (int i = i1; i >= i0; i--) {   // backward: x = L^-T (y - Le^T x_next)
     const double* F = a.frec + (size_t)i * a.fstride;
-    double w[BS], x[BS];
+    double w[BS], x[BS], M[BS * BS];
 #pragma unroll
-    for (int c = 0; c < BS; c++) {
-      double sacc = a.xsol[(size_t)i * BS + c];
-      if (hn) {
+    for (int c = 0; c < BS; c += 2) { const double2 yv = *reinterpret_cast<const double2*>(a.xsol + (size_t)i * BS + c); w[c] = yv.x; w[c + 1] = yv.y; }
+    if (hn) {
 #pragma unroll
-        for (int r = 0; r < BS; r++) sacc = fma(-F[BS * BS + r + c * BS], xq[r], sacc);
+      for (int k = 0; k < BS * BS; k += 2) { const double2 m = *reinterpret_cast<const double2*>(F + BS * BS + k); M[k] = m.x; M[k + 1] = m.y; }   // Le
+#pragma unroll
+      for (int c = 0; c < BS; c++) {
+        double sacc = w[c];
+#pragma unroll
+        for (int r = 0; r < BS; r++) sacc = fma(-M[r + c * BS], xq[r], sacc);
+        w[c] = sacc;
       }
-      w[c] = sacc;
     }
+#pragma unroll
+    for (int k = 0; k < BS * BS; k += 2) { const double2 m = *reinterpret_cast<const double2*>(F + k); M[k] = m.x; M[k + 1] = m.y; }   // L^-1
 #pragma unroll
     for (int c = 0; c < BS; c++) {
       double sacc = 0.0;
 #pragma unroll
-      for (int r = c; r < BS; r++) sacc = fma(F[r + c * BS], w[r], sacc);
+      for (int r = c; r < BS; r++) sacc = fma(M[r + c * BS], w[r], sacc);
       x[c] = sacc;
     }
 #pragma unroll
-    for (int c = 0; c < BS; c++) { a.xsol[(size_t)i * BS + c] = x[c]; xq[c] = x[c]; }
+    for (int c = 0; c < BS; c += 2) { st128(a.xsol + (size_t)i * BS + c, x[c], x[c + 1]); xq[c] = x[c]; xq[c + 1] = x[c + 1]; }
     hn = true;
   }
 }
