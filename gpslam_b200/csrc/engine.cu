@@ -131,6 +131,7 @@ struct gpb_graph {
   int *d_pair_a = nullptr, *d_pair_b = nullptr, *d_pairoff = nullptr, *d_pairrow = nullptr;
   bool generic_fwd = false, force_blocked = false, old_assemble = false, split_levels = false, no_tiny = false, fuse_l0 = false, old_bwd = false;
   int tiny_mode = 0;
+  bool fma_syrk = false;      // A/B switch GPB_FMA_SYRK: trailing update of the multi-CTA dense solve on FP64 FMAs (round 1) instead of the tensor pipe
   bool thread_chain = false;  // 6 x 6 chains without a landmark border: thread-per-segment kernels (k_fwd6t / k_bwd6t); GPB_NO_THREAD_CHAIN = generic kernels
   int panel0_occ = 4;         // CTAs per SM the level-0 active-column panel kernel is compiled for (GPB_PANEL0_OCC = 4: 128 registers, no spills)
   bool dense_panel = false;   // A/B switch GPB_DENSE_PANEL: k_panel4 (all 64 columns at every state) instead of k_panel0 (active columns only)
@@ -738,6 +739,7 @@ int gpb_graph_finalize(gpb_graph* g, int device) {
   g->dense_panel = getenv("GPB_DENSE_PANEL") != nullptr || g->old_bwd;
   if (const char* ev = getenv("GPB_PANEL0_OCC")) g->panel0_occ = atoi(ev) == 5 ? 5 : 4;  // the Y-reading back-substitution needs the dense kernel's Y layout  // A/B switch: back-substitution from a stored Y (k_bwd) instead of re-eliminating the right-hand side (k_bwd2)  // A/B switch: level 0 as ONE warp-specialised kernel (spine warp + panel warps per CTA)
   g->no_tiny = getenv("GPB_NO_TINY_SOLVE") != nullptr;
+  g->fma_syrk = getenv("GPB_FMA_SYRK") != nullptr;
   g->tiny_mode = g->no_tiny ? 2 : (getenv("GPB_OLD_TINY") != nullptr ? 1 : 0);  // reduced-system solver in shared memory: blocked (default) / register-blocked per column / plain per column  // A/B switch: the plain-loop instantiation of k_small_solve instead of the register-blocked ones
   g->qc_diag = 1;
   for (const auto& R : g->Rq) for (int c = 0; c < D; c++) for (int r = 0; r < D; r++) if (r != c && R[r + c * D] != 0.0) g->qc_diag = 0;
@@ -1125,7 +1127,8 @@ static int solve_top_dense(gpb_graph* g) {
     g->launches += 2;
     if (j0 + n < R) {
       const int nt = (below + DNB - 1) / DNB;
-      k_dense_syrk<<<dim3(nt, nt), 256, 0, g->stream>>>(g->d_topbuf, ld, R, j0);
+      if (g->fma_syrk) k_dense_syrk<<<dim3(nt, nt), 256, 0, g->stream>>>(g->d_topbuf, ld, R, j0);
+      else k_dense_syrk_mma<<<dim3(nt, nt), 128, 0, g->stream>>>(g->d_topbuf, ld, R, j0);
       g->launches++;
     }
   }
@@ -1633,6 +1636,7 @@ int gpb_debug_dense_solve(int device, int R, const double* A, const double* b, d
   CUDA_TRY(cudaFuncSetAttribute(k_small_solve<256, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_solve_smem(95)));
   CUDA_TRY(cudaFuncSetAttribute(k_small_solve<256, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_solve_smem(143)));
   gpb_graph g;
+  g.fma_syrk = getenv("GPB_FMA_SYRK") != nullptr;
   g.R = R; g.bs = 1; g.ntop = loff; g.force_blocked = force_blocked == 1; g.no_tiny = force_blocked == 2; g.tiny_mode = force_blocked == 2 ? 2 : (force_blocked == 3 ? 1 : 0);  // 2: plain per-column loops, 3: register-blocked per-column kernel, 0: blocked factorisation
   CUDA_TRY(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
   int rc = GPB_OK;

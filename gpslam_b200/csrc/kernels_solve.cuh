@@ -2365,6 +2365,52 @@ __global__ void __launch_bounds__(256) k_dense_syrk(double* __restrict__ T, int 
       if (r <= R && c < R && r >= c) T[r + (size_t)c * ld] -= acc[i][j];
     }
 }
+// The same trailing update on the FP64 tensor pipe (default; north_star: "tensor cores ... where that panel is a genuine dense
+// contraction" - this SYRK over 64-column panels is the one place in the path that is).  CTA = 4 warps, one 64 x 64 tile of the
+// trailing matrix, K = 64 staged through shared memory in 16-deep chunks; warp w owns row tiles 2w, 2w+1 x the 8 column tiles
+// (16 accumulator fragments); per k-slice 2 + 8 fragment loads feed 16 mma.sync.m8n8k4.f64.
+__global__ void __launch_bounds__(128) k_dense_syrk_mma(double* __restrict__ T, int ld, int R, int j0) {
+  if (blockIdx.y > blockIdx.x) return;
+  constexpr int KC = 16, LDS_ = DNB + 8;   // row stride 72 doubles: the four k rows of a fragment load fall into two bank halves
+  __shared__ double As[KC][LDS_], Bs[KC][LDS_];
+  const int n = min(DNB, R - j0), base = j0 + n;
+  const int r0 = base + blockIdx.x * DNB, c0 = base + blockIdx.y * DNB;  // tile origin (rows, cols)
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gi = lane >> 2, ti = lane & 3;
+  double acc[2][8][2];
+#pragma unroll
+  for (int i = 0; i < 2; i++)
+#pragma unroll
+    for (int j = 0; j < 8; j++) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+  for (int k0 = 0; k0 < n; k0 += KC) {
+    for (int e = tid; e < KC * DNB; e += 128) {
+      const int rr = e % DNB, kk = e / DNB;
+      const bool kv = k0 + kk < n;
+      As[kk][rr] = (kv && r0 + rr <= R) ? T[(r0 + rr) + (size_t)(j0 + k0 + kk) * ld] : 0.0;
+      Bs[kk][rr] = (kv && c0 + rr < R) ? T[(c0 + rr) + (size_t)(j0 + k0 + kk) * ld] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int sK = 0; sK < KC / 4; sK++) {
+      const double a0 = As[4 * sK + ti][8 * (2 * warp) + gi], a1 = As[4 * sK + ti][8 * (2 * warp + 1) + gi];
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const double b = Bs[4 * sK + ti][8 * j + gi];   // B[k][n] = A_J[n][k]
+        dmma884(acc[0][j][0], acc[0][j][1], a0, b);
+        dmma884(acc[1][j][0], acc[1][j][1], a1, b);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 2; i++)
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const int r = r0 + 8 * (2 * warp + i) + gi, c = c0 + 8 * j + 2 * ti + h;
+        if (r <= R && c < R && r >= c) T[r + (size_t)c * ld] -= acc[i][j][h];
+      }
+}
 // back-substitution step for block column j0: x_j = L_jj^-T y_j (every CTA, redundantly, by its first warp), then
 // y_c -= L[j-rows][c]^T x_j for the columns c < j0 (one per thread).  y lives in row R of T; x goes to xout.
 __global__ void __launch_bounds__(256) k_dense_bwd(double* __restrict__ T, int ld, int R, int j0, double* __restrict__ xout) {

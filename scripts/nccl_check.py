@@ -61,7 +61,7 @@ def main():
                 halos_ok = all(np.array_equal(gathered[r][1][0], P[shard.owned_range(n, r, world)[0] - 1]) and np.array_equal(gathered[r][1][1], V[shard.owned_range(n, r, world)[0] - 1])
                                for r in range(1, world))
                 its = [x[3] for x in gathered]; nars = [x[4] for x in gathered]
-                good = d_single < (1e-7 if use_lm else 1e-9) and d_oracle < 1e-6 and halos_ok and all(k == sr.iterations for k in its) and sr.iterations == so.iterations
+                good = d_single < (1e-7 if use_lm else 1e-8) and d_oracle < 1e-6 and halos_ok and all(k == sr.iterations for k in its) and sr.iterations == so.iterations
                 if not use_lm:
                     good = good and all(k == iters + 2 for k in nars)
                 ok = ok and good

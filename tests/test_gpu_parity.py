@@ -281,6 +281,21 @@ def test_reduced_system_solvers(R):
             capi.dense_solve(-A, b, 0.0, 0, force_small=True)
 
 
+def test_dense_solve_trailing_update_variants(monkeypatch):
+    """the multi-CTA dense solve with its trailing update on the tensor pipe (default) and on FP64 FMAs (GPB_FMA_SYRK) against numpy"""
+    from gpslam_b200 import capi
+    rng = np.random.default_rng(77)
+    for R in (130, 449, 1000):
+        B = rng.normal(size=(R, R + 5)); A = B @ B.T + 0.1 * np.eye(R); b = rng.normal(size=R)
+        ref = np.linalg.solve(A + 0.3 * np.diag((np.arange(R) >= R // 3).astype(float)), b)
+        x_mma = capi.dense_solve(A, b, 0.3, R // 3, True)
+        monkeypatch.setenv("GPB_FMA_SYRK", "1")
+        x_fma = capi.dense_solve(A, b, 0.3, R // 3, True)
+        monkeypatch.delenv("GPB_FMA_SYRK")
+        for x in (x_mma, x_fma):
+            assert np.abs(x - ref).max() <= 1e-9 * max(1.0, np.abs(ref).max()), (R, np.abs(x - ref).max())
+
+
 def test_reference_two_state_optimizations():
     """the reference's 'Optimization' unit tests through the CUDA path (gp/tests/testGaussianProcessPriorPose3.cpp:146-195,
     slam/tests/testGPInterpolatedRangeFactorPose3.cpp:177-260 incl. extrapolation tau = -0.1 and 0.2)"""
