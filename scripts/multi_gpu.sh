@@ -8,8 +8,9 @@ if [ "$N" = "1" ]; then LAUNCH="python"; else LAUNCH="python -m torch.distribute
 for s in $STEPS; do
   case $s in
     check) timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 scripts/nccl_check.py > gpurun_out/${TAG}_nccl_check_n$N.log 2>&1; echo "nccl_check rc=$?"; grep -E "PASS|FAIL|Error|error" gpurun_out/${TAG}_nccl_check_n$N.log | head -12;;
-    c3|c3_1m|c4|c5)
-      case $s in c3) ARGS="";; c3_1m) ARGS="--states 1000000";; c4) ARGS="--config C4";; c5) ARGS="--config C5";; esac
+    c3|c3_fuse|c3_1m|c4|c5)
+      unset GPB_FUSE_L0
+      case $s in c3) ARGS="";; c3_fuse) ARGS=""; export GPB_FUSE_L0=1;; c3_1m) ARGS="--states 1000000";; c4) ARGS="--config C4";; c5) ARGS="--config C5";; esac
       timeout 900 $LAUNCH bench.py --gpus $N --steps 20 --warmup 3 --no-cpu $ARGS > gpurun_out/${TAG}_bench_${s}_n$N.json 2> gpurun_out/${TAG}_bench_${s}_n$N.err; echo "bench $s N=$N rc=$?"
       python - <<PY
 import json
