@@ -1432,7 +1432,17 @@ __global__ void __launch_bounds__(128, 4) k_bwd2(const BwdArgs a) {
     };
     auto slot = [&](int i) -> double* { return (i - i0 < YC) ? &ysm[yw][(i - i0) * BS] : a.xsol + (size_t)i * BS; };
     // the (L^-1 | Le) of the first states start streaming in while the right-hand sides are formed
-    if (sweeper) {
+    // CTA per segment and the segment fits the staging buffers (NW * NST states: every upper level with M <= 12): all of its
+    // (L^-1 | Le) are loaded once, by the whole CTA, and both sweeps run out of shared memory with no memory latency in the chain
+    const bool resident = CTASEG && (i1 - i0 + 1) <= NW * NST;
+    double* const Fall = &Fb[0][0][0];
+    if (resident) {
+      for (int sidx = 0; sidx <= i1 - i0; sidx++) {
+        const double* src = a.frec + (size_t)(i0 + sidx) * a.fstride;
+        for (int k = threadIdx.x; k < F2 / 2; k += 128) cp_async16(Fall + (size_t)sidx * F2 + 2 * k, src + 2 * k);
+      }
+      cp_async_commit();
+    } else if (sweeper) {
       fetch(i0, 0); cp_async_commit();
       if (i0 + 1 <= i1) fetch(i0 + 1, 1);
       cp_async_commit();
@@ -1495,6 +1505,7 @@ __global__ void __launch_bounds__(128, 4) k_bwd2(const BwdArgs a) {
         if (rl) { const double* g = a.rec + (size_t)i * REC1 + oG; slot(i)[lane] = g[lane] + g[BS + lane] - sum; }
       }
     }
+    if (resident) cp_async_wait<0>();
     if constexpr (CTASEG) __syncthreads(); else __syncwarp();
     if (sweeper) {
     // ---- forward sweep:  z_i = o_i - [i == i0] E_p x_p - Le_{i-1} y_{i-1},  y_i = L_i^-1 z_i
@@ -1507,13 +1518,13 @@ __global__ void __launch_bounds__(128, 4) k_bwd2(const BwdArgs a) {
     }
     int st = 0;
     for (int i = i0; i <= i1; i++) {
-      if (i + 2 <= i1) fetch(i + 2, st == 0 ? 2 : st - 1);
+      if (!resident && i + 2 <= i1) fetch(i + 2, st == 0 ? 2 : st - 1);
       cp_async_commit();
       double* ys = slot(i);
       const double own = rl ? ys[lane] : 0.0;
       cp_async_wait<2>();
       __syncwarp();
-      const double* Li = Fb[yw][st];
+      const double* Li = resident ? Fall + (size_t)(i - i0) * F2 : Fb[yw][st];
       if (rl) v[lane] = own - t;
       __syncwarp();
       const double y = matvec(Li, false);   // the strictly-upper part of L^-1 is stored as zeros
@@ -1527,19 +1538,21 @@ __global__ void __launch_bounds__(128, 4) k_bwd2(const BwdArgs a) {
     cp_async_wait<0>();
     __syncwarp();
     // ---- backward sweep:  x_i = L_i^-T (y_i - Le_i^T x_{i+1}),  x_{i1+1} = x_q
-    fetch(i1, 0); cp_async_commit();
-    if (i1 - 1 >= i0) fetch(i1 - 1, 1);
-    cp_async_commit();
+    if (!resident) {
+      fetch(i1, 0); cp_async_commit();
+      if (i1 - 1 >= i0) fetch(i1 - 1, 1);
+      cp_async_commit();
+    }
     bool hn = q >= 0;
     double xn = xq;   // lane r: entry r of x_{i+1}
     st = 0;
     for (int i = i1; i >= i0; i--) {
-      if (i - 2 >= i0) fetch(i - 2, st == 0 ? 2 : st - 1);
+      if (!resident && i - 2 >= i0) fetch(i - 2, st == 0 ? 2 : st - 1);
       cp_async_commit();
       const double ycur = rl ? slot(i)[lane] : 0.0;
       cp_async_wait<2>();
       __syncwarp();
-      const double* Li = Fb[yw][st];
+      const double* Li = resident ? Fall + (size_t)(i - i0) * F2 : Fb[yw][st];
       double w = ycur;
       if (hn) {
         if (rl) v[lane] = xn;
