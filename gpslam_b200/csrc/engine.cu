@@ -134,6 +134,7 @@ struct gpb_graph {
   bool fma_syrk = false;      // A/B switch GPB_FMA_SYRK: trailing update of the multi-CTA dense solve on FP64 FMAs (round 1) instead of the tensor pipe
   bool thread_chain = false;  // 6 x 6 chains without a landmark border: thread-per-segment kernels (k_fwd6t / k_bwd6t); GPB_NO_THREAD_CHAIN = generic kernels
   int panel0_occ = 4;         // CTAs per SM the level-0 active-column panel kernel is compiled for (GPB_PANEL0_OCC = 4: 128 registers, no spills)
+  bool panelw = false;        // A/B switch GPB_PANELW: register-resident two-warp level-0 panel kernel (k_panel_w)
   bool dense_panel = false;   // A/B switch GPB_DENSE_PANEL: k_panel4 (all 64 columns at every state) instead of k_panel0 (active columns only)
   unsigned char *d_lorder = nullptr, *d_ntile = nullptr;  // k_panel0: per-segment landmark order [nseg][17], active column tiles per state [N]
   int fstride = 0;  // doubles per state of a level's factor record: (L^-1 | Le), + Y for the Y-reading back-substitution
@@ -563,9 +564,10 @@ static int bwd_blocks_per_sm(int bs, int W) {
   if (bs == 12) return W == 16 ? occ_bwd<12, 16>() : W == 32 ? occ_bwd<12, 32>() : W == 64 ? occ_bwd<12, 64>() : occ_bwd<12, 128>();
   return W == 16 ? occ_bwd<6, 16>() : W == 32 ? occ_bwd<6, 32>() : W == 64 ? occ_bwd<6, 64>() : occ_bwd<6, 128>();
 }
-static int fwd_blocks_per_sm(int bs, int W, bool fuse_l0 = false, int panel0_occ = 4) {
+static int fwd_blocks_per_sm(int bs, int W, bool fuse_l0 = false, int panel0_occ = 4, bool panelw = false) {
   if (bs == 12 && W == 64) {
     int nb = 0;
+    if (panelw) { if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_panel_w<12>, 64, 0) != cudaSuccess) { cudaGetLastError(); nb = 4; } return nb < 1 ? 1 : nb; }
     if (fuse_l0) { if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_level0_ws<12>, 160, 0) != cudaSuccess) { cudaGetLastError(); nb = 4; } return nb < 1 ? 1 : nb; }
     int nb0 = 0;
     if ((panel0_occ == 4 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb0, k_panel0<12, 4>, 128, 0) : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb0, k_panel0<12, 5>, 128, 0)) != cudaSuccess) { cudaGetLastError(); nb0 = 4; }
@@ -737,6 +739,7 @@ int gpb_graph_finalize(gpb_graph* g, int device) {
   g->fuse_l0 = getenv("GPB_FUSE_L0") != nullptr;
   g->old_bwd = getenv("GPB_OLD_BWD") != nullptr;
   g->dense_panel = getenv("GPB_DENSE_PANEL") != nullptr || g->old_bwd;
+  g->panelw = getenv("GPB_PANELW") != nullptr && !g->dense_panel;
   if (const char* ev = getenv("GPB_PANEL0_OCC")) g->panel0_occ = atoi(ev) == 5 ? 5 : 4;  // the Y-reading back-substitution needs the dense kernel's Y layout  // A/B switch: back-substitution from a stored Y (k_bwd) instead of re-eliminating the right-hand side (k_bwd2)  // A/B switch: level 0 as ONE warp-specialised kernel (spine warp + panel warps per CTA)
   g->no_tiny = getenv("GPB_NO_TINY_SOLVE") != nullptr;
   g->fma_syrk = getenv("GPB_FMA_SYRK") != nullptr;
@@ -760,7 +763,7 @@ int gpb_graph_finalize(gpb_graph* g, int device) {
     // the panel kernel runs one resident wave of persistent CTAs, each walking ceil(nseg / slots) segments of M0 (+ a closing
     // separator) states one after the other: pick the segment length that minimises that serial depth (whole rounds - a
     // 100k-state chain on 148 x 5 slots wants 46, not 32); ties go to the longer segment (fewer separators for the next level)
-    const int slots = sms * fwd_blocks_per_sm(bs, g->W, g->fuse_l0, g->panel0_occ), m0 = g->N - g->pinL - g->pinR;
+    const int slots = sms * fwd_blocks_per_sm(bs, g->W, g->fuse_l0, g->panel0_occ, g->panelw), m0 = g->N - g->pinL - g->pinR;
     long long best = -1;
     for (int M = 12; M <= 63; M++) {
       const int nseg = (m0 > 0 ? (m0 - 1) / M : 0) + 1;
@@ -818,7 +821,7 @@ int gpb_graph_finalize(gpb_graph* g, int device) {
         if ((rc = dev_upload(g, &g->d_lorder, lorder))) return rc;
         if ((rc = dev_upload(g, &g->d_ntile, ntile))) return rc;
       }
-      L.ncta = std::min(L.nseg, sms * fwd_blocks_per_sm(bs, g->W, g->fuse_l0 && lev == 0, g->panel0_occ));  // persistent CTAs: one resident wave
+      L.ncta = std::min(L.nseg, sms * fwd_blocks_per_sm(bs, g->W, g->fuse_l0 && lev == 0, g->panel0_occ, g->panelw && lev == 0));  // persistent CTAs: one resident wave
       L.ncta_bwd = std::min(L.nseg, sms * bwd_blocks_per_sm(bs, g->W));
       if ((rc = dev_upload(g, &L.d_sep, sep))) return rc;
       if ((rc = dev_alloc(g, &L.frec, (size_t)n * fstride))) return rc;
@@ -1049,7 +1052,8 @@ static int launch_fwd_level(gpb_graph* g, int buf, double lambda, int lev, int p
     } else {
       if (parts & 1) { if (lev == 0) k_spine<12, true><<<spine_ctas, 32, 0, g->stream>>>(a); else k_spine<12, false><<<spine_ctas, 32, 0, g->stream>>>(a); g->launches++; }
       if (parts & 2) {
-        if (lev == 0 && !g->dense_panel) { if (g->panel0_occ == 4) k_panel0<12, 4><<<L.ncta, 128, 0, g->stream>>>(a, g->d_lorder, g->d_ntile); else k_panel0<12, 5><<<L.ncta, 128, 0, g->stream>>>(a, g->d_lorder, g->d_ntile); }
+        if (lev == 0 && g->panelw) k_panel_w<12><<<L.ncta, 64, 0, g->stream>>>(a, g->d_lorder, g->d_ntile);
+        else if (lev == 0 && !g->dense_panel) { if (g->panel0_occ == 4) k_panel0<12, 4><<<L.ncta, 128, 0, g->stream>>>(a, g->d_lorder, g->d_ntile); else k_panel0<12, 5><<<L.ncta, 128, 0, g->stream>>>(a, g->d_lorder, g->d_ntile); }
         else k_panel4<12><<<L.ncta, 128, 0, g->stream>>>(a);
         g->launches++;
       }

@@ -1270,6 +1270,212 @@ __global__ void __launch_bounds__(128, MINB) k_panel0(const FwdArgs a, const uns
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Level-0 panel, register-resident (A/B switch GPB_PANELW).  Two warps per segment (one 64-thread CTA); the panel P and
+// Y = L^-1 P never touch shared memory as matrices: each warp keeps its four column tiles of P^T as mma A-fragments
+// (pa[j][s] = P[k(s, ti)][8 T + gi], T = 2 j + warp), computes Y^T = P^T L^-T and P'^T = -Y^T Le^T with the (L^-1, Le) fragments
+// loaded straight from L2 one state ahead, and turns each C-fragment back into an A/B-fragment with ONE shuffle per tile thanks
+// to the k-slot order k(0, ti) = 2 ti, k(1, ti) = 2 ti + 1, k(2, ti) = {8, 10, 9, 11}[ti] (a permutation of the summation index
+// applied to both operands of every product).  The only exchange is Y's fragments (12 doubles per lane and state, double
+// buffered, one 64-thread barrier per state) so that both warps can form their 18 tiles of S += Y^T Y.  Column order, active
+// tiles and the end-of-segment hand-off are k_panel0's.
+template <int W>
+__device__ __forceinline__ void panelw_body(const FwdArgs& a, const unsigned char* __restrict__ lorder, const unsigned char* __restrict__ ntile,
+                                            double* Csm, int* gdim, int* lrank, unsigned char* nts, double (*Yx)[8][3][32]) {
+  constexpr int BS = 12, REC0 = 2 * BS * BS + BS, REC1 = 3 * BS * BS + 2 * BS, C0 = BS + 1, DL = 3, LMAX = 17;
+  const int tid = threadIdx.x, lane = tid & 31, gi = lane >> 2, ti = lane & 3;
+  const int nb = a.nb, nl = nb / DL;
+  const int ks[3] = {2 * ti, 2 * ti + 1, ti < 2 ? 8 + 2 * ti : 9 + 2 * (ti - 2)};
+  const int shsrc = (lane & ~3) | (ti & 1);   // lane holding rows 9 / 11 of this column (second register of its rows-8..11 fragment)
+  double acc[18][2];
+#pragma unroll
+  for (int u = 0; u < 18; u++) { acc[u][0] = 0.0; acc[u][1] = 0.0; }
+  for (int seg = blockIdx.x; seg < a.nseg; seg += gridDim.x) {
+    const SegGeom sg = seg_geom(seg, a.n, a.sep, a.S, a.extL, a.extR);
+    const int p = sg.p, q = sg.q, i0 = sg.i0, i1 = sg.i1;
+    if (tid < 64) gdim[tid] = (tid >= C0 && tid < C0 + nb) ? (int)lorder[(size_t)seg * LMAX + (tid - C0) / DL] * DL + (tid - C0) % DL : -1;
+    if (tid < nl) lrank[(int)lorder[(size_t)seg * LMAX + tid]] = tid;
+    if (i0 + tid <= i1) nts[tid] = ntile[i0 + tid];
+    __syncthreads();
+    double pa[4][3];
+    {  // spike columns start as the coupling to the left separator
+      const double* E = a.rec + (size_t)(p >= 0 ? p : 0) * REC0 + BS * BS;
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+#pragma unroll
+        for (int s = 0; s < 3; s++) { const int col = 8 * (2 * j + W) + gi; pa[j][s] = (p >= 0 && col < BS) ? E[ks[s] + col * BS] : 0.0; }
+    }
+    // own part of state i added into the fragments: right-hand side (column 12) and the border entries of the state
+    auto add_own = [&](int i, int e0, int e1) {
+      if (W == 1 && gi == 4) {
+        const double* g = a.rec + (size_t)i * REC0 + 2 * BS * BS;
+#pragma unroll
+        for (int s = 0; s < 3; s++) pa[0][s] += g[ks[s]];
+      }
+      for (int e = e0; e < e1; e++) {
+        const double* en = a.bent + (size_t)e * 16;
+        const int k = lrank[(int)en[15]];
+        const double a0 = en[ks[0]], a1 = en[ks[1]], a2 = en[ks[2]];
+#pragma unroll
+        for (int d = 0; d < DL; d++) {
+          const int col = C0 + DL * k + d, T = col >> 3;
+          if ((T & 1) == W && (col & 7) == gi) {
+            const double h = en[BS + d];
+#pragma unroll
+            for (int j = 0; j < 4; j++) if (j == (T >> 1)) { pa[j][0] = fma(a0, h, pa[j][0]); pa[j][1] = fma(a1, h, pa[j][1]); pa[j][2] = fma(a2, h, pa[j][2]); }
+          }
+        }
+      }
+    };
+    // fragments of (L^-1 | Le) of one state, loaded straight from L2: B[k][n] = L^-1[n][k] (rows 0..7: slices 0, 1 only - the block is
+    // lower triangular; rows 8..11) and Le[n][k]
+    double fL0[2], fL1[3], fE0[3], fE1[3];
+    auto load_frags = [&](int i, double (&l0)[2], double (&l1)[3], double (&e0)[3], double (&e1)[3], bool want_e) {
+      const double* F = a.frec + (size_t)i * a.fstride;
+#pragma unroll
+      for (int s = 0; s < 3; s++) {
+        if (s < 2) l0[s] = F[gi + ks[s] * BS];
+        l1[s] = (gi < 4) ? F[(8 + gi) + ks[s] * BS] : 0.0;
+        e0[s] = want_e ? F[BS * BS + gi + ks[s] * BS] : 0.0;
+        e1[s] = (want_e && gi < 4) ? F[BS * BS + (8 + gi) + ks[s] * BS] : 0.0;
+      }
+    };
+    if (i0 <= i1) load_frags(i0, fL0, fL1, fE0, fE1, (i0 < i1) || (q >= 0));
+    int b0 = nb ? a.bsoff[i0 <= a.n ? i0 : a.n] : 0, b1 = nb ? a.bsoff[i0 + 1 <= a.n ? i0 + 1 : a.n] : 0, b2 = nb ? a.bsoff[i0 + 2 <= a.n ? i0 + 2 : a.n] : 0;
+    int par = 0, ntmax = 2;
+    for (int i = i0; i <= i1; i++) {
+      const bool has_next = (i < i1) || (q >= 0);
+      const int nt = (i - i0 < 64) ? (int)nts[i - i0] : (int)ntile[i];
+      ntmax = nt;
+      const int b3 = nb ? a.bsoff[i + 3 <= a.n ? i + 3 : a.n] : 0;
+      double nL0[2], nL1[3], nE0[3], nE1[3];
+      if (i + 1 <= i1) load_frags(i + 1, nL0, nL1, nE0, nE1, (i + 1 < i1) || (q >= 0));   // next state's fragments fly during this state
+      add_own(i, b0, b1);
+      double yall[8][3];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int T = 2 * j + W;
+        if (T < nt) {
+          double d0[2] = {0.0, 0.0}, d1[2] = {0.0, 0.0};
+#pragma unroll
+          for (int s = 0; s < 3; s++) { if (s < 2) dmma884(d0[0], d0[1], pa[j][s], fL0[s]); dmma884(d1[0], d1[1], pa[j][s], fL1[s]); }
+          const double v = __shfl_sync(0xffffffffu, d1[1], shsrc);
+          yall[T][0] = d0[0]; yall[T][1] = d0[1]; yall[T][2] = ti < 2 ? d1[0] : v;
+#pragma unroll
+          for (int s = 0; s < 3; s++) Yx[par][T][s][lane] = yall[T][s];
+          if (has_next) {
+            double e0[2] = {0.0, 0.0}, e1[2] = {0.0, 0.0};
+#pragma unroll
+            for (int s = 0; s < 3; s++) { dmma884(e0[0], e0[1], yall[T][s], fE0[s]); dmma884(e1[0], e1[1], yall[T][s], fE1[s]); }
+            const double v2 = __shfl_sync(0xffffffffu, e1[1], shsrc);
+            pa[j][0] = -e0[0]; pa[j][1] = -e0[1]; pa[j][2] = -(ti < 2 ? e1[0] : v2);
+          } else { pa[j][0] = 0.0; pa[j][1] = 0.0; pa[j][2] = 0.0; }
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int T = 2 * j + (1 - W);
+        if (T < nt) {
+#pragma unroll
+          for (int s = 0; s < 3; s++) yall[T][s] = Yx[par][T][s][lane];
+        }
+      }
+      static_for<0, 18>([&](auto U) {
+        constexpr int u = decltype(U)::value, t = 2 * u + W, I = tri_I(t), J = tri_J(t);
+        if (I < nt) {
+#pragma unroll
+          for (int s = 0; s < 3; s++) dmma884(acc[u][0], acc[u][1], yall[I][s], yall[J][s]);
+        }
+      });
+      par ^= 1;
+      b0 = b1; b1 = b2; b2 = b3;
+      if (i + 1 <= i1) {
+#pragma unroll
+        for (int s = 0; s < 3; s++) { if (s < 2) fL0[s] = nL0[s]; fL1[s] = nL1[s]; fE0[s] = nE0[s]; fE1[s] = nE1[s]; }
+      }
+    }
+    // ---- segment end: the closing separator's own border / rhs, then hand the panel off (D1 of q was written by k_spine)
+    if (q >= 0) {
+      double* R = a.rec_out + (size_t)sg.qo * REC1;
+      add_own(q, b0, b1);
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+#pragma unroll
+        for (int s = 0; s < 3; s++) {
+          const int col = 8 * (2 * j + W) + gi, r = ks[s];
+          if (col < BS) { if (p >= 0) a.rec_out[(size_t)sg.po * REC1 + 2 * BS * BS + r + col * BS] = pa[j][s]; }
+          else if (col == BS) R[3 * BS * BS + r] = pa[j][s];
+          else if (col < C0 + nb) a.brec_out[(size_t)sg.qo * (2 * BS * nb) + r + gdim[col] * BS] = pa[j][s];
+        }
+      if (a.extR && seg == a.S) {
+        for (int k = tid; k < BS * BS; k += 64) R[BS * BS + k] = 0.0;
+        if (tid < BS) R[3 * BS * BS + BS + tid] = 0.0;
+        for (int k = tid; k < BS * nb; k += 64) a.brec_out[(size_t)sg.qo * (2 * BS * nb) + BS * nb + k] = 0.0;
+      }
+    }
+    if (a.extL && seg == 0) {  // the left external separator (halo state p): its own blocks pass through to the next level
+      double* R = a.rec_out;
+      const double* src = a.rec + (size_t)p * REC0;
+      for (int k = tid; k < BS * BS; k += 64) R[k] = src[k] + ((a.lamL && (k % (BS + 1)) == 0) ? (*a.lambda_ptr) : 0.0);
+      if (tid < BS) R[3 * BS * BS + tid] = src[2 * BS * BS + tid];
+      for (int k = tid; k < BS * nb; k += 64) {
+        const int r = k % BS, gd = k / BS;
+        double v = 0.0;
+        for (int e = a.bsoff[p]; e < a.bsoff[p + 1]; e++) { const double* en = a.bent + (size_t)e * 16; if ((int)en[15] == gd / DL) v += en[r] * en[BS + gd % DL]; }
+        a.brec_out[k] = v;
+      }
+    }
+    {
+      double* Rp = (p >= 0) ? a.rec_out + (size_t)sg.po * REC1 : nullptr;
+      double* Bp = (p >= 0) ? a.brec_out + (size_t)sg.po * (2 * BS * nb) + BS * nb : nullptr;
+      auto flush = [&](int x, int y, double& av) {   // x >= y: physical columns
+        const double v = -av;
+        av = 0.0;
+        if (y < BS) {
+          if (p < 0) return;
+          if (x < BS) { Rp[BS * BS + y + x * BS] = v; Rp[BS * BS + x + y * BS] = v; }
+          else if (x == BS) Rp[3 * BS * BS + BS + y] = v;
+          else if (x < C0 + nb) Bp[y + gdim[x] * BS] = v;
+        } else if (x < C0 + nb && x > BS) {
+          const int gx = gdim[x];
+          if (y == BS) Csm[nb * (nb + 1) / 2 + gx] += v;
+          else { const int gy = gdim[y]; const int hi = gx > gy ? gx : gy, lo = gx > gy ? gy : gx; Csm[hi * (hi + 1) / 2 + lo] += v; }
+        }
+      };
+      static_for<0, 18>([&](auto U) {
+        constexpr int u = decltype(U)::value, t = 2 * u + W, I = tri_I(t), J = tri_J(t);
+        if (I < ntmax || J < 2) {
+          const int x = 8 * I + gi, y = 8 * J + 2 * ti;
+          if (x >= y) flush(x, y, acc[u][0]); else acc[u][0] = 0.0;
+          if (x >= y + 1) flush(x, y + 1, acc[u][1]); else acc[u][1] = 0.0;
+        }
+      });
+    }
+    __syncthreads();
+  }
+}
+template <int BS>
+__global__ void __launch_bounds__(64, 4) k_panel_w(const FwdArgs a, const unsigned char* __restrict__ lorder, const unsigned char* __restrict__ ntile) {
+  static_assert(BS == 12, "panel kernel is specialised for 12 x 12 state blocks");
+  constexpr int LMAX = 17, DL = 3, CSN = LMAX * DL * (LMAX * DL + 1) / 2 + LMAX * DL;
+  __shared__ double Csm[CSN];
+  __shared__ double Yx[2][8][3][32];
+  __shared__ int gdim[64], lrank[LMAX];
+  __shared__ unsigned char nts[64];
+  for (int k = threadIdx.x; k < CSN; k += 64) Csm[k] = 0.0;
+  __syncthreads();
+  if (threadIdx.x < 32) panelw_body<0>(a, lorder, ntile, Csm, gdim, lrank, nts, Yx);
+  else panelw_body<1>(a, lorder, ntile, Csm, gdim, lrank, nts, Yx);
+  __syncthreads();
+  const int nb = a.nb;
+  if (nb > 0) {
+    double* Cs = a.cseg + (size_t)blockIdx.x * (nb * nb + nb);
+    for (int e = threadIdx.x; e < nb * nb; e += 64) { const int r = e % nb, cc = e / nb, hi = r > cc ? r : cc, lo = r > cc ? cc : r; Cs[e] = Csm[hi * (hi + 1) / 2 + lo]; }
+    for (int e = threadIdx.x; e < nb; e += 64) Cs[nb * nb + e] = Csm[nb * (nb + 1) / 2 + e];
+  }
+}
+
 // Upper elimination levels (a few hundred segments at most: latency, not throughput): ONE kernel per level.  Warp 4 of each
 // CTA walks the spine of the CTA's segments and never waits; warps 0-3 run the panel a couple of states behind it, so a level
 // costs about one spine pass instead of a spine launch followed by a panel launch.
