@@ -1279,10 +1279,11 @@ __global__ void __launch_bounds__(128, MINB) k_panel0(const FwdArgs a, const uns
 // applied to both operands of every product).  The only exchange is Y's fragments (12 doubles per lane and state, double
 // buffered, one 64-thread barrier per state) so that both warps can form their 18 tiles of S += Y^T Y.  Column order, active
 // tiles and the end-of-segment hand-off are k_panel0's.
+constexpr int PW_MAXE = 6, PW_OWN = 12 + 16 * PW_MAXE;   // per-warp staging of a state's right-hand side and border entries
 template <int W>
 __device__ __forceinline__ void panelw_body(const FwdArgs& a, const unsigned char* __restrict__ lorder, const unsigned char* __restrict__ ntile,
-                                            double* Csm, int* gdim, int* lrank, unsigned char* nts, double (*Yx)[8][3][32]) {
-  constexpr int BS = 12, REC0 = 2 * BS * BS + BS, REC1 = 3 * BS * BS + 2 * BS, C0 = BS + 1, DL = 3, LMAX = 17;
+                                            double* Csm, int* gdim, int* lrank, unsigned char* nts, double (*Yx)[8][3][32], double (*Own)[PW_OWN]) {
+  constexpr int BS = 12, REC0 = 2 * BS * BS + BS, REC1 = 3 * BS * BS + 2 * BS, C0 = BS + 1, DL = 3, LMAX = 17, MAXE = PW_MAXE;
   const int tid = threadIdx.x, lane = tid & 31, gi = lane >> 2, ti = lane & 3;
   const int nb = a.nb, nl = nb / DL;
   const int ks[3] = {2 * ti, 2 * ti + 1, ti < 2 ? 8 + 2 * ti : 9 + 2 * (ti - 2)};
@@ -1305,15 +1306,23 @@ __device__ __forceinline__ void panelw_body(const FwdArgs& a, const unsigned cha
 #pragma unroll
         for (int s = 0; s < 3; s++) { const int col = 8 * (2 * j + W) + gi; pa[j][s] = (p >= 0 && col < BS) ? E[ks[s] + col * BS] : 0.0; }
     }
-    // own part of state i added into the fragments: right-hand side (column 12) and the border entries of the state
-    auto add_own = [&](int i, int e0, int e1) {
+    // own part of state i: right-hand side (column 12) and the border entries of the state.  Both were staged into this warp's
+    // shared-memory slot one state ahead with cp.async (a global load here would sit on the per-state critical path: in the first
+    // version of this kernel a third of the stall samples were exactly that)
+    auto stage_own = [&](int i, int e0, int e1, int st) {
+      double* dst = Own[st];
+      if (lane < BS / 2) cp_async16(dst + 2 * lane, a.rec + (size_t)i * REC0 + 2 * BS * BS + 2 * lane);
+      const int ne = min(e1 - e0, MAXE);
+      for (int k = lane; k < 8 * ne; k += 32) cp_async16(dst + BS + 2 * k, a.bent + (size_t)e0 * 16 + 2 * k);
+    };
+    auto add_own = [&](int st, int e0, int e1) {
+      const double* own = Own[st];
       if (W == 1 && gi == 4) {
-        const double* g = a.rec + (size_t)i * REC0 + 2 * BS * BS;
 #pragma unroll
-        for (int s = 0; s < 3; s++) pa[0][s] += g[ks[s]];
+        for (int s = 0; s < 3; s++) pa[0][s] += own[ks[s]];
       }
       for (int e = e0; e < e1; e++) {
-        const double* en = a.bent + (size_t)e * 16;
+        const double* en = (e - e0 < MAXE) ? own + BS + 16 * (e - e0) : a.bent + (size_t)e * 16;
         const int k = lrank[(int)en[15]];
         const double a0 = en[ks[0]], a1 = en[ks[1]], a2 = en[ks[2]];
 #pragma unroll
@@ -1342,7 +1351,11 @@ __device__ __forceinline__ void panelw_body(const FwdArgs& a, const unsigned cha
     };
     if (i0 <= i1) load_frags(i0, fL0, fL1, fE0, fE1, (i0 < i1) || (q >= 0));
     int b0 = nb ? a.bsoff[i0 <= a.n ? i0 : a.n] : 0, b1 = nb ? a.bsoff[i0 + 1 <= a.n ? i0 + 1 : a.n] : 0, b2 = nb ? a.bsoff[i0 + 2 <= a.n ? i0 + 2 : a.n] : 0;
-    int par = 0, ntmax = 2;
+    const int ilast = (q >= 0) ? q : i1;
+    int par = 0, ntmax = 2, ost = 0;
+    __syncwarp();
+    if (i0 <= ilast) stage_own(i0, b0, b1, 0);
+    cp_async_commit();
     for (int i = i0; i <= i1; i++) {
       const bool has_next = (i < i1) || (q >= 0);
       const int nt = (i - i0 < 64) ? (int)nts[i - i0] : (int)ntile[i];
@@ -1350,7 +1363,13 @@ __device__ __forceinline__ void panelw_body(const FwdArgs& a, const unsigned cha
       const int b3 = nb ? a.bsoff[i + 3 <= a.n ? i + 3 : a.n] : 0;
       double nL0[2], nL1[3], nE0[3], nE1[3];
       if (i + 1 <= i1) load_frags(i + 1, nL0, nL1, nE0, nE1, (i + 1 < i1) || (q >= 0));   // next state's fragments fly during this state
-      add_own(i, b0, b1);
+      if (i + 1 <= ilast) stage_own(i + 1, b1, b2, ost ^ 1);
+      cp_async_commit();
+      cp_async_wait<1>();
+      __syncwarp();
+      add_own(ost, b0, b1);
+      __syncwarp();
+      ost ^= 1;
       double yall[8][3];
 #pragma unroll
       for (int j = 0; j < 4; j++) {
@@ -1396,9 +1415,11 @@ __device__ __forceinline__ void panelw_body(const FwdArgs& a, const unsigned cha
       }
     }
     // ---- segment end: the closing separator's own border / rhs, then hand the panel off (D1 of q was written by k_spine)
+    cp_async_wait<0>();
+    __syncwarp();
     if (q >= 0) {
       double* R = a.rec_out + (size_t)sg.qo * REC1;
-      add_own(q, b0, b1);
+      add_own(ost, b0, b1);
 #pragma unroll
       for (int j = 0; j < 4; j++)
 #pragma unroll
@@ -1463,10 +1484,11 @@ __global__ void __launch_bounds__(64, 4) k_panel_w(const FwdArgs a, const unsign
   __shared__ double Yx[2][8][3][32];
   __shared__ int gdim[64], lrank[LMAX];
   __shared__ unsigned char nts[64];
+  __shared__ __align__(16) double Own[2][2][PW_OWN];   // [warp][stage]
   for (int k = threadIdx.x; k < CSN; k += 64) Csm[k] = 0.0;
   __syncthreads();
-  if (threadIdx.x < 32) panelw_body<0>(a, lorder, ntile, Csm, gdim, lrank, nts, Yx);
-  else panelw_body<1>(a, lorder, ntile, Csm, gdim, lrank, nts, Yx);
+  if (threadIdx.x < 32) panelw_body<0>(a, lorder, ntile, Csm, gdim, lrank, nts, Yx, Own[0]);
+  else panelw_body<1>(a, lorder, ntile, Csm, gdim, lrank, nts, Yx, Own[1]);
   __syncthreads();
   const int nb = a.nb;
   if (nb > 0) {
