@@ -1371,24 +1371,39 @@ __device__ __forceinline__ void panelw_body(const FwdArgs& a, const unsigned cha
       __syncwarp();
       ost ^= 1;
       double yall[8][3];
+      // own tiles two at a time, slice-outer: the mma chains of the two tiles (and of the two row halves) are independent and
+      // issue back to back instead of each waiting for its own accumulator
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const int T = 2 * j + W;
-        if (T < nt) {
-          double d0[2] = {0.0, 0.0}, d1[2] = {0.0, 0.0};
+      for (int jp = 0; jp < 4; jp += 2) {
+        const int TA = 2 * jp + W, TB = 2 * (jp + 1) + W;
+        const bool actA = TA < nt, actB = TB < nt;
+        if (actA) {
+          double dA0[2] = {0.0, 0.0}, dA1[2] = {0.0, 0.0}, dB0[2] = {0.0, 0.0}, dB1[2] = {0.0, 0.0};
 #pragma unroll
-          for (int s = 0; s < 3; s++) { if (s < 2) dmma884(d0[0], d0[1], pa[j][s], fL0[s]); dmma884(d1[0], d1[1], pa[j][s], fL1[s]); }
-          const double v = __shfl_sync(0xffffffffu, d1[1], shsrc);
-          yall[T][0] = d0[0]; yall[T][1] = d0[1]; yall[T][2] = ti < 2 ? d1[0] : v;
+          for (int s = 0; s < 3; s++) {
+            if (s < 2) dmma884(dA0[0], dA0[1], pa[jp][s], fL0[s]);
+            dmma884(dA1[0], dA1[1], pa[jp][s], fL1[s]);
+            if (actB) { if (s < 2) dmma884(dB0[0], dB0[1], pa[jp + 1][s], fL0[s]); dmma884(dB1[0], dB1[1], pa[jp + 1][s], fL1[s]); }
+          }
+          const double vA = __shfl_sync(0xffffffffu, dA1[1], shsrc), vB = __shfl_sync(0xffffffffu, dB1[1], shsrc);
+          yall[TA][0] = dA0[0]; yall[TA][1] = dA0[1]; yall[TA][2] = ti < 2 ? dA1[0] : vA;
+          yall[TB][0] = dB0[0]; yall[TB][1] = dB0[1]; yall[TB][2] = ti < 2 ? dB1[0] : vB;
 #pragma unroll
-          for (int s = 0; s < 3; s++) Yx[par][T][s][lane] = yall[T][s];
+          for (int s = 0; s < 3; s++) { Yx[par][TA][s][lane] = yall[TA][s]; if (actB) Yx[par][TB][s][lane] = yall[TB][s]; }
           if (has_next) {
-            double e0[2] = {0.0, 0.0}, e1[2] = {0.0, 0.0};
+            double eA0[2] = {0.0, 0.0}, eA1[2] = {0.0, 0.0}, eB0[2] = {0.0, 0.0}, eB1[2] = {0.0, 0.0};
 #pragma unroll
-            for (int s = 0; s < 3; s++) { dmma884(e0[0], e0[1], yall[T][s], fE0[s]); dmma884(e1[0], e1[1], yall[T][s], fE1[s]); }
-            const double v2 = __shfl_sync(0xffffffffu, e1[1], shsrc);
-            pa[j][0] = -e0[0]; pa[j][1] = -e0[1]; pa[j][2] = -(ti < 2 ? e1[0] : v2);
-          } else { pa[j][0] = 0.0; pa[j][1] = 0.0; pa[j][2] = 0.0; }
+            for (int s = 0; s < 3; s++) {
+              dmma884(eA0[0], eA0[1], yall[TA][s], fE0[s]); dmma884(eA1[0], eA1[1], yall[TA][s], fE1[s]);
+              if (actB) { dmma884(eB0[0], eB0[1], yall[TB][s], fE0[s]); dmma884(eB1[0], eB1[1], yall[TB][s], fE1[s]); }
+            }
+            const double wA = __shfl_sync(0xffffffffu, eA1[1], shsrc), wB = __shfl_sync(0xffffffffu, eB1[1], shsrc);
+            pa[jp][0] = -eA0[0]; pa[jp][1] = -eA0[1]; pa[jp][2] = -(ti < 2 ? eA1[0] : wA);
+            if (actB) { pa[jp + 1][0] = -eB0[0]; pa[jp + 1][1] = -eB0[1]; pa[jp + 1][2] = -(ti < 2 ? eB1[0] : wB); }
+          } else {
+#pragma unroll
+            for (int s = 0; s < 3; s++) { pa[jp][s] = 0.0; pa[jp + 1][s] = 0.0; }
+          }
         }
       }
       __syncthreads();
@@ -1400,13 +1415,15 @@ __device__ __forceinline__ void panelw_body(const FwdArgs& a, const unsigned cha
           for (int s = 0; s < 3; s++) yall[T][s] = Yx[par][T][s][lane];
         }
       }
-      static_for<0, 18>([&](auto U) {
-        constexpr int u = decltype(U)::value, t = 2 * u + W, I = tri_I(t), J = tri_J(t);
-        if (I < nt) {
+      // S += Y^T Y, slice-outer: this warp's active tiles (row tile I < nt; their number is monotone in u) form independent chains
+      int umax = 0;
+      static_for<0, 18>([&](auto U) { constexpr int u = decltype(U)::value, t = 2 * u + W; if (tri_I(t) < nt) umax = u + 1; });
 #pragma unroll
-          for (int s = 0; s < 3; s++) dmma884(acc[u][0], acc[u][1], yall[I][s], yall[J][s]);
-        }
-      });
+      for (int s = 0; s < 3; s++)
+        static_for<0, 18>([&](auto U) {
+          constexpr int u = decltype(U)::value, t = 2 * u + W, I = tri_I(t), J = tri_J(t);
+          if (u < umax) dmma884(acc[u][0], acc[u][1], yall[I][s], yall[J][s]);
+        });
       par ^= 1;
       b0 = b1; b1 = b2; b2 = b3;
       if (i + 1 <= i1) {
