@@ -91,3 +91,37 @@ def test_every_factor_owned_once():
                 total += sb.g.num_factors(); err += sb.g.error()
             assert total == full.num_factors()
             assert abs(err - full.error()) <= 1e-9 * full.error()
+
+
+def test_recorder_replays_the_same_graph():
+    """synth.record: the generator runs once, its construction calls replay into any number of graph objects (parity tests at
+    BASELINE sizes build the engine graph and the oracle graph from one recording)"""
+    from gpslam_b200 import synth
+    from oracle import pyoracle as po
+    cfg = synth.config("C5"); cfg.n_states = 600; cfg.n_landmarks = 4; cfg.n_closures = 3; cfg.closure_min_gap = 100
+    rec, truth = synth.record(cfg)
+    a = rec.replay(lambda grp, n, l: po.Graph(grp, n, l))
+    b, _ = synth.build(cfg, lambda grp, n, l: po.Graph(grp, n, l))
+    assert a.num_factors() == b.num_factors() and a.error() == b.error()
+    Pa, Va, La = a.get_values(); Pb, Vb, Lb = b.get_values()
+    assert np.array_equal(Pa, Pb) and np.array_equal(Va, Vb) and np.array_equal(La, Lb)
+
+
+def test_oracle_step_check_separates_right_from_wrong():
+    """oracle.check_step (the full-size parity instrument of tests/test_gpu_fullsize.py): the exact solution of the oracle's own
+    normal equations passes at rounding level, a step that is off by 1e-6 of its size in ONE entry fails by orders of magnitude"""
+    from gpslam_b200 import synth
+    from oracle import pyoracle as po
+    cfg = synth.config("C5"); cfg.n_states = 300; cfg.n_landmarks = 4; cfg.prior_every = 40; cfg.n_closures = 4; cfg.closure_min_gap = 50
+    o, _ = synth.build(cfg, lambda grp, n, l: po.Graph(grp, n, l))
+    o.set_threads(3)
+    o.optimize(n_iter=3, use_lm=True)
+    H, g = o.normal_equations_dense()
+    for lam in (0.0, 1e-2):
+        d = np.linalg.solve(H + lam * np.eye(len(g)), g)
+        ns = 300 * 12
+        c = o.check_step(d[:ns], d[ns:], lam)
+        assert c["residual"] <= 1e-12 * c["scale"], c
+        bad = d.copy(); k = int(np.argmax(np.abs(d))); bad[k] *= 1 + 1e-6
+        cb = o.check_step(bad[:ns], bad[ns:], lam)
+        assert cb["residual"] > 1e-8 * cb["scale"] and cb["residual"] > 1e3 * c["residual"]
