@@ -36,7 +36,7 @@ def cpu_sample_states(iterations, full=100000):
 # profiles/r1x_ncu_full_summary.csv: k_lin_gp 15.7 MB read + 180.6 MB written (the tail of the 240 MB of [A|b] is still in L2 at
 # kernel end); k_panel4 (level 0) 270.2 MB read + 557.1 MB written
 TRAFFIC_LIN_GP = 196.3e6
-TRAFFIC_PANEL = 282.2e6        # k_panel0<12,4>: 261.4 MB read + 20.9 MB written (profiles/r2f_ncu_full_summary.csv); k_panel4 in round 1: 827.3 MB
+TRAFFIC_PANEL = 282.2e6        # k_panel0<12,4>: 261.4 MB read + 20.9 MB written (profiles/rd2f_ncu_full_summary.csv); k_panel4 in round 1: 827.3 MB
 PANEL_EXECUTED_FRACTION = 0.58  # 11.38 M DMMA executed by k_panel0 on C3 (ncu source page, r2f) of the dense panel's 19.6 M
 # algorithmic FLOPs of the level-0 panel per state (SE(3), w = 61 columns): Y = L^-1 P (12*13/2*61 MAC), P' = Le Y (12*12*61),
 # S += Y^T Y (61*62/2*12)
