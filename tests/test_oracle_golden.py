@@ -180,8 +180,11 @@ def test_gp_prior_factor(group):
         e, H, Hnum = numeric_jacobians(g, 0, group, 1e-5 if group == POSE2 else 1e-6)
         if zero:
             np.testing.assert_allclose(e, 0, atol=1e-6)
-        for Ha, Hn in zip(H, Hnum):
-            np.testing.assert_allclose(Ha, Hn, atol=tol)
+        # per-block tolerances of the reference's "random" Pose3 case (testGaussianProcessPriorPose3.cpp:138-142): 1e-5 on H1,
+        # 1e-6 on H2, H3, H4; every other case 1e-6 throughout
+        tols = (1e-5, 1e-6, 1e-6, 1e-6) if (group == POSE3 and tol == 1e-5) else (tol,) * 4
+        for Ha, Hn, tb in zip(H, Hnum, tols):
+            np.testing.assert_allclose(Ha, Hn, atol=tb)
         # cheap path (no Jacobians requested) returns the same residual (gp/GaussianProcessPriorPose3.h:73-74)
         np.testing.assert_allclose(g.eval_factor(0, False)[0], e, atol=0)
 
