@@ -140,7 +140,7 @@ struct gpb_graph {
   int fstride = 0;  // doubles per state of a level's factor record: (L^-1 | Le), + Y for the Y-reading back-substitution
   gpb_allreduce_fn allreduce = nullptr; void* allreduce_ctx = nullptr;
   nccl_rt::Comm nccl = nullptr;   // engine-owned communicator (gpb_graph_init_nccl): the all-reduce is captured inside the iteration graph
-  cudaGraphExec_t gn_graph[2] = {nullptr, nullptr}; int gn_graph_launches[2] = {0, 0};  // whole asynchronous GN iteration per buffer parity
+  cudaGraphExec_t gn_graph[4] = {nullptr, nullptr, nullptr, nullptr}; int gn_graph_launches[4] = {0, 0, 0, 0};  // [parity + 2 * variant]  // whole asynchronous GN iteration per buffer parity
   bool failed = false;            // gpb_graph_finalize failed half-way: the graph can only be destroyed
   // pipelined batch interface (gpb_optimize_batch): staging buffers, copy streams, events
   double* d_stage_in[2] = {nullptr, nullptr}; double* d_stage_out[2] = {nullptr, nullptr}; double* h_batch_err = nullptr;
@@ -255,7 +255,7 @@ void gpb_graph_destroy(gpb_graph* g) {
   if (g->pinned) { cudaHostUnregister(g->h_X.data()); if (g->L) cudaHostUnregister(g->h_land.data()); }
   for (int k = 0; k < 2; k++) if (g->iter_graph[k]) cudaGraphExecDestroy(g->iter_graph[k]);
   for (int k = 0; k < 2; k++) for (int h = 0; h < 2; h++) if (g->dist_graph[k][h]) cudaGraphExecDestroy(g->dist_graph[k][h]);
-  for (int k = 0; k < 2; k++) if (g->gn_graph[k]) cudaGraphExecDestroy(g->gn_graph[k]);
+  for (int k = 0; k < 4; k++) if (g->gn_graph[k]) cudaGraphExecDestroy(g->gn_graph[k]);
   if (g->nccl && nccl_rt::CommDestroy) { if (g->stream) cudaStreamSynchronize(g->stream); nccl_rt::CommDestroy(g->nccl); }
   for (int k = 0; k < 2; k++) {
     if (g->ev_in_ready[k]) cudaEventDestroy(g->ev_in_ready[k]);
@@ -1344,9 +1344,10 @@ struct Capture {
 // caller checks after its last iteration.  The launch sequence is fixed per buffer parity and is replayed as ONE CUDA graph
 // (single GPU, or sharded with the engine's own NCCL communicator: the collective is captured with the kernels), or as two graphs
 // around a caller-supplied all-reduce callback (gpb_set_allreduce).
-static int gn_iteration_async(gpb_graph* g) {
+static int gn_iteration_async(gpb_graph* g, bool error_only = false) {
   int r = GPB_OK;
   const int par = g->cur;
+  const int var = error_only ? 1 : 0;   // graph variant: 1 = the new point's error only (residual pass without Jacobians: a batch step's values are replaced before the next solve)
   const bool dist = g->world > 1;
   const long long top_count = (long long)(g->R + 1) * g->R + 4;
   auto first_half = [&]() -> int {
@@ -1360,24 +1361,24 @@ static int gn_iteration_async(gpb_graph* g) {
     int rr = top_finish(g, nullptr);
     if (!rr) rr = solve_backward(g);
     if (!rr) rr = retract_dispatch(g);
-    if (!rr) rr = linearize_dispatch(g, g->d_Xt, g->d_landt, 1 - par, 1);
+    if (!rr) rr = linearize_dispatch(g, g->d_Xt, g->d_landt, 1 - par, error_only ? 0 : 1);
     return rr;
   };
   if (!dist || g->nccl) {
-    if (!g->gn_graph[par]) {
+    if (!g->gn_graph[par + 2 * var]) {
       const int l0 = g->launches;
       Capture cap(g->stream);
       if ((r = cap.begin(dist ? cudaStreamCaptureModeRelaxed : cudaStreamCaptureModeThreadLocal))) return r;
       r = first_half();
       if (!r && dist) r = dist_allreduce(g, g->d_topbuf, top_count);
       if (!r) r = second_half();
-      if ((r = cap.end(r, &g->gn_graph[par]))) return r;
-      g->gn_graph_launches[par] = g->launches - l0;
+      if ((r = cap.end(r, &g->gn_graph[par + 2 * var]))) return r;
+      g->gn_graph_launches[par + 2 * var] = g->launches - l0;
       g->launches = l0;
       if (dist) g->n_allreduce--;  // counted per replay below
     }
-    CUDA_TRY(cudaGraphLaunch(g->gn_graph[par], g->stream));
-    g->launches += g->gn_graph_launches[par];
+    CUDA_TRY(cudaGraphLaunch(g->gn_graph[par + 2 * var], g->stream));
+    g->launches += g->gn_graph_launches[par + 2 * var];
     if (dist) g->n_allreduce++;
   } else {
     if (!g->dist_graph[par][0]) {
@@ -1601,7 +1602,8 @@ int gpb_optimize_batch(gpb_graph* g, int K, const double* const* poses_in, const
     if (nl) CUDA_TRY(cudaMemcpyAsync(g->d_land, land_in[k], nl * sizeof(double), cudaMemcpyHostToDevice, g->stream));
     if ((rc = linearize_dispatch(g, g->d_X, g->d_land, g->cur, 1))) return rc;
     g->linearized = true; g->assembled = false;
-    if ((rc = gn_iteration_async(g))) return rc;
+    if ((rc = gn_iteration_async(g, /*error_only=*/(g->world == 1 || g->nccl != nullptr)))) return rc;
+    g->linearized = false;   // the new point's [A|b] was not formed (or, with a callback all-reduce, is about to be overwritten)
     if (k >= 2) CUDA_TRY(cudaStreamWaitEvent(g->stream, g->ev_out_free[b], 0));
     k_pack_values<<<nblk, 256, 0, g->stream>>>(g->d_stage_out[b], g->d_stage_out[b] + np, g->d_X, g->N, g->PS, g->D, 1); g->launches++;
     CUDA_TRY(cudaMemcpyAsync(herr + k, g->d_scal, sizeof(double), cudaMemcpyDeviceToHost, g->stream));  // local error at the new point

@@ -296,6 +296,37 @@ def test_dense_solve_trailing_update_variants(monkeypatch):
             assert np.abs(x - ref).max() <= 1e-9 * max(1.0, np.abs(ref).max()), (R, np.abs(x - ref).max())
 
 
+@pytest.mark.parametrize("case", ["pose3_wide", "pose2", "rot3"])
+def test_optimize_batch_matches_oracle(case):
+    """gpb_optimize_batch: K independent (values in -> one GN iteration -> values out) steps, copies pipelined against compute.  Two
+    different inputs alternate; every step's output and error equal the oracle's single iteration from that input"""
+    g, o = make_pair(case)
+    P0, V0, L0 = g.get_values()
+    inA = g.get_values(out=g.alloc_values())
+    inB = g.alloc_values()
+    rng = np.random.default_rng(3)
+    inB[0][:] = P0; inB[1][:] = V0 + rng.normal(size=V0.shape) * 0.01
+    if L0.size:
+        inB[2][:, :L0.shape[1]] = L0 + 0.05
+    outs = [g.alloc_values() for _ in range(4)]
+    st, errs = g.optimize_batch([inA, inB, inA, inB], outs)
+    assert st.status == 0 and st.iterations == 4
+    for k, (pin, vin, lin) in enumerate([inA, inB]):
+        o.set_values(pin, vin, lin[:, :L0.shape[1]] if L0.size else None)
+        so = o.optimize(n_iter=1, use_lm=False)
+        Po, Vo, Lo = o.get_values()
+        for kk in (k, k + 2):
+            assert np.abs(outs[kk][0] - Po).max() <= 1e-6 and np.abs(outs[kk][1] - Vo).max() <= 1e-6
+            if L0.size:
+                assert np.abs(outs[kk][2][:, :L0.shape[1]] - Lo).max() <= 1e-6
+            assert abs(errs[kk] - so.error_final) <= 1e-7 * max(1.0, so.error_final)
+        assert np.array_equal(outs[k][0], outs[k + 2][0]) and errs[k] == errs[k + 2]   # same input, same bits
+    # the graph is left at the last step's result and keeps working through the ordinary calls
+    Pn, Vn, Ln = g.get_values()
+    assert np.array_equal(Pn, outs[3][0])
+    assert abs(g.linearize() - errs[3]) <= 1e-9 * max(1.0, errs[3])
+
+
 def test_reference_two_state_optimizations():
     """the reference's 'Optimization' unit tests through the CUDA path (gp/tests/testGaussianProcessPriorPose3.cpp:146-195,
     slam/tests/testGPInterpolatedRangeFactorPose3.cpp:177-260 incl. extrapolation tau = -0.1 and 0.2)"""
