@@ -32,11 +32,12 @@ CPU_US_PER_STATE = 30.0
 
 def cpu_sample_states(iterations, full=100000):
     return int(max(10000, min(full, CPU_BUDGET_S / (max(1, iterations) * CPU_US_PER_STATE * 1e-6))))
-# dram__bytes_read.sum + dram__bytes_write.sum of one launch on C3, from the ncu --set full capture summarised in
-# profiles/r1x_ncu_full_summary.csv: k_lin_gp 15.7 MB read + 180.6 MB written (the tail of the 240 MB of [A|b] is still in L2 at
-# kernel end); k_panel4 (level 0) 270.2 MB read + 557.1 MB written
-TRAFFIC_LIN_GP = 196.3e6
-TRAFFIC_PANEL = 282.2e6        # k_panel0<12,4>: 261.4 MB read + 20.9 MB written (profiles/rd2f_ncu_full_summary.csv); k_panel4 in round 1: 827.3 MB
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch on C3, from the ncu --set full capture of THIS round's build summarised in
+# profiles/rd2w_ncu_full_summary.csv (ncu cannot run inside the timed bench, so these are constants tied to that capture):
+# k_lin_gp 15.7 MB read + 182.0 MB written (the tail of the 240 MB of [A|b] is still in L2 at kernel end and is written back during
+# the next kernel); k_panel0<12,4> (level 0) 261.4 MB read + 19.8 MB written (k_panel4 in round 1: 827.3 MB)
+TRAFFIC_LIN_GP = 197.7e6
+TRAFFIC_PANEL = 281.2e6
 PANEL_EXECUTED_FRACTION = 0.58  # 11.38 M DMMA executed by k_panel0 on C3 (ncu source page, r2f) of the dense panel's 19.6 M
 # algorithmic FLOPs of the level-0 panel per state (SE(3), w = 61 columns): Y = L^-1 P (12*13/2*61 MAC), P' = Le Y (12*12*61),
 # S += Y^T Y (61*62/2*12)
@@ -287,7 +288,7 @@ def run_engine(args, rank, world, local_rank):
     e2e_serial_s = max_over_ranks((time.perf_counter() - t0) / args.steps)
     # ---- per-stage device times and the linearise roofline (local shard)
     stages = {n: g.time_stage(k, 20) for k, n in ((0, "linearise_gp"), (1, "linearise_other"), (2, "assemble"), (3, "solve"), (4, "retract"), (5, "solve_fwd_level0"),
-                                                   (6, "solve_spine_level0"), (7, "solve_panel_level0"), (8, "solve_backward")) if se3_wide or k not in (6, 7)}
+                                                   (6, "solve_spine_level0"), (7, "solve_panel_level0"), (8, "solve_backward"), (9, "linearise_all")) if se3_wide or k not in (6, 7)}
     from gpslam_b200 import capi
     dmma_peak = capi.dmma_peak(local_rank)
     # what the [A|b] store pattern costs with no arithmetic in front of it, and a plain memset of the same bytes (context for
@@ -316,7 +317,12 @@ def run_engine(args, rank, world, local_rank):
         "gpu_launches": launches,
         "roofline": {"kernel": "k_lin_gp<%s> (batched GP-prior linearise%s)" % ({0: "POSE3", 1: "POSE2", 2: "ROT3", 3: "LINEAR"}[cfg.group], "; diagonal-Qc instantiation" if cfg.group == 0 else ""), "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "peak_source": peak_src, "algorithmic_bytes": gp_bytes, "ms": stages["linearise_gp"], "traffic": TRAFFIC_LIN_GP if world == 1 and args.config == "C3" and not args.states else None,
-                     "store_pattern_floor_ms": store_floor_us * 1e-3, "memset_same_bytes_ms": memset_us * 1e-3},
+                     "store_pattern_floor_ms": store_floor_us * 1e-3, "memset_same_bytes_ms": memset_us * 1e-3,
+                     # every factor of the graph (SURVEY §8d LINEARISE_BYTES incl. the measurement rows), timed as the iteration runs it:
+                     # k_lin_gp on the main stream, the other factors beside it on the side stream, joined before the error reduction
+                     "whole_linearise": {"algorithmic_bytes": sz.linearise_bytes, "ms": stages["linearise_all"],
+                                         "achieved": sz.linearise_bytes / (stages["linearise_all"] * 1e-3) / 1e9, "frac": sz.linearise_bytes / (stages["linearise_all"] * 1e-3) / 1e9 / peak,
+                                         "streams": "overlapped (two streams, fork / join inside the stage)"}},
         # the kernel that dominates the iteration by time: the level-0 panel, bound by the FP64 tensor pipe
         "stages_ms": stages, "clocks": clocks, "error": {"initial": err0, "final": st.error_final},
     }

@@ -163,7 +163,8 @@ struct gpb_graph {
   double *d_Cbase = nullptr, *d_xlm = nullptr, *d_Cpart = nullptr;
   std::vector<Level> levels;
   cudaStream_t stream = nullptr, stream2 = nullptr;  // stream2: forked side branch (joined back before anything consumes its output)
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr;
+  bool chunk_lin = true;  // GPB_NO_CHUNK: linearise and assemble as two whole-graph stages instead of the chunked pipeline
   double cur_error = 0;
   int launches = 0;
   size_t hbm_bytes = 0;
@@ -269,6 +270,7 @@ void gpb_graph_destroy(gpb_graph* g) {
   for (void* p : g->allocs) cudaFree(p);
   if (g->ev_fork) cudaEventDestroy(g->ev_fork);
   if (g->ev_join) cudaEventDestroy(g->ev_join);
+  if (g->ev_join2) cudaEventDestroy(g->ev_join2);
   if (g->stream2) cudaStreamDestroy(g->stream2);
   if (g->stream) cudaStreamDestroy(g->stream);
   delete g;
@@ -602,6 +604,8 @@ int gpb_graph_finalize(gpb_graph* g, int device) {
   CUDA_TRY(cudaStreamCreateWithFlags(&g->stream2, cudaStreamNonBlocking));
   CUDA_TRY(cudaEventCreateWithFlags(&g->ev_fork, cudaEventDisableTiming));
   CUDA_TRY(cudaEventCreateWithFlags(&g->ev_join, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&g->ev_join2, cudaEventDisableTiming));
+  g->chunk_lin = getenv("GPB_NO_CHUNK") == nullptr;
   CUDA_TRY(cudaFuncSetAttribute(k_small_solve<256, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_solve_smem(SMALL_SOLVE_MAX)));
   CUDA_TRY(cudaFuncSetAttribute(k_small_solve<256, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_solve_smem(SMALL_SOLVE_MAX)));
   CUDA_TRY(cudaFuncSetAttribute(k_small_solve<256, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_solve_smem(95)));
@@ -1000,7 +1004,7 @@ template <int G> static int launch_assemble(gpb_graph* g, int buf) {
     }
     CUDA_TRY(cudaEventRecord(g->ev_join, g->stream2));
   }
-  if (G == G_POSE3 && !g->old_assemble) k_assemble_mma<<<(g->N + 7) / 8, 128, 0, g->stream>>>(g->d_AB[buf], g->NX ? g->d_XR[buf] : nullptr, g->d_rowoff, g->d_HREC, g->N, g->NFp, g->NXRp, g->ncolsX - 1);
+  if (G == G_POSE3 && !g->old_assemble) k_assemble_mma<<<(g->N + 7) / 8, 128, 0, g->stream>>>(g->d_AB[buf], g->NX ? g->d_XR[buf] : nullptr, g->d_rowoff, g->d_HREC, g->N, g->NFp, g->NXRp, g->ncolsX - 1, 0);
   else k_assemble<G, NT><<<nblk, NT, 0, g->stream>>>(g->d_AB[buf], g->d_dt, g->NX ? g->d_XR[buf] : nullptr, g->d_rowoff, g->d_HREC, g->N, g->NFp, g->NXRp);
   g->launches++;
   if (g->nep) {  // loop closures: diagonal blocks / rhs of their endpoint states
@@ -1018,6 +1022,72 @@ static int assemble_dispatch(gpb_graph* g, int buf) {
     case GPB_ROT3: return launch_assemble<G_ROT3>(g, buf);
     default: return launch_assemble<G_LINEAR>(g, buf);
   }
+}
+
+// Linearise at (X, land) into buffer `buf` AND assemble its normal equations, as one pipelined stage (SE(3), body-velocity priors,
+// tensor-pipe assembly): the [A|b] of the GP priors is produced in chunks of tiles and each chunk is assembled two chunks later, while
+// it is still in L2 - the 240 MB of [A|b] are written once (HBM write-back) but not read back from HBM.  The other factors run on the
+// side stream as in launch_linearize and are joined before the first assembly launch (their rows enter the state records).
+// Falls back to linearize_dispatch + assemble_dispatch for every other graph (and with GPB_NO_CHUNK).
+static int linearize_assemble(gpb_graph* g, const double* X, const double* land, int buf) {
+  constexpr int NT = 128, NCH = 8, LA = 2;
+  const int nb1 = (g->nint + NT - 1) / NT;
+  const bool chunked = g->chunk_lin && g->group == GPB_POSE3 && !g->vw && !g->old_assemble && nb1 >= 8 * NCH;
+  int rc;
+  if (!chunked) {
+    if ((rc = linearize_dispatch(g, X, land, buf, 1))) return rc;
+    if ((rc = assemble_dispatch(g, buf))) return rc;
+    g->assembled = true;
+    return GPB_OK;
+  }
+  const int nbA = (g->nA + NT - 1) / NT, nbB = (int)(((size_t)g->nB * 32 + NT - 1) / NT), nbC = (g->nC + NT - 1) / NT;
+  const int SR = g->SR;
+  const bool fork = nbA > 0 || nbB > 0 || g->nb > 0;
+  if (fork) {
+    CUDA_TRY(cudaEventRecord(g->ev_fork, g->stream));
+    CUDA_TRY(cudaStreamWaitEvent(g->stream2, g->ev_fork, 0));
+    if (nbB > 0) { k_lin_extra<G_POSE3, 1, NT><<<nbB, NT, 0, g->stream2>>>(g->d_listB, g->nB, X, land, g->d_xkind, g->d_xsa, g->d_xsb, g->d_xl, g->d_xrow, g->d_xprm, g->d_XR[buf], g->d_errpart + nb1 + nbA, g->NX, g->NXRp, 1); g->launches++; }
+    if (nbA > 0) { k_lin_extra<G_POSE3, 0, NT><<<nbA, NT, 0, g->stream2>>>(g->d_listA, g->nA, X, land, g->d_xkind, g->d_xsa, g->d_xsb, g->d_xl, g->d_xrow, g->d_xprm, g->d_XR[buf], g->d_errpart + nb1, g->NX, g->NXRp, 1); g->launches++; }
+    CUDA_TRY(cudaEventRecord(g->ev_join, g->stream2));
+    if (g->nb) {  // landmark block / packed border entries: need the measurement rows only
+      CUDA_TRY(cudaMemsetAsync(g->d_Cbase, 0, (size_t)(g->nb * g->nb + g->nb) * sizeof(double), g->stream2));
+      k_landmark_base<512><<<g->L, 512, 0, g->stream2>>>(g->d_XR[buf], g->d_lmoff, g->d_lmrows, g->NXRp, 2 * g->bs, g->DL, g->nb, g->d_Cbase); g->launches++;
+      if (g->nbent > 0) { k_border_pack<<<(g->nbent * 16 + 255) / 256, 256, 0, g->stream2>>>(g->d_XR[buf], g->d_bsrow, g->d_bsside, g->d_rowland, g->nbent, g->bs, g->DL, g->NXRp, g->d_bent); g->launches++; }
+      CUDA_TRY(cudaEventRecord(g->ev_join2, g->stream2));
+    }
+  }
+  if (nbC > 0) { k_lin_extra<G_POSE3, 2, NT><<<nbC, NT, 0, g->stream>>>(g->d_listC, g->nC, X, land, g->d_xkind, g->d_xsa, g->d_xsb, g->d_xl, g->d_xrow, g->d_xprm, g->d_XR[buf], g->d_errpart + nb1 + nbA + nbB, g->NX, g->NXRp, 1); g->launches++; }
+  const int per = (nb1 + NCH - 1) / NCH;                    // linearise tiles (128 factors) per chunk
+  const int asm_total = (g->N + 7) / 8;                     // assembly tiles (8 states)
+  auto lin_chunk = [&](int c) {
+    const int b0 = c * per, b1 = std::min(nb1, b0 + per);
+    if (b0 >= b1) return;
+    const int f0 = b0 * NT, nf = std::min(g->nint, b1 * NT) - f0;
+    const size_t smem = (size_t)(NT + 1) * SR * sizeof(double);
+    double* AB = g->d_AB[buf] + ab_off(0, f0, (4 * 6 + 1) * 6);
+    if (g->lin_variant == 1) k_lin_gp<G_POSE3, NT, true, 1><<<b1 - b0, NT, smem, g->stream>>>(X + (size_t)f0 * SR, g->d_dt + f0, g->d_qc + f0, g->d_Rq, AB, g->d_errpart + b0, nf, g->NFp, 1);
+    else if (g->lin_variant == 2) k_lin_gp<G_POSE3, NT, false, 3><<<b1 - b0, NT, smem, g->stream>>>(X + (size_t)f0 * SR, g->d_dt + f0, g->d_qc + f0, g->d_Rq, AB, g->d_errpart + b0, nf, g->NFp, 1);
+    else if (g->lin_variant == 3) k_lin_gp<G_POSE3, NT, true, 3><<<b1 - b0, NT, smem, g->stream>>>(X + (size_t)f0 * SR, g->d_dt + f0, g->d_qc + f0, g->d_Rq, AB, g->d_errpart + b0, nf, g->NFp, 1);
+    else k_lin_gp<G_POSE3, NT, false, 1><<<b1 - b0, NT, smem, g->stream>>>(X + (size_t)f0 * SR, g->d_dt + f0, g->d_qc + f0, g->d_Rq, AB, g->d_errpart + b0, nf, g->NFp, 1);
+    g->launches++;
+  };
+  auto asm_chunk = [&](int c) {
+    // states whose two priors (intervals i-1, i) lie in chunks <= c: assembly tiles [16 b0, 16 b1); the last chunk takes the rest
+    const int b0 = c * per, b1 = std::min(nb1, b0 + per);
+    const int t0 = std::min(asm_total, 16 * b0), t1 = (c == NCH - 1 || b1 >= nb1) ? asm_total : std::min(asm_total, 16 * b1);
+    if (t0 >= t1) return;
+    k_assemble_mma<<<t1 - t0, 128, 0, g->stream>>>(g->d_AB[buf], g->NX ? g->d_XR[buf] : nullptr, g->d_rowoff, g->d_HREC, g->N, g->NFp, g->NXRp, g->ncolsX - 1, t0);
+    g->launches++;
+  };
+  for (int c = 0; c < LA; c++) lin_chunk(c);
+  if (fork) CUDA_TRY(cudaStreamWaitEvent(g->stream, g->ev_join, 0));   // the measurement rows are complete
+  for (int c = 0; c < NCH; c++) { asm_chunk(c); if (c + LA < NCH) lin_chunk(c + LA); }
+  k_sum_partials<<<1, 256, 0, g->stream>>>(g->d_errpart, nb1 + nbA + nbB + nbC, g->d_scal, 0); g->launches++;
+  if (g->nep) { k_assemble_closures<<<g->nep, 64, 0, g->stream>>>(g->d_XR[buf], g->NXRp, g->bs, 6, g->ncolsX - 1, g->d_epstate, g->d_epoff, g->d_eprow, g->d_epside, g->d_HREC); g->launches++; }
+  if (fork && g->nb) CUDA_TRY(cudaStreamWaitEvent(g->stream, g->ev_join2, 0));
+  CUDA_TRY(cudaGetLastError());
+  g->assembled = true;
+  return GPB_OK;
 }
 
 template <int BS, int W> static void launch_fwd(const FwdArgs& a, int ncta, cudaStream_t s) { k_fwd<BS, W><<<ncta, (W < 32 ? 32 : W), 0, s>>>(a); }
@@ -1350,8 +1420,11 @@ static int gn_iteration_async(gpb_graph* g, bool error_only = false) {
   const int var = error_only ? 1 : 0;   // graph variant: 1 = the new point's error only (residual pass without Jacobians: a batch step's values are replaced before the next solve)
   const bool dist = g->world > 1;
   const long long top_count = (long long)(g->R + 1) * g->R + 4;
+  // the normal equations of the current point are assembled at the END of the previous iteration (linearize_assemble: the [A|b]
+  // chunks are consumed while they are still in L2); only the first iteration of a run finds them missing
+  if (!g->assembled) { if ((r = assemble_dispatch(g, par))) return r; g->assembled = true; }
   auto first_half = [&]() -> int {
-    int rr = assemble_dispatch(g, par);
+    int rr = GPB_OK;
     k_set_scalar<<<1, 1, 0, g->stream>>>(g->d_lambda, 0.0); g->launches++;
     if (!rr) rr = solve_forward(g, par, 0.0);
     if (!rr) rr = top_pack(g, par, 0.0, true);
@@ -1361,7 +1434,7 @@ static int gn_iteration_async(gpb_graph* g, bool error_only = false) {
     int rr = top_finish(g, nullptr);
     if (!rr) rr = solve_backward(g);
     if (!rr) rr = retract_dispatch(g);
-    if (!rr) rr = linearize_dispatch(g, g->d_Xt, g->d_landt, 1 - par, error_only ? 0 : 1);
+    if (!rr) rr = error_only ? linearize_dispatch(g, g->d_Xt, g->d_landt, 1 - par, 0) : linearize_assemble(g, g->d_Xt, g->d_landt, 1 - par);
     return rr;
   };
   if (!dist || g->nccl) {
@@ -1398,7 +1471,7 @@ static int gn_iteration_async(gpb_graph* g, bool error_only = false) {
     g->launches += g->dist_graph_launches[par];
   }
   std::swap(g->d_X, g->d_Xt); std::swap(g->d_land, g->d_landt); g->cur = 1 - g->cur;
-  g->assembled = false; g->linearized = true;
+  g->assembled = !error_only; g->linearized = !error_only;
   return GPB_OK;
 }
 
@@ -1600,10 +1673,9 @@ int gpb_optimize_batch(gpb_graph* g, int K, const double* const* poses_in, const
     k_pack_values<<<nblk, 256, 0, g->stream>>>(g->d_stage_in[b], g->d_stage_in[b] + np, g->d_X, g->N, g->PS, g->D, 0); g->launches++;
     CUDA_TRY(cudaEventRecord(g->ev_in_free[b], g->stream));
     if (nl) CUDA_TRY(cudaMemcpyAsync(g->d_land, land_in[k], nl * sizeof(double), cudaMemcpyHostToDevice, g->stream));
-    if ((rc = linearize_dispatch(g, g->d_X, g->d_land, g->cur, 1))) return rc;
-    g->linearized = true; g->assembled = false;
+    if ((rc = linearize_assemble(g, g->d_X, g->d_land, g->cur))) return rc;
+    g->linearized = true; g->assembled = true;
     if ((rc = gn_iteration_async(g, /*error_only=*/(g->world == 1 || g->nccl != nullptr)))) return rc;
-    g->linearized = false;   // the new point's [A|b] was not formed (or, with a callback all-reduce, is about to be overwritten)
     if (k >= 2) CUDA_TRY(cudaStreamWaitEvent(g->stream, g->ev_out_free[b], 0));
     k_pack_values<<<nblk, 256, 0, g->stream>>>(g->d_stage_out[b], g->d_stage_out[b] + np, g->d_X, g->N, g->PS, g->D, 1); g->launches++;
     CUDA_TRY(cudaMemcpyAsync(herr + k, g->d_scal, sizeof(double), cudaMemcpyDeviceToHost, g->stream));  // local error at the new point
@@ -2010,6 +2082,7 @@ int gpb_time_stage(gpb_graph* g, int stage, int reps, double* ms_out) {
       case 6: if ((rc = launch_fwd_level(g, g->cur, 0.0, 0, 1))) return rc; break;  // spine only (SE(3), 64-column panel)
       case 7: if ((rc = launch_fwd_level(g, g->cur, 0.0, 0, 2))) return rc; break;  // panel only
       case 8: if ((rc = solve_backward(g))) return rc; break;
+      case 9: if ((rc = linearize_dispatch(g, g->d_X, g->d_land, other, 1))) return rc; break;  // the whole linearise as the iteration runs it: GP priors and the other factors on their two streams, error reduction
       default: return fail(GPB_ERR_ARG, "gpb_time_stage: unknown stage");
     }
   }

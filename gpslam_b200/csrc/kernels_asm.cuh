@@ -190,12 +190,12 @@ __device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsr
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(valid ? 16 : 0) : "memory");
 }
 __global__ void __launch_bounds__(128) k_assemble_mma(const double* __restrict__ AB, const double* __restrict__ XR,
-                                                      const int* __restrict__ rowoff, double* __restrict__ HREC, int N, int NFp, int NXRp, int xrhs) {
+                                                      const int* __restrict__ rowoff, double* __restrict__ HREC, int N, int NFp, int NXRp, int xrhs, int blk0) {
   constexpr int D = 6, bs = 12, REC = 2 * bs * bs + bs, TS = 8, NF = TS + 1, NCOL = 4 * D + 1, FS = NCOL * bs + 2;  // FS: doubles per staged factor (padded)
   __shared__ __align__(16) double Fsm[NF * FS];   // staged factors [factor][column][row]; re-used for the finished records
   static_assert(TS * REC <= NF * FS, "record staging must fit the factor staging");
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gi = lane >> 2, ti = lane & 3;
-  const int i0 = blockIdx.x * TS, nint = N - 1;
+  const int i0 = (blockIdx.x + blk0) * TS, nint = N - 1;   // blk0: first tile of this launch (the chunked linearise / assemble pipeline launches ranges of tiles)
   // ---- load: item = (row pair pr = column * D + rp, factor ff), 16 bytes each; consecutive threads take consecutive factors.
   // Thread (ff, g) = (tid % NF, tid / NF) of the first 14 * NF = 126 threads copies row pairs g, g + 14, ...: its source
   // (ab_off: + one row of the tile per row pair) and destination (Fsm[ff][2 pr]) advance by constants - no index arithmetic

@@ -229,7 +229,8 @@ int gpb_get_sizes(gpb_graph* g, gpb_sizes* s);
 /* profiling aid: average device milliseconds (CUDA events on the engine's stream) of one stage of the hot path over `reps`
  * launches at the current values.  stage: 0 batched GP-prior linearise kernel, 1 linearise of the other factors, 2 assembly,
  * 3 whole block solve (all levels, both sweeps), 4 retract, 5 level-0 forward elimination only, 6 / 7 its spine / panel kernel
- * alone (SE(3) graphs with a 64-column panel), 8 back-substitution (all levels). */
+ * alone (SE(3) graphs with a 64-column panel), 8 back-substitution (all levels), 9 the whole linearise as an iteration runs it
+ * (GP priors and the other factors on their two streams + the error reduction). */
 int gpb_time_stage(gpb_graph* g, int stage, int reps, double* ms_out);
 
 /* names and average device milliseconds of the kernels timed during the last gpb_optimize (profiling aid) */
