@@ -164,7 +164,7 @@ struct gpb_graph {
   std::vector<Level> levels;
   cudaStream_t stream = nullptr, stream2 = nullptr;  // stream2: forked side branch (joined back before anything consumes its output)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr;
-  bool chunk_lin = true;  // GPB_NO_CHUNK: linearise and assemble as two whole-graph stages instead of the chunked pipeline
+  bool chunk_lin = false;  // A/B switch GPB_CHUNK: linearise and assemble as a chunked pipeline (measured slower: DESIGN.md §7) instead of two whole-graph stages
   double cur_error = 0;
   int launches = 0;
   size_t hbm_bytes = 0;
@@ -605,7 +605,7 @@ int gpb_graph_finalize(gpb_graph* g, int device) {
   CUDA_TRY(cudaEventCreateWithFlags(&g->ev_fork, cudaEventDisableTiming));
   CUDA_TRY(cudaEventCreateWithFlags(&g->ev_join, cudaEventDisableTiming));
   CUDA_TRY(cudaEventCreateWithFlags(&g->ev_join2, cudaEventDisableTiming));
-  g->chunk_lin = getenv("GPB_NO_CHUNK") == nullptr;
+  g->chunk_lin = getenv("GPB_CHUNK") != nullptr;
   CUDA_TRY(cudaFuncSetAttribute(k_small_solve<256, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_solve_smem(SMALL_SOLVE_MAX)));
   CUDA_TRY(cudaFuncSetAttribute(k_small_solve<256, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_solve_smem(SMALL_SOLVE_MAX)));
   CUDA_TRY(cudaFuncSetAttribute(k_small_solve<256, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_solve_smem(95)));
@@ -1028,7 +1028,8 @@ static int assemble_dispatch(gpb_graph* g, int buf) {
 // tensor-pipe assembly): the [A|b] of the GP priors is produced in chunks of tiles and each chunk is assembled two chunks later, while
 // it is still in L2 - the 240 MB of [A|b] are written once (HBM write-back) but not read back from HBM.  The other factors run on the
 // side stream as in launch_linearize and are joined before the first assembly launch (their rows enter the state records).
-// Falls back to linearize_dispatch + assemble_dispatch for every other graph (and with GPB_NO_CHUNK).
+// Measured on C3: 1.20 ms per iteration against 1.13 ms for the two whole-graph stages (sixteen small launches and their tails cost
+// more than the L2 hits save) - so this is an A/B switch (GPB_CHUNK), and the default is linearize_dispatch + assemble_dispatch.
 static int linearize_assemble(gpb_graph* g, const double* X, const double* land, int buf) {
   constexpr int NT = 128, NCH = 8, LA = 2;
   const int nb1 = (g->nint + NT - 1) / NT;
