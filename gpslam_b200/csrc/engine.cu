@@ -131,6 +131,8 @@ struct gpb_graph {
   int *d_pair_a = nullptr, *d_pair_b = nullptr, *d_pairoff = nullptr, *d_pairrow = nullptr;
   bool generic_fwd = false, force_blocked = false, old_assemble = false, split_levels = false, no_tiny = false, fuse_l0 = false, old_bwd = false;
   int tiny_mode = 0;
+  bool asm_persist = false;   // A/B switch GPB_ASM_PERSIST: k_assemble_mma_p (persistent CTAs, next tile's copies in flight during the products)
+  int asm_occ = 6;            // A/B switch GPB_ASM_OCC: resident CTAs per SM of k_assemble_mma (5 / 6 / 7)
   bool fma_syrk = false;      // A/B switch GPB_FMA_SYRK: trailing update of the multi-CTA dense solve on FP64 FMAs (round 1) instead of the tensor pipe
   bool thread_chain = false;  // 6 x 6 chains without a landmark border: thread-per-segment kernels (k_fwd6t / k_bwd6t); GPB_NO_THREAD_CHAIN = generic kernels
   int panel0_occ = 4;         // CTAs per SM the level-0 active-column panel kernel is compiled for (GPB_PANEL0_OCC = 4: 128 registers, no spills)
@@ -747,6 +749,8 @@ int gpb_graph_finalize(gpb_graph* g, int device) {
   if (const char* ev = getenv("GPB_PANEL0_OCC")) g->panel0_occ = atoi(ev) == 5 ? 5 : 4;  // the Y-reading back-substitution needs the dense kernel's Y layout  // A/B switch: back-substitution from a stored Y (k_bwd) instead of re-eliminating the right-hand side (k_bwd2)  // A/B switch: level 0 as ONE warp-specialised kernel (spine warp + panel warps per CTA)
   g->no_tiny = getenv("GPB_NO_TINY_SOLVE") != nullptr;
   g->fma_syrk = getenv("GPB_FMA_SYRK") != nullptr;
+  if (const char* ev = getenv("GPB_ASM_OCC")) { const int v = atoi(ev); if (v >= 3 && v <= 7) g->asm_occ = v; }
+  g->asm_persist = getenv("GPB_ASM_PERSIST") != nullptr;
   g->tiny_mode = g->no_tiny ? 2 : (getenv("GPB_OLD_TINY") != nullptr ? 1 : 0);  // reduced-system solver in shared memory: blocked (default) / register-blocked per column / plain per column  // A/B switch: the plain-loop instantiation of k_small_solve instead of the register-blocked ones
   g->qc_diag = 1;
   for (const auto& R : g->Rq) for (int c = 0; c < D; c++) for (int r = 0; r < D; r++) if (r != c && R[r + c * D] != 0.0) g->qc_diag = 0;
@@ -985,6 +989,20 @@ static int linearize_dispatch(gpb_graph* g, const double* X, const double* land,
   }
 }
 
+// SE(3) assembly on the tensor pipe: `nblk` tiles of 8 states from tile `blk0`; resident CTAs per SM = g->asm_occ (register cap 96 / 80 / 72)
+static void launch_assemble_mma(gpb_graph* g, int buf, int blk0, int nblk) {
+  const double* xr = g->NX ? g->d_XR[buf] : nullptr;
+  if (g->asm_persist && blk0 == 0) {  // persistent, double-buffered: one resident wave (two staging buffers: 43.5 KB per CTA)
+    const int occ = g->asm_occ > 5 ? 5 : g->asm_occ, grid = std::min(nblk, g->sms * occ);
+    if (occ == 5) k_assemble_mma_p<5><<<grid, 128, 0, g->stream>>>(g->d_AB[buf], xr, g->d_rowoff, g->d_HREC, g->N, g->NFp, g->NXRp, g->ncolsX - 1, nblk);
+    else if (occ == 4) k_assemble_mma_p<4><<<grid, 128, 0, g->stream>>>(g->d_AB[buf], xr, g->d_rowoff, g->d_HREC, g->N, g->NFp, g->NXRp, g->ncolsX - 1, nblk);
+    else k_assemble_mma_p<3><<<grid, 128, 0, g->stream>>>(g->d_AB[buf], xr, g->d_rowoff, g->d_HREC, g->N, g->NFp, g->NXRp, g->ncolsX - 1, nblk);
+    return;
+  }
+  if (g->asm_occ == 5) k_assemble_mma<5><<<nblk, 128, 0, g->stream>>>(g->d_AB[buf], xr, g->d_rowoff, g->d_HREC, g->N, g->NFp, g->NXRp, g->ncolsX - 1, blk0);
+  else if (g->asm_occ == 7) k_assemble_mma<7><<<nblk, 128, 0, g->stream>>>(g->d_AB[buf], xr, g->d_rowoff, g->d_HREC, g->N, g->NFp, g->NXRp, g->ncolsX - 1, blk0);
+  else k_assemble_mma<6><<<nblk, 128, 0, g->stream>>>(g->d_AB[buf], xr, g->d_rowoff, g->d_HREC, g->N, g->NFp, g->NXRp, g->ncolsX - 1, blk0);
+}
 template <int G> static int launch_assemble(gpb_graph* g, int buf) {
   constexpr int NT = 128, bs = 2 * GroupTraits<G>::D, TILES = bs == 12 ? 4 : 1;
   const int states_per_cta = 32 * (NT / (32 * TILES));
@@ -1004,7 +1022,7 @@ template <int G> static int launch_assemble(gpb_graph* g, int buf) {
     }
     CUDA_TRY(cudaEventRecord(g->ev_join, g->stream2));
   }
-  if (G == G_POSE3 && !g->old_assemble) k_assemble_mma<<<(g->N + 7) / 8, 128, 0, g->stream>>>(g->d_AB[buf], g->NX ? g->d_XR[buf] : nullptr, g->d_rowoff, g->d_HREC, g->N, g->NFp, g->NXRp, g->ncolsX - 1, 0);
+  if (G == G_POSE3 && !g->old_assemble) launch_assemble_mma(g, buf, 0, (g->N + 7) / 8);
   else k_assemble<G, NT><<<nblk, NT, 0, g->stream>>>(g->d_AB[buf], g->d_dt, g->NX ? g->d_XR[buf] : nullptr, g->d_rowoff, g->d_HREC, g->N, g->NFp, g->NXRp);
   g->launches++;
   if (g->nep) {  // loop closures: diagonal blocks / rhs of their endpoint states
@@ -1077,7 +1095,7 @@ static int linearize_assemble(gpb_graph* g, const double* X, const double* land,
     const int b0 = c * per, b1 = std::min(nb1, b0 + per);
     const int t0 = std::min(asm_total, 16 * b0), t1 = (c == NCH - 1 || b1 >= nb1) ? asm_total : std::min(asm_total, 16 * b1);
     if (t0 >= t1) return;
-    k_assemble_mma<<<t1 - t0, 128, 0, g->stream>>>(g->d_AB[buf], g->NX ? g->d_XR[buf] : nullptr, g->d_rowoff, g->d_HREC, g->N, g->NFp, g->NXRp, g->ncolsX - 1, t0);
+    launch_assemble_mma(g, buf, t0, t1 - t0);
     g->launches++;
   };
   for (int c = 0; c < LA; c++) lin_chunk(c);

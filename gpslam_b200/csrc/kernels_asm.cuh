@@ -184,18 +184,19 @@ __global__ void __launch_bounds__(NT) k_assemble(const double* __restrict__ AB, 
 //             mma.sync.m8n8k4.f64 tiles (36 DMMA), Fa / Fp = priors of the intervals i / i-1, _a / _b their columns on the first /
 //             second state; the rhs rides along as column 12 of the second column tile.  The few measurement / prior rows of
 //             the two intervals are further k-steps of the same products, their fragments read straight from the row table.
-//   store   : the 8 finished records (8 x 2400 B, contiguous in HBM) leave through shared memory as coalesced 128-bit stores
+//   store   : each state's record straight from its accumulator fragments (whole 32-byte sectors per store instruction)
 // This replaces the thread-per-tile kernel for SE(3) (255 registers, 8 warps per SM: latency-bound at a quarter of the HBM rate).
 __device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsrc, bool valid) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(valid ? 16 : 0) : "memory");
 }
-__global__ void __launch_bounds__(128) k_assemble_mma(const double* __restrict__ AB, const double* __restrict__ XR,
-                                                      const int* __restrict__ rowoff, double* __restrict__ HREC, int N, int NFp, int NXRp, int xrhs, int blk0) {
-  constexpr int D = 6, bs = 12, REC = 2 * bs * bs + bs, TS = 8, NF = TS + 1, NCOL = 4 * D + 1, FS = NCOL * bs + 2;  // FS: doubles per staged factor (padded)
-  __shared__ __align__(16) double Fsm[NF * FS];   // staged factors [factor][column][row]; re-used for the finished records
-  static_assert(TS * REC <= NF * FS, "record staging must fit the factor staging");
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gi = lane >> 2, ti = lane & 3;
-  const int i0 = (blockIdx.x + blk0) * TS, nint = N - 1;   // blk0: first tile of this launch (the chunked linearise / assemble pipeline launches ranges of tiles)
+struct AsmGeom { static constexpr int D = 6, bs = 12, REC = 2 * bs * bs + bs, TS = 8, NF = TS + 1, NCOL = 4 * D + 1, FS = NCOL * bs + 2; };  // FS: doubles per staged factor (padded)
+struct AsmRows {   // per warp: row ranges of its two states and the prefetched first k-step of their extra rows
+  int rr0[2], rr1[2], rr2[2];
+  double xc0[2], xc1[2], xd0[2], xd1[2], xq0[2], xq1[2];
+};
+// issue the cp.async copies of the 9 GP priors of the tile starting at state i0 into one staging buffer and commit them as one group
+__device__ __forceinline__ void asm_issue_load(double* Fsm, const double* __restrict__ AB, int i0, int NFp, int tid) {
+  constexpr int D = AsmGeom::D, NF = AsmGeom::NF, NCOL = AsmGeom::NCOL, FS = AsmGeom::FS;
   // ---- load: item = (row pair pr = column * D + rp, factor ff), 16 bytes each; consecutive threads take consecutive factors.
   // Thread (ff, g) = (tid % NF, tid / NF) of the first 14 * NF = 126 threads copies row pairs g, g + 14, ...: its source
   // (ab_off: + one row of the tile per row pair) and destination (Fsm[ff][2 pr]) advance by constants - no index arithmetic
@@ -214,8 +215,13 @@ __global__ void __launch_bounds__(128) k_assemble_mma(const double* __restrict__
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   }
+}
+__device__ __forceinline__ void asm_prefetch_rows(AsmRows& R, const double* __restrict__ XR, const int* __restrict__ rowoff, int i0, int N, int NXRp, int xrhs,
+                                                  int warp, int gi, int ti) {
+  const int nint = N - 1;
+  int (&rr0)[2] = R.rr0, (&rr1)[2] = R.rr1, (&rr2)[2] = R.rr2;
+  double (&xc0)[2] = R.xc0, (&xc1)[2] = R.xc1, (&xd0)[2] = R.xd0, (&xd1)[2] = R.xd1, (&xq0)[2] = R.xq0, (&xq1)[2] = R.xq1;
   // row ranges of this warp's two states (interval i-1: [r0, r1), interval i: [r1, r2)) while the copies fly
-  int rr0[2], rr1[2], rr2[2];
 #pragma unroll
   for (int sidx = 0; sidx < 2; sidx++) {
     const int i = i0 + 2 * warp + sidx;
@@ -226,8 +232,35 @@ __global__ void __launch_bounds__(128) k_assemble_mma(const double* __restrict__
       rr2[sidx] = i < nint ? rowoff[i + 1] : rr1[sidx];
     }
   }
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  __syncthreads();
+  // first k-step of the extra rows of both states, fetched while the staged factors are still in flight: the measurement rows
+  // sit in a [column][row] table, each fragment is a scattered 8-byte load, and almost every interval has at most four rows -
+  // taken after the barrier these loads were the kernel's longest stall (long scoreboard 26 % of the samples).
+  // xc1 / xq1: column 8 + gi (resp. 20 + gi) for gi < 4, the rhs column for gi == 4
+#pragma unroll
+  for (int sidx = 0; sidx < 2; sidx++) {
+    {
+      const int base = rr1[sidx], row = base + ti;
+      const bool v = row < rr2[sidx];
+      const double* x = XR + (v ? row : base);
+      xc0[sidx] = v ? x[(size_t)gi * NXRp] : 0.0;
+      xc1[sidx] = (v && gi <= 4) ? x[(size_t)(gi < 4 ? 8 + gi : xrhs) * NXRp] : 0.0;
+      xd0[sidx] = v ? x[(size_t)(12 + gi) * NXRp] : 0.0;
+      xd1[sidx] = (v && gi < 4) ? x[(size_t)(20 + gi) * NXRp] : 0.0;
+    }
+    {
+      const int base = rr0[sidx], row = base + ti;
+      const bool v = row < rr1[sidx];
+      const double* x = XR + (v ? row : base);
+      xq0[sidx] = v ? x[(size_t)(12 + gi) * NXRp] : 0.0;
+      xq1[sidx] = (v && gi <= 4) ? x[(size_t)(gi < 4 ? 20 + gi : xrhs) * NXRp] : 0.0;
+    }
+  }
+}
+__device__ __forceinline__ void asm_compute_store(const double* Fsm, const AsmRows& R, const double* __restrict__ XR, double* __restrict__ HREC, int i0, int N,
+                                                  int NXRp, int xrhs, int warp, int gi, int ti) {
+  constexpr int bs = AsmGeom::bs, REC = AsmGeom::REC, FS = AsmGeom::FS;
+  const int (&rr0)[2] = R.rr0, (&rr1)[2] = R.rr1, (&rr2)[2] = R.rr2;
+  const double (&xc0)[2] = R.xc0, (&xc1)[2] = R.xc1, (&xd0)[2] = R.xd0, (&xd1)[2] = R.xd1, (&xq0)[2] = R.xq0, (&xq1)[2] = R.xq1;
   double accD[2][2][2][2], accE[2][2][2][2];  // [state][mt][nt][2]
 #pragma unroll
   for (int sidx = 0; sidx < 2; sidx++) {
@@ -266,8 +299,9 @@ __global__ void __launch_bounds__(128) k_assemble_mma(const double* __restrict__
       const double p0 = Fp[(12 + gi) * bs + k], p1 = (gi < 4) ? Fp[(20 + gi) * bs + k] : 0.0, p1b = (gi < 4) ? p1 : (gi == 4 ? Fp[24 * bs + k] : 0.0);
       kstep_prev(p0, p1, p1b);
     }
-    // extra rows, four per k-step, fragments straight from the row table XR[column][row]
-    for (int base = rr1[sidx]; base < rr2[sidx]; base += 4) {
+    // extra rows, four per k-step, fragments straight from the row table XR[column][row]; the first k-step was prefetched
+    if (rr1[sidx] < rr2[sidx]) kstep_cur(xc0[sidx], gi < 4 ? xc1[sidx] : 0.0, xc1[sidx], xd0[sidx], xd1[sidx]);
+    for (int base = rr1[sidx] + 4; base < rr2[sidx]; base += 4) {
       const int row = base + ti;
       const bool v = row < rr2[sidx];
       const double* x = XR + (v ? row : base);
@@ -276,7 +310,8 @@ __global__ void __launch_bounds__(128) k_assemble_mma(const double* __restrict__
       const double b0 = v ? x[(size_t)(12 + gi) * NXRp] : 0.0, b1 = (v && gi < 4) ? x[(size_t)(20 + gi) * NXRp] : 0.0;
       kstep_cur(a0, a1, a1b, b0, b1);
     }
-    for (int base = rr0[sidx]; base < rr1[sidx]; base += 4) {
+    if (rr0[sidx] < rr1[sidx]) kstep_prev(xq0[sidx], gi < 4 ? xq1[sidx] : 0.0, xq1[sidx]);
+    for (int base = rr0[sidx] + 4; base < rr1[sidx]; base += 4) {
       const int row = base + ti;
       const bool v = row < rr1[sidx];
       const double* x = XR + (v ? row : base);
@@ -284,30 +319,58 @@ __global__ void __launch_bounds__(128) k_assemble_mma(const double* __restrict__
       const double p1b = (gi < 4) ? p1 : ((v && gi == 4) ? x[(size_t)xrhs * NXRp] : 0.0);
       kstep_prev(p0, p1, p1b);
     }
-  }
-  __syncthreads();  // every warp is done reading the staged factors: the buffer becomes the record staging
-  double* Osm = Fsm;
+    // ---- store: straight from the accumulator fragments.  For one (mt, nt, h) the eight lanes of equal ti hold eight
+    // consecutive rows of one column - a 64-byte run (32 bytes for rows 8..11) that starts on a 32-byte boundary (records are
+    // 2400 bytes, columns 96) - so every store instruction writes whole sectors and nothing needs to pass through shared memory
+    if (i0 + sl < N) {
+      double* O = HREC + (size_t)(i0 + sl) * REC;
 #pragma unroll
-  for (int sidx = 0; sidx < 2; sidx++) {
-    double* O = Osm + (2 * warp + sidx) * REC;
+      for (int mt = 0; mt < 2; mt++)
 #pragma unroll
-    for (int mt = 0; mt < 2; mt++)
+        for (int nt = 0; nt < 2; nt++)
 #pragma unroll
-      for (int nt = 0; nt < 2; nt++)
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-          const int row = 8 * mt + gi, col = 8 * nt + 2 * ti + h;
-          if (row < bs) {
-            if (col < bs) { O[row + col * bs] = accD[sidx][mt][nt][h]; O[bs * bs + row + col * bs] = accE[sidx][mt][nt][h]; }
-            else if (col == bs) O[2 * bs * bs + row] = accD[sidx][mt][nt][h];
+          for (int h = 0; h < 2; h++) {
+            const int row = 8 * mt + gi, col = 8 * nt + 2 * ti + h;
+            if (row < bs) {
+              if (col < bs) { O[row + col * bs] = accD[sidx][mt][nt][h]; O[bs * bs + row + col * bs] = accE[sidx][mt][nt][h]; }
+              else if (col == bs) O[2 * bs * bs + row] = accD[sidx][mt][nt][h];
+            }
           }
-        }
+    }
   }
-  __syncthreads();
-  // ---- store: TS records are contiguous in HBM
-  const int nst = min(TS, N - i0);
-  double* dst = HREC + (size_t)i0 * REC;
-#pragma unroll 4
-  for (int k = tid; k < nst * REC / 2; k += 128) *reinterpret_cast<double2*>(dst + 2 * k) = *reinterpret_cast<const double2*>(Osm + 2 * k);
 }
-
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_assemble_mma(const double* __restrict__ AB, const double* __restrict__ XR,
+                                                      const int* __restrict__ rowoff, double* __restrict__ HREC, int N, int NFp, int NXRp, int xrhs, int blk0) {
+  __shared__ __align__(16) double Fsm[AsmGeom::NF * AsmGeom::FS];   // staged factors [factor][column][row]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gi = lane >> 2, ti = lane & 3;
+  const int i0 = (blockIdx.x + blk0) * AsmGeom::TS;   // blk0: first tile of this launch (the chunked linearise / assemble pipeline launches ranges of tiles)
+  asm_issue_load(Fsm, AB, i0, NFp, tid);
+  AsmRows R;
+  asm_prefetch_rows(R, XR, rowoff, i0, N, NXRp, xrhs, warp, gi, ti);
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  asm_compute_store(Fsm, R, XR, HREC, i0, N, NXRp, xrhs, warp, gi, ti);
+}
+// The same tile pipeline as a persistent kernel: a resident wave of CTAs walks the tiles with stride gridDim.x, the copies of
+// the next tile in flight (second staging buffer) while the current one is multiplied and stored - the one-tile CTAs above spend
+// most of their ~10 us life between launch, the first copy landing and the barrier, with nothing on the SM saturated.
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_assemble_mma_p(const double* __restrict__ AB, const double* __restrict__ XR,
+                                                        const int* __restrict__ rowoff, double* __restrict__ HREC, int N, int NFp, int NXRp, int xrhs, int ntiles) {
+  __shared__ __align__(16) double Fsm[2][AsmGeom::NF * AsmGeom::FS];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gi = lane >> 2, ti = lane & 3;
+  int tile = blockIdx.x, st = 0;
+  if (tile < ntiles) asm_issue_load(Fsm[0], AB, tile * AsmGeom::TS, NFp, tid);
+  for (; tile < ntiles; tile += gridDim.x, st ^= 1) {
+    const int i0 = tile * AsmGeom::TS, next = tile + gridDim.x;
+    if (next < ntiles) asm_issue_load(Fsm[st ^ 1], AB, next * AsmGeom::TS, NFp, tid);   // that buffer was released by the barrier closing the previous round
+    else asm volatile("cp.async.commit_group;" ::: "memory");                           // keep one group per round
+    AsmRows R;
+    asm_prefetch_rows(R, XR, rowoff, i0, N, NXRp, xrhs, warp, gi, ti);
+    asm volatile("cp.async.wait_group 1;" ::: "memory");   // everything but the newest group: this tile has landed
+    __syncthreads();
+    asm_compute_store(Fsm[st], R, XR, HREC, i0, N, NXRp, xrhs, warp, gi, ti);
+    __syncthreads();                                       // every warp is done with this buffer before the next round refills it
+  }
+}
