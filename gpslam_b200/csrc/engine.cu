@@ -739,26 +739,28 @@ int gpb_graph_finalize(gpb_graph* g, int device) {
   g->sms = sms;
   // segment lengths: explicit setting > environment (tuning aid) > defaults
   const char* em0 = getenv("GPB_M0"); const char* emu = getenv("GPB_MUP");
-  g->split_levels = getenv("GPB_SPLIT_LEVELS") != nullptr;  // A/B switch: spine and panel as two launches on the upper levels too
-  g->old_assemble = getenv("GPB_OLD_ASSEMBLE") != nullptr;  // A/B switch: thread-per-tile assembly instead of the DMMA kernel
-  g->generic_fwd = getenv("GPB_GENERIC_FWD") != nullptr;
-  g->fuse_l0 = getenv("GPB_FUSE_L0") != nullptr;
-  g->old_bwd = getenv("GPB_OLD_BWD") != nullptr;
-  g->dense_panel = getenv("GPB_DENSE_PANEL") != nullptr || g->old_bwd;
-  g->panelw = getenv("GPB_PANELW") != nullptr && !g->dense_panel;
-  if (const char* ev = getenv("GPB_PANEL0_OCC")) g->panel0_occ = atoi(ev) == 5 ? 5 : 4;  // the Y-reading back-substitution needs the dense kernel's Y layout  // A/B switch: back-substitution from a stored Y (k_bwd) instead of re-eliminating the right-hand side (k_bwd2)  // A/B switch: level 0 as ONE warp-specialised kernel (spine warp + panel warps per CTA)
-  g->no_tiny = getenv("GPB_NO_TINY_SOLVE") != nullptr;
-  g->fma_syrk = getenv("GPB_FMA_SYRK") != nullptr;
-  if (const char* ev = getenv("GPB_ASM_OCC")) { const int v = atoi(ev); if (v >= 3 && v <= 7) g->asm_occ = v; }
-  g->asm_persist = getenv("GPB_ASM_PERSIST") != nullptr;
-  g->tiny_mode = g->no_tiny ? 2 : (getenv("GPB_OLD_TINY") != nullptr ? 1 : 0);  // reduced-system solver in shared memory: blocked (default) / register-blocked per column / plain per column  // A/B switch: the plain-loop instantiation of k_small_solve instead of the register-blocked ones
+  // A/B switches (tuning aids read once here; every non-default arm is a measured alternative recorded in DESIGN.md §7):
+  g->split_levels = getenv("GPB_SPLIT_LEVELS") != nullptr;   // spine and panel as two launches on the upper levels too
+  g->old_assemble = getenv("GPB_OLD_ASSEMBLE") != nullptr;   // thread-per-tile assembly instead of the DMMA kernel
+  g->generic_fwd = getenv("GPB_GENERIC_FWD") != nullptr;     // one-kernel generic forward sweep (k_fwd<12,64>)
+  g->fuse_l0 = getenv("GPB_FUSE_L0") != nullptr;             // level 0 as ONE warp-specialised kernel (spine warp + panel warps per CTA)
+  g->old_bwd = getenv("GPB_OLD_BWD") != nullptr;             // back-substitution from a stored Y (k_bwd) instead of re-eliminating the rhs (k_bwd2)
+  g->dense_panel = getenv("GPB_DENSE_PANEL") != nullptr || g->old_bwd;   // k_panel4 on all 64 columns (the Y-reading k_bwd needs its Y layout)
+  g->panelw = getenv("GPB_PANELW") != nullptr && !g->dense_panel;        // two-warp register-resident panel kernel
+  if (const char* ev = getenv("GPB_PANEL0_OCC")) g->panel0_occ = atoi(ev) == 5 ? 5 : 4;   // resident CTAs per SM of k_panel0
+  g->no_tiny = getenv("GPB_NO_TINY_SOLVE") != nullptr;       // reduced system always through the multi-CTA dense solver
+  g->fma_syrk = getenv("GPB_FMA_SYRK") != nullptr;           // dense trailing update on FP64 FMAs instead of the tensor pipe
+  if (const char* ev = getenv("GPB_ASM_OCC")) { const int v = atoi(ev); if (v >= 3 && v <= 7) g->asm_occ = v; }   // resident CTAs per SM of k_assemble_mma
+  g->asm_persist = getenv("GPB_ASM_PERSIST") != nullptr;     // persistent double-buffered assembly kernel
+  // reduced-system solver in shared memory: 0 blocked (default) / 1 register-blocked per column (GPB_OLD_TINY) / 2 off
+  g->tiny_mode = g->no_tiny ? 2 : (getenv("GPB_OLD_TINY") != nullptr ? 1 : 0);
   g->qc_diag = 1;
   for (const auto& R : g->Rq) for (int c = 0; c < D; c++) for (int r = 0; r < D; r++) if (r != c && R[r + c * D] != 0.0) g->qc_diag = 0;
   g->lin_variant = g->qc_diag ? 1 : 0;
   if (const char* ev = getenv("GPB_LIN_VARIANT")) {  // A/B switch: 0 dense Rq, 1 diagonal Rq, +2: three CTAs per SM (<= 168 registers)
     const int v = atoi(ev);
     if (v >= 0 && v <= 3 && (!(v & 1) || g->qc_diag)) g->lin_variant = v;
-  }  // A/B switch: one-kernel generic forward sweep (k_fwd<12,64>)
+  }
   int M0 = g->M0 ? g->M0 : (em0 ? std::max(2, atoi(em0)) : (g->nb > 0 ? 32 : 16));
   g->thread_chain = bs == 6 && g->nb == 0 && !g->generic_fwd && !g->old_bwd && getenv("GPB_NO_THREAD_CHAIN") == nullptr;
   // one thread per segment: about one resident wave of 256 threads per SM, segments of 8 .. 64 states
