@@ -14,15 +14,18 @@
 #include <array>
 #include <cmath>
 #include <cstdint>
+#include <fstream>
 #include <functional>
 #include <iostream>
 #include <map>
 #include <memory>
+#include <sstream>
 #include <stdexcept>
 #include <string>
 #include <vector>
 
 #include "../gpb.h"
+#include "archive.h"
 
 namespace gpslam_b200 {
 namespace gtsam {
@@ -46,15 +49,34 @@ struct Matrix {  // dynamic, column-major (Eigen's default)
   double& operator()(int r, int c) { return a[r + static_cast<size_t>(c) * rows]; }
   double operator()(int r, int c) const { return a[r + static_cast<size_t>(c) * rows]; }
   static Matrix Identity(int n, int m) { Matrix I(n, m); for (int k = 0; k < (n < m ? n : m); k++) I(k, k) = 1.0; return I; }
+  template <class ARCHIVE> void serialize(ARCHIVE& ar, const unsigned int /*version*/) {
+    ar & GPSLAM_B200_NVP(rows); ar & GPSLAM_B200_NVP(cols); ar & make_nvp("data", a);
+    if (rows < 0 || cols < 0 || a.size() != static_cast<size_t>(rows) * cols) throw std::runtime_error("gpslam_b200 archive: matrix data does not match its shape");
+  }
 };
 inline Matrix operator*(double s, Matrix m) { for (double& v : m.a) v *= s; return m; }
 
 template <int N> using VectorN = std::array<double, N>;
 using Vector3 = VectorN<3>;
 using Vector6 = VectorN<6>;
-struct Point2 { double x = 0, y = 0; Point2() {} Point2(double x_, double y_) : x(x_), y(y_) {} };
-struct Point3 { double x = 0, y = 0, z = 0; Point3() {} Point3(double x_, double y_, double z_) : x(x_), y(y_), z(z_) {} };
-struct Unit3 { double x = 0, y = 0, z = 1; Unit3() {} Unit3(double x_, double y_, double z_) { const double n = std::sqrt(x_ * x_ + y_ * y_ + z_ * z_); x = x_ / n; y = y_ / n; z = z_ / n; } };
+struct Point2 {
+  double x = 0, y = 0;
+  Point2() {}
+  Point2(double x_, double y_) : x(x_), y(y_) {}
+  template <class ARCHIVE> void serialize(ARCHIVE& ar, const unsigned int) { ar & GPSLAM_B200_NVP(x); ar & GPSLAM_B200_NVP(y); }
+};
+struct Point3 {
+  double x = 0, y = 0, z = 0;
+  Point3() {}
+  Point3(double x_, double y_, double z_) : x(x_), y(y_), z(z_) {}
+  template <class ARCHIVE> void serialize(ARCHIVE& ar, const unsigned int) { ar & GPSLAM_B200_NVP(x); ar & GPSLAM_B200_NVP(y); ar & GPSLAM_B200_NVP(z); }
+};
+struct Unit3 {
+  double x = 0, y = 0, z = 1;
+  Unit3() {}
+  Unit3(double x_, double y_, double z_) { const double n = std::sqrt(x_ * x_ + y_ * y_ + z_ * z_); x = x_ / n; y = y_ / n; z = z_ / n; }
+  template <class ARCHIVE> void serialize(ARCHIVE& ar, const unsigned int) { ar & GPSLAM_B200_NVP(x); ar & GPSLAM_B200_NVP(y); ar & GPSLAM_B200_NVP(z); }
+};
 
 struct Rot3 {
   double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};  // column-major
@@ -65,6 +87,9 @@ struct Rot3 {
     for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) o.R[i + 3 * j] = m[i][j];
     return o;
   }
+  template <class ARCHIVE> void serialize(ARCHIVE& ar, const unsigned int) {
+    ar.array("R", R, 9, [&](size_t n) { if (n != 9) throw std::runtime_error("gpslam_b200 archive: a rotation has nine entries"); return R; });
+  }
 };
 struct Pose3 {
   Rot3 r; Point3 t;
@@ -72,8 +97,14 @@ struct Pose3 {
   Pose3(const Rot3& r_, const Point3& t_) : r(r_), t(t_) {}
   void wire(double* p) const { for (int k = 0; k < 9; k++) p[k] = r.R[k]; p[9] = t.x; p[10] = t.y; p[11] = t.z; }
   static Pose3 fromWire(const double* p) { Pose3 T; for (int k = 0; k < 9; k++) T.r.R[k] = p[k]; T.t = Point3(p[9], p[10], p[11]); return T; }
+  template <class ARCHIVE> void serialize(ARCHIVE& ar, const unsigned int) { ar & make_nvp("R_", r); ar & make_nvp("t_", t); }
 };
-struct Pose2 { double x = 0, y = 0, theta = 0; Pose2() {} Pose2(double x_, double y_, double th) : x(x_), y(y_), theta(th) {} };
+struct Pose2 {
+  double x = 0, y = 0, theta = 0;
+  Pose2() {}
+  Pose2(double x_, double y_, double th) : x(x_), y(y_), theta(th) {}
+  template <class ARCHIVE> void serialize(ARCHIVE& ar, const unsigned int) { ar & GPSLAM_B200_NVP(x); ar & GPSLAM_B200_NVP(y); ar & GPSLAM_B200_NVP(theta); }
+};
 
 namespace noiseModel {
 // Every model the gpslam call sites use reduces to a Gaussian with upper-triangular square-root information R.
@@ -92,6 +123,7 @@ struct Gaussian {
     else m->R = Matrix();  // dense covariance: valid as a Qc model (the engine factors it itself), not as a measurement model
     return m;
   }
+  template <class ARCHIVE> void serialize(ARCHIVE& ar, const unsigned int) { ar & GPSLAM_B200_NVP(dim); ar & GPSLAM_B200_NVP(cov); ar & make_nvp("sqrt_information", R); }
 };
 struct Isotropic { static Gaussian::shared_ptr Sigma(int dim, double sigma) { return Gaussian::Covariance((sigma * sigma) * Matrix::Identity(dim, dim)); } };
 struct Diagonal {
@@ -163,10 +195,28 @@ class NonlinearFactor {
   // lowering hook used by the optimisers: add this factor to g; idx maps a state key to its chain index, lidx a landmark key
   virtual void lower(gpb_graph* g, int qc_of(void*, const gtsam::Matrix&), void* ctx, const std::map<gtsam::Key, int>& sidx,
                      const std::map<gtsam::Key, int>& lidx) const = 0;
+  /// archives (archive.h): the type name a graph archive stores in front of the factor, and the factor's own serialize() reached
+  /// through the base pointer (what boost's export / void_cast registration does for the reference's classes)
+  virtual std::string archiveTag() const = 0;
+  virtual void save(OArchive& ar) const = 0;
+  virtual void load(IArchive& ar) = 0;
 };
-#define GPSLAM_B200_FACTOR(CLASS, TEXT)                                                                   \
+#define GPSLAM_B200_FACTOR(CLASS, TEXT, TAG)                                                              \
   NonlinearFactor::shared_ptr clone() const override { return std::make_shared<CLASS>(*this); }           \
-  std::string describe() const override { return TEXT; }
+  std::string describe() const override { return TEXT; }                                                  \
+  std::string archiveTag() const override { return TAG; }                                                 \
+  void save(OArchive& ar) const override { archiveIO(ar, "factor", const_cast<CLASS&>(*this)); }          \
+  void load(IArchive& ar) override { archiveIO(ar, "factor", *this); }
+
+/// type name -> default-constructed factor, for loading a graph archive; every factor class of this header is registered, user
+/// classes join with FactorRegistry::add<F>()
+class FactorRegistry {
+ public:
+  using Maker = std::function<NonlinearFactor::shared_ptr()>;
+  static std::map<std::string, Maker>& table() { static std::map<std::string, Maker> t; return t; }
+  template <class F> static void add() { table()[F().archiveTag()] = [] { return NonlinearFactor::shared_ptr(std::make_shared<F>()); }; }
+  static inline NonlinearFactor::shared_ptr make(const std::string& tag);
+};
 
 namespace detail {
 inline int stateOf(const std::map<gtsam::Key, int>& m, gtsam::Key k) {
@@ -174,6 +224,34 @@ inline int stateOf(const std::map<gtsam::Key, int>& m, gtsam::Key k) {
   if (it == m.end()) throw std::runtime_error("gpslam_b200: factor refers to a key that is not in Values");
   return it->second;
 }
+// archive pieces shared by the factor classes: the NoiseModelFactorN base (keys and, for measurement factors, the noise model),
+// the interpolator a GPInterpolated* factor holds (GPbase_), and an optional sensor pose (boost::optional<POSE> in the reference)
+template <class AR> void ioBase(AR& ar, std::vector<gtsam::Key>& keys, size_t nkeys, gtsam::SharedNoiseModel* model) {
+  ar.begin("Base");
+  ar & make_nvp("keys_", keys);
+  if (keys.size() != nkeys) throw std::runtime_error("gpslam_b200 archive: wrong number of keys for this factor type");
+  if (model) ar & make_nvp("noiseModel_", *model);
+  ar.end();
+}
+template <class AR> void ioGPbase(AR& ar, double& delta_t, double& tau, gtsam::SharedNoiseModel& Qc) {
+  ar.begin("GPbase_");
+  ar & make_nvp("delta_t_", delta_t); ar & make_nvp("tau_", tau); ar & make_nvp("Qc", Qc);
+  ar.end();
+}
+template <class AR, class P> void ioOptional(AR& ar, const char* name, bool& has, P& value) {
+  ar.begin(name);
+  ar & make_nvp("initialized", has);
+  if (has) ar & make_nvp("value", value);
+  ar.end();
+}
+template <class T> struct TypeName;
+template <> struct TypeName<gtsam::Pose3> { static const char* name() { return "Pose3"; } };
+template <> struct TypeName<gtsam::Pose2> { static const char* name() { return "Pose2"; } };
+template <> struct TypeName<gtsam::Rot3> { static const char* name() { return "Rot3"; } };
+template <> struct TypeName<gtsam::Vector3> { static const char* name() { return "Vector3"; } };
+template <> struct TypeName<gtsam::Vector6> { static const char* name() { return "Vector6"; } };
+template <> struct TypeName<gtsam::Point3> { static const char* name() { return "Point3"; } };
+template <> struct TypeName<gtsam::Point2> { static const char* name() { return "Point2"; } };
 }  // namespace detail
 
 /// 4-way GP prior factors — gp/GaussianProcessPrior{Pose3,Pose2,Rot3,Linear}.h (constructor: :43-49)
@@ -181,16 +259,24 @@ template <class POSE>
 class GaussianProcessPriorT : public NonlinearFactor {
   using G = detail::GroupOf<POSE>;
   std::vector<gtsam::Key> keys_;
-  double delta_t_;
+  double delta_t_ = 0;
   gtsam::SharedNoiseModel Qc_;
 
  public:
+  GaussianProcessPriorT() {}  ///< default constructor, for loading from an archive only (gp/GaussianProcessPriorPose3.h:40)
   GaussianProcessPriorT(gtsam::Key poseKey1, gtsam::Key velKey1, gtsam::Key poseKey2, gtsam::Key velKey2, double delta_t, const gtsam::SharedNoiseModel& Qc_model)
       : keys_{poseKey1, velKey1, poseKey2, velKey2}, delta_t_(delta_t), Qc_(Qc_model) {
     if (!Qc_model) throw std::runtime_error("gpslam_b200: Qc model is not Gaussian");  // getQc dereferences a failed dynamic_cast in the reference (gp/GPutils.cpp:17-19)
   }
   const std::vector<gtsam::Key>& keys() const override { return keys_; }
-  GPSLAM_B200_FACTOR(GaussianProcessPriorT, std::string("4-way Gaussian Process Factor ") + G::name())
+  GPSLAM_B200_FACTOR(GaussianProcessPriorT, std::string("4-way Gaussian Process Factor ") + G::name(), std::string("GaussianProcessPrior") + detail::TypeName<POSE>::name())
+  /// gp/GaussianProcessPriorPose3.h:118-125 (Base, delta_t_); the base's noise model there is Q(delta_t, Qc) - here the Qc model itself
+  template <class ARCHIVE> void serialize(ARCHIVE& ar, const unsigned int /*version*/) {
+    detail::ioBase(ar, keys_, 4, nullptr);
+    ar & GPSLAM_B200_NVP(delta_t_);
+    ar & GPSLAM_B200_NVP(Qc_);
+    if (!Qc_) throw std::runtime_error("gpslam_b200 archive: GP prior without a Qc model");
+  }
   size_t size() const override { return 4; }
   double delta_t() const { return delta_t_; }
   bool chainLink(ChainLink& c) const override { c = ChainLink{keys_[0], keys_[1], 0, keys_[2], keys_[3], 0, false}; return true; }
@@ -273,6 +359,9 @@ class GaussianProcessInterpolatorT {
     return v;
   }
   void print(const std::string& s = "") const { std::cout << s << "GaussianProcessInterpolator" << G::name() << std::endl; }
+  /// gp/GaussianProcessInterpolatorPose3.h:148-159 (delta_t_, tau_, Qc; Lambda and Psi are functions of these three and are
+  /// evaluated on the device at every query, so they are not stored)
+  template <class ARCHIVE> void serialize(ARCHIVE& ar, const unsigned int /*version*/) { ar & GPSLAM_B200_NVP(delta_t_); ar & GPSLAM_B200_NVP(tau_); ar & make_nvp("Qc", Qc_); }
   bool equals(const GaussianProcessInterpolatorT& e, double tol = 1e-9) const {
     return std::fabs(delta_t_ - e.delta_t_) < tol && std::fabs(tau_ - e.tau_) < tol && Qc_ && e.Qc_ && Qc_->cov.a == e.Qc_->cov.a;
   }
@@ -287,12 +376,13 @@ template <class POSE>
 class GPInterpolatedRangeFactorT : public NonlinearFactor {
   using G = detail::GroupOf<POSE>;
   std::vector<gtsam::Key> keys_;
-  double measured_, delta_t_, tau_;
+  double measured_ = 0, delta_t_ = 0, tau_ = 0;
   gtsam::SharedNoiseModel meas_, Qc_;
   bool has_sensor_ = false;
-  POSE body_P_sensor_;
+  POSE body_P_sensor_{};
 
  public:
+  GPInterpolatedRangeFactorT() {}  ///< for loading from an archive only (slam/GPInterpolatedRangeFactorPose3.h:43)
   GPInterpolatedRangeFactorT(double measured, const gtsam::SharedNoiseModel& meas_model, const gtsam::SharedNoiseModel& Qc_model, gtsam::Key poseKey1,
                              gtsam::Key velKey1, gtsam::Key poseKey2, gtsam::Key velKey2, gtsam::Key pointKey, double delta_t, double tau,
                              const POSE* body_P_sensor = nullptr)
@@ -300,7 +390,14 @@ class GPInterpolatedRangeFactorT : public NonlinearFactor {
     if (body_P_sensor) { has_sensor_ = true; body_P_sensor_ = *body_P_sensor; }
   }
   const std::vector<gtsam::Key>& keys() const override { return keys_; }
-  GPSLAM_B200_FACTOR(GPInterpolatedRangeFactorT, "RangeFactor, range = " + std::to_string(measured_))
+  GPSLAM_B200_FACTOR(GPInterpolatedRangeFactorT, "RangeFactor, range = " + std::to_string(measured_), std::string("GPInterpolatedRangeFactor") + detail::TypeName<POSE>::name())
+  /// slam/GPInterpolatedRangeFactorPose3.h:125-135 (Base, GPbase_, measured_, body_P_sensor_)
+  template <class ARCHIVE> void serialize(ARCHIVE& ar, const unsigned int /*version*/) {
+    detail::ioBase(ar, keys_, 5, &meas_);
+    detail::ioGPbase(ar, delta_t_, tau_, Qc_);
+    ar & GPSLAM_B200_NVP(measured_);
+    detail::ioOptional(ar, "body_P_sensor_", has_sensor_, body_P_sensor_);
+  }
   double measured() const { return measured_; }
   gtsam::Vector evaluateError(const POSE& pose1, const typename G::Vel& vel1, const POSE& pose2, const typename G::Vel& vel2, const typename G::Land& point,
                               gtsam::Matrix* H1 = nullptr, gtsam::Matrix* H2 = nullptr, gtsam::Matrix* H3 = nullptr, gtsam::Matrix* H4 = nullptr,
@@ -325,10 +422,11 @@ using GPInterpolatedRangeFactorPose2 = GPInterpolatedRangeFactorT<gtsam::Pose2>;
 /// slam/GPInterpolatedRangeFactor2DLinear.h:42-50 — note the reference's different argument order
 class GPInterpolatedRangeFactor2DLinear : public GPInterpolatedRangeFactorT<gtsam::Vector3> {
  public:
+  GPInterpolatedRangeFactor2DLinear() {}
   GPInterpolatedRangeFactor2DLinear(double measured, gtsam::Key pose1Key, gtsam::Key vel1Key, gtsam::Key pose2Key, gtsam::Key vel2Key, gtsam::Key pointKey,
                                     const gtsam::SharedNoiseModel& meas_model, const gtsam::SharedNoiseModel& Qc_model, double delta_t, double tau)
       : GPInterpolatedRangeFactorT<gtsam::Vector3>(measured, meas_model, Qc_model, pose1Key, vel1Key, pose2Key, vel2Key, pointKey, delta_t, tau) {}
-  GPSLAM_B200_FACTOR(GPInterpolatedRangeFactor2DLinear, "RangeFactor, range = " + std::to_string(measured()))
+  GPSLAM_B200_FACTOR(GPInterpolatedRangeFactor2DLinear, "RangeFactor, range = " + std::to_string(measured()), "GPInterpolatedRangeFactor2DLinear")
 };
 
 /// gtsam::Cal3_S2 (fx, fy, s, u0, v0) — the calibration the reference's projection-factor tests use
@@ -337,6 +435,9 @@ struct Cal3_S2 {
   double fx = 1, fy = 1, s = 0, u0 = 0, v0 = 0;
   Cal3_S2() {}
   Cal3_S2(double fx_, double fy_, double s_, double u0_, double v0_) : fx(fx_), fy(fy_), s(s_), u0(u0_), v0(v0_) {}
+  template <class ARCHIVE> void serialize(ARCHIVE& ar, const unsigned int) {
+    ar & make_nvp("fx_", fx); ar & make_nvp("fy_", fy); ar & make_nvp("s_", s); ar & make_nvp("u0_", u0); ar & make_nvp("v0_", v0);
+  }
 };
 }  // namespace gtsam
 
@@ -344,12 +445,13 @@ struct Cal3_S2 {
 class GPInterpolatedGPSFactorPose3 : public NonlinearFactor {
   std::vector<gtsam::Key> keys_;
   gtsam::Point3 measured_;
-  double delta_t_, tau_;
+  double delta_t_ = 0, tau_ = 0;
   gtsam::SharedNoiseModel meas_, Qc_;
   bool has_sensor_ = false;
   gtsam::Pose3 body_P_sensor_;
 
  public:
+  GPInterpolatedGPSFactorPose3() {}  ///< for loading from an archive only
   GPInterpolatedGPSFactorPose3(const gtsam::Point3& measured_point3, const gtsam::SharedNoiseModel& meas_model, const gtsam::SharedNoiseModel& Qc_model,
                                gtsam::Key poseKey1, gtsam::Key velKey1, gtsam::Key poseKey2, gtsam::Key velKey2, double delta_t, double tau,
                                const gtsam::Pose3* body_P_sensor = nullptr)
@@ -357,7 +459,14 @@ class GPInterpolatedGPSFactorPose3 : public NonlinearFactor {
     if (body_P_sensor) { has_sensor_ = true; body_P_sensor_ = *body_P_sensor; }
   }
   const std::vector<gtsam::Key>& keys() const override { return keys_; }
-  GPSLAM_B200_FACTOR(GPInterpolatedGPSFactorPose3, "GPSFactor, point = (" + std::to_string(measured_.x) + ", " + std::to_string(measured_.y) + ", " + std::to_string(measured_.z) + ")")
+  GPSLAM_B200_FACTOR(GPInterpolatedGPSFactorPose3, "GPSFactor, point = (" + std::to_string(measured_.x) + ", " + std::to_string(measured_.y) + ", " + std::to_string(measured_.z) + ")", "GPInterpolatedGPSFactorPose3")
+  /// slam/GPInterpolatedGPSFactorPose3.h:123-130 (Base, GPbase_, measured_, body_P_sensor_)
+  template <class ARCHIVE> void serialize(ARCHIVE& ar, const unsigned int /*version*/) {
+    detail::ioBase(ar, keys_, 4, &meas_);
+    detail::ioGPbase(ar, delta_t_, tau_, Qc_);
+    ar & GPSLAM_B200_NVP(measured_);
+    detail::ioOptional(ar, "body_P_sensor_", has_sensor_, body_P_sensor_);
+  }
   gtsam::Point3 measured() const { return measured_; }
   gtsam::Vector evaluateError(const gtsam::Pose3& pose1, const gtsam::Vector6& vel1, const gtsam::Pose3& pose2, const gtsam::Vector6& vel2,
                               gtsam::Matrix* H1 = nullptr, gtsam::Matrix* H2 = nullptr, gtsam::Matrix* H3 = nullptr, gtsam::Matrix* H4 = nullptr) const {
@@ -381,14 +490,16 @@ template <class CALIBRATION = gtsam::Cal3_S2>
 class GPInterpolatedProjectionFactorPose3 : public NonlinearFactor {
   std::vector<gtsam::Key> keys_;
   gtsam::Point2 measured_;
-  double delta_t_, tau_;
+  double delta_t_ = 0, tau_ = 0;
   gtsam::SharedNoiseModel meas_, Qc_;
   std::shared_ptr<CALIBRATION> K_;
   bool has_sensor_ = false;
   gtsam::Pose3 body_P_sensor_;
+  bool throwCheirality_ = false, verboseCheirality_ = false;  // kept for the archive's member list: the device path is the no-throw one
   void calib(double* k) const { k[0] = K_->fx; k[1] = K_->fy; k[2] = K_->s; k[3] = K_->u0; k[4] = K_->v0; }
 
  public:
+  GPInterpolatedProjectionFactorPose3() {}  ///< for loading from an archive only
   GPInterpolatedProjectionFactorPose3(const gtsam::Point2& measured, const gtsam::SharedNoiseModel& cam_model, const gtsam::SharedNoiseModel& Qc_model,
                                       gtsam::Key poseKey1, gtsam::Key velKey1, gtsam::Key poseKey2, gtsam::Key velKey2, gtsam::Key pointKey, double delta_t,
                                       double tau, const std::shared_ptr<CALIBRATION>& K, const gtsam::Pose3* body_P_sensor = nullptr)
@@ -397,7 +508,18 @@ class GPInterpolatedProjectionFactorPose3 : public NonlinearFactor {
     if (body_P_sensor) { has_sensor_ = true; body_P_sensor_ = *body_P_sensor; }
   }
   const std::vector<gtsam::Key>& keys() const override { return keys_; }
-  GPSLAM_B200_FACTOR(GPInterpolatedProjectionFactorPose3, "GPInterpolatedProjectionFactor, z = (" + std::to_string(measured_.x) + ", " + std::to_string(measured_.y) + ")")
+  GPSLAM_B200_FACTOR(GPInterpolatedProjectionFactorPose3, "GPInterpolatedProjectionFactor, z = (" + std::to_string(measured_.x) + ", " + std::to_string(measured_.y) + ")", "GPInterpolatedProjectionFactorPose3")
+  /// slam/GPInterpolatedProjectionFactorPose3.h:186-195 (Base, GPbase_, measured_, K_, throwCheirality_, verboseCheirality_) + the sensor pose
+  template <class ARCHIVE> void serialize(ARCHIVE& ar, const unsigned int /*version*/) {
+    detail::ioBase(ar, keys_, 5, &meas_);
+    detail::ioGPbase(ar, delta_t_, tau_, Qc_);
+    ar & GPSLAM_B200_NVP(measured_);
+    ar & GPSLAM_B200_NVP(K_);
+    ar & GPSLAM_B200_NVP(throwCheirality_);
+    ar & GPSLAM_B200_NVP(verboseCheirality_);
+    detail::ioOptional(ar, "body_P_sensor_", has_sensor_, body_P_sensor_);
+    if (!K_) throw std::runtime_error("gpslam_b200 archive: projection factor without a calibration");
+  }
   const gtsam::Point2& measured() const { return measured_; }
   const std::shared_ptr<CALIBRATION> calibration() const { return K_; }
   gtsam::Vector evaluateError(const gtsam::Pose3& pose1, const gtsam::Vector6& vel1, const gtsam::Pose3& pose2, const gtsam::Vector6& vel2, const gtsam::Point3& point,
@@ -452,17 +574,25 @@ inline void checkVWKeys(const std::map<gtsam::Key, int>& sidx, const std::vector
 /// gp/GaussianProcessPriorPose3VW.h:43-51 (6-way factor; evaluateError :62-117)
 class GaussianProcessPriorPose3VW : public NonlinearFactor {
   std::vector<gtsam::Key> keys_;
-  double delta_t_;
+  double delta_t_ = 0;
   gtsam::SharedNoiseModel Qc_;
 
  public:
+  GaussianProcessPriorPose3VW() {}  ///< for loading from an archive only
   GaussianProcessPriorPose3VW(gtsam::Key poseKey1, gtsam::Key velKey1, gtsam::Key omegaKey1, gtsam::Key poseKey2, gtsam::Key velKey2, gtsam::Key omegaKey2, double delta_t,
                               const gtsam::SharedNoiseModel& Qc_model)
       : keys_{poseKey1, velKey1, omegaKey1, poseKey2, velKey2, omegaKey2}, delta_t_(delta_t), Qc_(Qc_model) {
     if (!Qc_model) throw std::runtime_error("gpslam_b200: Qc model is not Gaussian");
   }
   const std::vector<gtsam::Key>& keys() const override { return keys_; }
-  GPSLAM_B200_FACTOR(GaussianProcessPriorPose3VW, "4-way Gaussian Process Factor Pose3 VW")
+  GPSLAM_B200_FACTOR(GaussianProcessPriorPose3VW, "4-way Gaussian Process Factor Pose3 VW", "GaussianProcessPriorPose3VW")
+  /// gp/GaussianProcessPriorPose3VW.h:139-144 (Base, delta_t_)
+  template <class ARCHIVE> void serialize(ARCHIVE& ar, const unsigned int /*version*/) {
+    detail::ioBase(ar, keys_, 6, nullptr);
+    ar & GPSLAM_B200_NVP(delta_t_);
+    ar & GPSLAM_B200_NVP(Qc_);
+    if (!Qc_) throw std::runtime_error("gpslam_b200 archive: GP prior without a Qc model");
+  }
   bool chainLink(ChainLink& c) const override { c = ChainLink{keys_[0], keys_[1], keys_[2], keys_[3], keys_[4], keys_[5], true}; return true; }
   size_t size() const override { return 6; }
   gtsam::Vector evaluateError(const gtsam::Pose3& pose1, const gtsam::Vector3& vel1, const gtsam::Vector3& omega1, const gtsam::Pose3& pose2, const gtsam::Vector3& vel2,
@@ -503,6 +633,8 @@ class GaussianProcessInterpolatorPose3VW {
     if (H5 || H6) detail::splitVW(Hvw2, H5, H6);
     return gtsam::Pose3::fromWire(out);
   }
+  /// gp/GaussianProcessInterpolatorPose3VW.h:175-184 (delta_t_, tau_, Qc)
+  template <class ARCHIVE> void serialize(ARCHIVE& ar, const unsigned int /*version*/) { ar & GPSLAM_B200_NVP(delta_t_); ar & GPSLAM_B200_NVP(tau_); ar & make_nvp("Qc", Qc_); }
   bool equals(const GaussianProcessInterpolatorPose3VW& e, double tol = 1e-9) const {
     return std::fabs(delta_t_ - e.delta_t_) < tol && std::fabs(tau_ - e.tau_) < tol && Qc_ && e.Qc_ && Qc_->cov.a == e.Qc_->cov.a;
   }
@@ -518,6 +650,7 @@ class GPInterpolatedGPSFactorPose3VW : public NonlinearFactor {
   gtsam::Pose3 body_P_sensor_;
 
  public:
+  GPInterpolatedGPSFactorPose3VW() {}  ///< for loading from an archive only
   GPInterpolatedGPSFactorPose3VW(const gtsam::Point3& measured_point3, const gtsam::SharedNoiseModel& meas_model, const gtsam::SharedNoiseModel& Qc_model,
                                  gtsam::Key poseKey1, gtsam::Key velKey1, gtsam::Key omegaKey1, gtsam::Key poseKey2, gtsam::Key velKey2, gtsam::Key omegaKey2, double delta_t,
                                  double tau, const gtsam::Pose3* body_P_sensor = nullptr)
@@ -525,7 +658,14 @@ class GPInterpolatedGPSFactorPose3VW : public NonlinearFactor {
     if (body_P_sensor) { has_sensor_ = true; body_P_sensor_ = *body_P_sensor; }
   }
   const std::vector<gtsam::Key>& keys() const override { return keys_; }
-  GPSLAM_B200_FACTOR(GPInterpolatedGPSFactorPose3VW, "GPSFactor, point = (" + std::to_string(measured_.x) + ", " + std::to_string(measured_.y) + ", " + std::to_string(measured_.z) + ")")
+  GPSLAM_B200_FACTOR(GPInterpolatedGPSFactorPose3VW, "GPSFactor, point = (" + std::to_string(measured_.x) + ", " + std::to_string(measured_.y) + ", " + std::to_string(measured_.z) + ")", "GPInterpolatedGPSFactorPose3VW")
+  /// slam/GPInterpolatedGPSFactorPose3VW.h:132-139 (Base, GPbase_, measured_, body_P_sensor_)
+  template <class ARCHIVE> void serialize(ARCHIVE& ar, const unsigned int /*version*/) {
+    detail::ioBase(ar, keys_, 6, &meas_);
+    ar & GPSLAM_B200_NVP(GPbase_);
+    ar & GPSLAM_B200_NVP(measured_);
+    detail::ioOptional(ar, "body_P_sensor_", has_sensor_, body_P_sensor_);
+  }
   size_t size() const override { return 6; }
   gtsam::Point3 measured() const { return measured_; }
   gtsam::Vector evaluateError(const gtsam::Pose3& pose1, const gtsam::Vector3& vel1, const gtsam::Vector3& omega1, const gtsam::Pose3& pose2, const gtsam::Vector3& vel2,
@@ -551,17 +691,24 @@ class GPInterpolatedGPSFactorPose3VW : public NonlinearFactor {
 /// slam/GPInterpolatedAttitudeFactorRot3.h:44-51
 class GPInterpolatedAttitudeFactorRot3 : public NonlinearFactor {
   std::vector<gtsam::Key> keys_;
-  double delta_t_, tau_;
+  double delta_t_ = 0, tau_ = 0;
   gtsam::SharedNoiseModel Qc_, meas_;
   gtsam::Unit3 nZ_, bRef_;
 
  public:
+  GPInterpolatedAttitudeFactorRot3() {}  ///< for loading from an archive only
   GPInterpolatedAttitudeFactorRot3(gtsam::Key poseKey1, gtsam::Key velKey1, gtsam::Key poseKey2, gtsam::Key velKey2, double delta_t, double tau,
                                    const gtsam::SharedNoiseModel& Qc_model, const gtsam::SharedNoiseModel& meas_model, const gtsam::Unit3& nZ,
                                    const gtsam::Unit3& bRef = gtsam::Unit3(0, 0, 1))
       : keys_{poseKey1, velKey1, poseKey2, velKey2}, delta_t_(delta_t), tau_(tau), Qc_(Qc_model), meas_(meas_model), nZ_(nZ), bRef_(bRef) {}
   const std::vector<gtsam::Key>& keys() const override { return keys_; }
-  GPSLAM_B200_FACTOR(GPInterpolatedAttitudeFactorRot3, "GP Interpolated AttitudeFactor")
+  GPSLAM_B200_FACTOR(GPInterpolatedAttitudeFactorRot3, "GP Interpolated AttitudeFactor", "GPInterpolatedAttitudeFactorRot3")
+  /// slam/GPInterpolatedAttitudeFactorRot3.h:103-112 (NoiseModelFactor4, AttitudeFactor {nZ_, bRef_}, GPbase_)
+  template <class ARCHIVE> void serialize(ARCHIVE& ar, const unsigned int /*version*/) {
+    detail::ioBase(ar, keys_, 4, &meas_);
+    ar.begin("AttitudeFactor"); ar & GPSLAM_B200_NVP(nZ_); ar & GPSLAM_B200_NVP(bRef_); ar.end();
+    detail::ioGPbase(ar, delta_t_, tau_, Qc_);
+  }
   gtsam::Vector evaluateError(const gtsam::Rot3& pose1, const gtsam::Vector3& vel1, const gtsam::Rot3& pose2, const gtsam::Vector3& vel2, gtsam::Matrix* H1 = nullptr,
                               gtsam::Matrix* H2 = nullptr, gtsam::Matrix* H3 = nullptr, gtsam::Matrix* H4 = nullptr) const {
     double x1[9], x2[9], prm[20] = {0};
@@ -585,6 +732,7 @@ struct Rot2 {
   explicit Rot2(double theta) : theta_(theta) {}
   static Rot2 fromAngle(double theta) { return Rot2(theta); }
   double theta() const { return theta_; }
+  template <class ARCHIVE> void serialize(ARCHIVE& ar, const unsigned int) { ar & GPSLAM_B200_NVP(theta_); }
 };
 }  // namespace gtsam
 
@@ -594,14 +742,17 @@ template <class POSE>
 class RangeFactor2DT : public NonlinearFactor {
   using G = detail::GroupOf<POSE>;
   std::vector<gtsam::Key> keys_;
-  double measured_;
+  double measured_ = 0;
   gtsam::SharedNoiseModel model_;
 
  public:
+  RangeFactor2DT() {}  ///< for loading from an archive only
   RangeFactor2DT(gtsam::Key poseKey, gtsam::Key pointKey, double measured, const gtsam::SharedNoiseModel& model)
       : keys_{poseKey, pointKey}, measured_(measured), model_(model) {}
   const std::vector<gtsam::Key>& keys() const override { return keys_; }
-  GPSLAM_B200_FACTOR(RangeFactor2DT, "RangeFactor, range = " + std::to_string(measured_))
+  GPSLAM_B200_FACTOR(RangeFactor2DT, "RangeFactor, range = " + std::to_string(measured_), std::string("RangeFactor2D") + detail::TypeName<POSE>::name())
+  /// slam/RangeFactor2DLinear.h:79-84 (Base, measured_)
+  template <class ARCHIVE> void serialize(ARCHIVE& ar, const unsigned int /*version*/) { detail::ioBase(ar, keys_, 2, &model_); ar & GPSLAM_B200_NVP(measured_); }
   double measured() const { return measured_; }
   gtsam::Vector evaluateError(const POSE& pose, const gtsam::Point2& point, gtsam::Matrix* H1 = nullptr, gtsam::Matrix* H2 = nullptr) const {
     double x[3], l[2], prm[48] = {0};
@@ -619,15 +770,18 @@ using RangeFactorPose2 = RangeFactor2DT<gtsam::Pose2>;
 /// slam/RangeBearingFactor2DLinear.h:33-38 (evaluateError :47-84): residual (bearing, range)
 class RangeBearingFactor2DLinear : public NonlinearFactor {
   std::vector<gtsam::Key> keys_;
-  double range_;
+  double range_ = 0;
   gtsam::Rot2 bearing_;
   gtsam::SharedNoiseModel model_;
 
  public:
+  RangeBearingFactor2DLinear() {}  ///< for loading from an archive only
   RangeBearingFactor2DLinear(gtsam::Key poseKey, gtsam::Key pointKey, double range, const gtsam::Rot2& bearing, const gtsam::SharedNoiseModel& model)
       : keys_{poseKey, pointKey}, range_(range), bearing_(bearing), model_(model) {}
   const std::vector<gtsam::Key>& keys() const override { return keys_; }
-  GPSLAM_B200_FACTOR(RangeBearingFactor2DLinear, "RangeBearingFactor, range = " + std::to_string(range_))
+  GPSLAM_B200_FACTOR(RangeBearingFactor2DLinear, "RangeBearingFactor, range = " + std::to_string(range_), "RangeBearingFactor2DLinear")
+  /// slam/RangeBearingFactor2DLinear.h:112-118 (Base, range_, bearing_)
+  template <class ARCHIVE> void serialize(ARCHIVE& ar, const unsigned int /*version*/) { detail::ioBase(ar, keys_, 2, &model_); ar & GPSLAM_B200_NVP(range_); ar & GPSLAM_B200_NVP(bearing_); }
   gtsam::Vector evaluateError(const gtsam::Vector3& pose, const gtsam::Point2& point, gtsam::Matrix* H1 = nullptr, gtsam::Matrix* H2 = nullptr) const {
     double x[3], l[2], prm[48] = {0};
     detail::wire(pose, x); detail::wire(point, l);
@@ -642,14 +796,17 @@ class RangeBearingFactor2DLinear : public NonlinearFactor {
 /// slam/OdometryFactor2DLinear.h:36-40 (evaluateError :50-75): body-frame odometry (dx, dy, dtheta) between two Vector3 states
 class OdometryFactor2DLinear : public NonlinearFactor {
   std::vector<gtsam::Key> keys_;
-  gtsam::Vector3 measured_;
+  gtsam::Vector3 measured_{};
   gtsam::SharedNoiseModel model_;
 
  public:
+  OdometryFactor2DLinear() {}  ///< for loading from an archive only
   OdometryFactor2DLinear(gtsam::Key pose1Key, gtsam::Key pose2Key, const gtsam::Vector3& betweenMeasured, const gtsam::SharedNoiseModel& model)
       : keys_{pose1Key, pose2Key}, measured_(betweenMeasured), model_(model) {}
   const std::vector<gtsam::Key>& keys() const override { return keys_; }
-  GPSLAM_B200_FACTOR(OdometryFactor2DLinear, "2-way projected odometry factor")
+  GPSLAM_B200_FACTOR(OdometryFactor2DLinear, "2-way projected odometry factor", "OdometryFactor2DLinear")
+  /// slam/OdometryFactor2DLinear.h:104-110 (NoiseModelFactor2, measured_)
+  template <class ARCHIVE> void serialize(ARCHIVE& ar, const unsigned int /*version*/) { detail::ioBase(ar, keys_, 2, &model_); ar & GPSLAM_B200_NVP(measured_); }
   gtsam::Vector evaluateError(const gtsam::Vector3& pose1, const gtsam::Vector3& pose2, gtsam::Matrix* H1 = nullptr, gtsam::Matrix* H2 = nullptr) const {
     double x1[3], x2[3], prm[48] = {0};
     detail::wire(pose1, x1); detail::wire(pose2, x2); detail::wire(measured_, prm + 4);
@@ -666,13 +823,16 @@ class OdometryFactor2DLinear : public NonlinearFactor {
 template <class T>
 class PriorFactor : public NonlinearFactor {
   std::vector<gtsam::Key> keys_;
-  T prior_;
+  T prior_{};
   gtsam::SharedNoiseModel model_;
 
  public:
+  PriorFactor() {}  ///< for loading from an archive only
   PriorFactor(gtsam::Key key, const T& prior, const gtsam::SharedNoiseModel& model) : keys_{key}, prior_(prior), model_(model) {}
   const std::vector<gtsam::Key>& keys() const override { return keys_; }
-  GPSLAM_B200_FACTOR(PriorFactor, "PriorFactor")
+  GPSLAM_B200_FACTOR(PriorFactor, "PriorFactor", std::string("PriorFactor") + detail::TypeName<T>::name())
+  /// gtsam/slam/PriorFactor.h (Base, prior_)
+  template <class ARCHIVE> void serialize(ARCHIVE& ar, const unsigned int /*version*/) { detail::ioBase(ar, keys_, 1, &model_); ar & GPSLAM_B200_NVP(prior_); }
   void lower(gpb_graph* g, int (*)(void*, const gtsam::Matrix&), void*, const std::map<gtsam::Key, int>& sidx, const std::map<gtsam::Key, int>& lidx) const override {
     double v[12];
     detail::wire(prior_, v);
@@ -700,13 +860,16 @@ class PriorFactor : public NonlinearFactor {
 template <class POSE>
 class BetweenFactor : public NonlinearFactor {
   std::vector<gtsam::Key> keys_;
-  POSE measured_;
+  POSE measured_{};
   gtsam::SharedNoiseModel model_;
 
  public:
+  BetweenFactor() {}  ///< for loading from an archive only
   BetweenFactor(gtsam::Key key1, gtsam::Key key2, const POSE& measured, const gtsam::SharedNoiseModel& model) : keys_{key1, key2}, measured_(measured), model_(model) {}
   const std::vector<gtsam::Key>& keys() const override { return keys_; }
-  GPSLAM_B200_FACTOR(BetweenFactor, "BetweenFactor")
+  GPSLAM_B200_FACTOR(BetweenFactor, "BetweenFactor", std::string("BetweenFactor") + detail::TypeName<POSE>::name())
+  /// gtsam/slam/BetweenFactor.h (Base, measured_)
+  template <class ARCHIVE> void serialize(ARCHIVE& ar, const unsigned int /*version*/) { detail::ioBase(ar, keys_, 2, &model_); ar & GPSLAM_B200_NVP(measured_); }
   void lower(gpb_graph* g, int (*)(void*, const gtsam::Matrix&), void*, const std::map<gtsam::Key, int>& sidx, const std::map<gtsam::Key, int>&) const override {
     double v[12];
     detail::wire(measured_, v);
@@ -723,6 +886,22 @@ class NonlinearFactorGraph {
   void push_back(const NonlinearFactor::shared_ptr& f) { factors_.push_back(f); }
   size_t size() const { return factors_.size(); }
   const std::vector<NonlinearFactor::shared_ptr>& factors() const { return factors_; }
+  /// every factor behind its type name (FactorRegistry restores the class on loading); noise models and calibrations shared between
+  /// factors are written once and stay shared after loading
+  template <class ARCHIVE> void serialize(ARCHIVE& ar, const unsigned int /*version*/) {
+    std::uint64_t size = factors_.size();
+    ar & GPSLAM_B200_NVP(size);
+    if constexpr (ARCHIVE::is_loading) {
+      if (size > (std::uint64_t(1) << 32)) throw std::runtime_error("gpslam_b200 archive: implausible factor count");
+      factors_.assign(static_cast<size_t>(size), nullptr);
+    }
+    for (auto& f : factors_) {
+      std::string type = f ? f->archiveTag() : std::string();
+      ar & GPSLAM_B200_NVP(type);
+      if constexpr (ARCHIVE::is_loading) { f = FactorRegistry::make(type); f->load(ar); }
+      else { if (!f) throw std::runtime_error("gpslam_b200 archive: null factor in the graph"); f->save(ar); }
+    }
+  }
 };
 
 /// gtsam::Values restricted to the variable types of a gpslam trajectory: poses 'x', velocities 'v', landmarks 'l'
@@ -745,6 +924,21 @@ class Values {
   template <class T> T at(gtsam::Key k) const;
   const std::map<gtsam::Key, std::vector<double>>& all() const { return v_; }
   std::map<gtsam::Key, std::vector<double>>& all() { return v_; }
+  /// key -> value in wire layout (the value's type follows from its length and the trajectory group, as everywhere in this class)
+  template <class ARCHIVE> void serialize(ARCHIVE& ar, const unsigned int /*version*/) {
+    std::uint64_t size = v_.size();
+    ar & GPSLAM_B200_NVP(size);
+    if constexpr (ARCHIVE::is_loading) {
+      v_.clear();
+      for (std::uint64_t k = 0; k < size; k++) {
+        gtsam::Key key = 0; std::vector<double> value;
+        ar & GPSLAM_B200_NVP(key); ar & GPSLAM_B200_NVP(value);
+        if (value.empty() || value.size() > 12 || !v_.emplace(key, std::move(value)).second) throw std::runtime_error("gpslam_b200 archive: bad or duplicate entry in Values");
+      }
+    } else {
+      for (auto& kv : v_) { gtsam::Key key = kv.first; ar & GPSLAM_B200_NVP(key); ar & make_nvp("value", kv.second); }
+    }
+  }
 };
 template <> inline gtsam::Pose3 Values::at<gtsam::Pose3>(gtsam::Key k) const { return gtsam::Pose3::fromWire(wire(k).data()); }
 template <> inline gtsam::Rot3 Values::at<gtsam::Rot3>(gtsam::Key k) const { gtsam::Rot3 r; for (int i = 0; i < 9; i++) r.R[i] = wire(k)[i]; return r; }
@@ -904,5 +1098,80 @@ class LevenbergMarquardtOptimizer : public NonlinearOptimizer {
     params_.min_model_fidelity = p.minModelFidelity;
   }
 };
+
+// ================================================================================== archives: registry and the gtsam-style helpers
+namespace detail {
+inline void registerBuiltinFactors() {
+  static const bool once = [] {
+    FactorRegistry::add<GaussianProcessPriorPose3>(); FactorRegistry::add<GaussianProcessPriorPose2>(); FactorRegistry::add<GaussianProcessPriorRot3>();
+    FactorRegistry::add<GaussianProcessPriorLinear<3>>(); FactorRegistry::add<GaussianProcessPriorPose3VW>();
+    FactorRegistry::add<GPInterpolatedRangeFactorPose3>(); FactorRegistry::add<GPInterpolatedRangeFactorPose2>();
+    FactorRegistry::add<GPInterpolatedRangeFactorT<gtsam::Vector3>>(); FactorRegistry::add<GPInterpolatedRangeFactor2DLinear>();
+    FactorRegistry::add<GPInterpolatedGPSFactorPose3>(); FactorRegistry::add<GPInterpolatedGPSFactorPose3VW>();
+    FactorRegistry::add<GPInterpolatedProjectionFactorPose3<gtsam::Cal3_S2>>(); FactorRegistry::add<GPInterpolatedAttitudeFactorRot3>();
+    FactorRegistry::add<RangeFactor2DLinear>(); FactorRegistry::add<RangeFactorPose2>(); FactorRegistry::add<RangeBearingFactor2DLinear>();
+    FactorRegistry::add<OdometryFactor2DLinear>();
+    FactorRegistry::add<PriorFactor<gtsam::Pose3>>(); FactorRegistry::add<PriorFactor<gtsam::Pose2>>(); FactorRegistry::add<PriorFactor<gtsam::Rot3>>();
+    FactorRegistry::add<PriorFactor<gtsam::Vector3>>(); FactorRegistry::add<PriorFactor<gtsam::Vector6>>(); FactorRegistry::add<PriorFactor<gtsam::Point3>>();
+    FactorRegistry::add<PriorFactor<gtsam::Point2>>();
+    FactorRegistry::add<BetweenFactor<gtsam::Pose3>>(); FactorRegistry::add<BetweenFactor<gtsam::Pose2>>(); FactorRegistry::add<BetweenFactor<gtsam::Rot3>>();
+    FactorRegistry::add<BetweenFactor<gtsam::Vector3>>();
+    return true;
+  }();
+  (void)once;
+}
+}  // namespace detail
+inline NonlinearFactor::shared_ptr FactorRegistry::make(const std::string& tag) {
+  detail::registerBuiltinFactors();
+  auto it = table().find(tag);
+  if (it == table().end()) throw std::runtime_error("gpslam_b200 archive: unknown factor type '" + tag + "' (FactorRegistry::add<F>() registers a user class)");
+  return it->second();
+}
+
+/// gtsam/base/serialization.h: serialize / deserialize to a string, serializeToFile / deserializeFromFile
+template <class T> std::string serialize(const T& input) {
+  std::ostringstream os;
+  OArchive ar(os);
+  ar & make_nvp("data", input);
+  return os.str();
+}
+template <class T> void deserialize(const std::string& serialized, T& output) {
+  std::istringstream is(serialized);
+  IArchive ar(is);
+  ar & make_nvp("data", output);
+}
+template <class T> bool serializeToFile(const T& input, const std::string& filename) {
+  std::ofstream os(filename.c_str());
+  if (!os.is_open()) return false;
+  OArchive ar(os);
+  ar & make_nvp("data", input);
+  os.flush();
+  return os.good();
+}
+template <class T> bool deserializeFromFile(const std::string& filename, T& output) {
+  std::ifstream is(filename.c_str());
+  if (!is.is_open()) return false;
+  IArchive ar(is);
+  ar & make_nvp("data", output);
+  return true;
+}
+/// one factor behind a base pointer (what a graph archive does per entry)
+inline std::string serializeFactor(const NonlinearFactor& f) {
+  std::ostringstream os;
+  OArchive ar(os);
+  std::string type = f.archiveTag();
+  ar & GPSLAM_B200_NVP(type);
+  f.save(ar);
+  return os.str();
+}
+inline NonlinearFactor::shared_ptr deserializeFactor(const std::string& serialized) {
+  std::istringstream is(serialized);
+  IArchive ar(is);
+  std::string type;
+  ar & GPSLAM_B200_NVP(type);
+  NonlinearFactor::shared_ptr f = FactorRegistry::make(type);
+  f->load(ar);
+  return f;
+}
 
 }  // namespace gpslam_b200

@@ -25,6 +25,20 @@ def test_facade_compiles_and_fails_loudly_without_gpu():
     assert r.returncode == 2 and "no CUDA device" in r.stdout
 
 
+def test_facade_archives_round_trip():
+    """include/gpslam_b200/archive.h + the serialize() members of every facade class (the reference's classes are
+    boost-serializable): object -> text -> object for every factor class, interpolator, value type, a graph and Values; type
+    restoration behind the base pointer, shared noise models, files, and loud failure on damaged input.  No device call: runs here."""
+    import __graft_entry__ as ge
+    ge.build()
+    exe = os.path.join(ROOT, "tests", "cpp", "test_archive")
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "test_archive.cpp"),
+                        "-L" + os.path.join(ROOT, "gpslam_b200"), "-lgpb", "-Wl,-rpath," + os.path.join(ROOT, "gpslam_b200"), "-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "archive tests passed" in r.stdout, r.stdout + r.stderr
+
+
 @pytest.mark.gpu
 def test_facade_reference_style_tests():
     _build()
