@@ -132,6 +132,12 @@ struct Diagonal {
 }  // namespace noiseModel
 using SharedNoiseModel = noiseModel::Gaussian::shared_ptr;
 
+/// gtsam::traits<T> for the Testable types of this header (gp/GaussianProcessPriorPose3.h:134-137): Equals / Print forward to the members
+template <class T> struct traits {
+  static bool Equals(const T& a, const T& b, double tol = 1e-8) { return a.equals(b, tol); }
+  static void Print(const T& a, const std::string& s = "") { a.print(s); }
+};
+
 }  // namespace gtsam
 
 namespace detail {
@@ -189,6 +195,10 @@ class NonlinearFactor {
     std::cout << " }" << std::endl;
   }
   virtual std::string describe() const { return "NonlinearFactor"; }
+  /// same class, same keys, members equal up to tol (gp/GaussianProcessPriorPose3.h:106-109 and its siblings)
+  virtual bool equals(const NonlinearFactor& expected, double tol = 1e-9) const = 0;
+  /// dimension of the residual (gtsam::NoiseModelFactor::dim(): the noise model's)
+  virtual size_t dim() const = 0;
   /// a GP prior ties (pose, velocity[, angular velocity]) of one state to the next: the optimiser reads the chain order from these links
   struct ChainLink { gtsam::Key x1, v1, w1, x2, v2, w2; bool vw; };
   virtual bool chainLink(ChainLink&) const { return false; }
@@ -204,6 +214,10 @@ class NonlinearFactor {
 #define GPSLAM_B200_FACTOR(CLASS, TEXT, TAG)                                                              \
   NonlinearFactor::shared_ptr clone() const override { return std::make_shared<CLASS>(*this); }           \
   std::string describe() const override { return TEXT; }                                                  \
+  bool equals(const NonlinearFactor& expected, double tol = 1e-9) const override {                        \
+    const CLASS* e = dynamic_cast<const CLASS*>(&expected);                                               \
+    return e != nullptr && keys() == e->keys() && sameMembers(*e, tol);                                   \
+  }                                                                                                       \
   std::string archiveTag() const override { return TAG; }                                                 \
   void save(OArchive& ar) const override { archiveIO(ar, "factor", const_cast<CLASS&>(*this)); }          \
   void load(IArchive& ar) override { archiveIO(ar, "factor", *this); }
@@ -224,6 +238,24 @@ inline int stateOf(const std::map<gtsam::Key, int>& m, gtsam::Key k) {
   if (it == m.end()) throw std::runtime_error("gpslam_b200: factor refers to a key that is not in Values");
   return it->second;
 }
+// member comparison for equals(): numbers, value types through their wire layout, noise models through their covariance
+inline bool same(double a, double b, double tol) { return std::fabs(a - b) <= tol; }
+inline bool same(const std::vector<double>& a, const std::vector<double>& b, double tol) {
+  if (a.size() != b.size()) return false;
+  for (size_t k = 0; k < a.size(); k++) if (!same(a[k], b[k], tol)) return false;
+  return true;
+}
+template <class T> bool sameValue(const T& a, const T& b, double tol) {
+  double wa[12] = {0}, wb[12] = {0};
+  wire(a, wa); wire(b, wb);
+  for (int k = 0; k < 12; k++) if (!same(wa[k], wb[k], tol)) return false;
+  return true;
+}
+inline bool sameModel(const gtsam::SharedNoiseModel& a, const gtsam::SharedNoiseModel& b, double tol) {
+  if (!a || !b) return !a && !b;
+  return a->dim == b->dim && same(a->cov.a, b->cov.a, tol);
+}
+inline size_t modelDim(const gtsam::SharedNoiseModel& m) { return m ? static_cast<size_t>(m->dim) : 0; }
 // archive pieces shared by the factor classes: the NoiseModelFactorN base (keys and, for measurement factors, the noise model),
 // the interpolator a GPInterpolated* factor holds (GPbase_), and an optional sensor pose (boost::optional<POSE> in the reference)
 template <class AR> void ioBase(AR& ar, std::vector<gtsam::Key>& keys, size_t nkeys, gtsam::SharedNoiseModel* model) {
@@ -288,7 +320,8 @@ class GaussianProcessPriorT : public NonlinearFactor {
     prm[0] = delta_t_;
     return detail::eval(G::group, GPB_F_GP_PRIOR, x1, v1, x2, v2, nullptr, prm, {H1, H2, H3, H4});
   }
-  bool equals(const GaussianProcessPriorT& e, double tol = 1e-9) const { return keys_ == e.keys_ && std::fabs(delta_t_ - e.delta_t_) < tol; }
+  bool sameMembers(const GaussianProcessPriorT& e, double tol) const { return detail::same(delta_t_, e.delta_t_, tol) && detail::sameModel(Qc_, e.Qc_, tol); }
+  size_t dim() const override { return 2 * G::D; }
   void lower(gpb_graph* g, int qc_of(void*, const gtsam::Matrix&), void* ctx, const std::map<gtsam::Key, int>& sidx, const std::map<gtsam::Key, int>&) const override {
     const int i = detail::stateOf(sidx, keys_[0]), j = detail::stateOf(sidx, keys_[2]);
     if (j != i + 1 || detail::stateOf(sidx, keys_[1]) != i || detail::stateOf(sidx, keys_[3]) != j) throw std::runtime_error("gpslam_b200: GP prior must join consecutive states");
@@ -363,7 +396,7 @@ class GaussianProcessInterpolatorT {
   /// evaluated on the device at every query, so they are not stored)
   template <class ARCHIVE> void serialize(ARCHIVE& ar, const unsigned int /*version*/) { ar & GPSLAM_B200_NVP(delta_t_); ar & GPSLAM_B200_NVP(tau_); ar & make_nvp("Qc", Qc_); }
   bool equals(const GaussianProcessInterpolatorT& e, double tol = 1e-9) const {
-    return std::fabs(delta_t_ - e.delta_t_) < tol && std::fabs(tau_ - e.tau_) < tol && Qc_ && e.Qc_ && Qc_->cov.a == e.Qc_->cov.a;
+    return detail::same(delta_t_, e.delta_t_, tol) && detail::same(tau_, e.tau_, tol) && detail::sameModel(Qc_, e.Qc_, tol);
   }
 };
 using GaussianProcessInterpolatorPose3 = GaussianProcessInterpolatorT<gtsam::Pose3>;
@@ -399,6 +432,12 @@ class GPInterpolatedRangeFactorT : public NonlinearFactor {
     detail::ioOptional(ar, "body_P_sensor_", has_sensor_, body_P_sensor_);
   }
   double measured() const { return measured_; }
+  /// slam/GPInterpolatedRangeFactorPose3.h:107-113 (Base, measured_, body_P_sensor_) + the interpolator's members
+  bool sameMembers(const GPInterpolatedRangeFactorT& e, double tol) const {
+    return detail::same(measured_, e.measured_, tol) && detail::same(delta_t_, e.delta_t_, tol) && detail::same(tau_, e.tau_, tol) && detail::sameModel(meas_, e.meas_, tol) &&
+           detail::sameModel(Qc_, e.Qc_, tol) && has_sensor_ == e.has_sensor_ && (!has_sensor_ || detail::sameValue(body_P_sensor_, e.body_P_sensor_, tol));
+  }
+  size_t dim() const override { return 1; }
   gtsam::Vector evaluateError(const POSE& pose1, const typename G::Vel& vel1, const POSE& pose2, const typename G::Vel& vel2, const typename G::Land& point,
                               gtsam::Matrix* H1 = nullptr, gtsam::Matrix* H2 = nullptr, gtsam::Matrix* H3 = nullptr, gtsam::Matrix* H4 = nullptr,
                               gtsam::Matrix* H5 = nullptr) const {
@@ -468,6 +507,11 @@ class GPInterpolatedGPSFactorPose3 : public NonlinearFactor {
     detail::ioOptional(ar, "body_P_sensor_", has_sensor_, body_P_sensor_);
   }
   gtsam::Point3 measured() const { return measured_; }
+  bool sameMembers(const GPInterpolatedGPSFactorPose3& e, double tol) const {
+    return detail::sameValue(measured_, e.measured_, tol) && detail::same(delta_t_, e.delta_t_, tol) && detail::same(tau_, e.tau_, tol) && detail::sameModel(meas_, e.meas_, tol) &&
+           detail::sameModel(Qc_, e.Qc_, tol) && has_sensor_ == e.has_sensor_ && (!has_sensor_ || detail::sameValue(body_P_sensor_, e.body_P_sensor_, tol));
+  }
+  size_t dim() const override { return 3; }
   gtsam::Vector evaluateError(const gtsam::Pose3& pose1, const gtsam::Vector6& vel1, const gtsam::Pose3& pose2, const gtsam::Vector6& vel2,
                               gtsam::Matrix* H1 = nullptr, gtsam::Matrix* H2 = nullptr, gtsam::Matrix* H3 = nullptr, gtsam::Matrix* H4 = nullptr) const {
     double x1[12], x2[12], v1[6], v2[6], prm[48] = {0};
@@ -522,6 +566,15 @@ class GPInterpolatedProjectionFactorPose3 : public NonlinearFactor {
   }
   const gtsam::Point2& measured() const { return measured_; }
   const std::shared_ptr<CALIBRATION> calibration() const { return K_; }
+  bool sameMembers(const GPInterpolatedProjectionFactorPose3& e, double tol) const {
+    double ka[5], kb[5];
+    if (!K_ || !e.K_) return false;
+    calib(ka); e.calib(kb);
+    for (int k = 0; k < 5; k++) if (!detail::same(ka[k], kb[k], tol)) return false;
+    return detail::sameValue(measured_, e.measured_, tol) && detail::same(delta_t_, e.delta_t_, tol) && detail::same(tau_, e.tau_, tol) && detail::sameModel(meas_, e.meas_, tol) &&
+           detail::sameModel(Qc_, e.Qc_, tol) && has_sensor_ == e.has_sensor_ && (!has_sensor_ || detail::sameValue(body_P_sensor_, e.body_P_sensor_, tol));
+  }
+  size_t dim() const override { return 2; }
   gtsam::Vector evaluateError(const gtsam::Pose3& pose1, const gtsam::Vector6& vel1, const gtsam::Pose3& pose2, const gtsam::Vector6& vel2, const gtsam::Point3& point,
                               gtsam::Matrix* H1 = nullptr, gtsam::Matrix* H2 = nullptr, gtsam::Matrix* H3 = nullptr, gtsam::Matrix* H4 = nullptr,
                               gtsam::Matrix* H5 = nullptr) const {
@@ -602,7 +655,8 @@ class GaussianProcessPriorPose3VW : public NonlinearFactor {
     prm[0] = delta_t_;
     return detail::evalVW(GPB_F_GP_PRIOR, pose1, vel1, omega1, pose2, vel2, omega2, prm, H1, H2, H3, H4, H5, H6);
   }
-  bool equals(const GaussianProcessPriorPose3VW& e, double tol = 1e-9) const { return keys_ == e.keys_ && std::fabs(delta_t_ - e.delta_t_) < tol; }
+  bool sameMembers(const GaussianProcessPriorPose3VW& e, double tol) const { return detail::same(delta_t_, e.delta_t_, tol) && detail::sameModel(Qc_, e.Qc_, tol); }
+  size_t dim() const override { return 12; }
   void lower(gpb_graph* g, int qc_of(void*, const gtsam::Matrix&), void* ctx, const std::map<gtsam::Key, int>& sidx, const std::map<gtsam::Key, int>&) const override {
     if (gpb_graph_group(g) != GPB_POSE3VW) throw std::runtime_error("gpslam_b200: GaussianProcessPriorPose3VW needs an optimiser created with group GPB_POSE3VW");
     detail::checkVWKeys(sidx, keys_);
@@ -636,8 +690,9 @@ class GaussianProcessInterpolatorPose3VW {
   /// gp/GaussianProcessInterpolatorPose3VW.h:175-184 (delta_t_, tau_, Qc)
   template <class ARCHIVE> void serialize(ARCHIVE& ar, const unsigned int /*version*/) { ar & GPSLAM_B200_NVP(delta_t_); ar & GPSLAM_B200_NVP(tau_); ar & make_nvp("Qc", Qc_); }
   bool equals(const GaussianProcessInterpolatorPose3VW& e, double tol = 1e-9) const {
-    return std::fabs(delta_t_ - e.delta_t_) < tol && std::fabs(tau_ - e.tau_) < tol && Qc_ && e.Qc_ && Qc_->cov.a == e.Qc_->cov.a;
+    return detail::same(delta_t_, e.delta_t_, tol) && detail::same(tau_, e.tau_, tol) && detail::sameModel(Qc_, e.Qc_, tol);
   }
+  void print(const std::string& s = "") const { std::cout << s << "GaussianProcessInterpolatorPose3VW" << std::endl; }
 };
 
 /// slam/GPInterpolatedGPSFactorPose3VW.h:50-61 (evaluateError :71-106)
@@ -668,6 +723,11 @@ class GPInterpolatedGPSFactorPose3VW : public NonlinearFactor {
   }
   size_t size() const override { return 6; }
   gtsam::Point3 measured() const { return measured_; }
+  bool sameMembers(const GPInterpolatedGPSFactorPose3VW& e, double tol) const {
+    return detail::sameValue(measured_, e.measured_, tol) && GPbase_.equals(e.GPbase_, tol) && detail::sameModel(meas_, e.meas_, tol) && has_sensor_ == e.has_sensor_ &&
+           (!has_sensor_ || detail::sameValue(body_P_sensor_, e.body_P_sensor_, tol));
+  }
+  size_t dim() const override { return 3; }
   gtsam::Vector evaluateError(const gtsam::Pose3& pose1, const gtsam::Vector3& vel1, const gtsam::Vector3& omega1, const gtsam::Pose3& pose2, const gtsam::Vector3& vel2,
                               const gtsam::Vector3& omega2, gtsam::Matrix* H1 = nullptr, gtsam::Matrix* H2 = nullptr, gtsam::Matrix* H3 = nullptr, gtsam::Matrix* H4 = nullptr,
                               gtsam::Matrix* H5 = nullptr, gtsam::Matrix* H6 = nullptr) const {
@@ -709,6 +769,12 @@ class GPInterpolatedAttitudeFactorRot3 : public NonlinearFactor {
     ar.begin("AttitudeFactor"); ar & GPSLAM_B200_NVP(nZ_); ar & GPSLAM_B200_NVP(bRef_); ar.end();
     detail::ioGPbase(ar, delta_t_, tau_, Qc_);
   }
+  bool sameMembers(const GPInterpolatedAttitudeFactorRot3& e, double tol) const {
+    return detail::same(delta_t_, e.delta_t_, tol) && detail::same(tau_, e.tau_, tol) && detail::sameModel(Qc_, e.Qc_, tol) && detail::sameModel(meas_, e.meas_, tol) &&
+           detail::same(nZ_.x, e.nZ_.x, tol) && detail::same(nZ_.y, e.nZ_.y, tol) && detail::same(nZ_.z, e.nZ_.z, tol) && detail::same(bRef_.x, e.bRef_.x, tol) &&
+           detail::same(bRef_.y, e.bRef_.y, tol) && detail::same(bRef_.z, e.bRef_.z, tol);
+  }
+  size_t dim() const override { return 2; }
   gtsam::Vector evaluateError(const gtsam::Rot3& pose1, const gtsam::Vector3& vel1, const gtsam::Rot3& pose2, const gtsam::Vector3& vel2, gtsam::Matrix* H1 = nullptr,
                               gtsam::Matrix* H2 = nullptr, gtsam::Matrix* H3 = nullptr, gtsam::Matrix* H4 = nullptr) const {
     double x1[9], x2[9], prm[20] = {0};
@@ -754,6 +820,8 @@ class RangeFactor2DT : public NonlinearFactor {
   /// slam/RangeFactor2DLinear.h:79-84 (Base, measured_)
   template <class ARCHIVE> void serialize(ARCHIVE& ar, const unsigned int /*version*/) { detail::ioBase(ar, keys_, 2, &model_); ar & GPSLAM_B200_NVP(measured_); }
   double measured() const { return measured_; }
+  bool sameMembers(const RangeFactor2DT& e, double tol) const { return detail::same(measured_, e.measured_, tol) && detail::sameModel(model_, e.model_, tol); }
+  size_t dim() const override { return 1; }
   gtsam::Vector evaluateError(const POSE& pose, const gtsam::Point2& point, gtsam::Matrix* H1 = nullptr, gtsam::Matrix* H2 = nullptr) const {
     double x[3], l[2], prm[48] = {0};
     detail::wire(pose, x); detail::wire(point, l);
@@ -782,6 +850,10 @@ class RangeBearingFactor2DLinear : public NonlinearFactor {
   GPSLAM_B200_FACTOR(RangeBearingFactor2DLinear, "RangeBearingFactor, range = " + std::to_string(range_), "RangeBearingFactor2DLinear")
   /// slam/RangeBearingFactor2DLinear.h:112-118 (Base, range_, bearing_)
   template <class ARCHIVE> void serialize(ARCHIVE& ar, const unsigned int /*version*/) { detail::ioBase(ar, keys_, 2, &model_); ar & GPSLAM_B200_NVP(range_); ar & GPSLAM_B200_NVP(bearing_); }
+  bool sameMembers(const RangeBearingFactor2DLinear& e, double tol) const {
+    return detail::same(range_, e.range_, tol) && detail::same(bearing_.theta(), e.bearing_.theta(), tol) && detail::sameModel(model_, e.model_, tol);
+  }
+  size_t dim() const override { return 2; }
   gtsam::Vector evaluateError(const gtsam::Vector3& pose, const gtsam::Point2& point, gtsam::Matrix* H1 = nullptr, gtsam::Matrix* H2 = nullptr) const {
     double x[3], l[2], prm[48] = {0};
     detail::wire(pose, x); detail::wire(point, l);
@@ -807,6 +879,8 @@ class OdometryFactor2DLinear : public NonlinearFactor {
   GPSLAM_B200_FACTOR(OdometryFactor2DLinear, "2-way projected odometry factor", "OdometryFactor2DLinear")
   /// slam/OdometryFactor2DLinear.h:104-110 (NoiseModelFactor2, measured_)
   template <class ARCHIVE> void serialize(ARCHIVE& ar, const unsigned int /*version*/) { detail::ioBase(ar, keys_, 2, &model_); ar & GPSLAM_B200_NVP(measured_); }
+  bool sameMembers(const OdometryFactor2DLinear& e, double tol) const { return detail::sameValue(measured_, e.measured_, tol) && detail::sameModel(model_, e.model_, tol); }
+  size_t dim() const override { return 3; }
   gtsam::Vector evaluateError(const gtsam::Vector3& pose1, const gtsam::Vector3& pose2, gtsam::Matrix* H1 = nullptr, gtsam::Matrix* H2 = nullptr) const {
     double x1[3], x2[3], prm[48] = {0};
     detail::wire(pose1, x1); detail::wire(pose2, x2); detail::wire(measured_, prm + 4);
@@ -833,6 +907,9 @@ class PriorFactor : public NonlinearFactor {
   GPSLAM_B200_FACTOR(PriorFactor, "PriorFactor", std::string("PriorFactor") + detail::TypeName<T>::name())
   /// gtsam/slam/PriorFactor.h (Base, prior_)
   template <class ARCHIVE> void serialize(ARCHIVE& ar, const unsigned int /*version*/) { detail::ioBase(ar, keys_, 1, &model_); ar & GPSLAM_B200_NVP(prior_); }
+  const T& prior() const { return prior_; }
+  bool sameMembers(const PriorFactor& e, double tol) const { return detail::sameValue(prior_, e.prior_, tol) && detail::sameModel(model_, e.model_, tol); }
+  size_t dim() const override { return detail::modelDim(model_); }
   void lower(gpb_graph* g, int (*)(void*, const gtsam::Matrix&), void*, const std::map<gtsam::Key, int>& sidx, const std::map<gtsam::Key, int>& lidx) const override {
     double v[12];
     detail::wire(prior_, v);
@@ -870,6 +947,9 @@ class BetweenFactor : public NonlinearFactor {
   GPSLAM_B200_FACTOR(BetweenFactor, "BetweenFactor", std::string("BetweenFactor") + detail::TypeName<POSE>::name())
   /// gtsam/slam/BetweenFactor.h (Base, measured_)
   template <class ARCHIVE> void serialize(ARCHIVE& ar, const unsigned int /*version*/) { detail::ioBase(ar, keys_, 2, &model_); ar & GPSLAM_B200_NVP(measured_); }
+  const POSE& measured() const { return measured_; }
+  bool sameMembers(const BetweenFactor& e, double tol) const { return detail::sameValue(measured_, e.measured_, tol) && detail::sameModel(model_, e.model_, tol); }
+  size_t dim() const override { return detail::modelDim(model_); }
   void lower(gpb_graph* g, int (*)(void*, const gtsam::Matrix&), void*, const std::map<gtsam::Key, int>& sidx, const std::map<gtsam::Key, int>&) const override {
     double v[12];
     detail::wire(measured_, v);

@@ -4,7 +4,8 @@
 //     second archive being byte-identical to the first (doubles are written with 17 significant digits: exact round trip);
 //   * factors are restored behind the base pointer from their type name; shared noise models / calibrations stay shared;
 //   * file round trip (serializeToFile / deserializeFromFile);
-//   * damaged input fails loudly: truncated archive, wrong member name, wrong key count, unknown factor type, newer class version.
+//   * damaged input fails loudly: truncated archive, wrong member name, wrong key count, unknown factor type, newer class version;
+//   * equals(other, tol) / dim() / traits<T> of every factor class and the interpolators.
 // Nothing here touches the device (no evaluateError, no optimiser): it runs on a box without a GPU.  Exit code 0 = all passed.
 #include <cmath>
 #include <cstdio>
@@ -184,6 +185,8 @@ class MyFactor : public NonlinearFactor {
   const std::vector<Key>& keys() const override { return keys_; }
   GPSLAM_B200_FACTOR(MyFactor, "MyFactor", "test::MyFactor")
   double weight() const { return weight_; }
+  bool sameMembers(const MyFactor& e, double tol) const { return std::fabs(weight_ - e.weight_) <= tol; }
+  size_t dim() const override { return 1; }
   template <class ARCHIVE> void serialize(ARCHIVE& ar, const unsigned int) { detail::ioBase(ar, keys_, 1, nullptr); ar & GPSLAM_B200_NVP(weight_); }
   void lower(gpb_graph*, int (*)(void*, const Matrix&), void*, const std::map<Key, int>&, const std::map<Key, int>&) const override {}
 };
@@ -201,6 +204,40 @@ static void testUserFactorAndStrings() {
     std::istringstream is(os.str()); IArchive ar(is); std::string t; ar & make_nvp("text", t);
     EXPECT(t == s);
   }
+}
+
+// equals / dim / traits (SURVEY §8b "other virtuals to honour": gp/GaussianProcessPriorPose3.h:101-115,134-137)
+static void testEqualsDimTraits() {
+  const NonlinearFactorGraph g = everyFactor();
+  const size_t dims[] = {12, 6, 6, 6, 12, 1, 1, 1, 1, 3, 3, 2, 2, 2, 1, 1, 2, 3, 6, 3, 3, 3, 6, 3, 2, 6, 3};
+  EXPECT(g.size() == sizeof(dims) / sizeof(dims[0]));
+  for (size_t k = 0; k < g.size(); k++) {
+    const auto& f = g.factors()[k];
+    EXPECT(f->dim() == dims[k]);
+    EXPECT(f->equals(*f));
+    EXPECT(f->equals(*f->clone()));
+    EXPECT(deserializeFactor(serializeFactor(*f))->equals(*f, 0.0));     // archives are exact
+    for (size_t j = 0; j < g.size(); j++) if (j != k) EXPECT(!f->equals(*g.factors()[j]));   // another class, other keys or other members
+  }
+  // a member off by more than the tolerance, the same member inside it, other keys
+  auto Qc = noiseModel::Isotropic::Sigma(6, 0.2), Qc2 = noiseModel::Isotropic::Sigma(6, 0.21), m1 = noiseModel::Isotropic::Sigma(1, 0.05);
+  const GaussianProcessPriorPose3 a(1, 2, 3, 4, 0.1, Qc), b(1, 2, 3, 4, 0.1 + 1e-12, Qc), c(1, 2, 3, 4, 0.1 + 1e-6, Qc), d(1, 2, 3, 5, 0.1, Qc), e(1, 2, 3, 4, 0.1, Qc2);
+  EXPECT(a.equals(b) && !a.equals(c) && a.equals(c, 1e-5) && !a.equals(d) && !a.equals(e));
+  const Pose3 s1(Rot3::Ypr(0.1, 0.2, 0.3), Point3(1, 2, 3)), s2(Rot3::Ypr(0.1, 0.2, 0.3), Point3(1, 2, 3.001));
+  const GPInterpolatedRangeFactorPose3 r0(2.0, m1, Qc, 1, 2, 3, 4, 5, 0.1, 0.04), r1(2.0, m1, Qc, 1, 2, 3, 4, 5, 0.1, 0.04, &s1), r2(2.0, m1, Qc, 1, 2, 3, 4, 5, 0.1, 0.04, &s2),
+      r3(2.0, m1, Qc, 1, 2, 3, 4, 5, 0.1, 0.05), r4(2.5, m1, Qc, 1, 2, 3, 4, 5, 0.1, 0.04);
+  EXPECT(r0.equals(r0) && !r0.equals(r1) && !r1.equals(r2) && r1.equals(r2, 0.01) && !r0.equals(r3) && !r0.equals(r4) && !r0.equals(a));
+  // the 2-D linear range factor is its own class although it shares its members with the Vector3 instantiation of the template
+  auto Qc3 = noiseModel::Isotropic::Sigma(3, 0.2);
+  const GPInterpolatedRangeFactor2DLinear l1(4.5, 1, 2, 3, 4, 5, m1, Qc3, 0.2, 0.15);
+  const GPInterpolatedRangeFactorT<Vector3> l2(4.5, m1, Qc3, 1, 2, 3, 4, 5, 0.2, 0.15);
+  EXPECT(l1.equals(l1) && !l1.equals(l2) && l2.equals(l1));   // as with any derived class: the base accepts the derived object, not the reverse
+  // traits forward to the members; interpolators are Testable value types
+  EXPECT(traits<GaussianProcessPriorPose3>::Equals(a, b) && !traits<GaussianProcessPriorPose3>::Equals(a, c));
+  const GaussianProcessInterpolatorPose3 i1(Qc, 0.1, 0.04), i2(Qc, 0.1, 0.04), i3(Qc, 0.1, 0.05), i4(Qc2, 0.1, 0.04);
+  EXPECT(traits<GaussianProcessInterpolatorPose3>::Equals(i1, i2) && !traits<GaussianProcessInterpolatorPose3>::Equals(i1, i3) && !i1.equals(i4));
+  const GaussianProcessInterpolatorPose3VW w1(Qc, 0.1, 0.04), w2(Qc, 0.1, 0.04), w3(Qc, 0.2, 0.04);
+  EXPECT(traits<GaussianProcessInterpolatorPose3VW>::Equals(w1, w2) && !w1.equals(w3));
 }
 
 static void testDamagedInput() {
@@ -243,6 +280,7 @@ int main() {
   testEveryFactorClass();
   testGraphAndValues();
   testUserFactorAndStrings();
+  testEqualsDimTraits();
   testDamagedInput();
   if (failures) { std::printf("%d EXPECT(s) failed\n", failures); return 1; }
   std::printf("archive tests passed\n");
