@@ -126,6 +126,7 @@ struct Gaussian {
   template <class ARCHIVE> void serialize(ARCHIVE& ar, const unsigned int) { ar & GPSLAM_B200_NVP(dim); ar & GPSLAM_B200_NVP(cov); ar & make_nvp("sqrt_information", R); }
 };
 struct Isotropic { static Gaussian::shared_ptr Sigma(int dim, double sigma) { return Gaussian::Covariance((sigma * sigma) * Matrix::Identity(dim, dim)); } };
+struct Unit { static Gaussian::shared_ptr Create(int dim) { return Isotropic::Sigma(dim, 1.0); } };
 struct Diagonal {
   static Gaussian::shared_ptr Sigmas(const Vector& s) { Matrix c(static_cast<int>(s.size()), static_cast<int>(s.size())); for (size_t k = 0; k < s.size(); k++) c(static_cast<int>(k), static_cast<int>(k)) = s[k] * s[k]; return Gaussian::Covariance(c); }
 };
@@ -795,7 +796,7 @@ namespace gtsam {
 struct Rot2 {
   double theta_ = 0;
   Rot2() {}
-  explicit Rot2(double theta) : theta_(theta) {}
+  Rot2(double theta) : theta_(theta) {}  // implicit, as GTSAM's (slam/tests/testSerializationSLAM.cpp:52 passes a double for the bearing)
   static Rot2 fromAngle(double theta) { return Rot2(theta); }
   double theta() const { return theta_; }
   template <class ARCHIVE> void serialize(ARCHIVE& ar, const unsigned int) { ar & GPSLAM_B200_NVP(theta_); }

@@ -174,6 +174,40 @@ static void testGraphAndValues() {
   std::remove(path.c_str());
 }
 
+// gp/tests/testSerializationGP.cpp:38-92 and slam/tests/testSerializationSLAM.cpp:33-83 with their objects and constructor
+// arguments (the GP test's commented-out objects included; Linear<6> is not a group of this engine: Linear<3> stands in).
+// equalsObj (gtsam/base/serializationTestHelpers.h) = write, read into a default-constructed object, compare with equals().
+template <class T> static bool equalsObj(const T& input) {
+  T output;
+  deserialize(serialize(input), output);
+  return input.equals(output) && output.equals(input);
+}
+static void testReferenceSerializationTests() {
+  SharedNoiseModel Qcmodel_6 = noiseModel::Isotropic::Sigma(6, 0.1), Qcmodel_3 = noiseModel::Isotropic::Sigma(3, 0.1);
+  // bases (the reference's GaussianProcessFactorBase* are today's GaussianProcessInterpolator*)
+  EXPECT(equalsObj(GaussianProcessInterpolatorLinear<3>(Qcmodel_3, 0.1, 0.04)));
+  EXPECT(equalsObj(GaussianProcessInterpolatorPose3(Qcmodel_6, 0.1, 0.04)));
+  EXPECT(equalsObj(GaussianProcessInterpolatorPose3VW(Qcmodel_6, 0.1, 0.04)));
+  EXPECT(equalsObj(GaussianProcessInterpolatorPose2(Qcmodel_3, 0.1, 0.04)));
+  EXPECT(equalsObj(GaussianProcessInterpolatorRot3(Qcmodel_3, 0.1, 0.04)));
+  // factors
+  EXPECT(equalsObj(GaussianProcessPriorLinear<3>(1, 2, 3, 4, 0.1, Qcmodel_3)));
+  EXPECT(equalsObj(GaussianProcessPriorPose3(1, 2, 3, 4, 0.1, Qcmodel_6)));
+  EXPECT(equalsObj(GaussianProcessPriorPose3VW(1, 2, 3, 4, 5, 6, 0.1, Qcmodel_6)));
+  EXPECT(equalsObj(GaussianProcessPriorPose2(1, 2, 3, 4, 0.1, Qcmodel_3)));
+  EXPECT(equalsObj(GaussianProcessPriorRot3(1, 2, 3, 4, 0.1, Qcmodel_3)));
+  // slam
+  SharedNoiseModel unit1 = noiseModel::Unit::Create(1), unit2 = noiseModel::Unit::Create(2), unit3 = noiseModel::Unit::Create(3);
+  std::shared_ptr<Cal3_S2> K(new Cal3_S2());
+  EXPECT(equalsObj(GPInterpolatedGPSFactorPose3(Point3(0.3, 0.6, 0.9), unit2, Qcmodel_6, 1, 2, 3, 4, 0.1, 0.04)));
+  EXPECT(equalsObj(GPInterpolatedGPSFactorPose3VW(Point3(0.3, 0.6, 0.9), unit2, Qcmodel_6, 1, 2, 3, 4, 5, 6, 0.1, 0.04)));
+  EXPECT(equalsObj(GPInterpolatedProjectionFactorPose3<Cal3_S2>(Point2(10, 20), unit2, Qcmodel_6, 1, 2, 3, 4, 5, 0.1, 0.04, K)));
+  EXPECT(equalsObj(GPInterpolatedRangeFactorPose3(10.0, unit1, Qcmodel_6, 1, 2, 3, 4, 5, 0.1, 0.04)));
+  EXPECT(equalsObj(OdometryFactor2DLinear(1, 2, Vector3{0.1, 0.2, 3.0}, unit3)));
+  EXPECT(equalsObj(RangeFactor2DLinear(1, 2, 10.0, unit1)));
+  EXPECT(equalsObj(RangeBearingFactor2DLinear(1, 2, 0.1, 10.0, unit2)));
+}
+
 // a user-defined factor joins through FactorRegistry::add
 class MyFactor : public NonlinearFactor {
   std::vector<Key> keys_;
@@ -279,6 +313,7 @@ int main() {
   testInterpolators();
   testEveryFactorClass();
   testGraphAndValues();
+  testReferenceSerializationTests();
   testUserFactorAndStrings();
   testEqualsDimTraits();
   testDamagedInput();
