@@ -270,6 +270,16 @@ static void testEqualsDimTraits() {
   EXPECT(traits<GaussianProcessPriorPose3>::Equals(a, b) && !traits<GaussianProcessPriorPose3>::Equals(a, c));
   const GaussianProcessInterpolatorPose3 i1(Qc, 0.1, 0.04), i2(Qc, 0.1, 0.04), i3(Qc, 0.1, 0.05), i4(Qc2, 0.1, 0.04);
   EXPECT(traits<GaussianProcessInterpolatorPose3>::Equals(i1, i2) && !traits<GaussianProcessInterpolatorPose3>::Equals(i1, i3) && !i1.equals(i4));
+  {  // gp/tests/testGaussianProcessInterpolatorLinear.cpp:25-45, the reference's own equals test
+    typedef GaussianProcessInterpolatorLinear<3> GPBase3;
+    auto Qc_model = noiseModel::Gaussian::Covariance(0.01 * Matrix::Identity(3, 3)), Qc2_model = noiseModel::Gaussian::Covariance(0.02 * Matrix::Identity(3, 3));
+    double dt = 0.1, tau = 0.03;
+    GPBase3 base1(Qc_model, dt, tau), base2(Qc_model, dt, tau), base3(Qc2_model, dt, tau), base4(Qc_model, 0.2, 0.03), base5(Qc_model, 0.1, 0.06);
+    EXPECT(base1.equals(base2, 1e-9));
+    EXPECT(!base1.equals(base3, 1e-9));
+    EXPECT(!base1.equals(base4, 1e-9));
+    EXPECT(!base1.equals(base5, 1e-9));
+  }
   const GaussianProcessInterpolatorPose3VW w1(Qc, 0.1, 0.04), w2(Qc, 0.1, 0.04), w3(Qc, 0.2, 0.04);
   EXPECT(traits<GaussianProcessInterpolatorPose3VW>::Equals(w1, w2) && !w1.equals(w3));
 }
