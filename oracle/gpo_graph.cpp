@@ -504,13 +504,13 @@ struct Solver {
     std::vector<double> Dnext(bs * bs);
     bool have_next = false;
     for (int k = 0; k < nc; k++) {
-      const double* Din = &sys.Dg[(size_t)k * bs * bs];
+      const double* Din = sys.Dg.data() + (size_t)k * bs * bs;
       if (have_next) for (int t = 0; t < bs * bs; t++) Dk[t] = Dnext[t];
       else { for (int t = 0; t < bs * bs; t++) Dk[t] = Din[t]; for (int r = 0; r < bs; r++) Dk[r + r * bs] += lambda; }
       if (!have_next) { for (int c = 0; c < nb; c++) for (int r = 0; r < bs; r++) Pk[r + (size_t)c * bs] = sys.B[(size_t)k * bs * nb + r + (size_t)c * bs]; for (int r = 0; r < bs; r++) Pk[r + (size_t)nb * bs] = sys.gc[(size_t)k * bs + r]; }
       else Pk.swap(Pn);
       // Cholesky (lower) of Dk
-      double* Lk = &Lf[(size_t)k * bs * bs];
+      double* Lk = Lf.data() + (size_t)k * bs * bs;
       for (int t = 0; t < bs * bs; t++) Lk[t] = 0;
       for (int j = 0; j < bs; j++) {
         double d = Dk[j + j * bs];
@@ -521,7 +521,7 @@ struct Solver {
         for (int r = j + 1; r < bs; r++) { double s = Dk[r + j * bs]; for (int t = 0; t < j; t++) s -= Lk[r + t * bs] * Lk[j + t * bs]; Lk[r + j * bs] = s / ljj; }
       }
       // Y_k = L^-1 [B_k | g_k]
-      double* Yk = &Y[(size_t)k * bs * w];
+      double* Yk = Y.data() + (size_t)k * bs * w;
       for (int c = 0; c < w; c++) for (int r = 0; r < bs; r++) { double s = Pk[r + (size_t)c * bs]; for (int t = 0; t < r; t++) s -= Lk[r + t * bs] * Yk[t + (size_t)c * bs]; Yk[r + (size_t)c * bs] = s / Lk[r + r * bs]; }
       // border Schur: S -= Yb^T Yb ; sb -= Yb^T y
       for (int c2 = 0; c2 < nb; c2++) for (int c1 = c2; c1 < nb; c1++) { double s = 0; for (int r = 0; r < bs; r++) s += Yk[r + (size_t)c1 * bs] * Yk[r + (size_t)c2 * bs]; S[c1 + (size_t)c2 * nb] -= s; }
@@ -529,10 +529,10 @@ struct Solver {
       have_next = false;
       if (k + 1 < nc) {
         // Le = E_k L^-T  (E_k: rows k+1, cols k)
-        const double* Ek = &sys.E[(size_t)k * bs * bs];
-        double* Lek = &Le[(size_t)k * bs * bs];
+        const double* Ek = sys.E.data() + (size_t)k * bs * bs;
+        double* Lek = Le.data() + (size_t)k * bs * bs;
         for (int r = 0; r < bs; r++) for (int c = 0; c < bs; c++) { double s = Ek[r + c * bs]; for (int t = 0; t < c; t++) s -= Lek[r + t * bs] * Lk[c + t * bs]; Lek[r + c * bs] = s / Lk[c + c * bs]; }
-        const double* Dn = &sys.Dg[(size_t)(k + 1) * bs * bs];
+        const double* Dn = sys.Dg.data() + (size_t)(k + 1) * bs * bs;
         for (int c = 0; c < bs; c++) for (int r = 0; r < bs; r++) { double s = 0; for (int t = 0; t < bs; t++) s += Lek[r + t * bs] * Lek[c + t * bs]; Dnext[r + c * bs] = Dn[r + c * bs] - s + (r == c ? lambda : 0.0); }
         for (int c = 0; c < w; c++) for (int r = 0; r < bs; r++) {
           double s = (c < nb) ? sys.B[(size_t)(k + 1) * bs * nb + r + (size_t)c * bs] : sys.gc[(size_t)(k + 1) * bs + r];
@@ -556,10 +556,10 @@ struct Solver {
     // back-substitute chain
     std::vector<double> rhs(bs);
     for (int k = nc - 1; k >= 0; k--) {
-      const double* Lk = &Lf[(size_t)k * bs * bs];
-      const double* Yk = &Y[(size_t)k * bs * w];
+      const double* Lk = Lf.data() + (size_t)k * bs * bs;
+      const double* Yk = Y.data() + (size_t)k * bs * w;
       for (int r = 0; r < bs; r++) { double s = Yk[r + (size_t)nb * bs]; for (int c = 0; c < nb; c++) s -= Yk[r + (size_t)c * bs] * dborder[c]; rhs[r] = s; }
-      if (k + 1 < nc) { const double* Lek = &Le[(size_t)k * bs * bs]; for (int c = 0; c < bs; c++) { double s = 0; for (int r = 0; r < bs; r++) s += Lek[r + c * bs] * dchain[(size_t)(k + 1) * bs + r]; rhs[c] -= s; } }
+      if (k + 1 < nc) { const double* Lek = Le.data() + (size_t)k * bs * bs; for (int c = 0; c < bs; c++) { double s = 0; for (int r = 0; r < bs; r++) s += Lek[r + c * bs] * dchain[(size_t)(k + 1) * bs + r]; rhs[c] -= s; } }
       for (int r = bs - 1; r >= 0; r--) { double s = rhs[r]; for (int t = r + 1; t < bs; t++) s -= Lk[t + r * bs] * dchain[(size_t)k * bs + t]; dchain[(size_t)k * bs + r] = s / Lk[r + r * bs]; }
     }
     return true;
@@ -570,12 +570,12 @@ struct Solver {
     const int nc = sys.nc, bs = sys.bs, nb = sys.nb;
     double gd = 0, dHd = 0;
     for (int k = 0; k < nc; k++) {
-      const double* d = &dchain[(size_t)k * bs];
+      const double* d = dchain.data() + (size_t)k * bs;
       for (int r = 0; r < bs; r++) gd += sys.gc[(size_t)k * bs + r] * d[r];
-      const double* Dk = &sys.Dg[(size_t)k * bs * bs];
+      const double* Dk = sys.Dg.data() + (size_t)k * bs * bs;
       for (int c = 0; c < bs; c++) for (int r = 0; r < bs; r++) dHd += d[r] * Dk[r + c * bs] * d[c];
-      if (k + 1 < nc) { const double* Ek = &sys.E[(size_t)k * bs * bs]; const double* dn = &dchain[(size_t)(k + 1) * bs]; for (int c = 0; c < bs; c++) for (int r = 0; r < bs; r++) dHd += 2.0 * dn[r] * Ek[r + c * bs] * d[c]; }
-      const double* Bk = &sys.B[(size_t)k * bs * nb];
+      if (k + 1 < nc) { const double* Ek = sys.E.data() + (size_t)k * bs * bs; const double* dn = dchain.data() + (size_t)(k + 1) * bs; for (int c = 0; c < bs; c++) for (int r = 0; r < bs; r++) dHd += 2.0 * dn[r] * Ek[r + c * bs] * d[c]; }
+      const double* Bk = sys.B.data() + (size_t)k * bs * nb;
       for (int c = 0; c < nb; c++) for (int r = 0; r < bs; r++) dHd += 2.0 * d[r] * Bk[r + (size_t)c * bs] * dborder[c];
     }
     for (int r = 0; r < nb; r++) gd += sys.gb[r] * dborder[r];
